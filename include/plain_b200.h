@@ -1,0 +1,195 @@
+/* plain_b200.h - C-ABI of the B200 frame-path backend.
+ *
+ * Drop-in boundary for the per-pixel frame path of Gaukler/PlainRenderer: every entry point replaces one
+ * public method of `class RenderBackend` (reference Plain/src/Runtime/Rendering/Backend/RenderBackend.h:33-110)
+ * for the compute-pass subset the frame path uses. Passes are identified by the reference's shader file name
+ * (ResourceDescriptions.h:112-149), resources by integer handle + per-shader binding number
+ * (ResourceDescriptions.h:9-78), executions are replayed in submission order (RenderBackend.cpp:259-265,
+ * 769-786). Plain pointers and sizes only; no C++/torch types cross this boundary.
+ *
+ * All functions return 0 on success, non-zero on failure; plain_last_error() returns the message
+ * (the reference prints + throws instead, RenderBackend.cpp:442-445). Nothing throws across the ABI.
+ *
+ * The same header is implemented twice: by the CUDA backend (libplain_b200.so, symbols plain_*) and by the
+ * CPU oracle used only as the checker in tests/bench (oracle/, symbols oracle_*; select with
+ * -DPLAIN_FN_PREFIX=oracle_).
+ */
+#ifndef PLAIN_B200_H
+#define PLAIN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#ifndef PLAIN_FN_PREFIX
+#define PLAIN_FN_PREFIX plain_
+#endif
+#define PLAIN_CAT2(a, b) a##b
+#define PLAIN_CAT(a, b) PLAIN_CAT2(a, b)
+#define PLAIN_FN(name) PLAIN_CAT(PLAIN_FN_PREFIX, name)
+
+#if defined(__GNUC__)
+#define PLAIN_EXPORT __attribute__((visibility("default")))
+#else
+#define PLAIN_EXPORT
+#endif
+
+typedef struct plain_ctx plain_ctx;
+
+#define PLAIN_INVALID_INDEX 0xFFFFFFFFu /* RenderHandles.h:4 */
+
+/* ImageDescription.h:4-5 */
+typedef enum { PLAIN_IMAGE_TYPE_1D = 0, PLAIN_IMAGE_TYPE_2D = 1, PLAIN_IMAGE_TYPE_3D = 2, PLAIN_IMAGE_TYPE_CUBE = 3 } plain_image_type;
+typedef enum { PLAIN_MIPS_ONE = 0, PLAIN_MIPS_FULL_CHAIN = 1, PLAIN_MIPS_MANUAL = 2, PLAIN_MIPS_FULL_CHAIN_ALREADY_IN_DATA = 3 } plain_mip_count;
+/* ImageDescription.h:7-11 */
+enum { PLAIN_USAGE_STORAGE = 1, PLAIN_USAGE_SAMPLED = 2, PLAIN_USAGE_ATTACHMENT = 4 };
+
+/* ImageDescription.h:16, same order. PLAIN_FORMAT_RGBA32_UINT is new: the packed G-buffer texel. */
+typedef enum {
+    PLAIN_FORMAT_R8 = 0,
+    PLAIN_FORMAT_RG8,
+    PLAIN_FORMAT_RGBA8,
+    PLAIN_FORMAT_R16_SFLOAT,
+    PLAIN_FORMAT_RG16_SFLOAT,
+    PLAIN_FORMAT_RG32_SFLOAT,
+    PLAIN_FORMAT_RG16_SNORM,
+    PLAIN_FORMAT_RGBA16_SFLOAT,
+    PLAIN_FORMAT_RGBA16_SNORM,
+    PLAIN_FORMAT_RGBA32_SFLOAT,
+    PLAIN_FORMAT_R11G11B10_UFLOAT,
+    PLAIN_FORMAT_DEPTH16,
+    PLAIN_FORMAT_DEPTH32,
+    PLAIN_FORMAT_BC1,
+    PLAIN_FORMAT_BC3,
+    PLAIN_FORMAT_BC5,
+    PLAIN_FORMAT_BGRA8_UNORM,
+    PLAIN_FORMAT_RGBA32_UINT,
+    PLAIN_FORMAT_COUNT
+} plain_image_format;
+
+/* ImageDescription.h:18-30 */
+typedef struct {
+    uint32_t width, height, depth;
+    uint32_t type;             /* plain_image_type */
+    uint32_t format;           /* plain_image_format */
+    uint32_t usage_flags;      /* PLAIN_USAGE_* */
+    uint32_t mip_count;        /* plain_mip_count */
+    uint32_t manual_mip_count; /* only if mip_count == PLAIN_MIPS_MANUAL */
+    uint32_t auto_create_mips;
+} plain_image_desc;
+
+/* RenderHandles.h:16-21 */
+typedef enum { PLAIN_IMAGE_HANDLE_DEFAULT = 0, PLAIN_IMAGE_HANDLE_TRANSIENT = 1, PLAIN_IMAGE_HANDLE_SWAPCHAIN = 2 } plain_image_handle_type;
+typedef struct {
+    uint32_t type; /* plain_image_handle_type */
+    uint32_t index;
+} plain_image_handle;
+typedef uint32_t plain_handle; /* {uint32_t index} handles: pass, sampler, uniform buffer, storage buffer */
+
+/* ResourceDescriptions.h:163-172 */
+typedef enum { PLAIN_SAMPLER_NEAREST = 0, PLAIN_SAMPLER_LINEAR = 1 } plain_sampler_interpolation;
+typedef enum { PLAIN_WRAP_CLAMP = 0, PLAIN_WRAP_COLOR = 1, PLAIN_WRAP_REPEAT = 2 } plain_sampler_wrapping;
+typedef enum { PLAIN_BORDER_WHITE = 0, PLAIN_BORDER_BLACK = 1 } plain_sampler_border;
+typedef struct {
+    uint32_t interpolation, wrapping, use_anisotropy;
+    float max_anisotropy;
+    uint32_t border_color, max_mip;
+} plain_sampler_desc;
+
+/* ResourceDescriptions.h:112-120 */
+typedef struct {
+    uint32_t location;
+    const void* data;
+    uint32_t size;
+} plain_spec_const;
+
+/* ResourceDescriptions.h:9-53 */
+typedef struct { plain_handle buffer; uint32_t read_only; uint32_t binding; } plain_storage_buffer_resource;
+typedef struct { plain_handle buffer; uint32_t binding; } plain_uniform_buffer_resource;
+typedef struct { plain_image_handle image; uint32_t mip_level; uint32_t binding; } plain_image_resource;
+typedef struct { plain_handle sampler; uint32_t binding; } plain_sampler_resource;
+
+typedef struct {
+    const plain_sampler_resource* samplers; uint32_t n_samplers;
+    const plain_storage_buffer_resource* storage_buffers; uint32_t n_storage_buffers;
+    const plain_uniform_buffer_resource* uniform_buffers; uint32_t n_uniform_buffers;
+    const plain_image_resource* sampled_images; uint32_t n_sampled_images;
+    const plain_image_resource* storage_images; uint32_t n_storage_images;
+} plain_pass_resources;
+
+/* ComputePassExecution, ResourceDescriptions.h:73-78 */
+typedef struct {
+    plain_handle pass;
+    plain_pass_resources resources;
+    const void* push_constants; uint32_t push_constant_size;
+    uint32_t dispatch_count[3];
+} plain_compute_pass_execution;
+
+/* VulkanTimestampQueries.h:16-20 */
+typedef struct {
+    char name[64];
+    float time_ms;
+} plain_pass_time;
+
+/* ---- lifetime: RenderBackend::setup / shutdown (RenderBackend.cpp:47-92); output size replaces the swapchain ---- */
+PLAIN_EXPORT int PLAIN_FN(backend_create)(int device, uint32_t width, uint32_t height, plain_ctx** out_ctx);
+PLAIN_EXPORT void PLAIN_FN(backend_destroy)(plain_ctx* ctx);
+PLAIN_EXPORT const char* PLAIN_FN(last_error)(plain_ctx* ctx);
+/* recreateSwapchain (RenderBackend.h:37) */
+PLAIN_EXPORT int PLAIN_FN(recreate_swapchain)(plain_ctx* ctx, uint32_t width, uint32_t height);
+
+/* ---- resources (RenderBackend.h:84-110) ---- */
+PLAIN_EXPORT int PLAIN_FN(create_image)(plain_ctx* ctx, const plain_image_desc* desc, const void* initial_data, size_t initial_data_size, plain_image_handle* out);
+PLAIN_EXPORT int PLAIN_FN(create_temporary_image)(plain_ctx* ctx, const plain_image_desc* desc, plain_image_handle* out);
+PLAIN_EXPORT int PLAIN_FN(resize_images)(plain_ctx* ctx, const plain_image_handle* images, uint32_t n, uint32_t width, uint32_t height);
+PLAIN_EXPORT int PLAIN_FN(get_image_description)(plain_ctx* ctx, plain_image_handle image, plain_image_desc* out);
+PLAIN_EXPORT int PLAIN_FN(get_image_global_texture_array_index)(plain_ctx* ctx, plain_image_handle image, uint32_t* out);
+PLAIN_EXPORT int PLAIN_FN(create_uniform_buffer)(plain_ctx* ctx, size_t size, const void* initial_data, plain_handle* out);
+PLAIN_EXPORT int PLAIN_FN(create_storage_buffer)(plain_ctx* ctx, size_t size, const void* initial_data, plain_handle* out);
+PLAIN_EXPORT int PLAIN_FN(create_sampler)(plain_ctx* ctx, const plain_sampler_desc* desc, plain_handle* out);
+PLAIN_EXPORT int PLAIN_FN(get_swapchain_input_image)(plain_ctx* ctx, plain_image_handle* out);
+
+/* ---- passes: createComputePass / updateComputePassShaderDescription (RenderBackend.h:77-96) ---- */
+PLAIN_EXPORT int PLAIN_FN(create_compute_pass)(plain_ctx* ctx, const char* shader_src_path_relative, const plain_spec_const* consts, uint32_t n_consts, const char* debug_name, plain_handle* out);
+PLAIN_EXPORT int PLAIN_FN(update_compute_pass_shader_description)(plain_ctx* ctx, plain_handle pass, const char* shader_src_path_relative, const plain_spec_const* consts, uint32_t n_consts);
+/* setGlobalDescriptorSetResources (RenderBackend.h:73): set 0 = global UBO + the 8 immutable samplers (global.inc:4-42) */
+PLAIN_EXPORT int PLAIN_FN(set_global_descriptor_set_resources)(plain_ctx* ctx, const plain_pass_resources* resources);
+
+/* ---- frame protocol (RenderBackend.h:49-82) ---- */
+PLAIN_EXPORT int PLAIN_FN(new_frame)(plain_ctx* ctx);
+PLAIN_EXPORT int PLAIN_FN(set_compute_pass_execution)(plain_ctx* ctx, const plain_compute_pass_execution* execution);
+PLAIN_EXPORT int PLAIN_FN(prepare_for_drawcall_recording)(plain_ctx* ctx);
+/* data is copied before the call returns; the device copy lands before any pass of the frame (RenderBackend.cpp:315-321, 896-911) */
+PLAIN_EXPORT int PLAIN_FN(set_uniform_buffer_data)(plain_ctx* ctx, plain_handle buffer, const void* data, size_t size);
+PLAIN_EXPORT int PLAIN_FN(set_storage_buffer_data)(plain_ctx* ctx, plain_handle buffer, const void* data, size_t size);
+PLAIN_EXPORT int PLAIN_FN(render_frame)(plain_ctx* ctx, int present_to_screen);
+PLAIN_EXPORT int PLAIN_FN(wait_for_gpu_idle)(plain_ctx* ctx);
+PLAIN_EXPORT int PLAIN_FN(get_renderpass_timings)(plain_ctx* ctx, plain_pass_time* out, uint32_t capacity, uint32_t* out_count);
+PLAIN_EXPORT int PLAIN_FN(set_timing_enabled)(plain_ctx* ctx, int enabled);
+
+/* ---- additions (not in the reference): the raster passes that produce depth/motion/normal/shadow maps/G-buffer are
+ * out of scope, so their outputs are uploaded; read-back exists for parity tests and the e2e bench leg. Synchronous. ---- */
+PLAIN_EXPORT int PLAIN_FN(write_image)(plain_ctx* ctx, plain_image_handle image, uint32_t mip_level, const void* data, size_t size);
+PLAIN_EXPORT int PLAIN_FN(read_image)(plain_ctx* ctx, plain_image_handle image, uint32_t mip_level, void* out, size_t size);
+PLAIN_EXPORT int PLAIN_FN(read_storage_buffer)(plain_ctx* ctx, plain_handle buffer, void* out, size_t size);
+/* async variants on the backend stream with caller-pinned host memory (e2e leg: upload of the frame inputs, read-back of the frame) */
+PLAIN_EXPORT int PLAIN_FN(write_image_async)(plain_ctx* ctx, plain_image_handle image, uint32_t mip_level, const void* pinned_data, size_t size);
+PLAIN_EXPORT int PLAIN_FN(read_image_async)(plain_ctx* ctx, plain_image_handle image, uint32_t mip_level, void* pinned_out, size_t size);
+/* device pointer of mip 0 (CUDA backend only; oracle returns the host pointer). Lets a caller that owns device memory
+ * (e.g. a torch tensor holding a shard received over NCCL) fill an image without a host round trip. */
+PLAIN_EXPORT int PLAIN_FN(get_image_device_pointer)(plain_ctx* ctx, plain_image_handle image, uint32_t mip_level, void** out_ptr, size_t* out_size);
+PLAIN_EXPORT int PLAIN_FN(get_storage_buffer_device_pointer)(plain_ctx* ctx, plain_handle buffer, void** out_ptr, size_t* out_size);
+/* number of kernels launched by the last render_frame (bench "gpu_launches") */
+PLAIN_EXPORT int PLAIN_FN(get_last_frame_launch_count)(plain_ctx* ctx, uint32_t* out);
+/* enable replay of an unchanged pass list through a captured CUDA graph (CUDA backend; no-op in the oracle) */
+PLAIN_EXPORT int PLAIN_FN(set_graph_replay_enabled)(plain_ctx* ctx, int enabled);
+/* the stream all passes run on (cudaStream_t as void*), for callers that time with CUDA events */
+PLAIN_EXPORT int PLAIN_FN(get_stream)(plain_ctx* ctx, void** out_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PLAIN_B200_H */

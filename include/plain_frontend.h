@@ -1,0 +1,103 @@
+/* plain_frontend.h - C entry points of the host-side frame driver (mirror of the reference's RenderFrontend +
+ * technique classes, plainrenderer_b200/host/), for callers that are not C++ (tests, bench.py). One frame =
+ * main.cpp:79-90 of the reference: markNewFrame -> prepareNewFrame -> setCameraExtrinsic -> prepareForDrawcalls ->
+ * renderScene -> renderFrame, with the raster passes' outputs supplied by the caller.
+ *
+ * Built twice from the same sources: against the CUDA backend (symbols plain_frontend_*) and, for tests/bench
+ * cpu_baseline only, against the CPU oracle backend (symbols oracle_frontend_*; -DPLAIN_FRONTEND_PREFIX=oracle_frontend_).
+ */
+#ifndef PLAIN_FRONTEND_H
+#define PLAIN_FRONTEND_H
+#include "plain_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#ifndef PLAIN_FRONTEND_PREFIX
+#define PLAIN_FRONTEND_PREFIX plain_frontend_
+#endif
+#define PLAIN_FE(name) PLAIN_CAT(PLAIN_FRONTEND_PREFIX, name)
+
+typedef struct plain_frontend plain_frontend;
+
+/* defaults = the reference's default member initialisers (SURVEY.md section 5 "Config / flags") */
+typedef struct {
+    uint32_t width, height;
+    int32_t diffuse_brdf;             /* 0 lambert, 1 disney, 2 CoD WWII (default), 3 titanfall 2 */
+    int32_t direct_multiscatter;      /* 0 McAuley (default) */
+    int32_t indirect_lighting_tech;   /* 0 SDF trace (default), 1 constant ambient */
+    int32_t use_geometry_aa;          /* default 1 */
+    int32_t sun_shadow_cascade_count; /* default 3 */
+    int32_t half_res_trace;           /* default 1 */
+    int32_t strict_influence_radius_cutoff; /* default 1 */
+    float trace_influence_radius;     /* default 5 */
+    int32_t taa_enabled;              /* default 1 */
+    int32_t taa_use_clipping, taa_use_motion_vector_dilation, taa_history_sampling_tech, taa_filter_use_tonemapping; /* 1,1,4,1 */
+    int32_t bloom_enabled;            /* default 1 */
+    float bloom_strength, bloom_radius; /* 0.05, 1.5 */
+    float sun_direction_deg[2];       /* (phi, theta) as RenderFrontend::m_sunDirection */
+    float camera_fov_deg, camera_near, camera_far; /* 35, 0.1, 300 */
+    uint32_t noise_seed;
+} plain_frontend_settings;
+
+/* host pointers to the outputs of the out-of-scope raster passes for one frame */
+typedef struct {
+    const void* depth;        /* D32F, w*h*4 (depthPrepass) */
+    const void* motion;       /* RG16_SNORM, w*h*4 */
+    const void* normal;       /* RGBA8 world-space geometric normal, w*h*4 */
+    const void* gbuffer;      /* RGBA32_UINT packed G-buffer, w*h*16 (include/plain_frame_types.h) */
+    const void* shadow_maps[4]; /* D16 2048x2048 each, may be NULL to keep the previous contents */
+    int32_t async_upload;     /* 1: pointers are pinned host memory, copies go through the backend stream */
+} plain_frame_inputs;
+
+typedef struct {
+    float position[3], forward[3], right[3], up[3];
+} plain_camera_extrinsic;
+
+PLAIN_EXPORT void PLAIN_FE(default_settings)(plain_frontend_settings* out, uint32_t width, uint32_t height);
+PLAIN_EXPORT int PLAIN_FE(create)(int device, const plain_frontend_settings* settings, plain_frontend** out);
+PLAIN_EXPORT void PLAIN_FE(destroy)(plain_frontend* fe);
+PLAIN_EXPORT const char* PLAIN_FE(last_error)(plain_frontend* fe);
+PLAIN_EXPORT plain_ctx* PLAIN_FE(backend)(plain_frontend* fe);
+
+/* scene: SDF meshes (3-D R16F bricks) and objects instancing them (RenderFrontend::registerMeshes / App scene) */
+PLAIN_EXPORT int PLAIN_FE(register_sdf_mesh)(plain_frontend* fe, const uint16_t* r16f_texels, uint32_t rx, uint32_t ry, uint32_t rz,
+                                             const float local_bb_min[3], const float local_bb_max[3], const float mean_albedo[3], uint32_t* out_mesh);
+PLAIN_EXPORT int PLAIN_FE(set_scene)(plain_frontend* fe, uint32_t n_objects, const uint32_t* mesh_indices, const float* model_matrices /* 16 each, column-major */,
+                                     const float* bb_world_min /* 3 each */, const float* bb_world_max /* 3 each */);
+
+/* one frame */
+PLAIN_EXPORT int PLAIN_FE(render_frame)(plain_frontend* fe, const plain_camera_extrinsic* camera, float time, float delta_time, const plain_frame_inputs* inputs);
+/* read back the tonemapped B8G8R8A8 frame (w*h*4) */
+PLAIN_EXPORT int PLAIN_FE(read_output)(plain_frontend* fe, void* out, size_t size, int32_t async_pinned);
+
+/* named resources, for parity tests: images "color0|color1|depth0|depth1|motion0|motion1|post0|post1|normal|gbuffer|depthHalf|hiz|
+ * brdfLut|skyTransmission|skyMultiscatter|skyLut|shadow0..3|giY0|giY1|giC0|giC1|giHistY0|giHistY1|giHistC0|giHistC1|giFullY|giFullC|
+ * froxelMaterial|froxelScatter|froxelHist0|froxelHist1|froxelIntegration|taaHist0|taaHist1|bloomDown|bloomUp|output";
+ * buffers "histogram|histogramPerTile|light|sunShadowInfo|sdfInstances|sdfCulled|sdfTiles" */
+PLAIN_EXPORT int PLAIN_FE(get_image)(plain_frontend* fe, const char* name, plain_image_handle* out);
+PLAIN_EXPORT int PLAIN_FE(get_storage_buffer)(plain_frontend* fe, const char* name, plain_handle* out);
+PLAIN_EXPORT int PLAIN_FE(get_global_shader_info)(plain_frontend* fe, void* out_340_bytes);
+PLAIN_EXPORT int PLAIN_FE(get_resolve_weights)(plain_frontend* fe, float out[9]);
+/* preset the exposure state (LightBuffer.previousFrameExposure) so short test sequences start adapted */
+PLAIN_EXPORT int PLAIN_FE(set_exposure)(plain_frontend* fe, float previous_frame_exposure);
+
+/* ---- synthetic scene (stand-in for the .plain loader + raster passes): boxes with analytic SDF bricks,
+ * and a CPU ray caster producing depth / motion / normal / G-buffer / shadow maps for a camera. Host-only. ---- */
+typedef struct plain_synthetic_scene plain_synthetic_scene;
+PLAIN_EXPORT int PLAIN_FE(synthetic_scene_create)(uint32_t seed, uint32_t n_instances, plain_synthetic_scene** out);
+PLAIN_EXPORT void PLAIN_FE(synthetic_scene_destroy)(plain_synthetic_scene* s);
+/* registers meshes + objects of the scene with the frontend */
+PLAIN_EXPORT int PLAIN_FE(synthetic_scene_attach)(plain_synthetic_scene* s, plain_frontend* fe);
+/* ray-casts the raster-pass outputs for one frame into caller buffers (sizes as in plain_frame_inputs). frame_index selects the
+ * TAA jitter (Halton(2,3)[frame_index % 8]); previous_camera may be NULL (static camera). shadow maps are rendered when the
+ * pointers are non-NULL. threads = 0 -> all cores */
+PLAIN_EXPORT int PLAIN_FE(synthetic_scene_render_inputs)(plain_synthetic_scene* s, const plain_frontend_settings* settings, const plain_camera_extrinsic* camera,
+                                                         const plain_camera_extrinsic* previous_camera, uint32_t frame_index, void* depth, void* motion, void* normal,
+                                                         void* gbuffer, void* const shadow_maps[4], int32_t threads);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,413 @@
+"""ctypes bindings for the C-ABI in include/plain_b200.h and include/plain_frontend.h.
+
+`Api(path, fn_prefix, fe_prefix)` binds one shared library. The product library is bound by
+`plainrenderer_b200.load()` (prefixes ``plain_`` / ``plain_frontend_``); tests bind the CPU oracle with the
+same class and the ``oracle_`` prefixes - the structures are identical by construction (one header).
+"""
+import ctypes as C
+import numpy as np
+
+u32, i32, f32 = C.c_uint32, C.c_int32, C.c_float
+
+# plain_image_format (ImageDescription.h:16 order + RGBA32_UINT)
+FORMATS = ["R8", "RG8", "RGBA8", "R16_SFLOAT", "RG16_SFLOAT", "RG32_SFLOAT", "RG16_SNORM", "RGBA16_SFLOAT", "RGBA16_SNORM",
+           "RGBA32_SFLOAT", "R11G11B10_UFLOAT", "DEPTH16", "DEPTH32", "BC1", "BC3", "BC5", "BGRA8_UNORM", "RGBA32_UINT"]
+FORMAT = {n: i for i, n in enumerate(FORMATS)}
+BYTES_PER_TEXEL = {"R8": 1, "RG8": 2, "RGBA8": 4, "R16_SFLOAT": 2, "RG16_SFLOAT": 4, "RG32_SFLOAT": 8, "RG16_SNORM": 4, "RGBA16_SFLOAT": 8,
+                   "RGBA16_SNORM": 8, "RGBA32_SFLOAT": 16, "R11G11B10_UFLOAT": 4, "DEPTH16": 2, "DEPTH32": 4, "BGRA8_UNORM": 4, "RGBA32_UINT": 16}
+IMAGE_1D, IMAGE_2D, IMAGE_3D, IMAGE_CUBE = 0, 1, 2, 3
+MIPS_ONE, MIPS_FULL_CHAIN, MIPS_MANUAL, MIPS_IN_DATA = 0, 1, 2, 3
+USAGE_STORAGE, USAGE_SAMPLED, USAGE_ATTACHMENT = 1, 2, 4
+
+
+class ImageDesc(C.Structure):
+    _fields_ = [("width", u32), ("height", u32), ("depth", u32), ("type", u32), ("format", u32), ("usage_flags", u32),
+                ("mip_count", u32), ("manual_mip_count", u32), ("auto_create_mips", u32)]
+
+
+class ImageHandle(C.Structure):
+    _fields_ = [("type", u32), ("index", u32)]
+
+
+class SamplerDesc(C.Structure):
+    _fields_ = [("interpolation", u32), ("wrapping", u32), ("use_anisotropy", u32), ("max_anisotropy", f32), ("border_color", u32), ("max_mip", u32)]
+
+
+class SpecConst(C.Structure):
+    _fields_ = [("location", u32), ("data", C.c_void_p), ("size", u32)]
+
+
+class StorageBufferResource(C.Structure):
+    _fields_ = [("buffer", u32), ("read_only", u32), ("binding", u32)]
+
+
+class UniformBufferResource(C.Structure):
+    _fields_ = [("buffer", u32), ("binding", u32)]
+
+
+class ImageResource(C.Structure):
+    _fields_ = [("image", ImageHandle), ("mip_level", u32), ("binding", u32)]
+
+
+class SamplerResource(C.Structure):
+    _fields_ = [("sampler", u32), ("binding", u32)]
+
+
+class PassResources(C.Structure):
+    _fields_ = [("samplers", C.POINTER(SamplerResource)), ("n_samplers", u32),
+                ("storage_buffers", C.POINTER(StorageBufferResource)), ("n_storage_buffers", u32),
+                ("uniform_buffers", C.POINTER(UniformBufferResource)), ("n_uniform_buffers", u32),
+                ("sampled_images", C.POINTER(ImageResource)), ("n_sampled_images", u32),
+                ("storage_images", C.POINTER(ImageResource)), ("n_storage_images", u32)]
+
+
+class ComputePassExecution(C.Structure):
+    _fields_ = [("pass_", u32), ("resources", PassResources), ("push_constants", C.c_void_p), ("push_constant_size", u32), ("dispatch_count", u32 * 3)]
+
+
+class PassTime(C.Structure):
+    _fields_ = [("name", C.c_char * 64), ("time_ms", f32)]
+
+
+class GlobalShaderInfo(C.Structure):  # include/plain_frame_types.h plain_global_shader_info
+    _fields_ = [("viewProjection", f32 * 16), ("viewProjectionPrevious", f32 * 16), ("sunDirection", f32 * 4), ("cameraPosition", f32 * 4),
+                ("cameraPositionPrevious", f32 * 4), ("cameraRight", f32 * 4), ("cameraUp", f32 * 4), ("cameraForward", f32 * 4),
+                ("cameraForwardPrevious", f32 * 4), ("noiseTextureIndices", i32 * 4), ("currentFrameCameraJitter", f32 * 2),
+                ("previousFrameCameraJitter", f32 * 2), ("screenResolution", i32 * 2), ("cameraTanFovHalf", f32), ("cameraAspectRatio", f32),
+                ("nearPlane", f32), ("farPlane", f32), ("sunStrength", f32), ("exposureOffset", f32), ("exposureAdaptionSpeedEvPerSec", f32),
+                ("deltaTime", f32), ("time", f32), ("mipBias", f32), ("cameraCut", u32), ("frameIndex", u32), ("frameIndexMod2", u32),
+                ("frameIndexMod3", u32), ("frameIndexMod4", u32)]
+
+
+class FrontendSettings(C.Structure):
+    _fields_ = [("width", u32), ("height", u32), ("diffuse_brdf", i32), ("direct_multiscatter", i32), ("indirect_lighting_tech", i32),
+                ("use_geometry_aa", i32), ("sun_shadow_cascade_count", i32), ("half_res_trace", i32), ("strict_influence_radius_cutoff", i32),
+                ("trace_influence_radius", f32), ("taa_enabled", i32), ("taa_use_clipping", i32), ("taa_use_motion_vector_dilation", i32),
+                ("taa_history_sampling_tech", i32), ("taa_filter_use_tonemapping", i32), ("bloom_enabled", i32), ("bloom_strength", f32),
+                ("bloom_radius", f32), ("sun_direction_deg", f32 * 2), ("camera_fov_deg", f32), ("camera_near", f32), ("camera_far", f32),
+                ("noise_seed", u32)]
+
+
+class FrameInputs(C.Structure):
+    _fields_ = [("depth", C.c_void_p), ("motion", C.c_void_p), ("normal", C.c_void_p), ("gbuffer", C.c_void_p), ("shadow_maps", C.c_void_p * 4), ("async_upload", i32)]
+
+
+class CameraExtrinsic(C.Structure):
+    _fields_ = [("position", f32 * 3), ("forward", f32 * 3), ("right", f32 * 3), ("up", f32 * 3)]
+
+
+BACKEND_SYMBOLS = [
+    "backend_create", "backend_destroy", "last_error", "recreate_swapchain", "create_image", "create_temporary_image", "resize_images",
+    "get_image_description", "get_image_global_texture_array_index", "create_uniform_buffer", "create_storage_buffer", "create_sampler",
+    "get_swapchain_input_image", "create_compute_pass", "update_compute_pass_shader_description", "set_global_descriptor_set_resources",
+    "new_frame", "set_compute_pass_execution", "prepare_for_drawcall_recording", "set_uniform_buffer_data", "set_storage_buffer_data",
+    "render_frame", "wait_for_gpu_idle", "get_renderpass_timings", "set_timing_enabled", "write_image", "read_image", "read_storage_buffer",
+    "write_image_async", "read_image_async", "get_image_device_pointer", "get_storage_buffer_device_pointer", "get_last_frame_launch_count",
+    "set_graph_replay_enabled", "get_stream"]
+FRONTEND_SYMBOLS = [
+    "default_settings", "create", "destroy", "last_error", "backend", "register_sdf_mesh", "set_scene", "render_frame", "read_output", "get_image",
+    "get_storage_buffer", "get_global_shader_info", "get_resolve_weights", "set_exposure", "synthetic_scene_create", "synthetic_scene_destroy",
+    "synthetic_scene_attach", "synthetic_scene_render_inputs"]
+
+
+class ApiError(RuntimeError):
+    pass
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+class Api:
+    """One loaded library exposing the backend C-ABI (`b_*`) and the frontend C API (`f_*`)."""
+
+    def __init__(self, path, fn_prefix="plain_", fe_prefix="plain_frontend_"):
+        self.path = str(path)
+        self.lib = C.CDLL(self.path, mode=C.RTLD_LOCAL)
+        self.fn_prefix, self.fe_prefix = fn_prefix, fe_prefix
+        self.b, self.f = {}, {}
+        for s in BACKEND_SYMBOLS:
+            self.b[s] = getattr(self.lib, fn_prefix + s)  # AttributeError if the library does not export it
+        for s in FRONTEND_SYMBOLS:
+            fn = getattr(self.lib, fe_prefix + s, None)
+            if fn is not None:
+                self.f[s] = fn
+        self.b["last_error"].restype = C.c_char_p
+        self.b["backend_destroy"].restype = None
+        if "last_error" in self.f:
+            self.f["last_error"].restype = C.c_char_p
+            self.f["backend"].restype = C.c_void_p
+            self.f["destroy"].restype = None
+            self.f["default_settings"].restype = None
+            self.f["synthetic_scene_destroy"].restype = None
+
+
+class Backend:
+    """Thin object wrapper over a `plain_ctx*` (reference `RenderBackend` method names, snake_case)."""
+
+    def __init__(self, api, device=0, width=64, height=64, ctx=None):
+        self.api = api
+        self.owned = ctx is None
+        if ctx is None:
+            p = C.c_void_p()
+            if api.b["backend_create"](C.c_int(device), u32(width), u32(height), C.byref(p)):
+                raise ApiError("backend_create failed")
+            ctx = p
+        self.ctx = C.c_void_p(ctx) if not isinstance(ctx, C.c_void_p) else ctx
+        self._keep = []
+
+    def close(self):
+        if self.owned and self.ctx:
+            self.api.b["backend_destroy"](self.ctx)
+        self.ctx = None
+
+    def _check(self, rc, what):
+        if rc:
+            raise ApiError("%s: %s" % (what, self.api.b["last_error"](self.ctx).decode()))
+
+    def create_image(self, width, height, fmt, depth=1, type_=IMAGE_2D, usage=USAGE_STORAGE | USAGE_SAMPLED, mips=MIPS_ONE, manual_mips=1, data=None):
+        d = ImageDesc(width, height, depth, type_, FORMAT[fmt], usage, mips, manual_mips, 0)
+        h = ImageHandle()
+        if data is not None:
+            data = np.ascontiguousarray(data)
+        self._check(self.api.b["create_image"](self.ctx, C.byref(d), _ptr(data), C.c_size_t(0 if data is None else data.nbytes), C.byref(h)), "create_image")
+        return h
+
+    def create_temporary_image(self, width, height, fmt, mips=MIPS_ONE, manual_mips=1):
+        d = ImageDesc(width, height, 1, IMAGE_2D, FORMAT[fmt], USAGE_STORAGE | USAGE_SAMPLED, mips, manual_mips, 0)
+        h = ImageHandle()
+        self._check(self.api.b["create_temporary_image"](self.ctx, C.byref(d), C.byref(h)), "create_temporary_image")
+        return h
+
+    def image_description(self, h):
+        d = ImageDesc()
+        self._check(self.api.b["get_image_description"](self.ctx, h, C.byref(d)), "get_image_description")
+        return d
+
+    def mip_shape(self, h, mip=0):
+        d = self.image_description(h)
+        return max(d.width >> mip, 1), max(d.height >> mip, 1), max(max(d.depth, 1) >> mip, 1), FORMATS[d.format]
+
+    def global_texture_index(self, h):
+        i = u32()
+        self._check(self.api.b["get_image_global_texture_array_index"](self.ctx, h, C.byref(i)), "global texture index")
+        return i.value
+
+    def create_storage_buffer(self, size, data=None):
+        h = u32()
+        if data is not None:
+            data = np.ascontiguousarray(data)
+        self._check(self.api.b["create_storage_buffer"](self.ctx, C.c_size_t(size), _ptr(data), C.byref(h)), "create_storage_buffer")
+        return h.value
+
+    def create_uniform_buffer(self, size, data=None):
+        h = u32()
+        if data is not None:
+            data = np.ascontiguousarray(data)
+        self._check(self.api.b["create_uniform_buffer"](self.ctx, C.c_size_t(size), _ptr(data), C.byref(h)), "create_uniform_buffer")
+        return h.value
+
+    def swapchain_image(self):
+        h = ImageHandle()
+        self._check(self.api.b["get_swapchain_input_image"](self.ctx, C.byref(h)), "get_swapchain_input_image")
+        return h
+
+    def create_compute_pass(self, shader, spec=None, name=None):
+        """spec: {location: bytes-like or numpy scalar}"""
+        spec = spec or {}
+        keep = [np.frombuffer(bytes(v) if isinstance(v, (bytes, bytearray)) else np.asarray(v).tobytes(), np.uint8).copy() for v in spec.values()]
+        arr = (SpecConst * max(len(spec), 1))()
+        for i, (loc, k) in enumerate(zip(spec.keys(), keep)):
+            arr[i] = SpecConst(loc, k.ctypes.data, k.nbytes)
+        h = u32()
+        self._check(self.api.b["create_compute_pass"](self.ctx, shader.encode(), arr, u32(len(spec)), (name or shader).encode(), C.byref(h)), "create_compute_pass(%s)" % shader)
+        return h.value
+
+    def set_global_uniform_buffer(self, buffer):
+        ub = (UniformBufferResource * 1)(UniformBufferResource(buffer, 0))
+        r = PassResources()
+        r.uniform_buffers, r.n_uniform_buffers = ub, 1
+        self._check(self.api.b["set_global_descriptor_set_resources"](self.ctx, C.byref(r)), "set_global_descriptor_set_resources")
+
+    def new_frame(self):
+        self._check(self.api.b["new_frame"](self.ctx), "new_frame")
+
+    def set_compute_pass_execution(self, pass_, dispatch, sampled=(), storage=(), storage_buffers=(), uniform_buffers=(), push=None):
+        """sampled/storage: [(handle, mip, binding)]; storage_buffers: [(handle, read_only, binding)]; uniform_buffers: [(handle, binding)]"""
+        e = ComputePassExecution()
+        e.pass_ = pass_
+        si = (ImageResource * max(len(sampled), 1))(*[ImageResource(h, m, b) for h, m, b in sampled])
+        st = (ImageResource * max(len(storage), 1))(*[ImageResource(h, m, b) for h, m, b in storage])
+        sb = (StorageBufferResource * max(len(storage_buffers), 1))(*[StorageBufferResource(h, int(ro), b) for h, ro, b in storage_buffers])
+        ub = (UniformBufferResource * max(len(uniform_buffers), 1))(*[UniformBufferResource(h, b) for h, b in uniform_buffers])
+        e.resources.sampled_images, e.resources.n_sampled_images = si, len(sampled)
+        e.resources.storage_images, e.resources.n_storage_images = st, len(storage)
+        e.resources.storage_buffers, e.resources.n_storage_buffers = sb, len(storage_buffers)
+        e.resources.uniform_buffers, e.resources.n_uniform_buffers = ub, len(uniform_buffers)
+        pc = None
+        if push is not None:
+            pc = np.frombuffer(bytes(push), np.uint8).copy()
+            e.push_constants, e.push_constant_size = pc.ctypes.data, pc.nbytes
+        for i in range(3):
+            e.dispatch_count[i] = dispatch[i] if i < len(dispatch) else 1
+        self._check(self.api.b["set_compute_pass_execution"](self.ctx, C.byref(e)), "set_compute_pass_execution")
+
+    def set_uniform_buffer_data(self, h, data):
+        data = np.frombuffer(bytes(data), np.uint8) if not isinstance(data, np.ndarray) else np.ascontiguousarray(data)
+        self._check(self.api.b["set_uniform_buffer_data"](self.ctx, u32(h), _ptr(data), C.c_size_t(data.nbytes)), "set_uniform_buffer_data")
+
+    def set_storage_buffer_data(self, h, data):
+        data = np.frombuffer(bytes(data), np.uint8) if not isinstance(data, np.ndarray) else np.ascontiguousarray(data)
+        self._check(self.api.b["set_storage_buffer_data"](self.ctx, u32(h), _ptr(data), C.c_size_t(data.nbytes)), "set_storage_buffer_data")
+
+    def render_frame(self):
+        self._check(self.api.b["prepare_for_drawcall_recording"](self.ctx), "prepare_for_drawcall_recording")
+        self._check(self.api.b["render_frame"](self.ctx, C.c_int(1)), "render_frame")
+        self._check(self.api.b["wait_for_gpu_idle"](self.ctx), "wait_for_gpu_idle")
+
+    def write_image(self, h, data, mip=0):
+        data = np.ascontiguousarray(data)
+        self._check(self.api.b["write_image"](self.ctx, h, u32(mip), _ptr(data), C.c_size_t(data.nbytes)), "write_image")
+
+    def read_image(self, h, mip=0, dtype=np.uint8):
+        w, hh, d, fmt = self.mip_shape(h, mip)
+        out = np.empty(w * hh * d * BYTES_PER_TEXEL[fmt], np.uint8)
+        self._check(self.api.b["read_image"](self.ctx, h, u32(mip), _ptr(out), C.c_size_t(out.nbytes)), "read_image")
+        return out.view(dtype)
+
+    def read_storage_buffer(self, h, size, dtype=np.uint8):
+        out = np.empty(size, np.uint8)
+        self._check(self.api.b["read_storage_buffer"](self.ctx, u32(h), _ptr(out), C.c_size_t(size)), "read_storage_buffer")
+        return out.view(dtype)
+
+    def set_timing_enabled(self, on):
+        self._check(self.api.b["set_timing_enabled"](self.ctx, C.c_int(int(on))), "set_timing_enabled")
+
+    def pass_timings(self):
+        arr = (PassTime * 128)()
+        n = u32()
+        self._check(self.api.b["get_renderpass_timings"](self.ctx, arr, u32(128), C.byref(n)), "get_renderpass_timings")
+        return [(arr[i].name.decode(), arr[i].time_ms) for i in range(min(n.value, 128))]
+
+    def last_frame_launch_count(self):
+        n = u32()
+        self._check(self.api.b["get_last_frame_launch_count"](self.ctx, C.byref(n)), "get_last_frame_launch_count")
+        return n.value
+
+    def set_graph_replay_enabled(self, on):
+        self._check(self.api.b["set_graph_replay_enabled"](self.ctx, C.c_int(int(on))), "set_graph_replay_enabled")
+
+
+def default_settings(api, width, height, **overrides):
+    s = FrontendSettings()
+    api.f["default_settings"](C.byref(s), u32(width), u32(height))
+    for k, v in overrides.items():
+        if k == "sun_direction_deg":
+            s.sun_direction_deg[0], s.sun_direction_deg[1] = v
+        else:
+            setattr(s, k, v)
+    return s
+
+
+def camera(position, forward, right, up):
+    c = CameraExtrinsic()
+    for i in range(3):
+        c.position[i], c.forward[i], c.right[i], c.up[i] = position[i], forward[i], right[i], up[i]
+    return c
+
+
+class Frontend:
+    """Frame driver (RenderFrontend mirror) of one library."""
+
+    def __init__(self, api, settings, device=0):
+        self.api, self.settings = api, settings
+        p = C.c_void_p()
+        if api.f["create"](C.c_int(device), C.byref(settings), C.byref(p)):
+            raise ApiError("frontend create failed (see stderr)")
+        self.fe = p
+        self.backend = Backend(api, ctx=api.f["backend"](self.fe))
+        self.width, self.height = settings.width, settings.height
+
+    def close(self):
+        if self.fe:
+            self.api.f["destroy"](self.fe)
+        self.fe = None
+
+    def _check(self, rc, what):
+        if rc:
+            raise ApiError("%s: %s" % (what, self.api.f["last_error"](self.fe).decode()))
+
+    def render_frame(self, cam, time, delta_time, depth=None, motion=None, normal=None, gbuffer=None, shadow_maps=None, async_upload=False):
+        fi = FrameInputs()
+        fi.depth, fi.motion, fi.normal, fi.gbuffer = _ptr(depth), _ptr(motion), _ptr(normal), _ptr(gbuffer)
+        for i in range(4):
+            fi.shadow_maps[i] = _ptr(shadow_maps[i]) if shadow_maps is not None and i < len(shadow_maps) and shadow_maps[i] is not None else None
+        fi.async_upload = int(async_upload)
+        self._check(self.api.f["render_frame"](self.fe, C.byref(cam), f32(time), f32(delta_time), C.byref(fi)), "render_frame")
+
+    def read_output(self, out=None, async_pinned=False):
+        if out is None:
+            out = np.empty(self.width * self.height * 4, np.uint8)
+        self._check(self.api.f["read_output"](self.fe, _ptr(out), C.c_size_t(out.nbytes), i32(int(async_pinned))), "read_output")
+        return out
+
+    def image(self, name):
+        h = ImageHandle()
+        self._check(self.api.f["get_image"](self.fe, name.encode(), C.byref(h)), "get_image(%s)" % name)
+        return h
+
+    def storage_buffer(self, name):
+        h = u32()
+        self._check(self.api.f["get_storage_buffer"](self.fe, name.encode(), C.byref(h)), "get_storage_buffer(%s)" % name)
+        return h.value
+
+    def global_shader_info(self):
+        g = GlobalShaderInfo()
+        self.api.f["get_global_shader_info"](self.fe, C.byref(g))
+        return g
+
+    def resolve_weights(self):
+        w = (f32 * 9)()
+        self.api.f["get_resolve_weights"](self.fe, w)
+        return np.array(list(w), np.float32)
+
+    def set_exposure(self, e):
+        self._check(self.api.f["set_exposure"](self.fe, f32(e)), "set_exposure")
+
+
+class SyntheticScene:
+    def __init__(self, api, seed=0x504C4149, n_instances=100):
+        self.api = api
+        p = C.c_void_p()
+        if api.f["synthetic_scene_create"](u32(seed), u32(n_instances), C.byref(p)):
+            raise ApiError("synthetic_scene_create failed")
+        self.s = p
+
+    def close(self):
+        if self.s:
+            self.api.f["synthetic_scene_destroy"](self.s)
+        self.s = None
+
+    def attach(self, frontend):
+        if self.api.f["synthetic_scene_attach"](self.s, frontend.fe):
+            raise ApiError("synthetic_scene_attach: " + self.api.f["last_error"](frontend.fe).decode())
+
+    def render_inputs(self, settings, cam, frame_index, prev_cam=None, shadows=True, threads=0, out=None):
+        """Returns dict(depth, motion, normal, gbuffer, shadow_maps[list]) of numpy arrays (reused from `out` if given)."""
+        w, h = settings.width, settings.height
+        o = out or {}
+        o.setdefault("depth", np.empty(w * h, np.float32))
+        o.setdefault("motion", np.empty(w * h * 2, np.int16))
+        o.setdefault("normal", np.empty(w * h * 4, np.uint8))
+        o.setdefault("gbuffer", np.empty(w * h * 4, np.uint32))
+        n_casc = settings.sun_shadow_cascade_count
+        if shadows:
+            o.setdefault("shadow_maps", [np.zeros(2048 * 2048, np.uint16) for _ in range(n_casc)])
+        sm = (C.c_void_p * 4)()
+        for i in range(4):
+            sm[i] = _ptr(o["shadow_maps"][i]) if shadows and i < n_casc else None
+        rc = self.api.f["synthetic_scene_render_inputs"](self.s, C.byref(settings), C.byref(cam), C.byref(prev_cam) if prev_cam is not None else None,
+                                                         u32(frame_index), _ptr(o["depth"]), _ptr(o["motion"]), _ptr(o["normal"]), _ptr(o["gbuffer"]), sm, i32(threads))
+        if rc:
+            raise ApiError("synthetic_scene_render_inputs failed")
+        return o

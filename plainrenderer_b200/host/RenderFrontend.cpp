@@ -1,0 +1,540 @@
+// RenderFrontend.cpp - see RenderFrontend.h. Follows Plain/src/Runtime/Rendering/RenderFrontend.cpp: setup :156-192,
+// pass list :313-406, camera/jitter :423-454, histogram :707-754, exposure :776-790, depth pyramid :804-838 and
+// :1770-1827, light matrices :840-871, depth downscale :873-892, forward shading :894-929 (recast), tonemapping
+// :931-945, global shader info :1158-1184, images/buffers :1186-1516.
+#include "RenderFrontend.h"
+#include <cstring>
+
+static const uint32_t shadowMapRes = 2048;
+static const uint32_t brdfLutRes = 512;
+static const uint32_t nHistogramBins = 128;
+static const int maxSunShadowCascadeCount = 4;
+static const uint32_t histogramTileSizeX = 32, histogramTileSizeY = 32;
+static const uint32_t noiseTextureCount = 4, noiseTextureWidth = 32, noiseTextureHeight = 32;
+static const float histogramMinValue = 0.001f, histogramMaxValue = 200000.f;  // createHistogramSettings :1063-1073
+
+static uint32_t ceilDiv(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
+
+// ---- small host utilities (MathUtils.cpp, sdfUtilities.cpp, ViewFrustum.cpp) ----
+static float radicalInverseBase2(uint32_t in) {
+    uint32_t out = (in << 16) | (in >> 16);
+    out = ((out & 0x00ff00ffu) << 8) | ((out & 0xff00ff00u) >> 8);
+    out = ((out & 0x0f0f0f0fu) << 4) | ((out & 0xf0f0f0f0u) >> 4);
+    out = ((out & 0x33333333u) << 2) | ((out & 0xccccccccu) >> 2);
+    out = ((out & 0x55555555u) << 1) | ((out & 0xaaaaaaaau) >> 1);
+    return (float)out * 2.3283064365386963e-10f;
+}
+static float radicalInverseBase3(uint32_t in) {
+    const float inverseBase = 1.f / 3.f;
+    uint32_t reversedDigits = 0, current = in;
+    float inverseBasePowerN = 1.f;
+    while (current) {
+        uint32_t next = current / 3;
+        reversedDigits = reversedDigits * 3 + (current - next * 3);
+        inverseBasePowerN *= inverseBase;
+        current = next;
+    }
+    return (float)reversedDigits * inverseBasePowerN;
+}
+hm::Vec2 hammersley2D(uint32_t index) { hm::Vec2 r; r.x = radicalInverseBase2(index); r.y = radicalInverseBase3(index); return r; }
+hm::Vec3 directionToVector(hm::Vec2 d) {
+    float theta = hm::radians(d.y), phi = hm::radians(d.x);
+    return hm::Vec3(dm::sin(theta) * dm::cos(phi), -dm::cos(theta), dm::sin(theta) * dm::sin(phi));
+}
+uint32_t mipCountFromResolution(uint32_t w, uint32_t h, uint32_t d) {
+    uint32_t m = w > h ? w : h;
+    if (d > m) m = d;
+    uint32_t n = 1;
+    while (m > 1) { m >>= 1; n++; }
+    return n;
+}
+hm::AABB padSDFBoundingBox(const hm::AABB& bb) {
+    hm::Vec3 padding = (bb.max - bb.min) * 0.075f;
+    padding = hm::vmax(padding, hm::Vec3(0.5f));
+    hm::AABB p;
+    p.min = bb.min - padding;
+    p.max = bb.max + padding;
+    return p;
+}
+ViewFrustum computeViewFrustum(const CameraExtrinsic& e, const CameraIntrinsic& in) {
+    using namespace hm;
+    Vec3 nearC = e.position + e.forward * in.near, farC = e.position + e.forward * in.far;
+    float tanFoV = dm::tan(radians(in.fov) * 0.5f);
+    float hn = tanFoV * in.near, hf = tanFoV * in.far, wn = hn * in.aspectRatio, wf = hf * in.aspectRatio;
+    ViewFrustum f;
+    f.r_u_f = farC + e.up * hf + e.right * wf;   f.l_u_f = farC + e.up * hf - e.right * wf;
+    f.r_l_f = farC - e.up * hf + e.right * wf;   f.l_l_f = farC - e.up * hf - e.right * wf;
+    f.r_u_n = nearC + e.up * hn + e.right * wn;  f.l_u_n = nearC + e.up * hn - e.right * wn;
+    f.r_l_n = nearC - e.up * hn + e.right * wn;  f.l_l_n = nearC - e.up * hn - e.right * wn;
+    f.top = normalize(cross(f.r_u_f - f.r_u_n, f.r_u_n - f.l_u_n));
+    f.bot = normalize(cross(f.r_l_n - f.l_l_n, f.r_l_f - f.r_l_n));
+    f.right = normalize(cross(f.r_u_n - f.r_l_n, f.r_l_f - f.r_l_n));
+    f.left = normalize(cross(f.l_l_f - f.l_l_n, f.l_u_n - f.l_l_n));
+    f.near = normalize(cross(f.r_u_n - f.r_l_n, f.r_l_n - f.l_l_n));
+    f.far = normalize(cross(f.r_l_f - f.l_l_f, f.r_u_f - f.r_l_f));
+    return f;
+}
+static hm::Mat4 viewMatrixFromCameraExtrinsic(const CameraExtrinsic& e) {  // Camera.cpp:4-12
+    hm::Mat4 v = hm::Mat4::identity();
+    v.at(0, 0) = e.right.x; v.at(0, 1) = e.right.y; v.at(0, 2) = e.right.z;
+    v.at(1, 0) = e.up.x; v.at(1, 1) = e.up.y; v.at(1, 2) = e.up.z;
+    v.at(2, 0) = -e.forward.x; v.at(2, 1) = -e.forward.y; v.at(2, 2) = -e.forward.z;
+    v = hm::transpose(v);
+    return v * hm::translate(-e.position);
+}
+static hm::Mat4 projectionMatrixFromCameraIntrinsic(const CameraIntrinsic& in) {  // Camera.cpp:14-27: y flip, reverse z
+    hm::Mat4 p = hm::perspective(hm::radians(in.fov), in.aspectRatio, in.near, in.far);
+    hm::Mat4 c = hm::Mat4::identity();
+    c.at(1, 1) = -1.f; c.at(2, 2) = -0.5f; c.at(3, 2) = 0.5f;
+    return c * p;
+}
+
+// deterministic fixture noise (the reference seeds its blue/Perlin noise with C rand())
+static uint32_t pcg(uint32_t& s) {
+    s = s * 747796405u + 2891336453u;
+    uint32_t w = ((s >> ((s >> 28u) + 4u)) ^ s) * 277803737u;
+    return (w >> 22u) ^ w;
+}
+
+void RenderFrontend::setup(int device, uint32_t width, uint32_t height, uint32_t noiseSeed) {
+    m_screenWidth = width;
+    m_screenHeight = height;
+    m_cameraIntrinsic.aspectRatio = (float)width / (float)height;
+    m_sunDirection.x = 0.f; m_sunDirection.y = 0.f;
+    std::memset(&m_globalShaderInfo, 0, sizeof(m_globalShaderInfo));
+    // GlobalShaderInfo defaults, ResourceDescriptions.h:174-203
+    m_globalShaderInfo.sunDirection[1] = -1.f;
+    m_globalShaderInfo.cameraRight[0] = 1.f; m_globalShaderInfo.cameraUp[1] = -1.f;
+    m_globalShaderInfo.cameraForward[2] = -1.f; m_globalShaderInfo.cameraForwardPrevious[2] = -1.f;
+    m_globalShaderInfo.cameraTanFovHalf = 1.f; m_globalShaderInfo.cameraAspectRatio = 1.f;
+    m_globalShaderInfo.nearPlane = 0.1f; m_globalShaderInfo.farPlane = 100.f;
+    m_globalShaderInfo.sunStrength = 128000.f; m_globalShaderInfo.exposureOffset = 1.f;
+    m_globalShaderInfo.exposureAdaptionSpeedEvPerSec = 2.f; m_globalShaderInfo.deltaTime = 0.016f;
+    // AtmosphereSettings defaults, Sky.h:6-15
+    plain_atmosphere_settings& a = m_atmosphereSettings;
+    a.scatteringRayleighGround[0] = 0.0058f; a.scatteringRayleighGround[1] = 0.0135f; a.scatteringRayleighGround[2] = 0.0331f;
+    a.earthRadius = 6371.f;
+    for (int i = 0; i < 3; i++) a.extinctionRayleighGround[i] = a.scatteringRayleighGround[i];
+    a.atmosphereHeight = 100.f;
+    a.ozoneExtinction[0] = 0.000650f; a.ozoneExtinction[1] = 0.001881f; a.ozoneExtinction[2] = 0.000085f;
+    a.scatteringMieGround = 0.006f;
+    a.extinctionMieGround = 1.11f * a.scatteringMieGround;
+    a.mieScatteringExponent = 0.76f;
+
+    backend.setup(device, width, height);
+    // the 8 global samplers, RenderFrontend.cpp:1300-1397 (binding order global.inc:35-42)
+    const plain_sampler_desc descs[8] = {
+        {PLAIN_SAMPLER_LINEAR, PLAIN_WRAP_REPEAT, 1, 8.f, PLAIN_BORDER_WHITE, 20},   // anisotropicRepeat
+        {PLAIN_SAMPLER_NEAREST, PLAIN_WRAP_COLOR, 0, 0.f, PLAIN_BORDER_BLACK, 20},   // nearestBlackBorder
+        {PLAIN_SAMPLER_LINEAR, PLAIN_WRAP_REPEAT, 0, 0.f, PLAIN_BORDER_WHITE, 20},   // linearRepeat
+        {PLAIN_SAMPLER_LINEAR, PLAIN_WRAP_CLAMP, 0, 0.f, PLAIN_BORDER_WHITE, 20},    // linearClamp
+        {PLAIN_SAMPLER_NEAREST, PLAIN_WRAP_CLAMP, 0, 8.f, PLAIN_BORDER_BLACK, 20},   // nearestClamp
+        {PLAIN_SAMPLER_LINEAR, PLAIN_WRAP_COLOR, 0, 8.f, PLAIN_BORDER_WHITE, 20},    // linearWhiteBorder
+        {PLAIN_SAMPLER_NEAREST, PLAIN_WRAP_REPEAT, 0, 8.f, PLAIN_BORDER_BLACK, 20},  // nearestRepeat
+        {PLAIN_SAMPLER_NEAREST, PLAIN_WRAP_COLOR, 0, 0.f, PLAIN_BORDER_WHITE, 20},   // nearestWhiteBorder
+    };
+    for (int i = 0; i < 8; i++) m_samplers[i] = backend.createSampler(descs[i]);
+    initImages(noiseSeed);
+    initBuffers();
+    initRenderpasses();
+    m_sky.init(backend);
+    m_bloom.init(backend);
+    m_volumetrics.init(backend, (int)width, (int)height, noiseSeed ^ 0x9e3779b9u);
+    m_taa.init(backend, (int)width, (int)height, m_taaSettings);
+    m_sdfGi.init(backend, (int)width, (int)height, m_sdfTraceSettings, m_shadingConfig.sunShadowCascadeCount - 1);
+
+    RenderPassResources globalResources;  // setupGlobalShaderInfoResources :295-311
+    globalResources.uniformBuffers = {UniformBufferResource(m_globalUniformBuffer, 0)};
+    for (uint32_t i = 0; i < 8; i++) globalResources.samplers.push_back(SamplerResource(m_samplers[i], i + 1));
+    backend.setGlobalDescriptorSetResources(globalResources);
+
+    backend.newFrame();
+    computeBRDFLut();
+    backend.prepareForDrawcallRecording();
+    backend.renderFrame(false);
+}
+
+void RenderFrontend::shutdown() { backend.shutdown(); }
+
+void RenderFrontend::initImages(uint32_t noiseSeed) {
+    const uint32_t w = m_screenWidth, h = m_screenHeight;
+    const uint32_t SS = PLAIN_USAGE_SAMPLED | PLAIN_USAGE_STORAGE;
+    for (int i = 0; i < 2; i++) m_postProcessBuffers[i] = backend.createImage(imageDesc2D(w, h, PLAIN_FORMAT_R11G11B10_UFLOAT, SS), nullptr, 0);
+    for (int i = 0; i < maxSunShadowCascadeCount; i++)
+        m_shadowMaps.push_back(backend.createImage(imageDesc2D(shadowMapRes, shadowMapRes, PLAIN_FORMAT_DEPTH16, PLAIN_USAGE_ATTACHMENT | PLAIN_USAGE_SAMPLED), nullptr, 0));
+    m_brdfLut = backend.createImage(imageDesc2D(brdfLutRes, brdfLutRes, PLAIN_FORMAT_RGBA16_SFLOAT, SS), nullptr, 0);
+    m_minMaxDepthPyramid = backend.createImage(imageDesc2D(w / 2, h / 2, PLAIN_FORMAT_RG32_SFLOAT, SS, PLAIN_MIPS_FULL_CHAIN), nullptr, 0);
+    uint32_t s = noiseSeed;
+    for (uint32_t i = 0; i < noiseTextureCount; i++) {
+        std::vector<uint8_t> noise(noiseTextureWidth * noiseTextureHeight * 2);
+        for (auto& v : noise) v = (uint8_t)(pcg(s) & 0xff);
+        m_noiseTextures.push_back(backend.createImage(imageDesc2D(noiseTextureWidth, noiseTextureHeight, PLAIN_FORMAT_RG8, PLAIN_USAGE_SAMPLED), noise.data(), noise.size()));
+        m_globalShaderInfo.noiseTextureIndices[i] = (int32_t)backend.getImageGlobalTextureArrayIndex(m_noiseTextures.back());
+    }
+    m_worldSpaceNormalImage = backend.createImage(imageDesc2D(w, h, PLAIN_FORMAT_RGBA8, PLAIN_USAGE_ATTACHMENT | PLAIN_USAGE_SAMPLED), nullptr, 0);
+    m_depthHalfRes = backend.createImage(imageDesc2D(w / 2, h / 2, PLAIN_FORMAT_R16_SFLOAT, SS), nullptr, 0);
+    // packed G-buffer: the post-raster inputs of triangle.frag (new in this build)
+    m_gbuffer = backend.createImage(imageDesc2D(w, h, PLAIN_FORMAT_RGBA32_UINT, PLAIN_USAGE_ATTACHMENT | PLAIN_USAGE_SAMPLED), nullptr, 0);
+    for (int i = 0; i < 2; i++) {  // initRenderTargets :1399-1447
+        m_frameRenderTargets[i].motionBuffer = backend.createImage(imageDesc2D(w, h, PLAIN_FORMAT_RG16_SNORM, PLAIN_USAGE_ATTACHMENT | PLAIN_USAGE_SAMPLED), nullptr, 0);
+        m_frameRenderTargets[i].colorBuffer = backend.createImage(imageDesc2D(w, h, PLAIN_FORMAT_R11G11B10_UFLOAT, PLAIN_USAGE_ATTACHMENT | SS), nullptr, 0);
+        m_frameRenderTargets[i].depthBuffer = backend.createImage(imageDesc2D(w, h, PLAIN_FORMAT_DEPTH32, PLAIN_USAGE_ATTACHMENT | PLAIN_USAGE_SAMPLED), nullptr, 0);
+    }
+}
+
+void RenderFrontend::initBuffers() {
+    m_histogramBuffer = backend.createStorageBuffer(nHistogramBins * sizeof(uint32_t));
+    plain_light_buffer initialLight{};
+    m_lightBuffer = backend.createStorageBuffer(sizeof(plain_light_buffer), &initialLight);
+    // the reference sizes this for 1920x1080 (:1069-1070 FIXME); sized by the actual resolution here
+    const size_t tiles = (size_t)ceilDiv(m_screenWidth, histogramTileSizeX) * ceilDiv(m_screenHeight, histogramTileSizeY);
+    m_histogramPerTileBuffer = backend.createStorageBuffer(tiles * nHistogramBins * sizeof(uint32_t));
+    uint32_t zero = 0;
+    m_depthPyramidSyncBuffer = backend.createStorageBuffer(sizeof(uint32_t), &zero);
+    m_sunShadowInfoBuffer = backend.createStorageBuffer(sizeof(plain_shadow_cascade_info));
+    m_globalUniformBuffer = backend.createUniformBuffer(sizeof(plain_global_shader_info));
+}
+
+template <typename T> static SpecialisationConstant specConst(uint32_t location, const T& v) { return SpecialisationConstant{location, dataToCharArray(&v, sizeof(T))}; }
+
+ShaderDescription RenderFrontend::createDepthPyramidShaderDescription(uint32_t* outThreadgroupCount) const {
+    ShaderDescription desc;
+    desc.srcPathRelative = "depthHiZPyramid.comp";
+    const uint32_t width = m_screenWidth / 2, height = m_screenHeight / 2;
+    const uint32_t depthMipCount = mipCountFromResolution(width, height, 1);
+    uint32_t dc[2];
+    computeSinglePassMipChainDispatchCount(width, height, depthMipCount, 11, dc);
+    *outThreadgroupCount = dc[0] * dc[1];
+    desc.specialisationConstants = {specConst(0, depthMipCount), specConst(1, m_screenWidth), specConst(2, m_screenHeight), specConst(3, *outThreadgroupCount)};
+    return desc;
+}
+
+void RenderFrontend::computeSinglePassMipChainDispatchCount(uint32_t w, uint32_t h, uint32_t mipCount, uint32_t maxMipCount, uint32_t out[2]) const {
+    const uint32_t unusedMips = maxMipCount > mipCount ? maxMipCount - mipCount : 0;
+    if (unusedMips >= 6) { out[0] = 1; out[1] = 1; return; }
+    const uint32_t localThreadGroupExtent = 32u >> unusedMips;
+    out[0] = ceilDiv(w, localThreadGroupExtent);
+    out[1] = ceilDiv(h, localThreadGroupExtent);
+}
+
+void RenderFrontend::initRenderpasses() {
+    {   // deferred recast of the "Forward shading" graphic pass; constants as createForwardPassShaderDescription :1099-1135
+        ComputePassDescription d;
+        d.name = "Forward shading";
+        d.shaderDescription.srcPathRelative = "gbufferShading.comp";
+        const int diffuse = (int)m_shadingConfig.diffuseBRDF, multi = (int)m_shadingConfig.directMultiscatter, tech = (int)m_shadingConfig.indirectLightingTech;
+        const uint32_t geoAA = m_shadingConfig.useGeometryAA ? 1u : 0u;
+        const uint32_t cascades = (uint32_t)m_shadingConfig.sunShadowCascadeCount;
+        d.shaderDescription.specialisationConstants = {specConst(0, diffuse), specConst(1, multi), specConst(2, geoAA), specConst(3, tech), specConst(4, cascades)};
+        m_shadingPass = backend.createComputePass(d);
+    }
+    {
+        ComputePassDescription d;
+        d.name = "BRDF Lut creation";
+        d.shaderDescription.srcPathRelative = "brdfLut.comp";
+        d.shaderDescription.specialisationConstants = {specConst(0, (int)m_shadingConfig.diffuseBRDF)};
+        m_brdfLutPass = backend.createComputePass(d);
+    }
+    const uint32_t maxTileCount = ceilDiv(m_screenWidth, histogramTileSizeX) * ceilDiv(m_screenHeight, histogramTileSizeY);
+    {
+        ComputePassDescription d;
+        d.name = "Histogram per tile";
+        d.shaderDescription.srcPathRelative = "histogramPerTile.comp";
+        d.shaderDescription.specialisationConstants = {specConst(0, nHistogramBins), specConst(1, histogramMinValue), specConst(2, histogramMaxValue), specConst(3, (int)maxTileCount)};
+        m_histogramPerTilePass = backend.createComputePass(d);
+    }
+    {
+        ComputePassDescription d;
+        d.name = "Histogram reset";
+        d.shaderDescription.srcPathRelative = "histogramReset.comp";
+        d.shaderDescription.specialisationConstants = {specConst(0, nHistogramBins)};
+        m_histogramResetPass = backend.createComputePass(d);
+    }
+    {
+        ComputePassDescription d;
+        d.name = "Histogram combine tiles";
+        d.shaderDescription.srcPathRelative = "histogramCombineTiles.comp";
+        d.shaderDescription.specialisationConstants = {specConst(0, nHistogramBins), specConst(1, (int)maxTileCount)};
+        m_histogramCombinePass = backend.createComputePass(d);
+    }
+    {
+        ComputePassDescription d;
+        d.name = "Pre-expose lights";
+        d.shaderDescription.srcPathRelative = "preExposeLights.comp";
+        d.shaderDescription.specialisationConstants = {specConst(0, (int)nHistogramBins), specConst(1, histogramMinValue), specConst(2, histogramMaxValue)};
+        m_preExposeLightsPass = backend.createComputePass(d);
+    }
+    {
+        ComputePassDescription d;
+        d.name = "Depth min/max pyramid creation";
+        uint32_t threadgroupCount = 0;
+        d.shaderDescription = createDepthPyramidShaderDescription(&threadgroupCount);
+        m_depthPyramidPass = backend.createComputePass(d);
+    }
+    {
+        ComputePassDescription d;
+        d.name = "Compute light matrix";
+        d.shaderDescription.srcPathRelative = "lightMatrix.comp";
+        d.shaderDescription.specialisationConstants = {specConst(0, (uint32_t)m_shadingConfig.sunShadowCascadeCount)};
+        m_lightMatrixPass = backend.createComputePass(d);
+    }
+    {
+        ComputePassDescription d;
+        d.name = "Tonemapping";
+        d.shaderDescription.srcPathRelative = "tonemapping.comp";
+        m_tonemappingPass = backend.createComputePass(d);
+    }
+    {
+        ComputePassDescription d;
+        d.name = "Depth downscale";
+        d.shaderDescription.srcPathRelative = "depthDownscale.comp";
+        m_depthDownscalePass = backend.createComputePass(d);
+    }
+}
+
+void RenderFrontend::markNewFrame(float time, float deltaTime) {
+    m_time = time;
+    m_deltaTime = deltaTime;
+    m_frameIndex.markNewFrame();
+}
+
+void RenderFrontend::prepareNewFrame() {
+    backend.newFrame();
+    prepareRenderpasses();
+    backend.prepareForDrawcallRecording();
+}
+
+// the ordered pass list, RenderFrontend.cpp:313-406
+void RenderFrontend::prepareRenderpasses() {
+    const FrameRenderTargets previousRenderTarget = m_frameRenderTargets[m_sceneRenderTargetIndex];
+    m_sceneRenderTargetIndex = (m_sceneRenderTargetIndex + 1) % 2;
+    const FrameRenderTargets currentRenderTarget = m_frameRenderTargets[m_sceneRenderTargetIndex];
+
+    computeColorBufferHistogram(previousRenderTarget.colorBuffer);
+    m_sky.updateTransmissionLut(backend);
+    computeExposure();
+    m_sky.updateSkyLut(backend, m_lightBuffer, m_atmosphereSettings);
+    // renderDepthPrepass: rasterisation, out of scope - depth/motion/normal/G-buffer of this frame are uploaded
+    computeDepthPyramid(currentRenderTarget.depthBuffer);
+    computeSunLightMatrices();
+    // renderSunShadowCascades: rasterisation, out of scope - shadow maps are uploaded
+    if (m_shadingConfig.indirectLightingTech == IndirectLightingTech::SDFTrace) {
+        if (m_sdfTraceSettings.halfResTrace) downscaleDepth(currentRenderTarget);
+        SDFTraceDependencies dep;  // fillOutSdfGiDependencies :1075-1092
+        dep.currentFrame = currentRenderTarget;
+        dep.previousFrame = previousRenderTarget;
+        dep.cameraFrustum = m_cameraFrustum;
+        dep.depthHalfRes = m_depthHalfRes;
+        dep.worldSpaceNormals = m_worldSpaceNormalImage;
+        dep.skyLut = m_sky.m_skyLut;
+        dep.shadowMap = m_shadowMaps[m_shadingConfig.sunShadowCascadeCount - 1];
+        dep.lightBuffer = m_lightBuffer;
+        dep.sunShadowInfoBuffer = m_sunShadowInfoBuffer;
+        dep.depthMinMaxPyramid = m_minMaxDepthPyramid;
+        m_sdfGi.computeIndirectLighting(backend, dep, m_sdfTraceSettings, m_frameIndex);
+    }
+    Volumetrics::Dependencies vd;
+    vd.lightBuffer = m_lightBuffer;
+    vd.shadowMap = m_shadowMaps[m_shadingConfig.sunShadowCascadeCount - 1];
+    vd.sunShadowInfoBuffer = m_sunShadowInfoBuffer;
+    m_volumetrics.computeVolumetricLighting(backend, m_volumetricsSettings, m_windSettings, vd, m_frameIndex, m_deltaTime);
+
+    shadeGBuffer(currentRenderTarget.colorBuffer);  // renderForwardShading + m_sky.renderSky
+
+    ImageHandle currentSrc = currentRenderTarget.colorBuffer;
+    if (m_taaSettings.enabled) {
+        m_taa.computeTemporalFilter(backend, currentSrc, currentRenderTarget, m_postProcessBuffers[1], m_frameIndex);
+        currentSrc = m_postProcessBuffers[1];
+    }
+    if (m_bloomSettings.enabled) m_bloom.computeBloom(backend, currentSrc, m_bloomSettings);
+    computeTonemapping(currentSrc);
+}
+
+void RenderFrontend::setCameraExtrinsic(const CameraExtrinsic& extrinsic) {
+    std::memcpy(m_globalShaderInfo.previousFrameCameraJitter, m_globalShaderInfo.currentFrameCameraJitter, sizeof(float) * 2);
+    m_cameraExtrinsic = extrinsic;
+    const hm::Mat4 viewMatrix = viewMatrixFromCameraExtrinsic(extrinsic);
+    const hm::Mat4 projectionMatrix = projectionMatrixFromCameraIntrinsic(m_cameraIntrinsic);
+    if (m_taaSettings.enabled) {
+        const hm::Vec2 jitterInPixels = m_taa.computeProjectionMatrixJitter(m_frameIndex);
+        m_taa.updateTaaResolveWeights(backend, jitterInPixels);
+        m_globalShaderInfo.currentFrameCameraJitter[0] = jitterInPixels.x * (1.f / (float)m_screenWidth);
+        m_globalShaderInfo.currentFrameCameraJitter[1] = jitterInPixels.y * (1.f / (float)m_screenHeight);
+        hm::Vec2 off;
+        off.x = m_globalShaderInfo.currentFrameCameraJitter[0]; off.y = m_globalShaderInfo.currentFrameCameraJitter[1];
+        m_viewProjectionMatrix = m_taa.applyProjectionMatrixJitter(projectionMatrix, off) * viewMatrix;
+    } else {
+        m_globalShaderInfo.currentFrameCameraJitter[0] = 0.f; m_globalShaderInfo.currentFrameCameraJitter[1] = 0.f;
+        m_viewProjectionMatrix = projectionMatrix * viewMatrix;
+    }
+    std::memcpy(m_globalShaderInfo.viewProjectionPrevious, m_globalShaderInfo.viewProjection, sizeof(float) * 16);
+    std::memcpy(m_globalShaderInfo.viewProjection, m_viewProjectionMatrix.m, sizeof(float) * 16);
+    CameraIntrinsic in = m_cameraIntrinsic;
+    m_cameraFrustum = computeViewFrustum(extrinsic, in);
+}
+
+void RenderFrontend::prepareForDrawcalls() { updateGlobalShaderInfo(); }
+
+void RenderFrontend::updateGlobalShaderInfo() {
+    plain_global_shader_info& g = m_globalShaderInfo;
+    const hm::Vec3 sun = directionToVector(m_sunDirection);
+    g.sunDirection[0] = sun.x; g.sunDirection[1] = sun.y; g.sunDirection[2] = sun.z; g.sunDirection[3] = 0.f;
+    std::memcpy(g.cameraPositionPrevious, g.cameraPosition, sizeof(float) * 4);
+    g.cameraPosition[0] = m_cameraExtrinsic.position.x; g.cameraPosition[1] = m_cameraExtrinsic.position.y; g.cameraPosition[2] = m_cameraExtrinsic.position.z; g.cameraPosition[3] = 1.f;
+    g.deltaTime = m_deltaTime;
+    g.time = m_time;
+    g.nearPlane = m_cameraIntrinsic.near;
+    g.farPlane = m_cameraIntrinsic.far;
+    g.cameraRight[0] = m_cameraExtrinsic.right.x; g.cameraRight[1] = m_cameraExtrinsic.right.y; g.cameraRight[2] = m_cameraExtrinsic.right.z; g.cameraRight[3] = 0.f;
+    g.cameraUp[0] = m_cameraExtrinsic.up.x; g.cameraUp[1] = m_cameraExtrinsic.up.y; g.cameraUp[2] = m_cameraExtrinsic.up.z; g.cameraUp[3] = 0.f;
+    std::memcpy(g.cameraForwardPrevious, g.cameraForward, sizeof(float) * 4);
+    g.cameraForward[0] = m_cameraExtrinsic.forward.x; g.cameraForward[1] = m_cameraExtrinsic.forward.y; g.cameraForward[2] = m_cameraExtrinsic.forward.z; g.cameraForward[3] = 0.f;
+    g.cameraTanFovHalf = dm::tan(hm::radians(m_cameraIntrinsic.fov) * 0.5f);
+    g.cameraAspectRatio = m_cameraIntrinsic.aspectRatio;
+    g.screenResolution[0] = (int32_t)m_screenWidth; g.screenResolution[1] = (int32_t)m_screenHeight;
+    g.mipBias = (m_taaSettings.enabled && m_taaSettings.useMipBias) ? dm::log2(0.5f) : 0.f;
+    backend.setUniformBufferData(m_globalUniformBuffer, &g, sizeof(g));
+}
+
+void RenderFrontend::renderScene(const std::vector<RenderObject>& scene) { m_sdfGi.updateSDFScene(backend, scene, m_frontendMeshes); }
+
+void RenderFrontend::renderFrame() {  // RenderFrontend.cpp:685-705
+    m_globalShaderInfo.frameIndex++;
+    m_globalShaderInfo.frameIndexMod2 = m_globalShaderInfo.frameIndex % 2;
+    m_globalShaderInfo.frameIndexMod3 = m_globalShaderInfo.frameIndex % 3;
+    m_globalShaderInfo.frameIndexMod4 = m_globalShaderInfo.frameIndex % 4;
+    backend.renderFrame(true);
+    m_globalShaderInfo.cameraCut = 0;
+}
+
+uint32_t RenderFrontend::registerSdfMesh(const uint16_t* texels, uint32_t rx, uint32_t ry, uint32_t rz, const hm::AABB& localBB, hm::Vec3 meanAlbedo) {
+    ImageHandle img = backend.createImage(imageDesc3D(rx, ry, rz, PLAIN_FORMAT_R16_SFLOAT, PLAIN_USAGE_SAMPLED), texels, (size_t)rx * ry * rz * 2);
+    MeshFrontend m;
+    m.sdfTextureIndex = (int)backend.getImageGlobalTextureArrayIndex(img);
+    m.meanAlbedo = meanAlbedo;
+    m.localBB = localBB;
+    m_frontendMeshes.push_back(m);
+    return (uint32_t)m_frontendMeshes.size() - 1;
+}
+
+void RenderFrontend::computeColorBufferHistogram(ImageHandle lastFrameColor) {
+    StorageBufferResource histogramPerTileResource(m_histogramPerTileBuffer, false, 0);
+    StorageBufferResource histogramResource(m_histogramBuffer, false, 1);
+    {
+        ComputePassExecution e;
+        e.genericInfo.handle = m_histogramPerTilePass;
+        e.genericInfo.resources.storageBuffers = {histogramPerTileResource, StorageBufferResource(m_lightBuffer, true, 3)};
+        e.genericInfo.resources.sampledImages = {ImageResource(lastFrameColor, 0, 2)};
+        e.dispatchCount[0] = ceilDiv(m_screenWidth, histogramTileSizeX);
+        e.dispatchCount[1] = ceilDiv(m_screenHeight, histogramTileSizeY);
+        backend.setComputePassExecution(e);
+    }
+    {
+        ComputePassExecution e;
+        e.genericInfo.handle = m_histogramResetPass;
+        e.genericInfo.resources.storageBuffers = {histogramResource};
+        e.dispatchCount[0] = ceilDiv(nHistogramBins, 64);
+        backend.setComputePassExecution(e);
+    }
+    {
+        ComputePassExecution e;
+        e.genericInfo.handle = m_histogramCombinePass;
+        e.genericInfo.resources.storageBuffers = {histogramPerTileResource, histogramResource};
+        e.dispatchCount[0] = ceilDiv(m_screenWidth, histogramTileSizeX) * ceilDiv(m_screenHeight, histogramTileSizeY);
+        e.dispatchCount[1] = ceilDiv(nHistogramBins, 64);
+        backend.setComputePassExecution(e);
+    }
+}
+
+void RenderFrontend::computeExposure() {
+    ComputePassExecution e;
+    e.genericInfo.handle = m_preExposeLightsPass;
+    e.genericInfo.resources.storageBuffers = {StorageBufferResource(m_histogramBuffer, false, 1), StorageBufferResource(m_lightBuffer, false, 0)};
+    e.genericInfo.resources.sampledImages = {ImageResource(m_sky.m_skyTransmissionLut, 0, 2)};
+    backend.setComputePassExecution(e);
+}
+
+void RenderFrontend::computeDepthPyramid(ImageHandle depthBuffer) {
+    ComputePassExecution e;
+    e.genericInfo.handle = m_depthPyramidPass;
+    const uint32_t width = m_screenWidth / 2, height = m_screenHeight / 2, maxMipCount = 11;
+    const uint32_t mipCount = mipCountFromResolution(width, height, 1);
+    uint32_t dc[2];
+    computeSinglePassMipChainDispatchCount(width, height, mipCount, maxMipCount, dc);
+    e.dispatchCount[0] = dc[0]; e.dispatchCount[1] = dc[1];
+    e.genericInfo.resources.sampledImages = {ImageResource(depthBuffer, 0, 13), ImageResource(m_minMaxDepthPyramid, 0, 15)};
+    e.genericInfo.resources.storageBuffers = {StorageBufferResource(m_depthPyramidSyncBuffer, false, 16)};
+    const uint32_t unusedMipCount = maxMipCount > mipCount ? maxMipCount - mipCount : 0;
+    for (uint32_t i = 0; i < maxMipCount; i++) {
+        const uint32_t mipLevel = i >= unusedMipCount ? i - unusedMipCount : 0;
+        e.genericInfo.resources.storageImages.push_back(ImageResource(m_minMaxDepthPyramid, mipLevel, i));
+    }
+    backend.setComputePassExecution(e);
+}
+
+void RenderFrontend::computeSunLightMatrices() {
+    ComputePassExecution e;
+    e.genericInfo.handle = m_lightMatrixPass;
+    const uint32_t depthPyramidMipCount = mipCountFromResolution(m_screenWidth / 2, m_screenHeight / 2, 1);
+    e.genericInfo.resources.storageImages = {ImageResource(m_minMaxDepthPyramid, depthPyramidMipCount - 1, 1)};
+    e.genericInfo.resources.storageBuffers = {StorageBufferResource(m_sunShadowInfoBuffer, false, 0)};
+    float pc[2];
+    pc[0] = m_sdfTraceSettings.traceInfluenceRadius;
+    pc[1] = m_volumetricsSettings.maxDistance;
+    if (!m_sdfTraceSettings.strictInfluenceRadiusCutoff) pc[0] += m_sdfTraceSettings.additionalSunShadowMapPadding;
+    e.pushConstants = dataToCharArray(pc, sizeof(pc));
+    backend.setComputePassExecution(e);
+}
+
+void RenderFrontend::downscaleDepth(const FrameRenderTargets& current) {
+    ComputePassExecution e;
+    e.genericInfo.handle = m_depthDownscalePass;
+    e.dispatchCount[0] = ceilDiv(m_screenWidth / 2, 8);
+    e.dispatchCount[1] = ceilDiv(m_screenHeight / 2, 8);
+    e.genericInfo.resources.storageImages = {ImageResource(m_depthHalfRes, 0, 0)};
+    e.genericInfo.resources.sampledImages = {ImageResource(current.depthBuffer, 0, 1)};
+    backend.setComputePassExecution(e);
+}
+
+// renderForwardShading :894-929 + Sky::renderSky (Sky.cpp:318-352), as one full-screen pass over the G-buffer.
+// Bindings 3,7,8,9-12,15,16,18,19 are triangle.frag's; 0 = G-buffer, 20 = colour target, 21 = sky LUT (sky.frag
+// binding 0), 22 = transmission LUT (sunSprite.frag binding 1). Push constants = SunSpriteMatrices (Sky.cpp:256-262).
+void RenderFrontend::shadeGBuffer(ImageHandle colorTarget) {
+    ComputePassExecution e;
+    e.genericInfo.handle = m_shadingPass;
+    const SDFGI::IndirectLightingImages indirect = m_sdfGi.getIndirectLightingResults(m_sdfTraceSettings.halfResTrace);
+    e.genericInfo.resources.storageBuffers = {StorageBufferResource(m_lightBuffer, true, 7), StorageBufferResource(m_sunShadowInfoBuffer, true, 8)};
+    e.genericInfo.resources.sampledImages = {ImageResource(m_gbuffer, 0, 0), ImageResource(m_brdfLut, 0, 3), ImageResource(indirect.Y_SH, 0, 15), ImageResource(indirect.CoCg, 0, 16),
+                                             ImageResource(m_volumetrics.m_volumetricIntegrationVolume, 0, 18), ImageResource(m_sky.m_skyLut, 0, 21),
+                                             ImageResource(m_sky.m_skyTransmissionLut, 0, 22)};
+    for (uint32_t i = 0; i < (uint32_t)maxSunShadowCascadeCount; i++) e.genericInfo.resources.sampledImages.push_back(ImageResource(m_shadowMaps[i], 0, 9 + i));
+    e.genericInfo.resources.uniformBuffers = {UniformBufferResource(m_volumetrics.m_volumetricsSettingsUniforms, 19)};
+    e.genericInfo.resources.storageImages = {ImageResource(colorTarget, 0, 20)};
+    struct SunSpriteMatrices { hm::Mat4 model, mvp; } sun;
+    sun.model = m_sky.sunSpriteModelMatrix(m_sunDirection);
+    sun.mvp = hm::Mat4::identity();  // only the model matrix is used by the deferred recast; set in renderFrame order
+    e.pushConstants = dataToCharArray(&sun, sizeof(sun));
+    e.dispatchCount[0] = ceilDiv(m_screenWidth, 8);
+    e.dispatchCount[1] = ceilDiv(m_screenHeight, 8);
+    backend.setComputePassExecution(e);
+}
+
+void RenderFrontend::computeTonemapping(ImageHandle src) {
+    ComputePassExecution e;
+    e.genericInfo.handle = m_tonemappingPass;
+    e.genericInfo.resources.storageImages = {ImageResource(backend.getSwapchainInputImage(), 0, 0)};
+    e.genericInfo.resources.sampledImages = {ImageResource(src, 0, 1)};
+    e.dispatchCount[0] = ceilDiv(m_screenWidth, 8);
+    e.dispatchCount[1] = ceilDiv(m_screenHeight, 8);
+    backend.setComputePassExecution(e);
+    m_lastTonemapSource = src;
+}
+
+void RenderFrontend::computeBRDFLut() {
+    ComputePassExecution e;
+    e.genericInfo.handle = m_brdfLutPass;
+    e.genericInfo.resources.storageImages = {ImageResource(m_brdfLut, 0, 0)};
+    e.dispatchCount[0] = brdfLutRes / 8;
+    e.dispatchCount[1] = brdfLutRes / 8;
+    backend.setComputePassExecution(e);
+}

@@ -1,0 +1,188 @@
+// frontend_api.cpp - C entry points (include/plain_frontend.h) over the RenderFrontend mirror.
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include "RenderFrontend.h"
+#include "plain_frontend.h"
+
+struct plain_frontend {
+    RenderFrontend fe;
+    std::vector<RenderObject> scene;
+    std::string lastError;
+    plain_frontend_settings settings;
+};
+
+#define FE_TRY(fe, body)                          \
+    try { body; return 0; }                       \
+    catch (const std::exception& e) { (fe)->lastError = e.what(); return 1; }
+
+extern "C" {
+
+void PLAIN_FE(default_settings)(plain_frontend_settings* s, uint32_t width, uint32_t height) {
+    std::memset(s, 0, sizeof(*s));
+    s->width = width; s->height = height;
+    s->diffuse_brdf = 2; s->direct_multiscatter = 0; s->indirect_lighting_tech = 0; s->use_geometry_aa = 1; s->sun_shadow_cascade_count = 3;
+    s->half_res_trace = 1; s->strict_influence_radius_cutoff = 1; s->trace_influence_radius = 5.f;
+    s->taa_enabled = 1; s->taa_use_clipping = 1; s->taa_use_motion_vector_dilation = 1; s->taa_history_sampling_tech = 4; s->taa_filter_use_tonemapping = 1;
+    s->bloom_enabled = 1; s->bloom_strength = 0.05f; s->bloom_radius = 1.5f;
+    s->sun_direction_deg[0] = 0.f; s->sun_direction_deg[1] = 0.f;
+    s->camera_fov_deg = 35.f; s->camera_near = 0.1f; s->camera_far = 300.f;
+    s->noise_seed = 0x504c4149u;
+}
+
+int PLAIN_FE(create)(int device, const plain_frontend_settings* s, plain_frontend** out) {
+    if (!s || !out) return 1;
+    plain_frontend* p = new plain_frontend();
+    p->settings = *s;
+    RenderFrontend& f = p->fe;
+    f.m_shadingConfig.diffuseBRDF = (DiffuseBRDF)s->diffuse_brdf;
+    f.m_shadingConfig.directMultiscatter = (DirectSpecularMultiscattering)s->direct_multiscatter;
+    f.m_shadingConfig.indirectLightingTech = (IndirectLightingTech)s->indirect_lighting_tech;
+    f.m_shadingConfig.useGeometryAA = s->use_geometry_aa != 0;
+    f.m_shadingConfig.sunShadowCascadeCount = s->sun_shadow_cascade_count;
+    f.m_sdfTraceSettings.halfResTrace = s->half_res_trace != 0;
+    f.m_sdfTraceSettings.strictInfluenceRadiusCutoff = s->strict_influence_radius_cutoff != 0;
+    f.m_sdfTraceSettings.traceInfluenceRadius = s->trace_influence_radius;
+    f.m_taaSettings.enabled = s->taa_enabled != 0;
+    f.m_taaSettings.useClipping = s->taa_use_clipping != 0;
+    f.m_taaSettings.useMotionVectorDilation = s->taa_use_motion_vector_dilation != 0;
+    f.m_taaSettings.historySamplingTech = (HistorySamplingTech)s->taa_history_sampling_tech;
+    f.m_taaSettings.filterUseTonemapping = s->taa_filter_use_tonemapping != 0;
+    f.m_bloomSettings.enabled = s->bloom_enabled != 0;
+    f.m_bloomSettings.strength = s->bloom_strength;
+    f.m_bloomSettings.radius = s->bloom_radius;
+    f.m_cameraIntrinsic.fov = s->camera_fov_deg;
+    f.m_cameraIntrinsic.near = s->camera_near;
+    f.m_cameraIntrinsic.far = s->camera_far;
+    try {
+        f.setup(device, s->width, s->height, s->noise_seed);
+        f.m_sunDirection.x = s->sun_direction_deg[0];
+        f.m_sunDirection.y = s->sun_direction_deg[1];
+    } catch (const std::exception& e) {
+        static std::string createError;
+        createError = e.what();
+        fprintf(stderr, "plain_frontend create failed: %s\n", e.what());
+        delete p;
+        return 1;
+    }
+    *out = p;
+    return 0;
+}
+void PLAIN_FE(destroy)(plain_frontend* fe) {
+    if (!fe) return;
+    fe->fe.shutdown();
+    delete fe;
+}
+const char* PLAIN_FE(last_error)(plain_frontend* fe) { return fe ? fe->lastError.c_str() : "null frontend"; }
+plain_ctx* PLAIN_FE(backend)(plain_frontend* fe) { return fe->fe.backend.context(); }
+
+int PLAIN_FE(register_sdf_mesh)(plain_frontend* fe, const uint16_t* texels, uint32_t rx, uint32_t ry, uint32_t rz, const float mn[3], const float mx[3], const float albedo[3], uint32_t* out) {
+    FE_TRY(fe, {
+        hm::AABB bb;
+        bb.min = hm::Vec3(mn[0], mn[1], mn[2]);
+        bb.max = hm::Vec3(mx[0], mx[1], mx[2]);
+        *out = fe->fe.registerSdfMesh(texels, rx, ry, rz, bb, hm::Vec3(albedo[0], albedo[1], albedo[2]));
+    });
+}
+int PLAIN_FE(set_scene)(plain_frontend* fe, uint32_t n, const uint32_t* meshes, const float* mats, const float* bmin, const float* bmax) {
+    FE_TRY(fe, {
+        fe->scene.clear();
+        for (uint32_t i = 0; i < n; i++) {
+            RenderObject o;
+            o.mesh = meshes[i];
+            std::memcpy(o.modelMatrix.m, mats + 16 * i, sizeof(float) * 16);
+            o.bbWorld.min = hm::Vec3(bmin[3 * i], bmin[3 * i + 1], bmin[3 * i + 2]);
+            o.bbWorld.max = hm::Vec3(bmax[3 * i], bmax[3 * i + 1], bmax[3 * i + 2]);
+            fe->scene.push_back(o);
+        }
+    });
+}
+
+int PLAIN_FE(render_frame)(plain_frontend* fe, const plain_camera_extrinsic* cam, float time, float deltaTime, const plain_frame_inputs* in) {
+    FE_TRY(fe, {
+        RenderFrontend& f = fe->fe;
+        f.markNewFrame(time, deltaTime);
+        f.prepareNewFrame();
+        if (in) {  // what depthPrepass / sunShadow / the G-buffer producer write during the frame
+            const FrameRenderTargets& t = f.currentTargets();
+            const size_t px = (size_t)f.m_screenWidth * f.m_screenHeight;
+            auto up = [&](ImageHandle h, const void* p, size_t size) {
+                if (!p) return;
+                if (in->async_upload) f.backend.writeImageAsync(h, 0, p, size);
+                else f.backend.writeImage(h, 0, p, size);
+            };
+            up(t.depthBuffer, in->depth, px * 4);
+            up(t.motionBuffer, in->motion, px * 4);
+            up(f.m_worldSpaceNormalImage, in->normal, px * 4);
+            up(f.m_gbuffer, in->gbuffer, px * 16);
+            for (int i = 0; i < 4; i++) up(f.m_shadowMaps[i], in->shadow_maps[i], (size_t)2048 * 2048 * 2);
+        }
+        CameraExtrinsic e;
+        e.position = hm::Vec3(cam->position[0], cam->position[1], cam->position[2]);
+        e.forward = hm::Vec3(cam->forward[0], cam->forward[1], cam->forward[2]);
+        e.right = hm::Vec3(cam->right[0], cam->right[1], cam->right[2]);
+        e.up = hm::Vec3(cam->up[0], cam->up[1], cam->up[2]);
+        f.setCameraExtrinsic(e);
+        f.prepareForDrawcalls();
+        f.renderScene(fe->scene);
+        f.renderFrame();
+    });
+}
+int PLAIN_FE(read_output)(plain_frontend* fe, void* out, size_t size, int32_t asyncPinned) {
+    FE_TRY(fe, {
+        ImageHandle h = fe->fe.backend.getSwapchainInputImage();
+        if (asyncPinned) fe->fe.backend.readImageAsync(h, 0, out, size);
+        else fe->fe.backend.readImage(h, 0, out, size);
+    });
+}
+
+int PLAIN_FE(get_image)(plain_frontend* fe, const char* name, plain_image_handle* out) {
+    RenderFrontend& f = fe->fe;
+    std::map<std::string, ImageHandle> m = {
+        {"color0", f.m_frameRenderTargets[0].colorBuffer}, {"color1", f.m_frameRenderTargets[1].colorBuffer},
+        {"depth0", f.m_frameRenderTargets[0].depthBuffer}, {"depth1", f.m_frameRenderTargets[1].depthBuffer},
+        {"motion0", f.m_frameRenderTargets[0].motionBuffer}, {"motion1", f.m_frameRenderTargets[1].motionBuffer},
+        {"post0", f.m_postProcessBuffers[0]}, {"post1", f.m_postProcessBuffers[1]}, {"normal", f.m_worldSpaceNormalImage}, {"gbuffer", f.m_gbuffer},
+        {"depthHalf", f.m_depthHalfRes}, {"hiz", f.m_minMaxDepthPyramid}, {"brdfLut", f.m_brdfLut},
+        {"skyTransmission", f.m_sky.m_skyTransmissionLut}, {"skyMultiscatter", f.m_sky.m_skyMultiscatterLut}, {"skyLut", f.m_sky.m_skyLut},
+        {"shadow0", f.m_shadowMaps[0]}, {"shadow1", f.m_shadowMaps[1]}, {"shadow2", f.m_shadowMaps[2]}, {"shadow3", f.m_shadowMaps[3]},
+        {"giY0", f.m_sdfGi.m_indirectDiffuse_Y_SH[0]}, {"giY1", f.m_sdfGi.m_indirectDiffuse_Y_SH[1]}, {"giC0", f.m_sdfGi.m_indirectDiffuse_CoCg[0]}, {"giC1", f.m_sdfGi.m_indirectDiffuse_CoCg[1]},
+        {"giHistY0", f.m_sdfGi.m_indirectDiffuseHistory_Y_SH[0]}, {"giHistY1", f.m_sdfGi.m_indirectDiffuseHistory_Y_SH[1]},
+        {"giHistC0", f.m_sdfGi.m_indirectDiffuseHistory_CoCg[0]}, {"giHistC1", f.m_sdfGi.m_indirectDiffuseHistory_CoCg[1]},
+        {"giFullY", f.m_sdfGi.m_indirectLightingFullRes_Y_SH}, {"giFullC", f.m_sdfGi.m_indirectLightingFullRes_CoCg},
+        {"froxelMaterial", f.m_volumetrics.m_volumeMaterialVolume}, {"froxelScatter", f.m_volumetrics.m_scatteringTransmittanceVolume},
+        {"froxelHist0", f.m_volumetrics.m_volumetricLightingHistory[0]}, {"froxelHist1", f.m_volumetrics.m_volumetricLightingHistory[1]},
+        {"froxelIntegration", f.m_volumetrics.m_volumetricIntegrationVolume}, {"taaHist0", f.m_taa.m_historyBuffers[0]}, {"taaHist1", f.m_taa.m_historyBuffers[1]},
+        {"bloomDown", f.m_bloom.m_lastDownscaleTexture}, {"bloomUp", f.m_bloom.m_lastUpscaleTexture}, {"output", f.backend.getSwapchainInputImage()},
+    };
+    auto it = m.find(name);
+    if (it == m.end()) { fe->lastError = std::string("unknown image '") + name + "'"; return 1; }
+    *out = it->second;
+    return 0;
+}
+int PLAIN_FE(get_storage_buffer)(plain_frontend* fe, const char* name, plain_handle* out) {
+    RenderFrontend& f = fe->fe;
+    std::map<std::string, StorageBufferHandle> m = {
+        {"histogram", f.m_histogramBuffer}, {"histogramPerTile", f.m_histogramPerTileBuffer}, {"light", f.m_lightBuffer}, {"sunShadowInfo", f.m_sunShadowInfoBuffer},
+        {"sdfInstances", f.m_sdfGi.m_sdfInstanceBuffer}, {"sdfCulled", f.m_sdfGi.m_sdfCameraFrustumCulledInstances}, {"sdfTiles", f.m_sdfGi.m_sdfCameraCulledTiles},
+        {"sdfWorldBBs", f.m_sdfGi.m_sdfInstanceWorldBBBuffer},
+    };
+    auto it = m.find(name);
+    if (it == m.end()) { fe->lastError = std::string("unknown buffer '") + name + "'"; return 1; }
+    *out = it->second.index;
+    return 0;
+}
+int PLAIN_FE(get_global_shader_info)(plain_frontend* fe, void* out) { std::memcpy(out, &fe->fe.m_globalShaderInfo, sizeof(plain_global_shader_info)); return 0; }
+int PLAIN_FE(get_resolve_weights)(plain_frontend* fe, float out[9]) { std::memcpy(out, fe->fe.m_taa.m_lastResolveWeights.data(), sizeof(float) * 9); return 0; }
+int PLAIN_FE(set_exposure)(plain_frontend* fe, float previousFrameExposure) {
+    FE_TRY(fe, {
+        plain_light_buffer lb{};
+        lb.previousFrameExposure = previousFrameExposure;
+        lb.sunStrengthExposed = fe->fe.m_globalShaderInfo.sunStrength * previousFrameExposure;
+        lb.sunColor[0] = lb.sunColor[1] = lb.sunColor[2] = 1.f;
+        fe->fe.backend.setStorageBufferData(fe->fe.m_lightBuffer, &lb, sizeof(lb));
+    });
+}
+
+}  // extern "C"
