@@ -78,7 +78,7 @@ inline float smallFloatToFloat(uint32_t v, int mbits, bool hasSign) {
     return dm::u2f(out | (sign << 31));
 }
 
-inline uint16_t floatToHalf(float f) { return (uint16_t)floatToSmallFloat(f, 10, true, true); }
+inline uint16_t floatToHalf(float f) { return isnan(f) ? (uint16_t)0x7fffu : (uint16_t)floatToSmallFloat(f, 10, true, true); }  // NaN -> 0x7fff (what cvt.rn.f16.f32 gives)
 inline float halfToFloat(uint16_t h) { return smallFloatToFloat(h, 10, true); }
 inline uint32_t packR11G11B10(vec3 c) {
     return floatToSmallFloat(c.x, 6, false, false) | (floatToSmallFloat(c.y, 6, false, false) << 11) | (floatToSmallFloat(c.z, 5, false, false) << 22);

@@ -1,0 +1,618 @@
+// backend.cu - CUDA implementation of include/plain_b200.h (symbols plain_*): the drop-in for the compute-pass
+// subset of the reference's RenderBackend (Plain/src/Runtime/Rendering/Backend/RenderBackend.h:33-110).
+//
+//   * handles are indices into tables owned by the context (RenderHandles.h:4-33); no public destroy
+//   * set_*_buffer_data copies the bytes before returning and applies them at render_frame, before any pass of the
+//     frame (RenderBackend.cpp:315-321, 896-911): the fills of a frame are packed into one pinned staging block,
+//     moved with ONE host->device copy and scattered to their buffers by one kernel
+//   * executions are replayed in submission order on one stream (RenderBackend.cpp:769-786); the in-order stream
+//     replaces the reference's barriers
+//   * an unchanged pass list (same passes, resources, push constants) is replayed as an instantiated CUDA graph:
+//     kernels read uniform/storage buffers through pointers, so only buffer contents differ between frames
+//   * there is no CPU fallback: every pass is a CUDA kernel looked up by the reference's shader file name; an unknown
+//     shader name or a missing device is an error
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstring>
+#include <unordered_map>
+#include "pass_common.cuh"
+
+namespace pb {
+
+static std::map<std::string, LaunchFn>& registry() {
+    static std::map<std::string, LaunchFn> r;
+    return r;
+}
+PassRegistration::PassRegistration(const char* shader, LaunchFn fn) { registry()[shader] = fn; }
+
+struct FillOrder {
+    bool uniform;
+    uint32_t buffer;
+    size_t offsetInStaging, size;
+};
+struct FillSegment {  // one entry of the scatter table that travels at the head of the staging block
+    unsigned long long dst;
+    uint32_t srcOffset, size;
+};
+static const size_t kMaxFillSegments = 64;
+static const size_t kStagingHeader = kMaxFillSegments * sizeof(FillSegment);
+static const size_t kStagingBytes = 1u << 20;
+
+struct CachedGraph {
+    cudaGraphExec_t exec = nullptr;
+    uint32_t launches = 0;
+};
+
+struct Backend {
+    int device = 0;
+    int smCount = 148;
+    cudaStream_t stream = nullptr;
+    std::vector<DeviceImage> images, transientImages;
+    DeviceImage swapchain;
+    std::vector<DeviceBuffer> uniformBuffers, storageBuffers;
+    std::vector<plain_sampler_desc> samplers;
+    std::vector<PassRecord> passes;
+    std::vector<ExecRecord> execs;
+    std::vector<FillOrder> fills;
+    uint32_t globalUniformBuffer = PLAIN_INVALID_INDEX;
+    std::string lastError;
+
+    unsigned char* stagingHost = nullptr;  // pinned
+    unsigned char* stagingDevice = nullptr;
+    size_t stagingUsed = kStagingHeader;
+    cudaEvent_t stagingConsumed = nullptr;
+    bool stagingInFlight = false;
+
+    BindlessEntry* bindlessDevice = nullptr;
+    static const uint32_t kMaxBindless = 4096;
+
+    bool timingEnabled = false;
+    std::vector<plain_pass_time> timings;
+    std::vector<cudaEvent_t> timingEvents;
+
+    bool graphEnabled = false;
+    std::unordered_map<uint64_t, CachedGraph> graphs;
+    uint32_t passEpoch = 0;  // bumped when a pass description or an image allocation changes: invalidates cached graphs
+    uint32_t lastFrameLaunches = 0;
+    uint32_t launchCounter = 0;
+
+    DeviceImage* resolve(plain_image_handle h) {
+        if (h.type == PLAIN_IMAGE_HANDLE_SWAPCHAIN) return &swapchain;
+        if (h.type == PLAIN_IMAGE_HANDLE_TRANSIENT) return h.index < transientImages.size() ? &transientImages[h.index] : nullptr;
+        return h.index < images.size() ? &images[h.index] : nullptr;
+    }
+};
+
+static int formatBytesPerTexel(uint32_t fmt) {
+    switch (fmt) {
+        case PLAIN_FORMAT_R8: return 1;
+        case PLAIN_FORMAT_RG8: return 2;
+        case PLAIN_FORMAT_RGBA8: return 4;
+        case PLAIN_FORMAT_R16_SFLOAT: return 2;
+        case PLAIN_FORMAT_RG16_SFLOAT: return 4;
+        case PLAIN_FORMAT_RG32_SFLOAT: return 8;
+        case PLAIN_FORMAT_RG16_SNORM: return 4;
+        case PLAIN_FORMAT_RGBA16_SFLOAT: return 8;
+        case PLAIN_FORMAT_RGBA16_SNORM: return 8;
+        case PLAIN_FORMAT_RGBA32_SFLOAT: return 16;
+        case PLAIN_FORMAT_R11G11B10_UFLOAT: return 4;
+        case PLAIN_FORMAT_DEPTH16: return 2;
+        case PLAIN_FORMAT_DEPTH32: return 4;
+        case PLAIN_FORMAT_BGRA8_UNORM: return 4;
+        case PLAIN_FORMAT_RGBA32_UINT: return 16;
+        default: return 0;  // BCn: material textures are baked into the G-buffer, not on the frame path
+    }
+}
+
+static int computeMipCount(const plain_image_desc& d) {
+    if (d.mip_count == PLAIN_MIPS_ONE) return 1;
+    if (d.mip_count == PLAIN_MIPS_MANUAL) return (int)d.manual_mip_count;
+    uint32_t m = d.width > d.height ? d.width : d.height;
+    if (d.depth > m) m = d.depth;
+    int n = 1;
+    while (m > 1) { m >>= 1; n++; }  // 1 + floor(log2(max)), MathUtils.cpp:17-19
+    return n;
+}
+
+static bool allocateImage(Backend& b, DeviceImage& img, const plain_image_desc& d) {
+    if (img.ptr) { cudaStreamSynchronize(b.stream); cudaFree(img.ptr); img.ptr = nullptr; }
+    img.desc = d;
+    const int n = computeMipCount(d), bpt = formatBytesPerTexel(d.format);
+    img.mips.assign(n, MipInfo());
+    size_t off = 0;
+    for (int i = 0; i < n; i++) {
+        MipInfo& m = img.mips[i];
+        m.w = std::max((int)d.width >> i, 1);
+        m.h = std::max((int)d.height >> i, 1);
+        m.d = std::max((int)(d.depth ? d.depth : 1) >> i, 1);
+        m.offset = off;
+        m.bytes = (size_t)m.w * m.h * m.d * bpt;
+        off = (off + m.bytes + 255) & ~(size_t)255;
+    }
+    img.bytes = off;
+    if (cudaMalloc(&img.ptr, img.bytes ? img.bytes : 256) != cudaSuccess) return false;
+    cudaMemsetAsync(img.ptr, 0, img.bytes ? img.bytes : 256, b.stream);
+    b.passEpoch++;
+    return true;
+}
+
+static ImgView makeView(LaunchCtx& c, const plain_image_resource& r, int expectFormat, const char* what, uint32_t binding) {
+    ImgView v{nullptr, 0, 0, 0};
+    DeviceImage* img = c.be->resolve(r.image);
+    if (!img || r.mip_level >= img->mips.size()) {
+        c.fail(c.pass->shader + ": " + what + " binding " + std::to_string(binding) + " has an invalid image handle or mip level");
+        return v;
+    }
+    if (expectFormat >= 0 && (int)img->desc.format != expectFormat) {
+        c.fail(c.pass->shader + ": " + what + " binding " + std::to_string(binding) + " has format " + std::to_string(img->desc.format) + ", expected " + std::to_string(expectFormat));
+        return v;
+    }
+    const MipInfo& m = img->mips[r.mip_level];
+    v.ptr = img->ptr + m.offset;
+    v.w = m.w; v.h = m.h; v.d = m.d;
+    return v;
+}
+ImgView LaunchCtx::sampled(uint32_t binding, int expectFormat) {
+    for (auto& r : exec->sampledImages) if (r.binding == binding) return makeView(*this, r, expectFormat, "sampled image", binding);
+    fail(pass->shader + ": no sampled image at binding " + std::to_string(binding));
+    return ImgView{nullptr, 0, 0, 0};
+}
+ImgView LaunchCtx::storage(uint32_t binding, int expectFormat) {
+    for (auto& r : exec->storageImages) if (r.binding == binding) return makeView(*this, r, expectFormat, "storage image", binding);
+    fail(pass->shader + ": no storage image at binding " + std::to_string(binding));
+    return ImgView{nullptr, 0, 0, 0};
+}
+int LaunchCtx::sampledFormat(uint32_t binding) {
+    for (auto& r : exec->sampledImages)
+        if (r.binding == binding) { DeviceImage* img = be->resolve(r.image); return img ? (int)img->desc.format : -1; }
+    return -1;
+}
+void* LaunchCtx::sbufRaw(uint32_t binding, size_t* size) {
+    for (auto& r : exec->storageBuffers)
+        if (r.binding == binding && r.buffer < be->storageBuffers.size()) {
+            if (size) *size = be->storageBuffers[r.buffer].size;
+            return be->storageBuffers[r.buffer].ptr;
+        }
+    fail(pass->shader + ": no storage buffer at binding " + std::to_string(binding));
+    return nullptr;
+}
+const void* LaunchCtx::ubufRaw(uint32_t binding) {
+    for (auto& r : exec->uniformBuffers)
+        if (r.binding == binding && r.buffer < be->uniformBuffers.size()) return be->uniformBuffers[r.buffer].ptr;
+    fail(pass->shader + ": no uniform buffer at binding " + std::to_string(binding));
+    return nullptr;
+}
+void LaunchCtx::countLaunch(int n) { be->launchCounter += (uint32_t)n; }
+
+// scatter the staged fills to their buffers: one block per segment, 4-byte words (+ byte tail)
+__global__ void scatterFillsKernel(const unsigned char* __restrict__ staging, int nSegments) {
+    const FillSegment seg = ((const FillSegment*)staging)[blockIdx.x];
+    if ((int)blockIdx.x >= nSegments) return;
+    unsigned char* dst = (unsigned char*)seg.dst;
+    const unsigned char* src = staging + seg.srcOffset;
+    if ((((unsigned long long)dst | seg.srcOffset) & 3u) == 0) {
+        const uint32_t words = seg.size >> 2;
+        for (uint32_t i = threadIdx.x; i < words; i += blockDim.x) ((uint32_t*)dst)[i] = ((const uint32_t*)src)[i];
+        for (uint32_t i = (words << 2) + threadIdx.x; i < seg.size; i += blockDim.x) dst[i] = src[i];
+    } else {
+        for (uint32_t i = threadIdx.x; i < seg.size; i += blockDim.x) dst[i] = src[i];
+    }
+}
+
+static uint64_t fnv(uint64_t h, const void* data, size_t n) {
+    const uint8_t* p = (const uint8_t*)data;
+    for (size_t i = 0; i < n; i++) { h ^= p[i]; h *= 1099511628211ull; }
+    return h;
+}
+static uint64_t hashExecs(const Backend& b) {
+    uint64_t h = 1469598103934665603ull;
+    h = fnv(h, &b.passEpoch, sizeof(b.passEpoch));
+    h = fnv(h, &b.globalUniformBuffer, sizeof(uint32_t));
+    for (auto& e : b.execs) {
+        h = fnv(h, &e.pass, 4);
+        uint32_t n;
+        n = (uint32_t)e.storageBuffers.size(); h = fnv(h, &n, 4); h = fnv(h, e.storageBuffers.data(), n * sizeof(e.storageBuffers[0]));
+        n = (uint32_t)e.uniformBuffers.size(); h = fnv(h, &n, 4); h = fnv(h, e.uniformBuffers.data(), n * sizeof(e.uniformBuffers[0]));
+        n = (uint32_t)e.sampledImages.size(); h = fnv(h, &n, 4); h = fnv(h, e.sampledImages.data(), n * sizeof(e.sampledImages[0]));
+        n = (uint32_t)e.storageImages.size(); h = fnv(h, &n, 4); h = fnv(h, e.storageImages.data(), n * sizeof(e.storageImages[0]));
+        n = (uint32_t)e.pushConstants.size(); h = fnv(h, &n, 4); h = fnv(h, e.pushConstants.data(), n);
+        h = fnv(h, e.dispatch, sizeof(e.dispatch));
+    }
+    return h;
+}
+
+static bool runPasses(Backend& b, bool withTiming) {
+    size_t ev = 0;
+    for (auto& e : b.execs) {
+        LaunchCtx c;
+        c.be = &b;
+        c.pass = &b.passes[e.pass];
+        c.exec = &e;
+        c.stream = b.stream;
+        c.smCount = b.smCount;
+        c.g = b.globalUniformBuffer < b.uniformBuffers.size() ? (const plain_global_shader_info*)b.uniformBuffers[b.globalUniformBuffer].ptr : nullptr;
+        c.bindless = b.bindlessDevice;
+        if (!c.g) { b.lastError = "render_frame: no global uniform buffer bound (set_global_descriptor_set_resources)"; return false; }
+        if (withTiming) {
+            while (b.timingEvents.size() < ev + 2) { cudaEvent_t x; cudaEventCreate(&x); b.timingEvents.push_back(x); }
+            cudaEventRecord(b.timingEvents[ev], b.stream);
+        }
+        c.pass->fn(c);
+        if (withTiming) { cudaEventRecord(b.timingEvents[ev + 1], b.stream); ev += 2; }
+        if (c.failed) { b.lastError = c.error; return false; }
+    }
+    return true;
+}
+
+}  // namespace pb
+
+using namespace pb;
+
+struct plain_ctx {
+    Backend b;
+};
+
+static int fail(plain_ctx* ctx, const std::string& msg) {
+    if (ctx) ctx->b.lastError = msg;
+    return 1;
+}
+#define CU_CHECK(ctx, call)                                                                            \
+    do {                                                                                               \
+        cudaError_t e__ = (call);                                                                      \
+        if (e__ != cudaSuccess) return fail(ctx, std::string(#call) + ": " + cudaGetErrorString(e__)); \
+    } while (0)
+
+static void updateBindless(Backend& b, uint32_t index) {
+    if (index >= Backend::kMaxBindless) return;
+    const DeviceImage& img = b.images[index];
+    BindlessEntry e;
+    e.view.ptr = img.ptr; e.view.w = img.mips[0].w; e.view.h = img.mips[0].h; e.view.d = img.mips[0].d;
+    e.format = img.desc.format; e.pad = 0;
+    cudaMemcpyAsync(b.bindlessDevice + index, &e, sizeof(e), cudaMemcpyHostToDevice, b.stream);
+    cudaStreamSynchronize(b.stream);
+}
+
+extern "C" {
+
+int PLAIN_FN(backend_create)(int device, uint32_t width, uint32_t height, plain_ctx** out_ctx) {
+    if (!out_ctx) return 1;
+    *out_ctx = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) {
+        fprintf(stderr, "plain_backend_create: CUDA device %d not available (%d devices) - this backend has no CPU path\n", device, count);
+        return 1;
+    }
+    if (cudaSetDevice(device) != cudaSuccess) return 1;
+    plain_ctx* ctx = new plain_ctx();
+    Backend& b = ctx->b;
+    b.device = device;
+    cudaDeviceGetAttribute(&b.smCount, cudaDevAttrMultiProcessorCount, device);
+    if (cudaStreamCreateWithFlags(&b.stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return 1; }
+    cudaEventCreateWithFlags(&b.stagingConsumed, cudaEventDisableTiming);
+    if (cudaMallocHost(&b.stagingHost, kStagingBytes) != cudaSuccess || cudaMalloc(&b.stagingDevice, kStagingBytes) != cudaSuccess ||
+        cudaMalloc(&b.bindlessDevice, sizeof(BindlessEntry) * Backend::kMaxBindless) != cudaSuccess) {
+        fprintf(stderr, "plain_backend_create: allocation failed: %s\n", cudaGetErrorString(cudaGetLastError()));
+        delete ctx;
+        return 1;
+    }
+    cudaMemsetAsync(b.bindlessDevice, 0, sizeof(BindlessEntry) * Backend::kMaxBindless, b.stream);
+    plain_image_desc d{};
+    d.width = width; d.height = height; d.depth = 1;
+    d.type = PLAIN_IMAGE_TYPE_2D; d.format = PLAIN_FORMAT_BGRA8_UNORM;  // VulkanSurface.cpp:41-46
+    d.usage_flags = PLAIN_USAGE_STORAGE; d.mip_count = PLAIN_MIPS_ONE;
+    if (!allocateImage(b, b.swapchain, d)) { delete ctx; return 1; }
+    *out_ctx = ctx;
+    return 0;
+}
+void PLAIN_FN(backend_destroy)(plain_ctx* ctx) {
+    if (!ctx) return;
+    Backend& b = ctx->b;
+    cudaSetDevice(b.device);
+    cudaStreamSynchronize(b.stream);
+    for (auto& g : b.graphs) if (g.second.exec) cudaGraphExecDestroy(g.second.exec);
+    for (auto& i : b.images) cudaFree(i.ptr);
+    for (auto& i : b.transientImages) cudaFree(i.ptr);
+    cudaFree(b.swapchain.ptr);
+    for (auto& u : b.uniformBuffers) cudaFree(u.ptr);
+    for (auto& s : b.storageBuffers) cudaFree(s.ptr);
+    for (auto& e : b.timingEvents) cudaEventDestroy(e);
+    cudaFree(b.stagingDevice);
+    cudaFreeHost(b.stagingHost);
+    cudaFree(b.bindlessDevice);
+    cudaEventDestroy(b.stagingConsumed);
+    cudaStreamDestroy(b.stream);
+    delete ctx;
+}
+const char* PLAIN_FN(last_error)(plain_ctx* ctx) { return ctx ? ctx->b.lastError.c_str() : "null context"; }
+int PLAIN_FN(recreate_swapchain)(plain_ctx* ctx, uint32_t width, uint32_t height) {
+    plain_image_desc d = ctx->b.swapchain.desc;
+    d.width = width; d.height = height;
+    return allocateImage(ctx->b, ctx->b.swapchain, d) ? 0 : fail(ctx, "recreate_swapchain: allocation failed");
+}
+
+int PLAIN_FN(create_image)(plain_ctx* ctx, const plain_image_desc* desc, const void* initial_data, size_t initial_data_size, plain_image_handle* out) {
+    if (!desc || !out) return fail(ctx, "create_image: null argument");
+    if (formatBytesPerTexel(desc->format) == 0) return fail(ctx, "create_image: format not supported on the frame path");
+    Backend& b = ctx->b;
+    cudaSetDevice(b.device);
+    DeviceImage img;
+    if (!allocateImage(b, img, *desc)) return fail(ctx, std::string("create_image: cudaMalloc failed: ") + cudaGetErrorString(cudaGetLastError()));
+    if (initial_data) {
+        size_t off = 0;
+        const size_t levels = desc->mip_count == PLAIN_MIPS_FULL_CHAIN_ALREADY_IN_DATA ? img.mips.size() : 1;
+        for (size_t i = 0; i < levels; i++) {
+            if (off + img.mips[i].bytes > initial_data_size) { cudaFree(img.ptr); return fail(ctx, "create_image: initial data too small"); }
+            CU_CHECK(ctx, cudaMemcpyAsync(img.ptr + img.mips[i].offset, (const uint8_t*)initial_data + off, img.mips[i].bytes, cudaMemcpyHostToDevice, b.stream));
+            off += img.mips[i].bytes;
+        }
+        CU_CHECK(ctx, cudaStreamSynchronize(b.stream));  // the caller's memory may go away after the call (RenderBackend.cpp:315-321)
+    }
+    b.images.push_back(std::move(img));
+    out->type = PLAIN_IMAGE_HANDLE_DEFAULT;
+    out->index = (uint32_t)b.images.size() - 1;
+    updateBindless(b, out->index);
+    return 0;
+}
+int PLAIN_FN(create_temporary_image)(plain_ctx* ctx, const plain_image_desc* desc, plain_image_handle* out) {
+    // valid for one frame; the allocation is reused across frames when the description matches (RenderBackend.cpp:1026-1123)
+    Backend& b = ctx->b;
+    for (size_t i = 0; i < b.transientImages.size(); i++) {
+        DeviceImage& t = b.transientImages[i];
+        if (!t.inUse && memcmp(&t.desc, desc, sizeof(*desc)) == 0) {
+            t.inUse = true;
+            out->type = PLAIN_IMAGE_HANDLE_TRANSIENT; out->index = (uint32_t)i;
+            return 0;
+        }
+    }
+    if (formatBytesPerTexel(desc->format) == 0) return fail(ctx, "create_temporary_image: format not supported");
+    cudaSetDevice(b.device);
+    DeviceImage img;
+    if (!allocateImage(b, img, *desc)) return fail(ctx, "create_temporary_image: cudaMalloc failed");
+    img.inUse = true;
+    b.transientImages.push_back(std::move(img));
+    out->type = PLAIN_IMAGE_HANDLE_TRANSIENT;
+    out->index = (uint32_t)b.transientImages.size() - 1;
+    return 0;
+}
+int PLAIN_FN(resize_images)(plain_ctx* ctx, const plain_image_handle* images, uint32_t n, uint32_t width, uint32_t height) {
+    Backend& b = ctx->b;
+    cudaSetDevice(b.device);
+    for (uint32_t i = 0; i < n; i++) {
+        DeviceImage* img = b.resolve(images[i]);
+        if (!img) return fail(ctx, "resize_images: invalid handle");
+        plain_image_desc d = img->desc;
+        d.width = width; d.height = height;
+        if (!allocateImage(b, *img, d)) return fail(ctx, "resize_images: cudaMalloc failed");
+        if (images[i].type == PLAIN_IMAGE_HANDLE_DEFAULT) updateBindless(b, images[i].index);
+    }
+    return 0;
+}
+int PLAIN_FN(get_image_description)(plain_ctx* ctx, plain_image_handle image, plain_image_desc* out) {
+    DeviceImage* img = ctx->b.resolve(image);
+    if (!img) return fail(ctx, "get_image_description: invalid handle");
+    *out = img->desc;
+    return 0;
+}
+int PLAIN_FN(get_image_global_texture_array_index)(plain_ctx* ctx, plain_image_handle image, uint32_t* out) {
+    if (image.type != PLAIN_IMAGE_HANDLE_DEFAULT || image.index >= ctx->b.images.size() || image.index >= Backend::kMaxBindless) return fail(ctx, "global texture index: invalid handle");
+    *out = image.index;
+    return 0;
+}
+static int createBuffer(plain_ctx* ctx, std::vector<DeviceBuffer>& table, size_t size, const void* initial_data, plain_handle* out) {
+    Backend& b = ctx->b;
+    cudaSetDevice(b.device);
+    DeviceBuffer buf;
+    buf.size = size;
+    CU_CHECK(ctx, cudaMalloc(&buf.ptr, size ? size : 4));
+    CU_CHECK(ctx, cudaMemsetAsync(buf.ptr, 0, size ? size : 4, b.stream));
+    if (initial_data) {
+        CU_CHECK(ctx, cudaMemcpyAsync(buf.ptr, initial_data, size, cudaMemcpyHostToDevice, b.stream));
+        CU_CHECK(ctx, cudaStreamSynchronize(b.stream));
+    }
+    table.push_back(buf);
+    *out = (uint32_t)table.size() - 1;
+    b.passEpoch++;
+    return 0;
+}
+int PLAIN_FN(create_uniform_buffer)(plain_ctx* ctx, size_t size, const void* initial_data, plain_handle* out) { return createBuffer(ctx, ctx->b.uniformBuffers, size, initial_data, out); }
+int PLAIN_FN(create_storage_buffer)(plain_ctx* ctx, size_t size, const void* initial_data, plain_handle* out) { return createBuffer(ctx, ctx->b.storageBuffers, size, initial_data, out); }
+int PLAIN_FN(create_sampler)(plain_ctx* ctx, const plain_sampler_desc* desc, plain_handle* out) {
+    // samplers are compile-time policy of each kernel (the 8 immutable samplers of global.inc:35-42); the table only keeps handles valid
+    ctx->b.samplers.push_back(*desc);
+    *out = (uint32_t)ctx->b.samplers.size() - 1;
+    return 0;
+}
+int PLAIN_FN(get_swapchain_input_image)(plain_ctx* ctx, plain_image_handle* out) {
+    (void)ctx;
+    out->type = PLAIN_IMAGE_HANDLE_SWAPCHAIN;
+    out->index = 0;
+    return 0;
+}
+
+static int fillPass(plain_ctx* ctx, PassRecord& p, const char* shader, const plain_spec_const* consts, uint32_t n) {
+    p.shader = shader;
+    p.spec.clear();
+    for (uint32_t i = 0; i < n; i++) {
+        const uint8_t* d = (const uint8_t*)consts[i].data;
+        p.spec[consts[i].location] = std::vector<uint8_t>(d, d + consts[i].size);
+    }
+    auto it = registry().find(p.shader);
+    if (it == registry().end()) return fail(ctx, std::string("no CUDA kernel registered for shader '") + shader + "'");
+    p.fn = it->second;
+    ctx->b.passEpoch++;
+    return 0;
+}
+int PLAIN_FN(create_compute_pass)(plain_ctx* ctx, const char* shader, const plain_spec_const* consts, uint32_t n_consts, const char* debug_name, plain_handle* out) {
+    PassRecord p;
+    if (fillPass(ctx, p, shader, consts, n_consts)) return 1;
+    p.name = debug_name ? debug_name : shader;
+    ctx->b.passes.push_back(std::move(p));
+    *out = (uint32_t)ctx->b.passes.size() - 1;
+    return 0;
+}
+int PLAIN_FN(update_compute_pass_shader_description)(plain_ctx* ctx, plain_handle pass, const char* shader, const plain_spec_const* consts, uint32_t n_consts) {
+    if (pass >= ctx->b.passes.size()) return fail(ctx, "update pass: invalid handle");
+    return fillPass(ctx, ctx->b.passes[pass], shader, consts, n_consts);
+}
+int PLAIN_FN(set_global_descriptor_set_resources)(plain_ctx* ctx, const plain_pass_resources* r) {
+    for (uint32_t i = 0; i < r->n_uniform_buffers; i++)
+        if (r->uniform_buffers[i].binding == 0) ctx->b.globalUniformBuffer = r->uniform_buffers[i].buffer;
+    return 0;
+}
+
+int PLAIN_FN(new_frame)(plain_ctx* ctx) {
+    ctx->b.execs.clear();
+    for (auto& t : ctx->b.transientImages) t.inUse = false;
+    return 0;
+}
+int PLAIN_FN(set_compute_pass_execution)(plain_ctx* ctx, const plain_compute_pass_execution* e) {
+    if (e->pass >= ctx->b.passes.size()) return fail(ctx, "set_compute_pass_execution: invalid pass handle");
+    ExecRecord r;
+    r.pass = e->pass;
+    const plain_pass_resources& s = e->resources;
+    r.storageBuffers.assign(s.storage_buffers, s.storage_buffers + s.n_storage_buffers);
+    r.uniformBuffers.assign(s.uniform_buffers, s.uniform_buffers + s.n_uniform_buffers);
+    r.sampledImages.assign(s.sampled_images, s.sampled_images + s.n_sampled_images);
+    r.storageImages.assign(s.storage_images, s.storage_images + s.n_storage_images);
+    const uint8_t* pc = (const uint8_t*)e->push_constants;
+    if (pc) r.pushConstants.assign(pc, pc + e->push_constant_size);
+    for (int i = 0; i < 3; i++) r.dispatch[i] = e->dispatch_count[i];
+    ctx->b.execs.push_back(std::move(r));
+    return 0;
+}
+int PLAIN_FN(prepare_for_drawcall_recording)(plain_ctx* ctx) { (void)ctx; return 0; }
+
+static int stageFill(plain_ctx* ctx, bool uniform, plain_handle buffer, const void* data, size_t size) {
+    Backend& b = ctx->b;
+    std::vector<DeviceBuffer>& table = uniform ? b.uniformBuffers : b.storageBuffers;
+    if (buffer >= table.size() || size > table[buffer].size) return fail(ctx, "set_buffer_data: invalid buffer/size");
+    if (b.stagingInFlight) {  // the previous frame's staged copy must have left the pinned block before it is rewritten
+        cudaEventSynchronize(b.stagingConsumed);
+        b.stagingInFlight = false;
+    }
+    const size_t aligned = (size + 15) & ~(size_t)15;
+    if (b.fills.size() >= kMaxFillSegments || b.stagingUsed + aligned > kStagingBytes) return fail(ctx, "set_buffer_data: staging block full (too many / too large fills in one frame)");
+    memcpy(b.stagingHost + b.stagingUsed, data, size);
+    b.fills.push_back(FillOrder{uniform, buffer, b.stagingUsed, size});
+    b.stagingUsed += aligned;
+    return 0;
+}
+int PLAIN_FN(set_uniform_buffer_data)(plain_ctx* ctx, plain_handle buffer, const void* data, size_t size) { return stageFill(ctx, true, buffer, data, size); }
+int PLAIN_FN(set_storage_buffer_data)(plain_ctx* ctx, plain_handle buffer, const void* data, size_t size) { return stageFill(ctx, false, buffer, data, size); }
+
+int PLAIN_FN(render_frame)(plain_ctx* ctx, int present) {
+    (void)present;
+    Backend& b = ctx->b;
+    cudaSetDevice(b.device);
+    b.launchCounter = 0;
+    // all fills of the frame land before any pass (RenderBackend.cpp:896-911): one H2D copy + one scatter kernel
+    if (!b.fills.empty()) {
+        FillSegment* table = (FillSegment*)b.stagingHost;
+        for (size_t i = 0; i < b.fills.size(); i++) {
+            const FillOrder& f = b.fills[i];
+            DeviceBuffer& dst = f.uniform ? b.uniformBuffers[f.buffer] : b.storageBuffers[f.buffer];
+            table[i].dst = (unsigned long long)dst.ptr;
+            table[i].srcOffset = (uint32_t)f.offsetInStaging;
+            table[i].size = (uint32_t)f.size;
+        }
+        CU_CHECK(ctx, cudaMemcpyAsync(b.stagingDevice, b.stagingHost, b.stagingUsed, cudaMemcpyHostToDevice, b.stream));
+        cudaEventRecord(b.stagingConsumed, b.stream);
+        b.stagingInFlight = true;
+        scatterFillsKernel<<<(unsigned)b.fills.size(), 128, 0, b.stream>>>(b.stagingDevice, (int)b.fills.size());
+        b.launchCounter++;
+        b.fills.clear();
+        b.stagingUsed = kStagingHeader;
+    }
+    const uint32_t fillLaunches = b.launchCounter;
+    b.timings.clear();
+    if (b.timingEnabled) {
+        if (!runPasses(b, true)) return 1;
+        CU_CHECK(ctx, cudaStreamSynchronize(b.stream));
+        for (size_t i = 0; i < b.execs.size(); i++) {
+            plain_pass_time pt;
+            snprintf(pt.name, sizeof(pt.name), "%s", b.passes[b.execs[i].pass].name.c_str());
+            cudaEventElapsedTime(&pt.time_ms, b.timingEvents[2 * i], b.timingEvents[2 * i + 1]);
+            b.timings.push_back(pt);
+        }
+    } else if (b.graphEnabled) {
+        const uint64_t key = hashExecs(b);
+        auto it = b.graphs.find(key);
+        if (it == b.graphs.end()) {
+            cudaGraph_t graph = nullptr;
+            CU_CHECK(ctx, cudaStreamBeginCapture(b.stream, cudaStreamCaptureModeThreadLocal));
+            const bool ok = runPasses(b, false);
+            cudaError_t ce = cudaStreamEndCapture(b.stream, &graph);
+            if (!ok) { if (graph) cudaGraphDestroy(graph); return 1; }
+            if (ce != cudaSuccess) return fail(ctx, std::string("graph capture failed: ") + cudaGetErrorString(ce));
+            CachedGraph cg;
+            cg.launches = b.launchCounter - fillLaunches;
+            ce = cudaGraphInstantiate(&cg.exec, graph, 0);
+            cudaGraphDestroy(graph);
+            if (ce != cudaSuccess) return fail(ctx, std::string("cudaGraphInstantiate failed: ") + cudaGetErrorString(ce));
+            it = b.graphs.emplace(key, cg).first;
+        }
+        CU_CHECK(ctx, cudaGraphLaunch(it->second.exec, b.stream));
+        b.launchCounter = fillLaunches + it->second.launches;
+    } else {
+        if (!runPasses(b, false)) return 1;
+    }
+    cudaError_t e = cudaPeekAtLastError();
+    if (e != cudaSuccess) return fail(ctx, std::string("render_frame: ") + cudaGetErrorString(e));
+    b.lastFrameLaunches = b.launchCounter;
+    return 0;
+}
+int PLAIN_FN(wait_for_gpu_idle)(plain_ctx* ctx) {
+    cudaSetDevice(ctx->b.device);
+    CU_CHECK(ctx, cudaStreamSynchronize(ctx->b.stream));
+    return 0;
+}
+int PLAIN_FN(get_renderpass_timings)(plain_ctx* ctx, plain_pass_time* out, uint32_t capacity, uint32_t* out_count) {
+    const uint32_t n = (uint32_t)ctx->b.timings.size();
+    if (out_count) *out_count = n;
+    for (uint32_t i = 0; i < n && i < capacity; i++) out[i] = ctx->b.timings[i];
+    return 0;
+}
+int PLAIN_FN(set_timing_enabled)(plain_ctx* ctx, int enabled) { ctx->b.timingEnabled = enabled != 0; return 0; }
+
+static int imageCopy(plain_ctx* ctx, plain_image_handle image, uint32_t mip, void* host, size_t size, bool toDevice, bool sync, const char* what) {
+    Backend& b = ctx->b;
+    cudaSetDevice(b.device);
+    DeviceImage* img = b.resolve(image);
+    if (!img || mip >= img->mips.size()) return fail(ctx, std::string(what) + ": invalid handle/mip");
+    if (size != img->mips[mip].bytes) return fail(ctx, std::string(what) + ": size mismatch");
+    unsigned char* dev = img->ptr + img->mips[mip].offset;
+    if (toDevice) CU_CHECK(ctx, cudaMemcpyAsync(dev, host, size, cudaMemcpyHostToDevice, b.stream));
+    else CU_CHECK(ctx, cudaMemcpyAsync(host, dev, size, cudaMemcpyDeviceToHost, b.stream));
+    if (sync) CU_CHECK(ctx, cudaStreamSynchronize(b.stream));
+    return 0;
+}
+int PLAIN_FN(write_image)(plain_ctx* ctx, plain_image_handle image, uint32_t mip, const void* data, size_t size) { return imageCopy(ctx, image, mip, (void*)data, size, true, true, "write_image"); }
+int PLAIN_FN(read_image)(plain_ctx* ctx, plain_image_handle image, uint32_t mip, void* out, size_t size) { return imageCopy(ctx, image, mip, out, size, false, true, "read_image"); }
+int PLAIN_FN(write_image_async)(plain_ctx* ctx, plain_image_handle image, uint32_t mip, const void* data, size_t size) { return imageCopy(ctx, image, mip, (void*)data, size, true, false, "write_image_async"); }
+int PLAIN_FN(read_image_async)(plain_ctx* ctx, plain_image_handle image, uint32_t mip, void* out, size_t size) { return imageCopy(ctx, image, mip, out, size, false, false, "read_image_async"); }
+int PLAIN_FN(read_storage_buffer)(plain_ctx* ctx, plain_handle buffer, void* out, size_t size) {
+    Backend& b = ctx->b;
+    cudaSetDevice(b.device);
+    if (buffer >= b.storageBuffers.size() || size > b.storageBuffers[buffer].size) return fail(ctx, "read_storage_buffer: invalid buffer/size");
+    CU_CHECK(ctx, cudaMemcpyAsync(out, b.storageBuffers[buffer].ptr, size, cudaMemcpyDeviceToHost, b.stream));
+    CU_CHECK(ctx, cudaStreamSynchronize(b.stream));
+    return 0;
+}
+int PLAIN_FN(get_image_device_pointer)(plain_ctx* ctx, plain_image_handle image, uint32_t mip, void** out_ptr, size_t* out_size) {
+    DeviceImage* img = ctx->b.resolve(image);
+    if (!img || mip >= img->mips.size()) return fail(ctx, "get_image_device_pointer: invalid handle/mip");
+    *out_ptr = img->ptr + img->mips[mip].offset;
+    if (out_size) *out_size = img->mips[mip].bytes;
+    return 0;
+}
+int PLAIN_FN(get_storage_buffer_device_pointer)(plain_ctx* ctx, plain_handle buffer, void** out_ptr, size_t* out_size) {
+    if (buffer >= ctx->b.storageBuffers.size()) return fail(ctx, "get_storage_buffer_device_pointer: invalid buffer");
+    *out_ptr = ctx->b.storageBuffers[buffer].ptr;
+    if (out_size) *out_size = ctx->b.storageBuffers[buffer].size;
+    return 0;
+}
+int PLAIN_FN(get_last_frame_launch_count)(plain_ctx* ctx, uint32_t* out) { *out = ctx->b.lastFrameLaunches; return 0; }
+int PLAIN_FN(set_graph_replay_enabled)(plain_ctx* ctx, int enabled) { ctx->b.graphEnabled = enabled != 0; return 0; }
+int PLAIN_FN(get_stream)(plain_ctx* ctx, void** out_stream) { *out_stream = (void*)ctx->b.stream; return 0; }
+
+}  // extern "C"

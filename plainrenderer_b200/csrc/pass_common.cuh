@@ -1,0 +1,135 @@
+// pass_common.cuh - what every CUDA pass launcher sees: the execution record of one compute pass resolved to device
+// views (the counterpart of the descriptor sets the reference binds, RenderBackend.cpp:845-890), the launch helpers
+// and the registry that maps the reference's shader file name to a launcher (ResourceDescriptions.h:112-120).
+//
+// Memory model (DESIGN.md "Data layout"): every image is one HBM allocation, mip levels concatenated at 256-byte
+// aligned offsets, row-major, tightly packed. Uniform and storage buffers are plain device allocations; kernels read
+// them through pointers, never by value, so an unchanged pass list can be replayed as a CUDA graph while the host
+// only rewrites buffer contents (the global UBO, resolve weights, ... land through one staged copy per frame).
+#pragma once
+#include <cuda_runtime.h>
+#include <map>
+#include <string>
+#include <vector>
+#include "image_view.h"
+#include "plain_b200.h"
+#include "plain_frame_types.h"
+
+namespace pb {
+using namespace pv;
+
+struct BindlessEntry {  // set 2: global texture array (RenderBackend.cpp:45); index == image handle index
+    ImgView view;
+    uint32_t format;
+    uint32_t pad;
+};
+
+struct MipInfo { int w, h, d; size_t offset, bytes; };
+struct DeviceImage {
+    plain_image_desc desc{};
+    unsigned char* ptr = nullptr;
+    size_t bytes = 0;
+    std::vector<MipInfo> mips;
+    bool inUse = false;
+};
+struct DeviceBuffer {
+    unsigned char* ptr = nullptr;
+    size_t size = 0;
+};
+
+struct ExecRecord {
+    uint32_t pass;
+    std::vector<plain_storage_buffer_resource> storageBuffers;
+    std::vector<plain_uniform_buffer_resource> uniformBuffers;
+    std::vector<plain_image_resource> sampledImages;
+    std::vector<plain_image_resource> storageImages;
+    std::vector<uint8_t> pushConstants;
+    uint32_t dispatch[3];
+};
+
+struct Backend;
+struct LaunchCtx;
+typedef void (*LaunchFn)(LaunchCtx&);
+
+struct PassRecord {
+    std::string shader, name;
+    std::map<uint32_t, std::vector<uint8_t>> spec;
+    LaunchFn fn = nullptr;
+};
+
+struct LaunchCtx {
+    Backend* be;
+    const PassRecord* pass;
+    const ExecRecord* exec;
+    cudaStream_t stream;
+    const plain_global_shader_info* g;  // device pointer (set 0 binding 0)
+    const BindlessEntry* bindless;      // device pointer
+    int smCount;
+    bool failed = false;
+    std::string error;
+
+    ImgView sampled(uint32_t binding, int expectFormat = -1);
+    ImgView storage(uint32_t binding, int expectFormat = -1);
+    int sampledFormat(uint32_t binding);  // plain_image_format of the image bound at a sampled binding, -1 if none
+    template <typename T> T* sbuf(uint32_t binding, size_t* size = nullptr) { return (T*)sbufRaw(binding, size); }
+    template <typename T> const T* ubuf(uint32_t binding) { return (const T*)ubufRaw(binding); }
+    void* sbufRaw(uint32_t binding, size_t* size);
+    const void* ubufRaw(uint32_t binding);
+    template <typename T> T spec(uint32_t location, T def) const {
+        auto it = pass->spec.find(location);
+        if (it == pass->spec.end() || it->second.size() < sizeof(T)) return def;
+        T v;
+        memcpy(&v, it->second.data(), sizeof(T));
+        return v;
+    }
+    bool specBool(uint32_t location, bool def) const {  // VkBool32 or 1-byte bool
+        auto it = pass->spec.find(location);
+        if (it == pass->spec.end() || it->second.empty()) return def;
+        for (uint8_t b : it->second) if (b) return true;
+        return false;
+    }
+    template <typename T> T push(size_t offset = 0) const {
+        T v{};
+        if (exec->pushConstants.size() >= offset + sizeof(T)) memcpy(&v, exec->pushConstants.data() + offset, sizeof(T));
+        return v;
+    }
+    void fail(const std::string& msg) { if (!failed) { failed = true; error = msg; } }
+    void countLaunch(int n = 1);
+};
+
+struct PassRegistration { PassRegistration(const char* shader, LaunchFn fn); };
+#define PLAIN_PASS(fnname, shader)                       \
+    static void fnname(pb::LaunchCtx& c);                \
+    static pb::PassRegistration reg_##fnname(shader, fnname); \
+    static void fnname(pb::LaunchCtx& c)
+
+inline unsigned ceilDiv(unsigned a, unsigned b) { return (a + b - 1) / b; }
+
+// launch helper: counts the launch (bench "gpu_launches") and records launch errors into the context
+#define PLAIN_LAUNCH(c, kernel, grid, block, smem, ...)                                                   \
+    do {                                                                                                  \
+        kernel<<<(grid), (block), (smem), (c).stream>>>(__VA_ARGS__);                                     \
+        cudaError_t e__ = cudaPeekAtLastError();                                                          \
+        if (e__ != cudaSuccess) (c).fail(std::string(#kernel) + ": " + cudaGetErrorString(e__));          \
+        (c).countLaunch();                                                                                \
+    } while (0)
+
+// ---- device helpers shared by the pass kernels ----
+struct Globals {  // the fields of the global UBO (global.inc:4-33) most kernels need, loaded once per thread
+    vec3 camPos, fwd, up, right;
+    float tanFovHalf, aspect, nearPlane, farPlane;
+};
+__device__ __forceinline__ Globals loadGlobals(const plain_global_shader_info* __restrict__ g) {
+    Globals r;
+    r.camPos = v3(g->cameraPosition[0], g->cameraPosition[1], g->cameraPosition[2]);
+    r.fwd = v3(g->cameraForward[0], g->cameraForward[1], g->cameraForward[2]);
+    r.up = v3(g->cameraUp[0], g->cameraUp[1], g->cameraUp[2]);
+    r.right = v3(g->cameraRight[0], g->cameraRight[1], g->cameraRight[2]);
+    r.tanFovHalf = g->cameraTanFovHalf;
+    r.aspect = g->cameraAspectRatio;
+    r.nearPlane = g->nearPlane;
+    r.farPlane = g->farPlane;
+    return r;
+}
+
+}  // namespace pb

@@ -1,0 +1,617 @@
+// passes_gi.cu - SDF instance culling, diffuse SDF sphere trace, spatial/temporal denoise, upscale.
+//   sdfCameraFrustumCulling.comp:36-62, sdfCameraTileCulling.comp:37-99, sdfDiffuseTrace.comp:70-207 + SDF.inc:12-184,
+//   filterIndirectDiffuseSpatial.comp:21-135, filterIndirectDiffuseTemporal.comp:20-86, indirectLightUpscale.comp:17-71
+#include "shader_inc.cuh"
+
+namespace pb {
+
+// sdfCulling.inc:17-20: strides by the FULL screen resolution even when the trace runs at half resolution
+__device__ __forceinline__ uint32_t tileIndexFromTileUV(int tileX, int tileY, const plain_global_shader_info* g) {
+    const float t = (float)g->screenResolution[0] / 32.f;
+    const float fl = floorf_(t);
+    const uint32_t tileCountX = f2u(fl + ((fl < t) ? 1.f : 0.f));  // ceil
+    return (uint32_t)tileX + (uint32_t)tileY * tileCountX;
+}
+
+// ---------------- sdfCameraFrustumCulling.comp ----------------
+// The reference appends with atomicAdd (order undefined); here one warp appends in ascending instance order
+// (ballot + prefix popcount), so the list - and with it the 100-instance cut of the tile lists - is deterministic.
+__global__ void __launch_bounds__(32) sdfFrustumCullingKernel(const uint32_t* __restrict__ instanceBuffer, const plain_camera_frustum_buffer* __restrict__ frustum, uint32_t* culled,
+                                                               size_t culledCapacity, const plain_bounding_box* __restrict__ instanceBBs, const float* __restrict__ influenceRangePtr, uint32_t invocations) {
+    const uint32_t instanceCount = instanceBuffer[0];
+    const float influenceRange = *influenceRangePtr;
+    const uint32_t lane = threadIdx.x;
+    uint32_t count = culled[0];
+    const uint32_t n = min(instanceCount, invocations);
+    for (uint32_t base = 0; base < n; base += 32) {
+        const uint32_t instanceIndex = base + lane;
+        bool isInsideFrustum = false;
+        if (instanceIndex < n) {
+            const plain_bounding_box bb = instanceBBs[instanceIndex];
+            const vec3 bbMin = ld3(bb.bbMin), bbMax = ld3(bb.bbMax);
+            const vec3 boundingSphereCenter = (bbMax + bbMin) * 0.5f;
+            const vec3 bbExtends = (bbMax - bbMin);
+            float boundingSphereRadius = fmaxp(fmaxp(bbExtends.x, bbExtends.y), bbExtends.z) * 0.5f;
+            boundingSphereRadius += influenceRange;
+            isInsideFrustum = true;
+            for (int i = 0; i < 6; i++) {
+                const vec3 frustumPoint = ld3(frustum->frustumPoints[i]), frustumNormal = ld3(frustum->frustumNormals[i]);
+                const bool isOutsidePlane = dot(boundingSphereCenter - frustumPoint, frustumNormal) > boundingSphereRadius;
+                isInsideFrustum = isInsideFrustum && !isOutsidePlane;
+            }
+        }
+        const unsigned mask = __ballot_sync(0xffffffffu, isInsideFrustum);
+        if (isInsideFrustum) {
+            const uint32_t slot = count + __popc(mask & ((1u << lane) - 1u));
+            if (1 + slot < culledCapacity) culled[1 + slot] = instanceIndex;
+        }
+        count += __popc(mask);
+    }
+    __syncwarp();
+    if (lane == 0) culled[0] = count;
+}
+PLAIN_PASS(launch_sdfFrustumCulling, "sdfCameraFrustumCulling.comp") {
+    size_t culledSize = 0;
+    const uint32_t* instances = c.sbuf<uint32_t>(0);
+    const plain_camera_frustum_buffer* frustum = c.ubuf<plain_camera_frustum_buffer>(1);
+    uint32_t* culled = c.sbuf<uint32_t>(2, &culledSize);
+    const plain_bounding_box* bbs = c.sbuf<plain_bounding_box>(3);
+    const float* influence = c.ubuf<float>(4);
+    if (c.failed) return;
+    PLAIN_LAUNCH(c, sdfFrustumCullingKernel, 1, 32, 0, instances, frustum, culled, culledSize / 4, bbs, influence, c.exec->dispatch[0] * 64);
+}
+
+// ---------------- sdfCameraTileCulling.comp ----------------
+// one warp per 32x32-pixel tile; lanes test 32 instances at a time against the tile's cone, bounded by the HiZ depth
+// range of the tile, and append in list order up to maxObjectsPerTile (sdfCulling.inc:5)
+__global__ void __launch_bounds__(128) sdfTileCullingKernel(const uint32_t* __restrict__ culled, const plain_bounding_box* __restrict__ instanceBBs, plain_culled_instances_per_tile* cullingTiles,
+                                                             size_t tileCapacity, const float* __restrict__ influenceRangePtr, ImgView depthMinMaxTexture, const plain_global_shader_info* __restrict__ g,
+                                                             int useHiZ, uint32_t tileCountX, uint32_t tileCountY, uint32_t limitX, uint32_t limitY) {
+    const uint32_t warpGlobal = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (warpGlobal >= tileCountX * tileCountY) return;
+    const int tx = (int)(warpGlobal % tileCountX), ty = (int)(warpGlobal / tileCountX);
+    if ((uint32_t)tx >= limitX || (uint32_t)ty >= limitY) return;
+    const uint32_t tileIndex = tileIndexFromTileUV(tx, ty, g);
+    if ((size_t)tileIndex >= tileCapacity) return;  // out-of-bounds writes are dropped
+    const Globals G = loadGlobals(g);
+    const float influenceRange = *influenceRangePtr;
+    const vec2 res = v2((float)g->screenResolution[0], (float)g->screenResolution[1]);
+    auto VFromiUV = [&](int ix, int iy) {  // :37-40, normalised by the full screen resolution as in the reference
+        const vec2 pixelCoor = (v2((float)ix, (float)iy) / res - 0.5f) * 2.f;
+        return viewDirFromNDC(G, pixelCoor);
+    };
+    const int cullingTileSize = 32;
+    const vec3 cameraToPixel = -VFromiUV(tx * cullingTileSize + cullingTileSize / 2, ty * cullingTileSize + cullingTileSize / 2);
+    vec3 V_ll = -VFromiUV(tx * cullingTileSize, ty * cullingTileSize);
+    vec3 V_ur = -VFromiUV(tx * cullingTileSize + cullingTileSize, ty * cullingTileSize + cullingTileSize);
+    V_ll = V_ll / dot(cameraToPixel, V_ll);
+    V_ur = V_ur / dot(cameraToPixel, V_ur);
+    const float coneRadiusPerMeter = length(V_ll - V_ur) * 0.5f;
+    float depthMin = G.nearPlane, depthMax = G.farPlane;
+    const vec2 uv = v2((float)tx, (float)ty) / v2((float)tileCountX, (float)tileCountY);
+    if (useHiZ) {
+        const vec2 depthMinMax = sampleNearest2D<WRAP_CLAMP, vec2>([&](int x, int y) { return loadRG32F(depthMinMaxTexture, x, y); }, depthMinMaxTexture.w, depthMinMaxTexture.h, uv, v2(0.f));
+        depthMin = linearizeDepth(depthMinMax.y, G.nearPlane, G.farPlane);
+        depthMax = linearizeDepth(depthMinMax.x, G.nearPlane, G.farPlane);
+    }
+    depthMin *= dot(cameraToPixel, G.fwd);
+    depthMax *= dot(cameraToPixel, G.fwd);
+    plain_culled_instances_per_tile& tile = cullingTiles[tileIndex];
+    const uint32_t culledInstanceCount = culled[0];
+    uint32_t objectCount = 0;
+    for (uint32_t base = 0; base < culledInstanceCount && objectCount < PLAIN_MAX_OBJECTS_PER_TILE; base += 32) {
+        const uint32_t i = base + lane;
+        bool pass = false;
+        uint32_t instanceIndex = 0;
+        if (i < culledInstanceCount) {
+            instanceIndex = culled[1 + i];
+            const plain_bounding_box bb = instanceBBs[instanceIndex];
+            const vec3 bbMin = ld3(bb.bbMin), bbMax = ld3(bb.bbMax);
+            const vec3 boundingSphereCenter = (bbMax + bbMin) * 0.5f;
+            const vec3 bbExtends = (bbMax - bbMin) * 0.5f;
+            float boundingSphereRadius = fmaxp(fmaxp(bbExtends.x, bbExtends.y), bbExtends.z);
+            boundingSphereRadius += influenceRange;
+            float projection = dot(boundingSphereCenter - G.camPos, cameraToPixel);
+            projection = clampf(projection, depthMin, depthMax);
+            const float d = length(boundingSphereCenter - (projection * cameraToPixel + G.camPos));
+            pass = d < boundingSphereRadius + coneRadiusPerMeter * projection;
+        }
+        const unsigned mask = __ballot_sync(0xffffffffu, pass);
+        if (pass) {
+            const uint32_t slot = objectCount + __popc(mask & ((1u << lane) - 1u));
+            if (slot < PLAIN_MAX_OBJECTS_PER_TILE) tile.indices[slot] = instanceIndex;
+        }
+        objectCount = min(objectCount + (uint32_t)__popc(mask), (uint32_t)PLAIN_MAX_OBJECTS_PER_TILE);
+    }
+    if (lane == 0) tile.objectCount = objectCount;
+}
+PLAIN_PASS(launch_sdfTileCulling, "sdfCameraTileCulling.comp") {
+    size_t tilesSize = 0;
+    const uint32_t* culled = c.sbuf<uint32_t>(0);
+    const plain_bounding_box* bbs = c.sbuf<plain_bounding_box>(1);
+    plain_culled_instances_per_tile* tiles = c.sbuf<plain_culled_instances_per_tile>(2, &tilesSize);
+    const float* influence = c.ubuf<float>(3);
+    const ImgView hiz = c.sampled(4, PLAIN_FORMAT_RG32_SFLOAT);
+    if (c.failed) return;
+    const uint32_t tcx = c.push<uint32_t>(0), tcy = c.push<uint32_t>(4);
+    if (tcx == 0 || tcy == 0) return;
+    PLAIN_LAUNCH(c, sdfTileCullingKernel, ceilDiv(tcx * tcy, 4), 128, 0, culled, bbs, tiles, tilesSize / sizeof(plain_culled_instances_per_tile), influence, hiz, c.g,
+                 c.specBool(0, false) ? 1 : 0, tcx, tcy, c.exec->dispatch[0] * 8, c.exec->dispatch[1] * 8);
+}
+
+// ---------------- sdfDiffuseTrace.comp ----------------
+struct TraceInstance {  // one SDFInstance (SDF.inc:4-10) staged in shared memory together with its brick view
+    float worldToLocal[16];
+    vec3 localExtends;
+    vec3 meanAlbedo;
+    ImgView sdf;
+};
+struct TraceResult {
+    bool hit;
+    float closestHitDistance;
+    vec3 hitPos, N;
+    int hitCount;
+    vec3 albedo;
+};
+__device__ __forceinline__ float sampleSDF(const ImgView& sdf, vec3 uv) { return sampleR16FLinearClamp3D(sdf, uv); }  // SDF.inc:12-14
+__device__ __forceinline__ vec3 normalFromSDF(vec3 uv, vec3 extends, const ImgView& sdf) {  // SDF.inc:16-25
+    const float extendsMax = fmaxp(extends.x, fmaxp(extends.y, extends.z));
+    const vec3 extendsNormalized = extends / extendsMax;
+    const vec3 epsilon = v3(0.15f) / v3((float)sdf.w, (float)sdf.h, (float)sdf.d) / extendsNormalized;
+    return normalize(v3(sampleSDF(sdf, uv + v3(epsilon.x, 0, 0)) - sampleSDF(sdf, uv - v3(epsilon.x, 0, 0)),
+                        sampleSDF(sdf, uv + v3(0, epsilon.y, 0)) - sampleSDF(sdf, uv - v3(0, epsilon.y, 0)),
+                        sampleSDF(sdf, uv + v3(0, 0, epsilon.z)) - sampleSDF(sdf, uv - v3(0, 0, epsilon.z))));
+}
+__device__ __forceinline__ bool isPointInAABB(vec3 p, vec3 mn, vec3 mx) {  // SDF.inc:27-35
+    return p.x >= mn.x && p.y >= mn.y && p.z >= mn.z && p.x <= mx.x && p.y <= mx.y && p.z <= mx.z;
+}
+__device__ __forceinline__ bool rayAABBIntersection(vec3 rayOrigin, vec3 rayDirection, vec3 aabbMin, vec3 aabbMax, float& tOut) {  // SDF.inc:42-86
+    bool hit = false;
+    float t = 100000.f;
+    float intersection = rayOrigin.x < 0.f ? aabbMin.x : aabbMax.x;
+    const float tx = (intersection - rayOrigin.x) / rayDirection.x;
+    vec3 pI = rayOrigin + tx * rayDirection;
+    if (tx > 0.f && pI.y >= aabbMin.y && pI.y <= aabbMax.y && pI.z >= aabbMin.z && pI.z <= aabbMax.z) { t = fminp(t, tx); hit = true; }
+    intersection = rayOrigin.y < 0.f ? aabbMin.y : aabbMax.y;
+    const float ty = (intersection - rayOrigin.y) / rayDirection.y;
+    pI = rayOrigin + ty * rayDirection;
+    if (ty > 0.f && pI.x >= aabbMin.x && pI.x <= aabbMax.x && pI.z >= aabbMin.z && pI.z <= aabbMax.z) { t = fminp(t, ty); hit = true; }
+    intersection = rayOrigin.z < 0.f ? aabbMin.z : aabbMax.z;
+    const float tz = (intersection - rayOrigin.z) / rayDirection.z;
+    pI = rayOrigin + tz * rayDirection;
+    if (tz > 0.f && pI.x >= aabbMin.x && pI.x <= aabbMax.x && pI.y >= aabbMin.y && pI.y <= aabbMax.y) { t = fminp(t, tz); hit = true; }
+    tOut = t;
+    return hit;
+}
+// SDF.inc:101-184
+__device__ void traceRayTroughSDFInstance(const TraceInstance& inst, vec3 rayStartWorld, vec3 rayDirectionWorld, TraceResult& tr) {
+    const vec3 localExtends = inst.localExtends;
+    vec3 rayStartLocal = xyz(mulm4(inst.worldToLocal, v4(rayStartWorld, 1.f)));
+    const vec3 rayEndLocal = xyz(mulm4(inst.worldToLocal, v4(rayStartWorld + rayDirectionWorld, 1.f)));
+    vec3 rayDirection = rayEndLocal - rayStartLocal;
+    rayDirection = rayDirection / length(rayDirection);
+    const vec3 sdfMaxLocal = localExtends * 0.5f;
+    const vec3 sdfMinLocal = -sdfMaxLocal;
+    float hitDistanceLocal = 0.f;
+    if (!isPointInAABB(rayStartLocal, sdfMinLocal, sdfMaxLocal)) {
+        float t;
+        if (rayAABBIntersection(rayStartLocal, rayDirection, sdfMinLocal, sdfMaxLocal, t)) {
+            rayStartLocal = rayStartLocal + t * rayDirection;
+            hitDistanceLocal = t;
+        } else {
+            return;
+        }
+    }
+    vec3 localSamplePos = rayStartLocal;
+    const ImgView sdf = inst.sdf;
+    const vec3 sdfResolution = v3((float)sdf.w, (float)sdf.h, (float)sdf.d);
+    const float distanceThreshold = length(localExtends / sdfResolution) * 0.25f;
+    float dLast = 0.f, d = 0.f;
+    const float localToGlobalScale = 1.f / length(v3(inst.worldToLocal[0], inst.worldToLocal[1], inst.worldToLocal[2]));
+    if (localToGlobalScale * hitDistanceLocal > tr.closestHitDistance) return;
+    vec3 localExtendsHalf = localExtends * 0.5f;
+    localExtendsHalf = localExtendsHalf + 0.01f;
+    for (int i = 0; i < 128; i++) {
+        if (localSamplePos.x > localExtendsHalf.x || localSamplePos.y > localExtendsHalf.y || localSamplePos.z > localExtendsHalf.z ||
+            localSamplePos.x < -localExtendsHalf.x || localSamplePos.y < -localExtendsHalf.y || localSamplePos.z < -localExtendsHalf.z)
+            break;
+        vec3 sampleUV = localSamplePos / localExtends + 0.5f;
+        dLast = d;
+        d = sampleSDF(sdf, sampleUV);
+        if (d < distanceThreshold) {
+            tr.hit = true;
+            const float distanceGlobal = hitDistanceLocal * localToGlobalScale;
+            if (distanceGlobal < tr.closestHitDistance) {
+                tr.closestHitDistance = distanceGlobal;
+                tr.hitCount = i;
+                const float lastStepSizeLocal = d / (1.f - (d - dLast));
+                localSamplePos = localSamplePos + rayDirection * lastStepSizeLocal;
+                sampleUV = localSamplePos / localExtends + 0.5f;
+                vec3 N = normalFromSDF(sampleUV, localExtends, sdf);
+                // transpose(mat3(worldToLocal)) * N
+                const float* m = inst.worldToLocal;
+                tr.N = v3(m[0], m[4], m[8]) * N.x + v3(m[1], m[5], m[9]) * N.y + v3(m[2], m[6], m[10]) * N.z;
+                tr.albedo = vpow(inst.meanAlbedo, v3(2.2f));
+                const float lastStepSizeGlobal = lastStepSizeLocal * localToGlobalScale;
+                tr.hitPos = rayStartWorld + rayDirectionWorld * (distanceGlobal + lastStepSizeGlobal);
+            }
+            break;
+        }
+        localSamplePos = localSamplePos + rayDirection * absf(d);
+        hitDistanceLocal += absf(d);
+    }
+}
+
+struct TraceParams {
+    ImgView outYSH, outCoCg, depthTexture, normalTexture, skyLut, shadowMap;
+    const plain_light_buffer* light;
+    const unsigned char* instanceBuffer;  // uvec4 header + SDFInstance[]
+    const plain_culled_instances_per_tile* tiles;
+    size_t tileCapacity;
+    const float* influenceRange;
+    const plain_shadow_cascade_info* cascades;
+    const plain_global_shader_info* g;
+    const BindlessEntry* bindless;
+    int strictInfluenceRadiusCutoff, shadowCascadeIndex;
+    int groupsX, groupsY;
+};
+
+// A block traces a 16x16-pixel region = 2x2 of the reference's 8x8 workgroups; all four lie in one 32x32 culling tile
+// (:154), whose instance records and brick views are staged once in shared memory. Each 8x8 group keeps its own ray
+// cache for the 3x3 resolve (:70-116), exactly like the reference's shared arrays. Every invocation of a dispatched
+// group traces, also those beyond the image edge: they are neighbours in the resolve; only their stores are dropped.
+__global__ void __launch_bounds__(256) sdfDiffuseTraceKernel(const __grid_constant__ TraceParams p) {
+    __shared__ TraceInstance sInst[PLAIN_MAX_OBJECTS_PER_TILE];
+    __shared__ uint32_t sCount;
+    __shared__ float sRayNormal[4][8][8][3], sRayDepth[4][8][8], sRayColor[4][8][8][3];
+    const plain_global_shader_info* g = p.g;
+    const int sub = threadIdx.x >> 6;                  // which of the 2x2 groups
+    const int lx = threadIdx.x & 7, ly = (threadIdx.x >> 3) & 7;
+    const int gx = blockIdx.x * 2 + (sub & 1), gy = blockIdx.y * 2 + (sub >> 1);
+    const bool groupActive = gx < p.groupsX && gy < p.groupsY;
+    // tile of the block (identical for its four groups)
+    const int tileX = (blockIdx.x * 2) / 4, tileY = (blockIdx.y * 2) / 4;
+    const uint32_t tileIndex = tileIndexFromTileUV(tileX, tileY, g);
+    const bool tileValid = (size_t)tileIndex < p.tileCapacity;
+    if (threadIdx.x == 0) sCount = tileValid ? min(p.tiles[tileIndex].objectCount, (uint32_t)PLAIN_MAX_OBJECTS_PER_TILE) : 0u;
+    __syncthreads();
+    const uint32_t objectCount = sCount;
+    const plain_sdf_instance* instances = (const plain_sdf_instance*)(p.instanceBuffer + 16);
+    for (uint32_t i = threadIdx.x; i < objectCount; i += 256) {
+        const plain_sdf_instance in = instances[p.tiles[tileIndex].indices[i]];
+        TraceInstance t;
+        for (int k = 0; k < 16; k++) t.worldToLocal[k] = in.worldToLocal[k];
+        t.localExtends = ld3(in.localExtends);
+        t.meanAlbedo = ld3(in.meanAlbedo);
+        t.sdf = p.bindless[in.sdfTextureIndex].view;
+        sInst[i] = t;
+    }
+    __syncthreads();
+
+    const Globals G = loadGlobals(g);
+    const int ix = gx * 8 + lx, iy = gy * 8 + ly;
+    vec3 L = v3(0.f);
+    if (groupActive) {
+        const vec2 uv = v2((float)ix, (float)iy) / v2((float)p.outYSH.w, (float)p.outYSH.h);
+        const float depth = sampleNearest2D<WRAP_CLAMP, float>([&](int x, int y) { return loadD32(p.depthTexture, x, y); }, p.depthTexture.w, p.depthTexture.h, uv, 0.f);
+        const float depthLinear = linearizeDepth(depth, G.nearPlane, G.farPlane);
+        const vec2 pixelNDC = uv * 2.f - 1.f;
+        const vec3 V = -viewDirFromNDC(G, pixelNDC);
+        const vec3 pWorld = G.camPos + V / dot(V, G.fwd) * depthLinear;
+        const ImgView noiseTex = p.bindless[g->noiseTextureIndices[g->frameIndexMod4]].view;
+        const vec2 noiseUV = v2((float)ix, (float)iy) / v2((float)noiseTex.w, (float)noiseTex.h);
+        const vec2 xi = sampleNearest2D<WRAP_REPEAT, vec2>([&](int x, int y) { return loadRG8(noiseTex, x, y); }, noiseTex.w, noiseTex.h, noiseUV, v2(0.f));
+        const vec3 normalTexel = sampleNearest2D<WRAP_CLAMP, vec3>([&](int x, int y) { return loadRGBA8rgb(p.normalTexture, x, y); }, p.normalTexture.w, p.normalTexture.h, uv, v3(0.f));
+        const vec3 N = normalTexel * 2.f - 1.f;
+        sRayNormal[sub][lx][ly][0] = N.x; sRayNormal[sub][lx][ly][1] = N.y; sRayNormal[sub][lx][ly][2] = N.z;
+        sRayDepth[sub][lx][ly] = depthLinear;
+        const vec3 rayOrigin = pWorld + N * 0.2f;
+        L = importanceSampleCosine(xi, N);
+
+        TraceResult tr;
+        tr.hit = false;
+        tr.closestHitDistance = 10000.f;
+        tr.hitCount = 0;
+        tr.hitPos = v3(0.f); tr.N = v3(0.f); tr.albedo = v3(0.f);
+        for (uint32_t i = 0; i < objectCount; i++) traceRayTroughSDFInstance(sInst[i], rayOrigin, L, tr);
+        vec3 hitColor;
+        if (tr.hit) {
+            const float shadow = simpleShadow<true>(tr.hitPos, p.cascades->lightMatrices[p.shadowCascadeIndex], p.shadowMap);
+            const vec3 sunLight = shadow * p.light->sunStrengthExposed * ld3(p.light->sunColor);
+            hitColor = tr.albedo * sunLight;
+            bool hitInRange = tr.closestHitDistance < *p.influenceRange;
+            hitInRange = hitInRange || !p.strictInfluenceRadiusCutoff;
+            const bool selfIntersection = tr.closestHitDistance < 0.0001f;
+            if (!hitInRange || selfIntersection) hitColor = v3(0.f);
+        } else {
+            hitColor = sampleSkyLut(L, p.skyLut);
+        }
+        sRayColor[sub][lx][ly][0] = hitColor.x; sRayColor[sub][lx][ly][1] = hitColor.y; sRayColor[sub][lx][ly][2] = hitColor.z;
+    }
+    __syncthreads();
+    if (!groupActive) return;
+    // resolveColor :70-116
+    float weightTotal = 1.f;
+    vec3 color = v3(sRayColor[sub][lx][ly][0], sRayColor[sub][lx][ly][1], sRayColor[sub][lx][ly][2]);
+    const vec3 myN = v3(sRayNormal[sub][lx][ly][0], sRayNormal[sub][lx][ly][1], sRayNormal[sub][lx][ly][2]);
+    const float myDepth = sRayDepth[sub][lx][ly];
+    for (int x = -1; x <= 1; x++) {
+        for (int y = -1; y <= 1; y++) {
+            if (x == 0 && y == 0) continue;
+            const int rx = lx + x, ry = ly + y;
+            const bool isValidIndex = rx > 0 && ry > 0 && rx < 8 && ry < 8;  // greaterThan(rayIndex, 0): row/column 0 never used (:88)
+            if (!isValidIndex) continue;
+            const vec3 nN = v3(sRayNormal[sub][rx][ry][0], sRayNormal[sub][rx][ry][1], sRayNormal[sub][rx][ry][2]);
+            const float NoN = clampf(dot(myN, nN), 0.f, 1.f);
+            const bool normalsMatch = NoN > 0.9f;
+            const bool depthMatch = absf(myDepth - sRayDepth[sub][rx][ry]) < 0.5f;
+            if (normalsMatch && depthMatch) {
+                const float weightX = x == 0 ? 1.f : 0.5f, weightY = y == 0 ? 1.f : 0.5f;
+                const float weight = weightX * weightY;
+                color = color + weight * v3(sRayColor[sub][rx][ry][0], sRayColor[sub][rx][ry][1], sRayColor[sub][rx][ry][2]);
+                weightTotal += weight;
+            }
+        }
+    }
+    color = color / weightTotal;
+    const vec3 YCoCg = linearToYCoCg(color);
+    vec4 result_Y_SH = v4(0.f);
+    vec2 result_CoCg = v2(0.f);
+    result_Y_SH = result_Y_SH + YCoCg.x * directionToSH_L1(L);
+    result_CoCg = result_CoCg + v2(YCoCg.y, YCoCg.z);
+    if (inRange(p.outYSH, ix, iy)) storeRGBA16F(p.outYSH, ix, iy, 0, result_Y_SH);
+    if (inRange(p.outCoCg, ix, iy)) storeRG16F(p.outCoCg, ix, iy, result_CoCg);
+}
+PLAIN_PASS(launch_sdfDiffuseTrace, "sdfDiffuseTrace.comp") {
+    TraceParams p;
+    p.outYSH = c.storage(0, PLAIN_FORMAT_RGBA16_SFLOAT);
+    p.outCoCg = c.storage(1, PLAIN_FORMAT_RG16_SFLOAT);
+    p.depthTexture = c.sampled(2, PLAIN_FORMAT_DEPTH32);
+    p.normalTexture = c.sampled(3, PLAIN_FORMAT_RGBA8);
+    p.skyLut = c.sampled(4, PLAIN_FORMAT_R11G11B10_UFLOAT);
+    p.shadowMap = c.sampled(10, PLAIN_FORMAT_DEPTH16);
+    p.light = c.sbuf<plain_light_buffer>(5);
+    p.instanceBuffer = c.sbuf<unsigned char>(6);
+    size_t tilesSize = 0;
+    p.tiles = c.sbuf<plain_culled_instances_per_tile>(7, &tilesSize);
+    p.tileCapacity = tilesSize / sizeof(plain_culled_instances_per_tile);
+    p.influenceRange = c.ubuf<float>(8);
+    p.cascades = c.sbuf<plain_shadow_cascade_info>(9);
+    p.g = c.g;
+    p.bindless = c.bindless;
+    p.strictInfluenceRadiusCutoff = c.specBool(0, false) ? 1 : 0;
+    p.shadowCascadeIndex = c.spec<int>(1, 3);
+    p.groupsX = (int)c.exec->dispatch[0];
+    p.groupsY = (int)c.exec->dispatch[1];
+    if (c.failed) return;
+    if (p.shadowCascadeIndex < 0 || p.shadowCascadeIndex > 3) { c.fail("sdfDiffuseTrace.comp: shadow cascade index must be 0..3"); return; }
+    if (p.groupsX == 0 || p.groupsY == 0) return;
+    PLAIN_LAUNCH(c, sdfDiffuseTraceKernel, dim3(ceilDiv(p.groupsX, 2), ceilDiv(p.groupsY, 2)), 256, 0, p);
+}
+
+// ---------------- filterIndirectDiffuseSpatial.comp ----------------
+struct SpatialParams {
+    ImgView outYSH, outCoCg, texYSH, texCoCg, depthTexture, normalTexture;
+    const plain_global_shader_info* g;
+    int filterIndex;
+};
+template <bool DEPTH_IS_R16F>
+__device__ __forceinline__ vec3 giPixelToWorld(const ImgView& depthTexture, const Globals& G, vec2 uv) {
+    const float depth = sampleNearest2D<WRAP_CLAMP, float>([&](int x, int y) { return DEPTH_IS_R16F ? loadR16F(depthTexture, x, y) : loadD32(depthTexture, x, y); },
+                                                           depthTexture.w, depthTexture.h, uv, 0.f);
+    const float depthLinear = linearizeDepth(depth, G.nearPlane, G.farPlane);
+    const vec2 pixelNDC = uv * 2.f - 1.f;
+    const vec3 cameraToPixel = -viewDirFromNDC(G, pixelNDC);
+    return G.camPos + cameraToPixel / dot(cameraToPixel, G.fwd) * depthLinear;
+}
+// The 32 disc samples come from one xorshift sequence that is the same for every pixel (:60-70): the block computes
+// sqrt(rand), cos(angle), sin(angle) once into shared memory; each pixel only applies its own lengthModifier.
+template <bool DEPTH_IS_R16F>
+__global__ void __launch_bounds__(256) giSpatialFilterKernel(const __grid_constant__ SpatialParams p) {
+    __shared__ float sSqrtRand[32], sCos[32], sSin[32];
+    const plain_global_shader_info* g = p.g;
+    if (threadIdx.x == 0) {
+        uint32_t rngState = wang_hash(g->frameIndexMod4 + (uint32_t)p.filterIndex);
+        for (int i = 0; i < 32; i++) {
+            sSqrtRand[i] = sqrtf_(rand01(rngState));
+            const float angle = 2.f * PV_PI * rand01(rngState);
+            sCos[i] = dm::cos(angle);
+            sSin[i] = dm::sin(angle);
+        }
+    }
+    __syncthreads();
+    const int ix = blockIdx.x * 32 + (threadIdx.x & 31), iy = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (ix >= p.outYSH.w || iy >= p.outYSH.h) return;
+    const Globals G = loadGlobals(g);
+    const vec2 texelSize = 1.f / v2((float)p.outYSH.w, (float)p.outYSH.h);
+    const vec2 uv = (v2((float)ix, (float)iy) + 0.5f) * texelSize;
+    const vec3 pCenter = giPixelToWorld<DEPTH_IS_R16F>(p.depthTexture, G, uv);
+    const vec3 pRight = giPixelToWorld<DEPTH_IS_R16F>(p.depthTexture, G, uv + v2(1.f, 0.f) * texelSize);
+    const vec3 pUp = giPixelToWorld<DEPTH_IS_R16F>(p.depthTexture, G, uv + v2(0.f, 1.f) * texelSize);
+    const vec3 tangent = normalize(pCenter - pRight);
+    const vec3 bitangent = normalize(pCenter - pUp);
+    const vec3 N = 2.f * sampleNearest2D<WRAP_CLAMP, vec3>([&](int x, int y) { return loadRGBA8rgb(p.normalTexture, x, y); }, p.normalTexture.w, p.normalTexture.h, uv, v3(0.f)) - 1.f;
+    vec4 result_Y_SH = v4(0.f);
+    vec2 result_CoCg = v2(0.f);
+    float weightTotal = 0.f;
+    float radiusWorld = 1.5f;
+    if (p.filterIndex == 1) radiusWorld = 1.f;
+    float lengthModifier = 1.f;
+    for (int i = 0; i < 32; i++) {
+        const float d = sSqrtRand[i] * lengthModifier;
+        const vec2 offset = v2(sCos[i], sSin[i]) * d;
+        const vec3 sampleWorld = pCenter + radiusWorld * (offset.x * tangent + offset.y * bitangent);
+        const vec4 sampleProjected = mulm4(g->viewProjection, v4(sampleWorld, 1.f));
+        vec2 sampleUV = v2(sampleProjected.x, sampleProjected.y) / sampleProjected.w;
+        sampleUV = sampleUV * 0.5f + 0.5f;
+        sampleUV.x = sampleUV.x < 0.f ? uv.x - offset.x : sampleUV.x;
+        sampleUV.y = sampleUV.y < 0.f ? uv.y - offset.y : sampleUV.y;
+        sampleUV.x = sampleUV.x > 1.f ? uv.x - offset.x : sampleUV.x;
+        sampleUV.y = sampleUV.y > 1.f ? uv.y - offset.y : sampleUV.y;
+        const vec3 pixelWorld = giPixelToWorld<DEPTH_IS_R16F>(p.depthTexture, G, sampleUV);
+        const float distanceToTangentPlane = absf(dot(N, pixelWorld - pCenter));
+        const float maxDistance = 0.25f;
+        float weight = clampf(maxDistance / fmaxp(distanceToTangentPlane, 0.0001f), 0.f, 1.f);
+        weight *= weight;
+        if (sampleUV.x < 0.f || sampleUV.y < 0.f || sampleUV.x > 1.f || sampleUV.y > 1.f) {
+            weight = 0.f;
+            lengthModifier *= 0.98f;
+        }
+        if (weight > 0.f) {
+            const vec4 sample_Y_SH = sampleNearest2D<WRAP_CLAMP, vec4>([&](int x, int y) { return loadRGBA16F(p.texYSH, x, y); }, p.texYSH.w, p.texYSH.h, sampleUV, v4(0.f));
+            const vec2 sample_CoCg = sampleNearest2D<WRAP_CLAMP, vec2>([&](int x, int y) { return loadRG16F(p.texCoCg, x, y); }, p.texCoCg.w, p.texCoCg.h, sampleUV, v2(0.f));
+            if (!(anynan(sample_Y_SH) || anynan(sample_CoCg))) {
+                result_Y_SH = result_Y_SH + weight * sample_Y_SH;
+                result_CoCg = result_CoCg + weight * sample_CoCg;
+                weightTotal += weight;
+            }
+        }
+    }
+    weightTotal = fmaxp(weightTotal, 0.00001f);
+    result_Y_SH = result_Y_SH / weightTotal;
+    result_CoCg = result_CoCg / weightTotal;
+    storeRGBA16F(p.outYSH, ix, iy, 0, result_Y_SH);
+    if (inRange(p.outCoCg, ix, iy)) storeRG16F(p.outCoCg, ix, iy, result_CoCg);
+}
+PLAIN_PASS(launch_giSpatialFilter, "filterIndirectDiffuseSpatial.comp") {
+    SpatialParams p;
+    p.outYSH = c.storage(0, PLAIN_FORMAT_RGBA16_SFLOAT);
+    p.outCoCg = c.storage(1, PLAIN_FORMAT_RG16_SFLOAT);
+    p.texYSH = c.sampled(2, PLAIN_FORMAT_RGBA16_SFLOAT);
+    p.texCoCg = c.sampled(3, PLAIN_FORMAT_RG16_SFLOAT);
+    p.depthTexture = c.sampled(4);  // half-res R16F (halfResTrace) or the full-res D32F depth buffer
+    p.normalTexture = c.sampled(5, PLAIN_FORMAT_RGBA8);
+    p.g = c.g;
+    p.filterIndex = c.spec<int>(0, 0);
+    if (c.failed) return;
+    const int fmt = c.sampledFormat(4);
+    if ((int)c.exec->dispatch[0] * 8 < p.outYSH.w || (int)c.exec->dispatch[1] * 8 < p.outYSH.h) { c.fail("filterIndirectDiffuseSpatial.comp: dispatch does not cover the target"); return; }
+    dim3 grid(ceilDiv(p.outYSH.w, 32), ceilDiv(p.outYSH.h, 8));
+    if (fmt == PLAIN_FORMAT_R16_SFLOAT) PLAIN_LAUNCH(c, giSpatialFilterKernel<true>, grid, 256, 0, p);
+    else if (fmt == PLAIN_FORMAT_DEPTH32) PLAIN_LAUNCH(c, giSpatialFilterKernel<false>, grid, 256, 0, p);
+    else c.fail("filterIndirectDiffuseSpatial.comp: depth binding must be R16F or D32F");
+}
+
+// ---------------- filterIndirectDiffuseTemporal.comp ----------------
+struct TemporalParams {
+    ImgView targetYSH, targetCoCg, historyOutYSH, historyOutCoCg, inputYSH, inputCoCg, historyInYSH, historyInCoCg, velocityCurrent, velocityLastFrame;
+    const plain_global_shader_info* g;
+};
+__global__ void __launch_bounds__(256) giTemporalFilterKernel(const __grid_constant__ TemporalParams p) {
+    const int ix = blockIdx.x * 32 + (threadIdx.x & 31), iy = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (ix >= p.targetYSH.w || iy >= p.targetYSH.h) return;
+    const plain_global_shader_info* g = p.g;
+    const vec2 texelSize = 1.f / v2((float)p.targetYSH.w, (float)p.targetYSH.h);
+    const vec2 uv = (v2((float)ix, (float)iy) + 0.5f) * texelSize;
+    const vec4 current_Y_SH = sampleRGBA16FLinearClamp(p.inputYSH, uv);
+    const vec2 current_CoCg = sampleRG16FLinearClamp(p.inputCoCg, uv);
+    const vec2 motion = sampleLinear2D<WRAP_CLAMP, vec2>([&](int x, int y) { return loadRG16SNORM(p.velocityCurrent, x, y); }, p.velocityCurrent.w, p.velocityCurrent.h, uv, v2(0.f));
+    const vec2 uvReprojected = uv + motion;
+    vec4 history_Y_SH = sampleRGBA16FLinearClamp(p.historyInYSH, uvReprojected);
+    vec2 history_CoCg = sampleRG16FLinearClamp(p.historyInCoCg, uvReprojected);
+    const vec2 motionLastFrame = sampleLinear2D<WRAP_REPEAT, vec2>([&](int x, int y) { return loadRG16SNORM(p.velocityLastFrame, x, y); }, p.velocityLastFrame.w, p.velocityLastFrame.h, uvReprojected, v2(0.f));
+    const float motionDifference = sqrtf_(absf(length(motion) - length(motionLastFrame)));
+    const float K = 10.f;
+    const float motionDifferenceFactor = clampf(motionDifference * K, 0.f, 1.f);
+    const float alphaDefault = 0.8f;
+    float alphaMin = 0.6f;
+    alphaMin -= 0.3f * absf(length(current_Y_SH) - length(history_Y_SH));
+    alphaMin = fmaxp(alphaMin, 0.f);
+    float alpha = mixf(alphaDefault, alphaMin, motionDifferenceFactor);
+    const float pixelThreshold = 3.f;
+    const vec2 res = v2((float)g->screenResolution[0], (float)g->screenResolution[1]);
+    const vec2 am = vabs(motion) * res, al = vabs(motionLastFrame) * res;
+    if (am.x > pixelThreshold || am.y > pixelThreshold || al.x > pixelThreshold || al.y > pixelThreshold) alpha = alphaMin;
+    if (uvReprojected.x < 0.f || uvReprojected.y < 0.f || uvReprojected.x > 1.f || uvReprojected.y > 1.f) alpha = 0.f;
+    if (g->cameraCut) alpha = 0.f;
+    if (anynan(current_Y_SH) || anynan(current_CoCg)) {
+        alpha = 1.f;
+        if (anynan(history_Y_SH)) history_Y_SH = v4(0.f);
+        if (anynan(history_CoCg)) history_CoCg = v2(0.f);
+    }
+    const vec4 result_Y_SH = vmix(current_Y_SH, history_Y_SH, alpha);
+    const vec2 result_CoCg = vmix(current_CoCg, history_CoCg, alpha);
+    storeRGBA16F(p.targetYSH, ix, iy, 0, result_Y_SH);
+    if (inRange(p.targetCoCg, ix, iy)) storeRG16F(p.targetCoCg, ix, iy, result_CoCg);
+    if (inRange(p.historyOutYSH, ix, iy)) storeRGBA16F(p.historyOutYSH, ix, iy, 0, result_Y_SH);
+    if (inRange(p.historyOutCoCg, ix, iy)) storeRG16F(p.historyOutCoCg, ix, iy, result_CoCg);
+}
+PLAIN_PASS(launch_giTemporalFilter, "filterIndirectDiffuseTemporal.comp") {
+    TemporalParams p;
+    p.targetYSH = c.storage(0, PLAIN_FORMAT_RGBA16_SFLOAT);
+    p.targetCoCg = c.storage(1, PLAIN_FORMAT_RG16_SFLOAT);
+    p.historyOutYSH = c.storage(2, PLAIN_FORMAT_RGBA16_SFLOAT);
+    p.historyOutCoCg = c.storage(3, PLAIN_FORMAT_RG16_SFLOAT);
+    p.inputYSH = c.sampled(4, PLAIN_FORMAT_RGBA16_SFLOAT);
+    p.inputCoCg = c.sampled(5, PLAIN_FORMAT_RG16_SFLOAT);
+    p.historyInYSH = c.sampled(6, PLAIN_FORMAT_RGBA16_SFLOAT);
+    p.historyInCoCg = c.sampled(7, PLAIN_FORMAT_RG16_SFLOAT);
+    p.velocityCurrent = c.sampled(8, PLAIN_FORMAT_RG16_SNORM);
+    p.velocityLastFrame = c.sampled(9, PLAIN_FORMAT_RG16_SNORM);
+    p.g = c.g;
+    if (c.failed) return;
+    if ((int)c.exec->dispatch[0] * 8 < p.targetYSH.w || (int)c.exec->dispatch[1] * 8 < p.targetYSH.h) { c.fail("filterIndirectDiffuseTemporal.comp: dispatch does not cover the target"); return; }
+    PLAIN_LAUNCH(c, giTemporalFilterKernel, dim3(ceilDiv(p.targetYSH.w, 32), ceilDiv(p.targetYSH.h, 8)), 256, 0, p);
+}
+
+// ---------------- indirectLightUpscale.comp ----------------
+struct UpscaleParams {
+    ImgView dstYSH, dstCoCg, srcYSH, srcCoCg, fullResDepth, halfResDepth;
+    const plain_global_shader_info* g;
+};
+__global__ void __launch_bounds__(256) giUpscaleKernel(const __grid_constant__ UpscaleParams p) {
+    const int ix = blockIdx.x * 32 + (threadIdx.x & 31), iy = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (ix >= p.dstYSH.w || iy >= p.dstYSH.h) return;
+    const plain_global_shader_info* g = p.g;
+    const float nearP = g->nearPlane, farP = g->farPlane;
+    const vec2 uv = (v2((float)ix, (float)iy) + 0.5f) / v2((float)g->screenResolution[0], (float)g->screenResolution[1]);
+    float fullResDepth = sampleNearest2D<WRAP_CLAMP, float>([&](int x, int y) { return loadD32(p.fullResDepth, x, y); }, p.fullResDepth.w, p.fullResDepth.h, uv, 0.f);
+    fullResDepth = linearizeDepth(fullResDepth, nearP, farP);
+    const vec2 halfResTexelSize = 1.f / v2((float)p.halfResDepth.w, (float)p.halfResDepth.h);
+    // textureGather: (i0,j1), (i1,j1), (i1,j0), (i0,j0) with i0 = floor(u*w - 0.5), clamp-to-edge
+    const int gx0 = f2i(floorf_(sanitizeCoord(uv.x) * (float)p.halfResDepth.w - 0.5f));
+    const int gy0 = f2i(floorf_(sanitizeCoord(uv.y) * (float)p.halfResDepth.h - 0.5f));
+    auto G4 = [&](int x, int y) { return loadR16F(p.halfResDepth, iclamp(x, 0, p.halfResDepth.w - 1), iclamp(y, 0, p.halfResDepth.h - 1)); };
+    float depthSamples[4] = {G4(gx0, gy0 + 1), G4(gx0 + 1, gy0 + 1), G4(gx0 + 1, gy0), G4(gx0, gy0)};
+    for (int i = 0; i < 4; i++) depthSamples[i] = linearizeDepth(depthSamples[i], nearP, farP);
+    float minDepthDiff = 1000.f;
+    vec2 closestDepthTexel = v2(0.f);
+    const float edgeDepthThreshold = 0.5f;
+    bool isEdge = false;
+    const float offX[4] = {0.f, 1.f, 1.f, 0.f}, offY[4] = {1.f, 1.f, 0.f, 0.f};
+    for (int i = 0; i < 4; i++) {
+        const float depthDiff = absf(depthSamples[i] - fullResDepth);
+        isEdge = isEdge || depthDiff > edgeDepthThreshold;
+        if (depthDiff < minDepthDiff) {
+            minDepthDiff = depthDiff;
+            closestDepthTexel = v2(offX[i], offY[i]);
+        }
+    }
+    const vec2 uvClosestTexel = uv + closestDepthTexel * halfResTexelSize;
+    vec4 result_Y_SH;
+    vec2 result_CoCg;
+    if (isEdge) {
+        result_Y_SH = sampleNearest2D<WRAP_CLAMP, vec4>([&](int x, int y) { return loadRGBA16F(p.srcYSH, x, y); }, p.srcYSH.w, p.srcYSH.h, uvClosestTexel, v4(0.f));
+        result_CoCg = sampleNearest2D<WRAP_CLAMP, vec2>([&](int x, int y) { return loadRG16F(p.srcCoCg, x, y); }, p.srcCoCg.w, p.srcCoCg.h, uvClosestTexel, v2(0.f));
+    } else {
+        result_Y_SH = sampleRGBA16FLinearClamp(p.srcYSH, uv);
+        result_CoCg = sampleRG16FLinearClamp(p.srcCoCg, uv);
+    }
+    storeRGBA16F(p.dstYSH, ix, iy, 0, result_Y_SH);
+    if (inRange(p.dstCoCg, ix, iy)) storeRG16F(p.dstCoCg, ix, iy, result_CoCg);
+}
+PLAIN_PASS(launch_giUpscale, "indirectLightUpscale.comp") {
+    UpscaleParams p;
+    p.dstYSH = c.storage(0, PLAIN_FORMAT_RGBA16_SFLOAT);
+    p.dstCoCg = c.storage(1, PLAIN_FORMAT_RG16_SFLOAT);
+    p.srcYSH = c.sampled(2, PLAIN_FORMAT_RGBA16_SFLOAT);
+    p.srcCoCg = c.sampled(3, PLAIN_FORMAT_RG16_SFLOAT);
+    p.fullResDepth = c.sampled(4, PLAIN_FORMAT_DEPTH32);
+    p.halfResDepth = c.sampled(5, PLAIN_FORMAT_R16_SFLOAT);
+    p.g = c.g;
+    if (c.failed) return;
+    if ((int)c.exec->dispatch[0] * 8 < p.dstYSH.w || (int)c.exec->dispatch[1] * 8 < p.dstYSH.h) { c.fail("indirectLightUpscale.comp: dispatch does not cover the target"); return; }
+    PLAIN_LAUNCH(c, giUpscaleKernel, dim3(ceilDiv(p.dstYSH.w, 32), ceilDiv(p.dstYSH.h, 8)), 256, 0, p);
+}
+
+}  // namespace pb

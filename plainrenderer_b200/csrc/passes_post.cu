@@ -1,0 +1,291 @@
+// passes_post.cu - TAA resolve, bloom chain, tonemapping.
+//   temporalFilter.comp:84-179 + temporalReprojection.inc:8-87 + bicubicSampling.inc:4-181;
+//   bloomDownsample.comp:12-50, bloomUpsample.comp:19-58, applyBloom.comp:16-31; tonemapping.comp:17-27
+#include "shader_inc.cuh"
+
+namespace pb {
+
+// ---------------- tonemapping.comp ----------------
+// four pixels per thread: one 128-bit load of packed R11G11B10, one 128-bit store of B8G8R8A8
+__device__ __forceinline__ uint32_t tonemapTexel(uint32_t packed, int x, int y, float g_time) {
+    const vec3 linearColor = unpackR11G11B10(packed);
+    const vec3 tonemapped = ACESFitted(linearColor);
+    vec3 sRGB = linearTosRGB(tonemapped);
+    sRGB = ditherRGB8(sRGB, x, y, g_time);
+    return floatToUnorm8(sRGB.z) | (floatToUnorm8(sRGB.y) << 8) | (floatToUnorm8(sRGB.x) << 16) | (255u << 24);  // B8G8R8A8, alpha 1
+}
+__global__ void __launch_bounds__(256) tonemappingKernel(ImgView imageOut, ImgView imageIn, const plain_global_shader_info* __restrict__ g, int limitX, int limitY) {
+    const int x0 = (blockIdx.x * 32 + (threadIdx.x & 31)) * 4, y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    const int w = imin(imin(imageOut.w, imageIn.w), limitX), h = imin(imin(imageOut.h, imageIn.h), limitY);
+    if (y >= h || x0 >= w) return;
+    const float g_time = g->time;
+    const uint32_t* in = (const uint32_t*)imageIn.ptr + (size_t)y * imageIn.w + x0;
+    uint32_t* out = (uint32_t*)imageOut.ptr + (size_t)y * imageOut.w + x0;
+    if (x0 + 3 < w && ((imageIn.w | imageOut.w) & 3) == 0) {
+        const uint4 t = __ldg((const uint4*)in);
+        uint4 o;
+        o.x = tonemapTexel(t.x, x0, y, g_time); o.y = tonemapTexel(t.y, x0 + 1, y, g_time);
+        o.z = tonemapTexel(t.z, x0 + 2, y, g_time); o.w = tonemapTexel(t.w, x0 + 3, y, g_time);
+        *(uint4*)out = o;
+    } else {
+        for (int i = 0; i < 4 && x0 + i < w; i++) out[i] = tonemapTexel(__ldg(in + i), x0 + i, y, g_time);
+    }
+}
+PLAIN_PASS(launch_tonemapping, "tonemapping.comp") {
+    const ImgView out = c.storage(0, PLAIN_FORMAT_BGRA8_UNORM);
+    const ImgView in = c.sampled(1, PLAIN_FORMAT_R11G11B10_UFLOAT);
+    if (c.failed) return;
+    const int limX = (int)c.exec->dispatch[0] * 8, limY = (int)c.exec->dispatch[1] * 8;
+    dim3 grid(ceilDiv(std::min(out.w, limX), 128), ceilDiv(std::min(out.h, limY), 8));
+    PLAIN_LAUNCH(c, tonemappingKernel, grid, 256, 0, out, in, c.g, limX, limY);
+}
+
+// ---------------- bloom ----------------
+// bloomDownsample.comp: 13 bilinear taps of the finer mip. The bounds test is '>' in the reference (:16): the extra
+// row/column of invocations only produces stores outside the image, which are dropped.
+__global__ void __launch_bounds__(256) bloomDownsampleKernel(ImgView target, ImgView source) {
+    const int ix = blockIdx.x * 32 + (threadIdx.x & 31), iy = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (ix >= target.w || iy >= target.h) return;
+    const vec2 uv = (v2((float)ix, (float)iy) + 0.5f) / v2((float)target.w, (float)target.h);
+    const vec2 texelSize = 1.f / v2((float)source.w, (float)source.h);
+    vec3 color = v3(0.f);
+    auto T = [&](float ox, float oy) { return sampleR11LinearClamp(source, uv + texelSize * v2(ox, oy)); };
+    color = color + sampleR11LinearClamp(source, uv) * 0.125f;
+    color = color + T(0.5f, 0.5f) * 0.125f; color = color + T(0.5f, -0.5f) * 0.125f; color = color + T(-0.5f, 0.5f) * 0.125f; color = color + T(-0.5f, -0.5f) * 0.125f;
+    color = color + T(1.5f, 0.f) * 0.0625f; color = color + T(-1.5f, 0.f) * 0.0625f; color = color + T(0.f, 1.5f) * 0.0625f; color = color + T(0.f, -1.5f) * 0.0625f;
+    color = color + T(1.5f, 1.5f) * 0.03125f; color = color + T(1.5f, -1.5f) * 0.03125f; color = color + T(-1.5f, 1.5f) * 0.03125f; color = color + T(-1.5f, -1.5f) * 0.03125f;
+    storeR11(target, ix, iy, color);
+}
+PLAIN_PASS(launch_bloomDownsample, "bloomDownsample.comp") {
+    const ImgView target = c.storage(0, PLAIN_FORMAT_R11G11B10_UFLOAT), source = c.sampled(1, PLAIN_FORMAT_R11G11B10_UFLOAT);
+    if (c.failed) return;
+    if ((int)c.exec->dispatch[0] * 8 < target.w || (int)c.exec->dispatch[1] * 8 < target.h) { c.fail("bloomDownsample.comp: dispatch does not cover the target"); return; }
+    PLAIN_LAUNCH(c, bloomDownsampleKernel, dim3(ceilDiv(target.w, 32), ceilDiv(target.h, 8)), 256, 0, target, source);
+}
+
+// bloomUpsample.comp: 9-tap tent of the coarser downsample mip (+ 4-tap box of the coarser upsample mip)
+__global__ void __launch_bounds__(256) bloomUpsampleKernel(ImgView target, ImgView targetPreviousMip, ImgView source, int isLowestMip, float blurRadius) {
+    const int ix = blockIdx.x * 32 + (threadIdx.x & 31), iy = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (ix >= target.w || iy >= target.h) return;
+    const vec2 texelSize = 1.f / v2((float)source.w, (float)source.h);
+    const vec2 sampleStepSize = blurRadius * texelSize;
+    const vec2 uv = (v2((float)ix, (float)iy) + 0.5f) / v2((float)target.w, (float)target.h);
+    vec3 color = v3(0.f);
+    auto S = [&](float ox, float oy) { return sampleR11LinearClamp(source, uv + sampleStepSize * v2(ox, oy)); };
+    color = color + sampleR11LinearClamp(source, uv) * 0.25f;
+    color = color + S(1.f, 0.f) * 0.125f; color = color + S(-1.f, 0.f) * 0.125f; color = color + S(0.f, 1.f) * 0.125f; color = color + S(0.f, -1.f) * 0.125f;
+    color = color + S(1.f, 1.f) * 0.0625f; color = color + S(1.f, -1.f) * 0.0625f; color = color + S(-1.f, 1.f) * 0.0625f; color = color + S(-1.f, -1.f) * 0.0625f;
+    if (!isLowestMip) {
+        auto P = [&](float ox, float oy) { return sampleR11LinearClamp(targetPreviousMip, uv + texelSize * v2(ox, oy)); };
+        color = color + P(0.5f, 0.5f) * 0.25f; color = color + P(0.5f, -0.5f) * 0.25f; color = color + P(-0.5f, 0.5f) * 0.25f; color = color + P(-0.5f, -0.5f) * 0.25f;
+    }
+    storeR11(target, ix, iy, color);
+}
+PLAIN_PASS(launch_bloomUpsample, "bloomUpsample.comp") {
+    const ImgView target = c.storage(0, PLAIN_FORMAT_R11G11B10_UFLOAT);
+    const ImgView prev = c.sampled(1, PLAIN_FORMAT_R11G11B10_UFLOAT), source = c.sampled(2, PLAIN_FORMAT_R11G11B10_UFLOAT);
+    if (c.failed) return;
+    if ((int)c.exec->dispatch[0] * 8 < target.w || (int)c.exec->dispatch[1] * 8 < target.h) { c.fail("bloomUpsample.comp: dispatch does not cover the target"); return; }
+    PLAIN_LAUNCH(c, bloomUpsampleKernel, dim3(ceilDiv(target.w, 32), ceilDiv(target.h, 8)), 256, 0, target, prev, source, c.specBool(0, false) ? 1 : 0, c.push<float>(0));
+}
+
+// applyBloom.comp: mix(scene, bloom, strength) in place
+__global__ void __launch_bounds__(256) applyBloomKernel(ImgView target, ImgView bloomTexture, float bloomStrength) {
+    const int ix = blockIdx.x * 32 + (threadIdx.x & 31), iy = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (ix >= target.w || iy >= target.h) return;
+    const vec2 uv = (v2((float)ix, (float)iy) + 0.5f) / v2((float)target.w, (float)target.h);
+    const vec3 bloom = sampleR11LinearClamp(bloomTexture, uv);
+    const vec3 scene = loadR11(target, ix, iy);
+    storeR11(target, ix, iy, vmix(scene, bloom, bloomStrength));
+}
+PLAIN_PASS(launch_applyBloom, "applyBloom.comp") {
+    const ImgView target = c.storage(0, PLAIN_FORMAT_R11G11B10_UFLOAT), bloom = c.sampled(1, PLAIN_FORMAT_R11G11B10_UFLOAT);
+    if (c.failed) return;
+    if ((int)c.exec->dispatch[0] * 8 < target.w || (int)c.exec->dispatch[1] * 8 < target.h) { c.fail("applyBloom.comp: dispatch does not cover the target"); return; }
+    PLAIN_LAUNCH(c, applyBloomKernel, dim3(ceilDiv(target.w, 32), ceilDiv(target.h, 8)), 256, 0, target, bloom, c.push<float>(0));
+}
+
+// ---------------- temporalFilter.comp ----------------
+struct TaaParams {
+    ImgView currentFrame, historySrc, motionBuffer, depthBuffer, outputImage, historyDst;
+    const float* resolveWeights;  // 9 floats, uniform buffer binding 6 (TAA.cpp:181-202)
+    const plain_global_shader_info* g;
+    int useClipping, useMotionVectorDilation, historySampleTech, useTonemap;
+};
+__device__ __forceinline__ vec3 taaTonemap(vec3 color) { return color / (1.f + computeLuminance(color)); }         // temporalReprojection.inc:34-36
+__device__ __forceinline__ vec3 taaTonemapReverse(vec3 color) { return color / (1.f - computeLuminance(color)); }  // :38-40
+struct Nb { vec3 v[3][3]; };  // v[x+1][y+1]
+template <bool TONEMAP>
+__device__ __forceinline__ void sampleNeighbourhood(const ImgView& tex, vec2 uv, vec2 texelSize, Nb& n) {  // :42-52
+#pragma unroll
+    for (int x = -1; x <= 1; x++)
+#pragma unroll
+        for (int y = -1; y <= 1; y++) {
+            vec3 color = sampleR11LinearClamp(tex, uv + texelSize * v2((float)x, (float)y));
+            n.v[x + 1][y + 1] = TONEMAP ? taaTonemap(color) : color;
+        }
+}
+__device__ __forceinline__ vec3 clipAABB(vec3 target, vec3 bbMin, vec3 bbMax) {  // :8-30
+    const vec3 epsilon = v3(0.0001f);
+    const vec3 center = 0.5f * (bbMax + bbMin);
+    const vec3 extend = 0.5f * (bbMax - bbMin) + epsilon;
+    const vec3 toTarget = target - center;
+    const vec3 a = vabs(toTarget / extend);
+    const float maxComponent = fmaxp(a.x, fmaxp(a.y, a.z));
+    if (maxComponent < 1.f) return target;
+    return center + toTarget / maxComponent;
+}
+__device__ __forceinline__ float catmullRomWeight1D(float d) {  // bicubicSampling.inc:4-17
+    const float d1 = absf(d), d2 = d1 * d1, d3 = d2 * d1;
+    if (d1 <= 1.f) return (1.f / 6.f) * (9.f * d3 - 15.f * d2 + 6.f);
+    else if (d1 <= 2.f) return (1.f / 6.f) * (-3.f * d3 + 15.f * d2 - 24.f * d + 12.f);
+    return 0.f;
+}
+__device__ __forceinline__ float neighbourhoodContrast(const Nb& n) {  // temporalFilter.comp:59-69
+    const float c11 = computeLuminance(n.v[1][1]);
+    return absf(computeLuminance(n.v[0][0]) - c11) + absf(computeLuminance(n.v[1][0]) - c11) + absf(computeLuminance(n.v[2][0]) - c11) +
+           absf(computeLuminance(n.v[0][2]) - c11) + absf(computeLuminance(n.v[1][2]) - c11) + absf(computeLuminance(n.v[2][2]) - c11) +
+           absf(computeLuminance(n.v[0][1]) - c11) + absf(computeLuminance(n.v[2][1]) - c11);
+}
+struct BicubicW { vec2 w0, w1, w2, w3, wB, t, uvTrunc; };
+__device__ __forceinline__ vec2 vfloor(vec2 a) { return v2(floorf_(a.x), floorf_(a.y)); }
+__device__ __forceinline__ BicubicW bicubicWeights(vec2 iUV) {  // bicubicSampling.inc:74-85
+    BicubicW b;
+    b.uvTrunc = vfloor(iUV - 0.5f) + 0.5f;
+    const vec2 f = iUV - b.uvTrunc, f2 = f * f, f3 = f2 * f;
+    b.w0 = -0.5f * f3 + f2 - 0.5f * f;
+    b.w1 = 1.5f * f3 - 2.5f * f2 + 1.f;
+    b.w2 = -1.5f * f3 + 2.f * f2 + 0.5f * f;
+    b.w3 = 0.5f * f3 - 0.5f * f2;
+    b.wB = b.w1 + b.w2;
+    b.t = b.w2 / b.wB;
+    return b;
+}
+
+template <bool TONEMAP>
+__global__ void __launch_bounds__(256) temporalFilterKernel(TaaParams p) {
+    const int ix = blockIdx.x * 32 + (threadIdx.x & 31), iy = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (ix >= p.outputImage.w || iy >= p.outputImage.h) return;
+    const vec2 screenRes = v2((float)p.g->screenResolution[0], (float)p.g->screenResolution[1]);
+    const vec2 texelSize = 1.f / v2((float)p.outputImage.w, (float)p.outputImage.h);
+    const vec2 iUVf = v2((float)ix, (float)iy);
+    const vec2 uv = (iUVf + 0.5f) * texelSize;
+    Nb nb;
+    sampleNeighbourhood<TONEMAP>(p.currentFrame, uv, texelSize, nb);
+    vec3 mn = nb.v[0][0], mx = nb.v[0][0];  // minMaxFromNeighbourhood :54-65
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) { mn = vmin(mn, nb.v[i][j]); mx = vmax(mx, nb.v[i][j]); }
+    const float* rw = p.resolveWeights;  // resolveColor, temporalFilter.comp:41-57
+    vec3 currentColor = v3(0.f);
+    currentColor = currentColor + nb.v[0][0] * rw[0]; currentColor = currentColor + nb.v[1][0] * rw[1]; currentColor = currentColor + nb.v[2][0] * rw[2];
+    currentColor = currentColor + nb.v[0][1] * rw[3]; currentColor = currentColor + nb.v[1][1] * rw[4]; currentColor = currentColor + nb.v[2][1] * rw[5];
+    currentColor = currentColor + nb.v[0][2] * rw[6]; currentColor = currentColor + nb.v[1][2] * rw[7]; currentColor = currentColor + nb.v[2][2] * rw[8];
+
+    vec2 motion;
+    if (p.useMotionVectorDilation) {  // getClosestFragmentMotion, temporalReprojection.inc:67-83
+        float closestDepth = 0.f;
+        int offX = 0, offY = 0;
+        for (int x = -1; x <= 1; x++)
+            for (int y = -1; y <= 1; y++) {
+                const float depth = inRange(p.depthBuffer, ix + x, iy + y) ? loadD32(p.depthBuffer, ix + x, iy + y) : 0.f;
+                if (depth > closestDepth) { closestDepth = depth; offX = x; offY = y; }
+            }
+        motion = inRange(p.motionBuffer, ix + offX, iy + offY) ? loadRG16SNORM(p.motionBuffer, ix + offX, iy + offY) : v2(0.f);
+    } else {
+        motion = inRange(p.motionBuffer, ix, iy) ? loadRG16SNORM(p.motionBuffer, ix, iy) : v2(0.f);
+    }
+
+    auto H = [&](float x, float y) { return sampleR11LinearClamp(p.historySrc, v2(x, y)); };
+    vec3 historySample;
+    if (p.historySampleTech == 0) {
+        historySample = sampleR11LinearClamp(p.historySrc, uv + motion);
+    } else if (p.historySampleTech == 1) {  // 16 tap, bicubicSampling.inc:28-67
+        const vec2 pp = iUVf + 0.5f + motion * screenRes;
+        const vec2 uvTrunc = vfloor(pp - 0.5f) + 0.5f;
+        const vec2 ad = vabs(pp - uvTrunc);
+        const vec2 w[4] = {v2(catmullRomWeight1D(ad.x + 1.f), catmullRomWeight1D(ad.y + 1.f)), v2(catmullRomWeight1D(ad.x), catmullRomWeight1D(ad.y)),
+                           v2(catmullRomWeight1D(1.f - ad.x), catmullRomWeight1D(1.f - ad.y)), v2(catmullRomWeight1D(2.f - ad.x), catmullRomWeight1D(2.f - ad.y))};
+        const vec2 u[4] = {(uvTrunc - 1.f) * texelSize, uvTrunc * texelSize, (uvTrunc + 1.f) * texelSize, (uvTrunc + 2.f) * texelSize};
+        vec3 acc = v3(0.f);
+        bool first = true;
+        for (int yy = 0; yy < 4; yy++)
+            for (int xx = 0; xx < 4; xx++) {
+                const vec3 term = H(u[xx].x, u[yy].y) * w[xx].x * w[yy].y;
+                acc = first ? term : acc + term;
+                first = false;
+            }
+        historySample = acc;
+    } else if (p.historySampleTech == 2) {  // 9 tap :72-107
+        const BicubicW b = bicubicWeights(iUVf + 0.5f + motion * screenRes);
+        const vec2 uv0 = (b.uvTrunc - 1.f) * texelSize, uvT = (b.uvTrunc + b.t) * texelSize, uv3 = (b.uvTrunc + 2.f) * texelSize;
+        historySample = H(uv0.x, uv0.y) * b.w0.x * b.w0.y + H(uv0.x, uvT.y) * b.w0.x * b.wB.y + H(uv0.x, uv3.y) * b.w0.x * b.w3.y +
+                        H(uvT.x, uv0.y) * b.wB.x * b.w0.y + H(uvT.x, uvT.y) * b.wB.x * b.wB.y + H(uvT.x, uv3.y) * b.wB.x * b.w3.y +
+                        H(uv3.x, uv0.y) * b.w3.x * b.w0.y + H(uv3.x, uvT.y) * b.w3.x * b.wB.y + H(uv3.x, uv3.y) * b.w3.x * b.w3.y;
+    } else if (p.historySampleTech == 3) {  // 5 tap :112-145
+        const BicubicW b = bicubicWeights(iUVf + 0.5f + motion * screenRes);
+        const vec2 uv0 = (b.uvTrunc - 1.f) * texelSize, uvT = (b.uvTrunc + b.t) * texelSize, uv3 = (b.uvTrunc + 2.f) * texelSize;
+        auto T = [&](float x, float y) { return v4(H(x, y), 1.f); };
+        const vec4 result = T(uv0.x, uvT.y) * b.w0.x * b.wB.y + T(uvT.x, uv0.y) * b.wB.x * b.w0.y + T(uvT.x, uvT.y) * b.wB.x * b.wB.y +
+                            T(uvT.x, uv3.y) * b.wB.x * b.w3.y + T(uv3.x, uvT.y) * b.w3.x * b.wB.y;
+        historySample = xyz(result) / result.w;
+    } else if (p.historySampleTech == 4) {  // 1 tap :150-181
+        const BicubicW b = bicubicWeights(iUVf + 0.5f + motion * screenRes);
+        const vec2 uvT = (b.uvTrunc + b.t) * texelSize;
+        const vec3 hs = H(uvT.x, uvT.y);
+        const vec4 result = v4(hs + nb.v[0][1] - nb.v[1][1], 1.f) * b.w0.x * b.wB.y + v4(hs + nb.v[1][0] - nb.v[1][1], 1.f) * b.wB.x * b.w0.y +
+                            v4(hs, 1.f) * b.wB.x * b.wB.y + v4(hs + nb.v[1][2] - nb.v[1][1], 1.f) * b.wB.x * b.w3.y +
+                            v4(hs + nb.v[2][1] - nb.v[1][1], 1.f) * b.w3.x * b.wB.y;
+        historySample = xyz(result) / result.w;
+    } else {
+        historySample = v3(1.f, 0.f, 0.f);
+    }
+    if (TONEMAP) historySample = taaTonemap(historySample);
+    if (p.useClipping) historySample = clipAABB(historySample, mn, mx);
+    else historySample = vclamp(historySample, mn, mx);
+    if (anynan(historySample)) historySample = currentColor;
+
+    const float currentContrast = neighbourhoodContrast(nb);
+    Nb lastNb;
+    sampleNeighbourhood<TONEMAP>(p.historySrc, uv + motion, texelSize, lastNb);
+    const float lastContrast = neighbourhoodContrast(lastNb);
+    float contrastChange = absf(currentContrast - lastContrast);
+    contrastChange = clampf(contrastChange, 0.f, 1.f);
+    const float blendMin = 0.03f, blendMax = 0.13f;
+    float blendFactor = mixf(blendMax, blendMin, contrastChange);
+    if (p.g->cameraCut) blendFactor = 1.f;
+    const vec2 ur = uv + motion;
+    if (ur.x < 0.f || ur.y < 0.f || ur.x > 1.f || ur.y > 1.f) {  // isUVOutOfImage
+        blendFactor = 1.f;
+        currentColor = nb.v[0][0] * 0.0625f + nb.v[0][2] * 0.0625f + nb.v[2][0] * 0.0625f + nb.v[2][2] * 0.0625f + nb.v[1][0] * 0.125f +
+                       nb.v[0][1] * 0.125f + nb.v[1][2] * 0.125f + nb.v[2][1] * 0.125f + nb.v[1][1] * 0.25f;  // gaussianFilteredNeighbourhood :71-82
+    }
+    vec3 color = vmix(historySample, currentColor, blendFactor);
+    if (TONEMAP) color = taaTonemapReverse(color);
+    const uint32_t packed = packR11G11B10(color);
+    if (inRange(p.historyDst, ix, iy)) ((uint32_t*)p.historyDst.ptr)[texelIndex(p.historyDst, ix, iy)] = packed;
+    ((uint32_t*)p.outputImage.ptr)[texelIndex(p.outputImage, ix, iy)] = packed;
+}
+PLAIN_PASS(launch_temporalFilter, "temporalFilter.comp") {
+    TaaParams p;
+    p.currentFrame = c.sampled(0, PLAIN_FORMAT_R11G11B10_UFLOAT);
+    p.historySrc = c.sampled(3, PLAIN_FORMAT_R11G11B10_UFLOAT);
+    p.motionBuffer = c.sampled(4, PLAIN_FORMAT_RG16_SNORM);
+    p.depthBuffer = c.sampled(5, PLAIN_FORMAT_DEPTH32);
+    p.outputImage = c.storage(1, PLAIN_FORMAT_R11G11B10_UFLOAT);
+    p.historyDst = c.storage(2, PLAIN_FORMAT_R11G11B10_UFLOAT);
+    p.resolveWeights = c.ubuf<float>(6);
+    p.g = c.g;
+    p.useClipping = c.specBool(0, false);
+    p.useMotionVectorDilation = c.specBool(1, false);
+    p.historySampleTech = c.spec<int>(2, 0);
+    p.useTonemap = c.specBool(3, false);
+    if (c.failed) return;
+    if ((int)c.exec->dispatch[0] * 8 < p.outputImage.w || (int)c.exec->dispatch[1] * 8 < p.outputImage.h) { c.fail("temporalFilter.comp: dispatch does not cover the target"); return; }
+    dim3 grid(ceilDiv(p.outputImage.w, 32), ceilDiv(p.outputImage.h, 8));
+    if (p.useTonemap) PLAIN_LAUNCH(c, temporalFilterKernel<true>, grid, 256, 0, p);
+    else PLAIN_LAUNCH(c, temporalFilterKernel<false>, grid, 256, 0, p);
+}
+
+}  // namespace pb
