@@ -1,0 +1,328 @@
+#!/usr/bin/env python
+"""bench.py - frames/s of the full frame path at 3840x2160 (BASELINE.json metric, configs[2]) on N B200.
+
+One "step" = one frame: the ordered pass list of RenderFrontend::prepareRenderpasses (histogram, exposure, sky LUTs,
+HiZ, light matrices, SDF culling + trace, GI denoise + upscale, froxel volumetrics, G-buffer shading, TAA, bloom,
+tonemap) over the synthetic Sponza-sized scene, replayed through the C-ABI of include/plain_b200.h.
+
+  value : frames/s with the raster-pass outputs (depth, motion, normal, G-buffer, shadow maps) already resident in HBM
+  e2e   : the same frame driven through plain_frontend_render_frame with HOST buffers: every step uploads that frame's
+          raster-pass outputs from pinned host memory and reads the tonemapped 8-bit frame back, copies inside the
+          timed region
+  roofline     : the most expensive pass of the frame, algorithmic bytes (SURVEY.md 8d / DESIGN.md) / its mean duration
+  cpu_baseline : the scalar C++ oracle (oracle/, kind "port") on the host cores, bounded sample (rank 0, N = 1 only)
+
+`--impl reference` times the reference's own CPU implementation of the path: its per-pixel arithmetic is GLSL that
+cannot execute here (no Vulkan), so this is the oracle port on all host threads, on a bounded sample of the workload.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+WIDTH, HEIGHT, INSTANCES = 3840, 2160, 100
+CAMERA = ((-13.0, -1.7, 0.5), (1.0, 0.0, 0.0), (0.0, 0.0, 1.0), (0.0, -1.0, 0.0))  # eye height, looking down the atrium
+SUN_DEG = (40.0, 35.0)
+START_EXPOSURE = 2e-5
+METRIC = "frames/s at 3840x2160 (full pipeline)"
+HBM_FALLBACK_GBS = 6650.0  # B200_PROFILING.md fallback
+
+
+def algorithmic_bytes(w, h):
+    """Compulsory bytes per frame of each pass (every distinct input byte once + every output byte once), SURVEY.md 8d."""
+    N, n = w * h, (w // 2) * (h // 2)
+    F = ((w + 7) // 8) * ((h + 7) // 8) * 64
+    return {
+        "Histogram per tile": 4 * N + 512,
+        "Depth min/max pyramid creation": 4 * N + 8 * n * 4 // 3,
+        "Depth downscale": 4 * n + 2 * n,
+        "Indirect diffuse SDF trace": 8 * n + 12 * n,
+        "Indirect diffuse spatial filter": 18 * n + 12 * n,
+        "Indirect diffuse temporal filter": 32 * n + 24 * n,
+        "Indirect lighting upscale": 4 * N + 14 * n + 12 * N,
+        "Froxel volume material": 8 * F,
+        "Froxel light scattering": 16 * F,
+        "Volumetric lighting reprojection": 24 * F,
+        "Volumetric light integration": 16 * F,
+        "Forward shading": 32 * N + 8 * F,
+        "Temporal filtering": 24 * N,
+        "Apply bloom": 4 * N + 4 * N + N,
+        "Tonemapping": 8 * N,
+    }
+
+
+def measured_hbm_peak():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, device):
+        self.samples, self.proc, self.device = [], None, device
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = sorted(int(s[0]) for s in self.samples if s and s[0].isdigit())
+        mx = [int(s[1]) for s in self.samples if len(s) > 1 and s[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for s in self.samples if len(s) >= 6 for i in range(4) if s[2 + i].lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+
+
+def oracle_api():
+    """CPU oracle (test infrastructure): only for the cpu_baseline / --impl reference legs."""
+    from plainrenderer_b200 import ffi
+    lib = ROOT / "oracle" / "_build" / "liboracle.so"
+    if not lib.exists():
+        subprocess.run(["make", "-C", str(ROOT / "oracle")], check=True, capture_output=True)
+    return ffi.Api(str(lib), "oracle_", "oracle_frontend_")
+
+
+def time_oracle(width, height, frames, warm):
+    """Median seconds per frame of the CPU oracle on all host threads at width x height (same scene, camera, sequence)."""
+    from plainrenderer_b200 import ffi
+    api = oracle_api()
+    s = ffi.default_settings(api, width, height, sun_direction_deg=SUN_DEG)
+    fe = ffi.Frontend(api, s)
+    scene = ffi.SyntheticScene(api, n_instances=INSTANCES)
+    scene.attach(fe)
+    fe.set_exposure(START_EXPOSURE)
+    cam = ffi.camera(*CAMERA)
+    inputs = [scene.render_inputs(s, cam, f + 1, shadows=(f == 0)) for f in range(2)]
+    times = []
+    for f in range(warm + frames):
+        i = inputs[f % 2]
+        t0 = time.perf_counter()
+        fe.render_frame(cam, (f + 1) / 60.0, 1 / 60.0, i["depth"], i["motion"], i["normal"], i["gbuffer"], inputs[0]["shadow_maps"] if f == 0 else None)
+        fe.read_output()
+        if f >= warm:
+            times.append(time.perf_counter() - t0)
+    fe.close()
+    return float(np.median(times))
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    sw, sh = WIDTH // 8, HEIGHT // 8  # bounded sample: the same scene and camera at 480x270 = 1/64 of the pixels
+    cores = os.cpu_count() or 1
+    sec = time_oracle(sw, sh, max(args.steps, 1), max(args.warmup, 1))
+    scale = (WIDTH * HEIGHT) / float(sw * sh)
+    fps = 1.0 / (sec * scale)
+    sample = "%dx%d frame (1/%d of the 3840x2160 pixels, same scene/camera/pass list), frames/s divided by %d" % (sw, sh, int(scale), int(scale))
+    line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": sec * scale * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args.gpus),
+            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "note": "the reference's per-pixel path is GLSL under Vulkan and cannot execute here; this arm is the scalar C++ oracle port (oracle/) on all host threads"}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(n_gpus):
+    return {"workload": "configs[2]: 3840x2160 synthetic Sponza-sized scene (%d SDF instances), full pipeline (GI/TAA/sky/volumetrics/bloom), static camera with TAA jitter" % INSTANCES,
+            "resolution": [WIDTH, HEIGHT], "sdf_instances": INSTANCES, "parallelism": "1 GPU" if n_gpus == 1 else "%d GPUs, one whole frame per GPU per step (frame replicas, no collective)" % n_gpus,
+            "l2": "per-frame working set (>1.5 GB touched, G-buffer alone 133 MB) exceeds the 126 MB L2; no flush needed"}
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import plainrenderer_b200 as pr
+    from plainrenderer_b200 import ffi
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - the frame path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    api = pr.load()
+    s = ffi.default_settings(api, WIDTH, HEIGHT, sun_direction_deg=SUN_DEG)
+    fe = ffi.Frontend(api, s, device=local_rank)
+    scene = ffi.SyntheticScene(api, n_instances=INSTANCES)
+    scene.attach(fe)
+    fe.set_exposure(START_EXPOSURE)
+    cam = ffi.camera(*CAMERA)
+    be = fe.backend
+
+    # raster-pass outputs for the TAA jitter phases, ray cast on the host into pinned memory (untimed set-up)
+    def pinned(nbytes, dtype):
+        t = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+        return t, t.numpy().view(dtype)
+    keep, phases = [], []
+    t_setup = time.time()
+    n_phases = args.phases
+    for ph in range(n_phases):
+        bufs = {}
+        for name, nbytes, dt in (("depth", WIDTH * HEIGHT * 4, np.float32), ("motion", WIDTH * HEIGHT * 4, np.int16), ("normal", WIDTH * HEIGHT * 4, np.uint8), ("gbuffer", WIDTH * HEIGHT * 16, np.uint32)):
+            t, a = pinned(nbytes, dt)
+            keep.append(t)
+            bufs[name] = a
+        if ph == 0:
+            sm = []
+            for _ in range(s.sun_shadow_cascade_count):
+                t, a = pinned(2048 * 2048 * 2, np.uint16)
+                keep.append(t)
+                sm.append(a)
+            bufs["shadow_maps"] = sm
+        scene.render_inputs(s, cam, ph + 1, shadows=(ph == 0), out=bufs)
+        phases.append(bufs)
+    out_t, out_host = pinned(WIDTH * HEIGHT * 4, np.uint8)
+    setup_s = time.time() - t_setup
+
+    stream_ptr = C.c_void_p()
+    api.b["get_stream"](be.ctx, C.byref(stream_ptr))
+    stream = torch.cuda.ExternalStream(stream_ptr.value, device=torch.device("cuda", local_rank))
+
+    frame = [0]
+
+    def step(upload, readback):
+        f = frame[0]
+        frame[0] += 1
+        ph = phases[f % n_phases]
+        if upload:
+            fe.render_frame(cam, (f + 1) / 60.0, 1 / 60.0, ph["depth"], ph["motion"], ph["normal"], ph["gbuffer"], phases[0]["shadow_maps"] if f == 0 else None, async_upload=True)
+        else:
+            fe.render_frame(cam, (f + 1) / 60.0, 1 / 60.0)
+        if readback:
+            fe.read_output(out_host, async_pinned=True)
+
+    def barrier():
+        torch.cuda.synchronize()
+        be._check(api.b["wait_for_gpu_idle"](be.ctx), "idle")
+        if world > 1:
+            torch.distributed.barrier()
+            torch.cuda.synchronize()
+
+    def timed(k, upload, readback):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(k):
+            step(upload, readback)
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    # warm-up: uploads every phase once (fills both ping-pong targets, shadow maps), lets exposure/TAA/GI histories settle
+    be.set_graph_replay_enabled(not args.no_graph)
+    for _ in range(max(args.warmup, 3, n_phases if n_phases <= 8 else 8)):
+        step(True, True)
+    barrier()
+
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    ms_resident = timed(args.steps, upload=False, readback=False)
+    launches = be.last_frame_launch_count()
+    ms_e2e = timed(args.steps, upload=True, readback=True)
+    clock_info = clocks.stop()
+
+    # per-pass durations (CUDA events on the backend stream around every pass, mean over the same number of frames)
+    be.set_graph_replay_enabled(False)
+    be.set_timing_enabled(True)
+    acc, order = {}, []
+    tk = max(min(args.steps, 10), 1)
+    for _ in range(tk):
+        step(False, False)
+        for name, ms in be.pass_timings():
+            if name not in acc:
+                acc[name] = 0.0
+                order.append(name)
+            acc[name] += ms / tk
+    be.set_timing_enabled(False)
+
+    if rank == 0:
+        ms_step = ms_resident / args.steps
+        fps = world * 1000.0 / ms_step
+        ms_step_e2e = ms_e2e / args.steps
+        fps_e2e = world * 1000.0 / ms_step_e2e
+        h2d = WIDTH * HEIGHT * (4 + 4 + 4 + 16)
+        d2h = WIDTH * HEIGHT * 4
+        peak, peak_src = measured_hbm_peak()
+        alg = algorithmic_bytes(WIDTH, HEIGHT)
+        top = max(acc, key=lambda k: acc[k])
+        launches_of_top = 2 if top == "Indirect diffuse spatial filter" else 1
+        top_ms = acc[top] / launches_of_top
+        achieved = alg.get(top, 0) / (top_ms * 1e-3) / 1e9 if top_ms > 0 else 0.0
+        passes_sum = sum(acc.values())
+        line = {"metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(world),
+                "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_step_e2e},
+                "gpu_launches": launches * args.steps,
+                "clocks": clock_info,
+                "roofline": {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None, "traffic": None,
+                             "algorithmic_bytes_per_launch": alg.get(top, 0), "kernel_ms": top_ms, "share_of_frame": acc[top] / passes_sum if passes_sum else None, "peak_source": peak_src},
+                "passes_ms": {k: round(acc[k], 4) for k in order},
+                "frame_roofline": {"algorithmic_bytes_per_frame": int(sum(alg.values()) + alg["Indirect diffuse spatial filter"]), "hbm_bound_ms": (sum(alg.values()) + alg["Indirect diffuse spatial filter"]) / peak / 1e6},
+                "setup_s": round(setup_s, 1), "graph_replay": not args.no_graph}
+        if world == 1 and not args.no_cpu_baseline:
+            sw, sh = WIDTH // 8, HEIGHT // 8
+            sec = time_oracle(sw, sh, 3, 1)
+            scale = (WIDTH * HEIGHT) / float(sw * sh)
+            line["cpu_baseline"] = {"value": 1.0 / (sec * scale), "unit": "frames/s", "cores": os.cpu_count() or 1, "kind": "port",
+                                    "sample": "%dx%d frame of the same scene (1/%d of the pixels), oracle port on all host threads, frames/s divided by %d" % (sw, sh, int(scale), int(scale))}
+        print(json.dumps(line), flush=True)
+    fe.close()
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=8)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--phases", type=int, default=2, help="TAA jitter phases of raster-pass outputs generated on the host (each 232 MB at 4K)")
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+    else:
+        if world != args.gpus and world == 1 and args.gpus > 1:
+            print("bench.py: --gpus %d needs torchrun (one rank per GPU); running 1 rank" % args.gpus, file=sys.stderr)
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

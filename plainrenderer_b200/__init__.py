@@ -14,8 +14,8 @@ _api = None
 
 
 def build(force=False):
-    from . import build as _build
-    return _build.build(force=force)
+    import importlib
+    return importlib.import_module(__name__ + ".buildlib").build(force=force)
 
 
 def load():
@@ -23,6 +23,6 @@ def load():
     global _api
     if _api is None:
         if not LIB_PATH.exists():
-            raise RuntimeError("%s is missing - run `python -m plainrenderer_b200.build` (there is no CPU fallback)" % LIB_PATH)
+            raise RuntimeError("%s is missing - run `python -m plainrenderer_b200.buildlib` (there is no CPU fallback)" % LIB_PATH)
         _api = ffi.Api(LIB_PATH, "plain_", "plain_frontend_")
     return _api

@@ -1,7 +1,7 @@
 """Builds plainrenderer_b200/libplain_b200.so in-tree: the CUDA backend (csrc/*.cu, sm_100a) + the host-side frontend
 mirror (host/*.cpp) behind the C-ABI of include/plain_b200.h and include/plain_frontend.h.
 
-    python -m plainrenderer_b200.build [--force] [--jobs N]
+    python -m plainrenderer_b200.buildlib [--force] [--jobs N]
 
 nvcc cross-compiles without a GPU. Flags that are part of the numeric contract: -fmad=false (no
 contraction), default -prec-div/-prec-sqrt/-ftz=false; host side -ffp-contract=off.

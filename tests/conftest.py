@@ -1,0 +1,136 @@
+import subprocess
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT))
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+@pytest.fixture(scope="session")
+def ffi():
+    from plainrenderer_b200 import ffi as m
+    return m
+
+
+@pytest.fixture(scope="session")
+def oracle(ffi):
+    """CPU oracle (checker). Built on demand from oracle/*.cpp."""
+    lib = ROOT / "oracle" / "_build" / "liboracle.so"
+    if not lib.exists():
+        subprocess.run(["make", "-C", str(ROOT / "oracle")], check=True, capture_output=True)
+    return ffi.Api(str(lib), "oracle_", "oracle_frontend_")
+
+
+@pytest.fixture(scope="session")
+def product_lib():
+    import plainrenderer_b200 as pr
+    if not pr.LIB_PATH.exists():
+        pr.build()
+    return pr.LIB_PATH
+
+
+@pytest.fixture(scope="session")
+def cuda(product_lib):
+    """The product library on a CUDA device. GPU tests fail (not skip) if the library cannot create a backend."""
+    import plainrenderer_b200 as pr
+    return pr.load()
+
+
+# ---- independent numpy restatements of exactly specified pieces (texel formats) ----
+def decode_small_float(v, mbits):
+    v = np.asarray(v, np.uint32)
+    e = (v >> mbits).astype(np.int64)
+    m = (v & ((1 << mbits) - 1)).astype(np.float64)
+    out = np.where(e == 0, m * 2.0 ** (-14 - mbits), (1.0 + m / (1 << mbits)) * 2.0 ** (e - 15))
+    out = np.where(e == 31, np.where(m == 0, np.inf, np.nan), out)
+    return out
+
+
+def decode_r11g11b10(packed):
+    packed = np.asarray(packed, np.uint32)
+    return np.stack([decode_small_float(packed & 0x7FF, 6), decode_small_float((packed >> 11) & 0x7FF, 6), decode_small_float(packed >> 22, 5)], axis=-1)
+
+
+def random_r11g11b10(rng, n, finite=True):
+    """Random packed texels; with finite=True exponents stay below 31 (no inf/NaN)."""
+    def chan(mbits):
+        e = rng.integers(0, 31 if finite else 32, n, dtype=np.uint32)
+        m = rng.integers(0, 1 << mbits, n, dtype=np.uint32)
+        return (e << mbits) | m
+    return chan(6) | (chan(6) << 11) | (chan(5) << 22)
+
+
+CAMERA = ((-13.0, -1.7, 0.5), (1.0, 0.0, 0.0), (0.0, 0.0, 1.0), (0.0, -1.0, 0.0))
+ALL_IMAGES = ["skyTransmission", "skyMultiscatter", "skyLut", "hiz", "depthHalf", "giY0", "giC0", "giY1", "giC1", "giHistY0", "giHistC0", "giHistY1", "giHistC1", "giFullY", "giFullC",
+              "froxelMaterial", "froxelScatter", "froxelHist0", "froxelHist1", "froxelIntegration", "color0", "color1", "taaHist0", "taaHist1", "post1", "brdfLut", "output"]
+ALL_BUFFERS = [("histogram", 512), ("light", 20), ("sunShadowInfo", 304)]
+
+
+def image_mips(fe, h):
+    d = fe.backend.image_description(h)
+    if d.mip_count == 1:  # full chain
+        return 1 + int(np.floor(np.log2(max(d.width, d.height, d.depth))))
+    if d.mip_count == 2:
+        return d.manual_mip_count
+    return 1
+
+
+class Sequence:
+    """Drives the same frame sequence through one library (CUDA product or CPU oracle)."""
+
+    def __init__(self, ffi, api, w, h, instances=12, frames=None, **settings):
+        self.ffi, self.api, self.w, self.h = ffi, api, w, h
+        settings.setdefault("sun_direction_deg", (40.0, 35.0))
+        self.s = ffi.default_settings(api, w, h, **settings)
+        self.fe = ffi.Frontend(api, self.s)
+        self.scene = ffi.SyntheticScene(api, n_instances=instances)
+        self.scene.attach(self.fe)
+        self.fe.set_exposure(2e-5)
+        self.frame = 0
+        self.prev_cam = None
+
+    def camera(self, f, moving):
+        p, fw, r, u = CAMERA
+        if moving:
+            p = (p[0] + 0.35 * f, p[1] - 0.02 * f, p[2] + 0.11 * f)
+        return self.ffi.camera(p, fw, r, u)
+
+    def step(self, moving=False, inputs=None):
+        f = self.frame
+        cam = self.camera(f, moving)
+        if inputs is None:
+            inputs = self.scene.render_inputs(self.s, cam, f + 1, prev_cam=self.prev_cam, shadows=True, threads=0)
+        self.fe.render_frame(cam, (f + 1) / 60.0, 1 / 60.0, inputs["depth"], inputs["motion"], inputs["normal"], inputs["gbuffer"], inputs.get("shadow_maps"))
+        self.prev_cam = cam
+        self.frame += 1
+        return inputs
+
+    def snapshot(self, images=ALL_IMAGES, buffers=ALL_BUFFERS):
+        out = {}
+        for name in images:
+            h = self.fe.image(name)
+            for mip in range(image_mips(self.fe, h)):
+                out["%s/%d" % (name, mip)] = self.fe.backend.read_image(h, mip).copy()
+        for name, size in buffers:
+            out["buf:" + name] = self.fe.backend.read_storage_buffer(self.fe.storage_buffer(name), size).copy()
+        return out
+
+    def close(self):
+        self.scene.close()
+        self.fe.close()
+
+
+def assert_snapshots_equal(a, b, context=""):
+    bad = []
+    for k in a:
+        n = int((a[k] != b[k]).sum())
+        if n:
+            bad.append("%s: %d/%d bytes differ" % (k, n, a[k].size))
+    assert not bad, "%s differs from the oracle: %s" % (context, "; ".join(bad))

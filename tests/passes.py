@@ -1,0 +1,135 @@
+"""Single-pass drivers over the C-ABI (used with both the CUDA product and the CPU oracle): each builds the resources one
+reference shader binds, records one execution with the reference's binding numbers and returns the outputs."""
+import ctypes as C
+
+import numpy as np
+
+
+class PassRig:
+    def __init__(self, ffi, api, w=64, h=64, time=0.5, screen=None):
+        self.ffi, self.api = ffi, api
+        self.be = ffi.Backend(api, width=w, height=h)
+        g = ffi.GlobalShaderInfo()
+        g.time = time
+        g.screenResolution[0], g.screenResolution[1] = screen or (w, h)
+        g.nearPlane, g.farPlane = 0.1, 300.0
+        g.cameraTanFovHalf, g.cameraAspectRatio = 0.3153, (screen or (w, h))[0] / (screen or (w, h))[1]
+        g.cameraForward[2] = -1.0
+        g.cameraUp[1] = -1.0
+        g.cameraRight[0] = 1.0
+        g.sunDirection[1] = -1.0
+        g.deltaTime = 1 / 60.0
+        g.exposureAdaptionSpeedEvPerSec, g.exposureOffset, g.sunStrength = 2.0, 1.0, 128000.0
+        self.g = g
+        self.gbuf = self.be.create_uniform_buffer(C.sizeof(g), np.frombuffer(bytes(g), np.uint8))
+        self.be.set_global_uniform_buffer(self.gbuf)
+
+    def close(self):
+        self.be.close()
+
+    def run(self):
+        self.be.render_frame()
+
+
+def tonemap(ffi, api, packed, time=0.37):
+    h, w = packed.shape
+    rig = PassRig(ffi, api, w, h, time=time)
+    be = rig.be
+    src = be.create_image(w, h, "R11G11B10_UFLOAT", data=packed.astype(np.uint32))
+    p = be.create_compute_pass("tonemapping.comp")
+    be.new_frame()
+    be.set_compute_pass_execution(p, ((w + 7) // 8, (h + 7) // 8, 1), sampled=[(src, 0, 1)], storage=[(be.swapchain_image(), 0, 0)])
+    rig.run()
+    out = be.read_image(be.swapchain_image()).reshape(h, w, 4).copy()
+    rig.close()
+    return out
+
+
+def histogram(ffi, api, packed, exposure, n_bins=128, lum_min=0.001, lum_max=200000.0):
+    h, w = packed.shape
+    rig = PassRig(ffi, api, w, h)
+    be = rig.be
+    tx, ty = (w + 31) // 32, (h + 31) // 32
+    src = be.create_image(w, h, "R11G11B10_UFLOAT", data=packed.astype(np.uint32))
+    per_tile = be.create_storage_buffer(tx * ty * n_bins * 4)
+    hist = be.create_storage_buffer(n_bins * 4, np.full(n_bins, 77, np.uint32))
+    light = be.create_storage_buffer(20, np.array([1, 1, 1, exposure, 1], np.float32))
+    spec = {0: np.uint32(n_bins), 1: np.float32(lum_min), 2: np.float32(lum_max), 3: np.int32(tx * ty)}
+    p0 = be.create_compute_pass("histogramPerTile.comp", spec)
+    p1 = be.create_compute_pass("histogramReset.comp", {0: np.uint32(n_bins)})
+    p2 = be.create_compute_pass("histogramCombineTiles.comp", {0: np.uint32(n_bins), 1: np.int32(tx * ty)})
+    be.new_frame()
+    be.set_compute_pass_execution(p0, (tx, ty, 1), sampled=[(src, 0, 2)], storage_buffers=[(per_tile, False, 0), (light, True, 3)])
+    be.set_compute_pass_execution(p1, ((n_bins + 63) // 64, 1, 1), storage_buffers=[(hist, False, 1)])
+    be.set_compute_pass_execution(p2, (tx * ty, (n_bins + 63) // 64, 1), storage_buffers=[(per_tile, False, 0), (hist, False, 1)])
+    rig.run()
+    out = (be.read_storage_buffer(per_tile, tx * ty * n_bins * 4, np.uint32).reshape(ty, tx, n_bins).copy(), be.read_storage_buffer(hist, n_bins * 4, np.uint32).copy())
+    rig.close()
+    return out
+
+
+def mip_count(w, h):
+    return 1 + int(np.floor(np.log2(max(w, h))))
+
+
+def hiz(ffi, api, depth):
+    """depthHiZPyramid.comp with the bindings of RenderFrontend::computeDepthPyramid (RenderFrontend.cpp:804-838)."""
+    h, w = depth.shape
+    rig = PassRig(ffi, api, w, h)
+    be = rig.be
+    pw, ph = w // 2, h // 2
+    n = mip_count(pw, ph)
+    src = be.create_image(w, h, "DEPTH32", data=depth.astype(np.float32))
+    pyr = be.create_image(pw, ph, "RG32_SFLOAT", mips=ffi.MIPS_FULL_CHAIN)
+    sync = be.create_storage_buffer(4, np.zeros(1, np.uint32))
+    p = be.create_compute_pass("depthHiZPyramid.comp", {0: np.uint32(n), 1: np.uint32(w), 2: np.uint32(h), 3: np.uint32(1)})
+    unused = 11 - n
+    storage = [(pyr, max(i - unused, 0), i) for i in range(11)]
+    be.new_frame()
+    be.set_compute_pass_execution(p, ((pw + 31) // 32, (ph + 31) // 32, 1), sampled=[(src, 0, 13), (pyr, 0, 15)], storage=storage, storage_buffers=[(sync, False, 16)])
+    rig.run()
+    out = [be.read_image(pyr, m, np.float32).reshape(max(ph >> m, 1), max(pw >> m, 1), 2).copy() for m in range(n)]
+    rig.close()
+    return out
+
+
+def depth_downscale(ffi, api, depth):
+    h, w = depth.shape
+    rig = PassRig(ffi, api, w, h)
+    be = rig.be
+    src = be.create_image(w, h, "DEPTH32", data=depth.astype(np.float32))
+    dst = be.create_image(w // 2, h // 2, "R16_SFLOAT")
+    p = be.create_compute_pass("depthDownscale.comp")
+    be.new_frame()
+    be.set_compute_pass_execution(p, ((w // 2 + 7) // 8, (h // 2 + 7) // 8, 1), sampled=[(src, 0, 1)], storage=[(dst, 0, 0)])
+    rig.run()
+    out = be.read_image(dst, 0, np.float16).reshape(h // 2, w // 2).copy()
+    rig.close()
+    return out
+
+
+def bloom(ffi, api, packed, strength=0.05, radius=1.5, mips=6):
+    """Bloom::computeBloom (Bloom.cpp:56-144): 5 down, 5 up, apply. Returns (downscale mips, upscale mips, result)."""
+    h, w = packed.shape
+    rig = PassRig(ffi, api, w, h)
+    be = rig.be
+    target = be.create_image(w, h, "R11G11B10_UFLOAT", data=packed.astype(np.uint32))
+    down = be.create_temporary_image(w, h, "R11G11B10_UFLOAT", mips=ffi.MIPS_MANUAL, manual_mips=mips)
+    up = be.create_temporary_image(w, h, "R11G11B10_UFLOAT", mips=ffi.MIPS_MANUAL, manual_mips=mips)
+    pd = [be.create_compute_pass("bloomDownsample.comp") for _ in range(mips - 1)]
+    pu = [be.create_compute_pass("bloomUpsample.comp", {0: np.uint32(1 if i == 0 else 0)}) for i in range(mips - 1)]
+    pa = be.create_compute_pass("applyBloom.comp")
+    res = lambda m, v: max(v // (1 << m), 1)
+    be.new_frame()
+    for i in range(mips - 1):
+        be.set_compute_pass_execution(pd[i], ((res(i + 1, w) + 7) // 8, (res(i + 1, h) + 7) // 8, 1), sampled=[(target if i == 0 else down, i, 1)], storage=[(down, i + 1, 0)])
+    for i in range(mips - 1):
+        t = mips - 2 - i
+        be.set_compute_pass_execution(pu[i], ((res(t, w) + 7) // 8, (res(t, h) + 7) // 8, 1), sampled=[(up, t + 1, 1), (down, t + 1, 2)], storage=[(up, t, 0)],
+                                      push=np.float32(radius).tobytes())
+    be.set_compute_pass_execution(pa, ((w + 7) // 8, (h + 7) // 8, 1), sampled=[(up, 0, 1)], storage=[(target, 0, 0)], push=np.float32(strength).tobytes())
+    rig.run()
+    out = ([be.read_image(down, m, np.uint32).copy() for m in range(1, mips)], [be.read_image(up, m, np.uint32).copy() for m in range(mips - 1)],
+           be.read_image(target, 0, np.uint32).reshape(h, w).copy())
+    rig.close()
+    return out

