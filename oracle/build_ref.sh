@@ -1,0 +1,16 @@
+#!/bin/bash
+# ORACLE - test infrastructure only. Compiles the one part of the reference that builds here - the asset pipeline
+# (PlainAssetPipeline: glTF import + CPU SDF bake, BASELINE configs[0]) - from its sources where they lie under
+# /root/reference, into oracle/_ref/ (git-ignored, travels to the GPU box). No reference source is copied into the repo.
+set -e
+REF=${REF:-/root/reference}
+HERE="$(cd "$(dirname "$0")" && pwd)"
+OUT="$HERE/_ref"
+[ -d "$REF/Plain/src/AssetPipeline" ] || { echo "reference not present at $REF"; exit 0; }
+mkdir -p "$OUT"
+[ -x "$OUT/PlainAssetPipeline" ] && [ "$OUT/PlainAssetPipeline" -nt "$HERE/build_ref.sh" ] && { echo "up to date: $OUT/PlainAssetPipeline"; exit 0; }
+g++ -std=c++17 -O2 -w -fpermissive -include cassert -include cstring -include condition_variable -include stdexcept \
+    -I"$HERE/shim" -I"$REF/Plain/src" -I"$REF/Plain/src/Common" -I"$REF/Plain/vendor" -I"$REF/Plain/vendor/glm" -I"$REF/Plain/vendor/tinygltf" \
+    "$REF"/Plain/src/AssetPipeline/*.cpp "$REF"/Plain/src/Common/*.cpp "$REF"/Plain/src/Common/Utilities/*.cpp \
+    -lpthread -o "$OUT/PlainAssetPipeline"
+echo "built $OUT/PlainAssetPipeline"

@@ -45,14 +45,18 @@ DM_HD float u2f(uint32_t u) {
 
 DM_HD float nanf_() { return u2f(0x7fc00000u); }
 DM_HD float inff_() { return u2f(0x7f800000u); }
-DM_HD bool isnan_(float x) { return (f2u(x) & 0x7fffffffu) > 0x7f800000u; }
+DM_HD bool isnan_(float x) { return x != x; }
 DM_HD float abs_(float x) { return u2f(f2u(x) & 0x7fffffffu); }
 
 // floor for |x| < 2^31 via truncation (exact)
 DM_HD float floor_(float x) {
+#if defined(__CUDA_ARCH__)
+    return floorf(x) + 0.f;  // one FRND; "+ 0" turns floor(-0) = -0 into the +0 the portable sequence below yields
+#else
     if (!(abs_(x) < 8388608.f)) return x;  // already integral (or nan/inf)
     float t = (float)(int)x;
     return (t > x) ? t - 1.f : t;
+#endif
 }
 
 // x * 2^n, n roughly in [-300, 300]; handles results in the denormal range

@@ -42,11 +42,13 @@ PV_HD uint32_t encodeSmallFloat(float f, int mbits) {  // unsigned 5-bit-exponen
     }
     return value >= expAll ? maxFinite : value;
 }
-PV_HD float decodeSmallFloat(uint32_t v, int mbits) {
-    const uint32_t e = v >> mbits, m = v & ((1u << mbits) - 1u);
-    if (e == 0) return (float)m * ((mbits == 6) ? 9.5367431640625e-07f : 1.9073486328125e-06f);  // m * 2^-14 / 2^mbits, exact
-    if (e == 31) return dm::u2f(0x7f800000u | (m << (23 - mbits)));
-    return dm::u2f(((e + 112u) << 23) | (m << (23 - mbits)));
+PV_HD float decodeSmallFloat(uint32_t v, int mbits) {  // exact; branch-free: exponent and mantissa shifted into the binary32 fields
+    const uint32_t e = v >> mbits;
+    const uint32_t shifted = v << (23 - mbits);
+    const float normal = dm::u2f(shifted + (112u << 23));                                    // rebias 15 -> 127
+    const float denormal = dm::u2f(shifted + (113u << 23)) - dm::u2f(113u << 23);            // (1 + m/2^mbits) * 2^-14 - 2^-14, exact
+    const float special = dm::u2f(shifted | 0x7f800000u);                                    // inf / NaN keep their mantissa
+    return e == 0 ? denormal : (e == 31 ? special : normal);
 }
 PV_HD uint32_t packR11G11B10(vec3 c) { return encodeSmallFloat(c.x, 6) | (encodeSmallFloat(c.y, 6) << 11) | (encodeSmallFloat(c.z, 5) << 22); }
 PV_HD vec3 unpackR11G11B10(uint32_t v) { return v3(decodeSmallFloat(v & 0x7ffu, 6), decodeSmallFloat((v >> 11) & 0x7ffu, 6), decodeSmallFloat(v >> 22, 5)); }
