@@ -64,6 +64,7 @@ struct Backend {
     bool stagingInFlight = false;
 
     BindlessEntry* bindlessDevice = nullptr;
+    ShadingTables* tablesDevice = nullptr;
     static const uint32_t kMaxBindless = 4096;
 
     bool timingEnabled = false;
@@ -232,6 +233,7 @@ static bool runPasses(Backend& b, bool withTiming) {
         c.smCount = b.smCount;
         c.g = b.globalUniformBuffer < b.uniformBuffers.size() ? (const plain_global_shader_info*)b.uniformBuffers[b.globalUniformBuffer].ptr : nullptr;
         c.bindless = b.bindlessDevice;
+        c.tables = (const float*)b.tablesDevice;
         if (!c.g) { b.lastError = "render_frame: no global uniform buffer bound (set_global_descriptor_set_resources)"; return false; }
         if (withTiming) {
             while (b.timingEvents.size() < ev + 2) { cudaEvent_t x; cudaEventCreate(&x); b.timingEvents.push_back(x); }
@@ -290,12 +292,13 @@ int PLAIN_FN(backend_create)(int device, uint32_t width, uint32_t height, plain_
     if (cudaStreamCreateWithFlags(&b.stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return 1; }
     cudaEventCreateWithFlags(&b.stagingConsumed, cudaEventDisableTiming);
     if (cudaMallocHost(&b.stagingHost, kStagingBytes) != cudaSuccess || cudaMalloc(&b.stagingDevice, kStagingBytes) != cudaSuccess ||
-        cudaMalloc(&b.bindlessDevice, sizeof(BindlessEntry) * Backend::kMaxBindless) != cudaSuccess) {
+        cudaMalloc(&b.bindlessDevice, sizeof(BindlessEntry) * Backend::kMaxBindless) != cudaSuccess || cudaMalloc(&b.tablesDevice, sizeof(ShadingTables)) != cudaSuccess) {
         fprintf(stderr, "plain_backend_create: allocation failed: %s\n", cudaGetErrorString(cudaGetLastError()));
         delete ctx;
         return 1;
     }
     cudaMemsetAsync(b.bindlessDevice, 0, sizeof(BindlessEntry) * Backend::kMaxBindless, b.stream);
+    buildShadingTables(b.tablesDevice, b.stream);
     plain_image_desc d{};
     d.width = width; d.height = height; d.depth = 1;
     d.type = PLAIN_IMAGE_TYPE_2D; d.format = PLAIN_FORMAT_BGRA8_UNORM;  // VulkanSurface.cpp:41-46
@@ -319,6 +322,7 @@ void PLAIN_FN(backend_destroy)(plain_ctx* ctx) {
     cudaFree(b.stagingDevice);
     cudaFreeHost(b.stagingHost);
     cudaFree(b.bindlessDevice);
+    cudaFree(b.tablesDevice);
     cudaEventDestroy(b.stagingConsumed);
     cudaStreamDestroy(b.stream);
     delete ctx;

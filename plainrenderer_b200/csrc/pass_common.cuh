@@ -64,6 +64,7 @@ struct LaunchCtx {
     cudaStream_t stream;
     const plain_global_shader_info* g;  // device pointer (set 0 binding 0)
     const BindlessEntry* bindless;      // device pointer
+    const float* tables;                // device pointer: exact lookup tables over 8-bit domains, see ShadingTables
     int smCount;
     bool failed = false;
     std::string error;
@@ -96,6 +97,18 @@ struct LaunchCtx {
     void fail(const std::string& msg) { if (!failed) { failed = true; error = msg; } }
     void countLaunch(int n = 1);
 };
+
+// Exact tables over 8-bit input domains (built once per context by buildShadingTables, passes_shading.cu): tabulating a
+// function on its whole domain returns the same bits as evaluating it.
+//   unorm8[b]       = float(b) / 255                              (UNORM8 decode)
+//   srgbToLinear[b] = sRGBToLinear(unorm8[b])                     (colorConversion.inc:15-23 on an 8-bit albedo channel)
+//   pcf[b * 12 + i] = {cos(angle), sin(angle), sqrt(d), 0} of tap i of calcShadow for blue-noise byte b (triangle.frag:107-116)
+struct ShadingTables {
+    float unorm8[256];
+    float srgbToLinear[256];
+    float4 pcf[256 * 12];
+};
+void buildShadingTables(ShadingTables* deviceTables, cudaStream_t stream);
 
 struct PassRegistration { PassRegistration(const char* shader, LaunchFn fn); };
 #define PLAIN_PASS(fnname, shader)                       \

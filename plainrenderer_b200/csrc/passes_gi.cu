@@ -145,6 +145,12 @@ struct TraceInstance {  // one SDFInstance (SDF.inc:4-10) staged in shared memor
     vec3 localExtends;
     vec3 meanAlbedo;
     ImgView sdf;
+    vec3 sphereCenter;  // world-space bounding sphere of the brick's box (conservative: radius padded), see instanceBoundingSphere
+    float sphereR2;
+    // per-instance values of SDF.inc:131-141, evaluated once when the instance is staged (same expressions)
+    vec3 localExtendsHalfPadded;   // localExtends * 0.5 + 0.01
+    float distanceThreshold;       // length(localExtends / sdfResolution) * 0.25
+    float localToGlobalScale;      // 1 / length(worldToLocal[0].xyz)
 };
 struct TraceResult {
     bool hit;
@@ -183,8 +189,15 @@ __device__ __forceinline__ bool rayAABBIntersection(vec3 rayOrigin, vec3 rayDire
     tOut = t;
     return hit;
 }
-// SDF.inc:101-184
-__device__ void traceRayTroughSDFInstance(const TraceInstance& inst, vec3 rayStartWorld, vec3 rayDirectionWorld, TraceResult& tr) {
+// SDF.inc:101-184, split at the head of the sphere-trace loop so that a warp can interleave lanes that are marching
+// through different instances (see sdfDiffuseTraceKernel). The per-lane operation sequence is the reference's.
+struct MarchState {
+    vec3 localSamplePos, rayDirection;
+    float hitDistanceLocal, d, dLast;
+    int k;
+};
+// SDF.inc:101-141: transform the ray, clip it to the box, early-outs. Returns true when the lane has to march.
+__device__ __forceinline__ bool traceSetup(const TraceInstance& inst, vec3 rayStartWorld, vec3 rayDirectionWorld, const TraceResult& tr, MarchState& st) {
     const vec3 localExtends = inst.localExtends;
     vec3 rayStartLocal = xyz(mulm4(inst.worldToLocal, v4(rayStartWorld, 1.f)));
     const vec3 rayEndLocal = xyz(mulm4(inst.worldToLocal, v4(rayStartWorld + rayDirectionWorld, 1.f)));
@@ -199,47 +212,81 @@ __device__ void traceRayTroughSDFInstance(const TraceInstance& inst, vec3 raySta
             rayStartLocal = rayStartLocal + t * rayDirection;
             hitDistanceLocal = t;
         } else {
-            return;
+            return false;
         }
     }
-    vec3 localSamplePos = rayStartLocal;
-    const ImgView sdf = inst.sdf;
-    const vec3 sdfResolution = v3((float)sdf.w, (float)sdf.h, (float)sdf.d);
-    const float distanceThreshold = length(localExtends / sdfResolution) * 0.25f;
-    float dLast = 0.f, d = 0.f;
-    const float localToGlobalScale = 1.f / length(v3(inst.worldToLocal[0], inst.worldToLocal[1], inst.worldToLocal[2]));
-    if (localToGlobalScale * hitDistanceLocal > tr.closestHitDistance) return;
-    vec3 localExtendsHalf = localExtends * 0.5f;
-    localExtendsHalf = localExtendsHalf + 0.01f;
-    for (int i = 0; i < 128; i++) {
-        if (localSamplePos.x > localExtendsHalf.x || localSamplePos.y > localExtendsHalf.y || localSamplePos.z > localExtendsHalf.z ||
-            localSamplePos.x < -localExtendsHalf.x || localSamplePos.y < -localExtendsHalf.y || localSamplePos.z < -localExtendsHalf.z)
-            break;
-        vec3 sampleUV = localSamplePos / localExtends + 0.5f;
-        dLast = d;
-        d = sampleSDF(sdf, sampleUV);
-        if (d < distanceThreshold) {
-            tr.hit = true;
-            const float distanceGlobal = hitDistanceLocal * localToGlobalScale;
-            if (distanceGlobal < tr.closestHitDistance) {
-                tr.closestHitDistance = distanceGlobal;
-                tr.hitCount = i;
-                const float lastStepSizeLocal = d / (1.f - (d - dLast));
-                localSamplePos = localSamplePos + rayDirection * lastStepSizeLocal;
-                sampleUV = localSamplePos / localExtends + 0.5f;
-                vec3 N = normalFromSDF(sampleUV, localExtends, sdf);
-                // transpose(mat3(worldToLocal)) * N
-                const float* m = inst.worldToLocal;
-                tr.N = v3(m[0], m[4], m[8]) * N.x + v3(m[1], m[5], m[9]) * N.y + v3(m[2], m[6], m[10]) * N.z;
-                tr.albedo = vpow(inst.meanAlbedo, v3(2.2f));
-                const float lastStepSizeGlobal = lastStepSizeLocal * localToGlobalScale;
-                tr.hitPos = rayStartWorld + rayDirectionWorld * (distanceGlobal + lastStepSizeGlobal);
-            }
-            break;
+    if (inst.localToGlobalScale * hitDistanceLocal > tr.closestHitDistance) return false;
+    st.localSamplePos = rayStartLocal;
+    st.rayDirection = rayDirection;
+    st.hitDistanceLocal = hitDistanceLocal;
+    st.d = 0.f;
+    st.dLast = 0.f;
+    st.k = 0;
+    return true;
+}
+// one iteration of the loop SDF.inc:144-183. Returns true while the lane keeps marching through this instance.
+__device__ __forceinline__ bool traceStep(const TraceInstance& inst, vec3 rayStartWorld, vec3 rayDirectionWorld, TraceResult& tr, MarchState& st) {
+    if (st.k >= 128) return false;
+    const vec3 localExtends = inst.localExtends, localExtendsHalf = inst.localExtendsHalfPadded;
+    const vec3 localSamplePos = st.localSamplePos;
+    if (localSamplePos.x > localExtendsHalf.x || localSamplePos.y > localExtendsHalf.y || localSamplePos.z > localExtendsHalf.z ||
+        localSamplePos.x < -localExtendsHalf.x || localSamplePos.y < -localExtendsHalf.y || localSamplePos.z < -localExtendsHalf.z)
+        return false;
+    vec3 sampleUV = localSamplePos / localExtends + 0.5f;
+    st.dLast = st.d;
+    const float d = sampleSDF(inst.sdf, sampleUV);
+    st.d = d;
+    if (d < inst.distanceThreshold) {
+        tr.hit = true;
+        const float distanceGlobal = st.hitDistanceLocal * inst.localToGlobalScale;
+        if (distanceGlobal < tr.closestHitDistance) {
+            tr.closestHitDistance = distanceGlobal;
+            tr.hitCount = st.k;
+            const float lastStepSizeLocal = d / (1.f - (d - st.dLast));
+            const vec3 hitSamplePos = localSamplePos + st.rayDirection * lastStepSizeLocal;
+            sampleUV = hitSamplePos / localExtends + 0.5f;
+            const vec3 N = normalFromSDF(sampleUV, localExtends, inst.sdf);
+            const float* m = inst.worldToLocal;  // transpose(mat3(worldToLocal)) * N
+            tr.N = v3(m[0], m[4], m[8]) * N.x + v3(m[1], m[5], m[9]) * N.y + v3(m[2], m[6], m[10]) * N.z;
+            tr.albedo = vpow(inst.meanAlbedo, v3(2.2f));
+            const float lastStepSizeGlobal = lastStepSizeLocal * inst.localToGlobalScale;
+            tr.hitPos = rayStartWorld + rayDirectionWorld * (distanceGlobal + lastStepSizeGlobal);
         }
-        localSamplePos = localSamplePos + rayDirection * absf(d);
-        hitDistanceLocal += absf(d);
+        return false;
     }
+    st.localSamplePos = localSamplePos + st.rayDirection * absf(d);
+    st.hitDistanceLocal += absf(d);
+    st.k++;
+    return true;
+}
+
+// World-space sphere around the image of the local box [-extends/2, extends/2] under inverse(worldToLocal), padded by
+// 0.1 % + 1 mm. Only used to SKIP instances whose box the ray cannot touch (the reference would run its slab test and
+// return at SDF.inc:115-126 with no effect), never to accept one; any NaN/inf (singular matrix) disables the skip.
+__device__ __forceinline__ void instanceBoundingSphere(TraceInstance& t) {
+    const float* m = t.worldToLocal;
+    const vec3 a0 = v3(m[0], m[1], m[2]), a1 = v3(m[4], m[5], m[6]), a2 = v3(m[8], m[9], m[10]), tr = v3(m[12], m[13], m[14]);
+    const vec3 c12 = cross(a1, a2), c20 = cross(a2, a0), c01 = cross(a0, a1);
+    const float invDet = 1.f / dot(a0, c12);
+    // rows of inverse(A) are c12, c20, c01 scaled by 1/det: x_w = invA * (x_l - tr)
+    auto invA = [&](vec3 v) { return v3(dot(c12, v), dot(c20, v), dot(c01, v)) * invDet; };
+    t.sphereCenter = invA(-tr);
+    const vec3 h = t.localExtends * 0.5f;
+    float r2 = 0.f;
+    for (int k = 0; k < 4; k++) {
+        const vec3 o = invA(v3(h.x, (k & 1) ? -h.y : h.y, (k & 2) ? -h.z : h.z));
+        r2 = fmaxf(r2, dot(o, o));
+    }
+    const float r = sqrtf(r2) * 1.001f + 0.001f;
+    t.sphereR2 = (r2 == r2) ? r * r : dm::nanf_();
+}
+__device__ __forceinline__ bool rayMissesSphere(const TraceInstance& t, vec3 o, vec3 L, float invLen2) {
+    const vec3 oc = t.sphereCenter - o;
+    const float oc2 = dot(oc, oc), tca = dot(oc, L);
+    const float R2 = t.sphereR2 + 1e-5f * oc2;  // slack for the cancellation in oc2 - tca^2
+    if (oc2 <= R2) return false;
+    if (tca < 0.f) return true;
+    return oc2 - tca * tca * invLen2 > R2;  // false when anything is NaN
 }
 
 struct TraceParams {
@@ -260,6 +307,15 @@ struct TraceParams {
 // (:154), whose instance records and brick views are staged once in shared memory. Each 8x8 group keeps its own ray
 // cache for the 3x3 resolve (:70-116), exactly like the reference's shared arrays. Every invocation of a dispatched
 // group traces, also those beyond the image edge: they are neighbours in the resolve; only their stores are dropped.
+//
+// Scheduling inside a warp: rays hit different instances with very different step counts, so the per-instance
+// trace of the reference (SDF.inc:101-184) is split into states that one loop interleaves:
+//   1. up front, convergent: every lane tests its ray against the bounding spheres of ALL listed instances and keeps
+//      a candidate bit mask (<= 100 bits) - the instances whose slab test could succeed
+//   2. MARCH: one sphere-trace step of the lane's current instance per iteration (the hot, convergent code)
+//   3. SETUP: transform/clip the ray for the lane's next candidate (lowest set bit: list order is kept because the
+//      closest-hit early-out of SDF.inc:141 depends on it); runs only when a quarter of the warp waits for it
+// The per-ray operation sequence is exactly the reference's, so results do not depend on the schedule.
 __global__ void __launch_bounds__(256) sdfDiffuseTraceKernel(const __grid_constant__ TraceParams p) {
     __shared__ TraceInstance sInst[PLAIN_MAX_OBJECTS_PER_TILE];
     __shared__ uint32_t sCount;
@@ -284,6 +340,10 @@ __global__ void __launch_bounds__(256) sdfDiffuseTraceKernel(const __grid_consta
         t.localExtends = ld3(in.localExtends);
         t.meanAlbedo = ld3(in.meanAlbedo);
         t.sdf = p.bindless[in.sdfTextureIndex].view;
+        instanceBoundingSphere(t);
+        t.localExtendsHalfPadded = t.localExtends * 0.5f + 0.01f;
+        t.distanceThreshold = length(t.localExtends / v3((float)t.sdf.w, (float)t.sdf.h, (float)t.sdf.d)) * 0.25f;
+        t.localToGlobalScale = 1.f / length(v3(t.worldToLocal[0], t.worldToLocal[1], t.worldToLocal[2]));
         sInst[i] = t;
     }
     __syncthreads();
@@ -291,7 +351,7 @@ __global__ void __launch_bounds__(256) sdfDiffuseTraceKernel(const __grid_consta
     const Globals G = loadGlobals(g);
     const int ix = gx * 8 + lx, iy = gy * 8 + ly;
     vec3 L = v3(0.f);
-    if (groupActive) {
+    if (groupActive) {  // uniform per warp: a group is two whole warps
         const vec2 uv = v2((float)ix, (float)iy) / v2((float)p.outYSH.w, (float)p.outYSH.h);
         const float depth = sampleNearest2D<WRAP_CLAMP, float>([&](int x, int y) { return loadD32(p.depthTexture, x, y); }, p.depthTexture.w, p.depthTexture.h, uv, 0.f);
         const float depthLinear = linearizeDepth(depth, G.nearPlane, G.farPlane);
@@ -313,7 +373,47 @@ __global__ void __launch_bounds__(256) sdfDiffuseTraceKernel(const __grid_consta
         tr.closestHitDistance = 10000.f;
         tr.hitCount = 0;
         tr.hitPos = v3(0.f); tr.N = v3(0.f); tr.albedo = v3(0.f);
-        for (uint32_t i = 0; i < objectCount; i++) traceRayTroughSDFInstance(sInst[i], rayOrigin, L, tr);
+
+        // 1. candidate mask, all lanes in lockstep over the tile's list
+        const float invLen2 = 1.f / dot(L, L);
+        uint32_t cand[4];
+#pragma unroll
+        for (int w = 0; w < 4; w++) {
+            uint32_t m = 0u;
+            const uint32_t base = (uint32_t)w * 32u;
+            if (base < objectCount) {
+                const uint32_t n = min(32u, objectCount - base);
+                for (uint32_t b = 0; b < n; b++)
+                    if (!rayMissesSphere(sInst[base + b], rayOrigin, L, invLen2)) m |= 1u << b;
+            }
+            cand[w] = m;
+        }
+        auto popCandidate = [&]() -> int {  // lowest listed candidate, -1 when none is left
+#pragma unroll
+            for (int w = 0; w < 4; w++)
+                if (cand[w]) { const int b = __ffs(cand[w]) - 1; cand[w] &= cand[w] - 1; return w * 32 + b; }
+            return -1;
+        };
+        // 2./3. interleaved march / set-up
+        int next = popCandidate(), cur = 0;
+        bool marching = false;
+        MarchState st;
+        st.localSamplePos = v3(0.f); st.rayDirection = v3(0.f); st.hitDistanceLocal = 0.f; st.d = 0.f; st.dLast = 0.f; st.k = 0;
+        while (true) {
+            const bool needSetup = !marching && next >= 0;
+            const unsigned marchMask = __ballot_sync(0xffffffffu, marching), setupMask = __ballot_sync(0xffffffffu, needSetup);
+            if ((marchMask | setupMask) == 0u) break;
+            const int nSetup = __popc(setupMask), nMarch = __popc(marchMask);
+            if (nSetup > 0 && (nMarch == 0 || nSetup >= 8 || nSetup >= nMarch)) {
+                if (needSetup) {
+                    cur = next;
+                    marching = traceSetup(sInst[cur], rayOrigin, L, tr, st);
+                    next = popCandidate();
+                }
+                continue;
+            }
+            if (marching) marching = traceStep(sInst[cur], rayOrigin, L, tr, st);
+        }
         vec3 hitColor;
         if (tr.hit) {
             const float shadow = simpleShadow<true>(tr.hitPos, p.cascades->lightMatrices[p.shadowCascadeIndex], p.shadowMap);

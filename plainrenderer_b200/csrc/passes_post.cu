@@ -2,6 +2,7 @@
 //   temporalFilter.comp:84-179 + temporalReprojection.inc:8-87 + bicubicSampling.inc:4-181;
 //   bloomDownsample.comp:12-50, bloomUpsample.comp:19-58, applyBloom.comp:16-31; tonemapping.comp:17-27
 #include "shader_inc.cuh"
+#include "tile.cuh"
 
 namespace pb {
 
@@ -43,14 +44,22 @@ PLAIN_PASS(launch_tonemapping, "tonemapping.comp") {
 // ---------------- bloom ----------------
 // bloomDownsample.comp: 13 bilinear taps of the finer mip. The bounds test is '>' in the reference (:16): the extra
 // row/column of invocations only produces stores outside the image, which are dropped.
+// Block = 32x8 target texels; their 13 taps touch a (64 + 6) x (16 + 6) rectangle of the finer mip, staged once.
 __global__ void __launch_bounds__(256) bloomDownsampleKernel(ImgView target, ImgView source) {
-    const int ix = blockIdx.x * 32 + (threadIdx.x & 31), iy = blockIdx.y * 8 + (threadIdx.x >> 5);
+    constexpr int TW = 72, TH = 24;
+    __shared__ float4 sSrc[TW * TH];
+    const int bx = blockIdx.x * 32, by = blockIdx.y * 8;
+    const int sx0 = (int)(((long long)bx * source.w) / target.w) - 3, sy0 = (int)(((long long)by * source.h) / target.h) - 3;
+    tileLoadR11<TW, TH>(sSrc, source, sx0, sy0);
+    __syncthreads();
+    const TileR11<TW, TH> tile{sSrc, sx0, sy0};
+    const int ix = bx + (threadIdx.x & 31), iy = by + (threadIdx.x >> 5);
     if (ix >= target.w || iy >= target.h) return;
     const vec2 uv = (v2((float)ix, (float)iy) + 0.5f) / v2((float)target.w, (float)target.h);
     const vec2 texelSize = 1.f / v2((float)source.w, (float)source.h);
     vec3 color = v3(0.f);
-    auto T = [&](float ox, float oy) { return sampleR11LinearClamp(source, uv + texelSize * v2(ox, oy)); };
-    color = color + sampleR11LinearClamp(source, uv) * 0.125f;
+    auto T = [&](float ox, float oy) { return sampleR11LinearClampTile(tile, source, uv + texelSize * v2(ox, oy)); };
+    color = color + sampleR11LinearClampTile(tile, source, uv) * 0.125f;
     color = color + T(0.5f, 0.5f) * 0.125f; color = color + T(0.5f, -0.5f) * 0.125f; color = color + T(-0.5f, 0.5f) * 0.125f; color = color + T(-0.5f, -0.5f) * 0.125f;
     color = color + T(1.5f, 0.f) * 0.0625f; color = color + T(-1.5f, 0.f) * 0.0625f; color = color + T(0.f, 1.5f) * 0.0625f; color = color + T(0.f, -1.5f) * 0.0625f;
     color = color + T(1.5f, 1.5f) * 0.03125f; color = color + T(1.5f, -1.5f) * 0.03125f; color = color + T(-1.5f, 1.5f) * 0.03125f; color = color + T(-1.5f, -1.5f) * 0.03125f;
@@ -64,19 +73,28 @@ PLAIN_PASS(launch_bloomDownsample, "bloomDownsample.comp") {
 }
 
 // bloomUpsample.comp: 9-tap tent of the coarser downsample mip (+ 4-tap box of the coarser upsample mip)
+// Block = 32x8 target texels; the tent and box taps touch about (16 + 8) x (4 + 8) texels of the two coarser mips.
 __global__ void __launch_bounds__(256) bloomUpsampleKernel(ImgView target, ImgView targetPreviousMip, ImgView source, int isLowestMip, float blurRadius) {
-    const int ix = blockIdx.x * 32 + (threadIdx.x & 31), iy = blockIdx.y * 8 + (threadIdx.x >> 5);
+    constexpr int TW = 24, TH = 12;
+    __shared__ float4 sSrc[TW * TH], sPrev[TW * TH];
+    const int bx = blockIdx.x * 32, by = blockIdx.y * 8;
+    const int sx0 = (int)(((long long)bx * source.w) / target.w) - 3, sy0 = (int)(((long long)by * source.h) / target.h) - 3;
+    tileLoadR11<TW, TH>(sSrc, source, sx0, sy0);
+    if (!isLowestMip) tileLoadR11<TW, TH>(sPrev, targetPreviousMip, sx0, sy0);
+    __syncthreads();
+    const TileR11<TW, TH> srcTile{sSrc, sx0, sy0}, prevTile{sPrev, sx0, sy0};
+    const int ix = bx + (threadIdx.x & 31), iy = by + (threadIdx.x >> 5);
     if (ix >= target.w || iy >= target.h) return;
     const vec2 texelSize = 1.f / v2((float)source.w, (float)source.h);
     const vec2 sampleStepSize = blurRadius * texelSize;
     const vec2 uv = (v2((float)ix, (float)iy) + 0.5f) / v2((float)target.w, (float)target.h);
     vec3 color = v3(0.f);
-    auto S = [&](float ox, float oy) { return sampleR11LinearClamp(source, uv + sampleStepSize * v2(ox, oy)); };
-    color = color + sampleR11LinearClamp(source, uv) * 0.25f;
+    auto S = [&](float ox, float oy) { return sampleR11LinearClampTile(srcTile, source, uv + sampleStepSize * v2(ox, oy)); };
+    color = color + sampleR11LinearClampTile(srcTile, source, uv) * 0.25f;
     color = color + S(1.f, 0.f) * 0.125f; color = color + S(-1.f, 0.f) * 0.125f; color = color + S(0.f, 1.f) * 0.125f; color = color + S(0.f, -1.f) * 0.125f;
     color = color + S(1.f, 1.f) * 0.0625f; color = color + S(1.f, -1.f) * 0.0625f; color = color + S(-1.f, 1.f) * 0.0625f; color = color + S(-1.f, -1.f) * 0.0625f;
     if (!isLowestMip) {
-        auto P = [&](float ox, float oy) { return sampleR11LinearClamp(targetPreviousMip, uv + texelSize * v2(ox, oy)); };
+        auto P = [&](float ox, float oy) { return sampleR11LinearClampTile(prevTile, targetPreviousMip, uv + texelSize * v2(ox, oy)); };
         color = color + P(0.5f, 0.5f) * 0.25f; color = color + P(0.5f, -0.5f) * 0.25f; color = color + P(-0.5f, 0.5f) * 0.25f; color = color + P(-0.5f, -0.5f) * 0.25f;
     }
     storeR11(target, ix, iy, color);
@@ -115,13 +133,13 @@ struct TaaParams {
 __device__ __forceinline__ vec3 taaTonemap(vec3 color) { return color / (1.f + computeLuminance(color)); }         // temporalReprojection.inc:34-36
 __device__ __forceinline__ vec3 taaTonemapReverse(vec3 color) { return color / (1.f - computeLuminance(color)); }  // :38-40
 struct Nb { vec3 v[3][3]; };  // v[x+1][y+1]
-template <bool TONEMAP>
-__device__ __forceinline__ void sampleNeighbourhood(const ImgView& tex, vec2 uv, vec2 texelSize, Nb& n) {  // :42-52
+template <bool TONEMAP, int TW, int TH>
+__device__ __forceinline__ void sampleNeighbourhood(const TileR11<TW, TH>& tile, const ImgView& tex, vec2 uv, vec2 texelSize, Nb& n) {  // :42-52
 #pragma unroll
     for (int x = -1; x <= 1; x++)
 #pragma unroll
         for (int y = -1; y <= 1; y++) {
-            vec3 color = sampleR11LinearClamp(tex, uv + texelSize * v2((float)x, (float)y));
+            vec3 color = sampleR11LinearClampTile(tile, tex, uv + texelSize * v2((float)x, (float)y));
             n.v[x + 1][y + 1] = TONEMAP ? taaTonemap(color) : color;
         }
 }
@@ -162,16 +180,29 @@ __device__ __forceinline__ BicubicW bicubicWeights(vec2 iUV) {  // bicubicSampli
     return b;
 }
 
-template <bool TONEMAP>
-__global__ void __launch_bounds__(256) temporalFilterKernel(TaaParams p) {
-    const int ix = blockIdx.x * 32 + (threadIdx.x & 31), iy = blockIdx.y * 8 + (threadIdx.x >> 5);
+// Block = 32x8 pixels. The current frame is staged with a 2-texel halo (3x3 bilinear taps at texel centres touch
+// [-2, +2]); the history with a 6-texel halo, which covers the reprojected 3x3 neighbourhood and the bicubic tap for
+// motion up to ~4 pixels - larger motion falls back to global loads per tap corner (tile.cuh).
+#define TAA_CUR_HALO 2
+#define TAA_HIS_HALO 6
+template <bool TONEMAP, int TECH>
+__global__ void __launch_bounds__(256, 3) temporalFilterKernel(const __grid_constant__ TaaParams p) {
+    __shared__ float4 sCur[(32 + 2 * TAA_CUR_HALO) * (8 + 2 * TAA_CUR_HALO)];
+    __shared__ float4 sHis[(32 + 2 * TAA_HIS_HALO) * (8 + 2 * TAA_HIS_HALO)];
+    const int bx = blockIdx.x * 32, by = blockIdx.y * 8;
+    tileLoadR11<32 + 2 * TAA_CUR_HALO, 8 + 2 * TAA_CUR_HALO>(sCur, p.currentFrame, bx - TAA_CUR_HALO, by - TAA_CUR_HALO);
+    tileLoadR11<32 + 2 * TAA_HIS_HALO, 8 + 2 * TAA_HIS_HALO>(sHis, p.historySrc, bx - TAA_HIS_HALO, by - TAA_HIS_HALO);
+    __syncthreads();
+    const TileR11<32 + 2 * TAA_CUR_HALO, 8 + 2 * TAA_CUR_HALO> curTile{sCur, bx - TAA_CUR_HALO, by - TAA_CUR_HALO};
+    const TileR11<32 + 2 * TAA_HIS_HALO, 8 + 2 * TAA_HIS_HALO> hisTile{sHis, bx - TAA_HIS_HALO, by - TAA_HIS_HALO};
+    const int ix = bx + (threadIdx.x & 31), iy = by + (threadIdx.x >> 5);
     if (ix >= p.outputImage.w || iy >= p.outputImage.h) return;
     const vec2 screenRes = v2((float)p.g->screenResolution[0], (float)p.g->screenResolution[1]);
     const vec2 texelSize = 1.f / v2((float)p.outputImage.w, (float)p.outputImage.h);
     const vec2 iUVf = v2((float)ix, (float)iy);
     const vec2 uv = (iUVf + 0.5f) * texelSize;
     Nb nb;
-    sampleNeighbourhood<TONEMAP>(p.currentFrame, uv, texelSize, nb);
+    sampleNeighbourhood<TONEMAP>(curTile, p.currentFrame, uv, texelSize, nb);
     vec3 mn = nb.v[0][0], mx = nb.v[0][0];  // minMaxFromNeighbourhood :54-65
 #pragma unroll
     for (int i = 0; i < 3; i++)
@@ -197,11 +228,12 @@ __global__ void __launch_bounds__(256) temporalFilterKernel(TaaParams p) {
         motion = inRange(p.motionBuffer, ix, iy) ? loadRG16SNORM(p.motionBuffer, ix, iy) : v2(0.f);
     }
 
-    auto H = [&](float x, float y) { return sampleR11LinearClamp(p.historySrc, v2(x, y)); };
+    auto H = [&](float x, float y) { return sampleR11LinearClampTile(hisTile, p.historySrc, v2(x, y)); };
     vec3 historySample;
-    if (p.historySampleTech == 0) {
-        historySample = sampleR11LinearClamp(p.historySrc, uv + motion);
-    } else if (p.historySampleTech == 1) {  // 16 tap, bicubicSampling.inc:28-67
+    const int historySampleTech = TECH >= 0 ? TECH : p.historySampleTech;  // specialisation constant 2 -> template parameter
+    if (historySampleTech == 0) {
+        { const vec2 hu = uv + motion; historySample = H(hu.x, hu.y); }
+    } else if (historySampleTech == 1) {  // 16 tap, bicubicSampling.inc:28-67
         const vec2 pp = iUVf + 0.5f + motion * screenRes;
         const vec2 uvTrunc = vfloor(pp - 0.5f) + 0.5f;
         const vec2 ad = vabs(pp - uvTrunc);
@@ -217,20 +249,20 @@ __global__ void __launch_bounds__(256) temporalFilterKernel(TaaParams p) {
                 first = false;
             }
         historySample = acc;
-    } else if (p.historySampleTech == 2) {  // 9 tap :72-107
+    } else if (historySampleTech == 2) {  // 9 tap :72-107
         const BicubicW b = bicubicWeights(iUVf + 0.5f + motion * screenRes);
         const vec2 uv0 = (b.uvTrunc - 1.f) * texelSize, uvT = (b.uvTrunc + b.t) * texelSize, uv3 = (b.uvTrunc + 2.f) * texelSize;
         historySample = H(uv0.x, uv0.y) * b.w0.x * b.w0.y + H(uv0.x, uvT.y) * b.w0.x * b.wB.y + H(uv0.x, uv3.y) * b.w0.x * b.w3.y +
                         H(uvT.x, uv0.y) * b.wB.x * b.w0.y + H(uvT.x, uvT.y) * b.wB.x * b.wB.y + H(uvT.x, uv3.y) * b.wB.x * b.w3.y +
                         H(uv3.x, uv0.y) * b.w3.x * b.w0.y + H(uv3.x, uvT.y) * b.w3.x * b.wB.y + H(uv3.x, uv3.y) * b.w3.x * b.w3.y;
-    } else if (p.historySampleTech == 3) {  // 5 tap :112-145
+    } else if (historySampleTech == 3) {  // 5 tap :112-145
         const BicubicW b = bicubicWeights(iUVf + 0.5f + motion * screenRes);
         const vec2 uv0 = (b.uvTrunc - 1.f) * texelSize, uvT = (b.uvTrunc + b.t) * texelSize, uv3 = (b.uvTrunc + 2.f) * texelSize;
         auto T = [&](float x, float y) { return v4(H(x, y), 1.f); };
         const vec4 result = T(uv0.x, uvT.y) * b.w0.x * b.wB.y + T(uvT.x, uv0.y) * b.wB.x * b.w0.y + T(uvT.x, uvT.y) * b.wB.x * b.wB.y +
                             T(uvT.x, uv3.y) * b.wB.x * b.w3.y + T(uv3.x, uvT.y) * b.w3.x * b.wB.y;
         historySample = xyz(result) / result.w;
-    } else if (p.historySampleTech == 4) {  // 1 tap :150-181
+    } else if (historySampleTech == 4) {  // 1 tap :150-181
         const BicubicW b = bicubicWeights(iUVf + 0.5f + motion * screenRes);
         const vec2 uvT = (b.uvTrunc + b.t) * texelSize;
         const vec3 hs = H(uvT.x, uvT.y);
@@ -248,7 +280,7 @@ __global__ void __launch_bounds__(256) temporalFilterKernel(TaaParams p) {
 
     const float currentContrast = neighbourhoodContrast(nb);
     Nb lastNb;
-    sampleNeighbourhood<TONEMAP>(p.historySrc, uv + motion, texelSize, lastNb);
+    sampleNeighbourhood<TONEMAP>(hisTile, p.historySrc, uv + motion, texelSize, lastNb);
     const float lastContrast = neighbourhoodContrast(lastNb);
     float contrastChange = absf(currentContrast - lastContrast);
     contrastChange = clampf(contrastChange, 0.f, 1.f);
@@ -284,8 +316,9 @@ PLAIN_PASS(launch_temporalFilter, "temporalFilter.comp") {
     if (c.failed) return;
     if ((int)c.exec->dispatch[0] * 8 < p.outputImage.w || (int)c.exec->dispatch[1] * 8 < p.outputImage.h) { c.fail("temporalFilter.comp: dispatch does not cover the target"); return; }
     dim3 grid(ceilDiv(p.outputImage.w, 32), ceilDiv(p.outputImage.h, 8));
-    if (p.useTonemap) PLAIN_LAUNCH(c, temporalFilterKernel<true>, grid, 256, 0, p);
-    else PLAIN_LAUNCH(c, temporalFilterKernel<false>, grid, 256, 0, p);
+    if (p.useTonemap && p.historySampleTech == 4) PLAIN_LAUNCH(c, (temporalFilterKernel<true, 4>), grid, 256, 0, p);  // the reference's defaults (TAA.h:8-17)
+    else if (p.useTonemap) PLAIN_LAUNCH(c, (temporalFilterKernel<true, -1>), grid, 256, 0, p);
+    else PLAIN_LAUNCH(c, (temporalFilterKernel<false, -1>), grid, 256, 0, p);
 }
 
 }  // namespace pb

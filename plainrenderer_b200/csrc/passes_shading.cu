@@ -11,6 +11,24 @@
 
 namespace pb {
 
+__global__ void buildShadingTablesKernel(ShadingTables* t) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 256) {
+        t->unorm8[i] = unorm8((uint32_t)i);
+        t->srgbToLinear[i] = sRGBToLinear1(unorm8((uint32_t)i));
+    }
+    if (i < 256 * 12) {
+        const float noise = unorm8((uint32_t)(i / 12));
+        const int tap = i % 12;
+        const float sampleCount = 12.f;
+        float d = ((float)tap + 0.5f * noise) / sampleCount;
+        d = sqrtf_(d);
+        const float angle = noise * 2.f * PV_PI + 2.f * PV_PI * (float)tap / sampleCount;
+        t->pcf[i] = make_float4(dm::cos(angle), dm::sin(angle), d, 0.f);
+    }
+}
+void buildShadingTables(ShadingTables* deviceTables, cudaStream_t stream) { buildShadingTablesKernel<<<12, 256, 0, stream>>>(deviceTables); }
+
 struct ShadingParams {
     ImgView gbuffer, brdfLut, shadowMaps[4], ySH, coCg, volumetricLUT, skyLut, transmissionLut, colorOut;
     const plain_light_buffer* light;
@@ -18,6 +36,7 @@ struct ShadingParams {
     const plain_volumetric_lighting_settings* vol;
     const plain_global_shader_info* g;
     const BindlessEntry* bindless;
+    const ShadingTables* tables;
     int diffuseBRDF, directMultiscatterBRDF, geometricAA, indirectLightingTech;
     uint32_t sunShadowCascadeCount;
     float sunSpriteModel[16];
@@ -62,8 +81,9 @@ __device__ __forceinline__ vec3 computeSpecularMultiscatteringLobe(const Shading
     return v3(0.f);
 }
 
-// triangle.frag:92-120, 12-tap spiral PCF with a per-pixel blue-noise rotation
-__device__ __forceinline__ float calcShadow(const ImgView& shadowMap, const float* lightMatrix, vec2 lightSpaceScale, vec3 pos, float noise) {
+// triangle.frag:92-120, 12-tap spiral PCF with a per-pixel blue-noise rotation. cos/sin/sqrt of tap i depend only on the
+// 8-bit noise texel and i: they come from the exact table (ShadingTables::pcf).
+__device__ __forceinline__ float calcShadow(const ImgView& shadowMap, const float* lightMatrix, vec2 lightSpaceScale, vec3 pos, const float4* __restrict__ pcfRow) {
     vec4 posLightSpace = mulm4(lightMatrix, v4(pos, 1.f));
     posLightSpace = posLightSpace / posLightSpace.w;
     const vec2 plsXY = v2(posLightSpace.x, posLightSpace.y) * 0.5f + 0.5f;
@@ -71,12 +91,11 @@ __device__ __forceinline__ float calcShadow(const ImgView& shadowMap, const floa
     const vec2 offsetScale = PB_SHADOW_SAMPLE_RADIUS * lightSpaceScale;
     float shadow = 0.f;
     const float sampleCount = 12.f;
-    for (int i = 0; (float)i < sampleCount; i++) {
-        float d = ((float)i + 0.5f * noise) / sampleCount;
-        d = sqrtf_(d);
-        const float angle = noise * 2.f * PV_PI + 2.f * PV_PI * (float)i / sampleCount;
-        vec2 offset = v2(dm::cos(angle), dm::sin(angle));
-        offset = offset * (offsetScale * d);
+#pragma unroll
+    for (int i = 0; i < 12; i++) {
+        const float4 e = __ldg(pcfRow + i);  // {cos(angle), sin(angle), sqrt(d)}
+        vec2 offset = v2(e.x, e.y);
+        offset = offset * (offsetScale * e.z);
         const vec2 samplePosition = plsXY + offset;
         const float depthTexel = sampleNearest2D<WRAP_BORDER, float>([&](int x, int y) { return loadD16(shadowMap, x, y); }, shadowMap.w, shadowMap.h, samplePosition, 0.f);
         shadow += (actualDepth >= depthTexel) ? 1.f : 0.f;  // shadowTest :84-87
@@ -85,7 +104,7 @@ __device__ __forceinline__ float calcShadow(const ImgView& shadowMap, const floa
 }
 
 template <int DIFFUSE, int MULTI, int GEOAA, int TECH>
-__device__ __forceinline__ vec3 shadeGeometry(const ShadingParams& p, const Globals& G, int x, int y, uint4 texel, vec3 N, vec3 N_U, vec3 N_V, vec3 cameraToPixel, vec2 noiseTexel) {
+__device__ __forceinline__ vec3 shadeGeometry(const ShadingParams& p, const Globals& G, int x, int y, uint4 texel, vec3 N, vec3 N_U, vec3 N_V, vec3 cameraToPixel, uint32_t noiseBytes) {
     const plain_global_shader_info* g = p.g;
     const vec2 fragCoord = v2((float)x + 0.5f, (float)y + 0.5f);
     const float depth = dm::u2f(texel.x);
@@ -93,10 +112,12 @@ __device__ __forceinline__ vec3 shadeGeometry(const ShadingParams& p, const Glob
     const vec3 passPos = G.camPos + cameraToPixel / dot(cameraToPixel, G.fwd) * depthLinear;
 
     // triangle.frag:184-193
-    const float metalic = unorm8(texel.w & 0xffu);
-    float r = unorm8(texel.z >> 24);
+    const ShadingTables* T = p.tables;
+    const float metalic = __ldg(&T->unorm8[texel.w & 0xffu]);
+    float r = __ldg(&T->unorm8[texel.z >> 24]);
     r = fmaxp(r * r, 0.0045f);
-    const vec3 albedo = sRGBToLinear(v3(unorm8(texel.z & 0xffu), unorm8((texel.z >> 8) & 0xffu), unorm8((texel.z >> 16) & 0xffu)));
+    const vec3 albedo = v3(__ldg(&T->srgbToLinear[texel.z & 0xffu]), __ldg(&T->srgbToLinear[(texel.z >> 8) & 0xffu]), __ldg(&T->srgbToLinear[(texel.z >> 16) & 0xffu]));
+    const vec2 noiseTexel = v2(__ldg(&T->unorm8[noiseBytes & 0xffu]), __ldg(&T->unorm8[noiseBytes >> 8]));
     const vec3 diffuseColor = (1.f - metalic) * albedo;
     const vec3 L = normalize(v3(g->sunDirection[0], g->sunDirection[1], g->sunDirection[2]));
     vec3 V = G.camPos - passPos;
@@ -123,7 +144,7 @@ __device__ __forceinline__ vec3 shadeGeometry(const ShadingParams& p, const Glob
     int cascadeIndex = 0;
     for (uint32_t cascade = 0; cascade + 1 < p.sunShadowCascadeCount; cascade++) cascadeIndex += (pixelDepth >= p.cascades->splits[cascade]) ? 1 : 0;
     const float sunShadow = calcShadow(p.shadowMaps[cascadeIndex], p.cascades->lightMatrices[cascadeIndex],
-                                       v2(p.cascades->lightSpaceScale[cascadeIndex][0], p.cascades->lightSpaceScale[cascadeIndex][1]), passPos, noiseTexel.x);
+                                       v2(p.cascades->lightSpaceScale[cascadeIndex][0], p.cascades->lightSpaceScale[cascadeIndex][1]), passPos, T->pcf + (noiseBytes & 0xffu) * 12);
     const float sunStrengthExposed = p.light->sunStrengthExposed;
     const vec3 sunColor = ld3(p.light->sunColor);
     const vec3 directLighting = fmaxp(dot(N, L), 0.f) * sunShadow * sunColor;
@@ -276,8 +297,8 @@ __global__ void __launch_bounds__(256) gbufferShadingKernel(const __grid_constan
         // blue noise of this frame (global.inc noiseTextureIndices), nearest + repeat at fragCoord / textureSize
         const ImgView noiseTex = p.bindless[g->noiseTextureIndices[g->frameIndexMod4]].view;
         const vec2 noiseUV = v2((float)x + 0.5f, (float)y + 0.5f) / v2((float)noiseTex.w, (float)noiseTex.h);
-        const vec2 noiseTexel = sampleNearest2D<WRAP_REPEAT, vec2>([&](int tx, int ty) { return loadRG8(noiseTex, tx, ty); }, noiseTex.w, noiseTex.h, noiseUV, v2(0.f));
-        color = shadeGeometry<DIFFUSE, MULTI, GEOAA, TECH>(p, G, x, y, texel, N, N_U, N_V, cameraToPixel, noiseTexel);
+        const uint32_t noiseBytes = sampleNearest2D<WRAP_REPEAT, uint32_t>([&](int tx, int ty) { return (uint32_t)ldg((const uint16_t*)noiseTex.ptr + texelIndex(noiseTex, tx, ty)); }, noiseTex.w, noiseTex.h, noiseUV, 0u);
+        color = shadeGeometry<DIFFUSE, MULTI, GEOAA, TECH>(p, G, x, y, texel, N, N_U, N_V, cameraToPixel, noiseBytes);
     }
     storeR11(p.colorOut, x, y, color);
 }
@@ -298,6 +319,7 @@ PLAIN_PASS(launch_gbufferShading, "gbufferShading.comp") {
     p.vol = c.ubuf<plain_volumetric_lighting_settings>(19);
     p.g = c.g;
     p.bindless = c.bindless;
+    p.tables = (const ShadingTables*)c.tables;
     p.diffuseBRDF = c.spec<int>(0, 0);
     p.directMultiscatterBRDF = c.spec<int>(1, 0);
     p.geometricAA = c.specBool(2, false) ? 1 : 0;
