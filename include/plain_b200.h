@@ -126,6 +126,11 @@ typedef struct {
     plain_pass_resources resources;
     const void* push_constants; uint32_t push_constant_size;
     uint32_t dispatch_count[3];
+    /* additions for screen-space row sharding across GPUs (not in the reference; 0/0/0 = the whole pass):
+     * rows [row_begin, row_end) of the pass's output image are produced (units: rows of that image; for tile-based
+     * passes rows of tiles / workgroups as documented per kernel); shard_phase splits passes that mix a banded and a
+     * replicated part (depthHiZPyramid.comp: 1 = the levels reduced from the rank's own depth rows, 2 = the rest) */
+    uint32_t row_begin, row_end, shard_phase;
 } plain_compute_pass_execution;
 
 /* VulkanTimestampQueries.h:16-20 */
@@ -166,6 +171,10 @@ PLAIN_EXPORT int PLAIN_FN(prepare_for_drawcall_recording)(plain_ctx* ctx);
 PLAIN_EXPORT int PLAIN_FN(set_uniform_buffer_data)(plain_ctx* ctx, plain_handle buffer, const void* data, size_t size);
 PLAIN_EXPORT int PLAIN_FN(set_storage_buffer_data)(plain_ctx* ctx, plain_handle buffer, const void* data, size_t size);
 PLAIN_EXPORT int PLAIN_FN(render_frame)(plain_ctx* ctx, int present_to_screen);
+/* executes the executions recorded so far (after applying pending buffer fills) and clears the list without ending the
+ * frame: transient images stay valid. Lets a sharded caller interleave collectives (halo / all-gather / all-reduce over
+ * NCCL) between groups of passes of one frame. render_frame == submit of what is left. */
+PLAIN_EXPORT int PLAIN_FN(submit_recorded_passes)(plain_ctx* ctx);
 PLAIN_EXPORT int PLAIN_FN(wait_for_gpu_idle)(plain_ctx* ctx);
 PLAIN_EXPORT int PLAIN_FN(get_renderpass_timings)(plain_ctx* ctx, plain_pass_time* out, uint32_t capacity, uint32_t* out_count);
 PLAIN_EXPORT int PLAIN_FN(set_timing_enabled)(plain_ctx* ctx, int enabled);
@@ -178,6 +187,10 @@ PLAIN_EXPORT int PLAIN_FN(read_storage_buffer)(plain_ctx* ctx, plain_handle buff
 /* async variants on the backend stream with caller-pinned host memory (e2e leg: upload of the frame inputs, read-back of the frame) */
 PLAIN_EXPORT int PLAIN_FN(write_image_async)(plain_ctx* ctx, plain_image_handle image, uint32_t mip_level, const void* pinned_data, size_t size);
 PLAIN_EXPORT int PLAIN_FN(read_image_async)(plain_ctx* ctx, plain_image_handle image, uint32_t mip_level, void* pinned_out, size_t size);
+/* rows [row_begin, row_end) of a 2-D image level (images are row-major and tightly packed): a rank of a row-sharded frame
+ * uploads / reads back only its band (+ halo). `data` points at the first transferred row. */
+PLAIN_EXPORT int PLAIN_FN(write_image_rows_async)(plain_ctx* ctx, plain_image_handle image, uint32_t mip_level, uint32_t row_begin, uint32_t row_end, const void* pinned_data, size_t size);
+PLAIN_EXPORT int PLAIN_FN(read_image_rows_async)(plain_ctx* ctx, plain_image_handle image, uint32_t mip_level, uint32_t row_begin, uint32_t row_end, void* pinned_out, size_t size);
 /* device pointer of mip 0 (CUDA backend only; oracle returns the host pointer). Lets a caller that owns device memory
  * (e.g. a torch tensor holding a shard received over NCCL) fill an image without a host round trip. */
 PLAIN_EXPORT int PLAIN_FN(get_image_device_pointer)(plain_ctx* ctx, plain_image_handle image, uint32_t mip_level, void** out_ptr, size_t* out_size);

@@ -39,6 +39,10 @@ typedef struct {
     float sun_direction_deg[2];       /* (phi, theta) as RenderFrontend::m_sunDirection */
     float camera_fov_deg, camera_near, camera_far; /* 35, 0.1, 300 */
     uint32_t noise_seed;
+    /* screen-space row sharding across GPUs: this frontend renders the rows of rank shard_rank out of
+     * shard_count bands (bands are multiples of 64 rows); 0 / 0 or count 1 = the whole frame. The caller drives the frame
+     * with begin_frame / run_segment and performs the exchanges between segments. */
+    uint32_t shard_rank, shard_count;
 } plain_frontend_settings;
 
 /* host pointers to the outputs of the out-of-scope raster passes for one frame */
@@ -49,6 +53,9 @@ typedef struct {
     const void* gbuffer;      /* RGBA32_UINT packed G-buffer, w*h*16 (include/plain_frame_types.h) */
     const void* shadow_maps[4]; /* D16 2048x2048 each, may be NULL to keep the previous contents */
     int32_t async_upload;     /* 1: pointers are pinned host memory, copies go through the backend stream */
+    /* rows of depth / normal / gbuffer to upload (the pointers always address row 0 of full-frame buffers); 0, 0 = all rows.
+     * A sharded rank uploads its band plus the halo its stencils read. motion and shadow maps are always uploaded whole. */
+    uint32_t row_begin, row_end;
 } plain_frame_inputs;
 
 typedef struct {
@@ -69,6 +76,33 @@ PLAIN_EXPORT int PLAIN_FE(set_scene)(plain_frontend* fe, uint32_t n_objects, con
 
 /* one frame */
 PLAIN_EXPORT int PLAIN_FE(render_frame)(plain_frontend* fe, const plain_camera_extrinsic* camera, float time, float delta_time, const plain_frame_inputs* inputs);
+/* ---- row-sharded frames: one frame = begin_frame, then run_segment until it reports no pending exchange. Between two
+ * segments the caller performs the exchange described by *out over its communicator (NCCL / gloo / local copies): every
+ * rank calls the same sequence. render_frame == begin_frame + run_segment (a frontend with shard_count <= 1 never
+ * reports an exchange). ---- */
+typedef enum {
+    PLAIN_EXCHANGE_NONE = 0,
+    PLAIN_EXCHANGE_ALLREDUCE_SUM_U32 = 1, /* storage buffer of u32 counters: element-wise sum over ranks (luminance histogram) */
+    PLAIN_EXCHANGE_ALLGATHER_ROWS = 2,    /* every rank contributes the rows of its band, afterwards all ranks hold all rows */
+    PLAIN_EXCHANGE_HALO_ROWS = 3          /* halo_rows rows on each side of the band boundary are copied from the neighbouring ranks */
+} plain_exchange_kind;
+typedef struct {
+    uint32_t kind;          /* plain_exchange_kind */
+    uint32_t n_images;      /* images exchanged together (e.g. Y_SH + CoCg) */
+    void* device_ptr[4];    /* base of the image level (row 0); for ALLREDUCE device_ptr[0] = the buffer */
+    uint32_t row_pitch_bytes[4];
+    uint32_t rows[4];       /* height of the level */
+    uint32_t row_divisor[4];/* the band of rank r in this level is [Y0(r) / divisor, ceil(Y1(r) / divisor)) clipped to rows, see shard_band */
+    uint32_t halo_rows;
+    uint32_t element_count; /* ALLREDUCE: number of u32 */
+    char name[32];
+} plain_exchange;
+PLAIN_EXPORT int PLAIN_FE(begin_frame)(plain_frontend* fe, const plain_camera_extrinsic* camera, float time, float delta_time, const plain_frame_inputs* inputs);
+PLAIN_EXPORT int PLAIN_FE(run_segment)(plain_frontend* fe, plain_exchange* out);
+/* rows [*out_begin, *out_end) of an image level with `rows` rows and the given divisor that belong to `rank` */
+PLAIN_EXPORT void PLAIN_FE(shard_band)(uint32_t full_height, uint32_t shard_count, uint32_t rank, uint32_t divisor, uint32_t rows, uint32_t* out_begin, uint32_t* out_end);
+PLAIN_EXPORT int PLAIN_FE(read_output_rows)(plain_frontend* fe, void* out_full_frame, uint32_t row_begin, uint32_t row_end, int32_t async_pinned);
+
 /* read back the tonemapped B8G8R8A8 frame (w*h*4) */
 PLAIN_EXPORT int PLAIN_FE(read_output)(plain_frontend* fe, void* out, size_t size, int32_t async_pinned);
 

@@ -314,6 +314,11 @@ int PLAIN_FN(render_frame)(plain_ctx* ctx, int present) {
     }
     return 0;
 }
+int PLAIN_FN(submit_recorded_passes)(plain_ctx* ctx) {
+    const int rc = PLAIN_FN(render_frame)(ctx, 0);
+    ctx->c.execs.clear();
+    return rc;
+}
 int PLAIN_FN(wait_for_gpu_idle)(plain_ctx* ctx) { (void)ctx; return 0; }
 int PLAIN_FN(get_renderpass_timings)(plain_ctx* ctx, plain_pass_time* out, uint32_t capacity, uint32_t* out_count) {
     uint32_t n = (uint32_t)ctx->c.timings.size();
@@ -344,6 +349,19 @@ int PLAIN_FN(read_storage_buffer)(plain_ctx* ctx, plain_handle buffer, void* out
 }
 int PLAIN_FN(write_image_async)(plain_ctx* ctx, plain_image_handle image, uint32_t mip, const void* data, size_t size) { return PLAIN_FN(write_image)(ctx, image, mip, data, size); }
 int PLAIN_FN(read_image_async)(plain_ctx* ctx, plain_image_handle image, uint32_t mip, void* out, size_t size) { return PLAIN_FN(read_image)(ctx, image, mip, out, size); }
+static int imageRows(plain_ctx* ctx, plain_image_handle image, uint32_t mip, uint32_t rowBegin, uint32_t rowEnd, void* host, size_t size, bool toImage) {
+    Image* img = ctx->c.resolve(image);
+    if (!img || mip >= img->mips.size()) return fail(ctx, "image rows: invalid handle/mip");
+    MipLevel& m = img->mips[mip];
+    if (m.d != 1 || rowBegin > rowEnd || rowEnd > (uint32_t)m.h) return fail(ctx, "image rows: invalid row range");
+    const size_t pitch = m.data.size() / (size_t)m.h;
+    if (size != pitch * (rowEnd - rowBegin)) return fail(ctx, "image rows: size mismatch");
+    if (toImage) memcpy(m.data.data() + pitch * rowBegin, host, size);
+    else memcpy(host, m.data.data() + pitch * rowBegin, size);
+    return 0;
+}
+int PLAIN_FN(write_image_rows_async)(plain_ctx* ctx, plain_image_handle image, uint32_t mip, uint32_t rowBegin, uint32_t rowEnd, const void* data, size_t size) { return imageRows(ctx, image, mip, rowBegin, rowEnd, (void*)data, size, true); }
+int PLAIN_FN(read_image_rows_async)(plain_ctx* ctx, plain_image_handle image, uint32_t mip, uint32_t rowBegin, uint32_t rowEnd, void* out, size_t size) { return imageRows(ctx, image, mip, rowBegin, rowEnd, out, size, false); }
 int PLAIN_FN(get_image_device_pointer)(plain_ctx* ctx, plain_image_handle image, uint32_t mip, void** out_ptr, size_t* out_size) {
     Image* img = ctx->c.resolve(image);
     if (!img || mip >= img->mips.size()) return fail(ctx, "get_image_device_pointer: invalid handle/mip");

@@ -218,6 +218,7 @@ static uint64_t hashExecs(const Backend& b) {
         n = (uint32_t)e.storageImages.size(); h = fnv(h, &n, 4); h = fnv(h, e.storageImages.data(), n * sizeof(e.storageImages[0]));
         n = (uint32_t)e.pushConstants.size(); h = fnv(h, &n, 4); h = fnv(h, e.pushConstants.data(), n);
         h = fnv(h, e.dispatch, sizeof(e.dispatch));
+        h = fnv(h, &e.rowBegin, 12);
     }
     return h;
 }
@@ -481,6 +482,7 @@ int PLAIN_FN(set_compute_pass_execution)(plain_ctx* ctx, const plain_compute_pas
     const uint8_t* pc = (const uint8_t*)e->push_constants;
     if (pc) r.pushConstants.assign(pc, pc + e->push_constant_size);
     for (int i = 0; i < 3; i++) r.dispatch[i] = e->dispatch_count[i];
+    r.rowBegin = e->row_begin; r.rowEnd = e->row_end; r.shardPhase = e->shard_phase;
     ctx->b.execs.push_back(std::move(r));
     return 0;
 }
@@ -565,6 +567,11 @@ int PLAIN_FN(render_frame)(plain_ctx* ctx, int present) {
     b.lastFrameLaunches = b.launchCounter;
     return 0;
 }
+int PLAIN_FN(submit_recorded_passes)(plain_ctx* ctx) {
+    const int rc = PLAIN_FN(render_frame)(ctx, 0);
+    ctx->b.execs.clear();
+    return rc;
+}
 int PLAIN_FN(wait_for_gpu_idle)(plain_ctx* ctx) {
     cudaSetDevice(ctx->b.device);
     CU_CHECK(ctx, cudaStreamSynchronize(ctx->b.stream));
@@ -594,6 +601,23 @@ int PLAIN_FN(write_image)(plain_ctx* ctx, plain_image_handle image, uint32_t mip
 int PLAIN_FN(read_image)(plain_ctx* ctx, plain_image_handle image, uint32_t mip, void* out, size_t size) { return imageCopy(ctx, image, mip, out, size, false, true, "read_image"); }
 int PLAIN_FN(write_image_async)(plain_ctx* ctx, plain_image_handle image, uint32_t mip, const void* data, size_t size) { return imageCopy(ctx, image, mip, (void*)data, size, true, false, "write_image_async"); }
 int PLAIN_FN(read_image_async)(plain_ctx* ctx, plain_image_handle image, uint32_t mip, void* out, size_t size) { return imageCopy(ctx, image, mip, out, size, false, false, "read_image_async"); }
+static int imageRowsCopy(plain_ctx* ctx, plain_image_handle image, uint32_t mip, uint32_t rowBegin, uint32_t rowEnd, void* host, size_t size, bool toDevice, const char* what) {
+    Backend& b = ctx->b;
+    cudaSetDevice(b.device);
+    DeviceImage* img = b.resolve(image);
+    if (!img || mip >= img->mips.size()) return fail(ctx, std::string(what) + ": invalid handle/mip");
+    const MipInfo& m = img->mips[mip];
+    if (m.d != 1 || rowBegin > rowEnd || rowEnd > (uint32_t)m.h) return fail(ctx, std::string(what) + ": invalid row range");
+    const size_t pitch = m.bytes / (size_t)m.h;
+    if (size != pitch * (rowEnd - rowBegin)) return fail(ctx, std::string(what) + ": size mismatch");
+    if (size == 0) return 0;
+    unsigned char* dev = img->ptr + m.offset + pitch * rowBegin;
+    if (toDevice) CU_CHECK(ctx, cudaMemcpyAsync(dev, host, size, cudaMemcpyHostToDevice, b.stream));
+    else CU_CHECK(ctx, cudaMemcpyAsync(host, dev, size, cudaMemcpyDeviceToHost, b.stream));
+    return 0;
+}
+int PLAIN_FN(write_image_rows_async)(plain_ctx* ctx, plain_image_handle image, uint32_t mip, uint32_t rowBegin, uint32_t rowEnd, const void* data, size_t size) { return imageRowsCopy(ctx, image, mip, rowBegin, rowEnd, (void*)data, size, true, "write_image_rows_async"); }
+int PLAIN_FN(read_image_rows_async)(plain_ctx* ctx, plain_image_handle image, uint32_t mip, uint32_t rowBegin, uint32_t rowEnd, void* out, size_t size) { return imageRowsCopy(ctx, image, mip, rowBegin, rowEnd, out, size, false, "read_image_rows_async"); }
 int PLAIN_FN(read_storage_buffer)(plain_ctx* ctx, plain_handle buffer, void* out, size_t size) {
     Backend& b = ctx->b;
     cudaSetDevice(b.device);

@@ -45,6 +45,7 @@ struct ExecRecord {
     std::vector<plain_image_resource> storageImages;
     std::vector<uint8_t> pushConstants;
     uint32_t dispatch[3];
+    uint32_t rowBegin = 0, rowEnd = 0, shardPhase = 0;  // row sharding (plain_compute_pass_execution), 0/0/0 = whole pass
 };
 
 struct Backend;
@@ -95,6 +96,13 @@ struct LaunchCtx {
         return v;
     }
     void fail(const std::string& msg) { if (!failed) { failed = true; error = msg; } }
+    // rows [y0, y1) of an output with `rows` rows that this execution has to produce (row sharding; whole range by default)
+    void window(int rows, int& y0, int& y1) const {
+        if (exec->rowBegin == 0 && exec->rowEnd == 0) { y0 = 0; y1 = rows; return; }
+        y0 = std::min((int)exec->rowBegin, rows);
+        y1 = std::min((int)exec->rowEnd, rows);
+        if (y1 < y0) y1 = y0;
+    }
     void countLaunch(int n = 1);
 };
 

@@ -29,12 +29,13 @@ __device__ __forceinline__ void accumMinMax(vec2 t, float& mn, float& mx) {
 }
 
 template <int FUSED>
-__global__ void __launch_bounds__(256) hizFusedKernel(ImgView depth, HizLevels L) {
+__global__ void __launch_bounds__(256) hizFusedKernel(ImgView depth, HizLevels L, int blockRowOffset) {
     __shared__ float2 s0[16][16];
     __shared__ float2 s1[8][8];
     __shared__ float2 s2[4][4];
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-    const int x = blockIdx.x * 16 + tx, y = blockIdx.y * 16 + ty;
+    const int blockRow = (int)blockIdx.y + blockRowOffset;  // row sharding: block rows of 32 depth rows
+    const int x = blockIdx.x * 16 + tx, y = blockRow * 16 + ty;
     float mn = 1.f, mx = 0.f;
     if (x < L.mip[0].w && y < L.mip[0].h) {
         const float* r0 = (const float*)depth.ptr + (size_t)(2 * y) * depth.w + 2 * x;
@@ -47,7 +48,7 @@ __global__ void __launch_bounds__(256) hizFusedKernel(ImgView depth, HizLevels L
     __syncthreads();
     if (threadIdx.x < 64) {
         const int qx = threadIdx.x & 7, qy = threadIdx.x >> 3;
-        const int ox = blockIdx.x * 8 + qx, oy = blockIdx.y * 8 + qy;
+        const int ox = blockIdx.x * 8 + qx, oy = blockRow * 8 + qy;
         float n1 = 1.f, x1 = 0.f;
         if (ox < L.mip[1].w && oy < L.mip[1].h) {
             for (int j = 0; j < 2; j++)
@@ -60,7 +61,7 @@ __global__ void __launch_bounds__(256) hizFusedKernel(ImgView depth, HizLevels L
     __syncthreads();
     if (threadIdx.x < 16) {
         const int qx = threadIdx.x & 3, qy = threadIdx.x >> 2;
-        const int ox = blockIdx.x * 4 + qx, oy = blockIdx.y * 4 + qy;
+        const int ox = blockIdx.x * 4 + qx, oy = blockRow * 4 + qy;
         float n2 = 1.f, x2 = 0.f;
         if (ox < L.mip[2].w && oy < L.mip[2].h) {
             for (int j = 0; j < 2; j++)
@@ -73,7 +74,7 @@ __global__ void __launch_bounds__(256) hizFusedKernel(ImgView depth, HizLevels L
     __syncthreads();
     if (threadIdx.x < 4) {
         const int qx = threadIdx.x & 1, qy = threadIdx.x >> 1;
-        const int ox = blockIdx.x * 2 + qx, oy = blockIdx.y * 2 + qy;
+        const int ox = blockIdx.x * 2 + qx, oy = blockRow * 2 + qy;
         if (ox < L.mip[3].w && oy < L.mip[3].h) {
             float n3 = 1.f, x3 = 0.f;
             for (int j = 0; j < 2; j++)
@@ -149,17 +150,29 @@ PLAIN_PASS(launch_depthHiZPyramid, "depthHiZPyramid.comp") {
         if (evenSoFar && k < 4) fused = k + 1;
         srcW = w; srcH = h;
     }
+    // Row sharding (shard_phase): 1 = only the fused levels, for level-0 rows [row_begin, row_end) (multiples of 16: the
+    // rank's own depth rows); 2 = only the remaining levels (replicated on every rank after the last fused level has been
+    // all-gathered); 0 = everything.
+    const uint32_t phase = c.exec->shardPhase;
     int next = 0;
     if (fused > 0) {
-        dim3 grid(ceilDiv(L.mip[0].w, 16), ceilDiv(L.mip[0].h, 16));
-        switch (fused) {
-            case 1: PLAIN_LAUNCH(c, hizFusedKernel<1>, grid, 256, 0, depth, L); break;
-            case 2: PLAIN_LAUNCH(c, hizFusedKernel<2>, grid, 256, 0, depth, L); break;
-            case 3: PLAIN_LAUNCH(c, hizFusedKernel<3>, grid, 256, 0, depth, L); break;
-            default: PLAIN_LAUNCH(c, hizFusedKernel<4>, grid, 256, 0, depth, L); break;
+        int y0, y1;
+        c.window(L.mip[0].h, y0, y1);
+        if (phase == 2) y1 = y0;
+        if (y0 % 16 != 0) { c.fail("depthHiZPyramid.comp: row window must start at a multiple of 16 level-0 rows"); return; }
+        dim3 grid(ceilDiv(L.mip[0].w, 16), ceilDiv((unsigned)(y1 - y0), 16));
+        if (y1 > y0) switch (fused) {
+            case 1: PLAIN_LAUNCH(c, hizFusedKernel<1>, grid, 256, 0, depth, L, y0 / 16); break;
+            case 2: PLAIN_LAUNCH(c, hizFusedKernel<2>, grid, 256, 0, depth, L, y0 / 16); break;
+            case 3: PLAIN_LAUNCH(c, hizFusedKernel<3>, grid, 256, 0, depth, L, y0 / 16); break;
+            default: PLAIN_LAUNCH(c, hizFusedKernel<4>, grid, 256, 0, depth, L, y0 / 16); break;
         }
         next = fused;
+    } else if (phase != 0) {
+        c.fail("depthHiZPyramid.comp: row sharding needs even depth extents (no level can be reduced from a rank's own rows)");
+        return;
     }
+    if (phase == 1) return;
     while (next < mipCount && (next == 0 || L.mip[next].w * L.mip[next].h > 1024)) {
         dim3 grid(ceilDiv(L.mip[next].w, 16), ceilDiv(L.mip[next].h, 16));
         if (next == 0) PLAIN_LAUNCH(c, hizLevelKernel<true>, grid, 256, 0, depth, L.mip[0]);
@@ -267,9 +280,9 @@ PLAIN_PASS(launch_lightMatrix, "lightMatrix.comp") {
 
 // ---------------- depthDownscale.comp:12-20 ----------------
 // uv = (2*x + 0.5) / size lands half a texel inside texel 2*x: the nearest fetch is an exact strided copy.
-__global__ void __launch_bounds__(256) depthDownscaleKernel(ImgView dst, ImgView src, int limitX, int limitY) {
-    const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
-    if (x >= dst.w || y >= dst.h || x >= limitX || y >= limitY) return;
+__global__ void __launch_bounds__(256) depthDownscaleKernel(ImgView dst, ImgView src, int limitX, int limitY, int y0) {
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = y0 + blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x >= dst.w || y >= limitY || x >= limitX) return;
     const int sx = imin(2 * x, src.w - 1), sy = imin(2 * y, src.h - 1);
     storeR16F(dst, x, y, loadD32(src, sx, sy));
 }
@@ -278,8 +291,11 @@ PLAIN_PASS(launch_depthDownscale, "depthDownscale.comp") {
     const ImgView src = c.sampled(1, PLAIN_FORMAT_DEPTH32);
     if (c.failed) return;
     const int limX = (int)c.exec->dispatch[0] * 8, limY = (int)c.exec->dispatch[1] * 8;
-    dim3 grid(ceilDiv(std::min(dst.w, limX), 32), ceilDiv(std::min(dst.h, limY), 8));
-    PLAIN_LAUNCH(c, depthDownscaleKernel, grid, 256, 0, dst, src, limX, limY);
+    int y0, y1;
+    c.window(std::min(dst.h, limY), y0, y1);
+    if (y1 <= y0) return;
+    dim3 grid(ceilDiv(std::min(dst.w, limX), 32), ceilDiv((unsigned)(y1 - y0), 8));
+    PLAIN_LAUNCH(c, depthDownscaleKernel, grid, 256, 0, dst, src, limX, y1, y0);
 }
 
 }  // namespace pb

@@ -11,7 +11,7 @@ namespace pb {
 // pixels mostly share a bin, so a warp issues a handful of shared atomics instead of 32.
 template <int NBINS_MAX>
 __global__ void __launch_bounds__(256) histogramPerTileKernel(ImgView src, uint32_t* __restrict__ perTile, size_t perTileCount, const plain_light_buffer* __restrict__ light,
-                                                               uint32_t nBins, float minLuminance, float maxLuminance) {
+                                                               uint32_t nBins, float minLuminance, float maxLuminance, int tileRowOffset) {
     __shared__ uint32_t hist[NBINS_MAX];
     for (uint32_t i = threadIdx.x; i < nBins; i += 256) hist[i] = 0;
     __syncthreads();
@@ -19,7 +19,8 @@ __global__ void __launch_bounds__(256) histogramPerTileKernel(ImgView src, uint3
     const float minLuminanceLog = dm::log(minLuminance), maxLuminanceLog = dm::log(maxLuminance);
     const float range = maxLuminanceLog - minLuminanceLog;
     const uint32_t maxIndex = nBins - 1;
-    const int tx = blockIdx.x * 32, ty = blockIdx.y * 32;
+    const int tileRow = (int)blockIdx.y + tileRowOffset;  // row sharding: this launch covers tile rows [tileRowOffset, tileRowOffset + gridDim.y)
+    const int tx = blockIdx.x * 32, ty = tileRow * 32;
     const int lx = (threadIdx.x & 7) * 4, ly = threadIdx.x >> 3;  // 8 threads x 4 px per row, 32 rows
     const int x0 = tx + lx, y = ty + ly;
     uint32_t texels[4];
@@ -49,7 +50,7 @@ __global__ void __launch_bounds__(256) histogramPerTileKernel(ImgView src, uint3
     }
     __syncthreads();
     // invocation (b % 32, b / 32) of the reference's 32x32 group writes bin b unless it left the image (:37-39, :58-64)
-    const uint32_t tileIndex = blockIdx.x + blockIdx.y * ((src.w + 31) / 32);
+    const uint32_t tileIndex = blockIdx.x + (uint32_t)tileRow * ((src.w + 31) / 32);
     for (uint32_t b = threadIdx.x; b < nBins; b += 256) {
         const int px = tx + (int)(b % 32), py = ty + (int)(b / 32);
         if (px >= src.w || py >= src.h) continue;
@@ -67,8 +68,11 @@ PLAIN_PASS(launch_histogramPerTile, "histogramPerTile.comp") {
     const plain_light_buffer* light = c.sbuf<plain_light_buffer>(3);
     if (c.failed) return;
     if (nBins > 256) { c.fail("histogramPerTile.comp: at most 256 bins"); return; }
-    dim3 grid(c.exec->dispatch[0], c.exec->dispatch[1]);
-    PLAIN_LAUNCH(c, histogramPerTileKernel<256>, grid, 256, 0, src, perTile, perTileSize / 4, light, nBins, minLum, maxLum);
+    int ty0, ty1;
+    c.window((int)c.exec->dispatch[1], ty0, ty1);  // row sharding unit: rows of 32x32 tiles
+    if (ty1 <= ty0 || c.exec->dispatch[0] == 0) return;
+    dim3 grid(c.exec->dispatch[0], ty1 - ty0);
+    PLAIN_LAUNCH(c, histogramPerTileKernel<256>, grid, 256, 0, src, perTile, perTileSize / 4, light, nBins, minLum, maxLum, ty0);
 }
 
 __global__ void histogramResetKernel(uint32_t* histogram, uint32_t nBins, uint32_t invocations) {
@@ -86,12 +90,12 @@ PLAIN_PASS(launch_histogramReset, "histogramReset.comp") {
 // histogramCombineTiles.comp: one thread per bin and a slab of tiles per block; coalesced over bins, one global
 // atomic per (block, bin). Integer sums are order independent, so the result equals the reference's atomicAdd chain.
 __global__ void __launch_bounds__(256) histogramCombineKernel(const uint32_t* __restrict__ perTile, size_t perTileCount, uint32_t* histogram, size_t histCount,
-                                                               uint32_t nBins, uint32_t tileCount, uint32_t binInvocations, uint32_t tilesPerBlock) {
+                                                               uint32_t nBins, uint32_t tileBegin, uint32_t tileCount, uint32_t binInvocations, uint32_t tilesPerBlock) {
     const uint32_t binsPerRow = min(nBins + 1, binInvocations);  // bin == nBins passes the reference's '>' test (:29) and falls outside both buffers
     const uint32_t rowsPerIter = 256 / binsPerRow > 0 ? 256 / binsPerRow : 1;
     const uint32_t bin = threadIdx.x % binsPerRow, sub = threadIdx.x / binsPerRow;
     if (binsPerRow > 256 || sub >= rowsPerIter) return;
-    const uint32_t t0 = blockIdx.x * tilesPerBlock, t1 = min(t0 + tilesPerBlock, tileCount);
+    const uint32_t t0 = tileBegin + blockIdx.x * tilesPerBlock, t1 = min(t0 + tilesPerBlock, tileCount);  // tiles [tileBegin, tileCount)
     uint32_t sum = 0;
     for (uint32_t t = t0 + sub; t < t1; t += rowsPerIter) {
         const size_t idx = (size_t)t * nBins + bin;
@@ -108,7 +112,10 @@ PLAIN_PASS(launch_histogramCombine, "histogramCombineTiles.comp") {
     const uint32_t tiles = c.exec->dispatch[0], binInv = c.exec->dispatch[1] * 64;
     if (nBins + 1 > 256) { c.fail("histogramCombineTiles.comp: at most 255 bins"); return; }
     const uint32_t tilesPerBlock = 64;
-    PLAIN_LAUNCH(c, histogramCombineKernel, ceilDiv(tiles, tilesPerBlock), 256, 0, perTile, perTileSize / 4, histogram, histSize / 4, nBins, tiles, binInv, tilesPerBlock);
+    int t0, t1;
+    c.window((int)tiles, t0, t1);  // row sharding unit: tile indices (a rank sums the tiles of its own tile rows; the partial histograms are all-reduced)
+    if (t1 <= t0) return;
+    PLAIN_LAUNCH(c, histogramCombineKernel, ceilDiv((unsigned)(t1 - t0), tilesPerBlock), 256, 0, perTile, perTileSize / 4, histogram, histSize / 4, nBins, (uint32_t)t0, (uint32_t)t1, binInv, tilesPerBlock);
 }
 
 // ---------------- preExposeLights.comp:28-88 (single thread in the reference) ----------------

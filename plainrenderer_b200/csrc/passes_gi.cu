@@ -301,6 +301,7 @@ struct TraceParams {
     const BindlessEntry* bindless;
     int strictInfluenceRadiusCutoff, shadowCascadeIndex;
     int groupsX, groupsY;
+    int blockRowOffset;  // row sharding: first 16-row block row of this launch
 };
 
 // A block traces a 16x16-pixel region = 2x2 of the reference's 8x8 workgroups; all four lie in one 32x32 culling tile
@@ -323,10 +324,11 @@ __global__ void __launch_bounds__(256) sdfDiffuseTraceKernel(const __grid_consta
     const plain_global_shader_info* g = p.g;
     const int sub = threadIdx.x >> 6;                  // which of the 2x2 groups
     const int lx = threadIdx.x & 7, ly = (threadIdx.x >> 3) & 7;
-    const int gx = blockIdx.x * 2 + (sub & 1), gy = blockIdx.y * 2 + (sub >> 1);
+    const int blockRow = (int)blockIdx.y + p.blockRowOffset;
+    const int gx = blockIdx.x * 2 + (sub & 1), gy = blockRow * 2 + (sub >> 1);
     const bool groupActive = gx < p.groupsX && gy < p.groupsY;
     // tile of the block (identical for its four groups)
-    const int tileX = (blockIdx.x * 2) / 4, tileY = (blockIdx.y * 2) / 4;
+    const int tileX = (blockIdx.x * 2) / 4, tileY = (blockRow * 2) / 4;
     const uint32_t tileIndex = tileIndexFromTileUV(tileX, tileY, g);
     const bool tileValid = (size_t)tileIndex < p.tileCapacity;
     if (threadIdx.x == 0) sCount = tileValid ? min(p.tiles[tileIndex].objectCount, (uint32_t)PLAIN_MAX_OBJECTS_PER_TILE) : 0u;
@@ -486,7 +488,12 @@ PLAIN_PASS(launch_sdfDiffuseTrace, "sdfDiffuseTrace.comp") {
     if (c.failed) return;
     if (p.shadowCascadeIndex < 0 || p.shadowCascadeIndex > 3) { c.fail("sdfDiffuseTrace.comp: shadow cascade index must be 0..3"); return; }
     if (p.groupsX == 0 || p.groupsY == 0) return;
-    PLAIN_LAUNCH(c, sdfDiffuseTraceKernel, dim3(ceilDiv(p.groupsX, 2), ceilDiv(p.groupsY, 2)), 256, 0, p);
+    int y0, y1;
+    c.window(p.groupsY * 8, y0, y1);  // row sharding unit: rows of the (half-res) trace target, in multiples of the 16-row blocks
+    if (y0 % 16 != 0) { c.fail("sdfDiffuseTrace.comp: row window must start at a multiple of 16 rows"); return; }
+    if (y1 <= y0) return;
+    p.blockRowOffset = y0 / 16;
+    PLAIN_LAUNCH(c, sdfDiffuseTraceKernel, dim3(ceilDiv(p.groupsX, 2), ceilDiv((unsigned)(y1 - y0), 16)), 256, 0, p);
 }
 
 // ---------------- filterIndirectDiffuseSpatial.comp ----------------
@@ -494,6 +501,7 @@ struct SpatialParams {
     ImgView outYSH, outCoCg, texYSH, texCoCg, depthTexture, normalTexture;
     const plain_global_shader_info* g;
     int filterIndex;
+    int y0, y1;  // rows to produce (row sharding)
 };
 template <bool DEPTH_IS_R16F>
 __device__ __forceinline__ vec3 giPixelToWorld(const ImgView& depthTexture, const Globals& G, vec2 uv) {
@@ -520,8 +528,8 @@ __global__ void __launch_bounds__(256) giSpatialFilterKernel(const __grid_consta
         }
     }
     __syncthreads();
-    const int ix = blockIdx.x * 32 + (threadIdx.x & 31), iy = blockIdx.y * 8 + (threadIdx.x >> 5);
-    if (ix >= p.outYSH.w || iy >= p.outYSH.h) return;
+    const int ix = blockIdx.x * 32 + (threadIdx.x & 31), iy = p.y0 + blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (ix >= p.outYSH.w || iy >= p.y1) return;
     const Globals G = loadGlobals(g);
     const vec2 texelSize = 1.f / v2((float)p.outYSH.w, (float)p.outYSH.h);
     const vec2 uv = (v2((float)ix, (float)iy) + 0.5f) * texelSize;
@@ -586,7 +594,9 @@ PLAIN_PASS(launch_giSpatialFilter, "filterIndirectDiffuseSpatial.comp") {
     if (c.failed) return;
     const int fmt = c.sampledFormat(4);
     if ((int)c.exec->dispatch[0] * 8 < p.outYSH.w || (int)c.exec->dispatch[1] * 8 < p.outYSH.h) { c.fail("filterIndirectDiffuseSpatial.comp: dispatch does not cover the target"); return; }
-    dim3 grid(ceilDiv(p.outYSH.w, 32), ceilDiv(p.outYSH.h, 8));
+    c.window(p.outYSH.h, p.y0, p.y1);
+    if (p.y1 <= p.y0) return;
+    dim3 grid(ceilDiv(p.outYSH.w, 32), ceilDiv((unsigned)(p.y1 - p.y0), 8));
     if (fmt == PLAIN_FORMAT_R16_SFLOAT) PLAIN_LAUNCH(c, giSpatialFilterKernel<true>, grid, 256, 0, p);
     else if (fmt == PLAIN_FORMAT_DEPTH32) PLAIN_LAUNCH(c, giSpatialFilterKernel<false>, grid, 256, 0, p);
     else c.fail("filterIndirectDiffuseSpatial.comp: depth binding must be R16F or D32F");
@@ -596,10 +606,11 @@ PLAIN_PASS(launch_giSpatialFilter, "filterIndirectDiffuseSpatial.comp") {
 struct TemporalParams {
     ImgView targetYSH, targetCoCg, historyOutYSH, historyOutCoCg, inputYSH, inputCoCg, historyInYSH, historyInCoCg, velocityCurrent, velocityLastFrame;
     const plain_global_shader_info* g;
+    int y0, y1;  // rows to produce (row sharding)
 };
 __global__ void __launch_bounds__(256) giTemporalFilterKernel(const __grid_constant__ TemporalParams p) {
-    const int ix = blockIdx.x * 32 + (threadIdx.x & 31), iy = blockIdx.y * 8 + (threadIdx.x >> 5);
-    if (ix >= p.targetYSH.w || iy >= p.targetYSH.h) return;
+    const int ix = blockIdx.x * 32 + (threadIdx.x & 31), iy = p.y0 + blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (ix >= p.targetYSH.w || iy >= p.y1) return;
     const plain_global_shader_info* g = p.g;
     const vec2 texelSize = 1.f / v2((float)p.targetYSH.w, (float)p.targetYSH.h);
     const vec2 uv = (v2((float)ix, (float)iy) + 0.5f) * texelSize;
@@ -651,17 +662,20 @@ PLAIN_PASS(launch_giTemporalFilter, "filterIndirectDiffuseTemporal.comp") {
     p.g = c.g;
     if (c.failed) return;
     if ((int)c.exec->dispatch[0] * 8 < p.targetYSH.w || (int)c.exec->dispatch[1] * 8 < p.targetYSH.h) { c.fail("filterIndirectDiffuseTemporal.comp: dispatch does not cover the target"); return; }
-    PLAIN_LAUNCH(c, giTemporalFilterKernel, dim3(ceilDiv(p.targetYSH.w, 32), ceilDiv(p.targetYSH.h, 8)), 256, 0, p);
+    c.window(p.targetYSH.h, p.y0, p.y1);
+    if (p.y1 <= p.y0) return;
+    PLAIN_LAUNCH(c, giTemporalFilterKernel, dim3(ceilDiv(p.targetYSH.w, 32), ceilDiv((unsigned)(p.y1 - p.y0), 8)), 256, 0, p);
 }
 
 // ---------------- indirectLightUpscale.comp ----------------
 struct UpscaleParams {
     ImgView dstYSH, dstCoCg, srcYSH, srcCoCg, fullResDepth, halfResDepth;
     const plain_global_shader_info* g;
+    int y0, y1;  // rows to produce (row sharding)
 };
 __global__ void __launch_bounds__(256) giUpscaleKernel(const __grid_constant__ UpscaleParams p) {
-    const int ix = blockIdx.x * 32 + (threadIdx.x & 31), iy = blockIdx.y * 8 + (threadIdx.x >> 5);
-    if (ix >= p.dstYSH.w || iy >= p.dstYSH.h) return;
+    const int ix = blockIdx.x * 32 + (threadIdx.x & 31), iy = p.y0 + blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (ix >= p.dstYSH.w || iy >= p.y1) return;
     const plain_global_shader_info* g = p.g;
     const float nearP = g->nearPlane, farP = g->farPlane;
     const vec2 uv = (v2((float)ix, (float)iy) + 0.5f) / v2((float)g->screenResolution[0], (float)g->screenResolution[1]);
@@ -711,7 +725,9 @@ PLAIN_PASS(launch_giUpscale, "indirectLightUpscale.comp") {
     p.g = c.g;
     if (c.failed) return;
     if ((int)c.exec->dispatch[0] * 8 < p.dstYSH.w || (int)c.exec->dispatch[1] * 8 < p.dstYSH.h) { c.fail("indirectLightUpscale.comp: dispatch does not cover the target"); return; }
-    PLAIN_LAUNCH(c, giUpscaleKernel, dim3(ceilDiv(p.dstYSH.w, 32), ceilDiv(p.dstYSH.h, 8)), 256, 0, p);
+    c.window(p.dstYSH.h, p.y0, p.y1);
+    if (p.y1 <= p.y0) return;
+    PLAIN_LAUNCH(c, giUpscaleKernel, dim3(ceilDiv(p.dstYSH.w, 32), ceilDiv((unsigned)(p.y1 - p.y0), 8)), 256, 0, p);
 }
 
 }  // namespace pb

@@ -15,8 +15,8 @@ __device__ __forceinline__ uint32_t tonemapTexel(uint32_t packed, int x, int y, 
     sRGB = ditherRGB8(sRGB, x, y, g_time);
     return floatToUnorm8(sRGB.z) | (floatToUnorm8(sRGB.y) << 8) | (floatToUnorm8(sRGB.x) << 16) | (255u << 24);  // B8G8R8A8, alpha 1
 }
-__global__ void __launch_bounds__(256) tonemappingKernel(ImgView imageOut, ImgView imageIn, const plain_global_shader_info* __restrict__ g, int limitX, int limitY) {
-    const int x0 = (blockIdx.x * 32 + (threadIdx.x & 31)) * 4, y = blockIdx.y * 8 + (threadIdx.x >> 5);
+__global__ void __launch_bounds__(256) tonemappingKernel(ImgView imageOut, ImgView imageIn, const plain_global_shader_info* __restrict__ g, int limitX, int limitY, int yBegin) {
+    const int x0 = (blockIdx.x * 32 + (threadIdx.x & 31)) * 4, y = yBegin + blockIdx.y * 8 + (threadIdx.x >> 5);
     const int w = imin(imin(imageOut.w, imageIn.w), limitX), h = imin(imin(imageOut.h, imageIn.h), limitY);
     if (y >= h || x0 >= w) return;
     const float g_time = g->time;
@@ -37,24 +37,27 @@ PLAIN_PASS(launch_tonemapping, "tonemapping.comp") {
     const ImgView in = c.sampled(1, PLAIN_FORMAT_R11G11B10_UFLOAT);
     if (c.failed) return;
     const int limX = (int)c.exec->dispatch[0] * 8, limY = (int)c.exec->dispatch[1] * 8;
-    dim3 grid(ceilDiv(std::min(out.w, limX), 128), ceilDiv(std::min(out.h, limY), 8));
-    PLAIN_LAUNCH(c, tonemappingKernel, grid, 256, 0, out, in, c.g, limX, limY);
+    int y0, y1;
+    c.window(std::min(out.h, limY), y0, y1);
+    if (y1 <= y0) return;
+    dim3 grid(ceilDiv(std::min(out.w, limX), 128), ceilDiv((unsigned)(y1 - y0), 8));
+    PLAIN_LAUNCH(c, tonemappingKernel, grid, 256, 0, out, in, c.g, limX, y1, y0);
 }
 
 // ---------------- bloom ----------------
 // bloomDownsample.comp: 13 bilinear taps of the finer mip. The bounds test is '>' in the reference (:16): the extra
 // row/column of invocations only produces stores outside the image, which are dropped.
 // Block = 32x8 target texels; their 13 taps touch a (64 + 6) x (16 + 6) rectangle of the finer mip, staged once.
-__global__ void __launch_bounds__(256) bloomDownsampleKernel(ImgView target, ImgView source) {
+__global__ void __launch_bounds__(256) bloomDownsampleKernel(ImgView target, ImgView source, int yBegin, int yEnd) {
     constexpr int TW = 72, TH = 24;
     __shared__ float4 sSrc[TW * TH];
-    const int bx = blockIdx.x * 32, by = blockIdx.y * 8;
+    const int bx = blockIdx.x * 32, by = yBegin + blockIdx.y * 8;
     const int sx0 = (int)(((long long)bx * source.w) / target.w) - 3, sy0 = (int)(((long long)by * source.h) / target.h) - 3;
     tileLoadR11<TW, TH>(sSrc, source, sx0, sy0);
     __syncthreads();
     const TileR11<TW, TH> tile{sSrc, sx0, sy0};
     const int ix = bx + (threadIdx.x & 31), iy = by + (threadIdx.x >> 5);
-    if (ix >= target.w || iy >= target.h) return;
+    if (ix >= target.w || iy >= yEnd) return;
     const vec2 uv = (v2((float)ix, (float)iy) + 0.5f) / v2((float)target.w, (float)target.h);
     const vec2 texelSize = 1.f / v2((float)source.w, (float)source.h);
     vec3 color = v3(0.f);
@@ -69,22 +72,25 @@ PLAIN_PASS(launch_bloomDownsample, "bloomDownsample.comp") {
     const ImgView target = c.storage(0, PLAIN_FORMAT_R11G11B10_UFLOAT), source = c.sampled(1, PLAIN_FORMAT_R11G11B10_UFLOAT);
     if (c.failed) return;
     if ((int)c.exec->dispatch[0] * 8 < target.w || (int)c.exec->dispatch[1] * 8 < target.h) { c.fail("bloomDownsample.comp: dispatch does not cover the target"); return; }
-    PLAIN_LAUNCH(c, bloomDownsampleKernel, dim3(ceilDiv(target.w, 32), ceilDiv(target.h, 8)), 256, 0, target, source);
+    int y0, y1;
+    c.window(target.h, y0, y1);
+    if (y1 <= y0) return;
+    PLAIN_LAUNCH(c, bloomDownsampleKernel, dim3(ceilDiv(target.w, 32), ceilDiv((unsigned)(y1 - y0), 8)), 256, 0, target, source, y0, y1);
 }
 
 // bloomUpsample.comp: 9-tap tent of the coarser downsample mip (+ 4-tap box of the coarser upsample mip)
 // Block = 32x8 target texels; the tent and box taps touch about (16 + 8) x (4 + 8) texels of the two coarser mips.
-__global__ void __launch_bounds__(256) bloomUpsampleKernel(ImgView target, ImgView targetPreviousMip, ImgView source, int isLowestMip, float blurRadius) {
+__global__ void __launch_bounds__(256) bloomUpsampleKernel(ImgView target, ImgView targetPreviousMip, ImgView source, int isLowestMip, float blurRadius, int yBegin, int yEnd) {
     constexpr int TW = 24, TH = 12;
     __shared__ float4 sSrc[TW * TH], sPrev[TW * TH];
-    const int bx = blockIdx.x * 32, by = blockIdx.y * 8;
+    const int bx = blockIdx.x * 32, by = yBegin + blockIdx.y * 8;
     const int sx0 = (int)(((long long)bx * source.w) / target.w) - 3, sy0 = (int)(((long long)by * source.h) / target.h) - 3;
     tileLoadR11<TW, TH>(sSrc, source, sx0, sy0);
     if (!isLowestMip) tileLoadR11<TW, TH>(sPrev, targetPreviousMip, sx0, sy0);
     __syncthreads();
     const TileR11<TW, TH> srcTile{sSrc, sx0, sy0}, prevTile{sPrev, sx0, sy0};
     const int ix = bx + (threadIdx.x & 31), iy = by + (threadIdx.x >> 5);
-    if (ix >= target.w || iy >= target.h) return;
+    if (ix >= target.w || iy >= yEnd) return;
     const vec2 texelSize = 1.f / v2((float)source.w, (float)source.h);
     const vec2 sampleStepSize = blurRadius * texelSize;
     const vec2 uv = (v2((float)ix, (float)iy) + 0.5f) / v2((float)target.w, (float)target.h);
@@ -104,13 +110,16 @@ PLAIN_PASS(launch_bloomUpsample, "bloomUpsample.comp") {
     const ImgView prev = c.sampled(1, PLAIN_FORMAT_R11G11B10_UFLOAT), source = c.sampled(2, PLAIN_FORMAT_R11G11B10_UFLOAT);
     if (c.failed) return;
     if ((int)c.exec->dispatch[0] * 8 < target.w || (int)c.exec->dispatch[1] * 8 < target.h) { c.fail("bloomUpsample.comp: dispatch does not cover the target"); return; }
-    PLAIN_LAUNCH(c, bloomUpsampleKernel, dim3(ceilDiv(target.w, 32), ceilDiv(target.h, 8)), 256, 0, target, prev, source, c.specBool(0, false) ? 1 : 0, c.push<float>(0));
+    int y0, y1;
+    c.window(target.h, y0, y1);
+    if (y1 <= y0) return;
+    PLAIN_LAUNCH(c, bloomUpsampleKernel, dim3(ceilDiv(target.w, 32), ceilDiv((unsigned)(y1 - y0), 8)), 256, 0, target, prev, source, c.specBool(0, false) ? 1 : 0, c.push<float>(0), y0, y1);
 }
 
 // applyBloom.comp: mix(scene, bloom, strength) in place
-__global__ void __launch_bounds__(256) applyBloomKernel(ImgView target, ImgView bloomTexture, float bloomStrength) {
-    const int ix = blockIdx.x * 32 + (threadIdx.x & 31), iy = blockIdx.y * 8 + (threadIdx.x >> 5);
-    if (ix >= target.w || iy >= target.h) return;
+__global__ void __launch_bounds__(256) applyBloomKernel(ImgView target, ImgView bloomTexture, float bloomStrength, int yBegin, int yEnd) {
+    const int ix = blockIdx.x * 32 + (threadIdx.x & 31), iy = yBegin + blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (ix >= target.w || iy >= yEnd) return;
     const vec2 uv = (v2((float)ix, (float)iy) + 0.5f) / v2((float)target.w, (float)target.h);
     const vec3 bloom = sampleR11LinearClamp(bloomTexture, uv);
     const vec3 scene = loadR11(target, ix, iy);
@@ -120,7 +129,10 @@ PLAIN_PASS(launch_applyBloom, "applyBloom.comp") {
     const ImgView target = c.storage(0, PLAIN_FORMAT_R11G11B10_UFLOAT), bloom = c.sampled(1, PLAIN_FORMAT_R11G11B10_UFLOAT);
     if (c.failed) return;
     if ((int)c.exec->dispatch[0] * 8 < target.w || (int)c.exec->dispatch[1] * 8 < target.h) { c.fail("applyBloom.comp: dispatch does not cover the target"); return; }
-    PLAIN_LAUNCH(c, applyBloomKernel, dim3(ceilDiv(target.w, 32), ceilDiv(target.h, 8)), 256, 0, target, bloom, c.push<float>(0));
+    int y0, y1;
+    c.window(target.h, y0, y1);
+    if (y1 <= y0) return;
+    PLAIN_LAUNCH(c, applyBloomKernel, dim3(ceilDiv(target.w, 32), ceilDiv((unsigned)(y1 - y0), 8)), 256, 0, target, bloom, c.push<float>(0), y0, y1);
 }
 
 // ---------------- temporalFilter.comp ----------------
@@ -129,6 +141,7 @@ struct TaaParams {
     const float* resolveWeights;  // 9 floats, uniform buffer binding 6 (TAA.cpp:181-202)
     const plain_global_shader_info* g;
     int useClipping, useMotionVectorDilation, historySampleTech, useTonemap;
+    int y0, y1;  // rows to produce (row sharding)
 };
 __device__ __forceinline__ vec3 taaTonemap(vec3 color) { return color / (1.f + computeLuminance(color)); }         // temporalReprojection.inc:34-36
 __device__ __forceinline__ vec3 taaTonemapReverse(vec3 color) { return color / (1.f - computeLuminance(color)); }  // :38-40
@@ -189,14 +202,14 @@ template <bool TONEMAP, int TECH>
 __global__ void __launch_bounds__(256, 3) temporalFilterKernel(const __grid_constant__ TaaParams p) {
     __shared__ float4 sCur[(32 + 2 * TAA_CUR_HALO) * (8 + 2 * TAA_CUR_HALO)];
     __shared__ float4 sHis[(32 + 2 * TAA_HIS_HALO) * (8 + 2 * TAA_HIS_HALO)];
-    const int bx = blockIdx.x * 32, by = blockIdx.y * 8;
+    const int bx = blockIdx.x * 32, by = p.y0 + blockIdx.y * 8;
     tileLoadR11<32 + 2 * TAA_CUR_HALO, 8 + 2 * TAA_CUR_HALO>(sCur, p.currentFrame, bx - TAA_CUR_HALO, by - TAA_CUR_HALO);
     tileLoadR11<32 + 2 * TAA_HIS_HALO, 8 + 2 * TAA_HIS_HALO>(sHis, p.historySrc, bx - TAA_HIS_HALO, by - TAA_HIS_HALO);
     __syncthreads();
     const TileR11<32 + 2 * TAA_CUR_HALO, 8 + 2 * TAA_CUR_HALO> curTile{sCur, bx - TAA_CUR_HALO, by - TAA_CUR_HALO};
     const TileR11<32 + 2 * TAA_HIS_HALO, 8 + 2 * TAA_HIS_HALO> hisTile{sHis, bx - TAA_HIS_HALO, by - TAA_HIS_HALO};
     const int ix = bx + (threadIdx.x & 31), iy = by + (threadIdx.x >> 5);
-    if (ix >= p.outputImage.w || iy >= p.outputImage.h) return;
+    if (ix >= p.outputImage.w || iy >= p.y1) return;
     const vec2 screenRes = v2((float)p.g->screenResolution[0], (float)p.g->screenResolution[1]);
     const vec2 texelSize = 1.f / v2((float)p.outputImage.w, (float)p.outputImage.h);
     const vec2 iUVf = v2((float)ix, (float)iy);
@@ -315,7 +328,9 @@ PLAIN_PASS(launch_temporalFilter, "temporalFilter.comp") {
     p.useTonemap = c.specBool(3, false);
     if (c.failed) return;
     if ((int)c.exec->dispatch[0] * 8 < p.outputImage.w || (int)c.exec->dispatch[1] * 8 < p.outputImage.h) { c.fail("temporalFilter.comp: dispatch does not cover the target"); return; }
-    dim3 grid(ceilDiv(p.outputImage.w, 32), ceilDiv(p.outputImage.h, 8));
+    c.window(p.outputImage.h, p.y0, p.y1);
+    if (p.y1 <= p.y0) return;
+    dim3 grid(ceilDiv(p.outputImage.w, 32), ceilDiv((unsigned)(p.y1 - p.y0), 8));
     if (p.useTonemap && p.historySampleTech == 4) PLAIN_LAUNCH(c, (temporalFilterKernel<true, 4>), grid, 256, 0, p);  // the reference's defaults (TAA.h:8-17)
     else if (p.useTonemap) PLAIN_LAUNCH(c, (temporalFilterKernel<true, -1>), grid, 256, 0, p);
     else PLAIN_LAUNCH(c, (temporalFilterKernel<false, -1>), grid, 256, 0, p);

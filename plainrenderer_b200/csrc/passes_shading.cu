@@ -265,14 +265,15 @@ __device__ __forceinline__ vec3 shadeSky(const ShadingParams& p, int x, int y, v
 }
 
 template <int DIFFUSE, int MULTI, int GEOAA, int TECH>
-__global__ void __launch_bounds__(256) gbufferShadingKernel(const __grid_constant__ ShadingParams p, int limitX, int limitY) {
+__global__ void __launch_bounds__(256) gbufferShadingKernel(const __grid_constant__ ShadingParams p, int limitX, int limitY, int y0) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int x = blockIdx.x * 32 + (warp & 1) * 16 + (lane & 15);
-    const int y = blockIdx.y * 8 + (warp >> 1) * 2 + (lane >> 4);
+    const int y = y0 + blockIdx.y * 8 + (warp >> 1) * 2 + (lane >> 4);  // y0: first row of the launch (even; row sharding)
     const int W = p.colorOut.w, Hh = p.colorOut.h;
-    const bool inside = x < W && y < Hh && x < limitX && y < limitY;
+    const bool inImage = x < W && y < Hh;                        // quad partners are loaded even when they lie outside the row window
+    const bool inside = inImage && x < limitX && y < limitY;
     uint4 texel = make_uint4(0, 0, 0, 0);
-    if (inside) texel = loadU4(p.gbuffer, x, y);
+    if (inImage) texel = loadU4(p.gbuffer, x, y);
     const vec3 N = decodeOctNormal(texel.y);
     // quad partners: dFdx = right - left within the pixel pair, dFdy = bottom - top; a partner outside the image is the pixel itself
     const bool rightOk = ((x | 1) < W), bottomOk = ((y | 1) < Hh);
@@ -332,13 +333,17 @@ PLAIN_PASS(launch_gbufferShading, "gbufferShading.comp") {
     if (p.gbuffer.w != p.colorOut.w || p.gbuffer.h != p.colorOut.h) { c.fail("gbufferShading.comp: G-buffer and colour target extents differ"); return; }
     if (p.sunShadowCascadeCount < 1 || p.sunShadowCascadeCount > 4) { c.fail("gbufferShading.comp: cascade count must be 1..4"); return; }
     const int limX = (int)c.exec->dispatch[0] * 8, limY = (int)c.exec->dispatch[1] * 8;
-    dim3 grid(ceilDiv(p.colorOut.w, 32), ceilDiv(p.colorOut.h, 8));
+    int y0, y1;
+    c.window(std::min(p.colorOut.h, limY), y0, y1);
+    if (y0 % 2 != 0) { c.fail("gbufferShading.comp: row window must start at an even row (2x2 quads)"); return; }
+    if (y1 <= y0) return;
+    dim3 grid(ceilDiv(p.colorOut.w, 32), ceilDiv((unsigned)(y1 - y0), 8));
     if (p.diffuseBRDF == 2 && p.directMultiscatterBRDF == 0 && p.geometricAA && p.indirectLightingTech == 0)
-        PLAIN_LAUNCH(c, (gbufferShadingKernel<2, 0, 1, 0>), grid, 256, 0, p, limX, limY);
+        PLAIN_LAUNCH(c, (gbufferShadingKernel<2, 0, 1, 0>), grid, 256, 0, p, limX, y1, y0);
     else if (p.diffuseBRDF == 2 && p.directMultiscatterBRDF == 0 && p.geometricAA && p.indirectLightingTech == 1)
-        PLAIN_LAUNCH(c, (gbufferShadingKernel<2, 0, 1, 1>), grid, 256, 0, p, limX, limY);
+        PLAIN_LAUNCH(c, (gbufferShadingKernel<2, 0, 1, 1>), grid, 256, 0, p, limX, y1, y0);
     else
-        PLAIN_LAUNCH(c, (gbufferShadingKernel<-1, -1, -1, -1>), grid, 256, 0, p, limX, limY);
+        PLAIN_LAUNCH(c, (gbufferShadingKernel<-1, -1, -1, -1>), grid, 256, 0, p, limX, y1, y0);
 }
 
 // ---------------- brdfLut.comp:20-101 (startup / on diffuse-BRDF change) ----------------

@@ -62,7 +62,8 @@ class PassResources(C.Structure):
 
 
 class ComputePassExecution(C.Structure):
-    _fields_ = [("pass_", u32), ("resources", PassResources), ("push_constants", C.c_void_p), ("push_constant_size", u32), ("dispatch_count", u32 * 3)]
+    _fields_ = [("pass_", u32), ("resources", PassResources), ("push_constants", C.c_void_p), ("push_constant_size", u32), ("dispatch_count", u32 * 3),
+                ("row_begin", u32), ("row_end", u32), ("shard_phase", u32)]
 
 
 class PassTime(C.Structure):
@@ -85,11 +86,19 @@ class FrontendSettings(C.Structure):
                 ("trace_influence_radius", f32), ("taa_enabled", i32), ("taa_use_clipping", i32), ("taa_use_motion_vector_dilation", i32),
                 ("taa_history_sampling_tech", i32), ("taa_filter_use_tonemapping", i32), ("bloom_enabled", i32), ("bloom_strength", f32),
                 ("bloom_radius", f32), ("sun_direction_deg", f32 * 2), ("camera_fov_deg", f32), ("camera_near", f32), ("camera_far", f32),
-                ("noise_seed", u32)]
+                ("noise_seed", u32), ("shard_rank", u32), ("shard_count", u32)]
 
 
 class FrameInputs(C.Structure):
-    _fields_ = [("depth", C.c_void_p), ("motion", C.c_void_p), ("normal", C.c_void_p), ("gbuffer", C.c_void_p), ("shadow_maps", C.c_void_p * 4), ("async_upload", i32)]
+    _fields_ = [("depth", C.c_void_p), ("motion", C.c_void_p), ("normal", C.c_void_p), ("gbuffer", C.c_void_p), ("shadow_maps", C.c_void_p * 4), ("async_upload", i32), ("row_begin", u32), ("row_end", u32)]
+
+
+EXCHANGE_NONE, EXCHANGE_ALLREDUCE_SUM_U32, EXCHANGE_ALLGATHER_ROWS, EXCHANGE_HALO_ROWS = 0, 1, 2, 3
+
+
+class Exchange(C.Structure):  # include/plain_frontend.h plain_exchange
+    _fields_ = [("kind", u32), ("n_images", u32), ("device_ptr", C.c_void_p * 4), ("row_pitch_bytes", u32 * 4), ("rows", u32 * 4), ("row_divisor", u32 * 4),
+                ("halo_rows", u32), ("element_count", u32), ("name", C.c_char * 32)]
 
 
 class CameraExtrinsic(C.Structure):
@@ -101,11 +110,12 @@ BACKEND_SYMBOLS = [
     "get_image_description", "get_image_global_texture_array_index", "create_uniform_buffer", "create_storage_buffer", "create_sampler",
     "get_swapchain_input_image", "create_compute_pass", "update_compute_pass_shader_description", "set_global_descriptor_set_resources",
     "new_frame", "set_compute_pass_execution", "prepare_for_drawcall_recording", "set_uniform_buffer_data", "set_storage_buffer_data",
-    "render_frame", "wait_for_gpu_idle", "get_renderpass_timings", "set_timing_enabled", "write_image", "read_image", "read_storage_buffer",
-    "write_image_async", "read_image_async", "get_image_device_pointer", "get_storage_buffer_device_pointer", "get_last_frame_launch_count",
+    "render_frame", "submit_recorded_passes", "wait_for_gpu_idle", "get_renderpass_timings", "set_timing_enabled", "write_image", "read_image", "read_storage_buffer",
+    "write_image_async", "read_image_async", "write_image_rows_async", "read_image_rows_async", "get_image_device_pointer", "get_storage_buffer_device_pointer", "get_last_frame_launch_count",
     "set_graph_replay_enabled", "get_stream"]
 FRONTEND_SYMBOLS = [
-    "default_settings", "create", "destroy", "last_error", "backend", "register_sdf_mesh", "set_scene", "render_frame", "read_output", "get_image",
+    "default_settings", "create", "destroy", "last_error", "backend", "register_sdf_mesh", "set_scene", "render_frame", "begin_frame", "run_segment", "shard_band",
+    "read_output_rows", "read_output", "get_image",
     "get_storage_buffer", "get_global_shader_info", "get_resolve_weights", "set_exposure", "synthetic_scene_create", "synthetic_scene_destroy",
     "synthetic_scene_attach", "synthetic_scene_render_inputs"]
 
@@ -140,6 +150,7 @@ class Api:
             self.f["destroy"].restype = None
             self.f["default_settings"].restype = None
             self.f["synthetic_scene_destroy"].restype = None
+            self.f["shard_band"].restype = None
 
 
 class Backend:
@@ -232,7 +243,7 @@ class Backend:
     def new_frame(self):
         self._check(self.api.b["new_frame"](self.ctx), "new_frame")
 
-    def set_compute_pass_execution(self, pass_, dispatch, sampled=(), storage=(), storage_buffers=(), uniform_buffers=(), push=None):
+    def set_compute_pass_execution(self, pass_, dispatch, sampled=(), storage=(), storage_buffers=(), uniform_buffers=(), push=None, rows=None, shard_phase=0):
         """sampled/storage: [(handle, mip, binding)]; storage_buffers: [(handle, read_only, binding)]; uniform_buffers: [(handle, binding)]"""
         e = ComputePassExecution()
         e.pass_ = pass_
@@ -250,6 +261,9 @@ class Backend:
             e.push_constants, e.push_constant_size = pc.ctypes.data, pc.nbytes
         for i in range(3):
             e.dispatch_count[i] = dispatch[i] if i < len(dispatch) else 1
+        if rows is not None:
+            e.row_begin, e.row_end = rows
+        e.shard_phase = shard_phase
         self._check(self.api.b["set_compute_pass_execution"](self.ctx, C.byref(e)), "set_compute_pass_execution")
 
     def set_uniform_buffer_data(self, h, data):
@@ -336,6 +350,32 @@ class Frontend:
     def _check(self, rc, what):
         if rc:
             raise ApiError("%s: %s" % (what, self.api.f["last_error"](self.fe).decode()))
+
+    def _inputs(self, depth, motion, normal, gbuffer, shadow_maps, async_upload, rows):
+        fi = FrameInputs()
+        fi.depth, fi.motion, fi.normal, fi.gbuffer = _ptr(depth), _ptr(motion), _ptr(normal), _ptr(gbuffer)
+        for i in range(4):
+            fi.shadow_maps[i] = _ptr(shadow_maps[i]) if shadow_maps is not None and i < len(shadow_maps) and shadow_maps[i] is not None else None
+        fi.async_upload = int(async_upload)
+        if rows is not None:
+            fi.row_begin, fi.row_end = rows
+        return fi
+
+    def begin_frame(self, cam, time, delta_time, depth=None, motion=None, normal=None, gbuffer=None, shadow_maps=None, async_upload=False, rows=None):
+        """Row-sharded frames: records the frame; then call run_segment() until it returns None, performing each returned Exchange."""
+        fi = self._inputs(depth, motion, normal, gbuffer, shadow_maps, async_upload, rows)
+        self._check(self.api.f["begin_frame"](self.fe, C.byref(cam), f32(time), f32(delta_time), C.byref(fi)), "begin_frame")
+
+    def run_segment(self):
+        x = Exchange()
+        rc = self.api.f["run_segment"](self.fe, C.byref(x))
+        if rc < 0:
+            self._check(1, "run_segment")
+        return x if rc == 1 else None
+
+    def read_output_rows(self, out, rows, async_pinned=False):
+        self._check(self.api.f["read_output_rows"](self.fe, _ptr(out), u32(rows[0]), u32(rows[1]), i32(int(async_pinned))), "read_output_rows")
+        return out
 
     def render_frame(self, cam, time, delta_time, depth=None, motion=None, normal=None, gbuffer=None, shadow_maps=None, async_upload=False):
         fi = FrameInputs()

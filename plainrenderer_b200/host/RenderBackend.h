@@ -3,10 +3,13 @@
 // the frontend/technique mirrors below read like the reference callers. Every method is one C-ABI call; failures
 // throw std::runtime_error carrying plain_last_error() (the reference prints and throws, RenderBackend.cpp:442-445).
 #pragma once
+#include <cstdio>
+#include <cstring>
 #include <stdexcept>
 #include <string>
 #include <vector>
 #include "plain_b200.h"
+#include "plain_frontend.h"
 
 typedef plain_image_handle ImageHandle;
 struct RenderPassHandle { uint32_t index = PLAIN_INVALID_INDEX; };
@@ -44,6 +47,7 @@ struct ComputePassExecution {
     RenderPassExecution genericInfo;
     std::vector<char> pushConstants;
     uint32_t dispatchCount[3] = {1, 1, 1};
+    uint32_t rowBegin = 0, rowEnd = 0, shardPhase = 0;  // row sharding (plain_compute_pass_execution), 0/0/0 = whole pass
 };
 struct SpecialisationConstant { uint32_t location; std::vector<char> data; };
 struct ShaderDescription { std::string srcPathRelative; std::vector<SpecialisationConstant> specialisationConstants; };
@@ -54,8 +58,41 @@ inline std::vector<char> dataToCharArray(const void* data, size_t size) {  // Ge
     return std::vector<char>(p, p + size);
 }
 
+// what a row-sharded frame is made of: compute pass executions and the exchanges between them
+struct ExchangeRequest {
+    uint32_t kind = PLAIN_EXCHANGE_NONE;
+    std::vector<ImageHandle> images;
+    std::vector<uint32_t> mips, divisors;
+    uint32_t buffer = PLAIN_INVALID_INDEX, elementCount = 0, haloRows = 0;
+    std::string name;
+};
+struct ShardInfo {
+    uint32_t rank = 0, count = 1, fullHeight = 0, y0 = 0, y1 = 0;  // [y0, y1): full-resolution rows of this rank
+    bool active() const { return count > 1; }
+};
+inline void shardBandRows(uint32_t fullHeight, uint32_t count, uint32_t rank, uint32_t* y0, uint32_t* y1) {
+    const uint32_t unit = 64, units = (fullHeight + unit - 1) / unit;  // 64 rows: 32x32 tiles at half resolution, 8-pixel froxel rows, 4 fused HiZ levels
+    const uint32_t u0 = (uint32_t)((uint64_t)rank * units / count), u1 = (uint32_t)((uint64_t)(rank + 1) * units / count);
+    *y0 = u0 * unit < fullHeight ? u0 * unit : fullHeight;
+    *y1 = u1 * unit < fullHeight ? u1 * unit : fullHeight;
+}
+
 class RenderBackend {
 public:
+    // ---- row sharding helpers (no counterpart in the reference) ----
+    ShardInfo shard;
+    // rows of an image whose height is fullHeight / divisor (or tiles of `divisor` rows) that belong to this rank, optionally
+    // extended by `extend` rows on both sides (overlapped computation instead of a halo exchange); {0, 0} when not sharded
+    void band(uint32_t divisor, uint32_t rows, uint32_t extend, uint32_t* a, uint32_t* b) const {
+        if (!shard.active()) { *a = 0; *b = 0; return; }
+        uint32_t lo = shard.y0 / divisor, hi = (shard.y1 + divisor - 1) / divisor;
+        lo = lo > extend ? lo - extend : 0;
+        hi = hi + extend < rows ? hi + extend : rows;
+        if (lo > rows) lo = rows;
+        *a = lo; *b = hi > lo ? hi : lo;
+        if (*a == 0 && *b == 0) *b = 0;
+    }
+
     void setup(int device, uint32_t width, uint32_t height) { if (PLAIN_FN(backend_create)(device, width, height, &m_ctx)) throw std::runtime_error("backend_create failed"); }
     void shutdown() { if (m_ctx) PLAIN_FN(backend_destroy)(m_ctx); m_ctx = nullptr; }
     plain_ctx* context() const { return m_ctx; }
@@ -63,6 +100,48 @@ public:
     void resizeImages(const std::vector<ImageHandle>& images, uint32_t w, uint32_t h) { check(PLAIN_FN(resize_images)(m_ctx, images.data(), (uint32_t)images.size(), w, h)); }
     void newFrame() { check(PLAIN_FN(new_frame)(m_ctx)); }
     void setComputePassExecution(const ComputePassExecution& e) {
+        if (m_recording) { m_recorded.push_back(Recorded{false, e, ExchangeRequest()}); return; }
+        sendExecution(e);
+    }
+    void addExchange(const ExchangeRequest& x) { if (m_recording && shard.active()) m_recorded.push_back(Recorded{true, ComputePassExecution(), x}); }
+    // deferred frames: executions are kept on the host and sent segment by segment (run until the next exchange)
+    void beginRecording() { m_recording = true; m_recorded.clear(); m_cursor = 0; }
+    void endRecording() { m_recording = false; }
+    bool hasRecorded() const { return m_cursor < m_recorded.size(); }
+    // sends executions up to the next exchange and submits them; returns true and fills `out` when an exchange is pending
+    bool runSegment(plain_exchange* out) {
+        while (m_cursor < m_recorded.size()) {
+            const Recorded& r = m_recorded[m_cursor++];
+            if (!r.isExchange) { sendExecution(r.exec); continue; }
+            check(PLAIN_FN(submit_recorded_passes)(m_ctx));
+            std::memset(out, 0, sizeof(*out));
+            out->kind = r.exchange.kind;
+            out->halo_rows = r.exchange.haloRows;
+            out->element_count = r.exchange.elementCount;
+            std::snprintf(out->name, sizeof(out->name), "%s", r.exchange.name.c_str());
+            if (r.exchange.kind == PLAIN_EXCHANGE_ALLREDUCE_SUM_U32) {
+                size_t size = 0;
+                check(PLAIN_FN(get_storage_buffer_device_pointer)(m_ctx, r.exchange.buffer, &out->device_ptr[0], &size));
+                out->n_images = 1;
+            } else {
+                out->n_images = (uint32_t)r.exchange.images.size();
+                for (uint32_t i = 0; i < out->n_images && i < 4; i++) {
+                    size_t size = 0;
+                    check(PLAIN_FN(get_image_device_pointer)(m_ctx, r.exchange.images[i], r.exchange.mips[i], &out->device_ptr[i], &size));
+                    ImageDescription d = getImageDescription(r.exchange.images[i]);
+                    uint32_t rows = d.height >> r.exchange.mips[i];
+                    if (rows < 1) rows = 1;
+                    out->rows[i] = rows;
+                    out->row_pitch_bytes[i] = (uint32_t)(size / rows);
+                    out->row_divisor[i] = r.exchange.divisors[i];
+                }
+            }
+            return true;
+        }
+        check(PLAIN_FN(render_frame)(m_ctx, 1));
+        return false;
+    }
+    void sendExecution(const ComputePassExecution& e) {
         std::vector<plain_sampler_resource> sm;
         std::vector<plain_storage_buffer_resource> sb;
         std::vector<plain_uniform_buffer_resource> ub;
@@ -73,6 +152,7 @@ public:
         x.push_constants = e.pushConstants.empty() ? nullptr : e.pushConstants.data();
         x.push_constant_size = (uint32_t)e.pushConstants.size();
         for (int i = 0; i < 3; i++) x.dispatch_count[i] = e.dispatchCount[i];
+        x.row_begin = e.rowBegin; x.row_end = e.rowEnd; x.shard_phase = e.shardPhase;
         check(PLAIN_FN(set_compute_pass_execution)(m_ctx, &x));
     }
     void prepareForDrawcallRecording() { check(PLAIN_FN(prepare_for_drawcall_recording)(m_ctx)); }
@@ -109,6 +189,8 @@ public:
     // additions of this build (inputs the out-of-scope raster passes would have written, read-back)
     void writeImage(ImageHandle h, uint32_t mip, const void* data, size_t size) { check(PLAIN_FN(write_image)(m_ctx, h, mip, data, size)); }
     void writeImageAsync(ImageHandle h, uint32_t mip, const void* data, size_t size) { check(PLAIN_FN(write_image_async)(m_ctx, h, mip, data, size)); }
+    void writeImageRowsAsync(ImageHandle h, uint32_t mip, uint32_t r0, uint32_t r1, const void* data, size_t size) { check(PLAIN_FN(write_image_rows_async)(m_ctx, h, mip, r0, r1, data, size)); }
+    void readImageRowsAsync(ImageHandle h, uint32_t mip, uint32_t r0, uint32_t r1, void* out, size_t size) { check(PLAIN_FN(read_image_rows_async)(m_ctx, h, mip, r0, r1, out, size)); }
     void readImage(ImageHandle h, uint32_t mip, void* out, size_t size) { check(PLAIN_FN(read_image)(m_ctx, h, mip, out, size)); }
     void readImageAsync(ImageHandle h, uint32_t mip, void* out, size_t size) { check(PLAIN_FN(read_image_async)(m_ctx, h, mip, out, size)); }
     void waitForGPUIdle() { check(PLAIN_FN(wait_for_gpu_idle)(m_ctx)); }
@@ -134,6 +216,10 @@ private:
         x.storage_images = st.data(); x.n_storage_images = (uint32_t)st.size();
     }
     plain_ctx* m_ctx = nullptr;
+    struct Recorded { bool isExchange; ComputePassExecution exec; ExchangeRequest exchange; };
+    std::vector<Recorded> m_recorded;
+    size_t m_cursor = 0;
+    bool m_recording = false;
 };
 
 inline ImageDescription imageDesc2D(uint32_t w, uint32_t h, plain_image_format f, uint32_t usage, plain_mip_count mips = PLAIN_MIPS_ONE, uint32_t manualMips = 1) {

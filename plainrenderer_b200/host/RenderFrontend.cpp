@@ -14,6 +14,14 @@ static const uint32_t noiseTextureCount = 4, noiseTextureWidth = 32, noiseTextur
 static const float histogramMinValue = 0.001f, histogramMaxValue = 200000.f;  // createHistogramSettings :1063-1073
 
 static uint32_t ceilDiv(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
+static void setRows(RenderBackend& b, ComputePassExecution& e, uint32_t divisor, uint32_t rows, uint32_t extend = 0) { b.band(divisor, rows, extend, &e.rowBegin, &e.rowEnd); }
+static ExchangeRequest gatherRows(const char* name, std::initializer_list<ImageHandle> images, uint32_t mip, uint32_t divisor) {
+    ExchangeRequest x;
+    x.kind = PLAIN_EXCHANGE_ALLGATHER_ROWS;
+    x.name = name;
+    for (ImageHandle h : images) { x.images.push_back(h); x.mips.push_back(mip); x.divisors.push_back(divisor); }
+    return x;
+}
 
 // ---- small host utilities (MathUtils.cpp, sdfUtilities.cpp, ViewFrustum.cpp) ----
 static float radicalInverseBase2(uint32_t in) {
@@ -122,6 +130,12 @@ void RenderFrontend::setup(int device, uint32_t width, uint32_t height, uint32_t
     a.mieScatteringExponent = 0.76f;
 
     backend.setup(device, width, height);
+    if (m_shardCount > 1) {
+        if ((height + 63) / 64 < m_shardCount) throw std::runtime_error("row sharding: fewer 64-row units than ranks");
+        if (width % 16 != 0 || height % 16 != 0) throw std::runtime_error("row sharding needs a resolution that is a multiple of 16 (four HiZ levels reduced from a rank's own rows)");
+        backend.shard.rank = m_shardRank; backend.shard.count = m_shardCount; backend.shard.fullHeight = height;
+        shardBandRows(height, m_shardCount, m_shardRank, &backend.shard.y0, &backend.shard.y1);
+    }
     // the 8 global samplers, RenderFrontend.cpp:1300-1397 (binding order global.inc:35-42)
     const plain_sampler_desc descs[8] = {
         {PLAIN_SAMPLER_LINEAR, PLAIN_WRAP_REPEAT, 1, 8.f, PLAIN_BORDER_WHITE, 20},   // anisotropicRepeat
@@ -153,6 +167,7 @@ void RenderFrontend::setup(int device, uint32_t width, uint32_t height, uint32_t
     backend.prepareForDrawcallRecording();
     backend.renderFrame(false);
 }
+
 
 void RenderFrontend::shutdown() { backend.shutdown(); }
 
@@ -300,7 +315,9 @@ void RenderFrontend::markNewFrame(float time, float deltaTime) {
 
 void RenderFrontend::prepareNewFrame() {
     backend.newFrame();
+    backend.beginRecording();  // executions are kept on the host and sent segment by segment in renderFrameSegment
     prepareRenderpasses();
+    backend.endRecording();
     backend.prepareForDrawcallRecording();
 }
 
@@ -399,12 +416,22 @@ void RenderFrontend::updateGlobalShaderInfo() {
 void RenderFrontend::renderScene(const std::vector<RenderObject>& scene) { m_sdfGi.updateSDFScene(backend, scene, m_frontendMeshes); }
 
 void RenderFrontend::renderFrame() {  // RenderFrontend.cpp:685-705
-    m_globalShaderInfo.frameIndex++;
-    m_globalShaderInfo.frameIndexMod2 = m_globalShaderInfo.frameIndex % 2;
-    m_globalShaderInfo.frameIndexMod3 = m_globalShaderInfo.frameIndex % 3;
-    m_globalShaderInfo.frameIndexMod4 = m_globalShaderInfo.frameIndex % 4;
-    backend.renderFrame(true);
+    plain_exchange x;
+    while (renderFrameSegment(&x)) {}  // an unsharded frame has no exchanges: one segment
+}
+// runs the recorded passes up to the next exchange (row sharding); returns false when the frame has been submitted completely
+bool RenderFrontend::renderFrameSegment(plain_exchange* pending) {
+    if (!m_frameOpen) {
+        m_frameOpen = true;
+        m_globalShaderInfo.frameIndex++;
+        m_globalShaderInfo.frameIndexMod2 = m_globalShaderInfo.frameIndex % 2;
+        m_globalShaderInfo.frameIndexMod3 = m_globalShaderInfo.frameIndex % 3;
+        m_globalShaderInfo.frameIndexMod4 = m_globalShaderInfo.frameIndex % 4;
+    }
+    if (backend.runSegment(pending)) return true;
     m_globalShaderInfo.cameraCut = 0;
+    m_frameOpen = false;
+    return false;
 }
 
 uint32_t RenderFrontend::registerSdfMesh(const uint16_t* texels, uint32_t rx, uint32_t ry, uint32_t rz, const hm::AABB& localBB, hm::Vec3 meanAlbedo) {
@@ -427,6 +454,7 @@ void RenderFrontend::computeColorBufferHistogram(ImageHandle lastFrameColor) {
         e.genericInfo.resources.sampledImages = {ImageResource(lastFrameColor, 0, 2)};
         e.dispatchCount[0] = ceilDiv(m_screenWidth, histogramTileSizeX);
         e.dispatchCount[1] = ceilDiv(m_screenHeight, histogramTileSizeY);
+        setRows(backend, e, histogramTileSizeY, e.dispatchCount[1]);  // a rank bins the tile rows of its own band
         backend.setComputePassExecution(e);
     }
     {
@@ -442,8 +470,20 @@ void RenderFrontend::computeColorBufferHistogram(ImageHandle lastFrameColor) {
         e.genericInfo.resources.storageBuffers = {histogramPerTileResource, histogramResource};
         e.dispatchCount[0] = ceilDiv(m_screenWidth, histogramTileSizeX) * ceilDiv(m_screenHeight, histogramTileSizeY);
         e.dispatchCount[1] = ceilDiv(nHistogramBins, 64);
+        if (backend.shard.active()) {  // sums the rank's own tiles; the 128 partial counters are all-reduced below
+            uint32_t a, b;
+            backend.band(histogramTileSizeY, ceilDiv(m_screenHeight, histogramTileSizeY), 0, &a, &b);
+            e.rowBegin = a * ceilDiv(m_screenWidth, histogramTileSizeX);
+            e.rowEnd = b * ceilDiv(m_screenWidth, histogramTileSizeX);
+        }
         backend.setComputePassExecution(e);
     }
+    ExchangeRequest x;
+    x.kind = PLAIN_EXCHANGE_ALLREDUCE_SUM_U32;
+    x.name = "histogram";
+    x.buffer = m_histogramBuffer.index;
+    x.elementCount = nHistogramBins;
+    backend.addExchange(x);
 }
 
 void RenderFrontend::computeExposure() {
@@ -469,7 +509,22 @@ void RenderFrontend::computeDepthPyramid(ImageHandle depthBuffer) {
         const uint32_t mipLevel = i >= unusedMipCount ? i - unusedMipCount : 0;
         e.genericInfo.resources.storageImages.push_back(ImageResource(m_minMaxDepthPyramid, mipLevel, i));
     }
-    backend.setComputePassExecution(e);
+    if (!backend.shard.active()) {
+        backend.setComputePassExecution(e);
+        return;
+    }
+    // sharded: the levels reduced from a rank's own depth rows (up to four: band boundaries are multiples of 64 rows), then
+    // an all-gather of the last of them, then the remaining small levels on every rank
+    uint32_t fused = 0, sw = m_screenWidth, sh = m_screenHeight;
+    for (uint32_t k = 0; k < mipCount && k < 4 && sw % 2 == 0 && sh % 2 == 0 && sw >= 2 && sh >= 2; k++) { fused = k + 1; sw /= 2; sh /= 2; }
+    ComputePassExecution local = e;
+    local.shardPhase = 1;
+    setRows(backend, local, 2, height);
+    backend.setComputePassExecution(local);
+    backend.addExchange(gatherRows("hiz", {m_minMaxDepthPyramid}, fused - 1, 2u << (fused - 1)));
+    ComputePassExecution rest = e;
+    rest.shardPhase = 2;
+    backend.setComputePassExecution(rest);
 }
 
 void RenderFrontend::computeSunLightMatrices() {
@@ -493,7 +548,9 @@ void RenderFrontend::downscaleDepth(const FrameRenderTargets& current) {
     e.dispatchCount[1] = ceilDiv(m_screenHeight / 2, 8);
     e.genericInfo.resources.storageImages = {ImageResource(m_depthHalfRes, 0, 0)};
     e.genericInfo.resources.sampledImages = {ImageResource(current.depthBuffer, 0, 1)};
+    setRows(backend, e, 2, m_screenHeight / 2);
     backend.setComputePassExecution(e);
+    backend.addExchange(gatherRows("depthHalf", {m_depthHalfRes}, 0, 2));  // the spatial GI filter reads it at arbitrary rows
 }
 
 // renderForwardShading :894-929 + Sky::renderSky (Sky.cpp:318-352), as one full-screen pass over the G-buffer.
@@ -516,6 +573,7 @@ void RenderFrontend::shadeGBuffer(ImageHandle colorTarget) {
     e.pushConstants = dataToCharArray(&sun, sizeof(sun));
     e.dispatchCount[0] = ceilDiv(m_screenWidth, 8);
     e.dispatchCount[1] = ceilDiv(m_screenHeight, 8);
+    setRows(backend, e, 1, m_screenHeight, 8);  // 8 extra rows on both sides: the TAA resolve (+-4 rows, for bloom) reads +-2 rows of colour
     backend.setComputePassExecution(e);
 }
 
@@ -526,6 +584,7 @@ void RenderFrontend::computeTonemapping(ImageHandle src) {
     e.genericInfo.resources.sampledImages = {ImageResource(src, 0, 1)};
     e.dispatchCount[0] = ceilDiv(m_screenWidth, 8);
     e.dispatchCount[1] = ceilDiv(m_screenHeight, 8);
+    setRows(backend, e, 1, m_screenHeight);
     backend.setComputePassExecution(e);
     m_lastTonemapSource = src;
 }

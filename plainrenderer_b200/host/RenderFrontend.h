@@ -168,6 +168,8 @@ public:
     void prepareForDrawcalls();                      // updateGlobalShaderInfo
     void renderScene(const std::vector<RenderObject>& scene);
     void renderFrame();
+    bool renderFrameSegment(plain_exchange* pending);  // row-sharded frames: run up to the next exchange
+    uint32_t m_shardRank = 0, m_shardCount = 1;
 
     uint32_t registerSdfMesh(const uint16_t* r16fTexels, uint32_t rx, uint32_t ry, uint32_t rz, const hm::AABB& localBB, hm::Vec3 meanAlbedo);
     const FrameRenderTargets& currentTargets() const { return m_frameRenderTargets[m_sceneRenderTargetIndex]; }
@@ -218,6 +220,7 @@ private:
     void computeSinglePassMipChainDispatchCount(uint32_t w, uint32_t h, uint32_t mipCount, uint32_t maxMipCount, uint32_t out[2]) const;
 
     CameraExtrinsic m_cameraExtrinsic;
+    bool m_frameOpen = false;
     hm::Mat4 m_viewProjectionMatrix = hm::Mat4::zero();
     ViewFrustum m_cameraFrustum;
     float m_time = 0.f, m_deltaTime = 0.016f;

@@ -6,6 +6,15 @@
 
 static const uint32_t SS = PLAIN_USAGE_SAMPLED | PLAIN_USAGE_STORAGE;
 static uint32_t ceilDivU(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
+static void setRows(RenderBackend& b, ComputePassExecution& e, uint32_t divisor, uint32_t rows, uint32_t extend = 0) { b.band(divisor, rows, extend, &e.rowBegin, &e.rowEnd); }
+static ExchangeRequest exchangeRows(uint32_t kind, const char* name, std::initializer_list<ImageHandle> images, uint32_t mip, uint32_t divisor, uint32_t halo = 0) {
+    ExchangeRequest x;
+    x.kind = kind;
+    x.name = name;
+    x.haloRows = halo;
+    for (ImageHandle h : images) { x.images.push_back(h); x.mips.push_back(mip); x.divisors.push_back(divisor); }
+    return x;
+}
 template <typename T> static SpecialisationConstant specConst(uint32_t location, const T& v) { return SpecialisationConstant{location, dataToCharArray(&v, sizeof(T))}; }
 static RenderPassHandle makePass(RenderBackend& b, const char* name, const char* shader, std::vector<SpecialisationConstant> consts = {}) {
     ComputePassDescription d;
@@ -103,7 +112,11 @@ void SDFGI::diffuseSDFTrace(RenderBackend& b, const SDFTraceDependencies& d, con
     e.genericInfo.resources.uniformBuffers = {UniformBufferResource(m_sdfTraceInfluenceRangeBuffer, 8)};
     e.dispatchCount[0] = ceilDivU(target.width, 8);
     e.dispatchCount[1] = ceilDivU(target.height, 8);
+    const uint32_t div = s.halfResTrace ? 2 : 1;  // the GI buffers' rows per full-resolution row
+    setRows(b, e, div, e.dispatchCount[1] * 8);
     b.setComputePassExecution(e);
+    // the spatial filter gathers in a world-space disc (no bound in pixels): every rank needs the whole traced image
+    b.addExchange(exchangeRows(PLAIN_EXCHANGE_ALLGATHER_ROWS, "giTrace", {m_indirectDiffuse_Y_SH[0], m_indirectDiffuse_CoCg[0]}, 0, div));
 }
 
 void SDFGI::filterIndirectDiffuse(RenderBackend& b, const SDFTraceDependencies& d, const SDFTraceSettings& s, const FrameIndex& fi) const {  // SDFGI.cpp:421-536
@@ -111,6 +124,7 @@ void SDFGI::filterIndirectDiffuse(RenderBackend& b, const SDFTraceDependencies& 
     const ImageHandle depthSrc = s.halfResTrace ? d.depthHalfRes : d.currentFrame.depthBuffer;
     const ImageDescription target = b.getImageDescription(m_indirectDiffuse_Y_SH[1]);
     const uint32_t gx = ceilDivU(target.width, 8), gy = ceilDivU(target.height, 8);
+    const uint32_t div = s.halfResTrace ? 2 : 1;
     {   // spatial filter on input
         ComputePassExecution e;
         e.genericInfo.handle = m_indirectDiffuseFilterSpatialPass[0];
@@ -118,7 +132,10 @@ void SDFGI::filterIndirectDiffuse(RenderBackend& b, const SDFTraceDependencies& 
         e.genericInfo.resources.sampledImages = {ImageResource(m_indirectDiffuse_Y_SH[0], 0, 2), ImageResource(m_indirectDiffuse_CoCg[0], 0, 3), ImageResource(depthSrc, 0, 4),
                                                  ImageResource(d.worldSpaceNormals, 0, 5)};
         e.dispatchCount[0] = gx; e.dispatchCount[1] = gy;
+        setRows(b, e, div, target.height);
         b.setComputePassExecution(e);
+        // the temporal filter reads its input bilinearly at the pixel's own position: one row beyond the band
+        b.addExchange(exchangeRows(PLAIN_EXCHANGE_HALO_ROWS, "giSpatial0", {m_indirectDiffuse_Y_SH[1], m_indirectDiffuse_CoCg[1]}, 0, div, 2));
     }
     {   // temporal filter
         ComputePassExecution e;
@@ -129,7 +146,9 @@ void SDFGI::filterIndirectDiffuse(RenderBackend& b, const SDFTraceDependencies& 
                                                  ImageResource(m_indirectDiffuseHistory_Y_SH[0], 0, 6), ImageResource(m_indirectDiffuseHistory_CoCg[0], 0, 7),
                                                  ImageResource(d.currentFrame.motionBuffer, 0, 8), ImageResource(d.previousFrame.motionBuffer, 0, 9)};
         e.dispatchCount[0] = gx; e.dispatchCount[1] = gy;
+        setRows(b, e, div, target.height);
         b.setComputePassExecution(e);
+        b.addExchange(exchangeRows(PLAIN_EXCHANGE_ALLGATHER_ROWS, "giTemporal", {m_indirectDiffuseHistory_Y_SH[1], m_indirectDiffuseHistory_CoCg[1]}, 0, div));  // input of the second spatial filter
     }
     {   // spatial filter on history
         ComputePassExecution e;
@@ -138,7 +157,10 @@ void SDFGI::filterIndirectDiffuse(RenderBackend& b, const SDFTraceDependencies& 
         e.genericInfo.resources.sampledImages = {ImageResource(m_indirectDiffuseHistory_Y_SH[1], 0, 2), ImageResource(m_indirectDiffuseHistory_CoCg[1], 0, 3), ImageResource(depthSrc, 0, 4),
                                                  ImageResource(d.worldSpaceNormals, 0, 5)};
         e.dispatchCount[0] = gx; e.dispatchCount[1] = gy;
+        setRows(b, e, div, target.height);
         b.setComputePassExecution(e);
+        // read by the upscale (+-1 row) and, reprojected, by the next frame's temporal filter
+        b.addExchange(exchangeRows(PLAIN_EXCHANGE_ALLGATHER_ROWS, "giSpatial1", {m_indirectDiffuseHistory_Y_SH[0], m_indirectDiffuseHistory_CoCg[0]}, 0, div));
     }
     if (s.halfResTrace) {  // upscale
         ComputePassExecution e;
@@ -149,6 +171,7 @@ void SDFGI::filterIndirectDiffuse(RenderBackend& b, const SDFTraceDependencies& 
         const ImageDescription full = b.getImageDescription(m_indirectLightingFullRes_Y_SH);
         e.dispatchCount[0] = ceilDivU(full.width, 8);
         e.dispatchCount[1] = ceilDivU(full.height, 8);
+        setRows(b, e, 1, full.height, 8);  // the shading pass runs 8 rows beyond the band
         b.setComputePassExecution(e);
     }
 }
@@ -207,7 +230,10 @@ void TAA::computeTemporalFilter(RenderBackend& b, ImageHandle colorSrc, const Fr
     const ImageDescription td = b.getImageDescription(target);
     e.dispatchCount[0] = ceilDivU(td.width, 8);
     e.dispatchCount[1] = ceilDivU(td.height, 8);
+    setRows(b, e, 1, td.height, 4);  // 4 rows beyond the band: the first bloom downsample reads +-3 rows of the resolved image
     b.setComputePassExecution(e);
+    // next frame's resolve reads the history at reprojected positions
+    b.addExchange(exchangeRows(PLAIN_EXCHANGE_ALLGATHER_ROWS, "taaHistory", {m_historyBuffers[(m2 + 1) % 2]}, 0, 1));
 }
 hm::Vec2 TAA::computeProjectionMatrixJitter(const FrameIndex& fi) const {  // TAA.cpp:168-170
     hm::Vec2 h = hammersley2D((uint32_t)fi.mod8());
@@ -396,7 +422,9 @@ void Bloom::computeBloom(RenderBackend& b, ImageHandle targetImage, const BloomS
         e.genericInfo.resources.sampledImages = {ImageResource(i == 0 ? targetImage : downscaleTexture, sourceMip, 1)};
         e.dispatchCount[0] = ceilDivU((uint32_t)mipRes(targetMip, width), 8);
         e.dispatchCount[1] = ceilDivU((uint32_t)mipRes(targetMip, height), 8);
+        if (i == 0) setRows(b, e, 2, (uint32_t)mipRes(1, height));  // mip 1 from the rank's own rows; the small mips below are computed by every rank
         b.setComputePassExecution(e);
+        if (i == 0) b.addExchange(exchangeRows(PLAIN_EXCHANGE_ALLGATHER_ROWS, "bloomMip1", {downscaleTexture}, 1, 2));
     }
     const ImageHandle upscaleTexture = b.createTemporaryImage(desc);
     for (int i = 0; i < (int)m_bloomUpsamplePasses.size(); i++) {
@@ -408,6 +436,7 @@ void Bloom::computeBloom(RenderBackend& b, ImageHandle targetImage, const BloomS
         e.dispatchCount[0] = ceilDivU((uint32_t)mipRes(targetMip, width), 8);
         e.dispatchCount[1] = ceilDivU((uint32_t)mipRes(targetMip, height), 8);
         e.pushConstants = dataToCharArray(&s.radius, sizeof(s.radius));
+        if (targetMip == 0) setRows(b, e, 1, (uint32_t)height, 1);  // +-1 row: applyBloom samples it bilinearly at the pixel centre
         b.setComputePassExecution(e);
     }
     {
@@ -418,6 +447,7 @@ void Bloom::computeBloom(RenderBackend& b, ImageHandle targetImage, const BloomS
         e.dispatchCount[0] = ceilDivU((uint32_t)width, 8);
         e.dispatchCount[1] = ceilDivU((uint32_t)height, 8);
         e.pushConstants = dataToCharArray(&s.strength, sizeof(s.strength));
+        setRows(b, e, 1, (uint32_t)height);
         b.setComputePassExecution(e);
     }
     m_lastDownscaleTexture = downscaleTexture;

@@ -55,6 +55,8 @@ int PLAIN_FE(create)(int device, const plain_frontend_settings* s, plain_fronten
     f.m_cameraIntrinsic.fov = s->camera_fov_deg;
     f.m_cameraIntrinsic.near = s->camera_near;
     f.m_cameraIntrinsic.far = s->camera_far;
+    f.m_shardRank = s->shard_rank;
+    f.m_shardCount = s->shard_count > 1 ? s->shard_count : 1;
     try {
         f.setup(device, s->width, s->height, s->noise_seed);
         f.m_sunDirection.x = s->sun_direction_deg[0];
@@ -99,41 +101,84 @@ int PLAIN_FE(set_scene)(plain_frontend* fe, uint32_t n, const uint32_t* meshes, 
     });
 }
 
+static void beginFrame(plain_frontend* fe, const plain_camera_extrinsic* cam, float time, float deltaTime, const plain_frame_inputs* in) {
+    RenderFrontend& f = fe->fe;
+    f.markNewFrame(time, deltaTime);
+    f.prepareNewFrame();
+    if (in) {  // what depthPrepass / sunShadow / the G-buffer producer write during the frame
+        const FrameRenderTargets& t = f.currentTargets();
+        const size_t W = f.m_screenWidth, H = f.m_screenHeight;
+        const uint32_t r0 = (in->row_begin == 0 && in->row_end == 0) ? 0u : (in->row_begin < H ? in->row_begin : (uint32_t)H);
+        const uint32_t r1 = (in->row_begin == 0 && in->row_end == 0) ? (uint32_t)H : (in->row_end < H ? in->row_end : (uint32_t)H);
+        auto upRows = [&](ImageHandle h, const void* p, size_t bytesPerTexel) {  // rows [r0, r1) of a full-frame host buffer
+            if (!p || r1 <= r0) return;
+            const size_t pitch = W * bytesPerTexel;
+            const unsigned char* src = (const unsigned char*)p + pitch * r0;
+            if (in->async_upload) f.backend.writeImageRowsAsync(h, 0, r0, r1, src, pitch * (r1 - r0));
+            else { f.backend.writeImageRowsAsync(h, 0, r0, r1, src, pitch * (r1 - r0)); f.backend.waitForGPUIdle(); }
+        };
+        auto up = [&](ImageHandle h, const void* p, size_t size) {
+            if (!p) return;
+            if (in->async_upload) f.backend.writeImageAsync(h, 0, p, size);
+            else f.backend.writeImage(h, 0, p, size);
+        };
+        upRows(t.depthBuffer, in->depth, 4);
+        up(t.motionBuffer, in->motion, W * H * 4);
+        upRows(f.m_worldSpaceNormalImage, in->normal, 4);
+        upRows(f.m_gbuffer, in->gbuffer, 16);
+        for (int i = 0; i < 4; i++) up(f.m_shadowMaps[i], in->shadow_maps[i], (size_t)2048 * 2048 * 2);
+    }
+    CameraExtrinsic e;
+    e.position = hm::Vec3(cam->position[0], cam->position[1], cam->position[2]);
+    e.forward = hm::Vec3(cam->forward[0], cam->forward[1], cam->forward[2]);
+    e.right = hm::Vec3(cam->right[0], cam->right[1], cam->right[2]);
+    e.up = hm::Vec3(cam->up[0], cam->up[1], cam->up[2]);
+    f.setCameraExtrinsic(e);
+    f.prepareForDrawcalls();
+    f.renderScene(fe->scene);
+}
 int PLAIN_FE(render_frame)(plain_frontend* fe, const plain_camera_extrinsic* cam, float time, float deltaTime, const plain_frame_inputs* in) {
     FE_TRY(fe, {
-        RenderFrontend& f = fe->fe;
-        f.markNewFrame(time, deltaTime);
-        f.prepareNewFrame();
-        if (in) {  // what depthPrepass / sunShadow / the G-buffer producer write during the frame
-            const FrameRenderTargets& t = f.currentTargets();
-            const size_t px = (size_t)f.m_screenWidth * f.m_screenHeight;
-            auto up = [&](ImageHandle h, const void* p, size_t size) {
-                if (!p) return;
-                if (in->async_upload) f.backend.writeImageAsync(h, 0, p, size);
-                else f.backend.writeImage(h, 0, p, size);
-            };
-            up(t.depthBuffer, in->depth, px * 4);
-            up(t.motionBuffer, in->motion, px * 4);
-            up(f.m_worldSpaceNormalImage, in->normal, px * 4);
-            up(f.m_gbuffer, in->gbuffer, px * 16);
-            for (int i = 0; i < 4; i++) up(f.m_shadowMaps[i], in->shadow_maps[i], (size_t)2048 * 2048 * 2);
-        }
-        CameraExtrinsic e;
-        e.position = hm::Vec3(cam->position[0], cam->position[1], cam->position[2]);
-        e.forward = hm::Vec3(cam->forward[0], cam->forward[1], cam->forward[2]);
-        e.right = hm::Vec3(cam->right[0], cam->right[1], cam->right[2]);
-        e.up = hm::Vec3(cam->up[0], cam->up[1], cam->up[2]);
-        f.setCameraExtrinsic(e);
-        f.prepareForDrawcalls();
-        f.renderScene(fe->scene);
-        f.renderFrame();
+        if (fe->fe.backend.shard.active()) throw std::runtime_error("render_frame: a row-sharded frontend is driven with begin_frame / run_segment");
+        beginFrame(fe, cam, time, deltaTime, in);
+        fe->fe.renderFrame();
     });
+}
+int PLAIN_FE(begin_frame)(plain_frontend* fe, const plain_camera_extrinsic* cam, float time, float deltaTime, const plain_frame_inputs* in) {
+    FE_TRY(fe, { beginFrame(fe, cam, time, deltaTime, in); });
+}
+int PLAIN_FE(run_segment)(plain_frontend* fe, plain_exchange* out) {
+    try {
+        std::memset(out, 0, sizeof(*out));
+        return fe->fe.renderFrameSegment(out) ? 1 : 0;  // 1: perform the exchange in *out, then call again
+    } catch (const std::exception& e) {
+        fe->lastError = e.what();
+        return -1;
+    }
+}
+void PLAIN_FE(shard_band)(uint32_t fullHeight, uint32_t count, uint32_t rank, uint32_t divisor, uint32_t rows, uint32_t* a, uint32_t* b) {
+    uint32_t y0 = 0, y1 = fullHeight;
+    if (count > 1) shardBandRows(fullHeight, count, rank, &y0, &y1);
+    if (divisor < 1) divisor = 1;
+    uint32_t lo = y0 / divisor, hi = (y1 + divisor - 1) / divisor;
+    if (hi > rows) hi = rows;
+    if (lo > hi) lo = hi;
+    *a = lo; *b = hi;
 }
 int PLAIN_FE(read_output)(plain_frontend* fe, void* out, size_t size, int32_t asyncPinned) {
     FE_TRY(fe, {
         ImageHandle h = fe->fe.backend.getSwapchainInputImage();
         if (asyncPinned) fe->fe.backend.readImageAsync(h, 0, out, size);
         else fe->fe.backend.readImage(h, 0, out, size);
+    });
+}
+int PLAIN_FE(read_output_rows)(plain_frontend* fe, void* outFullFrame, uint32_t r0, uint32_t r1, int32_t asyncPinned) {
+    FE_TRY(fe, {
+        ImageHandle h = fe->fe.backend.getSwapchainInputImage();
+        const size_t pitch = (size_t)fe->fe.m_screenWidth * 4;
+        if (r1 > fe->fe.m_screenHeight) r1 = fe->fe.m_screenHeight;
+        if (r1 > r0) fe->fe.backend.readImageRowsAsync(h, 0, r0, r1, (unsigned char*)outFullFrame + pitch * r0, pitch * (r1 - r0));
+        if (!asyncPinned) fe->fe.backend.waitForGPUIdle();
     });
 }
 

@@ -1,0 +1,93 @@
+"""Row-sharded frames on the GPU: R frontends (one per rank) on ONE device with the exchanges done by local copies
+(sharding.LocalComm) must reproduce the unsharded frame bit for bit - validates the row windows of every kernel, the
+overlapped computation and the exchange schedule. The same schedule runs over NCCL in bench.py --gpus N."""
+import numpy as np
+import pytest
+
+from conftest import CAMERA, image_mips
+
+pytestmark = pytest.mark.gpu
+
+GATHERED_IMAGES = ["hiz", "depthHalf", "giHistY1", "giHistC1", "giHistY0", "giHistC0", "skyLut", "froxelIntegration", "brdfLut"]
+BANDED_IMAGES = [("hiz", 2, 0), ("hiz", 2, 1), ("hiz", 2, 2), ("output", 1, 0), ("post1", 1, 0), ("giFullY", 1, 0), ("giFullC", 1, 0), ("giY1", 2, 0), ("giC1", 2, 0),
+                 ("giY0", 2, 0), ("giC0", 2, 0), ("color0", 1, 0), ("color1", 1, 0)]  # giY0/giC0: the temporal filter overwrites the gathered trace result with its banded target  # (name, divisor, mip): compared on the rank's own rows
+
+
+def make(ffi, api, W, H, instances, rank=0, count=1, **settings):
+    s = ffi.default_settings(api, W, H, sun_direction_deg=(40.0, 35.0), shard_rank=rank, shard_count=count, **settings)
+    fe = ffi.Frontend(api, s)
+    scene = ffi.SyntheticScene(api, n_instances=instances)
+    scene.attach(fe)
+    fe.set_exposure(2e-5)
+    return s, fe, scene
+
+
+def camera(ffi, f, moving):
+    p, fw, r, u = CAMERA
+    if moving:
+        p = (p[0] + 0.02 * f, p[1], p[2] + 0.01 * f)  # about a pixel per frame at this resolution: inside the TAA history halo
+    return ffi.camera(p, fw, r, u)
+
+
+@pytest.mark.parametrize("W,H,R,moving", [(256, 192, 2, False), (256, 192, 3, True), (320, 256, 4, True)])
+def test_sharded_frame_equals_unsharded(ffi, cuda, W, H, R, moving):
+    import torch
+    from plainrenderer_b200 import sharding
+    s0, ref, scene0 = make(ffi, cuda, W, H, 14)
+    ranks = [make(ffi, cuda, W, H, 14, rank=r, count=R) for r in range(R)]
+    fes = [x[1] for x in ranks]
+    comm = sharding.LocalComm(cuda, H, R, torch.device("cuda", 0))
+    prev = None
+    for f in range(4):
+        cam = camera(ffi, f, moving)
+        inputs = scene0.render_inputs(s0, cam, f + 1, prev_cam=prev, shadows=True)
+        prev = cam
+        ref.render_frame(cam, (f + 1) / 60.0, 1 / 60.0, inputs["depth"], inputs["motion"], inputs["normal"], inputs["gbuffer"], inputs["shadow_maps"])
+        # every rank uploads only its band + 16 halo rows of depth / normal / G-buffer
+        upload = []
+        for r in range(R):
+            a, b = sharding.full_res_band(cuda, H, R, r)
+            upload.append((max(a - 16, 0), min(b + 16, H)))
+        n_exchanges = sharding.run_frame_local(fes, comm, cam, (f + 1) / 60.0, 1 / 60.0, inputs, upload_rows=upload)
+        assert n_exchanges == 9
+        torch.cuda.synchronize()
+        # images every rank holds completely
+        for name in GATHERED_IMAGES:
+            h = ref.image(name)
+            for mip in range(image_mips(ref, h)):
+                if name == "hiz" and mip < 3:
+                    continue  # pyramid levels 0-2 stay banded (checked below); level 3 is all-gathered, the rest is replicated
+                want = ref.backend.read_image(h, mip)
+                for r, fe in enumerate(fes):
+                    got = fe.backend.read_image(fe.image(name), mip)
+                    assert np.array_equal(got, want), "frame %d rank %d: %s mip %d" % (f, r, name, mip)
+        for name, size in (("histogram", 512), ("light", 20), ("sunShadowInfo", 304)):
+            want = ref.backend.read_storage_buffer(ref.storage_buffer(name), size)
+            for r, fe in enumerate(fes):
+                assert np.array_equal(fe.backend.read_storage_buffer(fe.storage_buffer(name), size), want), "frame %d rank %d: buffer %s" % (f, r, name)
+        # images a rank holds for its own rows
+        for name, div, mip in BANDED_IMAGES:
+            h = ref.image(name)
+            d = ref.backend.image_description(h)
+            rows = d.height >> mip
+            want = ref.backend.read_image(h, mip).reshape(rows, -1)
+            for r, fe in enumerate(fes):
+                a, b = sharding.shard_band(cuda, H, R, r, div << mip, rows)
+                got = fe.backend.read_image(fe.image(name), mip).reshape(rows, -1)
+                assert np.array_equal(got[a:b], want[a:b]), "frame %d rank %d: %s rows [%d, %d)" % (f, r, name, a, b)
+        # TAA history of this frame (all-gathered for the next one)
+        hist_name = "taaHist%d" % (f % 2)  # written this frame: m_historyBuffers[(frameIndex % 2 + 1) % 2], frameIndex = f + 1
+        want = ref.backend.read_image(ref.image(hist_name))
+        for r, fe in enumerate(fes):
+            assert np.array_equal(fe.backend.read_image(fe.image(hist_name)), want), "frame %d rank %d: %s" % (f, r, hist_name)
+    # assemble the frame from the ranks' bands (what a gather to rank 0 would deliver)
+    frame = np.zeros((H, W * 4), np.uint8)
+    for r, fe in enumerate(fes):
+        a, b = sharding.full_res_band(cuda, H, R, r)
+        fe.read_output_rows(frame, (a, b))
+    assert np.array_equal(frame.ravel(), ref.read_output())
+    for _, fe, sc in ranks:
+        sc.close()
+        fe.close()
+    scene0.close()
+    ref.close()
