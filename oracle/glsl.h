@@ -1,9 +1,12 @@
 // ORACLE - test infrastructure only (see oracle/README.md). Never linked into the product library.
 //
 // glsl.h - the GLSL built-ins the reference shaders use, as scalar C++. Operation order is the numeric
-// contract of DESIGN.md section "Numeric contract": every built-in lowers to the IEEE binary32 operation
-// sequence written here (compiled with -ffp-contract=off), transcendental functions come from
-// plainrenderer_b200/csrc/detmath.h (the pinned libm).
+// contract of DESIGN.md section "Numeric contract" (version 2): every built-in lowers to the IEEE binary32
+// operation sequence written here (compiled with -ffp-contract=off: nothing contracts implicitly):
+//   * dot, matrix * vector, mix and the sampler's blends are fma chains (fma_ = one correctly rounded fmaf)
+//   * a division with a vector operand multiplies by the correctly rounded reciprocal of the divisor
+//     (v / s = v * (1/s), v / w = v * (1/w) per component, s / v = s * (1/v)); float / float is IEEE division
+//   * transcendental functions come from plainrenderer_b200/csrc/detmath.h (the pinned libm).
 #pragma once
 #include <stdint.h>
 #include "detmath.h"
@@ -28,15 +31,15 @@ struct uvec3 { uint x, y, z; uvec3() : x(0), y(0), z(0) {} uvec3(uint a, uint b,
     inline V operator+(V a, V b) { V r; for (int i = 0; i < N; i++) (&r.x)[i] = (&a.x)[i] + (&b.x)[i]; return r; }      \
     inline V operator-(V a, V b) { V r; for (int i = 0; i < N; i++) (&r.x)[i] = (&a.x)[i] - (&b.x)[i]; return r; }      \
     inline V operator*(V a, V b) { V r; for (int i = 0; i < N; i++) (&r.x)[i] = (&a.x)[i] * (&b.x)[i]; return r; }      \
-    inline V operator/(V a, V b) { V r; for (int i = 0; i < N; i++) (&r.x)[i] = (&a.x)[i] / (&b.x)[i]; return r; }      \
+    inline V operator/(V a, V b) { V r; for (int i = 0; i < N; i++) (&r.x)[i] = (&a.x)[i] * (1.f / (&b.x)[i]); return r; } \
     inline V operator+(V a, float b) { V r; for (int i = 0; i < N; i++) (&r.x)[i] = (&a.x)[i] + b; return r; }          \
     inline V operator-(V a, float b) { V r; for (int i = 0; i < N; i++) (&r.x)[i] = (&a.x)[i] - b; return r; }          \
     inline V operator*(V a, float b) { V r; for (int i = 0; i < N; i++) (&r.x)[i] = (&a.x)[i] * b; return r; }          \
-    inline V operator/(V a, float b) { V r; for (int i = 0; i < N; i++) (&r.x)[i] = (&a.x)[i] / b; return r; }          \
+    inline V operator/(V a, float b) { V r; const float rb = 1.f / b; for (int i = 0; i < N; i++) (&r.x)[i] = (&a.x)[i] * rb; return r; } \
     inline V operator+(float a, V b) { V r; for (int i = 0; i < N; i++) (&r.x)[i] = a + (&b.x)[i]; return r; }          \
     inline V operator-(float a, V b) { V r; for (int i = 0; i < N; i++) (&r.x)[i] = a - (&b.x)[i]; return r; }          \
     inline V operator*(float a, V b) { V r; for (int i = 0; i < N; i++) (&r.x)[i] = a * (&b.x)[i]; return r; }          \
-    inline V operator/(float a, V b) { V r; for (int i = 0; i < N; i++) (&r.x)[i] = a / (&b.x)[i]; return r; }          \
+    inline V operator/(float a, V b) { V r; for (int i = 0; i < N; i++) (&r.x)[i] = a * (1.f / (&b.x)[i]); return r; }  \
     inline V operator-(V a) { V r; for (int i = 0; i < N; i++) (&r.x)[i] = -(&a.x)[i]; return r; }                      \
     inline V& operator+=(V& a, V b) { a = a + b; return a; }                                                            \
     inline V& operator-=(V& a, V b) { a = a - b; return a; }                                                            \
@@ -49,6 +52,12 @@ struct uvec3 { uint x, y, z; uvec3() : x(0), y(0), z(0) {} uvec3(uint a, uint b,
 GL_VEC_OPS(vec2, 2)
 GL_VEC_OPS(vec3, 3)
 GL_VEC_OPS(vec4, 4)
+// fused multiply-add: one rounding. vfma(a, s, c) = a * s + c per component
+inline float fma_(float a, float b, float c) { return __builtin_fmaf(a, b, c); }
+inline float vfma(float a, float s, float c) { return fma_(a, s, c); }
+inline vec2 vfma(vec2 a, float s, vec2 c) { return vec2(fma_(a.x, s, c.x), fma_(a.y, s, c.y)); }
+inline vec3 vfma(vec3 a, float s, vec3 c) { return vec3(fma_(a.x, s, c.x), fma_(a.y, s, c.y), fma_(a.z, s, c.z)); }
+inline vec4 vfma(vec4 a, float s, vec4 c) { return vec4(fma_(a.x, s, c.x), fma_(a.y, s, c.y), fma_(a.z, s, c.z), fma_(a.w, s, c.w)); }
 
 inline ivec2 operator+(ivec2 a, ivec2 b) { return ivec2(a.x + b.x, a.y + b.y); }
 inline ivec2 operator*(ivec2 a, int b) { return ivec2(a.x * b, a.y * b); }
@@ -72,7 +81,7 @@ inline float sign(float x) { return (x > 0.f) ? 1.f : ((x < 0.f) ? -1.f : 0.f); 
 inline float floor(float x) { return dm::floor_(x); }
 inline float fract(float x) { return x - dm::floor_(x); }
 inline float sqrt(float x) { return dm::sqrt_(x); }
-inline float mix(float a, float b, float t) { return a * (1.f - t) + b * t; }
+inline float mix(float a, float b, float t) { return fma_(b, t, a * (1.f - t)); }
 inline float exp(float x) { return dm::exp(x); }
 inline float exp2(float x) { return dm::exp2(x); }
 inline float log(float x) { return dm::log(x); }
@@ -97,20 +106,20 @@ GL_MAP2(vec3, 3, pow)
 inline vec3 clamp(vec3 x, float lo, float hi) { return vec3(clamp(x.x, lo, hi), clamp(x.y, lo, hi), clamp(x.z, lo, hi)); }
 inline vec3 clamp(vec3 x, vec3 lo, vec3 hi) { return vec3(clamp(x.x, lo.x, hi.x), clamp(x.y, lo.y, hi.y), clamp(x.z, lo.z, hi.z)); }
 inline vec2 clamp(vec2 x, float lo, float hi) { return vec2(clamp(x.x, lo, hi), clamp(x.y, lo, hi)); }
-inline vec3 mix(vec3 a, vec3 b, float t) { return a * (1.f - t) + b * t; }
-inline vec4 mix(vec4 a, vec4 b, float t) { return a * (1.f - t) + b * t; }
-inline vec2 mix(vec2 a, vec2 b, float t) { return a * (1.f - t) + b * t; }
-inline vec3 mix(vec3 a, vec3 b, vec3 t) { return a * (1.f - t) + b * t; }
+inline vec3 mix(vec3 a, vec3 b, float t) { return vfma(b, t, a * (1.f - t)); }
+inline vec4 mix(vec4 a, vec4 b, float t) { return vfma(b, t, a * (1.f - t)); }
+inline vec2 mix(vec2 a, vec2 b, float t) { return vfma(b, t, a * (1.f - t)); }
+inline vec3 mix(vec3 a, vec3 b, vec3 t) { return vec3(mix(a.x, b.x, t.x), mix(a.y, b.y, t.y), mix(a.z, b.z, t.z)); }
 
-// dot = ((a.x*b.x + a.y*b.y) + a.z*b.z) + a.w*b.w, left to right
-inline float dot(vec2 a, vec2 b) { return a.x * b.x + a.y * b.y; }
-inline float dot(vec3 a, vec3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
-inline float dot(vec4 a, vec4 b) { return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w; }
+// dot = fma(a.w,b.w, fma(a.z,b.z, fma(a.y,b.y, a.x*b.x))), left to right
+inline float dot(vec2 a, vec2 b) { return fma_(a.y, b.y, a.x * b.x); }
+inline float dot(vec3 a, vec3 b) { return fma_(a.z, b.z, fma_(a.y, b.y, a.x * b.x)); }
+inline float dot(vec4 a, vec4 b) { return fma_(a.w, b.w, fma_(a.z, b.z, fma_(a.y, b.y, a.x * b.x))); }
 inline float length(vec2 a) { return sqrt(dot(a, a)); }
 inline float length(vec3 a) { return sqrt(dot(a, a)); }
 inline float length(vec4 a) { return sqrt(dot(a, a)); }
 inline float distance(vec3 a, vec3 b) { return length(a - b); }
-// normalize(v) = v / length(v)
+// normalize(v) = v / length(v) = v * (1 / sqrt(dot(v, v)))
 inline vec3 normalize(vec3 a) { return a / length(a); }
 inline vec4 normalize(vec4 a) { return a / length(a); }
 inline vec3 cross(vec3 a, vec3 b) { return vec3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
@@ -127,8 +136,8 @@ struct mat4 {
     const vec4& operator[](int i) const { return c[i]; }
 };
 inline mat4 mat4_diag(float d) { mat4 m; m.c[0] = vec4(d, 0, 0, 0); m.c[1] = vec4(0, d, 0, 0); m.c[2] = vec4(0, 0, d, 0); m.c[3] = vec4(0, 0, 0, d); return m; }
-// M * v = ((c0*v.x + c1*v.y) + c2*v.z) + c3*v.w
-inline vec4 operator*(const mat4& m, vec4 v) { return m.c[0] * v.x + m.c[1] * v.y + m.c[2] * v.z + m.c[3] * v.w; }
+// M * v = fma(c3, v.w, fma(c2, v.z, fma(c1, v.y, c0*v.x))) per row
+inline vec4 operator*(const mat4& m, vec4 v) { return vfma(m.c[3], v.w, vfma(m.c[2], v.z, vfma(m.c[1], v.y, m.c[0] * v.x))); }
 inline mat4 operator*(const mat4& a, const mat4& b) { mat4 r; for (int j = 0; j < 4; j++) r.c[j] = a * b.c[j]; return r; }
 inline mat4 transpose(const mat4& m) { mat4 r; for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++) r.c[i][j] = m.c[j][i]; return r; }
 

@@ -5,7 +5,7 @@
 //   * float -> UNORM8: uint(clamp(x,0,1)*255 + 0.5); float -> half / R11G11B10: round to nearest even,
 //     negative -> 0, > max finite -> max finite (R11G11B10) / inf (half), NaN kept
 //   * nearest: texel = floor(u*size); linear: x = u*size - 0.5, i0 = floor(x), f = x - i0 in full fp32,
-//     result = ((t00*((1-fx)*(1-fy)) + t10*(fx*(1-fy))) + t01*((1-fx)*fy)) + t11*(fx*fy)
+//     (x = fma(u, size, -0.5)), result = fma(t11, fx*fy, fma(t01, (1-fx)*fy, fma(t10, fx*(1-fy), t00*((1-fx)*(1-fy)))))
 //   * clamp-to-edge clamps the integer texel index; repeat wraps it; border returns opaque black/white
 //   * texelFetch/imageLoad out of range -> 0; imageStore out of range is dropped
 // Formats follow VulkanImageFormats.cpp:4-25 (R11G11B10 = B10G11R11_UFLOAT_PACK32: R bits 0-10, G 11-21, B 22-31).
@@ -250,19 +250,19 @@ inline vec4 texture(const View& v, const Sampler& s, vec2 uv) {
         int y = f2int(floor(uv.y * (float)v.h()));
         return sampleTexel(v, s, x, y, 0);
     }
-    float fx = uv.x * (float)v.w() - 0.5f;
-    float fy = uv.y * (float)v.h() - 0.5f;
+    float fx = fma_(uv.x, (float)v.w(), -0.5f);
+    float fy = fma_(uv.y, (float)v.h(), -0.5f);
     float x0f = floor(fx), y0f = floor(fy);
     float ax = fx - x0f, ay = fy - y0f;
     int x0 = f2int(x0f), y0 = f2int(y0f);
     vec4 t00 = sampleTexel(v, s, x0, y0, 0), t10 = sampleTexel(v, s, x0 + 1, y0, 0);
     vec4 t01 = sampleTexel(v, s, x0, y0 + 1, 0), t11 = sampleTexel(v, s, x0 + 1, y0 + 1, 0);
     float bx = 1.f - ax, by = 1.f - ay;
-    return t00 * (bx * by) + t10 * (ax * by) + t01 * (bx * ay) + t11 * (ax * ay);
+    return vfma(t11, ax * ay, vfma(t01, bx * ay, vfma(t10, ax * by, t00 * (bx * by))));
 }
 
 // texture(sampler3D, uvw): trilinear = lerp of the two bilinear slices in z:
-// r = slice0*(1-fz) + slice1*fz with each slice as in the 2D rule
+// r = fma(slice1, fz, slice0*(1-fz)) with each slice as in the 2D rule
 inline vec4 texture3D(const View& v, const Sampler& s, vec3 uvw) {
     uvw = vec3(sanitizeCoord(uvw.x), sanitizeCoord(uvw.y), sanitizeCoord(uvw.z));
     if (!s.linear) {
@@ -271,9 +271,9 @@ inline vec4 texture3D(const View& v, const Sampler& s, vec3 uvw) {
         int z = f2int(floor(uvw.z * (float)v.d()));
         return sampleTexel(v, s, x, y, z);
     }
-    float fx = uvw.x * (float)v.w() - 0.5f;
-    float fy = uvw.y * (float)v.h() - 0.5f;
-    float fz = uvw.z * (float)v.d() - 0.5f;
+    float fx = fma_(uvw.x, (float)v.w(), -0.5f);
+    float fy = fma_(uvw.y, (float)v.h(), -0.5f);
+    float fz = fma_(uvw.z, (float)v.d(), -0.5f);
     float x0f = floor(fx), y0f = floor(fy), z0f = floor(fz);
     float ax = fx - x0f, ay = fy - y0f, az = fz - z0f;
     int x0 = f2int(x0f), y0 = f2int(y0f), z0 = f2int(z0f);
@@ -282,9 +282,9 @@ inline vec4 texture3D(const View& v, const Sampler& s, vec3 uvw) {
     for (int k = 0; k < 2; k++) {
         vec4 t00 = sampleTexel(v, s, x0, y0, z0 + k), t10 = sampleTexel(v, s, x0 + 1, y0, z0 + k);
         vec4 t01 = sampleTexel(v, s, x0, y0 + 1, z0 + k), t11 = sampleTexel(v, s, x0 + 1, y0 + 1, z0 + k);
-        sl[k] = t00 * (bx * by) + t10 * (ax * by) + t01 * (bx * ay) + t11 * (ax * ay);
+        sl[k] = vfma(t11, ax * ay, vfma(t01, bx * ay, vfma(t10, ax * by, t00 * (bx * by))));
     }
-    return sl[0] * bz + sl[1] * az;
+    return vfma(sl[1], az, sl[0] * bz);
 }
 
 // textureGather(sampler2D, uv) component 0: (i0,j1), (i1,j1), (i1,j0), (i0,j0) with i0 = floor(u*w - 0.5)

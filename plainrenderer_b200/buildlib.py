@@ -7,6 +7,7 @@ nvcc cross-compiles without a GPU. Flags that are part of the numeric contract (
 contraction), default -prec-div/-prec-sqrt/-ftz=false; host side -ffp-contract=off.
 """
 import os
+import platform
 import subprocess
 import sys
 from concurrent.futures import ThreadPoolExecutor
@@ -19,9 +20,11 @@ LIB = PKG / "libplain_b200.so"
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 CXX = os.environ.get("CXX", "g++")
 INCLUDES = ["-I%s" % (ROOT / "include"), "-I%s" % (PKG / "csrc"), "-I%s" % (PKG / "host")]
+# the contract's explicit fmaf (pvec.h / detmath.h) must be the hardware instruction on the host too: -mfma on x86-64
+HOST_FMA = ["-mfma"] if platform.machine() in ("x86_64", "AMD64") else []
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false", "--extended-lambda", "--expt-relaxed-constexpr",
-              "-Xcompiler", "-fPIC,-fvisibility=hidden,-ffp-contract=off", "-Xptxas", "-v", "-diag-suppress", "177,550"]
-CXX_FLAGS = ["-std=c++17", "-O2", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-fvisibility=hidden", "-Wall", "-Wno-unused-function"]
+              "-Xcompiler", ",".join(["-fPIC", "-fvisibility=hidden", "-ffp-contract=off"] + HOST_FMA), "-Xptxas", "-v", "-diag-suppress", "177,550"]
+CXX_FLAGS = ["-std=c++17", "-O2", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-fvisibility=hidden", "-Wall", "-Wno-unused-function"] + HOST_FMA
 
 
 def _newer(src, deps, obj):

@@ -4,8 +4,9 @@
 // acos/atan precision is implementation defined. To make "bit-exact histogram bins"
 // (histogramPerTile.comp:49-56 depends on log()) and frame parity testable, every transcendental on
 // the frame path is pinned to the functions in this header. Each is a fixed sequence of IEEE-754
-// binary32 add/mul/div/sqrt plus integer bit operations, so the same bits come out of nvcc
-// (-fmad=false) and gcc (-ffp-contract=off). It plays the role of "the libm both sides link":
+// binary32 add/mul/fma/div/sqrt plus integer bit operations (fma only where written: dm::fma_, one
+// correctly rounded operation on both sides), so the same bits come out of nvcc (-fmad=false) and
+// gcc (-ffp-contract=off). It plays the role of "the libm both sides link":
 // the CUDA kernels use it on the device and the CPU oracle includes it instead of glibc's libm.
 // tests/test_detmath.py checks every function against float64 numpy (max error in ulp).
 //
@@ -40,6 +41,15 @@ DM_HD float u2f(uint32_t u) {
     float f;
     memcpy(&f, &u, 4);
     return f;
+#endif
+}
+
+// fused multiply-add, written explicitly where the contract contracts (Horner steps, Cody-Waite reduction)
+DM_HD float fma_(float a, float b, float c) {
+#if defined(__CUDA_ARCH__)
+    return __fmaf_rn(a, b, c);
+#else
+    return __builtin_fmaf(a, b, c);
 #endif
 }
 
@@ -100,12 +110,12 @@ DM_HD float frexp_pos(float x, int* e) {
 DM_HD float exp_core(float r) {
     float z = r * r;
     float p = 1.9875691500E-4f;
-    p = p * r + 1.3981999507E-3f;
-    p = p * r + 8.3334519073E-3f;
-    p = p * r + 4.1665795894E-2f;
-    p = p * r + 1.6666665459E-1f;
-    p = p * r + 5.0000001201E-1f;
-    p = p * z + r;
+    p = fma_(p, r, 1.3981999507E-3f);
+    p = fma_(p, r, 8.3334519073E-3f);
+    p = fma_(p, r, 4.1665795894E-2f);
+    p = fma_(p, r, 1.6666665459E-1f);
+    p = fma_(p, r, 5.0000001201E-1f);
+    p = fma_(p, z, r);
     return p + 1.f;
 }
 
@@ -113,9 +123,9 @@ DM_HD float exp(float x) {
     if (isnan_(x)) return x;
     if (x > 88.72283905206835f) return inff_();
     if (x < -103.972084f) return 0.f;
-    float z = floor_(1.44269504088896341f * x + 0.5f);
-    float r = x - z * 0.693359375f;
-    r = r - z * -2.12194440e-4f;
+    float z = floor_(fma_(1.44269504088896341f, x, 0.5f));
+    float r = fma_(z, -0.693359375f, x);
+    r = fma_(z, 2.12194440e-4f, r);
     return ldexp_(exp_core(r), (int)z);
 }
 
@@ -140,14 +150,14 @@ DM_HD float log_reduced(float m, int* e, float* xr) {
     }
     float z = x * x;
     float y = 7.0376836292E-2f;
-    y = y * x + -1.1514610310E-1f;
-    y = y * x + 1.1676998740E-1f;
-    y = y * x + -1.2420140846E-1f;
-    y = y * x + 1.4249322787E-1f;
-    y = y * x + -1.6668057665E-1f;
-    y = y * x + 2.0000714765E-1f;
-    y = y * x + -2.4999993993E-1f;
-    y = y * x + 3.3333331174E-1f;
+    y = fma_(y, x, -1.1514610310E-1f);
+    y = fma_(y, x, 1.1676998740E-1f);
+    y = fma_(y, x, -1.2420140846E-1f);
+    y = fma_(y, x, 1.4249322787E-1f);
+    y = fma_(y, x, -1.6668057665E-1f);
+    y = fma_(y, x, 2.0000714765E-1f);
+    y = fma_(y, x, -2.4999993993E-1f);
+    y = fma_(y, x, 3.3333331174E-1f);
     y = y * x * z;
     *xr = x;
     return y;  // ln(1+x) = x - z/2 + y
@@ -165,10 +175,10 @@ DM_HD float log(float x) {
     float y = log_reduced(m, &e, &xr);
     z = xr * xr;
     float fe = (float)e;
-    y = y + -2.12194440e-4f * fe;
-    y = y + -0.5f * z;
+    y = fma_(-2.12194440e-4f, fe, y);
+    y = fma_(-0.5f, z, y);
     z = xr + y;
-    z = z + 0.693359375f * fe;
+    z = fma_(0.693359375f, fe, z);
     return z;
 }
 
@@ -182,10 +192,10 @@ DM_HD float log2(float x) {
     float xr;
     float y = log_reduced(m, &e, &xr);
     float z = xr * xr;
-    y = y + -0.5f * z;
+    y = fma_(-0.5f, z, y);
     // ln(1+x) = xr + y ; log2 = e + (xr + y) * log2(e), split for accuracy
     float r = y * 1.44269504088896341f;
-    r = r + xr * 0.44269504088896341f;
+    r = fma_(xr, 0.44269504088896341f, r);
     r = r + xr;
     return r + (float)e;
 }
@@ -210,26 +220,26 @@ DM_HD float sincos_reduce(float ax, int* jout) {
         y += 1.f;
     }
     *jout = j;
-    float r = ax - y * 0.78515625f;
-    r = r - y * 2.4187564849853515625e-4f;
-    r = r - y * 3.77489497744594108e-8f;
+    float r = fma_(y, -0.78515625f, ax);
+    r = fma_(y, -2.4187564849853515625e-4f, r);
+    r = fma_(y, -3.77489497744594108e-8f, r);
     return r;
 }
 
 DM_HD float sin_poly(float x, float z) {
     float y = -1.9515295891E-4f;
-    y = y * z + 8.3321608736E-3f;
-    y = y * z + -1.6666654611E-1f;
-    y = y * z * x;
-    return y + x;
+    y = fma_(y, z, 8.3321608736E-3f);
+    y = fma_(y, z, -1.6666654611E-1f);
+    y = y * z;
+    return fma_(y, x, x);
 }
 
 DM_HD float cos_poly(float z) {
     float y = 2.443315711809948E-005f;
-    y = y * z + -1.388731625493765E-003f;
-    y = y * z + 4.166664568298827E-002f;
+    y = fma_(y, z, -1.388731625493765E-003f);
+    y = fma_(y, z, 4.166664568298827E-002f);
     y = y * z * z;
-    y = y - 0.5f * z;
+    y = fma_(-0.5f, z, y);
     return y + 1.f;
 }
 
@@ -296,12 +306,12 @@ DM_HD float asin(float x) {
         z = s * s;
     }
     float p = 4.2163199048E-2f;
-    p = p * z + 2.4181311049E-2f;
-    p = p * z + 4.5470025998E-2f;
-    p = p * z + 7.4953002686E-2f;
-    p = p * z + 1.6666752422E-1f;
-    p = p * z * s;
-    p = p + s;
+    p = fma_(p, z, 2.4181311049E-2f);
+    p = fma_(p, z, 4.5470025998E-2f);
+    p = fma_(p, z, 7.4953002686E-2f);
+    p = fma_(p, z, 1.6666752422E-1f);
+    p = p * z;
+    p = fma_(p, s, s);
     if (flag) {
         p = p + p;
         p = DM_PIO2F - p;
@@ -335,11 +345,11 @@ DM_HD float atan(float x) {
     }
     float z = a * a;
     float p = 8.05374449538e-2f;
-    p = p * z + -1.38776856032E-1f;
-    p = p * z + 1.99777106478E-1f;
-    p = p * z + -3.33329491539E-1f;
-    p = p * z * a;
-    p = p + a;
+    p = fma_(p, z, -1.38776856032E-1f);
+    p = fma_(p, z, 1.99777106478E-1f);
+    p = fma_(p, z, -3.33329491539E-1f);
+    p = p * z;
+    p = fma_(p, a, a);
     y = y + p;
     return neg ? -y : y;
 }

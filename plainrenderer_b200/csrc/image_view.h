@@ -2,7 +2,8 @@
 // Layout in HBM: every image is one allocation, mip levels concatenated (256-byte aligned), each level row-major and
 // tightly packed (x fastest, then y, then z). A view is one mip level: base pointer + extent.
 // Codec and sampler rules are the ones of DESIGN.md "Numeric contract" (RNE to half / R11G11B10, UNORM8 =
-// uint(clamp(x)*255+0.5), nearest = floor(u*size), linear with full fp32 weights, NaN coordinate -> 0).
+// uint(clamp(x)*255+0.5), nearest = floor(u*size), linear with full fp32 weights blended as
+// fma(t11,w11, fma(t01,w01, fma(t10,w10, t00*w00))), trilinear fma(slice1, fz, slice0*(1-fz)), NaN coordinate -> 0).
 #pragma once
 #include "pvec.h"
 #if defined(__CUDACC__)
@@ -150,7 +151,21 @@ PV_HD uint4 loadU4(const ImgView& v, int x, int y) { return ldg((const uint4*)v.
 
 // ---------------- sampler ----------------
 enum Wrap { WRAP_CLAMP = 0, WRAP_BORDER = 1, WRAP_REPEAT = 2 };
-PV_HD float sanitizeCoord(float u) { return isnanf_(u) ? 0.f : clampf(u, -65536.f, 65536.f); }
+PV_HD float sanitizeCoord(float u) {
+#if defined(__CUDA_ARCH__)
+    return isnanf_(u) ? 0.f : fminf(fmaxf(u, -65536.f), 65536.f);  // two FMNMX + select; the bounds are non-zero, so the +-0 rule of fminp/fmaxp cannot matter
+#else
+    return isnanf_(u) ? 0.f : clampf(u, -65536.f, 65536.f);
+#endif
+}
+// f2i(floor(x)) in one conversion on the device: cvt.rmi.s32.f32 rounds down, saturates, NaN -> 0 (and -0 -> 0)
+PV_HD int floor2i(float x) {
+#if defined(__CUDA_ARCH__)
+    return __float2int_rd(x);
+#else
+    return f2i(floorf_(x));
+#endif
+}
 template <int WRAP> PV_HD bool wrapIndex(int& i, int size) {
     if (WRAP == WRAP_CLAMP) { i = iclamp(i, 0, size - 1); return true; }
     if (WRAP == WRAP_REPEAT) { i %= size; if (i < 0) i += size; return true; }
@@ -159,7 +174,7 @@ template <int WRAP> PV_HD bool wrapIndex(int& i, int size) {
 struct Bilerp { int x0, y0; float w00, w10, w01, w11; };
 PV_HD Bilerp bilerpSetup(vec2 uv, int w, int h) {
     Bilerp b;
-    const float fx = sanitizeCoord(uv.x) * (float)w - 0.5f, fy = sanitizeCoord(uv.y) * (float)h - 0.5f;
+    const float fx = fmaf_(sanitizeCoord(uv.x), (float)w, -0.5f), fy = fmaf_(sanitizeCoord(uv.y), (float)h, -0.5f);
     const float x0f = floorf_(fx), y0f = floorf_(fy);
     const float ax = fx - x0f, ay = fy - y0f, bx = 1.f - ax, by = 1.f - ay;
     b.x0 = f2i(x0f); b.y0 = f2i(y0f);
@@ -168,8 +183,8 @@ PV_HD Bilerp bilerpSetup(vec2 uv, int w, int h) {
 }
 PV_HD ivec2 nearestTexel(vec2 uv, int w, int h) {
     ivec2 r;
-    r.x = f2i(floorf_(sanitizeCoord(uv.x) * (float)w));
-    r.y = f2i(floorf_(sanitizeCoord(uv.y) * (float)h));
+    r.x = floor2i(sanitizeCoord(uv.x) * (float)w);
+    r.y = floor2i(sanitizeCoord(uv.y) * (float)h);
     return r;
 }
 
@@ -180,17 +195,17 @@ template <int WRAP, typename T, typename F> PV_HD T sampleLinear2D(F fetch, int 
     const bool okx0 = wrapIndex<WRAP>(x0, w), okx1 = wrapIndex<WRAP>(x1, w), oky0 = wrapIndex<WRAP>(y0, h), oky1 = wrapIndex<WRAP>(y1, h);
     const T t00 = (okx0 && oky0) ? fetch(x0, y0) : border, t10 = (okx1 && oky0) ? fetch(x1, y0) : border;
     const T t01 = (okx0 && oky1) ? fetch(x0, y1) : border, t11 = (okx1 && oky1) ? fetch(x1, y1) : border;
-    return t00 * b.w00 + t10 * b.w10 + t01 * b.w01 + t11 * b.w11;
+    return vfma(t11, b.w11, vfma(t01, b.w01, vfma(t10, b.w10, t00 * b.w00)));
 }
 template <int WRAP, typename T, typename F> PV_HD T sampleNearest2D(F fetch, int w, int h, vec2 uv, T border) {
     ivec2 t = nearestTexel(uv, w, h);
     const bool ok = wrapIndex<WRAP>(t.x, w) & wrapIndex<WRAP>(t.y, h);
     return ok ? fetch(t.x, t.y) : border;
 }
-// trilinear over a fetch functor F(x, y, z) -> T: slice0*(1-fz) + slice1*fz
+// trilinear over a fetch functor F(x, y, z) -> T: fma(slice1, fz, slice0*(1-fz))
 template <int WRAP, typename T, typename F> PV_HD T sampleLinear3D(F fetch, int w, int h, int d, vec3 uvw, T border) {
     const Bilerp b = bilerpSetup(v2(uvw.x, uvw.y), w, h);
-    const float fz = sanitizeCoord(uvw.z) * (float)d - 0.5f;
+    const float fz = fmaf_(sanitizeCoord(uvw.z), (float)d, -0.5f);
     const float z0f = floorf_(fz);
     const float az = fz - z0f, bz = 1.f - az;
     int x0 = b.x0, x1 = b.x0 + 1, y0 = b.y0, y1 = b.y0 + 1, z0 = f2i(z0f), z1 = z0 + 1;
@@ -200,9 +215,9 @@ template <int WRAP, typename T, typename F> PV_HD T sampleLinear3D(F fetch, int 
     const T a01 = (okx0 && oky1 && okz0) ? fetch(x0, y1, z0) : border, a11 = (okx1 && oky1 && okz0) ? fetch(x1, y1, z0) : border;
     const T b00 = (okx0 && oky0 && okz1) ? fetch(x0, y0, z1) : border, b10 = (okx1 && oky0 && okz1) ? fetch(x1, y0, z1) : border;
     const T b01 = (okx0 && oky1 && okz1) ? fetch(x0, y1, z1) : border, b11 = (okx1 && oky1 && okz1) ? fetch(x1, y1, z1) : border;
-    const T s0 = a00 * b.w00 + a10 * b.w10 + a01 * b.w01 + a11 * b.w11;
-    const T s1 = b00 * b.w00 + b10 * b.w10 + b01 * b.w01 + b11 * b.w11;
-    return s0 * bz + s1 * az;
+    const T s0 = vfma(a11, b.w11, vfma(a01, b.w01, vfma(a10, b.w10, a00 * b.w00)));
+    const T s1 = vfma(b11, b.w11, vfma(b01, b.w01, vfma(b10, b.w10, b00 * b.w00)));
+    return vfma(s1, az, s0 * bz);
 }
 
 // common instantiations

@@ -185,7 +185,7 @@ PLAIN_PASS(launch_depthHiZPyramid, "depthHiZPyramid.comp") {
 
 // ---------------- lightMatrix.comp:57-138 (single thread in the reference) ----------------
 struct M4 { vec4 c[4]; };
-__device__ vec4 mulM4(const M4& m, vec4 v) { return m.c[0] * v.x + m.c[1] * v.y + m.c[2] * v.z + m.c[3] * v.w; }
+__device__ vec4 mulM4(const M4& m, vec4 v) { return vfma(m.c[3], v.w, vfma(m.c[2], v.z, vfma(m.c[1], v.y, m.c[0] * v.x))); }  // the contract's M * v
 __device__ M4 mulM4(const M4& a, const M4& b) { M4 r; for (int j = 0; j < 4; j++) r.c[j] = mulM4(a, b.c[j]); return r; }
 __device__ float& comp(vec4& v, int i) { return (&v.x)[i]; }
 

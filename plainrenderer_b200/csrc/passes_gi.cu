@@ -151,6 +151,7 @@ struct TraceInstance {  // one SDFInstance (SDF.inc:4-10) staged in shared memor
     vec3 localExtendsHalfPadded;   // localExtends * 0.5 + 0.01
     float distanceThreshold;       // length(localExtends / sdfResolution) * 0.25
     float localToGlobalScale;      // 1 / length(worldToLocal[0].xyz)
+    vec3 invLocalExtends;          // 1 / localExtends per component: "pos / localExtends" multiplies by it (contract 2)
 };
 struct TraceResult {
     bool hit;
@@ -232,7 +233,7 @@ __device__ __forceinline__ bool traceStep(const TraceInstance& inst, vec3 raySta
     if (localSamplePos.x > localExtendsHalf.x || localSamplePos.y > localExtendsHalf.y || localSamplePos.z > localExtendsHalf.z ||
         localSamplePos.x < -localExtendsHalf.x || localSamplePos.y < -localExtendsHalf.y || localSamplePos.z < -localExtendsHalf.z)
         return false;
-    vec3 sampleUV = localSamplePos / localExtends + 0.5f;
+    vec3 sampleUV = localSamplePos * inst.invLocalExtends + 0.5f;  // localSamplePos / localExtends + 0.5
     st.dLast = st.d;
     const float d = sampleSDF(inst.sdf, sampleUV);
     st.d = d;
@@ -244,7 +245,7 @@ __device__ __forceinline__ bool traceStep(const TraceInstance& inst, vec3 raySta
             tr.hitCount = st.k;
             const float lastStepSizeLocal = d / (1.f - (d - st.dLast));
             const vec3 hitSamplePos = localSamplePos + st.rayDirection * lastStepSizeLocal;
-            sampleUV = hitSamplePos / localExtends + 0.5f;
+            sampleUV = hitSamplePos * inst.invLocalExtends + 0.5f;
             const vec3 N = normalFromSDF(sampleUV, localExtends, inst.sdf);
             const float* m = inst.worldToLocal;  // transpose(mat3(worldToLocal)) * N
             tr.N = v3(m[0], m[4], m[8]) * N.x + v3(m[1], m[5], m[9]) * N.y + v3(m[2], m[6], m[10]) * N.z;
@@ -346,6 +347,7 @@ __global__ void __launch_bounds__(256) sdfDiffuseTraceKernel(const __grid_consta
         t.localExtendsHalfPadded = t.localExtends * 0.5f + 0.01f;
         t.distanceThreshold = length(t.localExtends / v3((float)t.sdf.w, (float)t.sdf.h, (float)t.sdf.d)) * 0.25f;
         t.localToGlobalScale = 1.f / length(v3(t.worldToLocal[0], t.worldToLocal[1], t.worldToLocal[2]));
+        t.invLocalExtends = 1.f / t.localExtends;
         sInst[i] = t;
     }
     __syncthreads();
@@ -503,17 +505,30 @@ struct SpatialParams {
     int filterIndex;
     int y0, y1;  // rows to produce (row sharding)
 };
-template <bool DEPTH_IS_R16F>
-__device__ __forceinline__ vec3 giPixelToWorld(const ImgView& depthTexture, const Globals& G, vec2 uv) {
-    const float depth = sampleNearest2D<WRAP_CLAMP, float>([&](int x, int y) { return DEPTH_IS_R16F ? loadR16F(depthTexture, x, y) : loadD32(depthTexture, x, y); },
-                                                           depthTexture.w, depthTexture.h, uv, 0.f);
+// depth texel -> world position for a pixel at uv (filterIndirectDiffuseSpatial.comp:21-28); the nearest-sampled depth is passed in
+__device__ __forceinline__ vec3 giDepthToWorld(float depth, const Globals& G, vec2 uv) {
     const float depthLinear = linearizeDepth(depth, G.nearPlane, G.farPlane);
     const vec2 pixelNDC = uv * 2.f - 1.f;
     const vec3 cameraToPixel = -viewDirFromNDC(G, pixelNDC);
     return G.camPos + cameraToPixel / dot(cameraToPixel, G.fwd) * depthLinear;
 }
+// nearest + clamp-to-edge texel of a (sanitised) coordinate: image_view.h nearestTexel + wrapIndex<WRAP_CLAMP>
+__device__ __forceinline__ ivec2 nearestClampTexel(vec2 uvSanitized, int w, int h) {
+    ivec2 t;
+    t.x = iclamp(floor2i(uvSanitized.x * (float)w), 0, w - 1);
+    t.y = iclamp(floor2i(uvSanitized.y * (float)h), 0, h - 1);
+    return t;
+}
+template <bool DEPTH_IS_R16F>
+__device__ __forceinline__ vec3 giPixelToWorld(const ImgView& depthTexture, const Globals& G, vec2 uv) {
+    const ivec2 t = nearestClampTexel(v2(sanitizeCoord(uv.x), sanitizeCoord(uv.y)), depthTexture.w, depthTexture.h);
+    return giDepthToWorld(DEPTH_IS_R16F ? loadR16F(depthTexture, t.x, t.y) : loadD32(depthTexture, t.x, t.y), G, uv);
+}
 // The 32 disc samples come from one xorshift sequence that is the same for every pixel (:60-70): the block computes
 // sqrt(rand), cos(angle), sin(angle) once into shared memory; each pixel only applies its own lengthModifier.
+// Per sample the coordinate is sanitised once and - when the depth, Y_SH and CoCg images have the same extent, which
+// is how the frontend creates them - the nearest texel is computed once for the three fetches (same expression,
+// same operands: same result).
 template <bool DEPTH_IS_R16F>
 __global__ void __launch_bounds__(256) giSpatialFilterKernel(const __grid_constant__ SpatialParams p) {
     __shared__ float sSqrtRand[32], sCos[32], sSin[32];
@@ -531,6 +546,9 @@ __global__ void __launch_bounds__(256) giSpatialFilterKernel(const __grid_consta
     const int ix = blockIdx.x * 32 + (threadIdx.x & 31), iy = p.y0 + blockIdx.y * 8 + (threadIdx.x >> 5);
     if (ix >= p.outYSH.w || iy >= p.y1) return;
     const Globals G = loadGlobals(g);
+    float VP[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) VP[k] = g->viewProjection[k];
     const vec2 texelSize = 1.f / v2((float)p.outYSH.w, (float)p.outYSH.h);
     const vec2 uv = (v2((float)ix, (float)iy) + 0.5f) * texelSize;
     const vec3 pCenter = giPixelToWorld<DEPTH_IS_R16F>(p.depthTexture, G, uv);
@@ -539,6 +557,7 @@ __global__ void __launch_bounds__(256) giSpatialFilterKernel(const __grid_consta
     const vec3 tangent = normalize(pCenter - pRight);
     const vec3 bitangent = normalize(pCenter - pUp);
     const vec3 N = 2.f * sampleNearest2D<WRAP_CLAMP, vec3>([&](int x, int y) { return loadRGBA8rgb(p.normalTexture, x, y); }, p.normalTexture.w, p.normalTexture.h, uv, v3(0.f)) - 1.f;
+    const bool sameExtent = p.texYSH.w == p.depthTexture.w && p.texYSH.h == p.depthTexture.h && p.texCoCg.w == p.depthTexture.w && p.texCoCg.h == p.depthTexture.h;
     vec4 result_Y_SH = v4(0.f);
     vec2 result_CoCg = v2(0.f);
     float weightTotal = 0.f;
@@ -549,14 +568,16 @@ __global__ void __launch_bounds__(256) giSpatialFilterKernel(const __grid_consta
         const float d = sSqrtRand[i] * lengthModifier;
         const vec2 offset = v2(sCos[i], sSin[i]) * d;
         const vec3 sampleWorld = pCenter + radiusWorld * (offset.x * tangent + offset.y * bitangent);
-        const vec4 sampleProjected = mulm4(g->viewProjection, v4(sampleWorld, 1.f));
+        const vec4 sampleProjected = mulm4(VP, v4(sampleWorld, 1.f));
         vec2 sampleUV = v2(sampleProjected.x, sampleProjected.y) / sampleProjected.w;
         sampleUV = sampleUV * 0.5f + 0.5f;
         sampleUV.x = sampleUV.x < 0.f ? uv.x - offset.x : sampleUV.x;
         sampleUV.y = sampleUV.y < 0.f ? uv.y - offset.y : sampleUV.y;
         sampleUV.x = sampleUV.x > 1.f ? uv.x - offset.x : sampleUV.x;
         sampleUV.y = sampleUV.y > 1.f ? uv.y - offset.y : sampleUV.y;
-        const vec3 pixelWorld = giPixelToWorld<DEPTH_IS_R16F>(p.depthTexture, G, sampleUV);
+        const vec2 sampleUVSanitized = v2(sanitizeCoord(sampleUV.x), sanitizeCoord(sampleUV.y));
+        const ivec2 td = nearestClampTexel(sampleUVSanitized, p.depthTexture.w, p.depthTexture.h);
+        const vec3 pixelWorld = giDepthToWorld(DEPTH_IS_R16F ? loadR16F(p.depthTexture, td.x, td.y) : loadD32(p.depthTexture, td.x, td.y), G, sampleUV);
         const float distanceToTangentPlane = absf(dot(N, pixelWorld - pCenter));
         const float maxDistance = 0.25f;
         float weight = clampf(maxDistance / fmaxp(distanceToTangentPlane, 0.0001f), 0.f, 1.f);
@@ -566,8 +587,10 @@ __global__ void __launch_bounds__(256) giSpatialFilterKernel(const __grid_consta
             lengthModifier *= 0.98f;
         }
         if (weight > 0.f) {
-            const vec4 sample_Y_SH = sampleNearest2D<WRAP_CLAMP, vec4>([&](int x, int y) { return loadRGBA16F(p.texYSH, x, y); }, p.texYSH.w, p.texYSH.h, sampleUV, v4(0.f));
-            const vec2 sample_CoCg = sampleNearest2D<WRAP_CLAMP, vec2>([&](int x, int y) { return loadRG16F(p.texCoCg, x, y); }, p.texCoCg.w, p.texCoCg.h, sampleUV, v2(0.f));
+            const ivec2 ty = sameExtent ? td : nearestClampTexel(sampleUVSanitized, p.texYSH.w, p.texYSH.h);
+            const ivec2 tc = sameExtent ? td : nearestClampTexel(sampleUVSanitized, p.texCoCg.w, p.texCoCg.h);
+            const vec4 sample_Y_SH = loadRGBA16F(p.texYSH, ty.x, ty.y);
+            const vec2 sample_CoCg = loadRG16F(p.texCoCg, tc.x, tc.y);
             if (!(anynan(sample_Y_SH) || anynan(sample_CoCg))) {
                 result_Y_SH = result_Y_SH + weight * sample_Y_SH;
                 result_CoCg = result_CoCg + weight * sample_CoCg;

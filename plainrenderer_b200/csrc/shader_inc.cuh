@@ -13,9 +13,9 @@ PV_HD float linearTosRGB1(float l) {  // :5-13
     return l <= 0.0031308f ? lo : hi;
 }
 PV_HD vec3 linearTosRGB(vec3 c) { return v3(linearTosRGB1(c.x), linearTosRGB1(c.y), linearTosRGB1(c.z)); }
-PV_HD float sRGBToLinear1(float s) {  // :15-23
-    const float lo = s / 12.92f;
-    const float hi = dm::pow(absf(s + 0.055f) / 1.055f, 2.4f);
+PV_HD float sRGBToLinear1(float s) {  // :15-23; vec3 / float in the shader: multiplies by the rounded reciprocal (contract 2)
+    const float lo = s * rcpf_(12.92f);
+    const float hi = dm::pow(absf(s + 0.055f) * rcpf_(1.055f), 2.4f);
     return s <= 0.004045f ? lo : hi;
 }
 PV_HD vec3 sRGBToLinear(vec3 c) { return v3(sRGBToLinear1(c.x), sRGBToLinear1(c.y), sRGBToLinear1(c.z)); }

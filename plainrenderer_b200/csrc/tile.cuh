@@ -50,7 +50,7 @@ __device__ __forceinline__ vec3 sampleR11LinearClampTile(const TileR11<TW, TH>& 
     } else {
         tapCornersGlobalR11(img, x0, x1, y0, y1, t00, t10, t01, t11);
     }
-    return t00 * b.w00 + t10 * b.w10 + t01 * b.w01 + t11 * b.w11;
+    return vfma(t11, b.w11, vfma(t01, b.w01, vfma(t10, b.w10, t00 * b.w00)));
 }
 
 }  // namespace pb

@@ -186,10 +186,10 @@ void RenderFrontend::initImages(uint32_t noiseSeed) {
         m_noiseTextures.push_back(backend.createImage(imageDesc2D(noiseTextureWidth, noiseTextureHeight, PLAIN_FORMAT_RG8, PLAIN_USAGE_SAMPLED), noise.data(), noise.size()));
         m_globalShaderInfo.noiseTextureIndices[i] = (int32_t)backend.getImageGlobalTextureArrayIndex(m_noiseTextures.back());
     }
-    m_worldSpaceNormalImage = backend.createImage(imageDesc2D(w, h, PLAIN_FORMAT_RGBA8, PLAIN_USAGE_ATTACHMENT | PLAIN_USAGE_SAMPLED), nullptr, 0);
+    for (int i = 0; i < 2; i++) m_worldSpaceNormalImages[i] = backend.createImage(imageDesc2D(w, h, PLAIN_FORMAT_RGBA8, PLAIN_USAGE_ATTACHMENT | PLAIN_USAGE_SAMPLED), nullptr, 0);
     m_depthHalfRes = backend.createImage(imageDesc2D(w / 2, h / 2, PLAIN_FORMAT_R16_SFLOAT, SS), nullptr, 0);
     // packed G-buffer: the post-raster inputs of triangle.frag (new in this build)
-    m_gbuffer = backend.createImage(imageDesc2D(w, h, PLAIN_FORMAT_RGBA32_UINT, PLAIN_USAGE_ATTACHMENT | PLAIN_USAGE_SAMPLED), nullptr, 0);
+    for (int i = 0; i < 2; i++) m_gbuffers[i] = backend.createImage(imageDesc2D(w, h, PLAIN_FORMAT_RGBA32_UINT, PLAIN_USAGE_ATTACHMENT | PLAIN_USAGE_SAMPLED), nullptr, 0);
     for (int i = 0; i < 2; i++) {  // initRenderTargets :1399-1447
         m_frameRenderTargets[i].motionBuffer = backend.createImage(imageDesc2D(w, h, PLAIN_FORMAT_RG16_SNORM, PLAIN_USAGE_ATTACHMENT | PLAIN_USAGE_SAMPLED), nullptr, 0);
         m_frameRenderTargets[i].colorBuffer = backend.createImage(imageDesc2D(w, h, PLAIN_FORMAT_R11G11B10_UFLOAT, PLAIN_USAGE_ATTACHMENT | SS), nullptr, 0);
@@ -342,7 +342,7 @@ void RenderFrontend::prepareRenderpasses() {
         dep.previousFrame = previousRenderTarget;
         dep.cameraFrustum = m_cameraFrustum;
         dep.depthHalfRes = m_depthHalfRes;
-        dep.worldSpaceNormals = m_worldSpaceNormalImage;
+        dep.worldSpaceNormals = worldSpaceNormalImage();
         dep.skyLut = m_sky.m_skyLut;
         dep.shadowMap = m_shadowMaps[m_shadingConfig.sunShadowCascadeCount - 1];
         dep.lightBuffer = m_lightBuffer;
@@ -561,7 +561,7 @@ void RenderFrontend::shadeGBuffer(ImageHandle colorTarget) {
     e.genericInfo.handle = m_shadingPass;
     const SDFGI::IndirectLightingImages indirect = m_sdfGi.getIndirectLightingResults(m_sdfTraceSettings.halfResTrace);
     e.genericInfo.resources.storageBuffers = {StorageBufferResource(m_lightBuffer, true, 7), StorageBufferResource(m_sunShadowInfoBuffer, true, 8)};
-    e.genericInfo.resources.sampledImages = {ImageResource(m_gbuffer, 0, 0), ImageResource(m_brdfLut, 0, 3), ImageResource(indirect.Y_SH, 0, 15), ImageResource(indirect.CoCg, 0, 16),
+    e.genericInfo.resources.sampledImages = {ImageResource(gbuffer(), 0, 0), ImageResource(m_brdfLut, 0, 3), ImageResource(indirect.Y_SH, 0, 15), ImageResource(indirect.CoCg, 0, 16),
                                              ImageResource(m_volumetrics.m_volumetricIntegrationVolume, 0, 18), ImageResource(m_sky.m_skyLut, 0, 21),
                                              ImageResource(m_sky.m_skyTransmissionLut, 0, 22)};
     for (uint32_t i = 0; i < (uint32_t)maxSunShadowCascadeCount; i++) e.genericInfo.resources.sampledImages.push_back(ImageResource(m_shadowMaps[i], 0, 9 + i));

@@ -190,7 +190,12 @@ public:
     uint32_t m_screenWidth = 0, m_screenHeight = 0;
     FrameRenderTargets m_frameRenderTargets[2];
     int m_sceneRenderTargetIndex = 0;
-    ImageHandle m_postProcessBuffers[2], m_brdfLut, m_minMaxDepthPyramid, m_worldSpaceNormalImage, m_depthHalfRes, m_gbuffer;
+    ImageHandle m_postProcessBuffers[2], m_brdfLut, m_minMaxDepthPyramid, m_depthHalfRes;
+    // raster-pass outputs the caller uploads every frame; two of each, indexed like m_frameRenderTargets, so that the upload
+    // of frame N+1 (copy engine) overlaps the passes of frame N instead of waiting for them to release a single image
+    ImageHandle m_worldSpaceNormalImages[2], m_gbuffers[2];
+    ImageHandle worldSpaceNormalImage() const { return m_worldSpaceNormalImages[m_sceneRenderTargetIndex]; }
+    ImageHandle gbuffer() const { return m_gbuffers[m_sceneRenderTargetIndex]; }
     std::vector<ImageHandle> m_shadowMaps, m_noiseTextures;
     StorageBufferHandle m_histogramBuffer, m_lightBuffer, m_histogramPerTileBuffer, m_depthPyramidSyncBuffer, m_sunShadowInfoBuffer;
     UniformBufferHandle m_globalUniformBuffer;

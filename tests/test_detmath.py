@@ -15,7 +15,7 @@ def dm():
     out.mkdir(exist_ok=True)
     lib = out / "libdetmath_c.so"
     src = ROOT / "tests" / "emul" / "detmath_c.cpp"
-    subprocess.run(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-I", str(ROOT / "plainrenderer_b200" / "csrc"), str(src), "-o", str(lib)], check=True)
+    subprocess.run(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-mfma", "-fPIC", "-shared", "-I", str(ROOT / "plainrenderer_b200" / "csrc"), str(src), "-o", str(lib)], check=True)
     return C.CDLL(str(lib))
 
 
