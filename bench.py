@@ -255,6 +255,7 @@ def run_ours(args, rank, world, local_rank):
         e0.record(stream)
         for _ in range(k):
             step(upload, readback)
+        be._check(api.b["join_transfers"](be.ctx), "join_transfers")  # the end event also covers the copies on the upload / download streams
         e1.record(stream)
         barrier()
         ms = e0.elapsed_time(e1)

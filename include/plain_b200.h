@@ -184,7 +184,11 @@ PLAIN_EXPORT int PLAIN_FN(set_timing_enabled)(plain_ctx* ctx, int enabled);
 PLAIN_EXPORT int PLAIN_FN(write_image)(plain_ctx* ctx, plain_image_handle image, uint32_t mip_level, const void* data, size_t size);
 PLAIN_EXPORT int PLAIN_FN(read_image)(plain_ctx* ctx, plain_image_handle image, uint32_t mip_level, void* out, size_t size);
 PLAIN_EXPORT int PLAIN_FN(read_storage_buffer)(plain_ctx* ctx, plain_handle buffer, void* out, size_t size);
-/* async variants on the backend stream with caller-pinned host memory (e2e leg: upload of the frame inputs, read-back of the frame) */
+/* async variants with caller-pinned host memory (e2e leg: upload of the frame inputs, read-back of the frame). In the CUDA
+ * backend they run on dedicated upload / download streams so the copy engines overlap the passes: an upload waits for the
+ * last submission that referenced the image, a submission waits for the uploads issued before it, a read-back sees the
+ * passes submitted before it. The host buffer of a read-back is valid after wait_for_gpu_idle (or once an event recorded
+ * on the pass stream after join_transfers has completed). */
 PLAIN_EXPORT int PLAIN_FN(write_image_async)(plain_ctx* ctx, plain_image_handle image, uint32_t mip_level, const void* pinned_data, size_t size);
 PLAIN_EXPORT int PLAIN_FN(read_image_async)(plain_ctx* ctx, plain_image_handle image, uint32_t mip_level, void* pinned_out, size_t size);
 /* rows [row_begin, row_end) of a 2-D image level (images are row-major and tightly packed): a rank of a row-sharded frame
@@ -199,6 +203,9 @@ PLAIN_EXPORT int PLAIN_FN(get_storage_buffer_device_pointer)(plain_ctx* ctx, pla
 PLAIN_EXPORT int PLAIN_FN(get_last_frame_launch_count)(plain_ctx* ctx, uint32_t* out);
 /* enable replay of an unchanged pass list through a captured CUDA graph (CUDA backend; no-op in the oracle) */
 PLAIN_EXPORT int PLAIN_FN(set_graph_replay_enabled)(plain_ctx* ctx, int enabled);
+/* makes the pass stream wait for every asynchronous upload and read-back issued so far (no host synchronisation): an event
+ * recorded on the pass stream afterwards covers them. No-op in the oracle. */
+PLAIN_EXPORT int PLAIN_FN(join_transfers)(plain_ctx* ctx);
 /* the stream all passes run on (cudaStream_t as void*), for callers that time with CUDA events */
 PLAIN_EXPORT int PLAIN_FN(get_stream)(plain_ctx* ctx, void** out_stream);
 

@@ -377,6 +377,7 @@ int PLAIN_FN(get_storage_buffer_device_pointer)(plain_ctx* ctx, plain_handle buf
 }
 int PLAIN_FN(get_last_frame_launch_count)(plain_ctx* ctx, uint32_t* out) { (void)ctx; *out = 0; return 0; }
 int PLAIN_FN(set_graph_replay_enabled)(plain_ctx* ctx, int enabled) { (void)ctx; (void)enabled; return 0; }
+int PLAIN_FN(join_transfers)(plain_ctx* ctx) { (void)ctx; return 0; }
 int PLAIN_FN(get_stream)(plain_ctx* ctx, void** out_stream) { (void)ctx; *out_stream = nullptr; return 0; }
 
 }  // extern "C"

@@ -47,8 +47,22 @@ struct Backend {
     int device = 0;
     int smCount = 148;
     cudaStream_t stream = nullptr;
+    // Asynchronous image uploads / read-backs run on their own streams (copy engines) so that the raster-pass outputs of
+    // frame N+1 travel while the passes of frame N execute. Ordering: an upload into an image waits for the last
+    // submission that referenced it (submissionDone ring) and for a pending read-back of it; a submission waits for
+    // every upload issued before it and for the read-backs still in flight; a read-back waits for the passes
+    // submitted so far.
+    cudaStream_t uploadStream = nullptr, downloadStream = nullptr;
+    static const int kSubmissionRing = 8;
+    cudaEvent_t submissionDone[kSubmissionRing] = {};
+    cudaEvent_t uploadsDone = nullptr, computeMark = nullptr;
+    long long submissionCounter = 0;
+    bool uploadsPending = false;
     std::vector<DeviceImage> images, transientImages;
-    DeviceImage swapchain;
+    // two presentable images, flipped by new_frame (a swapchain hands out a different image every frame): the read-back of
+    // frame N does not hold up the tonemapping pass of frame N+1
+    DeviceImage swapchainImages[2];
+    int swapchainCurrent = 0;
     std::vector<DeviceBuffer> uniformBuffers, storageBuffers;
     std::vector<plain_sampler_desc> samplers;
     std::vector<PassRecord> passes;
@@ -78,7 +92,7 @@ struct Backend {
     uint32_t launchCounter = 0;
 
     DeviceImage* resolve(plain_image_handle h) {
-        if (h.type == PLAIN_IMAGE_HANDLE_SWAPCHAIN) return &swapchain;
+        if (h.type == PLAIN_IMAGE_HANDLE_SWAPCHAIN) return &swapchainImages[swapchainCurrent];
         if (h.type == PLAIN_IMAGE_HANDLE_TRANSIENT) return h.index < transientImages.size() ? &transientImages[h.index] : nullptr;
         return h.index < images.size() ? &images[h.index] : nullptr;
     }
@@ -116,7 +130,7 @@ static int computeMipCount(const plain_image_desc& d) {
 }
 
 static bool allocateImage(Backend& b, DeviceImage& img, const plain_image_desc& d) {
-    if (img.ptr) { cudaStreamSynchronize(b.stream); cudaFree(img.ptr); img.ptr = nullptr; }
+    if (img.ptr) { cudaStreamSynchronize(b.uploadStream); cudaStreamSynchronize(b.downloadStream); cudaStreamSynchronize(b.stream); cudaFree(img.ptr); img.ptr = nullptr; }
     img.desc = d;
     const int n = computeMipCount(d), bpt = formatBytesPerTexel(d.format);
     img.mips.assign(n, MipInfo());
@@ -209,6 +223,7 @@ static uint64_t hashExecs(const Backend& b) {
     uint64_t h = 1469598103934665603ull;
     h = fnv(h, &b.passEpoch, sizeof(b.passEpoch));
     h = fnv(h, &b.globalUniformBuffer, sizeof(uint32_t));
+    h = fnv(h, &b.swapchainCurrent, sizeof(int));  // the swapchain handle resolves to a different allocation every other frame
     for (auto& e : b.execs) {
         h = fnv(h, &e.pass, 4);
         uint32_t n;
@@ -221,6 +236,52 @@ static uint64_t hashExecs(const Backend& b) {
         h = fnv(h, &e.rowBegin, 12);
     }
     return h;
+}
+
+// the compute stream waits for the uploads and read-backs issued so far
+static void joinTransfers(Backend& b) {
+    if (b.uploadsPending) {
+        cudaEventRecord(b.uploadsDone, b.uploadStream);
+        cudaStreamWaitEvent(b.stream, b.uploadsDone, 0);
+        b.uploadsPending = false;
+    }
+}
+// a submission that references an image with a read-back in flight waits for that read-back (write-after-read)
+static void orderAfterDownload(Backend& b, DeviceImage* img) {
+    if (img && img->downloadPending) {
+        cudaStreamWaitEvent(b.stream, img->downloadDone, 0);
+        img->downloadPending = false;
+    }
+}
+// stream for an asynchronous copy of `img`, ordered against the passes and the other copy direction
+static cudaStream_t transferStream(Backend& b, DeviceImage& img, bool toDevice) {
+    if (toDevice) {
+        if (img.lastUsedSubmission >= 0) {
+            // the ring slot holds this submission's event or, once overwritten, a later one: either completes after it
+            cudaStreamWaitEvent(b.uploadStream, b.submissionDone[img.lastUsedSubmission % Backend::kSubmissionRing], 0);
+        }
+        if (img.downloadPending) cudaStreamWaitEvent(b.uploadStream, img.downloadDone, 0);
+        b.uploadsPending = true;
+        return b.uploadStream;
+    }
+    cudaEventRecord(b.computeMark, b.stream);
+    cudaStreamWaitEvent(b.downloadStream, b.computeMark, 0);
+    if (b.uploadsPending) {  // a read-back of an image that is being uploaded sees the upload
+        cudaEventRecord(b.uploadsDone, b.uploadStream);
+        cudaStreamWaitEvent(b.downloadStream, b.uploadsDone, 0);
+    }
+    return b.downloadStream;
+}
+static void markDownloaded(Backend& b, DeviceImage& img) {
+    if (!img.downloadDone) cudaEventCreateWithFlags(&img.downloadDone, cudaEventDisableTiming);
+    cudaEventRecord(img.downloadDone, b.downloadStream);
+    img.downloadPending = true;
+}
+// blocking operations on the compute stream first drain the transfer streams
+static void drainTransfers(Backend& b) {
+    cudaStreamSynchronize(b.uploadStream);
+    cudaStreamSynchronize(b.downloadStream);
+    joinTransfers(b);
 }
 
 static bool runPasses(Backend& b, bool withTiming) {
@@ -290,8 +351,12 @@ int PLAIN_FN(backend_create)(int device, uint32_t width, uint32_t height, plain_
     Backend& b = ctx->b;
     b.device = device;
     cudaDeviceGetAttribute(&b.smCount, cudaDevAttrMultiProcessorCount, device);
-    if (cudaStreamCreateWithFlags(&b.stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return 1; }
+    if (cudaStreamCreateWithFlags(&b.stream, cudaStreamNonBlocking) != cudaSuccess || cudaStreamCreateWithFlags(&b.uploadStream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&b.downloadStream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return 1; }
     cudaEventCreateWithFlags(&b.stagingConsumed, cudaEventDisableTiming);
+    for (auto& e : b.submissionDone) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&b.uploadsDone, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&b.computeMark, cudaEventDisableTiming);
     if (cudaMallocHost(&b.stagingHost, kStagingBytes) != cudaSuccess || cudaMalloc(&b.stagingDevice, kStagingBytes) != cudaSuccess ||
         cudaMalloc(&b.bindlessDevice, sizeof(BindlessEntry) * Backend::kMaxBindless) != cudaSuccess || cudaMalloc(&b.tablesDevice, sizeof(ShadingTables)) != cudaSuccess) {
         fprintf(stderr, "plain_backend_create: allocation failed: %s\n", cudaGetErrorString(cudaGetLastError()));
@@ -304,7 +369,7 @@ int PLAIN_FN(backend_create)(int device, uint32_t width, uint32_t height, plain_
     d.width = width; d.height = height; d.depth = 1;
     d.type = PLAIN_IMAGE_TYPE_2D; d.format = PLAIN_FORMAT_BGRA8_UNORM;  // VulkanSurface.cpp:41-46
     d.usage_flags = PLAIN_USAGE_STORAGE; d.mip_count = PLAIN_MIPS_ONE;
-    if (!allocateImage(b, b.swapchain, d)) { delete ctx; return 1; }
+    for (auto& sc : b.swapchainImages) if (!allocateImage(b, sc, d)) { delete ctx; return 1; }
     *out_ctx = ctx;
     return 0;
 }
@@ -312,11 +377,15 @@ void PLAIN_FN(backend_destroy)(plain_ctx* ctx) {
     if (!ctx) return;
     Backend& b = ctx->b;
     cudaSetDevice(b.device);
+    cudaStreamSynchronize(b.uploadStream);
+    cudaStreamSynchronize(b.downloadStream);
     cudaStreamSynchronize(b.stream);
     for (auto& g : b.graphs) if (g.second.exec) cudaGraphExecDestroy(g.second.exec);
     for (auto& i : b.images) cudaFree(i.ptr);
     for (auto& i : b.transientImages) cudaFree(i.ptr);
-    cudaFree(b.swapchain.ptr);
+    for (auto& sc : b.swapchainImages) { cudaFree(sc.ptr); if (sc.downloadDone) cudaEventDestroy(sc.downloadDone); }
+    for (auto& i : b.images) if (i.downloadDone) cudaEventDestroy(i.downloadDone);
+    for (auto& i : b.transientImages) if (i.downloadDone) cudaEventDestroy(i.downloadDone);
     for (auto& u : b.uniformBuffers) cudaFree(u.ptr);
     for (auto& s : b.storageBuffers) cudaFree(s.ptr);
     for (auto& e : b.timingEvents) cudaEventDestroy(e);
@@ -325,14 +394,20 @@ void PLAIN_FN(backend_destroy)(plain_ctx* ctx) {
     cudaFree(b.bindlessDevice);
     cudaFree(b.tablesDevice);
     cudaEventDestroy(b.stagingConsumed);
+    for (auto& e : b.submissionDone) cudaEventDestroy(e);
+    cudaEventDestroy(b.uploadsDone);
+    cudaEventDestroy(b.computeMark);
+    cudaStreamDestroy(b.uploadStream);
+    cudaStreamDestroy(b.downloadStream);
     cudaStreamDestroy(b.stream);
     delete ctx;
 }
 const char* PLAIN_FN(last_error)(plain_ctx* ctx) { return ctx ? ctx->b.lastError.c_str() : "null context"; }
 int PLAIN_FN(recreate_swapchain)(plain_ctx* ctx, uint32_t width, uint32_t height) {
-    plain_image_desc d = ctx->b.swapchain.desc;
+    plain_image_desc d = ctx->b.swapchainImages[0].desc;
     d.width = width; d.height = height;
-    return allocateImage(ctx->b, ctx->b.swapchain, d) ? 0 : fail(ctx, "recreate_swapchain: allocation failed");
+    for (auto& sc : ctx->b.swapchainImages) if (!allocateImage(ctx->b, sc, d)) return fail(ctx, "recreate_swapchain: allocation failed");
+    return 0;
 }
 
 int PLAIN_FN(create_image)(plain_ctx* ctx, const plain_image_desc* desc, const void* initial_data, size_t initial_data_size, plain_image_handle* out) {
@@ -467,6 +542,7 @@ int PLAIN_FN(set_global_descriptor_set_resources)(plain_ctx* ctx, const plain_pa
 
 int PLAIN_FN(new_frame)(plain_ctx* ctx) {
     ctx->b.execs.clear();
+    ctx->b.swapchainCurrent ^= 1;  // the next presentable image (RenderBackend.cpp:608-612 getSwapchainInputImage)
     for (auto& t : ctx->b.transientImages) t.inUse = false;
     return 0;
 }
@@ -511,6 +587,11 @@ int PLAIN_FN(render_frame)(plain_ctx* ctx, int present) {
     Backend& b = ctx->b;
     cudaSetDevice(b.device);
     b.launchCounter = 0;
+    joinTransfers(b);  // uploads issued before this submission are visible to its passes; read-backs in flight keep their source
+    for (auto& e : b.execs) {
+        for (auto& r : e.sampledImages) if (DeviceImage* img = b.resolve(r.image)) img->lastUsedSubmission = b.submissionCounter;
+        for (auto& r : e.storageImages) if (DeviceImage* img = b.resolve(r.image)) { img->lastUsedSubmission = b.submissionCounter; orderAfterDownload(b, img); }
+    }
     // all fills of the frame land before any pass (RenderBackend.cpp:896-911): one H2D copy + one scatter kernel
     if (!b.fills.empty()) {
         FillSegment* table = (FillSegment*)b.stagingHost;
@@ -565,6 +646,8 @@ int PLAIN_FN(render_frame)(plain_ctx* ctx, int present) {
     cudaError_t e = cudaPeekAtLastError();
     if (e != cudaSuccess) return fail(ctx, std::string("render_frame: ") + cudaGetErrorString(e));
     b.lastFrameLaunches = b.launchCounter;
+    cudaEventRecord(b.submissionDone[b.submissionCounter % Backend::kSubmissionRing], b.stream);
+    b.submissionCounter++;
     return 0;
 }
 int PLAIN_FN(submit_recorded_passes)(plain_ctx* ctx) {
@@ -574,7 +657,16 @@ int PLAIN_FN(submit_recorded_passes)(plain_ctx* ctx) {
 }
 int PLAIN_FN(wait_for_gpu_idle)(plain_ctx* ctx) {
     cudaSetDevice(ctx->b.device);
+    drainTransfers(ctx->b);
     CU_CHECK(ctx, cudaStreamSynchronize(ctx->b.stream));
+    return 0;
+}
+int PLAIN_FN(join_transfers)(plain_ctx* ctx) {  // the compute stream waits for every asynchronous upload and read-back issued so far
+    Backend& b = ctx->b;
+    cudaSetDevice(b.device);
+    joinTransfers(b);
+    cudaEventRecord(b.computeMark, b.downloadStream);
+    cudaStreamWaitEvent(b.stream, b.computeMark, 0);
     return 0;
 }
 int PLAIN_FN(get_renderpass_timings)(plain_ctx* ctx, plain_pass_time* out, uint32_t capacity, uint32_t* out_count) {
@@ -592,8 +684,11 @@ static int imageCopy(plain_ctx* ctx, plain_image_handle image, uint32_t mip, voi
     if (!img || mip >= img->mips.size()) return fail(ctx, std::string(what) + ": invalid handle/mip");
     if (size != img->mips[mip].bytes) return fail(ctx, std::string(what) + ": size mismatch");
     unsigned char* dev = img->ptr + img->mips[mip].offset;
-    if (toDevice) CU_CHECK(ctx, cudaMemcpyAsync(dev, host, size, cudaMemcpyHostToDevice, b.stream));
-    else CU_CHECK(ctx, cudaMemcpyAsync(host, dev, size, cudaMemcpyDeviceToHost, b.stream));
+    if (sync) drainTransfers(b);
+    cudaStream_t st = sync ? b.stream : transferStream(b, *img, toDevice);
+    if (toDevice) CU_CHECK(ctx, cudaMemcpyAsync(dev, host, size, cudaMemcpyHostToDevice, st));
+    else CU_CHECK(ctx, cudaMemcpyAsync(host, dev, size, cudaMemcpyDeviceToHost, st));
+    if (!sync && !toDevice) markDownloaded(b, *img);
     if (sync) CU_CHECK(ctx, cudaStreamSynchronize(b.stream));
     return 0;
 }
@@ -612,8 +707,10 @@ static int imageRowsCopy(plain_ctx* ctx, plain_image_handle image, uint32_t mip,
     if (size != pitch * (rowEnd - rowBegin)) return fail(ctx, std::string(what) + ": size mismatch");
     if (size == 0) return 0;
     unsigned char* dev = img->ptr + m.offset + pitch * rowBegin;
-    if (toDevice) CU_CHECK(ctx, cudaMemcpyAsync(dev, host, size, cudaMemcpyHostToDevice, b.stream));
-    else CU_CHECK(ctx, cudaMemcpyAsync(host, dev, size, cudaMemcpyDeviceToHost, b.stream));
+    cudaStream_t st = transferStream(b, *img, toDevice);
+    if (toDevice) CU_CHECK(ctx, cudaMemcpyAsync(dev, host, size, cudaMemcpyHostToDevice, st));
+    else CU_CHECK(ctx, cudaMemcpyAsync(host, dev, size, cudaMemcpyDeviceToHost, st));
+    if (!toDevice) markDownloaded(b, *img);
     return 0;
 }
 int PLAIN_FN(write_image_rows_async)(plain_ctx* ctx, plain_image_handle image, uint32_t mip, uint32_t rowBegin, uint32_t rowEnd, const void* data, size_t size) { return imageRowsCopy(ctx, image, mip, rowBegin, rowEnd, (void*)data, size, true, "write_image_rows_async"); }
@@ -622,6 +719,7 @@ int PLAIN_FN(read_storage_buffer)(plain_ctx* ctx, plain_handle buffer, void* out
     Backend& b = ctx->b;
     cudaSetDevice(b.device);
     if (buffer >= b.storageBuffers.size() || size > b.storageBuffers[buffer].size) return fail(ctx, "read_storage_buffer: invalid buffer/size");
+    drainTransfers(b);
     CU_CHECK(ctx, cudaMemcpyAsync(out, b.storageBuffers[buffer].ptr, size, cudaMemcpyDeviceToHost, b.stream));
     CU_CHECK(ctx, cudaStreamSynchronize(b.stream));
     return 0;

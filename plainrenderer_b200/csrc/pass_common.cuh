@@ -31,6 +31,9 @@ struct DeviceImage {
     size_t bytes = 0;
     std::vector<MipInfo> mips;
     bool inUse = false;
+    long long lastUsedSubmission = -1;  // index of the last submission (render_frame) whose passes referenced the image
+    cudaEvent_t downloadDone = nullptr; // recorded after the last asynchronous read-back of the image (created on first use)
+    bool downloadPending = false;       // that read-back has not been ordered before a later writer yet
 };
 struct DeviceBuffer {
     unsigned char* ptr = nullptr;

@@ -159,6 +159,11 @@ struct TraceResult {
     vec3 hitPos, N;
     int hitCount;
     vec3 albedo;
+    // march state of the hit that currently holds closestHitDistance: hit position, normal and albedo (SDF.inc:165-176)
+    // are evaluated from it once, after all instances, instead of at every improvement (only the last one survives)
+    int winner;  // index into the tile's list, -1: none
+    vec3 winnerSamplePos, winnerRayDirection;
+    float winnerD, winnerDLast;
 };
 __device__ __forceinline__ float sampleSDF(const ImgView& sdf, vec3 uv) { return sampleR16FLinearClamp3D(sdf, uv); }  // SDF.inc:12-14
 __device__ __forceinline__ vec3 normalFromSDF(vec3 uv, vec3 extends, const ImgView& sdf) {  // SDF.inc:16-25
@@ -226,32 +231,31 @@ __device__ __forceinline__ bool traceSetup(const TraceInstance& inst, vec3 raySt
     return true;
 }
 // one iteration of the loop SDF.inc:144-183. Returns true while the lane keeps marching through this instance.
-__device__ __forceinline__ bool traceStep(const TraceInstance& inst, vec3 rayStartWorld, vec3 rayDirectionWorld, TraceResult& tr, MarchState& st) {
+// `listIndex` is the position of the instance in the tile's list. The reference visits the list in order and replaces the
+// closest hit only by a strictly closer one, so of two hits at the same distance the one listed first wins; this kernel
+// visits the instances in a different order (sdfDiffuseTraceKernel) and applies that rule explicitly.
+__device__ __forceinline__ bool traceStep(const TraceInstance& inst, int listIndex, TraceResult& tr, MarchState& st) {
     if (st.k >= 128) return false;
-    const vec3 localExtends = inst.localExtends, localExtendsHalf = inst.localExtendsHalfPadded;
+    const vec3 localExtendsHalf = inst.localExtendsHalfPadded;
     const vec3 localSamplePos = st.localSamplePos;
     if (localSamplePos.x > localExtendsHalf.x || localSamplePos.y > localExtendsHalf.y || localSamplePos.z > localExtendsHalf.z ||
         localSamplePos.x < -localExtendsHalf.x || localSamplePos.y < -localExtendsHalf.y || localSamplePos.z < -localExtendsHalf.z)
         return false;
-    vec3 sampleUV = localSamplePos * inst.invLocalExtends + 0.5f;  // localSamplePos / localExtends + 0.5
+    const vec3 sampleUV = localSamplePos * inst.invLocalExtends + 0.5f;  // localSamplePos / localExtends + 0.5
     st.dLast = st.d;
     const float d = sampleSDF(inst.sdf, sampleUV);
     st.d = d;
     if (d < inst.distanceThreshold) {
         tr.hit = true;
         const float distanceGlobal = st.hitDistanceLocal * inst.localToGlobalScale;
-        if (distanceGlobal < tr.closestHitDistance) {
+        if (distanceGlobal < tr.closestHitDistance || (distanceGlobal == tr.closestHitDistance && listIndex < tr.winner)) {
             tr.closestHitDistance = distanceGlobal;
             tr.hitCount = st.k;
-            const float lastStepSizeLocal = d / (1.f - (d - st.dLast));
-            const vec3 hitSamplePos = localSamplePos + st.rayDirection * lastStepSizeLocal;
-            sampleUV = hitSamplePos * inst.invLocalExtends + 0.5f;
-            const vec3 N = normalFromSDF(sampleUV, localExtends, inst.sdf);
-            const float* m = inst.worldToLocal;  // transpose(mat3(worldToLocal)) * N
-            tr.N = v3(m[0], m[4], m[8]) * N.x + v3(m[1], m[5], m[9]) * N.y + v3(m[2], m[6], m[10]) * N.z;
-            tr.albedo = vpow(inst.meanAlbedo, v3(2.2f));
-            const float lastStepSizeGlobal = lastStepSizeLocal * inst.localToGlobalScale;
-            tr.hitPos = rayStartWorld + rayDirectionWorld * (distanceGlobal + lastStepSizeGlobal);
+            tr.winner = listIndex;
+            tr.winnerSamplePos = localSamplePos;
+            tr.winnerRayDirection = st.rayDirection;
+            tr.winnerD = d;
+            tr.winnerDLast = st.dLast;
         }
         return false;
     }
@@ -259,6 +263,19 @@ __device__ __forceinline__ bool traceStep(const TraceInstance& inst, vec3 raySta
     st.hitDistanceLocal += absf(d);
     st.k++;
     return true;
+}
+// SDF.inc:165-176 for the hit that ended up closest
+__device__ __forceinline__ void shadeWinner(const TraceInstance& inst, vec3 rayStartWorld, vec3 rayDirectionWorld, TraceResult& tr) {
+    const float d = tr.winnerD;
+    const float lastStepSizeLocal = d / (1.f - (d - tr.winnerDLast));
+    const vec3 hitSamplePos = tr.winnerSamplePos + tr.winnerRayDirection * lastStepSizeLocal;
+    const vec3 sampleUV = hitSamplePos * inst.invLocalExtends + 0.5f;
+    const vec3 N = normalFromSDF(sampleUV, inst.localExtends, inst.sdf);
+    const float* m = inst.worldToLocal;  // transpose(mat3(worldToLocal)) * N
+    tr.N = v3(m[0], m[4], m[8]) * N.x + v3(m[1], m[5], m[9]) * N.y + v3(m[2], m[6], m[10]) * N.z;
+    tr.albedo = vpow(inst.meanAlbedo, v3(2.2f));
+    const float lastStepSizeGlobal = lastStepSizeLocal * inst.localToGlobalScale;
+    tr.hitPos = rayStartWorld + rayDirectionWorld * (tr.closestHitDistance + lastStepSizeGlobal);
 }
 
 // World-space sphere around the image of the local box [-extends/2, extends/2] under inverse(worldToLocal), padded by
@@ -311,14 +328,11 @@ struct TraceParams {
 // group traces, also those beyond the image edge: they are neighbours in the resolve; only their stores are dropped.
 //
 // Scheduling inside a warp: rays hit different instances with very different step counts, so the per-instance
-// trace of the reference (SDF.inc:101-184) is split into states that one loop interleaves:
-//   1. up front, convergent: every lane tests its ray against the bounding spheres of ALL listed instances and keeps
-//      a candidate bit mask (<= 100 bits) - the instances whose slab test could succeed
-//   2. MARCH: one sphere-trace step of the lane's current instance per iteration (the hot, convergent code)
-//   3. SETUP: transform/clip the ray for the lane's next candidate (lowest set bit: list order is kept because the
-//      closest-hit early-out of SDF.inc:141 depends on it); runs only when a quarter of the warp waits for it
-// The per-ray operation sequence is exactly the reference's, so results do not depend on the schedule.
-__global__ void __launch_bounds__(256) sdfDiffuseTraceKernel(const __grid_constant__ TraceParams p) {
+// trace of the reference (SDF.inc:101-184) is split into states that one loop interleaves (steps 1-4 in the kernel).
+// Per (ray, instance) the operation sequence is exactly the reference's; across instances the result of a ray is the
+// closest hit with ties going to the instance listed first - what the reference's in-order loop computes - so it does
+// not depend on the order in which the instances are visited, and the kernel visits the nearest box first.
+__global__ void __launch_bounds__(256, 3) sdfDiffuseTraceKernel(const __grid_constant__ TraceParams p) {
     __shared__ TraceInstance sInst[PLAIN_MAX_OBJECTS_PER_TILE];
     __shared__ uint32_t sCount;
     __shared__ float sRayNormal[4][8][8][3], sRayDepth[4][8][8], sRayColor[4][8][8][3];
@@ -378,6 +392,9 @@ __global__ void __launch_bounds__(256) sdfDiffuseTraceKernel(const __grid_consta
         tr.hitCount = 0;
         tr.hitPos = v3(0.f); tr.N = v3(0.f); tr.albedo = v3(0.f);
 
+        tr.winner = -1;
+        tr.winnerSamplePos = v3(0.f); tr.winnerRayDirection = v3(0.f); tr.winnerD = 0.f; tr.winnerDLast = 0.f;
+
         // 1. candidate mask, all lanes in lockstep over the tile's list
         const float invLen2 = 1.f / dot(L, L);
         uint32_t cand[4];
@@ -392,17 +409,35 @@ __global__ void __launch_bounds__(256) sdfDiffuseTraceKernel(const __grid_consta
             }
             cand[w] = m;
         }
-        auto popCandidate = [&]() -> int {  // lowest listed candidate, -1 when none is left
+        uint32_t scan[4] = {cand[0], cand[1], cand[2], cand[3]};
+        auto popLowest = [](uint32_t (&m)[4]) -> int {  // lowest listed candidate, -1 when none is left
 #pragma unroll
             for (int w = 0; w < 4; w++)
-                if (cand[w]) { const int b = __ffs(cand[w]) - 1; cand[w] &= cand[w] - 1; return w * 32 + b; }
+                if (m[w]) { const int b = __ffs(m[w]) - 1; m[w] &= m[w] - 1; return w * 32 + b; }
             return -1;
         };
-        // 2./3. interleaved march / set-up
-        int next = popCandidate(), cur = 0;
-        bool marching = false;
-        MarchState st;
+        auto clearBit = [](uint32_t (&m)[4], int idx) {
+#pragma unroll
+            for (int w = 0; w < 4; w++)
+                if (w == (idx >> 5)) m[w] &= ~(1u << (idx & 31));
+        };
+        // 2. SCAN: set-up (SDF.inc:101-141) of every candidate in list order; candidates whose box the ray misses are
+        //    dropped, the one with the nearest entry point is remembered together with its march state
+        // 3. the nearest candidate is marched first: once it has produced a hit, SDF.inc:141 (entry point beyond the
+        //    closest hit) rejects most of the others without a single step
+        // 4. the remaining candidates in list order: set-up again (with the early-out against the closest hit), march
+        // SET-UP and MARCH of different lanes are interleaved: a march step is the hot, convergent code; set-ups run
+        // when a quarter of the warp waits for one. Visiting order does not change the result: the closest hit wins, a
+        // tie goes to the instance listed first (traceStep), and an instance skipped by SDF.inc:141 could only have
+        // produced a hit farther away than the one that caused the skip.
+        int next = popLowest(scan), cur = 0;
+        bool scanning = true, marching = false;
+        float bestEntry = 3.402823466e+38f;
+        int bestIdx = -1;
+        MarchState st, bestSt;
         st.localSamplePos = v3(0.f); st.rayDirection = v3(0.f); st.hitDistanceLocal = 0.f; st.d = 0.f; st.dLast = 0.f; st.k = 0;
+        bestSt = st;
+        if (next < 0) scanning = false;
         while (true) {
             const bool needSetup = !marching && next >= 0;
             const unsigned marchMask = __ballot_sync(0xffffffffu, marching), setupMask = __ballot_sync(0xffffffffu, needSetup);
@@ -411,13 +446,35 @@ __global__ void __launch_bounds__(256) sdfDiffuseTraceKernel(const __grid_consta
             if (nSetup > 0 && (nMarch == 0 || nSetup >= 8 || nSetup >= nMarch)) {
                 if (needSetup) {
                     cur = next;
-                    marching = traceSetup(sInst[cur], rayOrigin, L, tr, st);
-                    next = popCandidate();
+                    const bool ok = traceSetup(sInst[cur], rayOrigin, L, tr, st);
+                    if (scanning) {
+                        if (!ok) {
+                            clearBit(cand, cur);
+                        } else {
+                            const float entry = sInst[cur].localToGlobalScale * st.hitDistanceLocal;
+                            if (entry < bestEntry) { bestEntry = entry; bestIdx = cur; bestSt = st; }
+                        }
+                        next = popLowest(scan);
+                        if (next < 0) {  // scan complete: march the nearest candidate, then the others
+                            scanning = false;
+                            if (bestIdx >= 0) {
+                                clearBit(cand, bestIdx);
+                                cur = bestIdx;
+                                st = bestSt;
+                                marching = true;
+                            }
+                            next = popLowest(cand);
+                        }
+                    } else {
+                        marching = ok;
+                        next = popLowest(cand);
+                    }
                 }
                 continue;
             }
-            if (marching) marching = traceStep(sInst[cur], rayOrigin, L, tr, st);
+            if (marching) marching = traceStep(sInst[cur], cur, tr, st);
         }
+        if (tr.winner >= 0) shadeWinner(sInst[tr.winner], rayOrigin, L, tr);
         vec3 hitColor;
         if (tr.hit) {
             const float shadow = simpleShadow<true>(tr.hitPos, p.cascades->lightMatrices[p.shadowCascadeIndex], p.shadowMap);
@@ -528,10 +585,19 @@ __device__ __forceinline__ vec3 giPixelToWorld(const ImgView& depthTexture, cons
 // sqrt(rand), cos(angle), sin(angle) once into shared memory; each pixel only applies its own lengthModifier.
 // Per sample the coordinate is sanitised once and - when the depth, Y_SH and CoCg images have the same extent, which
 // is how the frontend creates them - the nearest texel is computed once for the three fetches (same expression,
-// same operands: same result).
+// same operands: same result). The loop is software-pipelined: the three texels of sample i+1 are requested before the
+// arithmetic of sample i runs (the position of sample i+1 depends on sample i only through lengthModifier, which is known
+// as soon as sample i's coordinate is); Y_SH / CoCg are fetched speculatively (clamped addresses are always valid) and
+// only used when the reference would have sampled them.
+struct SpatialFetch {
+    vec2 uv;        // sampleUV after the border fix-up (unsanitised: the NDC of giDepthToWorld uses it as is)
+    float depth;
+    uint2 ysh;
+    uint32_t cocg;
+};
 template <bool DEPTH_IS_R16F>
-__global__ void __launch_bounds__(256) giSpatialFilterKernel(const __grid_constant__ SpatialParams p) {
-    __shared__ float sSqrtRand[32], sCos[32], sSin[32];
+__global__ void __launch_bounds__(256, 4) giSpatialFilterKernel(const __grid_constant__ SpatialParams p) {
+    __shared__ float sSqrtRand[32], sCos[32], sSin[32], sVP[16];
     const plain_global_shader_info* g = p.g;
     if (threadIdx.x == 0) {
         uint32_t rngState = wang_hash(g->frameIndexMod4 + (uint32_t)p.filterIndex);
@@ -542,13 +608,11 @@ __global__ void __launch_bounds__(256) giSpatialFilterKernel(const __grid_consta
             sSin[i] = dm::sin(angle);
         }
     }
+    if (threadIdx.x >= 32 && threadIdx.x < 48) sVP[threadIdx.x - 32] = g->viewProjection[threadIdx.x - 32];
     __syncthreads();
     const int ix = blockIdx.x * 32 + (threadIdx.x & 31), iy = p.y0 + blockIdx.y * 8 + (threadIdx.x >> 5);
     if (ix >= p.outYSH.w || iy >= p.y1) return;
     const Globals G = loadGlobals(g);
-    float VP[16];
-#pragma unroll
-    for (int k = 0; k < 16; k++) VP[k] = g->viewProjection[k];
     const vec2 texelSize = 1.f / v2((float)p.outYSH.w, (float)p.outYSH.h);
     const vec2 uv = (v2((float)ix, (float)iy) + 0.5f) * texelSize;
     const vec3 pCenter = giPixelToWorld<DEPTH_IS_R16F>(p.depthTexture, G, uv);
@@ -558,39 +622,51 @@ __global__ void __launch_bounds__(256) giSpatialFilterKernel(const __grid_consta
     const vec3 bitangent = normalize(pCenter - pUp);
     const vec3 N = 2.f * sampleNearest2D<WRAP_CLAMP, vec3>([&](int x, int y) { return loadRGBA8rgb(p.normalTexture, x, y); }, p.normalTexture.w, p.normalTexture.h, uv, v3(0.f)) - 1.f;
     const bool sameExtent = p.texYSH.w == p.depthTexture.w && p.texYSH.h == p.depthTexture.h && p.texCoCg.w == p.depthTexture.w && p.texCoCg.h == p.depthTexture.h;
-    vec4 result_Y_SH = v4(0.f);
-    vec2 result_CoCg = v2(0.f);
-    float weightTotal = 0.f;
     float radiusWorld = 1.5f;
     if (p.filterIndex == 1) radiusWorld = 1.f;
-    float lengthModifier = 1.f;
-    for (int i = 0; i < 32; i++) {
+    // position + texel requests of sample i for the current lengthModifier (:72-98)
+    auto fetchSample = [&](int i, float lengthModifier) {
+        SpatialFetch f;
         const float d = sSqrtRand[i] * lengthModifier;
         const vec2 offset = v2(sCos[i], sSin[i]) * d;
         const vec3 sampleWorld = pCenter + radiusWorld * (offset.x * tangent + offset.y * bitangent);
-        const vec4 sampleProjected = mulm4(VP, v4(sampleWorld, 1.f));
+        const vec4 sampleProjected = mulm4(sVP, v4(sampleWorld, 1.f));
         vec2 sampleUV = v2(sampleProjected.x, sampleProjected.y) / sampleProjected.w;
         sampleUV = sampleUV * 0.5f + 0.5f;
         sampleUV.x = sampleUV.x < 0.f ? uv.x - offset.x : sampleUV.x;
         sampleUV.y = sampleUV.y < 0.f ? uv.y - offset.y : sampleUV.y;
         sampleUV.x = sampleUV.x > 1.f ? uv.x - offset.x : sampleUV.x;
         sampleUV.y = sampleUV.y > 1.f ? uv.y - offset.y : sampleUV.y;
+        f.uv = sampleUV;
         const vec2 sampleUVSanitized = v2(sanitizeCoord(sampleUV.x), sanitizeCoord(sampleUV.y));
         const ivec2 td = nearestClampTexel(sampleUVSanitized, p.depthTexture.w, p.depthTexture.h);
-        const vec3 pixelWorld = giDepthToWorld(DEPTH_IS_R16F ? loadR16F(p.depthTexture, td.x, td.y) : loadD32(p.depthTexture, td.x, td.y), G, sampleUV);
+        const ivec2 ty = sameExtent ? td : nearestClampTexel(sampleUVSanitized, p.texYSH.w, p.texYSH.h);
+        const ivec2 tc = sameExtent ? td : nearestClampTexel(sampleUVSanitized, p.texCoCg.w, p.texCoCg.h);
+        f.depth = DEPTH_IS_R16F ? loadR16F(p.depthTexture, td.x, td.y) : loadD32(p.depthTexture, td.x, td.y);
+        f.ysh = ldg((const uint2*)p.texYSH.ptr + texelIndex(p.texYSH, ty.x, ty.y));
+        f.cocg = ldg((const uint32_t*)p.texCoCg.ptr + texelIndex(p.texCoCg, tc.x, tc.y));
+        return f;
+    };
+    vec4 result_Y_SH = v4(0.f);
+    vec2 result_CoCg = v2(0.f);
+    float weightTotal = 0.f;
+    float lengthModifier = 1.f;
+    SpatialFetch next = fetchSample(0, lengthModifier);
+#pragma unroll 1
+    for (int i = 0; i < 32; i++) {
+        const SpatialFetch cur = next;
+        const bool outside = cur.uv.x < 0.f || cur.uv.y < 0.f || cur.uv.x > 1.f || cur.uv.y > 1.f;
+        if (outside) lengthModifier *= 0.98f;
+        if (i + 1 < 32) next = fetchSample(i + 1, lengthModifier);
+        const vec3 pixelWorld = giDepthToWorld(cur.depth, G, cur.uv);
         const float distanceToTangentPlane = absf(dot(N, pixelWorld - pCenter));
         const float maxDistance = 0.25f;
         float weight = clampf(maxDistance / fmaxp(distanceToTangentPlane, 0.0001f), 0.f, 1.f);
         weight *= weight;
-        if (sampleUV.x < 0.f || sampleUV.y < 0.f || sampleUV.x > 1.f || sampleUV.y > 1.f) {
-            weight = 0.f;
-            lengthModifier *= 0.98f;
-        }
+        if (outside) weight = 0.f;
         if (weight > 0.f) {
-            const ivec2 ty = sameExtent ? td : nearestClampTexel(sampleUVSanitized, p.texYSH.w, p.texYSH.h);
-            const ivec2 tc = sameExtent ? td : nearestClampTexel(sampleUVSanitized, p.texCoCg.w, p.texCoCg.h);
-            const vec4 sample_Y_SH = loadRGBA16F(p.texYSH, ty.x, ty.y);
-            const vec2 sample_CoCg = loadRG16F(p.texCoCg, tc.x, tc.y);
+            const vec4 sample_Y_SH = v4(halfToFloat((uint16_t)(cur.ysh.x & 0xffffu)), halfToFloat((uint16_t)(cur.ysh.x >> 16)), halfToFloat((uint16_t)(cur.ysh.y & 0xffffu)), halfToFloat((uint16_t)(cur.ysh.y >> 16)));
+            const vec2 sample_CoCg = v2(halfToFloat((uint16_t)(cur.cocg & 0xffffu)), halfToFloat((uint16_t)(cur.cocg >> 16)));
             if (!(anynan(sample_Y_SH) || anynan(sample_CoCg))) {
                 result_Y_SH = result_Y_SH + weight * sample_Y_SH;
                 result_CoCg = result_CoCg + weight * sample_CoCg;

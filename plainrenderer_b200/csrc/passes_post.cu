@@ -148,12 +148,18 @@ __device__ __forceinline__ vec3 taaTonemapReverse(vec3 color) { return color / (
 struct Nb { vec3 v[3][3]; };  // v[x+1][y+1]
 template <bool TONEMAP, int TW, int TH>
 __device__ __forceinline__ void sampleNeighbourhood(const TileR11<TW, TH>& tile, const ImgView& tex, vec2 uv, vec2 texelSize, Nb& n) {  // :42-52
+    AxisTap X[3], Y[3];  // separable set-up of the nine taps (tile.cuh)
 #pragma unroll
-    for (int x = -1; x <= 1; x++)
+    for (int i = 0; i < 3; i++) {
+        X[i] = axisTap(uv.x + texelSize.x * (float)(i - 1), tex.w, tile.x0);
+        Y[i] = axisTap(uv.y + texelSize.y * (float)(i - 1), tex.h, tile.y0);
+    }
 #pragma unroll
-        for (int y = -1; y <= 1; y++) {
-            vec3 color = sampleR11LinearClampTile(tile, tex, uv + texelSize * v2((float)x, (float)y));
-            n.v[x + 1][y + 1] = TONEMAP ? taaTonemap(color) : color;
+    for (int x = 0; x < 3; x++)
+#pragma unroll
+        for (int y = 0; y < 3; y++) {
+            const vec3 color = tapR11Tile(tile, tex, X[x], Y[y]);
+            n.v[x][y] = TONEMAP ? taaTonemap(color) : color;
         }
 }
 __device__ __forceinline__ vec3 clipAABB(vec3 target, vec3 bbMin, vec3 bbMax) {  // :8-30

@@ -53,4 +53,40 @@ __device__ __forceinline__ vec3 sampleR11LinearClampTile(const TileR11<TW, TH>& 
     return vfma(t11, b.w11, vfma(t01, b.w01, vfma(t10, b.w10, t00 * b.w00)));
 }
 
+// ---- separable set-up for a 3x3 block of taps at uv + texelSize * (i - 1, j - 1) ----
+// The bilinear set-up of image_view.h bilerpSetup works per axis: the coordinate, its floor, the two weights and the two
+// clamped texel indices of the x axis depend only on i, those of the y axis only on j. Computing the three x axes and the
+// three y axes once (6 set-ups instead of 18) and combining them per tap evaluates the same expressions on the same
+// operands as nine calls of sampleR11LinearClampTile - the results are identical.
+struct AxisTap {
+    float a, b;      // weight of texel i1 / i0 (ax, 1 - ax)
+    unsigned l0, l1; // clamped texel indices relative to the tile origin (unsigned: one compare tests the range)
+    int i0, i1;      // clamped absolute texel indices (global fallback)
+};
+__device__ __forceinline__ AxisTap axisTap(float u, int size, int tileOrigin) {
+    AxisTap t;
+    const float f = fmaf_(sanitizeCoord(u), (float)size, -0.5f);
+    const float f0 = floorf_(f);
+    t.a = f - f0;
+    t.b = 1.f - t.a;
+    const int i = f2i(f0);
+    t.i0 = iclamp(i, 0, size - 1);
+    t.i1 = iclamp(i + 1, 0, size - 1);
+    t.l0 = (unsigned)(t.i0 - tileOrigin);
+    t.l1 = (unsigned)(t.i1 - tileOrigin);
+    return t;
+}
+template <int TW, int TH>
+__device__ __forceinline__ vec3 tapR11Tile(const TileR11<TW, TH>& t, const ImgView& img, const AxisTap& X, const AxisTap& Y) {
+    const float w00 = X.b * Y.b, w10 = X.a * Y.b, w01 = X.b * Y.a, w11 = X.a * Y.a;
+    vec3 t00, t10, t01, t11;
+    if (X.l0 < (unsigned)TW && X.l1 < (unsigned)TW && Y.l0 < (unsigned)TH && Y.l1 < (unsigned)TH) {
+        const float4 a = t.s[Y.l0 * TW + X.l0], bq = t.s[Y.l0 * TW + X.l1], c = t.s[Y.l1 * TW + X.l0], d = t.s[Y.l1 * TW + X.l1];
+        t00 = v3(a.x, a.y, a.z); t10 = v3(bq.x, bq.y, bq.z); t01 = v3(c.x, c.y, c.z); t11 = v3(d.x, d.y, d.z);
+    } else {
+        tapCornersGlobalR11(img, X.i0, X.i1, Y.i0, Y.i1, t00, t10, t01, t11);
+    }
+    return vfma(t11, w11, vfma(t01, w01, vfma(t10, w10, t00 * w00)));
+}
+
 }  // namespace pb

@@ -190,8 +190,9 @@ void RenderFrontend::initImages(uint32_t noiseSeed) {
     m_depthHalfRes = backend.createImage(imageDesc2D(w / 2, h / 2, PLAIN_FORMAT_R16_SFLOAT, SS), nullptr, 0);
     // packed G-buffer: the post-raster inputs of triangle.frag (new in this build)
     for (int i = 0; i < 2; i++) m_gbuffers[i] = backend.createImage(imageDesc2D(w, h, PLAIN_FORMAT_RGBA32_UINT, PLAIN_USAGE_ATTACHMENT | PLAIN_USAGE_SAMPLED), nullptr, 0);
+    for (int i = 0; i < 3; i++) m_motionBuffers[i] = backend.createImage(imageDesc2D(w, h, PLAIN_FORMAT_RG16_SNORM, PLAIN_USAGE_ATTACHMENT | PLAIN_USAGE_SAMPLED), nullptr, 0);
     for (int i = 0; i < 2; i++) {  // initRenderTargets :1399-1447
-        m_frameRenderTargets[i].motionBuffer = backend.createImage(imageDesc2D(w, h, PLAIN_FORMAT_RG16_SNORM, PLAIN_USAGE_ATTACHMENT | PLAIN_USAGE_SAMPLED), nullptr, 0);
+        m_frameRenderTargets[i].motionBuffer = m_motionBuffers[i];
         m_frameRenderTargets[i].colorBuffer = backend.createImage(imageDesc2D(w, h, PLAIN_FORMAT_R11G11B10_UFLOAT, PLAIN_USAGE_ATTACHMENT | SS), nullptr, 0);
         m_frameRenderTargets[i].depthBuffer = backend.createImage(imageDesc2D(w, h, PLAIN_FORMAT_DEPTH32, PLAIN_USAGE_ATTACHMENT | PLAIN_USAGE_SAMPLED), nullptr, 0);
     }
@@ -325,6 +326,10 @@ void RenderFrontend::prepareNewFrame() {
 void RenderFrontend::prepareRenderpasses() {
     const FrameRenderTargets previousRenderTarget = m_frameRenderTargets[m_sceneRenderTargetIndex];
     m_sceneRenderTargetIndex = (m_sceneRenderTargetIndex + 1) % 2;
+    // the motion buffer rotates through three images: the one frame N-1 wrote is still read by frame N (velocityLastFrame of
+    // the GI temporal filter), so with two the upload of frame N+1's motion vectors would have to wait for frame N to end
+    m_motionBufferIndex = (m_motionBufferIndex + 1) % 3;
+    m_frameRenderTargets[m_sceneRenderTargetIndex].motionBuffer = m_motionBuffers[m_motionBufferIndex];
     const FrameRenderTargets currentRenderTarget = m_frameRenderTargets[m_sceneRenderTargetIndex];
 
     computeColorBufferHistogram(previousRenderTarget.colorBuffer);

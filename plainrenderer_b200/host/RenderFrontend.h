@@ -193,7 +193,8 @@ public:
     ImageHandle m_postProcessBuffers[2], m_brdfLut, m_minMaxDepthPyramid, m_depthHalfRes;
     // raster-pass outputs the caller uploads every frame; two of each, indexed like m_frameRenderTargets, so that the upload
     // of frame N+1 (copy engine) overlaps the passes of frame N instead of waiting for them to release a single image
-    ImageHandle m_worldSpaceNormalImages[2], m_gbuffers[2];
+    ImageHandle m_worldSpaceNormalImages[2], m_gbuffers[2], m_motionBuffers[3];
+    int m_motionBufferIndex = 0;
     ImageHandle worldSpaceNormalImage() const { return m_worldSpaceNormalImages[m_sceneRenderTargetIndex]; }
     ImageHandle gbuffer() const { return m_gbuffers[m_sceneRenderTargetIndex]; }
     std::vector<ImageHandle> m_shadowMaps, m_noiseTextures;

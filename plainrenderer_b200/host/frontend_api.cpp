@@ -123,9 +123,9 @@ static void beginFrame(plain_frontend* fe, const plain_camera_extrinsic* cam, fl
             else f.backend.writeImage(h, 0, p, size);
         };
         upRows(t.depthBuffer, in->depth, 4);
-        up(t.motionBuffer, in->motion, W * H * 4);
         upRows(f.worldSpaceNormalImage(), in->normal, 4);
         upRows(f.gbuffer(), in->gbuffer, 16);
+        up(t.motionBuffer, in->motion, W * H * 4);
         for (int i = 0; i < 4; i++) up(f.m_shadowMaps[i], in->shadow_maps[i], (size_t)2048 * 2048 * 2);
     }
     CameraExtrinsic e;
@@ -187,7 +187,7 @@ int PLAIN_FE(get_image)(plain_frontend* fe, const char* name, plain_image_handle
     std::map<std::string, ImageHandle> m = {
         {"color0", f.m_frameRenderTargets[0].colorBuffer}, {"color1", f.m_frameRenderTargets[1].colorBuffer},
         {"depth0", f.m_frameRenderTargets[0].depthBuffer}, {"depth1", f.m_frameRenderTargets[1].depthBuffer},
-        {"motion0", f.m_frameRenderTargets[0].motionBuffer}, {"motion1", f.m_frameRenderTargets[1].motionBuffer},
+        {"motion0", f.m_motionBuffers[0]}, {"motion1", f.m_motionBuffers[1]}, {"motion2", f.m_motionBuffers[2]},
         {"post0", f.m_postProcessBuffers[0]}, {"post1", f.m_postProcessBuffers[1]}, {"normal", f.worldSpaceNormalImage()}, {"gbuffer", f.gbuffer()},
         {"depthHalf", f.m_depthHalfRes}, {"hiz", f.m_minMaxDepthPyramid}, {"brdfLut", f.m_brdfLut},
         {"skyTransmission", f.m_sky.m_skyTransmissionLut}, {"skyMultiscatter", f.m_sky.m_skyMultiscatterLut}, {"skyLut", f.m_sky.m_skyLut},
