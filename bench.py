@@ -29,6 +29,7 @@ import numpy as np
 
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
+_REAL_STDOUT = sys.stdout
 
 WIDTH, HEIGHT, INSTANCES = 3840, 2160, 100
 CAMERA = ((-13.0, -1.7, 0.5), (1.0, 0.0, 0.0), (0.0, 0.0, 1.0), (0.0, -1.0, 0.0))  # eye height, looking down the atrium
@@ -147,13 +148,13 @@ def run_reference(args, rank):
             "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "note": "the reference's per-pixel path is GLSL under Vulkan and cannot execute here; this arm is the scalar C++ oracle port (oracle/) on all host threads"}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_REAL_STDOUT, flush=True)
 
 
 def workload_config(n_gpus):
     return {"workload": "configs[2]: 3840x2160 synthetic Sponza-sized scene (%d SDF instances), full pipeline (GI/TAA/sky/volumetrics/bloom), static camera with TAA jitter" % INSTANCES,
             "resolution": [WIDTH, HEIGHT], "sdf_instances": INSTANCES,
-            "parallelism": "1 GPU" if n_gpus == 1 else "%d GPUs: every frame split into %d screen-space row bands (multiples of 64 rows), 9 NCCL exchanges per frame (histogram all-reduce, row all-gathers, halos); froxel volumetrics, LUTs and small mips replicated" % (n_gpus, n_gpus),
+            "parallelism": "1 GPU" if n_gpus == 1 else "%d GPUs: every frame split into %d screen-space row bands (multiples of 64 rows), 9 exchanges per frame over NVLink (histogram all-reduce, row all-gathers, halos); froxel volumetrics, LUTs and small mips replicated" % (n_gpus, n_gpus),
             "l2": "per-frame working set (>1.5 GB touched, G-buffer alone 133 MB) exceeds the 126 MB L2; no flush needed"}
 
 
@@ -209,7 +210,8 @@ def run_ours(args, rank, world, local_rank):
     stream_ptr = C.c_void_p()
     api.b["get_stream"](be.ctx, C.byref(stream_ptr))
     stream = torch.cuda.ExternalStream(stream_ptr.value, device=torch.device("cuda", local_rank))
-    comm = sharding.DistComm(api, HEIGHT, device=torch.device("cuda", local_rank), stream=stream) if sharded else None
+    comm = sharding.DistComm(api, HEIGHT, device=torch.device("cuda", local_rank), stream=stream, frontend=fe, peer=not args.nccl_exchange) if sharded else None
+    bytes_first_frame = [None]
 
     frame = [0]
     pass_acc, pass_order = {}, []
@@ -230,11 +232,13 @@ def run_ours(args, rank, world, local_rank):
             fe.begin_frame(cam, (f + 1) / 60.0, 1 / 60.0, *args, async_upload=True, rows=upload_rows)
             while True:
                 x = fe.run_segment()
-                if timing_weight is not None:
-                    collect_timings(timing_weight)
                 if x is None:
                     break
                 comm.exchange(x)
+            if timing_weight is not None:
+                collect_timings(timing_weight)  # the backend accumulates the timings of all segments of the frame
+            if bytes_first_frame[0] is None:
+                bytes_first_frame[0] = comm.bytes_sent  # the first frame runs every exchange through Python: its byte count is the per-frame figure
         else:
             fe.render_frame(cam, (f + 1) / 60.0, 1 / 60.0, *args, async_upload=True)
             if timing_weight is not None:
@@ -313,7 +317,10 @@ def run_ours(args, rank, world, local_rank):
                 "frame_roofline": {"algorithmic_bytes_per_frame": int(sum(alg.values()) + alg["Indirect diffuse spatial filter"]), "hbm_bound_ms": (sum(alg.values()) + alg["Indirect diffuse spatial filter"]) / peak / 1e6},
                 "setup_s": round(setup_s, 1), "graph_replay": not args.no_graph}
         if sharded:
-            line["sharding"] = {"rows_of_rank0": list(band), "exchanges_per_frame": 9, "bytes_sent_per_frame_rank0": comm.bytes_sent // max(frame[0], 1),
+            comm.check_peer_error()
+            line["sharding"] = {"rows_of_rank0": list(band), "exchanges_per_frame": 9, "bytes_sent_per_frame_rank0": bytes_first_frame[0],
+                                "transport": "peer pushes over NVLink (CUDA IPC) + flag barriers, enqueued by run_segment" if comm.peer else "NCCL send/recv batches issued from Python",
+                                "exchanges_through_python": comm.python_exchanges,
                                 "note": "passes_ms are rank 0's kernels only (its band); e2e byte counts are per rank"}
         if world == 1 and not args.no_cpu_baseline:
             sw, sh = WIDTH // 8, HEIGHT // 8
@@ -321,7 +328,7 @@ def run_ours(args, rank, world, local_rank):
             scale = (WIDTH * HEIGHT) / float(sw * sh)
             line["cpu_baseline"] = {"value": 1.0 / (sec * scale), "unit": "frames/s", "cores": os.cpu_count() or 1, "kind": "port",
                                     "sample": "%dx%d frame of the same scene (1/%d of the pixels), oracle port on all host threads, frames/s divided by %d" % (sw, sh, int(scale), int(scale))}
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=_REAL_STDOUT, flush=True)
     fe.close()
     if world > 1:
         torch.distributed.destroy_process_group()
@@ -335,8 +342,14 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--phases", type=int, default=2, help="TAA jitter phases of raster-pass outputs generated on the host (each 232 MB at 4K)")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--nccl-exchange", action="store_true", help="N > 1: exchange over NCCL send/recv from Python instead of peer pushes over NVLink")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    # the driver parses ONE JSON line from stdout: everything else a library prints there (e.g. the NCCL version banner) goes to stderr
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -206,6 +206,39 @@ PLAIN_EXPORT int PLAIN_FN(set_graph_replay_enabled)(plain_ctx* ctx, int enabled)
 /* makes the pass stream wait for every asynchronous upload and read-back issued so far (no host synchronisation): an event
  * recorded on the pass stream afterwards covers them. No-op in the oracle. */
 PLAIN_EXPORT int PLAIN_FN(join_transfers)(plain_ctx* ctx);
+
+/* ---- peer exchange over NVLink (row-sharded frames, one process per GPU; no counterpart in the reference) ----
+ * The ranks map each other's images (CUDA IPC) once; an exchange is then a kernel that stores this rank's rows straight into
+ * the peers' copies of the image (peer_push_rows) followed by a flag barrier in peer memory (peer_barrier): no host round
+ * trip, no library collective on the frame path. Everything is enqueued on the pass stream.
+ *   set-up (collective, the caller ships the 64-byte handles between the processes, e.g. with torch.distributed):
+ *     peer_init -> peer_get_sync_handle -> [exchange] -> peer_open_sync for every other rank
+ *     per exchanged image: peer_get_image_handle -> [exchange] -> peer_open_image for every other rank
+ *   per exchange: peer_push_rows (rows of image levels to given peers) + peer_barrier, or peer_allreduce_sum_u32.
+ * The oracle backend returns an error from all of them. */
+#define PLAIN_IPC_HANDLE_BYTES 64
+#define PLAIN_MAX_PEERS 16
+typedef struct {
+    plain_image_handle image;
+    uint32_t mip_level;
+    uint32_t row_begin, row_end; /* rows of the level, copied to the same rows of the peer's image */
+    uint32_t peer;               /* destination rank */
+} plain_peer_push;
+PLAIN_EXPORT int PLAIN_FN(peer_init)(plain_ctx* ctx, uint32_t rank, uint32_t count);
+PLAIN_EXPORT int PLAIN_FN(peer_get_sync_handle)(plain_ctx* ctx, void* out_handle);
+PLAIN_EXPORT int PLAIN_FN(peer_open_sync)(plain_ctx* ctx, uint32_t peer, const void* handle);
+PLAIN_EXPORT int PLAIN_FN(peer_get_image_handle)(plain_ctx* ctx, plain_image_handle image, void* out_handle);
+PLAIN_EXPORT int PLAIN_FN(peer_open_image)(plain_ctx* ctx, plain_image_handle image, uint32_t peer, const void* handle);
+/* 1 when every other rank's copy of the image is mapped */
+PLAIN_EXPORT int PLAIN_FN(peer_image_ready)(plain_ctx* ctx, plain_image_handle image);
+PLAIN_EXPORT int PLAIN_FN(peer_push_rows)(plain_ctx* ctx, uint32_t n, const plain_peer_push* pushes);
+/* every rank signals every other rank and waits for all of them: pushes enqueued before it on any rank are visible to the
+ * passes enqueued after it on every rank */
+PLAIN_EXPORT int PLAIN_FN(peer_barrier)(plain_ctx* ctx);
+/* element-wise sum over the ranks of `count` (<= 256) u32 at the start of a storage buffer; includes its own barrier */
+PLAIN_EXPORT int PLAIN_FN(peer_allreduce_sum_u32)(plain_ctx* ctx, plain_handle storage_buffer, uint32_t count);
+/* non-zero once a barrier gave up waiting for a peer (about 2 s): the frame is invalid, the caller must abort */
+PLAIN_EXPORT int PLAIN_FN(peer_error)(plain_ctx* ctx, uint32_t* out_error);
 /* the stream all passes run on (cudaStream_t as void*), for callers that time with CUDA events */
 PLAIN_EXPORT int PLAIN_FN(get_stream)(plain_ctx* ctx, void** out_stream);
 

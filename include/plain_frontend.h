@@ -96,9 +96,17 @@ typedef struct {
     uint32_t halo_rows;
     uint32_t element_count; /* ALLREDUCE: number of u32 */
     char name[32];
+    plain_image_handle image[4]; /* the exchanged images (for peer_get_image_handle / peer_open_image) */
+    uint32_t mip_level[4];
+    plain_handle buffer;         /* ALLREDUCE: the storage buffer */
 } plain_exchange;
 PLAIN_EXPORT int PLAIN_FE(begin_frame)(plain_frontend* fe, const plain_camera_extrinsic* camera, float time, float delta_time, const plain_frame_inputs* inputs);
 PLAIN_EXPORT int PLAIN_FE(run_segment)(plain_frontend* fe, plain_exchange* out);
+/* With peer exchange enabled (after plain_peer_init and the sync blocks are mapped, include/plain_b200.h) run_segment performs
+ * every exchange whose images are mapped on all ranks itself - row pushes into the peers' images + a flag barrier, enqueued
+ * on the pass stream - and only returns the ones it cannot do yet, so that the caller can map their images (and perform that
+ * one exchange itself). Once everything is mapped a whole frame is one run_segment call without a host round trip. */
+PLAIN_EXPORT int PLAIN_FE(set_peer_exchange)(plain_frontend* fe, int32_t enabled);
 /* rows [*out_begin, *out_end) of an image level with `rows` rows and the given divisor that belong to `rank` */
 PLAIN_EXPORT void PLAIN_FE(shard_band)(uint32_t full_height, uint32_t shard_count, uint32_t rank, uint32_t divisor, uint32_t rows, uint32_t* out_begin, uint32_t* out_end);
 PLAIN_EXPORT int PLAIN_FE(read_output_rows)(plain_frontend* fe, void* out_full_frame, uint32_t row_begin, uint32_t row_end, int32_t async_pinned);

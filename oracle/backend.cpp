@@ -377,6 +377,18 @@ int PLAIN_FN(get_storage_buffer_device_pointer)(plain_ctx* ctx, plain_handle buf
 }
 int PLAIN_FN(get_last_frame_launch_count)(plain_ctx* ctx, uint32_t* out) { (void)ctx; *out = 0; return 0; }
 int PLAIN_FN(set_graph_replay_enabled)(plain_ctx* ctx, int enabled) { (void)ctx; (void)enabled; return 0; }
+// peer exchange over NVLink: CUDA backend only
+static int peerUnsupported(plain_ctx* ctx) { ctx->c.lastError = "peer exchange is not available in the CPU oracle"; return 1; }
+int PLAIN_FN(peer_init)(plain_ctx* ctx, uint32_t, uint32_t) { return peerUnsupported(ctx); }
+int PLAIN_FN(peer_get_sync_handle)(plain_ctx* ctx, void*) { return peerUnsupported(ctx); }
+int PLAIN_FN(peer_open_sync)(plain_ctx* ctx, uint32_t, const void*) { return peerUnsupported(ctx); }
+int PLAIN_FN(peer_get_image_handle)(plain_ctx* ctx, plain_image_handle, void*) { return peerUnsupported(ctx); }
+int PLAIN_FN(peer_open_image)(plain_ctx* ctx, plain_image_handle, uint32_t, const void*) { return peerUnsupported(ctx); }
+int PLAIN_FN(peer_image_ready)(plain_ctx*, plain_image_handle) { return 0; }
+int PLAIN_FN(peer_push_rows)(plain_ctx* ctx, uint32_t, const plain_peer_push*) { return peerUnsupported(ctx); }
+int PLAIN_FN(peer_barrier)(plain_ctx* ctx) { return peerUnsupported(ctx); }
+int PLAIN_FN(peer_allreduce_sum_u32)(plain_ctx* ctx, plain_handle, uint32_t) { return peerUnsupported(ctx); }
+int PLAIN_FN(peer_error)(plain_ctx*, uint32_t* out_error) { *out_error = 0; return 0; }
 int PLAIN_FN(join_transfers)(plain_ctx* ctx) { (void)ctx; return 0; }
 int PLAIN_FN(get_stream)(plain_ctx* ctx, void** out_stream) { (void)ctx; *out_stream = nullptr; return 0; }
 

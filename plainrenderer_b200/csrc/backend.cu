@@ -58,6 +58,16 @@ struct Backend {
     cudaEvent_t uploadsDone = nullptr, computeMark = nullptr;
     long long submissionCounter = 0;
     bool uploadsPending = false;
+    // peer exchange over NVLink (row-sharded frames): a sync block per rank, mapped by every other rank
+    //   u32 flags[PLAIN_MAX_PEERS]   flags[p] = epoch of the last barrier rank p has signalled (written by rank p)
+    //   u32 error                    set when a barrier gave up waiting
+    //   u32 scratch[2][PLAIN_MAX_PEERS][kPeerReduceMax]   all-reduce partials, double-buffered by all-reduce parity
+    static const uint32_t kPeerReduceMax = 256;
+    static const size_t kPeerFlagsOffset = 0, kPeerErrorOffset = PLAIN_MAX_PEERS, kPeerScratchOffset = 2 * PLAIN_MAX_PEERS;
+    static const size_t kPeerSyncWords = 2 * PLAIN_MAX_PEERS + 2 * PLAIN_MAX_PEERS * kPeerReduceMax;
+    uint32_t peerRank = 0, peerCount = 0;
+    uint32_t* peerSync[PLAIN_MAX_PEERS] = {};  // [peerRank] = own block
+    uint32_t peerEpoch = 0, peerReduceCount = 0;
     std::vector<DeviceImage> images, transientImages;
     // two presentable images, flipped by new_frame (a swapchain hands out a different image every frame): the read-back of
     // frame N does not hold up the tonemapping pass of frame N+1
@@ -308,6 +318,63 @@ static bool runPasses(Backend& b, bool withTiming) {
     return true;
 }
 
+
+// ---------------- peer exchange kernels ----------------
+struct PushSegment { const unsigned char* src; unsigned char* dst; unsigned long long bytes; };
+static const int kMaxPushSegments = 28;
+struct PushArgs { PushSegment seg[kMaxPushSegments]; };
+// blockIdx.y = segment; the blocks of a segment stride over it. Rows of an image level are contiguous, and all levels on
+// the frame path have 16-byte aligned rows, so the copy is 128-bit loads from local HBM and 128-bit stores over NVLink.
+__global__ void __launch_bounds__(256) peerPushKernel(const __grid_constant__ PushArgs a) {
+    const PushSegment sg = a.seg[blockIdx.y];
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+    if ((((size_t)sg.src | (size_t)sg.dst | (size_t)sg.bytes) & 15) == 0) {
+        const uint4* s = (const uint4*)sg.src;
+        uint4* d = (uint4*)sg.dst;
+        const size_t n = sg.bytes / 16;
+        for (size_t i = tid; i < n; i += stride) d[i] = s[i];
+    } else {
+        for (size_t i = tid; i < sg.bytes; i += stride) sg.dst[i] = sg.src[i];
+    }
+}
+struct BarrierArgs {
+    uint32_t* peerFlags[PLAIN_MAX_PEERS];  // flags array of every rank's sync block
+    uint32_t* localError;
+    uint32_t rank, count, epoch;
+    long long timeoutCycles;
+};
+// one warp: lane p signals rank p (release: the pushes enqueued before this kernel have completed, the fence orders them
+// before the flag at system scope), then waits until rank p has signalled this rank
+__global__ void peerBarrierKernel(const __grid_constant__ BarrierArgs a) {
+    const uint32_t p = threadIdx.x;
+    if (p < a.count && p != a.rank) {
+        __threadfence_system();
+        *(volatile uint32_t*)(a.peerFlags[p] + a.rank) = a.epoch;
+        const volatile uint32_t* mine = a.peerFlags[a.rank] + p;
+        const long long start = clock64();
+        while ((int)(*mine - a.epoch) < 0) {
+            if (clock64() - start > a.timeoutCycles) { atomicExch(a.localError, 1u); break; }
+            __nanosleep(64);
+        }
+        __threadfence_system();
+    }
+}
+struct ReduceArgs {
+    uint32_t* peerScratch[PLAIN_MAX_PEERS];  // scratch[parity] of every rank's sync block
+    uint32_t* buffer;
+    uint32_t rank, count, n;
+};
+__global__ void peerReducePushKernel(const __grid_constant__ ReduceArgs a) {  // block p writes this rank's partials into rank p's scratch
+    for (uint32_t i = threadIdx.x; i < a.n; i += blockDim.x) a.peerScratch[blockIdx.x][(size_t)a.rank * Backend::kPeerReduceMax + i] = a.buffer[i];
+}
+__global__ void peerReduceSumKernel(const __grid_constant__ ReduceArgs a) {  // ascending rank order: integer sums, deterministic
+    for (uint32_t i = threadIdx.x; i < a.n; i += blockDim.x) {
+        uint32_t sum = 0;
+        for (uint32_t r = 0; r < a.count; r++) sum += a.peerScratch[a.rank][(size_t)r * Backend::kPeerReduceMax + i];
+        a.buffer[i] = sum;
+    }
+}
+
 }  // namespace pb
 
 using namespace pb;
@@ -381,6 +448,12 @@ void PLAIN_FN(backend_destroy)(plain_ctx* ctx) {
     cudaStreamSynchronize(b.downloadStream);
     cudaStreamSynchronize(b.stream);
     for (auto& g : b.graphs) if (g.second.exec) cudaGraphExecDestroy(g.second.exec);
+    for (uint32_t p = 0; p < b.peerCount; p++) {
+        for (auto& i : b.images) if (i.peerPtr[p]) cudaIpcCloseMemHandle(i.peerPtr[p]);
+        for (auto& i : b.transientImages) if (i.peerPtr[p]) cudaIpcCloseMemHandle(i.peerPtr[p]);
+        if (p != b.peerRank && b.peerSync[p]) cudaIpcCloseMemHandle(b.peerSync[p]);
+    }
+    if (b.peerCount) cudaFree(b.peerSync[b.peerRank]);
     for (auto& i : b.images) cudaFree(i.ptr);
     for (auto& i : b.transientImages) cudaFree(i.ptr);
     for (auto& sc : b.swapchainImages) { cudaFree(sc.ptr); if (sc.downloadDone) cudaEventDestroy(sc.downloadDone); }
@@ -542,6 +615,8 @@ int PLAIN_FN(set_global_descriptor_set_resources)(plain_ctx* ctx, const plain_pa
 
 int PLAIN_FN(new_frame)(plain_ctx* ctx) {
     ctx->b.execs.clear();
+    ctx->b.launchCounter = 0;  // kernels of the frame: all submissions + the peer exchange kernels between them
+    ctx->b.timings.clear();  // pass timings accumulate over the submissions of a frame (a row-sharded frame has one per segment)
     ctx->b.swapchainCurrent ^= 1;  // the next presentable image (RenderBackend.cpp:608-612 getSwapchainInputImage)
     for (auto& t : ctx->b.transientImages) t.inUse = false;
     return 0;
@@ -586,7 +661,6 @@ int PLAIN_FN(render_frame)(plain_ctx* ctx, int present) {
     (void)present;
     Backend& b = ctx->b;
     cudaSetDevice(b.device);
-    b.launchCounter = 0;
     joinTransfers(b);  // uploads issued before this submission are visible to its passes; read-backs in flight keep their source
     for (auto& e : b.execs) {
         for (auto& r : e.sampledImages) if (DeviceImage* img = b.resolve(r.image)) img->lastUsedSubmission = b.submissionCounter;
@@ -611,7 +685,6 @@ int PLAIN_FN(render_frame)(plain_ctx* ctx, int present) {
         b.stagingUsed = kStagingHeader;
     }
     const uint32_t fillLaunches = b.launchCounter;
-    b.timings.clear();
     if (b.timingEnabled) {
         if (!runPasses(b, true)) return 1;
         CU_CHECK(ctx, cudaStreamSynchronize(b.stream));
@@ -739,6 +812,155 @@ int PLAIN_FN(get_storage_buffer_device_pointer)(plain_ctx* ctx, plain_handle buf
 }
 int PLAIN_FN(get_last_frame_launch_count)(plain_ctx* ctx, uint32_t* out) { *out = ctx->b.lastFrameLaunches; return 0; }
 int PLAIN_FN(set_graph_replay_enabled)(plain_ctx* ctx, int enabled) { ctx->b.graphEnabled = enabled != 0; return 0; }
+
+// ---------------- peer exchange over NVLink ----------------
+int PLAIN_FN(peer_init)(plain_ctx* ctx, uint32_t rank, uint32_t count) {
+    Backend& b = ctx->b;
+    cudaSetDevice(b.device);
+    if (count < 1 || count > PLAIN_MAX_PEERS || rank >= count) return fail(ctx, "peer_init: invalid rank/count");
+    if (b.peerSync[b.peerRank]) return fail(ctx, "peer_init: already initialised");
+    uint32_t* block = nullptr;
+    CU_CHECK(ctx, cudaMalloc(&block, Backend::kPeerSyncWords * 4));
+    CU_CHECK(ctx, cudaMemset(block, 0, Backend::kPeerSyncWords * 4));
+    b.peerRank = rank; b.peerCount = count;
+    b.peerSync[rank] = block;
+    return 0;
+}
+int PLAIN_FN(peer_get_sync_handle)(plain_ctx* ctx, void* out_handle) {
+    Backend& b = ctx->b;
+    cudaSetDevice(b.device);
+    if (!b.peerCount) return fail(ctx, "peer_get_sync_handle: peer_init first");
+    static_assert(sizeof(cudaIpcMemHandle_t) == PLAIN_IPC_HANDLE_BYTES, "IPC handle size");
+    CU_CHECK(ctx, cudaIpcGetMemHandle((cudaIpcMemHandle_t*)out_handle, b.peerSync[b.peerRank]));
+    return 0;
+}
+int PLAIN_FN(peer_open_sync)(plain_ctx* ctx, uint32_t peer, const void* handle) {
+    Backend& b = ctx->b;
+    cudaSetDevice(b.device);
+    if (peer >= b.peerCount || peer == b.peerRank) return fail(ctx, "peer_open_sync: invalid peer");
+    if (b.peerSync[peer]) return 0;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof(h));
+    void* p = nullptr;
+    CU_CHECK(ctx, cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    b.peerSync[peer] = (uint32_t*)p;
+    return 0;
+}
+int PLAIN_FN(peer_get_image_handle)(plain_ctx* ctx, plain_image_handle image, void* out_handle) {
+    Backend& b = ctx->b;
+    cudaSetDevice(b.device);
+    DeviceImage* img = b.resolve(image);
+    if (!img || !img->ptr || image.type == PLAIN_IMAGE_HANDLE_SWAPCHAIN) return fail(ctx, "peer_get_image_handle: invalid image");
+    CU_CHECK(ctx, cudaIpcGetMemHandle((cudaIpcMemHandle_t*)out_handle, img->ptr));
+    return 0;
+}
+int PLAIN_FN(peer_open_image)(plain_ctx* ctx, plain_image_handle image, uint32_t peer, const void* handle) {
+    Backend& b = ctx->b;
+    cudaSetDevice(b.device);
+    DeviceImage* img = b.resolve(image);
+    if (!img || image.type == PLAIN_IMAGE_HANDLE_SWAPCHAIN) return fail(ctx, "peer_open_image: invalid image");
+    if (peer >= b.peerCount || peer == b.peerRank) return fail(ctx, "peer_open_image: invalid peer");
+    if (img->peerPtr[peer]) return 0;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof(h));
+    void* p = nullptr;
+    CU_CHECK(ctx, cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    img->peerPtr[peer] = (unsigned char*)p;
+    return 0;
+}
+int PLAIN_FN(peer_image_ready)(plain_ctx* ctx, plain_image_handle image) {
+    Backend& b = ctx->b;
+    DeviceImage* img = b.resolve(image);
+    if (!img || b.peerCount < 2) return 0;
+    for (uint32_t p = 0; p < b.peerCount; p++)
+        if (p != b.peerRank && !img->peerPtr[p]) return 0;
+    return 1;
+}
+int PLAIN_FN(peer_push_rows)(plain_ctx* ctx, uint32_t n, const plain_peer_push* pushes) {
+    Backend& b = ctx->b;
+    cudaSetDevice(b.device);
+    if (b.peerCount < 2) return fail(ctx, "peer_push_rows: peer_init first");
+    PushArgs args;
+    int used = 0;
+    auto flush = [&]() {
+        if (!used) return;
+        const unsigned blocksPerSegment = (unsigned)std::max(1, 4 * b.smCount / used);
+        peerPushKernel<<<dim3(blocksPerSegment, (unsigned)used), 256, 0, b.stream>>>(args);
+        b.launchCounter++;
+        used = 0;
+    };
+    for (uint32_t i = 0; i < n; i++) {
+        const plain_peer_push& q = pushes[i];
+        DeviceImage* img = b.resolve(q.image);
+        if (!img || q.mip_level >= img->mips.size()) return fail(ctx, "peer_push_rows: invalid image/mip");
+        if (q.peer >= b.peerCount || q.peer == b.peerRank || !img->peerPtr[q.peer]) return fail(ctx, "peer_push_rows: peer image not mapped (peer_open_image)");
+        const MipInfo& m = img->mips[q.mip_level];
+        if (m.d != 1 || q.row_begin > q.row_end || q.row_end > (uint32_t)m.h) return fail(ctx, "peer_push_rows: invalid row range");
+        if (q.row_end == q.row_begin) continue;
+        const size_t pitch = m.bytes / (size_t)m.h, off = m.offset + pitch * q.row_begin;
+        args.seg[used].src = img->ptr + off;
+        args.seg[used].dst = img->peerPtr[q.peer] + off;
+        args.seg[used].bytes = (unsigned long long)(pitch * (q.row_end - q.row_begin));
+        if (++used == kMaxPushSegments) flush();
+    }
+    flush();
+    cudaError_t e = cudaPeekAtLastError();
+    if (e != cudaSuccess) return fail(ctx, std::string("peer_push_rows: ") + cudaGetErrorString(e));
+    return 0;
+}
+static int peerBarrier(plain_ctx* ctx) {
+    Backend& b = ctx->b;
+    BarrierArgs a{};
+    for (uint32_t p = 0; p < b.peerCount; p++) {
+        if (!b.peerSync[p]) return fail(ctx, "peer_barrier: sync block of a peer not mapped (peer_open_sync)");
+        a.peerFlags[p] = b.peerSync[p] + Backend::kPeerFlagsOffset;
+    }
+    a.localError = b.peerSync[b.peerRank] + Backend::kPeerErrorOffset;
+    a.rank = b.peerRank; a.count = b.peerCount; a.epoch = ++b.peerEpoch;
+    a.timeoutCycles = 4000000000ll;  // about 2 s
+    peerBarrierKernel<<<1, 32, 0, b.stream>>>(a);
+    b.launchCounter++;
+    cudaError_t e = cudaPeekAtLastError();
+    if (e != cudaSuccess) return fail(ctx, std::string("peer_barrier: ") + cudaGetErrorString(e));
+    return 0;
+}
+int PLAIN_FN(peer_barrier)(plain_ctx* ctx) {
+    cudaSetDevice(ctx->b.device);
+    if (ctx->b.peerCount < 2) return fail(ctx, "peer_barrier: peer_init first");
+    return peerBarrier(ctx);
+}
+int PLAIN_FN(peer_allreduce_sum_u32)(plain_ctx* ctx, plain_handle storage_buffer, uint32_t count) {
+    Backend& b = ctx->b;
+    cudaSetDevice(b.device);
+    if (b.peerCount < 2) return fail(ctx, "peer_allreduce_sum_u32: peer_init first");
+    if (storage_buffer >= b.storageBuffers.size() || count > Backend::kPeerReduceMax || (size_t)count * 4 > b.storageBuffers[storage_buffer].size) return fail(ctx, "peer_allreduce_sum_u32: invalid buffer/count");
+    ReduceArgs a{};
+    const size_t parity = (b.peerReduceCount++ & 1u) * (size_t)PLAIN_MAX_PEERS * Backend::kPeerReduceMax;
+    for (uint32_t p = 0; p < b.peerCount; p++) {
+        if (!b.peerSync[p]) return fail(ctx, "peer_allreduce_sum_u32: sync block of a peer not mapped (peer_open_sync)");
+        a.peerScratch[p] = b.peerSync[p] + Backend::kPeerScratchOffset + parity;
+    }
+    a.buffer = (uint32_t*)b.storageBuffers[storage_buffer].ptr;
+    a.rank = b.peerRank; a.count = b.peerCount; a.n = count;
+    peerReducePushKernel<<<b.peerCount, 256, 0, b.stream>>>(a);
+    b.launchCounter++;
+    if (peerBarrier(ctx)) return 1;
+    peerReduceSumKernel<<<1, 256, 0, b.stream>>>(a);
+    b.launchCounter++;
+    cudaError_t e = cudaPeekAtLastError();
+    if (e != cudaSuccess) return fail(ctx, std::string("peer_allreduce_sum_u32: ") + cudaGetErrorString(e));
+    return 0;
+}
+int PLAIN_FN(peer_error)(plain_ctx* ctx, uint32_t* out_error) {
+    Backend& b = ctx->b;
+    cudaSetDevice(b.device);
+    *out_error = 0;
+    if (!b.peerCount) return 0;
+    drainTransfers(b);
+    CU_CHECK(ctx, cudaMemcpyAsync(out_error, b.peerSync[b.peerRank] + Backend::kPeerErrorOffset, 4, cudaMemcpyDeviceToHost, b.stream));
+    CU_CHECK(ctx, cudaStreamSynchronize(b.stream));
+    return 0;
+}
 int PLAIN_FN(get_stream)(plain_ctx* ctx, void** out_stream) { *out_stream = (void*)ctx->b.stream; return 0; }
 
 }  // extern "C"

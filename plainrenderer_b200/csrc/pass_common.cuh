@@ -32,6 +32,7 @@ struct DeviceImage {
     std::vector<MipInfo> mips;
     bool inUse = false;
     long long lastUsedSubmission = -1;  // index of the last submission (render_frame) whose passes referenced the image
+    unsigned char* peerPtr[PLAIN_MAX_PEERS] = {};  // the other ranks' copies of this image (CUDA IPC mappings), row sharding
     cudaEvent_t downloadDone = nullptr; // recorded after the last asynchronous read-back of the image (created on first use)
     bool downloadPending = false;       // that read-back has not been ordered before a later writer yet
 };

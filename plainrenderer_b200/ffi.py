@@ -98,7 +98,7 @@ EXCHANGE_NONE, EXCHANGE_ALLREDUCE_SUM_U32, EXCHANGE_ALLGATHER_ROWS, EXCHANGE_HAL
 
 class Exchange(C.Structure):  # include/plain_frontend.h plain_exchange
     _fields_ = [("kind", u32), ("n_images", u32), ("device_ptr", C.c_void_p * 4), ("row_pitch_bytes", u32 * 4), ("rows", u32 * 4), ("row_divisor", u32 * 4),
-                ("halo_rows", u32), ("element_count", u32), ("name", C.c_char * 32)]
+                ("halo_rows", u32), ("element_count", u32), ("name", C.c_char * 32), ("image", ImageHandle * 4), ("mip_level", u32 * 4), ("buffer", u32)]
 
 
 class CameraExtrinsic(C.Structure):
@@ -112,9 +112,11 @@ BACKEND_SYMBOLS = [
     "new_frame", "set_compute_pass_execution", "prepare_for_drawcall_recording", "set_uniform_buffer_data", "set_storage_buffer_data",
     "render_frame", "submit_recorded_passes", "wait_for_gpu_idle", "get_renderpass_timings", "set_timing_enabled", "write_image", "read_image", "read_storage_buffer",
     "write_image_async", "read_image_async", "write_image_rows_async", "read_image_rows_async", "get_image_device_pointer", "get_storage_buffer_device_pointer", "get_last_frame_launch_count",
-    "set_graph_replay_enabled", "join_transfers", "get_stream"]
+    "set_graph_replay_enabled", "join_transfers", "get_stream",
+    "peer_init", "peer_get_sync_handle", "peer_open_sync", "peer_get_image_handle", "peer_open_image", "peer_image_ready", "peer_push_rows", "peer_barrier",
+    "peer_allreduce_sum_u32", "peer_error"]
 FRONTEND_SYMBOLS = [
-    "default_settings", "create", "destroy", "last_error", "backend", "register_sdf_mesh", "set_scene", "render_frame", "begin_frame", "run_segment", "shard_band",
+    "default_settings", "create", "destroy", "last_error", "backend", "register_sdf_mesh", "set_scene", "render_frame", "begin_frame", "run_segment", "set_peer_exchange", "shard_band",
     "read_output_rows", "read_output", "get_image",
     "get_storage_buffer", "get_global_shader_info", "get_resolve_weights", "set_exposure", "synthetic_scene_create", "synthetic_scene_destroy",
     "synthetic_scene_attach", "synthetic_scene_render_inputs"]

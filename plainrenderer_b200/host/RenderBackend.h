@@ -114,6 +114,7 @@ public:
             const Recorded& r = m_recorded[m_cursor++];
             if (!r.isExchange) { sendExecution(r.exec); continue; }
             check(PLAIN_FN(submit_recorded_passes)(m_ctx));
+            if (peerExchange(r.exchange)) continue;  // done on the device: rows pushed into the peers' images + flag barrier
             std::memset(out, 0, sizeof(*out));
             out->kind = r.exchange.kind;
             out->halo_rows = r.exchange.haloRows;
@@ -123,6 +124,7 @@ public:
                 size_t size = 0;
                 check(PLAIN_FN(get_storage_buffer_device_pointer)(m_ctx, r.exchange.buffer, &out->device_ptr[0], &size));
                 out->n_images = 1;
+                out->buffer = r.exchange.buffer;
             } else {
                 out->n_images = (uint32_t)r.exchange.images.size();
                 for (uint32_t i = 0; i < out->n_images && i < 4; i++) {
@@ -134,12 +136,59 @@ public:
                     out->rows[i] = rows;
                     out->row_pitch_bytes[i] = (uint32_t)(size / rows);
                     out->row_divisor[i] = r.exchange.divisors[i];
+                    out->image[i].index = r.exchange.images[i].index;
+                    out->image[i].type = (uint32_t)r.exchange.images[i].type;
+                    out->mip_level[i] = r.exchange.mips[i];
                 }
             }
             return true;
         }
         check(PLAIN_FN(render_frame)(m_ctx, 1));
         return false;
+    }
+    // ---- peer exchange over NVLink (include/plain_b200.h): the sends of sharding.plan_row_exchange as row pushes ----
+    bool m_peerExchange = false;
+    void bandOf(uint32_t rank, uint32_t divisor, uint32_t rows, uint32_t* a, uint32_t* b) const {
+        uint32_t y0 = 0, y1 = shard.fullHeight;
+        shardBandRows(shard.fullHeight, shard.count, rank, &y0, &y1);
+        if (divisor < 1) divisor = 1;
+        uint32_t lo = y0 / divisor, hi = (y1 + divisor - 1) / divisor;
+        if (hi > rows) hi = rows;
+        if (lo > hi) lo = hi;
+        *a = lo; *b = hi;
+    }
+    bool peerExchange(const ExchangeRequest& x) {
+        if (!m_peerExchange || !shard.active()) return false;
+        if (x.kind == PLAIN_EXCHANGE_ALLREDUCE_SUM_U32) {
+            check(PLAIN_FN(peer_allreduce_sum_u32)(m_ctx, x.buffer, x.elementCount));
+            return true;
+        }
+        std::vector<plain_peer_push> pushes;
+        for (size_t i = 0; i < x.images.size(); i++) {
+            plain_image_handle h;
+            h.type = (uint32_t)x.images[i].type;
+            h.index = x.images[i].index;
+            if (!PLAIN_FN(peer_image_ready)(m_ctx, h)) return false;
+            const ImageDescription d = getImageDescription(x.images[i]);
+            uint32_t rows = d.height >> x.mips[i];
+            if (rows < 1) rows = 1;
+            uint32_t a, b;
+            bandOf(shard.rank, x.divisors[i], rows, &a, &b);
+            auto push = [&](uint32_t peer, uint32_t r0, uint32_t r1) {
+                if (r1 > r0) pushes.push_back(plain_peer_push{h, x.mips[i], r0, r1, peer});
+            };
+            if (x.kind == PLAIN_EXCHANGE_ALLGATHER_ROWS) {
+                for (uint32_t p = 0; p < shard.count; p++)
+                    if (p != shard.rank) push(p, a, b);
+            } else if (x.kind == PLAIN_EXCHANGE_HALO_ROWS) {
+                const uint32_t halo = x.haloRows;
+                if (shard.rank > 0) push(shard.rank - 1, a, a + halo < b ? a + halo : b);                // the neighbour above needs my first rows
+                if (shard.rank + 1 < shard.count) push(shard.rank + 1, b > a + halo ? b - halo : a, b);  // the neighbour below my last rows
+            }
+        }
+        check(PLAIN_FN(peer_push_rows)(m_ctx, (uint32_t)pushes.size(), pushes.data()));
+        check(PLAIN_FN(peer_barrier)(m_ctx));
+        return true;
     }
     void sendExecution(const ComputePassExecution& e) {
         std::vector<plain_sampler_resource> sm;

@@ -437,6 +437,9 @@ void Bloom::computeBloom(RenderBackend& b, ImageHandle targetImage, const BloomS
         e.dispatchCount[1] = ceilDivU((uint32_t)mipRes(targetMip, height), 8);
         e.pushConstants = dataToCharArray(&s.radius, sizeof(s.radius));
         if (targetMip == 0) setRows(b, e, 1, (uint32_t)height, 1);  // +-1 row: applyBloom samples it bilinearly at the pixel centre
+        // mip 1 reads only replicated mips (>= 2): every rank computes the rows its mip-0 window samples (the band +-1 row is
+        // +-1 row of mip 1; the 9-tap tent reaches 1.5 texels + the bilinear footprint: 5 rows cover it)
+        if (targetMip == 1) setRows(b, e, 2, (uint32_t)mipRes(1, height), 5);
         b.setComputePassExecution(e);
     }
     {

@@ -156,6 +156,10 @@ int PLAIN_FE(run_segment)(plain_frontend* fe, plain_exchange* out) {
         return -1;
     }
 }
+int PLAIN_FE(set_peer_exchange)(plain_frontend* fe, int32_t enabled) {
+    fe->fe.backend.m_peerExchange = enabled != 0;
+    return 0;
+}
 void PLAIN_FE(shard_band)(uint32_t fullHeight, uint32_t count, uint32_t rank, uint32_t divisor, uint32_t rows, uint32_t* a, uint32_t* b) {
     uint32_t y0 = 0, y1 = fullHeight;
     if (count > 1) shardBandRows(fullHeight, count, rank, &y0, &y1);

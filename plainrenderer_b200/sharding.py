@@ -12,6 +12,15 @@ boundaries, over `torch.distributed` (NCCL over NVLink on GPUs, gloo in the CPU 
 Stencils with a small fixed footprint (shading -> TAA -> bloom mip 1, upscale, bloom upsample mip 0) use overlapped
 computation instead of an exchange: the frontend extends the row window of the producing pass.
 The exchanges write straight into the images' device memory (tensors aliasing the pointers of the C-ABI).
+
+Two transports:
+  * `DistComm(..., peer=False)`: every exchange is a batch of NCCL send/recv issued from Python between two segments
+  * `DistComm(..., peer=True)` (default on GPUs): **peer exchange over NVLink** (include/plain_b200.h). The ranks map each other's
+    images with CUDA IPC (handles shipped once with torch.distributed); from then on `run_segment` performs the exchanges on
+    the device - a kernel stores the rank's rows into the peers' copies of the image, a flag barrier in peer memory orders
+    it - and a whole frame is enqueued by one call without a host round trip. Images are mapped lazily: the first time an
+    exchange names an unmapped image it is returned to Python, which maps it on all ranks and performs that one exchange
+    over NCCL.
 """
 import ctypes as C
 
@@ -93,12 +102,55 @@ def plan_row_exchange(kind, halo, bands, me):
 class DistComm:
     """Exchanges over torch.distributed (one rank per process)."""
 
-    def __init__(self, api, full_height, device=None, stream=None):
+    def __init__(self, api, full_height, device=None, stream=None, frontend=None, peer=False):
         import torch.distributed as dist
         self.api, self.H, self.device, self.stream = api, full_height, device, stream
         self.rank, self.world = dist.get_rank(), dist.get_world_size()
         self.cache = {}
         self.bytes_sent = 0
+        self.fe, self.peer = frontend, False
+        self.python_exchanges = 0  # exchanges that went through Python (all of them without peer exchange)
+        if peer and self.world > 1:
+            self._peer_setup()
+
+    # ---- peer exchange over NVLink: CUDA IPC set-up (collective) ----
+    def _all_gather_handles(self, handle_bytes):
+        import torch.distributed as dist
+        out = [None] * self.world
+        dist.all_gather_object(out, bytes(handle_bytes))
+        return out
+
+    def _peer_setup(self):
+        be = self.fe.backend
+        be._check(self.api.b["peer_init"](be.ctx, ffi.u32(self.rank), ffi.u32(self.world)), "peer_init")
+        h = (C.c_uint8 * 64)()
+        be._check(self.api.b["peer_get_sync_handle"](be.ctx, h), "peer_get_sync_handle")
+        for r, hb in enumerate(self._all_gather_handles(h)):
+            if r != self.rank:
+                buf = (C.c_uint8 * 64).from_buffer_copy(hb)
+                be._check(self.api.b["peer_open_sync"](be.ctx, ffi.u32(r), buf), "peer_open_sync")
+        self.fe._check(self.api.f["set_peer_exchange"](self.fe.fe, C.c_int32(1)), "set_peer_exchange")
+        self.peer = True
+
+    def _peer_map_images(self, x):
+        """Maps the images of exchange x on all ranks (every rank reaches the same exchange: the calls below are collective)."""
+        be = self.fe.backend
+        for i in range(x.n_images):
+            img = x.image[i]
+            h = (C.c_uint8 * 64)()
+            be._check(self.api.b["peer_get_image_handle"](be.ctx, img, h), "peer_get_image_handle")
+            for r, hb in enumerate(self._all_gather_handles(h)):
+                if r != self.rank:
+                    buf = (C.c_uint8 * 64).from_buffer_copy(hb)
+                    be._check(self.api.b["peer_open_image"](be.ctx, img, ffi.u32(r), buf), "peer_open_image")
+
+    def check_peer_error(self):
+        if not self.peer:
+            return
+        e = ffi.u32()
+        self.fe.backend._check(self.api.b["peer_error"](self.fe.backend.ctx, C.byref(e)), "peer_error")
+        if e.value:
+            raise RuntimeError("peer exchange: a barrier timed out waiting for another rank")
 
     def bands(self, rows, divisor):
         return [shard_band(self.api, self.H, self.world, r, divisor, rows) for r in range(self.world)]
@@ -106,6 +158,9 @@ class DistComm:
     def exchange(self, x):
         import torch
         import torch.distributed as dist
+        self.python_exchanges += 1
+        if self.peer and x.kind != ffi.EXCHANGE_ALLREDUCE_SUM_U32:
+            self._peer_map_images(x)  # from the next frame on run_segment performs this exchange on the device
         ctx = torch.cuda.stream(self.stream) if self.stream is not None else _Null()
         with ctx:
             if x.kind == ffi.EXCHANGE_ALLREDUCE_SUM_U32:

@@ -26,7 +26,10 @@ def main():
     import plainrenderer_b200 as pr
     from plainrenderer_b200 import ffi, sharding
 
-    W, H = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) > 2 else (512, 512)
+    args = [a for a in sys.argv[1:] if not a.startswith("--")]
+    peer = "--nccl" not in sys.argv  # default: peer pushes over NVLink (CUDA IPC); --nccl: send/recv batches from Python
+    W, H = (int(args[0]), int(args[1])) if len(args) > 1 else (512, 512)
+    frames = int(args[2]) if len(args) > 2 else 6
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -45,12 +48,12 @@ def main():
     stream_ptr = C.c_void_p()
     api.b["get_stream"](fe.backend.ctx, C.byref(stream_ptr))
     stream = torch.cuda.ExternalStream(stream_ptr.value, device=torch.device("cuda", local))
-    comm = sharding.DistComm(api, H, device=torch.device("cuda", local), stream=stream)
+    comm = sharding.DistComm(api, H, device=torch.device("cuda", local), stream=stream, frontend=fe, peer=peer)
     band = sharding.full_res_band(api, H, world, rank)
     upload = (max(band[0] - 16, 0), min(band[1] + 16, H))
     ok = True
     prev = None
-    for f in range(4):
+    for f in range(frames):
         p, fw, r, u = CAMERA
         cam = ffi.camera((p[0] + 0.02 * f, p[1], p[2] + 0.01 * f), fw, r, u)
         inputs = scene0.render_inputs(s0, cam, f + 1, prev_cam=prev, shadows=True)
@@ -68,13 +71,14 @@ def main():
         hname = "taaHist%d" % (f % 2)
         same_hist = np.array_equal(hist_w, hist_g)
         same_taa = np.array_equal(ref.backend.read_image(ref.image(hname)), fe.backend.read_image(fe.image(hname)))
-        print("rank %d/%d frame %d: %d exchanges, band [%d,%d) frame %s, histogram %s, TAA history %s" %
+        print("rank %d/%d frame %d: %d exchanges through Python, band [%d,%d) frame %s, histogram %s, TAA history %s" %
               (rank, world, f, n, a, b, "equal" if same_frame else "DIFFERS", "equal" if same_hist else "DIFFERS", "equal" if same_taa else "DIFFERS"), flush=True)
         ok = ok and same_frame and same_hist and same_taa
+    comm.check_peer_error()
     t = torch.tensor([0 if ok else 1], device="cuda")
     dist.all_reduce(t)
     if rank == 0:
-        print("SHARDED_NCCL_PARITY %s (%d ranks, %dx%d)" % ("OK" if int(t.item()) == 0 else "FAILED", world, W, H), flush=True)
+        print("SHARDED_%s_PARITY %s (%d ranks, %dx%d, %d frames)" % ("PEER" if peer else "NCCL", "OK" if int(t.item()) == 0 else "FAILED", world, W, H, frames), flush=True)
     for sc, f_ in ((scene0, ref), (scene1, fe)):
         sc.close()
         f_.close()
