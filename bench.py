@@ -154,7 +154,7 @@ def run_reference(args, rank):
 def workload_config(n_gpus):
     return {"workload": "configs[2]: 3840x2160 synthetic Sponza-sized scene (%d SDF instances), full pipeline (GI/TAA/sky/volumetrics/bloom), static camera with TAA jitter" % INSTANCES,
             "resolution": [WIDTH, HEIGHT], "sdf_instances": INSTANCES,
-            "parallelism": "1 GPU" if n_gpus == 1 else "%d GPUs: every frame split into %d screen-space row bands (multiples of 64 rows), 9 exchanges per frame over NVLink (histogram all-reduce, row all-gathers, halos); froxel volumetrics, LUTs and small mips replicated" % (n_gpus, n_gpus),
+            "parallelism": "1 GPU" if n_gpus == 1 else "%d GPUs: every frame split into %d screen-space row bands (multiples of 32 rows), 10 exchanges per frame over NVLink (histogram all-reduce, row all-gathers, halos); sky LUTs, culling lists and bloom mips >= 2 replicated" % (n_gpus, n_gpus),
             "l2": "per-frame working set (>1.5 GB touched, G-buffer alone 133 MB) exceeds the 126 MB L2; no flush needed"}
 
 
@@ -318,7 +318,7 @@ def run_ours(args, rank, world, local_rank):
                 "setup_s": round(setup_s, 1), "graph_replay": not args.no_graph}
         if sharded:
             comm.check_peer_error()
-            line["sharding"] = {"rows_of_rank0": list(band), "exchanges_per_frame": 9, "bytes_sent_per_frame_rank0": bytes_first_frame[0],
+            line["sharding"] = {"rows_of_rank0": list(band), "exchanges_per_frame": 10, "bytes_sent_per_frame_rank0": bytes_first_frame[0],
                                 "transport": "peer pushes over NVLink (CUDA IPC) + flag barriers, enqueued by run_segment" if comm.peer else "NCCL send/recv batches issued from Python",
                                 "exchanges_through_python": comm.python_exchanges,
                                 "note": "passes_ms are rank 0's kernels only (its band); e2e byte counts are per rank"}

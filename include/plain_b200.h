@@ -221,7 +221,7 @@ PLAIN_EXPORT int PLAIN_FN(join_transfers)(plain_ctx* ctx);
 typedef struct {
     plain_image_handle image;
     uint32_t mip_level;
-    uint32_t row_begin, row_end; /* rows of the level, copied to the same rows of the peer's image */
+    uint32_t row_begin, row_end; /* rows of the level (of every slice of a 3-D level), copied to the same rows of the peer's image */
     uint32_t peer;               /* destination rank */
 } plain_peer_push;
 PLAIN_EXPORT int PLAIN_FN(peer_init)(plain_ctx* ctx, uint32_t rank, uint32_t count);

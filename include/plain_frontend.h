@@ -99,6 +99,8 @@ typedef struct {
     plain_image_handle image[4]; /* the exchanged images (for peer_get_image_handle / peer_open_image) */
     uint32_t mip_level[4];
     plain_handle buffer;         /* ALLREDUCE: the storage buffer */
+    uint32_t depth[4];           /* slices of the level (1 for 2-D images): a row range means those rows in EVERY slice; slices are
+                                    rows * row_pitch_bytes apart */
 } plain_exchange;
 PLAIN_EXPORT int PLAIN_FE(begin_frame)(plain_frontend* fe, const plain_camera_extrinsic* camera, float time, float delta_time, const plain_frame_inputs* inputs);
 PLAIN_EXPORT int PLAIN_FE(run_segment)(plain_frontend* fe, plain_exchange* out);

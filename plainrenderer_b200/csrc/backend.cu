@@ -53,7 +53,7 @@ struct Backend {
     // every upload issued before it and for the read-backs still in flight; a read-back waits for the passes
     // submitted so far.
     cudaStream_t uploadStream = nullptr, downloadStream = nullptr;
-    static const int kSubmissionRing = 8;
+    static const int kSubmissionRing = 64;  // a row-sharded frame is ~11 submissions; an image is reused after 2 frames
     cudaEvent_t submissionDone[kSubmissionRing] = {};
     cudaEvent_t uploadsDone = nullptr, computeMark = nullptr;
     long long submissionCounter = 0;
@@ -320,7 +320,7 @@ static bool runPasses(Backend& b, bool withTiming) {
 
 
 // ---------------- peer exchange kernels ----------------
-struct PushSegment { const unsigned char* src; unsigned char* dst; unsigned long long bytes; };
+struct PushSegment { const unsigned char* src; unsigned char* dst; unsigned long long bytes, sliceStride; unsigned int slices; };  // `bytes` contiguous bytes in each of `slices` slices
 static const int kMaxPushSegments = 28;
 struct PushArgs { PushSegment seg[kMaxPushSegments]; };
 // blockIdx.y = segment; the blocks of a segment stride over it. Rows of an image level are contiguous, and all levels on
@@ -328,13 +328,20 @@ struct PushArgs { PushSegment seg[kMaxPushSegments]; };
 __global__ void __launch_bounds__(256) peerPushKernel(const __grid_constant__ PushArgs a) {
     const PushSegment sg = a.seg[blockIdx.y];
     const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
-    if ((((size_t)sg.src | (size_t)sg.dst | (size_t)sg.bytes) & 15) == 0) {
+    if ((((size_t)sg.src | (size_t)sg.dst | (size_t)sg.bytes | (size_t)sg.sliceStride) & 15) == 0) {
+        const size_t perSlice = sg.bytes / 16, n = perSlice * sg.slices, strideVec = sg.sliceStride / 16;
         const uint4* s = (const uint4*)sg.src;
         uint4* d = (uint4*)sg.dst;
-        const size_t n = sg.bytes / 16;
-        for (size_t i = tid; i < n; i += stride) d[i] = s[i];
+        for (size_t i = tid; i < n; i += stride) {
+            const size_t slice = i / perSlice, off = slice * strideVec + (i - slice * perSlice);
+            d[off] = s[off];
+        }
     } else {
-        for (size_t i = tid; i < sg.bytes; i += stride) sg.dst[i] = sg.src[i];
+        const size_t n = (size_t)sg.bytes * sg.slices;
+        for (size_t i = tid; i < n; i += stride) {
+            const size_t slice = i / sg.bytes, off = slice * sg.sliceStride + (i - slice * sg.bytes);
+            sg.dst[off] = sg.src[off];
+        }
     }
 }
 struct BarrierArgs {
@@ -895,12 +902,14 @@ int PLAIN_FN(peer_push_rows)(plain_ctx* ctx, uint32_t n, const plain_peer_push* 
         if (!img || q.mip_level >= img->mips.size()) return fail(ctx, "peer_push_rows: invalid image/mip");
         if (q.peer >= b.peerCount || q.peer == b.peerRank || !img->peerPtr[q.peer]) return fail(ctx, "peer_push_rows: peer image not mapped (peer_open_image)");
         const MipInfo& m = img->mips[q.mip_level];
-        if (m.d != 1 || q.row_begin > q.row_end || q.row_end > (uint32_t)m.h) return fail(ctx, "peer_push_rows: invalid row range");
+        if (q.row_begin > q.row_end || q.row_end > (uint32_t)m.h) return fail(ctx, "peer_push_rows: invalid row range");
         if (q.row_end == q.row_begin) continue;
-        const size_t pitch = m.bytes / (size_t)m.h, off = m.offset + pitch * q.row_begin;
+        const size_t pitch = m.bytes / ((size_t)m.h * m.d), off = m.offset + pitch * q.row_begin;  // 3-D levels: the rows in every slice
         args.seg[used].src = img->ptr + off;
         args.seg[used].dst = img->peerPtr[q.peer] + off;
         args.seg[used].bytes = (unsigned long long)(pitch * (q.row_end - q.row_begin));
+        args.seg[used].sliceStride = (unsigned long long)(pitch * m.h);
+        args.seg[used].slices = (unsigned int)m.d;
         if (++used == kMaxPushSegments) flush();
     }
     flush();

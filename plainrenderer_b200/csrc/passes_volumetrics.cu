@@ -12,13 +12,14 @@ __device__ __forceinline__ vec3 froxelWorldPos(const Globals& G, vec3 uv, float 
     return G.camPos - V / dot(-V, G.fwd) * froxelUVToDepth(uv.z, maxDistance);
 }
 
+// yBegin / limY: froxel rows [yBegin, limY) of this launch (row sharding: the rank's band of froxel rows + a few rows of overlap)
 #define FROXEL_COORDS(vol)                                                                                     \
-    const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 4 + (threadIdx.x >> 5), z = blockIdx.z; \
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = yBegin + blockIdx.y * 4 + (threadIdx.x >> 5), z = blockIdx.z; \
     if (x >= (vol).w || y >= (vol).h || z >= (vol).d || x >= limX || y >= limY || z >= limZ) return;
 
 // ---------------- froxelVolumeMaterial.comp ----------------
 __global__ void __launch_bounds__(128) froxelVolumeMaterialKernel(ImgView materialVolume, ImgView noiseTexture, const plain_volumetric_lighting_settings* __restrict__ sp,
-                                                                   const plain_global_shader_info* __restrict__ g, int limX, int limY, int limZ) {
+                                                                   const plain_global_shader_info* __restrict__ g, int limX, int limY, int limZ, int yBegin) {
     FROXEL_COORDS(materialVolume)
     const plain_volumetric_lighting_settings s = *sp;
     const Globals G = loadGlobals(g);
@@ -42,14 +43,17 @@ PLAIN_PASS(launch_froxelVolumeMaterial, "froxelVolumeMaterial.comp") {
     const plain_volumetric_lighting_settings* s = c.ubuf<plain_volumetric_lighting_settings>(2);
     if (c.failed) return;
     const int limX = (int)c.exec->dispatch[0] * 4, limY = (int)c.exec->dispatch[1] * 4, limZ = (int)c.exec->dispatch[2] * 4;
-    dim3 grid(ceilDiv(vol.w, 32), ceilDiv(vol.h, 4), vol.d);
-    PLAIN_LAUNCH(c, froxelVolumeMaterialKernel, grid, 128, 0, vol, noise, s, c.g, limX, limY, limZ);
+    int y0, y1;
+    c.window(std::min(vol.h, limY), y0, y1);
+    if (y1 <= y0) return;
+    dim3 grid(ceilDiv(vol.w, 32), ceilDiv((unsigned)(y1 - y0), 4), vol.d);
+    PLAIN_LAUNCH(c, froxelVolumeMaterialKernel, grid, 128, 0, vol, noise, s, c.g, limX, y1, limZ, y0);
 }
 
 // ---------------- froxelLightScattering.comp ----------------
 __global__ void __launch_bounds__(128) froxelLightScatteringKernel(ImgView outVolume, ImgView sunShadowMap, ImgView materialVolume, const plain_shadow_cascade_info* __restrict__ cascades,
                                                                     const plain_light_buffer* __restrict__ light, const plain_volumetric_lighting_settings* __restrict__ sp,
-                                                                    const plain_global_shader_info* __restrict__ g, int limX, int limY, int limZ) {
+                                                                    const plain_global_shader_info* __restrict__ g, int limX, int limY, int limZ, int yBegin) {
     FROXEL_COORDS(outVolume)
     const plain_volumetric_lighting_settings s = *sp;
     const Globals G = loadGlobals(g);
@@ -80,13 +84,16 @@ PLAIN_PASS(launch_froxelLightScattering, "froxelLightScattering.comp") {
     const plain_volumetric_lighting_settings* s = c.ubuf<plain_volumetric_lighting_settings>(5);
     if (c.failed) return;
     const int limX = (int)c.exec->dispatch[0] * 4, limY = (int)c.exec->dispatch[1] * 4, limZ = (int)c.exec->dispatch[2] * 4;
-    dim3 grid(ceilDiv(out.w, 32), ceilDiv(out.h, 4), out.d);
-    PLAIN_LAUNCH(c, froxelLightScatteringKernel, grid, 128, 0, out, shadow, material, cascades, light, s, c.g, limX, limY, limZ);
+    int y0, y1;
+    c.window(std::min(out.h, limY), y0, y1);
+    if (y1 <= y0) return;
+    dim3 grid(ceilDiv(out.w, 32), ceilDiv((unsigned)(y1 - y0), 4), out.d);
+    PLAIN_LAUNCH(c, froxelLightScatteringKernel, grid, 128, 0, out, shadow, material, cascades, light, s, c.g, limX, y1, limZ, y0);
 }
 
 // ---------------- volumeLightingReprojection.comp ----------------
 __global__ void __launch_bounds__(128) volumeLightingReprojectionKernel(ImgView targetImage, ImgView inputVolume, ImgView historyVolume, const plain_volumetric_lighting_settings* __restrict__ sp,
-                                                                         const plain_global_shader_info* __restrict__ g, int limX, int limY, int limZ) {
+                                                                         const plain_global_shader_info* __restrict__ g, int limX, int limY, int limZ, int yBegin) {
     FROXEL_COORDS(targetImage)
     const float maxDistance = sp->maxDistance;
     const Globals G = loadGlobals(g);
@@ -113,16 +120,19 @@ PLAIN_PASS(launch_volumeLightingReprojection, "volumeLightingReprojection.comp")
     const plain_volumetric_lighting_settings* s = c.ubuf<plain_volumetric_lighting_settings>(3);
     if (c.failed) return;
     const int limX = (int)c.exec->dispatch[0] * 4, limY = (int)c.exec->dispatch[1] * 4, limZ = (int)c.exec->dispatch[2] * 4;
-    dim3 grid(ceilDiv(target.w, 32), ceilDiv(target.h, 4), target.d);
-    PLAIN_LAUNCH(c, volumeLightingReprojectionKernel, grid, 128, 0, target, input, history, s, c.g, limX, limY, limZ);
+    int y0, y1;
+    c.window(std::min(target.h, limY), y0, y1);
+    if (y1 <= y0) return;
+    dim3 grid(ceilDiv(target.w, 32), ceilDiv((unsigned)(y1 - y0), 4), target.d);
+    PLAIN_LAUNCH(c, volumeLightingReprojectionKernel, grid, 128, 0, target, input, history, s, c.g, limX, y1, limZ, y0);
 }
 
 // ---------------- volumetricLightingIntegration.comp ----------------
 // front-to-back scan along z, one thread per froxel column. The reference loops z <= res.z (:28): the extra iteration
 // fetches and stores out of range and has no effect.
 __global__ void __launch_bounds__(128) volumetricLightingIntegrationKernel(ImgView integrationVolume, ImgView scatteringTransmittanceVolume, const plain_volumetric_lighting_settings* __restrict__ sp,
-                                                                            int limX, int limY) {
-    const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 4 + (threadIdx.x >> 5);
+                                                                            int limX, int limY, int yBegin) {
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = yBegin + blockIdx.y * 4 + (threadIdx.x >> 5);
     if (x >= integrationVolume.w || y >= integrationVolume.h || x >= limX || y >= limY) return;
     const float maxDistance = sp->maxDistance;
     vec3 inscatteringTotal = v3(0.f);
@@ -145,8 +155,11 @@ PLAIN_PASS(launch_volumetricLightingIntegration, "volumetricLightingIntegration.
     const plain_volumetric_lighting_settings* s = c.ubuf<plain_volumetric_lighting_settings>(2);
     if (c.failed) return;
     const int limX = (int)c.exec->dispatch[0] * 8, limY = (int)c.exec->dispatch[1] * 8;
-    dim3 grid(ceilDiv(integration.w, 32), ceilDiv(integration.h, 4));
-    PLAIN_LAUNCH(c, volumetricLightingIntegrationKernel, grid, 128, 0, integration, src, s, limX, limY);
+    int y0, y1;
+    c.window(std::min(integration.h, limY), y0, y1);
+    if (y1 <= y0) return;
+    dim3 grid(ceilDiv(integration.w, 32), ceilDiv((unsigned)(y1 - y0), 4));
+    PLAIN_LAUNCH(c, volumetricLightingIntegrationKernel, grid, 128, 0, integration, src, s, limX, y1, y0);
 }
 
 }  // namespace pb

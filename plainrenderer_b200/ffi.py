@@ -98,7 +98,7 @@ EXCHANGE_NONE, EXCHANGE_ALLREDUCE_SUM_U32, EXCHANGE_ALLGATHER_ROWS, EXCHANGE_HAL
 
 class Exchange(C.Structure):  # include/plain_frontend.h plain_exchange
     _fields_ = [("kind", u32), ("n_images", u32), ("device_ptr", C.c_void_p * 4), ("row_pitch_bytes", u32 * 4), ("rows", u32 * 4), ("row_divisor", u32 * 4),
-                ("halo_rows", u32), ("element_count", u32), ("name", C.c_char * 32), ("image", ImageHandle * 4), ("mip_level", u32 * 4), ("buffer", u32)]
+                ("halo_rows", u32), ("element_count", u32), ("name", C.c_char * 32), ("image", ImageHandle * 4), ("mip_level", u32 * 4), ("buffer", u32), ("depth", u32 * 4)]
 
 
 class CameraExtrinsic(C.Structure):

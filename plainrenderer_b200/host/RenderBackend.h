@@ -70,8 +70,12 @@ struct ShardInfo {
     uint32_t rank = 0, count = 1, fullHeight = 0, y0 = 0, y1 = 0;  // [y0, y1): full-resolution rows of this rank
     bool active() const { return count > 1; }
 };
+#define PLAIN_SHARD_ROW_UNIT 32u
 inline void shardBandRows(uint32_t fullHeight, uint32_t count, uint32_t rank, uint32_t* y0, uint32_t* y1) {
-    const uint32_t unit = 64, units = (fullHeight + unit - 1) / unit;  // 64 rows: 32x32 tiles at half resolution, 8-pixel froxel rows, 4 fused HiZ levels
+    // 32 rows: a 32x32 histogram tile, one 16-row block of the half-res trace, 4 fused HiZ levels (16 / 8 / 4 / 2 rows of the
+    // half-res pyramid), 4 froxel rows. (The 32x32 culling tiles of the half-res trace span 64 rows: their lists are
+    // computed by every rank.) Finer units balance the bands better: 2160 rows on 8 ranks = 256..288 rows instead of 256..320
+    const uint32_t unit = PLAIN_SHARD_ROW_UNIT, units = (fullHeight + unit - 1) / unit;
     const uint32_t u0 = (uint32_t)((uint64_t)rank * units / count), u1 = (uint32_t)((uint64_t)(rank + 1) * units / count);
     *y0 = u0 * unit < fullHeight ? u0 * unit : fullHeight;
     *y1 = u1 * unit < fullHeight ? u1 * unit : fullHeight;
@@ -133,8 +137,11 @@ public:
                     ImageDescription d = getImageDescription(r.exchange.images[i]);
                     uint32_t rows = d.height >> r.exchange.mips[i];
                     if (rows < 1) rows = 1;
+                    uint32_t slices = d.depth >> r.exchange.mips[i];
+                    if (slices < 1) slices = 1;
                     out->rows[i] = rows;
-                    out->row_pitch_bytes[i] = (uint32_t)(size / rows);
+                    out->depth[i] = slices;
+                    out->row_pitch_bytes[i] = (uint32_t)(size / ((size_t)rows * slices));
                     out->row_divisor[i] = r.exchange.divisors[i];
                     out->image[i].index = r.exchange.images[i].index;
                     out->image[i].type = (uint32_t)r.exchange.images[i].type;

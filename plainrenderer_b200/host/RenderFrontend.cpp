@@ -131,7 +131,7 @@ void RenderFrontend::setup(int device, uint32_t width, uint32_t height, uint32_t
 
     backend.setup(device, width, height);
     if (m_shardCount > 1) {
-        if ((height + 63) / 64 < m_shardCount) throw std::runtime_error("row sharding: fewer 64-row units than ranks");
+        if ((height + PLAIN_SHARD_ROW_UNIT - 1) / PLAIN_SHARD_ROW_UNIT < m_shardCount) throw std::runtime_error("row sharding: fewer 32-row units than ranks");
         if (width % 16 != 0 || height % 16 != 0) throw std::runtime_error("row sharding needs a resolution that is a multiple of 16 (four HiZ levels reduced from a rank's own rows)");
         backend.shard.rank = m_shardRank; backend.shard.count = m_shardCount; backend.shard.fullHeight = height;
         shardBandRows(height, m_shardCount, m_shardRank, &backend.shard.y0, &backend.shard.y1);
@@ -518,7 +518,7 @@ void RenderFrontend::computeDepthPyramid(ImageHandle depthBuffer) {
         backend.setComputePassExecution(e);
         return;
     }
-    // sharded: the levels reduced from a rank's own depth rows (up to four: band boundaries are multiples of 64 rows), then
+    // sharded: the levels reduced from a rank's own depth rows (up to four: band boundaries are multiples of 32 rows), then
     // an all-gather of the last of them, then the remaining small levels on every rank
     uint32_t fused = 0, sw = m_screenWidth, sh = m_screenHeight;
     for (uint32_t k = 0; k < mipCount && k < 4 && sw % 2 == 0 && sh % 2 == 0 && sw >= 2 && sh >= 2; k++) { fused = k + 1; sw /= 2; sh /= 2; }

@@ -355,6 +355,12 @@ void Volumetrics::computeVolumetricLighting(RenderBackend& b, const VolumetricsS
     b.setUniformBufferData(m_volumetricsSettingsUniforms, &u, sizeof(u));
     const ImageDescription fd = b.getImageDescription(m_volumeMaterialVolume);
     const uint32_t g4[3] = {ceilDivU(fd.width, 4), ceilDivU(fd.height, 4), ceilDivU(fd.depth, 4)};
+    // Row sharding: every pass works on the rank's band of froxel rows (8 screen rows each) extended by froxelOverlap rows,
+    // which covers what the rank's pixels read from the integrated volume (shading runs on the band +-8 screen rows = 1 froxel
+    // row, its lookup is jittered by +-0.0065 of the screen height = 1.8 froxel rows at 4K, plus the trilinear footprint). The
+    // reprojection reads LAST frame's result at reprojected positions, anywhere in the volume: the band rows of this frame's
+    // result are all-gathered for the next frame.
+    const uint32_t froxelRowPixels = 8, froxelOverlap = 5;
     {
         ComputePassExecution e;
         e.genericInfo.handle = m_froxelVolumeMaterialPass;
@@ -362,6 +368,7 @@ void Volumetrics::computeVolumetricLighting(RenderBackend& b, const VolumetricsS
         e.genericInfo.resources.sampledImages = {ImageResource(m_perlinNoise3D, 0, 1)};
         e.genericInfo.resources.uniformBuffers = {UniformBufferResource(m_volumetricsSettingsUniforms, 2)};
         for (int i = 0; i < 3; i++) e.dispatchCount[i] = g4[i];
+        setRows(b, e, froxelRowPixels, fd.height, froxelOverlap);
         b.setComputePassExecution(e);
     }
     {
@@ -372,6 +379,7 @@ void Volumetrics::computeVolumetricLighting(RenderBackend& b, const VolumetricsS
         e.genericInfo.resources.storageBuffers = {StorageBufferResource(d.sunShadowInfoBuffer, true, 3), StorageBufferResource(d.lightBuffer, true, 4)};
         e.genericInfo.resources.uniformBuffers = {UniformBufferResource(m_volumetricsSettingsUniforms, 5)};
         for (int i = 0; i < 3; i++) e.dispatchCount[i] = g4[i];
+        setRows(b, e, froxelRowPixels, fd.height, froxelOverlap);
         b.setComputePassExecution(e);
     }
     const size_t m2 = fi.mod2();
@@ -384,6 +392,7 @@ void Volumetrics::computeVolumetricLighting(RenderBackend& b, const VolumetricsS
         e.genericInfo.resources.sampledImages = {ImageResource(m_scatteringTransmittanceVolume, 0, 1), ImageResource(reprojectionHistory, 0, 2)};
         e.genericInfo.resources.uniformBuffers = {UniformBufferResource(m_volumetricsSettingsUniforms, 3)};
         for (int i = 0; i < 3; i++) e.dispatchCount[i] = g4[i];
+        setRows(b, e, froxelRowPixels, fd.height, froxelOverlap);
         b.setComputePassExecution(e);
     }
     {
@@ -394,8 +403,11 @@ void Volumetrics::computeVolumetricLighting(RenderBackend& b, const VolumetricsS
         e.genericInfo.resources.uniformBuffers = {UniformBufferResource(m_volumetricsSettingsUniforms, 2)};
         e.dispatchCount[0] = ceilDivU(fd.width, 8);
         e.dispatchCount[1] = ceilDivU(fd.height, 8);
+        setRows(b, e, froxelRowPixels, fd.height, froxelOverlap);
         b.setComputePassExecution(e);
     }
+    // next frame's reprojection history: every rank contributes the froxel rows of its band (in every z slice)
+    b.addExchange(exchangeRows(PLAIN_EXCHANGE_ALLGATHER_ROWS, "froxelHistory", {reprojectionTarget}, 0, froxelRowPixels));
 }
 
 // =============================== Bloom ===============================

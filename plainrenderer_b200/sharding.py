@@ -1,6 +1,6 @@
 """Row-sharded frames across GPUs (DESIGN.md "Multi-GPU").
 
-One process per GPU. Each rank owns a band of screen rows (multiples of 64) and drives its frontend segment by segment
+One process per GPU. Each rank owns a band of screen rows (multiples of 32) and drives its frontend segment by segment
 (`Frontend.begin_frame` / `run_segment`); between segments the ranks exchange what the next passes read across band
 boundaries, over `torch.distributed` (NCCL over NVLink on GPUs, gloo in the CPU tests):
 
@@ -53,13 +53,15 @@ def alias_tensor(ptr, nbytes, device):
 
 
 def exchange_views(x, device, cache=None):
-    """[(tensor(rows, pitch) uint8, rows, divisor)] for the images of a plain_exchange."""
+    """[(tensor(rows, slices, pitch) uint8, rows, divisor)] for the images of a plain_exchange. Rows come first so that
+    t[r0:r1] is a row range in every slice of a 3-D level (contiguous for 2-D images, strided for 3-D ones)."""
     out = []
     for i in range(x.n_images):
-        key = (x.device_ptr[i], x.rows[i], x.row_pitch_bytes[i])
+        slices = max(int(x.depth[i]), 1)
+        key = (x.device_ptr[i], x.rows[i], x.row_pitch_bytes[i], slices)
         t = cache.get(key) if cache is not None else None
         if t is None:
-            t = alias_tensor(x.device_ptr[i], x.rows[i] * x.row_pitch_bytes[i], device).view(x.rows[i], x.row_pitch_bytes[i])
+            t = alias_tensor(x.device_ptr[i], slices * x.rows[i] * x.row_pitch_bytes[i], device).view(slices, x.rows[i], x.row_pitch_bytes[i]).permute(1, 0, 2)
             if cache is not None:
                 cache[key] = t
         out.append((t, x.rows[i], x.row_divisor[i]))
@@ -168,17 +170,25 @@ class DistComm:
                 dist.all_reduce(t, op=dist.ReduceOp.SUM)
                 self.bytes_sent += x.element_count * 4
                 return
-            ops = []
+            ops, staged = [], []
             for t, rows, div in exchange_views(x, self.device, self.cache):
                 sends, recvs = plan_row_exchange(x.kind, x.halo_rows, self.bands(rows, div), self.rank)
                 for p, r0, r1 in sends:
-                    ops.append(dist.P2POp(dist.isend, t[r0:r1], p))
-                    self.bytes_sent += (r1 - r0) * t.shape[1]
+                    ops.append(dist.P2POp(dist.isend, t[r0:r1].contiguous(), p))  # a copy only for 3-D levels (strided row ranges)
+                    self.bytes_sent += (r1 - r0) * t.shape[1] * t.shape[2]
                 for p, r0, r1 in recvs:
-                    ops.append(dist.P2POp(dist.irecv, t[r0:r1], p))
+                    dst = t[r0:r1]
+                    if dst.is_contiguous():
+                        ops.append(dist.P2POp(dist.irecv, dst, p))
+                    else:
+                        tmp = torch.empty(dst.shape, dtype=dst.dtype, device=dst.device)
+                        staged.append((dst, tmp))
+                        ops.append(dist.P2POp(dist.irecv, tmp, p))
             if ops:
                 for w in dist.batch_isend_irecv(ops):
                     w.wait()
+            for dst, tmp in staged:
+                dst.copy_(tmp)
 
 
 class _Null:

@@ -22,9 +22,9 @@ def test_bands_partition_every_level(cuda, H, count):
         for (a0, b0), (a1, b1) in zip(bands, bands[1:]):
             assert b0 == a1 and b0 >= a0  # contiguous, ordered, no overlap
     full = [sharding.full_res_band(cuda, H, count, r) for r in range(count)]
-    assert all(a % 64 == 0 for a, _ in full)  # 32x32 half-res tiles, froxel rows, 4 fused HiZ levels never straddle ranks
+    assert all(a % 32 == 0 for a, _ in full)  # histogram tiles, 16-row trace blocks, froxel rows, 4 fused HiZ levels never straddle ranks
     sizes = [b - a for a, b in full]
-    assert max(sizes) - min(sizes) <= 64 + (64 - H % 64) % 64
+    assert max(sizes) - min(sizes) <= 32 + (32 - H % 32) % 32
 
 
 def test_exchange_plans_are_consistent(cuda):

@@ -8,7 +8,7 @@ from conftest import CAMERA, image_mips
 
 pytestmark = pytest.mark.gpu
 
-GATHERED_IMAGES = ["hiz", "depthHalf", "giHistY1", "giHistC1", "giHistY0", "giHistC0", "skyLut", "froxelIntegration", "brdfLut"]
+GATHERED_IMAGES = ["hiz", "depthHalf", "giHistY1", "giHistC1", "giHistY0", "giHistC0", "skyLut", "brdfLut"]
 BANDED_IMAGES = [("hiz", 2, 0), ("hiz", 2, 1), ("hiz", 2, 2), ("output", 1, 0), ("post1", 1, 0), ("giFullY", 1, 0), ("giFullC", 1, 0), ("giY1", 2, 0), ("giC1", 2, 0),
                  ("giY0", 2, 0), ("giC0", 2, 0), ("color0", 1, 0), ("color1", 1, 0)]  # giY0/giC0: the temporal filter overwrites the gathered trace result with its banded target  # (name, divisor, mip): compared on the rank's own rows
 
@@ -49,7 +49,7 @@ def test_sharded_frame_equals_unsharded(ffi, cuda, W, H, R, moving):
             a, b = sharding.full_res_band(cuda, H, R, r)
             upload.append((max(a - 16, 0), min(b + 16, H)))
         n_exchanges = sharding.run_frame_local(fes, comm, cam, (f + 1) / 60.0, 1 / 60.0, inputs, upload_rows=upload)
-        assert n_exchanges == 9
+        assert n_exchanges == 10
         torch.cuda.synchronize()
         # images every rank holds completely
         for name in GATHERED_IMAGES:
@@ -75,6 +75,19 @@ def test_sharded_frame_equals_unsharded(ffi, cuda, W, H, R, moving):
                 a, b = sharding.shard_band(cuda, H, R, r, div << mip, rows)
                 got = fe.backend.read_image(fe.image(name), mip).reshape(rows, -1)
                 assert np.array_equal(got[a:b], want[a:b]), "frame %d rank %d: %s rows [%d, %d)" % (f, r, name, a, b)
+        # froxel volumes: the integrated volume on the rank's band of froxel rows (8 screen rows each), this frame's reprojection
+        # result (next frame's history) all-gathered
+        want = ref.backend.read_image(ref.image("froxelIntegration"))
+        d = ref.backend.image_description(ref.image("froxelIntegration"))
+        want = want.reshape(d.depth, d.height, -1)
+        for r, fe in enumerate(fes):
+            a, b = sharding.shard_band(cuda, H, R, r, 8, d.height)
+            got = fe.backend.read_image(fe.image("froxelIntegration")).reshape(d.depth, d.height, -1)
+            assert np.array_equal(got[:, a:b], want[:, a:b]), "frame %d rank %d: froxelIntegration rows [%d, %d)" % (f, r, a, b)
+        froxel_hist = "froxelHist%d" % ((f + 1) % 2)  # m_volumetricLightingHistory[frameIndex % 2], frameIndex = f + 1
+        want = ref.backend.read_image(ref.image(froxel_hist))
+        for r, fe in enumerate(fes):
+            assert np.array_equal(fe.backend.read_image(fe.image(froxel_hist)), want), "frame %d rank %d: %s" % (f, r, froxel_hist)
         # TAA history of this frame (all-gathered for the next one)
         hist_name = "taaHist%d" % (f % 2)  # written this frame: m_historyBuffers[(frameIndex % 2 + 1) % 2], frameIndex = f + 1
         want = ref.backend.read_image(ref.image(hist_name))
