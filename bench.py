@@ -62,6 +62,20 @@ def algorithmic_bytes(w, h):
     }
 
 
+NCU_KERNEL_OF_PASS = {"Indirect diffuse spatial filter": "giSpatialFilterKernel<1>", "Indirect diffuse SDF trace": "sdfDiffuseTraceKernel",
+                      "Temporal filtering": "temporalFilterKernel<1, 4>", "Forward shading": "gbufferShadingKernel<2, 0, 1, 0>"}
+
+
+def ncu_traffic(pass_name):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the pass's kernel from the committed `ncu --set full` capture
+    (profiles/r1g_ncu_top_kernels.json, same command and workload); None when the kernel was not captured."""
+    try:
+        table = json.loads((ROOT / "profiles" / "r1g_ncu_top_kernels.json").read_text())
+        return int(table[NCU_KERNEL_OF_PASS[pass_name]][0]["dram_bytes"])
+    except Exception:
+        return None
+
+
 def measured_hbm_peak():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -311,7 +325,7 @@ def run_ours(args, rank, world, local_rank):
                 "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_step_e2e},
                 "gpu_launches": launches * args.steps,
                 "clocks": clock_info,
-                "roofline": {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None, "traffic": None,
+                "roofline": {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None, "traffic": ncu_traffic(top),
                              "algorithmic_bytes_per_launch": alg.get(top, 0), "kernel_ms": top_ms, "share_of_frame": acc[top] / passes_sum if passes_sum else None, "peak_source": peak_src},
                 "passes_ms": {k: round(acc[k], 4) for k in order},
                 "frame_roofline": {"algorithmic_bytes_per_frame": int(sum(alg.values()) + alg["Indirect diffuse spatial filter"]), "hbm_bound_ms": (sum(alg.values()) + alg["Indirect diffuse spatial filter"]) / peak / 1e6},
