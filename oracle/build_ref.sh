@@ -9,7 +9,10 @@ OUT="$HERE/_ref"
 [ -d "$REF/Plain/src/AssetPipeline" ] || { echo "reference not present at $REF"; exit 0; }
 mkdir -p "$OUT"
 [ -x "$OUT/PlainAssetPipeline" ] && [ "$OUT/PlainAssetPipeline" -nt "$HERE/build_ref.sh" ] && { echo "up to date: $OUT/PlainAssetPipeline"; exit 0; }
-g++ -std=c++17 -O2 -w -fpermissive -include cassert -include cstring -include condition_variable -include stdexcept \
+# -include math.h / stdlib.h: libstdc++'s C++ wrappers pull the float overloads of abs/sin/cos/sqrt into the global namespace, as
+# MSVC's headers do for the reference's own build. Without them the unqualified abs(float) calls of SceneSDF.cpp resolve to
+# int abs(int) under g++ (every ray is rejected as "parallel", distances come out as square roots of integers).
+g++ -std=c++17 -O2 -w -fpermissive -include cassert -include cstring -include condition_variable -include stdexcept -include math.h -include stdlib.h \
     -I"$HERE/shim" -I"$REF/Plain/src" -I"$REF/Plain/src/Common" -I"$REF/Plain/vendor" -I"$REF/Plain/vendor/glm" -I"$REF/Plain/vendor/tinygltf" \
     "$REF"/Plain/src/AssetPipeline/*.cpp "$REF"/Plain/src/Common/*.cpp "$REF"/Plain/src/Common/Utilities/*.cpp \
     -lpthread -o "$OUT/PlainAssetPipeline"
