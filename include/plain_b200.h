@@ -203,6 +203,10 @@ PLAIN_EXPORT int PLAIN_FN(get_storage_buffer_device_pointer)(plain_ctx* ctx, pla
 PLAIN_EXPORT int PLAIN_FN(get_last_frame_launch_count)(plain_ctx* ctx, uint32_t* out);
 /* enable replay of an unchanged pass list through a captured CUDA graph (CUDA backend; no-op in the oracle) */
 PLAIN_EXPORT int PLAIN_FN(set_graph_replay_enabled)(plain_ctx* ctx, int enabled);
+/* schedule the passes of a submission onto several streams from the hazards between their declared resources (default on):
+ * a pass waits only for the passes it conflicts with, like the barriers the reference derives (RenderBackend.cpp:632-767).
+ * Off: strictly in submission order on one stream. No-op in the oracle. */
+PLAIN_EXPORT int PLAIN_FN(set_concurrent_passes_enabled)(plain_ctx* ctx, int enabled);
 /* makes the pass stream wait for every asynchronous upload and read-back issued so far (no host synchronisation): an event
  * recorded on the pass stream afterwards covers them. No-op in the oracle. */
 PLAIN_EXPORT int PLAIN_FN(join_transfers)(plain_ctx* ctx);

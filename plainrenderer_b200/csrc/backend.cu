@@ -12,6 +12,7 @@
 //   * there is no CPU fallback: every pass is a CUDA kernel looked up by the reference's shader file name; an unknown
 //     shader name or a missing device is an error
 #include <cuda_runtime.h>
+#include <algorithm>
 #include <cstdio>
 #include <cstring>
 #include <unordered_map>
@@ -58,6 +59,15 @@ struct Backend {
     cudaEvent_t uploadsDone = nullptr, computeMark = nullptr;
     long long submissionCounter = 0;
     bool uploadsPending = false;
+    // Passes of one submission are scheduled onto the pass stream + side streams from the hazards between their declared
+    // resources (what the reference derives its barriers from, RenderBackend.cpp:632-767): a pass waits for the passes it
+    // conflicts with and nothing else, so the small low-occupancy passes (sky LUTs, histogram, HiZ tail, culling) run next to
+    // each other and next to the froxel / GI chains instead of serially. Captured into the frame's CUDA graph as parallel branches.
+    static const int kSideStreams = 2;
+    cudaStream_t sideStreams[kSideStreams] = {};
+    std::vector<cudaEvent_t> passEvents;
+    cudaEvent_t forkEvent = nullptr;
+    bool concurrentPasses = true;
     // peer exchange over NVLink (row-sharded frames): a sync block per rank, mapped by every other rank
     //   u32 flags[PLAIN_MAX_PEERS]   flags[p] = epoch of the last barrier rank p has signalled (written by rank p)
     //   u32 error                    set when a barrier gave up waiting
@@ -294,9 +304,62 @@ static void drainTransfers(Backend& b) {
     joinTransfers(b);
 }
 
+// hazards between the passes of a submission, from their declared resources: storage images and writable storage buffers are
+// read-write, sampled images and read-only storage buffers are reads (uniform buffers change only through the fills, which
+// land before the first pass). deps[i] = earlier passes that pass i must wait for (RAW, WAR, WAW).
+static void passDependencies(Backend& b, std::vector<std::vector<int>>& deps) {
+    struct Use { int lastWriter = -1; std::vector<int> readers; };
+    std::unordered_map<uint64_t, Use> uses;
+    auto imageKey = [](const plain_image_resource& r) { return ((uint64_t)(r.image.type & 3u) << 60) | ((uint64_t)r.image.index << 8) | (uint64_t)(r.mip_level & 0xffu); };
+    deps.assign(b.execs.size(), {});
+    for (size_t i = 0; i < b.execs.size(); i++) {
+        const ExecRecord& e = b.execs[i];
+        std::vector<int>& d = deps[i];
+        auto read = [&](uint64_t key) {
+            Use& u = uses[key];
+            if (u.lastWriter >= 0 && u.lastWriter != (int)i) d.push_back(u.lastWriter);
+            u.readers.push_back((int)i);
+        };
+        auto write = [&](uint64_t key) {
+            Use& u = uses[key];
+            if (u.lastWriter >= 0 && u.lastWriter != (int)i) d.push_back(u.lastWriter);  // a pass may bind one resource twice
+            for (int r : u.readers) if (r != (int)i) d.push_back(r);
+            u.readers.clear();
+            u.lastWriter = (int)i;
+        };
+        for (auto& r : e.sampledImages) read(imageKey(r));
+        for (auto& r : e.storageBuffers) if (r.read_only) read((1ull << 63) | r.buffer);
+        for (auto& r : e.storageImages) write(imageKey(r));
+        for (auto& r : e.storageBuffers) if (!r.read_only) write((1ull << 63) | r.buffer);
+        std::sort(d.begin(), d.end());
+        d.erase(std::unique(d.begin(), d.end()), d.end());
+    }
+}
+
+#define SCHED_CHECK(call, what)                                                                                         \
+    do {                                                                                                                \
+        cudaError_t e__ = (call);                                                                                       \
+        if (e__ != cudaSuccess) { b.lastError = std::string("pass scheduling: ") + what + ": " + cudaGetErrorString(e__); return false; } \
+    } while (0)
 static bool runPasses(Backend& b, bool withTiming) {
+    const bool concurrent = b.concurrentPasses && !withTiming && b.execs.size() > 1;
+    std::vector<std::vector<int>> deps;
+    std::vector<int> streamOf;
+    cudaStream_t streams[1 + Backend::kSideStreams];
+    int tail[1 + Backend::kSideStreams];
+    bool forked[1 + Backend::kSideStreams];
+    int nextSide = 0;
+    if (concurrent) {
+        passDependencies(b, deps);
+        streamOf.assign(b.execs.size(), 0);
+        streams[0] = b.stream;
+        for (int k = 0; k < Backend::kSideStreams; k++) streams[1 + k] = b.sideStreams[k];
+        for (int k = 0; k <= Backend::kSideStreams; k++) { tail[k] = -1; forked[k] = k == 0; }
+        SCHED_CHECK(cudaEventRecord(b.forkEvent, b.stream), "fork record");  // everything enqueued before this submission (fills, uploads, exchanges)
+    }
     size_t ev = 0;
-    for (auto& e : b.execs) {
+    for (size_t i = 0; i < b.execs.size(); i++) {
+        ExecRecord& e = b.execs[i];
         LaunchCtx c;
         c.be = &b;
         c.pass = &b.passes[e.pass];
@@ -307,17 +370,37 @@ static bool runPasses(Backend& b, bool withTiming) {
         c.bindless = b.bindlessDevice;
         c.tables = (const float*)b.tablesDevice;
         if (!c.g) { b.lastError = "render_frame: no global uniform buffer bound (set_global_descriptor_set_resources)"; return false; }
+        int s = 0;
+        if (concurrent) {
+            // the pass follows a pass it depends on when that pass is the tail of a stream (the pass stream first); a pass that
+            // depends on no tail starts a parallel branch on a side stream
+            const std::vector<int>& d = deps[i];
+            auto dependsOn = [&](int p) { return p >= 0 && std::binary_search(d.begin(), d.end(), p); };
+            if (i == 0 || dependsOn(tail[0])) s = 0;
+            else {
+                s = -1;
+                for (int k = 1; k <= Backend::kSideStreams && s < 0; k++) if (dependsOn(tail[k])) s = k;
+                if (s < 0) { s = 1 + nextSide; nextSide = (nextSide + 1) % Backend::kSideStreams; }
+            }
+            if (!forked[s]) { SCHED_CHECK(cudaStreamWaitEvent(streams[s], b.forkEvent, 0), "fork wait"); forked[s] = true; }
+            for (int p : d) if (streamOf[(size_t)p] != s) SCHED_CHECK(cudaStreamWaitEvent(streams[s], b.passEvents[(size_t)p], 0), "dependency wait");  // same stream: ordered already
+            streamOf[i] = s;
+            tail[s] = (int)i;
+            c.stream = streams[s];
+        }
         if (withTiming) {
             while (b.timingEvents.size() < ev + 2) { cudaEvent_t x; cudaEventCreate(&x); b.timingEvents.push_back(x); }
             cudaEventRecord(b.timingEvents[ev], b.stream);
         }
         c.pass->fn(c);
         if (withTiming) { cudaEventRecord(b.timingEvents[ev + 1], b.stream); ev += 2; }
-        if (c.failed) { b.lastError = c.error; return false; }
+        if (concurrent) SCHED_CHECK(cudaEventRecord(b.passEvents[i], c.stream), "pass event record");
+        if (c.failed) { b.lastError = c.error; if (concurrent) for (int k = 1; k <= Backend::kSideStreams; k++) if (forked[k] && tail[k] >= 0) cudaStreamWaitEvent(b.stream, b.passEvents[(size_t)tail[k]], 0); return false; }
     }
+    if (concurrent)  // join: whatever follows on the pass stream (next submission, exchanges, read-backs) sees every pass
+        for (int k = 1; k <= Backend::kSideStreams; k++) if (tail[k] >= 0) SCHED_CHECK(cudaStreamWaitEvent(b.stream, b.passEvents[(size_t)tail[k]], 0), "join");
     return true;
 }
-
 
 // ---------------- peer exchange kernels ----------------
 struct PushSegment { const unsigned char* src; unsigned char* dst; unsigned long long bytes, sliceStride; unsigned int slices; };  // `bytes` contiguous bytes in each of `slices` slices
@@ -429,6 +512,8 @@ int PLAIN_FN(backend_create)(int device, uint32_t width, uint32_t height, plain_
         cudaStreamCreateWithFlags(&b.downloadStream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return 1; }
     cudaEventCreateWithFlags(&b.stagingConsumed, cudaEventDisableTiming);
     for (auto& e : b.submissionDone) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    for (auto& st : b.sideStreams) cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&b.forkEvent, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&b.uploadsDone, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&b.computeMark, cudaEventDisableTiming);
     if (cudaMallocHost(&b.stagingHost, kStagingBytes) != cudaSuccess || cudaMalloc(&b.stagingDevice, kStagingBytes) != cudaSuccess ||
@@ -475,6 +560,9 @@ void PLAIN_FN(backend_destroy)(plain_ctx* ctx) {
     cudaFree(b.tablesDevice);
     cudaEventDestroy(b.stagingConsumed);
     for (auto& e : b.submissionDone) cudaEventDestroy(e);
+    for (auto& st : b.sideStreams) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
+    for (auto& e : b.passEvents) cudaEventDestroy(e);
+    cudaEventDestroy(b.forkEvent);
     cudaEventDestroy(b.uploadsDone);
     cudaEventDestroy(b.computeMark);
     cudaStreamDestroy(b.uploadStream);
@@ -669,6 +757,7 @@ int PLAIN_FN(render_frame)(plain_ctx* ctx, int present) {
     Backend& b = ctx->b;
     cudaSetDevice(b.device);
     joinTransfers(b);  // uploads issued before this submission are visible to its passes; read-backs in flight keep their source
+    while (b.passEvents.size() < b.execs.size()) { cudaEvent_t x; cudaEventCreateWithFlags(&x, cudaEventDisableTiming); b.passEvents.push_back(x); }
     for (auto& e : b.execs) {
         for (auto& r : e.sampledImages) if (DeviceImage* img = b.resolve(r.image)) img->lastUsedSubmission = b.submissionCounter;
         for (auto& r : e.storageImages) if (DeviceImage* img = b.resolve(r.image)) { img->lastUsedSubmission = b.submissionCounter; orderAfterDownload(b, img); }
@@ -819,6 +908,11 @@ int PLAIN_FN(get_storage_buffer_device_pointer)(plain_ctx* ctx, plain_handle buf
 }
 int PLAIN_FN(get_last_frame_launch_count)(plain_ctx* ctx, uint32_t* out) { *out = ctx->b.lastFrameLaunches; return 0; }
 int PLAIN_FN(set_graph_replay_enabled)(plain_ctx* ctx, int enabled) { ctx->b.graphEnabled = enabled != 0; return 0; }
+int PLAIN_FN(set_concurrent_passes_enabled)(plain_ctx* ctx, int enabled) {
+    if ((enabled != 0) != ctx->b.concurrentPasses) ctx->b.passEpoch++;  // cached graphs were captured with the other schedule
+    ctx->b.concurrentPasses = enabled != 0;
+    return 0;
+}
 
 // ---------------- peer exchange over NVLink ----------------
 int PLAIN_FN(peer_init)(plain_ctx* ctx, uint32_t rank, uint32_t count) {

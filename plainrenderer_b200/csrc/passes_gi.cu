@@ -332,7 +332,7 @@ struct TraceParams {
 // Per (ray, instance) the operation sequence is exactly the reference's; across instances the result of a ray is the
 // closest hit with ties going to the instance listed first - what the reference's in-order loop computes - so it does
 // not depend on the order in which the instances are visited, and the kernel visits the nearest box first.
-__global__ void __launch_bounds__(256, 3) sdfDiffuseTraceKernel(const __grid_constant__ TraceParams p) {
+__global__ void __launch_bounds__(256, 4) sdfDiffuseTraceKernel(const __grid_constant__ TraceParams p) {
     __shared__ TraceInstance sInst[PLAIN_MAX_OBJECTS_PER_TILE];
     __shared__ uint32_t sCount;
     __shared__ float sRayNormal[4][8][8][3], sRayDepth[4][8][8], sRayColor[4][8][8][3];

@@ -123,6 +123,19 @@ def test_graph_replay_is_identical(ffi, cuda):
     assert_snapshots_equal(outs[0], outs[1], "graph replay")
 
 
+def test_concurrent_pass_schedule_is_identical(ffi, cuda):
+    """Scheduling the passes onto several streams from their resource hazards produces the same bytes as strict submission order."""
+    outs = []
+    for concurrent in (False, True):
+        s = Sequence(ffi, cuda, 192, 108, 10)
+        s.fe.backend._check(cuda.b["set_concurrent_passes_enabled"](s.fe.backend.ctx, 1 if concurrent else 0), "set_concurrent_passes_enabled")
+        for _ in range(4):
+            s.step(moving=True)
+        outs.append(s.snapshot())
+        s.close()
+    assert_snapshots_equal(outs[0], outs[1], "concurrent pass schedule")
+
+
 # ---------------- full size (BASELINE 3840x2160): size-independent properties ----------------
 def test_full_size_properties(ffi, cuda):
     W, H = 3840, 2160
