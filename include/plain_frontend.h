@@ -43,6 +43,13 @@ typedef struct {
      * shard_count bands (bands are multiples of 64 rows); 0 / 0 or count 1 = the whole frame. The caller drives the frame
      * with begin_frame / run_segment and performs the exchanges between segments. */
     uint32_t shard_rank, shard_count;
+    /* the non-default passes beside the frame path (single GPU only) */
+    int32_t taa_use_separate_supersampling;  /* default 0: colorToLuminance.comp + temporalSupersampling.comp before the resolve (TAA.cpp:85-137) */
+    int32_t taa_supersample_use_tonemapping; /* default 1 */
+    int32_t sdf_debug_mode;                  /* SDFVisualisationMode: 0 none (default), 1 SDF, 2 camera tile usage, 3 normals, 4 raymarching count;
+                                                != 0 replaces the frame by RenderFrontend.cpp:321-340 (sdfDebugVisualisation.comp + tonemap) */
+    int32_t sdf_debug_show_tile_usage_with_hiz; /* default 1 */
+    int32_t sdf_debug_use_influence_radius;     /* default 0 */
 } plain_frontend_settings;
 
 /* host pointers to the outputs of the out-of-scope raster passes for one frame */
@@ -118,7 +125,7 @@ PLAIN_EXPORT int PLAIN_FE(read_output)(plain_frontend* fe, void* out, size_t siz
 
 /* named resources, for parity tests: images "color0|color1|depth0|depth1|motion0|motion1|post0|post1|normal|gbuffer|depthHalf|hiz|
  * brdfLut|skyTransmission|skyMultiscatter|skyLut|shadow0..3|giY0|giY1|giC0|giC1|giHistY0|giHistY1|giHistC0|giHistC1|giFullY|giFullC|
- * froxelMaterial|froxelScatter|froxelHist0|froxelHist1|froxelIntegration|taaHist0|taaHist1|bloomDown|bloomUp|output";
+ * froxelMaterial|froxelScatter|froxelHist0|froxelHist1|froxelIntegration|taaHist0|taaHist1|taaLum0|taaLum1|bloomDown|bloomUp|output";
  * buffers "histogram|histogramPerTile|light|sunShadowInfo|sdfInstances|sdfCulled|sdfTiles" */
 PLAIN_EXPORT int PLAIN_FE(get_image)(plain_frontend* fe, const char* name, plain_image_handle* out);
 PLAIN_EXPORT int PLAIN_FE(get_storage_buffer)(plain_frontend* fe, const char* name, plain_handle* out);

@@ -190,6 +190,8 @@ struct View {
         if (!inRange(x, y, z)) return;
         uint8_t* p = texelPtr(x, y, z);
         switch (format()) {
+            case PLAIN_FORMAT_R8: p[0] = floatToUnorm8(c.x); break;
+            case PLAIN_FORMAT_RG8: p[0] = floatToUnorm8(c.x); p[1] = floatToUnorm8(c.y); break;
             case PLAIN_FORMAT_RGBA8: p[0] = floatToUnorm8(c.x); p[1] = floatToUnorm8(c.y); p[2] = floatToUnorm8(c.z); p[3] = floatToUnorm8(c.w); break;
             case PLAIN_FORMAT_BGRA8_UNORM: p[2] = floatToUnorm8(c.x); p[1] = floatToUnorm8(c.y); p[0] = floatToUnorm8(c.z); p[3] = floatToUnorm8(c.w); break;
             case PLAIN_FORMAT_R16_SFLOAT: { uint16_t v = floatToHalf(c.x); memcpy(p, &v, 2); break; }

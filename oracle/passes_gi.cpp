@@ -321,6 +321,64 @@ ORACLE_PASS(pass_sdfDiffuseTrace, "sdfDiffuseTrace.comp") {
     });
 }
 
+// ---------------- sdfDebugVisualisation.comp:74-133 ----------------
+ORACLE_PASS(pass_sdfDebugVisualisation, "sdfDebugVisualisation.comp") {
+    const int debugMode = c.spec<int>(0, 0);
+    const int shadowCascadeIndex = c.spec<int>(1, 3);
+    View imageOut = c.storage(0), skyLut = c.sampled(2), shadowMap = c.sampled(7);
+    plain_light_buffer light;
+    memcpy(&light, c.sbuf(1), sizeof(light));
+    const plain_sdf_instance* sdfInstances = (const plain_sdf_instance*)(c.sbuf(3) + 16);
+    size_t tilesSize = 0;
+    const plain_culled_instances_per_tile* cameraCulledTiles = (const plain_culled_instances_per_tile*)c.sbuf(4, &tilesSize);
+    plain_shadow_cascade_info cascades;
+    memcpy(&cascades, c.sbuf(6), sizeof(cascades));
+    const plain_global_shader_info& g = c.g;
+    vec3 fwd = c.gv3(g.cameraForward), up = c.gv3(g.cameraUp), right = c.gv3(g.cameraRight), camPos = c.gv3(g.cameraPosition);
+    const mat4 shadowMatrix = c.gm4(cascades.lightMatrices[shadowCascadeIndex]);
+    const vec3 sunDirection = c.gv3(g.sunDirection);
+    c.forEachInvocation(8, 8, 1, [&](int ix, int iy, int) {
+        if (ix >= imageOut.w() || iy >= imageOut.h()) return;  // stores outside the image are dropped
+        vec2 pixelCoor = (vec2((float)ix, (float)iy) / vec2((float)g.screenResolution[0], (float)g.screenResolution[1]) - 0.5f) * 2.f;
+        vec3 cameraToPixel = -calculateViewDirectionFromPixel(pixelCoor, fwd, up, right, g.cameraTanFovHalf, g.cameraAspectRatio);
+        ivec2 tileUV(ix / 32, iy / 32);
+        uint32_t tileIndex = tileIndexFromTileUV(tileUV, g);
+        vec3 rayStart = camPos + g.nearPlane * cameraToPixel;
+        TraceResult traceResult;
+        traceResult.hit = false;
+        traceResult.closestHitDistance = 10000.f;
+        traceResult.hitCount = 0;  // hitPos / N / albedo / hitCount are undefined in the reference until a hit; pinned to 0
+        plain_culled_instances_per_tile cullingTile;
+        memset(&cullingTile, 0, sizeof(cullingTile));
+        if ((size_t)(tileIndex + 1) * sizeof(cullingTile) <= tilesSize) cullingTile = cameraCulledTiles[tileIndex];
+        for (uint32_t i = 0; i < cullingTile.objectCount; i++) {
+            const plain_sdf_instance& instance = sdfInstances[cullingTile.indices[i]];
+            traceRayTroughSDFInstance(instance, c.gm4(instance.worldToLocal), rayStart, c.bindless(instance.sdfTextureIndex), cameraToPixel, traceResult);
+        }
+        float shadow = simpleShadow(traceResult.hitPos, shadowMatrix, shadowMap, s_nearestBlackBorder);
+        vec3 color = vec3(0.f);
+        if (traceResult.hit || debugMode == 2) {
+            if (debugMode == 1) {
+                vec3 sunLight = light.sunStrengthExposed * vec3(light.sunColor[0], light.sunColor[1], light.sunColor[2]);
+                sunLight = sunLight * shadow;
+                vec3 ambient = vec3(0.15f);
+                float NoL = clamp(dot(traceResult.N, sunDirection), 0.f, 1.f);
+                color = traceResult.albedo * (ambient + sunLight * NoL);
+            } else if (debugMode == 2) {
+                float percentage = (float)cullingTile.objectCount / (float)PLAIN_MAX_OBJECTS_PER_TILE;
+                color = percentage >= 1.f ? vec3(1.f, 0.f, 0.f) : vec3(percentage);
+            } else if (debugMode == 3) {
+                color = traceResult.N * 0.5f + 0.5f;
+            } else if (debugMode == 4) {
+                color = vec3((float)traceResult.hitCount / 128.f);
+            }
+        } else {
+            color = sampleSkyLut(cameraToPixel, skyLut);
+        }
+        imageOut.store(ix, iy, 0, vec4(color, 1.f));
+    });
+}
+
 // ---------------- filterIndirectDiffuseSpatial.comp:21-135 ----------------
 ORACLE_PASS(pass_filterIndirectDiffuseSpatial, "filterIndirectDiffuseSpatial.comp") {
     const int filterIndex = c.spec<int>(0, 0);

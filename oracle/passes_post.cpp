@@ -304,6 +304,75 @@ ORACLE_PASS(pass_temporalFilter, "temporalFilter.comp") {
     });
 }
 
+// ---------------- colorToLuminance.comp:13-21 ----------------
+ORACLE_PASS(pass_colorToLuminance, "colorToLuminance.comp") {
+    View srcTexture = c.sampled(0), dstImage = c.storage(1);
+    c.forEachInvocation(8, 8, 1, [&](int ix, int iy, int) {
+        if (ix >= dstImage.w() || iy >= dstImage.h()) return;
+        vec3 color = srcTexture.fetch(ix, iy).xyz();
+        float l = computeLuminance(color);
+        dstImage.store(ix, iy, 0, vec4(l, 0.f, 0.f, 0.f));
+    });
+}
+
+// ---------------- temporalSupersampling.comp:21-110 ----------------
+static float minAbsoluteDifference(float s, vec4 v) {  // :22-28 (as written: differences of absolute values, not absolute differences)
+    return min(abs(s) - abs(v.x), min(abs(s) - abs(v.y), min(abs(s) - abs(v.z), abs(s) - abs(v.w))));
+}
+static float computeLuminanceBlockDifference(vec4 cur, vec4 last) {  // :30-36
+    return minAbsoluteDifference(cur.x, last) + minAbsoluteDifference(cur.y, last) + minAbsoluteDifference(cur.z, last) + minAbsoluteDifference(cur.w, last);
+}
+static float getClosestNeighbourhoodDepth(const View& depthBuffer, vec2 uv, const plain_global_shader_info& g) {  // :38-55
+    vec2 texelSize = 1.f / vec2((float)g.screenResolution[0], (float)g.screenResolution[1]);
+    float closestDepth = texture(depthBuffer, s_nearestClamp, uv + vec2(-1.f, -1.f) * texelSize).x;
+    static const int off[8][2] = {{0, -1}, {1, -1}, {-1, 0}, {0, 0}, {1, 0}, {-1, 1}, {0, 1}, {1, 1}};
+    for (int i = 0; i < 8; i++) closestDepth = max(texture(depthBuffer, s_nearestClamp, uv + vec2((float)off[i][0], (float)off[i][1]) * texelSize).x, closestDepth);
+    return linearizeDepth(closestDepth, g.nearPlane, g.farPlane);
+}
+ORACLE_PASS(pass_temporalSupersampling, "temporalSupersampling.comp") {
+    const bool useTonemap = c.specBool(0, false);
+    View currentFrame = c.sampled(1), lastFrame = c.sampled(2), velocityBuffer = c.sampled(4), currentDepthBuffer = c.sampled(5), lastDepthBuffer = c.sampled(6);
+    View currentLuminanceTexture = c.sampled(7), lastLuminanceTexture = c.sampled(8);
+    View targetImage = c.storage(3);
+    const plain_global_shader_info& g = c.g;
+    c.forEachInvocation(8, 8, 1, [&](int ix, int iy, int) {
+        if (ix >= targetImage.w() || iy >= targetImage.h()) return;
+        vec2 texelSize = 1.f / vec2((float)g.screenResolution[0], (float)g.screenResolution[1]);
+        vec2 uvCurrent = (vec2((float)ix, (float)iy) + vec2(0.5f)) * texelSize;
+        // getClosestFragmentMotion, temporalReprojection.inc:67-83
+        float closestDepth = 0.f;
+        ivec2 closestDepthOffset(0, 0);
+        for (int x = -1; x <= 1; x++)
+            for (int y = -1; y <= 1; y++) {
+                float depth = currentDepthBuffer.fetch(ix + x, iy + y).x;
+                if (depth > closestDepth) { closestDepth = depth; closestDepthOffset = ivec2(x, y); }
+            }
+        vec2 motion = velocityBuffer.fetch(ix + closestDepthOffset.x, iy + closestDepthOffset.y).xy();
+        vec2 uvLast = uvCurrent + motion;
+        vec3 currentSample = texture(currentFrame, s_linearClamp, uvCurrent).xyz();
+        vec3 lastSample = texture(lastFrame, s_linearClamp, uvLast).xyz();
+        if (useTonemap) {
+            currentSample = taaTonemap(currentSample);
+            lastSample = taaTonemap(lastSample);
+        }
+        // acceptLastFrameSample :57-84
+        vec4 currentLuminance = textureGather(currentLuminanceTexture, s_nearestClamp, uvCurrent);
+        vec4 lastLuminance = textureGather(lastLuminanceTexture, s_nearestClamp, uvLast);
+        float contrast = computeLuminanceBlockDifference(currentLuminance, lastLuminance);
+        bool contrastTest = contrast < 0.5f;
+        float currentDepth = getClosestNeighbourhoodDepth(currentDepthBuffer, uvCurrent, g);
+        float lastDepth = getClosestNeighbourhoodDepth(lastDepthBuffer, uvLast, g);
+        float depthDifference = abs(currentDepth - lastDepth);
+        bool depthTest = depthDifference < 1.f;
+        bool outOfScreen = uvLast.x < 0.f || uvLast.y < 0.f || uvLast.x > 1.f || uvLast.y > 1.f;
+        bool acceptSample = contrastTest && depthTest && !outOfScreen;
+        float blendFactor = acceptSample ? 0.5f : 0.f;
+        vec3 color = mix(currentSample, lastSample, blendFactor);
+        if (useTonemap) color = taaTonemapReverse(color);
+        targetImage.store(ix, iy, 0, vec4(color, 1.f));
+    });
+}
+
 // ---------------- bloomDownsample.comp:12-50 ----------------
 ORACLE_PASS(pass_bloomDownsample, "bloomDownsample.comp") {
     View target = c.storage(0);

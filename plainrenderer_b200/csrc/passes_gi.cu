@@ -555,6 +555,113 @@ PLAIN_PASS(launch_sdfDiffuseTrace, "sdfDiffuseTrace.comp") {
     PLAIN_LAUNCH(c, sdfDiffuseTraceKernel, dim3(ceilDiv(p.groupsX, 2), ceilDiv((unsigned)(y1 - y0), 16)), 256, 0, p);
 }
 
+// ---------------- sdfDebugVisualisation.comp ----------------
+struct DebugVisParams {
+    ImgView imageOut, skyLut, shadowMap;
+    const plain_light_buffer* light;
+    const unsigned char* instanceBuffer;  // uvec4 header + SDFInstance[]
+    const plain_culled_instances_per_tile* tiles;
+    size_t tileCapacity;
+    const plain_shadow_cascade_info* cascades;
+    const plain_global_shader_info* g;
+    const BindlessEntry* bindless;
+    int debugMode, shadowCascadeIndex;
+    int y0, y1;
+};
+// Primary rays through the SDF scene (:74-133). Block = 32x8 pixels of one 32x32 culling tile, whose instance records are
+// staged once in shared memory (as in sdfDiffuseTraceKernel); every pixel walks the tile's list in the reference's order.
+__global__ void __launch_bounds__(256) sdfDebugVisualisationKernel(const __grid_constant__ DebugVisParams p) {
+    __shared__ TraceInstance sInst[PLAIN_MAX_OBJECTS_PER_TILE];
+    __shared__ uint32_t sCount;
+    const plain_global_shader_info* g = p.g;
+    const int ix = blockIdx.x * 32 + (threadIdx.x & 31), iy = p.y0 + blockIdx.y * 8 + (threadIdx.x >> 5);
+    const uint32_t tileIndex = tileIndexFromTileUV(blockIdx.x, (p.y0 + blockIdx.y * 8) / 32, g);
+    const bool tileValid = (size_t)tileIndex < p.tileCapacity;
+    if (threadIdx.x == 0) sCount = tileValid ? p.tiles[tileIndex].objectCount : 0u;
+    __syncthreads();
+    const uint32_t objectCountRaw = sCount;  // the tile culling pass caps it at maxObjectsPerTile
+    const uint32_t objectCount = min(objectCountRaw, (uint32_t)PLAIN_MAX_OBJECTS_PER_TILE);
+    const plain_sdf_instance* instances = (const plain_sdf_instance*)(p.instanceBuffer + 16);
+    for (uint32_t i = threadIdx.x; i < objectCount; i += 256) {
+        const plain_sdf_instance in = instances[p.tiles[tileIndex].indices[i]];
+        TraceInstance t;
+        for (int k = 0; k < 16; k++) t.worldToLocal[k] = in.worldToLocal[k];
+        t.localExtends = ld3(in.localExtends);
+        t.meanAlbedo = ld3(in.meanAlbedo);
+        t.sdf = p.bindless[in.sdfTextureIndex].view;
+        t.sphereCenter = v3(0.f);
+        t.sphereR2 = 0.f;
+        t.localExtendsHalfPadded = t.localExtends * 0.5f + 0.01f;
+        t.distanceThreshold = length(t.localExtends / v3((float)t.sdf.w, (float)t.sdf.h, (float)t.sdf.d)) * 0.25f;
+        t.localToGlobalScale = 1.f / length(v3(t.worldToLocal[0], t.worldToLocal[1], t.worldToLocal[2]));
+        t.invLocalExtends = 1.f / t.localExtends;
+        sInst[i] = t;
+    }
+    __syncthreads();
+    if (ix >= p.imageOut.w || iy >= p.y1) return;
+    const Globals G = loadGlobals(g);
+    const vec2 pixelCoor = (v2((float)ix, (float)iy) / v2((float)g->screenResolution[0], (float)g->screenResolution[1]) - 0.5f) * 2.f;
+    const vec3 cameraToPixel = -viewDirFromNDC(G, pixelCoor);
+    const vec3 rayStart = G.camPos + G.nearPlane * cameraToPixel;
+    TraceResult tr;
+    tr.hit = false;
+    tr.closestHitDistance = 10000.f;
+    tr.hitCount = 0;
+    tr.hitPos = v3(0.f); tr.N = v3(0.f); tr.albedo = v3(0.f);
+    tr.winner = -1;
+    tr.winnerSamplePos = v3(0.f); tr.winnerRayDirection = v3(0.f); tr.winnerD = 0.f; tr.winnerDLast = 0.f;
+    for (uint32_t i = 0; i < objectCount; i++) {
+        MarchState st;
+        if (!traceSetup(sInst[i], rayStart, cameraToPixel, tr, st)) continue;
+        while (traceStep(sInst[i], (int)i, tr, st)) {}
+    }
+    if (tr.winner >= 0) shadeWinner(sInst[tr.winner], rayStart, cameraToPixel, tr);
+    const float shadow = simpleShadow<false>(tr.hitPos, p.cascades->lightMatrices[p.shadowCascadeIndex], p.shadowMap);
+    vec3 color = v3(0.f);
+    if (tr.hit || p.debugMode == 2) {
+        if (p.debugMode == 1) {
+            vec3 sunLight = p.light->sunStrengthExposed * ld3(p.light->sunColor);
+            sunLight = sunLight * shadow;
+            const vec3 ambient = v3(0.15f);
+            const float NoL = clampf(dot(tr.N, v3(g->sunDirection[0], g->sunDirection[1], g->sunDirection[2])), 0.f, 1.f);
+            color = tr.albedo * (ambient + sunLight * NoL);
+        } else if (p.debugMode == 2) {
+            const float percentage = (float)objectCountRaw / (float)PLAIN_MAX_OBJECTS_PER_TILE;
+            color = percentage >= 1.f ? v3(1.f, 0.f, 0.f) : v3(percentage);
+        } else if (p.debugMode == 3) {
+            color = tr.N * 0.5f + 0.5f;
+        } else if (p.debugMode == 4) {
+            color = v3((float)tr.hitCount / 128.f);
+        }
+    } else {
+        color = sampleSkyLut(cameraToPixel, p.skyLut);
+    }
+    storeR11(p.imageOut, ix, iy, color);
+}
+PLAIN_PASS(launch_sdfDebugVisualisation, "sdfDebugVisualisation.comp") {
+    DebugVisParams p;
+    p.imageOut = c.storage(0, PLAIN_FORMAT_R11G11B10_UFLOAT);
+    p.skyLut = c.sampled(2, PLAIN_FORMAT_R11G11B10_UFLOAT);
+    p.shadowMap = c.sampled(7, PLAIN_FORMAT_DEPTH16);
+    p.light = c.sbuf<plain_light_buffer>(1);
+    p.instanceBuffer = c.sbuf<unsigned char>(3);
+    size_t tilesSize = 0;
+    p.tiles = c.sbuf<plain_culled_instances_per_tile>(4, &tilesSize);
+    p.tileCapacity = tilesSize / sizeof(plain_culled_instances_per_tile);
+    p.cascades = c.sbuf<plain_shadow_cascade_info>(6);
+    p.g = c.g;
+    p.bindless = c.bindless;
+    p.debugMode = c.spec<int>(0, 0);
+    p.shadowCascadeIndex = c.spec<int>(1, 3);
+    if (c.failed) return;
+    if (p.shadowCascadeIndex < 0 || p.shadowCascadeIndex > 3) { c.fail("sdfDebugVisualisation.comp: shadow cascade index must be 0..3"); return; }
+    if ((int)c.exec->dispatch[0] * 8 < p.imageOut.w || (int)c.exec->dispatch[1] * 8 < p.imageOut.h) { c.fail("sdfDebugVisualisation.comp: dispatch does not cover the target"); return; }
+    c.window(p.imageOut.h, p.y0, p.y1);
+    if (p.y0 % 8 != 0) { c.fail("sdfDebugVisualisation.comp: row window must start at a multiple of 8 rows"); return; }
+    if (p.y1 <= p.y0) return;
+    PLAIN_LAUNCH(c, sdfDebugVisualisationKernel, dim3(ceilDiv(p.imageOut.w, 32), ceilDiv((unsigned)(p.y1 - p.y0), 8)), 256, 0, p);
+}
+
 // ---------------- filterIndirectDiffuseSpatial.comp ----------------
 struct SpatialParams {
     ImgView outYSH, outCoCg, texYSH, texCoCg, depthTexture, normalTexture;

@@ -342,4 +342,110 @@ PLAIN_PASS(launch_temporalFilter, "temporalFilter.comp") {
     else PLAIN_LAUNCH(c, (temporalFilterKernel<false, -1>), grid, 256, 0, p);
 }
 
+// ---------------- colorToLuminance.comp ----------------
+// R11G11B10 colour -> R8 luminance (the contrast test of temporalSupersampling.comp reads it with textureGather)
+__global__ void __launch_bounds__(256) colorToLuminanceKernel(ImgView dst, ImgView src, int yBegin, int yEnd) {
+    const int ix = blockIdx.x * 32 + (threadIdx.x & 31), iy = yBegin + blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (ix >= dst.w || iy >= yEnd) return;
+    const vec3 color = inRange(src, ix, iy) ? loadR11(src, ix, iy) : v3(0.f);  // texelFetch
+    ((uint8_t*)dst.ptr)[texelIndex(dst, ix, iy)] = (uint8_t)floatToUnorm8(computeLuminance(color));
+}
+PLAIN_PASS(launch_colorToLuminance, "colorToLuminance.comp") {
+    const ImgView src = c.sampled(0, PLAIN_FORMAT_R11G11B10_UFLOAT), dst = c.storage(1, PLAIN_FORMAT_R8);
+    if (c.failed) return;
+    if ((int)c.exec->dispatch[0] * 8 < dst.w || (int)c.exec->dispatch[1] * 8 < dst.h) { c.fail("colorToLuminance.comp: dispatch does not cover the target"); return; }
+    int y0, y1;
+    c.window(dst.h, y0, y1);
+    if (y1 <= y0) return;
+    PLAIN_LAUNCH(c, colorToLuminanceKernel, dim3(ceilDiv(dst.w, 32), ceilDiv((unsigned)(y1 - y0), 8)), 256, 0, dst, src, y0, y1);
+}
+
+// ---------------- temporalSupersampling.comp ----------------
+struct SupersampleParams {
+    ImgView currentFrame, lastFrame, targetImage, velocityBuffer, currentDepth, lastDepth, currentLuminance, lastLuminance;
+    const plain_global_shader_info* g;
+    int y0, y1;
+};
+__device__ __forceinline__ float minAbsoluteDifference(float s, vec4 v) {  // :22-28, as written (differences of absolute values)
+    return fminp(absf(s) - absf(v.x), fminp(absf(s) - absf(v.y), fminp(absf(s) - absf(v.z), absf(s) - absf(v.w))));
+}
+__device__ __forceinline__ float luminanceBlockDifference(vec4 cur, vec4 last) {  // :30-36
+    return minAbsoluteDifference(cur.x, last) + minAbsoluteDifference(cur.y, last) + minAbsoluteDifference(cur.z, last) + minAbsoluteDifference(cur.w, last);
+}
+// textureGather on an R8 image with the nearest-clamp sampler: (i0,j1), (i1,j1), (i1,j0), (i0,j0), i0 = floor(u*w - 0.5)
+__device__ __forceinline__ vec4 gatherR8Clamp(const ImgView& t, vec2 uv) {
+    const int x0 = f2i(floorf_(sanitizeCoord(uv.x) * (float)t.w - 0.5f)), y0 = f2i(floorf_(sanitizeCoord(uv.y) * (float)t.h - 0.5f));
+    const int xa = iclamp(x0, 0, t.w - 1), xb = iclamp(x0 + 1, 0, t.w - 1), ya = iclamp(y0, 0, t.h - 1), yb = iclamp(y0 + 1, 0, t.h - 1);
+    return v4(loadR8(t, xa, yb), loadR8(t, xb, yb), loadR8(t, xb, ya), loadR8(t, xa, ya));
+}
+// :38-55: closest (largest, reverse z) depth of the 3x3 nearest-clamp taps around uv, linearised
+__device__ __forceinline__ float closestNeighbourhoodDepth(const ImgView& depthBuffer, vec2 uv, vec2 texelSize, float nearP, float farP) {
+    auto tap = [&](float dx, float dy) {
+        return sampleNearest2D<WRAP_CLAMP, float>([&](int x, int y) { return loadD32(depthBuffer, x, y); }, depthBuffer.w, depthBuffer.h, uv + v2(dx, dy) * texelSize, 0.f);
+    };
+    float closestDepth = tap(-1.f, -1.f);
+    closestDepth = fmaxp(tap(0.f, -1.f), closestDepth);
+    closestDepth = fmaxp(tap(1.f, -1.f), closestDepth);
+    closestDepth = fmaxp(tap(-1.f, 0.f), closestDepth);
+    closestDepth = fmaxp(tap(0.f, 0.f), closestDepth);
+    closestDepth = fmaxp(tap(1.f, 0.f), closestDepth);
+    closestDepth = fmaxp(tap(-1.f, 1.f), closestDepth);
+    closestDepth = fmaxp(tap(0.f, 1.f), closestDepth);
+    closestDepth = fmaxp(tap(1.f, 1.f), closestDepth);
+    return linearizeDepth(closestDepth, nearP, farP);
+}
+template <bool TONEMAP>
+__global__ void __launch_bounds__(256) temporalSupersamplingKernel(const __grid_constant__ SupersampleParams p) {
+    const int ix = blockIdx.x * 32 + (threadIdx.x & 31), iy = p.y0 + blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (ix >= p.targetImage.w || iy >= p.y1) return;
+    const plain_global_shader_info* g = p.g;
+    const vec2 texelSize = 1.f / v2((float)g->screenResolution[0], (float)g->screenResolution[1]);
+    const vec2 uvCurrent = (v2((float)ix, (float)iy) + v2(0.5f)) * texelSize;
+    float closestDepth = 0.f;  // getClosestFragmentMotion, temporalReprojection.inc:67-83
+    int offX = 0, offY = 0;
+    for (int x = -1; x <= 1; x++)
+        for (int y = -1; y <= 1; y++) {
+            const float depth = inRange(p.currentDepth, ix + x, iy + y) ? loadD32(p.currentDepth, ix + x, iy + y) : 0.f;
+            if (depth > closestDepth) { closestDepth = depth; offX = x; offY = y; }
+        }
+    const vec2 motion = inRange(p.velocityBuffer, ix + offX, iy + offY) ? loadRG16SNORM(p.velocityBuffer, ix + offX, iy + offY) : v2(0.f);
+    const vec2 uvLast = uvCurrent + motion;
+    vec3 currentSample = sampleR11LinearClamp(p.currentFrame, uvCurrent);
+    vec3 lastSample = sampleR11LinearClamp(p.lastFrame, uvLast);
+    if (TONEMAP) {
+        currentSample = taaTonemap(currentSample);
+        lastSample = taaTonemap(lastSample);
+    }
+    // acceptLastFrameSample :57-84
+    const float contrast = luminanceBlockDifference(gatherR8Clamp(p.currentLuminance, uvCurrent), gatherR8Clamp(p.lastLuminance, uvLast));
+    const bool contrastTest = contrast < 0.5f;
+    const float currentDepth = closestNeighbourhoodDepth(p.currentDepth, uvCurrent, texelSize, g->nearPlane, g->farPlane);
+    const float lastDepth = closestNeighbourhoodDepth(p.lastDepth, uvLast, texelSize, g->nearPlane, g->farPlane);
+    const bool depthTest = absf(currentDepth - lastDepth) < 1.f;
+    const bool outOfScreen = uvLast.x < 0.f || uvLast.y < 0.f || uvLast.x > 1.f || uvLast.y > 1.f;
+    const bool acceptSample = contrastTest && depthTest && !outOfScreen;
+    vec3 color = vmix(currentSample, lastSample, acceptSample ? 0.5f : 0.f);
+    if (TONEMAP) color = taaTonemapReverse(color);
+    storeR11(p.targetImage, ix, iy, color);
+}
+PLAIN_PASS(launch_temporalSupersampling, "temporalSupersampling.comp") {
+    SupersampleParams p;
+    p.currentFrame = c.sampled(1, PLAIN_FORMAT_R11G11B10_UFLOAT);
+    p.lastFrame = c.sampled(2, PLAIN_FORMAT_R11G11B10_UFLOAT);
+    p.targetImage = c.storage(3, PLAIN_FORMAT_R11G11B10_UFLOAT);
+    p.velocityBuffer = c.sampled(4, PLAIN_FORMAT_RG16_SNORM);
+    p.currentDepth = c.sampled(5, PLAIN_FORMAT_DEPTH32);
+    p.lastDepth = c.sampled(6, PLAIN_FORMAT_DEPTH32);
+    p.currentLuminance = c.sampled(7, PLAIN_FORMAT_R8);
+    p.lastLuminance = c.sampled(8, PLAIN_FORMAT_R8);
+    p.g = c.g;
+    if (c.failed) return;
+    if ((int)c.exec->dispatch[0] * 8 < p.targetImage.w || (int)c.exec->dispatch[1] * 8 < p.targetImage.h) { c.fail("temporalSupersampling.comp: dispatch does not cover the target"); return; }
+    c.window(p.targetImage.h, p.y0, p.y1);
+    if (p.y1 <= p.y0) return;
+    dim3 grid(ceilDiv(p.targetImage.w, 32), ceilDiv((unsigned)(p.y1 - p.y0), 8));
+    if (c.specBool(0, false)) PLAIN_LAUNCH(c, temporalSupersamplingKernel<true>, grid, 256, 0, p);
+    else PLAIN_LAUNCH(c, temporalSupersamplingKernel<false>, grid, 256, 0, p);
+}
+
 }  // namespace pb

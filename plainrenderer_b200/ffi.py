@@ -86,7 +86,8 @@ class FrontendSettings(C.Structure):
                 ("trace_influence_radius", f32), ("taa_enabled", i32), ("taa_use_clipping", i32), ("taa_use_motion_vector_dilation", i32),
                 ("taa_history_sampling_tech", i32), ("taa_filter_use_tonemapping", i32), ("bloom_enabled", i32), ("bloom_strength", f32),
                 ("bloom_radius", f32), ("sun_direction_deg", f32 * 2), ("camera_fov_deg", f32), ("camera_near", f32), ("camera_far", f32),
-                ("noise_seed", u32), ("shard_rank", u32), ("shard_count", u32)]
+                ("noise_seed", u32), ("shard_rank", u32), ("shard_count", u32), ("taa_use_separate_supersampling", i32), ("taa_supersample_use_tonemapping", i32),
+                ("sdf_debug_mode", i32), ("sdf_debug_show_tile_usage_with_hiz", i32), ("sdf_debug_use_influence_radius", i32)]
 
 
 class FrameInputs(C.Structure):

@@ -133,6 +133,8 @@ void RenderFrontend::setup(int device, uint32_t width, uint32_t height, uint32_t
     if (m_shardCount > 1) {
         if ((height + PLAIN_SHARD_ROW_UNIT - 1) / PLAIN_SHARD_ROW_UNIT < m_shardCount) throw std::runtime_error("row sharding: fewer 32-row units than ranks");
         if (width % 16 != 0 || height % 16 != 0) throw std::runtime_error("row sharding needs a resolution that is a multiple of 16 (four HiZ levels reduced from a rank's own rows)");
+        if (m_taaSettings.useSeparateSupersampling || m_sdfDebugSettings.visualisationMode != SDFVisualisationMode::None)
+            throw std::runtime_error("row sharding: the separate temporal supersampling pass and the SDF debug visualisation are single-GPU only");
         backend.shard.rank = m_shardRank; backend.shard.count = m_shardCount; backend.shard.fullHeight = height;
         shardBandRows(height, m_shardCount, m_shardRank, &backend.shard.y0, &backend.shard.y1);
     }
@@ -155,7 +157,7 @@ void RenderFrontend::setup(int device, uint32_t width, uint32_t height, uint32_t
     m_bloom.init(backend);
     m_volumetrics.init(backend, (int)width, (int)height, noiseSeed ^ 0x9e3779b9u);
     m_taa.init(backend, (int)width, (int)height, m_taaSettings);
-    m_sdfGi.init(backend, (int)width, (int)height, m_sdfTraceSettings, m_shadingConfig.sunShadowCascadeCount - 1);
+    m_sdfGi.init(backend, (int)width, (int)height, m_sdfTraceSettings, m_sdfDebugSettings, m_shadingConfig.sunShadowCascadeCount - 1);
 
     RenderPassResources globalResources;  // setupGlobalShaderInfoResources :295-311
     globalResources.uniformBuffers = {UniformBufferResource(m_globalUniformBuffer, 0)};
@@ -332,17 +334,8 @@ void RenderFrontend::prepareRenderpasses() {
     m_frameRenderTargets[m_sceneRenderTargetIndex].motionBuffer = m_motionBuffers[m_motionBufferIndex];
     const FrameRenderTargets currentRenderTarget = m_frameRenderTargets[m_sceneRenderTargetIndex];
 
-    computeColorBufferHistogram(previousRenderTarget.colorBuffer);
-    m_sky.updateTransmissionLut(backend);
-    computeExposure();
-    m_sky.updateSkyLut(backend, m_lightBuffer, m_atmosphereSettings);
-    // renderDepthPrepass: rasterisation, out of scope - depth/motion/normal/G-buffer of this frame are uploaded
-    computeDepthPyramid(currentRenderTarget.depthBuffer);
-    computeSunLightMatrices();
-    // renderSunShadowCascades: rasterisation, out of scope - shadow maps are uploaded
-    if (m_shadingConfig.indirectLightingTech == IndirectLightingTech::SDFTrace) {
-        if (m_sdfTraceSettings.halfResTrace) downscaleDepth(currentRenderTarget);
-        SDFTraceDependencies dep;  // fillOutSdfGiDependencies :1075-1092
+    auto fillOutSdfGiDependencies = [&]() {  // :1075-1092
+        SDFTraceDependencies dep;
         dep.currentFrame = currentRenderTarget;
         dep.previousFrame = previousRenderTarget;
         dep.cameraFrustum = m_cameraFrustum;
@@ -353,7 +346,33 @@ void RenderFrontend::prepareRenderpasses() {
         dep.lightBuffer = m_lightBuffer;
         dep.sunShadowInfoBuffer = m_sunShadowInfoBuffer;
         dep.depthMinMaxPyramid = m_minMaxDepthPyramid;
-        m_sdfGi.computeIndirectLighting(backend, dep, m_sdfTraceSettings, m_frameIndex);
+        return dep;
+    };
+    if (m_sdfDebugSettings.visualisationMode != SDFVisualisationMode::None) {  // :321-340, primary rays through the SDF scene instead of the frame
+        // renderDepthPrepass: uploaded
+        computeDepthPyramid(currentRenderTarget.depthBuffer);
+        computeColorBufferHistogram(m_postProcessBuffers[0]);
+        m_sky.updateTransmissionLut(backend);
+        computeExposure();
+        m_sky.updateSkyLut(backend, m_lightBuffer, m_atmosphereSettings);
+        computeSunLightMatrices();
+        // renderSunShadowCascades: uploaded
+        m_sdfGi.renderSDFVisualization(backend, m_postProcessBuffers[0], fillOutSdfGiDependencies(), m_sdfDebugSettings, m_sdfTraceSettings);
+        computeTonemapping(m_postProcessBuffers[0]);
+        return;
+    }
+
+    computeColorBufferHistogram(previousRenderTarget.colorBuffer);
+    m_sky.updateTransmissionLut(backend);
+    computeExposure();
+    m_sky.updateSkyLut(backend, m_lightBuffer, m_atmosphereSettings);
+    // renderDepthPrepass: rasterisation, out of scope - depth/motion/normal/G-buffer of this frame are uploaded
+    computeDepthPyramid(currentRenderTarget.depthBuffer);
+    computeSunLightMatrices();
+    // renderSunShadowCascades: rasterisation, out of scope - shadow maps are uploaded
+    if (m_shadingConfig.indirectLightingTech == IndirectLightingTech::SDFTrace) {
+        if (m_sdfTraceSettings.halfResTrace) downscaleDepth(currentRenderTarget);
+        m_sdfGi.computeIndirectLighting(backend, fillOutSdfGiDependencies(), m_sdfTraceSettings, m_frameIndex);
     }
     Volumetrics::Dependencies vd;
     vd.lightBuffer = m_lightBuffer;
@@ -365,6 +384,10 @@ void RenderFrontend::prepareRenderpasses() {
 
     ImageHandle currentSrc = currentRenderTarget.colorBuffer;
     if (m_taaSettings.enabled) {
+        if (m_taaSettings.useSeparateSupersampling) {
+            m_taa.computeTemporalSuperSampling(backend, currentRenderTarget, previousRenderTarget, m_postProcessBuffers[0], m_frameIndex);
+            currentSrc = m_postProcessBuffers[0];
+        }
         m_taa.computeTemporalFilter(backend, currentSrc, currentRenderTarget, m_postProcessBuffers[1], m_frameIndex);
         currentSrc = m_postProcessBuffers[1];
     }

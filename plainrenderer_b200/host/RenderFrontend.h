@@ -28,6 +28,12 @@ struct SDFTraceSettings {  // SDFGI.h:17-29
     float traceInfluenceRadius = 5.f;
     float additionalSunShadowMapPadding = 3.f;
 };
+enum class SDFVisualisationMode : int { None = 0, VisualizeSDF = 1, CameraTileUsage = 2, SDFNormals = 3, RaymarchingCount = 4 };  // SDFGI.h:9
+struct SDFDebugSettings {  // SDFGI.h:11-15
+    SDFVisualisationMode visualisationMode = SDFVisualisationMode::None;
+    bool showCameraTileUsageWithHiZ = true;
+    bool useInfluenceRadiusForDebug = false;
+};
 enum class HistorySamplingTech : int { Bilinear = 0, Bicubic16Tap = 1, Bicubic9Tap = 2, Bicubic5Tap = 3, Bicubic1Tap = 4 };
 struct TAASettings {  // TAA.h:8-17
     bool enabled = true;
@@ -90,7 +96,9 @@ struct SDFTraceDependencies {
 
 class SDFGI {
 public:
-    void init(RenderBackend& b, int w, int h, const SDFTraceSettings& s, int sunShadowCascadeIndex);
+    void init(RenderBackend& b, int w, int h, const SDFTraceSettings& s, const SDFDebugSettings& debug, int sunShadowCascadeIndex);
+    void renderSDFVisualization(RenderBackend& b, ImageHandle target, const SDFTraceDependencies& d, const SDFDebugSettings& debug, const SDFTraceSettings& s) const;
+    void updateSDFDebugSettings(RenderBackend& b, const SDFDebugSettings& debug, int sunShadowCascadeIndex);
     void updateSDFScene(RenderBackend& b, const std::vector<RenderObject>& scene, const std::vector<MeshFrontend>& meshes);
     struct IndirectLightingImages { ImageHandle Y_SH, CoCg; };
     IndirectLightingImages getIndirectLightingResults(bool tracedHalfRes) const;
@@ -105,20 +113,22 @@ private:
     void filterIndirectDiffuse(RenderBackend& b, const SDFTraceDependencies& d, const SDFTraceSettings& s, const FrameIndex& fi) const;
     uint32_t m_sdfInstanceCount = 0;
     RenderPassHandle m_diffuseSDFTracePass, m_indirectDiffuseFilterSpatialPass[2], m_indirectDiffuseFilterTemporalPass, m_indirectLightingUpscale;
-    RenderPassHandle m_sdfCameraFrustumCulling, m_sdfCameraTileCulling, m_sdfCameraTileCullingHiZ;
+    RenderPassHandle m_sdfCameraFrustumCulling, m_sdfCameraTileCulling, m_sdfCameraTileCullingHiZ, m_sdfDebugVisualisationPass;
 };
 
 class TAA {
 public:
     void init(RenderBackend& b, int w, int h, const TAASettings& s);
+    void updateSettings(RenderBackend& b, const TAASettings& s);
+    void computeTemporalSuperSampling(RenderBackend& b, const FrameRenderTargets& currentFrame, const FrameRenderTargets& lastFrame, ImageHandle target, const FrameIndex& fi) const;
     void computeTemporalFilter(RenderBackend& b, ImageHandle colorSrc, const FrameRenderTargets& currentFrame, ImageHandle target, const FrameIndex& fi) const;
     hm::Vec2 computeProjectionMatrixJitter(const FrameIndex& fi) const;
     hm::Mat4 applyProjectionMatrixJitter(const hm::Mat4& projection, hm::Vec2 offset) const;
     void updateTaaResolveWeights(RenderBackend& b, hm::Vec2 cameraJitterInPixels);
-    ImageHandle m_historyBuffers[2];
+    ImageHandle m_historyBuffers[2], m_sceneLuminance[2];
     std::array<float, 9> m_lastResolveWeights{};
 private:
-    RenderPassHandle m_temporalFilterPass;
+    RenderPassHandle m_temporalFilterPass, m_temporalSupersamplingPass, m_colorToLuminancePass;
     UniformBufferHandle m_taaResolveWeightBuffer;
 };
 
@@ -177,6 +187,7 @@ public:
     RenderBackend backend;
     ShadingConfig m_shadingConfig;
     SDFTraceSettings m_sdfTraceSettings;
+    SDFDebugSettings m_sdfDebugSettings;
     TAASettings m_taaSettings;
     BloomSettings m_bloomSettings;
     VolumetricsSettings m_volumetricsSettings;

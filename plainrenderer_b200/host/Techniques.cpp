@@ -28,7 +28,11 @@ static RenderPassHandle makePass(RenderBackend& b, const char* name, const char*
 static const uint32_t sdfCameraCullingTileSize = 32;
 static const uint32_t maxObjectCountMainScene = 1200;  // SceneConfig.h
 
-void SDFGI::init(RenderBackend& b, int w, int h, const SDFTraceSettings& s, int sunShadowCascadeIndex) {
+static std::vector<SpecialisationConstant> sdfDebugSpecConstants(const SDFDebugSettings& debug, int sunShadowCascadeIndex) {  // SDFGI.cpp:13-29
+    return {specConst(0, (int)debug.visualisationMode), specConst(1, sunShadowCascadeIndex)};
+}
+
+void SDFGI::init(RenderBackend& b, int w, int h, const SDFTraceSettings& s, const SDFDebugSettings& debug, int sunShadowCascadeIndex) {
     const uint32_t tw = s.halfResTrace ? w / 2 : w, th = s.halfResTrace ? h / 2 : h;
     for (int i = 0; i < 2; i++) {
         m_indirectDiffuseHistory_Y_SH[i] = b.createImage(imageDesc2D(tw, th, PLAIN_FORMAT_RGBA16_SFLOAT, SS), nullptr, 0);
@@ -55,6 +59,30 @@ void SDFGI::init(RenderBackend& b, int w, int h, const SDFTraceSettings& s, int 
     m_sdfCameraFrustumCulling = makePass(b, "SDF camera frustum culling", "sdfCameraFrustumCulling.comp");
     m_sdfCameraTileCulling = makePass(b, "SDF camera tile culling", "sdfCameraTileCulling.comp", {specConst(0, 0u)});
     m_sdfCameraTileCullingHiZ = makePass(b, "SDF camera tile culling", "sdfCameraTileCulling.comp", {specConst(0, 1u)});
+    m_sdfDebugVisualisationPass = makePass(b, "SDF debug visualisation", "sdfDebugVisualisation.comp", sdfDebugSpecConstants(debug, sunShadowCascadeIndex));
+}
+
+void SDFGI::updateSDFDebugSettings(RenderBackend& b, const SDFDebugSettings& debug, int sunShadowCascadeIndex) {  // SDFGI.cpp:371-373
+    ShaderDescription d;
+    d.srcPathRelative = "sdfDebugVisualisation.comp";
+    d.specialisationConstants = sdfDebugSpecConstants(debug, sunShadowCascadeIndex);
+    b.updateComputePassShaderDescription(m_sdfDebugVisualisationPass, d);
+}
+
+void SDFGI::renderSDFVisualization(RenderBackend& b, ImageHandle target, const SDFTraceDependencies& d, const SDFDebugSettings& debug, const SDFTraceSettings& s) const {  // SDFGI.cpp:334-369
+    const float sdfInfluenceRadius = debug.useInfluenceRadiusForDebug ? s.traceInfluenceRadius : 0.f;
+    const ImageDescription targetDescription = b.getImageDescription(m_indirectLightingFullRes_CoCg);
+    const bool useHiZCulling = debug.visualisationMode == SDFVisualisationMode::CameraTileUsage && debug.showCameraTileUsageWithHiZ;
+    sdfInstanceCulling(b, d, (int)targetDescription.width, (int)targetDescription.height, sdfInfluenceRadius, useHiZCulling);
+    ComputePassExecution e;
+    e.genericInfo.handle = m_sdfDebugVisualisationPass;
+    e.genericInfo.resources.storageImages = {ImageResource(target, 0, 0)};
+    e.genericInfo.resources.sampledImages = {ImageResource(d.skyLut, 0, 2), ImageResource(d.shadowMap, 0, 7)};
+    e.genericInfo.resources.storageBuffers = {StorageBufferResource(d.lightBuffer, true, 1), StorageBufferResource(m_sdfInstanceBuffer, true, 3), StorageBufferResource(m_sdfCameraCulledTiles, true, 4),
+                                              StorageBufferResource(m_sdfCameraFrustumCulledInstances, true, 5), StorageBufferResource(d.sunShadowInfoBuffer, true, 6)};
+    e.dispatchCount[0] = ceilDivU(targetDescription.width, 8);
+    e.dispatchCount[1] = ceilDivU(targetDescription.height, 8);
+    b.setComputePassExecution(e);
 }
 
 void SDFGI::updateSDFScene(RenderBackend& b, const std::vector<RenderObject>& scene, const std::vector<MeshFrontend>& meshes) {  // SDFGI.cpp:260-313
@@ -219,6 +247,45 @@ void TAA::init(RenderBackend& b, int w, int h, const TAASettings& s) {
     m_taaResolveWeightBuffer = b.createUniformBuffer(sizeof(float) * 9);
     const uint32_t clip = s.useClipping, dil = s.useMotionVectorDilation, tm = s.filterUseTonemapping;
     m_temporalFilterPass = makePass(b, "Temporal filtering", "temporalFilter.comp", {specConst(0, clip), specConst(1, dil), specConst(2, (int)s.historySamplingTech), specConst(3, tm)});
+    const uint32_t ssTm = s.supersampleUseTonemapping;
+    m_temporalSupersamplingPass = makePass(b, "Temporal supersampling", "temporalSupersampling.comp", {specConst(0, ssTm)});
+    for (int i = 0; i < 2; i++) m_sceneLuminance[i] = b.createImage(imageDesc2D(w, h, PLAIN_FORMAT_R8, SS), nullptr, 0);
+    m_colorToLuminancePass = makePass(b, "Color to Luminance", "colorToLuminance.comp");
+}
+void TAA::updateSettings(RenderBackend& b, const TAASettings& s) {  // TAA.cpp:80-83
+    const uint32_t clip = s.useClipping, dil = s.useMotionVectorDilation, tm = s.filterUseTonemapping, ssTm = s.supersampleUseTonemapping;
+    ShaderDescription filter;
+    filter.srcPathRelative = "temporalFilter.comp";
+    filter.specialisationConstants = {specConst(0, clip), specConst(1, dil), specConst(2, (int)s.historySamplingTech), specConst(3, tm)};
+    b.updateComputePassShaderDescription(m_temporalFilterPass, filter);
+    ShaderDescription supersampling;
+    supersampling.srcPathRelative = "temporalSupersampling.comp";
+    supersampling.specialisationConstants = {specConst(0, ssTm)};
+    b.updateComputePassShaderDescription(m_temporalSupersamplingPass, supersampling);
+}
+void TAA::computeTemporalSuperSampling(RenderBackend& b, const FrameRenderTargets& cur, const FrameRenderTargets& last, ImageHandle target, const FrameIndex& fi) const {  // TAA.cpp:85-137
+    const ImageDescription td = b.getImageDescription(target);
+    const size_t m2 = fi.mod2();
+    const ImageHandle currentLuminance = m_sceneLuminance[m2], historyLuminance = m_sceneLuminance[(m2 + 1) % 2];
+    {   // scene luminance
+        ComputePassExecution e;
+        e.genericInfo.handle = m_colorToLuminancePass;
+        e.genericInfo.resources.storageImages = {ImageResource(currentLuminance, 0, 1)};
+        e.genericInfo.resources.sampledImages = {ImageResource(cur.colorBuffer, 0, 0)};
+        e.dispatchCount[0] = ceilDivU(td.width, 8);
+        e.dispatchCount[1] = ceilDivU(td.height, 8);
+        b.setComputePassExecution(e);
+    }
+    {   // temporal supersampling
+        ComputePassExecution e;
+        e.genericInfo.handle = m_temporalSupersamplingPass;
+        e.genericInfo.resources.storageImages = {ImageResource(target, 0, 3)};
+        e.genericInfo.resources.sampledImages = {ImageResource(cur.colorBuffer, 0, 1), ImageResource(last.colorBuffer, 0, 2), ImageResource(cur.motionBuffer, 0, 4), ImageResource(cur.depthBuffer, 0, 5),
+                                                 ImageResource(last.depthBuffer, 0, 6), ImageResource(currentLuminance, 0, 7), ImageResource(historyLuminance, 0, 8)};
+        e.dispatchCount[0] = ceilDivU(td.width, 8);
+        e.dispatchCount[1] = ceilDivU(td.height, 8);
+        b.setComputePassExecution(e);
+    }
 }
 void TAA::computeTemporalFilter(RenderBackend& b, ImageHandle colorSrc, const FrameRenderTargets& cur, ImageHandle target, const FrameIndex& fi) const {  // TAA.cpp:139-166
     const size_t m2 = fi.mod2();

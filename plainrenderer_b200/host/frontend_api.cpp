@@ -29,6 +29,8 @@ void PLAIN_FE(default_settings)(plain_frontend_settings* s, uint32_t width, uint
     s->sun_direction_deg[0] = 0.f; s->sun_direction_deg[1] = 0.f;
     s->camera_fov_deg = 35.f; s->camera_near = 0.1f; s->camera_far = 300.f;
     s->noise_seed = 0x504c4149u;
+    s->taa_use_separate_supersampling = 0; s->taa_supersample_use_tonemapping = 1;
+    s->sdf_debug_mode = 0; s->sdf_debug_show_tile_usage_with_hiz = 1; s->sdf_debug_use_influence_radius = 0;
 }
 
 int PLAIN_FE(create)(int device, const plain_frontend_settings* s, plain_frontend** out) {
@@ -49,6 +51,11 @@ int PLAIN_FE(create)(int device, const plain_frontend_settings* s, plain_fronten
     f.m_taaSettings.useMotionVectorDilation = s->taa_use_motion_vector_dilation != 0;
     f.m_taaSettings.historySamplingTech = (HistorySamplingTech)s->taa_history_sampling_tech;
     f.m_taaSettings.filterUseTonemapping = s->taa_filter_use_tonemapping != 0;
+    f.m_taaSettings.useSeparateSupersampling = s->taa_use_separate_supersampling != 0;
+    f.m_taaSettings.supersampleUseTonemapping = s->taa_supersample_use_tonemapping != 0;
+    f.m_sdfDebugSettings.visualisationMode = (SDFVisualisationMode)s->sdf_debug_mode;
+    f.m_sdfDebugSettings.showCameraTileUsageWithHiZ = s->sdf_debug_show_tile_usage_with_hiz != 0;
+    f.m_sdfDebugSettings.useInfluenceRadiusForDebug = s->sdf_debug_use_influence_radius != 0;
     f.m_bloomSettings.enabled = s->bloom_enabled != 0;
     f.m_bloomSettings.strength = s->bloom_strength;
     f.m_bloomSettings.radius = s->bloom_radius;
@@ -203,6 +210,7 @@ int PLAIN_FE(get_image)(plain_frontend* fe, const char* name, plain_image_handle
         {"froxelMaterial", f.m_volumetrics.m_volumeMaterialVolume}, {"froxelScatter", f.m_volumetrics.m_scatteringTransmittanceVolume},
         {"froxelHist0", f.m_volumetrics.m_volumetricLightingHistory[0]}, {"froxelHist1", f.m_volumetrics.m_volumetricLightingHistory[1]},
         {"froxelIntegration", f.m_volumetrics.m_volumetricIntegrationVolume}, {"taaHist0", f.m_taa.m_historyBuffers[0]}, {"taaHist1", f.m_taa.m_historyBuffers[1]},
+        {"taaLum0", f.m_taa.m_sceneLuminance[0]}, {"taaLum1", f.m_taa.m_sceneLuminance[1]},
         {"bloomDown", f.m_bloom.m_lastDownscaleTexture}, {"bloomUp", f.m_bloom.m_lastUpscaleTexture}, {"output", f.backend.getSwapchainInputImage()},
     };
     auto it = m.find(name);

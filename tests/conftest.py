@@ -69,8 +69,12 @@ def random_r11g11b10(rng, n, finite=True):
 
 CAMERA = ((-13.0, -1.7, 0.5), (1.0, 0.0, 0.0), (0.0, 0.0, 1.0), (0.0, -1.0, 0.0))
 ALL_IMAGES = ["skyTransmission", "skyMultiscatter", "skyLut", "hiz", "depthHalf", "giY0", "giC0", "giY1", "giC1", "giHistY0", "giHistC0", "giHistY1", "giHistC1", "giFullY", "giFullC",
-              "froxelMaterial", "froxelScatter", "froxelHist0", "froxelHist1", "froxelIntegration", "color0", "color1", "taaHist0", "taaHist1", "post1", "brdfLut", "output"]
+              "froxelMaterial", "froxelScatter", "froxelHist0", "froxelHist1", "froxelIntegration", "color0", "color1", "taaHist0", "taaHist1", "taaLum0", "taaLum1", "post0", "post1", "brdfLut", "output"]
 ALL_BUFFERS = [("histogram", 512), ("light", 20), ("sunShadowInfo", 304)]
+# the non-default passes beside the frame path (temporalSupersampling.comp + colorToLuminance.comp, sdfDebugVisualisation.comp)
+N4_VARIANTS = [dict(taa_use_separate_supersampling=1), dict(taa_use_separate_supersampling=1, taa_supersample_use_tonemapping=0),
+               dict(sdf_debug_mode=1), dict(sdf_debug_mode=2), dict(sdf_debug_mode=3), dict(sdf_debug_mode=4),
+               dict(sdf_debug_mode=2, sdf_debug_show_tile_usage_with_hiz=0), dict(sdf_debug_mode=1, sdf_debug_use_influence_radius=1)]
 
 
 def image_mips(fe, h):

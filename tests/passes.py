@@ -133,3 +133,40 @@ def bloom(ffi, api, packed, strength=0.05, radius=1.5, mips=6):
            be.read_image(target, 0, np.uint32).reshape(h, w).copy())
     rig.close()
     return out
+
+
+def color_to_luminance(ffi, api, packed):
+    """colorToLuminance.comp with the bindings of TAA::computeTemporalSuperSampling (TAA.cpp:94-107): R11G11B10 -> R8."""
+    h, w = packed.shape
+    rig = PassRig(ffi, api, w, h)
+    be = rig.be
+    src = be.create_image(w, h, "R11G11B10_UFLOAT", data=packed.astype(np.uint32))
+    dst = be.create_image(w, h, "R8")
+    p = be.create_compute_pass("colorToLuminance.comp")
+    be.new_frame()
+    be.set_compute_pass_execution(p, ((w + 7) // 8, (h + 7) // 8, 1), sampled=[(src, 0, 0)], storage=[(dst, 0, 1)])
+    rig.run()
+    out = be.read_image(dst, 0, np.uint8).reshape(h, w).copy()
+    rig.close()
+    return out
+
+
+def temporal_supersampling(ffi, api, current, last, motion, depth_current, depth_last, lum_current, lum_last, use_tonemap=True):
+    """temporalSupersampling.comp with the bindings of TAA.cpp:109-136. current/last: packed R11G11B10 (h, w) uint32; motion: (h, w, 2)
+    int16 SNORM; depths: float32 D32F; luminance: uint8 R8. Returns the packed target."""
+    h, w = current.shape
+    rig = PassRig(ffi, api, w, h)
+    be = rig.be
+    img = lambda fmt, data: be.create_image(w, h, fmt, data=np.ascontiguousarray(data))
+    cur, las = img("R11G11B10_UFLOAT", current.astype(np.uint32)), img("R11G11B10_UFLOAT", last.astype(np.uint32))
+    vel = img("RG16_SNORM", motion.astype(np.int16))
+    dc, dl = img("DEPTH32", depth_current.astype(np.float32)), img("DEPTH32", depth_last.astype(np.float32))
+    lc, ll = img("R8", lum_current.astype(np.uint8)), img("R8", lum_last.astype(np.uint8))
+    target = be.create_image(w, h, "R11G11B10_UFLOAT")
+    p = be.create_compute_pass("temporalSupersampling.comp", {0: np.uint32(1 if use_tonemap else 0)})
+    be.new_frame()
+    be.set_compute_pass_execution(p, ((w + 7) // 8, (h + 7) // 8, 1), sampled=[(cur, 0, 1), (las, 0, 2), (vel, 0, 4), (dc, 0, 5), (dl, 0, 6), (lc, 0, 7), (ll, 0, 8)], storage=[(target, 0, 3)])
+    rig.run()
+    out = be.read_image(target, 0, np.uint32).reshape(h, w).copy()
+    rig.close()
+    return out

@@ -33,3 +33,23 @@ def test_oracle_reproduces_golden(oracle):
 def test_cuda_reproduces_golden(cuda):
     want = json.loads((GOLDEN / "frame_sequence.json").read_text())
     _check(_generator().run(cuda), want, "CUDA")
+
+
+def _check_n4(got, want, who):
+    assert [g["settings"] for g in got] == [w["settings"] for w in want]
+    for g, w in zip(got, want):
+        for f, (a, b) in enumerate(zip(g["frames"], w["frames"])):
+            bad = [k for k in b if a[k] != b[k]]
+            assert not bad, "%s: %s frame %d differs from the golden vectors: %s" % (who, w["settings"], f, bad)
+
+
+def test_oracle_reproduces_n4_golden(oracle):
+    """temporal supersampling + SDF debug visualiser variants, tests/golden/n4_variants.json"""
+    want = json.loads((GOLDEN / "n4_variants.json").read_text())
+    _check_n4(_generator().run_n4(oracle), want, "oracle")
+
+
+@pytest.mark.gpu
+def test_cuda_reproduces_n4_golden(cuda):
+    want = json.loads((GOLDEN / "n4_variants.json").read_text())
+    _check_n4(_generator().run_n4(cuda), want, "CUDA")

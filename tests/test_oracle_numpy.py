@@ -173,3 +173,66 @@ def test_halton_jitter_and_resolve_weights(ffi, oracle):
         assert np.allclose(fe.resolve_weights(), wts / wts.sum(), rtol=2e-5)
         assert g.frameIndexMod4 == frame % 4
     fe.close()
+
+
+# ---------------- colorToLuminance.comp + temporalSupersampling.comp ----------------
+def test_color_to_luminance_matches_numpy(ffi, oracle):
+    rng = np.random.default_rng(21)
+    w, h = 70, 37
+    packed = random_r11g11b10(rng, w * h).reshape(h, w)
+    packed[rng.uniform(size=(h, w)) < 0.5] &= np.uint32(0x0FF3FDFF)  # half of the texels below ~2 so that the R8 target is not saturated everywhere
+    got = passes.color_to_luminance(ffi, oracle, packed)
+    lum = decode_r11g11b10(packed) @ np.array([0.21, 0.72, 0.07])  # luminance.inc:5-7
+    want = np.floor(np.clip(lum, 0, 1) * 255 + 0.5).astype(np.int32)
+    diff = np.abs(got.astype(np.int32) - want)
+    assert diff.max() <= 1 and (diff == 0).mean() > 0.99  # float32 vs float64 may flip a rounding
+    assert 0.1 < (got == 255).mean() < 0.9
+
+
+def pack_r11g11b10_exact(r, g, b):
+    """pack values that are exactly representable (powers of two times small integers)"""
+    def chan(v, mbits):
+        m, e = np.frexp(np.float64(v))  # v = m * 2^e, m in [0.5, 1)
+        return (int(e - 1 + 15) << mbits) | int(round((m * 2 - 1) * (1 << mbits)))
+    return np.uint32(chan(r, 6) | (chan(g, 6) << 11) | (chan(b, 5) << 22))
+
+
+@pytest.mark.parametrize("use_tonemap", [False, True])
+def test_temporal_supersampling_accept_and_reject(ffi, oracle, use_tonemap):
+    """temporalSupersampling.comp:86-110: an accepted history sample is blended 50:50, a rejected one (depth difference >= 1 m,
+    2x2 luminance block contrast >= 0.5, reprojected position off screen) leaves the current sample."""
+    w, h = 48, 32
+    A, B = (0.5, 0.25, 0.125), (0.25, 0.75, 0.5)
+    cur = np.full((h, w), pack_r11g11b10_exact(*A), np.uint32)
+    last = np.full((h, w), pack_r11g11b10_exact(*B), np.uint32)
+    zero_motion = np.zeros((h, w, 2), np.int16)
+    near, far = 0.1, 300.0
+    depth_of = lambda z: np.float32(1.0 - (near * far / z - far) / (near - far))  # inverse of linearDepth.inc:5-8
+    d10, d12 = np.full((h, w), depth_of(10.0), np.float32), np.full((h, w), depth_of(12.0), np.float32)
+    lum = np.full((h, w), 100, np.uint8)
+
+    def tm(c):
+        c = np.asarray(c, np.float64)
+        return c / (1 + c @ np.array([0.21, 0.72, 0.07])) if use_tonemap else c
+
+    def tm_inv(c):
+        return c / (1 - c @ np.array([0.21, 0.72, 0.07])) if use_tonemap else c
+    blended, kept = tm_inv(0.5 * tm(A) + 0.5 * tm(B)), np.asarray(A, np.float64)
+    run = lambda **kw: decode_r11g11b10(passes.temporal_supersampling(ffi, oracle, **{**dict(current=cur, last=last, motion=zero_motion, depth_current=d10, depth_last=d10,
+                                                                                           lum_current=lum, lum_last=lum, use_tonemap=use_tonemap), **kw}))
+    tol = dict(rtol=2.0 ** -5, atol=0)  # R11G11B10 keeps 6 / 5 mantissa bits
+    assert np.allclose(run(), blended, **tol)
+    assert np.allclose(run(depth_last=d12), kept, **tol)                                   # depth test
+    assert np.allclose(run(lum_current=np.full((h, w), 250, np.uint8), lum_last=np.full((h, w), 10, np.uint8)), kept, **tol)  # contrast test: 4 * (250 - 10) / 255 >= 0.5
+    # the contrast is a difference of absolute values (:22-28), so a darker current block always passes
+    assert np.allclose(run(lum_current=np.full((h, w), 10, np.uint8), lum_last=np.full((h, w), 250, np.uint8)), blended, **tol)
+    off = zero_motion.copy()
+    off[..., 0] = 32767  # motion of +1 screen width: every reprojected position is off screen
+    assert np.allclose(run(motion=off), kept, **tol)
+    # motion dilation picks the motion of the closest (largest, reverse z) depth in the 3x3 neighbourhood
+    dil = zero_motion.copy()
+    dil[10, 20, 0] = 32767
+    dc = d10.copy()
+    dc[10, 20] = depth_of(2.0)
+    out = run(motion=dil, depth_current=dc, depth_last=dc)
+    assert np.allclose(out[9:12, 19:22], kept, **tol) and np.allclose(out[0:8], blended, **tol)

@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 
 import passes
-from conftest import Sequence, assert_snapshots_equal, decode_r11g11b10, random_r11g11b10
+from conftest import N4_VARIANTS, Sequence, assert_snapshots_equal, decode_r11g11b10, random_r11g11b10
 
 pytestmark = pytest.mark.gpu
 
@@ -58,6 +58,28 @@ def test_depth_downscale_bit_exact(ffi, cuda, oracle):
     assert np.array_equal(passes.depth_downscale(ffi, cuda, depth).view(np.uint16), passes.depth_downscale(ffi, oracle, depth).view(np.uint16))
 
 
+@pytest.mark.parametrize("w,h", [(96, 40), (70, 37), (5, 3), (513, 65)])
+def test_color_to_luminance_bit_exact(ffi, cuda, oracle, w, h):
+    rng = np.random.default_rng(w * 7 + h)
+    packed = random_r11g11b10(rng, w * h, finite=False).reshape(h, w)  # includes inf / NaN texels
+    assert np.array_equal(passes.color_to_luminance(ffi, cuda, packed), passes.color_to_luminance(ffi, oracle, packed))
+
+
+@pytest.mark.parametrize("w,h,use_tonemap", [(96, 40, True), (70, 37, False), (9, 5, True), (260, 130, True)])
+def test_temporal_supersampling_bit_exact(ffi, cuda, oracle, w, h, use_tonemap):
+    """random colours (inf / NaN included), random motion up to +-1/8 screen with some vectors leaving the screen, depth steps"""
+    rng = np.random.default_rng(w * 13 + h)
+    kw = dict(current=random_r11g11b10(rng, w * h, finite=False).reshape(h, w), last=random_r11g11b10(rng, w * h, finite=False).reshape(h, w),
+              motion=rng.integers(-4096, 4096, (h, w, 2)).astype(np.int16), depth_current=rng.uniform(0.0003, 0.05, (h, w)).astype(np.float32),
+              depth_last=rng.uniform(0.0003, 0.05, (h, w)).astype(np.float32), lum_current=rng.integers(0, 256, (h, w)).astype(np.uint8),
+              lum_last=rng.integers(0, 256, (h, w)).astype(np.uint8), use_tonemap=use_tonemap)
+    kw["depth_current"][rng.uniform(size=(h, w)) < 0.2] = 0.0  # sky
+    kw["motion"][rng.uniform(size=(h, w)) < 0.05] = 32767
+    kw["lum_last"][: h // 2] = kw["lum_current"][: h // 2]      # upper half passes the contrast test
+    kw["depth_last"][:, : w // 2] = kw["depth_current"][:, : w // 2]
+    assert np.array_equal(passes.temporal_supersampling(ffi, cuda, **kw), passes.temporal_supersampling(ffi, oracle, **kw))
+
+
 # ---------------- whole frames: every resource of every pass ----------------
 def run_both(ffi, cuda, oracle, w, h, frames, moving, instances=12, **settings):
     a, b = Sequence(ffi, cuda, w, h, instances, **settings), Sequence(ffi, oracle, w, h, instances, **settings)
@@ -94,6 +116,19 @@ def test_frame_many_instances_hits_tile_cap(ffi, cuda, oracle):
 ])
 def test_frame_setting_variants(ffi, cuda, oracle, settings):
     run_both(ffi, cuda, oracle, 128, 72, frames=2, moving=True, instances=8, **settings)
+
+
+@pytest.mark.parametrize("settings", N4_VARIANTS)
+def test_frame_n4_variants(ffi, cuda, oracle, settings):
+    """separate temporal supersampling (colorToLuminance.comp + temporalSupersampling.comp) and the SDF debug
+    visualiser (sdfDebugVisualisation.comp, primary rays through the SDF scene), every resource of a 3-frame moving sequence."""
+    run_both(ffi, cuda, oracle, 160, 90, frames=3, moving=True, instances=14, **settings)
+
+
+def test_debug_visualisation_many_instances(ffi, cuda, oracle):
+    """tiles at the 100-instance cap (camera tile usage shows red) and ties between overlapping bricks"""
+    run_both(ffi, cuda, oracle, 128, 72, frames=1, moving=False, instances=160, sdf_debug_mode=2)
+    run_both(ffi, cuda, oracle, 128, 72, frames=1, moving=False, instances=160, sdf_debug_mode=4, sdf_debug_use_influence_radius=1)
 
 
 def test_config1_shade_and_tonemap_1080p(ffi, cuda, oracle):
