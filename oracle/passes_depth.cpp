@@ -49,8 +49,10 @@ ORACLE_PASS(pass_depthHiZPyramid, "depthHiZPyramid.comp") {
     int srcMipLevel = 0;
     ivec2 srcMipRes(depthBufferResX, depthBufferResY);
     ivec2 currentMipRes(max(srcMipRes.x / 2, 1), max(srcMipRes.y / 2, 1));
-    for (int k = 0; k <= 10; k++) {
-        if (!(mipCount >= 11 - k)) continue;
+    // 11 bindings in the reference (:21-31); a 12th level at binding 11 is the extension for 7680x4320
+    const int bindingCount = mipCount > 11 ? mipCount : 11;
+    for (int k = 0; k < bindingCount; k++) {
+        if (!(mipCount >= bindingCount - k)) continue;
         View target = c.storage((uint32_t)k);
         View src = depthBuffer;
         if (!fromDepthBuffer) { src = pyramidTexture; src.mip = pyramidTexture.mip + srcMipLevel; }

@@ -133,7 +133,10 @@ PLAIN_PASS(launch_depthHiZPyramid, "depthHiZPyramid.comp") {
     const int resX = c.spec<int>(1, 0), resY = c.spec<int>(2, 0);
     const ImgView depth = c.sampled(13, PLAIN_FORMAT_DEPTH32);
     if (c.failed) return;
-    if (mipCount < 1 || mipCount > 11) { c.fail("depthHiZPyramid.comp: mip count must be 1..11 (depthHiZPyramid.comp:16-19)"); return; }
+    // the reference binds 11 levels (depthHiZPyramid.comp:16-31: up to 4096x4096); a 12th level at binding 11 is this build's
+    // extension for BASELINE configs[4] (7680x4320: the half-resolution pyramid has 12 levels), defined level by level like the rest
+    if (mipCount < 1 || mipCount > 12) { c.fail("depthHiZPyramid.comp: mip count must be 1..12 (depthHiZPyramid.comp:16-19, + one extension level)"); return; }
+    const int bindingCount = mipCount > 11 ? mipCount : 11;
     if (depth.w != resX || depth.h != resY) { c.fail("depthHiZPyramid.comp: depth buffer extent differs from the specialisation constants"); return; }
     HizLevels L;
     L.count = mipCount;
@@ -142,7 +145,7 @@ PLAIN_PASS(launch_depthHiZPyramid, "depthHiZPyramid.comp") {
     bool evenSoFar = true;
     for (int k = 0; k < mipCount; k++) {
         // the shader's image binding k' = 11 - mipCount + k holds pyramid level k (RenderFrontend.cpp:825-833)
-        L.mip[k] = c.storage((uint32_t)(11 - mipCount + k), PLAIN_FORMAT_RG32_SFLOAT);
+        L.mip[k] = c.storage((uint32_t)(bindingCount - mipCount + k), PLAIN_FORMAT_RG32_SFLOAT);
         if (c.failed) return;
         const int w = std::max(srcW / 2, 1), h = std::max(srcH / 2, 1);
         if (L.mip[k].w != w || L.mip[k].h != h) { c.fail("depthHiZPyramid.comp: pyramid level extent mismatch"); return; }

@@ -221,7 +221,7 @@ ShaderDescription RenderFrontend::createDepthPyramidShaderDescription(uint32_t* 
     const uint32_t width = m_screenWidth / 2, height = m_screenHeight / 2;
     const uint32_t depthMipCount = mipCountFromResolution(width, height, 1);
     uint32_t dc[2];
-    computeSinglePassMipChainDispatchCount(width, height, depthMipCount, 11, dc);
+    computeSinglePassMipChainDispatchCount(width, height, depthMipCount, depthMipCount > 11 ? depthMipCount : 11, dc);
     *outThreadgroupCount = dc[0] * dc[1];
     desc.specialisationConstants = {specConst(0, depthMipCount), specConst(1, m_screenWidth), specConst(2, m_screenHeight), specConst(3, *outThreadgroupCount)};
     return desc;
@@ -525,8 +525,10 @@ void RenderFrontend::computeExposure() {
 void RenderFrontend::computeDepthPyramid(ImageHandle depthBuffer) {
     ComputePassExecution e;
     e.genericInfo.handle = m_depthPyramidPass;
-    const uint32_t width = m_screenWidth / 2, height = m_screenHeight / 2, maxMipCount = 11;
+    const uint32_t width = m_screenWidth / 2, height = m_screenHeight / 2;
     const uint32_t mipCount = mipCountFromResolution(width, height, 1);
+    // 11 in the reference (RenderFrontend.cpp:806); 7680x4320 (BASELINE configs[4]) needs a 12th level, bound at binding 11
+    const uint32_t maxMipCount = mipCount > 11 ? mipCount : 11;
     uint32_t dc[2];
     computeSinglePassMipChainDispatchCount(width, height, mipCount, maxMipCount, dc);
     e.dispatchCount[0] = dc[0]; e.dispatchCount[1] = dc[1];

@@ -83,8 +83,9 @@ def hiz(ffi, api, depth):
     pyr = be.create_image(pw, ph, "RG32_SFLOAT", mips=ffi.MIPS_FULL_CHAIN)
     sync = be.create_storage_buffer(4, np.zeros(1, np.uint32))
     p = be.create_compute_pass("depthHiZPyramid.comp", {0: np.uint32(n), 1: np.uint32(w), 2: np.uint32(h), 3: np.uint32(1)})
-    unused = 11 - n
-    storage = [(pyr, max(i - unused, 0), i) for i in range(11)]
+    bindings = max(11, n)  # 11 in the reference; a 12th level (binding 11) is the extension for 7680x4320
+    unused = bindings - n
+    storage = [(pyr, max(i - unused, 0), i) for i in range(bindings)]
     be.new_frame()
     be.set_compute_pass_execution(p, ((pw + 31) // 32, (ph + 31) // 32, 1), sampled=[(src, 0, 13), (pyr, 0, 15)], storage=storage, storage_buffers=[(sync, False, 16)])
     rig.run()

@@ -47,7 +47,7 @@ def np_hiz(depth):
     return levels
 
 
-@pytest.mark.parametrize("w,h", [(64, 36), (50, 30), (37, 23), (130, 66), (2, 2), (18, 5)])
+@pytest.mark.parametrize("w,h", [(64, 36), (50, 30), (37, 23), (130, 66), (2, 2), (18, 5), (4096, 4), (4098, 6)])  # the last two: 12 levels
 def test_hiz_matches_numpy(ffi, oracle, w, h):
     rng = np.random.default_rng(w * 1000 + h)
     depth = rng.uniform(0.0005, 0.9, (h, w)).astype(np.float32)

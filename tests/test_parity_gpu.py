@@ -11,7 +11,7 @@ pytestmark = pytest.mark.gpu
 
 
 # ---------------- single passes on adversarial inputs ----------------
-@pytest.mark.parametrize("w,h", [(64, 36), (50, 30), (37, 23), (130, 66), (2, 2), (18, 5), (257, 129), (512, 256)])
+@pytest.mark.parametrize("w,h", [(64, 36), (50, 30), (37, 23), (130, 66), (2, 2), (18, 5), (257, 129), (512, 256), (4096, 4), (4098, 6), (7680, 64)])  # the last three: 12 levels
 def test_hiz_bit_exact(ffi, cuda, oracle, w, h):
     rng = np.random.default_rng(w * 1000 + h)
     depth = rng.uniform(0.0005, 0.9, (h, w)).astype(np.float32)

@@ -104,3 +104,55 @@ def test_sharded_frame_equals_unsharded(ffi, cuda, W, H, R, moving):
         fe.close()
     scene0.close()
     ref.close()
+
+
+def test_config4_8k_256_instances(ffi, cuda):
+    """BASELINE configs[4] on one device: 7680x4320, 256 SDF instances (the 100-instances-per-tile cap is active), a half-resolution
+    depth pyramid of 12 levels (one more than the reference binds). Size-independent properties of the unsharded frame, and the
+    frame split into 2 row bands (LocalComm exchanges) reproduces it bit for bit."""
+    import torch
+    from plainrenderer_b200 import sharding
+    W, H, R = 7680, 4320, 2
+    s0, ref, scene0 = make(ffi, cuda, W, H, 256)
+    ranks = [make(ffi, cuda, W, H, 256, rank=r, count=R) for r in range(R)]
+    fes = [x[1] for x in ranks]
+    comm = sharding.LocalComm(cuda, H, R, torch.device("cuda", 0))
+    cam = camera(ffi, 0, False)
+    inputs = scene0.render_inputs(s0, cam, 1, prev_cam=None, shadows=True)
+    for f in range(2):
+        ref.render_frame(cam, (f + 1) / 60.0, 1 / 60.0, inputs["depth"], inputs["motion"], inputs["normal"], inputs["gbuffer"], inputs["shadow_maps"])
+        upload = []
+        for r in range(R):
+            a, b = sharding.full_res_band(cuda, H, R, r)
+            upload.append((max(a - 16, 0), min(b + 16, H)))
+        sharding.run_frame_local(fes, comm, cam, (f + 1) / 60.0, 1 / 60.0, inputs, upload_rows=upload)
+    torch.cuda.synchronize()
+    be = ref.backend
+    hist = be.read_storage_buffer(ref.storage_buffer("histogram"), 512, np.uint32)
+    assert int(hist.sum()) == W * H  # 240 x 135 whole tiles: every pixel of the previous frame's colour lands in exactly one bin
+    depth = inputs["depth"].reshape(H, W)
+    assert image_mips(ref, ref.image("hiz")) == 12
+    hiz0 = be.read_image(ref.image("hiz"), 0, np.float32).reshape(H // 2, W // 2, 2)
+    d4 = depth.reshape(H // 2, 2, W // 2, 2)
+    assert np.array_equal(hiz0[..., 0], np.minimum(np.where(d4 == 0, np.float32(1.0), d4).min(axis=(1, 3)), np.float32(1.0)))
+    assert np.array_equal(hiz0[..., 1], d4.max(axis=(1, 3)))
+    top = be.read_image(ref.image("hiz"), 11, np.float32)
+    assert top.size == 2 and top[1] == depth.max() and top[0] == depth[depth > 0].min()
+    # half-res trace: 120 x 68 tiles, indexed with the full-resolution stride of 240 tiles per row (sdfCulling.inc:17-20); unused entries stay 0
+    tiles = be.read_storage_buffer(ref.storage_buffer("sdfTiles"), 404 * 240 * 135, np.uint32).reshape(-1, 101)
+    assert tiles[:, 0].max() == 100, "the per-tile instance cap (sdfCulling.inc:5) should be reached with 256 instances"
+    out = ref.read_output().reshape(H, W, 4)
+    assert out[..., :3].mean() > 5 and (out[..., 3] == 255).all()
+    frame = np.zeros((H, W * 4), np.uint8)
+    for r, fe in enumerate(fes):
+        a, b = sharding.full_res_band(cuda, H, R, r)
+        fe.read_output_rows(frame, (a, b))
+    assert np.array_equal(frame.reshape(H, W, 4), out)
+    for r, fe in enumerate(fes):
+        assert np.array_equal(fe.backend.read_storage_buffer(fe.storage_buffer("histogram"), 512, np.uint32), hist), "rank %d histogram" % r
+        assert np.array_equal(fe.backend.read_storage_buffer(fe.storage_buffer("sunShadowInfo"), 304), be.read_storage_buffer(ref.storage_buffer("sunShadowInfo"), 304))
+    for _, fe, sc in ranks:
+        sc.close()
+        fe.close()
+    scene0.close()
+    ref.close()
