@@ -142,7 +142,7 @@ def test_config4_8k_256_instances(ffi, cuda):
     tiles = be.read_storage_buffer(ref.storage_buffer("sdfTiles"), 404 * 240 * 135, np.uint32).reshape(-1, 101)
     assert tiles[:, 0].max() == 100, "the per-tile instance cap (sdfCulling.inc:5) should be reached with 256 instances"
     out = ref.read_output().reshape(H, W, 4)
-    assert out[..., :3].mean() > 5 and (out[..., 3] == 255).all()
+    assert out[..., :3].mean() > 1 and out[..., :3].std() > 1 and (out[..., 3] == 255).all()  # second frame: the exposure is still adapting (dark, not black)
     frame = np.zeros((H, W * 4), np.uint8)
     for r, fe in enumerate(fes):
         a, b = sharding.full_res_band(cuda, H, R, r)
