@@ -133,6 +133,46 @@ typedef struct {
     uint32_t row_begin, row_end, shard_phase;
 } plain_compute_pass_execution;
 
+/* ---- graphic passes (the rasterisation passes that feed the frame path) ----
+ * MeshBinary, MeshData.h:27-35: index buffer u16 when index_count < 65535 else u32 (RenderBackend.cpp:483-488); vertex buffer
+ * 28 bytes per vertex: position 3 x f32, uv 2 x f16, normal / tangent / bitangent A2R10G10B10_SNORM (VertexInput.h:27-31,
+ * VulkanVertexInput.cpp:4-10, MeshProcessing.cpp:52-106). Both are copied before the call returns. */
+typedef struct {
+    uint32_t index_count, vertex_count;
+    const void* index_buffer;
+    const void* vertex_buffer;
+} plain_mesh_binary;
+
+/* ResourceDescriptions.h:80-103 */
+typedef enum { PLAIN_CULL_NONE = 0, PLAIN_CULL_FRONT = 1, PLAIN_CULL_BACK = 2 } plain_cull_mode;
+typedef enum { PLAIN_DEPTH_NEVER = 0, PLAIN_DEPTH_ALWAYS, PLAIN_DEPTH_LESS, PLAIN_DEPTH_GREATER, PLAIN_DEPTH_LESS_EQUAL, PLAIN_DEPTH_GREATER_EQUAL, PLAIN_DEPTH_EQUAL } plain_depth_function;
+typedef enum { PLAIN_LOAD_OP_LOAD = 0, PLAIN_LOAD_OP_CLEAR = 1, PLAIN_LOAD_OP_DONT_CARE = 2 } plain_attachment_load_op;
+typedef struct { uint32_t format; uint32_t load_op; } plain_attachment;
+/* GraphicPassDescription, ResourceDescriptions.h:129-143 (vertex + fragment stage; fill mode, no blending, VertexFormat::Full).
+ * Passes that exist as CUDA rasteriser programs (csrc/passes_raster.cu), by shader pair:
+ *   depthPrepass.vert + depthPrepass.frag   attachments {RG16_SNORM motion, RGBA8 normal, DEPTH32}, cull back, GREATER_EQUAL
+ *   sunShadow.vert    + sunShadow.frag      attachment  {DEPTH16}, cull front, depth clamp, GREATER_EQUAL; spec constant 0 = cascade
+ *   triangle.vert     + gbufferFill.frag    attachments {RGBA32_UINT packed G-buffer, DEPTH32 (load)}, depth EQUAL against the
+ *                                           prepass: the raster half of the reference's main pass (triangle.frag:178-193: the
+ *                                           interpolated inputs and material texels), recast for the deferred shading kernel */
+typedef struct {
+    const char* vertex_shader; const plain_spec_const* vertex_consts; uint32_t n_vertex_consts;
+    const char* fragment_shader; const plain_spec_const* fragment_consts; uint32_t n_fragment_consts;
+    const plain_attachment* attachments; uint32_t n_attachments;
+    uint32_t cull_mode;      /* plain_cull_mode; front face = counter clockwise (VulkanPipeline.cpp:61) */
+    uint32_t clamp_depth;
+    uint32_t depth_function; /* plain_depth_function */
+    uint32_t depth_write;
+    const char* debug_name;
+} plain_graphic_pass_desc;
+/* GraphicPassExecution, ResourceDescriptions.h:55-71: targets in attachment order */
+typedef struct { plain_image_handle image; uint32_t mip_level; } plain_render_target;
+typedef struct {
+    plain_handle pass;
+    plain_pass_resources resources;
+    const plain_render_target* targets; uint32_t n_targets;
+} plain_graphic_pass_execution;
+
 /* VulkanTimestampQueries.h:16-20 */
 typedef struct {
     char name[64];
@@ -178,6 +218,15 @@ PLAIN_EXPORT int PLAIN_FN(submit_recorded_passes)(plain_ctx* ctx);
 PLAIN_EXPORT int PLAIN_FN(wait_for_gpu_idle)(plain_ctx* ctx);
 PLAIN_EXPORT int PLAIN_FN(get_renderpass_timings)(plain_ctx* ctx, plain_pass_time* out, uint32_t capacity, uint32_t* out_count);
 PLAIN_EXPORT int PLAIN_FN(set_timing_enabled)(plain_ctx* ctx, int enabled);
+
+/* ---- meshes and graphic passes (RenderBackend.h:57-96): createMeshes, createGraphicPass, setGraphicPassExecution (after
+ * new_frame, before prepare_for_drawcall_recording), drawMeshes (after it; one push-constant block per mesh, its size fixed by
+ * the pass: 16 bytes for depthPrepass / triangle, 8 for sunShadow; worker_index is accepted and ignored - draws are ordered by
+ * call). A graphic pass runs where its execution was set in the pass order, with the draws recorded for it this frame. ---- */
+PLAIN_EXPORT int PLAIN_FN(create_meshes)(plain_ctx* ctx, const plain_mesh_binary* meshes, uint32_t n, plain_handle* out_handles);
+PLAIN_EXPORT int PLAIN_FN(create_graphic_pass)(plain_ctx* ctx, const plain_graphic_pass_desc* desc, plain_handle* out);
+PLAIN_EXPORT int PLAIN_FN(set_graphic_pass_execution)(plain_ctx* ctx, const plain_graphic_pass_execution* execution);
+PLAIN_EXPORT int PLAIN_FN(draw_meshes)(plain_ctx* ctx, const plain_handle* meshes, uint32_t n, const void* push_constants, plain_handle pass, int32_t worker_index);
 
 /* ---- additions (not in the reference): the raster passes that produce depth/motion/normal/shadow maps/G-buffer are
  * out of scope, so their outputs are uploaded; read-back exists for parity tests and the e2e bench leg. Synchronous. ---- */

@@ -53,6 +53,11 @@ static View makeView(Ctx* ctx, const plain_image_resource& r) {
     v.mip = (int)r.mip_level;
     return v;
 }
+View PassCtx::target(uint32_t attachment) const {
+    if (attachment >= exec->targets.size()) return View();
+    plain_image_resource r{exec->targets[attachment].image, exec->targets[attachment].mip_level, 0};
+    return makeView(ctx, r);
+}
 View PassCtx::sampled(uint32_t binding) const {
     for (auto& r : exec->sampledImages) if (r.binding == binding) return makeView(ctx, r);
     return View();
@@ -270,6 +275,78 @@ int PLAIN_FN(set_compute_pass_execution)(plain_ctx* ctx, const plain_compute_pas
     return 0;
 }
 int PLAIN_FN(prepare_for_drawcall_recording)(plain_ctx* ctx) { (void)ctx; return 0; }
+
+// ---- meshes and graphic passes (RenderBackend.h:57-96) ----
+int PLAIN_FN(create_meshes)(plain_ctx* ctx, const plain_mesh_binary* meshes, uint32_t n, plain_handle* out) {
+    for (uint32_t i = 0; i < n; i++) {
+        const plain_mesh_binary& m = meshes[i];
+        if (m.index_count % 3 != 0 || !m.index_buffer || !m.vertex_buffer) return fail(ctx, "create_meshes: triangle list with index and vertex data expected");
+        Mesh r;
+        r.indexCount = m.index_count; r.vertexCount = m.vertex_count;
+        r.index32 = !(m.index_count < 65535u);  // RenderBackend.cpp:483-488
+        const size_t ib = (size_t)m.index_count * (r.index32 ? 4 : 2), vb = (size_t)m.vertex_count * 28;
+        r.indices.assign((const uint8_t*)m.index_buffer, (const uint8_t*)m.index_buffer + ib);
+        r.vertices.assign((const uint8_t*)m.vertex_buffer, (const uint8_t*)m.vertex_buffer + vb);
+        for (uint32_t k = 0; k < m.index_count; k++) {
+            uint32_t idx = r.index32 ? ((const uint32_t*)r.indices.data())[k] : ((const uint16_t*)r.indices.data())[k];
+            if (idx >= m.vertex_count) return fail(ctx, "create_meshes: index out of range");
+        }
+        ctx->c.meshes.push_back(std::move(r));
+        out[i] = (uint32_t)ctx->c.meshes.size() - 1;
+    }
+    return 0;
+}
+int PLAIN_FN(create_graphic_pass)(plain_ctx* ctx, const plain_graphic_pass_desc* d, plain_handle* out) {
+    if (!d || !d->vertex_shader || !d->fragment_shader) return fail(ctx, "create_graphic_pass: vertex and fragment shader expected");
+    PassRecord p;
+    p.graphic = true;
+    p.shader = std::string(d->vertex_shader) + "+" + d->fragment_shader;
+    p.name = d->debug_name ? d->debug_name : p.shader;
+    for (uint32_t i = 0; i < d->n_vertex_consts; i++) {
+        const uint8_t* s = (const uint8_t*)d->vertex_consts[i].data;
+        p.spec[d->vertex_consts[i].location] = std::vector<uint8_t>(s, s + d->vertex_consts[i].size);
+    }
+    p.cullMode = d->cull_mode; p.clampDepth = d->clamp_depth; p.depthFunction = d->depth_function; p.depthWrite = d->depth_write;
+    p.attachments.assign(d->attachments, d->attachments + d->n_attachments);
+    p.pushSize = p.shader.rfind("sunShadow.vert", 0) == 0 ? 8u : 16u;
+    p.fn = findPass(p.shader);
+    if (!p.fn) return fail(ctx, std::string("no oracle rasteriser program for the shader pair '") + p.shader + "'");
+    ctx->c.passes.push_back(std::move(p));
+    *out = (uint32_t)ctx->c.passes.size() - 1;
+    return 0;
+}
+int PLAIN_FN(set_graphic_pass_execution)(plain_ctx* ctx, const plain_graphic_pass_execution* e) {
+    if (e->pass >= ctx->c.passes.size() || !ctx->c.passes[e->pass].graphic) return fail(ctx, "set_graphic_pass_execution: not a graphic pass");
+    if (e->n_targets != ctx->c.passes[e->pass].attachments.size()) return fail(ctx, "set_graphic_pass_execution: one target per attachment expected");
+    ExecRecord r;
+    r.pass = e->pass;
+    const plain_pass_resources& s = e->resources;
+    r.storageBuffers.assign(s.storage_buffers, s.storage_buffers + s.n_storage_buffers);
+    r.uniformBuffers.assign(s.uniform_buffers, s.uniform_buffers + s.n_uniform_buffers);
+    r.sampledImages.assign(s.sampled_images, s.sampled_images + s.n_sampled_images);
+    r.storageImages.assign(s.storage_images, s.storage_images + s.n_storage_images);
+    r.targets.assign(e->targets, e->targets + e->n_targets);
+    r.dispatch[0] = r.dispatch[1] = r.dispatch[2] = 0;
+    ctx->c.execs.push_back(std::move(r));
+    return 0;
+}
+int PLAIN_FN(draw_meshes)(plain_ctx* ctx, const plain_handle* meshes, uint32_t n, const void* push_constants, plain_handle pass, int32_t worker_index) {
+    (void)worker_index;
+    if (pass >= ctx->c.passes.size() || !ctx->c.passes[pass].graphic) return fail(ctx, "draw_meshes: not a graphic pass");
+    ExecRecord* rec = nullptr;
+    for (auto& e : ctx->c.execs) if (e.pass == pass) rec = &e;
+    if (!rec) return fail(ctx, "draw_meshes: the pass has no execution this frame (set_graphic_pass_execution)");
+    const uint32_t ps = ctx->c.passes[pass].pushSize;
+    for (uint32_t i = 0; i < n; i++) {
+        if (meshes[i] >= ctx->c.meshes.size()) return fail(ctx, "draw_meshes: invalid mesh handle");
+        DrawRecord d;
+        d.mesh = meshes[i];
+        memset(d.push, 0, sizeof(d.push));
+        memcpy(d.push, (const uint8_t*)push_constants + (size_t)i * ps, ps);
+        rec->draws.push_back(d);
+    }
+    return 0;
+}
 int PLAIN_FN(set_uniform_buffer_data)(plain_ctx* ctx, plain_handle buffer, const void* data, size_t size) {
     if (buffer >= ctx->c.uniformBuffers.size() || size > ctx->c.uniformBuffers[buffer].data.size()) return fail(ctx, "set_uniform_buffer_data: invalid buffer/size");
     FillOrder f{true, buffer, std::vector<uint8_t>((const uint8_t*)data, (const uint8_t*)data + size)};

@@ -17,8 +17,20 @@ struct Buffer {
     std::vector<uint8_t> data;
 };
 
+struct Mesh {  // MeshBinary (MeshData.h:27-35) as uploaded by create_meshes
+    uint32_t indexCount = 0, vertexCount = 0;
+    bool index32 = false;
+    std::vector<uint8_t> indices, vertices;
+};
+struct DrawRecord {  // one mesh of a drawMeshes call with its push-constant block
+    uint32_t mesh;
+    uint8_t push[16];
+};
+
 struct ExecRecord {
     uint32_t pass;
+    std::vector<plain_render_target> targets;  // graphic passes: attachments in order
+    std::vector<DrawRecord> draws;
     std::vector<plain_storage_buffer_resource> storageBuffers;
     std::vector<plain_uniform_buffer_resource> uniformBuffers;
     std::vector<plain_image_resource> sampledImages;
@@ -35,6 +47,10 @@ struct PassRecord {
     std::string name;
     std::map<uint32_t, std::vector<uint8_t>> spec;
     PassFn fn = nullptr;
+    // graphic passes (GraphicPassDescription, ResourceDescriptions.h:129-143); spec holds the vertex stage's constants
+    bool graphic = false;
+    uint32_t cullMode = 0, clampDepth = 0, depthFunction = 0, depthWrite = 0, pushSize = 0;
+    std::vector<plain_attachment> attachments;
 };
 
 struct FillOrder {
@@ -51,6 +67,8 @@ struct Ctx {
     std::vector<Buffer> storageBuffers;
     std::vector<plain_sampler_desc> samplers;
     std::vector<PassRecord> passes;
+    std::vector<Mesh> meshes;
+    std::map<uint32_t, std::vector<uint64_t>> visibility;  // per depth image (handle index): depth bits << 32 | primitive + 1 of the last raster pass
     std::vector<ExecRecord> execs;
     std::vector<FillOrder> fills;
     uint32_t globalUniformBuffer = PLAIN_INVALID_INDEX;
@@ -70,6 +88,7 @@ struct PassCtx {
     const ExecRecord* exec;
     plain_global_shader_info g;
 
+    View target(uint32_t attachment) const;  // graphic passes
     View sampled(uint32_t binding) const;
     View storage(uint32_t binding) const;
     View bindless(uint32_t index) const;  // set 2: global texture array, index == image handle index

@@ -66,6 +66,57 @@ class ComputePassExecution(C.Structure):
                 ("row_begin", u32), ("row_end", u32), ("shard_phase", u32)]
 
 
+class ShadowCascadeInfo(C.Structure):  # plain_shadow_cascade_info (sunShadowCascades.inc:7-11)
+    _fields_ = [("splits", f32 * 4), ("lightMatrices", (f32 * 16) * 4), ("lightSpaceScale", (f32 * 2) * 4)]
+
+
+class MeshBinary(C.Structure):  # plain_mesh_binary
+    _fields_ = [("index_count", u32), ("vertex_count", u32), ("index_buffer", C.c_void_p), ("vertex_buffer", C.c_void_p)]
+
+
+class Attachment(C.Structure):
+    _fields_ = [("format", u32), ("load_op", u32)]
+
+
+class GraphicPassDesc(C.Structure):  # plain_graphic_pass_desc
+    _fields_ = [("vertex_shader", C.c_char_p), ("vertex_consts", C.POINTER(SpecConst)), ("n_vertex_consts", u32),
+                ("fragment_shader", C.c_char_p), ("fragment_consts", C.POINTER(SpecConst)), ("n_fragment_consts", u32),
+                ("attachments", C.POINTER(Attachment)), ("n_attachments", u32), ("cull_mode", u32), ("clamp_depth", u32),
+                ("depth_function", u32), ("depth_write", u32), ("debug_name", C.c_char_p)]
+
+
+class RenderTarget(C.Structure):
+    _fields_ = [("image", ImageHandle), ("mip_level", u32)]
+
+
+class GraphicPassExecution(C.Structure):
+    _fields_ = [("pass_", u32), ("resources", PassResources), ("targets", C.POINTER(RenderTarget)), ("n_targets", u32)]
+
+
+CULL_NONE, CULL_FRONT, CULL_BACK = 0, 1, 2
+DEPTH_GREATER_EQUAL, DEPTH_EQUAL = 5, 6
+LOAD_OP_LOAD, LOAD_OP_CLEAR = 0, 1
+
+
+def pack_vertices(positions, uvs=None, normals=None, tangents=None, bitangents=None):
+    """28-byte vertices of MeshBinary (MeshProcessing.cpp:52-106): f32 x 3, f16 x 2, three A2R10G10B10_SNORM (CompressedTypes.cpp:24-46)."""
+    positions = np.asarray(positions, np.float32).reshape(-1, 3)
+    n = len(positions)
+
+    def pack_snorm(v):
+        v = np.zeros((n, 3), np.float32) if v is None else np.asarray(v, np.float32).reshape(n, 3)
+        bits = (np.clip(v, -1, 1) * 0.5 + 0.5) * np.float32(511 + 510) + np.float32(-510)
+        bits = bits.astype(np.int32) & 1023
+        return (bits[:, 0].astype(np.uint32) << 20) | (bits[:, 1].astype(np.uint32) << 10) | bits[:, 2].astype(np.uint32)
+    out = np.zeros((n, 28), np.uint8)
+    out[:, 0:12] = positions.view(np.uint8).reshape(n, 12)
+    uv = np.zeros((n, 2), np.float16) if uvs is None else np.asarray(uvs, np.float32).reshape(n, 2).astype(np.float16)
+    out[:, 12:16] = uv.view(np.uint8).reshape(n, 4)
+    for k, v in enumerate((normals, tangents, bitangents)):
+        out[:, 16 + 4 * k:20 + 4 * k] = pack_snorm(v).astype("<u4").view(np.uint8).reshape(n, 4)
+    return out
+
+
 class PassTime(C.Structure):
     _fields_ = [("name", C.c_char * 64), ("time_ms", f32)]
 
@@ -112,6 +163,7 @@ BACKEND_SYMBOLS = [
     "get_swapchain_input_image", "create_compute_pass", "update_compute_pass_shader_description", "set_global_descriptor_set_resources",
     "new_frame", "set_compute_pass_execution", "prepare_for_drawcall_recording", "set_uniform_buffer_data", "set_storage_buffer_data",
     "render_frame", "submit_recorded_passes", "wait_for_gpu_idle", "get_renderpass_timings", "set_timing_enabled", "write_image", "read_image", "read_storage_buffer",
+    "create_meshes", "create_graphic_pass", "set_graphic_pass_execution", "draw_meshes",
     "write_image_async", "read_image_async", "write_image_rows_async", "read_image_rows_async", "get_image_device_pointer", "get_storage_buffer_device_pointer", "get_last_frame_launch_count",
     "set_graph_replay_enabled", "set_concurrent_passes_enabled", "join_transfers", "get_stream",
     "peer_init", "peer_get_sync_handle", "peer_open_sync", "peer_get_image_handle", "peer_open_image", "peer_image_ready", "peer_push_rows", "peer_barrier",
@@ -268,6 +320,51 @@ class Backend:
             e.row_begin, e.row_end = rows
         e.shard_phase = shard_phase
         self._check(self.api.b["set_compute_pass_execution"](self.ctx, C.byref(e)), "set_compute_pass_execution")
+
+    def create_meshes(self, meshes):
+        """meshes: [(indices uint array, 28-byte vertex array from pack_vertices)]; indices travel as u16 when there are fewer than 65535"""
+        arr = (MeshBinary * max(len(meshes), 1))()
+        keep = []
+        for i, (idx, vtx) in enumerate(meshes):
+            idx = np.ascontiguousarray(np.asarray(idx).ravel().astype(np.uint16 if len(np.asarray(idx).ravel()) < 65535 else np.uint32))
+            vtx = np.ascontiguousarray(np.asarray(vtx, np.uint8).reshape(-1, 28))
+            keep += [idx, vtx]
+            arr[i] = MeshBinary(len(idx), len(vtx), idx.ctypes.data, vtx.ctypes.data)
+        out = (u32 * max(len(meshes), 1))()
+        self._check(self.api.b["create_meshes"](self.ctx, arr, u32(len(meshes)), out), "create_meshes")
+        return [out[i] for i in range(len(meshes))]
+
+    def create_graphic_pass(self, vertex_shader, fragment_shader, attachments, cull_mode, clamp_depth=False, depth_function=DEPTH_GREATER_EQUAL, vertex_spec=None, name=None):
+        """attachments: [(format name, load op)]"""
+        spec = vertex_spec or {}
+        keep = [np.frombuffer(np.asarray(v).tobytes(), np.uint8).copy() for v in spec.values()]
+        sc = (SpecConst * max(len(spec), 1))()
+        for i, (loc, k) in enumerate(zip(spec.keys(), keep)):
+            sc[i] = SpecConst(loc, k.ctypes.data, k.nbytes)
+        at = (Attachment * max(len(attachments), 1))(*[Attachment(FORMAT[f], op) for f, op in attachments])
+        d = GraphicPassDesc(vertex_shader.encode(), sc, len(spec), fragment_shader.encode(), None, 0, at, len(attachments), cull_mode, int(clamp_depth), depth_function, 1,
+                            (name or vertex_shader).encode())
+        h = u32()
+        self._check(self.api.b["create_graphic_pass"](self.ctx, C.byref(d), C.byref(h)), "create_graphic_pass(%s + %s)" % (vertex_shader, fragment_shader))
+        return h.value
+
+    def set_graphic_pass_execution(self, pass_, targets, storage_buffers=(), sampled=()):
+        """targets: [(image handle, mip)] in attachment order"""
+        e = GraphicPassExecution()
+        e.pass_ = pass_
+        sb = (StorageBufferResource * max(len(storage_buffers), 1))(*[StorageBufferResource(h, int(ro), b) for h, ro, b in storage_buffers])
+        si = (ImageResource * max(len(sampled), 1))(*[ImageResource(h, m, b) for h, m, b in sampled])
+        tg = (RenderTarget * max(len(targets), 1))(*[RenderTarget(h, m) for h, m in targets])
+        e.resources.storage_buffers, e.resources.n_storage_buffers = sb, len(storage_buffers)
+        e.resources.sampled_images, e.resources.n_sampled_images = si, len(sampled)
+        e.targets, e.n_targets = tg, len(targets)
+        self._check(self.api.b["set_graphic_pass_execution"](self.ctx, C.byref(e)), "set_graphic_pass_execution")
+
+    def draw_meshes(self, meshes, push_constants, pass_):
+        """push_constants: uint32 array, one block per mesh (4 words for depthPrepass / triangle, 2 for sunShadow)"""
+        m = (u32 * max(len(meshes), 1))(*meshes)
+        pc = np.ascontiguousarray(np.asarray(push_constants, np.uint32))
+        self._check(self.api.b["draw_meshes"](self.ctx, m, u32(len(meshes)), _ptr(pc), u32(pass_), i32(0)), "draw_meshes")
 
     def set_uniform_buffer_data(self, h, data):
         data = np.frombuffer(bytes(data), np.uint8) if not isinstance(data, np.ndarray) else np.ascontiguousarray(data)

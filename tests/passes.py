@@ -171,3 +171,73 @@ def temporal_supersampling(ffi, api, current, last, motion, depth_current, depth
     out = be.read_image(target, 0, np.uint32).reshape(h, w).copy()
     rig.close()
     return out
+
+
+# ---------------- the rasterisation passes (graphic passes of the C-ABI) ----------------
+def _raster_rig(ffi, api, w, h, jitter=((0.0, 0.0), (0.0, 0.0))):
+    rig = PassRig(ffi, api, w, h)
+    rig.g.currentFrameCameraJitter[0], rig.g.currentFrameCameraJitter[1] = jitter[0]
+    rig.g.previousFrameCameraJitter[0], rig.g.previousFrameCameraJitter[1] = jitter[1]
+    rig.be.set_uniform_buffer_data(rig.gbuf, np.frombuffer(bytes(rig.g), np.uint8))
+    return rig
+
+
+def raster_prepass(ffi, api, w, h, meshes, draws, matrices, jitter=((0.0, 0.0), (0.0, 0.0)), textures=None, gbuffer=False):
+    """depthPrepass.vert/.frag (RenderFrontend.cpp:792-802, 1716-1735) and, with gbuffer=True, the G-buffer fill of the main pass.
+    meshes: [(indices, vertices)]; draws: [(mesh number, transform index)] or [(mesh, transform, albedo, normal, specular texture numbers)];
+    matrices: float32 (n, 3, 16) MainPassMatrices {model, mvp, mvpPrevious} column-major; textures: [(w, h, RGBA8 bytes)].
+    Returns depth (h, w) f32, motion (h, w, 2) i16, normal (h, w, 4) u8 [, gbuffer (h, w, 4) u32]."""
+    rig = _raster_rig(ffi, api, w, h, jitter)
+    be = rig.be
+    handles = be.create_meshes(meshes)
+    tex = [be.create_image(tw, th, "RGBA8", data=np.asarray(d, np.uint8)) for tw, th, d in (textures or [(1, 1, [255, 255, 255, 255])])]
+    tex_index = [be.global_texture_index(t) for t in tex]
+    depth, motion, normal = be.create_image(w, h, "DEPTH32"), be.create_image(w, h, "RG16_SNORM"), be.create_image(w, h, "RGBA8")
+    transforms = be.create_storage_buffer(max(len(matrices), 1) * 192, np.asarray(matrices, np.float32))
+    pre = be.create_graphic_pass("depthPrepass.vert", "depthPrepass.frag", [("RG16_SNORM", ffi.LOAD_OP_CLEAR), ("RGBA8", ffi.LOAD_OP_CLEAR), ("DEPTH32", ffi.LOAD_OP_CLEAR)], ffi.CULL_BACK, name="Depth prepass")
+    push = np.array([[tex_index[d[2]] if len(d) > 2 else tex_index[0], tex_index[d[3]] if len(d) > 2 else tex_index[0], tex_index[d[4]] if len(d) > 2 else tex_index[0], d[1]] for d in draws], np.uint32)
+    be.new_frame()
+    be.set_graphic_pass_execution(pre, [(motion, 0), (normal, 0), (depth, 0)], storage_buffers=[(transforms, True, 0)])
+    if gbuffer:
+        gb = be.create_image(w, h, "RGBA32_UINT")
+        fill = be.create_graphic_pass("triangle.vert", "gbufferFill.frag", [("RGBA32_UINT", ffi.LOAD_OP_CLEAR), ("DEPTH32", ffi.LOAD_OP_LOAD)], ffi.CULL_BACK, depth_function=ffi.DEPTH_EQUAL, name="G-buffer fill")
+        be.set_graphic_pass_execution(fill, [(gb, 0), (depth, 0)], storage_buffers=[(transforms, True, 17)])
+    be._check(api.b["prepare_for_drawcall_recording"](be.ctx), "prepare_for_drawcall_recording")
+    be.draw_meshes([handles[d[0]] for d in draws], push, pre)
+    if gbuffer:
+        be.draw_meshes([handles[d[0]] for d in draws], push, fill)
+    rig.run()
+    out = [be.read_image(depth, 0, np.float32).reshape(h, w).copy(), be.read_image(motion, 0, np.int16).reshape(h, w, 2).copy(), be.read_image(normal).reshape(h, w, 4).copy()]
+    if gbuffer:
+        out.append(be.read_image(gb, 0, np.uint32).reshape(h, w, 4).copy())
+    rig.close()
+    return out
+
+
+def raster_shadow(ffi, api, size, meshes, draws, model_matrices, light_matrices, cascade=0):
+    """sunShadow.vert/.frag (RenderFrontend.cpp:760-775, 1563-1590): one D16 cascade. draws: [(mesh number, transform index)];
+    model_matrices float32 (n, 16); light_matrices float32 (4, 16)."""
+    rig = _raster_rig(ffi, api, size, size)
+    be = rig.be
+    handles = be.create_meshes(meshes)
+    shadow_map = be.create_image(size, size, "DEPTH16")
+    cascades = be.create_storage_buffer(304, _shadow_cascade_info(ffi, light_matrices))
+    transforms = be.create_storage_buffer(max(len(model_matrices), 1) * 64, np.asarray(model_matrices, np.float32))
+    p = be.create_graphic_pass("sunShadow.vert", "sunShadow.frag", [("DEPTH16", ffi.LOAD_OP_CLEAR)], ffi.CULL_FRONT, clamp_depth=True, vertex_spec={0: np.uint32(cascade)}, name="Shadow map cascade %d" % cascade)
+    be.new_frame()
+    be.set_graphic_pass_execution(p, [(shadow_map, 0)], storage_buffers=[(cascades, True, 0), (transforms, True, 1)])
+    be._check(api.b["prepare_for_drawcall_recording"](be.ctx), "prepare_for_drawcall_recording")
+    be.draw_meshes([handles[d[0]] for d in draws], np.array([[0, d[1]] for d in draws], np.uint32), p)
+    rig.run()
+    out = be.read_image(shadow_map, 0, np.uint16).reshape(size, size).copy()
+    rig.close()
+    return out
+
+
+def _shadow_cascade_info(ffi, light_matrices):
+    info = ffi.ShadowCascadeInfo()
+    lm = np.asarray(light_matrices, np.float32).reshape(4, 16)
+    for c in range(4):
+        for k in range(16):
+            info.lightMatrices[c][k] = float(lm[c, k])
+    return np.frombuffer(bytes(info), np.uint8).copy()
