@@ -86,6 +86,12 @@ struct Backend {
     std::vector<DeviceBuffer> uniformBuffers, storageBuffers;
     std::vector<plain_sampler_desc> samplers;
     std::vector<PassRecord> passes;
+    std::vector<DeviceMesh> meshes;
+    struct RasterScratch { RasterDraw* draws = nullptr; size_t drawCapacity = 0; uint32_t* triInfo = nullptr; size_t triCapacity = 0; };
+    std::unordered_map<uint32_t, RasterScratch> rasterScratch;  // by pass handle
+    struct VisBuffer { unsigned long long* ptr = nullptr; size_t texels = 0; };
+    std::unordered_map<uint64_t, VisBuffer> visBuffers;         // by depth target (image handle + mip): shared by the prepass and the G-buffer fill
+    std::vector<RasterDraw> rasterDrawStaging;
     std::vector<ExecRecord> execs;
     std::vector<FillOrder> fills;
     uint32_t globalUniformBuffer = PLAIN_INVALID_INDEX;
@@ -187,6 +193,11 @@ static ImgView makeView(LaunchCtx& c, const plain_image_resource& r, int expectF
     v.w = m.w; v.h = m.h; v.d = m.d;
     return v;
 }
+ImgView LaunchCtx::target(uint32_t attachment, int expectFormat) {
+    if (attachment >= exec->targets.size()) { fail(pass->shader + ": no render target for attachment " + std::to_string(attachment)); return ImgView{nullptr, 0, 0, 0}; }
+    const plain_image_resource r{exec->targets[attachment].image, exec->targets[attachment].mip_level, attachment};
+    return makeView(*this, r, expectFormat, "render target", attachment);
+}
 ImgView LaunchCtx::sampled(uint32_t binding, int expectFormat) {
     for (auto& r : exec->sampledImages) if (r.binding == binding) return makeView(*this, r, expectFormat, "sampled image", binding);
     fail(pass->shader + ": no sampled image at binding " + std::to_string(binding));
@@ -218,6 +229,8 @@ const void* LaunchCtx::ubufRaw(uint32_t binding) {
     return nullptr;
 }
 void LaunchCtx::countLaunch(int n) { be->launchCounter += (uint32_t)n; }
+size_t LaunchCtx::be_imageCount() const { return be->images.size(); }
+int LaunchCtx::be_imageFormat(uint32_t index) const { return index < be->images.size() ? (int)be->images[index].desc.format : -1; }
 
 // scatter the staged fills to their buffers: one block per segment, 4-byte words (+ byte tail)
 __global__ void scatterFillsKernel(const unsigned char* __restrict__ staging, int nSegments) {
@@ -254,6 +267,8 @@ static uint64_t hashExecs(const Backend& b) {
         n = (uint32_t)e.pushConstants.size(); h = fnv(h, &n, 4); h = fnv(h, e.pushConstants.data(), n);
         h = fnv(h, e.dispatch, sizeof(e.dispatch));
         h = fnv(h, &e.rowBegin, 12);
+        n = (uint32_t)e.targets.size(); h = fnv(h, &n, 4); h = fnv(h, e.targets.data(), n * sizeof(e.targets[0]));
+        n = (uint32_t)e.draws.size(); h = fnv(h, &n, 4); h = fnv(h, e.draws.data(), n * sizeof(e.draws[0]));
     }
     return h;
 }
@@ -330,6 +345,7 @@ static void passDependencies(Backend& b, std::vector<std::vector<int>>& deps) {
         for (auto& r : e.sampledImages) read(imageKey(r));
         for (auto& r : e.storageBuffers) if (r.read_only) read((1ull << 63) | r.buffer);
         for (auto& r : e.storageImages) write(imageKey(r));
+        for (auto& t : e.targets) write(imageKey(plain_image_resource{t.image, t.mip_level, 0}));  // attachments (a loaded depth attachment is read and written)
         for (auto& r : e.storageBuffers) if (!r.read_only) write((1ull << 63) | r.buffer);
         std::sort(d.begin(), d.end());
         d.erase(std::unique(d.begin(), d.end()), d.end());
@@ -551,6 +567,9 @@ void PLAIN_FN(backend_destroy)(plain_ctx* ctx) {
     for (auto& sc : b.swapchainImages) { cudaFree(sc.ptr); if (sc.downloadDone) cudaEventDestroy(sc.downloadDone); }
     for (auto& i : b.images) if (i.downloadDone) cudaEventDestroy(i.downloadDone);
     for (auto& i : b.transientImages) if (i.downloadDone) cudaEventDestroy(i.downloadDone);
+    for (auto& m : b.meshes) { cudaFree(m.indices); cudaFree(m.vertices); }
+    for (auto& kv : b.rasterScratch) { cudaFree(kv.second.draws); cudaFree(kv.second.triInfo); }
+    for (auto& kv : b.visBuffers) cudaFree(kv.second.ptr);
     for (auto& u : b.uniformBuffers) cudaFree(u.ptr);
     for (auto& s : b.storageBuffers) cudaFree(s.ptr);
     for (auto& e : b.timingEvents) cudaEventDestroy(e);
@@ -734,6 +753,143 @@ int PLAIN_FN(set_compute_pass_execution)(plain_ctx* ctx, const plain_compute_pas
 }
 int PLAIN_FN(prepare_for_drawcall_recording)(plain_ctx* ctx) { (void)ctx; return 0; }
 
+// ---- meshes and graphic passes (RenderBackend.h:57-96) ----
+int PLAIN_FN(create_meshes)(plain_ctx* ctx, const plain_mesh_binary* meshes, uint32_t n, plain_handle* out) {
+    Backend& b = ctx->b;
+    cudaSetDevice(b.device);
+    for (uint32_t i = 0; i < n; i++) {
+        const plain_mesh_binary& m = meshes[i];
+        if (m.index_count % 3 != 0 || !m.index_buffer || !m.vertex_buffer) return fail(ctx, "create_meshes: triangle list with index and vertex data expected");
+        DeviceMesh d;
+        d.indexCount = m.index_count; d.vertexCount = m.vertex_count;
+        d.index32 = m.index_count < 65535u ? 0u : 1u;
+        const size_t ib = (size_t)m.index_count * (d.index32 ? 4 : 2), vb = (size_t)m.vertex_count * 28;
+        for (uint32_t k = 0; k < m.index_count; k++) {
+            const uint32_t idx = d.index32 ? ((const uint32_t*)m.index_buffer)[k] : ((const uint16_t*)m.index_buffer)[k];
+            if (idx >= m.vertex_count) return fail(ctx, "create_meshes: index out of range");
+        }
+        CU_CHECK(ctx, cudaMalloc(&d.indices, ib ? ib : 4));
+        CU_CHECK(ctx, cudaMalloc(&d.vertices, vb ? vb : 4));
+        CU_CHECK(ctx, cudaMemcpy(d.indices, m.index_buffer, ib, cudaMemcpyHostToDevice));
+        CU_CHECK(ctx, cudaMemcpy(d.vertices, m.vertex_buffer, vb, cudaMemcpyHostToDevice));
+        b.meshes.push_back(d);
+        out[i] = (uint32_t)b.meshes.size() - 1;
+    }
+    return 0;
+}
+int PLAIN_FN(create_graphic_pass)(plain_ctx* ctx, const plain_graphic_pass_desc* d, plain_handle* out) {
+    if (!d || !d->vertex_shader || !d->fragment_shader) return fail(ctx, "create_graphic_pass: vertex and fragment shader expected");
+    PassRecord p;
+    p.graphic = true;
+    p.shader = std::string(d->vertex_shader) + "+" + d->fragment_shader;
+    p.name = d->debug_name ? d->debug_name : p.shader;
+    for (uint32_t i = 0; i < d->n_vertex_consts; i++) {
+        const uint8_t* s = (const uint8_t*)d->vertex_consts[i].data;
+        p.spec[d->vertex_consts[i].location] = std::vector<uint8_t>(s, s + d->vertex_consts[i].size);
+    }
+    p.cullMode = d->cull_mode; p.clampDepth = d->clamp_depth; p.depthFunction = d->depth_function; p.depthWrite = d->depth_write;
+    p.attachments.assign(d->attachments, d->attachments + d->n_attachments);
+    p.pushSize = p.shader.rfind("sunShadow.vert", 0) == 0 ? 8u : 16u;
+    p.depthAttachment = PLAIN_INVALID_INDEX;
+    for (uint32_t i = 0; i < d->n_attachments; i++)
+        if (d->attachments[i].format == PLAIN_FORMAT_DEPTH32 || d->attachments[i].format == PLAIN_FORMAT_DEPTH16) p.depthAttachment = i;
+    if (p.depthAttachment == PLAIN_INVALID_INDEX) return fail(ctx, "create_graphic_pass: a depth attachment is required (the rasteriser resolves visibility through it)");
+    auto it = registry().find(p.shader);
+    if (it == registry().end()) return fail(ctx, std::string("no CUDA rasteriser program registered for the shader pair '") + p.shader + "'");
+    p.fn = it->second;
+    ctx->b.passes.push_back(std::move(p));
+    ctx->b.passEpoch++;
+    *out = (uint32_t)ctx->b.passes.size() - 1;
+    return 0;
+}
+int PLAIN_FN(set_graphic_pass_execution)(plain_ctx* ctx, const plain_graphic_pass_execution* e) {
+    Backend& b = ctx->b;
+    if (e->pass >= b.passes.size() || !b.passes[e->pass].graphic) return fail(ctx, "set_graphic_pass_execution: not a graphic pass");
+    if (e->n_targets != b.passes[e->pass].attachments.size()) return fail(ctx, "set_graphic_pass_execution: one target per attachment expected");
+    ExecRecord r;
+    r.pass = e->pass;
+    const plain_pass_resources& s = e->resources;
+    r.storageBuffers.assign(s.storage_buffers, s.storage_buffers + s.n_storage_buffers);
+    r.uniformBuffers.assign(s.uniform_buffers, s.uniform_buffers + s.n_uniform_buffers);
+    r.sampledImages.assign(s.sampled_images, s.sampled_images + s.n_sampled_images);
+    r.storageImages.assign(s.storage_images, s.storage_images + s.n_storage_images);
+    r.targets.assign(e->targets, e->targets + e->n_targets);
+    r.dispatch[0] = r.dispatch[1] = r.dispatch[2] = 0;
+    b.execs.push_back(std::move(r));
+    return 0;
+}
+int PLAIN_FN(draw_meshes)(plain_ctx* ctx, const plain_handle* meshes, uint32_t n, const void* push_constants, plain_handle pass, int32_t worker_index) {
+    (void)worker_index;
+    Backend& b = ctx->b;
+    if (pass >= b.passes.size() || !b.passes[pass].graphic) return fail(ctx, "draw_meshes: not a graphic pass");
+    ExecRecord* rec = nullptr;
+    for (auto& e : b.execs) if (e.pass == pass) rec = &e;
+    if (!rec) return fail(ctx, "draw_meshes: the pass has no execution this frame (set_graphic_pass_execution)");
+    const uint32_t ps = b.passes[pass].pushSize;
+    for (uint32_t i = 0; i < n; i++) {
+        if (meshes[i] >= b.meshes.size()) return fail(ctx, "draw_meshes: invalid mesh handle");
+        DrawRecord d;
+        d.mesh = meshes[i];
+        memset(d.push, 0, sizeof(d.push));
+        memcpy(d.push, (const uint8_t*)push_constants + (size_t)i * ps, ps);
+        rec->draws.push_back(d);
+    }
+    return 0;
+}
+// draw tables, per-primitive scratch and visibility buffers of the graphic passes of this submission: allocated and uploaded
+// before the passes run (nothing may allocate while the pass list is captured into a graph)
+static int prepareRaster(plain_ctx* ctx) {
+    Backend& b = ctx->b;
+    for (auto& e : b.execs) {
+        const PassRecord& p = b.passes[e.pass];
+        if (!p.graphic) continue;
+        Backend::RasterScratch& sc = b.rasterScratch[e.pass];
+        b.rasterDrawStaging.clear();
+        uint32_t first = 0;
+        for (auto& d : e.draws) {
+            const DeviceMesh& m = b.meshes[d.mesh];
+            RasterDraw rd;
+            rd.indices = m.indices; rd.vertices = m.vertices;
+            rd.firstPrimitive = first; rd.triCount = m.indexCount / 3; rd.index32 = m.index32; rd.pad = 0;
+            memcpy(rd.push, d.push, 16);
+            b.rasterDrawStaging.push_back(rd);
+            first += rd.triCount;
+        }
+        if (b.rasterDrawStaging.size() > sc.drawCapacity) {
+            if (sc.draws) cudaFree(sc.draws);
+            sc.drawCapacity = b.rasterDrawStaging.size() * 2 + 16;
+            CU_CHECK(ctx, cudaMalloc(&sc.draws, sc.drawCapacity * sizeof(RasterDraw)));
+            b.passEpoch++;
+        }
+        const size_t triWords = (size_t)first * 2 + 2;  // rows per primitive, the big-triangle counter, the big-triangle list
+        if (triWords > sc.triCapacity) {
+            if (sc.triInfo) cudaFree(sc.triInfo);
+            sc.triCapacity = triWords * 2 + 1024;
+            CU_CHECK(ctx, cudaMalloc(&sc.triInfo, sc.triCapacity * sizeof(uint32_t)));
+            b.passEpoch++;
+        }
+        if (!b.rasterDrawStaging.empty())  // pageable source: the copy has left the host vector when the call returns
+            CU_CHECK(ctx, cudaMemcpyAsync(sc.draws, b.rasterDrawStaging.data(), b.rasterDrawStaging.size() * sizeof(RasterDraw), cudaMemcpyHostToDevice, b.stream));
+        const plain_render_target& dt = e.targets[p.depthAttachment];
+        DeviceImage* img = b.resolve(dt.image);
+        if (!img || dt.mip_level >= img->mips.size()) return fail(ctx, p.shader + ": invalid depth target");
+        const size_t texels = (size_t)img->mips[dt.mip_level].w * img->mips[dt.mip_level].h;
+        Backend::VisBuffer& vb = b.visBuffers[((uint64_t)(dt.image.type & 3u) << 60) | ((uint64_t)dt.image.index << 8) | (uint64_t)(dt.mip_level & 0xffu)];
+        if (vb.texels != texels) {
+            if (vb.ptr) cudaFree(vb.ptr);
+            CU_CHECK(ctx, cudaMalloc(&vb.ptr, (texels ? texels : 1) * sizeof(unsigned long long)));
+            CU_CHECK(ctx, cudaMemsetAsync(vb.ptr, 0, (texels ? texels : 1) * sizeof(unsigned long long), b.stream));
+            vb.texels = texels;
+            b.passEpoch++;
+        }
+        e.rasterDraws = sc.draws;
+        e.rasterTriInfo = sc.triInfo;
+        e.rasterVis = vb.ptr;
+        e.rasterTotalTris = first;
+    }
+    return 0;
+}
+
 static int stageFill(plain_ctx* ctx, bool uniform, plain_handle buffer, const void* data, size_t size) {
     Backend& b = ctx->b;
     std::vector<DeviceBuffer>& table = uniform ? b.uniformBuffers : b.storageBuffers;
@@ -758,7 +914,9 @@ int PLAIN_FN(render_frame)(plain_ctx* ctx, int present) {
     cudaSetDevice(b.device);
     joinTransfers(b);  // uploads issued before this submission are visible to its passes; read-backs in flight keep their source
     while (b.passEvents.size() < b.execs.size()) { cudaEvent_t x; cudaEventCreateWithFlags(&x, cudaEventDisableTiming); b.passEvents.push_back(x); }
+    if (prepareRaster(ctx)) return 1;
     for (auto& e : b.execs) {
+        for (auto& t : e.targets) if (DeviceImage* img = b.resolve(t.image)) { img->lastUsedSubmission = b.submissionCounter; orderAfterDownload(b, img); }
         for (auto& r : e.sampledImages) if (DeviceImage* img = b.resolve(r.image)) img->lastUsedSubmission = b.submissionCounter;
         for (auto& r : e.storageImages) if (DeviceImage* img = b.resolve(r.image)) { img->lastUsedSubmission = b.submissionCounter; orderAfterDownload(b, img); }
     }

@@ -41,8 +41,29 @@ struct DeviceBuffer {
     size_t size = 0;
 };
 
+// ---- graphic passes: meshes, draws and the rasteriser's scratch ----
+struct DeviceMesh {  // MeshBinary (MeshData.h:27-35) in HBM
+    unsigned char* indices = nullptr;   // u16 when indexCount < 65535, else u32 (RenderBackend.cpp:483-488)
+    unsigned char* vertices = nullptr;  // 28 bytes per vertex
+    uint32_t indexCount = 0, vertexCount = 0, index32 = 0;
+};
+struct RasterDraw {  // one entry of the device draw table of a graphic pass execution
+    const unsigned char* indices;
+    const unsigned char* vertices;
+    uint32_t firstPrimitive, triCount, index32, pad;
+    uint32_t push[4];
+};
+struct DrawRecord { uint32_t mesh; uint8_t push[16]; };
+
 struct ExecRecord {
     uint32_t pass;
+    std::vector<plain_render_target> targets;  // graphic passes: attachments in order
+    std::vector<DrawRecord> draws;
+    // resolved by render_frame before the passes run (allocations are not allowed while a graph is being captured)
+    const RasterDraw* rasterDraws = nullptr;
+    uint32_t* rasterTriInfo = nullptr;          // per primitive: covered rows (y0 | y1 << 16) or ~0u; [totalTris] = big-triangle count; then the big-triangle list
+    unsigned long long* rasterVis = nullptr;    // per pixel of the depth target: depth bits << 32 | primitive + 1
+    uint32_t rasterTotalTris = 0;
     std::vector<plain_storage_buffer_resource> storageBuffers;
     std::vector<plain_uniform_buffer_resource> uniformBuffers;
     std::vector<plain_image_resource> sampledImages;
@@ -60,6 +81,10 @@ struct PassRecord {
     std::string shader, name;
     std::map<uint32_t, std::vector<uint8_t>> spec;
     LaunchFn fn = nullptr;
+    // graphic passes (GraphicPassDescription, ResourceDescriptions.h:129-143); spec holds the vertex stage's constants
+    bool graphic = false;
+    uint32_t cullMode = 0, clampDepth = 0, depthFunction = 0, depthWrite = 0, pushSize = 0, depthAttachment = 0;
+    std::vector<plain_attachment> attachments;
 };
 
 struct LaunchCtx {
@@ -74,6 +99,7 @@ struct LaunchCtx {
     bool failed = false;
     std::string error;
 
+    ImgView target(uint32_t attachment, int expectFormat = -1);  // graphic passes
     ImgView sampled(uint32_t binding, int expectFormat = -1);
     ImgView storage(uint32_t binding, int expectFormat = -1);
     int sampledFormat(uint32_t binding);  // plain_image_format of the image bound at a sampled binding, -1 if none
@@ -108,6 +134,8 @@ struct LaunchCtx {
         if (y1 < y0) y1 = y0;
     }
     void countLaunch(int n = 1);
+    size_t be_imageCount() const;               // image table of the backend (bindless slot == image handle index)
+    int be_imageFormat(uint32_t index) const;
 };
 
 // Exact tables over 8-bit input domains (built once per context by buildShadingTables, passes_shading.cu): tabulating a

@@ -1,0 +1,442 @@
+// passes_raster.cu - the rasterisation passes that feed the frame path as a visibility-buffer software
+// rasteriser for sm_100a:
+//   depthPrepass.vert + depthPrepass.frag   depth (D32F reverse z), motion (RG16_SNORM), geometric normal (RGBA8)
+//   sunShadow.vert + sunShadow.frag         one D16 shadow cascade (front faces culled, depth clamp)
+//   triangle.vert + gbufferFill.frag        the packed G-buffer (include/plain_frame_types.h): the interpolated inputs and material
+//                                           texels of triangle.frag:178-193 for the fragment that won the prepass (depth EQUAL)
+// Per pass: (1) rasterSetupKernel, a thread per triangle: vertex stage, clipping, window-space bounding rows; triangles taller
+// than 64 rows are appended to a list. (2) rasterCoverKernel<false>, a warp per small triangle: lanes = 32 consecutive pixels of
+// a row, exact integer edge functions, depth from the triangle's homogeneous plane equation in binary64, one 64-bit atomicMax of
+// (depth bits << 32 | primitive + 1) per covered pixel - the depth test GREATER_EQUAL in draw order. (3) rasterCoverKernel<true>,
+// persistent warps over (big triangle, 64-row band) pairs, so a wall-sized triangle is spread over the whole GPU. (4) a resolve
+// kernel, a thread per pixel: the winning primitive's vertices are fetched again, perspective-correct barycentrics from the same
+// plane equations, the fragment stage, one coalesced store per attachment. The G-buffer fill reuses the prepass's visibility
+// buffer (the reference rasterises everything twice, with depth test EQUAL the second time).
+// The rules the reference leaves to the Vulkan rasteriser are stated in oracle/passes_raster.cpp (header); this file follows them
+// operation by operation (binary64 clipping / plane equations, -fmad=false), so the results are bit-identical.
+#include "pass_common.cuh"
+#include "shader_inc.cuh"
+
+namespace pb {
+
+struct D3 { double x, y, z; };
+__device__ __forceinline__ D3 crossd(D3 a, D3 b) { return D3{a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
+struct ClipV { double x, y, z, w; };
+
+// ---- vertex fetch: VertexInput.h:27-31, VulkanVertexInput.cpp:4-10 ----
+struct VertexIn { vec3 pos; vec2 uv; vec3 normal, tangent, bitangent; };
+__device__ __forceinline__ float snorm10(uint32_t bits) {
+    int v = (int)(bits & 1023u);
+    if (v >= 512) v -= 1024;
+    return fmaxp((float)v / 511.f, -1.f);
+}
+__device__ __forceinline__ vec3 unpackA2R10G10B10Snorm(uint32_t p) { return v3(snorm10(p >> 20), snorm10(p >> 10), snorm10(p)); }
+__device__ __forceinline__ uint32_t fetchIndex(const RasterDraw& d, uint32_t k) { return d.index32 ? ldg((const uint32_t*)d.indices + k) : (uint32_t)ldg((const uint16_t*)d.indices + k); }
+__device__ __forceinline__ vec3 fetchPosition(const RasterDraw& d, uint32_t index) {
+    const float* p = (const float*)(d.vertices + (size_t)index * 28);
+    return v3(ldg(p), ldg(p + 1), ldg(p + 2));
+}
+__device__ __forceinline__ VertexIn fetchVertex(const RasterDraw& d, uint32_t index) {
+    const uint32_t* p = (const uint32_t*)(d.vertices + (size_t)index * 28);
+    VertexIn v;
+    v.pos = v3(__uint_as_float(ldg(p)), __uint_as_float(ldg(p + 1)), __uint_as_float(ldg(p + 2)));
+    const uint32_t uv = ldg(p + 3);
+    v.uv = v2(halfToFloat((uint16_t)(uv & 0xffffu)), halfToFloat((uint16_t)(uv >> 16)));
+    v.normal = unpackA2R10G10B10Snorm(ldg(p + 4));
+    v.tangent = unpackA2R10G10B10Snorm(ldg(p + 5));
+    v.bitangent = unpackA2R10G10B10Snorm(ldg(p + 6));
+    return v;
+}
+__device__ __forceinline__ vec3 mulMat3(const float* m, vec3 v) {  // mat3(model) * v, the contract's M * v
+    return vfma(v3(m[8], m[9], m[10]), v.z, vfma(v3(m[4], m[5], m[6]), v.y, v3(m[0], m[1], m[2]) * v.x));
+}
+__device__ __forceinline__ const RasterDraw& drawOfPrimitive(const RasterDraw* draws, uint32_t drawCount, uint32_t primitive) {
+    uint32_t lo = 0, hi = drawCount;
+    while (hi - lo > 1) { const uint32_t mid = (lo + hi) / 2; if (draws[mid].firstPrimitive <= primitive) lo = mid; else hi = mid; }
+    return draws[lo];
+}
+
+struct MainPassMatrices { float model[16], mvp[16], mvpPrevious[16]; };  // MainPassMatrices.inc
+struct RasterParams {
+    const RasterDraw* draws;
+    uint32_t drawCount, totalTris;
+    uint32_t* triInfo;
+    unsigned long long* vis;
+    int W, H;
+    int clipNear, clampDepth, cullMode;
+    int shadowProgram;                       // 0: clip = transforms[push[3]].mvp * pos; 1: clip = lightMatrices[cascade] * transforms[push[1]] * pos
+    const MainPassMatrices* mainTransforms;
+    const float* shadowTransforms;
+    const plain_shadow_cascade_info* cascades;
+    uint32_t cascade;
+};
+// vertex stage of the three positions of one triangle (depthPrepass.vert:29, triangle.vert:30, sunShadow.vert:30)
+__device__ __forceinline__ void triangleClipPositions(const RasterParams& p, const RasterDraw& d, uint32_t tri, vec4 clip[3]) {
+    vec3 pos[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) pos[k] = fetchPosition(d, fetchIndex(d, tri * 3 + k));
+    if (!p.shadowProgram) {
+        const float* mvp = p.mainTransforms[d.push[3]].mvp;
+#pragma unroll
+        for (int k = 0; k < 3; k++) clip[k] = mulm4(mvp, v4(pos[k], 1.f));
+    } else {
+        const float* L = p.cascades->lightMatrices[p.cascade];
+        const float* T = p.shadowTransforms + (size_t)d.push[1] * 16;
+        float M[16];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const vec4 c = mulm4(L, v4(T[j * 4], T[j * 4 + 1], T[j * 4 + 2], T[j * 4 + 3]));
+            M[j * 4] = c.x; M[j * 4 + 1] = c.y; M[j * 4 + 2] = c.z; M[j * 4 + 3] = c.w;
+        }
+#pragma unroll
+        for (int k = 0; k < 3; k++) clip[k] = mulm4(M, v4(pos[k], 1.f));
+    }
+}
+
+// ---- homogeneous plane equations of one (unclipped) triangle ----
+struct TriPlanes { D3 c0, c1, c2, num, den; };
+__device__ __forceinline__ TriPlanes trianglePlanes(const vec4 clip[3]) {
+    D3 v[3];
+    double z[3], w[3];
+#pragma unroll
+    for (int i = 0; i < 3; i++) { v[i] = D3{(double)clip[i].x, (double)clip[i].y, (double)clip[i].w}; z[i] = (double)clip[i].z; w[i] = (double)clip[i].w; }
+    TriPlanes t;
+    t.c0 = crossd(v[1], v[2]); t.c1 = crossd(v[2], v[0]); t.c2 = crossd(v[0], v[1]);
+    t.num = D3{t.c0.x * z[0] + t.c1.x * z[1] + t.c2.x * z[2], t.c0.y * z[0] + t.c1.y * z[1] + t.c2.y * z[2], t.c0.z * z[0] + t.c1.z * z[1] + t.c2.z * z[2]};
+    t.den = D3{t.c0.x * w[0] + t.c1.x * w[1] + t.c2.x * w[2], t.c0.y * w[0] + t.c1.y * w[1] + t.c2.y * w[2], t.c0.z * w[0] + t.c1.z * w[1] + t.c2.z * w[2]};
+    return t;
+}
+__device__ __forceinline__ double pixelNdc(int i, int size) { return ((double)i + 0.5) / (double)size * 2.0 - 1.0; }
+__device__ __forceinline__ void barycentrics(const TriPlanes& t, double px, double py, float l[3]) {
+    const double e0 = t.c0.x * px + t.c0.y * py + t.c0.z, e1 = t.c1.x * px + t.c1.y * py + t.c1.z, e2 = t.c2.x * px + t.c2.y * py + t.c2.z;
+    const double sum = e0 + e1 + e2;
+    l[0] = (float)(e0 / sum); l[1] = (float)(e1 / sum); l[2] = (float)(e2 / sum);
+}
+__device__ __forceinline__ float lerp3(const float l[3], float a, float b, float c) { return fmaf_(l[2], c, fmaf_(l[1], b, l[0] * a)); }
+__device__ __forceinline__ vec3 lerp3(const float l[3], vec3 a, vec3 b, vec3 c) { return v3(lerp3(l, a.x, b.x, c.x), lerp3(l, a.y, b.y, c.y), lerp3(l, a.z, b.z, c.z)); }
+
+// ---- clipping + snapping: the window-space polygon of one triangle (fanned from its first vertex) ----
+struct ScreenPoly { int n; long long X[12], Y[12]; };
+__device__ __forceinline__ double clipDistance(int plane, const ClipV& p, double gx, double gy, bool clipNear) {
+    switch (plane) {
+        case 0: return p.w - 1e-6;
+        case 1: return clipNear ? p.w - p.z : 1.0;
+        case 2: return gx * p.w - p.x;
+        case 3: return gx * p.w + p.x;
+        case 4: return gy * p.w - p.y;
+        default: return gy * p.w + p.y;
+    }
+}
+__device__ void clipAndSnap(const RasterParams& p, const vec4 clip[3], ScreenPoly& sp) {
+    ClipV poly[12], tmp[12];
+    int n = 3;
+    for (int i = 0; i < 3; i++) poly[i] = ClipV{(double)clip[i].x, (double)clip[i].y, (double)clip[i].z, (double)clip[i].w};
+    const double gx = 32768.0 / (double)p.W, gy = 32768.0 / (double)p.H;
+    for (int plane = 0; plane < 6 && n >= 3; plane++) {
+        bool allIn = true;
+        for (int i = 0; i < n; i++) allIn = allIn && clipDistance(plane, poly[i], gx, gy, p.clipNear != 0) >= 0.0;
+        if (allIn) continue;
+        int m = 0;
+        for (int i = 0; i < n; i++) {
+            const ClipV a = poly[i], b = poly[(i + 1) % n];
+            const double da = clipDistance(plane, a, gx, gy, p.clipNear != 0), db = clipDistance(plane, b, gx, gy, p.clipNear != 0);
+            if (da >= 0.0) tmp[m++] = a;
+            if ((da >= 0.0) != (db >= 0.0)) {
+                const double t = da / (da - db);
+                tmp[m++] = ClipV{a.x + t * (b.x - a.x), a.y + t * (b.y - a.y), a.z + t * (b.z - a.z), a.w + t * (b.w - a.w)};
+            }
+        }
+        n = m;
+        for (int i = 0; i < n; i++) poly[i] = tmp[i];
+    }
+    sp.n = n < 3 ? 0 : n;
+    for (int i = 0; i < sp.n; i++) {
+        const double inv = 1.0 / poly[i].w;
+        const double xs = (poly[i].x * inv * 0.5 + 0.5) * (double)p.W, ys = (poly[i].y * inv * 0.5 + 0.5) * (double)p.H;
+        sp.X[i] = (long long)floor(xs * 256.0 + 0.5);
+        sp.Y[i] = (long long)floor(ys * 256.0 + 0.5);
+    }
+}
+// one triangle of the fan: orientation, culling, the pixel rectangle it can cover. Returns false when it covers nothing.
+struct SubTriangle { long long ax[3], ay[3], ex[3], ey[3], bias[3]; int ix0, ix1, iy0, iy1; };
+__device__ __forceinline__ long long llmin(long long a, long long b) { return a < b ? a : b; }
+__device__ __forceinline__ long long llmax(long long a, long long b) { return a > b ? a : b; }
+__device__ __forceinline__ bool subTriangle(const RasterParams& p, const ScreenPoly& sp, int k, SubTriangle& s) {
+    long long x0 = sp.X[0], y0 = sp.Y[0], x1 = sp.X[k], y1 = sp.Y[k], x2 = sp.X[k + 1], y2 = sp.Y[k + 1];
+    const long long area2 = (x1 - x0) * (y2 - y0) - (x2 - x0) * (y1 - y0);
+    if (area2 == 0) return false;
+    const bool front = area2 < 0;  // counter clockwise on the y-down screen (VulkanPipeline.cpp:61)
+    if ((p.cullMode == PLAIN_CULL_BACK && !front) || (p.cullMode == PLAIN_CULL_FRONT && front)) return false;
+    if (area2 < 0) { long long t = x1; x1 = x2; x2 = t; t = y1; y1 = y2; y2 = t; }
+    s.ax[0] = x0; s.ax[1] = x1; s.ax[2] = x2; s.ay[0] = y0; s.ay[1] = y1; s.ay[2] = y2;
+    s.ex[0] = x1 - x0; s.ex[1] = x2 - x1; s.ex[2] = x0 - x2; s.ey[0] = y1 - y0; s.ey[1] = y2 - y1; s.ey[2] = y0 - y2;
+#pragma unroll
+    for (int e = 0; e < 3; e++) s.bias[e] = (s.ey[e] < 0 || (s.ey[e] == 0 && s.ex[e] > 0)) ? 0 : -1;  // top-left rule
+    const long long minX = llmin(x0, llmin(x1, x2)), maxX = llmax(x0, llmax(x1, x2)), minY = llmin(y0, llmin(y1, y2)), maxY = llmax(y0, llmax(y1, y2));
+    s.ix0 = (int)llmax(0, (minX - 128 + 255) >> 8); s.ix1 = (int)llmin(p.W - 1, (maxX - 128) >> 8);
+    s.iy0 = (int)llmax(0, (minY - 128 + 255) >> 8); s.iy1 = (int)llmin(p.H - 1, (maxY - 128) >> 8);
+    return s.ix0 <= s.ix1 && s.iy0 <= s.iy1;
+}
+
+#define RASTER_BAND_ROWS 64
+// (1) a thread per triangle: the rows it can cover; tall triangles go to the list behind the counter at triInfo[totalTris]
+__global__ void __launch_bounds__(128) rasterSetupKernel(const __grid_constant__ RasterParams p) {
+    const uint32_t prim = blockIdx.x * 128 + threadIdx.x;
+    if (prim >= p.totalTris) return;
+    const RasterDraw& d = drawOfPrimitive(p.draws, p.drawCount, prim);
+    vec4 clip[3];
+    triangleClipPositions(p, d, prim - d.firstPrimitive, clip);
+    ScreenPoly sp;
+    clipAndSnap(p, clip, sp);
+    int y0 = 0x7fffffff, y1 = -1;
+    for (int k = 1; k + 1 < sp.n; k++) {
+        SubTriangle s;
+        if (!subTriangle(p, sp, k, s)) continue;
+        y0 = imin(y0, s.iy0); y1 = imax(y1, s.iy1);
+    }
+    uint32_t info = 0xffffffffu;
+    if (y1 >= y0) {
+        info = (uint32_t)y0 | ((uint32_t)y1 << 16);
+        if (y1 - y0 + 1 > RASTER_BAND_ROWS) p.triInfo[p.totalTris + 1 + atomicAdd(&p.triInfo[p.totalTris], 1u)] = prim;
+    }
+    p.triInfo[prim] = info;
+}
+// coverage of rows [rowBegin, rowEnd] of one triangle by one warp
+__device__ void coverTriangle(const RasterParams& p, uint32_t prim, int rowBegin, int rowEnd) {
+    const int lane = threadIdx.x & 31;
+    const RasterDraw& d = drawOfPrimitive(p.draws, p.drawCount, prim);
+    vec4 clip[3];
+    triangleClipPositions(p, d, prim - d.firstPrimitive, clip);
+    const TriPlanes tp = trianglePlanes(clip);
+    ScreenPoly sp;
+    clipAndSnap(p, clip, sp);
+    const unsigned long long keyLow = (unsigned long long)(prim + 1u);
+    for (int k = 1; k + 1 < sp.n; k++) {
+        SubTriangle s;
+        if (!subTriangle(p, sp, k, s)) continue;
+        const int ya = imax(s.iy0, rowBegin), yb = imin(s.iy1, rowEnd);
+        for (int iy = ya; iy <= yb; iy++) {
+            const long long py = (long long)iy * 256 + 128;
+            const double ny = pixelNdc(iy, p.H);
+            // edge functions along the row: E_e(px) = rowTerm_e - ey_e * (px - ax_e)
+            long long rowTerm[3];
+#pragma unroll
+            for (int e = 0; e < 3; e++) rowTerm[e] = s.ex[e] * (py - s.ay[e]) + s.bias[e];
+            for (int xb = s.ix0 & ~31; xb <= s.ix1; xb += 32) {
+                const int ix = xb + lane;
+                if (ix < s.ix0 || ix > s.ix1) continue;
+                const long long px = (long long)ix * 256 + 128;
+                bool inside = true;
+#pragma unroll
+                for (int e = 0; e < 3; e++) inside = inside && (rowTerm[e] - s.ey[e] * (px - s.ax[e]) >= 0);
+                if (!inside) continue;
+                const double nx = pixelNdc(ix, p.W);
+                const double num = tp.num.x * nx + tp.num.y * ny + tp.num.z, den = tp.den.x * nx + tp.den.y * ny + tp.den.z;
+                float dep = (float)(num / den);
+                if (dep != dep) continue;
+                if (p.clampDepth) dep = dep < 0.f ? 0.f : (dep > 1.f ? 1.f : dep);
+                else if (dep < 0.f || dep > 1.f) continue;
+                const unsigned long long key = ((unsigned long long)(__float_as_uint(dep) & 0x7fffffffu) << 32) | keyLow;
+                atomicMax(p.vis + (size_t)iy * p.W + ix, key);
+            }
+        }
+    }
+}
+// (2) BIG = false: a warp per triangle, the ones that fit a band; (3) BIG = true: persistent warps over (listed triangle, band)
+template <bool BIG>
+__global__ void __launch_bounds__(256) rasterCoverKernel(const __grid_constant__ RasterParams p) {
+    const uint32_t warp = (blockIdx.x * 256 + threadIdx.x) >> 5;
+    if (!BIG) {
+        if (warp >= p.totalTris) return;
+        const uint32_t info = p.triInfo[warp];
+        if (info == 0xffffffffu) return;
+        const int y0 = (int)(info & 0xffffu), y1 = (int)(info >> 16);
+        if (y1 - y0 + 1 > RASTER_BAND_ROWS) return;
+        coverTriangle(p, warp, y0, y1);
+    } else {
+        const uint32_t bigCount = p.triInfo[p.totalTris], warps = gridDim.x * 8u;
+        const uint32_t bands = ((uint32_t)p.H + RASTER_BAND_ROWS - 1) / RASTER_BAND_ROWS;
+        for (uint32_t item = warp; item < bigCount * bands; item += warps) {
+            const uint32_t prim = p.triInfo[p.totalTris + 1 + item / bands], band = item % bands;
+            const uint32_t info = p.triInfo[prim];
+            const int y0 = (int)(info & 0xffffu), y1 = (int)(info >> 16);
+            const int ra = (int)band * RASTER_BAND_ROWS, rb = ra + RASTER_BAND_ROWS - 1;
+            if (rb < y0 || ra > y1) continue;
+            coverTriangle(p, prim, imax(ra, y0), imin(rb, y1));
+        }
+    }
+}
+static void launchCoverage(LaunchCtx& c, const RasterParams& p) {
+    cudaMemsetAsync(p.vis, 0, (size_t)p.W * p.H * sizeof(unsigned long long), c.stream);  // attachments are cleared (RenderPass.cpp:95-110)
+    if (p.totalTris == 0) return;
+    cudaMemsetAsync(p.triInfo + p.totalTris, 0, sizeof(uint32_t), c.stream);
+    PLAIN_LAUNCH(c, rasterSetupKernel, ceilDiv(p.totalTris, 128), 128, 0, p);
+    PLAIN_LAUNCH(c, rasterCoverKernel<false>, ceilDiv(p.totalTris, 8), 256, 0, p);
+    PLAIN_LAUNCH(c, rasterCoverKernel<true>, (unsigned)c.smCount * 4, 256, 0, p);
+}
+static bool fillRasterParams(LaunchCtx& c, RasterParams& p, const ImgView& depthTarget) {
+    p.draws = c.exec->rasterDraws;
+    p.drawCount = (uint32_t)c.exec->draws.size();
+    p.totalTris = c.exec->rasterTotalTris;
+    p.triInfo = c.exec->rasterTriInfo;
+    p.vis = c.exec->rasterVis;
+    p.W = depthTarget.w; p.H = depthTarget.h;
+    p.clipNear = c.pass->clampDepth ? 0 : 1;
+    p.clampDepth = c.pass->clampDepth ? 1 : 0;
+    p.cullMode = (int)c.pass->cullMode;
+    p.shadowProgram = 0; p.mainTransforms = nullptr; p.shadowTransforms = nullptr; p.cascades = nullptr; p.cascade = 0;
+    if (!p.vis || (p.totalTris && (!p.draws || !p.triInfo))) { c.fail(c.pass->shader + ": rasteriser scratch missing (render_frame prepares it)"); return false; }
+    if (p.W > 65535 || p.H > 65535) { c.fail(c.pass->shader + ": render targets beyond 65535 pixels are not supported"); return false; }
+    return true;
+}
+__device__ __forceinline__ int toSnorm16(float v) { if (v != v) return 0; return (int)floorf_(clampf(v, -1.f, 1.f) * 32767.f + 0.5f); }
+
+// ---------------- depthPrepass.vert:28-42 + depthPrepass.frag:27-49 ----------------
+__global__ void __launch_bounds__(256) depthPrepassResolveKernel(const __grid_constant__ RasterParams p, ImgView motionT, ImgView normalT, ImgView depthT, const plain_global_shader_info* __restrict__ g) {
+    const int ix = blockIdx.x * 32 + (threadIdx.x & 31), iy = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (ix >= p.W || iy >= p.H) return;
+    const unsigned long long key = p.vis[(size_t)iy * p.W + ix];
+    float depth = 0.f;
+    uint32_t motion = 0u, normal = 0u;
+    if (key) {
+        depth = __uint_as_float((uint32_t)(key >> 32));
+        const uint32_t primitive = (uint32_t)(key & 0xffffffffu) - 1u;
+        const RasterDraw& d = drawOfPrimitive(p.draws, p.drawCount, primitive);
+        const MainPassMatrices& tr = p.mainTransforms[d.push[3]];
+        vec4 passPos[3], passPosPrevious[3];
+        vec3 N[3];
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            const VertexIn v = fetchVertex(d, fetchIndex(d, (primitive - d.firstPrimitive) * 3 + k));
+            passPos[k] = mulm4(tr.mvp, v4(v.pos, 1.f));
+            passPosPrevious[k] = mulm4(tr.mvpPrevious, v4(v.pos, 1.f));
+            N[k] = normalize(mulMat3(tr.model, v.normal));
+        }
+        float l[3];
+        barycentrics(trianglePlanes(passPos), pixelNdc(ix, p.W), pixelNdc(iy, p.H), l);
+        const vec3 pos = v3(lerp3(l, passPos[0].x, passPos[1].x, passPos[2].x), lerp3(l, passPos[0].y, passPos[1].y, passPos[2].y), lerp3(l, passPos[0].w, passPos[1].w, passPos[2].w));
+        const vec3 posPrev = v3(lerp3(l, passPosPrevious[0].x, passPosPrevious[1].x, passPosPrevious[2].x), lerp3(l, passPosPrevious[0].y, passPosPrevious[1].y, passPosPrevious[2].y),
+                                lerp3(l, passPosPrevious[0].w, passPosPrevious[1].w, passPosPrevious[2].w));
+        vec2 ndcCurrent = v2(pos.x, pos.y) / pos.z;
+        vec2 ndcPrevious = v2(posPrev.x, posPrev.y) / posPrev.z;
+        ndcCurrent = ndcCurrent + v2(g->currentFrameCameraJitter[0], g->currentFrameCameraJitter[1]);
+        ndcPrevious = ndcPrevious + v2(g->previousFrameCameraJitter[0], g->previousFrameCameraJitter[1]);
+        const vec2 mv = (ndcPrevious - ndcCurrent) * v2(0.5f, 0.5f);
+        motion = ((uint32_t)toSnorm16(mv.x) & 0xffffu) | ((uint32_t)toSnorm16(mv.y) << 16);
+        const vec3 nOut = normalize(lerp3(l, N[0], N[1], N[2])) * 0.5f + 0.5f;  // :48, the geometric normal overwrites the normal-mapped one
+        normal = floatToUnorm8(nOut.x) | (floatToUnorm8(nOut.y) << 8) | (floatToUnorm8(nOut.z) << 16);
+    }
+    const size_t i = (size_t)iy * p.W + ix;
+    ((float*)depthT.ptr)[i] = depth;
+    ((uint32_t*)motionT.ptr)[i] = motion;
+    ((uint32_t*)normalT.ptr)[i] = normal;
+}
+PLAIN_PASS(launch_depthPrepass, "depthPrepass.vert+depthPrepass.frag") {
+    const ImgView motionT = c.target(0, PLAIN_FORMAT_RG16_SNORM), normalT = c.target(1, PLAIN_FORMAT_RGBA8), depthT = c.target(2, PLAIN_FORMAT_DEPTH32);
+    if (c.failed) return;
+    if (motionT.w != depthT.w || motionT.h != depthT.h || normalT.w != depthT.w || normalT.h != depthT.h) { c.fail("depthPrepass: attachments of different extent"); return; }
+    RasterParams p;
+    if (!fillRasterParams(c, p, depthT)) return;
+    p.mainTransforms = c.sbuf<MainPassMatrices>(0);
+    if (c.failed) return;
+    launchCoverage(c, p);
+    PLAIN_LAUNCH(c, depthPrepassResolveKernel, dim3(ceilDiv(p.W, 32), ceilDiv(p.H, 8)), 256, 0, p, motionT, normalT, depthT, c.g);
+}
+
+// ---------------- sunShadow.vert:29-32 + sunShadow.frag ----------------
+__global__ void __launch_bounds__(256) shadowResolveKernel(const unsigned long long* __restrict__ vis, ImgView shadowMap) {
+    const int ix = blockIdx.x * 32 + (threadIdx.x & 31), iy = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (ix >= shadowMap.w || iy >= shadowMap.h) return;
+    const unsigned long long key = vis[(size_t)iy * shadowMap.w + ix];
+    ((uint16_t*)shadowMap.ptr)[(size_t)iy * shadowMap.w + ix] = key ? (uint16_t)(uint32_t)(__uint_as_float((uint32_t)(key >> 32)) * 65535.f + 0.5f) : (uint16_t)0;
+}
+PLAIN_PASS(launch_sunShadow, "sunShadow.vert+sunShadow.frag") {
+    const ImgView shadowMap = c.target(0, PLAIN_FORMAT_DEPTH16);
+    if (c.failed) return;
+    RasterParams p;
+    if (!fillRasterParams(c, p, shadowMap)) return;
+    p.shadowProgram = 1;
+    p.cascades = c.sbuf<plain_shadow_cascade_info>(0);
+    p.shadowTransforms = c.sbuf<float>(1);
+    p.cascade = c.spec<uint32_t>(0, 0);
+    if (c.failed) return;
+    if (p.cascade > 3) { c.fail("sunShadow.vert: cascade index must be 0..3"); return; }
+    launchCoverage(c, p);
+    PLAIN_LAUNCH(c, shadowResolveKernel, dim3(ceilDiv(p.W, 32), ceilDiv(p.H, 8)), 256, 0, p.vis, shadowMap);
+}
+
+// ---------------- triangle.vert:29-40 + the fetches of triangle.frag:178-193 -> packed G-buffer ----------------
+__device__ __forceinline__ uint32_t octEncodeSnorm16(vec3 n) {  // inverse of the decode in gbufferShading (include/plain_frame_types.h)
+    const float l1 = absf(n.x) + absf(n.y) + absf(n.z);
+    float x = n.x / l1, y = n.y / l1;
+    if (n.z < 0.f) {
+        const float ox = (1.f - absf(y)) * (x >= 0.f ? 1.f : -1.f), oy = (1.f - absf(x)) * (y >= 0.f ? 1.f : -1.f);
+        x = ox; y = oy;
+    }
+    return ((uint32_t)toSnorm16(x) & 0xffffu) | ((uint32_t)toSnorm16(y) << 16);
+}
+__device__ __forceinline__ vec4 sampleRGBA8LinearRepeat(const ImgView& t, vec2 uv) {
+    return sampleLinear2D<WRAP_REPEAT, vec4>([&](int x, int y) {
+        const uint32_t v = ldg((const uint32_t*)t.ptr + texelIndex(t, x, y));
+        return v4(unorm8(v & 0xffu), unorm8((v >> 8) & 0xffu), unorm8((v >> 16) & 0xffu), unorm8(v >> 24));
+    }, t.w, t.h, uv, v4(0.f));
+}
+__global__ void __launch_bounds__(256) gbufferFillResolveKernel(const __grid_constant__ RasterParams p, ImgView gbuffer, const BindlessEntry* __restrict__ bindless) {
+    const int ix = blockIdx.x * 32 + (threadIdx.x & 31), iy = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (ix >= p.W || iy >= p.H) return;
+    const unsigned long long key = p.vis[(size_t)iy * p.W + ix];
+    uint4 texel = make_uint4(0u, 0u, 0u, 0u);
+    if (key) {
+        const uint32_t primitive = (uint32_t)(key & 0xffffffffu) - 1u;
+        const RasterDraw& d = drawOfPrimitive(p.draws, p.drawCount, primitive);
+        const MainPassMatrices& tr = p.mainTransforms[d.push[3]];
+        vec4 clip[3];
+        vec2 uv[3];
+        vec3 T[3], B[3], N[3];
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            const VertexIn v = fetchVertex(d, fetchIndex(d, (primitive - d.firstPrimitive) * 3 + k));
+            clip[k] = mulm4(tr.mvp, v4(v.pos, 1.f));
+            uv[k] = v.uv;
+            T[k] = normalize(mulMat3(tr.model, v.tangent));
+            N[k] = normalize(mulMat3(tr.model, v.normal));
+            B[k] = normalize(mulMat3(tr.model, v.bitangent));
+        }
+        float l[3];
+        barycentrics(trianglePlanes(clip), pixelNdc(ix, p.W), pixelNdc(iy, p.H), l);
+        const vec2 passUV = v2(lerp3(l, uv[0].x, uv[1].x, uv[2].x), lerp3(l, uv[0].y, uv[1].y, uv[2].y));
+        const vec3 tbnT = lerp3(l, T[0], T[1], T[2]), tbnB = lerp3(l, B[0], B[1], B[2]), tbnN = lerp3(l, N[0], N[1], N[2]);
+        const vec4 albedoTexel = sampleRGBA8LinearRepeat(bindless[d.push[0]].view, passUV);
+        const vec4 normalTexel = sampleRGBA8LinearRepeat(bindless[d.push[1]].view, passUV);
+        const vec4 specularTexel = sampleRGBA8LinearRepeat(bindless[d.push[2]].view, passUV);
+        vec3 nrm = v3(normalTexel.x, normalTexel.y, sqrtf_(1.f - normalTexel.x * normalTexel.x + normalTexel.y + normalTexel.y));  // triangle.frag:181, as written
+        nrm = nrm * 2.f - 1.f;
+        vec3 Nw = normalize(tbnT * nrm.x + tbnB * nrm.y + tbnN * nrm.z);  // passTBN * normalTexelReconstructed
+        if (anynan(Nw)) Nw = tbnN;                                        // :190-192
+        texel.x = (uint32_t)(key >> 32);
+        texel.y = octEncodeSnorm16(Nw);
+        texel.z = floatToUnorm8(albedoTexel.x) | (floatToUnorm8(albedoTexel.y) << 8) | (floatToUnorm8(albedoTexel.z) << 16) | (floatToUnorm8(specularTexel.y) << 24);
+        texel.w = floatToUnorm8(specularTexel.z);
+    }
+    ((uint4*)gbuffer.ptr)[(size_t)iy * p.W + ix] = texel;
+}
+PLAIN_PASS(launch_gbufferFill, "triangle.vert+gbufferFill.frag") {
+    const ImgView gbuffer = c.target(0, PLAIN_FORMAT_RGBA32_UINT), depthT = c.target(1, PLAIN_FORMAT_DEPTH32);
+    if (c.failed) return;
+    if (gbuffer.w != depthT.w || gbuffer.h != depthT.h) { c.fail("gbufferFill: attachments of different extent"); return; }
+    if (c.pass->depthFunction != PLAIN_DEPTH_EQUAL) { c.fail("gbufferFill: depth test EQUAL against the prepass expected (RenderFrontend.cpp:1555)"); return; }
+    RasterParams p;
+    if (!fillRasterParams(c, p, depthT)) return;
+    p.mainTransforms = c.sbuf<MainPassMatrices>(17);
+    if (c.failed) return;
+    for (auto& d : c.exec->draws)  // material textures: bindless slot == image handle index, RGBA8
+        for (int k = 0; k < 3; k++) {
+            uint32_t index;
+            memcpy(&index, d.push + 4 * k, 4);
+            if (index >= c.be_imageCount() || c.be_imageFormat(index) != PLAIN_FORMAT_RGBA8) { c.fail("gbufferFill: material textures must be RGBA8 images (bindless index = image handle index)"); return; }
+        }
+    // no coverage pass: the visibility buffer of the prepass over the same draws decides (depth test EQUAL)
+    PLAIN_LAUNCH(c, gbufferFillResolveKernel, dim3(ceilDiv(p.W, 32), ceilDiv(p.H, 8)), 256, 0, p, gbuffer, c.bindless);
+}
+
+}  // namespace pb
