@@ -47,6 +47,9 @@ PLAIN_EXPORT int PLAIN_ASSET(scene_object)(const plain_scene* scene, uint64_t in
 PLAIN_EXPORT int PLAIN_ASSET(scene_mesh_info)(const plain_scene* scene, uint64_t mesh, plain_mesh_info* out);
 /* positions: vertex_count * 3 floats; indices: index_count u32 (16-bit indices of the file are widened) */
 PLAIN_EXPORT int PLAIN_ASSET(scene_mesh_geometry)(const plain_scene* scene, uint64_t mesh, float* out_positions, uint32_t* out_indices);
+/* the vertex buffer as stored: vertex_count * 28 bytes (position 3 x f32, uv 2 x f16, normal / tangent / bitangent A2R10G10B10_SNORM),
+ * what plain_create_meshes / plain_frontend_set_mesh_geometry consume */
+PLAIN_EXPORT int PLAIN_ASSET(scene_mesh_vertices)(const plain_scene* scene, uint64_t mesh, void* out_vertices);
 
 /* ---- N1: R16F 3-D .dds bricks (148-byte DDS + DX10 header, DXGI_FORMAT_R16_FLOAT) ---- */
 PLAIN_EXPORT int PLAIN_ASSET(dds_r16f_info)(const char* path, uint32_t out_extent[3]);

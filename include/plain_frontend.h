@@ -50,6 +50,10 @@ typedef struct {
                                                 != 0 replaces the frame by RenderFrontend.cpp:321-340 (sdfDebugVisualisation.comp + tonemap) */
     int32_t sdf_debug_show_tile_usage_with_hiz; /* default 1 */
     int32_t sdf_debug_use_influence_radius;     /* default 0 */
+    /* 1 = depth / motion / normal, the shadow cascades and the packed G-buffer are rasterised from the meshes'
+     * geometry (set_mesh_geometry) by the backend's graphic passes; render_frame is then called with inputs = NULL. Default 0:
+     * the caller uploads them (plain_frame_inputs). Single GPU only. */
+    int32_t raster_inputs;
 } plain_frontend_settings;
 
 /* host pointers to the outputs of the out-of-scope raster passes for one frame */
@@ -78,6 +82,10 @@ PLAIN_EXPORT plain_ctx* PLAIN_FE(backend)(plain_frontend* fe);
 /* scene: SDF meshes (3-D R16F bricks) and objects instancing them (RenderFrontend::registerMeshes / App scene) */
 PLAIN_EXPORT int PLAIN_FE(register_sdf_mesh)(plain_frontend* fe, const uint16_t* r16f_texels, uint32_t rx, uint32_t ry, uint32_t rz,
                                              const float local_bb_min[3], const float local_bb_max[3], const float mean_albedo[3], uint32_t* out_mesh);
+/* geometry + material of a registered mesh (RenderFrontend::registerMeshes, RenderFrontend.cpp:456-531): MeshBinary index / vertex
+ * buffers (include/plain_b200.h plain_mesh_binary) and the bindless slots (plain_get_image_global_texture_array_index) of its RGBA8
+ * albedo / normal / specular textures; PLAIN_INVALID_INDEX = the reference's 1x1 default texture (RenderFrontend.cpp:86-150) */
+PLAIN_EXPORT int PLAIN_FE(set_mesh_geometry)(plain_frontend* fe, uint32_t mesh, const plain_mesh_binary* geometry, uint32_t albedo_texture, uint32_t normal_texture, uint32_t specular_texture);
 PLAIN_EXPORT int PLAIN_FE(set_scene)(plain_frontend* fe, uint32_t n_objects, const uint32_t* mesh_indices, const float* model_matrices /* 16 each, column-major */,
                                      const float* bb_world_min /* 3 each */, const float* bb_world_max /* 3 each */);
 

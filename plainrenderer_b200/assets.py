@@ -27,6 +27,7 @@ class Mesh:
     bb_max: np.ndarray
     mean_albedo: np.ndarray
     paths: dict = field(default_factory=dict)
+    vertices: np.ndarray = None  # (n, 28) uint8: the vertex buffer as stored
 
 
 @dataclass
@@ -39,7 +40,7 @@ class AssetError(RuntimeError):
     pass
 
 
-SYMBOLS = ["last_error", "scene_load", "scene_destroy", "scene_counts", "scene_object", "scene_mesh_info", "scene_mesh_geometry", "dds_r16f_info", "dds_r16f_load",
+SYMBOLS = ["last_error", "scene_load", "scene_destroy", "scene_counts", "scene_object", "scene_mesh_info", "scene_mesh_geometry", "scene_mesh_vertices", "dds_r16f_info", "dds_r16f_load",
            "dds_r16f_save", "sdf_resolution", "sdf_bake"]
 
 
@@ -77,8 +78,10 @@ class Assets:
                 pos = np.zeros((info.vertex_count, 3), np.float32)
                 idx = np.zeros(info.index_count, np.uint32)
                 self._check(self.f["scene_mesh_geometry"](p, C.c_uint64(m), pos.ctypes.data_as(C.c_void_p), idx.ctypes.data_as(C.c_void_p)), "scene_mesh_geometry")
+                vtx = np.zeros((info.vertex_count, 28), np.uint8)
+                self._check(self.f["scene_mesh_vertices"](p, C.c_uint64(m), vtx.ctypes.data_as(C.c_void_p)), "scene_mesh_vertices")
                 meshes.append(Mesh(pos, idx, np.array(info.bb_min, np.float32), np.array(info.bb_max, np.float32), np.array(info.mean_albedo, np.float32),
-                                   {k: getattr(info, k + "_path").decode() for k in ("albedo", "normal", "specular", "sdf")}))
+                                   {k: getattr(info, k + "_path").decode() for k in ("albedo", "normal", "specular", "sdf")}, vtx))
             return Scene(objects, meshes)
         finally:
             self.f["scene_destroy"](p)

@@ -138,7 +138,7 @@ class FrontendSettings(C.Structure):
                 ("taa_history_sampling_tech", i32), ("taa_filter_use_tonemapping", i32), ("bloom_enabled", i32), ("bloom_strength", f32),
                 ("bloom_radius", f32), ("sun_direction_deg", f32 * 2), ("camera_fov_deg", f32), ("camera_near", f32), ("camera_far", f32),
                 ("noise_seed", u32), ("shard_rank", u32), ("shard_count", u32), ("taa_use_separate_supersampling", i32), ("taa_supersample_use_tonemapping", i32),
-                ("sdf_debug_mode", i32), ("sdf_debug_show_tile_usage_with_hiz", i32), ("sdf_debug_use_influence_radius", i32)]
+                ("sdf_debug_mode", i32), ("sdf_debug_show_tile_usage_with_hiz", i32), ("sdf_debug_use_influence_radius", i32), ("raster_inputs", i32)]
 
 
 class FrameInputs(C.Structure):
@@ -169,7 +169,7 @@ BACKEND_SYMBOLS = [
     "peer_init", "peer_get_sync_handle", "peer_open_sync", "peer_get_image_handle", "peer_open_image", "peer_image_ready", "peer_push_rows", "peer_barrier",
     "peer_allreduce_sum_u32", "peer_error"]
 FRONTEND_SYMBOLS = [
-    "default_settings", "create", "destroy", "last_error", "backend", "register_sdf_mesh", "set_scene", "render_frame", "begin_frame", "run_segment", "set_peer_exchange", "shard_band",
+    "default_settings", "create", "destroy", "last_error", "backend", "register_sdf_mesh", "set_mesh_geometry", "set_scene", "render_frame", "begin_frame", "run_segment", "set_peer_exchange", "shard_band",
     "read_output_rows", "read_output", "get_image",
     "get_storage_buffer", "get_global_shader_info", "get_resolve_weights", "set_exposure", "synthetic_scene_create", "synthetic_scene_destroy",
     "synthetic_scene_attach", "synthetic_scene_render_inputs"]
@@ -476,6 +476,31 @@ class Frontend:
     def read_output_rows(self, out, rows, async_pinned=False):
         self._check(self.api.f["read_output_rows"](self.fe, _ptr(out), u32(rows[0]), u32(rows[1]), i32(int(async_pinned))), "read_output_rows")
         return out
+
+    def register_sdf_mesh(self, texels, bb_min, bb_max, mean_albedo):
+        """texels: uint16 half floats (d, h, w); returns the frontend mesh number"""
+        texels = np.ascontiguousarray(texels, np.uint16)
+        d, h, w = texels.shape
+        out = u32()
+        self._check(self.api.f["register_sdf_mesh"](self.fe, _ptr(texels), u32(w), u32(h), u32(d), (f32 * 3)(*bb_min), (f32 * 3)(*bb_max), (f32 * 3)(*mean_albedo), C.byref(out)), "register_sdf_mesh")
+        return out.value
+
+    def set_mesh_geometry(self, mesh, indices, vertices, textures=(None, None, None)):
+        """indices: uint array; vertices: (n, 28) uint8 (pack_vertices / assets.Mesh.vertices); textures: bindless slots of RGBA8 albedo / normal / specular images or None"""
+        idx = np.ascontiguousarray(np.asarray(indices).ravel().astype(np.uint16 if np.asarray(indices).size < 65535 else np.uint32))
+        vtx = np.ascontiguousarray(np.asarray(vertices, np.uint8).reshape(-1, 28))
+        mb = MeshBinary(len(idx), len(vtx), idx.ctypes.data, vtx.ctypes.data)
+        t = [0xFFFFFFFF if x is None else int(x) for x in textures]
+        self._check(self.api.f["set_mesh_geometry"](self.fe, u32(mesh), C.byref(mb), u32(t[0]), u32(t[1]), u32(t[2])), "set_mesh_geometry")
+
+    def set_scene(self, objects):
+        """objects: [(mesh number, model matrix float32[16] column-major, world bb min, world bb max)]"""
+        n = len(objects)
+        meshes = np.array([o[0] for o in objects], np.uint32)
+        mats = np.ascontiguousarray(np.array([np.asarray(o[1], np.float32).ravel() for o in objects], np.float32).reshape(n, 16))
+        bmin = np.ascontiguousarray(np.array([o[2] for o in objects], np.float32).reshape(n, 3))
+        bmax = np.ascontiguousarray(np.array([o[3] for o in objects], np.float32).reshape(n, 3))
+        self._check(self.api.f["set_scene"](self.fe, u32(n), _ptr(meshes), _ptr(mats), _ptr(bmin), _ptr(bmax)), "set_scene")
 
     def render_frame(self, cam, time, delta_time, depth=None, motion=None, normal=None, gbuffer=None, shadow_maps=None, async_upload=False):
         fi = FrameInputs()

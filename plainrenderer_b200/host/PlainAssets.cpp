@@ -18,6 +18,7 @@ struct Mesh {
     plain_mesh_info info{};
     std::vector<uint32_t> indices;
     std::vector<float> positions;
+    std::vector<unsigned char> vertices;  // the 28-byte vertices as stored (MeshProcessing.cpp:52-106)
 };
 bool readAll(const char* path, std::vector<unsigned char>& out) {
     std::ifstream f(path, std::ios::binary | std::ios::ate);
@@ -91,6 +92,7 @@ int PLAIN_ASSET(scene_load)(const char* path, plain_scene** out) {
         p += indexBytes;
         mesh.positions.resize((size_t)mesh.info.vertex_count * 3);
         for (uint32_t i = 0; i < mesh.info.vertex_count; i++) std::memcpy(&mesh.positions[3 * (size_t)i], d.data() + p + (size_t)i * kVertexBytes, 12);
+        mesh.vertices.assign(d.data() + p, d.data() + p + vertexBytes);
         p += vertexBytes;
         s->meshes.push_back(std::move(mesh));
     }
@@ -118,6 +120,12 @@ int PLAIN_ASSET(scene_mesh_geometry)(const plain_scene* s, uint64_t m, float* po
     const Mesh& mesh = s->meshes[m];
     if (positions) std::memcpy(positions, mesh.positions.data(), mesh.positions.size() * 4);
     if (indices) std::memcpy(indices, mesh.indices.data(), mesh.indices.size() * 4);
+    return 0;
+}
+
+int PLAIN_ASSET(scene_mesh_vertices)(const plain_scene* s, uint64_t m, void* vertices) {
+    if (m >= s->meshes.size()) return failAsset("scene_mesh_vertices: index out of range");
+    std::memcpy(vertices, s->meshes[m].vertices.data(), s->meshes[m].vertices.size());
     return 0;
 }
 

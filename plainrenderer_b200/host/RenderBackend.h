@@ -49,9 +49,29 @@ struct ComputePassExecution {
     uint32_t dispatchCount[3] = {1, 1, 1};
     uint32_t rowBegin = 0, rowEnd = 0, shardPhase = 0;  // row sharding (plain_compute_pass_execution), 0/0/0 = whole pass
 };
+// graphic passes (ResourceDescriptions.h:55-71, 80-143)
+struct MeshHandle { uint32_t index = PLAIN_INVALID_INDEX; };
+struct RenderTarget { ImageHandle image; uint32_t mipLevel; };
+struct GraphicPassExecution { RenderPassExecution genericInfo; std::vector<RenderTarget> targets; };
 struct SpecialisationConstant { uint32_t location; std::vector<char> data; };
 struct ShaderDescription { std::string srcPathRelative; std::vector<SpecialisationConstant> specialisationConstants; };
 struct ComputePassDescription { ShaderDescription shaderDescription; std::string name; };
+struct GraphicPassShaderDescriptions { ShaderDescription vertex, fragment; };
+struct Attachment { plain_image_format format; plain_attachment_load_op loadOp; };
+struct RasterizationConfig { plain_cull_mode cullMode = PLAIN_CULL_NONE; bool clampDepth = false; };
+struct DepthTest { plain_depth_function function = PLAIN_DEPTH_ALWAYS; bool write = false; };
+struct GraphicPassDescription {
+    GraphicPassShaderDescriptions shaderDescriptions;
+    std::vector<Attachment> attachments;
+    RasterizationConfig rasterization;
+    DepthTest depthTest;
+    std::string name;
+};
+struct MeshBinary {  // MeshData.h:27-35 (geometry part)
+    uint32_t indexCount = 0, vertexCount = 0;
+    std::vector<uint16_t> indexBuffer;  // 16 or 32 bit indices, as stored
+    std::vector<uint8_t> vertexBuffer;
+};
 
 inline std::vector<char> dataToCharArray(const void* data, size_t size) {  // GeneralUtils.cpp:8-12
     const char* p = (const char*)data;
@@ -83,6 +103,10 @@ inline void shardBandRows(uint32_t fullHeight, uint32_t count, uint32_t rank, ui
 
 class RenderBackend {
 public:
+    struct Recorded {  // one entry of a recorded frame: a compute execution, an exchange or a graphic execution with its draws
+        bool isExchange; ComputePassExecution exec; ExchangeRequest exchange;
+        bool isGraphic = false; GraphicPassExecution graphic; std::vector<plain_handle> drawMeshes; std::vector<char> drawPush;
+    };
     // ---- row sharding helpers (no counterpart in the reference) ----
     ShardInfo shard;
     // rows of an image whose height is fullHeight / divisor (or tiles of `divisor` rows) that belong to this rank, optionally
@@ -107,6 +131,52 @@ public:
         if (m_recording) { m_recorded.push_back(Recorded{false, e, ExchangeRequest()}); return; }
         sendExecution(e);
     }
+    // graphic passes: the execution is recorded where the frontend sets it; drawMeshes (called later, from renderScene) attaches
+    // the draws to it; both reach the C-ABI when the segment is sent
+    void setGraphicPassExecution(const GraphicPassExecution& e) {
+        Recorded r{false, ComputePassExecution(), ExchangeRequest()};
+        r.isGraphic = true;
+        r.graphic = e;
+        if (m_recording) { m_recorded.push_back(r); return; }
+        m_immediateGraphic.push_back(r);
+    }
+    void drawMeshes(const std::vector<MeshHandle>& meshHandles, const char* pushConstantData, RenderPassHandle pass, int workerIndex) {
+        (void)workerIndex;
+        const uint32_t ps = pass.index < m_graphicPushSize.size() ? m_graphicPushSize[pass.index] : 0;
+        if (!ps) throw std::runtime_error("drawMeshes: not a graphic pass");
+        Recorded* rec = nullptr;
+        for (auto& r : m_recorded) if (r.isGraphic && r.graphic.genericInfo.handle.index == pass.index) rec = &r;
+        for (auto& r : m_immediateGraphic) if (r.graphic.genericInfo.handle.index == pass.index) rec = &r;
+        if (!rec) throw std::runtime_error("drawMeshes: the pass has no execution this frame");
+        for (auto& m : meshHandles) rec->drawMeshes.push_back(m.index);
+        rec->drawPush.insert(rec->drawPush.end(), pushConstantData, pushConstantData + (size_t)ps * meshHandles.size());
+    }
+    std::vector<MeshHandle> createMeshes(const std::vector<MeshBinary>& meshes) {
+        std::vector<plain_mesh_binary> in;
+        for (auto& m : meshes) in.push_back(plain_mesh_binary{m.indexCount, m.vertexCount, m.indexBuffer.data(), m.vertexBuffer.data()});
+        std::vector<plain_handle> out(meshes.size());
+        check(PLAIN_FN(create_meshes)(m_ctx, in.data(), (uint32_t)in.size(), out.data()));
+        std::vector<MeshHandle> handles(meshes.size());
+        for (size_t i = 0; i < out.size(); i++) handles[i].index = out[i];
+        return handles;
+    }
+    RenderPassHandle createGraphicPass(const GraphicPassDescription& d) {
+        std::vector<plain_spec_const> vs = specs(d.shaderDescriptions.vertex), fs = specs(d.shaderDescriptions.fragment);
+        std::vector<plain_attachment> at;
+        for (auto& a : d.attachments) at.push_back(plain_attachment{(uint32_t)a.format, (uint32_t)a.loadOp});
+        plain_graphic_pass_desc x{};
+        x.vertex_shader = d.shaderDescriptions.vertex.srcPathRelative.c_str(); x.vertex_consts = vs.data(); x.n_vertex_consts = (uint32_t)vs.size();
+        x.fragment_shader = d.shaderDescriptions.fragment.srcPathRelative.c_str(); x.fragment_consts = fs.data(); x.n_fragment_consts = (uint32_t)fs.size();
+        x.attachments = at.data(); x.n_attachments = (uint32_t)at.size();
+        x.cull_mode = d.rasterization.cullMode; x.clamp_depth = d.rasterization.clampDepth ? 1u : 0u;
+        x.depth_function = d.depthTest.function; x.depth_write = d.depthTest.write ? 1u : 0u;
+        x.debug_name = d.name.c_str();
+        RenderPassHandle h;
+        check(PLAIN_FN(create_graphic_pass)(m_ctx, &x, &h.index));
+        if (m_graphicPushSize.size() <= h.index) m_graphicPushSize.resize(h.index + 1, 0);
+        m_graphicPushSize[h.index] = d.shaderDescriptions.vertex.srcPathRelative == "sunShadow.vert" ? 8u : 16u;
+        return h;
+    }
     void addExchange(const ExchangeRequest& x) { if (m_recording && shard.active()) m_recorded.push_back(Recorded{true, ComputePassExecution(), x}); }
     // deferred frames: executions are kept on the host and sent segment by segment (run until the next exchange)
     void beginRecording() { m_recording = true; m_recorded.clear(); m_cursor = 0; }
@@ -116,6 +186,7 @@ public:
     bool runSegment(plain_exchange* out) {
         while (m_cursor < m_recorded.size()) {
             const Recorded& r = m_recorded[m_cursor++];
+            if (r.isGraphic) { sendGraphic(r); continue; }
             if (!r.isExchange) { sendExecution(r.exec); continue; }
             check(PLAIN_FN(submit_recorded_passes)(m_ctx));
             if (peerExchange(r.exchange)) continue;  // done on the device: rows pushed into the peers' images + flag barrier
@@ -197,6 +268,7 @@ public:
         check(PLAIN_FN(peer_barrier)(m_ctx));
         return true;
     }
+    void sendGraphic(const Recorded& r);
     void sendExecution(const ComputePassExecution& e) {
         std::vector<plain_sampler_resource> sm;
         std::vector<plain_storage_buffer_resource> sb;
@@ -227,7 +299,11 @@ public:
         std::vector<plain_spec_const> sc = specs(d);
         check(PLAIN_FN(update_compute_pass_shader_description)(m_ctx, pass.index, d.srcPathRelative.c_str(), sc.data(), (uint32_t)sc.size()));
     }
-    void renderFrame(bool present) { check(PLAIN_FN(render_frame)(m_ctx, present ? 1 : 0)); }
+    void renderFrame(bool present) {
+        for (auto& r : m_immediateGraphic) sendGraphic(r);
+        m_immediateGraphic.clear();
+        check(PLAIN_FN(render_frame)(m_ctx, present ? 1 : 0));
+    }
     uint32_t getImageGlobalTextureArrayIndex(ImageHandle image) { uint32_t i = 0; check(PLAIN_FN(get_image_global_texture_array_index)(m_ctx, image, &i)); return i; }
     RenderPassHandle createComputePass(const ComputePassDescription& d) {
         std::vector<plain_spec_const> sc = specs(d.shaderDescription);
@@ -272,11 +348,26 @@ private:
         x.storage_images = st.data(); x.n_storage_images = (uint32_t)st.size();
     }
     plain_ctx* m_ctx = nullptr;
-    struct Recorded { bool isExchange; ComputePassExecution exec; ExchangeRequest exchange; };
-    std::vector<Recorded> m_recorded;
+    std::vector<Recorded> m_recorded, m_immediateGraphic;
+    std::vector<uint32_t> m_graphicPushSize;  // by pass handle; 0 = not a graphic pass
     size_t m_cursor = 0;
     bool m_recording = false;
 };
+
+inline void RenderBackend::sendGraphic(const Recorded& r) {
+    std::vector<plain_sampler_resource> sm;
+    std::vector<plain_storage_buffer_resource> sb;
+    std::vector<plain_uniform_buffer_resource> ub;
+    std::vector<plain_image_resource> si, st;
+    plain_graphic_pass_execution x{};
+    fill(r.graphic.genericInfo.resources, x.resources, sm, sb, ub, si, st);
+    x.pass = r.graphic.genericInfo.handle.index;
+    std::vector<plain_render_target> tg;
+    for (auto& t : r.graphic.targets) tg.push_back(plain_render_target{t.image, t.mipLevel});
+    x.targets = tg.data(); x.n_targets = (uint32_t)tg.size();
+    check(PLAIN_FN(set_graphic_pass_execution)(m_ctx, &x));
+    if (!r.drawMeshes.empty()) check(PLAIN_FN(draw_meshes)(m_ctx, r.drawMeshes.data(), (uint32_t)r.drawMeshes.size(), r.drawPush.data(), x.pass, 0));
+}
 
 inline ImageDescription imageDesc2D(uint32_t w, uint32_t h, plain_image_format f, uint32_t usage, plain_mip_count mips = PLAIN_MIPS_ONE, uint32_t manualMips = 1) {
     ImageDescription d{};

@@ -133,8 +133,8 @@ void RenderFrontend::setup(int device, uint32_t width, uint32_t height, uint32_t
     if (m_shardCount > 1) {
         if ((height + PLAIN_SHARD_ROW_UNIT - 1) / PLAIN_SHARD_ROW_UNIT < m_shardCount) throw std::runtime_error("row sharding: fewer 32-row units than ranks");
         if (width % 16 != 0 || height % 16 != 0) throw std::runtime_error("row sharding needs a resolution that is a multiple of 16 (four HiZ levels reduced from a rank's own rows)");
-        if (m_taaSettings.useSeparateSupersampling || m_sdfDebugSettings.visualisationMode != SDFVisualisationMode::None)
-            throw std::runtime_error("row sharding: the separate temporal supersampling pass and the SDF debug visualisation are single-GPU only");
+        if (m_taaSettings.useSeparateSupersampling || m_sdfDebugSettings.visualisationMode != SDFVisualisationMode::None || m_rasterInputs)
+            throw std::runtime_error("row sharding: the separate temporal supersampling pass, the SDF debug visualisation and rasterised inputs are single-GPU only");
         backend.shard.rank = m_shardRank; backend.shard.count = m_shardCount; backend.shard.fullHeight = height;
         shardBandRows(height, m_shardCount, m_shardRank, &backend.shard.y0, &backend.shard.y1);
     }
@@ -211,6 +211,9 @@ void RenderFrontend::initBuffers() {
     m_depthPyramidSyncBuffer = backend.createStorageBuffer(sizeof(uint32_t), &zero);
     m_sunShadowInfoBuffer = backend.createStorageBuffer(sizeof(plain_shadow_cascade_info));
     m_globalUniformBuffer = backend.createUniformBuffer(sizeof(plain_global_shader_info));
+    const size_t maxObjectCountMainScene = 1200;  // SceneConfig.h
+    m_mainPassTransformsBuffer = backend.createStorageBuffer(maxObjectCountMainScene * 3 * sizeof(hm::Mat4));  // MainPassMatrices {model, mvp, mvpPrevious}
+    m_shadowPassTransformsBuffer = backend.createStorageBuffer(maxObjectCountMainScene * sizeof(hm::Mat4));
 }
 
 template <typename T> static SpecialisationConstant specConst(uint32_t location, const T& v) { return SpecialisationConstant{location, dataToCharArray(&v, sizeof(T))}; }
@@ -236,6 +239,42 @@ void RenderFrontend::computeSinglePassMipChainDispatchCount(uint32_t w, uint32_t
 }
 
 void RenderFrontend::initRenderpasses() {
+    {   // depth prepass :1716-1735, shadow cascades :1563-1590, and the raster half of the main pass :1537-1561 (depth test EQUAL)
+        GraphicPassDescription d;
+        d.attachments = {Attachment{PLAIN_FORMAT_RG16_SNORM, PLAIN_LOAD_OP_CLEAR}, Attachment{PLAIN_FORMAT_RGBA8, PLAIN_LOAD_OP_CLEAR}, Attachment{PLAIN_FORMAT_DEPTH32, PLAIN_LOAD_OP_CLEAR}};
+        d.depthTest.function = PLAIN_DEPTH_GREATER_EQUAL; d.depthTest.write = true;
+        d.name = "Depth prepass";
+        d.rasterization.cullMode = PLAIN_CULL_BACK;
+        d.shaderDescriptions.vertex.srcPathRelative = "depthPrepass.vert";
+        d.shaderDescriptions.fragment.srcPathRelative = "depthPrepass.frag";
+        m_depthPrePass = backend.createGraphicPass(d);
+        GraphicPassDescription m;
+        m.attachments = {Attachment{PLAIN_FORMAT_RGBA32_UINT, PLAIN_LOAD_OP_CLEAR}, Attachment{PLAIN_FORMAT_DEPTH32, PLAIN_LOAD_OP_LOAD}};
+        m.depthTest.function = PLAIN_DEPTH_EQUAL; m.depthTest.write = true;
+        m.name = "G-buffer fill";
+        m.rasterization.cullMode = PLAIN_CULL_BACK;
+        m.shaderDescriptions.vertex.srcPathRelative = "triangle.vert";
+        m.shaderDescriptions.fragment.srcPathRelative = "gbufferFill.frag";
+        m_gbufferFillPass = backend.createGraphicPass(m);
+        for (uint32_t cascade = 0; cascade < (uint32_t)maxSunShadowCascadeCount; cascade++) {
+            GraphicPassDescription s;
+            s.name = "Shadow map cascade " + std::to_string(cascade);
+            s.attachments = {Attachment{PLAIN_FORMAT_DEPTH16, PLAIN_LOAD_OP_CLEAR}};
+            s.shaderDescriptions.vertex.srcPathRelative = "sunShadow.vert";
+            s.shaderDescriptions.fragment.srcPathRelative = "sunShadow.frag";
+            s.shaderDescriptions.vertex.specialisationConstants = {specConst(0, cascade)};
+            s.depthTest.function = PLAIN_DEPTH_GREATER_EQUAL; s.depthTest.write = true;
+            s.rasterization.cullMode = PLAIN_CULL_FRONT;
+            s.rasterization.clampDepth = true;
+            m_shadowPasses[cascade] = backend.createGraphicPass(s);
+        }
+        // createDefaultTextures :86-150 (the normal default is two-channel RG8 {128, 128} there; RGBA8 here, the material textures
+        // of the G-buffer fill are RGBA8)
+        const uint8_t diffuse[4] = {255, 255, 255, 255}, specular[4] = {0, 128, 255, 0}, normal[4] = {128, 128, 255, 255};
+        m_defaultTextures.diffuse = backend.createImage(imageDesc2D(1, 1, PLAIN_FORMAT_RGBA8, PLAIN_USAGE_SAMPLED), diffuse, 4);
+        m_defaultTextures.specular = backend.createImage(imageDesc2D(1, 1, PLAIN_FORMAT_RGBA8, PLAIN_USAGE_SAMPLED), specular, 4);
+        m_defaultTextures.normal = backend.createImage(imageDesc2D(1, 1, PLAIN_FORMAT_RGBA8, PLAIN_USAGE_SAMPLED), normal, 4);
+    }
     {   // deferred recast of the "Forward shading" graphic pass; constants as createForwardPassShaderDescription :1099-1135
         ComputePassDescription d;
         d.name = "Forward shading";
@@ -349,14 +388,14 @@ void RenderFrontend::prepareRenderpasses() {
         return dep;
     };
     if (m_sdfDebugSettings.visualisationMode != SDFVisualisationMode::None) {  // :321-340, primary rays through the SDF scene instead of the frame
-        // renderDepthPrepass: uploaded
+        if (m_rasterInputs) renderDepthPrepass(currentRenderTarget.depthBuffer, worldSpaceNormalImage(), currentRenderTarget.motionBuffer);  // else: uploaded
         computeDepthPyramid(currentRenderTarget.depthBuffer);
         computeColorBufferHistogram(m_postProcessBuffers[0]);
         m_sky.updateTransmissionLut(backend);
         computeExposure();
         m_sky.updateSkyLut(backend, m_lightBuffer, m_atmosphereSettings);
         computeSunLightMatrices();
-        // renderSunShadowCascades: uploaded
+        if (m_rasterInputs) renderSunShadowCascades();  // else: uploaded
         m_sdfGi.renderSDFVisualization(backend, m_postProcessBuffers[0], fillOutSdfGiDependencies(), m_sdfDebugSettings, m_sdfTraceSettings);
         computeTonemapping(m_postProcessBuffers[0]);
         return;
@@ -366,10 +405,11 @@ void RenderFrontend::prepareRenderpasses() {
     m_sky.updateTransmissionLut(backend);
     computeExposure();
     m_sky.updateSkyLut(backend, m_lightBuffer, m_atmosphereSettings);
-    // renderDepthPrepass: rasterisation, out of scope - depth/motion/normal/G-buffer of this frame are uploaded
+    // depth / motion / normal / G-buffer / shadow maps of this frame: rasterised from the meshes (m_rasterInputs) or uploaded
+    if (m_rasterInputs) renderDepthPrepass(currentRenderTarget.depthBuffer, worldSpaceNormalImage(), currentRenderTarget.motionBuffer);
     computeDepthPyramid(currentRenderTarget.depthBuffer);
     computeSunLightMatrices();
-    // renderSunShadowCascades: rasterisation, out of scope - shadow maps are uploaded
+    if (m_rasterInputs) renderSunShadowCascades();
     if (m_shadingConfig.indirectLightingTech == IndirectLightingTech::SDFTrace) {
         if (m_sdfTraceSettings.halfResTrace) downscaleDepth(currentRenderTarget);
         m_sdfGi.computeIndirectLighting(backend, fillOutSdfGiDependencies(), m_sdfTraceSettings, m_frameIndex);
@@ -380,6 +420,7 @@ void RenderFrontend::prepareRenderpasses() {
     vd.sunShadowInfoBuffer = m_sunShadowInfoBuffer;
     m_volumetrics.computeVolumetricLighting(backend, m_volumetricsSettings, m_windSettings, vd, m_frameIndex, m_deltaTime);
 
+    if (m_rasterInputs) fillGBuffer(gbuffer(), currentRenderTarget.depthBuffer);
     shadeGBuffer(currentRenderTarget.colorBuffer);  // renderForwardShading + m_sky.renderSky
 
     ImageHandle currentSrc = currentRenderTarget.colorBuffer;
@@ -441,7 +482,101 @@ void RenderFrontend::updateGlobalShaderInfo() {
     backend.setUniformBufferData(m_globalUniformBuffer, &g, sizeof(g));
 }
 
-void RenderFrontend::renderScene(const std::vector<RenderObject>& scene) { m_sdfGi.updateSDFScene(backend, scene, m_frontendMeshes); }
+bool isAxisAlignedBoundingBoxIntersectingViewFrustum(const ViewFrustum& f, const hm::AABB& bb) {  // Culling.cpp:5-42
+    const hm::Vec3 planes[6][2] = {{f.l_u_f, f.top}, {f.l_l_f, f.bot}, {f.l_u_n, f.near}, {f.l_u_f, f.far}, {f.l_u_f, f.left}, {f.r_u_f, f.right}};
+    for (int i = 0; i < 6; i++) {
+        bool isBBOutsidePlane = true;
+        for (int k = 0; k < 8; k++) {
+            const hm::Vec3 bp((k & 1) ? bb.max.x : bb.min.x, (k & 2) ? bb.max.y : bb.min.y, (k & 4) ? bb.max.z : bb.min.z);
+            isBBOutsidePlane = isBBOutsidePlane && hm::dot(bp - planes[i][0], planes[i][1]) > 0.f;
+        }
+        if (isBBOutsidePlane) return false;
+    }
+    return true;
+}
+
+// RenderFrontend.cpp:533-683: SDF instance table, then - when the raster passes run here - frustum culling, the per-draw matrices
+// and the draw calls of the depth prepass, the G-buffer fill (the reference's main pass) and the shadow cascades
+void RenderFrontend::renderScene(const std::vector<RenderObject>& scene) {
+    m_sdfGi.updateSDFScene(backend, scene, m_frontendMeshes);
+    if (!m_rasterInputs) return;
+    struct MainPassPushConstants { uint32_t albedoTextureIndex, normalTextureIndex, specularTextureIndex, transformIndex; };
+    struct MainPassMatrices { hm::Mat4 model, mvp, mvpPrevious; };
+    std::vector<MainPassPushConstants> mainPassPushConstants;
+    std::vector<MeshHandle> mainPassCulledMeshes;
+    std::vector<MainPassMatrices> mainPassMatrices;
+    hm::Mat4 previousViewProjection;
+    std::memcpy(previousViewProjection.m, m_globalShaderInfo.viewProjectionPrevious, sizeof(float) * 16);
+    for (const RenderObject& obj : scene) {
+        const MeshFrontend& mesh = m_frontendMeshes[obj.mesh];
+        if (mesh.backendHandle.index == PLAIN_INVALID_INDEX) continue;  // an SDF-only mesh
+        if (!isAxisAlignedBoundingBoxIntersectingViewFrustum(m_cameraFrustum, obj.bbWorld)) continue;
+        m_currentMainPassDrawcallCount++;
+        mainPassCulledMeshes.push_back(mesh.backendHandle);
+        mainPassPushConstants.push_back({mesh.material.albedoTextureIndex, mesh.material.normalTextureIndex, mesh.material.specularTextureIndex, (uint32_t)mainPassMatrices.size()});
+        mainPassMatrices.push_back({obj.modelMatrix, m_viewProjectionMatrix * obj.modelMatrix, previousViewProjection * obj.previousModelMatrix});
+    }
+    backend.drawMeshes(mainPassCulledMeshes, (const char*)mainPassPushConstants.data(), m_gbufferFillPass, 0);
+    backend.drawMeshes(mainPassCulledMeshes, (const char*)mainPassPushConstants.data(), m_depthPrePass, 0);
+    if (!mainPassMatrices.empty()) backend.setStorageBufferData(m_mainPassTransformsBuffer, mainPassMatrices.data(), sizeof(MainPassMatrices) * mainPassMatrices.size());
+    // shadow pass: the reference culls against a frustum fitted to the camera frustum and pushed 10 km towards the sun (:613-645);
+    // culling does not change the maps, every object with geometry is drawn here
+    struct ShadowPushConstants { uint32_t albedoTextureIndex, transformIndex; };
+    std::vector<MeshHandle> shadowCulledMeshes;
+    std::vector<ShadowPushConstants> shadowPushConstantData;
+    std::vector<hm::Mat4> shadowModelMatrices;
+    for (const RenderObject& obj : scene) {
+        const MeshFrontend& mesh = m_frontendMeshes[obj.mesh];
+        if (mesh.backendHandle.index == PLAIN_INVALID_INDEX) continue;
+        m_currentShadowPassDrawcallCount++;
+        shadowCulledMeshes.push_back(mesh.backendHandle);
+        shadowPushConstantData.push_back({mesh.material.albedoTextureIndex, (uint32_t)shadowModelMatrices.size()});
+        shadowModelMatrices.push_back(obj.modelMatrix);
+    }
+    for (int shadowPass = 0; shadowPass < m_shadingConfig.sunShadowCascadeCount; shadowPass++)
+        backend.drawMeshes(shadowCulledMeshes, (const char*)shadowPushConstantData.data(), m_shadowPasses[shadowPass], 0);
+    if (!shadowModelMatrices.empty()) backend.setStorageBufferData(m_shadowPassTransformsBuffer, shadowModelMatrices.data(), sizeof(hm::Mat4) * shadowModelMatrices.size());
+}
+
+void RenderFrontend::renderDepthPrepass(ImageHandle depth, ImageHandle normal, ImageHandle motion) {  // :792-802
+    GraphicPassExecution e;
+    e.genericInfo.handle = m_depthPrePass;
+    e.targets = {RenderTarget{motion, 0}, RenderTarget{normal, 0}, RenderTarget{depth, 0}};
+    e.genericInfo.resources.storageBuffers = {StorageBufferResource(m_mainPassTransformsBuffer, true, 0)};
+    backend.setGraphicPassExecution(e);
+}
+void RenderFrontend::renderSunShadowCascades() {  // :760-775
+    for (int i = 0; i < m_shadingConfig.sunShadowCascadeCount; i++) {
+        GraphicPassExecution e;
+        e.genericInfo.handle = m_shadowPasses[i];
+        e.genericInfo.resources.storageBuffers = {StorageBufferResource(m_sunShadowInfoBuffer, true, 0), StorageBufferResource(m_shadowPassTransformsBuffer, true, 1)};
+        e.targets = {RenderTarget{m_shadowMaps[i], 0}};
+        backend.setGraphicPassExecution(e);
+    }
+}
+// the raster half of the reference's main pass (renderForwardShading: triangle.vert/.frag with depth test EQUAL, :1537-1561): the
+// interpolated inputs and material texels land in the packed G-buffer, the shading itself runs in gbufferShading.comp
+void RenderFrontend::fillGBuffer(ImageHandle gbuffer, ImageHandle depth) {
+    GraphicPassExecution e;
+    e.genericInfo.handle = m_gbufferFillPass;
+    e.targets = {RenderTarget{gbuffer, 0}, RenderTarget{depth, 0}};
+    e.genericInfo.resources.storageBuffers = {StorageBufferResource(m_mainPassTransformsBuffer, true, 17)};
+    backend.setGraphicPassExecution(e);
+}
+void RenderFrontend::setMeshGeometry(uint32_t mesh, const MeshBinary& geometry, const Material* material) {
+    if (mesh >= m_frontendMeshes.size()) throw std::runtime_error("setMeshGeometry: invalid mesh");
+    m_frontendMeshes[mesh].backendHandle = backend.createMeshes({geometry})[0];
+    Material m;
+    m.albedoTextureIndex = backend.getImageGlobalTextureArrayIndex(m_defaultTextures.diffuse);
+    m.normalTextureIndex = backend.getImageGlobalTextureArrayIndex(m_defaultTextures.normal);
+    m.specularTextureIndex = backend.getImageGlobalTextureArrayIndex(m_defaultTextures.specular);
+    if (material) {
+        if (material->albedoTextureIndex != PLAIN_INVALID_INDEX) m.albedoTextureIndex = material->albedoTextureIndex;
+        if (material->normalTextureIndex != PLAIN_INVALID_INDEX) m.normalTextureIndex = material->normalTextureIndex;
+        if (material->specularTextureIndex != PLAIN_INVALID_INDEX) m.specularTextureIndex = material->specularTextureIndex;
+    }
+    m_frontendMeshes[mesh].material = m;
+}
 
 void RenderFrontend::renderFrame() {  // RenderFrontend.cpp:685-705
     plain_exchange x;

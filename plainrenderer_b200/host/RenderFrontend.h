@@ -84,8 +84,11 @@ uint32_t mipCountFromResolution(uint32_t w, uint32_t h, uint32_t d);
 hm::AABB padSDFBoundingBox(const hm::AABB& bb);  // sdfUtilities.cpp:5-19
 
 // scene objects with an SDF (RuntimeScene.h RenderObject + MeshFrontend.h)
-struct MeshFrontend { int sdfTextureIndex = -1; hm::Vec3 meanAlbedo = hm::Vec3(0.5f); hm::AABB localBB; };
-struct RenderObject { uint32_t mesh = 0; hm::AABB bbWorld; hm::Mat4 modelMatrix; };
+struct Material { uint32_t albedoTextureIndex = 0, normalTextureIndex = 0, specularTextureIndex = 0; };  // MeshFrontend.h: bindless slots
+struct MeshFrontend { int sdfTextureIndex = -1; hm::Vec3 meanAlbedo = hm::Vec3(0.5f); hm::AABB localBB; MeshHandle backendHandle; Material material; };
+struct RenderObject { uint32_t mesh = 0; hm::AABB bbWorld; hm::Mat4 modelMatrix; hm::Mat4 previousModelMatrix; };
+struct DefaultTextures { ImageHandle diffuse, specular, normal; };  // RenderFrontend.cpp:86-150
+bool isAxisAlignedBoundingBoxIntersectingViewFrustum(const ViewFrustum& frustum, const hm::AABB& bb);  // Culling.cpp:5-42
 
 struct SDFTraceDependencies {
     FrameRenderTargets currentFrame, previousFrame;
@@ -181,6 +184,12 @@ public:
     bool renderFrameSegment(plain_exchange* pending);  // row-sharded frames: run up to the next exchange
     uint32_t m_shardRank = 0, m_shardCount = 1;
 
+    // with m_rasterInputs the depth prepass, the sun shadow cascades and the G-buffer are rasterised from the
+    // registered meshes by the backend's graphic passes instead of being uploaded
+    bool m_rasterInputs = false;
+    void setMeshGeometry(uint32_t mesh, const MeshBinary& geometry, const Material* material);  // registerMeshes :456-531 (geometry + material part)
+    DefaultTextures m_defaultTextures;
+    uint32_t m_currentMainPassDrawcallCount = 0, m_currentShadowPassDrawcallCount = 0;
     uint32_t registerSdfMesh(const uint16_t* r16fTexels, uint32_t rx, uint32_t ry, uint32_t rz, const hm::AABB& localBB, hm::Vec3 meanAlbedo);
     const FrameRenderTargets& currentTargets() const { return m_frameRenderTargets[m_sceneRenderTargetIndex]; }
 
@@ -230,6 +239,9 @@ private:
     void computeSunLightMatrices();
     void downscaleDepth(const FrameRenderTargets& current);
     void shadeGBuffer(ImageHandle colorTarget);
+    void renderDepthPrepass(ImageHandle depth, ImageHandle normal, ImageHandle motion);  // :792-802
+    void renderSunShadowCascades();                                                     // :760-775
+    void fillGBuffer(ImageHandle gbuffer, ImageHandle depth);                           // the raster half of renderForwardShading :840-...
     void computeTonemapping(ImageHandle src);
     void computeBRDFLut();
     void updateGlobalShaderInfo();
@@ -243,5 +255,7 @@ private:
     float m_time = 0.f, m_deltaTime = 0.016f;
     RenderPassHandle m_shadingPass, m_brdfLutPass, m_histogramPerTilePass, m_histogramResetPass, m_histogramCombinePass, m_preExposeLightsPass;
     RenderPassHandle m_depthPyramidPass, m_lightMatrixPass, m_tonemappingPass, m_depthDownscalePass;
+    RenderPassHandle m_depthPrePass, m_gbufferFillPass, m_shadowPasses[4];
+    StorageBufferHandle m_mainPassTransformsBuffer, m_shadowPassTransformsBuffer;
     SamplerHandle m_samplers[8];
 };

@@ -31,6 +31,7 @@ void PLAIN_FE(default_settings)(plain_frontend_settings* s, uint32_t width, uint
     s->noise_seed = 0x504c4149u;
     s->taa_use_separate_supersampling = 0; s->taa_supersample_use_tonemapping = 1;
     s->sdf_debug_mode = 0; s->sdf_debug_show_tile_usage_with_hiz = 1; s->sdf_debug_use_influence_radius = 0;
+    s->raster_inputs = 0;
 }
 
 int PLAIN_FE(create)(int device, const plain_frontend_settings* s, plain_frontend** out) {
@@ -56,6 +57,7 @@ int PLAIN_FE(create)(int device, const plain_frontend_settings* s, plain_fronten
     f.m_sdfDebugSettings.visualisationMode = (SDFVisualisationMode)s->sdf_debug_mode;
     f.m_sdfDebugSettings.showCameraTileUsageWithHiZ = s->sdf_debug_show_tile_usage_with_hiz != 0;
     f.m_sdfDebugSettings.useInfluenceRadiusForDebug = s->sdf_debug_use_influence_radius != 0;
+    f.m_rasterInputs = s->raster_inputs != 0;
     f.m_bloomSettings.enabled = s->bloom_enabled != 0;
     f.m_bloomSettings.strength = s->bloom_strength;
     f.m_bloomSettings.radius = s->bloom_radius;
@@ -94,6 +96,19 @@ int PLAIN_FE(register_sdf_mesh)(plain_frontend* fe, const uint16_t* texels, uint
         *out = fe->fe.registerSdfMesh(texels, rx, ry, rz, bb, hm::Vec3(albedo[0], albedo[1], albedo[2]));
     });
 }
+int PLAIN_FE(set_mesh_geometry)(plain_frontend* fe, uint32_t mesh, const plain_mesh_binary* g, uint32_t albedoTexture, uint32_t normalTexture, uint32_t specularTexture) {
+    FE_TRY(fe, {
+        MeshBinary mb;
+        mb.indexCount = g->index_count; mb.vertexCount = g->vertex_count;
+        const bool wide = !(g->index_count < 65535u);
+        mb.indexBuffer.resize((size_t)g->index_count * (wide ? 2 : 1));
+        std::memcpy(mb.indexBuffer.data(), g->index_buffer, (size_t)g->index_count * (wide ? 4 : 2));
+        mb.vertexBuffer.assign((const uint8_t*)g->vertex_buffer, (const uint8_t*)g->vertex_buffer + (size_t)g->vertex_count * 28);
+        Material m;
+        m.albedoTextureIndex = albedoTexture; m.normalTextureIndex = normalTexture; m.specularTextureIndex = specularTexture;
+        fe->fe.setMeshGeometry(mesh, mb, &m);
+    });
+}
 int PLAIN_FE(set_scene)(plain_frontend* fe, uint32_t n, const uint32_t* meshes, const float* mats, const float* bmin, const float* bmax) {
     FE_TRY(fe, {
         fe->scene.clear();
@@ -101,6 +116,7 @@ int PLAIN_FE(set_scene)(plain_frontend* fe, uint32_t n, const uint32_t* meshes, 
             RenderObject o;
             o.mesh = meshes[i];
             std::memcpy(o.modelMatrix.m, mats + 16 * i, sizeof(float) * 16);
+            o.previousModelMatrix = o.modelMatrix;  // static objects (RuntimeScene.h keeps the last frame's matrix per object)
             o.bbWorld.min = hm::Vec3(bmin[3 * i], bmin[3 * i + 1], bmin[3 * i + 2]);
             o.bbWorld.max = hm::Vec3(bmax[3 * i], bmax[3 * i + 1], bmax[3 * i + 2]);
             fe->scene.push_back(o);

@@ -138,3 +138,62 @@ def assert_snapshots_equal(a, b, context=""):
         if n:
             bad.append("%s: %d/%d bytes differ" % (k, n, a[k].size))
     assert not bad, "%s differs from the oracle: %s" % (context, "; ".join(bad))
+
+
+class PlainSceneSequence:
+    """frames rendered end to end from `.plain` meshes - depth / motion / normal, the shadow cascades and the packed
+    G-buffer come from the backend's rasteriser (settings.raster_inputs = 1), nothing is uploaded. Scene: the three golden assets
+    of tests/golden/sdf (written by the reference's asset pipeline), instanced with translations / scales / a rotation."""
+    PLACEMENT = [("slab", (0.0, 2.6, 0.0), (4.0, 0.4, 4.0), 0.0), ("cube", (-6.0, 0.0, 1.5), (1.0, 1.0, 1.0), 0.5), ("tall", (-4.0, -1.0, -3.0), (1.0, 0.5, 1.0), 0.0),
+                 ("cube", (-9.5, 0.8, -0.5), (0.6, 0.6, 0.6), -0.8), ("cube", (-3.0, 1.2, 3.5), (1.5, 1.0, 0.7), 1.1), ("tall", (-14.0, 0.0, 4.0), (1.0, 0.6, 1.5), 0.3)]
+
+    def __init__(self, ffi, api, asset_lib, w, h, **settings):
+        self.ffi, self.w, self.h = ffi, w, h
+        settings.setdefault("sun_direction_deg", (40.0, 35.0))
+        self.s = ffi.default_settings(api, w, h, raster_inputs=1, **settings)
+        self.fe = ffi.Frontend(api, self.s)
+        be = self.fe.backend
+        rng = np.random.default_rng(5)
+        checker = np.zeros((4, 4, 4), np.uint8)
+        checker[..., :3] = rng.integers(60, 255, (4, 4, 3))
+        checker[..., 3] = 255
+        rough = np.zeros((2, 2, 4), np.uint8)
+        rough[..., 1], rough[..., 2] = rng.integers(60, 230, (2, 2)), 0
+        bumps = np.zeros((4, 4, 4), np.uint8)
+        bumps[..., :2] = rng.integers(108, 148, (4, 4, 2))
+        bumps[..., 2:] = 255
+        tex = [be.global_texture_index(be.create_image(t.shape[1], t.shape[0], "RGBA8", data=t)) for t in (checker, bumps, rough)]
+        golden = ROOT / "tests" / "golden" / "sdf"
+        self.meshes = {}
+        for k, name in enumerate(("cube", "slab", "tall")):
+            m = asset_lib.load_scene(golden / (name + ".plain")).meshes[0]
+            brick = asset_lib.load_brick(golden / (name + ".dds"))
+            fm = self.fe.register_sdf_mesh(brick, m.bb_min, m.bb_max, m.mean_albedo)
+            self.fe.set_mesh_geometry(fm, m.indices, m.vertices, textures=(tex[0], tex[1], tex[2]) if k != 1 else (None, None, tex[2]))
+            self.meshes[name] = (fm, m)
+        objects = []
+        for name, t, sc, rot in self.PLACEMENT:
+            fm, m = self.meshes[name]
+            c, s_ = np.cos(rot), np.sin(rot)
+            M = np.array([[c * sc[0], 0, s_ * sc[2], t[0]], [0, sc[1], 0, t[1]], [-s_ * sc[0], 0, c * sc[2], t[2]], [0, 0, 0, 1]], np.float32)
+            corners = np.array([[x, y, z, 1] for x in (m.bb_min[0], m.bb_max[0]) for y in (m.bb_min[1], m.bb_max[1]) for z in (m.bb_min[2], m.bb_max[2])], np.float32) @ M.T
+            objects.append((fm, M.T.ravel(), corners[:, :3].min(0), corners[:, :3].max(0)))
+        self.fe.set_scene(objects)
+        self.fe.set_exposure(2e-5)
+        self.frame = 0
+
+    def step(self, moving=False):
+        f = self.frame
+        p, fw, r, u = CAMERA
+        if moving:
+            p = (p[0] + 0.3 * f, p[1] - 0.02 * f, p[2] + 0.1 * f)
+        self.fe.render_frame(self.ffi.camera(p, fw, r, u), (f + 1) / 60.0, 1 / 60.0)
+        self.frame += 1
+
+    RASTER_IMAGES = ["depth0", "depth1", "motion0", "motion1", "motion2", "normal", "gbuffer", "shadow0", "shadow1", "shadow2"]
+
+    def snapshot(self, images=None, buffers=ALL_BUFFERS):
+        return Sequence.snapshot(self, images or (self.RASTER_IMAGES + ALL_IMAGES), buffers)
+
+    def close(self):
+        self.fe.close()

@@ -78,5 +78,39 @@ def test_shadow_cascade_bit_exact(ffi, cuda, oracle, size, n_tris):
     for cascade in (0, 2):
         got = passes.raster_shadow(ffi, cuda, size, meshes, [(0, 0), (0, 1)], [IDENTITY, model.T.ravel()], lm, cascade=cascade)
         want = passes.raster_shadow(ffi, oracle, size, meshes, [(0, 0), (0, 1)], [IDENTITY, model.T.ravel()], lm, cascade=cascade)
-        assert (want > 0).mean() > 0.1
+        assert (want > 0).mean() > 0.02
         assert np.array_equal(got, want), "cascade %d: %d texels differ" % (cascade, int((got != want).sum()))
+
+
+@pytest.mark.parametrize("w,h,moving,settings", [(192, 108, True, {}), (250, 142, False, {}), (160, 90, True, dict(sdf_debug_mode=1)), (128, 72, True, dict(sun_shadow_cascade_count=4, taa_enabled=0))])
+def test_frames_from_plain_meshes_bit_exact(ffi, cuda, oracle, w, h, moving, settings):
+    """frames rendered end to end from `.plain` geometry (raster_inputs = 1): every rasterised input and every resource of the
+    frame path after it, CUDA against the oracle"""
+    from conftest import PlainSceneSequence, ROOT, assert_snapshots_equal
+    from plainrenderer_b200 import assets
+    a = PlainSceneSequence(ffi, cuda, assets.Assets(), w, h, **settings)
+    b = PlainSceneSequence(ffi, oracle, assets.Assets(ROOT / "oracle" / "_build" / "liboracle.so", "oracle_asset_"), w, h, **settings)
+    try:
+        for f in range(3):
+            a.step(moving=moving)
+            b.step(moving=moving)
+            assert_snapshots_equal(a.snapshot(), b.snapshot(), "frame %d of %dx%d from .plain meshes %s" % (f, w, h, settings))
+    finally:
+        a.close()
+        b.close()
+
+
+def test_raster_graph_replay_is_identical(ffi, cuda):
+    """the rasteriser's launches inside the captured pass list (CUDA graph) produce the same bytes as direct launches"""
+    from conftest import PlainSceneSequence
+    from plainrenderer_b200 import assets
+    outs = []
+    for graph in (False, True):
+        s = PlainSceneSequence(ffi, cuda, assets.Assets(), 192, 108)
+        s.fe.backend.set_graph_replay_enabled(graph)
+        for _ in range(4):
+            s.step(moving=True)
+        outs.append(s.snapshot())
+        s.close()
+    for k in outs[0]:
+        assert np.array_equal(outs[0][k], outs[1][k]), k

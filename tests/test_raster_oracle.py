@@ -147,3 +147,34 @@ def test_shadow_cascade_keeps_the_back_faces_and_clamps_depth(ffi, oracle):
     want[16:56, 16:56] = int(0.25 * 65535 + 0.5)
     want[2:10, 40:60] = 65535
     assert np.array_equal(sm, want)
+
+
+def test_frame_from_plain_meshes(ffi, oracle):
+    """a frame rendered end to end from `.plain` geometry (raster_inputs = 1): what the rasterised inputs must look like"""
+    from conftest import PlainSceneSequence, ROOT
+    from plainrenderer_b200 import assets
+    lib = assets.Assets(ROOT / "oracle" / "_build" / "liboracle.so", "oracle_asset_")
+    w, h = 96, 54
+    s = PlainSceneSequence(ffi, oracle, lib, w, h)
+    for _ in range(3):
+        s.step()
+    snap = s.snapshot(["depth0", "depth1", "motion0", "motion1", "motion2", "normal", "gbuffer", "shadow2", "output", "giFullY"], [("sunShadowInfo", 304)])
+    s.close()
+    depth = snap["depth1/0"].view(np.float32).reshape(h, w)  # frame 3 renders into target 1
+    covered = depth > 0
+    assert 0.2 < covered.mean() < 0.99, "the slab floor and the boxes cover part of the view, the sky the rest"
+    assert depth.max() < 1.0
+    gb = snap["gbuffer/0"].view(np.uint32).reshape(h, w, 4)
+    assert np.array_equal(gb[..., 0], depth.view(np.uint32)) and (gb[~covered] == 0).all()
+    normal = snap["normal/0"].reshape(h, w, 4)
+    n = normal[covered][:, :3].astype(np.float64) / 255 * 2 - 1
+    assert np.abs(np.linalg.norm(n, axis=1) - 1).max() < 0.02 and (normal[~covered] == 0).all()
+    assert (n[:, 1] < -0.98).mean() > 0.05   # y points down in this world: the top faces' normal is (0, -1, 0)
+    assert (n[:, 0] < -0.5).mean() > 0.2     # the camera looks down +x: many faces look back at it
+    motions = [snap["motion%d/0" % i].view(np.int16) for i in range(3)]
+    assert max(np.abs(m).max() for m in motions) <= 1, "static camera: the jitter cancels (depthPrepass.frag:36-39)"
+    shadow = snap["shadow2/0"].view(np.uint16)
+    assert 0.001 < (shadow > 0).mean() < 0.9
+    out = snap["output/0"].reshape(h, w, 4)
+    assert out[..., :3].std() > 2 and (out[..., 3] == 255).all()
+    assert np.isfinite(snap["giFullY/0"].view(np.float16).astype(np.float32)).all()
