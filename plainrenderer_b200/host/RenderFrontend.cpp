@@ -516,7 +516,9 @@ void RenderFrontend::renderScene(const std::vector<RenderObject>& scene) {
         mainPassPushConstants.push_back({mesh.material.albedoTextureIndex, mesh.material.normalTextureIndex, mesh.material.specularTextureIndex, (uint32_t)mainPassMatrices.size()});
         mainPassMatrices.push_back({obj.modelMatrix, m_viewProjectionMatrix * obj.modelMatrix, previousViewProjection * obj.previousModelMatrix});
     }
-    backend.drawMeshes(mainPassCulledMeshes, (const char*)mainPassPushConstants.data(), m_gbufferFillPass, 0);
+    // only the prepass draws are needed for the SDF debug visualisation (:588-601)
+    const bool renderingSDFVisualisation = m_sdfDebugSettings.visualisationMode != SDFVisualisationMode::None;
+    if (!renderingSDFVisualisation) backend.drawMeshes(mainPassCulledMeshes, (const char*)mainPassPushConstants.data(), m_gbufferFillPass, 0);
     backend.drawMeshes(mainPassCulledMeshes, (const char*)mainPassPushConstants.data(), m_depthPrePass, 0);
     if (!mainPassMatrices.empty()) backend.setStorageBufferData(m_mainPassTransformsBuffer, mainPassMatrices.data(), sizeof(MainPassMatrices) * mainPassMatrices.size());
     // shadow pass: the reference culls against a frustum fitted to the camera frustum and pushed 10 km towards the sun (:613-645);
