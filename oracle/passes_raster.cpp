@@ -11,8 +11,10 @@
 //   * window coordinates are snapped to 1/256 pixel, coverage = exact integer edge functions at pixel centres, top-left rule
 //   * front face = counter clockwise = negative sum of x_i*y_j - x_j*y_i in window coordinates (VulkanPipeline.cpp:61)
 //   * depth and the perspective-correct barycentrics come from the plane equations of the UNCLIPPED triangle in homogeneous
-//     coordinates (2-D homogeneous rasterisation), evaluated in binary64 at the pixel centre; depth is rounded to binary32,
-//     fragments outside [0, 1] are dropped (clamped when depth clamp is on)
+//     coordinates (2-D homogeneous rasterisation), evaluated in binary64 at the pixel centre: with v_i = (x_i, y_i, w_i),
+//     c_0 = v_1 x v_2 (cyclic), e_i = c_i . (px, py, 1): lambda_i = e_i * (1 / (e_0 + e_1 + e_2)); depth is the affine function
+//     (sum z_i c_i) / det . (px, py, 1) with det = (sum w_i c_i).z (its x and y components vanish analytically), rounded to
+//     binary32; fragments outside [0, 1] are dropped (clamped when depth clamp is on)
 //   * depth test GREATER_EQUAL in draw order = per pixel the maximum of (depth bits, primitive number): of two fragments at the
 //     same depth the one drawn later wins; draws are ordered by draw_meshes call, triangles by index-buffer position
 //   * texture fetches of gbufferFill are bilinear, repeat, mip 0 (the reference samples anisotropically with a mip bias);
@@ -52,22 +54,23 @@ static VertexIn fetchVertex(const Mesh& m, uint32_t index) {
 static vec3 mulMat3(const mat4& m, vec3 v) { return vfma(m.c[2].xyz(), v.z, vfma(m.c[1].xyz(), v.y, m.c[0].xyz() * v.x)); }  // mat3(model) * v, the contract's M * v
 
 // ---- homogeneous plane equations of one (unclipped) triangle ----
-struct TriPlanes { D3 c0, c1, c2, num, den; };
+struct TriPlanes { D3 c0, c1, c2, depth; };
 static TriPlanes trianglePlanes(const vec4 clip[3]) {
     D3 v[3];
     double z[3], w[3];
     for (int i = 0; i < 3; i++) { v[i] = {(double)clip[i].x, (double)clip[i].y, (double)clip[i].w}; z[i] = (double)clip[i].z; w[i] = (double)clip[i].w; }
     TriPlanes t;
     t.c0 = crossd(v[1], v[2]); t.c1 = crossd(v[2], v[0]); t.c2 = crossd(v[0], v[1]);
-    t.num = {t.c0.x * z[0] + t.c1.x * z[1] + t.c2.x * z[2], t.c0.y * z[0] + t.c1.y * z[1] + t.c2.y * z[2], t.c0.z * z[0] + t.c1.z * z[1] + t.c2.z * z[2]};
-    t.den = {t.c0.x * w[0] + t.c1.x * w[1] + t.c2.x * w[2], t.c0.y * w[0] + t.c1.y * w[1] + t.c2.y * w[2], t.c0.z * w[0] + t.c1.z * w[1] + t.c2.z * w[2]};
+    const D3 num = {t.c0.x * z[0] + t.c1.x * z[1] + t.c2.x * z[2], t.c0.y * z[0] + t.c1.y * z[1] + t.c2.y * z[2], t.c0.z * z[0] + t.c1.z * z[1] + t.c2.z * z[2]};
+    const double det = t.c0.z * w[0] + t.c1.z * w[1] + t.c2.z * w[2];
+    t.depth = {num.x / det, num.y / det, num.z / det};
     return t;
 }
-static double pixelNdc(int i, int size) { return ((double)i + 0.5) / (double)size * 2.0 - 1.0; }
+static double pixelNdc(int i, int size) { return ((double)i + 0.5) * (2.0 / (double)size) - 1.0; }  // NDC of a pixel centre
 static void barycentrics(const TriPlanes& t, double px, double py, float l[3]) {
     const double e0 = t.c0.x * px + t.c0.y * py + t.c0.z, e1 = t.c1.x * px + t.c1.y * py + t.c1.z, e2 = t.c2.x * px + t.c2.y * py + t.c2.z;
-    const double sum = e0 + e1 + e2;
-    l[0] = (float)(e0 / sum); l[1] = (float)(e1 / sum); l[2] = (float)(e2 / sum);
+    const double inv = 1.0 / (e0 + e1 + e2);
+    l[0] = (float)(e0 * inv); l[1] = (float)(e1 * inv); l[2] = (float)(e2 * inv);
 }
 static float lerp3(const float l[3], float a, float b, float c) { return fma_(l[2], c, fma_(l[1], b, l[0] * a)); }
 static vec3 lerp3(const float l[3], vec3 a, vec3 b, vec3 c) { return vec3(lerp3(l, a.x, b.x, c.x), lerp3(l, a.y, b.y, c.y), lerp3(l, a.z, b.z, c.z)); }
@@ -136,8 +139,7 @@ static void rasterTriangle(const RasterTarget& rt, const vec4 clip[3], uint32_t 
                 for (int e = 0; e < 3; e++) inside = inside && (ex[e] * (py - ay[e]) - ey[e] * (px - ax[e]) + bias[e] >= 0);
                 if (!inside) continue;
                 const double nx = pixelNdc((int)ix, rt.W), ny = pixelNdc((int)iy, rt.H);
-                const double num = tp.num.x * nx + tp.num.y * ny + tp.num.z, den = tp.den.x * nx + tp.den.y * ny + tp.den.z;
-                float d = (float)(num / den);
+                float d = (float)(tp.depth.x * nx + (tp.depth.y * ny + tp.depth.z));  // the row term first (it is constant along a row)
                 if (d != d) continue;
                 if (rt.clampDepth) d = d < 0.f ? 0.f : (d > 1.f ? 1.f : d);
                 else if (d < 0.f || d > 1.f) continue;

@@ -87,7 +87,7 @@ struct Backend {
     std::vector<plain_sampler_desc> samplers;
     std::vector<PassRecord> passes;
     std::vector<DeviceMesh> meshes;
-    struct RasterScratch { RasterDraw* draws = nullptr; size_t drawCapacity = 0; uint32_t* triInfo = nullptr; size_t triCapacity = 0; };
+    struct RasterScratch { RasterDraw* draws = nullptr; size_t drawCapacity = 0; uint32_t* triInfo = nullptr; size_t triCapacity = 0; float* vertexCache = nullptr; size_t vertexCapacity = 0; };
     std::unordered_map<uint32_t, RasterScratch> rasterScratch;  // by pass handle
     struct VisBuffer { unsigned long long* ptr = nullptr; size_t texels = 0; };
     std::unordered_map<uint64_t, VisBuffer> visBuffers;         // by depth target (image handle + mip): shared by the prepass and the G-buffer fill
@@ -568,7 +568,7 @@ void PLAIN_FN(backend_destroy)(plain_ctx* ctx) {
     for (auto& i : b.images) if (i.downloadDone) cudaEventDestroy(i.downloadDone);
     for (auto& i : b.transientImages) if (i.downloadDone) cudaEventDestroy(i.downloadDone);
     for (auto& m : b.meshes) { cudaFree(m.indices); cudaFree(m.vertices); }
-    for (auto& kv : b.rasterScratch) { cudaFree(kv.second.draws); cudaFree(kv.second.triInfo); }
+    for (auto& kv : b.rasterScratch) { cudaFree(kv.second.draws); cudaFree(kv.second.triInfo); cudaFree(kv.second.vertexCache); }
     for (auto& kv : b.visBuffers) cudaFree(kv.second.ptr);
     for (auto& u : b.uniformBuffers) cudaFree(u.ptr);
     for (auto& s : b.storageBuffers) cudaFree(s.ptr);
@@ -845,15 +845,23 @@ static int prepareRaster(plain_ctx* ctx) {
         if (!p.graphic) continue;
         Backend::RasterScratch& sc = b.rasterScratch[e.pass];
         b.rasterDrawStaging.clear();
-        uint32_t first = 0;
+        uint32_t first = 0, firstVertex = 0;
         for (auto& d : e.draws) {
             const DeviceMesh& m = b.meshes[d.mesh];
             RasterDraw rd;
             rd.indices = m.indices; rd.vertices = m.vertices;
-            rd.firstPrimitive = first; rd.triCount = m.indexCount / 3; rd.index32 = m.index32; rd.pad = 0;
+            rd.firstPrimitive = first; rd.triCount = m.indexCount / 3; rd.index32 = m.index32;
+            rd.firstVertex = firstVertex; rd.vertexCount = m.vertexCount; rd.pad = 0;
             memcpy(rd.push, d.push, 16);
             b.rasterDrawStaging.push_back(rd);
             first += rd.triCount;
+            firstVertex += rd.vertexCount;
+        }
+        if ((size_t)firstVertex > sc.vertexCapacity) {
+            if (sc.vertexCache) cudaFree(sc.vertexCache);
+            sc.vertexCapacity = (size_t)firstVertex * 2 + 1024;
+            CU_CHECK(ctx, cudaMalloc(&sc.vertexCache, sc.vertexCapacity * PLAIN_RASTER_VERTEX_FLOATS * sizeof(float)));
+            b.passEpoch++;
         }
         if (b.rasterDrawStaging.size() > sc.drawCapacity) {
             if (sc.draws) cudaFree(sc.draws);
@@ -886,6 +894,8 @@ static int prepareRaster(plain_ctx* ctx) {
         e.rasterTriInfo = sc.triInfo;
         e.rasterVis = vb.ptr;
         e.rasterTotalTris = first;
+        e.rasterVertexCache = sc.vertexCache;
+        e.rasterTotalVertices = firstVertex;
     }
     return 0;
 }

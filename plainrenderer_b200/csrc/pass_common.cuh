@@ -50,9 +50,10 @@ struct DeviceMesh {  // MeshBinary (MeshData.h:27-35) in HBM
 struct RasterDraw {  // one entry of the device draw table of a graphic pass execution
     const unsigned char* indices;
     const unsigned char* vertices;
-    uint32_t firstPrimitive, triCount, index32, pad;
+    uint32_t firstPrimitive, triCount, index32, firstVertex, vertexCount, pad;
     uint32_t push[4];
 };
+#define PLAIN_RASTER_VERTEX_FLOATS 16  // one entry of a pass's post-transform vertex cache (64 bytes)
 struct DrawRecord { uint32_t mesh; uint8_t push[16]; };
 
 struct ExecRecord {
@@ -63,7 +64,8 @@ struct ExecRecord {
     const RasterDraw* rasterDraws = nullptr;
     uint32_t* rasterTriInfo = nullptr;          // per primitive: covered rows (y0 | y1 << 16) or ~0u; [totalTris] = big-triangle count; then the big-triangle list
     unsigned long long* rasterVis = nullptr;    // per pixel of the depth target: depth bits << 32 | primitive + 1
-    uint32_t rasterTotalTris = 0;
+    float* rasterVertexCache = nullptr;         // per (draw, vertex): the vertex stage's outputs, PLAIN_RASTER_VERTEX_FLOATS floats each
+    uint32_t rasterTotalTris = 0, rasterTotalVertices = 0;
     std::vector<plain_storage_buffer_resource> storageBuffers;
     std::vector<plain_uniform_buffer_resource> uniformBuffers;
     std::vector<plain_image_resource> sampledImages;

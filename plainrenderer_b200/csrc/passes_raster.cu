@@ -4,13 +4,16 @@
 //   sunShadow.vert + sunShadow.frag         one D16 shadow cascade (front faces culled, depth clamp)
 //   triangle.vert + gbufferFill.frag        the packed G-buffer (include/plain_frame_types.h): the interpolated inputs and material
 //                                           texels of triangle.frag:178-193 for the fragment that won the prepass (depth EQUAL)
-// Per pass: (1) rasterSetupKernel, a thread per triangle: vertex stage, clipping, window-space bounding rows; triangles taller
-// than 64 rows are appended to a list. (2) rasterCoverKernel<false>, a warp per small triangle: lanes = 32 consecutive pixels of
-// a row, exact integer edge functions, depth from the triangle's homogeneous plane equation in binary64, one 64-bit atomicMax of
-// (depth bits << 32 | primitive + 1) per covered pixel - the depth test GREATER_EQUAL in draw order. (3) rasterCoverKernel<true>,
+// Per pass: (0) rasterVertexKernel, a thread per (draw, vertex): the vertex stage once per vertex into a post-transform cache
+// (64 B per entry: clip position + what the fragment stage interpolates, tangent frame already normalised). (1) rasterSetupKernel,
+// a thread per triangle: clipping, window-space bounding rows; triangles taller than 64 rows are appended to a list.
+// (2) rasterCoverKernel<false>, a warp per small triangle: lanes = 32 consecutive pixels of a row, the row's span estimated from
+// the edge equations in binary64 (one pixel of slack) and decided by exact 64-bit integer edge functions, depth from the
+// triangle's affine depth plane in binary64, a read of the visibility texel and - only when the fragment would win - one 64-bit
+// atomicMax of (depth bits << 32 | primitive + 1): the depth test GREATER_EQUAL in draw order. (3) rasterCoverKernel<true>,
 // persistent warps over (big triangle, 64-row band) pairs, so a wall-sized triangle is spread over the whole GPU. (4) a resolve
-// kernel, a thread per pixel: the winning primitive's vertices are fetched again, perspective-correct barycentrics from the same
-// plane equations, the fragment stage, one coalesced store per attachment. The G-buffer fill reuses the prepass's visibility
+// kernel, a thread per pixel: the winning primitive's three cache entries, perspective-correct barycentrics from the same plane
+// equations, the fragment stage, one coalesced store per attachment. The G-buffer fill reuses the prepass's visibility
 // buffer (the reference rasterises everything twice, with depth test EQUAL the second time).
 // The rules the reference leaves to the Vulkan rasteriser are stated in oracle/passes_raster.cpp (header); this file follows them
 // operation by operation (binary64 clipping / plane equations, -fmad=false), so the results are bit-identical.
@@ -62,6 +65,8 @@ struct RasterParams {
     uint32_t drawCount, totalTris;
     uint32_t* triInfo;
     unsigned long long* vis;
+    float* vertexCache;
+    uint32_t totalVertices;
     int W, H;
     int clipNear, clampDepth, cullMode;
     int shadowProgram;                       // 0: clip = transforms[push[3]].mvp * pos; 1: clip = lightMatrices[cascade] * transforms[push[1]] * pos
@@ -70,31 +75,59 @@ struct RasterParams {
     const plain_shadow_cascade_info* cascades;
     uint32_t cascade;
 };
-// vertex stage of the three positions of one triangle (depthPrepass.vert:29, triangle.vert:30, sunShadow.vert:30)
-__device__ __forceinline__ void triangleClipPositions(const RasterParams& p, const RasterDraw& d, uint32_t tri, vec4 clip[3]) {
-    vec3 pos[3];
-#pragma unroll
-    for (int k = 0; k < 3; k++) pos[k] = fetchPosition(d, fetchIndex(d, tri * 3 + k));
-    if (!p.shadowProgram) {
-        const float* mvp = p.mainTransforms[d.push[3]].mvp;
-#pragma unroll
-        for (int k = 0; k < 3; k++) clip[k] = mulm4(mvp, v4(pos[k], 1.f));
-    } else {
+// ---- (0) vertex stage, once per (draw, vertex): depthPrepass.vert:28-42, triangle.vert:29-40, sunShadow.vert:29-32 ----
+// cache entry (16 floats): [0..3] clip position; KIND 0 (prepass): [4..7] previous clip position, [8..10] N;
+// KIND 1 (G-buffer fill): [4..6] T, [7..9] B, [10..12] N, [13..14] uv; KIND 2 (shadow): clip only
+__device__ __forceinline__ const RasterDraw& drawOfVertex(const RasterDraw* draws, uint32_t drawCount, uint32_t entry) {
+    uint32_t lo = 0, hi = drawCount;
+    while (hi - lo > 1) { const uint32_t mid = (lo + hi) / 2; if (draws[mid].firstVertex <= entry) lo = mid; else hi = mid; }
+    return draws[lo];
+}
+template <int KIND>
+__global__ void __launch_bounds__(256) rasterVertexKernel(const __grid_constant__ RasterParams p) {
+    const uint32_t entry = blockIdx.x * 256 + threadIdx.x;
+    if (entry >= p.totalVertices) return;
+    const RasterDraw& d = drawOfVertex(p.draws, p.drawCount, entry);
+    const VertexIn v = fetchVertex(d, entry - d.firstVertex);
+    float4* out = (float4*)(p.vertexCache + (size_t)entry * PLAIN_RASTER_VERTEX_FLOATS);
+    if (KIND == 2) {
         const float* L = p.cascades->lightMatrices[p.cascade];
         const float* T = p.shadowTransforms + (size_t)d.push[1] * 16;
-        float M[16];
+        float M[16];  // lightMatrices[cascadeIndex] * transforms[transformIndex]
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             const vec4 c = mulm4(L, v4(T[j * 4], T[j * 4 + 1], T[j * 4 + 2], T[j * 4 + 3]));
             M[j * 4] = c.x; M[j * 4 + 1] = c.y; M[j * 4 + 2] = c.z; M[j * 4 + 3] = c.w;
         }
-#pragma unroll
-        for (int k = 0; k < 3; k++) clip[k] = mulm4(M, v4(pos[k], 1.f));
+        const vec4 clip = mulm4(M, v4(v.pos, 1.f));
+        out[0] = make_float4(clip.x, clip.y, clip.z, clip.w);
+        return;
     }
+    const MainPassMatrices& tr = p.mainTransforms[d.push[3]];
+    const vec4 clip = mulm4(tr.mvp, v4(v.pos, 1.f));
+    out[0] = make_float4(clip.x, clip.y, clip.z, clip.w);
+    const vec3 N = normalize(mulMat3(tr.model, v.normal));
+    if (KIND == 0) {
+        const vec4 prev = mulm4(tr.mvpPrevious, v4(v.pos, 1.f));
+        out[1] = make_float4(prev.x, prev.y, prev.z, prev.w);
+        out[2] = make_float4(N.x, N.y, N.z, 0.f);
+    } else {
+        const vec3 T = normalize(mulMat3(tr.model, v.tangent)), B = normalize(mulMat3(tr.model, v.bitangent));
+        out[1] = make_float4(T.x, T.y, T.z, B.x);
+        out[2] = make_float4(B.y, B.z, N.x, N.y);
+        out[3] = make_float4(N.z, v.uv.x, v.uv.y, 0.f);
+    }
+}
+__device__ __forceinline__ const float4* cacheEntry(const RasterParams& p, const RasterDraw& d, uint32_t tri, int k) {
+    return (const float4*)(p.vertexCache + (size_t)(d.firstVertex + fetchIndex(d, tri * 3 + k)) * PLAIN_RASTER_VERTEX_FLOATS);
+}
+__device__ __forceinline__ void triangleClipPositions(const RasterParams& p, const RasterDraw& d, uint32_t tri, vec4 clip[3]) {
+#pragma unroll
+    for (int k = 0; k < 3; k++) { const float4 c = cacheEntry(p, d, tri, k)[0]; clip[k] = v4(c.x, c.y, c.z, c.w); }
 }
 
 // ---- homogeneous plane equations of one (unclipped) triangle ----
-struct TriPlanes { D3 c0, c1, c2, num, den; };
+struct TriPlanes { D3 c0, c1, c2, depth; };
 __device__ __forceinline__ TriPlanes trianglePlanes(const vec4 clip[3]) {
     D3 v[3];
     double z[3], w[3];
@@ -102,15 +135,16 @@ __device__ __forceinline__ TriPlanes trianglePlanes(const vec4 clip[3]) {
     for (int i = 0; i < 3; i++) { v[i] = D3{(double)clip[i].x, (double)clip[i].y, (double)clip[i].w}; z[i] = (double)clip[i].z; w[i] = (double)clip[i].w; }
     TriPlanes t;
     t.c0 = crossd(v[1], v[2]); t.c1 = crossd(v[2], v[0]); t.c2 = crossd(v[0], v[1]);
-    t.num = D3{t.c0.x * z[0] + t.c1.x * z[1] + t.c2.x * z[2], t.c0.y * z[0] + t.c1.y * z[1] + t.c2.y * z[2], t.c0.z * z[0] + t.c1.z * z[1] + t.c2.z * z[2]};
-    t.den = D3{t.c0.x * w[0] + t.c1.x * w[1] + t.c2.x * w[2], t.c0.y * w[0] + t.c1.y * w[1] + t.c2.y * w[2], t.c0.z * w[0] + t.c1.z * w[1] + t.c2.z * w[2]};
+    const D3 num = D3{t.c0.x * z[0] + t.c1.x * z[1] + t.c2.x * z[2], t.c0.y * z[0] + t.c1.y * z[1] + t.c2.y * z[2], t.c0.z * z[0] + t.c1.z * z[1] + t.c2.z * z[2]};
+    const double det = t.c0.z * w[0] + t.c1.z * w[1] + t.c2.z * w[2];
+    t.depth = D3{num.x / det, num.y / det, num.z / det};
     return t;
 }
-__device__ __forceinline__ double pixelNdc(int i, int size) { return ((double)i + 0.5) / (double)size * 2.0 - 1.0; }
+__device__ __forceinline__ double pixelNdc(int i, int size) { return ((double)i + 0.5) * (2.0 / (double)size) - 1.0; }  // NDC of a pixel centre
 __device__ __forceinline__ void barycentrics(const TriPlanes& t, double px, double py, float l[3]) {
     const double e0 = t.c0.x * px + t.c0.y * py + t.c0.z, e1 = t.c1.x * px + t.c1.y * py + t.c1.z, e2 = t.c2.x * px + t.c2.y * py + t.c2.z;
-    const double sum = e0 + e1 + e2;
-    l[0] = (float)(e0 / sum); l[1] = (float)(e1 / sum); l[2] = (float)(e2 / sum);
+    const double inv = 1.0 / (e0 + e1 + e2);
+    l[0] = (float)(e0 * inv); l[1] = (float)(e1 * inv); l[2] = (float)(e2 * inv);
 }
 __device__ __forceinline__ float lerp3(const float l[3], float a, float b, float c) { return fmaf_(l[2], c, fmaf_(l[1], b, l[0] * a)); }
 __device__ __forceinline__ vec3 lerp3(const float l[3], vec3 a, vec3 b, vec3 c) { return v3(lerp3(l, a.x, b.x, c.x), lerp3(l, a.y, b.y, c.y), lerp3(l, a.z, b.z, c.z)); }
@@ -218,26 +252,36 @@ __device__ void coverTriangle(const RasterParams& p, uint32_t prim, int rowBegin
         for (int iy = ya; iy <= yb; iy++) {
             const long long py = (long long)iy * 256 + 128;
             const double ny = pixelNdc(iy, p.H);
-            // edge functions along the row: E_e(px) = rowTerm_e - ey_e * (px - ax_e)
-            long long rowTerm[3];
+            // edge functions along the row, in pixels: E_e(ix) = base_e - step_e * ix (exact, 64-bit integers)
+            long long base[3], step[3];
+            double lo = (double)s.ix0, hi = (double)s.ix1;
+            bool rowEmpty = false;
 #pragma unroll
-            for (int e = 0; e < 3; e++) rowTerm[e] = s.ex[e] * (py - s.ay[e]) + s.bias[e];
-            for (int xb = s.ix0 & ~31; xb <= s.ix1; xb += 32) {
+            for (int e = 0; e < 3; e++) {
+                step[e] = s.ey[e] * 256;
+                base[e] = s.ex[e] * (py - s.ay[e]) + s.bias[e] - s.ey[e] * (128 - s.ax[e]);
+                // the span of the row from the real-valued inequality step * ix <= base, one pixel of slack: only narrows the loop
+                if (step[e] > 0) hi = fmin(hi, (double)base[e] / (double)step[e] + 1.0);
+                else if (step[e] < 0) lo = fmax(lo, (double)base[e] / (double)step[e] - 1.0);
+                else if (base[e] < 0) rowEmpty = true;
+            }
+            if (rowEmpty || !(lo <= hi)) continue;
+            const int xa = imax(s.ix0, (int)floor(lo)), xe = imin(s.ix1, (int)ceil(hi));
+            const double rowDepth = tp.depth.y * ny + tp.depth.z;
+            for (int xb = xa & ~31; xb <= xe; xb += 32) {
                 const int ix = xb + lane;
-                if (ix < s.ix0 || ix > s.ix1) continue;
-                const long long px = (long long)ix * 256 + 128;
+                if (ix < xa || ix > xe) continue;
                 bool inside = true;
 #pragma unroll
-                for (int e = 0; e < 3; e++) inside = inside && (rowTerm[e] - s.ey[e] * (px - s.ax[e]) >= 0);
+                for (int e = 0; e < 3; e++) inside = inside && (base[e] - step[e] * (long long)ix >= 0);
                 if (!inside) continue;
-                const double nx = pixelNdc(ix, p.W);
-                const double num = tp.num.x * nx + tp.num.y * ny + tp.num.z, den = tp.den.x * nx + tp.den.y * ny + tp.den.z;
-                float dep = (float)(num / den);
+                float dep = (float)(tp.depth.x * pixelNdc(ix, p.W) + rowDepth);
                 if (dep != dep) continue;
                 if (p.clampDepth) dep = dep < 0.f ? 0.f : (dep > 1.f ? 1.f : dep);
                 else if (dep < 0.f || dep > 1.f) continue;
                 const unsigned long long key = ((unsigned long long)(__float_as_uint(dep) & 0x7fffffffu) << 32) | keyLow;
-                atomicMax(p.vis + (size_t)iy * p.W + ix, key);
+                unsigned long long* slot = p.vis + (size_t)iy * p.W + ix;
+                if (key > *(volatile unsigned long long*)slot) atomicMax(slot, key);  // the texel only grows: a stale read can only cost an atomic
             }
         }
     }
@@ -266,10 +310,12 @@ __global__ void __launch_bounds__(256) rasterCoverKernel(const __grid_constant__
         }
     }
 }
+template <int KIND>
 static void launchCoverage(LaunchCtx& c, const RasterParams& p) {
     cudaMemsetAsync(p.vis, 0, (size_t)p.W * p.H * sizeof(unsigned long long), c.stream);  // attachments are cleared (RenderPass.cpp:95-110)
     if (p.totalTris == 0) return;
     cudaMemsetAsync(p.triInfo + p.totalTris, 0, sizeof(uint32_t), c.stream);
+    PLAIN_LAUNCH(c, rasterVertexKernel<KIND>, ceilDiv(p.totalVertices, 256), 256, 0, p);
     PLAIN_LAUNCH(c, rasterSetupKernel, ceilDiv(p.totalTris, 128), 128, 0, p);
     PLAIN_LAUNCH(c, rasterCoverKernel<false>, ceilDiv(p.totalTris, 8), 256, 0, p);
     PLAIN_LAUNCH(c, rasterCoverKernel<true>, (unsigned)c.smCount * 4, 256, 0, p);
@@ -280,12 +326,14 @@ static bool fillRasterParams(LaunchCtx& c, RasterParams& p, const ImgView& depth
     p.totalTris = c.exec->rasterTotalTris;
     p.triInfo = c.exec->rasterTriInfo;
     p.vis = c.exec->rasterVis;
+    p.vertexCache = c.exec->rasterVertexCache;
+    p.totalVertices = c.exec->rasterTotalVertices;
     p.W = depthTarget.w; p.H = depthTarget.h;
     p.clipNear = c.pass->clampDepth ? 0 : 1;
     p.clampDepth = c.pass->clampDepth ? 1 : 0;
     p.cullMode = (int)c.pass->cullMode;
     p.shadowProgram = 0; p.mainTransforms = nullptr; p.shadowTransforms = nullptr; p.cascades = nullptr; p.cascade = 0;
-    if (!p.vis || (p.totalTris && (!p.draws || !p.triInfo))) { c.fail(c.pass->shader + ": rasteriser scratch missing (render_frame prepares it)"); return false; }
+    if (!p.vis || (p.totalTris && (!p.draws || !p.triInfo || !p.vertexCache))) { c.fail(c.pass->shader + ": rasteriser scratch missing (render_frame prepares it)"); return false; }
     if (p.W > 65535 || p.H > 65535) { c.fail(c.pass->shader + ": render targets beyond 65535 pixels are not supported"); return false; }
     return true;
 }
@@ -302,15 +350,15 @@ __global__ void __launch_bounds__(256) depthPrepassResolveKernel(const __grid_co
         depth = __uint_as_float((uint32_t)(key >> 32));
         const uint32_t primitive = (uint32_t)(key & 0xffffffffu) - 1u;
         const RasterDraw& d = drawOfPrimitive(p.draws, p.drawCount, primitive);
-        const MainPassMatrices& tr = p.mainTransforms[d.push[3]];
         vec4 passPos[3], passPosPrevious[3];
         vec3 N[3];
 #pragma unroll
         for (int k = 0; k < 3; k++) {
-            const VertexIn v = fetchVertex(d, fetchIndex(d, (primitive - d.firstPrimitive) * 3 + k));
-            passPos[k] = mulm4(tr.mvp, v4(v.pos, 1.f));
-            passPosPrevious[k] = mulm4(tr.mvpPrevious, v4(v.pos, 1.f));
-            N[k] = normalize(mulMat3(tr.model, v.normal));
+            const float4* e = cacheEntry(p, d, primitive - d.firstPrimitive, k);
+            const float4 a = e[0], b = e[1], n = e[2];
+            passPos[k] = v4(a.x, a.y, a.z, a.w);
+            passPosPrevious[k] = v4(b.x, b.y, b.z, b.w);
+            N[k] = v3(n.x, n.y, n.z);
         }
         float l[3];
         barycentrics(trianglePlanes(passPos), pixelNdc(ix, p.W), pixelNdc(iy, p.H), l);
@@ -339,7 +387,7 @@ PLAIN_PASS(launch_depthPrepass, "depthPrepass.vert+depthPrepass.frag") {
     if (!fillRasterParams(c, p, depthT)) return;
     p.mainTransforms = c.sbuf<MainPassMatrices>(0);
     if (c.failed) return;
-    launchCoverage(c, p);
+    launchCoverage<0>(c, p);
     PLAIN_LAUNCH(c, depthPrepassResolveKernel, dim3(ceilDiv(p.W, 32), ceilDiv(p.H, 8)), 256, 0, p, motionT, normalT, depthT, c.g);
 }
 
@@ -361,7 +409,7 @@ PLAIN_PASS(launch_sunShadow, "sunShadow.vert+sunShadow.frag") {
     p.cascade = c.spec<uint32_t>(0, 0);
     if (c.failed) return;
     if (p.cascade > 3) { c.fail("sunShadow.vert: cascade index must be 0..3"); return; }
-    launchCoverage(c, p);
+    launchCoverage<2>(c, p);
     PLAIN_LAUNCH(c, shadowResolveKernel, dim3(ceilDiv(p.W, 32), ceilDiv(p.H, 8)), 256, 0, p.vis, shadowMap);
 }
 
@@ -389,18 +437,18 @@ __global__ void __launch_bounds__(256) gbufferFillResolveKernel(const __grid_con
     if (key) {
         const uint32_t primitive = (uint32_t)(key & 0xffffffffu) - 1u;
         const RasterDraw& d = drawOfPrimitive(p.draws, p.drawCount, primitive);
-        const MainPassMatrices& tr = p.mainTransforms[d.push[3]];
         vec4 clip[3];
         vec2 uv[3];
         vec3 T[3], B[3], N[3];
 #pragma unroll
         for (int k = 0; k < 3; k++) {
-            const VertexIn v = fetchVertex(d, fetchIndex(d, (primitive - d.firstPrimitive) * 3 + k));
-            clip[k] = mulm4(tr.mvp, v4(v.pos, 1.f));
-            uv[k] = v.uv;
-            T[k] = normalize(mulMat3(tr.model, v.tangent));
-            N[k] = normalize(mulMat3(tr.model, v.normal));
-            B[k] = normalize(mulMat3(tr.model, v.bitangent));
+            const float4* e = cacheEntry(p, d, primitive - d.firstPrimitive, k);
+            const float4 a = e[0], b = e[1], c2 = e[2], c3 = e[3];
+            clip[k] = v4(a.x, a.y, a.z, a.w);
+            T[k] = v3(b.x, b.y, b.z);
+            B[k] = v3(b.w, c2.x, c2.y);
+            N[k] = v3(c2.z, c2.w, c3.x);
+            uv[k] = v2(c3.y, c3.z);
         }
         float l[3];
         barycentrics(trianglePlanes(clip), pixelNdc(ix, p.W), pixelNdc(iy, p.H), l);
@@ -436,6 +484,7 @@ PLAIN_PASS(launch_gbufferFill, "triangle.vert+gbufferFill.frag") {
             if (index >= c.be_imageCount() || c.be_imageFormat(index) != PLAIN_FORMAT_RGBA8) { c.fail("gbufferFill: material textures must be RGBA8 images (bindless index = image handle index)"); return; }
         }
     // no coverage pass: the visibility buffer of the prepass over the same draws decides (depth test EQUAL)
+    if (p.totalVertices) PLAIN_LAUNCH(c, rasterVertexKernel<1>, ceilDiv(p.totalVertices, 256), 256, 0, p);
     PLAIN_LAUNCH(c, gbufferFillResolveKernel, dim3(ceilDiv(p.W, 32), ceilDiv(p.H, 8)), 256, 0, p, gbuffer, c.bindless);
 }
 
