@@ -212,8 +212,26 @@ __device__ __forceinline__ bool subTriangle(const RasterParams& p, const ScreenP
     return s.ix0 <= s.ix1 && s.iy0 <= s.iy1;
 }
 
-#define RASTER_BAND_ROWS 64
-// (1) a thread per triangle: the rows it can cover; tall triangles go to the list behind the counter at triInfo[totalTris]
+// depth of a covered pixel + the depth test: GREATER_EQUAL in draw order = maximum of (depth bits, primitive + 1)
+__device__ __forceinline__ void emitFragment(const RasterParams& p, const TriPlanes& tp, int ix, int iy, double rowDepth, unsigned long long keyLow) {
+    float dep = (float)(tp.depth.x * pixelNdc(ix, p.W) + rowDepth);
+    if (dep != dep) return;
+    if (p.clampDepth) dep = dep < 0.f ? 0.f : (dep > 1.f ? 1.f : dep);
+    else if (dep < 0.f || dep > 1.f) return;
+    const unsigned long long key = ((unsigned long long)(__float_as_uint(dep) & 0x7fffffffu) << 32) | keyLow;
+    unsigned long long* slot = p.vis + (size_t)iy * p.W + ix;
+    if (key > *(volatile unsigned long long*)slot) atomicMax(slot, key);  // the texel only grows: a stale read can only cost an atomic
+}
+
+// A triangle whose window-space bounding box is at most 256 pixels is "tiny": the set-up thread rasterises it on the spot.
+#define RASTER_TINY_MAX_AREA 256
+// A triangle whose window-space bounding box is taller than 64 rows or larger than 8192 pixels is "big": it is rasterised by the
+// persistent kernel in bands of 8 rows (one warp per band), so that a screen-wide wall is spread over a few hundred warps.
+#define RASTER_SMALL_MAX_ROWS 64
+#define RASTER_SMALL_MAX_AREA 8192
+#define RASTER_BIG_BAND_ROWS 8
+#define RASTER_BIG_FLAG 0x80000000u
+// (1) a thread per triangle: the rows it can cover (y0 | y1 << 16 | big flag); big triangles go to the list behind the counter at triInfo[totalTris]
 __global__ void __launch_bounds__(128) rasterSetupKernel(const __grid_constant__ RasterParams p) {
     const uint32_t prim = blockIdx.x * 128 + threadIdx.x;
     if (prim >= p.totalTris) return;
@@ -222,16 +240,45 @@ __global__ void __launch_bounds__(128) rasterSetupKernel(const __grid_constant__
     triangleClipPositions(p, d, prim - d.firstPrimitive, clip);
     ScreenPoly sp;
     clipAndSnap(p, clip, sp);
-    int y0 = 0x7fffffff, y1 = -1;
+    int y0 = 0x7fffffff, y1 = -1, x0 = 0x7fffffff, x1 = -1;
     for (int k = 1; k + 1 < sp.n; k++) {
         SubTriangle s;
         if (!subTriangle(p, sp, k, s)) continue;
         y0 = imin(y0, s.iy0); y1 = imax(y1, s.iy1);
+        x0 = imin(x0, s.ix0); x1 = imax(x1, s.ix1);
     }
     uint32_t info = 0xffffffffu;
-    if (y1 >= y0) {
+    if (y1 >= y0 && (long long)(y1 - y0 + 1) * (x1 - x0 + 1) <= RASTER_TINY_MAX_AREA) {
+        // tiny: this thread walks the few pixels itself (no second set-up by a warp); nothing is left for the coverage kernels
+        const TriPlanes tp = trianglePlanes(clip);
+        const unsigned long long keyLow = (unsigned long long)(prim + 1u);
+        for (int k = 1; k + 1 < sp.n; k++) {
+            SubTriangle s;
+            if (!subTriangle(p, sp, k, s)) continue;
+            for (int iy = s.iy0; iy <= s.iy1; iy++) {
+                const long long py = (long long)iy * 256 + 128;
+                const double rowDepth = tp.depth.y * pixelNdc(iy, p.H) + tp.depth.z;
+                long long base[3], step[3];
+#pragma unroll
+                for (int e = 0; e < 3; e++) {
+                    step[e] = s.ey[e] * 256;
+                    base[e] = s.ex[e] * (py - s.ay[e]) + s.bias[e] - s.ey[e] * (128 - s.ax[e]);
+                }
+                for (int ix = s.ix0; ix <= s.ix1; ix++) {
+                    bool inside = true;
+#pragma unroll
+                    for (int e = 0; e < 3; e++) inside = inside && (base[e] - step[e] * (long long)ix >= 0);
+                    if (inside) emitFragment(p, tp, ix, iy, rowDepth, keyLow);
+                }
+            }
+        }
+    } else if (y1 >= y0) {
         info = (uint32_t)y0 | ((uint32_t)y1 << 16);
-        if (y1 - y0 + 1 > RASTER_BAND_ROWS) p.triInfo[p.totalTris + 1 + atomicAdd(&p.triInfo[p.totalTris], 1u)] = prim;
+        const int rows = y1 - y0 + 1;
+        if (rows > RASTER_SMALL_MAX_ROWS || (long long)rows * (x1 - x0 + 1) > RASTER_SMALL_MAX_AREA) {
+            info |= RASTER_BIG_FLAG;
+            p.triInfo[p.totalTris + 1 + atomicAdd(&p.triInfo[p.totalTris], 1u)] = prim;
+        }
     }
     p.triInfo[prim] = info;
 }
@@ -254,19 +301,26 @@ __device__ void coverTriangle(const RasterParams& p, uint32_t prim, int rowBegin
             const double ny = pixelNdc(iy, p.H);
             // edge functions along the row, in pixels: E_e(ix) = base_e - step_e * ix (exact, 64-bit integers)
             long long base[3], step[3];
-            double lo = (double)s.ix0, hi = (double)s.ix1;
-            bool rowEmpty = false;
 #pragma unroll
             for (int e = 0; e < 3; e++) {
                 step[e] = s.ey[e] * 256;
                 base[e] = s.ex[e] * (py - s.ay[e]) + s.bias[e] - s.ey[e] * (128 - s.ax[e]);
-                // the span of the row from the real-valued inequality step * ix <= base, one pixel of slack: only narrows the loop
-                if (step[e] > 0) hi = fmin(hi, (double)base[e] / (double)step[e] + 1.0);
-                else if (step[e] < 0) lo = fmax(lo, (double)base[e] / (double)step[e] - 1.0);
-                else if (base[e] < 0) rowEmpty = true;
             }
-            if (rowEmpty || !(lo <= hi)) continue;
-            const int xa = imax(s.ix0, (int)floor(lo)), xe = imin(s.ix1, (int)ceil(hi));
+            int xa = s.ix0, xe = s.ix1;
+            if (xe - xa >= 96) {
+                // wide rows: the span from the real-valued inequality step * ix <= base with one pixel of slack; it only narrows
+                // the loop, the exact test below decides
+                double lo = (double)xa, hi = (double)xe;
+                bool rowEmpty = false;
+#pragma unroll
+                for (int e = 0; e < 3; e++) {
+                    if (step[e] > 0) hi = fmin(hi, (double)base[e] / (double)step[e] + 1.0);
+                    else if (step[e] < 0) lo = fmax(lo, (double)base[e] / (double)step[e] - 1.0);
+                    else if (base[e] < 0) rowEmpty = true;
+                }
+                if (rowEmpty || !(lo <= hi)) continue;
+                xa = imax(xa, (int)floor(lo)); xe = imin(xe, (int)ceil(hi));
+            }
             const double rowDepth = tp.depth.y * ny + tp.depth.z;
             for (int xb = xa & ~31; xb <= xe; xb += 32) {
                 const int ix = xb + lane;
@@ -274,14 +328,7 @@ __device__ void coverTriangle(const RasterParams& p, uint32_t prim, int rowBegin
                 bool inside = true;
 #pragma unroll
                 for (int e = 0; e < 3; e++) inside = inside && (base[e] - step[e] * (long long)ix >= 0);
-                if (!inside) continue;
-                float dep = (float)(tp.depth.x * pixelNdc(ix, p.W) + rowDepth);
-                if (dep != dep) continue;
-                if (p.clampDepth) dep = dep < 0.f ? 0.f : (dep > 1.f ? 1.f : dep);
-                else if (dep < 0.f || dep > 1.f) continue;
-                const unsigned long long key = ((unsigned long long)(__float_as_uint(dep) & 0x7fffffffu) << 32) | keyLow;
-                unsigned long long* slot = p.vis + (size_t)iy * p.W + ix;
-                if (key > *(volatile unsigned long long*)slot) atomicMax(slot, key);  // the texel only grows: a stale read can only cost an atomic
+                if (inside) emitFragment(p, tp, ix, iy, rowDepth, keyLow);
             }
         }
     }
@@ -293,18 +340,17 @@ __global__ void __launch_bounds__(256) rasterCoverKernel(const __grid_constant__
     if (!BIG) {
         if (warp >= p.totalTris) return;
         const uint32_t info = p.triInfo[warp];
-        if (info == 0xffffffffu) return;
-        const int y0 = (int)(info & 0xffffu), y1 = (int)(info >> 16);
-        if (y1 - y0 + 1 > RASTER_BAND_ROWS) return;
-        coverTriangle(p, warp, y0, y1);
+        if (info == 0xffffffffu || (info & RASTER_BIG_FLAG)) return;
+        coverTriangle(p, warp, (int)(info & 0xffffu), (int)(info >> 16));
     } else {
         const uint32_t bigCount = p.triInfo[p.totalTris], warps = gridDim.x * 8u;
-        const uint32_t bands = ((uint32_t)p.H + RASTER_BAND_ROWS - 1) / RASTER_BAND_ROWS;
-        for (uint32_t item = warp; item < bigCount * bands; item += warps) {
-            const uint32_t prim = p.triInfo[p.totalTris + 1 + item / bands], band = item % bands;
+        const uint32_t bands = ((uint32_t)p.H + RASTER_BIG_BAND_ROWS - 1) / RASTER_BIG_BAND_ROWS;
+        const unsigned long long items = (unsigned long long)bigCount * bands;
+        for (unsigned long long item = warp; item < items; item += warps) {
+            const uint32_t prim = p.triInfo[p.totalTris + 1 + (uint32_t)(item / bands)], band = (uint32_t)(item % bands);
             const uint32_t info = p.triInfo[prim];
-            const int y0 = (int)(info & 0xffffu), y1 = (int)(info >> 16);
-            const int ra = (int)band * RASTER_BAND_ROWS, rb = ra + RASTER_BAND_ROWS - 1;
+            const int y0 = (int)(info & 0xffffu), y1 = (int)((info & ~RASTER_BIG_FLAG) >> 16);
+            const int ra = (int)band * RASTER_BIG_BAND_ROWS, rb = ra + RASTER_BIG_BAND_ROWS - 1;
             if (rb < y0 || ra > y1) continue;
             coverTriangle(p, prim, imax(ra, y0), imin(rb, y1));
         }
@@ -334,7 +380,7 @@ static bool fillRasterParams(LaunchCtx& c, RasterParams& p, const ImgView& depth
     p.cullMode = (int)c.pass->cullMode;
     p.shadowProgram = 0; p.mainTransforms = nullptr; p.shadowTransforms = nullptr; p.cascades = nullptr; p.cascade = 0;
     if (!p.vis || (p.totalTris && (!p.draws || !p.triInfo || !p.vertexCache))) { c.fail(c.pass->shader + ": rasteriser scratch missing (render_frame prepares it)"); return false; }
-    if (p.W > 65535 || p.H > 65535) { c.fail(c.pass->shader + ": render targets beyond 65535 pixels are not supported"); return false; }
+    if (p.W > 32767 || p.H > 32767) { c.fail(c.pass->shader + ": render targets beyond 32767 pixels are not supported"); return false; }
     return true;
 }
 __device__ __forceinline__ int toSnorm16(float v) { if (v != v) return 0; return (int)floorf_(clampf(v, -1.f, 1.f) * 32767.f + 0.5f); }
