@@ -6,12 +6,14 @@
 //                                           texels of triangle.frag:178-193 for the fragment that won the prepass (depth EQUAL)
 // Per pass: (0) rasterVertexKernel, a thread per (draw, vertex): the vertex stage once per vertex into a post-transform cache
 // (64 B per entry: clip position + what the fragment stage interpolates, tangent frame already normalised). (1) rasterSetupKernel,
-// a thread per triangle: clipping, window-space bounding rows; triangles taller than 64 rows are appended to a list.
-// (2) rasterCoverKernel<false>, a warp per small triangle: lanes = 32 consecutive pixels of a row, the row's span estimated from
-// the edge equations in binary64 (one pixel of slack) and decided by exact 64-bit integer edge functions, depth from the
-// triangle's affine depth plane in binary64, a read of the visibility texel and - only when the fragment would win - one 64-bit
-// atomicMax of (depth bits << 32 | primitive + 1): the depth test GREATER_EQUAL in draw order. (3) rasterCoverKernel<true>,
-// persistent warps over (big triangle, 64-row band) pairs, so a wall-sized triangle is spread over the whole GPU. (4) a resolve
+// a thread per triangle: clipping, snapping, culling, the window-space bounding box. Three classes by that box: TINY (<= 1024
+// pixels) is rasterised by the set-up thread on the spot; BIG (taller than 64 rows or more than 8192 pixels) is appended to a
+// list; the rest is SMALL. (2) rasterCoverKernel<false>, a warp per small triangle: lanes = 32 consecutive pixels of a row,
+// exact 64-bit integer edge functions (rows wider than 96 pixels first narrow their span from the edge equations in binary64,
+// one pixel of slack), depth from the triangle's affine depth plane in binary64, a read of the visibility texel and - only when
+// the fragment would win - one 64-bit atomicMax of (depth bits << 32 | primitive + 1): the depth test GREATER_EQUAL in draw
+// order. (3) rasterCoverKernel<true>, persistent warps over (big triangle, 8-row band) pairs, so a wall-sized triangle is
+// spread over a few hundred warps. (4) a resolve
 // kernel, a thread per pixel: the winning primitive's three cache entries, perspective-correct barycentrics from the same plane
 // equations, the fragment stage, one coalesced store per attachment. The G-buffer fill reuses the prepass's visibility
 // buffer (the reference rasterises everything twice, with depth test EQUAL the second time).
@@ -223,8 +225,8 @@ __device__ __forceinline__ void emitFragment(const RasterParams& p, const TriPla
     if (key > *(volatile unsigned long long*)slot) atomicMax(slot, key);  // the texel only grows: a stale read can only cost an atomic
 }
 
-// A triangle whose window-space bounding box is at most 256 pixels is "tiny": the set-up thread rasterises it on the spot.
-#define RASTER_TINY_MAX_AREA 256
+// A triangle whose window-space bounding box is at most 1024 pixels is "tiny": the set-up thread rasterises it on the spot.
+#define RASTER_TINY_MAX_AREA 1024
 // A triangle whose window-space bounding box is taller than 64 rows or larger than 8192 pixels is "big": it is rasterised by the
 // persistent kernel in bands of 8 rows (one warp per band), so that a screen-wide wall is spread over a few hundred warps.
 #define RASTER_SMALL_MAX_ROWS 64
