@@ -471,13 +471,14 @@ __device__ __forceinline__ uint32_t octEncodeSnorm16(vec3 n) {  // inverse of th
     }
     return ((uint32_t)toSnorm16(x) & 0xffffu) | ((uint32_t)toSnorm16(y) << 16);
 }
-__device__ __forceinline__ vec4 sampleRGBA8LinearRepeat(const ImgView& t, vec2 uv) {
+// unorm8 = the exact table float(b) / 255 over the 256 byte values (pass_common.cuh ShadingTables): same bits as the division
+__device__ __forceinline__ vec4 sampleRGBA8LinearRepeat(const ImgView& t, vec2 uv, const float* __restrict__ unorm8Table) {
     return sampleLinear2D<WRAP_REPEAT, vec4>([&](int x, int y) {
         const uint32_t v = ldg((const uint32_t*)t.ptr + texelIndex(t, x, y));
-        return v4(unorm8(v & 0xffu), unorm8((v >> 8) & 0xffu), unorm8((v >> 16) & 0xffu), unorm8(v >> 24));
+        return v4(ldg(unorm8Table + (v & 0xffu)), ldg(unorm8Table + ((v >> 8) & 0xffu)), ldg(unorm8Table + ((v >> 16) & 0xffu)), ldg(unorm8Table + (v >> 24)));
     }, t.w, t.h, uv, v4(0.f));
 }
-__global__ void __launch_bounds__(256) gbufferFillResolveKernel(const __grid_constant__ RasterParams p, ImgView gbuffer, const BindlessEntry* __restrict__ bindless) {
+__global__ void __launch_bounds__(256) gbufferFillResolveKernel(const __grid_constant__ RasterParams p, ImgView gbuffer, const BindlessEntry* __restrict__ bindless, const float* __restrict__ unorm8Table) {
     const int ix = blockIdx.x * 32 + (threadIdx.x & 31), iy = blockIdx.y * 8 + (threadIdx.x >> 5);
     if (ix >= p.W || iy >= p.H) return;
     const unsigned long long key = p.vis[(size_t)iy * p.W + ix];
@@ -502,9 +503,9 @@ __global__ void __launch_bounds__(256) gbufferFillResolveKernel(const __grid_con
         barycentrics(trianglePlanes(clip), pixelNdc(ix, p.W), pixelNdc(iy, p.H), l);
         const vec2 passUV = v2(lerp3(l, uv[0].x, uv[1].x, uv[2].x), lerp3(l, uv[0].y, uv[1].y, uv[2].y));
         const vec3 tbnT = lerp3(l, T[0], T[1], T[2]), tbnB = lerp3(l, B[0], B[1], B[2]), tbnN = lerp3(l, N[0], N[1], N[2]);
-        const vec4 albedoTexel = sampleRGBA8LinearRepeat(bindless[d.push[0]].view, passUV);
-        const vec4 normalTexel = sampleRGBA8LinearRepeat(bindless[d.push[1]].view, passUV);
-        const vec4 specularTexel = sampleRGBA8LinearRepeat(bindless[d.push[2]].view, passUV);
+        const vec4 albedoTexel = sampleRGBA8LinearRepeat(bindless[d.push[0]].view, passUV, unorm8Table);
+        const vec4 normalTexel = sampleRGBA8LinearRepeat(bindless[d.push[1]].view, passUV, unorm8Table);
+        const vec4 specularTexel = sampleRGBA8LinearRepeat(bindless[d.push[2]].view, passUV, unorm8Table);
         vec3 nrm = v3(normalTexel.x, normalTexel.y, sqrtf_(1.f - normalTexel.x * normalTexel.x + normalTexel.y + normalTexel.y));  // triangle.frag:181, as written
         nrm = nrm * 2.f - 1.f;
         vec3 Nw = normalize(tbnT * nrm.x + tbnB * nrm.y + tbnN * nrm.z);  // passTBN * normalTexelReconstructed
@@ -533,7 +534,7 @@ PLAIN_PASS(launch_gbufferFill, "triangle.vert+gbufferFill.frag") {
         }
     // no coverage pass: the visibility buffer of the prepass over the same draws decides (depth test EQUAL)
     if (p.totalVertices) PLAIN_LAUNCH(c, rasterVertexKernel<1>, ceilDiv(p.totalVertices, 256), 256, 0, p);
-    PLAIN_LAUNCH(c, gbufferFillResolveKernel, dim3(ceilDiv(p.W, 32), ceilDiv(p.H, 8)), 256, 0, p, gbuffer, c.bindless);
+    PLAIN_LAUNCH(c, gbufferFillResolveKernel, dim3(ceilDiv(p.W, 32), ceilDiv(p.H, 8)), 256, 0, p, gbuffer, c.bindless, c.tables);
 }
 
 }  // namespace pb
