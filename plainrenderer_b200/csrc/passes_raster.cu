@@ -215,6 +215,9 @@ __device__ __forceinline__ bool subTriangle(const RasterParams& p, const ScreenP
 }
 
 // depth of a covered pixel + the depth test: GREATER_EQUAL in draw order = maximum of (depth bits, primitive + 1)
+// READ_FIRST: look at the texel before the atomic (it only grows, so a stale value can only cost an atomic): saves most atomics of
+// occluded fragments in the warp-parallel paths; the serial tiny path skips it (a dependent load per pixel is all latency there)
+template <bool READ_FIRST>
 __device__ __forceinline__ void emitFragment(const RasterParams& p, const TriPlanes& tp, int ix, int iy, double rowDepth, unsigned long long keyLow) {
     float dep = (float)(tp.depth.x * pixelNdc(ix, p.W) + rowDepth);
     if (dep != dep) return;
@@ -222,7 +225,7 @@ __device__ __forceinline__ void emitFragment(const RasterParams& p, const TriPla
     else if (dep < 0.f || dep > 1.f) return;
     const unsigned long long key = ((unsigned long long)(__float_as_uint(dep) & 0x7fffffffu) << 32) | keyLow;
     unsigned long long* slot = p.vis + (size_t)iy * p.W + ix;
-    if (key > *(volatile unsigned long long*)slot) atomicMax(slot, key);  // the texel only grows: a stale read can only cost an atomic
+    if (!READ_FIRST || key > *(volatile unsigned long long*)slot) atomicMax(slot, key);
 }
 
 // A triangle whose window-space bounding box is at most 1024 pixels is "tiny": the set-up thread rasterises it on the spot.
@@ -270,7 +273,7 @@ __global__ void __launch_bounds__(128) rasterSetupKernel(const __grid_constant__
                     bool inside = true;
 #pragma unroll
                     for (int e = 0; e < 3; e++) inside = inside && (base[e] - step[e] * (long long)ix >= 0);
-                    if (inside) emitFragment(p, tp, ix, iy, rowDepth, keyLow);
+                    if (inside) emitFragment<false>(p, tp, ix, iy, rowDepth, keyLow);
                 }
             }
         }
@@ -298,27 +301,37 @@ __device__ void coverTriangle(const RasterParams& p, uint32_t prim, int rowBegin
         SubTriangle s;
         if (!subTriangle(p, sp, k, s)) continue;
         const int ya = imax(s.iy0, rowBegin), yb = imin(s.iy1, rowEnd);
-        for (int iy = ya; iy <= yb; iy++) {
-            const long long py = (long long)iy * 256 + 128;
-            const double ny = pixelNdc(iy, p.H);
-            // edge functions along the row, in pixels: E_e(ix) = base_e - step_e * ix (exact, 64-bit integers)
-            long long base[3], step[3];
+        if (ya > yb) continue;
+        // edge functions in pixels: E_e(ix, iy) = base_e(iy) - step_e * ix, base_e(iy + 1) = base_e(iy) + 256 * ex_e (exact, 64-bit integers)
+        long long base[3], step[3], baseStep[3];
+        double q0[3], slope[3];  // wide triangles: the real-valued crossing base_e(iy) / step_e = q0_e + slope_e * (iy - ya)
+        const bool wide = s.ix1 - s.ix0 >= 96;
 #pragma unroll
-            for (int e = 0; e < 3; e++) {
-                step[e] = s.ey[e] * 256;
-                base[e] = s.ex[e] * (py - s.ay[e]) + s.bias[e] - s.ey[e] * (128 - s.ax[e]);
-            }
+        for (int e = 0; e < 3; e++) {
+            step[e] = s.ey[e] * 256;
+            baseStep[e] = s.ex[e] * 256;
+            base[e] = s.ex[e] * ((long long)ya * 256 + 128 - s.ay[e]) + s.bias[e] - s.ey[e] * (128 - s.ax[e]);
+            q0[e] = 0.0; slope[e] = 0.0;
+            if (wide && step[e] != 0) { q0[e] = (double)base[e] / (double)step[e]; slope[e] = (double)baseStep[e] / (double)step[e]; }
+        }
+        for (int iy = ya; iy <= yb; iy++) {
+            const double ny = pixelNdc(iy, p.H);
+            long long rowBase[3];
+#pragma unroll
+            for (int e = 0; e < 3; e++) { rowBase[e] = base[e]; base[e] += baseStep[e]; }
             int xa = s.ix0, xe = s.ix1;
-            if (xe - xa >= 96) {
-                // wide rows: the span from the real-valued inequality step * ix <= base with one pixel of slack; it only narrows
-                // the loop, the exact test below decides
+            if (wide) {
+                // the span of the row from the real-valued inequality step * ix <= base with one pixel of slack; it only narrows the
+                // loop, the exact test below decides
                 double lo = (double)xa, hi = (double)xe;
                 bool rowEmpty = false;
+                const double dy = (double)(iy - ya);
 #pragma unroll
                 for (int e = 0; e < 3; e++) {
-                    if (step[e] > 0) hi = fmin(hi, (double)base[e] / (double)step[e] + 1.0);
-                    else if (step[e] < 0) lo = fmax(lo, (double)base[e] / (double)step[e] - 1.0);
-                    else if (base[e] < 0) rowEmpty = true;
+                    const double q = q0[e] + slope[e] * dy;
+                    if (step[e] > 0) hi = fmin(hi, q + 1.0);
+                    else if (step[e] < 0) lo = fmax(lo, q - 1.0);
+                    else if (rowBase[e] < 0) rowEmpty = true;
                 }
                 if (rowEmpty || !(lo <= hi)) continue;
                 xa = imax(xa, (int)floor(lo)); xe = imin(xe, (int)ceil(hi));
@@ -329,8 +342,8 @@ __device__ void coverTriangle(const RasterParams& p, uint32_t prim, int rowBegin
                 if (ix < xa || ix > xe) continue;
                 bool inside = true;
 #pragma unroll
-                for (int e = 0; e < 3; e++) inside = inside && (base[e] - step[e] * (long long)ix >= 0);
-                if (inside) emitFragment(p, tp, ix, iy, rowDepth, keyLow);
+                for (int e = 0; e < 3; e++) inside = inside && (rowBase[e] - step[e] * (long long)ix >= 0);
+                if (inside) emitFragment<true>(p, tp, ix, iy, rowDepth, keyLow);
             }
         }
     }
