@@ -37,10 +37,6 @@ __device__ __forceinline__ float snorm10(uint32_t bits) {
 }
 __device__ __forceinline__ vec3 unpackA2R10G10B10Snorm(uint32_t p) { return v3(snorm10(p >> 20), snorm10(p >> 10), snorm10(p)); }
 __device__ __forceinline__ uint32_t fetchIndex(const RasterDraw& d, uint32_t k) { return d.index32 ? ldg((const uint32_t*)d.indices + k) : (uint32_t)ldg((const uint16_t*)d.indices + k); }
-__device__ __forceinline__ vec3 fetchPosition(const RasterDraw& d, uint32_t index) {
-    const float* p = (const float*)(d.vertices + (size_t)index * 28);
-    return v3(ldg(p), ldg(p + 1), ldg(p + 2));
-}
 __device__ __forceinline__ VertexIn fetchVertex(const RasterDraw& d, uint32_t index) {
     const uint32_t* p = (const uint32_t*)(d.vertices + (size_t)index * 28);
     VertexIn v;
@@ -71,7 +67,6 @@ struct RasterParams {
     uint32_t totalVertices;
     int W, H;
     int clipNear, clampDepth, cullMode;
-    int shadowProgram;                       // 0: clip = transforms[push[3]].mvp * pos; 1: clip = lightMatrices[cascade] * transforms[push[1]] * pos
     const MainPassMatrices* mainTransforms;
     const float* shadowTransforms;
     const plain_shadow_cascade_info* cascades;
@@ -393,7 +388,7 @@ static bool fillRasterParams(LaunchCtx& c, RasterParams& p, const ImgView& depth
     p.clipNear = c.pass->clampDepth ? 0 : 1;
     p.clampDepth = c.pass->clampDepth ? 1 : 0;
     p.cullMode = (int)c.pass->cullMode;
-    p.shadowProgram = 0; p.mainTransforms = nullptr; p.shadowTransforms = nullptr; p.cascades = nullptr; p.cascade = 0;
+    p.mainTransforms = nullptr; p.shadowTransforms = nullptr; p.cascades = nullptr; p.cascade = 0;
     if (!p.vis || (p.totalTris && (!p.draws || !p.triInfo || !p.vertexCache))) { c.fail(c.pass->shader + ": rasteriser scratch missing (render_frame prepares it)"); return false; }
     if (p.W > 32767 || p.H > 32767) { c.fail(c.pass->shader + ": render targets beyond 32767 pixels are not supported"); return false; }
     return true;
@@ -464,7 +459,6 @@ PLAIN_PASS(launch_sunShadow, "sunShadow.vert+sunShadow.frag") {
     if (c.failed) return;
     RasterParams p;
     if (!fillRasterParams(c, p, shadowMap)) return;
-    p.shadowProgram = 1;
     p.cascades = c.sbuf<plain_shadow_cascade_info>(0);
     p.shadowTransforms = c.sbuf<float>(1);
     p.cascade = c.spec<uint32_t>(0, 0);
