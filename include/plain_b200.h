@@ -171,6 +171,9 @@ typedef struct {
     plain_handle pass;
     plain_pass_resources resources;
     const plain_render_target* targets; uint32_t n_targets;
+    /* addition for screen-space row sharding (0 / 0 = all rows): only rows [row_begin, row_end) of the targets are rasterised and
+     * resolved, the other rows keep their contents (a rank renders its band + the halo its stencils read) */
+    uint32_t row_begin, row_end;
 } plain_graphic_pass_execution;
 
 /* VulkanTimestampQueries.h:16-20 */

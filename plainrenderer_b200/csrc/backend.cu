@@ -815,6 +815,7 @@ int PLAIN_FN(set_graphic_pass_execution)(plain_ctx* ctx, const plain_graphic_pas
     r.storageImages.assign(s.storage_images, s.storage_images + s.n_storage_images);
     r.targets.assign(e->targets, e->targets + e->n_targets);
     r.dispatch[0] = r.dispatch[1] = r.dispatch[2] = 0;
+    r.rowBegin = e->row_begin; r.rowEnd = e->row_end;
     b.execs.push_back(std::move(r));
     return 0;
 }

@@ -66,6 +66,7 @@ struct RasterParams {
     float* vertexCache;
     uint32_t totalVertices;
     int W, H;
+    int yMin, yMax;                          // rows of the targets this execution renders (row sharding), inclusive
     int clipNear, clampDepth, cullMode;
     const MainPassMatrices* mainTransforms;
     const float* shadowTransforms;
@@ -205,7 +206,7 @@ __device__ __forceinline__ bool subTriangle(const RasterParams& p, const ScreenP
     for (int e = 0; e < 3; e++) s.bias[e] = (s.ey[e] < 0 || (s.ey[e] == 0 && s.ex[e] > 0)) ? 0 : -1;  // top-left rule
     const long long minX = llmin(x0, llmin(x1, x2)), maxX = llmax(x0, llmax(x1, x2)), minY = llmin(y0, llmin(y1, y2)), maxY = llmax(y0, llmax(y1, y2));
     s.ix0 = (int)llmax(0, (minX - 128 + 255) >> 8); s.ix1 = (int)llmin(p.W - 1, (maxX - 128) >> 8);
-    s.iy0 = (int)llmax(0, (minY - 128 + 255) >> 8); s.iy1 = (int)llmin(p.H - 1, (maxY - 128) >> 8);
+    s.iy0 = (int)llmax(p.yMin, (minY - 128 + 255) >> 8); s.iy1 = (int)llmin(p.yMax, (maxY - 128) >> 8);
     return s.ix0 <= s.ix1 && s.iy0 <= s.iy1;
 }
 
@@ -385,6 +386,9 @@ static bool fillRasterParams(LaunchCtx& c, RasterParams& p, const ImgView& depth
     p.vertexCache = c.exec->rasterVertexCache;
     p.totalVertices = c.exec->rasterTotalVertices;
     p.W = depthTarget.w; p.H = depthTarget.h;
+    int y0, y1;
+    c.window(p.H, y0, y1);
+    p.yMin = y0; p.yMax = y1 - 1;
     p.clipNear = c.pass->clampDepth ? 0 : 1;
     p.clampDepth = c.pass->clampDepth ? 1 : 0;
     p.cullMode = (int)c.pass->cullMode;
@@ -397,8 +401,8 @@ __device__ __forceinline__ int toSnorm16(float v) { if (v != v) return 0; return
 
 // ---------------- depthPrepass.vert:28-42 + depthPrepass.frag:27-49 ----------------
 __global__ void __launch_bounds__(256) depthPrepassResolveKernel(const __grid_constant__ RasterParams p, ImgView motionT, ImgView normalT, ImgView depthT, const plain_global_shader_info* __restrict__ g) {
-    const int ix = blockIdx.x * 32 + (threadIdx.x & 31), iy = blockIdx.y * 8 + (threadIdx.x >> 5);
-    if (ix >= p.W || iy >= p.H) return;
+    const int ix = blockIdx.x * 32 + (threadIdx.x & 31), iy = p.yMin + blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (ix >= p.W || iy > p.yMax) return;
     const unsigned long long key = p.vis[(size_t)iy * p.W + ix];
     float depth = 0.f;
     uint32_t motion = 0u, normal = 0u;
@@ -444,7 +448,8 @@ PLAIN_PASS(launch_depthPrepass, "depthPrepass.vert+depthPrepass.frag") {
     p.mainTransforms = c.sbuf<MainPassMatrices>(0);
     if (c.failed) return;
     launchCoverage<0>(c, p);
-    PLAIN_LAUNCH(c, depthPrepassResolveKernel, dim3(ceilDiv(p.W, 32), ceilDiv(p.H, 8)), 256, 0, p, motionT, normalT, depthT, c.g);
+    if (p.yMax < p.yMin) return;
+    PLAIN_LAUNCH(c, depthPrepassResolveKernel, dim3(ceilDiv(p.W, 32), ceilDiv((unsigned)(p.yMax - p.yMin + 1), 8)), 256, 0, p, motionT, normalT, depthT, c.g);
 }
 
 // ---------------- sunShadow.vert:29-32 + sunShadow.frag ----------------
@@ -486,8 +491,8 @@ __device__ __forceinline__ vec4 sampleRGBA8LinearRepeat(const ImgView& t, vec2 u
     }, t.w, t.h, uv, v4(0.f));
 }
 __global__ void __launch_bounds__(256) gbufferFillResolveKernel(const __grid_constant__ RasterParams p, ImgView gbuffer, const BindlessEntry* __restrict__ bindless, const float* __restrict__ unorm8Table) {
-    const int ix = blockIdx.x * 32 + (threadIdx.x & 31), iy = blockIdx.y * 8 + (threadIdx.x >> 5);
-    if (ix >= p.W || iy >= p.H) return;
+    const int ix = blockIdx.x * 32 + (threadIdx.x & 31), iy = p.yMin + blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (ix >= p.W || iy > p.yMax) return;
     const unsigned long long key = p.vis[(size_t)iy * p.W + ix];
     uint4 texel = make_uint4(0u, 0u, 0u, 0u);
     if (key) {
@@ -541,7 +546,8 @@ PLAIN_PASS(launch_gbufferFill, "triangle.vert+gbufferFill.frag") {
         }
     // no coverage pass: the visibility buffer of the prepass over the same draws decides (depth test EQUAL)
     if (p.totalVertices) PLAIN_LAUNCH(c, rasterVertexKernel<1>, ceilDiv(p.totalVertices, 256), 256, 0, p);
-    PLAIN_LAUNCH(c, gbufferFillResolveKernel, dim3(ceilDiv(p.W, 32), ceilDiv(p.H, 8)), 256, 0, p, gbuffer, c.bindless, c.tables);
+    if (p.yMax < p.yMin) return;
+    PLAIN_LAUNCH(c, gbufferFillResolveKernel, dim3(ceilDiv(p.W, 32), ceilDiv((unsigned)(p.yMax - p.yMin + 1), 8)), 256, 0, p, gbuffer, c.bindless, c.tables);
 }
 
 }  // namespace pb

@@ -90,7 +90,7 @@ class RenderTarget(C.Structure):
 
 
 class GraphicPassExecution(C.Structure):
-    _fields_ = [("pass_", u32), ("resources", PassResources), ("targets", C.POINTER(RenderTarget)), ("n_targets", u32)]
+    _fields_ = [("pass_", u32), ("resources", PassResources), ("targets", C.POINTER(RenderTarget)), ("n_targets", u32), ("row_begin", u32), ("row_end", u32)]
 
 
 CULL_NONE, CULL_FRONT, CULL_BACK = 0, 1, 2
@@ -348,10 +348,12 @@ class Backend:
         self._check(self.api.b["create_graphic_pass"](self.ctx, C.byref(d), C.byref(h)), "create_graphic_pass(%s + %s)" % (vertex_shader, fragment_shader))
         return h.value
 
-    def set_graphic_pass_execution(self, pass_, targets, storage_buffers=(), sampled=()):
-        """targets: [(image handle, mip)] in attachment order"""
+    def set_graphic_pass_execution(self, pass_, targets, storage_buffers=(), sampled=(), rows=None):
+        """targets: [(image handle, mip)] in attachment order; rows: (begin, end) of the targets to render (row sharding)"""
         e = GraphicPassExecution()
         e.pass_ = pass_
+        if rows is not None:
+            e.row_begin, e.row_end = rows
         sb = (StorageBufferResource * max(len(storage_buffers), 1))(*[StorageBufferResource(h, int(ro), b) for h, ro, b in storage_buffers])
         si = (ImageResource * max(len(sampled), 1))(*[ImageResource(h, m, b) for h, m, b in sampled])
         tg = (RenderTarget * max(len(targets), 1))(*[RenderTarget(h, m) for h, m in targets])

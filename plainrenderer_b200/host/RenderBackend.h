@@ -52,7 +52,7 @@ struct ComputePassExecution {
 // graphic passes (ResourceDescriptions.h:55-71, 80-143)
 struct MeshHandle { uint32_t index = PLAIN_INVALID_INDEX; };
 struct RenderTarget { ImageHandle image; uint32_t mipLevel; };
-struct GraphicPassExecution { RenderPassExecution genericInfo; std::vector<RenderTarget> targets; };
+struct GraphicPassExecution { RenderPassExecution genericInfo; std::vector<RenderTarget> targets; uint32_t rowBegin = 0, rowEnd = 0; /* row sharding, 0/0 = all rows */ };
 struct SpecialisationConstant { uint32_t location; std::vector<char> data; };
 struct ShaderDescription { std::string srcPathRelative; std::vector<SpecialisationConstant> specialisationConstants; };
 struct ComputePassDescription { ShaderDescription shaderDescription; std::string name; };
@@ -365,6 +365,7 @@ inline void RenderBackend::sendGraphic(const Recorded& r) {
     std::vector<plain_render_target> tg;
     for (auto& t : r.graphic.targets) tg.push_back(plain_render_target{t.image, t.mipLevel});
     x.targets = tg.data(); x.n_targets = (uint32_t)tg.size();
+    x.row_begin = r.graphic.rowBegin; x.row_end = r.graphic.rowEnd;
     check(PLAIN_FN(set_graphic_pass_execution)(m_ctx, &x));
     if (!r.drawMeshes.empty()) check(PLAIN_FN(draw_meshes)(m_ctx, r.drawMeshes.data(), (uint32_t)r.drawMeshes.size(), r.drawPush.data(), x.pass, 0));
 }

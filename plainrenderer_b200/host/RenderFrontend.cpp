@@ -133,8 +133,8 @@ void RenderFrontend::setup(int device, uint32_t width, uint32_t height, uint32_t
     if (m_shardCount > 1) {
         if ((height + PLAIN_SHARD_ROW_UNIT - 1) / PLAIN_SHARD_ROW_UNIT < m_shardCount) throw std::runtime_error("row sharding: fewer 32-row units than ranks");
         if (width % 16 != 0 || height % 16 != 0) throw std::runtime_error("row sharding needs a resolution that is a multiple of 16 (four HiZ levels reduced from a rank's own rows)");
-        if (m_taaSettings.useSeparateSupersampling || m_sdfDebugSettings.visualisationMode != SDFVisualisationMode::None || m_rasterInputs)
-            throw std::runtime_error("row sharding: the separate temporal supersampling pass, the SDF debug visualisation and rasterised inputs are single-GPU only");
+        if (m_taaSettings.useSeparateSupersampling || m_sdfDebugSettings.visualisationMode != SDFVisualisationMode::None)
+            throw std::runtime_error("row sharding: the separate temporal supersampling pass and the SDF debug visualisation are single-GPU only");
         backend.shard.rank = m_shardRank; backend.shard.count = m_shardCount; backend.shard.fullHeight = height;
         shardBandRows(height, m_shardCount, m_shardRank, &backend.shard.y0, &backend.shard.y1);
     }
@@ -545,7 +545,17 @@ void RenderFrontend::renderDepthPrepass(ImageHandle depth, ImageHandle normal, I
     e.genericInfo.handle = m_depthPrePass;
     e.targets = {RenderTarget{motion, 0}, RenderTarget{normal, 0}, RenderTarget{depth, 0}};
     e.genericInfo.resources.storageBuffers = {StorageBufferResource(m_mainPassTransformsBuffer, true, 0)};
+    // row sharding: the rank's band + 16 rows (what a sharded caller uploads otherwise: the stencils of HiZ, trace, shading, TAA read
+    // that far); the motion vectors are read at reprojected positions by the GI temporal filter and the TAA resolve: all-gathered
+    backend.band(1, m_screenHeight, 16, &e.rowBegin, &e.rowEnd);
     backend.setGraphicPassExecution(e);
+    if (backend.shard.active()) {
+        ExchangeRequest x;
+        x.kind = PLAIN_EXCHANGE_ALLGATHER_ROWS;
+        x.name = "motion";
+        x.images.push_back(motion); x.mips.push_back(0); x.divisors.push_back(1);
+        backend.addExchange(x);
+    }
 }
 void RenderFrontend::renderSunShadowCascades() {  // :760-775
     for (int i = 0; i < m_shadingConfig.sunShadowCascadeCount; i++) {
@@ -563,6 +573,7 @@ void RenderFrontend::fillGBuffer(ImageHandle gbuffer, ImageHandle depth) {
     e.genericInfo.handle = m_gbufferFillPass;
     e.targets = {RenderTarget{gbuffer, 0}, RenderTarget{depth, 0}};
     e.genericInfo.resources.storageBuffers = {StorageBufferResource(m_mainPassTransformsBuffer, true, 17)};
+    backend.band(1, m_screenHeight, 16, &e.rowBegin, &e.rowEnd);  // the same rows as the prepass whose visibility buffer it resolves
     backend.setGraphicPassExecution(e);
 }
 void RenderFrontend::setMeshGeometry(uint32_t mesh, const MeshBinary& geometry, const Material* material) {

@@ -182,12 +182,15 @@ class PlainSceneSequence:
         self.fe.set_exposure(2e-5)
         self.frame = 0
 
-    def step(self, moving=False):
-        f = self.frame
+    def camera_at(self, f, moving, speed=1.0):
         p, fw, r, u = CAMERA
         if moving:
-            p = (p[0] + 0.3 * f, p[1] - 0.02 * f, p[2] + 0.1 * f)
-        self.fe.render_frame(self.ffi.camera(p, fw, r, u), (f + 1) / 60.0, 1 / 60.0)
+            p = (p[0] + 0.3 * speed * f, p[1] - 0.02 * speed * f, p[2] + 0.1 * speed * f)
+        return self.ffi.camera(p, fw, r, u)
+
+    def step(self, moving=False):
+        f = self.frame
+        self.fe.render_frame(self.camera_at(f, moving), (f + 1) / 60.0, 1 / 60.0)
         self.frame += 1
 
     RASTER_IMAGES = ["depth0", "depth1", "motion0", "motion1", "motion2", "normal", "gbuffer", "shadow0", "shadow1", "shadow2"]

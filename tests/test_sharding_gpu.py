@@ -156,3 +156,51 @@ def test_config4_8k_256_instances(ffi, cuda):
         fe.close()
     scene0.close()
     ref.close()
+
+
+@pytest.mark.parametrize("W,H,R,moving", [(256, 192, 2, False), (320, 256, 3, True)])
+def test_sharded_frame_from_meshes_equals_unsharded(ffi, cuda, W, H, R, moving):
+    """SURVEY.md 8f N3 + 8e: with rasterised inputs (raster_inputs = 1) a rank rasterises its band + 16 rows of depth / normal / motion /
+    G-buffer, the motion vectors are all-gathered (an 11th exchange), the shadow cascades are rendered by every rank: bit for bit the
+    unsharded frame"""
+    import torch
+    from conftest import PlainSceneSequence
+    from plainrenderer_b200 import assets, sharding
+    lib = assets.Assets()
+    ref = PlainSceneSequence(ffi, cuda, lib, W, H)
+    ranks = [PlainSceneSequence(ffi, cuda, lib, W, H, shard_rank=r, shard_count=R) for r in range(R)]
+    fes = [x.fe for x in ranks]
+    comm = sharding.LocalComm(cuda, H, R, torch.device("cuda", 0))
+    for f in range(4):
+        cam = ref.camera_at(f, moving, speed=0.05)  # about a pixel per frame: inside the TAA history halo, as in the uploaded-input tests
+        ref.fe.render_frame(cam, (f + 1) / 60.0, 1 / 60.0)
+        assert sharding.run_frame_local(fes, comm, cam, (f + 1) / 60.0, 1 / 60.0) == 11
+        torch.cuda.synchronize()
+        cur = (f + 1) % 2  # m_sceneRenderTargetIndex after frame f + 1
+        for name in ["motion%d" % ((f + 1) % 3), "shadow0", "shadow1", "shadow2", "hiz"]:  # held completely by every rank
+            h = ref.fe.image(name)
+            for mip in range(image_mips(ref.fe, h)):
+                if name == "hiz" and mip < 3:
+                    continue
+                want = ref.fe.backend.read_image(h, mip)
+                for r, fe in enumerate(fes):
+                    assert np.array_equal(fe.backend.read_image(fe.image(name), mip), want), "frame %d rank %d: %s mip %d" % (f, r, name, mip)
+        for name, size in (("histogram", 512), ("light", 20), ("sunShadowInfo", 304)):
+            want = ref.fe.backend.read_storage_buffer(ref.fe.storage_buffer(name), size)
+            for r, fe in enumerate(fes):
+                assert np.array_equal(fe.backend.read_storage_buffer(fe.storage_buffer(name), size), want), "frame %d rank %d: buffer %s" % (f, r, name)
+        for name in ["depth%d" % cur, "normal", "gbuffer", "color%d" % cur, "post1", "giFullY", "output"]:  # the rank's own rows
+            h = ref.fe.image(name)
+            want = ref.fe.backend.read_image(h, 0).reshape(H, -1)
+            for r, fe in enumerate(fes):
+                a, b = sharding.full_res_band(cuda, H, R, r)
+                got = fe.backend.read_image(fe.image(name), 0).reshape(H, -1)
+                assert np.array_equal(got[a:b], want[a:b]), "frame %d rank %d: %s rows [%d, %d)" % (f, r, name, a, b)
+    frame = np.zeros((H, W * 4), np.uint8)
+    for r, fe in enumerate(fes):
+        a, b = sharding.full_res_band(cuda, H, R, r)
+        fe.read_output_rows(frame, (a, b))
+    assert np.array_equal(frame.ravel(), ref.fe.read_output())
+    for x in ranks:
+        x.close()
+    ref.close()
