@@ -147,11 +147,11 @@ class PlainSceneSequence:
     PLACEMENT = [("slab", (0.0, 2.6, 0.0), (4.0, 0.4, 4.0), 0.0), ("cube", (-6.0, 0.0, 1.5), (1.0, 1.0, 1.0), 0.5), ("tall", (-4.0, -1.0, -3.0), (1.0, 0.5, 1.0), 0.0),
                  ("cube", (-9.5, 0.8, -0.5), (0.6, 0.6, 0.6), -0.8), ("cube", (-3.0, 1.2, 3.5), (1.5, 1.0, 0.7), 1.1), ("tall", (-14.0, 0.0, 4.0), (1.0, 0.6, 1.5), 0.3)]
 
-    def __init__(self, ffi, api, asset_lib, w, h, **settings):
+    def __init__(self, ffi, api, asset_lib, w, h, device=0, **settings):
         self.ffi, self.w, self.h = ffi, w, h
         settings.setdefault("sun_direction_deg", (40.0, 35.0))
         self.s = ffi.default_settings(api, w, h, raster_inputs=1, **settings)
-        self.fe = ffi.Frontend(api, self.s)
+        self.fe = ffi.Frontend(api, self.s, device=device)
         be = self.fe.backend
         rng = np.random.default_rng(5)
         checker = np.zeros((4, 4, 4), np.uint8)

@@ -6,6 +6,8 @@
 Every rank renders the same 4-frame sequence twice on its own GPU: unsharded (whole frame, no exchange) and as rank r of
 N with the exchanges of plainrenderer_b200.sharding.DistComm over NCCL. The rank's band of the tonemapped frame, the
 all-reduced histogram and the all-gathered TAA history must equal the unsharded result bit for bit.
+--raster: the frames are rendered from `.plain` meshes (raster_inputs = 1): nothing is uploaded, every rank
+rasterises its band + halo, the motion vectors travel as an 11th exchange.
 """
 import ctypes as C
 import os
@@ -43,8 +45,17 @@ def main():
         fe.set_exposure(2e-5)
         return s, fe, scene
 
-    s0, ref, scene0 = make(0, 0)
-    s1, fe, scene1 = make(rank, world)
+    raster = "--raster" in sys.argv
+    if raster:
+        sys.path.insert(0, str(ROOT / "tests"))
+        from conftest import PlainSceneSequence  # the scene of tests/test_raster_gpu.py: the golden .plain assets, instanced
+        from plainrenderer_b200 import assets
+        seq0 = PlainSceneSequence(ffi, api, assets.Assets(), W, H, device=local)
+        seq1 = PlainSceneSequence(ffi, api, assets.Assets(), W, H, device=local, shard_rank=rank, shard_count=world)
+        s0, ref, scene0, s1, fe, scene1 = seq0.s, seq0.fe, None, seq1.s, seq1.fe, None
+    else:
+        s0, ref, scene0 = make(0, 0)
+        s1, fe, scene1 = make(rank, world)
     stream_ptr = C.c_void_p()
     api.b["get_stream"](fe.backend.ctx, C.byref(stream_ptr))
     stream = torch.cuda.ExternalStream(stream_ptr.value, device=torch.device("cuda", local))
@@ -56,10 +67,14 @@ def main():
     for f in range(frames):
         p, fw, r, u = CAMERA
         cam = ffi.camera((p[0] + 0.02 * f, p[1], p[2] + 0.01 * f), fw, r, u)
-        inputs = scene0.render_inputs(s0, cam, f + 1, prev_cam=prev, shadows=True)
-        prev = cam
-        ref.render_frame(cam, (f + 1) / 60.0, 1 / 60.0, inputs["depth"], inputs["motion"], inputs["normal"], inputs["gbuffer"], inputs["shadow_maps"])
-        n = sharding.run_frame(fe, comm, cam, (f + 1) / 60.0, 1 / 60.0, inputs, upload_rows=upload)
+        if raster:
+            ref.render_frame(cam, (f + 1) / 60.0, 1 / 60.0)
+            n = sharding.run_frame(fe, comm, cam, (f + 1) / 60.0, 1 / 60.0)
+        else:
+            inputs = scene0.render_inputs(s0, cam, f + 1, prev_cam=prev, shadows=True)
+            prev = cam
+            ref.render_frame(cam, (f + 1) / 60.0, 1 / 60.0, inputs["depth"], inputs["motion"], inputs["normal"], inputs["gbuffer"], inputs["shadow_maps"])
+            n = sharding.run_frame(fe, comm, cam, (f + 1) / 60.0, 1 / 60.0, inputs, upload_rows=upload)
         torch.cuda.synchronize()
         want = ref.read_output().reshape(H, W * 4)
         got = np.zeros((H, W * 4), np.uint8)
@@ -71,6 +86,9 @@ def main():
         hname = "taaHist%d" % (f % 2)
         same_hist = np.array_equal(hist_w, hist_g)
         same_taa = np.array_equal(ref.backend.read_image(ref.image(hname)), fe.backend.read_image(fe.image(hname)))
+        if raster:  # the all-gathered motion vectors of this frame
+            mname = "motion%d" % ((f + 1) % 3)
+            same_taa = same_taa and np.array_equal(ref.backend.read_image(ref.image(mname)), fe.backend.read_image(fe.image(mname)))
         print("rank %d/%d frame %d: %d exchanges through Python, band [%d,%d) frame %s, histogram %s, TAA history %s" %
               (rank, world, f, n, a, b, "equal" if same_frame else "DIFFERS", "equal" if same_hist else "DIFFERS", "equal" if same_taa else "DIFFERS"), flush=True)
         ok = ok and same_frame and same_hist and same_taa
@@ -78,9 +96,10 @@ def main():
     t = torch.tensor([0 if ok else 1], device="cuda")
     dist.all_reduce(t)
     if rank == 0:
-        print("SHARDED_%s_PARITY %s (%d ranks, %dx%d, %d frames)" % ("PEER" if peer else "NCCL", "OK" if int(t.item()) == 0 else "FAILED", world, W, H, frames), flush=True)
+        print("SHARDED_%s_PARITY %s (%d ranks, %dx%d, %d frames%s)" % ("PEER" if peer else "NCCL", "OK" if int(t.item()) == 0 else "FAILED", world, W, H, frames, ", rasterised inputs" if raster else ""), flush=True)
     for sc, f_ in ((scene0, ref), (scene1, fe)):
-        sc.close()
+        if sc is not None:
+            sc.close()
         f_.close()
     dist.destroy_process_group()
     sys.exit(0 if int(t.item()) == 0 else 1)
