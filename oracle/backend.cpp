@@ -152,6 +152,8 @@ int PLAIN_FN(create_image)(plain_ctx* ctx, const plain_image_desc* desc, const v
             memcpy(img.mips[i].data.data(), src + off, n);
             off += n;
         }
+        if (desc->format == PLAIN_FORMAT_RGBA8)
+            for (size_t t = 3; t < img.mips[0].data.size(); t += 4) if (img.mips[0].data[t] != 255) { img.transparentTexels = true; break; }
     }
     ctx->c.images.push_back(std::move(img));
     out->type = PLAIN_IMAGE_HANDLE_DEFAULT;

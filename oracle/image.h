@@ -125,6 +125,7 @@ struct Image {
     plain_image_desc desc{};
     std::vector<MipLevel> mips;
     bool inUse = false;  // transient pool
+    bool transparentTexels = false;  // RGBA8 created with initial data containing a texel of alpha < 255 (alpha test of the raster passes)
 
     static int computeMipCount(const plain_image_desc& d) {
         if (d.mip_count == PLAIN_MIPS_ONE) return 1;

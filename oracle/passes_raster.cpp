@@ -17,8 +17,10 @@
 //     binary32; fragments outside [0, 1] are dropped (clamped when depth clamp is on)
 //   * depth test GREATER_EQUAL in draw order = per pixel the maximum of (depth bits, primitive number): of two fragments at the
 //     same depth the one drawn later wins; draws are ordered by draw_meshes call, triangles by index-buffer position
-//   * texture fetches of gbufferFill are bilinear, repeat, mip 0 (the reference samples anisotropically with a mip bias);
-//     the alpha test of depthPrepass.frag:28-31 / sunShadow.frag:19-22 is not applied (every texel opaque)
+//   * texture fetches (the material texels of gbufferFill, the alpha test of depthPrepass.frag:28-31 / sunShadow.frag:19-22) are
+//     bilinear, repeat, mip 0 of RGBA8 images (the reference samples BC-compressed mip chains anisotropically with a mip bias);
+//     the alpha test interpolates uv with the pixel's perspective-correct barycentrics and drops the fragment before the depth
+//     test when alpha < 0.5; it is skipped for albedo textures without a texel of alpha < 255 (it could not drop anything)
 #include <cmath>
 #include "backend.h"
 #include "shader_inc.h"
@@ -77,7 +79,8 @@ static vec3 lerp3(const float l[3], vec3 a, vec3 b, vec3 c) { return vec3(lerp3(
 
 // ---- coverage ----
 struct RasterTarget { int W, H; bool clipNear, clampDepth; uint32_t cullMode; uint64_t* vis; };
-static void rasterTriangle(const RasterTarget& rt, const vec4 clip[3], uint32_t primitive) {
+struct AlphaTest { bool enabled; View albedo; vec2 uv[3]; };
+static void rasterTriangle(const RasterTarget& rt, const vec4 clip[3], uint32_t primitive, const AlphaTest& alphaTest) {
     const TriPlanes tp = trianglePlanes(clip);
     ClipV poly[12], tmp[12];
     int n = 3;
@@ -139,6 +142,12 @@ static void rasterTriangle(const RasterTarget& rt, const vec4 clip[3], uint32_t 
                 for (int e = 0; e < 3; e++) inside = inside && (ex[e] * (py - ay[e]) - ey[e] * (px - ax[e]) + bias[e] >= 0);
                 if (!inside) continue;
                 const double nx = pixelNdc((int)ix, rt.W), ny = pixelNdc((int)iy, rt.H);
+                if (alphaTest.enabled) {
+                    float l[3];
+                    barycentrics(tp, nx, ny, l);
+                    const vec2 passUV(lerp3(l, alphaTest.uv[0].x, alphaTest.uv[1].x, alphaTest.uv[2].x), lerp3(l, alphaTest.uv[0].y, alphaTest.uv[1].y, alphaTest.uv[2].y));
+                    if (texture(alphaTest.albedo, s_linearRepeat, passUV).w < 0.5f) continue;  // discard
+                }
                 float d = (float)(tp.depth.x * nx + (tp.depth.y * ny + tp.depth.z));  // the row term first (it is constant along a row)
                 if (d != d) continue;
                 if (rt.clampDepth) d = d < 0.f ? 0.f : (d > 1.f ? 1.f : d);
@@ -166,18 +175,28 @@ static const DrawInfo& drawOfPrimitive(const std::vector<DrawInfo>& t, uint32_t 
     while (hi - lo > 1) { const size_t mid = (lo + hi) / 2; if (t[mid].firstPrimitive <= primitive) lo = mid; else hi = mid; }
     return t[lo];
 }
+static uint32_t pushU32(const DrawInfo& d, int i) { uint32_t v; memcpy(&v, d.push + i * 4, 4); return v; }
+static bool hasTransparentTexel(const View& albedo) {  // RGBA8 whose initial data (create_image) had a texel of alpha < 255 in mip 0
+    return albedo.valid() && albedo.format() == PLAIN_FORMAT_RGBA8 && albedo.img->transparentTexels;
+}
 template <typename MatrixOfDraw>
 static void rasterDraws(const PassCtx& c, const std::vector<DrawInfo>& draws, const RasterTarget& rt, MatrixOfDraw matrixOfDraw) {
     for (auto& d : draws) {
         const mat4 M = matrixOfDraw(d);
+        AlphaTest at;
+        at.albedo = c.bindless(pushU32(d, 0));  // push constant 0 of both vertex programs
+        at.enabled = hasTransparentTexel(at.albedo);
         for (uint32_t t = 0; t < d.mesh->indexCount / 3; t++) {
             vec4 clip[3];
-            for (int k = 0; k < 3; k++) clip[k] = M * vec4(fetchVertex(*d.mesh, fetchIndex(*d.mesh, t * 3 + k)).pos, 1.f);
-            rasterTriangle(rt, clip, d.firstPrimitive + t);
+            for (int k = 0; k < 3; k++) {
+                const VertexIn v = fetchVertex(*d.mesh, fetchIndex(*d.mesh, t * 3 + k));
+                clip[k] = M * vec4(v.pos, 1.f);
+                at.uv[k] = v.uv;
+            }
+            rasterTriangle(rt, clip, d.firstPrimitive + t, at);
         }
     }
 }
-static uint32_t pushU32(const DrawInfo& d, int i) { uint32_t v; memcpy(&v, d.push + i * 4, 4); return v; }
 static int16_t toSnorm16(float v) { if (v != v) return 0; return (int16_t)(int)dm::floor_(clamp(v, -1.f, 1.f) * 32767.f + 0.5f); }
 struct MainPassMatrices { float model[16], mvp[16], mvpPrevious[16]; };  // MainPassMatrices.inc
 

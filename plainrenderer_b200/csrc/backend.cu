@@ -268,7 +268,7 @@ static uint64_t hashExecs(const Backend& b) {
         h = fnv(h, e.dispatch, sizeof(e.dispatch));
         h = fnv(h, &e.rowBegin, 12);
         n = (uint32_t)e.targets.size(); h = fnv(h, &n, 4); h = fnv(h, e.targets.data(), n * sizeof(e.targets[0]));
-        n = (uint32_t)e.draws.size(); h = fnv(h, &n, 4); h = fnv(h, e.draws.data(), n * sizeof(e.draws[0]));
+        n = (uint32_t)e.draws.size(); h = fnv(h, &n, 4); h = fnv(h, e.draws.data(), n * sizeof(e.draws[0]));  // (the alpha-test variant follows from the draws' textures, fixed at create_image)
     }
     return h;
 }
@@ -613,6 +613,8 @@ int PLAIN_FN(create_image)(plain_ctx* ctx, const plain_image_desc* desc, const v
             off += img.mips[i].bytes;
         }
         CU_CHECK(ctx, cudaStreamSynchronize(b.stream));  // the caller's memory may go away after the call (RenderBackend.cpp:315-321)
+        if (desc->format == PLAIN_FORMAT_RGBA8)
+            for (size_t t = 3; t < img.mips[0].bytes; t += 4) if (((const uint8_t*)initial_data)[t] != 255) { img.transparentTexels = true; break; }
     }
     b.images.push_back(std::move(img));
     out->type = PLAIN_IMAGE_HANDLE_DEFAULT;
@@ -847,13 +849,16 @@ static int prepareRaster(plain_ctx* ctx) {
         Backend::RasterScratch& sc = b.rasterScratch[e.pass];
         b.rasterDrawStaging.clear();
         uint32_t first = 0, firstVertex = 0;
+        bool anyAlpha = false;
         for (auto& d : e.draws) {
             const DeviceMesh& m = b.meshes[d.mesh];
             RasterDraw rd;
             rd.indices = m.indices; rd.vertices = m.vertices;
             rd.firstPrimitive = first; rd.triCount = m.indexCount / 3; rd.index32 = m.index32;
-            rd.firstVertex = firstVertex; rd.vertexCount = m.vertexCount; rd.pad = 0;
+            rd.firstVertex = firstVertex; rd.vertexCount = m.vertexCount;
             memcpy(rd.push, d.push, 16);
+            rd.alphaTest = (rd.push[0] < b.images.size() && b.images[rd.push[0]].desc.format == PLAIN_FORMAT_RGBA8 && b.images[rd.push[0]].transparentTexels) ? 1u : 0u;
+            anyAlpha = anyAlpha || rd.alphaTest != 0u;
             b.rasterDrawStaging.push_back(rd);
             first += rd.triCount;
             firstVertex += rd.vertexCount;
@@ -897,6 +902,7 @@ static int prepareRaster(plain_ctx* ctx) {
         e.rasterTotalTris = first;
         e.rasterVertexCache = sc.vertexCache;
         e.rasterTotalVertices = firstVertex;
+        e.rasterAnyAlphaTest = anyAlpha;
     }
     return 0;
 }

@@ -31,6 +31,7 @@ struct DeviceImage {
     size_t bytes = 0;
     std::vector<MipInfo> mips;
     bool inUse = false;
+    bool transparentTexels = false;  // RGBA8 created with initial data containing a texel of alpha < 255 (alpha test of the raster passes)
     long long lastUsedSubmission = -1;  // index of the last submission (render_frame) whose passes referenced the image
     unsigned char* peerPtr[PLAIN_MAX_PEERS] = {};  // the other ranks' copies of this image (CUDA IPC mappings), row sharding
     cudaEvent_t downloadDone = nullptr; // recorded after the last asynchronous read-back of the image (created on first use)
@@ -50,7 +51,7 @@ struct DeviceMesh {  // MeshBinary (MeshData.h:27-35) in HBM
 struct RasterDraw {  // one entry of the device draw table of a graphic pass execution
     const unsigned char* indices;
     const unsigned char* vertices;
-    uint32_t firstPrimitive, triCount, index32, firstVertex, vertexCount, pad;
+    uint32_t firstPrimitive, triCount, index32, firstVertex, vertexCount, alphaTest;  // alphaTest: the albedo texture (push[0]) has transparent texels
     uint32_t push[4];
 };
 #define PLAIN_RASTER_VERTEX_FLOATS 16  // one entry of a pass's post-transform vertex cache (64 bytes)
@@ -66,6 +67,7 @@ struct ExecRecord {
     unsigned long long* rasterVis = nullptr;    // per pixel of the depth target: depth bits << 32 | primitive + 1
     float* rasterVertexCache = nullptr;         // per (draw, vertex): the vertex stage's outputs, PLAIN_RASTER_VERTEX_FLOATS floats each
     uint32_t rasterTotalTris = 0, rasterTotalVertices = 0;
+    bool rasterAnyAlphaTest = false;            // a draw's albedo texture has transparent texels: the alpha-testing kernel variants run
     std::vector<plain_storage_buffer_resource> storageBuffers;
     std::vector<plain_uniform_buffer_resource> uniformBuffers;
     std::vector<plain_image_resource> sampledImages;

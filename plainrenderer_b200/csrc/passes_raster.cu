@@ -72,10 +72,13 @@ struct RasterParams {
     const float* shadowTransforms;
     const plain_shadow_cascade_info* cascades;
     uint32_t cascade;
+    int shadowKind;                          // layout of the cache entries: 1 = sunShadow (uv at [4..5]), 0 = prepass (uv at [11..12])
+    const BindlessEntry* bindless;           // material textures: slot == image handle index
+    const float* unorm8Table;                // exact float(b) / 255 (pass_common.cuh ShadingTables)
 };
 // ---- (0) vertex stage, once per (draw, vertex): depthPrepass.vert:28-42, triangle.vert:29-40, sunShadow.vert:29-32 ----
-// cache entry (16 floats): [0..3] clip position; KIND 0 (prepass): [4..7] previous clip position, [8..10] N;
-// KIND 1 (G-buffer fill): [4..6] T, [7..9] B, [10..12] N, [13..14] uv; KIND 2 (shadow): clip only
+// cache entry (16 floats): [0..3] clip position; KIND 0 (prepass): [4..7] previous clip position, [8..10] N, [11..12] uv;
+// KIND 1 (G-buffer fill): [4..6] T, [7..9] B, [10..12] N, [13..14] uv; KIND 2 (shadow): [4..5] uv (uv: the alpha test)
 __device__ __forceinline__ const RasterDraw& drawOfVertex(const RasterDraw* draws, uint32_t drawCount, uint32_t entry) {
     uint32_t lo = 0, hi = drawCount;
     while (hi - lo > 1) { const uint32_t mid = (lo + hi) / 2; if (draws[mid].firstVertex <= entry) lo = mid; else hi = mid; }
@@ -99,6 +102,7 @@ __global__ void __launch_bounds__(256) rasterVertexKernel(const __grid_constant_
         }
         const vec4 clip = mulm4(M, v4(v.pos, 1.f));
         out[0] = make_float4(clip.x, clip.y, clip.z, clip.w);
+        out[1] = make_float4(v.uv.x, v.uv.y, 0.f, 0.f);
         return;
     }
     const MainPassMatrices& tr = p.mainTransforms[d.push[3]];
@@ -108,7 +112,8 @@ __global__ void __launch_bounds__(256) rasterVertexKernel(const __grid_constant_
     if (KIND == 0) {
         const vec4 prev = mulm4(tr.mvpPrevious, v4(v.pos, 1.f));
         out[1] = make_float4(prev.x, prev.y, prev.z, prev.w);
-        out[2] = make_float4(N.x, N.y, N.z, 0.f);
+        out[2] = make_float4(N.x, N.y, N.z, v.uv.x);
+        out[3] = make_float4(v.uv.y, 0.f, 0.f, 0.f);
     } else {
         const vec3 T = normalize(mulMat3(tr.model, v.tangent)), B = normalize(mulMat3(tr.model, v.bitangent));
         out[1] = make_float4(T.x, T.y, T.z, B.x);
@@ -213,8 +218,29 @@ __device__ __forceinline__ bool subTriangle(const RasterParams& p, const ScreenP
 // depth of a covered pixel + the depth test: GREATER_EQUAL in draw order = maximum of (depth bits, primitive + 1)
 // READ_FIRST: look at the texel before the atomic (it only grows, so a stale value can only cost an atomic): saves most atomics of
 // occluded fragments in the warp-parallel paths; the serial tiny path skips it (a dependent load per pixel is all latency there)
-template <bool READ_FIRST>
-__device__ __forceinline__ void emitFragment(const RasterParams& p, const TriPlanes& tp, int ix, int iy, double rowDepth, unsigned long long keyLow) {
+// the alpha test of depthPrepass.frag:28-31 / sunShadow.frag:19-22 for draws whose albedo texture has transparent texels
+// (out of line and self-contained - it fetches the triangle's uv itself - so that opaque draws carry nothing but the flag)
+struct AlphaTest { const RasterDraw* draw; uint32_t tri; };  // draw == nullptr: opaque
+__device__ __forceinline__ AlphaTest alphaTestOf(const RasterDraw& d, uint32_t tri) { return AlphaTest{d.alphaTest ? &d : nullptr, tri}; }
+__device__ __noinline__ bool alphaTestDiscards(const RasterParams& p, const TriPlanes& tp, AlphaTest a, int ix, int iy) {
+    vec2 uv[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const float4* e = cacheEntry(p, *a.draw, a.tri, k);
+        if (p.shadowKind) { const float4 u = e[1]; uv[k] = v2(u.x, u.y); }
+        else { const float4 n = e[2], u = e[3]; uv[k] = v2(n.w, u.x); }
+    }
+    float l[3];
+    barycentrics(tp, pixelNdc(ix, p.W), pixelNdc(iy, p.H), l);
+    const vec2 passUV = v2(lerp3(l, uv[0].x, uv[1].x, uv[2].x), lerp3(l, uv[0].y, uv[1].y, uv[2].y));
+    const ImgView albedo = p.bindless[a.draw->push[0]].view;
+    const float alpha = sampleLinear2D<WRAP_REPEAT, float>([&](int x, int y) { return ldg(p.unorm8Table + (ldg((const uint32_t*)albedo.ptr + texelIndex(albedo, x, y)) >> 24)); },
+                                                             albedo.w, albedo.h, passUV, 0.f);
+    return alpha < 0.5f;
+}
+template <bool READ_FIRST, bool ALPHA>
+__device__ __forceinline__ void emitFragment(const RasterParams& p, const TriPlanes& tp, const AlphaTest& alpha, int ix, int iy, double rowDepth, unsigned long long keyLow) {
+    if (ALPHA && alpha.draw && alphaTestDiscards(p, tp, alpha, ix, iy)) return;
     float dep = (float)(tp.depth.x * pixelNdc(ix, p.W) + rowDepth);
     if (dep != dep) return;
     if (p.clampDepth) dep = dep < 0.f ? 0.f : (dep > 1.f ? 1.f : dep);
@@ -233,6 +259,7 @@ __device__ __forceinline__ void emitFragment(const RasterParams& p, const TriPla
 #define RASTER_BIG_BAND_ROWS 8
 #define RASTER_BIG_FLAG 0x80000000u
 // (1) a thread per triangle: the rows it can cover (y0 | y1 << 16 | big flag); big triangles go to the list behind the counter at triInfo[totalTris]
+template <bool ALPHA>
 __global__ void __launch_bounds__(128) rasterSetupKernel(const __grid_constant__ RasterParams p) {
     const uint32_t prim = blockIdx.x * 128 + threadIdx.x;
     if (prim >= p.totalTris) return;
@@ -252,6 +279,7 @@ __global__ void __launch_bounds__(128) rasterSetupKernel(const __grid_constant__
     if (y1 >= y0 && (long long)(y1 - y0 + 1) * (x1 - x0 + 1) <= RASTER_TINY_MAX_AREA) {
         // tiny: this thread walks the few pixels itself (no second set-up by a warp); nothing is left for the coverage kernels
         const TriPlanes tp = trianglePlanes(clip);
+        const AlphaTest alpha = alphaTestOf(d, prim - d.firstPrimitive);
         const unsigned long long keyLow = (unsigned long long)(prim + 1u);
         for (int k = 1; k + 1 < sp.n; k++) {
             SubTriangle s;
@@ -269,7 +297,7 @@ __global__ void __launch_bounds__(128) rasterSetupKernel(const __grid_constant__
                     bool inside = true;
 #pragma unroll
                     for (int e = 0; e < 3; e++) inside = inside && (base[e] - step[e] * (long long)ix >= 0);
-                    if (inside) emitFragment<false>(p, tp, ix, iy, rowDepth, keyLow);
+                    if (inside) emitFragment<false, ALPHA>(p, tp, alpha, ix, iy, rowDepth, keyLow);
                 }
             }
         }
@@ -284,12 +312,14 @@ __global__ void __launch_bounds__(128) rasterSetupKernel(const __grid_constant__
     p.triInfo[prim] = info;
 }
 // coverage of rows [rowBegin, rowEnd] of one triangle by one warp
+template <bool ALPHA>
 __device__ void coverTriangle(const RasterParams& p, uint32_t prim, int rowBegin, int rowEnd) {
     const int lane = threadIdx.x & 31;
     const RasterDraw& d = drawOfPrimitive(p.draws, p.drawCount, prim);
     vec4 clip[3];
     triangleClipPositions(p, d, prim - d.firstPrimitive, clip);
     const TriPlanes tp = trianglePlanes(clip);
+    const AlphaTest alpha = alphaTestOf(d, prim - d.firstPrimitive);
     ScreenPoly sp;
     clipAndSnap(p, clip, sp);
     const unsigned long long keyLow = (unsigned long long)(prim + 1u);
@@ -339,20 +369,20 @@ __device__ void coverTriangle(const RasterParams& p, uint32_t prim, int rowBegin
                 bool inside = true;
 #pragma unroll
                 for (int e = 0; e < 3; e++) inside = inside && (rowBase[e] - step[e] * (long long)ix >= 0);
-                if (inside) emitFragment<true>(p, tp, ix, iy, rowDepth, keyLow);
+                if (inside) emitFragment<true, ALPHA>(p, tp, alpha, ix, iy, rowDepth, keyLow);
             }
         }
     }
 }
 // (2) BIG = false: a warp per triangle, the ones that fit a band; (3) BIG = true: persistent warps over (listed triangle, band)
-template <bool BIG>
+template <bool BIG, bool ALPHA>
 __global__ void __launch_bounds__(256) rasterCoverKernel(const __grid_constant__ RasterParams p) {
     const uint32_t warp = (blockIdx.x * 256 + threadIdx.x) >> 5;
     if (!BIG) {
         if (warp >= p.totalTris) return;
         const uint32_t info = p.triInfo[warp];
         if (info == 0xffffffffu || (info & RASTER_BIG_FLAG)) return;
-        coverTriangle(p, warp, (int)(info & 0xffffu), (int)(info >> 16));
+        coverTriangle<ALPHA>(p, warp, (int)(info & 0xffffu), (int)(info >> 16));
     } else {
         const uint32_t bigCount = p.triInfo[p.totalTris], warps = gridDim.x * 8u;
         const uint32_t bands = ((uint32_t)p.H + RASTER_BIG_BAND_ROWS - 1) / RASTER_BIG_BAND_ROWS;
@@ -363,7 +393,7 @@ __global__ void __launch_bounds__(256) rasterCoverKernel(const __grid_constant__
             const int y0 = (int)(info & 0xffffu), y1 = (int)((info & ~RASTER_BIG_FLAG) >> 16);
             const int ra = (int)band * RASTER_BIG_BAND_ROWS, rb = ra + RASTER_BIG_BAND_ROWS - 1;
             if (rb < y0 || ra > y1) continue;
-            coverTriangle(p, prim, imax(ra, y0), imin(rb, y1));
+            coverTriangle<ALPHA>(p, prim, imax(ra, y0), imin(rb, y1));
         }
     }
 }
@@ -373,9 +403,15 @@ static void launchCoverage(LaunchCtx& c, const RasterParams& p) {
     if (p.totalTris == 0) return;
     cudaMemsetAsync(p.triInfo + p.totalTris, 0, sizeof(uint32_t), c.stream);
     PLAIN_LAUNCH(c, rasterVertexKernel<KIND>, ceilDiv(p.totalVertices, 256), 256, 0, p);
-    PLAIN_LAUNCH(c, rasterSetupKernel, ceilDiv(p.totalTris, 128), 128, 0, p);
-    PLAIN_LAUNCH(c, rasterCoverKernel<false>, ceilDiv(p.totalTris, 8), 256, 0, p);
-    PLAIN_LAUNCH(c, rasterCoverKernel<true>, (unsigned)c.smCount * 4, 256, 0, p);
+    if (c.exec->rasterAnyAlphaTest) {  // a draw with a cut-out albedo texture: the variants that carry the alpha test
+        PLAIN_LAUNCH(c, rasterSetupKernel<true>, ceilDiv(p.totalTris, 128), 128, 0, p);
+        PLAIN_LAUNCH(c, (rasterCoverKernel<false, true>), ceilDiv(p.totalTris, 8), 256, 0, p);
+        PLAIN_LAUNCH(c, (rasterCoverKernel<true, true>), (unsigned)c.smCount * 4, 256, 0, p);
+    } else {
+        PLAIN_LAUNCH(c, rasterSetupKernel<false>, ceilDiv(p.totalTris, 128), 128, 0, p);
+        PLAIN_LAUNCH(c, (rasterCoverKernel<false, false>), ceilDiv(p.totalTris, 8), 256, 0, p);
+        PLAIN_LAUNCH(c, (rasterCoverKernel<true, false>), (unsigned)c.smCount * 4, 256, 0, p);
+    }
 }
 static bool fillRasterParams(LaunchCtx& c, RasterParams& p, const ImgView& depthTarget) {
     p.draws = c.exec->rasterDraws;
@@ -393,6 +429,7 @@ static bool fillRasterParams(LaunchCtx& c, RasterParams& p, const ImgView& depth
     p.clampDepth = c.pass->clampDepth ? 1 : 0;
     p.cullMode = (int)c.pass->cullMode;
     p.mainTransforms = nullptr; p.shadowTransforms = nullptr; p.cascades = nullptr; p.cascade = 0;
+    p.shadowKind = 0; p.bindless = c.bindless; p.unorm8Table = c.tables;
     if (!p.vis || (p.totalTris && (!p.draws || !p.triInfo || !p.vertexCache))) { c.fail(c.pass->shader + ": rasteriser scratch missing (render_frame prepares it)"); return false; }
     if (p.W > 32767 || p.H > 32767) { c.fail(c.pass->shader + ": render targets beyond 32767 pixels are not supported"); return false; }
     return true;
@@ -467,6 +504,7 @@ PLAIN_PASS(launch_sunShadow, "sunShadow.vert+sunShadow.frag") {
     p.cascades = c.sbuf<plain_shadow_cascade_info>(0);
     p.shadowTransforms = c.sbuf<float>(1);
     p.cascade = c.spec<uint32_t>(0, 0);
+    p.shadowKind = 1;
     if (c.failed) return;
     if (p.cascade > 3) { c.fail("sunShadow.vert: cascade index must be 0..3"); return; }
     launchCoverage<2>(c, p);

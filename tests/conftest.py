@@ -157,6 +157,7 @@ class PlainSceneSequence:
         checker = np.zeros((4, 4, 4), np.uint8)
         checker[..., :3] = rng.integers(60, 255, (4, 4, 3))
         checker[..., 3] = 255
+        checker[0, 0, 3], checker[2, 1, 3], checker[3, 3, 3] = 0, 90, 160  # cut-out texels: the alpha test of the prepass / shadow passes
         rough = np.zeros((2, 2, 4), np.uint8)
         rough[..., 1], rough[..., 2] = rng.integers(60, 230, (2, 2)), 0
         bumps = np.zeros((4, 4, 4), np.uint8)

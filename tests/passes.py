@@ -214,7 +214,7 @@ def raster_prepass(ffi, api, w, h, meshes, draws, matrices, jitter=((0.0, 0.0), 
     return out
 
 
-def raster_shadow(ffi, api, size, meshes, draws, model_matrices, light_matrices, cascade=0):
+def raster_shadow(ffi, api, size, meshes, draws, model_matrices, light_matrices, cascade=0, albedo=None):
     """sunShadow.vert/.frag (RenderFrontend.cpp:760-775, 1563-1590): one D16 cascade. draws: [(mesh number, transform index)];
     model_matrices float32 (n, 16); light_matrices float32 (4, 16)."""
     rig = _raster_rig(ffi, api, size, size)
@@ -227,7 +227,10 @@ def raster_shadow(ffi, api, size, meshes, draws, model_matrices, light_matrices,
     be.new_frame()
     be.set_graphic_pass_execution(p, [(shadow_map, 0)], storage_buffers=[(cascades, True, 0), (transforms, True, 1)])
     be._check(api.b["prepare_for_drawcall_recording"](be.ctx), "prepare_for_drawcall_recording")
-    be.draw_meshes([handles[d[0]] for d in draws], np.array([[0, d[1]] for d in draws], np.uint32), p)
+    tex = 0
+    if albedo is not None:  # (w, h, RGBA8 bytes): the albedo texture of every draw (alpha test)
+        tex = be.global_texture_index(be.create_image(albedo[0], albedo[1], "RGBA8", data=np.asarray(albedo[2], np.uint8)))
+    be.draw_meshes([handles[d[0]] for d in draws], np.array([[tex, d[1]] for d in draws], np.uint32), p)
     rig.run()
     out = be.read_image(shadow_map, 0, np.uint16).reshape(size, size).copy()
     rig.close()

@@ -75,9 +75,11 @@ def test_shadow_cascade_bit_exact(ffi, cuda, oracle, size, n_tris):
     lm[2] = ortho.astype(np.float32).T.ravel()
     model = np.eye(4, dtype=np.float32)
     model[0, 3] = 0.1
+    cutout = (4, 2, rng.integers(0, 256, 4 * 2 * 4).astype(np.uint8))  # random alpha: the alpha test of sunShadow.frag
     for cascade in (0, 2):
-        got = passes.raster_shadow(ffi, cuda, size, meshes, [(0, 0), (0, 1)], [IDENTITY, model.T.ravel()], lm, cascade=cascade)
-        want = passes.raster_shadow(ffi, oracle, size, meshes, [(0, 0), (0, 1)], [IDENTITY, model.T.ravel()], lm, cascade=cascade)
+        albedo = cutout if cascade == 2 else None
+        got = passes.raster_shadow(ffi, cuda, size, meshes, [(0, 0), (0, 1)], [IDENTITY, model.T.ravel()], lm, cascade=cascade, albedo=albedo)
+        want = passes.raster_shadow(ffi, oracle, size, meshes, [(0, 0), (0, 1)], [IDENTITY, model.T.ravel()], lm, cascade=cascade, albedo=albedo)
         assert (want > 0).mean() > 0.02
         assert np.array_equal(got, want), "cascade %d: %d texels differ" % (cascade, int((got != want).sum()))
 

@@ -178,3 +178,25 @@ def test_frame_from_plain_meshes(ffi, oracle):
     out = snap["output/0"].reshape(h, w, 4)
     assert out[..., :3].std() > 2 and (out[..., 3] == 255).all()
     assert np.isfinite(snap["giFullY/0"].view(np.float16).astype(np.float32)).all()
+
+
+def test_alpha_test_discards_before_the_depth_test(ffi, oracle):
+    """depthPrepass.frag:28-31: fragments whose albedo alpha (bilinear, repeat) is below 0.5 are discarded - what lies behind shows"""
+    w, h = 32, 16
+    cutout = (2, 1, [255, 255, 255, 0, 255, 255, 255, 255])   # left texel transparent, right texel opaque
+    opaque = (1, 1, [255, 255, 255, 255])
+    front, back = quad(ffi, 0, w, 0, h, w, h, z=0.75), quad(ffi, 0, w, 0, h, w, h, z=0.25)
+    depth, _, _, gb = passes.raster_prepass(ffi, oracle, w, h, [front, back], [(0, 0, 0, 1, 1), (1, 0, 1, 1, 1)], mats(), textures=[cutout, opaque], gbuffer=True)
+    u = (np.arange(w) + 0.5) / w
+    fx = u * 2 - 0.5
+    wgt = fx - np.floor(fx)
+    a0, a1 = np.array([0.0, 1.0])[np.floor(fx).astype(int) % 2], np.array([0.0, 1.0])[(np.floor(fx).astype(int) + 1) % 2]
+    alpha = a0 * (1 - wgt) + a1 * wgt
+    sure = np.abs(alpha - 0.5) > 1e-3
+    want = np.where(alpha >= 0.5, 0.75, 0.25).astype(np.float32)
+    assert (depth[:, sure] == want[None, sure]).all()
+    assert 0.3 < (depth == 0.25).mean() < 0.7
+    assert np.array_equal(gb[..., 0], depth.view(np.uint32))  # the G-buffer fill resolves the surviving fragments
+    # the shadow pass applies the same test (sunShadow.frag:19-22)
+    sm = passes.raster_shadow(ffi, oracle, 32, [quad(ffi, 0, 32, 0, 32, 32, 32, z=0.5, front=False)], [(0, 0)], [IDENTITY], np.tile(IDENTITY, (4, 1)), albedo=cutout)
+    assert ((sm > 0).mean(axis=0)[sure] == (alpha >= 0.5)[sure]).all()
