@@ -47,7 +47,7 @@ def test_prepass_and_gbuffer_bit_exact(ffi, cuda, oracle, w, h, n_tris, big):
     kw = dict(jitter=((0.5 / w, -0.25 / h), (-0.125 / w, 0.375 / h)), textures=random_textures(rng), gbuffer=True)
     got = passes.raster_prepass(ffi, cuda, w, h, meshes, draws, m, **kw)
     want = passes.raster_prepass(ffi, oracle, w, h, meshes, draws, m, **kw)
-    assert (want[0] > 0).mean() > 0.2, "the test scene should cover a good part of the frame"
+    assert (want[0] > 0).mean() > 0.05, "the test scene should cover part of the frame (the random-alpha albedo textures cut holes)"
     for name, a, b in zip(("depth", "motion", "normal", "gbuffer"), got, want):
         assert np.array_equal(a.view(np.uint8), b.view(np.uint8)), "%s: %d texels differ" % (name, int((a != b).reshape(h * w, -1).any(-1).sum()))
 
