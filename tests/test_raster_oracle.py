@@ -200,3 +200,73 @@ def test_alpha_test_discards_before_the_depth_test(ffi, oracle):
     # the shadow pass applies the same test (sunShadow.frag:19-22)
     sm = passes.raster_shadow(ffi, oracle, 32, [quad(ffi, 0, 32, 0, 32, 32, 32, z=0.5, front=False)], [(0, 0)], [IDENTITY], np.tile(IDENTITY, (4, 1)), albedo=cutout)
     assert ((sm > 0).mean(axis=0)[sure] == (alpha >= 0.5)[sure]).all()
+
+
+def test_fan_of_triangles_is_watertight(ffi, oracle):
+    """a fan of triangles tiling a convex polygon at arbitrary sub-pixel positions: every pixel centre strictly inside the polygon
+    is covered (no cracks along the shared edges), every centre strictly outside is not"""
+    w, h = 64, 48
+    rng = np.random.default_rng(7)
+    for trial in range(4):
+        n = 9
+        ang = np.sort(rng.uniform(0, 2 * np.pi, n))
+        rad = rng.uniform(14, 22, n)
+        centre = np.array([32.3, 24.6]) + rng.uniform(-0.5, 0.5, 2)
+        ring = centre + np.stack([np.cos(ang), np.sin(ang)], -1) * rad[:, None]      # pixel coordinates, counter clockwise for y up
+        pts = np.concatenate([[centre], ring])
+        pos = np.stack([ndc(pts[:, 0], w), ndc(pts[:, 1], h), np.full(len(pts), 0.5)], -1).astype(np.float32)
+        idx = []
+        for k in range(n):
+            a, b = 1 + k, 1 + (k + 1) % n
+            idx += [0, b, a]  # front faces: counter clockwise on the y-down screen
+        depth, _, _ = passes.raster_prepass(ffi, oracle, w, h, [(idx, ffi.pack_vertices(pos, normals=np.tile([[0, 0, 1]], (len(pts), 1))))], [(0, 0)], mats())
+        if not (depth > 0).any():
+            idx = [i for t in np.array(idx).reshape(-1, 3)[:, ::-1] for i in t]
+            depth, _, _ = passes.raster_prepass(ffi, oracle, w, h, [(idx, ffi.pack_vertices(pos, normals=np.tile([[0, 0, 1]], (len(pts), 1))))], [(0, 0)], mats())
+        # the snapped polygon (1/256 pixel) is what is rasterised: test against it with a margin of one snap step
+        snapped = np.floor(((pos[:, :2].astype(np.float64) * 0.5 + 0.5) * [w, h]) * 256 + 0.5) / 256
+        ys, xs = np.mgrid[0:h, 0:w]
+        c = np.stack([xs + 0.5, ys + 0.5], -1)
+        inside_all = np.zeros((h, w), bool)
+        near_edge = np.zeros((h, w), bool)
+        for t in np.array(idx).reshape(-1, 3):
+            a, b, cc = snapped[t]
+            e = lambda p, q: (q[0] - p[0]) * (c[..., 1] - p[1]) - (q[1] - p[1]) * (c[..., 0] - p[0])
+            e0, e1, e2 = e(a, b), e(b, cc), e(cc, a)
+            s = np.sign((b[0] - a[0]) * (cc[1] - a[1]) - (cc[0] - a[0]) * (b[1] - a[1]))
+            inside_all |= (s * e0 >= 0) & (s * e1 >= 0) & (s * e2 >= 0)
+        # polygon boundary = ring edges only
+        ringp = snapped[1:]
+        for k in range(n):
+            p, q = ringp[k], ringp[(k + 1) % n]
+            d = np.abs((q[0] - p[0]) * (c[..., 1] - p[1]) - (q[1] - p[1]) * (c[..., 0] - p[0])) / np.hypot(*(q - p))
+            near_edge |= d < 0.02
+        assert ((depth > 0) == inside_all)[~near_edge].all(), "trial %d: %d pixels differ" % (trial, int((((depth > 0) != inside_all) & ~near_edge).sum()))
+
+
+def test_guard_band_far_plane_and_depth_range(ffi, oracle):
+    """a triangle reaching 10^6 pixels off screen is clipped to the guard band without disturbing what is visible; fragments
+    behind the far plane (depth < 0) are dropped by the prepass"""
+    w, h = 32, 16
+    # x from -0.5 NDC to 60000 NDC: the visible part must be exactly the half plane right of x = -0.5, between the two slanted edges
+    pos = np.array([[-0.5, -0.75, 0.5], [60000.0, -30000.0, 0.5], [60000.0, 30000.0, 0.5]], np.float32)
+    for idx in ([0, 1, 2], [0, 2, 1]):
+        depth, _, _ = passes.raster_prepass(ffi, oracle, w, h, [(idx, ffi.pack_vertices(pos, normals=np.tile([[0, 0, 1]], (3, 1))))], [(0, 0)], mats())
+        if (depth > 0).any():
+            break
+    ys, xs = np.mgrid[0:h, 0:w]
+    nx, ny = (xs + 0.5) / w * 2 - 1, (ys + 0.5) / h * 2 - 1
+    t = (nx + 0.5) / 60000.5
+    lo, hi = -0.75 + t * (-30000 + 0.75), -0.75 + t * (30000 + 0.75)
+    inside = (nx > -0.5 + 1e-3) & (ny > lo + 1e-3) & (ny < hi - 1e-3)
+    outside = (nx < -0.5 - 1e-3) | (ny < lo - 1e-3) | (ny > hi + 1e-3)
+    assert (depth[inside] == 0.5).all() and (depth[outside] == 0).all() and inside.sum() > 100
+    # depth from 0.5 at the left edge to -0.5 at the right edge: the part behind the far plane (depth < 0) is dropped
+    q = quad(ffi, 0, w, 0, h, w, h)
+    vtx = np.array(q[1]).copy()
+    zs = np.array([0.5, -0.5, -0.5, 0.5], np.float32)  # per corner (x0, x1, x1, x0)
+    vtx[:, 8:12] = zs.view(np.uint8).reshape(4, 4)
+    depth2, _, _ = passes.raster_prepass(ffi, oracle, w, h, [(q[0], vtx)], [(0, 0)], mats())
+    want = 0.5 - (np.arange(w) + 0.5) / w
+    assert ((depth2 > 0) == (want > 0)[None, :]).all()
+    assert np.allclose(depth2[:, want > 0], want[None, want > 0], atol=1e-6)
