@@ -89,6 +89,19 @@ PLAIN_EXPORT int PLAIN_FE(set_mesh_geometry)(plain_frontend* fe, uint32_t mesh, 
 PLAIN_EXPORT int PLAIN_FE(set_scene)(plain_frontend* fe, uint32_t n_objects, const uint32_t* mesh_indices, const float* model_matrices /* 16 each, column-major */,
                                      const float* bb_world_min /* 3 each */, const float* bb_world_max /* 3 each */);
 
+/* ---- the host-side functions of the frame driver, exposed so that tests can hold them against the reference's own host code
+ * (oracle/ref/ref_host_shim.cpp over Camera.cpp, ViewFrustum.cpp, Culling.cpp, MathUtils.cpp, sdfUtilities.cpp). Frustum layout: points
+ * l_l_n, l_l_f, l_u_n, l_u_f, r_l_n, r_l_f, r_u_n, r_u_f; normals top, bot, right, left, near, far (ViewFrustum.h:6-30). ---- */
+PLAIN_EXPORT void PLAIN_FE(host_hammersley2d)(uint32_t index, float out[2]);                                  /* MathUtils.cpp:25-70 */
+PLAIN_EXPORT void PLAIN_FE(host_direction_to_vector)(const float angles_deg[2], float out[3]);                /* MathUtils.cpp:4-15 */
+PLAIN_EXPORT uint32_t PLAIN_FE(host_mip_count_from_resolution)(uint32_t width, uint32_t height, uint32_t depth); /* MathUtils.cpp:17-19 */
+PLAIN_EXPORT void PLAIN_FE(host_camera_matrices)(const plain_camera_extrinsic* camera, float fov_deg, float aspect, float near_plane, float far_plane,
+                                                 float out_view[16], float out_projection[16]);               /* Camera.cpp:4-27 */
+PLAIN_EXPORT void PLAIN_FE(host_view_frustum)(const plain_camera_extrinsic* camera, float fov_deg, float aspect, float near_plane, float far_plane,
+                                              float out_points[24], float out_normals[18]);                   /* ViewFrustum.cpp:4-60 */
+PLAIN_EXPORT int PLAIN_FE(host_aabb_intersects_frustum)(const float points[24], const float normals[18], const float bb_min[3], const float bb_max[3]); /* Culling.cpp:5-42 */
+PLAIN_EXPORT void PLAIN_FE(host_pad_sdf_bounding_box)(const float bb_min[3], const float bb_max[3], float out_min[3], float out_max[3]); /* sdfUtilities.cpp:5-19 */
+
 /* one frame */
 PLAIN_EXPORT int PLAIN_FE(render_frame)(plain_frontend* fe, const plain_camera_extrinsic* camera, float time, float delta_time, const plain_frame_inputs* inputs);
 /* ---- row-sharded frames: one frame = begin_frame, then run_segment until it reports no pending exchange. Between two

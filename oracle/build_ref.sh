@@ -8,6 +8,16 @@ HERE="$(cd "$(dirname "$0")" && pwd)"
 OUT="$HERE/_ref"
 [ -d "$REF/Plain/src/AssetPipeline" ] || { echo "reference not present at $REF"; exit 0; }
 mkdir -p "$OUT"
+# the reference's own host-side functions that feed the frame path (camera matrices, view frustum, culling, Hammersley jitter, SDF
+# bounding-box padding, vertex compression) behind the C entry points of oracle/ref/ref_host_shim.cpp: tests/test_host_vs_reference.py
+if [ ! -f "$OUT/libref_host.so" ] || [ "$HERE/ref/ref_host_shim.cpp" -nt "$OUT/libref_host.so" ] || [ "$HERE/build_ref.sh" -nt "$OUT/libref_host.so" ]; then
+    g++ -std=c++17 -O2 -w -fpermissive -shared -fPIC -fvisibility=hidden -include cassert -include cstring -include stdexcept -include math.h -include stdlib.h \
+        -I"$HERE/shim" -I"$REF/Plain/src" -I"$REF/Plain/src/Common" -I"$REF/Plain/src/Runtime/Rendering" -I"$REF/Plain/vendor" -I"$REF/Plain/vendor/glm" \
+        "$HERE/ref/ref_host_shim.cpp" "$REF"/Plain/src/Runtime/Rendering/Camera.cpp "$REF"/Plain/src/Runtime/Rendering/ViewFrustum.cpp "$REF"/Plain/src/Runtime/Rendering/Culling.cpp \
+        "$REF"/Plain/src/Common/Utilities/MathUtils.cpp "$REF"/Plain/src/Common/sdfUtilities.cpp "$REF"/Plain/src/Common/CompressedTypes.cpp "$REF"/Plain/src/Common/AABB.cpp \
+        -o "$OUT/libref_host.so"
+    echo "built $OUT/libref_host.so"
+fi
 [ -x "$OUT/PlainAssetPipeline" ] && [ "$OUT/PlainAssetPipeline" -nt "$HERE/build_ref.sh" ] && { echo "up to date: $OUT/PlainAssetPipeline"; exit 0; }
 # -include math.h / stdlib.h: libstdc++'s C++ wrappers pull the float overloads of abs/sin/cos/sqrt into the global namespace, as
 # MSVC's headers do for the reference's own build. Without them the unqualified abs(float) calls of SceneSDF.cpp resolve to

@@ -172,7 +172,9 @@ FRONTEND_SYMBOLS = [
     "default_settings", "create", "destroy", "last_error", "backend", "register_sdf_mesh", "set_mesh_geometry", "set_scene", "render_frame", "begin_frame", "run_segment", "set_peer_exchange", "shard_band",
     "read_output_rows", "read_output", "get_image",
     "get_storage_buffer", "get_global_shader_info", "get_resolve_weights", "set_exposure", "synthetic_scene_create", "synthetic_scene_destroy",
-    "synthetic_scene_attach", "synthetic_scene_render_inputs"]
+    "synthetic_scene_attach", "synthetic_scene_render_inputs",
+    "host_hammersley2d", "host_direction_to_vector", "host_mip_count_from_resolution", "host_camera_matrices", "host_view_frustum", "host_aabb_intersects_frustum",
+    "host_pad_sdf_bounding_box"]
 
 
 class ApiError(RuntimeError):

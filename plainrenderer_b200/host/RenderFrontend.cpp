@@ -82,7 +82,7 @@ ViewFrustum computeViewFrustum(const CameraExtrinsic& e, const CameraIntrinsic& 
     f.far = normalize(cross(f.r_l_f - f.l_l_f, f.r_u_f - f.r_l_f));
     return f;
 }
-static hm::Mat4 viewMatrixFromCameraExtrinsic(const CameraExtrinsic& e) {  // Camera.cpp:4-12
+hm::Mat4 viewMatrixFromCameraExtrinsic(const CameraExtrinsic& e) {  // Camera.cpp:4-12
     hm::Mat4 v = hm::Mat4::identity();
     v.at(0, 0) = e.right.x; v.at(0, 1) = e.right.y; v.at(0, 2) = e.right.z;
     v.at(1, 0) = e.up.x; v.at(1, 1) = e.up.y; v.at(1, 2) = e.up.z;
@@ -90,7 +90,7 @@ static hm::Mat4 viewMatrixFromCameraExtrinsic(const CameraExtrinsic& e) {  // Ca
     v = hm::transpose(v);
     return v * hm::translate(-e.position);
 }
-static hm::Mat4 projectionMatrixFromCameraIntrinsic(const CameraIntrinsic& in) {  // Camera.cpp:14-27: y flip, reverse z
+hm::Mat4 projectionMatrixFromCameraIntrinsic(const CameraIntrinsic& in) {  // Camera.cpp:14-27: y flip, reverse z
     hm::Mat4 p = hm::perspective(hm::radians(in.fov), in.aspectRatio, in.near, in.far);
     hm::Mat4 c = hm::Mat4::identity();
     c.at(1, 1) = -1.f; c.at(2, 2) = -0.5f; c.at(3, 2) = 0.5f;

@@ -70,6 +70,8 @@ struct ViewFrustum {  // ViewFrustum.h:6-30
     hm::Vec3 top, bot, right, left, near, far;
 };
 ViewFrustum computeViewFrustum(const CameraExtrinsic& e, const CameraIntrinsic& i);
+hm::Mat4 viewMatrixFromCameraExtrinsic(const CameraExtrinsic& e);      // Camera.cpp:4-12
+hm::Mat4 projectionMatrixFromCameraIntrinsic(const CameraIntrinsic& i);  // Camera.cpp:14-27
 
 // frame counters of the reference's main loop (FrameIndex.cpp:12-18), owned by the frontend instead of a global
 struct FrameIndex {

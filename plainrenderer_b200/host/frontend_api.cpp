@@ -248,6 +248,53 @@ int PLAIN_FE(get_storage_buffer)(plain_frontend* fe, const char* name, plain_han
 }
 int PLAIN_FE(get_global_shader_info)(plain_frontend* fe, void* out) { std::memcpy(out, &fe->fe.m_globalShaderInfo, sizeof(plain_global_shader_info)); return 0; }
 int PLAIN_FE(get_resolve_weights)(plain_frontend* fe, float out[9]) { std::memcpy(out, fe->fe.m_taa.m_lastResolveWeights.data(), sizeof(float) * 9); return 0; }
+// ---- host-side functions, for tests against the reference's own host code ----
+static CameraExtrinsic extrinsicOf(const plain_camera_extrinsic* c) {
+    CameraExtrinsic e;
+    e.position = hm::Vec3(c->position[0], c->position[1], c->position[2]);
+    e.forward = hm::Vec3(c->forward[0], c->forward[1], c->forward[2]);
+    e.right = hm::Vec3(c->right[0], c->right[1], c->right[2]);
+    e.up = hm::Vec3(c->up[0], c->up[1], c->up[2]);
+    return e;
+}
+static CameraIntrinsic intrinsicOf(float fov, float aspect, float nearPlane, float farPlane) {
+    CameraIntrinsic i;
+    i.fov = fov; i.aspectRatio = aspect; i.near = nearPlane; i.far = farPlane;
+    return i;
+}
+static void put3(float* out, hm::Vec3 v) { out[0] = v.x; out[1] = v.y; out[2] = v.z; }
+void PLAIN_FE(host_hammersley2d)(uint32_t index, float out[2]) { const hm::Vec2 h = hammersley2D(index); out[0] = h.x; out[1] = h.y; }
+void PLAIN_FE(host_direction_to_vector)(const float deg[2], float out[3]) { hm::Vec2 d; d.x = deg[0]; d.y = deg[1]; put3(out, directionToVector(d)); }
+uint32_t PLAIN_FE(host_mip_count_from_resolution)(uint32_t w, uint32_t h, uint32_t d) { return mipCountFromResolution(w, h, d); }
+void PLAIN_FE(host_camera_matrices)(const plain_camera_extrinsic* c, float fov, float aspect, float nearPlane, float farPlane, float outView[16], float outProjection[16]) {
+    const hm::Mat4 v = viewMatrixFromCameraExtrinsic(extrinsicOf(c)), p = projectionMatrixFromCameraIntrinsic(intrinsicOf(fov, aspect, nearPlane, farPlane));
+    std::memcpy(outView, v.m, 64);
+    std::memcpy(outProjection, p.m, 64);
+}
+void PLAIN_FE(host_view_frustum)(const plain_camera_extrinsic* c, float fov, float aspect, float nearPlane, float farPlane, float outPoints[24], float outNormals[18]) {
+    const ViewFrustum f = computeViewFrustum(extrinsicOf(c), intrinsicOf(fov, aspect, nearPlane, farPlane));
+    const hm::Vec3 p[8] = {f.l_l_n, f.l_l_f, f.l_u_n, f.l_u_f, f.r_l_n, f.r_l_f, f.r_u_n, f.r_u_f}, n[6] = {f.top, f.bot, f.right, f.left, f.near, f.far};
+    for (int i = 0; i < 8; i++) put3(outPoints + 3 * i, p[i]);
+    for (int i = 0; i < 6; i++) put3(outNormals + 3 * i, n[i]);
+}
+int PLAIN_FE(host_aabb_intersects_frustum)(const float points[24], const float normals[18], const float bbMin[3], const float bbMax[3]) {
+    ViewFrustum f;
+    hm::Vec3* p[8] = {&f.l_l_n, &f.l_l_f, &f.l_u_n, &f.l_u_f, &f.r_l_n, &f.r_l_f, &f.r_u_n, &f.r_u_f};
+    hm::Vec3* n[6] = {&f.top, &f.bot, &f.right, &f.left, &f.near, &f.far};
+    for (int i = 0; i < 8; i++) *p[i] = hm::Vec3(points[3 * i], points[3 * i + 1], points[3 * i + 2]);
+    for (int i = 0; i < 6; i++) *n[i] = hm::Vec3(normals[3 * i], normals[3 * i + 1], normals[3 * i + 2]);
+    hm::AABB bb;
+    bb.min = hm::Vec3(bbMin[0], bbMin[1], bbMin[2]);
+    bb.max = hm::Vec3(bbMax[0], bbMax[1], bbMax[2]);
+    return isAxisAlignedBoundingBoxIntersectingViewFrustum(f, bb) ? 1 : 0;
+}
+void PLAIN_FE(host_pad_sdf_bounding_box)(const float bbMin[3], const float bbMax[3], float outMin[3], float outMax[3]) {
+    hm::AABB bb;
+    bb.min = hm::Vec3(bbMin[0], bbMin[1], bbMin[2]);
+    bb.max = hm::Vec3(bbMax[0], bbMax[1], bbMax[2]);
+    const hm::AABB r = padSDFBoundingBox(bb);
+    put3(outMin, r.min); put3(outMax, r.max);
+}
 int PLAIN_FE(set_exposure)(plain_frontend* fe, float previousFrameExposure) {
     FE_TRY(fe, {
         plain_light_buffer lb{};
