@@ -102,6 +102,8 @@ PLAIN_EXPORT void PLAIN_FE(host_view_frustum)(const plain_camera_extrinsic* came
 PLAIN_EXPORT int PLAIN_FE(host_aabb_intersects_frustum)(const float points[24], const float normals[18], const float bb_min[3], const float bb_max[3]); /* Culling.cpp:5-42 */
 PLAIN_EXPORT void PLAIN_FE(host_pad_sdf_bounding_box)(const float bb_min[3], const float bb_max[3], float out_min[3], float out_max[3]); /* sdfUtilities.cpp:5-19 */
 
+PLAIN_EXPORT void PLAIN_FE(host_sdf_world_to_local)(const float model_matrix[16], const float bb_offset[3], float out[16]);  /* SDFGI.cpp:288-292 */
+
 /* one frame */
 PLAIN_EXPORT int PLAIN_FE(render_frame)(plain_frontend* fe, const plain_camera_extrinsic* camera, float time, float delta_time, const plain_frame_inputs* inputs);
 /* ---- row-sharded frames: one frame = begin_frame, then run_segment until it reports no pending exchange. Between two

@@ -63,5 +63,13 @@ __attribute__((visibility("default"))) void ref_padSDFBoundingBox(const float bb
     const AxisAlignedBoundingBox r = padSDFBoundingBox(bb);
     put(outMin, r.min); put(outMax, r.max);
 }
+// SDFGI.cpp:288-292 computes worldToLocal = glm::inverse(modelMatrix * glm::translate(glm::mat4(1.f), bbOffset)) inline in
+// SDFGI::updateSDFScene (a method that needs the Vulkan backend); the same glm calls on the same operands
+__attribute__((visibility("default"))) void ref_sdfWorldToLocal(const float model[16], const float bbOffset[3], float out[16]) {
+    glm::mat4 m;
+    memcpy(&m[0][0], model, 64);
+    const glm::mat4 r = glm::inverse(m * glm::translate(glm::mat4(1.f), glm::vec3(bbOffset[0], bbOffset[1], bbOffset[2])));
+    memcpy(out, &r[0][0], 64);
+}
 __attribute__((visibility("default"))) uint32_t ref_vec3ToNormalizedR10B10G10A2(const float v[3]) { return vec3ToNormalizedR10B10G10A2(glm::vec3(v[0], v[1], v[2])).value; }
 }

@@ -174,7 +174,7 @@ FRONTEND_SYMBOLS = [
     "get_storage_buffer", "get_global_shader_info", "get_resolve_weights", "set_exposure", "synthetic_scene_create", "synthetic_scene_destroy",
     "synthetic_scene_attach", "synthetic_scene_render_inputs",
     "host_hammersley2d", "host_direction_to_vector", "host_mip_count_from_resolution", "host_camera_matrices", "host_view_frustum", "host_aabb_intersects_frustum",
-    "host_pad_sdf_bounding_box"]
+    "host_pad_sdf_bounding_box", "host_sdf_world_to_local"]
 
 
 class ApiError(RuntimeError):

@@ -295,6 +295,12 @@ void PLAIN_FE(host_pad_sdf_bounding_box)(const float bbMin[3], const float bbMax
     const hm::AABB r = padSDFBoundingBox(bb);
     put3(outMin, r.min); put3(outMax, r.max);
 }
+void PLAIN_FE(host_sdf_world_to_local)(const float model[16], const float bbOffset[3], float out[16]) {  // as SDFGI::updateSDFScene (Techniques.cpp)
+    hm::Mat4 m;
+    std::memcpy(m.m, model, 64);
+    const hm::Mat4 r = hm::inverse(m * hm::translate(hm::Vec3(bbOffset[0], bbOffset[1], bbOffset[2])));
+    std::memcpy(out, r.m, 64);
+}
 int PLAIN_FE(set_exposure)(plain_frontend* fe, float previousFrameExposure) {
     FE_TRY(fe, {
         plain_light_buffer lb{};

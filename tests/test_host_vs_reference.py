@@ -107,3 +107,21 @@ def test_vertex_normal_packing(ffi, ref):
     got = np.frombuffer(packed[:, 16:20].tobytes(), np.uint32)
     want = np.array([ref.ref_vec3ToNormalizedR10B10G10A2(vec(x)) for x in v], np.uint32)
     assert np.array_equal(got, want)
+
+
+def test_sdf_instance_world_to_local(ffi, oracle, ref):
+    """worldToLocal of an SDF instance = inverse(model * translate(bbOffset)) (SDFGI.cpp:288-292): the mirror's 4x4 inverse against glm's"""
+    rng = np.random.default_rng(9)
+    for _ in range(40):
+        ang = rng.uniform(0, 2 * np.pi, 3)
+        rx = np.array([[1, 0, 0], [0, np.cos(ang[0]), -np.sin(ang[0])], [0, np.sin(ang[0]), np.cos(ang[0])]])
+        ry = np.array([[np.cos(ang[1]), 0, np.sin(ang[1])], [0, 1, 0], [-np.sin(ang[1]), 0, np.cos(ang[1])]])
+        M = np.eye(4)
+        M[:3, :3] = (rx @ ry) * rng.uniform(0.3, 4.0, 3)[None, :]
+        M[:3, 3] = rng.uniform(-30, 30, 3)
+        model = vec(M.T.ravel())
+        off = vec(rng.uniform(-3, 3, 3))
+        a, b = arr(16), arr(16)
+        oracle.f["host_sdf_world_to_local"](model, off, a)
+        ref.ref_sdfWorldToLocal(model, off, b)
+        assert np.allclose(list(a), list(b), rtol=2e-5, atol=2e-5)
