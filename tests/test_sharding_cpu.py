@@ -116,3 +116,34 @@ def test_exchanges_over_gloo_world_size_2(cuda):
             assert np.array_equal(img[lo:hi], expect(rows, img.shape[1], i)[lo:hi])  # own band + 3 halo rows
             assert not img[:lo].any() and not img[hi:].any()                         # nothing else was touched
         assert np.array_equal(out[r]["hist"], np.arange(128, dtype=np.uint32) * 3)
+
+
+def test_exchange_schedule_of_a_sharded_frame(ffi, oracle):
+    """the exchanges a row-sharded frontend asks for, in order - with uploaded inputs (10) and with rasterised inputs (the motion
+    vectors become an 11th, right after the depth prepass). Driven against the CPU backend: the schedule is host-side logic."""
+    from conftest import PlainSceneSequence
+    from plainrenderer_b200 import assets
+
+    def schedule(fe, cam):
+        names = []
+        fe.begin_frame(cam, 1 / 60.0, 1 / 60.0)
+        while True:
+            x = fe.run_segment()
+            if x is None:
+                return names
+            names.append((x.name.decode(), x.kind, x.n_images))
+    lib = assets.Assets(ROOT / "oracle" / "_build" / "liboracle.so", "oracle_asset_")
+    seq = PlainSceneSequence(ffi, oracle, lib, 64, 64, shard_rank=0, shard_count=2)
+    raster = schedule(seq.fe, seq.camera_at(0, False))
+    seq.close()
+    s = ffi.default_settings(oracle, 64, 64, shard_rank=1, shard_count=2)
+    fe = ffi.Frontend(oracle, s)
+    scene = ffi.SyntheticScene(oracle, n_instances=4)
+    scene.attach(fe)
+    uploaded = schedule(fe, ffi.camera((-13.0, -1.7, 0.5), (1, 0, 0), (0, 0, 1), (0, -1, 0)))
+    scene.close()
+    fe.close()
+    assert [n for n, _, _ in uploaded] == ["histogram", "hiz", "depthHalf", "giTrace", "giSpatial0", "giTemporal", "giSpatial1", "froxelHistory", "taaHistory", "bloomMip1"]
+    assert [n for n, _, _ in raster] == ["histogram", "motion"] + [n for n, _, _ in uploaded][1:]
+    assert dict((n, k) for n, k, _ in raster)["motion"] == ffi.EXCHANGE_ALLGATHER_ROWS
+    assert uploaded[0][1] == ffi.EXCHANGE_ALLREDUCE_SUM_U32
