@@ -99,10 +99,16 @@ PLAIN_EXPORT void PLAIN_FE(host_camera_matrices)(const plain_camera_extrinsic* c
                                                  float out_view[16], float out_projection[16]);               /* Camera.cpp:4-27 */
 PLAIN_EXPORT void PLAIN_FE(host_view_frustum)(const plain_camera_extrinsic* camera, float fov_deg, float aspect, float near_plane, float far_plane,
                                               float out_points[24], float out_normals[18]);                   /* ViewFrustum.cpp:4-60 */
+PLAIN_EXPORT void PLAIN_FE(host_orthogonal_frustum_fitted_to_camera)(const float points[24], const float normals[18], const float light_direction[3],
+                                                                     float out_points[24], float out_normals[18]);  /* ViewFrustum.cpp:231-271 */
 PLAIN_EXPORT int PLAIN_FE(host_aabb_intersects_frustum)(const float points[24], const float normals[18], const float bb_min[3], const float bb_max[3]); /* Culling.cpp:5-42 */
 PLAIN_EXPORT void PLAIN_FE(host_pad_sdf_bounding_box)(const float bb_min[3], const float bb_max[3], float out_min[3], float out_max[3]); /* sdfUtilities.cpp:5-19 */
 
 PLAIN_EXPORT void PLAIN_FE(host_sdf_world_to_local)(const float model_matrix[16], const float bb_offset[3], float out[16]);  /* SDFGI.cpp:288-292 */
+
+/* draw calls recorded for the last frame: out[0] main pass / prepass (after camera-frustum culling), out[1] per shadow cascade (after
+ * culling against the sun shadow frustum): the reference's m_currentMainPassDrawcallCount / m_currentShadowPassDrawcallCount */
+PLAIN_EXPORT int PLAIN_FE(get_drawcall_counts)(plain_frontend* fe, uint32_t out[2]);
 
 /* one frame */
 PLAIN_EXPORT int PLAIN_FE(render_frame)(plain_frontend* fe, const plain_camera_extrinsic* camera, float time, float delta_time, const plain_frame_inputs* inputs);

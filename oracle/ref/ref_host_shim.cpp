@@ -50,6 +50,9 @@ __attribute__((visibility("default"))) void ref_viewFrustum(const float* pos, co
                                                              float outPoints[24], float outNormals[18]) {
     frustumOut(computeViewFrustum(makeCamera(pos, fwd, right, up, fov, aspect, nearPlane, farPlane)), outPoints, outNormals);
 }
+__attribute__((visibility("default"))) void ref_orthogonalFrustumFittedToCamera(const float points[24], const float normals[18], const float lightDirection[3], float outPoints[24], float outNormals[18]) {
+    frustumOut(computeOrthogonalFrustumFittedToCamera(frustumIn(points, normals), glm::vec3(lightDirection[0], lightDirection[1], lightDirection[2])), outPoints, outNormals);
+}
 __attribute__((visibility("default"))) int ref_aabbIntersectsFrustum(const float points[24], const float normals[18], const float bbMin[3], const float bbMax[3]) {
     AxisAlignedBoundingBox bb;
     bb.min = glm::vec3(bbMin[0], bbMin[1], bbMin[2]);

@@ -174,7 +174,7 @@ FRONTEND_SYMBOLS = [
     "get_storage_buffer", "get_global_shader_info", "get_resolve_weights", "set_exposure", "synthetic_scene_create", "synthetic_scene_destroy",
     "synthetic_scene_attach", "synthetic_scene_render_inputs",
     "host_hammersley2d", "host_direction_to_vector", "host_mip_count_from_resolution", "host_camera_matrices", "host_view_frustum", "host_aabb_intersects_frustum",
-    "host_pad_sdf_bounding_box", "host_sdf_world_to_local"]
+    "host_pad_sdf_bounding_box", "host_sdf_world_to_local", "host_orthogonal_frustum_fitted_to_camera", "get_drawcall_counts"]
 
 
 class ApiError(RuntimeError):
@@ -513,6 +513,12 @@ class Frontend:
             fi.shadow_maps[i] = _ptr(shadow_maps[i]) if shadow_maps is not None and i < len(shadow_maps) and shadow_maps[i] is not None else None
         fi.async_upload = int(async_upload)
         self._check(self.api.f["render_frame"](self.fe, C.byref(cam), f32(time), f32(delta_time), C.byref(fi)), "render_frame")
+
+    def drawcall_counts(self):
+        """(main pass / prepass draws, draws per shadow cascade) of the last frame, after the host-side culling"""
+        out = (u32 * 2)()
+        self._check(self.api.f["get_drawcall_counts"](self.fe, out), "get_drawcall_counts")
+        return out[0], out[1]
 
     def read_output(self, out=None, async_pinned=False):
         if out is None:

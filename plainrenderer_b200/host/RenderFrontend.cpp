@@ -82,6 +82,48 @@ ViewFrustum computeViewFrustum(const CameraExtrinsic& e, const CameraIntrinsic& 
     f.far = normalize(cross(f.r_l_f - f.l_l_f, f.r_u_f - f.r_l_f));
     return f;
 }
+static void computeViewFrustumNormals(ViewFrustum& f) {  // ViewFrustum.cpp:39-51
+    using namespace hm;
+    f.top = normalize(cross(f.r_u_f - f.r_u_n, f.r_u_n - f.l_u_n));
+    f.bot = normalize(cross(f.r_l_n - f.l_l_n, f.r_l_f - f.r_l_n));
+    f.right = normalize(cross(f.r_u_n - f.r_l_n, f.r_l_f - f.r_l_n));
+    f.left = normalize(cross(f.l_l_f - f.l_l_n, f.l_u_n - f.l_l_n));
+    f.near = normalize(cross(f.r_u_n - f.r_l_n, f.r_l_n - f.l_l_n));
+    f.far = normalize(cross(f.r_l_f - f.l_l_f, f.r_u_f - f.r_l_f));
+}
+// the orthographic box, in the light's view space, around the eight corners of the camera frustum (ViewFrustum.cpp:231-271)
+ViewFrustum computeOrthogonalFrustumFittedToCamera(const ViewFrustum& c, hm::Vec3 lightDirection) {
+    using namespace hm;
+    const Vec3 up = dm::abs_(lightDirection.y) < 0.999f ? Vec3(0.f, -1.f, 0.f) : Vec3(0.f, 0.f, -1.f);
+    // glm::lookAt(eye = -lightDirection, center = 0, up), right-handed
+    const Vec3 eye = -lightDirection;
+    const Vec3 fw = normalize(Vec3(0.f) - eye), s = normalize(cross(fw, up)), u = cross(s, fw);
+    Mat4 V = Mat4::identity();
+    V.at(0, 0) = s.x; V.at(1, 0) = s.y; V.at(2, 0) = s.z;
+    V.at(0, 1) = u.x; V.at(1, 1) = u.y; V.at(2, 1) = u.z;
+    V.at(0, 2) = -fw.x; V.at(1, 2) = -fw.y; V.at(2, 2) = -fw.z;
+    V.at(3, 0) = -dot(s, eye); V.at(3, 1) = -dot(u, eye); V.at(3, 2) = dot(fw, eye);
+    const float inf = dm::inff_();
+    Vec3 maxP(-inf), minP(inf);
+    const Vec3 corners[8] = {c.l_l_f, c.l_l_n, c.r_l_f, c.r_l_n, c.l_u_f, c.l_u_n, c.r_u_f, c.r_u_n};
+    for (const Vec3& p : corners) {
+        const Vec4 t = V * Vec4(p, 1.f);
+        minP = vmin(minP, Vec3(t.x, t.y, t.z));
+        maxP = vmax(maxP, Vec3(t.x, t.y, t.z));
+    }
+    const Vec3 scale(2.f / (maxP.x - minP.x), 2.f / (maxP.y - minP.y), 2.f / (maxP.z - minP.z));
+    const Vec3 offset = (maxP + minP) * -0.5f * scale;
+    Mat4 clip = Mat4::identity();
+    clip.at(0, 0) = scale.x; clip.at(1, 1) = scale.y; clip.at(2, 2) = scale.z;
+    clip.at(3, 0) = offset.x; clip.at(3, 1) = offset.y; clip.at(3, 2) = offset.z;
+    const Mat4 clipToWorld = inverse(clip * V);
+    auto corner = [&](float x, float y, float z) { const Vec4 t = clipToWorld * Vec4(x, y, z, 1.f); return Vec3(t.x, t.y, t.z); };
+    ViewFrustum r;
+    r.l_l_n = corner(-1, -1, -1); r.r_l_n = corner(1, -1, -1); r.l_u_n = corner(-1, 1, -1); r.r_u_n = corner(1, 1, -1);
+    r.l_l_f = corner(-1, -1, 1); r.r_l_f = corner(1, -1, 1); r.l_u_f = corner(-1, 1, 1); r.r_u_f = corner(1, 1, 1);
+    computeViewFrustumNormals(r);
+    return r;
+}
 hm::Mat4 viewMatrixFromCameraExtrinsic(const CameraExtrinsic& e) {  // Camera.cpp:4-12
     hm::Mat4 v = hm::Mat4::identity();
     v.at(0, 0) = e.right.x; v.at(0, 1) = e.right.y; v.at(0, 2) = e.right.z;
@@ -356,6 +398,8 @@ void RenderFrontend::markNewFrame(float time, float deltaTime) {
 }
 
 void RenderFrontend::prepareNewFrame() {
+    m_currentMainPassDrawcallCount = 0;    // :275-277
+    m_currentShadowPassDrawcallCount = 0;
     backend.newFrame();
     backend.beginRecording();  // executions are kept on the host and sent segment by segment in renderFrameSegment
     prepareRenderpasses();
@@ -457,6 +501,7 @@ void RenderFrontend::setCameraExtrinsic(const CameraExtrinsic& extrinsic) {
     std::memcpy(m_globalShaderInfo.viewProjection, m_viewProjectionMatrix.m, sizeof(float) * 16);
     CameraIntrinsic in = m_cameraIntrinsic;
     m_cameraFrustum = computeViewFrustum(extrinsic, in);
+    m_sunShadowFrustum = computeOrthogonalFrustumFittedToCamera(m_cameraFrustum, directionToVector(m_sunDirection));  // updateShadowFrustum :1054-1056
 }
 
 void RenderFrontend::prepareForDrawcalls() { updateGlobalShaderInfo(); }
@@ -521,15 +566,21 @@ void RenderFrontend::renderScene(const std::vector<RenderObject>& scene) {
     if (!renderingSDFVisualisation) backend.drawMeshes(mainPassCulledMeshes, (const char*)mainPassPushConstants.data(), m_gbufferFillPass, 0);
     backend.drawMeshes(mainPassCulledMeshes, (const char*)mainPassPushConstants.data(), m_depthPrePass, 0);
     if (!mainPassMatrices.empty()) backend.setStorageBufferData(m_mainPassTransformsBuffer, mainPassMatrices.data(), sizeof(MainPassMatrices) * mainPassMatrices.size());
-    // shadow pass: the reference culls against a frustum fitted to the camera frustum and pushed 10 km towards the sun (:613-645);
-    // culling does not change the maps, every object with geometry is drawn here
+    // shadow pass (:607-652): coarse culling against the orthographic frustum fitted to the camera frustum, its near plane pushed
+    // 10 km towards the sun so that casters outside the view are kept (the normals are those of the unshifted box, as in the reference)
     struct ShadowPushConstants { uint32_t albedoTextureIndex, transformIndex; };
     std::vector<MeshHandle> shadowCulledMeshes;
     std::vector<ShadowPushConstants> shadowPushConstantData;
     std::vector<hm::Mat4> shadowModelMatrices;
+    const hm::Vec3 nearPlaneOffset = directionToVector(m_sunDirection) * 10000.f;
+    m_sunShadowFrustum.l_l_n = m_sunShadowFrustum.l_l_n + nearPlaneOffset;
+    m_sunShadowFrustum.r_l_n = m_sunShadowFrustum.r_l_n + nearPlaneOffset;
+    m_sunShadowFrustum.l_u_n = m_sunShadowFrustum.l_u_n + nearPlaneOffset;
+    m_sunShadowFrustum.r_u_n = m_sunShadowFrustum.r_u_n + nearPlaneOffset;
     for (const RenderObject& obj : scene) {
         const MeshFrontend& mesh = m_frontendMeshes[obj.mesh];
         if (mesh.backendHandle.index == PLAIN_INVALID_INDEX) continue;
+        if (!isAxisAlignedBoundingBoxIntersectingViewFrustum(m_sunShadowFrustum, obj.bbWorld)) continue;
         m_currentShadowPassDrawcallCount++;
         shadowCulledMeshes.push_back(mesh.backendHandle);
         shadowPushConstantData.push_back({mesh.material.albedoTextureIndex, (uint32_t)shadowModelMatrices.size()});

@@ -70,6 +70,7 @@ struct ViewFrustum {  // ViewFrustum.h:6-30
     hm::Vec3 top, bot, right, left, near, far;
 };
 ViewFrustum computeViewFrustum(const CameraExtrinsic& e, const CameraIntrinsic& i);
+ViewFrustum computeOrthogonalFrustumFittedToCamera(const ViewFrustum& cameraFrustum, hm::Vec3 lightDirection);  // ViewFrustum.cpp:231-271
 hm::Mat4 viewMatrixFromCameraExtrinsic(const CameraExtrinsic& e);      // Camera.cpp:4-12
 hm::Mat4 projectionMatrixFromCameraIntrinsic(const CameraIntrinsic& i);  // Camera.cpp:14-27
 
@@ -253,7 +254,7 @@ private:
     CameraExtrinsic m_cameraExtrinsic;
     bool m_frameOpen = false;
     hm::Mat4 m_viewProjectionMatrix = hm::Mat4::zero();
-    ViewFrustum m_cameraFrustum;
+    ViewFrustum m_cameraFrustum, m_sunShadowFrustum;
     float m_time = 0.f, m_deltaTime = 0.016f;
     RenderPassHandle m_shadingPass, m_brdfLutPass, m_histogramPerTilePass, m_histogramResetPass, m_histogramCombinePass, m_preExposeLightsPass;
     RenderPassHandle m_depthPyramidPass, m_lightMatrixPass, m_tonemappingPass, m_depthDownscalePass;

@@ -277,12 +277,22 @@ void PLAIN_FE(host_view_frustum)(const plain_camera_extrinsic* c, float fov, flo
     for (int i = 0; i < 8; i++) put3(outPoints + 3 * i, p[i]);
     for (int i = 0; i < 6; i++) put3(outNormals + 3 * i, n[i]);
 }
-int PLAIN_FE(host_aabb_intersects_frustum)(const float points[24], const float normals[18], const float bbMin[3], const float bbMax[3]) {
+static ViewFrustum frustumIn(const float points[24], const float normals[18]) {
     ViewFrustum f;
     hm::Vec3* p[8] = {&f.l_l_n, &f.l_l_f, &f.l_u_n, &f.l_u_f, &f.r_l_n, &f.r_l_f, &f.r_u_n, &f.r_u_f};
     hm::Vec3* n[6] = {&f.top, &f.bot, &f.right, &f.left, &f.near, &f.far};
     for (int i = 0; i < 8; i++) *p[i] = hm::Vec3(points[3 * i], points[3 * i + 1], points[3 * i + 2]);
     for (int i = 0; i < 6; i++) *n[i] = hm::Vec3(normals[3 * i], normals[3 * i + 1], normals[3 * i + 2]);
+    return f;
+}
+void PLAIN_FE(host_orthogonal_frustum_fitted_to_camera)(const float points[24], const float normals[18], const float lightDirection[3], float outPoints[24], float outNormals[18]) {
+    const ViewFrustum f = computeOrthogonalFrustumFittedToCamera(frustumIn(points, normals), hm::Vec3(lightDirection[0], lightDirection[1], lightDirection[2]));
+    const hm::Vec3 p[8] = {f.l_l_n, f.l_l_f, f.l_u_n, f.l_u_f, f.r_l_n, f.r_l_f, f.r_u_n, f.r_u_f}, n[6] = {f.top, f.bot, f.right, f.left, f.near, f.far};
+    for (int i = 0; i < 8; i++) put3(outPoints + 3 * i, p[i]);
+    for (int i = 0; i < 6; i++) put3(outNormals + 3 * i, n[i]);
+}
+int PLAIN_FE(host_aabb_intersects_frustum)(const float points[24], const float normals[18], const float bbMin[3], const float bbMax[3]) {
+    const ViewFrustum f = frustumIn(points, normals);
     hm::AABB bb;
     bb.min = hm::Vec3(bbMin[0], bbMin[1], bbMin[2]);
     bb.max = hm::Vec3(bbMax[0], bbMax[1], bbMax[2]);
@@ -300,6 +310,11 @@ void PLAIN_FE(host_sdf_world_to_local)(const float model[16], const float bbOffs
     std::memcpy(m.m, model, 64);
     const hm::Mat4 r = hm::inverse(m * hm::translate(hm::Vec3(bbOffset[0], bbOffset[1], bbOffset[2])));
     std::memcpy(out, r.m, 64);
+}
+int PLAIN_FE(get_drawcall_counts)(plain_frontend* fe, uint32_t out[2]) {
+    out[0] = fe->fe.m_currentMainPassDrawcallCount;
+    out[1] = fe->fe.m_currentShadowPassDrawcallCount;
+    return 0;
 }
 int PLAIN_FE(set_exposure)(plain_frontend* fe, float previousFrameExposure) {
     FE_TRY(fe, {

@@ -125,3 +125,20 @@ def test_sdf_instance_world_to_local(ffi, oracle, ref):
         oracle.f["host_sdf_world_to_local"](model, off, a)
         ref.ref_sdfWorldToLocal(model, off, b)
         assert np.allclose(list(a), list(b), rtol=2e-5, atol=2e-5)
+
+
+def test_sun_shadow_frustum(ffi, oracle, ref):
+    """the orthographic frustum fitted to the camera frustum in the sun's view space (ViewFrustum.cpp:231-271), against which the
+    shadow draws are culled (RenderFrontend.cpp:613-645)"""
+    for pos, fwd, right, up, fov, aspect, near, far in CAMERAS:
+        pts, nrm = arr(24), arr(18)
+        ref.ref_viewFrustum(vec(pos), vec(fwd), vec(right), vec(up), f32(fov), f32(aspect), f32(near), f32(far), pts, nrm)
+        for deg in [(40.0, 35.0), (0.0, 0.0), (200.0, 80.0), (90.0, 179.99)]:
+            light = arr(3)
+            ref.ref_directionToVector(vec(deg), light)
+            p0, n0, p1, n1 = arr(24), arr(18), arr(24), arr(18)
+            oracle.f["host_orthogonal_frustum_fitted_to_camera"](pts, nrm, light, p0, n0)
+            ref.ref_orthogonalFrustumFittedToCamera(pts, nrm, light, p1, n1)
+            scale = np.abs(np.array(list(p1))).max()
+            assert np.allclose(list(p0), list(p1), rtol=0, atol=2e-4 * scale), (pos, deg)  # a float 4x4 inverse on both sides
+            assert np.allclose(list(n0), list(n1), rtol=0, atol=2e-4), (pos, deg)

@@ -2,6 +2,8 @@
 coverage with the top-left rule, face culling, homogeneous (near-plane crossing) triangles against per-pixel ray casting,
 the depth test, motion vectors, the geometric normal and the packed G-buffer. The reference leaves all of this to the Vulkan
 rasteriser; oracle/passes_raster.cpp states the rules, these tests pin them."""
+import ctypes as C
+
 import numpy as np
 import pytest
 
@@ -159,6 +161,31 @@ def test_frame_from_plain_meshes(ffi, oracle):
     for _ in range(3):
         s.step()
     snap = s.snapshot(["depth0", "depth1", "motion0", "motion1", "motion2", "normal", "gbuffer", "shadow2", "output", "giFullY"], [("sunShadowInfo", 304)])
+    main_draws, shadow_draws = s.fe.drawcall_counts()
+    assert 3 <= main_draws <= shadow_draws <= len(s.PLACEMENT), "camera-frustum culling keeps what is in view, the fitted shadow frustum a superset"
+    # an object 500 m towards the sun is not in view but casts into it: kept by the shadow pass only (the near plane of the fitted frustum
+    # is pushed 10 km towards the sun, RenderFrontend.cpp:616-623); an object 2 km to the side is culled from both
+    fm, m = s.meshes["cube"]
+    sun = (C.c_float * 3)()
+    oracle.f["host_direction_to_vector"]((C.c_float * 2)(40.0, 35.0), sun)
+    up_sun = np.array(list(sun)) * 500.0 + np.array([0.0, 0.0, 0.0])
+    def placed(t):
+        M = np.eye(4, dtype=np.float32)
+        M[:3, 3] = t
+        return (fm, M.T.ravel(), np.array(t) + m.bb_min, np.array(t) + m.bb_max)
+    extra = [placed(up_sun), placed(np.array([0.0, 0.0, 2000.0]))]
+    base = []
+    for name, t, sc, rot in s.PLACEMENT:
+        f2, m2 = s.meshes[name]
+        c, s_ = np.cos(rot), np.sin(rot)
+        M = np.array([[c * sc[0], 0, s_ * sc[2], t[0]], [0, sc[1], 0, t[1]], [-s_ * sc[0], 0, c * sc[2], t[2]], [0, 0, 0, 1]], np.float32)
+        corners = np.array([[x, y, z, 1] for x in (m2.bb_min[0], m2.bb_max[0]) for y in (m2.bb_min[1], m2.bb_max[1]) for z in (m2.bb_min[2], m2.bb_max[2])], np.float32) @ M.T
+        base.append((f2, M.T.ravel(), corners[:, :3].min(0), corners[:, :3].max(0)))
+    s.fe.set_scene(base + extra)
+    s.step()
+    main2, shadow2 = s.fe.drawcall_counts()
+    assert main2 == main_draws, "neither extra object is in view"
+    assert shadow2 == shadow_draws + 1, "the object towards the sun still casts into the fitted frustum, the one 2 km to the side does not"
     s.close()
     depth = snap["depth1/0"].view(np.float32).reshape(h, w)  # frame 3 renders into target 1
     covered = depth > 0
