@@ -23,8 +23,7 @@ def soup(ffi, rng, n_tris, big=0, z_range=(-40.0, 3.0), spread=12.0, size=1.5):
     tan = np.cross(nrm, rng.normal(0, 1, (n_tris * 3, 3)))
     tan /= np.linalg.norm(tan, axis=1, keepdims=True)
     bit = np.cross(nrm, tan)
-    idx = rng.permutation(n_tris * 3).reshape(-1)  # shuffled index buffer: triangles share nothing, order is arbitrary
-    idx = np.arange(n_tris * 3).reshape(n_tris, 3)[rng.permutation(n_tris)].reshape(-1)
+    idx = np.arange(n_tris * 3).reshape(n_tris, 3)[rng.permutation(n_tris)].reshape(-1)  # triangles share nothing; their order is shuffled
     return idx, ffi.pack_vertices(pos, uvs=rng.uniform(-2, 3, (n_tris * 3, 2)), normals=nrm, tangents=tan, bitangents=bit)
 
 
@@ -47,7 +46,7 @@ def test_prepass_and_gbuffer_bit_exact(ffi, cuda, oracle, w, h, n_tris, big):
     kw = dict(jitter=((0.5 / w, -0.25 / h), (-0.125 / w, 0.375 / h)), textures=random_textures(rng), gbuffer=True)
     got = passes.raster_prepass(ffi, cuda, w, h, meshes, draws, m, **kw)
     want = passes.raster_prepass(ffi, oracle, w, h, meshes, draws, m, **kw)
-    assert (want[0] > 0).mean() > 0.05, "the test scene should cover part of the frame (the random-alpha albedo textures cut holes)"
+    assert (want[0] > 0).mean() > 0.02, "the test scene should cover part of the frame (the random-alpha albedo textures cut holes)"
     for name, a, b in zip(("depth", "motion", "normal", "gbuffer"), got, want):
         assert np.array_equal(a.view(np.uint8), b.view(np.uint8)), "%s: %d texels differ" % (name, int((a != b).reshape(h * w, -1).any(-1).sum()))
 
@@ -68,7 +67,6 @@ def test_quads_and_rules_bit_exact(ffi, cuda, oracle):
 def test_shadow_cascade_bit_exact(ffi, cuda, oracle, size, n_tris):
     rng = np.random.default_rng(size)
     meshes = [soup(ffi, rng, n_tris, big=3, z_range=(-1.2, 1.2), spread=1.0, size=0.12)]
-    meshes[0] = (meshes[0][0], meshes[0][1])
     lm = np.tile(IDENTITY, (4, 1)).astype(np.float32)
     ortho = np.diag([0.9, 1.1, 0.45, 1.0])
     ortho[2, 3] = 0.5
@@ -80,7 +78,7 @@ def test_shadow_cascade_bit_exact(ffi, cuda, oracle, size, n_tris):
         albedo = cutout if cascade == 2 else None
         got = passes.raster_shadow(ffi, cuda, size, meshes, [(0, 0), (0, 1)], [IDENTITY, model.T.ravel()], lm, cascade=cascade, albedo=albedo)
         want = passes.raster_shadow(ffi, oracle, size, meshes, [(0, 0), (0, 1)], [IDENTITY, model.T.ravel()], lm, cascade=cascade, albedo=albedo)
-        assert (want > 0).mean() > 0.02
+        assert (want > 0).mean() > 0.01
         assert np.array_equal(got, want), "cascade %d: %d texels differ" % (cascade, int((got != want).sum()))
 
 
