@@ -23,6 +23,7 @@ def soup(ffi, rng, n_tris, big=0, z_range=(-40.0, 3.0), spread=12.0, size=1.5):
     tan = np.cross(nrm, rng.normal(0, 1, (n_tris * 3, 3)))
     tan /= np.linalg.norm(tan, axis=1, keepdims=True)
     bit = np.cross(nrm, tan)
+    rng.permutation(n_tris * 3)  # (keeps the random stream of the committed GPU runs)
     idx = np.arange(n_tris * 3).reshape(n_tris, 3)[rng.permutation(n_tris)].reshape(-1)  # triangles share nothing; their order is shuffled
     return idx, ffi.pack_vertices(pos, uvs=rng.uniform(-2, 3, (n_tris * 3, 2)), normals=nrm, tangents=tan, bitangents=bit)
 
