@@ -244,3 +244,53 @@ def _shadow_cascade_info(ffi, light_matrices):
         for k in range(16):
             info.lightMatrices[c][k] = float(lm[c, k])
     return np.frombuffer(bytes(info), np.uint8).copy()
+
+
+# ---------------- gbufferShading.comp (triangle.frag recast over the packed G-buffer) as a single pass ----------------
+def shade(ffi, api, gbuffer, y_sh, co_cg, noise_rg8, sun_direction, camera_position, diffuse_brdf=2, direct_multiscatter=0, geometry_aa=0,
+          indirect_tech=0, sun_color=(1.0, 0.9, 0.8), sun_strength_exposed=2.5, brdf_res=512):
+    """Bindings of RenderFrontend::shadeGBuffer: G-buffer (h, w, 4) uint32, full-res Y_SH (h, w, 4) / CoCg (h, w, 2) float16, the BRDF LUT
+    computed by brdfLut.comp in the same rig, shadow maps without casters (everything lit), an identity froxel volume (no fog).
+    Returns (R11G11B10 colour (h, w) uint32, BRDF LUT (res, res, 4) float16, the global shader info used)."""
+    h, w = gbuffer.shape[:2]
+    rig = PassRig(ffi, api, w, h)
+    be, g = rig.be, rig.g
+    noise = be.create_image(noise_rg8.shape[1], noise_rg8.shape[0], "RG8", data=np.ascontiguousarray(noise_rg8, np.uint8))
+    for i in range(4):
+        g.noiseTextureIndices[i] = be.global_texture_index(noise)
+    g.frameIndexMod4 = 1
+    for i in range(3):
+        g.sunDirection[i] = float(sun_direction[i])
+        g.cameraPosition[i] = float(camera_position[i])
+    be.set_uniform_buffer_data(rig.gbuf, np.frombuffer(bytes(g), np.uint8))
+    gb = be.create_image(w, h, "RGBA32_UINT", data=np.ascontiguousarray(gbuffer, np.uint32))
+    ysh = be.create_image(w, h, "RGBA16_SFLOAT", data=np.ascontiguousarray(y_sh, np.float16))
+    cocg = be.create_image(w, h, "RG16_SFLOAT", data=np.ascontiguousarray(co_cg, np.float16))
+    lut = be.create_image(brdf_res, brdf_res, "RGBA16_SFLOAT")
+    shadow = [be.create_image(64, 64, "DEPTH16", data=np.zeros((64, 64), np.uint16)) for _ in range(4)]
+    identity = np.zeros((4, 4, 8, 4), np.float16)
+    identity[..., 3] = 1.0  # in-scattering 0, transmittance 1
+    froxels = be.create_image(8, 4, "RGBA16_SFLOAT", depth=4, type_=ffi.IMAGE_3D, data=identity)
+    sky = be.create_image(8, 4, "R11G11B10_UFLOAT", data=np.zeros((4, 8), np.uint32))
+    transmission = be.create_image(8, 8, "R11G11B10_UFLOAT", data=np.zeros((8, 8), np.uint32))
+    color = be.create_image(w, h, "R11G11B10_UFLOAT")
+    light = be.create_storage_buffer(20, np.array([sun_color[0], sun_color[1], sun_color[2], 1.0, sun_strength_exposed], np.float32))
+    info = ffi.ShadowCascadeInfo()
+    for c in range(4):
+        info.splits[c] = 1e9  # every pixel in cascade 0
+        for k in range(16):
+            info.lightMatrices[c][k] = 1.0 if k % 5 == 0 else 0.0
+        info.lightSpaceScale[c][0] = info.lightSpaceScale[c][1] = 1.0
+    cascades = be.create_storage_buffer(304, np.frombuffer(bytes(info), np.uint8).copy())
+    vol = be.create_uniform_buffer(52, np.array([0, 0, 0, 0, 1, 1, 1, 30.0, 1.0, 0.003, 0.008, 0.5, 0.2], np.float32))
+    p_lut = be.create_compute_pass("brdfLut.comp", {0: np.int32(diffuse_brdf)})
+    p = be.create_compute_pass("gbufferShading.comp", {0: np.int32(diffuse_brdf), 1: np.int32(direct_multiscatter), 2: np.uint32(geometry_aa), 3: np.int32(indirect_tech), 4: np.uint32(3)})
+    be.new_frame()
+    be.set_compute_pass_execution(p_lut, (brdf_res // 8, brdf_res // 8, 1), storage=[(lut, 0, 0)])
+    sampled = [(gb, 0, 0), (lut, 0, 3), (ysh, 0, 15), (cocg, 0, 16), (froxels, 0, 18), (sky, 0, 21), (transmission, 0, 22)] + [(shadow[i], 0, 9 + i) for i in range(4)]
+    be.set_compute_pass_execution(p, ((w + 7) // 8, (h + 7) // 8, 1), sampled=sampled, storage=[(color, 0, 20)], storage_buffers=[(light, True, 7), (cascades, True, 8)],
+                                  uniform_buffers=[(vol, 19)])
+    rig.run()
+    out = (be.read_image(color, 0, np.uint32).reshape(h, w).copy(), be.read_image(lut, 0, np.float16).reshape(brdf_res, brdf_res, 4).copy(), g)
+    rig.close()
+    return out
