@@ -48,7 +48,7 @@ def box_mesh(ffi, tess, outward_is_cross):
 
 def box_sdf(res=16):
     """analytic SDF brick of the unit box padded like the asset pipeline pads (half floats, (d, h, w))"""
-    c = (np.arange(res) + 0.5) / res * 2.4 - 1.2
+    c = (np.arange(res) + 0.5) / res * 3.0 - 1.5  # the brick spans the padded box: padSDFBoundingBox adds max(7.5 %, 0.5 m) per side
     z, y, x = np.meshgrid(c, c, c, indexing="ij")
     q = np.stack([np.abs(x) - 1, np.abs(y) - 1, np.abs(z) - 1], -1)
     d = np.linalg.norm(np.maximum(q, 0), axis=-1) + np.minimum(q.max(-1), 0)
