@@ -294,3 +294,27 @@ def shade(ffi, api, gbuffer, y_sh, co_cg, noise_rg8, sun_direction, camera_posit
     out = (be.read_image(color, 0, np.uint32).reshape(h, w).copy(), be.read_image(lut, 0, np.float16).reshape(brdf_res, brdf_res, 4).copy(), g)
     rig.close()
     return out
+
+
+def taa_resolve(ffi, api, current, history, motion, depth, weights, use_clipping=True, use_dilation=True, history_tech=0, use_tonemap=True, camera_cut=False):
+    """temporalFilter.comp with the bindings of TAA::computeTemporalFilter (TAA.cpp:139-166). current / history: packed R11G11B10 (h, w);
+    motion (h, w, 2) int16 SNORM; depth (h, w) float32; weights: 9 floats. Returns (output, new history), packed."""
+    h, w = current.shape
+    rig = PassRig(ffi, api, w, h)
+    be = rig.be
+    if camera_cut:
+        rig.g.cameraCut = 1
+        be.set_uniform_buffer_data(rig.gbuf, np.frombuffer(bytes(rig.g), np.uint8))
+    img = lambda fmt, data: be.create_image(w, h, fmt, data=np.ascontiguousarray(data))
+    cur, his = img("R11G11B10_UFLOAT", current.astype(np.uint32)), img("R11G11B10_UFLOAT", history.astype(np.uint32))
+    vel, dep = img("RG16_SNORM", motion.astype(np.int16)), img("DEPTH32", depth.astype(np.float32))
+    out, his_dst = be.create_image(w, h, "R11G11B10_UFLOAT"), be.create_image(w, h, "R11G11B10_UFLOAT")
+    wbuf = be.create_uniform_buffer(36, np.asarray(weights, np.float32))
+    p = be.create_compute_pass("temporalFilter.comp", {0: np.uint32(int(use_clipping)), 1: np.uint32(int(use_dilation)), 2: np.int32(history_tech), 3: np.uint32(int(use_tonemap))})
+    be.new_frame()
+    be.set_compute_pass_execution(p, ((w + 7) // 8, (h + 7) // 8, 1), sampled=[(cur, 0, 0), (his, 0, 3), (vel, 0, 4), (dep, 0, 5)], storage=[(out, 0, 1), (his_dst, 0, 2)],
+                                  uniform_buffers=[(wbuf, 6)])
+    rig.run()
+    res = (be.read_image(out, 0, np.uint32).reshape(h, w).copy(), be.read_image(his_dst, 0, np.uint32).reshape(h, w).copy())
+    rig.close()
+    return res
