@@ -318,3 +318,29 @@ def taa_resolve(ffi, api, current, history, motion, depth, weights, use_clipping
     res = (be.read_image(out, 0, np.uint32).reshape(h, w).copy(), be.read_image(his_dst, 0, np.uint32).reshape(h, w).copy())
     rig.close()
     return res
+
+
+def gi_spatial_filter(ffi, api, y_sh, co_cg, depth_half, normal_rgba8, filter_index, camera_position, view_projection, frame_index_mod4=2):
+    """filterIndirectDiffuseSpatial.comp with the bindings of SDFGI::filterIndirectDiffuse (SDFGI.cpp:430-447): half-res Y_SH (h, w, 4) /
+    CoCg (h, w, 2) float16, R16F half-res depth (h, w) float16, RGBA8 normals (h, w, 4). Returns (Y_SH, CoCg) float16 and the globals used."""
+    h, w = depth_half.shape
+    rig = PassRig(ffi, api, w, h, screen=(2 * w, 2 * h))
+    be, g = rig.be, rig.g
+    g.frameIndexMod4 = frame_index_mod4
+    for i in range(3):
+        g.cameraPosition[i] = float(camera_position[i])
+    for i, v in enumerate(np.asarray(view_projection, np.float32).T.ravel()):
+        g.viewProjection[i] = float(v)
+    be.set_uniform_buffer_data(rig.gbuf, np.frombuffer(bytes(g), np.uint8))
+    src_y = be.create_image(w, h, "RGBA16_SFLOAT", data=np.ascontiguousarray(y_sh, np.float16))
+    src_c = be.create_image(w, h, "RG16_SFLOAT", data=np.ascontiguousarray(co_cg, np.float16))
+    dep = be.create_image(w, h, "R16_SFLOAT", data=np.ascontiguousarray(depth_half, np.float16))
+    nrm = be.create_image(w, h, "RGBA8", data=np.ascontiguousarray(normal_rgba8, np.uint8))
+    out_y, out_c = be.create_image(w, h, "RGBA16_SFLOAT"), be.create_image(w, h, "RG16_SFLOAT")
+    p = be.create_compute_pass("filterIndirectDiffuseSpatial.comp", {0: np.int32(filter_index)})
+    be.new_frame()
+    be.set_compute_pass_execution(p, ((w + 7) // 8, (h + 7) // 8, 1), sampled=[(src_y, 0, 2), (src_c, 0, 3), (dep, 0, 4), (nrm, 0, 5)], storage=[(out_y, 0, 0), (out_c, 0, 1)])
+    rig.run()
+    res = (be.read_image(out_y, 0, np.float16).reshape(h, w, 4).copy(), be.read_image(out_c, 0, np.float16).reshape(h, w, 2).copy(), g)
+    rig.close()
+    return res
