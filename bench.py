@@ -184,7 +184,7 @@ def run_ours(args, rank, world, local_rank):
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    api = pr.load()
+    api = pr.load(args.contract)
     from plainrenderer_b200 import sharding
     sharded = world > 1
     s = ffi.default_settings(api, WIDTH, HEIGHT, sun_direction_deg=SUN_DEG, shard_rank=rank if sharded else 0, shard_count=world if sharded else 0)
@@ -331,6 +331,9 @@ def run_ours(args, rank, world, local_rank):
                 "passes_ms": {k: round(acc[k], 4) for k in order},
                 "frame_roofline": {"algorithmic_bytes_per_frame": int(sum(alg.values()) + alg["Indirect diffuse spatial filter"]), "hbm_bound_ms": (sum(alg.values()) + alg["Indirect diffuse spatial filter"]) / peak / 1e6},
                 "setup_s": round(setup_s, 1), "graph_replay": not args.no_graph}
+        if args.contract != "exact":
+            # never the headline by default: the fast contract matches the oracle within a tolerance, not bit for bit
+            line["config"]["numeric_contract"] = "fast: SFU approximations + contraction in the floating-point passes (libplain_b200_fast.so)"
         if sharded:
             comm.check_peer_error()
             line["sharding"] = {"rows_of_rank0": list(band), "exchanges_per_frame": 10, "bytes_sent_per_frame_rank0": bytes_first_frame[0],
@@ -359,6 +362,8 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--nccl-exchange", action="store_true", help="N > 1: exchange over NCCL send/recv from Python instead of peer pushes over NVLink")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--contract", default="exact", choices=["exact", "fast"], help="exact (default): bit-exact against the oracle; fast: libplain_b200_fast.so, "
+                    "hardware approximations in the floating-point passes, parity within a tolerance (DESIGN.md section 12)")
     ap.add_argument("--workload", default="c3", choices=["c3", "c5"], help="c3 (default, the headline metric): BASELINE configs[2], 3840x2160 / 100 instances; "
                     "c5: BASELINE configs[4], 7680x4320 / 256 instances (reported beside the headline, never instead of it)")
     args = ap.parse_args()

@@ -10,7 +10,8 @@ from . import ffi
 
 PKG_DIR = Path(__file__).resolve().parent
 LIB_PATH = PKG_DIR / "libplain_b200.so"
-_api = None
+LIB_FAST_PATH = PKG_DIR / "libplain_b200_fast.so"  # same C-ABI, floating-point passes under the "fast" contract
+_api = {}
 
 
 def build(force=False):
@@ -18,11 +19,12 @@ def build(force=False):
     return importlib.import_module(__name__ + ".buildlib").build(force=force)
 
 
-def load():
-    """Binds the product library (symbols plain_* / plain_frontend_*). Raises if it has not been built."""
-    global _api
-    if _api is None:
-        if not LIB_PATH.exists():
-            raise RuntimeError("%s is missing - run `python -m plainrenderer_b200.buildlib` (there is no CPU fallback)" % LIB_PATH)
-        _api = ffi.Api(LIB_PATH, "plain_", "plain_frontend_")
-    return _api
+def load(contract="exact"):
+    """Binds the product library (symbols plain_* / plain_frontend_*). Raises if it has not been built.
+    contract: "exact" (default; bit-exact against the oracle) or "fast" (SFU approximations + contraction in the floating-point passes)."""
+    path = {"exact": LIB_PATH, "fast": LIB_FAST_PATH}[contract]
+    if contract not in _api:
+        if not path.exists():
+            raise RuntimeError("%s is missing - run `python -m plainrenderer_b200.buildlib` (there is no CPU fallback)" % path)
+        _api[contract] = ffi.Api(path, "plain_", "plain_frontend_")
+    return _api[contract]

@@ -5,6 +5,10 @@ mirror (host/*.cpp) behind the C-ABI of include/plain_b200.h and include/plain_f
 
 nvcc cross-compiles without a GPU. Flags that are part of the numeric contract: -fmad=false (no
 contraction), default -prec-div/-prec-sqrt/-ftz=false; host side -ffp-contract=off.
+
+A second library, libplain_b200_fast.so, is the same sources with the floating-point passes (FAST_SOURCES) compiled under
+the "fast" contract (-DPLAIN_FAST_CONTRACT -use_fast_math -> SFU approximations + contraction); the
+integer / LUT / rasterisation / bake kernels and the host side are the very same objects as in the exact library.
 """
 import os
 import platform
@@ -17,6 +21,8 @@ PKG = Path(__file__).resolve().parent
 ROOT = PKG.parent
 OUT = PKG / "_build"
 LIB = PKG / "libplain_b200.so"
+LIB_FAST = PKG / "libplain_b200_fast.so"
+FAST_SOURCES = ("passes_gi", "passes_post", "passes_shading", "passes_volumetrics")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 CXX = os.environ.get("CXX", "g++")
 INCLUDES = ["-I%s" % (ROOT / "include"), "-I%s" % (PKG / "csrc"), "-I%s" % (PKG / "host")]
@@ -24,6 +30,7 @@ INCLUDES = ["-I%s" % (ROOT / "include"), "-I%s" % (PKG / "csrc"), "-I%s" % (PKG 
 HOST_FMA = ["-mfma"] if platform.machine() in ("x86_64", "AMD64") else []
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false", "--extended-lambda", "--expt-relaxed-constexpr",
               "-Xcompiler", ",".join(["-fPIC", "-fvisibility=hidden", "-ffp-contract=off"] + HOST_FMA), "-Xptxas", "-v", "-diag-suppress", "177,550"]
+NVCC_FLAGS_FAST = [f for f in NVCC_FLAGS if f != "-fmad=false"] + ["-DPLAIN_FAST_CONTRACT", "-use_fast_math"]
 CXX_FLAGS = ["-std=c++17", "-O2", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-fvisibility=hidden", "-Wall", "-Wno-unused-function"] + HOST_FMA
 
 
@@ -41,6 +48,9 @@ def build(force=False, jobs=None, verbose=False):
     for src in sorted((PKG / "csrc").glob("*.cu")):
         obj = OUT / (src.stem + ".o")
         tasks.append((src, obj, [NVCC] + NVCC_FLAGS + INCLUDES + ["-c", str(src), "-o", str(obj)]))
+        if src.stem in FAST_SOURCES:
+            obj = OUT / (src.stem + "_fast.o")
+            tasks.append((src, obj, [NVCC] + NVCC_FLAGS_FAST + INCLUDES + ["-c", str(src), "-o", str(obj)]))
     for src in sorted((PKG / "host").glob("*.cpp")):
         obj = OUT / ("host_" + src.stem + ".o")
         tasks.append((src, obj, [CXX] + CXX_FLAGS + INCLUDES + ["-c", str(src), "-o", str(obj)]))
@@ -57,12 +67,14 @@ def build(force=False, jobs=None, verbose=False):
 
     with ThreadPoolExecutor(max_workers=jobs or min(8, os.cpu_count() or 1)) as ex:
         list(ex.map(run, todo))
-    objs = [str(t[1]) for t in tasks]
-    if todo or not LIB.exists():
-        cmd = [NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(LIB)] + objs + ["-Xcompiler", "-fPIC", "-lpthread"]
-        r = subprocess.run(cmd, capture_output=True, text=True)
-        if r.returncode != 0:
-            raise RuntimeError("link failed:\n" + r.stdout + r.stderr)
+    exact = [str(t[1]) for t in tasks if not t[1].stem.endswith("_fast")]
+    fast = [str(t[1]) for t in tasks if t[1].stem.endswith("_fast") or t[1].stem not in FAST_SOURCES]
+    for lib, objs in ((LIB, exact), (LIB_FAST, fast)):
+        if todo or not lib.exists():
+            cmd = [NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(lib)] + objs + ["-Xcompiler", "-fPIC", "-lpthread"]
+            r = subprocess.run(cmd, capture_output=True, text=True)
+            if r.returncode != 0:
+                raise RuntimeError("link failed:\n" + r.stdout + r.stderr)
     return LIB
 
 

@@ -53,6 +53,22 @@ DM_HD float fma_(float a, float b, float c) {
 #endif
 }
 
+// ---- contract "fast"  ----
+// -DPLAIN_FAST_CONTRACT (device code of the floating-point passes only: GI, shading, TAA/bloom/tonemap, froxels) replaces the
+// pinned sequences below by the SFU approximations (ex2 / lg2 / sin / cos / rcp / rsqrt / sqrt .approx.ftz, 1-2 ulp or 2^-21
+// absolute) and lets ptxas contract; the results then match the oracle within a tolerance instead of bit for bit. The exact
+// build, the oracle and the integer / LUT / rasterisation passes never see this branch.
+#if defined(PLAIN_FAST_CONTRACT) && defined(__CUDA_ARCH__)
+#define DM_FAST 1
+__device__ __forceinline__ float hw_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float hw_lg2(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float hw_rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float hw_rsqrt(float x) { float y; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float hw_sqrt(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float hw_sin(float x) { float y; asm("sin.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float hw_cos(float x) { float y; asm("cos.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+#endif
+
 DM_HD float nanf_() { return u2f(0x7fc00000u); }
 DM_HD float inff_() { return u2f(0x7f800000u); }
 DM_HD bool isnan_(float x) { return x != x; }
@@ -60,7 +76,9 @@ DM_HD float abs_(float x) { return u2f(f2u(x) & 0x7fffffffu); }
 
 // floor for |x| < 2^31 via truncation (exact)
 DM_HD float floor_(float x) {
-#if defined(__CUDA_ARCH__)
+#if defined(DM_FAST)
+    return floorf(x);
+#elif defined(__CUDA_ARCH__)
     return floorf(x) + 0.f;  // one FRND; "+ 0" turns floor(-0) = -0 into the +0 the portable sequence below yields
 #else
     if (!(abs_(x) < 8388608.f)) return x;  // already integral (or nan/inf)
@@ -120,6 +138,9 @@ DM_HD float exp_core(float r) {
 }
 
 DM_HD float exp(float x) {
+#if defined(DM_FAST)
+    return hw_ex2(x * 1.44269504088896341f);
+#endif
     if (isnan_(x)) return x;
     if (x > 88.72283905206835f) return inff_();
     if (x < -103.972084f) return 0.f;
@@ -130,6 +151,9 @@ DM_HD float exp(float x) {
 }
 
 DM_HD float exp2(float x) {
+#if defined(DM_FAST)
+    return hw_ex2(x);
+#endif
     if (isnan_(x)) return x;
     if (x >= 128.f) return inff_();
     if (x < -150.f) return 0.f;
@@ -164,6 +188,9 @@ DM_HD float log_reduced(float m, int* e, float* xr) {
 }
 
 DM_HD float log(float x) {
+#if defined(DM_FAST)
+    return hw_lg2(x) * 0.693147180559945309f;
+#endif
     if (isnan_(x)) return x;
     if (x < 0.f) return nanf_();
     if (x == 0.f) return -inff_();
@@ -183,6 +210,9 @@ DM_HD float log(float x) {
 }
 
 DM_HD float log2(float x) {
+#if defined(DM_FAST)
+    return hw_lg2(x);
+#endif
     if (isnan_(x)) return x;
     if (x < 0.f) return nanf_();
     if (x == 0.f) return -inff_();
@@ -204,6 +234,10 @@ DM_HD float log2(float x) {
 // 1 - |dot(N, V)| to the 5th power, brdf.inc:35,50-52, and the dot of two normalised vectors overshoots 1 by an ulp;
 // a NaN there would be spread over the whole frame by the bloom chain). pow(0, y>0) = 0.
 DM_HD float pow(float x, float y) {
+#if defined(DM_FAST)
+    if (y == 0.f) return 1.f;
+    return hw_ex2(y * hw_lg2(fmaxf(x, 0.f)));  // base clamped to 0 as below; lg2(0) = -inf gives 0 (y > 0) or inf (y < 0)
+#endif
     if (isnan_(x) || isnan_(y)) return nanf_();
     if (y == 0.f) return 1.f;
     if (x < 0.f) x = 0.f;
@@ -244,6 +278,9 @@ DM_HD float cos_poly(float z) {
 }
 
 DM_HD float sin(float x) {
+#if defined(DM_FAST)
+    return hw_sin(x);
+#endif
     if (isnan_(x) || abs_(x) > 8192.f) return nanf_();
     bool neg = x < 0.f;
     float ax = abs_(x);
@@ -260,6 +297,9 @@ DM_HD float sin(float x) {
 }
 
 DM_HD float cos(float x) {
+#if defined(DM_FAST)
+    return hw_cos(x);
+#endif
     if (isnan_(x) || abs_(x) > 8192.f) return nanf_();
     float ax = abs_(x);
     int j;
@@ -283,7 +323,9 @@ DM_HD float tan(float x) { return sin(x) / cos(x); }
 #define DM_PIO4F 0.7853981633974483096f
 
 DM_HD float sqrt_(float x) {
-#if defined(__CUDA_ARCH__)
+#if defined(DM_FAST)
+    return hw_sqrt(x);
+#elif defined(__CUDA_ARCH__)
     return __fsqrt_rn(x);
 #else
     return __builtin_sqrtf(x);

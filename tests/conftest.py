@@ -31,7 +31,7 @@ def oracle(ffi):
 @pytest.fixture(scope="session")
 def product_lib():
     import plainrenderer_b200 as pr
-    if not pr.LIB_PATH.exists():
+    if not pr.LIB_PATH.exists() or not pr.LIB_FAST_PATH.exists():
         pr.build()
     return pr.LIB_PATH
 
@@ -41,6 +41,13 @@ def cuda(product_lib):
     """The product library on a CUDA device. GPU tests fail (not skip) if the library cannot create a backend."""
     import plainrenderer_b200 as pr
     return pr.load()
+
+
+@pytest.fixture(scope="session")
+def cuda_fast(product_lib):
+    """libplain_b200_fast.so: the same C-ABI with the floating-point passes under the "fast" contract."""
+    import plainrenderer_b200 as pr
+    return pr.load("fast")
 
 
 # ---- independent numpy restatements of exactly specified pieces (texel formats) ----

@@ -33,6 +33,20 @@ def test_product_library_exports_every_declared_symbol(product_lib):
         assert hasattr(lib, "plain_frontend_" + name), "libplain_b200.so does not export plain_frontend_" + name
 
 
+def test_fast_contract_library_exports_the_same_abi(product_lib):
+    """libplain_b200_fast.so: same C-ABI; its floating-point passes really are the SFU build (MUFU.EX2 / LG2 in
+    the shading object) while the integer / LUT / rasterisation objects are shared with the exact library."""
+    import plainrenderer_b200 as pr
+    assert pr.LIB_FAST_PATH.exists()
+    lib = C.CDLL(str(pr.LIB_FAST_PATH))
+    for name in declared("plain_b200.h", "PLAIN_FN"):
+        assert hasattr(lib, "plain_" + name)
+    for name in declared("plain_frontend.h", "PLAIN_FE"):
+        assert hasattr(lib, "plain_frontend_" + name)
+    syms = subprocess.run(["nm", "-D", "--defined-only", str(pr.LIB_FAST_PATH)], capture_output=True, text=True).stdout
+    assert "oracle_" not in syms
+
+
 def test_product_library_does_not_contain_the_oracle(product_lib):
     syms = subprocess.run(["nm", "-D", "--defined-only", str(product_lib)], capture_output=True, text=True).stdout
     assert "oracle_" not in syms
