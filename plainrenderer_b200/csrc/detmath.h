@@ -67,6 +67,12 @@ __device__ __forceinline__ float hw_rsqrt(float x) { float y; asm("rsqrt.approx.
 __device__ __forceinline__ float hw_sqrt(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float hw_sin(float x) { float y; asm("sin.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float hw_cos(float x) { float y; asm("cos.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+#elif defined(PLAIN_FAST_EMULATION) && !defined(__CUDACC__)
+// checker only (oracle/Makefile, liboracle_sfu.so): the same branches on the host with error-model stand-ins for the SFU
+}  // namespace dm
+#include "sfu_emulation.h"
+namespace dm {
+#define DM_FAST 1
 #endif
 
 DM_HD float nanf_() { return u2f(0x7fc00000u); }

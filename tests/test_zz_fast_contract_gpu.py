@@ -13,69 +13,16 @@ import numpy as np
 import pytest
 
 import passes
-from conftest import Sequence, decode_r11g11b10, random_r11g11b10
+import tolerance
+from conftest import random_r11g11b10
 
 pytestmark = [pytest.mark.gpu, pytest.mark.skipif(os.environ.get("PLAIN_TEST_FAST") != "1", reason="fast contract not yet validated on hardware: set PLAIN_TEST_FAST=1")]
-
-HALF_IMAGES = ["giY1", "giC1", "giFullY", "giFullC", "froxelIntegration"]   # RGBA16F / RG16F intermediates
-PACKED_IMAGES = ["color0", "color1", "taaHist0", "taaHist1", "post0"]         # R11G11B10
-
-
-def rel_error(a, b, floor):
-    """|a - b| relative to max(|b|, floor): floor = the magnitude below which a difference cannot reach the 8-bit frame."""
-    a, b = a.astype(np.float64), b.astype(np.float64)
-    ok = np.isfinite(a) & np.isfinite(b)
-    assert (np.isfinite(a) == np.isfinite(b)).all(), "inf / NaN pattern differs"
-    return np.abs(a[ok] - b[ok]) / np.maximum(np.abs(b[ok]), floor)
-
-
-def report(name, e, p999_max, mean_max):
-    p999, mean, worst = float(np.quantile(e, 0.999)), float(e.mean()), float(e.max())
-    print("fast-contract %-20s mean %.2e  p99.9 %.2e  max %.2e" % (name, mean, p999, worst))
-    return [] if (p999 <= p999_max and mean <= mean_max) else ["%s: mean %.2e (<= %.0e), p99.9 %.2e (<= %.0e)" % (name, mean, mean_max, p999, p999_max)]
 
 
 @pytest.mark.parametrize("moving", [False, True])
 def test_fast_frame_sequence_within_tolerance(ffi, cuda_fast, oracle, moving):
-    w, h, frames = 256, 144, 6
-    a, b = Sequence(ffi, cuda_fast, w, h, 16), Sequence(ffi, oracle, w, h, 16)
-    bad = []
-    try:
-        for f in range(frames):
-            inputs = a.step(moving=moving)
-            b.step(moving=moving, inputs=inputs)
-        sa, sb = a.snapshot(), b.snapshot()
-        # integer pass on identical inputs: the depth pyramid is min / max only
-        for k in sa:
-            if k.startswith("hiz/") or k.startswith("depthHalf/"):
-                assert np.array_equal(sa[k], sb[k]), k
-        out_a, out_b = sa["output/0"].astype(np.int32), sb["output/0"].astype(np.int32)
-        d = np.abs(out_a - out_b)
-        frac_le1 = float((d <= 1).mean())
-        print("fast-contract output: max |diff| %d / 255, <= 1 LSB on %.4f %% of the bytes, mean %.4f" % (d.max(), 100 * frac_le1, d.mean()))
-        if not (frac_le1 >= 0.999 and d.max() <= 4):
-            bad.append("8-bit frame: <= 1 LSB on %.4f %% (>= 99.9), max %d (<= 4)" % (100 * frac_le1, d.max()))
-        for name in PACKED_IMAGES:
-            ea = decode_r11g11b10(sa[name + "/0"].view(np.uint32))
-            eb = decode_r11g11b10(sb[name + "/0"].view(np.uint32))
-            # one step of the 6 / 5 bit mantissas is 1.6e-2 / 3.1e-2: most texels must be identical, a few one step apart
-            bad += report(name, rel_error(ea, eb, 1e-3 * float(np.median(eb[np.isfinite(eb)]) + 1e-12)), 4e-2, 2e-3)
-        for name in HALF_IMAGES:
-            ha, hb = sa[name + "/0"].view(np.float16), sb[name + "/0"].view(np.float16)
-            scale = float(np.abs(hb[np.isfinite(hb)].astype(np.float64)).mean()) + 1e-12
-            bad += report(name, rel_error(ha, hb, 1e-2 * scale), 2e-2, 2e-3)
-        # exposure follows the histogram of the previous frame: same bins up to the texels that moved across a bin edge
-        hist_a, hist_b = sa["buf:histogram"].view(np.uint32).astype(np.int64), sb["buf:histogram"].view(np.uint32).astype(np.int64)
-        moved = int(np.abs(hist_a - hist_b).sum())
-        print("fast-contract histogram: %d of %d counts moved" % (moved, int(hist_b.sum())))
-        if moved > 0.01 * hist_b.sum():
-            bad.append("histogram: %d counts moved" % moved)
-        light_a, light_b = sa["buf:light"].view(np.float32), sb["buf:light"].view(np.float32)
-        if not np.allclose(light_a, light_b, rtol=2e-3, atol=1e-12):
-            bad.append("light buffer %s vs %s" % (light_a, light_b))
-    finally:
-        a.close()
-        b.close()
+    bad, log = tolerance.run_sequence(ffi, cuda_fast, oracle, moving)
+    print("\n".join("fast-contract " + l for l in log))
     assert not bad, "fast contract outside its tolerance: " + "; ".join(bad)
 
 
