@@ -344,3 +344,46 @@ def gi_spatial_filter(ffi, api, y_sh, co_cg, depth_half, normal_rgba8, filter_in
     res = (be.read_image(out_y, 0, np.float16).reshape(h, w, 4).copy(), be.read_image(out_c, 0, np.float16).reshape(h, w, 2).copy(), g)
     rig.close()
     return res
+
+
+def gi_temporal_filter(ffi, api, y_sh, co_cg, hist_y, hist_c, motion_current, motion_last, camera_cut=False):
+    """filterIndirectDiffuseTemporal.comp with the bindings of SDFGI::filterIndirectDiffuse (SDFGI.cpp:449-474): half-res Y_SH (h, w, 4) /
+    CoCg (h, w, 2) float16 inputs and histories, full-res RG16_SNORM motion (2h, 2w, 2) int16 of this and of the last frame.
+    Returns (Y_SH, CoCg, historyOut_Y_SH, historyOut_CoCg) float16."""
+    h, w = y_sh.shape[:2]
+    rig = PassRig(ffi, api, w, h, screen=(2 * w, 2 * h))
+    be, g = rig.be, rig.g
+    g.cameraCut = int(camera_cut)
+    be.set_uniform_buffer_data(rig.gbuf, np.frombuffer(bytes(g), np.uint8))
+    img = lambda a, fmt, dt, ww=w, hh=h: be.create_image(ww, hh, fmt, data=np.ascontiguousarray(a, dt))
+    srcs = [img(y_sh, "RGBA16_SFLOAT", np.float16), img(co_cg, "RG16_SFLOAT", np.float16), img(hist_y, "RGBA16_SFLOAT", np.float16), img(hist_c, "RG16_SFLOAT", np.float16),
+            img(motion_current, "RG16_SNORM", np.int16, 2 * w, 2 * h), img(motion_last, "RG16_SNORM", np.int16, 2 * w, 2 * h)]
+    outs = [be.create_image(w, h, f) for f in ("RGBA16_SFLOAT", "RG16_SFLOAT", "RGBA16_SFLOAT", "RG16_SFLOAT")]
+    p = be.create_compute_pass("filterIndirectDiffuseTemporal.comp")
+    be.new_frame()
+    be.set_compute_pass_execution(p, ((w + 7) // 8, (h + 7) // 8, 1), sampled=[(s, 0, 4 + i) for i, s in enumerate(srcs)], storage=[(o, 0, i) for i, o in enumerate(outs)])
+    rig.run()
+    res = tuple(be.read_image(o, 0, np.float16).reshape(h, w, c).copy() for o, c in zip(outs, (4, 2, 4, 2)))
+    rig.close()
+    return res
+
+
+def gi_upscale(ffi, api, y_sh, co_cg, depth_full, depth_half):
+    """indirectLightUpscale.comp with the bindings of SDFGI::filterIndirectDiffuse (SDFGI.cpp:476-497): half-res Y_SH / CoCg float16 and
+    R16F depth (h, w), full-res D32F depth (H, W). Returns full-res (Y_SH, CoCg) float16 and the globals used."""
+    H, W = depth_full.shape
+    h, w = depth_half.shape
+    rig = PassRig(ffi, api, W, H)
+    be = rig.be
+    src_y = be.create_image(w, h, "RGBA16_SFLOAT", data=np.ascontiguousarray(y_sh, np.float16))
+    src_c = be.create_image(w, h, "RG16_SFLOAT", data=np.ascontiguousarray(co_cg, np.float16))
+    d_full = be.create_image(W, H, "DEPTH32", data=np.ascontiguousarray(depth_full, np.float32))
+    d_half = be.create_image(w, h, "R16_SFLOAT", data=np.ascontiguousarray(depth_half, np.float16))
+    out_y, out_c = be.create_image(W, H, "RGBA16_SFLOAT"), be.create_image(W, H, "RG16_SFLOAT")
+    p = be.create_compute_pass("indirectLightUpscale.comp")
+    be.new_frame()
+    be.set_compute_pass_execution(p, ((W + 7) // 8, (H + 7) // 8, 1), sampled=[(src_y, 0, 2), (src_c, 0, 3), (d_full, 0, 4), (d_half, 0, 5)], storage=[(out_y, 0, 0), (out_c, 0, 1)])
+    rig.run()
+    res = (be.read_image(out_y, 0, np.float16).reshape(H, W, 4).copy(), be.read_image(out_c, 0, np.float16).reshape(H, W, 2).copy(), rig.g)
+    rig.close()
+    return res

@@ -5,18 +5,16 @@ final tonemapped frame" read on the frame's own scale (a unit of 1/255 is 3.9e-3
 than 0 or 1 LSB), plus bounds on the HDR intermediates - and the integer passes stay bit-exact on the same inputs.
 
 This library was written and cross-compiled when the round's GPU minutes were spent: the tests below are enabled with
-PLAIN_TEST_FAST=1 until they have been seen green on a B200 (the default contract of bench.py and of every other test is
+PLAIN_TEST_UNVERIFIED=1 until they have been seen green on a B200 (the default contract of bench.py and of every other test is
 "exact")."""
-import os
-
 import numpy as np
 import pytest
 
 import passes
 import tolerance
-from conftest import random_r11g11b10
+from conftest import random_r11g11b10, unverified_on_hardware
 
-pytestmark = [pytest.mark.gpu, pytest.mark.skipif(os.environ.get("PLAIN_TEST_FAST") != "1", reason="fast contract not yet validated on hardware: set PLAIN_TEST_FAST=1")]
+pytestmark = [pytest.mark.gpu, unverified_on_hardware]
 
 
 @pytest.mark.parametrize("moving", [False, True])

@@ -1,0 +1,41 @@
+"""Single passes of the GI denoiser on adversarial inputs (NaN texels, fast / off-screen motion, camera cut, depth edges), CUDA against
+the oracle through the C-ABI, bit-exact - the inputs of tests/test_gi_temporal_upscale_numpy.py, which pins the oracle side.
+Written after the round's GPU minutes were spent: enabled with PLAIN_TEST_UNVERIFIED=1 until seen green on a B200."""
+import numpy as np
+import pytest
+
+import passes
+from conftest import unverified_on_hardware
+from test_gi_temporal_upscale_numpy import gi_inputs
+
+pytestmark = [pytest.mark.gpu, unverified_on_hardware]
+
+
+@pytest.mark.parametrize("w,h,max_px,cut", [(48, 30, 2.0, False), (37, 23, 6.0, False), (40, 24, 0.0, False), (32, 20, 2.0, True), (130, 70, 3.0, False)])
+def test_gi_temporal_filter_bit_exact(ffi, cuda, oracle, w, h, max_px, cut):
+    rng = np.random.default_rng(w * 100 + h)
+    y_sh, co_cg, hist_y, hist_c, cur, last = gi_inputs(rng, w, h, max_px)
+    y_sh[3, 5, 1] = np.nan
+    hist_y[7, 2, :] = np.nan
+    co_cg[9, 9, 0] = np.nan
+    hist_c[9, 9, 1] = np.nan
+    a = passes.gi_temporal_filter(ffi, cuda, y_sh, co_cg, hist_y, hist_c, cur, last, camera_cut=cut)
+    b = passes.gi_temporal_filter(ffi, oracle, y_sh, co_cg, hist_y, hist_c, cur, last, camera_cut=cut)
+    for x, y in zip(a, b):
+        assert np.array_equal(x.view(np.uint16), y.view(np.uint16))
+
+
+@pytest.mark.parametrize("W,H", [(64, 40), (50, 30), (33, 21), (258, 130)])
+def test_gi_upscale_bit_exact(ffi, cuda, oracle, W, H):
+    rng = np.random.default_rng(W + H)
+    w, h = W // 2, H // 2
+    ys, xs = np.mgrid[0:H, 0:W]
+    lin = np.where(xs + 0.6 * ys > 0.55 * W, 9.0, 2.0) + 0.05 * rng.random((H, W))
+    depth_full = (1 - (0.1 * 300.0 / lin - 300.0) / (0.1 - 300.0)).astype(np.float32)
+    depth_full[0:3, 0:4] = 0.0
+    depth_half = depth_full[::2, ::2][:h, :w].astype(np.float16)
+    y_sh = (rng.random((h, w, 4)) * 2 - 0.5).astype(np.float16)
+    co_cg = (rng.random((h, w, 2)) - 0.5).astype(np.float16)
+    y_sh[2, 3, 0] = np.nan
+    a, b = passes.gi_upscale(ffi, cuda, y_sh, co_cg, depth_full, depth_half), passes.gi_upscale(ffi, oracle, y_sh, co_cg, depth_full, depth_half)
+    assert np.array_equal(a[0].view(np.uint16), b[0].view(np.uint16)) and np.array_equal(a[1].view(np.uint16), b[1].view(np.uint16))
