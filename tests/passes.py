@@ -387,3 +387,47 @@ def gi_upscale(ffi, api, y_sh, co_cg, depth_full, depth_half):
     res = (be.read_image(out_y, 0, np.float16).reshape(H, W, 4).copy(), be.read_image(out_c, 0, np.float16).reshape(H, W, 2).copy(), rig.g)
     rig.close()
     return res
+
+
+def froxels(ffi, api, res, noise_r8, shadow_d16, light_matrix2, light, settings13, history, camera, prev, sun_direction, camera_cut=False):
+    """The four froxel passes with the bindings of Volumetrics::computeVolumetricLighting (Volumetrics.cpp:136-247) in one frame:
+    froxelVolumeMaterial -> froxelLightScattering -> volumeLightingReprojection -> volumetricLightingIntegration.
+    res = (w, h, d) of the volumes; noise_r8 (n, n, n) uint8; shadow_d16 (s, s) uint16; light_matrix2 = column-major 16 floats of cascade 2;
+    light = (sunColor rgb, previousFrameExposure, sunStrengthExposed) (lightBuffer.inc:4-8); settings13 = the 13 floats of VolumetricLightingSettings;
+    history (d, h, w, 4) float16; camera = dict(position, forward, up, right, tan_fov_half, aspect); prev = dict(view_projection (4x4, row-major
+    numpy), position, forward). Returns (material, scattering, reprojected, integrated) float16 volumes (d, h, w, 4) and the globals."""
+    w, h, d = res
+    rig = PassRig(ffi, api, w * 8, h * 8)
+    be, g = rig.be, rig.g
+    for i in range(3):
+        g.cameraPosition[i], g.cameraForward[i], g.cameraUp[i], g.cameraRight[i] = (float(camera[k][i]) for k in ("position", "forward", "up", "right"))
+        g.cameraPositionPrevious[i], g.cameraForwardPrevious[i] = float(prev["position"][i]), float(prev["forward"][i])
+        g.sunDirection[i] = float(sun_direction[i])
+    g.cameraTanFovHalf, g.cameraAspectRatio = float(camera["tan_fov_half"]), float(camera["aspect"])
+    for i, v in enumerate(np.asarray(prev["view_projection"], np.float32).T.ravel()):
+        g.viewProjectionPrevious[i] = float(v)
+    g.cameraCut = int(camera_cut)
+    be.set_uniform_buffer_data(rig.gbuf, np.frombuffer(bytes(g), np.uint8))
+    n = noise_r8.shape[0]
+    noise = be.create_image(n, n, "R8", depth=n, type_=ffi.IMAGE_3D, data=np.ascontiguousarray(noise_r8, np.uint8))
+    s = shadow_d16.shape[0]
+    shadow = be.create_image(s, s, "DEPTH16", data=np.ascontiguousarray(shadow_d16, np.uint16))
+    vol = lambda data=None: be.create_image(w, h, "RGBA16_SFLOAT", depth=d, type_=ffi.IMAGE_3D, data=data)
+    material, scatter, target, integrated = vol(), vol(), vol(), vol()
+    hist = vol(np.ascontiguousarray(history, np.float16))
+    lm = np.zeros((4, 16), np.float32)
+    lm[2] = np.asarray(light_matrix2, np.float32)
+    info = be.create_storage_buffer(304, _shadow_cascade_info(ffi, lm))
+    lightbuf = be.create_storage_buffer(20, np.asarray(light, np.float32))
+    ubo = be.create_uniform_buffer(52, np.asarray(settings13, np.float32).view(np.uint8))
+    p = [be.create_compute_pass(name) for name in ("froxelVolumeMaterial.comp", "froxelLightScattering.comp", "volumeLightingReprojection.comp", "volumetricLightingIntegration.comp")]
+    g4 = ((w + 3) // 4, (h + 3) // 4, (d + 3) // 4)
+    be.new_frame()
+    be.set_compute_pass_execution(p[0], g4, storage=[(material, 0, 0)], sampled=[(noise, 0, 1)], uniform_buffers=[(ubo, 2)])
+    be.set_compute_pass_execution(p[1], g4, storage=[(scatter, 0, 0)], sampled=[(shadow, 0, 1), (material, 0, 2)], storage_buffers=[(info, True, 3), (lightbuf, True, 4)], uniform_buffers=[(ubo, 5)])
+    be.set_compute_pass_execution(p[2], g4, storage=[(target, 0, 0)], sampled=[(scatter, 0, 1), (hist, 0, 2)], uniform_buffers=[(ubo, 3)])
+    be.set_compute_pass_execution(p[3], ((w + 7) // 8, (h + 7) // 8, 1), storage=[(integrated, 0, 0)], sampled=[(target, 0, 1)], uniform_buffers=[(ubo, 2)])
+    rig.run()
+    out = tuple(be.read_image(v, 0, np.float16).reshape(d, h, w, 4).copy() for v in (material, scatter, target, integrated)) + (g,)
+    rig.close()
+    return out

@@ -39,3 +39,24 @@ def test_gi_upscale_bit_exact(ffi, cuda, oracle, W, H):
     y_sh[2, 3, 0] = np.nan
     a, b = passes.gi_upscale(ffi, cuda, y_sh, co_cg, depth_full, depth_half), passes.gi_upscale(ffi, oracle, y_sh, co_cg, depth_full, depth_half)
     assert np.array_equal(a[0].view(np.uint16), b[0].view(np.uint16)) and np.array_equal(a[1].view(np.uint16), b[1].view(np.uint16))
+
+
+@pytest.mark.parametrize("res,moving,cut", [((12, 7, 16), False, False), ((10, 6, 8), True, False), ((9, 5, 8), True, True), ((60, 34, 64), True, False)])
+def test_froxel_passes_bit_exact(ffi, cuda, oracle, res, moving, cut):
+    from test_froxels_numpy import scene
+    cam, prev, noise, shadow, L, settings, light, history, sun = scene(res[0] * 10 + res[2], res, moving)
+    history[1, 2, 3, :] = np.nan
+    a = passes.froxels(ffi, cuda, res, noise, shadow, L.T.ravel(), light, settings, history, cam, prev, sun, camera_cut=cut)
+    b = passes.froxels(ffi, oracle, res, noise, shadow, L.T.ravel(), light, settings, history, cam, prev, sun, camera_cut=cut)
+    for name, x, y in zip(("material", "scattering", "reprojection", "integration"), a, b):
+        assert np.array_equal(x.view(np.uint16), y.view(np.uint16)), name
+
+
+@pytest.mark.parametrize("w,h,radius,strength", [(64, 48, 1.5, 0.05), (100, 75, 1.0, 0.3), (33, 17, 2.5, 1.0)])
+def test_bloom_with_hot_texels_bit_exact(ffi, cuda, oracle, w, h, radius, strength):
+    rng = np.random.default_rng(w + h)
+    from conftest import random_r11g11b10
+    packed = random_r11g11b10(rng, w * h, finite=False).reshape(h, w)   # inf / NaN texels included
+    a, b = passes.bloom(ffi, cuda, packed, strength=strength, radius=radius), passes.bloom(ffi, oracle, packed, strength=strength, radius=radius)
+    for x, y in zip(a[0] + a[1] + [a[2]], b[0] + b[1] + [b[2]]):
+        assert np.array_equal(x, y)
