@@ -431,3 +431,47 @@ def froxels(ffi, api, res, noise_r8, shadow_d16, light_matrix2, light, settings1
     out = tuple(be.read_image(v, 0, np.float16).reshape(d, h, w, 4).copy() for v in (material, scatter, target, integrated)) + (g,)
     rig.close()
     return out
+
+
+def pre_expose_lights(ffi, api, histogram_u32, light, transmission_packed, sun_direction_y, screen, lum_min=0.001, lum_max=200000.0,
+                      exposure_offset=1.0, adaption_speed=2.0, delta_time=1 / 60.0, sun_strength=128000.0):
+    """preExposeLights.comp with the bindings of RenderFrontend::computeColorBufferHistogram (RenderFrontend.cpp:741-752).
+    Returns the light buffer after the pass (5 floats: sunColor, previousFrameExposure, sunStrengthExposed)."""
+    rig = PassRig(ffi, api, 64, 64, screen=screen)
+    be, g = rig.be, rig.g
+    g.sunDirection[0], g.sunDirection[1], g.sunDirection[2] = 0.0, float(sun_direction_y), 0.0
+    g.exposureOffset, g.exposureAdaptionSpeedEvPerSec, g.deltaTime, g.sunStrength = exposure_offset, adaption_speed, delta_time, sun_strength
+    be.set_uniform_buffer_data(rig.gbuf, np.frombuffer(bytes(g), np.uint8))
+    n_bins = len(histogram_u32)
+    lh, lw = transmission_packed.shape
+    lut = be.create_image(lw, lh, "R11G11B10_UFLOAT", data=np.ascontiguousarray(transmission_packed, np.uint32))
+    hist = be.create_storage_buffer(n_bins * 4, np.ascontiguousarray(histogram_u32, np.uint32))
+    lightbuf = be.create_storage_buffer(20, np.asarray(light, np.float32))
+    p = be.create_compute_pass("preExposeLights.comp", {0: np.int32(n_bins), 1: np.float32(lum_min), 2: np.float32(lum_max)})
+    be.new_frame()
+    be.set_compute_pass_execution(p, (1, 1, 1), sampled=[(lut, 0, 2)], storage_buffers=[(lightbuf, False, 0), (hist, False, 1)])
+    rig.run()
+    out = be.read_storage_buffer(lightbuf, 20, np.float32).copy()
+    rig.close()
+    return out
+
+
+def light_matrix(ffi, api, depth_min_max, camera, sun_direction, cascades=4, extra_padding=5.0, min_far_plane=30.0, near=0.1, far=300.0):
+    """lightMatrix.comp with the bindings of RenderFrontend::computeSunLightMatrices (RenderFrontend.cpp:840-861): depth_min_max = the single
+    RG32F texel of the lowest HiZ mip (min, max of the reverse-z depth). Returns the 304-byte ShadowCascadeInfo as ffi.ShadowCascadeInfo."""
+    rig = PassRig(ffi, api, 64, 64)
+    be, g = rig.be, rig.g
+    for i in range(3):
+        g.cameraPosition[i], g.cameraForward[i], g.cameraUp[i], g.cameraRight[i] = (float(camera[k][i]) for k in ("position", "forward", "up", "right"))
+        g.sunDirection[i] = float(sun_direction[i])
+    g.cameraTanFovHalf, g.cameraAspectRatio, g.nearPlane, g.farPlane = float(camera["tan_fov_half"]), float(camera["aspect"]), near, far
+    be.set_uniform_buffer_data(rig.gbuf, np.frombuffer(bytes(g), np.uint8))
+    top = be.create_image(1, 1, "RG32_SFLOAT", data=np.asarray(depth_min_max, np.float32))
+    info = be.create_storage_buffer(304, np.zeros(304, np.uint8))
+    p = be.create_compute_pass("lightMatrix.comp", {0: np.uint32(cascades)})
+    be.new_frame()
+    be.set_compute_pass_execution(p, (1, 1, 1), storage=[(top, 0, 1)], storage_buffers=[(info, False, 0)], push=np.array([extra_padding, min_far_plane], np.float32).tobytes())
+    rig.run()
+    out = ffi.ShadowCascadeInfo.from_buffer_copy(be.read_storage_buffer(info, 304).tobytes())
+    rig.close()
+    return out

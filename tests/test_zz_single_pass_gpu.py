@@ -60,3 +60,32 @@ def test_bloom_with_hot_texels_bit_exact(ffi, cuda, oracle, w, h, radius, streng
     a, b = passes.bloom(ffi, cuda, packed, strength=strength, radius=radius), passes.bloom(ffi, oracle, packed, strength=strength, radius=radius)
     for x, y in zip(a[0] + a[1] + [a[2]], b[0] + b[1] + [b[2]]):
         assert np.array_equal(x, y)
+
+
+@pytest.mark.parametrize("case", ["bright", "single_bin", "adapting_up"])
+def test_pre_expose_lights_bit_exact(ffi, cuda, oracle, case):
+    from conftest import random_r11g11b10
+    rng = np.random.default_rng(3)
+    screen = (320, 180)
+    hist = np.zeros(128, np.uint32)
+    if case == "single_bin":
+        hist[80] = screen[0] * screen[1]
+    else:
+        hist = np.bincount(np.clip(rng.normal(95, 6, screen[0] * screen[1]).round(), 0, 127).astype(int), minlength=128).astype(np.uint32)
+    light = np.array([1, 1, 1, 1e-6 if case == "adapting_up" else 2e-5, 1], np.float32)
+    lut = random_r11g11b10(rng, 16 * 24).reshape(24, 16)
+    a, b = passes.pre_expose_lights(ffi, cuda, hist, light, lut, -0.61, screen), passes.pre_expose_lights(ffi, oracle, hist, light, lut, -0.61, screen)
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+@pytest.mark.parametrize("sun,cascades", [((0.35, -0.8, 0.48), 4), ((0.0, -1.0, 0.0), 4), ((-0.6, -0.3, -0.74), 3)])
+def test_light_matrix_bit_exact(ffi, cuda, oracle, sun, cascades):
+    sun = np.array(sun) / np.linalg.norm(sun)
+    fwd = np.array([0.6, 0.1, -0.79])
+    fwd /= np.linalg.norm(fwd)
+    right = np.cross(fwd, [0, -1.0, 0])
+    right /= np.linalg.norm(right)
+    cam = dict(position=np.array([3.0, -2.0, 1.0]), forward=fwd, up=np.cross(right, fwd), right=right, tan_fov_half=0.41, aspect=16 / 9)
+    dmm = np.array([0.0021, 0.083], np.float32)
+    a, b = passes.light_matrix(ffi, cuda, dmm, cam, sun, cascades=cascades), passes.light_matrix(ffi, oracle, dmm, cam, sun, cascades=cascades)
+    assert bytes(a) == bytes(b)
