@@ -475,3 +475,29 @@ def light_matrix(ffi, api, depth_min_max, camera, sun_direction, cascades=4, ext
     out = ffi.ShadowCascadeInfo.from_buffer_copy(be.read_storage_buffer(info, 304).tobytes())
     rig.close()
     return out
+
+
+ATMOSPHERE_DEFAULT = [0.0058, 0.0135, 0.0331, 6371.0, 0.0058, 0.0135, 0.0331, 100.0, 0.000650, 0.001881, 0.000085, 0.006, 1.11 * 0.006, 0.75]  # Sky.h:6-15
+
+
+def sky_luts(ffi, api, sun_direction, sun_strength_exposed, atmosphere=ATMOSPHERE_DEFAULT):
+    """skyTransmissionLut.comp -> skyMultiscatterLut.comp -> skyLut.comp in one frame with the bindings and dispatch sizes of
+    Sky::updateTransmissionLut / updateSkyLut (Sky.cpp:260-316). Returns the three LUTs as packed R11G11B10 (128x128, 32x32, 100x200)."""
+    rig = PassRig(ffi, api, 64, 64)
+    be, g = rig.be, rig.g
+    for i in range(3):
+        g.sunDirection[i] = float(sun_direction[i])
+    be.set_uniform_buffer_data(rig.gbuf, np.frombuffer(bytes(g), np.uint8))
+    trans, multi = be.create_image(128, 128, "R11G11B10_UFLOAT"), be.create_image(32, 32, "R11G11B10_UFLOAT")
+    sky = be.create_image(200, 100, "R11G11B10_UFLOAT", data=np.zeros(200 * 100, np.uint32))
+    ubo = be.create_uniform_buffer(56, np.asarray(atmosphere, np.float32).view(np.uint8))
+    light = be.create_storage_buffer(20, np.array([1, 1, 1, 1, sun_strength_exposed], np.float32))
+    p = [be.create_compute_pass(n) for n in ("skyTransmissionLut.comp", "skyMultiscatterLut.comp", "skyLut.comp")]
+    be.new_frame()
+    be.set_compute_pass_execution(p[0], (16, 16, 1), storage=[(trans, 0, 0)], uniform_buffers=[(ubo, 1)])
+    be.set_compute_pass_execution(p[1], (4, 4, 1), storage=[(multi, 0, 0)], sampled=[(trans, 0, 1)], uniform_buffers=[(ubo, 3)])
+    be.set_compute_pass_execution(p[2], (25, 12, 1), storage=[(sky, 0, 0)], sampled=[(trans, 0, 1), (multi, 0, 2)], uniform_buffers=[(ubo, 4)], storage_buffers=[(light, True, 5)])
+    rig.run()
+    out = (be.read_image(trans, 0, np.uint32).reshape(128, 128).copy(), be.read_image(multi, 0, np.uint32).reshape(32, 32).copy(), be.read_image(sky, 0, np.uint32).reshape(100, 200).copy())
+    rig.close()
+    return out

@@ -89,3 +89,10 @@ def test_light_matrix_bit_exact(ffi, cuda, oracle, sun, cascades):
     dmm = np.array([0.0021, 0.083], np.float32)
     a, b = passes.light_matrix(ffi, cuda, dmm, cam, sun, cascades=cascades), passes.light_matrix(ffi, oracle, dmm, cam, sun, cascades=cascades)
     assert bytes(a) == bytes(b)
+
+
+@pytest.mark.parametrize("sun", [(0.3, -0.5, 0.81), (0.0, -1.0, 0.0), (0.7, 0.05, 0.7)])
+def test_sky_luts_bit_exact(ffi, cuda, oracle, sun):
+    sun = np.array(sun) / np.linalg.norm(sun)
+    for x, y in zip(passes.sky_luts(ffi, cuda, sun, 3.0), passes.sky_luts(ffi, oracle, sun, 3.0)):
+        assert np.array_equal(x, y)
