@@ -248,9 +248,12 @@ def _shadow_cascade_info(ffi, light_matrices):
 
 # ---------------- gbufferShading.comp (triangle.frag recast over the packed G-buffer) as a single pass ----------------
 def shade(ffi, api, gbuffer, y_sh, co_cg, noise_rg8, sun_direction, camera_position, diffuse_brdf=2, direct_multiscatter=0, geometry_aa=0,
-          indirect_tech=0, sun_color=(1.0, 0.9, 0.8), sun_strength_exposed=2.5, brdf_res=512):
+          indirect_tech=0, sun_color=(1.0, 0.9, 0.8), sun_strength_exposed=2.5, brdf_res=512, shadow_maps=None, cascade_info=None, froxel_volume=None,
+          froxel_max_distance=30.0, cascades=3):
     """Bindings of RenderFrontend::shadeGBuffer: G-buffer (h, w, 4) uint32, full-res Y_SH (h, w, 4) / CoCg (h, w, 2) float16, the BRDF LUT
     computed by brdfLut.comp in the same rig, shadow maps without casters (everything lit), an identity froxel volume (no fog).
+    Optional: shadow_maps = 4 square uint16 D16 images + cascade_info = ffi.ShadowCascadeInfo (splits, light matrices, light-space scales),
+    froxel_volume = (d, h, w, 4) float16 integrated in-scattering / transmittance.
     Returns (R11G11B10 colour (h, w) uint32, BRDF LUT (res, res, 4) float16, the global shader info used)."""
     h, w = gbuffer.shape[:2]
     rig = PassRig(ffi, api, w, h)
@@ -267,28 +270,34 @@ def shade(ffi, api, gbuffer, y_sh, co_cg, noise_rg8, sun_direction, camera_posit
     ysh = be.create_image(w, h, "RGBA16_SFLOAT", data=np.ascontiguousarray(y_sh, np.float16))
     cocg = be.create_image(w, h, "RG16_SFLOAT", data=np.ascontiguousarray(co_cg, np.float16))
     lut = be.create_image(brdf_res, brdf_res, "RGBA16_SFLOAT")
-    shadow = [be.create_image(64, 64, "DEPTH16", data=np.zeros((64, 64), np.uint16)) for _ in range(4)]
-    identity = np.zeros((4, 4, 8, 4), np.float16)
-    identity[..., 3] = 1.0  # in-scattering 0, transmittance 1
-    froxels = be.create_image(8, 4, "RGBA16_SFLOAT", depth=4, type_=ffi.IMAGE_3D, data=identity)
+    if shadow_maps is None:
+        shadow_maps = [np.zeros((64, 64), np.uint16)] * 4
+    shadow = [be.create_image(m.shape[1], m.shape[0], "DEPTH16", data=np.ascontiguousarray(m, np.uint16)) for m in shadow_maps]
+    if froxel_volume is None:
+        froxel_volume = np.zeros((4, 4, 8, 4), np.float16)
+        froxel_volume[..., 3] = 1.0  # in-scattering 0, transmittance 1
+    fd, fh, fw = froxel_volume.shape[:3]
+    froxels = be.create_image(fw, fh, "RGBA16_SFLOAT", depth=fd, type_=ffi.IMAGE_3D, data=np.ascontiguousarray(froxel_volume, np.float16))
     sky = be.create_image(8, 4, "R11G11B10_UFLOAT", data=np.zeros((4, 8), np.uint32))
     transmission = be.create_image(8, 8, "R11G11B10_UFLOAT", data=np.zeros((8, 8), np.uint32))
     color = be.create_image(w, h, "R11G11B10_UFLOAT")
     light = be.create_storage_buffer(20, np.array([sun_color[0], sun_color[1], sun_color[2], 1.0, sun_strength_exposed], np.float32))
-    info = ffi.ShadowCascadeInfo()
-    for c in range(4):
-        info.splits[c] = 1e9  # every pixel in cascade 0
-        for k in range(16):
-            info.lightMatrices[c][k] = 1.0 if k % 5 == 0 else 0.0
-        info.lightSpaceScale[c][0] = info.lightSpaceScale[c][1] = 1.0
-    cascades = be.create_storage_buffer(304, np.frombuffer(bytes(info), np.uint8).copy())
-    vol = be.create_uniform_buffer(52, np.array([0, 0, 0, 0, 1, 1, 1, 30.0, 1.0, 0.003, 0.008, 0.5, 0.2], np.float32))
+    info = cascade_info
+    if info is None:
+        info = ffi.ShadowCascadeInfo()
+        for c in range(4):
+            info.splits[c] = 1e9  # every pixel in cascade 0
+            for k in range(16):
+                info.lightMatrices[c][k] = 1.0 if k % 5 == 0 else 0.0
+            info.lightSpaceScale[c][0] = info.lightSpaceScale[c][1] = 1.0
+    cascade_buf = be.create_storage_buffer(304, np.frombuffer(bytes(info), np.uint8).copy())
+    vol = be.create_uniform_buffer(52, np.array([0, 0, 0, 0, 1, 1, 1, froxel_max_distance, 1.0, 0.003, 0.008, 0.5, 0.2], np.float32))
     p_lut = be.create_compute_pass("brdfLut.comp", {0: np.int32(diffuse_brdf)})
-    p = be.create_compute_pass("gbufferShading.comp", {0: np.int32(diffuse_brdf), 1: np.int32(direct_multiscatter), 2: np.uint32(geometry_aa), 3: np.int32(indirect_tech), 4: np.uint32(3)})
+    p = be.create_compute_pass("gbufferShading.comp", {0: np.int32(diffuse_brdf), 1: np.int32(direct_multiscatter), 2: np.uint32(geometry_aa), 3: np.int32(indirect_tech), 4: np.uint32(cascades)})
     be.new_frame()
     be.set_compute_pass_execution(p_lut, (brdf_res // 8, brdf_res // 8, 1), storage=[(lut, 0, 0)])
     sampled = [(gb, 0, 0), (lut, 0, 3), (ysh, 0, 15), (cocg, 0, 16), (froxels, 0, 18), (sky, 0, 21), (transmission, 0, 22)] + [(shadow[i], 0, 9 + i) for i in range(4)]
-    be.set_compute_pass_execution(p, ((w + 7) // 8, (h + 7) // 8, 1), sampled=sampled, storage=[(color, 0, 20)], storage_buffers=[(light, True, 7), (cascades, True, 8)],
+    be.set_compute_pass_execution(p, ((w + 7) // 8, (h + 7) // 8, 1), sampled=sampled, storage=[(color, 0, 20)], storage_buffers=[(light, True, 7), (cascade_buf, True, 8)],
                                   uniform_buffers=[(vol, 19)])
     rig.run()
     out = (be.read_image(color, 0, np.uint32).reshape(h, w).copy(), be.read_image(lut, 0, np.float16).reshape(brdf_res, brdf_res, 4).copy(), g)

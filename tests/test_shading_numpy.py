@@ -58,7 +58,8 @@ def multiscatter(mode, r, NoL, f0, single, lut_rgb, lut_img):
     return np.zeros_like(single)
 
 
-def np_shade(gbuffer, y_sh, co_cg, lut_img, g, sun_color, sun_strength_exposed, diffuse_brdf, direct_multiscatter, indirect_tech):
+def np_shade(gbuffer, y_sh, co_cg, lut_img, g, sun_color, sun_strength_exposed, diffuse_brdf, direct_multiscatter, indirect_tech, sun_shadow=None, geometry_aa=False, fog=None):
+    """sun_shadow: callable(pos, pixel_depth) -> (h, w) shadow factor (calcShadow); fog: callable(colour, pixel_depth) -> colour"""
     h, w = gbuffer.shape[:2]
     depth = gbuffer[..., 0].view(np.float32).astype(np.float64)
     sn = np.stack([(gbuffer[..., 1] & 0xFFFF).astype(np.uint16).view(np.int16), (gbuffer[..., 1] >> 16).astype(np.uint16).view(np.int16)], -1).astype(np.float64) / 32767
@@ -79,6 +80,11 @@ def np_shade(gbuffer, y_sh, co_cg, lut_img, g, sun_color, sun_strength_exposed, 
     depth_linear = g.nearPlane * g.farPlane / (g.farPlane + (1 - depth) * (g.nearPlane - g.farPlane))
     pos = cam + to_pixel / (to_pixel @ fwd)[..., None] * depth_linear[..., None]
     r = np.maximum(rough * rough, 0.0045)
+    if geometry_aa:  # GeometricAA.inc:4-20; dFdxFine / dFdyFine = differences inside the pixel's 2x2 quad
+        xe, ye = (xs & ~1), (ys & ~1)
+        N_U, N_V = N[ys, xe + 1] - N[ys, xe], N[ye + 1, xs] - N[ye, xs]
+        variance = 0.25 * ((N_U * N_U).sum(-1) + (N_V * N_V).sum(-1))
+        r = np.clip(np.sqrt(r * r + np.minimum(2 * variance, 0.18)), 0, 1)
     diffuse_color = (1 - metal)[..., None] * albedo
     L = sun / np.linalg.norm(sun)
     V = cam - pos
@@ -89,7 +95,10 @@ def np_shade(gbuffer, y_sh, co_cg, lut_img, g, sun_color, sun_strength_exposed, 
     NoH, NoL, VoH, LoV = np.maximum(dot(N, H), 0), np.clip(dot(N, L), 0, 1), np.abs(dot(V, H)), np.maximum(dot(V, L), 0)
     NoV = np.maximum(np.abs(dot(N, V)), 0.0001)
     f0 = 0.04 * (1 - metal)[..., None] + albedo * metal[..., None]
-    direct = np.maximum(dot(N, L), 0)[..., None] * np.array(sun_color)  # sunShadow = 1: no casters
+    pixel_depth = dot(cam - pos, -fwd)  # triangle.frag:200
+    direct = np.maximum(dot(N, L), 0)[..., None] * np.array(sun_color)  # sunShadow = 1 without casters
+    if sun_shadow is not None:
+        direct = direct * sun_shadow(pos, pixel_depth)[..., None]
     lut_rgb = bilinear_clamp(lut_img, r, NoV)[..., :3]
     integral = lut_rgb[..., 2:3] * np.ones(3)
     if diffuse_brdf == 0:
@@ -135,7 +144,8 @@ def np_shade(gbuffer, y_sh, co_cg, lut_img, g, sun_color, sun_strength_exposed, 
     else:
         amb = 0.003 * sun_strength_exposed
         indirect = amb * diffuse_color * integral + (lut_rgb[..., 0:1] * (1 - f0) + lut_rgb[..., 1:2] * f0) * amb
-    return (diffuse_direct + specular_direct) * sun_strength_exposed + indirect
+    colour = (diffuse_direct + specular_direct) * sun_strength_exposed + indirect
+    return fog(colour, pixel_depth) if fog is not None else colour
 
 
 def oct_encode(n):
@@ -182,3 +192,97 @@ def test_shading_matches_float64_restatement(ffi, oracle, diffuse_brdf, direct_m
     assert rel[..., :2][bright[..., :2]].max() < 2.0 ** -6 * 1.25, "red / green: 6 mantissa bits"
     assert rel[..., 2][bright[..., 2]].max() < 2.0 ** -5 * 1.25, "blue: 5 mantissa bits"
     assert np.median(rel[bright]) < 2.0 ** -7
+
+
+def test_shadow_cascades_pcf_fog_and_geometric_aa(ffi, oracle):
+    """The rest of triangle.frag's main(): cascade selection by view depth (:224-239), the 12-tap spiral PCF with the blue-noise rotation
+    (calcShadow :92-120), geometric specular anti-aliasing from the quad's normal derivatives (GeometricAA.inc) and the froxel in-scattering /
+    transmittance applied at the jittered screen position (applyVolumetricLighting :133-144, volumetricFroxelLighting.inc:33-53)."""
+    from test_froxels_numpy import depth_to_uvz, trilinear
+    rng = np.random.default_rng(77)
+    w, h = 64, 40
+    cam = np.array([0.5, -1.0, 2.0])
+    near, far = 0.1, 300.0
+    ys, xs = np.mgrid[0:h, 0:w]
+    depth_linear = 3.0 + 36.0 * xs / (w - 1) + 0.3 * rng.random((h, w))           # 3 .. 39 m from left to right: all four cascades
+    depth = (1 - (near * far / depth_linear - far) / (near - far)).astype(np.float32)
+    # smooth normal field with a few creases (geometric AA widens the lobe only there)
+    nrm = np.stack([0.3 * np.sin(xs / 6.0), 0.3 * np.cos(ys / 5.0), np.ones((h, w))], -1)
+    nrm[:, 20:22, 0] += 0.8
+    nrm[12:14, :, 1] -= 0.7
+    nrm /= np.linalg.norm(nrm, axis=-1, keepdims=True)
+    gb = np.zeros((h, w, 4), np.uint32)
+    gb[..., 0] = depth.view(np.uint32)
+    gb[..., 1] = oct_encode(nrm)
+    alb = rng.integers(90, 250, (h, w, 3)).astype(np.uint32)
+    gb[..., 2] = alb[..., 0] | (alb[..., 1] << 8) | (alb[..., 2] << 16) | (rng.integers(20, 120, (h, w)).astype(np.uint32) << 24)   # rather smooth: a visible lobe
+    gb[..., 3] = np.where(rng.uniform(size=(h, w)) < 0.3, 255, 0).astype(np.uint32)
+    ysh = np.concatenate([rng.uniform(0.2, 1.0, (h, w, 1)), rng.uniform(-0.2, 0.2, (h, w, 3))], -1).astype(np.float16)
+    cocg = rng.uniform(-0.05, 0.05, (h, w, 2)).astype(np.float16)
+    noise = rng.integers(0, 256, (32, 32, 2)).astype(np.uint8)
+    sun = np.array([0.3, -0.6, 0.74])
+    sun_color, sse = (1.0, 0.9, 0.8), 2.5
+    # four cascades: top-down orthographic light matrices of different extent, maps of 8-texel blocks at two occluder depths
+    splits = [10.0, 20.0, 30.0]
+    info = ffi.ShadowCascadeInfo()
+    mats, scales, maps = [], [], []
+    for c in range(4):
+        ext = 25.0 + 10.0 * c
+        L = np.array([[1 / ext, 0, 0, 0.1 * c], [0, 0, 1 / ext, -0.05 * c], [0, 1 / 40.0, 0, 0.5], [0, 0, 0, 1]], np.float64)
+        mats.append(L)
+        scales.append(np.array([1.5 + 0.5 * c, 1.0 + 0.3 * c]))
+        block = ((np.add.outer(np.arange(64) // 8, np.arange(64) // 8) + c) % 3 == 0)
+        maps.append(np.where(block, 60000, 3000).astype(np.uint16))              # occluder depth 0.92 (shadows what is below) / 0.05
+        for k, v in enumerate(L.T.ravel()):
+            info.lightMatrices[c][k] = float(v)
+        info.lightSpaceScale[c][0], info.lightSpaceScale[c][1] = float(scales[c][0]), float(scales[c][1])
+    for c in range(3):
+        info.splits[c] = splits[c]
+    nz = noise[ys % 32, xs % 32].astype(np.float64) / 255.0                       # g_sampler_nearestRepeat at gl_FragCoord / textureSize
+
+    def sun_shadow(pos, pixel_depth):
+        cascade = sum((pixel_depth >= s).astype(int) for s in splits)
+        out = np.zeros((h, w))
+        for c in range(4):
+            pl = np.concatenate([pos, np.ones((h, w, 1))], -1) @ mats[c].T
+            pl = pl / pl[..., 3:4]
+            uv = pl[..., :2] * 0.5 + 0.5
+            actual = np.clip(pl[..., 2], 0, 1)
+            lit = np.zeros((h, w))
+            for i in range(12):
+                d = np.sqrt((i + 0.5 * nz[..., 0]) / 12)
+                angle = nz[..., 0] * 2 * PI + 2 * PI * i / 12
+                sp = uv + np.stack([np.cos(angle), np.sin(angle)], -1) * (0.03 * scales[c]) * d[..., None]
+                tx, ty = np.floor(sp[..., 0] * 64).astype(int), np.floor(sp[..., 1] * 64).astype(int)
+                inside = (tx >= 0) & (tx < 64) & (ty >= 0) & (ty < 64)
+                texel = np.where(inside, maps[c][np.clip(ty, 0, 63), np.clip(tx, 0, 63)] / 65535.0, 0.0)   # black border
+                lit += actual >= texel
+            out = np.where(cascade == c, lit / 12, out)
+        return out
+    volume = np.zeros((8, 5, 8, 4), np.float16)
+    zz, yy, xx = np.mgrid[0:8, 0:5, 0:8]
+    volume[..., :3] = (0.02 * (zz + 1) * (1 + 0.3 * np.sin(xx)))[..., None] * np.array([1.0, 0.8, 0.6])
+    volume[..., 3] = np.exp(-0.12 * (zz + 1) * (1 + 0.2 * np.cos(yy)))
+
+    def fog(colour, pixel_depth):
+        jitter = (nz - 0.5) * 0.013
+        suv = np.stack([(xs + 0.5) / w + jitter[..., 0], (ys + 0.5) / h + jitter[..., 1], depth_to_uvz(pixel_depth, 30.0)], -1)
+        it = trilinear(volume, suv, repeat=False)
+        return colour * it[..., 3:4] + it[..., :3]
+    kw = dict(shadow_maps=maps, cascade_info=info, froxel_volume=volume, cascades=4)
+    for aa in (0, 1):
+        packed, lut, g = passes.shade(ffi, oracle, gb, ysh, cocg, noise, sun, cam, 2, 0, aa, 0, sun_color, sse, brdf_res=128, **kw)
+        got = decode_r11g11b10(packed)
+        seen = {}
+        want = np_shade(gb, ysh, cocg, lut, g, sun_color, sse, 2, 0, 0, sun_shadow=lambda p, d: seen.setdefault("s", sun_shadow(p, d)), geometry_aa=bool(aa), fog=fog)
+        s = seen["s"]
+        assert 0.15 < s.mean() < 0.85 and ((s > 0.05) & (s < 0.95)).mean() > 0.05      # lit, shadowed and penumbra pixels
+        assert all(((s > 0) & (np.floor((depth_linear - 0.001) / 10).clip(0, 3) == c)).any() for c in range(4))
+        rel = np.abs(got - want) / np.maximum(want, 1e-6)
+        ok = (rel[..., :2].max(-1) < 2.0 ** -6 * 1.25) & (rel[..., 2] < 2.0 ** -5 * 1.25)
+        # a PCF tap within rounding distance of a texel border or a pixel on a cascade split may fall on the other side: a few pixels
+        print("geometric AA %d: %.4f of the pixels within the packed format, median rel %.5f" % (aa, ok.mean(), float(np.median(rel))))
+        assert ok.mean() > 0.995, "geometric AA %d: %d of %d pixels differ (median %.4f)" % (aa, int((~ok).sum()), ok.size, float(np.median(rel)))
+        if aa:
+            assert not np.array_equal(packed, first)                                   # the creases did widen some lobes
+        first = packed
