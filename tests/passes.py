@@ -510,3 +510,53 @@ def sky_luts(ffi, api, sun_direction, sun_strength_exposed, atmosphere=ATMOSPHER
     out = (be.read_image(trans, 0, np.uint32).reshape(128, 128).copy(), be.read_image(multi, 0, np.uint32).reshape(32, 32).copy(), be.read_image(sky, 0, np.uint32).reshape(100, 200).copy())
     rig.close()
     return out
+
+
+def sdf_diffuse_trace(ffi, api, depth, normal_rgba8, noise_rg8, sky_lut_packed, instances, bricks, shadow_d16, light_matrix, light, influence_range=5.0,
+                      strict_cutoff=False, camera_position=(0.0, 0.0, 0.0), frame_index_mod4=1, cascade=3):
+    """sdfDiffuseTrace.comp with the bindings of SDFGI::diffuseSDFTrace (SDFGI.cpp:380-419) at half resolution: depth (h, w) float32 and
+    RGBA8 normals (h, w, 4) sampled at uv = iUV / size, instances = [(localExtends, brick index into `bricks`, meanAlbedo, worldToLocal 4x4 numpy
+    row-major)], bricks = [(res, uint16 R16F volume (res, res, res))], every culling tile lists every instance. Returns (Y_SH, CoCg) float16, globals."""
+    h, w = depth.shape
+    rig = PassRig(ffi, api, w, h, screen=(2 * w, 2 * h))
+    be, g = rig.be, rig.g
+    noise = be.create_image(noise_rg8.shape[1], noise_rg8.shape[0], "RG8", data=np.ascontiguousarray(noise_rg8, np.uint8))
+    for i in range(4):
+        g.noiseTextureIndices[i] = be.global_texture_index(noise)
+    g.frameIndexMod4 = frame_index_mod4
+    for i in range(3):
+        g.cameraPosition[i] = float(camera_position[i])
+    be.set_uniform_buffer_data(rig.gbuf, np.frombuffer(bytes(g), np.uint8))
+    brick_index = []
+    for vol in bricks:
+        r = vol.shape[0]
+        brick_index.append(be.global_texture_index(be.create_image(r, r, "R16_SFLOAT", depth=r, type_=ffi.IMAGE_3D, data=np.ascontiguousarray(vol, np.uint16))))
+    inst = np.zeros(4 + 24 * max(len(instances), 1), np.float32)      # sdfDiffuseTrace.comp:35-41: uint instanceCount + 3 padding words, then SDFInstance[]
+    inst[0:1].view(np.uint32)[0] = len(instances)
+    for k, (ext, b, albedo, world_to_local) in enumerate(instances):
+        rec = inst[4 + 24 * k: 4 + 24 * (k + 1)]
+        rec[0:3], rec[4:7] = ext, albedo
+        rec[3:4].view(np.uint32)[0] = brick_index[b]
+        rec[8:24] = np.asarray(world_to_local, np.float32).T.ravel()
+    tiles_x, tiles_y = (2 * w + 31) // 32, (2 * h + 31) // 32          # tileIndexFromTileUV strides by the FULL-resolution width (sdfCulling.inc:17-20)
+    tiles = np.zeros((tiles_x * tiles_y, 101), np.uint32)
+    tiles[:, 0] = len(instances)
+    tiles[:, 1:1 + len(instances)] = np.arange(len(instances), dtype=np.uint32)
+    d_img = be.create_image(w, h, "DEPTH32", data=np.ascontiguousarray(depth, np.float32))
+    n_img = be.create_image(w, h, "RGBA8", data=np.ascontiguousarray(normal_rgba8, np.uint8))
+    sky = be.create_image(sky_lut_packed.shape[1], sky_lut_packed.shape[0], "R11G11B10_UFLOAT", data=np.ascontiguousarray(sky_lut_packed, np.uint32))
+    shadow = be.create_image(shadow_d16.shape[1], shadow_d16.shape[0], "DEPTH16", data=np.ascontiguousarray(shadow_d16, np.uint16))
+    out_y, out_c = be.create_image(w, h, "RGBA16_SFLOAT"), be.create_image(w, h, "RG16_SFLOAT")
+    lm = np.zeros((4, 16), np.float32)
+    lm[cascade] = np.asarray(light_matrix, np.float32)
+    bufs = [(be.create_storage_buffer(20, np.asarray(light, np.float32)), True, 5), (be.create_storage_buffer(inst.nbytes, inst.view(np.uint8)), True, 6),
+            (be.create_storage_buffer(tiles.nbytes, tiles.view(np.uint8)), True, 7), (be.create_storage_buffer(304, _shadow_cascade_info(ffi, lm)), True, 9)]
+    ubo = be.create_uniform_buffer(4, np.array([influence_range], np.float32).view(np.uint8))
+    p = be.create_compute_pass("sdfDiffuseTrace.comp", {0: np.uint32(int(strict_cutoff)), 1: np.int32(cascade)})
+    be.new_frame()
+    be.set_compute_pass_execution(p, ((w + 7) // 8, (h + 7) // 8, 1), storage=[(out_y, 0, 0), (out_c, 0, 1)], sampled=[(d_img, 0, 2), (n_img, 0, 3), (sky, 0, 4), (shadow, 0, 10)],
+                                  storage_buffers=bufs, uniform_buffers=[(ubo, 8)])
+    rig.run()
+    res = (be.read_image(out_y, 0, np.float16).reshape(h, w, 4).copy(), be.read_image(out_c, 0, np.float16).reshape(h, w, 2).copy(), g)
+    rig.close()
+    return res

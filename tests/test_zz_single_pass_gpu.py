@@ -96,3 +96,23 @@ def test_sky_luts_bit_exact(ffi, cuda, oracle, sun):
     sun = np.array(sun) / np.linalg.norm(sun)
     for x, y in zip(passes.sky_luts(ffi, cuda, sun, 3.0), passes.sky_luts(ffi, oracle, sun, 3.0)):
         assert np.array_equal(x, y)
+
+
+@pytest.mark.parametrize("strict,with_box", [(False, False), (False, True), (True, True)])
+def test_sdf_diffuse_trace_single_pass_bit_exact(ffi, cuda, oracle, strict, with_box):
+    from test_sdf_diffuse_trace_numpy import wall_inputs
+    from test_sdf_trace_analytic import box_brick
+    rng = np.random.default_rng(6)
+    depth, normal, noise, sky_p = wall_inputs(rng, 64, 40)
+    half, centre = np.array([1.6, 1.2, 0.9]), np.array([0.3, 0.2, -6.5])
+    pad = np.maximum(2 * half * 0.075, 0.5)
+    W2L = np.eye(4)
+    W2L[:3, 3] = -centre
+    Lm = np.array([[1 / 20.0, 0, 0, 0], [0, 0, 1 / 20.0, 0], [0, 1 / 40.0, 0, 0.5], [0, 0, 0, 1]], np.float64)
+    shadow = np.zeros((16, 16), np.uint16)
+    shadow[:, 8:] = 65535
+    inst = [(2 * (half + pad), 0, np.array([0.7, 0.5, 0.3]), W2L)] if with_box else []
+    bricks = [box_brick(half, 32).reshape(32, 32, 32)] if with_box else []
+    a = passes.sdf_diffuse_trace(ffi, cuda, depth, normal, noise, sky_p, inst, bricks, shadow, Lm.T.ravel(), [1.0, 0.9, 0.8, 1.0, 2.0], 3.4, strict)
+    b = passes.sdf_diffuse_trace(ffi, oracle, depth, normal, noise, sky_p, inst, bricks, shadow, Lm.T.ravel(), [1.0, 0.9, 0.8, 1.0, 2.0], 3.4, strict)
+    assert np.array_equal(a[0].view(np.uint16), b[0].view(np.uint16)) and np.array_equal(a[1].view(np.uint16), b[1].view(np.uint16))
