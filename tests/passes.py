@@ -560,3 +560,48 @@ def sdf_diffuse_trace(ffi, api, depth, normal_rgba8, noise_rg8, sky_lut_packed, 
     res = (be.read_image(out_y, 0, np.float16).reshape(h, w, 4).copy(), be.read_image(out_c, 0, np.float16).reshape(h, w, 2).copy(), g)
     rig.close()
     return res
+
+
+def sdf_culling(ffi, api, bbs, frustum_points, frustum_normals, influence_range, target_size, screen, camera, hiz_min_max=None, near=0.1, far=300.0):
+    """sdfCameraFrustumCulling.comp + sdfCameraTileCulling.comp with the bindings of SDFGI::sdfInstanceCulling (SDFGI.cpp:538-630).
+    bbs (n, 2, 3) world-space boxes; frustum_points / normals (6, 3); target_size = size of the traced image (tiles of 32 px);
+    hiz_min_max (ty, tx, 2) float32 = the depth pyramid level bound at binding 4 (None: useHiZ = false).
+    Returns (culled instance list, per-tile lists [(count, indices)] as an array (tiles, 101), tile stride)."""
+    n = len(bbs)
+    rig = PassRig(ffi, api, 64, 64, screen=screen)
+    be, g = rig.be, rig.g
+    for i in range(3):
+        g.cameraPosition[i], g.cameraForward[i], g.cameraUp[i], g.cameraRight[i] = (float(camera[k][i]) for k in ("position", "forward", "up", "right"))
+    g.cameraTanFovHalf, g.cameraAspectRatio, g.nearPlane, g.farPlane = float(camera["tan_fov_half"]), float(camera["aspect"]), near, far
+    be.set_uniform_buffer_data(rig.gbuf, np.frombuffer(bytes(g), np.uint8))
+    inst = np.zeros(4 + 24 * n, np.float32)
+    inst[0:1].view(np.uint32)[0] = n
+    bb = np.zeros((n, 8), np.float32)
+    bb[:, 0:3], bb[:, 4:7] = np.asarray(bbs)[:, 0], np.asarray(bbs)[:, 1]
+    fr = np.zeros((12, 4), np.float32)
+    fr[0:6, :3], fr[6:12, :3] = frustum_points, frustum_normals
+    tx, ty = (target_size[0] + 31) // 32, (target_size[1] + 31) // 32
+    stride = (screen[0] + 31) // 32                                      # tileIndexFromTileUV: full-resolution width
+    tiles_total = stride * max(ty, (screen[1] + 31) // 32)
+    b_inst = be.create_storage_buffer(inst.nbytes, inst.view(np.uint8))
+    b_list = be.create_storage_buffer(4 + 4 * max(n, 1), np.full(1 + max(n, 1), 0xFFFFFFFF, np.uint32).view(np.uint8))
+    be.set_storage_buffer_data(b_list, np.zeros(1, np.uint32).view(np.uint8))      # the host zeroes the counter every frame (SDFGI.cpp:557-558)
+    b_bb = be.create_storage_buffer(bb.nbytes, bb.view(np.uint8))
+    b_tiles = be.create_storage_buffer(tiles_total * 404, np.full(tiles_total * 101, 0xFFFFFFFF, np.uint32).view(np.uint8))
+    u_fr = be.create_uniform_buffer(192, fr.view(np.uint8))
+    u_inf = be.create_uniform_buffer(4, np.array([influence_range], np.float32).view(np.uint8))
+    use_hiz = hiz_min_max is not None
+    if not use_hiz:
+        hiz_min_max = np.zeros((1, 1, 2), np.float32)
+    hz = be.create_image(hiz_min_max.shape[1], hiz_min_max.shape[0], "RG32_SFLOAT", data=np.ascontiguousarray(hiz_min_max, np.float32))
+    p0 = be.create_compute_pass("sdfCameraFrustumCulling.comp")
+    p1 = be.create_compute_pass("sdfCameraTileCulling.comp", {0: np.uint32(int(use_hiz))})
+    be.new_frame()
+    be.set_compute_pass_execution(p0, ((n + 63) // 64, 1, 1), storage_buffers=[(b_inst, True, 0), (b_list, False, 2), (b_bb, True, 3)], uniform_buffers=[(u_fr, 1), (u_inf, 4)])
+    be.set_compute_pass_execution(p1, ((tx + 7) // 8, (ty + 7) // 8, 1), storage_buffers=[(b_list, True, 0), (b_bb, True, 1), (b_tiles, False, 2)], uniform_buffers=[(u_inf, 3)],
+                                  sampled=[(hz, 0, 4)], push=np.array([tx, ty], np.uint32).tobytes())
+    rig.run()
+    lst = be.read_storage_buffer(b_list, 4 + 4 * max(n, 1), np.uint32).copy()
+    tiles = be.read_storage_buffer(b_tiles, tiles_total * 404, np.uint32).reshape(tiles_total, 101).copy()
+    rig.close()
+    return lst[1:1 + lst[0]], tiles, stride

@@ -116,3 +116,22 @@ def test_sdf_diffuse_trace_single_pass_bit_exact(ffi, cuda, oracle, strict, with
     a = passes.sdf_diffuse_trace(ffi, cuda, depth, normal, noise, sky_p, inst, bricks, shadow, Lm.T.ravel(), [1.0, 0.9, 0.8, 1.0, 2.0], 3.4, strict)
     b = passes.sdf_diffuse_trace(ffi, oracle, depth, normal, noise, sky_p, inst, bricks, shadow, Lm.T.ravel(), [1.0, 0.9, 0.8, 1.0, 2.0], 3.4, strict)
     assert np.array_equal(a[0].view(np.uint16), b[0].view(np.uint16)) and np.array_equal(a[1].view(np.uint16), b[1].view(np.uint16))
+
+
+@pytest.mark.parametrize("n,use_hiz,influence", [(40, False, 5.0), (300, True, 2.0), (260, False, 40.0), (1200, True, 5.0)])
+def test_sdf_culling_bit_exact(ffi, cuda, oracle, n, use_hiz, influence):
+    from test_sdf_culling_numpy import camera_and_frustum
+    rng = np.random.default_rng(n + use_hiz)
+    cam, pts, nrm = camera_and_frustum()
+    centres = cam["position"] + rng.uniform(-60, 60, (n, 3)) * np.array([1.0, 0.3, 1.0])
+    halfs = rng.uniform(0.3, 4.0, (n, 3))
+    bbs = np.stack([centres - halfs, centres + halfs], 1)
+    hiz = rng.uniform(0.001, 0.09, (3, 5, 2)).astype(np.float32) if use_hiz else None
+    if hiz is not None:
+        hiz.sort(-1)
+    a = passes.sdf_culling(ffi, cuda, bbs, pts, nrm, influence, (160, 96), (320, 192), cam, hiz)
+    b = passes.sdf_culling(ffi, oracle, bbs, pts, nrm, influence, (160, 96), (320, 192), cam, hiz)
+    assert np.array_equal(a[0], b[0])
+    # entries beyond a tile's count are never written by either side
+    for ta, tb in zip(a[1], b[1]):
+        assert ta[0] == tb[0] and (ta[0] == 0xFFFFFFFF or np.array_equal(ta[1:1 + ta[0]], tb[1:1 + tb[0]]))
