@@ -51,8 +51,6 @@ PV_HD float decodeSmallFloat(uint32_t v, int mbits) {  // exact; branch-free: ex
     const float special = dm::u2f(shifted | 0x7f800000u);                                    // inf / NaN keep their mantissa
     return e == 0 ? denormal : (e == 31 ? special : normal);
 }
-PV_HD uint32_t packR11G11B10(vec3 c) { return encodeSmallFloat(c.x, 6) | (encodeSmallFloat(c.y, 6) << 11) | (encodeSmallFloat(c.z, 5) << 22); }
-PV_HD vec3 unpackR11G11B10(uint32_t v) { return v3(decodeSmallFloat(v & 0x7ffu, 6), decodeSmallFloat((v >> 11) & 0x7ffu, 6), decodeSmallFloat(v >> 22, 5)); }
 
 PV_HD uint16_t floatToHalf(float f) {
 #if defined(__CUDA_ARCH__)
@@ -89,6 +87,33 @@ PV_HD float halfToFloat(uint16_t h) {
     return dm::u2f(sign | ((e + 112u) << 23) | (m << 13));
 #endif
 }
+// The same codes with fewer instructions (used by the "fast" contract's device code; tests/test_codecs.py holds both
+// against the functions above on the host, exhaustively for the decoder and over every rounding boundary for the encoder):
+// encode = round to nearest even by integer arithmetic on the binary32 bits (codes below the smallest normal through one float add),
+// decode = the channel IS a half float without sign and with a short mantissa: shift it into place, one conversion.
+PV_HD uint32_t encodeSmallFloatFast(float f, int mbits) {
+    const uint32_t maxFinite = (30u << mbits) | ((1u << mbits) - 1u);
+    const uint32_t u = dm::f2u(f);
+    if ((u & 0x7fffffffu) > 0x7f800000u) return (31u << mbits) | 1u;
+    if (u >> 31) return 0u;
+    if (u == 0x7f800000u) return 31u << mbits;
+    const int shift = 23 - mbits;
+    if (u < (113u << 23)) {  // below 2^-14: in [2^(9-mbits), 2^(10-mbits)) one binary32 ulp is one denormal code step
+        const float magic = dm::u2f((uint32_t)(127 + 9 - mbits) << 23);
+        return dm::f2u(f + magic) - dm::f2u(magic);
+    }
+    const uint32_t r = u - (112u << 23);  // rebias 127 -> 15
+    const uint32_t v = (r + ((1u << (shift - 1)) - 1u) + ((r >> shift) & 1u)) >> shift;
+    return v > maxFinite ? maxFinite : v;
+}
+PV_HD float decodeSmallFloatFast(uint32_t v, int mbits) { return halfToFloat((uint16_t)(v << (10 - mbits))); }
+#if defined(DM_FAST) && defined(__CUDA_ARCH__)
+PV_HD uint32_t packR11G11B10(vec3 c) { return encodeSmallFloatFast(c.x, 6) | (encodeSmallFloatFast(c.y, 6) << 11) | (encodeSmallFloatFast(c.z, 5) << 22); }
+PV_HD vec3 unpackR11G11B10(uint32_t v) { return v3(decodeSmallFloatFast(v & 0x7ffu, 6), decodeSmallFloatFast((v >> 11) & 0x7ffu, 6), decodeSmallFloatFast(v >> 22, 5)); }
+#else
+PV_HD uint32_t packR11G11B10(vec3 c) { return encodeSmallFloat(c.x, 6) | (encodeSmallFloat(c.y, 6) << 11) | (encodeSmallFloat(c.z, 5) << 22); }
+PV_HD vec3 unpackR11G11B10(uint32_t v) { return v3(decodeSmallFloat(v & 0x7ffu, 6), decodeSmallFloat((v >> 11) & 0x7ffu, 6), decodeSmallFloat(v >> 22, 5)); }
+#endif
 PV_HD uint32_t floatToUnorm8(float x) { return isnanf_(x) ? 0u : (uint32_t)(clampf(x, 0.f, 1.f) * 255.f + 0.5f); }
 PV_HD float unorm8(uint32_t v) { return (float)v / 255.f; }
 PV_HD float snorm16(int16_t v) { return fmaxp((float)v / 32767.f, -1.f); }
