@@ -27,19 +27,30 @@ struct ivec2 { int x, y; ivec2() : x(0), y(0) {} ivec2(int a, int b) : x(a), y(b
 struct ivec3 { int x, y, z; ivec3() : x(0), y(0), z(0) {} ivec3(int a, int b, int c) : x(a), y(b), z(c) {} };
 struct uvec3 { uint x, y, z; uvec3() : x(0), y(0), z(0) {} uvec3(uint a, uint b, uint c) : x(a), y(b), z(c) {} };
 
+// reciprocal of a divisor: the correctly rounded 1/x. -DPLAIN_EMULATE_APPROX_RCP turns it into rcp.approx in the error-model build of the
+// "fast" contract (liboracle_sfu.so) - the experiment that showed why the fast contract must NOT do that: sdfDiffuseTrace.comp:120 and
+// sdfCameraTileCulling.comp:75 sample with NEAREST filtering at uv = iUV / size, exactly on texel borders, so one ulp in the reciprocal
+// moves a quarter of the pixels to the neighbouring texel (tests/test_fast_contract_emulation.py documents the numbers)
+inline float rcp_(float x) {
+#if defined(DM_FAST) && defined(PLAIN_EMULATE_APPROX_RCP)
+    return dm::hw_rcp(x);
+#else
+    return 1.f / x;
+#endif
+}
 #define GL_VEC_OPS(V, N)                                                                                                \
     inline V operator+(V a, V b) { V r; for (int i = 0; i < N; i++) (&r.x)[i] = (&a.x)[i] + (&b.x)[i]; return r; }      \
     inline V operator-(V a, V b) { V r; for (int i = 0; i < N; i++) (&r.x)[i] = (&a.x)[i] - (&b.x)[i]; return r; }      \
     inline V operator*(V a, V b) { V r; for (int i = 0; i < N; i++) (&r.x)[i] = (&a.x)[i] * (&b.x)[i]; return r; }      \
-    inline V operator/(V a, V b) { V r; for (int i = 0; i < N; i++) (&r.x)[i] = (&a.x)[i] * (1.f / (&b.x)[i]); return r; } \
+    inline V operator/(V a, V b) { V r; for (int i = 0; i < N; i++) (&r.x)[i] = (&a.x)[i] * rcp_((&b.x)[i]); return r; } \
     inline V operator+(V a, float b) { V r; for (int i = 0; i < N; i++) (&r.x)[i] = (&a.x)[i] + b; return r; }          \
     inline V operator-(V a, float b) { V r; for (int i = 0; i < N; i++) (&r.x)[i] = (&a.x)[i] - b; return r; }          \
     inline V operator*(V a, float b) { V r; for (int i = 0; i < N; i++) (&r.x)[i] = (&a.x)[i] * b; return r; }          \
-    inline V operator/(V a, float b) { V r; const float rb = 1.f / b; for (int i = 0; i < N; i++) (&r.x)[i] = (&a.x)[i] * rb; return r; } \
+    inline V operator/(V a, float b) { V r; const float rb = rcp_(b); for (int i = 0; i < N; i++) (&r.x)[i] = (&a.x)[i] * rb; return r; } \
     inline V operator+(float a, V b) { V r; for (int i = 0; i < N; i++) (&r.x)[i] = a + (&b.x)[i]; return r; }          \
     inline V operator-(float a, V b) { V r; for (int i = 0; i < N; i++) (&r.x)[i] = a - (&b.x)[i]; return r; }          \
     inline V operator*(float a, V b) { V r; for (int i = 0; i < N; i++) (&r.x)[i] = a * (&b.x)[i]; return r; }          \
-    inline V operator/(float a, V b) { V r; for (int i = 0; i < N; i++) (&r.x)[i] = a * (1.f / (&b.x)[i]); return r; }  \
+    inline V operator/(float a, V b) { V r; for (int i = 0; i < N; i++) (&r.x)[i] = a * rcp_((&b.x)[i]); return r; }  \
     inline V operator-(V a) { V r; for (int i = 0; i < N; i++) (&r.x)[i] = -(&a.x)[i]; return r; }                      \
     inline V& operator+=(V& a, V b) { a = a + b; return a; }                                                            \
     inline V& operator-=(V& a, V b) { a = a - b; return a; }                                                            \
@@ -120,8 +131,13 @@ inline float length(vec3 a) { return sqrt(dot(a, a)); }
 inline float length(vec4 a) { return sqrt(dot(a, a)); }
 inline float distance(vec3 a, vec3 b) { return length(a - b); }
 // normalize(v) = v / length(v) = v * (1 / sqrt(dot(v, v)))
+#if defined(DM_FAST)
+inline vec3 normalize(vec3 a) { return a * dm::hw_rsqrt(dot(a, a)); }
+inline vec4 normalize(vec4 a) { return a * dm::hw_rsqrt(dot(a, a)); }
+#else
 inline vec3 normalize(vec3 a) { return a / length(a); }
 inline vec4 normalize(vec4 a) { return a / length(a); }
+#endif
 inline vec3 cross(vec3 a, vec3 b) { return vec3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
 // reflect(I, N) = I - (2 * dot(N, I)) * N
 inline vec3 reflect(vec3 I, vec3 N) { return I - (2.f * dot(N, I)) * N; }

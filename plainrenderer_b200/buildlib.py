@@ -7,7 +7,7 @@ nvcc cross-compiles without a GPU. Flags that are part of the numeric contract (
 contraction), default -prec-div/-prec-sqrt/-ftz=false; host side -ffp-contract=off.
 
 A second library, libplain_b200_fast.so, is the same sources with the floating-point passes (FAST_SOURCES) compiled under
-the "fast" contract (-DPLAIN_FAST_CONTRACT -use_fast_math -> SFU approximations + contraction); the
+the "fast" contract (-DPLAIN_FAST_CONTRACT -fmad=true -ftz=true -prec-sqrt=false -> SFU approximations + contraction); the
 integer / LUT / rasterisation / bake kernels and the host side are the very same objects as in the exact library.
 """
 import os
@@ -30,7 +30,9 @@ INCLUDES = ["-I%s" % (ROOT / "include"), "-I%s" % (PKG / "csrc"), "-I%s" % (PKG 
 HOST_FMA = ["-mfma"] if platform.machine() in ("x86_64", "AMD64") else []
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false", "--extended-lambda", "--expt-relaxed-constexpr",
               "-Xcompiler", ",".join(["-fPIC", "-fvisibility=hidden", "-ffp-contract=off"] + HOST_FMA), "-Xptxas", "-v", "-diag-suppress", "177,550"]
-NVCC_FLAGS_FAST = [f for f in NVCC_FLAGS if f != "-fmad=false"] + ["-DPLAIN_FAST_CONTRACT", "-use_fast_math"]
+# fast contract: contraction, flush-to-zero, approximate sqrt, SFU transcendentals (detmath.h) - but IEEE division and correctly rounded
+# reciprocals stay (texel selection at uv = iUV / size sits exactly on texel borders)
+NVCC_FLAGS_FAST = [f for f in NVCC_FLAGS if f != "-fmad=false"] + ["-DPLAIN_FAST_CONTRACT", "-fmad=true", "-ftz=true", "-prec-sqrt=false", "-prec-div=true"]
 CXX_FLAGS = ["-std=c++17", "-O2", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-fvisibility=hidden", "-Wall", "-Wno-unused-function"] + HOST_FMA
 
 

@@ -34,3 +34,26 @@ def test_error_model_tonemap_within_one_lsb(ffi, oracle_sfu, oracle):
     packed = random_r11g11b10(rng, 130 * 67).reshape(67, 130)
     a, b = passes.tonemap(ffi, oracle_sfu, packed).astype(np.int32), passes.tonemap(ffi, oracle, packed).astype(np.int32)
     assert np.abs(a - b).max() <= 1 and (a != b).mean() < 0.05
+
+
+def test_approximate_reciprocals_are_rejected_for_a_reason(ffi, oracle_sfu, oracle):
+    """Why the fast contract keeps 1 / x correctly rounded: sdfDiffuseTrace.comp:120 samples depth and normals with NEAREST filtering at
+    uv = iUV / size - exactly on texel borders. With rcp.approx (one ulp) in that division a large part of the traced pixels read the
+    neighbouring texel; with the adopted model (same frame, same inputs) a fraction of a percent of the rays differ."""
+    lib = ROOT / "oracle" / "_build" / "liboracle_sfu_rcp.so"
+    subprocess.run(["make", "-C", str(ROOT / "oracle"), str(lib)], check=True, capture_output=True)
+    rejected = ffi.Api(str(lib), "oracle_", "oracle_frontend_")
+    from conftest import Sequence
+    seqs = [Sequence(ffi, api, 192, 108, 16) for api in (oracle, oracle_sfu, rejected)]
+    try:
+        inputs = seqs[0].step(moving=True)
+        for s in seqs[1:]:
+            s.step(moving=True, inputs=inputs)
+        ref, adopted, rej = (s.snapshot(["giY0"], [])["giY0/0"].view(np.float16).astype(np.float64) for s in seqs)   # the trace's own output
+        scale = 1e-2 * np.abs(ref).mean()
+        frac = lambda x: float((np.abs(x - ref) / np.maximum(np.abs(ref), scale) > 2e-2).mean())
+        print("traced texels further than 2e-2 from the exact oracle: adopted model %.4f, with rcp.approx %.4f" % (frac(adopted), frac(rej)))
+        assert frac(adopted) < 0.02 and frac(rej) > 0.10
+    finally:
+        for s in seqs:
+            s.close()
