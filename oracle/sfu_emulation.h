@@ -1,9 +1,9 @@
 // ORACLE - test infrastructure only (see oracle/README.md). Never linked into the product library.
 //
 // sfu_emulation.h - host stand-ins for the SFU approximations the "fast" contract uses on the device (detmath.h, DM_FAST;
-// DESIGN.md section 12). Included by detmath.h when an oracle translation unit is compiled with -DPLAIN_FAST_EMULATION (the
-// second checker library, liboracle_sfu.so): each function returns the correctly rounded result displaced by a deterministic
-// pseudo-random error of the size the PTX ISA documents for the instruction -
+// DESIGN.md section 12). Pre-included (`g++ -include`) in front of the oracle translation units of the second checker library,
+// liboracle_sfu.so, where it defines DM_FAST so that detmath.h / glsl.h take the fast contract's branches on the host: each
+// function returns the correctly rounded result displaced by a deterministic pseudo-random error of the size the PTX ISA documents for the instruction -
 //   ex2.approx / rsqrt.approx: 2 ulp;  rcp.approx / sqrt.approx: 1 ulp;  lg2.approx: 2^-22 absolute (2 ulp away from 1);
 //   sin.approx / cos.approx: 2^-20.9 absolute;  .ftz: denormal inputs and results flush to zero
 // so that the CPU suite can measure how far errors of that size, fed back through the TAA / GI / froxel / exposure histories,
@@ -50,3 +50,4 @@ inline float hw_sin(float x) { x = emu_ftz(x); return emu_ftz((float)(std::sin((
 inline float hw_cos(float x) { x = emu_ftz(x); return emu_ftz((float)(std::cos((double)x) + emu_unit(emu_hash(x, 8)) * 5.1e-7)); }
 
 }  // namespace dm
+#define DM_FAST 1

@@ -57,7 +57,8 @@ DM_HD float fma_(float a, float b, float c) {
 // -DPLAIN_FAST_CONTRACT (device code of the floating-point passes only: GI, shading, TAA/bloom/tonemap, froxels) replaces the
 // pinned sequences below by the SFU approximations (ex2 / lg2 / sin / cos / rcp / rsqrt / sqrt .approx.ftz, 1-2 ulp or 2^-21
 // absolute) and lets ptxas contract; the results then match the oracle within a tolerance instead of bit for bit. The exact
-// build, the oracle and the integer / LUT / rasterisation passes never see this branch.
+// build, the oracle and the integer / LUT / rasterisation passes never see this branch. (A host translation unit that defines DM_FAST and
+// the hw_* functions itself BEFORE this header takes the same branches: the test suite's error model of this contract does that.)
 #if defined(PLAIN_FAST_CONTRACT) && defined(__CUDA_ARCH__)
 #define DM_FAST 1
 __device__ __forceinline__ float hw_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
@@ -67,12 +68,6 @@ __device__ __forceinline__ float hw_rsqrt(float x) { float y; asm("rsqrt.approx.
 __device__ __forceinline__ float hw_sqrt(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float hw_sin(float x) { float y; asm("sin.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float hw_cos(float x) { float y; asm("cos.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-#elif defined(PLAIN_FAST_EMULATION) && !defined(__CUDACC__)
-// checker only (oracle/Makefile, liboracle_sfu.so): the same branches on the host with error-model stand-ins for the SFU
-}  // namespace dm
-#include "sfu_emulation.h"
-namespace dm {
-#define DM_FAST 1
 #endif
 
 DM_HD float nanf_() { return u2f(0x7fc00000u); }
