@@ -58,6 +58,28 @@ def np_taa(cur, his, motion, depth, weights, use_clipping, use_dilation, use_ton
     ur, vr = u + mot[..., 0], v + mot[..., 1]
     if history_tech == 0:
         hist = bilinear_clamp(his, ur, vr)
+    elif history_tech == 1:  # bicubicSample16Tap, bicubicSampling.inc:28-70: Catmull-Rom weights at distances |d| + 1, |d|, 1 - |d|, 2 - |d|
+        px, py = xs + 0.5 + mot[..., 0] * w, ys + 0.5 + mot[..., 1] * h
+
+        def cr(d):   # catmullRomWeight1D for d >= 0 (every argument above is: the signed `d` of its second branch is not observable)
+            return np.where(d <= 1, (9 * d ** 3 - 15 * d ** 2 + 6) / 6, np.where(d <= 2, (-3 * d ** 3 + 15 * d ** 2 - 24 * d + 12) / 6, 0.0))
+        tx, ty = np.floor(px - 0.5) + 0.5, np.floor(py - 0.5) + 0.5
+        dx, dy = np.abs(px - tx), np.abs(py - ty)
+        wx, wy = [cr(dx + 1), cr(dx), cr(1 - dx), cr(2 - dx)], [cr(dy + 1), cr(dy), cr(1 - dy), cr(2 - dy)]
+        hist = sum(bilinear_clamp(his, (tx + i - 1) / w, (ty + j - 1) / h) * (wx[i] * wy[j])[..., None] for j in range(4) for i in range(4))
+    elif history_tech in (2, 3):  # bicubicSample9Tap :75-110 / bicubicSample5Tap :115-145: the two middle taps merged into one bilinear tap
+        px, py = xs + 0.5 + mot[..., 0] * w, ys + 0.5 + mot[..., 1] * h
+
+        def taps_1d(p, n):
+            trunc = np.floor(p - 0.5) + 0.5
+            f = p - trunc
+            w0, w1 = -0.5 * f ** 3 + f ** 2 - 0.5 * f, 1.5 * f ** 3 - 2.5 * f ** 2 + 1
+            w2, w3 = -1.5 * f ** 3 + 2 * f ** 2 + 0.5 * f, 0.5 * f ** 3 - 0.5 * f ** 2
+            return [((trunc - 1) / n, w0), ((trunc + w2 / (w1 + w2)) / n, w1 + w2), ((trunc + 2) / n, w3)]
+        X, Y = taps_1d(px, w), taps_1d(py, h)
+        pairs = [(i, j) for i in range(3) for j in range(3) if history_tech == 2 or i == 1 or j == 1]   # the 5-tap variant drops the corners
+        acc = sum(bilinear_clamp(his, X[i][0], Y[j][0]) * (X[i][1] * Y[j][1])[..., None] for i, j in pairs)
+        hist = acc if history_tech == 2 else acc / sum(X[i][1] * Y[j][1] for i, j in pairs)[..., None]   # ... and renormalises
     else:  # bicubicSample1Tap (the default), bicubicSampling.inc:150-181: one bilinear tap + the current frame's cross neighbourhood
         px, py = xs + 0.5 + mot[..., 0] * w, ys + 0.5 + mot[..., 1] * h
 
@@ -97,7 +119,8 @@ def np_taa(cur, his, motion, depth, weights, use_clipping, use_dilation, use_ton
 
 
 @pytest.mark.parametrize("use_clipping,use_dilation,use_tonemap,camera_cut,history_tech", [(True, True, True, False, 4), (True, True, True, False, 0), (False, True, True, False, 0),
-                                                                                         (True, False, False, False, 4), (True, True, True, True, 0)])
+                                                                                         (True, False, False, False, 4), (True, True, True, True, 0),
+                                                                                         (True, True, True, False, 1), (True, True, True, False, 2), (True, True, True, False, 3)])
 def test_taa_resolve_matches_float64_restatement(ffi, oracle, use_clipping, use_dilation, use_tonemap, camera_cut, history_tech):
     rng = np.random.default_rng(40 + use_clipping * 2 + use_dilation)
     w, h = 48, 36
