@@ -43,8 +43,9 @@ def compare_snapshots(sa, sb):
         bad.append("8-bit frame: <= 1 LSB on %.4f %% (>= 99.9), max %d (<= 4)" % (100 * frac_le1, d.max()))
     for name in PACKED_IMAGES:
         ea, eb = decode_r11g11b10(sa[name + "/0"].view(np.uint32)), decode_r11g11b10(sb[name + "/0"].view(np.uint32))
-        # one step of the 6 / 5 bit mantissas is 1.6e-2 / 3.1e-2: most texels identical, a few one step apart
-        bad += check(name, rel_error(ea, eb, 1e-3 * float(np.median(eb[np.isfinite(eb)])) + 1e-12), 4e-2, 2e-3, log)
+        # one step of the 6 / 5 bit mantissas is 1.6e-2 / 3.1e-2: most texels identical, a few one or two steps apart
+        # (bounds with margin over the error model on a 100-instance scene with a moving camera: p99.9 4.4e-2, mean 5e-4)
+        bad += check(name, rel_error(ea, eb, 1e-3 * float(np.median(eb[np.isfinite(eb)])) + 1e-12), 6e-2, 2e-3, log)
     for name in HALF_IMAGES + GI_IMAGES:
         ha, hb = sa[name + "/0"].view(np.float16), sb[name + "/0"].view(np.float16)
         scale = float(np.abs(hb[np.isfinite(hb)].astype(np.float64)).mean()) + 1e-12
@@ -53,7 +54,7 @@ def compare_snapshots(sa, sb):
             # the sphere trace is a discrete process: an error of an ulp flips a few rays between hit and miss (or between two
             # instances), which the denoiser spreads over their neighbourhood - the median error is 0, a fraction of a percent of
             # the texels are simply different. Bounded as a fraction of outliers + the mean, not as a quantile
-            bad += check_outliers(name, e, 2e-2, 0.03, 5e-3, log)
+            bad += check_outliers(name, e, 2e-2, 0.05, 1e-2, log)   # error model, 100 instances, moving: 3.2 % outliers, mean 5.5e-3
         else:
             bad += check(name, e, 2e-2, 2e-3, log)
     # exposure follows the histogram of the previous frame: same bins up to the texels that moved across a bin edge
