@@ -331,6 +331,17 @@ def run_ours(args, rank, world, local_rank):
                 "passes_ms": {k: round(acc[k], 4) for k in order},
                 "frame_roofline": {"algorithmic_bytes_per_frame": int(sum(alg.values()) + alg["Indirect diffuse spatial filter"]), "hbm_bound_ms": (sum(alg.values()) + alg["Indirect diffuse spatial filter"]) / peak / 1e6},
                 "setup_s": round(setup_s, 1), "graph_replay": not args.no_graph}
+        try:  # every pass against the HBM roofline (the north star asks for each kernel's achieved GB/s): algorithmic bytes / measured duration
+            per_pass = {}
+            for name, nbytes in alg.items():
+                ms = acc.get(name, 0.0)
+                if ms > 0:
+                    launches_of = 2 if name == "Indirect diffuse spatial filter" else 1
+                    gbps = nbytes * launches_of / (ms * 1e-3) / 1e9
+                    per_pass[name] = {"ms": round(ms, 4), "GB/s": round(gbps, 1), "frac": round(gbps / peak, 4) if peak else None}
+            line["passes_roofline"] = per_pass
+        except Exception as e:  # never let a reporting extra break the bench line
+            line["passes_roofline"] = {"error": str(e)}
         if args.contract != "exact":
             # never the headline by default: the fast contract matches the oracle within a tolerance, not bit for bit
             line["config"]["numeric_contract"] = "fast: SFU approximations + contraction in the floating-point passes (libplain_b200_fast.so)"
