@@ -24,6 +24,15 @@ def test_fast_frame_sequence_within_tolerance(ffi, cuda_fast, oracle, moving):
     assert not bad, "fast contract outside its tolerance: " + "; ".join(bad)
 
 
+@pytest.mark.parametrize("settings", [dict(indirect_lighting_tech=1), dict(diffuse_brdf=3, direct_multiscatter=3), dict(half_res_trace=0), dict(sun_shadow_cascade_count=4),
+                                      dict(taa_history_sampling_tech=1), dict(taa_use_separate_supersampling=1), dict(strict_influence_radius_cutoff=1)])
+def test_fast_setting_variants_within_tolerance(ffi, cuda_fast, oracle, settings):
+    """the non-default configurations (all inside the tolerance under the CPU error model)"""
+    bad, log = tolerance.run_sequence(ffi, cuda_fast, oracle, True, w=160, h=90, frames=4, **settings)
+    print("\n".join("fast-contract %s " % settings + l for l in log[:1]))
+    assert not bad, "fast contract outside its tolerance with %s: %s" % (settings, "; ".join(bad))
+
+
 def test_fast_integer_passes_stay_bit_exact(ffi, cuda_fast, oracle):
     rng = np.random.default_rng(11)
     depth = rng.random((70, 130), dtype=np.float32)

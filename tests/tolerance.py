@@ -69,10 +69,10 @@ def compare_snapshots(sa, sb):
     return bad, log
 
 
-def run_sequence(ffi, approx_api, oracle_api, moving, w=256, h=144, frames=6, instances=16):
+def run_sequence(ffi, approx_api, oracle_api, moving, w=256, h=144, frames=6, instances=16, **settings):
     """Returns the comparison after the LAST frame: every history (TAA, GI, froxels, exposure) has been fed back frames - 1 times."""
     from conftest import Sequence
-    a, b = Sequence(ffi, approx_api, w, h, instances), Sequence(ffi, oracle_api, w, h, instances)
+    a, b = Sequence(ffi, approx_api, w, h, instances, **settings), Sequence(ffi, oracle_api, w, h, instances, **settings)
     try:
         for _ in range(frames):
             inputs = a.step(moving=moving)
