@@ -4,17 +4,16 @@ binary32 sequences. Parity is then a TOLERANCE against the oracle - the north st
 final tonemapped frame" read on the frame's own scale (a unit of 1/255 is 3.9e-3: the dithered 8-bit frame cannot be closer
 than 0 or 1 LSB), plus bounds on the HDR intermediates - and the integer passes stay bit-exact on the same inputs.
 
-This library was written and cross-compiled when the round's GPU minutes were spent: the tests below are enabled with
-PLAIN_TEST_UNVERIFIED=1 until they have been seen green on a B200 (the default contract of bench.py and of every other test is
-"exact")."""
+First seen green on a B200 in round 2 (profiles/r2a_staged_tests.md). The default contract of bench.py and of every other test is
+"exact"; the fast library is an experiment reported beside the headline, never instead of it."""
 import numpy as np
 import pytest
 
 import passes
 import tolerance
-from conftest import random_r11g11b10, unverified_on_hardware
+from conftest import random_r11g11b10
 
-pytestmark = [pytest.mark.gpu, unverified_on_hardware]
+pytestmark = [pytest.mark.gpu]
 
 
 @pytest.mark.parametrize("moving", [False, True])

@@ -1,14 +1,13 @@
 """Single passes of the GI denoiser on adversarial inputs (NaN texels, fast / off-screen motion, camera cut, depth edges), CUDA against
 the oracle through the C-ABI, bit-exact - the inputs of tests/test_gi_temporal_upscale_numpy.py, which pins the oracle side.
-Written after the round's GPU minutes were spent: enabled with PLAIN_TEST_UNVERIFIED=1 until seen green on a B200."""
+First seen green on a B200 in round 2 (profiles/r2a_staged_tests.md)."""
 import numpy as np
 import pytest
 
 import passes
-from conftest import unverified_on_hardware
 from test_gi_temporal_upscale_numpy import gi_inputs
 
-pytestmark = [pytest.mark.gpu, unverified_on_hardware]
+pytestmark = [pytest.mark.gpu]
 
 
 @pytest.mark.parametrize("w,h,max_px,cut", [(48, 30, 2.0, False), (37, 23, 6.0, False), (40, 24, 0.0, False), (32, 20, 2.0, True), (130, 70, 3.0, False)])
