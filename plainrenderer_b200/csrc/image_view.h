@@ -87,8 +87,9 @@ PV_HD float halfToFloat(uint16_t h) {
     return dm::u2f(sign | ((e + 112u) << 23) | (m << 13));
 #endif
 }
-// The same codes with fewer instructions (used by the "fast" contract's device code; tests/test_codecs.py holds both
-// against the functions above on the host, exhaustively for the decoder and over every rounding boundary for the encoder):
+// The same codes with fewer instructions (the device code of BOTH contracts uses them since round 2; tests/test_codecs.py holds both
+// against the functions above on the host, exhaustively for the decoder and for the encoder over all 2^32 binary32 values; on the
+// device only the payload of a NaN can differ, and every store canonicalises NaN):
 // encode = round to nearest even by integer arithmetic on the binary32 bits (codes below the smallest normal through one float add),
 // decode = the channel IS a half float without sign and with a short mantissa: shift it into place, one conversion.
 PV_HD uint32_t encodeSmallFloatFast(float f, int mbits) {
@@ -107,7 +108,7 @@ PV_HD uint32_t encodeSmallFloatFast(float f, int mbits) {
     return v > maxFinite ? maxFinite : v;
 }
 PV_HD float decodeSmallFloatFast(uint32_t v, int mbits) { return halfToFloat((uint16_t)(v << (10 - mbits))); }
-#if defined(DM_FAST) && defined(__CUDA_ARCH__)
+#if defined(__CUDA_ARCH__)
 PV_HD uint32_t packR11G11B10(vec3 c) { return encodeSmallFloatFast(c.x, 6) | (encodeSmallFloatFast(c.y, 6) << 11) | (encodeSmallFloatFast(c.z, 5) << 22); }
 PV_HD vec3 unpackR11G11B10(uint32_t v) { return v3(decodeSmallFloatFast(v & 0x7ffu, 6), decodeSmallFloatFast((v >> 11) & 0x7ffu, 6), decodeSmallFloatFast(v >> 22, 5)); }
 #else

@@ -147,10 +147,15 @@ struct LaunchCtx {
 //   unorm8[b]       = float(b) / 255                              (UNORM8 decode)
 //   srgbToLinear[b] = sRGBToLinear(unorm8[b])                     (colorConversion.inc:15-23 on an 8-bit albedo channel)
 //   pcf[b * 12 + i] = {cos(angle), sin(angle), sqrt(d), 0} of tap i of calcShadow for blue-noise byte b (triangle.frag:107-116)
+//   disc[s * 32 + i] = {sqrt(rand), cos(angle), sin(angle), 0} of sample i of the spatial GI filter's xorshift disc for seed
+//                     wang_hash(s), s = frameIndexMod4 + filterIndex in 0..7 (filterIndirectDiffuseSpatial.comp:60-70): the sequence is
+//                     the same for every pixel of a dispatch, so it is tabulated once per context instead of once per block
+#define PLAIN_DISC_SEEDS 8
 struct ShadingTables {
     float unorm8[256];
     float srgbToLinear[256];
     float4 pcf[256 * 12];
+    float4 disc[PLAIN_DISC_SEEDS * 32];
 };
 void buildShadingTables(ShadingTables* deviceTables, cudaStream_t stream);
 

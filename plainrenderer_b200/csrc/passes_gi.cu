@@ -666,6 +666,7 @@ PLAIN_PASS(launch_sdfDebugVisualisation, "sdfDebugVisualisation.comp") {
 struct SpatialParams {
     ImgView outYSH, outCoCg, texYSH, texCoCg, depthTexture, normalTexture;
     const plain_global_shader_info* g;
+    const ShadingTables* tables;
     int filterIndex;
     int y0, y1;  // rows to produce (row sharding)
 };
@@ -688,31 +689,37 @@ __device__ __forceinline__ vec3 giPixelToWorld(const ImgView& depthTexture, cons
     const ivec2 t = nearestClampTexel(v2(sanitizeCoord(uv.x), sanitizeCoord(uv.y)), depthTexture.w, depthTexture.h);
     return giDepthToWorld(DEPTH_IS_R16F ? loadR16F(depthTexture, t.x, t.y) : loadD32(depthTexture, t.x, t.y), G, uv);
 }
-// The 32 disc samples come from one xorshift sequence that is the same for every pixel (:60-70): the block computes
-// sqrt(rand), cos(angle), sin(angle) once into shared memory; each pixel only applies its own lengthModifier.
-// Per sample the coordinate is sanitised once and - when the depth, Y_SH and CoCg images have the same extent, which
-// is how the frontend creates them - the nearest texel is computed once for the three fetches (same expression,
-// same operands: same result). The loop is software-pipelined: the three texels of sample i+1 are requested before the
-// arithmetic of sample i runs (the position of sample i+1 depends on sample i only through lengthModifier, which is known
-// as soon as sample i's coordinate is); Y_SH / CoCg are fetched speculatively (clamped addresses are always valid) and
-// only used when the reference would have sampled them.
+// The 32 disc samples come from one xorshift sequence that is the same for every pixel (:60-70): sqrt(rand), cos(angle),
+// sin(angle) are tabulated once per context for the seeds a frame can use (ShadingTables::disc; any other seed is computed by
+// the block's first warp with the same functions); each pixel only applies its own lengthModifier.
+// Per sample, when the depth, Y_SH and CoCg images have the same extent - which is how the frontend creates them - the
+// nearest texel is computed once for the three fetches (same expression, same operands: same result). The coordinate is
+// NOT sanitised before the nearest + clamp-to-edge lookup: cvt.rmi saturates and maps NaN to 0, so
+// clamp(floor2i(u * w), 0, w - 1) returns the same texel for a NaN (0) and for |u| > 65536 (the edge) as the sanitised
+// coordinate does. The loop is software-pipelined by hand over two samples (A / B): the three texels of sample i+1 are
+// requested before the arithmetic of sample i runs (the position of sample i+1 depends on sample i only through
+// lengthModifier, which is known as soon as sample i's coordinate is); Y_SH / CoCg are fetched speculatively (clamped
+// addresses are always valid) and only used when the reference would have sampled them.
 struct SpatialFetch {
-    vec2 uv;        // sampleUV after the border fix-up (unsanitised: the NDC of giDepthToWorld uses it as is)
-    float depth;
+    vec2 uv;        // sampleUV after the border fix-up
+    uint32_t depth; // R16F: the half in the low 16 bits; D32F: the binary32 bits
     uint2 ysh;
     uint32_t cocg;
 };
-template <bool DEPTH_IS_R16F>
+template <bool DEPTH_IS_R16F, bool SAME_EXTENT>
 __global__ void __launch_bounds__(256, 4) giSpatialFilterKernel(const __grid_constant__ SpatialParams p) {
-    __shared__ float sSqrtRand[32], sCos[32], sSin[32], sVP[16];
+    __shared__ float4 sDisc[32];
+    __shared__ float sVP[16];
     const plain_global_shader_info* g = p.g;
-    if (threadIdx.x == 0) {
-        uint32_t rngState = wang_hash(g->frameIndexMod4 + (uint32_t)p.filterIndex);
+    const uint32_t seedIndex = g->frameIndexMod4 + (uint32_t)p.filterIndex;
+    if (seedIndex < PLAIN_DISC_SEEDS) {
+        if (threadIdx.x < 32) sDisc[threadIdx.x] = __ldg(&p.tables->disc[seedIndex * 32 + threadIdx.x]);
+    } else if (threadIdx.x == 0) {
+        uint32_t rngState = wang_hash(seedIndex);
         for (int i = 0; i < 32; i++) {
-            sSqrtRand[i] = sqrtf_(rand01(rngState));
+            const float sq = sqrtf_(rand01(rngState));
             const float angle = 2.f * PV_PI * rand01(rngState);
-            sCos[i] = dm::cos(angle);
-            sSin[i] = dm::sin(angle);
+            sDisc[i] = make_float4(sq, dm::cos(angle), dm::sin(angle), 0.f);
         }
     }
     if (threadIdx.x >= 32 && threadIdx.x < 48) sVP[threadIdx.x - 32] = g->viewProjection[threadIdx.x - 32];
@@ -728,50 +735,56 @@ __global__ void __launch_bounds__(256, 4) giSpatialFilterKernel(const __grid_con
     const vec3 tangent = normalize(pCenter - pRight);
     const vec3 bitangent = normalize(pCenter - pUp);
     const vec3 N = 2.f * sampleNearest2D<WRAP_CLAMP, vec3>([&](int x, int y) { return loadRGBA8rgb(p.normalTexture, x, y); }, p.normalTexture.w, p.normalTexture.h, uv, v3(0.f)) - 1.f;
-    const bool sameExtent = p.texYSH.w == p.depthTexture.w && p.texYSH.h == p.depthTexture.h && p.texCoCg.w == p.depthTexture.w && p.texCoCg.h == p.depthTexture.h;
     float radiusWorld = 1.5f;
     if (p.filterIndex == 1) radiusWorld = 1.f;
+    const float dW = (float)p.depthTexture.w, dH = (float)p.depthTexture.h;
+    const int dWm1 = p.depthTexture.w - 1, dHm1 = p.depthTexture.h - 1;
     // position + texel requests of sample i for the current lengthModifier (:72-98)
     auto fetchSample = [&](int i, float lengthModifier) {
         SpatialFetch f;
-        const float d = sSqrtRand[i] * lengthModifier;
-        const vec2 offset = v2(sCos[i], sSin[i]) * d;
+        const float4 disc = sDisc[i];
+        const float d = disc.x * lengthModifier;
+        const vec2 offset = v2(disc.y, disc.z) * d;
         const vec3 sampleWorld = pCenter + radiusWorld * (offset.x * tangent + offset.y * bitangent);
-        const vec4 sampleProjected = mulm4(sVP, v4(sampleWorld, 1.f));
-        vec2 sampleUV = v2(sampleProjected.x, sampleProjected.y) / sampleProjected.w;
+        // viewProjection * vec4(sampleWorld, 1): only x, y, w are used
+        const float px = fmaf_(sVP[12], 1.f, fmaf_(sVP[8], sampleWorld.z, fmaf_(sVP[4], sampleWorld.y, sVP[0] * sampleWorld.x)));
+        const float py = fmaf_(sVP[13], 1.f, fmaf_(sVP[9], sampleWorld.z, fmaf_(sVP[5], sampleWorld.y, sVP[1] * sampleWorld.x)));
+        const float pw = fmaf_(sVP[15], 1.f, fmaf_(sVP[11], sampleWorld.z, fmaf_(sVP[7], sampleWorld.y, sVP[3] * sampleWorld.x)));
+        const float rw = rcpf_(pw);
+        vec2 sampleUV = v2(px * rw, py * rw);
         sampleUV = sampleUV * 0.5f + 0.5f;
-        sampleUV.x = sampleUV.x < 0.f ? uv.x - offset.x : sampleUV.x;
-        sampleUV.y = sampleUV.y < 0.f ? uv.y - offset.y : sampleUV.y;
-        sampleUV.x = sampleUV.x > 1.f ? uv.x - offset.x : sampleUV.x;
-        sampleUV.y = sampleUV.y > 1.f ? uv.y - offset.y : sampleUV.y;
+        // x < 0 ? alt : x followed by x > 1 ? alt : x selects alt exactly when the first value is outside [0, 1] (NaN keeps itself)
+        const float altX = uv.x - offset.x, altY = uv.y - offset.y;
+        sampleUV.x = (sampleUV.x < 0.f || sampleUV.x > 1.f) ? altX : sampleUV.x;
+        sampleUV.y = (sampleUV.y < 0.f || sampleUV.y > 1.f) ? altY : sampleUV.y;
         f.uv = sampleUV;
-        const vec2 sampleUVSanitized = v2(sanitizeCoord(sampleUV.x), sanitizeCoord(sampleUV.y));
-        const ivec2 td = nearestClampTexel(sampleUVSanitized, p.depthTexture.w, p.depthTexture.h);
-        const ivec2 ty = sameExtent ? td : nearestClampTexel(sampleUVSanitized, p.texYSH.w, p.texYSH.h);
-        const ivec2 tc = sameExtent ? td : nearestClampTexel(sampleUVSanitized, p.texCoCg.w, p.texCoCg.h);
-        f.depth = DEPTH_IS_R16F ? loadR16F(p.depthTexture, td.x, td.y) : loadD32(p.depthTexture, td.x, td.y);
-        f.ysh = ldg((const uint2*)p.texYSH.ptr + texelIndex(p.texYSH, ty.x, ty.y));
-        f.cocg = ldg((const uint32_t*)p.texCoCg.ptr + texelIndex(p.texCoCg, tc.x, tc.y));
+        const int tx = iclamp(floor2i(sampleUV.x * dW), 0, dWm1), ty = iclamp(floor2i(sampleUV.y * dH), 0, dHm1);
+        const int texel = ty * p.depthTexture.w + tx;
+        f.depth = DEPTH_IS_R16F ? (uint32_t)ldg((const uint16_t*)p.depthTexture.ptr + texel) : ldg((const uint32_t*)p.depthTexture.ptr + texel);
+        if (SAME_EXTENT) {
+            f.ysh = ldg((const uint2*)p.texYSH.ptr + texel);
+            f.cocg = ldg((const uint32_t*)p.texCoCg.ptr + texel);
+        } else {
+            const ivec2 tyS = nearestClampTexel(sampleUV, p.texYSH.w, p.texYSH.h), tcS = nearestClampTexel(sampleUV, p.texCoCg.w, p.texCoCg.h);
+            f.ysh = ldg((const uint2*)p.texYSH.ptr + texelIndex(p.texYSH, tyS.x, tyS.y));
+            f.cocg = ldg((const uint32_t*)p.texCoCg.ptr + texelIndex(p.texCoCg, tcS.x, tcS.y));
+        }
         return f;
     };
     vec4 result_Y_SH = v4(0.f);
     vec2 result_CoCg = v2(0.f);
     float weightTotal = 0.f;
     float lengthModifier = 1.f;
-    SpatialFetch next = fetchSample(0, lengthModifier);
-#pragma unroll 1
-    for (int i = 0; i < 32; i++) {
-        const SpatialFetch cur = next;
-        const bool outside = cur.uv.x < 0.f || cur.uv.y < 0.f || cur.uv.x > 1.f || cur.uv.y > 1.f;
-        if (outside) lengthModifier *= 0.98f;
-        if (i + 1 < 32) next = fetchSample(i + 1, lengthModifier);
-        const vec3 pixelWorld = giDepthToWorld(cur.depth, G, cur.uv);
+    auto isOutside = [](const SpatialFetch& f) { return f.uv.x < 0.f || f.uv.y < 0.f || f.uv.x > 1.f || f.uv.y > 1.f; };
+    auto accumulate = [&](const SpatialFetch& cur, bool outside) {
+        const float depth = DEPTH_IS_R16F ? halfToFloat((uint16_t)cur.depth) : dm::u2f(cur.depth);
+        const vec3 pixelWorld = giDepthToWorld(depth, G, cur.uv);
         const float distanceToTangentPlane = absf(dot(N, pixelWorld - pCenter));
-        const float maxDistance = 0.25f;
-        float weight = clampf(maxDistance / fmaxp(distanceToTangentPlane, 0.0001f), 0.f, 1.f);
+        // clamp(0.25 / max(dist, 0.0001), 0, 1): the quotient is positive and never NaN (max drops a NaN distance), so the lower
+        // clamp is the identity and FMNMX against the non-zero constants returns the bits of the pinned min / max
+        float weight = fminf(0.25f / fmaxf(distanceToTangentPlane, 0.0001f), 1.f);
         weight *= weight;
-        if (outside) weight = 0.f;
-        if (weight > 0.f) {
+        if (!outside && weight > 0.f) {
             const vec4 sample_Y_SH = v4(halfToFloat((uint16_t)(cur.ysh.x & 0xffffu)), halfToFloat((uint16_t)(cur.ysh.x >> 16)), halfToFloat((uint16_t)(cur.ysh.y & 0xffffu)), halfToFloat((uint16_t)(cur.ysh.y >> 16)));
             const vec2 sample_CoCg = v2(halfToFloat((uint16_t)(cur.cocg & 0xffffu)), halfToFloat((uint16_t)(cur.cocg >> 16)));
             if (!(anynan(sample_Y_SH) || anynan(sample_CoCg))) {
@@ -780,6 +793,18 @@ __global__ void __launch_bounds__(256, 4) giSpatialFilterKernel(const __grid_con
                 weightTotal += weight;
             }
         }
+    };
+    SpatialFetch A = fetchSample(0, lengthModifier), B;
+#pragma unroll 1
+    for (int i = 0; i < 32; i += 2) {
+        const bool outsideA = isOutside(A);
+        if (outsideA) lengthModifier *= 0.98f;
+        B = fetchSample(i + 1, lengthModifier);
+        accumulate(A, outsideA);
+        const bool outsideB = isOutside(B);
+        if (outsideB) lengthModifier *= 0.98f;
+        if (i + 2 < 32) A = fetchSample(i + 2, lengthModifier);
+        accumulate(B, outsideB);
     }
     weightTotal = fmaxp(weightTotal, 0.00001f);
     result_Y_SH = result_Y_SH / weightTotal;
@@ -796,6 +821,7 @@ PLAIN_PASS(launch_giSpatialFilter, "filterIndirectDiffuseSpatial.comp") {
     p.depthTexture = c.sampled(4);  // half-res R16F (halfResTrace) or the full-res D32F depth buffer
     p.normalTexture = c.sampled(5, PLAIN_FORMAT_RGBA8);
     p.g = c.g;
+    p.tables = (const ShadingTables*)c.tables;
     p.filterIndex = c.spec<int>(0, 0);
     if (c.failed) return;
     const int fmt = c.sampledFormat(4);
@@ -803,8 +829,11 @@ PLAIN_PASS(launch_giSpatialFilter, "filterIndirectDiffuseSpatial.comp") {
     c.window(p.outYSH.h, p.y0, p.y1);
     if (p.y1 <= p.y0) return;
     dim3 grid(ceilDiv(p.outYSH.w, 32), ceilDiv((unsigned)(p.y1 - p.y0), 8));
-    if (fmt == PLAIN_FORMAT_R16_SFLOAT) PLAIN_LAUNCH(c, giSpatialFilterKernel<true>, grid, 256, 0, p);
-    else if (fmt == PLAIN_FORMAT_DEPTH32) PLAIN_LAUNCH(c, giSpatialFilterKernel<false>, grid, 256, 0, p);
+    const bool sameExtent = p.texYSH.w == p.depthTexture.w && p.texYSH.h == p.depthTexture.h && p.texCoCg.w == p.depthTexture.w && p.texCoCg.h == p.depthTexture.h;
+    if (fmt == PLAIN_FORMAT_R16_SFLOAT && sameExtent) PLAIN_LAUNCH(c, (giSpatialFilterKernel<true, true>), grid, 256, 0, p);
+    else if (fmt == PLAIN_FORMAT_R16_SFLOAT) PLAIN_LAUNCH(c, (giSpatialFilterKernel<true, false>), grid, 256, 0, p);
+    else if (fmt == PLAIN_FORMAT_DEPTH32 && sameExtent) PLAIN_LAUNCH(c, (giSpatialFilterKernel<false, true>), grid, 256, 0, p);
+    else if (fmt == PLAIN_FORMAT_DEPTH32) PLAIN_LAUNCH(c, (giSpatialFilterKernel<false, false>), grid, 256, 0, p);
     else c.fail("filterIndirectDiffuseSpatial.comp: depth binding must be R16F or D32F");
 }
 

@@ -26,6 +26,14 @@ __global__ void buildShadingTablesKernel(ShadingTables* t) {
         const float angle = noise * 2.f * PV_PI + 2.f * PV_PI * (float)tap / sampleCount;
         t->pcf[i] = make_float4(dm::cos(angle), dm::sin(angle), d, 0.f);
     }
+    if (i < PLAIN_DISC_SEEDS) {  // one thread per seed: the xorshift sequence is serial
+        uint32_t rngState = wang_hash((uint32_t)i);
+        for (int k = 0; k < 32; k++) {
+            const float sq = sqrtf_(rand01(rngState));
+            const float angle = 2.f * PV_PI * rand01(rngState);
+            t->disc[i * 32 + k] = make_float4(sq, dm::cos(angle), dm::sin(angle), 0.f);
+        }
+    }
 }
 void buildShadingTables(ShadingTables* deviceTables, cudaStream_t stream) { buildShadingTablesKernel<<<12, 256, 0, stream>>>(deviceTables); }
 
