@@ -298,6 +298,15 @@ PLAIN_EXPORT int PLAIN_FN(peer_error)(plain_ctx* ctx, uint32_t* out_error);
 /* the stream all passes run on (cudaStream_t as void*), for callers that time with CUDA events */
 PLAIN_EXPORT int PLAIN_FN(get_stream)(plain_ctx* ctx, void** out_stream);
 
+/* ---- device self test (new; no reference counterpart) ----
+ * Exhaustive on-device comparison of the instruction-lean sequences the kernels use with the functions of the numeric contract they
+ * stand for, over every binary32 value of their domain: [0] rcpf_nz vs __frcp_rn (every value that is not zero or denormal),
+ * [1] rcpf_normal vs __frcp_rn (2^-126 <= |x| < 2^126), [2] lean R11G11B10 channel encoder vs the contract's (all 2^32 values x both
+ * mantissa widths), [3] lean decoder vs the contract's (all codes), [4] floor2i + int->float vs floor_ + f2i (|x| < 2^24),
+ * [5] FMNMX vs the pinned min / max on non-negative-zero operands (2^26 random pairs). out_mismatches receives 8 counters (unused: 0).
+ * The CPU oracle returns zeros without running anything. */
+PLAIN_EXPORT int PLAIN_FN(device_selftest)(plain_ctx* ctx, uint64_t* out_mismatches);
+
 #ifdef __cplusplus
 }
 #endif

@@ -471,5 +471,6 @@ int PLAIN_FN(peer_error)(plain_ctx*, uint32_t* out_error) { *out_error = 0; retu
 int PLAIN_FN(set_concurrent_passes_enabled)(plain_ctx* ctx, int) { (void)ctx; return 0; }
 int PLAIN_FN(join_transfers)(plain_ctx* ctx) { (void)ctx; return 0; }
 int PLAIN_FN(get_stream)(plain_ctx* ctx, void** out_stream) { (void)ctx; *out_stream = nullptr; return 0; }
+int PLAIN_FN(device_selftest)(plain_ctx* ctx, uint64_t* out_mismatches) { (void)ctx; for (int i = 0; i < 8; i++) out_mismatches[i] = 0; return 0; }
 
 }  // extern "C"

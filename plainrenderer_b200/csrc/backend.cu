@@ -1240,5 +1240,13 @@ int PLAIN_FN(peer_error)(plain_ctx* ctx, uint32_t* out_error) {
     return 0;
 }
 int PLAIN_FN(get_stream)(plain_ctx* ctx, void** out_stream) { *out_stream = (void*)ctx->b.stream; return 0; }
+int PLAIN_FN(device_selftest)(plain_ctx* ctx, uint64_t* out_mismatches) {
+    if (!ctx || !out_mismatches) return 1;
+    cudaSetDevice(ctx->b.device);
+    unsigned long long counts[8] = {};
+    if (!pb::runDeviceSelftest(ctx->b.stream, counts, ctx->b.lastError)) return 1;
+    for (int i = 0; i < 8; i++) out_mismatches[i] = counts[i];
+    return 0;
+}
 
 }  // extern "C"

@@ -158,6 +158,7 @@ struct ShadingTables {
     float4 disc[PLAIN_DISC_SEEDS * 32];
 };
 void buildShadingTables(ShadingTables* deviceTables, cudaStream_t stream);
+bool runDeviceSelftest(cudaStream_t stream, unsigned long long* hostOut8, std::string& error);  // selftest.cu
 
 struct PassRegistration { PassRegistration(const char* shader, LaunchFn fn); };
 #define PLAIN_PASS(fnname, shader)                       \

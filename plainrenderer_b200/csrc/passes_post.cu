@@ -1,6 +1,7 @@
 // passes_post.cu - TAA resolve, bloom chain, tonemapping.
 //   temporalFilter.comp:84-179 + temporalReprojection.inc:8-87 + bicubicSampling.inc:4-181;
 //   bloomDownsample.comp:12-50, bloomUpsample.comp:19-58, applyBloom.comp:16-31; tonemapping.comp:17-27
+#include <cmath>
 #include "shader_inc.cuh"
 #include "tile.cuh"
 
@@ -48,16 +49,13 @@ PLAIN_PASS(launch_tonemapping, "tonemapping.comp") {
 // bloomDownsample.comp: 13 bilinear taps of the finer mip. The bounds test is '>' in the reference (:16): the extra
 // row/column of invocations only produces stores outside the image, which are dropped.
 // Block = 32x8 target texels; their 13 taps touch a (64 + 6) x (16 + 6) rectangle of the finer mip, staged once.
-__global__ void __launch_bounds__(256) bloomDownsampleKernel(ImgView target, ImgView source, int yBegin, int yEnd) {
-    constexpr int TW = 72, TH = 24;
-    __shared__ float4 sSrc[TW * TH];
-    const int bx = blockIdx.x * 32, by = yBegin + blockIdx.y * 8;
-    const int sx0 = (int)(((long long)bx * source.w) / target.w) - 3, sy0 = (int)(((long long)by * source.h) / target.h) - 3;
-    tileLoadR11<TW, TH>(sSrc, source, sx0, sy0);
-    __syncthreads();
-    const TileR11<TW, TH> tile{sSrc, sx0, sy0};
-    const int ix = bx + (threadIdx.x & 31), iy = by + (threadIdx.x >> 5);
-    if (ix >= target.w || iy >= yEnd) return;
+// The 13 taps use 5 distinct x and 5 distinct y coordinates (uv + texelSize * {0, +-0.5, +-1.5}): 10 axis set-ups instead of 26
+// (tile.cuh). FAST (block-uniform): the staged rectangle lies inside the source - no clamps, no bounds tests, no sanitising
+// (the coordinates are pixel centres plus fixed offsets); a pixel whose taps all lie inside the tile reads them with no test at all.
+#define BLOOM_DOWN_TW 72
+#define BLOOM_DOWN_TH 24
+__device__ __noinline__ void bloomDownsampleGeneric(ImgView target, ImgView source, const float4* sSrc, int sx0, int sy0, int ix, int iy) {
+    const TileR11<BLOOM_DOWN_TW, BLOOM_DOWN_TH> tile{sSrc, sx0, sy0};
     const vec2 uv = (v2((float)ix, (float)iy) + 0.5f) / v2((float)target.w, (float)target.h);
     const vec2 texelSize = 1.f / v2((float)source.w, (float)source.h);
     vec3 color = v3(0.f);
@@ -66,6 +64,41 @@ __global__ void __launch_bounds__(256) bloomDownsampleKernel(ImgView target, Img
     color = color + T(0.5f, 0.5f) * 0.125f; color = color + T(0.5f, -0.5f) * 0.125f; color = color + T(-0.5f, 0.5f) * 0.125f; color = color + T(-0.5f, -0.5f) * 0.125f;
     color = color + T(1.5f, 0.f) * 0.0625f; color = color + T(-1.5f, 0.f) * 0.0625f; color = color + T(0.f, 1.5f) * 0.0625f; color = color + T(0.f, -1.5f) * 0.0625f;
     color = color + T(1.5f, 1.5f) * 0.03125f; color = color + T(1.5f, -1.5f) * 0.03125f; color = color + T(-1.5f, 1.5f) * 0.03125f; color = color + T(-1.5f, -1.5f) * 0.03125f;
+    storeR11(target, ix, iy, color);
+}
+__global__ void __launch_bounds__(256) bloomDownsampleKernel(ImgView target, ImgView source, int yBegin, int yEnd) {
+    constexpr int TW = BLOOM_DOWN_TW, TH = BLOOM_DOWN_TH;
+    __shared__ float4 sSrc[TW * TH];
+    const int bx = blockIdx.x * 32, by = yBegin + blockIdx.y * 8;
+    const int sx0 = (int)(((long long)bx * source.w) / target.w) - 3, sy0 = (int)(((long long)by * source.h) / target.h) - 3;
+    const bool interior = tileIsInterior<TW, TH>(source, sx0, sy0);
+    if (interior) tileLoadR11<TW, TH, true>(sSrc, source, sx0, sy0);
+    else tileLoadR11<TW, TH, false>(sSrc, source, sx0, sy0);
+    __syncthreads();
+    const int ix = bx + (threadIdx.x & 31), iy = by + (threadIdx.x >> 5);
+    if (ix >= target.w || iy >= yEnd) return;
+    if (!interior) { bloomDownsampleGeneric(target, source, sSrc, sx0, sy0, ix, iy); return; }
+    const TileR11<TW, TH> tile{sSrc, sx0, sy0};
+    const vec2 uv = (v2((float)ix, (float)iy) + 0.5f) / v2((float)target.w, (float)target.h);
+    const vec2 texelSize = 1.f / v2((float)source.w, (float)source.h);
+    // axis k: offset {0, +0.5, -0.5, +1.5, -1.5}[k]; uv + texelSize * 0 == uv (uv > 0), so axis 0 is the centre tap's own set-up
+    AxisTap X[5], Y[5];
+    const float off[5] = {0.f, 0.5f, -0.5f, 1.5f, -1.5f};
+#pragma unroll
+    for (int k = 0; k < 5; k++) {
+        X[k] = axisTapT<false, true>(k == 0 ? uv.x : uv.x + texelSize.x * off[k], source.w, sx0);
+        Y[k] = axisTapT<false, true>(k == 0 ? uv.y : uv.y + texelSize.y * off[k], source.h, sy0);
+    }
+    bool inside = true;
+#pragma unroll
+    for (int k = 0; k < 5; k++) inside = inside && X[k].l0 < (unsigned)(TW - 1) && Y[k].l0 < (unsigned)(TH - 1);
+    if (!inside) { bloomDownsampleGeneric(target, source, sSrc, sx0, sy0, ix, iy); return; }  // cannot happen for 2:1 mip chains
+    vec3 color = v3(0.f);
+    auto T = [&](int kx, int ky) { return tapR11TileInside(tile, X[kx], Y[ky]); };
+    color = color + T(0, 0) * 0.125f;
+    color = color + T(1, 1) * 0.125f; color = color + T(1, 2) * 0.125f; color = color + T(2, 1) * 0.125f; color = color + T(2, 2) * 0.125f;
+    color = color + T(3, 0) * 0.0625f; color = color + T(4, 0) * 0.0625f; color = color + T(0, 3) * 0.0625f; color = color + T(0, 4) * 0.0625f;
+    color = color + T(3, 3) * 0.03125f; color = color + T(3, 4) * 0.03125f; color = color + T(4, 3) * 0.03125f; color = color + T(4, 4) * 0.03125f;
     storeR11(target, ix, iy, color);
 }
 PLAIN_PASS(launch_bloomDownsample, "bloomDownsample.comp") {
@@ -80,17 +113,11 @@ PLAIN_PASS(launch_bloomDownsample, "bloomDownsample.comp") {
 
 // bloomUpsample.comp: 9-tap tent of the coarser downsample mip (+ 4-tap box of the coarser upsample mip)
 // Block = 32x8 target texels; the tent and box taps touch about (16 + 8) x (4 + 8) texels of the two coarser mips.
-__global__ void __launch_bounds__(256) bloomUpsampleKernel(ImgView target, ImgView targetPreviousMip, ImgView source, int isLowestMip, float blurRadius, int yBegin, int yEnd) {
-    constexpr int TW = 24, TH = 12;
-    __shared__ float4 sSrc[TW * TH], sPrev[TW * TH];
-    const int bx = blockIdx.x * 32, by = yBegin + blockIdx.y * 8;
-    const int sx0 = (int)(((long long)bx * source.w) / target.w) - 3, sy0 = (int)(((long long)by * source.h) / target.h) - 3;
-    tileLoadR11<TW, TH>(sSrc, source, sx0, sy0);
-    if (!isLowestMip) tileLoadR11<TW, TH>(sPrev, targetPreviousMip, sx0, sy0);
-    __syncthreads();
-    const TileR11<TW, TH> srcTile{sSrc, sx0, sy0}, prevTile{sPrev, sx0, sy0};
-    const int ix = bx + (threadIdx.x & 31), iy = by + (threadIdx.x >> 5);
-    if (ix >= target.w || iy >= yEnd) return;
+// Tent: 3 x + 3 y axis set-ups (uv + sampleStepSize * {0, +1, -1}); box: 2 + 2 (uv + texelSize * {+0.5, -0.5}).
+#define BLOOM_UP_TW 24
+#define BLOOM_UP_TH 12
+__device__ __noinline__ void bloomUpsampleGeneric(ImgView target, ImgView targetPreviousMip, ImgView source, const float4* sSrc, const float4* sPrev, int sx0, int sy0, int isLowestMip, float blurRadius, int ix, int iy) {
+    const TileR11<BLOOM_UP_TW, BLOOM_UP_TH> srcTile{sSrc, sx0, sy0}, prevTile{sPrev, sx0, sy0};
     const vec2 texelSize = 1.f / v2((float)source.w, (float)source.h);
     const vec2 sampleStepSize = blurRadius * texelSize;
     const vec2 uv = (v2((float)ix, (float)iy) + 0.5f) / v2((float)target.w, (float)target.h);
@@ -105,6 +132,59 @@ __global__ void __launch_bounds__(256) bloomUpsampleKernel(ImgView target, ImgVi
     }
     storeR11(target, ix, iy, color);
 }
+__global__ void __launch_bounds__(256) bloomUpsampleKernel(ImgView target, ImgView targetPreviousMip, ImgView source, int isLowestMip, float blurRadius, int fastAllowed, int yBegin, int yEnd) {
+    constexpr int TW = BLOOM_UP_TW, TH = BLOOM_UP_TH;
+    __shared__ float4 sSrc[TW * TH], sPrev[TW * TH];
+    const int bx = blockIdx.x * 32, by = yBegin + blockIdx.y * 8;
+    const int sx0 = (int)(((long long)bx * source.w) / target.w) - 3, sy0 = (int)(((long long)by * source.h) / target.h) - 3;
+    // fastAllowed (launcher): the previous mip has the source's extent and blurRadius is a small finite number (bounded coordinates)
+    const bool interior = fastAllowed && tileIsInterior<TW, TH>(source, sx0, sy0);
+    if (interior) {
+        tileLoadR11<TW, TH, true>(sSrc, source, sx0, sy0);
+        if (!isLowestMip) tileLoadR11<TW, TH, true>(sPrev, targetPreviousMip, sx0, sy0);
+    } else {
+        tileLoadR11<TW, TH, false>(sSrc, source, sx0, sy0);
+        if (!isLowestMip) tileLoadR11<TW, TH, false>(sPrev, targetPreviousMip, sx0, sy0);
+    }
+    __syncthreads();
+    const int ix = bx + (threadIdx.x & 31), iy = by + (threadIdx.x >> 5);
+    if (ix >= target.w || iy >= yEnd) return;
+    if (!interior) { bloomUpsampleGeneric(target, targetPreviousMip, source, sSrc, sPrev, sx0, sy0, isLowestMip, blurRadius, ix, iy); return; }
+    const TileR11<TW, TH> srcTile{sSrc, sx0, sy0}, prevTile{sPrev, sx0, sy0};
+    const vec2 texelSize = 1.f / v2((float)source.w, (float)source.h);
+    const vec2 sampleStepSize = blurRadius * texelSize;
+    const vec2 uv = (v2((float)ix, (float)iy) + 0.5f) / v2((float)target.w, (float)target.h);
+    // tent axes k: offset {0, +1, -1}[k]; uv + sampleStepSize * 0 == uv (a finite step times 0 is +-0, uv > 0)
+    AxisTap X[3], Y[3], BX[2], BY[2];
+    const float off[3] = {0.f, 1.f, -1.f};
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        X[k] = axisTapT<false, true>(k == 0 ? uv.x : uv.x + sampleStepSize.x * off[k], source.w, sx0);
+        Y[k] = axisTapT<false, true>(k == 0 ? uv.y : uv.y + sampleStepSize.y * off[k], source.h, sy0);
+    }
+    bool inside = true;
+#pragma unroll
+    for (int k = 0; k < 3; k++) inside = inside && X[k].l0 < (unsigned)(TW - 1) && Y[k].l0 < (unsigned)(TH - 1);
+    if (!isLowestMip) {
+#pragma unroll
+        for (int k = 0; k < 2; k++) {  // box axes: offset {+0.5, -0.5}[k]
+            BX[k] = axisTapT<false, true>(uv.x + texelSize.x * (k == 0 ? 0.5f : -0.5f), targetPreviousMip.w, sx0);
+            BY[k] = axisTapT<false, true>(uv.y + texelSize.y * (k == 0 ? 0.5f : -0.5f), targetPreviousMip.h, sy0);
+            inside = inside && BX[k].l0 < (unsigned)(TW - 1) && BY[k].l0 < (unsigned)(TH - 1);
+        }
+    }
+    if (!inside) { bloomUpsampleGeneric(target, targetPreviousMip, source, sSrc, sPrev, sx0, sy0, isLowestMip, blurRadius, ix, iy); return; }
+    vec3 color = v3(0.f);
+    auto S = [&](int kx, int ky) { return tapR11TileInside(srcTile, X[kx], Y[ky]); };
+    color = color + S(0, 0) * 0.25f;
+    color = color + S(1, 0) * 0.125f; color = color + S(2, 0) * 0.125f; color = color + S(0, 1) * 0.125f; color = color + S(0, 2) * 0.125f;
+    color = color + S(1, 1) * 0.0625f; color = color + S(1, 2) * 0.0625f; color = color + S(2, 1) * 0.0625f; color = color + S(2, 2) * 0.0625f;
+    if (!isLowestMip) {
+        auto P = [&](int kx, int ky) { return tapR11TileInside(prevTile, BX[kx], BY[ky]); };
+        color = color + P(0, 0) * 0.25f; color = color + P(0, 1) * 0.25f; color = color + P(1, 0) * 0.25f; color = color + P(1, 1) * 0.25f;
+    }
+    storeR11(target, ix, iy, color);
+}
 PLAIN_PASS(launch_bloomUpsample, "bloomUpsample.comp") {
     const ImgView target = c.storage(0, PLAIN_FORMAT_R11G11B10_UFLOAT);
     const ImgView prev = c.sampled(1, PLAIN_FORMAT_R11G11B10_UFLOAT), source = c.sampled(2, PLAIN_FORMAT_R11G11B10_UFLOAT);
@@ -113,7 +193,10 @@ PLAIN_PASS(launch_bloomUpsample, "bloomUpsample.comp") {
     int y0, y1;
     c.window(target.h, y0, y1);
     if (y1 <= y0) return;
-    PLAIN_LAUNCH(c, bloomUpsampleKernel, dim3(ceilDiv(target.w, 32), ceilDiv((unsigned)(y1 - y0), 8)), 256, 0, target, prev, source, c.specBool(0, false) ? 1 : 0, c.push<float>(0), y0, y1);
+    const int isLowestMip = c.specBool(0, false) ? 1 : 0;
+    const float blurRadius = c.push<float>(0);
+    const int fastAllowed = (isLowestMip || (prev.w == source.w && prev.h == source.h)) && blurRadius == blurRadius && std::fabs(blurRadius) <= 64.f;
+    PLAIN_LAUNCH(c, bloomUpsampleKernel, dim3(ceilDiv(target.w, 32), ceilDiv((unsigned)(y1 - y0), 8)), 256, 0, target, prev, source, isLowestMip, blurRadius, fastAllowed, y0, y1);
 }
 
 // applyBloom.comp: mix(scene, bloom, strength) in place
@@ -142,32 +225,54 @@ struct TaaParams {
     const plain_global_shader_info* g;
     int useClipping, useMotionVectorDilation, historySampleTech, useTonemap;
     int y0, y1;  // rows to produce (row sharding)
+    int sameExtents;  // every bound image has the target's extent (set by the launcher)
 };
 __device__ __forceinline__ vec3 taaTonemap(vec3 color) { return color / (1.f + computeLuminance(color)); }         // temporalReprojection.inc:34-36
 __device__ __forceinline__ vec3 taaTonemapReverse(vec3 color) { return color / (1.f - computeLuminance(color)); }  // :38-40
+// taaTonemap of a FINITE colour without negative components (a texel of an unsigned format or a bilinear blend of such texels):
+// 1 + luminance lies in [1, 2^17), so the reciprocal needs no range test (pvec.h rcpf_normal: the same correctly rounded value)
+__device__ __forceinline__ vec3 taaTonemapFiniteNonNegative(vec3 color) { return color * rcpf_normal(1.f + computeLuminance(color)); }
 struct Nb { vec3 v[3][3]; };  // v[x+1][y+1]
-template <bool TONEMAP, int TW, int TH>
+// FAST (block-uniform, decided after staging): the tile lies inside the image and holds no inf / NaN texel.
+template <bool TONEMAP, bool FAST, int TW, int TH>
 __device__ __forceinline__ void sampleNeighbourhood(const TileR11<TW, TH>& tile, const ImgView& tex, vec2 uv, vec2 texelSize, Nb& n) {  // :42-52
     AxisTap X[3], Y[3];  // separable set-up of the nine taps (tile.cuh)
 #pragma unroll
     for (int i = 0; i < 3; i++) {
-        X[i] = axisTap(uv.x + texelSize.x * (float)(i - 1), tex.w, tile.x0);
-        Y[i] = axisTap(uv.y + texelSize.y * (float)(i - 1), tex.h, tile.y0);
+        // FAST: the coordinates are finite and bounded (pixel centre + SNORM16 motion + one texel): no sanitising, no clamps
+        X[i] = FAST ? axisTapT<false, true>(uv.x + texelSize.x * (float)(i - 1), tex.w, tile.x0) : axisTap(uv.x + texelSize.x * (float)(i - 1), tex.w, tile.x0);
+        Y[i] = FAST ? axisTapT<false, true>(uv.y + texelSize.y * (float)(i - 1), tex.h, tile.y0) : axisTap(uv.y + texelSize.y * (float)(i - 1), tex.h, tile.y0);
     }
+    if (FAST) {
+        if (window3x3Applies<TW, TH>(X, Y)) {
+            window3x3(tile, X, Y, [&](int x, int y, vec3 color) { n.v[x][y] = TONEMAP ? taaTonemapFiniteNonNegative(color) : color; });
+        } else {  // a tap leaves the tile (fast motion): every tap on its own, out of line
+            AxisTap Xc[3] = {X[0], X[1], X[2]}, Yc[3] = {Y[0], Y[1], Y[2]};
+            vec3 taps[9];
+            taps3x3Generic<TW, TH>(tile.s, tile.x0, tile.y0, tex, Xc, Yc, taps);
 #pragma unroll
-    for (int x = 0; x < 3; x++)
+            for (int x = 0; x < 3; x++)
 #pragma unroll
-        for (int y = 0; y < 3; y++) {
-            const vec3 color = tapR11Tile(tile, tex, X[x], Y[y]);
-            n.v[x][y] = TONEMAP ? taaTonemap(color) : color;
+                for (int y = 0; y < 3; y++) n.v[x][y] = TONEMAP ? taaTonemapFiniteNonNegative(taps[x * 3 + y]) : taps[x * 3 + y];
         }
+    } else {
+#pragma unroll
+        for (int x = 0; x < 3; x++)
+#pragma unroll
+            for (int y = 0; y < 3; y++) {
+                const vec3 color = tapR11Tile(tile, tex, X[x], Y[y]);
+                n.v[x][y] = TONEMAP ? taaTonemap(color) : color;
+            }
+    }
 }
+template <bool FAST>
 __device__ __forceinline__ vec3 clipAABB(vec3 target, vec3 bbMin, vec3 bbMax) {  // :8-30
     const vec3 epsilon = v3(0.0001f);
     const vec3 center = 0.5f * (bbMax + bbMin);
     const vec3 extend = 0.5f * (bbMax - bbMin) + epsilon;
     const vec3 toTarget = target - center;
-    const vec3 a = vabs(toTarget / extend);
+    // FAST: bbMin <= bbMax are finite, so extend lies in [0.0001, 2^17): the reciprocals of toTarget / extend need no range test
+    const vec3 a = FAST ? vabs(v3(toTarget.x * rcpf_normal(extend.x), toTarget.y * rcpf_normal(extend.y), toTarget.z * rcpf_normal(extend.z))) : vabs(toTarget / extend);
     const float maxComponent = fmaxp(a.x, fmaxp(a.y, a.z));
     if (maxComponent < 1.f) return target;
     return center + toTarget / maxComponent;
@@ -202,18 +307,22 @@ __device__ __forceinline__ BicubicW bicubicWeights(vec2 iUV) {  // bicubicSampli
 // Block = 32x8 pixels. The current frame is staged with a 2-texel halo (3x3 bilinear taps at texel centres touch
 // [-2, +2]); the history with a 6-texel halo, which covers the reprojected 3x3 neighbourhood and the bicubic tap for
 // motion up to ~4 pixels - larger motion falls back to global loads per tap corner (tile.cuh).
+// Two instantiations of one body, chosen per block after staging:
+//   FAST    - the history tile (and with it the current tile, the 3x3 depth neighbourhood and the block's own pixels) lies inside
+//             the image, all six images have the target's extent and no staged texel is inf / NaN: clamps, bounds tests, coordinate
+//             sanitising and reciprocal range tests are the identity and are left out; 3x3 neighbourhoods read a 4x4 window once
+//   !FAST   - image borders, odd configurations, inf / NaN texels: every rule spelled out (the round-1 kernel)
 #define TAA_CUR_HALO 2
 #define TAA_HIS_HALO 6
-template <bool TONEMAP, int TECH>
-__global__ void __launch_bounds__(256, 3) temporalFilterKernel(const __grid_constant__ TaaParams p) {
-    __shared__ float4 sCur[(32 + 2 * TAA_CUR_HALO) * (8 + 2 * TAA_CUR_HALO)];
-    __shared__ float4 sHis[(32 + 2 * TAA_HIS_HALO) * (8 + 2 * TAA_HIS_HALO)];
+#define TAA_CUR_W (32 + 2 * TAA_CUR_HALO)
+#define TAA_CUR_H (8 + 2 * TAA_CUR_HALO)
+#define TAA_HIS_W (32 + 2 * TAA_HIS_HALO)
+#define TAA_HIS_H (8 + 2 * TAA_HIS_HALO)
+template <bool TONEMAP, int TECH, bool FAST>
+__device__ __forceinline__ void temporalFilterPixel(const TaaParams& p, const float4* sCur, const float4* sHis, const float* sRw) {
     const int bx = blockIdx.x * 32, by = p.y0 + blockIdx.y * 8;
-    tileLoadR11<32 + 2 * TAA_CUR_HALO, 8 + 2 * TAA_CUR_HALO>(sCur, p.currentFrame, bx - TAA_CUR_HALO, by - TAA_CUR_HALO);
-    tileLoadR11<32 + 2 * TAA_HIS_HALO, 8 + 2 * TAA_HIS_HALO>(sHis, p.historySrc, bx - TAA_HIS_HALO, by - TAA_HIS_HALO);
-    __syncthreads();
-    const TileR11<32 + 2 * TAA_CUR_HALO, 8 + 2 * TAA_CUR_HALO> curTile{sCur, bx - TAA_CUR_HALO, by - TAA_CUR_HALO};
-    const TileR11<32 + 2 * TAA_HIS_HALO, 8 + 2 * TAA_HIS_HALO> hisTile{sHis, bx - TAA_HIS_HALO, by - TAA_HIS_HALO};
+    const TileR11<TAA_CUR_W, TAA_CUR_H> curTile{sCur, bx - TAA_CUR_HALO, by - TAA_CUR_HALO};
+    const TileR11<TAA_HIS_W, TAA_HIS_H> hisTile{sHis, bx - TAA_HIS_HALO, by - TAA_HIS_HALO};
     const int ix = bx + (threadIdx.x & 31), iy = by + (threadIdx.x >> 5);
     if (ix >= p.outputImage.w || iy >= p.y1) return;
     const vec2 screenRes = v2((float)p.g->screenResolution[0], (float)p.g->screenResolution[1]);
@@ -221,33 +330,50 @@ __global__ void __launch_bounds__(256, 3) temporalFilterKernel(const __grid_cons
     const vec2 iUVf = v2((float)ix, (float)iy);
     const vec2 uv = (iUVf + 0.5f) * texelSize;
     Nb nb;
-    sampleNeighbourhood<TONEMAP>(curTile, p.currentFrame, uv, texelSize, nb);
-    vec3 mn = nb.v[0][0], mx = nb.v[0][0];  // minMaxFromNeighbourhood :54-65
+    sampleNeighbourhood<TONEMAP, FAST>(curTile, p.currentFrame, uv, texelSize, nb);
+    // minMaxFromNeighbourhood :54-65. FAST: the neighbourhood has no negative component (hence no -0) and no NaN: FMNMX returns the pinned min / max
+    vec3 mn = nb.v[0][0], mx = nb.v[0][0];
 #pragma unroll
     for (int i = 0; i < 3; i++)
 #pragma unroll
-        for (int j = 0; j < 3; j++) { mn = vmin(mn, nb.v[i][j]); mx = vmax(mx, nb.v[i][j]); }
-    const float* rw = p.resolveWeights;  // resolveColor, temporalFilter.comp:41-57
+        for (int j = 0; j < 3; j++) {
+            if (FAST) {
+                mn = v3(fmin_nn(mn.x, nb.v[i][j].x), fmin_nn(mn.y, nb.v[i][j].y), fmin_nn(mn.z, nb.v[i][j].z));
+                mx = v3(fmax_nn(mx.x, nb.v[i][j].x), fmax_nn(mx.y, nb.v[i][j].y), fmax_nn(mx.z, nb.v[i][j].z));
+            } else {
+                mn = vmin(mn, nb.v[i][j]); mx = vmax(mx, nb.v[i][j]);
+            }
+        }
+    // resolveColor, temporalFilter.comp:41-57 (weights staged in shared memory by the kernel)
     vec3 currentColor = v3(0.f);
-    currentColor = currentColor + nb.v[0][0] * rw[0]; currentColor = currentColor + nb.v[1][0] * rw[1]; currentColor = currentColor + nb.v[2][0] * rw[2];
-    currentColor = currentColor + nb.v[0][1] * rw[3]; currentColor = currentColor + nb.v[1][1] * rw[4]; currentColor = currentColor + nb.v[2][1] * rw[5];
-    currentColor = currentColor + nb.v[0][2] * rw[6]; currentColor = currentColor + nb.v[1][2] * rw[7]; currentColor = currentColor + nb.v[2][2] * rw[8];
+    currentColor = currentColor + nb.v[0][0] * sRw[0]; currentColor = currentColor + nb.v[1][0] * sRw[1]; currentColor = currentColor + nb.v[2][0] * sRw[2];
+    currentColor = currentColor + nb.v[0][1] * sRw[3]; currentColor = currentColor + nb.v[1][1] * sRw[4]; currentColor = currentColor + nb.v[2][1] * sRw[5];
+    currentColor = currentColor + nb.v[0][2] * sRw[6]; currentColor = currentColor + nb.v[1][2] * sRw[7]; currentColor = currentColor + nb.v[2][2] * sRw[8];
 
     vec2 motion;
     if (p.useMotionVectorDilation) {  // getClosestFragmentMotion, temporalReprojection.inc:67-83
         float closestDepth = 0.f;
         int offX = 0, offY = 0;
+#pragma unroll
         for (int x = -1; x <= 1; x++)
+#pragma unroll
             for (int y = -1; y <= 1; y++) {
-                const float depth = inRange(p.depthBuffer, ix + x, iy + y) ? loadD32(p.depthBuffer, ix + x, iy + y) : 0.f;
+                const float depth = (FAST || inRange(p.depthBuffer, ix + x, iy + y)) ? loadD32(p.depthBuffer, ix + x, iy + y) : 0.f;
                 if (depth > closestDepth) { closestDepth = depth; offX = x; offY = y; }
             }
-        motion = inRange(p.motionBuffer, ix + offX, iy + offY) ? loadRG16SNORM(p.motionBuffer, ix + offX, iy + offY) : v2(0.f);
+        motion = (FAST || inRange(p.motionBuffer, ix + offX, iy + offY)) ? loadRG16SNORM(p.motionBuffer, ix + offX, iy + offY) : v2(0.f);
     } else {
-        motion = inRange(p.motionBuffer, ix, iy) ? loadRG16SNORM(p.motionBuffer, ix, iy) : v2(0.f);
+        motion = (FAST || inRange(p.motionBuffer, ix, iy)) ? loadRG16SNORM(p.motionBuffer, ix, iy) : v2(0.f);
     }
 
-    auto H = [&](float x, float y) { return sampleR11LinearClampTile(hisTile, p.historySrc, v2(x, y)); };
+    // texture(historyBuffer, uv) with the linear clamp sampler
+    auto H = [&](float x, float y) {
+        if (FAST) {  // finite, bounded coordinates: no sanitising; indices inside the tile need no clamp
+            const AxisTap X = axisTapT<false, true>(x, p.historySrc.w, hisTile.x0), Y = axisTapT<false, true>(y, p.historySrc.h, hisTile.y0);
+            return tapR11Tile(hisTile, p.historySrc, X, Y);
+        }
+        return sampleR11LinearClampTile(hisTile, p.historySrc, v2(x, y));
+    };
     vec3 historySample;
     const int historySampleTech = TECH >= 0 ? TECH : p.historySampleTech;  // specialisation constant 2 -> template parameter
     if (historySampleTech == 0) {
@@ -293,13 +419,16 @@ __global__ void __launch_bounds__(256, 3) temporalFilterKernel(const __grid_cons
         historySample = v3(1.f, 0.f, 0.f);
     }
     if (TONEMAP) historySample = taaTonemap(historySample);
-    if (p.useClipping) historySample = clipAABB(historySample, mn, mx);
+    if (p.useClipping) historySample = clipAABB<FAST>(historySample, mn, mx);
     else historySample = vclamp(historySample, mn, mx);
     if (anynan(historySample)) historySample = currentColor;
 
     const float currentContrast = neighbourhoodContrast(nb);
+    // gaussianFilteredNeighbourhood :71-82, used below when the history lies outside the image (same operands either way)
+    const vec3 gaussian = nb.v[0][0] * 0.0625f + nb.v[0][2] * 0.0625f + nb.v[2][0] * 0.0625f + nb.v[2][2] * 0.0625f + nb.v[1][0] * 0.125f +
+                          nb.v[0][1] * 0.125f + nb.v[1][2] * 0.125f + nb.v[2][1] * 0.125f + nb.v[1][1] * 0.25f;
     Nb lastNb;
-    sampleNeighbourhood<TONEMAP>(hisTile, p.historySrc, uv + motion, texelSize, lastNb);
+    sampleNeighbourhood<TONEMAP, FAST>(hisTile, p.historySrc, uv + motion, texelSize, lastNb);
     const float lastContrast = neighbourhoodContrast(lastNb);
     float contrastChange = absf(currentContrast - lastContrast);
     contrastChange = clampf(contrastChange, 0.f, 1.f);
@@ -309,14 +438,37 @@ __global__ void __launch_bounds__(256, 3) temporalFilterKernel(const __grid_cons
     const vec2 ur = uv + motion;
     if (ur.x < 0.f || ur.y < 0.f || ur.x > 1.f || ur.y > 1.f) {  // isUVOutOfImage
         blendFactor = 1.f;
-        currentColor = nb.v[0][0] * 0.0625f + nb.v[0][2] * 0.0625f + nb.v[2][0] * 0.0625f + nb.v[2][2] * 0.0625f + nb.v[1][0] * 0.125f +
-                       nb.v[0][1] * 0.125f + nb.v[1][2] * 0.125f + nb.v[2][1] * 0.125f + nb.v[1][1] * 0.25f;  // gaussianFilteredNeighbourhood :71-82
+        currentColor = gaussian;
     }
     vec3 color = vmix(historySample, currentColor, blendFactor);
     if (TONEMAP) color = taaTonemapReverse(color);
     const uint32_t packed = packR11G11B10(color);
-    if (inRange(p.historyDst, ix, iy)) ((uint32_t*)p.historyDst.ptr)[texelIndex(p.historyDst, ix, iy)] = packed;
+    if (FAST || inRange(p.historyDst, ix, iy)) ((uint32_t*)p.historyDst.ptr)[texelIndex(p.historyDst, ix, iy)] = packed;
     ((uint32_t*)p.outputImage.ptr)[texelIndex(p.outputImage, ix, iy)] = packed;
+}
+template <bool TONEMAP, int TECH>
+__device__ __noinline__ void temporalFilterPixelGeneric(const TaaParams& p, const float4* sCur, const float4* sHis, const float* sRw) {
+    temporalFilterPixel<TONEMAP, TECH, false>(p, sCur, sHis, sRw);
+}
+template <bool TONEMAP, int TECH>
+__global__ void __launch_bounds__(256, 3) temporalFilterKernel(const __grid_constant__ TaaParams p) {
+    __shared__ float4 sCur[TAA_CUR_W * TAA_CUR_H];
+    __shared__ float4 sHis[TAA_HIS_W * TAA_HIS_H];
+    __shared__ float sRw[9];
+    if (threadIdx.x < 9) sRw[threadIdx.x] = p.resolveWeights[threadIdx.x];
+    const int bx = blockIdx.x * 32, by = p.y0 + blockIdx.y * 8;
+    const bool interior = p.sameExtents && tileIsInterior<TAA_HIS_W, TAA_HIS_H>(p.historySrc, bx - TAA_HIS_HALO, by - TAA_HIS_HALO);
+    bool special;
+    if (interior) {
+        special = tileLoadR11<TAA_CUR_W, TAA_CUR_H, true>(sCur, p.currentFrame, bx - TAA_CUR_HALO, by - TAA_CUR_HALO);
+        special = tileLoadR11<TAA_HIS_W, TAA_HIS_H, true>(sHis, p.historySrc, bx - TAA_HIS_HALO, by - TAA_HIS_HALO) || special;
+    } else {
+        special = tileLoadR11<TAA_CUR_W, TAA_CUR_H, false>(sCur, p.currentFrame, bx - TAA_CUR_HALO, by - TAA_CUR_HALO);
+        special = tileLoadR11<TAA_HIS_W, TAA_HIS_H, false>(sHis, p.historySrc, bx - TAA_HIS_HALO, by - TAA_HIS_HALO) || special;
+    }
+    const bool anySpecial = __syncthreads_or(special ? 1 : 0) != 0;
+    if (interior && !anySpecial) temporalFilterPixel<TONEMAP, TECH, true>(p, sCur, sHis, sRw);
+    else temporalFilterPixelGeneric<TONEMAP, TECH>(p, sCur, sHis, sRw);
 }
 PLAIN_PASS(launch_temporalFilter, "temporalFilter.comp") {
     TaaParams p;
@@ -336,6 +488,8 @@ PLAIN_PASS(launch_temporalFilter, "temporalFilter.comp") {
     if ((int)c.exec->dispatch[0] * 8 < p.outputImage.w || (int)c.exec->dispatch[1] * 8 < p.outputImage.h) { c.fail("temporalFilter.comp: dispatch does not cover the target"); return; }
     c.window(p.outputImage.h, p.y0, p.y1);
     if (p.y1 <= p.y0) return;
+    auto same = [&](const ImgView& v) { return v.w == p.outputImage.w && v.h == p.outputImage.h; };
+    p.sameExtents = same(p.currentFrame) && same(p.historySrc) && same(p.motionBuffer) && same(p.depthBuffer) && same(p.historyDst);
     dim3 grid(ceilDiv(p.outputImage.w, 32), ceilDiv((unsigned)(p.y1 - p.y0), 8));
     if (p.useTonemap && p.historySampleTech == 4) PLAIN_LAUNCH(c, (temporalFilterKernel<true, 4>), grid, 256, 0, p);  // the reference's defaults (TAA.h:8-17)
     else if (p.useTonemap) PLAIN_LAUNCH(c, (temporalFilterKernel<true, -1>), grid, 256, 0, p);

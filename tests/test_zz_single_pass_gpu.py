@@ -134,3 +134,51 @@ def test_sdf_culling_bit_exact(ffi, cuda, oracle, n, use_hiz, influence):
     # entries beyond a tile's count are never written by either side
     for ta, tb in zip(a[1], b[1]):
         assert ta[0] == tb[0] and (ta[0] == 0xFFFFFFFF or np.array_equal(ta[1:1 + ta[0]], tb[1:1 + tb[0]]))
+
+
+def _taa_inputs(rng, w, h, max_px, special):
+    from conftest import random_r11g11b10
+    cur = random_r11g11b10(rng, w * h, finite=True).reshape(h, w)
+    his = random_r11g11b10(rng, w * h, finite=True).reshape(h, w)
+    # keep most values moderate so that the resolve is not dominated by 2^15-sized texels
+    cur = np.where(rng.random((h, w)) < 0.9, cur & np.uint32(0xBBFEFBFF), cur).astype(np.uint32)
+    his = np.where(rng.random((h, w)) < 0.9, his & np.uint32(0xBBFEFBFF), his).astype(np.uint32)
+    if special:  # a few inf / NaN texels: their blocks take the spelled-out path, the others the fast one
+        for img in (cur, his):
+            n = max(w * h // 700, 2)
+            ys, xs = rng.integers(0, h, n), rng.integers(0, w, n)
+            img[ys, xs] = random_r11g11b10(rng, n, finite=False) | np.uint32(0x7C0)
+    motion = np.zeros((h, w, 2), np.int16)
+    motion[..., 0] = np.clip(rng.normal(0, max_px, (h, w)) / w * 32767, -32767, 32767).astype(np.int16)
+    motion[..., 1] = np.clip(rng.normal(0, max_px, (h, w)) / h * 32767, -32767, 32767).astype(np.int16)
+    depth = rng.random((h, w)).astype(np.float32)
+    depth[rng.random((h, w)) < 0.1] = 0.0
+    wts = rng.random(9).astype(np.float32)
+    wts /= wts.sum()
+    return cur, his, motion, depth, wts
+
+
+@pytest.mark.parametrize("w,h,max_px,special,tech,clip,dil,tonemap", [
+    (200, 120, 0.7, False, 4, True, True, True),     # the default configuration: interior blocks on the fast path, a border ring on the generic one
+    (200, 120, 9.0, False, 4, True, True, True),     # motion beyond the staged history tile: taps fall back to global loads
+    (200, 120, 1.5, True, 4, True, True, True),      # inf / NaN texels
+    (131, 77, 2.0, True, 0, False, False, False),    # odd extent, bilinear history, clamp instead of clip, no dilation, no tonemap
+    (160, 96, 2.0, False, 1, True, True, True), (160, 96, 2.0, True, 2, True, False, True), (160, 96, 3.0, False, 3, False, True, False)])
+def test_taa_resolve_single_pass_bit_exact(ffi, cuda, oracle, w, h, max_px, special, tech, clip, dil, tonemap):
+    rng = np.random.default_rng(w * 7 + h + tech)
+    cur, his, motion, depth, wts = _taa_inputs(rng, w, h, max_px, special)
+    a = passes.taa_resolve(ffi, cuda, cur, his, motion, depth, wts, clip, dil, tech, tonemap)
+    b = passes.taa_resolve(ffi, oracle, cur, his, motion, depth, wts, clip, dil, tech, tonemap)
+    for name, x, y in zip(("output", "history"), a, b):
+        assert np.array_equal(x, y), "%s: %d of %d texels differ" % (name, int((x != y).sum()), x.size)
+
+
+@pytest.mark.parametrize("w,h,radius,finite", [(512, 288, 1.5, True), (480, 270, 1.5, False), (258, 130, 0.75, True), (300, 200, 100.0, True)])
+def test_bloom_chain_interior_blocks_bit_exact(ffi, cuda, oracle, w, h, radius, finite):
+    """Sizes with interior blocks in several mips (the fast path of the bloom kernels), odd mip extents, a blur radius beyond the fast path's bound."""
+    rng = np.random.default_rng(w + h)
+    from conftest import random_r11g11b10
+    packed = random_r11g11b10(rng, w * h, finite=finite).reshape(h, w)
+    a, b = passes.bloom(ffi, cuda, packed, strength=0.05, radius=radius), passes.bloom(ffi, oracle, packed, strength=0.05, radius=radius)
+    for x, y in zip(a[0] + a[1] + [a[2]], b[0] + b[1] + [b[2]]):
+        assert np.array_equal(x, y)
