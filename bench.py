@@ -10,10 +10,11 @@ tonemap) over the synthetic Sponza-sized scene, replayed throu
           raster-pass outputs from pinned host memory and reads the tonemapped 8-bit frame back, copies inside the
           timed region
   roofline     : the most expensive pass of the frame, algorithmic bytes (SURVEY.md 8d / DESIGN.md) / its mean duration
-  cpu_baseline : the scalar C++ oracle (oracle/, kind "port") on the host cores, bounded sample (rank 0, N = 1 only)
+  cpu_baseline : the scalar C++ oracle (oracle/, kind "port") on the host cores, one real frame of the workload (rank 0, N = 1 only)
 
 `--impl reference` times the reference's own CPU implementation of the path: its per-pixel arithmetic is GLSL that
-cannot execute here (no Vulkan), so this is the oracle port on all host threads, on a bounded sample of the workload.
+cannot execute here (no Vulkan), so this is the oracle port on all host threads, on real frames of the named
+configuration (1 warm-up + at most 3 timed frames: ~12 s each at 3840x2160).
 """
 import argparse
 import ctypes as C
@@ -43,7 +44,7 @@ def algorithmic_bytes(w, h):
     """Compulsory bytes per frame of each pass (every distinct input byte once + every output byte once), SURVEY.md 8d."""
     N, n = w * h, (w // 2) * (h // 2)
     F = ((w + 7) // 8) * ((h + 7) // 8) * 64
-    return {
+    b = {
         "Histogram per tile": 4 * N + 512,
         "Depth min/max pyramid creation": 4 * N + 8 * n * 4 // 3,
         "Depth downscale": 4 * n + 2 * n,
@@ -60,20 +61,40 @@ def algorithmic_bytes(w, h):
         "Apply bloom": 4 * N + 4 * N + N,
         "Tonemapping": 8 * N,
     }
+    # bloom chain (Bloom.cpp:56-144, 6 mips): downsample mip k reads mip k-1 and writes mip k; upsample mip k reads the downsample
+    # mip k+1 and - unless it is the lowest - the upsample mip k+1, writes mip k (R11G11B10, 4 bytes per texel)
+    mip = lambda k: max(w >> k, 1) * max(h >> k, 1)
+    for k in range(1, 6):
+        b["Bloom downsample mip %d" % k] = 4 * mip(k - 1) + 4 * mip(k)
+    for k in range(4, -1, -1):
+        b["Bloom Upsample mip %d" % k] = 4 * mip(k + 1) * (1 if k == 4 else 2) + 4 * mip(k)
+    return b
 
 
-NCU_KERNEL_OF_PASS = {"Indirect diffuse spatial filter": "giSpatialFilterKernel<1>", "Indirect diffuse SDF trace": "sdfDiffuseTraceKernel",
-                      "Temporal filtering": "temporalFilterKernel<1, 4>", "Forward shading": "gbufferShadingKernel<2, 0, 1, 0>"}
+# passes every rank computes in full when a frame is split into row bands; all others only cover the rank's band
+REPLICATED_PASSES = ("Sky ", "Pre-expose", "Histogram reset", "Histogram combine", "Compute light matrix", "SDF camera", "Bloom downsample mip 2", "Bloom downsample mip 3",
+                     "Bloom downsample mip 4", "Bloom downsample mip 5", "Bloom Upsample mip 4", "Bloom Upsample mip 3", "Bloom Upsample mip 2")
+
+
+NCU_KERNEL_OF_PASS = {"Indirect diffuse spatial filter": "giSpatialFilterKernel", "Indirect diffuse SDF trace": "sdfDiffuseTraceKernel",
+                      "Temporal filtering": "temporalFilterKernel", "Forward shading": "gbufferShadingKernel", "Bloom Upsample mip 0": "bloomUpsampleKernel"}
 
 
 def ncu_traffic(pass_name):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the pass's kernel from the committed `ncu --set full` capture
-    (profiles/r1g_ncu_top_kernels.json, same command and workload); None when the kernel was not captured."""
-    try:
-        table = json.loads((ROOT / "profiles" / "r1g_ncu_top_kernels.json").read_text())
-        return int(table[NCU_KERNEL_OF_PASS[pass_name]][0]["dram_bytes"])
-    except Exception:
-        return None
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the pass's kernel from the newest committed `ncu --set full` capture
+    of this workload (profiles/r2*_ncu_*.json, written by tools/ncu_summary.py): (bytes, file) or (None, None). A capture is a
+    separate run under the profiler - the bench line says which file the figure comes from."""
+    want = NCU_KERNEL_OF_PASS.get(pass_name)
+    if not want:
+        return None, None
+    for f in sorted((ROOT / "profiles").glob("r2*_ncu_*.json"), reverse=True):
+        try:
+            rows = [r for r in json.loads(f.read_text()) if want in r["kernel"]]
+        except Exception:
+            continue
+        if rows:
+            return int(max(r["dram_bytes"] for r in rows)), f.name  # the largest launch = the full-resolution one
+    return None, None
 
 
 def measured_hbm_peak():
@@ -87,32 +108,70 @@ def measured_hbm_peak():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe): NVML polled every 5 ms from a
+    thread (a 20-step region at 8 GPUs lasts tens of milliseconds - too short for nvidia-smi's 100 ms loop, the fallback)."""
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, device):
-        self.samples, self.proc, self.device = [], None, device
+        self.device, self.sm, self.max_sm, self.reasons = device, [], None, set()
+        self.stop_flag, self.thread, self.proc, self.source = False, None, None, None
+
+    def _nvml_loop(self, nv, h):
+        bits = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8), "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20), "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+        while not self.stop_flag:
+            try:
+                self.sm.append(int(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                r = int(nv.nvmlDeviceGetCurrentClocksEventReasons(h)) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") else int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                for name, bit in bits.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.005)
+
+    def _smi_loop(self):
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.proc.stdout:
+            f = [x.strip() for x in line.split(",")]
+            if f and f[0].isdigit():
+                self.sm.append(int(f[0]))
+            if len(f) > 1 and f[1].isdigit():
+                self.max_sm = int(f[1])
+            for i in range(4):
+                if len(f) >= 6 and f[2 + i].lower().startswith("active"):
+                    self.reasons.add(names[i])
 
     def start(self):
         try:
+            import pynvml as nv
+            nv.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            index = int(visible.split(",")[self.device]) if visible and all(x.strip().isdigit() for x in visible.split(",")) else self.device
+            h = nv.nvmlDeviceGetHandleByIndex(index)
+            self.max_sm = int(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            self.source = "nvml, 5 ms"
+            self.thread = threading.Thread(target=self._nvml_loop, args=(nv, h), daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            pass
+        try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
+            self.source = "nvidia-smi, 100 ms"
+            threading.Thread(target=self._smi_loop, daemon=True).start()
         except Exception:
             self.proc = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.samples.append([x.strip() for x in line.split(",")])
-
     def stop(self):
+        self.stop_flag = True
+        if self.thread:
+            self.thread.join(timeout=1.0)
         if self.proc:
             self.proc.terminate()
-        sm = sorted(int(s[0]) for s in self.samples if s and s[0].isdigit())
-        mx = [int(s[1]) for s in self.samples if len(s) > 1 and s[1].isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for s in self.samples if len(s) >= 6 for i in range(4) if s[2 + i].lower().startswith("active")})
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+        sm = sorted(self.sm)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_sm, "reasons": sorted(self.reasons), "samples": len(sm), "source": self.source}
 
 
 def oracle_api():
@@ -147,17 +206,23 @@ def time_oracle(width, height, frames, warm):
     return float(np.median(times))
 
 
+REFERENCE_MAX_TIMED_FRAMES = 3  # a 3840x2160 frame of the oracle takes ~12 s on 16 host threads: the arm stays within a few minutes
+
+
 def run_reference(args, rank):
+    """The reference's own CPU implementation of the path = the oracle port (its GLSL cannot execute here), timed on REAL frames of the
+    named configuration: 1 warm-up frame + min(--steps, 3) timed frames at WIDTH x HEIGHT, nothing extrapolated. `steps` / `warmup` in
+    the line are the counts actually run."""
     if rank != 0:
         return
-    sw, sh = WIDTH // 8, HEIGHT // 8  # bounded sample: the same scene and camera at 480x270 = 1/64 of the pixels
     cores = os.cpu_count() or 1
-    sec = time_oracle(sw, sh, max(args.steps, 1), max(args.warmup, 1))
-    scale = (WIDTH * HEIGHT) / float(sw * sh)
-    fps = 1.0 / (sec * scale)
-    sample = "%dx%d frame (1/%d of the full-size pixels, same scene/camera/pass list), frames/s divided by %d" % (sw, sh, int(scale), int(scale))
-    line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": sec * scale * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+    frames, warm = max(min(args.steps, REFERENCE_MAX_TIMED_FRAMES), 1), 1
+    sec = time_oracle(WIDTH, HEIGHT, frames, warm)
+    fps = 1.0 / sec
+    sample = "%d timed frame(s) after %d warm-up frame at the full %dx%d (median), same scene / camera / pass list, oracle port on all host threads" % (frames, warm, WIDTH, HEIGHT)
+    line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": frames, "warmup": warm,
+            "requested_steps": args.steps, "requested_warmup": args.warmup,
+            "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args.gpus),
             "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -315,21 +380,33 @@ def run_ours(args, rank, world, local_rank):
         h2d = WIDTH * (upload_rows[1] - upload_rows[0]) * (4 + 4 + 16) + WIDTH * HEIGHT * 4  # per rank: band + halo of depth/normal/G-buffer, motion whole
         d2h = WIDTH * (band[1] - band[0]) * 4
         peak, peak_src = measured_hbm_peak()
-        alg = algorithmic_bytes(WIDTH, HEIGHT)
+        alg_frame = algorithmic_bytes(WIDTH, HEIGHT)
+        # rank 0's kernels cover rank 0's band: the bytes a launch moves are the band's share of the pass (replicated passes move all of them)
+        band_share = (band[1] - band[0]) / float(HEIGHT)
+        alg = {k: (v if (not sharded or k.startswith(REPLICATED_PASSES)) else int(v * band_share)) for k, v in alg_frame.items()}
         top = max(acc, key=lambda k: acc[k])
         launches_of_top = 2 if top == "Indirect diffuse spatial filter" else 1
         top_ms = acc[top] / launches_of_top
         achieved = alg.get(top, 0) / (top_ms * 1e-3) / 1e9 if top_ms > 0 else 0.0
         passes_sum = sum(acc.values())
+        traffic, traffic_src = ncu_traffic(top) if not sharded else (None, None)
+        pair_ms = acc.get("Forward shading", 0.0) + acc.get("Indirect diffuse SDF trace", 0.0)
+        pair_bytes = alg["Forward shading"] + alg["Indirect diffuse SDF trace"]
+        pair_gbs = pair_bytes / (pair_ms * 1e-3) / 1e9 if pair_ms > 0 else 0.0
         line = {"metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
                 "higher_is_better": True, "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(world),
                 "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_step_e2e},
                 "gpu_launches": launches * args.steps,
                 "clocks": clock_info,
-                "roofline": {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None, "traffic": ncu_traffic(top),
+                "roofline": {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None, "traffic": traffic,
+                             "traffic_source": ("profiles/%s: a separate `ncu --set full` run of this workload, not this run" % traffic_src) if traffic_src else None,
                              "algorithmic_bytes_per_launch": alg.get(top, 0), "kernel_ms": top_ms, "share_of_frame": acc[top] / passes_sum if passes_sum else None, "peak_source": peak_src},
+                # the north star's target pair: bytes(S1 shading) + bytes(S2 trace) over the sum of their durations
+                "roofline_pair": {"kernels": ["Forward shading", "Indirect diffuse SDF trace"], "algorithmic_bytes": pair_bytes, "ms": round(pair_ms, 4), "achieved": pair_gbs, "unit": "GB/s",
+                                  "frac": pair_gbs / peak if peak else None},
                 "passes_ms": {k: round(acc[k], 4) for k in order},
-                "frame_roofline": {"algorithmic_bytes_per_frame": int(sum(alg.values()) + alg["Indirect diffuse spatial filter"]), "hbm_bound_ms": (sum(alg.values()) + alg["Indirect diffuse spatial filter"]) / peak / 1e6},
+                "frame_roofline": {"algorithmic_bytes_per_frame": int(sum(alg_frame.values()) + alg_frame["Indirect diffuse spatial filter"]),
+                                   "hbm_bound_ms": (sum(alg_frame.values()) + alg_frame["Indirect diffuse spatial filter"]) / peak / 1e6},
                 "setup_s": round(setup_s, 1), "graph_replay": not args.no_graph}
         try:  # every pass against the HBM roofline (the north star asks for each kernel's achieved GB/s): algorithmic bytes / measured duration
             per_pass = {}
@@ -352,11 +429,9 @@ def run_ours(args, rank, world, local_rank):
                                 "exchanges_through_python": comm.python_exchanges,
                                 "note": "passes_ms are rank 0's kernels only (its band); e2e byte counts are per rank"}
         if world == 1 and not args.no_cpu_baseline:
-            sw, sh = WIDTH // 8, HEIGHT // 8
-            sec = time_oracle(sw, sh, 3, 1)
-            scale = (WIDTH * HEIGHT) / float(sw * sh)
-            line["cpu_baseline"] = {"value": 1.0 / (sec * scale), "unit": "frames/s", "cores": os.cpu_count() or 1, "kind": "port",
-                                    "sample": "%dx%d frame of the same scene (1/%d of the pixels), oracle port on all host threads, frames/s divided by %d" % (sw, sh, int(scale), int(scale))}
+            sec = time_oracle(WIDTH, HEIGHT, 1, 1)
+            line["cpu_baseline"] = {"value": 1.0 / sec, "unit": "frames/s", "cores": os.cpu_count() or 1, "kind": "port",
+                                    "sample": "1 timed frame after 1 warm-up frame at the full %dx%d, same scene / camera / pass list, oracle port on all host threads" % (WIDTH, HEIGHT)}
         print(json.dumps(line), file=_REAL_STDOUT, flush=True)
     fe.close()
     if world > 1:

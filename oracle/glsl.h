@@ -15,10 +15,14 @@ namespace gl {
 
 typedef uint32_t uint;
 
-struct vec2 { float x, y; vec2() : x(0), y(0) {} vec2(float a, float b) : x(a), y(b) {} explicit vec2(float a) : x(a), y(a) {} };
+struct vec3;
+struct vec2 { float x, y; vec2() : x(0), y(0) {} vec2(float a, float b) : x(a), y(b) {} explicit vec2(float a) : x(a), y(a) {}
+    vec2 xy() const { return *this; } inline vec3 xyx() const; };
 struct vec3 { float x, y, z; vec3() : x(0), y(0), z(0) {} vec3(float a, float b, float c) : x(a), y(b), z(c) {} explicit vec3(float a) : x(a), y(a), z(a) {}
     vec3(vec2 v, float c) : x(v.x), y(v.y), z(c) {}
-    float& operator[](int i) { return (&x)[i]; } float operator[](int i) const { return (&x)[i]; } };
+    float& operator[](int i) { return (&x)[i]; } float operator[](int i) const { return (&x)[i]; }
+    vec2 xy() const { return vec2(x, y); } vec3 xyz() const { return *this; } };
+inline vec3 vec2::xyx() const { return vec3(x, y, x); }
 struct vec4 { float x, y, z, w; vec4() : x(0), y(0), z(0), w(0) {} vec4(float a, float b, float c, float d) : x(a), y(b), z(c), w(d) {} explicit vec4(float a) : x(a), y(a), z(a), w(a) {}
     vec4(vec3 v, float d) : x(v.x), y(v.y), z(v.z), w(d) {} vec4(vec2 v, float c, float d) : x(v.x), y(v.y), z(c), w(d) {}
     float& operator[](int i) { return (&x)[i]; } float operator[](int i) const { return (&x)[i]; }

@@ -542,3 +542,10 @@ ORACLE_PASS(pass_indirectLightUpscale, "indirectLightUpscale.comp") {
 }
 
 }  // namespace orc
+
+// the functions above that restate the reference's GLSL include files, behind the batch entry points the reference-pinning test uses
+#define INC_NS orc
+#define INC_PREFIX oracle_inc_
+#define INC_IS_REFERENCE 0
+#define INC_PART_SDF 1
+#include "inc_eval.h"

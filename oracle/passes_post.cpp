@@ -188,6 +188,56 @@ static BicubicW bicubicWeights(vec2 iUV) {  // bicubicSampling.inc:74-85
     return b;
 }
 
+// history sample of temporalFilter.comp:104-127: bilinear, or the bicubic samplers of bicubicSampling.inc:28-181 at the
+// reprojected pixel position p = iUV + 0.5 + motion * screenResolution
+static vec3 sampleHistory(int historySampleTech, const View& historyBufferSrc, vec2 uv, vec2 motion, vec2 p, vec2 texelSize, const Nb& nb) {
+    vec3 historySample;
+    if (historySampleTech == 0) {
+        historySample = texture(historyBufferSrc, s_linearClamp, uv + motion).xyz();
+    } else if (historySampleTech == 1) {  // 16 tap, bicubicSampling.inc:28-67
+        vec2 uvTrunc = floor(p - 0.5f) + 0.5f;
+        vec2 d = p - uvTrunc;
+        vec2 ad = abs(d);
+        vec2 w[4] = {vec2(catmullRomWeight1D(ad.x + 1.f), catmullRomWeight1D(ad.y + 1.f)), vec2(catmullRomWeight1D(ad.x), catmullRomWeight1D(ad.y)),
+                     vec2(catmullRomWeight1D(1.f - ad.x), catmullRomWeight1D(1.f - ad.y)), vec2(catmullRomWeight1D(2.f - ad.x), catmullRomWeight1D(2.f - ad.y))};
+        vec2 u[4] = {(uvTrunc - 1.f) * texelSize, uvTrunc * texelSize, (uvTrunc + 1.f) * texelSize, (uvTrunc + 2.f) * texelSize};
+        vec3 acc = vec3(0.f);
+        bool first = true;
+        for (int yy = 0; yy < 4; yy++)
+            for (int xx = 0; xx < 4; xx++) {
+                vec3 term = texture(historyBufferSrc, s_linearClamp, vec2(u[xx].x, u[yy].y)).xyz() * w[xx].x * w[yy].y;
+                acc = first ? term : acc + term;
+                first = false;
+            }
+        historySample = acc;
+    } else if (historySampleTech == 2) {  // 9 tap :72-107
+        BicubicW b = bicubicWeights(p);
+        vec2 uv0 = (b.uvTrunc - 1.f) * texelSize, uvT = (b.uvTrunc + b.t) * texelSize, uv3 = (b.uvTrunc + 2.f) * texelSize;
+        auto T = [&](float x, float y) { return texture(historyBufferSrc, s_linearClamp, vec2(x, y)).xyz(); };
+        historySample = T(uv0.x, uv0.y) * b.w0.x * b.w0.y + T(uv0.x, uvT.y) * b.w0.x * b.wB.y + T(uv0.x, uv3.y) * b.w0.x * b.w3.y +
+                        T(uvT.x, uv0.y) * b.wB.x * b.w0.y + T(uvT.x, uvT.y) * b.wB.x * b.wB.y + T(uvT.x, uv3.y) * b.wB.x * b.w3.y +
+                        T(uv3.x, uv0.y) * b.w3.x * b.w0.y + T(uv3.x, uvT.y) * b.w3.x * b.wB.y + T(uv3.x, uv3.y) * b.w3.x * b.w3.y;
+    } else if (historySampleTech == 3) {  // 5 tap :112-145
+        BicubicW b = bicubicWeights(p);
+        vec2 uv0 = (b.uvTrunc - 1.f) * texelSize, uvT = (b.uvTrunc + b.t) * texelSize, uv3 = (b.uvTrunc + 2.f) * texelSize;
+        auto T = [&](float x, float y) { return vec4(texture(historyBufferSrc, s_linearClamp, vec2(x, y)).xyz(), 1.f); };
+        vec4 result = T(uv0.x, uvT.y) * b.w0.x * b.wB.y + T(uvT.x, uv0.y) * b.wB.x * b.w0.y + T(uvT.x, uvT.y) * b.wB.x * b.wB.y +
+                      T(uvT.x, uv3.y) * b.wB.x * b.w3.y + T(uv3.x, uvT.y) * b.w3.x * b.wB.y;
+        historySample = result.xyz() / result.w;
+    } else if (historySampleTech == 4) {  // 1 tap :150-181
+        BicubicW b = bicubicWeights(p);
+        vec2 uvT = (b.uvTrunc + b.t) * texelSize;
+        vec3 hs = texture(historyBufferSrc, s_linearClamp, uvT).xyz();
+        vec4 result = vec4(hs + nb.v[0][1] - nb.v[1][1], 1.f) * b.w0.x * b.wB.y + vec4(hs + nb.v[1][0] - nb.v[1][1], 1.f) * b.wB.x * b.w0.y +
+                      vec4(hs, 1.f) * b.wB.x * b.wB.y + vec4(hs + nb.v[1][2] - nb.v[1][1], 1.f) * b.wB.x * b.w3.y +
+                      vec4(hs + nb.v[2][1] - nb.v[1][1], 1.f) * b.w3.x * b.wB.y;
+        historySample = result.xyz() / result.w;
+    } else {
+        historySample = vec3(1.f, 0.f, 0.f);
+    }
+    return historySample;
+}
+
 ORACLE_PASS(pass_temporalFilter, "temporalFilter.comp") {
     const bool useClipping = c.specBool(0, false);
     const bool useMotionVectorDilation = c.specBool(1, false);
@@ -228,54 +278,7 @@ ORACLE_PASS(pass_temporalFilter, "temporalFilter.comp") {
             motion = motionBuffer.fetch(ix, iy).xy();
         }
 
-        vec3 historySample;
-        if (historySampleTech == 0) {
-            historySample = texture(historyBufferSrc, s_linearClamp, uv + motion).xyz();
-        } else if (historySampleTech == 1) {  // 16 tap, bicubicSampling.inc:28-67
-            vec2 p = tovec2(iUV) + 0.5f + motion * screenRes;
-            vec2 uvTrunc = floor(p - 0.5f) + 0.5f;
-            vec2 d = p - uvTrunc;
-            vec2 ad = abs(d);
-            vec2 w[4] = {vec2(catmullRomWeight1D(ad.x + 1.f), catmullRomWeight1D(ad.y + 1.f)), vec2(catmullRomWeight1D(ad.x), catmullRomWeight1D(ad.y)),
-                         vec2(catmullRomWeight1D(1.f - ad.x), catmullRomWeight1D(1.f - ad.y)), vec2(catmullRomWeight1D(2.f - ad.x), catmullRomWeight1D(2.f - ad.y))};
-            vec2 u[4] = {(uvTrunc - 1.f) * texelSize, uvTrunc * texelSize, (uvTrunc + 1.f) * texelSize, (uvTrunc + 2.f) * texelSize};
-            vec3 acc = vec3(0.f);
-            bool first = true;
-            for (int yy = 0; yy < 4; yy++)
-                for (int xx = 0; xx < 4; xx++) {
-                    vec3 term = texture(historyBufferSrc, s_linearClamp, vec2(u[xx].x, u[yy].y)).xyz() * w[xx].x * w[yy].y;
-                    acc = first ? term : acc + term;
-                    first = false;
-                }
-            historySample = acc;
-        } else if (historySampleTech == 2) {  // 9 tap :72-107
-            vec2 p = tovec2(iUV) + 0.5f + motion * screenRes;
-            BicubicW b = bicubicWeights(p);
-            vec2 uv0 = (b.uvTrunc - 1.f) * texelSize, uvT = (b.uvTrunc + b.t) * texelSize, uv3 = (b.uvTrunc + 2.f) * texelSize;
-            auto T = [&](float x, float y) { return texture(historyBufferSrc, s_linearClamp, vec2(x, y)).xyz(); };
-            historySample = T(uv0.x, uv0.y) * b.w0.x * b.w0.y + T(uv0.x, uvT.y) * b.w0.x * b.wB.y + T(uv0.x, uv3.y) * b.w0.x * b.w3.y +
-                            T(uvT.x, uv0.y) * b.wB.x * b.w0.y + T(uvT.x, uvT.y) * b.wB.x * b.wB.y + T(uvT.x, uv3.y) * b.wB.x * b.w3.y +
-                            T(uv3.x, uv0.y) * b.w3.x * b.w0.y + T(uv3.x, uvT.y) * b.w3.x * b.wB.y + T(uv3.x, uv3.y) * b.w3.x * b.w3.y;
-        } else if (historySampleTech == 3) {  // 5 tap :112-145
-            vec2 p = tovec2(iUV) + 0.5f + motion * screenRes;
-            BicubicW b = bicubicWeights(p);
-            vec2 uv0 = (b.uvTrunc - 1.f) * texelSize, uvT = (b.uvTrunc + b.t) * texelSize, uv3 = (b.uvTrunc + 2.f) * texelSize;
-            auto T = [&](float x, float y) { return vec4(texture(historyBufferSrc, s_linearClamp, vec2(x, y)).xyz(), 1.f); };
-            vec4 result = T(uv0.x, uvT.y) * b.w0.x * b.wB.y + T(uvT.x, uv0.y) * b.wB.x * b.w0.y + T(uvT.x, uvT.y) * b.wB.x * b.wB.y +
-                          T(uvT.x, uv3.y) * b.wB.x * b.w3.y + T(uv3.x, uvT.y) * b.w3.x * b.wB.y;
-            historySample = result.xyz() / result.w;
-        } else if (historySampleTech == 4) {  // 1 tap :150-181
-            vec2 p = tovec2(iUV) + 0.5f + motion * screenRes;
-            BicubicW b = bicubicWeights(p);
-            vec2 uvT = (b.uvTrunc + b.t) * texelSize;
-            vec3 hs = texture(historyBufferSrc, s_linearClamp, uvT).xyz();
-            vec4 result = vec4(hs + nb.v[0][1] - nb.v[1][1], 1.f) * b.w0.x * b.wB.y + vec4(hs + nb.v[1][0] - nb.v[1][1], 1.f) * b.wB.x * b.w0.y +
-                          vec4(hs, 1.f) * b.wB.x * b.wB.y + vec4(hs + nb.v[1][2] - nb.v[1][1], 1.f) * b.wB.x * b.w3.y +
-                          vec4(hs + nb.v[2][1] - nb.v[1][1], 1.f) * b.w3.x * b.wB.y;
-            historySample = result.xyz() / result.w;
-        } else {
-            historySample = vec3(1.f, 0.f, 0.f);
-        }
+        vec3 historySample = sampleHistory(historySampleTech, historyBufferSrc, uv, motion, tovec2(iUV) + 0.5f + motion * screenRes, texelSize, nb);
         if (useTonemap) historySample = taaTonemap(historySample);
         if (useClipping) historySample = clipAABB(historySample, mn, mx);
         else historySample = clamp(historySample, mn, mx);
@@ -431,3 +434,10 @@ ORACLE_PASS(pass_applyBloom, "applyBloom.comp") {
 }
 
 }  // namespace orc
+
+// the functions above that restate the reference's GLSL include files, behind the batch entry points the reference-pinning test uses
+#define INC_NS orc
+#define INC_PREFIX oracle_inc_
+#define INC_IS_REFERENCE 0
+#define INC_PART_TAA 1
+#include "inc_eval.h"

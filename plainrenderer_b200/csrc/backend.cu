@@ -155,8 +155,10 @@ static int computeMipCount(const plain_image_desc& d) {
     return n;
 }
 
+static bool hasCornerBrick(const plain_image_desc& d) { return d.type == PLAIN_IMAGE_TYPE_3D && d.format == PLAIN_FORMAT_R16_SFLOAT; }
 static bool allocateImage(Backend& b, DeviceImage& img, const plain_image_desc& d) {
     if (img.ptr) { cudaStreamSynchronize(b.uploadStream); cudaStreamSynchronize(b.downloadStream); cudaStreamSynchronize(b.stream); cudaFree(img.ptr); img.ptr = nullptr; }
+    if (img.corners) { cudaFree(img.corners); img.corners = nullptr; }
     img.desc = d;
     const int n = computeMipCount(d), bpt = formatBytesPerTexel(d.format);
     img.mips.assign(n, MipInfo());
@@ -173,6 +175,12 @@ static bool allocateImage(Backend& b, DeviceImage& img, const plain_image_desc& 
     img.bytes = off;
     if (cudaMalloc(&img.ptr, img.bytes ? img.bytes : 256) != cudaSuccess) return false;
     cudaMemsetAsync(img.ptr, 0, img.bytes ? img.bytes : 256, b.stream);
+    if (hasCornerBrick(d)) {  // an all-zero brick has an all-zero copy
+        const size_t entries = (size_t)(img.mips[0].w + 1) * (img.mips[0].h + 1) * (img.mips[0].d + 1);
+        if (cudaMalloc(&img.corners, entries * sizeof(uint4)) != cudaSuccess) { cudaFree(img.ptr); img.ptr = nullptr; return false; }
+        cudaMemsetAsync(img.corners, 0, entries * sizeof(uint4), b.stream);
+        img.cornersStale = false;
+    }
     b.passEpoch++;
     return true;
 }
@@ -499,12 +507,21 @@ static int fail(plain_ctx* ctx, const std::string& msg) {
         if (e__ != cudaSuccess) return fail(ctx, std::string(#call) + ": " + cudaGetErrorString(e__)); \
     } while (0)
 
+// the corner-replicated copies of the SDF bricks written since they were built (enqueued on the pass stream; no allocation: capturable)
+static void refreshCornerBricks(Backend& b) {
+    for (DeviceImage& img : b.images)
+        if (img.corners && img.cornersStale) {
+            buildCornerBrick(img.corners, img.ptr, img.mips[0].w, img.mips[0].h, img.mips[0].d, b.stream);
+            img.cornersStale = false;
+        }
+}
 static void updateBindless(Backend& b, uint32_t index) {
     if (index >= Backend::kMaxBindless) return;
     const DeviceImage& img = b.images[index];
     BindlessEntry e;
     e.view.ptr = img.ptr; e.view.w = img.mips[0].w; e.view.h = img.mips[0].h; e.view.d = img.mips[0].d;
     e.format = img.desc.format; e.pad = 0;
+    e.corners = img.corners;
     cudaMemcpyAsync(b.bindlessDevice + index, &e, sizeof(e), cudaMemcpyHostToDevice, b.stream);
     cudaStreamSynchronize(b.stream);
 }
@@ -562,7 +579,7 @@ void PLAIN_FN(backend_destroy)(plain_ctx* ctx) {
         if (p != b.peerRank && b.peerSync[p]) cudaIpcCloseMemHandle(b.peerSync[p]);
     }
     if (b.peerCount) cudaFree(b.peerSync[b.peerRank]);
-    for (auto& i : b.images) cudaFree(i.ptr);
+    for (auto& i : b.images) { cudaFree(i.ptr); cudaFree(i.corners); }
     for (auto& i : b.transientImages) cudaFree(i.ptr);
     for (auto& sc : b.swapchainImages) { cudaFree(sc.ptr); if (sc.downloadDone) cudaEventDestroy(sc.downloadDone); }
     for (auto& i : b.images) if (i.downloadDone) cudaEventDestroy(i.downloadDone);
@@ -613,6 +630,7 @@ int PLAIN_FN(create_image)(plain_ctx* ctx, const plain_image_desc* desc, const v
             off += img.mips[i].bytes;
         }
         CU_CHECK(ctx, cudaStreamSynchronize(b.stream));  // the caller's memory may go away after the call (RenderBackend.cpp:315-321)
+        img.cornersStale = img.corners != nullptr;
         if (desc->format == PLAIN_FORMAT_RGBA8)
             for (size_t t = 3; t < img.mips[0].bytes; t += 4) if (((const uint8_t*)initial_data)[t] != 255) { img.transparentTexels = true; break; }
     }
@@ -930,12 +948,16 @@ int PLAIN_FN(render_frame)(plain_ctx* ctx, int present) {
     Backend& b = ctx->b;
     cudaSetDevice(b.device);
     joinTransfers(b);  // uploads issued before this submission are visible to its passes; read-backs in flight keep their source
+    refreshCornerBricks(b);  // SDF bricks written since the last submission (direct launches, outside the captured graph)
     while (b.passEvents.size() < b.execs.size()) { cudaEvent_t x; cudaEventCreateWithFlags(&x, cudaEventDisableTiming); b.passEvents.push_back(x); }
     if (prepareRaster(ctx)) return 1;
     for (auto& e : b.execs) {
         for (auto& t : e.targets) if (DeviceImage* img = b.resolve(t.image)) { img->lastUsedSubmission = b.submissionCounter; orderAfterDownload(b, img); }
         for (auto& r : e.sampledImages) if (DeviceImage* img = b.resolve(r.image)) img->lastUsedSubmission = b.submissionCounter;
-        for (auto& r : e.storageImages) if (DeviceImage* img = b.resolve(r.image)) { img->lastUsedSubmission = b.submissionCounter; orderAfterDownload(b, img); }
+        for (auto& r : e.storageImages) if (DeviceImage* img = b.resolve(r.image)) {
+            img->lastUsedSubmission = b.submissionCounter; orderAfterDownload(b, img);
+            if (img->corners) img->cornersStale = true;  // a pass writes an SDF brick: its corner copy is rebuilt before the NEXT submission
+        }
     }
     // all fills of the frame land before any pass (RenderBackend.cpp:896-911): one H2D copy + one scatter kernel
     if (!b.fills.empty()) {
@@ -1032,6 +1054,7 @@ static int imageCopy(plain_ctx* ctx, plain_image_handle image, uint32_t mip, voi
     cudaStream_t st = sync ? b.stream : transferStream(b, *img, toDevice);
     if (toDevice) CU_CHECK(ctx, cudaMemcpyAsync(dev, host, size, cudaMemcpyHostToDevice, st));
     else CU_CHECK(ctx, cudaMemcpyAsync(host, dev, size, cudaMemcpyDeviceToHost, st));
+    if (toDevice && img->corners) img->cornersStale = true;
     if (!sync && !toDevice) markDownloaded(b, *img);
     if (sync) CU_CHECK(ctx, cudaStreamSynchronize(b.stream));
     return 0;
@@ -1054,6 +1077,7 @@ static int imageRowsCopy(plain_ctx* ctx, plain_image_handle image, uint32_t mip,
     cudaStream_t st = transferStream(b, *img, toDevice);
     if (toDevice) CU_CHECK(ctx, cudaMemcpyAsync(dev, host, size, cudaMemcpyHostToDevice, st));
     else CU_CHECK(ctx, cudaMemcpyAsync(host, dev, size, cudaMemcpyDeviceToHost, st));
+    if (toDevice && img->corners) img->cornersStale = true;
     if (!toDevice) markDownloaded(b, *img);
     return 0;
 }

@@ -22,6 +22,10 @@ struct BindlessEntry {  // set 2: global texture array (RenderBackend.cpp:45); i
     ImgView view;
     uint32_t format;
     uint32_t pad;
+    // R16F 3-D images (SDF bricks) only: the corner-replicated copy, (w + 1) x (h + 1) x (d + 1) entries of eight halves. Entry
+    // (i, j, k) holds the 2x2x2 clamp-to-edge footprint of a trilinear tap whose lower texel is (i - 1, j - 1, k - 1), in the
+    // sampler's blend order, so a tap is ONE 128-bit load. Built by the backend whenever the image is written (backend.cu).
+    const uint4* corners;
 };
 
 struct MipInfo { int w, h, d; size_t offset, bytes; };
@@ -33,6 +37,8 @@ struct DeviceImage {
     bool inUse = false;
     bool transparentTexels = false;  // RGBA8 created with initial data containing a texel of alpha < 255 (alpha test of the raster passes)
     long long lastUsedSubmission = -1;  // index of the last submission (render_frame) whose passes referenced the image
+    uint4* corners = nullptr;           // R16F 3-D images: corner-replicated copy for the sphere tracer (BindlessEntry::corners)
+    bool cornersStale = false;          // the image was written since the copy was built
     unsigned char* peerPtr[PLAIN_MAX_PEERS] = {};  // the other ranks' copies of this image (CUDA IPC mappings), row sharding
     cudaEvent_t downloadDone = nullptr; // recorded after the last asynchronous read-back of the image (created on first use)
     bool downloadPending = false;       // that read-back has not been ordered before a later writer yet
@@ -159,6 +165,7 @@ struct ShadingTables {
 };
 void buildShadingTables(ShadingTables* deviceTables, cudaStream_t stream);
 bool runDeviceSelftest(cudaStream_t stream, unsigned long long* hostOut8, std::string& error);  // selftest.cu
+void buildCornerBrick(uint4* corners, const unsigned char* texels, int w, int h, int d, cudaStream_t stream);  // passes_gi.cu
 
 struct PassRegistration { PassRegistration(const char* shader, LaunchFn fn); };
 #define PLAIN_PASS(fnname, shader)                       \

@@ -203,7 +203,8 @@ struct MarchState {
     int k;
 };
 // SDF.inc:101-141: transform the ray, clip it to the box, early-outs. Returns true when the lane has to march.
-__device__ __forceinline__ bool traceSetup(const TraceInstance& inst, vec3 rayStartWorld, vec3 rayDirectionWorld, const TraceResult& tr, MarchState& st) {
+template <typename Inst>
+__device__ __forceinline__ bool traceSetup(const Inst& inst, vec3 rayStartWorld, vec3 rayDirectionWorld, const TraceResult& tr, MarchState& st) {
     const vec3 localExtends = inst.localExtends;
     vec3 rayStartLocal = xyz(mulm4(inst.worldToLocal, v4(rayStartWorld, 1.f)));
     const vec3 rayEndLocal = xyz(mulm4(inst.worldToLocal, v4(rayStartWorld + rayDirectionWorld, 1.f)));
@@ -234,7 +235,8 @@ __device__ __forceinline__ bool traceSetup(const TraceInstance& inst, vec3 raySt
 // `listIndex` is the position of the instance in the tile's list. The reference visits the list in order and replaces the
 // closest hit only by a strictly closer one, so of two hits at the same distance the one listed first wins; this kernel
 // visits the instances in a different order (sdfDiffuseTraceKernel) and applies that rule explicitly.
-__device__ __forceinline__ bool traceStep(const TraceInstance& inst, int listIndex, TraceResult& tr, MarchState& st) {
+template <typename Inst>
+__device__ __forceinline__ bool traceStep(const Inst& inst, int listIndex, TraceResult& tr, MarchState& st) {
     if (st.k >= 128) return false;
     const vec3 localExtendsHalf = inst.localExtendsHalfPadded;
     const vec3 localSamplePos = st.localSamplePos;
@@ -281,7 +283,8 @@ __device__ __forceinline__ void shadeWinner(const TraceInstance& inst, vec3 rayS
 // World-space sphere around the image of the local box [-extends/2, extends/2] under inverse(worldToLocal), padded by
 // 0.1 % + 1 mm. Only used to SKIP instances whose box the ray cannot touch (the reference would run its slab test and
 // return at SDF.inc:115-126 with no effect), never to accept one; any NaN/inf (singular matrix) disables the skip.
-__device__ __forceinline__ void instanceBoundingSphere(TraceInstance& t) {
+template <typename Inst>
+__device__ __forceinline__ void instanceBoundingSphere(Inst& t) {
     const float* m = t.worldToLocal;
     const vec3 a0 = v3(m[0], m[1], m[2]), a1 = v3(m[4], m[5], m[6]), a2 = v3(m[8], m[9], m[10]), tr = v3(m[12], m[13], m[14]);
     const vec3 c12 = cross(a1, a2), c20 = cross(a2, a0), c01 = cross(a0, a1);
@@ -298,7 +301,8 @@ __device__ __forceinline__ void instanceBoundingSphere(TraceInstance& t) {
     const float r = sqrtf(r2) * 1.001f + 0.001f;
     t.sphereR2 = (r2 == r2) ? r * r : dm::nanf_();
 }
-__device__ __forceinline__ bool rayMissesSphere(const TraceInstance& t, vec3 o, vec3 L, float invLen2) {
+template <typename Inst>
+__device__ __forceinline__ bool rayMissesSphere(const Inst& t, vec3 o, vec3 L, float invLen2) {
     const vec3 oc = t.sphereCenter - o;
     const float oc2 = dot(oc, oc), tca = dot(oc, L);
     const float R2 = t.sphereR2 + 1e-5f * oc2;  // slack for the cancellation in oc2 - tca^2
@@ -322,23 +326,189 @@ struct TraceParams {
     int blockRowOffset;  // row sharding: first 16-row block row of this launch
 };
 
-// A block traces a 16x16-pixel region = 2x2 of the reference's 8x8 workgroups; all four lie in one 32x32 culling tile
-// (:154), whose instance records and brick views are staged once in shared memory. Each 8x8 group keeps its own ray
-// cache for the 3x3 resolve (:70-116), exactly like the reference's shared arrays. Every invocation of a dispatched
-// group traces, also those beyond the image edge: they are neighbours in the resolve; only their stores are dropped.
+// ---- corner-replicated SDF bricks (BindlessEntry::corners) ----
+// Entry (i, j, k), 0 <= i <= w etc., holds the eight texels a trilinear tap with lower texel (i - 1, j - 1, k - 1) blends under
+// clamp-to-edge addressing, as halves in the sampler's order: x = a00 | a10 << 16, y = a01 | a11 << 16 (slice z0), z, w = slice z1.
+__global__ void __launch_bounds__(256) buildCornerBrickKernel(uint4* __restrict__ corners, const uint16_t* __restrict__ texels, int w, int h, int d) {
+    const int n = (w + 1) * (h + 1) * (d + 1);
+    const int e = blockIdx.x * 256 + threadIdx.x;
+    if (e >= n) return;
+    const int i = e % (w + 1), j = (e / (w + 1)) % (h + 1), k = e / ((w + 1) * (h + 1));
+    const int x0 = imax(i - 1, 0), x1 = imin(i, w - 1), y0 = imax(j - 1, 0), y1 = imin(j, h - 1), z0 = imax(k - 1, 0), z1 = imin(k, d - 1);
+    auto T = [&](int x, int y, int z) { return (uint32_t)__ldg(texels + ((size_t)z * h + y) * w + x); };
+    uint4 c;
+    c.x = T(x0, y0, z0) | (T(x1, y0, z0) << 16);
+    c.y = T(x0, y1, z0) | (T(x1, y1, z0) << 16);
+    c.z = T(x0, y0, z1) | (T(x1, y0, z1) << 16);
+    c.w = T(x0, y1, z1) | (T(x1, y1, z1) << 16);
+    corners[e] = c;
+}
+void buildCornerBrick(uint4* corners, const unsigned char* texels, int w, int h, int d, cudaStream_t stream) {
+    const int n = (w + 1) * (h + 1) * (d + 1);
+    buildCornerBrickKernel<<<ceilDiv((unsigned)n, 256), 256, 0, stream>>>(corners, (const uint16_t*)texels, w, h, d);
+}
+
+// One SDFInstance staged for the round-2 tracer: the fields of TraceInstance plus the corner-replicated brick, the albedo of a hit
+// (pow(meanAlbedo, 2.2), SDF.inc:174: it depends on the instance only) and whether the instance qualifies for the lean march.
+struct TraceInst2 {
+    float worldToLocal[16];
+    vec3 localExtends;           float distanceThreshold;
+    vec3 localExtendsHalfPadded; float localToGlobalScale;
+    vec3 invLocalExtends;        float sphereR2;
+    vec3 sphereCenter;           int fastOk;
+    vec3 albedo;                 int strideY;   // (w + 1)
+    vec3 dimsF;                  int strideZ;   // (w + 1) * (h + 1)
+    const uint4* corners;        int dimX, dimY;
+    ImgView sdf;                 // .d doubles as dimZ
+};
+// texture(sampler3D R16F, uvw) with the linear + clamp-to-edge sampler from the corner-replicated brick: the set-up and blend of
+// image_view.h sampleLinear3D<WRAP_CLAMP> (same expressions, same operands), the eight texels from ONE 128-bit load. The entry
+// index clamp(x0 + 1, 0, w) addresses exactly the clamped pair (clamp(x0), clamp(x0 + 1)) for every x0.
+// SANITIZE = false: the caller guarantees finite coordinates with |u| <= 65536 (sanitizeCoord is the identity).
+template <bool SANITIZE>
+__device__ __forceinline__ float sampleCornerBrick(const TraceInst2& t, vec3 uvw) {
+    const float fx = fmaf_(SANITIZE ? sanitizeCoord(uvw.x) : uvw.x, t.dimsF.x, -0.5f);
+    const float fy = fmaf_(SANITIZE ? sanitizeCoord(uvw.y) : uvw.y, t.dimsF.y, -0.5f);
+    const float fz = fmaf_(SANITIZE ? sanitizeCoord(uvw.z) : uvw.z, t.dimsF.z, -0.5f);
+    const int ix = floor2i(fx), iy = floor2i(fy), iz = floor2i(fz);  // |f| < 2^31: == f2i(floorf_(f)), and (float)i == floorf_(f)
+    const float ax = fx - (float)ix, ay = fy - (float)iy, az = fz - (float)iz;
+    const float bx = 1.f - ax, by = 1.f - ay, bz = 1.f - az;
+    const int ex = iclamp(ix + 1, 0, t.dimX), ey = iclamp(iy + 1, 0, t.dimY), ez = iclamp(iz + 1, 0, t.sdf.d);
+    const uint4 c = __ldg(t.corners + (ez * t.strideZ + ey * t.strideY + ex));
+    const float a00 = halfToFloat((uint16_t)(c.x & 0xffffu)), a10 = halfToFloat((uint16_t)(c.x >> 16)), a01 = halfToFloat((uint16_t)(c.y & 0xffffu)), a11 = halfToFloat((uint16_t)(c.y >> 16));
+    const float b00 = halfToFloat((uint16_t)(c.z & 0xffffu)), b10 = halfToFloat((uint16_t)(c.z >> 16)), b01 = halfToFloat((uint16_t)(c.w & 0xffffu)), b11 = halfToFloat((uint16_t)(c.w >> 16));
+    const float w00 = bx * by, w10 = ax * by, w01 = bx * ay, w11 = ax * ay;
+    const float s0 = fmaf_(a11, w11, fmaf_(a01, w01, fmaf_(a10, w10, a00 * w00)));
+    const float s1 = fmaf_(b11, w11, fmaf_(b01, w01, fmaf_(b10, w10, b00 * w00)));
+    return fmaf_(s1, az, s0 * bz);
+}
+__device__ __forceinline__ bool finite3(vec3 a) { return absf(a.x) < 3.0e38f && absf(a.y) < 3.0e38f && absf(a.z) < 3.0e38f; }
+// One iteration of SDF.inc:144-183 for a lean instance: traceStep with the brick tap from the corner copy and no coordinate
+// sanitising. Valid while the march state is finite (checked by the caller after the set-up) and d stays finite; a non-finite
+// d raises `poisoned` and leaves tr untouched, and the caller redoes this (ray, instance) with the spelled-out functions.
+__device__ __forceinline__ bool traceStepLean(const TraceInst2& inst, int listIndex, TraceResult& tr, MarchState& st, bool& poisoned) {
+    if (st.k >= 128) return false;
+    const vec3 h = inst.localExtendsHalfPadded;
+    const vec3 pos = st.localSamplePos;
+    if (absf(pos.x) > h.x || absf(pos.y) > h.y || absf(pos.z) > h.z) return false;  // x > h || x < -h for a finite x
+    const vec3 sampleUV = pos * inst.invLocalExtends + 0.5f;
+    st.dLast = st.d;
+    const float d = sampleCornerBrick<false>(inst, sampleUV);
+    if (!(absf(d) < 3.0e38f)) { poisoned = true; return false; }
+    st.d = d;
+    if (d < inst.distanceThreshold) {
+        tr.hit = true;
+        const float distanceGlobal = st.hitDistanceLocal * inst.localToGlobalScale;
+        if (distanceGlobal < tr.closestHitDistance || (distanceGlobal == tr.closestHitDistance && listIndex < tr.winner)) {
+            tr.closestHitDistance = distanceGlobal;
+            tr.hitCount = st.k;
+            tr.winner = listIndex;
+            tr.winnerSamplePos = pos;
+            tr.winnerRayDirection = st.rayDirection;
+            tr.winnerD = d;
+            tr.winnerDLast = st.dLast;
+        }
+        return false;
+    }
+    st.localSamplePos = pos + st.rayDirection * absf(d);
+    st.hitDistanceLocal += absf(d);
+    st.k++;
+    return true;
+}
+// SDF.inc:101-184 for one (ray, instance) with every rule spelled out (coordinate sanitising, the plain brick): the path of
+// instances, rays and bricks with non-finite values. Out of line: rare.
+__device__ __noinline__ void traceInstanceSpelledOutImpl(const TraceInst2* inst, int listIndex, vec3 rayOrigin, vec3 L, TraceResult* tr) {
+    MarchState st;
+    if (!traceSetup(*inst, rayOrigin, L, *tr, st)) return;
+    while (traceStep(*inst, listIndex, *tr, st)) {}
+}
+// the caller's TraceResult stays in registers: only a copy has its address taken
+__device__ __forceinline__ void traceInstanceSpelledOut(const TraceInst2* inst, int listIndex, vec3 rayOrigin, vec3 L, TraceResult* tr) {
+    TraceResult copy = *tr;
+    traceInstanceSpelledOutImpl(inst, listIndex, rayOrigin, L, &copy);
+    *tr = copy;
+}
+// SDF.inc:165-176 for the hit that ended up closest (normal from six taps of the corner copy, sanitised like the sampler)
+__device__ __forceinline__ void shadeWinner2(const TraceInst2& inst, vec3 rayStartWorld, vec3 rayDirectionWorld, TraceResult& tr) {
+    const float d = tr.winnerD;
+    const float lastStepSizeLocal = d / (1.f - (d - tr.winnerDLast));
+    const vec3 hitSamplePos = tr.winnerSamplePos + tr.winnerRayDirection * lastStepSizeLocal;
+    const vec3 uv = hitSamplePos * inst.invLocalExtends + 0.5f;
+    vec3 N;
+    if (inst.corners) {  // normalFromSDF, SDF.inc:16-25
+        const vec3 extends = inst.localExtends;
+        const float extendsMax = fmaxp(extends.x, fmaxp(extends.y, extends.z));
+        const vec3 extendsNormalized = extends / extendsMax;
+        const vec3 epsilon = v3(0.15f) / v3((float)inst.sdf.w, (float)inst.sdf.h, (float)inst.sdf.d) / extendsNormalized;
+        N = normalize(v3(sampleCornerBrick<true>(inst, uv + v3(epsilon.x, 0, 0)) - sampleCornerBrick<true>(inst, uv - v3(epsilon.x, 0, 0)),
+                         sampleCornerBrick<true>(inst, uv + v3(0, epsilon.y, 0)) - sampleCornerBrick<true>(inst, uv - v3(0, epsilon.y, 0)),
+                         sampleCornerBrick<true>(inst, uv + v3(0, 0, epsilon.z)) - sampleCornerBrick<true>(inst, uv - v3(0, 0, epsilon.z))));
+    } else {
+        N = normalFromSDF(uv, inst.localExtends, inst.sdf);
+    }
+    const float* m = inst.worldToLocal;  // transpose(mat3(worldToLocal)) * N
+    tr.N = v3(m[0], m[4], m[8]) * N.x + v3(m[1], m[5], m[9]) * N.y + v3(m[2], m[6], m[10]) * N.z;
+    tr.albedo = inst.albedo;
+    const float lastStepSizeGlobal = lastStepSizeLocal * inst.localToGlobalScale;
+    tr.hitPos = rayStartWorld + rayDirectionWorld * (tr.closestHitDistance + lastStepSizeGlobal);
+}
+
+// State of a hit as its marching lane leaves it for the ray's own thread: what shadeWinner2 needs (SDF.inc:165-176)
+struct HitRecord {
+    vec3 samplePos, rayDirection;
+    float d, dLast;
+    int hitCount;
+};
+#define TRACE_PAIR_CAP 2560  // (ray, candidate) pairs of one batch of rays; a ray has at most 100
+#define TRACE_HIT_POOL 448   // hit records per block; a block that reports more re-marches the winners that did not get one
+#define TRACE_NO_SLOT 0xffffu
+
+// key of a ray's closest hit: distance bits << 32 | (list index + 1) << 16 | hit record slot. The distance of a hit is a non-negative
+// float, so unsigned order is numeric order; the minimum over the hits of a ray is the closest hit, a tie going to the instance
+// listed first - the rule of the reference's in-order loop (traceStep). The initial key (10000, nothing) loses against every
+// hit closer than 10000 and wins against one at exactly 10000, like `distanceGlobal < closestHitDistance`.
+__device__ __forceinline__ unsigned long long traceKey(float distance, int listIndex, uint32_t slot) {
+    return ((unsigned long long)dm::f2u(distance) << 32) | ((unsigned long long)(uint32_t)(listIndex + 1) << 16) | (unsigned long long)slot;
+}
+
+// Round-2 tracer. A block traces a 16x16-pixel region = 2x2 of the reference's 8x8 workgroups; all four lie in one 32x32
+// culling tile (:154), whose instance records are staged once in shared memory. Each 8x8 group keeps its own ray cache for
+// the 3x3 resolve (:70-116). Every invocation of a dispatched group traces, also those beyond the image edge.
 //
-// Scheduling inside a warp: rays hit different instances with very different step counts, so the per-instance
-// trace of the reference (SDF.inc:101-184) is split into states that one loop interleaves (steps 1-4 in the kernel).
-// Per (ray, instance) the operation sequence is exactly the reference's; across instances the result of a ray is the
-// closest hit with ties going to the instance listed first - what the reference's in-order loop computes - so it does
-// not depend on the order in which the instances are visited, and the kernel visits the nearest box first.
-__global__ void __launch_bounds__(256, 4) sdfDiffuseTraceKernel(const __grid_constant__ TraceParams p) {
-    __shared__ TraceInstance sInst[PLAIN_MAX_OBJECTS_PER_TILE];
-    __shared__ uint32_t sCount;
-    __shared__ float sRayNormal[4][8][8][3], sRayDepth[4][8][8], sRayColor[4][8][8][3];
+// Per (ray, instance) the operation sequence is exactly the reference's (SDF.inc:101-184); across instances the result of a ray
+// is the closest hit with ties going to the instance listed first - what the reference's in-order loop computes - so it does not
+// depend on the order in which the instances are visited, on which lane visits them, or on whether an instance whose box lies
+// behind the closest hit is visited at all (SDF.inc:141 only ever skips work that cannot win; round 1 established that). The
+// work is therefore cut for the machine instead of for the pixel (ncu of the per-pixel kernel: 9 box tests and 2.7 short
+// marches per ray, 9 of 32 lanes busy in a march step because a warp lives as long as its slowest ray):
+//   B  every thread generates its ray and its candidate mask (bounding-sphere test over the tile's list), all lanes in lockstep
+//   C  the (ray, candidate) pairs of the block are compacted into one list (block-wide prefix sum of the candidate counts)
+//   D  lanes take pairs from the list with an atomic counter: box test (SDF.inc:101-141, with the early-out against the ray's
+//      closest hit so far), then the march. The box tests and the march steps of a warp's lanes are batched by ballots; a lane
+//      whose pair misses its box or whose march ends takes the next pair, so a warp stays populated until the list is empty.
+//      A hit enters the ray's key with one 64-bit atomicMin; its state goes to a hit record for the shading
+//   F  every thread shades its own ray from the winning hit record (normal, albedo, shadow or sky), then the resolve
+// A march step reads its eight brick texels with one 128-bit load of the corner-replicated brick (TraceInst2).
+__global__ void __launch_bounds__(256, 3) sdfDiffuseTraceKernel(const __grid_constant__ TraceParams p) {
+    extern __shared__ __align__(16) unsigned char smemRaw[];
+    TraceInst2* sInst = (TraceInst2*)smemRaw;                                         // [PLAIN_MAX_OBJECTS_PER_TILE]
+    unsigned long long* sKey = (unsigned long long*)(sInst + PLAIN_MAX_OBJECTS_PER_TILE);  // [256] closest hit of every ray
+    HitRecord* sHitPool = (HitRecord*)(sKey + 256);                                   // [TRACE_HIT_POOL]
+    float* sRayO = (float*)(sHitPool + TRACE_HIT_POOL);                               // [256][3]
+    float* sRayL = sRayO + 256 * 3;                                                   // [256][3]
+    float* sRayNormal = sRayL + 256 * 3;                                              // [4][8][8][3]
+    float* sRayDepth = sRayNormal + 256 * 3;                                          // [4][8][8]
+    float* sRayColor = sRayDepth + 256;                                               // [4][8][8][3]
+    uint32_t* sIncl = (uint32_t*)(sRayColor + 256 * 3);                               // [256] inclusive prefix sums of the candidate counts
+    uint16_t* sPairs = (uint16_t*)(sIncl + 256);                                      // [TRACE_PAIR_CAP] ray << 8 | list index
+    uint8_t* sHit = (uint8_t*)(sPairs + TRACE_PAIR_CAP);                              // [256] tr.hit: an instance reported d < threshold, closest or not
+    __shared__ uint32_t sCount, sWarpTotals[8];
+    __shared__ int sNextPair, sHitCount;
+
     const plain_global_shader_info* g = p.g;
-    const int sub = threadIdx.x >> 6;                  // which of the 2x2 groups
-    const int lx = threadIdx.x & 7, ly = (threadIdx.x >> 3) & 7;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int sub = tid >> 6;                  // which of the 2x2 groups
+    const int lx = tid & 7, ly = (tid >> 3) & 7;
     const int blockRow = (int)blockIdx.y + p.blockRowOffset;
     const int gx = blockIdx.x * 2 + (sub & 1), gy = blockRow * 2 + (sub >> 1);
     const bool groupActive = gx < p.groupsX && gy < p.groupsY;
@@ -346,29 +516,43 @@ __global__ void __launch_bounds__(256, 4) sdfDiffuseTraceKernel(const __grid_con
     const int tileX = (blockIdx.x * 2) / 4, tileY = (blockRow * 2) / 4;
     const uint32_t tileIndex = tileIndexFromTileUV(tileX, tileY, g);
     const bool tileValid = (size_t)tileIndex < p.tileCapacity;
-    if (threadIdx.x == 0) sCount = tileValid ? min(p.tiles[tileIndex].objectCount, (uint32_t)PLAIN_MAX_OBJECTS_PER_TILE) : 0u;
+    if (tid == 0) { sCount = tileValid ? min(p.tiles[tileIndex].objectCount, (uint32_t)PLAIN_MAX_OBJECTS_PER_TILE) : 0u; sHitCount = 0; }
     __syncthreads();
     const uint32_t objectCount = sCount;
+    // ---- A: stage the tile's instances ----
     const plain_sdf_instance* instances = (const plain_sdf_instance*)(p.instanceBuffer + 16);
-    for (uint32_t i = threadIdx.x; i < objectCount; i += 256) {
+    for (uint32_t i = tid; i < objectCount; i += 256) {
         const plain_sdf_instance in = instances[p.tiles[tileIndex].indices[i]];
-        TraceInstance t;
-        for (int k = 0; k < 16; k++) t.worldToLocal[k] = in.worldToLocal[k];
+        TraceInst2 t;
+        bool finite = true;
+        for (int k = 0; k < 16; k++) { t.worldToLocal[k] = in.worldToLocal[k]; finite = finite && absf(in.worldToLocal[k]) < 3.0e38f; }
         t.localExtends = ld3(in.localExtends);
-        t.meanAlbedo = ld3(in.meanAlbedo);
-        t.sdf = p.bindless[in.sdfTextureIndex].view;
+        const BindlessEntry be = p.bindless[in.sdfTextureIndex];
+        t.sdf = be.view;
+        t.corners = (be.format == PLAIN_FORMAT_R16_SFLOAT) ? be.corners : nullptr;
         instanceBoundingSphere(t);
         t.localExtendsHalfPadded = t.localExtends * 0.5f + 0.01f;
         t.distanceThreshold = length(t.localExtends / v3((float)t.sdf.w, (float)t.sdf.h, (float)t.sdf.d)) * 0.25f;
         t.localToGlobalScale = 1.f / length(v3(t.worldToLocal[0], t.worldToLocal[1], t.worldToLocal[2]));
         t.invLocalExtends = 1.f / t.localExtends;
+        t.albedo = vpow(ld3(in.meanAlbedo), v3(2.2f));
+        t.dimsF = v3((float)t.sdf.w, (float)t.sdf.h, (float)t.sdf.d);
+        t.dimX = t.sdf.w; t.dimY = t.sdf.h;
+        t.strideY = t.sdf.w + 1; t.strideZ = (t.sdf.w + 1) * (t.sdf.h + 1);
+        // lean march: finite transform, extents in [1e-6, 1e6] (texture coordinates of a point inside the padded box stay below 65536),
+        // a corner copy of a brick with sane extents
+        const vec3 e = t.localExtends;
+        t.fastOk = finite && t.corners != nullptr && e.x >= 1e-6f && e.y >= 1e-6f && e.z >= 1e-6f && e.x <= 1e6f && e.y <= 1e6f && e.z <= 1e6f &&
+                   t.sdf.w >= 1 && t.sdf.h >= 1 && t.sdf.d >= 1 && t.sdf.w <= 4096 && t.sdf.h <= 4096 && t.sdf.d <= 4096 && absf(t.distanceThreshold) < 3.0e38f && absf(t.localToGlobalScale) < 3.0e38f;
         sInst[i] = t;
     }
     __syncthreads();
 
+    // ---- B: the thread's own ray and its candidate mask ----
     const Globals G = loadGlobals(g);
     const int ix = gx * 8 + lx, iy = gy * 8 + ly;
-    vec3 L = v3(0.f);
+    vec3 L = v3(0.f), rayOrigin = v3(0.f);
+    uint32_t cand[4] = {0u, 0u, 0u, 0u};
     if (groupActive) {  // uniform per warp: a group is two whole warps
         const vec2 uv = v2((float)ix, (float)iy) / v2((float)p.outYSH.w, (float)p.outYSH.h);
         const float depth = sampleNearest2D<WRAP_CLAMP, float>([&](int x, int y) { return loadD32(p.depthTexture, x, y); }, p.depthTexture.w, p.depthTexture.h, uv, 0.f);
@@ -381,23 +565,11 @@ __global__ void __launch_bounds__(256, 4) sdfDiffuseTraceKernel(const __grid_con
         const vec2 xi = sampleNearest2D<WRAP_REPEAT, vec2>([&](int x, int y) { return loadRG8(noiseTex, x, y); }, noiseTex.w, noiseTex.h, noiseUV, v2(0.f));
         const vec3 normalTexel = sampleNearest2D<WRAP_CLAMP, vec3>([&](int x, int y) { return loadRGBA8rgb(p.normalTexture, x, y); }, p.normalTexture.w, p.normalTexture.h, uv, v3(0.f));
         const vec3 N = normalTexel * 2.f - 1.f;
-        sRayNormal[sub][lx][ly][0] = N.x; sRayNormal[sub][lx][ly][1] = N.y; sRayNormal[sub][lx][ly][2] = N.z;
-        sRayDepth[sub][lx][ly] = depthLinear;
-        const vec3 rayOrigin = pWorld + N * 0.2f;
+        sRayNormal[tid * 3 + 0] = N.x; sRayNormal[tid * 3 + 1] = N.y; sRayNormal[tid * 3 + 2] = N.z;
+        sRayDepth[tid] = depthLinear;
+        rayOrigin = pWorld + N * 0.2f;
         L = importanceSampleCosine(xi, N);
-
-        TraceResult tr;
-        tr.hit = false;
-        tr.closestHitDistance = 10000.f;
-        tr.hitCount = 0;
-        tr.hitPos = v3(0.f); tr.N = v3(0.f); tr.albedo = v3(0.f);
-
-        tr.winner = -1;
-        tr.winnerSamplePos = v3(0.f); tr.winnerRayDirection = v3(0.f); tr.winnerD = 0.f; tr.winnerDLast = 0.f;
-
-        // 1. candidate mask, all lanes in lockstep over the tile's list
         const float invLen2 = 1.f / dot(L, L);
-        uint32_t cand[4];
 #pragma unroll
         for (int w = 0; w < 4; w++) {
             uint32_t m = 0u;
@@ -409,72 +581,143 @@ __global__ void __launch_bounds__(256, 4) sdfDiffuseTraceKernel(const __grid_con
             }
             cand[w] = m;
         }
-        uint32_t scan[4] = {cand[0], cand[1], cand[2], cand[3]};
-        auto popLowest = [](uint32_t (&m)[4]) -> int {  // lowest listed candidate, -1 when none is left
+    }
+    sRayO[tid * 3 + 0] = rayOrigin.x; sRayO[tid * 3 + 1] = rayOrigin.y; sRayO[tid * 3 + 2] = rayOrigin.z;
+    sRayL[tid * 3 + 0] = L.x; sRayL[tid * 3 + 1] = L.y; sRayL[tid * 3 + 2] = L.z;
+    sKey[tid] = (unsigned long long)dm::f2u(10000.f) << 32;  // closestHitDistance = 10000, no winner
+    sHit[tid] = 0;
+    // ---- C: block-wide inclusive prefix sum of the candidate counts ----
+    const uint32_t cnt = (uint32_t)(__popc(cand[0]) + __popc(cand[1]) + __popc(cand[2]) + __popc(cand[3]));
+    uint32_t incl = cnt;
 #pragma unroll
-            for (int w = 0; w < 4; w++)
-                if (m[w]) { const int b = __ffs(m[w]) - 1; m[w] &= m[w] - 1; return w * 32 + b; }
-            return -1;
-        };
-        auto clearBit = [](uint32_t (&m)[4], int idx) {
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+    if (lane == 31) sWarpTotals[warp] = incl;
+    __syncthreads();
+    {
+        uint32_t before = 0;
 #pragma unroll
-            for (int w = 0; w < 4; w++)
-                if (w == (idx >> 5)) m[w] &= ~(1u << (idx & 31));
-        };
-        // 2. SCAN: set-up (SDF.inc:101-141) of every candidate in list order; candidates whose box the ray misses are
-        //    dropped, the one with the nearest entry point is remembered together with its march state
-        // 3. the nearest candidate is marched first: once it has produced a hit, SDF.inc:141 (entry point beyond the
-        //    closest hit) rejects most of the others without a single step
-        // 4. the remaining candidates in list order: set-up again (with the early-out against the closest hit), march
-        // SET-UP and MARCH of different lanes are interleaved: a march step is the hot, convergent code; set-ups run
-        // when a quarter of the warp waits for one. Visiting order does not change the result: the closest hit wins, a
-        // tie goes to the instance listed first (traceStep), and an instance skipped by SDF.inc:141 could only have
-        // produced a hit farther away than the one that caused the skip.
-        int next = popLowest(scan), cur = 0;
-        bool scanning = true, marching = false;
-        float bestEntry = 3.402823466e+38f;
-        int bestIdx = -1;
-        MarchState st, bestSt;
-        st.localSamplePos = v3(0.f); st.rayDirection = v3(0.f); st.hitDistanceLocal = 0.f; st.d = 0.f; st.dLast = 0.f; st.k = 0;
-        bestSt = st;
-        if (next < 0) scanning = false;
-        while (true) {
-            const bool needSetup = !marching && next >= 0;
-            const unsigned marchMask = __ballot_sync(0xffffffffu, marching), setupMask = __ballot_sync(0xffffffffu, needSetup);
-            if ((marchMask | setupMask) == 0u) break;
-            const int nSetup = __popc(setupMask), nMarch = __popc(marchMask);
-            if (nSetup > 0 && (nMarch == 0 || nSetup >= 8 || nSetup >= nMarch)) {
-                if (needSetup) {
-                    cur = next;
-                    const bool ok = traceSetup(sInst[cur], rayOrigin, L, tr, st);
-                    if (scanning) {
-                        if (!ok) {
-                            clearBit(cand, cur);
+        for (int w = 0; w < 8; w++) if (w < warp) before += sWarpTotals[w];
+        incl += before;
+    }
+    sIncl[tid] = incl;
+    __syncthreads();
+
+    // ---- batches of rays whose pairs fit the list (one batch unless the tile is crowded) ----
+    int batchBegin = 0;            // first ray of the batch
+    uint32_t pairBase = 0;         // pairs of the rays before the batch
+    while (batchBegin < 256) {
+        // rays [batchBegin, batchEnd): the longest run whose pairs fit; the prefix sums are monotone, so it is a count
+        const bool fits = tid >= batchBegin && incl - pairBase <= (uint32_t)TRACE_PAIR_CAP;
+        const int batchEnd = batchBegin + __syncthreads_count(fits ? 1 : 0);
+        const int pairEnd = (int)(sIncl[batchEnd - 1] - pairBase);  // pairs in the batch (a single ray always fits: <= 100)
+        if (tid == 0) sNextPair = 0;
+        if (tid >= batchBegin && tid < batchEnd) {  // write this ray's pairs in list order
+            uint32_t at = incl - cnt - pairBase;
+#pragma unroll
+            for (int w = 0; w < 4; w++) {
+                uint32_t m = cand[w];
+                while (m) { const int b = __ffs(m) - 1; m &= m - 1; sPairs[at++] = (uint16_t)((tid << 8) | (w * 32 + b)); }
+            }
+        }
+        __syncthreads();
+        // ---- D: box tests and marches, lanes take pairs from the list ----
+        {
+            bool marching = false, done = false;
+            int ray = 0, cur = 0;
+            TraceResult tr;
+            tr.hit = false; tr.closestHitDistance = 10000.f; tr.hitCount = 0; tr.hitPos = v3(0.f); tr.N = v3(0.f); tr.albedo = v3(0.f);
+            tr.winner = -1; tr.winnerSamplePos = v3(0.f); tr.winnerRayDirection = v3(0.f); tr.winnerD = 0.f; tr.winnerDLast = 0.f;
+            MarchState st;
+            st.localSamplePos = v3(0.f); st.rayDirection = v3(0.f); st.hitDistanceLocal = 0.f; st.d = 0.f; st.dLast = 0.f; st.k = 0;
+            // a hit that replaced the closest hit this lane knew of: into the ray's key (the atomicMin decides whether it really is the closest)
+            auto recordHit = [&]() {
+                sHit[ray] = 1;
+                if (tr.winner != cur) return;  // d < threshold, but not closer than the closest hit known when the pair was taken
+                uint32_t slot = (uint32_t)atomicAdd(&sHitCount, 1);
+                if (slot < (uint32_t)TRACE_HIT_POOL) {
+                    HitRecord h;
+                    h.samplePos = tr.winnerSamplePos; h.rayDirection = tr.winnerRayDirection; h.d = tr.winnerD; h.dLast = tr.winnerDLast; h.hitCount = tr.hitCount;
+                    sHitPool[slot] = h;
+                } else {
+                    slot = TRACE_NO_SLOT;
+                }
+                atomicMin(&sKey[ray], traceKey(tr.closestHitDistance, cur, slot));
+            };
+            while (true) {
+                const unsigned marchMask = __ballot_sync(0xffffffffu, marching), idleMask = __ballot_sync(0xffffffffu, !marching && !done);
+                if ((marchMask | idleMask) == 0u) break;
+                const int nMarch = __popc(marchMask), nIdle = __popc(idleMask);
+                if (nIdle > 0 && (nMarch == 0 || nIdle >= 12 || nIdle >= nMarch)) {
+                    // BOX TEST of one pair per idle lane
+                    if (!marching && !done) {
+                        const int q = atomicAdd(&sNextPair, 1);
+                        if (q >= pairEnd) {
+                            done = true;
                         } else {
-                            const float entry = sInst[cur].localToGlobalScale * st.hitDistanceLocal;
-                            if (entry < bestEntry) { bestEntry = entry; bestIdx = cur; bestSt = st; }
-                        }
-                        next = popLowest(scan);
-                        if (next < 0) {  // scan complete: march the nearest candidate, then the others
-                            scanning = false;
-                            if (bestIdx >= 0) {
-                                clearBit(cand, bestIdx);
-                                cur = bestIdx;
-                                st = bestSt;
+                            const uint32_t pr = sPairs[q];
+                            ray = (int)(pr >> 8); cur = (int)(pr & 0xffu);
+                            const vec3 o = v3(sRayO[ray * 3], sRayO[ray * 3 + 1], sRayO[ray * 3 + 2]), dir = v3(sRayL[ray * 3], sRayL[ray * 3 + 1], sRayL[ray * 3 + 2]);
+                            const unsigned long long key = sKey[ray];  // the ray's closest hit so far (other lanes may be improving it: any value is a valid bound)
+                            tr.closestHitDistance = dm::u2f((uint32_t)(key >> 32));
+                            tr.winner = (int)((key >> 16) & 0xffffu) - 1;
+                            tr.hit = false;
+                            const TraceInst2& inst = sInst[cur];
+                            bool lean = inst.fastOk && finite3(o) && finite3(dir);
+                            bool enters = false;
+                            if (lean) {
+                                enters = traceSetup(inst, o, dir, tr, st);
+                                lean = !enters || (finite3(st.localSamplePos) && finite3(st.rayDirection) && absf(st.hitDistanceLocal) < 3.0e38f);
+                            }
+                            if (!lean) {  // non-finite values somewhere: the whole (ray, instance) with every rule spelled out
+                                traceInstanceSpelledOut(&inst, cur, o, dir, &tr);
+                                if (tr.hit) recordHit();
+                            } else if (enters) {
                                 marching = true;
                             }
-                            next = popLowest(cand);
                         }
-                    } else {
-                        marching = ok;
-                        next = popLowest(cand);
                     }
+                    continue;
                 }
-                continue;
+                if (marching) {
+                    bool poisoned = false;
+                    marching = traceStepLean(sInst[cur], cur, tr, st, poisoned);
+                    if (poisoned) {  // a non-finite brick value: the whole (ray, instance) again, spelled out (tr is untouched so far)
+                        const vec3 o = v3(sRayO[ray * 3], sRayO[ray * 3 + 1], sRayO[ray * 3 + 2]), dir = v3(sRayL[ray * 3], sRayL[ray * 3 + 1], sRayL[ray * 3 + 2]);
+                        traceInstanceSpelledOut(&sInst[cur], cur, o, dir, &tr);
+                    }
+                    if (!marching && tr.hit) recordHit();
+                }
             }
-            if (marching) marching = traceStep(sInst[cur], cur, tr, st);
         }
-        if (tr.winner >= 0) shadeWinner(sInst[tr.winner], rayOrigin, L, tr);
+        __syncthreads();
+        pairBase += (uint32_t)pairEnd;
+        batchBegin = batchEnd;
+    }
+
+    // ---- F: every thread shades its own ray ----
+    if (groupActive) {
+        const unsigned long long key = sKey[tid];
+        TraceResult tr;
+        tr.hit = sHit[tid] != 0;
+        tr.closestHitDistance = dm::u2f((uint32_t)(key >> 32));
+        tr.winner = (int)((key >> 16) & 0xffffu) - 1;
+        tr.hitCount = 0; tr.hitPos = v3(0.f); tr.N = v3(0.f); tr.albedo = v3(0.f);
+        tr.winnerSamplePos = v3(0.f); tr.winnerRayDirection = v3(0.f); tr.winnerD = 0.f; tr.winnerDLast = 0.f;
+        if (tr.winner >= 0) {
+            const uint32_t slot = (uint32_t)(key & 0xffffu);
+            if (slot != TRACE_NO_SLOT) {
+                const HitRecord h = sHitPool[slot];
+                tr.winnerSamplePos = h.samplePos; tr.winnerRayDirection = h.rayDirection; tr.winnerD = h.d; tr.winnerDLast = h.dLast; tr.hitCount = h.hitCount;
+            } else {  // the block ran out of hit records: march the winning pair again (same operations, same state)
+                TraceResult again;
+                again.hit = false; again.closestHitDistance = 10000.f; again.hitCount = 0; again.winner = -1;
+                again.hitPos = v3(0.f); again.N = v3(0.f); again.albedo = v3(0.f);
+                again.winnerSamplePos = v3(0.f); again.winnerRayDirection = v3(0.f); again.winnerD = 0.f; again.winnerDLast = 0.f;
+                traceInstanceSpelledOut(&sInst[tr.winner], tr.winner, rayOrigin, L, &again);
+                tr.winnerSamplePos = again.winnerSamplePos; tr.winnerRayDirection = again.winnerRayDirection; tr.winnerD = again.winnerD; tr.winnerDLast = again.winnerDLast; tr.hitCount = again.hitCount;
+            }
+            shadeWinner2(sInst[tr.winner], rayOrigin, L, tr);
+        }
         vec3 hitColor;
         if (tr.hit) {
             const float shadow = simpleShadow<true>(tr.hitPos, p.cascades->lightMatrices[p.shadowCascadeIndex], p.shadowMap);
@@ -487,29 +730,31 @@ __global__ void __launch_bounds__(256, 4) sdfDiffuseTraceKernel(const __grid_con
         } else {
             hitColor = sampleSkyLut(L, p.skyLut);
         }
-        sRayColor[sub][lx][ly][0] = hitColor.x; sRayColor[sub][lx][ly][1] = hitColor.y; sRayColor[sub][lx][ly][2] = hitColor.z;
+        sRayColor[tid * 3 + 0] = hitColor.x; sRayColor[tid * 3 + 1] = hitColor.y; sRayColor[tid * 3 + 2] = hitColor.z;
     }
     __syncthreads();
     if (!groupActive) return;
-    // resolveColor :70-116
+    // resolveColor :70-116 (ray caches indexed [sub][ly][lx] = thread id)
+    auto rayIdx = [&](int rx, int ry) { return sub * 64 + ry * 8 + rx; };
     float weightTotal = 1.f;
-    vec3 color = v3(sRayColor[sub][lx][ly][0], sRayColor[sub][lx][ly][1], sRayColor[sub][lx][ly][2]);
-    const vec3 myN = v3(sRayNormal[sub][lx][ly][0], sRayNormal[sub][lx][ly][1], sRayNormal[sub][lx][ly][2]);
-    const float myDepth = sRayDepth[sub][lx][ly];
+    vec3 color = v3(sRayColor[tid * 3], sRayColor[tid * 3 + 1], sRayColor[tid * 3 + 2]);
+    const vec3 myN = v3(sRayNormal[tid * 3], sRayNormal[tid * 3 + 1], sRayNormal[tid * 3 + 2]);
+    const float myDepth = sRayDepth[tid];
     for (int x = -1; x <= 1; x++) {
         for (int y = -1; y <= 1; y++) {
             if (x == 0 && y == 0) continue;
             const int rx = lx + x, ry = ly + y;
             const bool isValidIndex = rx > 0 && ry > 0 && rx < 8 && ry < 8;  // greaterThan(rayIndex, 0): row/column 0 never used (:88)
             if (!isValidIndex) continue;
-            const vec3 nN = v3(sRayNormal[sub][rx][ry][0], sRayNormal[sub][rx][ry][1], sRayNormal[sub][rx][ry][2]);
+            const int ri = rayIdx(rx, ry);
+            const vec3 nN = v3(sRayNormal[ri * 3], sRayNormal[ri * 3 + 1], sRayNormal[ri * 3 + 2]);
             const float NoN = clampf(dot(myN, nN), 0.f, 1.f);
             const bool normalsMatch = NoN > 0.9f;
-            const bool depthMatch = absf(myDepth - sRayDepth[sub][rx][ry]) < 0.5f;
+            const bool depthMatch = absf(myDepth - sRayDepth[ri]) < 0.5f;
             if (normalsMatch && depthMatch) {
                 const float weightX = x == 0 ? 1.f : 0.5f, weightY = y == 0 ? 1.f : 0.5f;
                 const float weight = weightX * weightY;
-                color = color + weight * v3(sRayColor[sub][rx][ry][0], sRayColor[sub][rx][ry][1], sRayColor[sub][rx][ry][2]);
+                color = color + weight * v3(sRayColor[ri * 3], sRayColor[ri * 3 + 1], sRayColor[ri * 3 + 2]);
                 weightTotal += weight;
             }
         }
@@ -522,6 +767,10 @@ __global__ void __launch_bounds__(256, 4) sdfDiffuseTraceKernel(const __grid_con
     result_CoCg = result_CoCg + v2(YCoCg.y, YCoCg.z);
     if (inRange(p.outYSH, ix, iy)) storeRGBA16F(p.outYSH, ix, iy, 0, result_Y_SH);
     if (inRange(p.outCoCg, ix, iy)) storeRG16F(p.outCoCg, ix, iy, result_CoCg);
+}
+static size_t traceSharedBytes() {
+    return sizeof(TraceInst2) * PLAIN_MAX_OBJECTS_PER_TILE + sizeof(unsigned long long) * 256 + sizeof(HitRecord) * TRACE_HIT_POOL + sizeof(float) * (256 * 3 * 4 + 256) +
+           sizeof(uint32_t) * 256 + sizeof(uint16_t) * TRACE_PAIR_CAP + 256;
 }
 PLAIN_PASS(launch_sdfDiffuseTrace, "sdfDiffuseTrace.comp") {
     TraceParams p;
@@ -552,7 +801,9 @@ PLAIN_PASS(launch_sdfDiffuseTrace, "sdfDiffuseTrace.comp") {
     if (y0 % 16 != 0) { c.fail("sdfDiffuseTrace.comp: row window must start at a multiple of 16 rows"); return; }
     if (y1 <= y0) return;
     p.blockRowOffset = y0 / 16;
-    PLAIN_LAUNCH(c, sdfDiffuseTraceKernel, dim3(ceilDiv(p.groupsX, 2), ceilDiv((unsigned)(y1 - y0), 16)), 256, 0, p);
+    const size_t smem = traceSharedBytes();  // above the 48 KB static limit: opt in (per device; a host-side attribute, not a stream operation)
+    if (cudaFuncSetAttribute(sdfDiffuseTraceKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { c.fail("sdfDiffuseTrace.comp: cannot reserve shared memory"); return; }
+    PLAIN_LAUNCH(c, sdfDiffuseTraceKernel, dim3(ceilDiv(p.groupsX, 2), ceilDiv((unsigned)(y1 - y0), 16)), 256, smem, p);
 }
 
 // ---------------- sdfDebugVisualisation.comp ----------------
