@@ -18,6 +18,18 @@ if [ ! -f "$OUT/libref_host.so" ] || [ "$HERE/ref/ref_host_shim.cpp" -nt "$OUT/l
         -o "$OUT/libref_host.so"
     echo "built $OUT/libref_host.so"
 fi
+# the reference's pure GLSL include files compiled as C++ from where they lie (oracle/ref/glsl_to_cpp.py adapts spelling only; its output
+# is a build product under _ref/glsl/, never committed) against the oracle's built-ins and image sampler: tests/test_oracle_vs_reference_glsl.py
+if [ -d "$REF/resources/shaders" ]; then
+    if [ ! -f "$OUT/libref_glsl.so" ] || [ "$HERE/ref/ref_glsl_shim.cpp" -nt "$OUT/libref_glsl.so" ] || [ "$HERE/ref/glsl_ref.h" -nt "$OUT/libref_glsl.so" ] || \
+       [ "$HERE/ref/glsl_to_cpp.py" -nt "$OUT/libref_glsl.so" ] || [ "$HERE/inc_eval.h" -nt "$OUT/libref_glsl.so" ] || [ "$HERE/glsl.h" -nt "$OUT/libref_glsl.so" ] || [ "$HERE/image.h" -nt "$OUT/libref_glsl.so" ]; then
+        python3 "$HERE/ref/glsl_to_cpp.py" "$REF/resources/shaders" "$OUT/glsl/reference_inc.h"
+        FMA=""; [ "$(uname -m)" = "x86_64" ] && FMA="-mfma"
+        g++ -std=c++17 -O2 -ffp-contract=off $FMA -fno-fast-math -shared -fPIC -fvisibility=hidden -w -I"$HERE" -I"$HERE/ref" -I"$OUT/glsl" -I"$HERE/../include" -I"$HERE/../plainrenderer_b200/csrc" \
+            "$HERE/ref/ref_glsl_shim.cpp" -o "$OUT/libref_glsl.so"
+        echo "built $OUT/libref_glsl.so"
+    fi
+fi
 [ -x "$OUT/PlainAssetPipeline" ] && [ "$OUT/PlainAssetPipeline" -nt "$HERE/build_ref.sh" ] && { echo "up to date: $OUT/PlainAssetPipeline"; exit 0; }
 # -include math.h / stdlib.h: libstdc++'s C++ wrappers pull the float overloads of abs/sin/cos/sqrt into the global namespace, as
 # MSVC's headers do for the reference's own build. Without them the unqualified abs(float) calls of SceneSDF.cpp resolve to

@@ -459,9 +459,37 @@ struct HitRecord {
     float d, dLast;
     int hitCount;
 };
-#define TRACE_PAIR_CAP 2560  // (ray, candidate) pairs of one batch of rays; a ray has at most 100
-#define TRACE_HIT_POOL 448   // hit records per block; a block that reports more re-marches the winners that did not get one
+#define TRACE_PAIR_CAP 2048  // (ray, candidate) pairs of one batch of rays; a ray has at most 100
+#define TRACE_HIT_POOL 256   // hit records per block; a block that reports more re-marches the winners that did not get one
+#define TRACE_QUEUE_CAP 768  // marches waiting for a lane (pairs whose ray enters the box), per batch; more are marched on the spot
 #define TRACE_NO_SLOT 0xffffu
+struct MarchJob {            // MarchState at the box entry (SDF.inc:101-141 done) + which pair it belongs to
+    vec3 pos, dir;
+    float hitDistanceLocal;
+    uint32_t pair;           // ray << 8 | list index
+};
+// Conservative ray / box rejection in the instance's local space, BEFORE the reference's own test (SDF.inc:104-126): slabs against
+// the box inflated by 0.1 % + 1 mm + 1e-5 of the origin's magnitude, unnormalised direction, approximate reciprocals. It can only
+// say "certainly misses": the reference's test accepts a ray that starts inside the box or whose face intersection lies on the
+// closed box, up to the rounding of a few operations on these same operands - far inside the inflation. A rejected pair would have
+// returned at SDF.inc:123 with no effect. (oL, dL are the operands traceSetup forms; the compiler shares them.)
+__device__ __forceinline__ bool boxCertainlyMissed(const float* m, vec3 halfExtents, vec3 o, vec3 dirWorld) {
+    const vec3 oL = xyz(mulm4(m, v4(o, 1.f)));
+    const vec3 eL = xyz(mulm4(m, v4(o + dirWorld, 1.f)));
+    const vec3 dL = eL - oL;
+    const float slack = 1e-3f + 1e-5f * (absf(oL.x) + absf(oL.y) + absf(oL.z));
+    const vec3 h = halfExtents * 1.001f + slack;
+    float ix, iy, iz;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(ix) : "f"(dL.x));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(iy) : "f"(dL.y));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(iz) : "f"(dL.z));
+    const float ax = (-h.x - oL.x) * ix, bx = (h.x - oL.x) * ix;
+    const float ay = (-h.y - oL.y) * iy, by = (h.y - oL.y) * iy;
+    const float az = (-h.z - oL.z) * iz, bz = (h.z - oL.z) * iz;
+    const float tNear = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz));  // fminf / fmaxf drop a NaN (0 * inf on a slab boundary)
+    const float tFar = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
+    return tFar < fmaxf(tNear, 0.f);
+}
 
 // key of a ray's closest hit: distance bits << 32 | (list index + 1) << 16 | hit record slot. The distance of a hit is a non-negative
 // float, so unsigned order is numeric order; the minimum over the hits of a ray is the closest hit, a tie going to the instance
@@ -483,10 +511,11 @@ __device__ __forceinline__ unsigned long long traceKey(float distance, int listI
 // marches per ray, 9 of 32 lanes busy in a march step because a warp lives as long as its slowest ray):
 //   B  every thread generates its ray and its candidate mask (bounding-sphere test over the tile's list), all lanes in lockstep
 //   C  the (ray, candidate) pairs of the block are compacted into one list (block-wide prefix sum of the candidate counts)
-//   D  lanes take pairs from the list with an atomic counter: box test (SDF.inc:101-141, with the early-out against the ray's
-//      closest hit so far), then the march. The box tests and the march steps of a warp's lanes are batched by ballots; a lane
-//      whose pair misses its box or whose march ends takes the next pair, so a warp stays populated until the list is empty.
-//      A hit enters the ray's key with one 64-bit atomicMin; its state goes to a hit record for the shading
+//   D1 the box test of every pair (SDF.inc:101-141 behind a conservative slab rejection) with all 256 threads busy, whatever the
+//      spread of candidates per ray; a pair whose ray enters its box leaves a march job (the local ray at the entry) in a queue
+//   D2 lanes take march jobs from the queue with an atomic counter; a lane whose march ends takes the next job, so a warp stays
+//      populated until the queue is empty. SDF.inc:141 is applied again when a job is taken (against the closest hit found
+//      meanwhile). A hit enters the ray's key with one 64-bit atomicMin; its state goes to a hit record for the shading
 //   F  every thread shades its own ray from the winning hit record (normal, albedo, shadow or sky), then the resolve
 // A march step reads its eight brick texels with one 128-bit load of the corner-replicated brick (TraceInst2).
 __global__ void __launch_bounds__(256, 3) sdfDiffuseTraceKernel(const __grid_constant__ TraceParams p) {
@@ -502,8 +531,9 @@ __global__ void __launch_bounds__(256, 3) sdfDiffuseTraceKernel(const __grid_con
     uint32_t* sIncl = (uint32_t*)(sRayColor + 256 * 3);                               // [256] inclusive prefix sums of the candidate counts
     uint16_t* sPairs = (uint16_t*)(sIncl + 256);                                      // [TRACE_PAIR_CAP] ray << 8 | list index
     uint8_t* sHit = (uint8_t*)(sPairs + TRACE_PAIR_CAP);                              // [256] tr.hit: an instance reported d < threshold, closest or not
+    MarchJob* sQueue = (MarchJob*)(sHit + 256);                                       // [TRACE_QUEUE_CAP] marches waiting for a lane
     __shared__ uint32_t sCount, sWarpTotals[8];
-    __shared__ int sNextPair, sHitCount;
+    __shared__ int sQueueCount, sQueueNext, sHitCount;
 
     const plain_global_shader_info* g = p.g;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -610,7 +640,7 @@ __global__ void __launch_bounds__(256, 3) sdfDiffuseTraceKernel(const __grid_con
         const bool fits = tid >= batchBegin && incl - pairBase <= (uint32_t)TRACE_PAIR_CAP;
         const int batchEnd = batchBegin + __syncthreads_count(fits ? 1 : 0);
         const int pairEnd = (int)(sIncl[batchEnd - 1] - pairBase);  // pairs in the batch (a single ray always fits: <= 100)
-        if (tid == 0) sNextPair = 0;
+        if (tid == 0) { sQueueCount = 0; sQueueNext = 0; }
         if (tid >= batchBegin && tid < batchEnd) {  // write this ray's pairs in list order
             uint32_t at = incl - cnt - pairBase;
 #pragma unroll
@@ -620,17 +650,13 @@ __global__ void __launch_bounds__(256, 3) sdfDiffuseTraceKernel(const __grid_con
             }
         }
         __syncthreads();
-        // ---- D: box tests and marches, lanes take pairs from the list ----
+        // ---- D1: the box test of every pair, all 256 threads busy whatever the spread of candidates per ray ----
         {
-            bool marching = false, done = false;
-            int ray = 0, cur = 0;
             TraceResult tr;
             tr.hit = false; tr.closestHitDistance = 10000.f; tr.hitCount = 0; tr.hitPos = v3(0.f); tr.N = v3(0.f); tr.albedo = v3(0.f);
             tr.winner = -1; tr.winnerSamplePos = v3(0.f); tr.winnerRayDirection = v3(0.f); tr.winnerD = 0.f; tr.winnerDLast = 0.f;
-            MarchState st;
-            st.localSamplePos = v3(0.f); st.rayDirection = v3(0.f); st.hitDistanceLocal = 0.f; st.d = 0.f; st.dLast = 0.f; st.k = 0;
             // a hit that replaced the closest hit this lane knew of: into the ray's key (the atomicMin decides whether it really is the closest)
-            auto recordHit = [&]() {
+            auto recordHit = [&](int ray, int cur) {
                 sHit[ray] = 1;
                 if (tr.winner != cur) return;  // d < threshold, but not closer than the closest hit known when the pair was taken
                 uint32_t slot = (uint32_t)atomicAdd(&sHitCount, 1);
@@ -643,35 +669,67 @@ __global__ void __launch_bounds__(256, 3) sdfDiffuseTraceKernel(const __grid_con
                 }
                 atomicMin(&sKey[ray], traceKey(tr.closestHitDistance, cur, slot));
             };
+            // the ray's closest hit so far (other lanes may be improving it: any value read is a valid bound for SDF.inc:141)
+            auto loadClosest = [&](int ray) {
+                const unsigned long long key = sKey[ray];
+                tr.closestHitDistance = dm::u2f((uint32_t)(key >> 32));
+                tr.winner = (int)((key >> 16) & 0xffffu) - 1;
+                tr.hit = false;
+            };
+            // a whole march on the spot: the spelled-out path of non-finite values, and lean marches that found the queue full
+            auto marchHere = [&](int ray, int cur, vec3 o, vec3 dir, bool lean, MarchState& st) {
+                if (lean) {
+                    bool poisoned = false;
+                    while (traceStepLean(sInst[cur], cur, tr, st, poisoned)) {}
+                    lean = !poisoned;
+                }
+                if (!lean) traceInstanceSpelledOut(&sInst[cur], cur, o, dir, &tr);
+                if (tr.hit) recordHit(ray, cur);
+            };
+            for (int q = tid; q < pairEnd; q += 256) {
+                const uint32_t pr = sPairs[q];
+                const int ray = (int)(pr >> 8), cur = (int)(pr & 0xffu);
+                const vec3 o = v3(sRayO[ray * 3], sRayO[ray * 3 + 1], sRayO[ray * 3 + 2]), dir = v3(sRayL[ray * 3], sRayL[ray * 3 + 1], sRayL[ray * 3 + 2]);
+                const TraceInst2& inst = sInst[cur];
+                const bool lean = inst.fastOk && finite3(o) && finite3(dir);
+                if (lean && boxCertainlyMissed(inst.worldToLocal, inst.localExtends * 0.5f, o, dir)) continue;
+                loadClosest(ray);
+                MarchState st;
+                if (!lean) { marchHere(ray, cur, o, dir, false, st); continue; }
+                if (!traceSetup(inst, o, dir, tr, st)) continue;
+                if (!(finite3(st.localSamplePos) && finite3(st.rayDirection) && absf(st.hitDistanceLocal) < 3.0e38f)) { marchHere(ray, cur, o, dir, false, st); continue; }
+                const int slot = atomicAdd(&sQueueCount, 1);
+                if (slot < TRACE_QUEUE_CAP) {
+                    MarchJob j;
+                    j.pos = st.localSamplePos; j.dir = st.rayDirection; j.hitDistanceLocal = st.hitDistanceLocal; j.pair = pr;
+                    sQueue[slot] = j;
+                } else {
+                    marchHere(ray, cur, o, dir, true, st);
+                }
+            }
+            __syncthreads();
+            // ---- D2: the marches, lanes take jobs from the queue; a lane whose march ends takes the next job ----
+            const int nJobs = min(sQueueCount, TRACE_QUEUE_CAP);
+            bool marching = false, done = false;
+            int ray = 0, cur = 0;
+            MarchState st;
+            st.localSamplePos = v3(0.f); st.rayDirection = v3(0.f); st.hitDistanceLocal = 0.f; st.d = 0.f; st.dLast = 0.f; st.k = 0;
             while (true) {
                 const unsigned marchMask = __ballot_sync(0xffffffffu, marching), idleMask = __ballot_sync(0xffffffffu, !marching && !done);
                 if ((marchMask | idleMask) == 0u) break;
                 const int nMarch = __popc(marchMask), nIdle = __popc(idleMask);
-                if (nIdle > 0 && (nMarch == 0 || nIdle >= 12 || nIdle >= nMarch)) {
-                    // BOX TEST of one pair per idle lane
-                    if (!marching && !done) {
-                        const int q = atomicAdd(&sNextPair, 1);
-                        if (q >= pairEnd) {
+                if (nIdle > 0 && (nMarch == 0 || nIdle >= 8 || nIdle * 3 >= nMarch)) {
+                    if (!marching && !done) {  // refill
+                        const int i = atomicAdd(&sQueueNext, 1);
+                        if (i >= nJobs) {
                             done = true;
                         } else {
-                            const uint32_t pr = sPairs[q];
-                            ray = (int)(pr >> 8); cur = (int)(pr & 0xffu);
-                            const vec3 o = v3(sRayO[ray * 3], sRayO[ray * 3 + 1], sRayO[ray * 3 + 2]), dir = v3(sRayL[ray * 3], sRayL[ray * 3 + 1], sRayL[ray * 3 + 2]);
-                            const unsigned long long key = sKey[ray];  // the ray's closest hit so far (other lanes may be improving it: any value is a valid bound)
-                            tr.closestHitDistance = dm::u2f((uint32_t)(key >> 32));
-                            tr.winner = (int)((key >> 16) & 0xffffu) - 1;
-                            tr.hit = false;
-                            const TraceInst2& inst = sInst[cur];
-                            bool lean = inst.fastOk && finite3(o) && finite3(dir);
-                            bool enters = false;
-                            if (lean) {
-                                enters = traceSetup(inst, o, dir, tr, st);
-                                lean = !enters || (finite3(st.localSamplePos) && finite3(st.rayDirection) && absf(st.hitDistanceLocal) < 3.0e38f);
-                            }
-                            if (!lean) {  // non-finite values somewhere: the whole (ray, instance) with every rule spelled out
-                                traceInstanceSpelledOut(&inst, cur, o, dir, &tr);
-                                if (tr.hit) recordHit();
-                            } else if (enters) {
+                            const MarchJob j = sQueue[i];
+                            ray = (int)(j.pair >> 8); cur = (int)(j.pair & 0xffu);
+                            loadClosest(ray);
+                            // SDF.inc:141 against the closest hit found since the box test (the same product, the same comparison)
+                            if (!(sInst[cur].localToGlobalScale * j.hitDistanceLocal > tr.closestHitDistance)) {
+                                st.localSamplePos = j.pos; st.rayDirection = j.dir; st.hitDistanceLocal = j.hitDistanceLocal; st.d = 0.f; st.dLast = 0.f; st.k = 0;
                                 marching = true;
                             }
                         }
@@ -685,7 +743,7 @@ __global__ void __launch_bounds__(256, 3) sdfDiffuseTraceKernel(const __grid_con
                         const vec3 o = v3(sRayO[ray * 3], sRayO[ray * 3 + 1], sRayO[ray * 3 + 2]), dir = v3(sRayL[ray * 3], sRayL[ray * 3 + 1], sRayL[ray * 3 + 2]);
                         traceInstanceSpelledOut(&sInst[cur], cur, o, dir, &tr);
                     }
-                    if (!marching && tr.hit) recordHit();
+                    if (!marching && tr.hit) recordHit(ray, cur);
                 }
             }
         }
@@ -770,7 +828,7 @@ __global__ void __launch_bounds__(256, 3) sdfDiffuseTraceKernel(const __grid_con
 }
 static size_t traceSharedBytes() {
     return sizeof(TraceInst2) * PLAIN_MAX_OBJECTS_PER_TILE + sizeof(unsigned long long) * 256 + sizeof(HitRecord) * TRACE_HIT_POOL + sizeof(float) * (256 * 3 * 4 + 256) +
-           sizeof(uint32_t) * 256 + sizeof(uint16_t) * TRACE_PAIR_CAP + 256;
+           sizeof(uint32_t) * 256 + sizeof(uint16_t) * TRACE_PAIR_CAP + 256 + sizeof(MarchJob) * TRACE_QUEUE_CAP;
 }
 PLAIN_PASS(launch_sdfDiffuseTrace, "sdfDiffuseTrace.comp") {
     TraceParams p;
