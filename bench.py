@@ -315,6 +315,7 @@ def run_ours(args, rank, world, local_rank):
                 if x is None:
                     break
                 comm.exchange(x)
+            comm.check_peer_error(blocking=False)  # every frame, no synchronisation: a barrier time-out aborts the run instead of being timed
             if timing_weight is not None:
                 collect_timings(timing_weight)  # the backend accumulates the timings of all segments of the frame
             if bytes_first_frame[0] is None:

@@ -295,6 +295,9 @@ PLAIN_EXPORT int PLAIN_FN(peer_barrier)(plain_ctx* ctx);
 PLAIN_EXPORT int PLAIN_FN(peer_allreduce_sum_u32)(plain_ctx* ctx, plain_handle storage_buffer, uint32_t count);
 /* non-zero once a barrier gave up waiting for a peer (about 2 s): the frame is invalid, the caller must abort */
 PLAIN_EXPORT int PLAIN_FN(peer_error)(plain_ctx* ctx, uint32_t* out_error);
+/* the same word without blocking: returns what the previous poll fetched and enqueues the next read-back (call it once per frame; the
+ * word is sticky, so a time-out is seen one frame later at the latest). peer_error (blocking) also clears the word once it reported it */
+PLAIN_EXPORT int PLAIN_FN(peer_error_poll)(plain_ctx* ctx, uint32_t* out_error);
 /* the stream all passes run on (cudaStream_t as void*), for callers that time with CUDA events */
 PLAIN_EXPORT int PLAIN_FN(get_stream)(plain_ctx* ctx, void** out_stream);
 

@@ -468,6 +468,7 @@ int PLAIN_FN(peer_push_rows)(plain_ctx* ctx, uint32_t, const plain_peer_push*) {
 int PLAIN_FN(peer_barrier)(plain_ctx* ctx) { return peerUnsupported(ctx); }
 int PLAIN_FN(peer_allreduce_sum_u32)(plain_ctx* ctx, plain_handle, uint32_t) { return peerUnsupported(ctx); }
 int PLAIN_FN(peer_error)(plain_ctx*, uint32_t* out_error) { *out_error = 0; return 0; }
+int PLAIN_FN(peer_error_poll)(plain_ctx*, uint32_t* out_error) { *out_error = 0; return 0; }
 int PLAIN_FN(set_concurrent_passes_enabled)(plain_ctx* ctx, int) { (void)ctx; return 0; }
 int PLAIN_FN(join_transfers)(plain_ctx* ctx) { (void)ctx; return 0; }
 int PLAIN_FN(get_stream)(plain_ctx* ctx, void** out_stream) { (void)ctx; *out_stream = nullptr; return 0; }

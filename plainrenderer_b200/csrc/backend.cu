@@ -11,6 +11,7 @@
 //     kernels read uniform/storage buffers through pointers, so only buffer contents differ between frames
 //   * there is no CPU fallback: every pass is a CUDA kernel looked up by the reference's shader file name; an unknown
 //     shader name or a missing device is an error
+#include <cstdlib>
 #include <cuda_runtime.h>
 #include <algorithm>
 #include <cstdio>
@@ -42,6 +43,7 @@ static const size_t kStagingBytes = 1u << 20;
 struct CachedGraph {
     cudaGraphExec_t exec = nullptr;
     uint32_t launches = 0;
+    uint64_t lastUse = 0;  // submission counter of the last replay (least recently used entries are evicted, kMaxCachedGraphs)
 };
 
 struct Backend {
@@ -104,6 +106,7 @@ struct Backend {
     bool stagingInFlight = false;
 
     BindlessEntry* bindlessDevice = nullptr;
+    uint32_t* peerErrorHost = nullptr;  // pinned mirror of the peer error word (peer_error_poll)
     ShadingTables* tablesDevice = nullptr;
     static const uint32_t kMaxBindless = 4096;
 
@@ -113,6 +116,8 @@ struct Backend {
 
     bool graphEnabled = false;
     std::unordered_map<uint64_t, CachedGraph> graphs;
+    static const size_t kMaxCachedGraphs = 32;
+    uint64_t graphUseCounter = 0;
     uint32_t passEpoch = 0;  // bumped when a pass description or an image allocation changes: invalidates cached graphs
     uint32_t lastFrameLaunches = 0;
     uint32_t launchCounter = 0;
@@ -593,6 +598,7 @@ void PLAIN_FN(backend_destroy)(plain_ctx* ctx) {
     cudaFree(b.stagingDevice);
     cudaFreeHost(b.stagingHost);
     cudaFree(b.bindlessDevice);
+    if (b.peerErrorHost) cudaFreeHost(b.peerErrorHost);
     cudaFree(b.tablesDevice);
     cudaEventDestroy(b.stagingConsumed);
     for (auto& e : b.submissionDone) cudaEventDestroy(e);
@@ -1002,8 +1008,16 @@ int PLAIN_FN(render_frame)(plain_ctx* ctx, int present) {
             ce = cudaGraphInstantiate(&cg.exec, graph, 0);
             cudaGraphDestroy(graph);
             if (ce != cudaSuccess) return fail(ctx, std::string("cudaGraphInstantiate failed: ") + cudaGetErrorString(ce));
+            // a frame-varying push constant or draw list makes a new key every frame: keep the cache bounded (evict the least recently used)
+            if (b.graphs.size() >= Backend::kMaxCachedGraphs) {
+                auto victim = b.graphs.begin();
+                for (auto g = b.graphs.begin(); g != b.graphs.end(); ++g) if (g->second.lastUse < victim->second.lastUse) victim = g;
+                if (victim->second.exec) cudaGraphExecDestroy(victim->second.exec);
+                b.graphs.erase(victim);
+            }
             it = b.graphs.emplace(key, cg).first;
         }
+        it->second.lastUse = ++b.graphUseCounter;
         CU_CHECK(ctx, cudaGraphLaunch(it->second.exec, b.stream));
         b.launchCounter = fillLaunches + it->second.launches;
     } else {
@@ -1219,7 +1233,10 @@ static int peerBarrier(plain_ctx* ctx) {
     }
     a.localError = b.peerSync[b.peerRank] + Backend::kPeerErrorOffset;
     a.rank = b.peerRank; a.count = b.peerCount; a.epoch = ++b.peerEpoch;
-    a.timeoutCycles = 4000000000ll;  // about 2 s
+    // a rank that is late on the host (first graph instantiation, lazy IPC mapping, CPU contention) must not trip the others: 20 s by
+    // default, PLAIN_PEER_TIMEOUT_MS to change it. A timeout sets the sticky error word; callers poll it every frame (peer_error_poll)
+    static const long long timeoutMs = getenv("PLAIN_PEER_TIMEOUT_MS") ? atoll(getenv("PLAIN_PEER_TIMEOUT_MS")) : 20000ll;
+    a.timeoutCycles = timeoutMs * 1900000ll;  // SM clock ~1.9 GHz
     peerBarrierKernel<<<1, 32, 0, b.stream>>>(a);
     b.launchCounter++;
     cudaError_t e = cudaPeekAtLastError();
@@ -1253,6 +1270,21 @@ int PLAIN_FN(peer_allreduce_sum_u32)(plain_ctx* ctx, plain_handle storage_buffer
     if (e != cudaSuccess) return fail(ctx, std::string("peer_allreduce_sum_u32: ") + cudaGetErrorString(e));
     return 0;
 }
+int PLAIN_FN(peer_error_poll)(plain_ctx* ctx, uint32_t* out_error) {
+    // non-blocking: returns the value the PREVIOUS poll fetched (the word is sticky, so a time-out shows up one poll later at the latest)
+    // and enqueues the next 4-byte read-back behind the work submitted so far
+    Backend& b = ctx->b;
+    cudaSetDevice(b.device);
+    *out_error = 0;
+    if (!b.peerCount) return 0;
+    if (!b.peerErrorHost) {
+        if (cudaHostAlloc((void**)&b.peerErrorHost, 4, cudaHostAllocDefault) != cudaSuccess) return fail(ctx, "peer_error_poll: cudaHostAlloc failed");
+        *b.peerErrorHost = 0;
+    }
+    *out_error = *(volatile uint32_t*)b.peerErrorHost;
+    CU_CHECK(ctx, cudaMemcpyAsync(b.peerErrorHost, b.peerSync[b.peerRank] + Backend::kPeerErrorOffset, 4, cudaMemcpyDeviceToHost, b.stream));
+    return 0;
+}
 int PLAIN_FN(peer_error)(plain_ctx* ctx, uint32_t* out_error) {
     Backend& b = ctx->b;
     cudaSetDevice(b.device);
@@ -1261,6 +1293,10 @@ int PLAIN_FN(peer_error)(plain_ctx* ctx, uint32_t* out_error) {
     drainTransfers(b);
     CU_CHECK(ctx, cudaMemcpyAsync(out_error, b.peerSync[b.peerRank] + Backend::kPeerErrorOffset, 4, cudaMemcpyDeviceToHost, b.stream));
     CU_CHECK(ctx, cudaStreamSynchronize(b.stream));
+    if (*out_error) {  // reported: clear the sticky word so that a caller that recovers (re-handshake, retry) starts clean
+        CU_CHECK(ctx, cudaMemsetAsync(b.peerSync[b.peerRank] + Backend::kPeerErrorOffset, 0, 4, b.stream));
+        if (b.peerErrorHost) *b.peerErrorHost = 0;
+    }
     return 0;
 }
 int PLAIN_FN(get_stream)(plain_ctx* ctx, void** out_stream) { *out_stream = (void*)ctx->b.stream; return 0; }

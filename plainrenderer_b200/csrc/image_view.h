@@ -223,8 +223,18 @@ template <int WRAP, typename T, typename F> PV_HD T sampleLinear2D(F fetch, int 
     const T t01 = (okx0 && oky1) ? fetch(x0, y1) : border, t11 = (okx1 && oky1) ? fetch(x1, y1) : border;
     return vfma(t11, b.w11, vfma(t01, b.w01, vfma(t10, b.w10, t00 * b.w00)));
 }
+// nearest texel of an UNSANITISED coordinate, for clamp-to-edge and border addressing only: the float -> int conversion saturates
+// and maps NaN to 0, so floor2i(u * size) lands on the same side of [0, size) as the sanitised coordinate does for |u| > 65536
+// (both far outside: the edge texel / the border) and on texel 0 for a NaN (sanitised: 0 * size = 0). Sizes are below 65536.
+// Repeat addressing takes the index modulo the size and keeps the sanitised form.
+PV_HD ivec2 nearestTexelUnsanitized(vec2 uv, int w, int h) {
+    ivec2 r;
+    r.x = floor2i(uv.x * (float)w);
+    r.y = floor2i(uv.y * (float)h);
+    return r;
+}
 template <int WRAP, typename T, typename F> PV_HD T sampleNearest2D(F fetch, int w, int h, vec2 uv, T border) {
-    ivec2 t = nearestTexel(uv, w, h);
+    ivec2 t = (WRAP == WRAP_REPEAT) ? nearestTexel(uv, w, h) : nearestTexelUnsanitized(uv, w, h);
     const bool ok = wrapIndex<WRAP>(t.x, w) & wrapIndex<WRAP>(t.y, h);
     return ok ? fetch(t.x, t.y) : border;
 }

@@ -1,6 +1,7 @@
 // passes_gi.cu - SDF instance culling, diffuse SDF sphere trace, spatial/temporal denoise, upscale.
 //   sdfCameraFrustumCulling.comp:36-62, sdfCameraTileCulling.comp:37-99, sdfDiffuseTrace.comp:70-207 + SDF.inc:12-184,
 //   filterIndirectDiffuseSpatial.comp:21-135, filterIndirectDiffuseTemporal.comp:20-86, indirectLightUpscale.comp:17-71
+#include <cstdlib>
 #include "shader_inc.cuh"
 
 namespace pb {
@@ -324,6 +325,7 @@ struct TraceParams {
     int strictInfluenceRadiusCutoff, shadowCascadeIndex;
     int groupsX, groupsY;
     int blockRowOffset;  // row sharding: first 16-row block row of this launch
+    int variant;         // scheduling experiments (PLAIN_TRACE_VARIANT): bit 0 compact the slab survivors, bit 1 slice long marches, bit 2 lazier refill
 };
 
 // ---- corner-replicated SDF bricks (BindlessEntry::corners) ----
@@ -459,9 +461,16 @@ struct HitRecord {
     float d, dLast;
     int hitCount;
 };
-#define TRACE_PAIR_CAP 2048  // (ray, candidate) pairs of one batch of rays; a ray has at most 100
-#define TRACE_HIT_POOL 256   // hit records per block; a block that reports more re-marches the winners that did not get one
-#define TRACE_QUEUE_CAP 768  // marches waiting for a lane (pairs whose ray enters the box), per batch; more are marched on the spot
+#define TRACE_PAIR_CAP 2560  // (ray, candidate) pairs of one batch of rays; a ray has at most 100
+#define TRACE_HIT_POOL 192   // hit records per block; a block that reports more re-marches the winners that did not get one
+#define TRACE_QUEUE_CAP 896  // marches waiting for a lane (pairs whose ray enters the box), per batch; more are marched on the spot
+#define TRACE_LONG_CAP 16    // marches parked between two slices (<= 256: the compaction uses one thread per slot); slicing is off by default
+struct LongMarch {           // a march parked between two slices: the whole MarchState
+    vec3 pos, dir;
+    float hitDistanceLocal, d, dLast;
+    int k;
+    uint32_t pair;
+};
 #define TRACE_NO_SLOT 0xffffu
 struct MarchJob {            // MarchState at the box entry (SDF.inc:101-141 done) + which pair it belongs to
     vec3 pos, dir;
@@ -527,13 +536,16 @@ __global__ void __launch_bounds__(256, 3) sdfDiffuseTraceKernel(const __grid_con
     float* sRayL = sRayO + 256 * 3;                                                   // [256][3]
     float* sRayNormal = sRayL + 256 * 3;                                              // [4][8][8][3]
     float* sRayDepth = sRayNormal + 256 * 3;                                          // [4][8][8]
-    float* sRayColor = sRayDepth + 256;                                               // [4][8][8][3]
-    uint32_t* sIncl = (uint32_t*)(sRayColor + 256 * 3);                               // [256] inclusive prefix sums of the candidate counts
+    uint32_t* sIncl = (uint32_t*)(sRayDepth + 256);                                   // [256] inclusive prefix sums of the candidate counts
     uint16_t* sPairs = (uint16_t*)(sIncl + 256);                                      // [TRACE_PAIR_CAP] ray << 8 | list index
     uint8_t* sHit = (uint8_t*)(sPairs + TRACE_PAIR_CAP);                              // [256] tr.hit: an instance reported d < threshold, closest or not
     MarchJob* sQueue = (MarchJob*)(sHit + 256);                                       // [TRACE_QUEUE_CAP] marches waiting for a lane
+    LongMarch* sLong = (LongMarch*)(sQueue + TRACE_QUEUE_CAP);                        // [TRACE_LONG_CAP] marches parked between two slices
+    uint8_t* sLongFlag = (uint8_t*)(sLong + TRACE_LONG_CAP);                          // [TRACE_LONG_CAP] the parked march is unfinished
+    uint8_t* sLongList = sLongFlag + TRACE_LONG_CAP;                                  // [TRACE_LONG_CAP] compacted slots of the next slice
+    float* sRayColor = (float*)sPairs;                                                // [4][8][8][3], phase F only: the pair list is dead by then
     __shared__ uint32_t sCount, sWarpTotals[8];
-    __shared__ int sQueueCount, sQueueNext, sHitCount;
+    __shared__ int sQueueCount, sQueueNext, sHitCount, sSurvivors, sLongCount;
 
     const plain_global_shader_info* g = p.g;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -640,7 +652,7 @@ __global__ void __launch_bounds__(256, 3) sdfDiffuseTraceKernel(const __grid_con
         const bool fits = tid >= batchBegin && incl - pairBase <= (uint32_t)TRACE_PAIR_CAP;
         const int batchEnd = batchBegin + __syncthreads_count(fits ? 1 : 0);
         const int pairEnd = (int)(sIncl[batchEnd - 1] - pairBase);  // pairs in the batch (a single ray always fits: <= 100)
-        if (tid == 0) { sQueueCount = 0; sQueueNext = 0; }
+        if (tid == 0) { sQueueCount = 0; sQueueNext = 0; sSurvivors = 0; sLongCount = 0; }
         if (tid >= batchBegin && tid < batchEnd) {  // write this ray's pairs in list order
             uint32_t at = incl - cnt - pairBase;
 #pragma unroll
@@ -650,7 +662,7 @@ __global__ void __launch_bounds__(256, 3) sdfDiffuseTraceKernel(const __grid_con
             }
         }
         __syncthreads();
-        // ---- D1: the box test of every pair, all 256 threads busy whatever the spread of candidates per ray ----
+        // ---- D1a: conservative slab rejection of every pair; the survivors are compacted in place (all 256 threads busy) ----
         {
             TraceResult tr;
             tr.hit = false; tr.closestHitDistance = 10000.f; tr.hitCount = 0; tr.hitPos = v3(0.f); tr.N = v3(0.f); tr.albedo = v3(0.f);
@@ -676,7 +688,7 @@ __global__ void __launch_bounds__(256, 3) sdfDiffuseTraceKernel(const __grid_con
                 tr.winner = (int)((key >> 16) & 0xffffu) - 1;
                 tr.hit = false;
             };
-            // a whole march on the spot: the spelled-out path of non-finite values, and lean marches that found the queue full
+            // a whole march on the spot: the spelled-out path of non-finite values, and lean marches that found a queue full
             auto marchHere = [&](int ray, int cur, vec3 o, vec3 dir, bool lean, MarchState& st) {
                 if (lean) {
                     bool poisoned = false;
@@ -686,18 +698,17 @@ __global__ void __launch_bounds__(256, 3) sdfDiffuseTraceKernel(const __grid_con
                 if (!lean) traceInstanceSpelledOut(&sInst[cur], cur, o, dir, &tr);
                 if (tr.hit) recordHit(ray, cur);
             };
-            for (int q = tid; q < pairEnd; q += 256) {
-                const uint32_t pr = sPairs[q];
+            // the reference's box test (SDF.inc:101-141) of one surviving pair; a ray that enters its box leaves a march job
+            auto exactBoxTest = [&](uint32_t pr) {
                 const int ray = (int)(pr >> 8), cur = (int)(pr & 0xffu);
                 const vec3 o = v3(sRayO[ray * 3], sRayO[ray * 3 + 1], sRayO[ray * 3 + 2]), dir = v3(sRayL[ray * 3], sRayL[ray * 3 + 1], sRayL[ray * 3 + 2]);
                 const TraceInst2& inst = sInst[cur];
                 const bool lean = inst.fastOk && finite3(o) && finite3(dir);
-                if (lean && boxCertainlyMissed(inst.worldToLocal, inst.localExtends * 0.5f, o, dir)) continue;
                 loadClosest(ray);
                 MarchState st;
-                if (!lean) { marchHere(ray, cur, o, dir, false, st); continue; }
-                if (!traceSetup(inst, o, dir, tr, st)) continue;
-                if (!(finite3(st.localSamplePos) && finite3(st.rayDirection) && absf(st.hitDistanceLocal) < 3.0e38f)) { marchHere(ray, cur, o, dir, false, st); continue; }
+                if (!lean) { marchHere(ray, cur, o, dir, false, st); return; }
+                if (!traceSetup(inst, o, dir, tr, st)) return;
+                if (!(finite3(st.localSamplePos) && finite3(st.rayDirection) && absf(st.hitDistanceLocal) < 3.0e38f)) { marchHere(ray, cur, o, dir, false, st); return; }
                 const int slot = atomicAdd(&sQueueCount, 1);
                 if (slot < TRACE_QUEUE_CAP) {
                     MarchJob j;
@@ -706,45 +717,113 @@ __global__ void __launch_bounds__(256, 3) sdfDiffuseTraceKernel(const __grid_con
                 } else {
                     marchHere(ray, cur, o, dir, true, st);
                 }
+            };
+            const bool compactSurvivors = (p.variant & 1) != 0;
+            for (int base = 0; base < pairEnd; base += 256) {  // uniform trip count: the ballots below need whole warps
+                const int q = base + tid;
+                uint32_t pr = 0;
+                bool keep = false;
+                if (q < pairEnd) {
+                    pr = sPairs[q];
+                    const int ray = (int)(pr >> 8), cur = (int)(pr & 0xffu);
+                    const vec3 o = v3(sRayO[ray * 3], sRayO[ray * 3 + 1], sRayO[ray * 3 + 2]), dir = v3(sRayL[ray * 3], sRayL[ray * 3 + 1], sRayL[ray * 3 + 2]);
+                    const TraceInst2& inst = sInst[cur];
+                    const bool lean = inst.fastOk && finite3(o) && finite3(dir);
+                    keep = !(lean && boxCertainlyMissed(inst.worldToLocal, inst.localExtends * 0.5f, o, dir));
+                }
+                if (!compactSurvivors) {  // the survivor's box test right away (fewer barriers, emptier warps)
+                    if (keep) exactBoxTest(pr);
+                    continue;
+                }
+                // survivors go to the front of the same list: position base' <= q, so a warp never overwrites a pair that is still unread
+                // (every thread reads its pair of this pass before the block-wide barrier, and writes after it)
+                const unsigned m = __ballot_sync(0xffffffffu, keep);
+                int at = 0;
+                if (lane == 0 && m) at = atomicAdd(&sSurvivors, __popc(m));
+                at = __shfl_sync(0xffffffffu, at, 0);
+                __syncthreads();
+                if (keep) sPairs[at + __popc(m & ((1u << lane) - 1u))] = (uint16_t)pr;
+            }
+            if (compactSurvivors) {
+                __syncthreads();
+                const int nSurvivors = sSurvivors;
+                for (int q = tid; q < nSurvivors; q += 256) exactBoxTest(sPairs[q]);
             }
             __syncthreads();
-            // ---- D2: the marches, lanes take jobs from the queue; a lane whose march ends takes the next job ----
-            const int nJobs = min(sQueueCount, TRACE_QUEUE_CAP);
-            bool marching = false, done = false;
-            int ray = 0, cur = 0;
-            MarchState st;
-            st.localSamplePos = v3(0.f); st.rayDirection = v3(0.f); st.hitDistanceLocal = 0.f; st.d = 0.f; st.dLast = 0.f; st.k = 0;
-            while (true) {
-                const unsigned marchMask = __ballot_sync(0xffffffffu, marching), idleMask = __ballot_sync(0xffffffffu, !marching && !done);
-                if ((marchMask | idleMask) == 0u) break;
-                const int nMarch = __popc(marchMask), nIdle = __popc(idleMask);
-                if (nIdle > 0 && (nMarch == 0 || nIdle >= 8 || nIdle * 3 >= nMarch)) {
-                    if (!marching && !done) {  // refill
-                        const int i = atomicAdd(&sQueueNext, 1);
-                        if (i >= nJobs) {
-                            done = true;
-                        } else {
-                            const MarchJob j = sQueue[i];
-                            ray = (int)(j.pair >> 8); cur = (int)(j.pair & 0xffu);
-                            loadClosest(ray);
-                            // SDF.inc:141 against the closest hit found since the box test (the same product, the same comparison)
-                            if (!(sInst[cur].localToGlobalScale * j.hitDistanceLocal > tr.closestHitDistance)) {
-                                st.localSamplePos = j.pos; st.rayDirection = j.dir; st.hitDistanceLocal = j.hitDistanceLocal; st.d = 0.f; st.dLast = 0.f; st.k = 0;
+            // ---- D2: the marches, in three slices of 8 / 24 / 96 steps (SDF.inc:144: at most 128). Lanes take jobs from a list with an
+            //      atomic counter; a lane whose march ends (or whose slice is used up) takes the next job, so a warp stays populated until the
+            //      list is empty. A march that outlives its slice is parked in sLong and re-compacted with the other long marches for the next
+            //      slice, instead of keeping a warp alive for one lane: ncu showed the rare 100-step marches costing as many issue slots as
+            //      all the short ones together ----
+            int nJobs = min(sQueueCount, TRACE_QUEUE_CAP);
+#pragma unroll 1
+            for (int round = 0; round < 3; round++) {
+                const int sliceEnd = (p.variant & 2) ? (round == 0 ? 8 : (round == 1 ? 32 : 128)) : 128;  // a march of this round stops when st.k reaches it
+                bool marching = false, done = false;
+                int ray = 0, cur = 0, slotLong = -1;
+                MarchState st;
+                st.localSamplePos = v3(0.f); st.rayDirection = v3(0.f); st.hitDistanceLocal = 0.f; st.d = 0.f; st.dLast = 0.f; st.k = 0;
+                while (true) {
+                    const unsigned marchMask = __ballot_sync(0xffffffffu, marching), idleMask = __ballot_sync(0xffffffffu, !marching && !done);
+                    if ((marchMask | idleMask) == 0u) break;
+                    const int nMarch = __popc(marchMask), nIdle = __popc(idleMask);
+                    if (nIdle > 0 && (nMarch == 0 || ((p.variant & 4) ? (nIdle >= 16 || nIdle >= nMarch) : (nIdle >= 8 || nIdle * 3 >= nMarch)))) {
+                        if (!marching && !done) {  // refill
+                            const int i = atomicAdd(&sQueueNext, 1);
+                            if (i >= nJobs) {
+                                done = true;
+                            } else if (round == 0) {
+                                const MarchJob j = sQueue[i];
+                                ray = (int)(j.pair >> 8); cur = (int)(j.pair & 0xffu);
+                                loadClosest(ray);
+                                // SDF.inc:141 against the closest hit found since the box test (the same product, the same comparison)
+                                if (!(sInst[cur].localToGlobalScale * j.hitDistanceLocal > tr.closestHitDistance)) {
+                                    st.localSamplePos = j.pos; st.rayDirection = j.dir; st.hitDistanceLocal = j.hitDistanceLocal; st.d = 0.f; st.dLast = 0.f; st.k = 0;
+                                    marching = true; slotLong = -1;
+                                }
+                            } else {
+                                slotLong = sLongList[i];
+                                const LongMarch j = sLong[slotLong];
+                                ray = (int)(j.pair >> 8); cur = (int)(j.pair & 0xffu);
+                                loadClosest(ray);
+                                st.localSamplePos = j.pos; st.rayDirection = j.dir; st.hitDistanceLocal = j.hitDistanceLocal; st.d = j.d; st.dLast = j.dLast; st.k = j.k;
                                 marching = true;
                             }
                         }
+                        continue;
                     }
-                    continue;
-                }
-                if (marching) {
-                    bool poisoned = false;
-                    marching = traceStepLean(sInst[cur], cur, tr, st, poisoned);
-                    if (poisoned) {  // a non-finite brick value: the whole (ray, instance) again, spelled out (tr is untouched so far)
-                        const vec3 o = v3(sRayO[ray * 3], sRayO[ray * 3 + 1], sRayO[ray * 3 + 2]), dir = v3(sRayL[ray * 3], sRayL[ray * 3 + 1], sRayL[ray * 3 + 2]);
-                        traceInstanceSpelledOut(&sInst[cur], cur, o, dir, &tr);
+                    if (marching) {
+                        bool poisoned = false;
+                        marching = traceStepLean(sInst[cur], cur, tr, st, poisoned);
+                        if (poisoned) {  // a non-finite brick value: the whole (ray, instance) again, spelled out (tr is untouched so far)
+                            const vec3 o = v3(sRayO[ray * 3], sRayO[ray * 3 + 1], sRayO[ray * 3 + 2]), dir = v3(sRayL[ray * 3], sRayL[ray * 3 + 1], sRayL[ray * 3 + 2]);
+                            traceInstanceSpelledOut(&sInst[cur], cur, o, dir, &tr);
+                        }
+                        if (!marching) {
+                            if (tr.hit) recordHit(ray, cur);
+                            if (slotLong >= 0) sLongFlag[slotLong] = 0;
+                        } else if (st.k >= sliceEnd) {  // the slice is used up: park the march (its own slot again if it already has one)
+                            if (slotLong < 0) { slotLong = atomicAdd(&sLongCount, 1); if (slotLong >= TRACE_LONG_CAP) slotLong = -1; }
+                            if (slotLong >= 0) {
+                                LongMarch j;
+                                j.pos = st.localSamplePos; j.dir = st.rayDirection; j.hitDistanceLocal = st.hitDistanceLocal; j.d = st.d; j.dLast = st.dLast; j.k = st.k;
+                                j.pair = (uint32_t)((ray << 8) | cur);
+                                sLong[slotLong] = j;
+                                sLongFlag[slotLong] = 1;
+                                marching = false;
+                            }  // no slot left: the lane keeps the march to its end
+                        }
                     }
-                    if (!marching && tr.hit) recordHit(ray, cur);
                 }
+                __syncthreads();
+                // the parked marches, compacted into the list of the next slice
+                if (tid == 0) { sQueueNext = 0; sSurvivors = 0; }
+                __syncthreads();
+                const int nLong = min(sLongCount, TRACE_LONG_CAP);
+                if (tid < nLong && sLongFlag[tid]) sLongList[atomicAdd(&sSurvivors, 1)] = (uint8_t)tid;
+                __syncthreads();
+                nJobs = sSurvivors;
+                if (nJobs == 0) break;
             }
         }
         __syncthreads();
@@ -827,8 +906,9 @@ __global__ void __launch_bounds__(256, 3) sdfDiffuseTraceKernel(const __grid_con
     if (inRange(p.outCoCg, ix, iy)) storeRG16F(p.outCoCg, ix, iy, result_CoCg);
 }
 static size_t traceSharedBytes() {
-    return sizeof(TraceInst2) * PLAIN_MAX_OBJECTS_PER_TILE + sizeof(unsigned long long) * 256 + sizeof(HitRecord) * TRACE_HIT_POOL + sizeof(float) * (256 * 3 * 4 + 256) +
-           sizeof(uint32_t) * 256 + sizeof(uint16_t) * TRACE_PAIR_CAP + 256 + sizeof(MarchJob) * TRACE_QUEUE_CAP;
+    static_assert(sizeof(uint16_t) * TRACE_PAIR_CAP >= sizeof(float) * 256 * 3, "the ray colours reuse the pair list");
+    return sizeof(TraceInst2) * PLAIN_MAX_OBJECTS_PER_TILE + sizeof(unsigned long long) * 256 + sizeof(HitRecord) * TRACE_HIT_POOL + sizeof(float) * (256 * 3 * 3 + 256) +
+           sizeof(uint32_t) * 256 + sizeof(uint16_t) * TRACE_PAIR_CAP + 256 + sizeof(MarchJob) * TRACE_QUEUE_CAP + sizeof(LongMarch) * TRACE_LONG_CAP + 2 * TRACE_LONG_CAP;
 }
 PLAIN_PASS(launch_sdfDiffuseTrace, "sdfDiffuseTrace.comp") {
     TraceParams p;
@@ -859,6 +939,9 @@ PLAIN_PASS(launch_sdfDiffuseTrace, "sdfDiffuseTrace.comp") {
     if (y0 % 16 != 0) { c.fail("sdfDiffuseTrace.comp: row window must start at a multiple of 16 rows"); return; }
     if (y1 <= y0) return;
     p.blockRowOffset = y0 / 16;
+    // default 1: survivors compacted, long marches not sliced (measured slower: profiles/r2_trace_variants.md), eager refill
+    static const int variant = getenv("PLAIN_TRACE_VARIANT") ? atoi(getenv("PLAIN_TRACE_VARIANT")) : 1;
+    p.variant = variant;
     const size_t smem = traceSharedBytes();  // above the 48 KB static limit: opt in (per device; a host-side attribute, not a stream operation)
     if (cudaFuncSetAttribute(sdfDiffuseTraceKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { c.fail("sdfDiffuseTrace.comp: cannot reserve shared memory"); return; }
     PLAIN_LAUNCH(c, sdfDiffuseTraceKernel, dim3(ceilDiv(p.groupsX, 2), ceilDiv((unsigned)(y1 - y0), 16)), 256, smem, p);

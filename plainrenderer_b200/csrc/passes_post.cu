@@ -2,6 +2,9 @@
 //   temporalFilter.comp:84-179 + temporalReprojection.inc:8-87 + bicubicSampling.inc:4-181;
 //   bloomDownsample.comp:12-50, bloomUpsample.comp:19-58, applyBloom.comp:16-31; tonemapping.comp:17-27
 #include <cmath>
+#include <cstdlib>
+#include <cuda.h>
+#include <cudaTypedefs.h>
 #include "shader_inc.cuh"
 #include "tile.cuh"
 
@@ -72,7 +75,7 @@ __global__ void __launch_bounds__(256) bloomDownsampleKernel(ImgView target, Img
     const int bx = blockIdx.x * 32, by = yBegin + blockIdx.y * 8;
     const int sx0 = (int)(((long long)bx * source.w) / target.w) - 3, sy0 = (int)(((long long)by * source.h) / target.h) - 3;
     const bool interior = tileIsInterior<TW, TH>(source, sx0, sy0);
-    if (interior) tileLoadR11<TW, TH, true>(sSrc, source, sx0, sy0);
+    if (interior) tileLoadR11<TW, TH, true, true>(sSrc, source, sx0, sy0);  // swizzled columns: neighbouring lanes read columns two apart
     else tileLoadR11<TW, TH, false>(sSrc, source, sx0, sy0);
     __syncthreads();
     const int ix = bx + (threadIdx.x & 31), iy = by + (threadIdx.x >> 5);
@@ -92,7 +95,12 @@ __global__ void __launch_bounds__(256) bloomDownsampleKernel(ImgView target, Img
     bool inside = true;
 #pragma unroll
     for (int k = 0; k < 5; k++) inside = inside && X[k].l0 < (unsigned)(TW - 1) && Y[k].l0 < (unsigned)(TH - 1);
-    if (!inside) { bloomDownsampleGeneric(target, source, sSrc, sx0, sy0, ix, iy); return; }  // cannot happen for 2:1 mip chains
+    if (!inside) {  // cannot happen for 2:1 mip chains; the swizzled tile is not what the generic taps expect: they read the image itself
+        bloomDownsampleGeneric(target, source, sSrc, source.w + TW, source.h + TH, ix, iy);  // a tile origin no texel can lie in
+        return;
+    }
+#pragma unroll
+    for (int k = 0; k < 5; k++) { X[k].l0 = tileSwizzle<TW>(X[k].l0); X[k].l1 = tileSwizzle<TW>(X[k].l1); }
     vec3 color = v3(0.f);
     auto T = [&](int kx, int ky) { return tapR11TileInside(tile, X[kx], Y[ky]); };
     color = color + T(0, 0) * 0.125f;
@@ -101,6 +109,98 @@ __global__ void __launch_bounds__(256) bloomDownsampleKernel(ImgView target, Img
     color = color + T(3, 3) * 0.03125f; color = color + T(3, 4) * 0.03125f; color = color + T(4, 3) * 0.03125f; color = color + T(4, 4) * 0.03125f;
     storeR11(target, ix, iy, color);
 }
+// ---- the same pass with the source tile staged by TMA (the default when the source rows are 16-byte multiples; PLAIN_BLOOM_TMA=0
+//      selects the plain loader; A / B in profiles/r2_tma_ab.md) ----
+// One elected thread issues cp.async.bulk.tensor.2d for the RAW packed tile (72 x 24 texels x 4 bytes; texels outside the image are
+// zero-filled by the descriptor, which decode to (0, 0, 0) like the loader's) and the block waits on an mbarrier; a second pass decodes
+// shared -> shared into the float4 tile the taps read. Against the plain loader it trades the per-texel address arithmetic, bounds
+// tests and LDG for an LDS + one more block-wide hand-over.
+__device__ __forceinline__ uint32_t smemAddr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+#define BLOOM_DOWN_TMA_TW 76  // the TMA box starts at a multiple of 4 texels (16-byte aligned innermost coordinate): up to 3 more columns on the left
+__global__ void __launch_bounds__(256) bloomDownsampleTmaKernel(const __grid_constant__ CUtensorMap sourceMap, ImgView target, ImgView source, int yBegin, int yEnd) {
+    constexpr int TW = BLOOM_DOWN_TMA_TW, TH = BLOOM_DOWN_TH;
+    __shared__ __align__(128) uint32_t sRaw[TW * TH];
+    __shared__ float4 sSrc[TW * TH];
+    __shared__ __align__(8) unsigned long long sBar;
+    const int bx = blockIdx.x * 32, by = yBegin + blockIdx.y * 8;
+    // the innermost box coordinate must be a multiple of 16 bytes (a box at x = 125 or x = -3 faults with "illegal instruction",
+    // tools/microbench/tma_probe.cu); negative and overflowing coordinates are fine: those texels arrive as zeros
+    const int sx0 = ((int)(((long long)bx * source.w) / target.w) - 3) & ~3, sy0 = (int)(((long long)by * source.h) / target.h) - 3;
+    const bool interior = tileIsInterior<TW, TH>(source, sx0, sy0);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smemAddr(&sBar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smemAddr(&sBar)), "r"((uint32_t)(TW * TH * 4)) : "memory");
+        asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                     ::"r"(smemAddr(sRaw)), "l"(&sourceMap), "r"(sx0), "r"(sy0), "r"(smemAddr(&sBar)) : "memory");
+    }
+    {   // every thread waits for the bytes to land (phase 0 of the barrier)
+        uint32_t done = 0, spins = 0;
+        while (!done) {
+            if (++spins > (1u << 22)) __trap();  // a descriptor fault must end the kernel, not hang the GPU
+            asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(done) : "r"(smemAddr(&sBar)) : "memory");
+        }
+    }
+    // decode shared -> shared (swizzled columns in interior blocks, like the plain loader)
+    for (int i = threadIdx.x; i < TW * TH; i += 256) {
+        const int tx = i % TW, ty = i / TW;
+        sSrc[ty * TW + (interior ? (int)tileSwizzle<TW>((unsigned)tx) : tx)] = decodeR11Texel(sRaw[i]);
+    }
+    __syncthreads();
+    const int ix = bx + (threadIdx.x & 31), iy = by + (threadIdx.x >> 5);
+    if (ix >= target.w || iy >= yEnd) return;
+    const TileR11<TW, TH> tile{sSrc, sx0, sy0};
+    const vec2 uv = (v2((float)ix, (float)iy) + 0.5f) / v2((float)target.w, (float)target.h);
+    const vec2 texelSize = 1.f / v2((float)source.w, (float)source.h);
+    if (!interior) {  // the spelled-out taps on the (unswizzled) tile, global loads for anything outside it
+        vec3 color = v3(0.f);
+        auto T = [&](float ox, float oy) { return sampleR11LinearClampTile(tile, source, uv + texelSize * v2(ox, oy)); };
+        color = color + sampleR11LinearClampTile(tile, source, uv) * 0.125f;
+        color = color + T(0.5f, 0.5f) * 0.125f; color = color + T(0.5f, -0.5f) * 0.125f; color = color + T(-0.5f, 0.5f) * 0.125f; color = color + T(-0.5f, -0.5f) * 0.125f;
+        color = color + T(1.5f, 0.f) * 0.0625f; color = color + T(-1.5f, 0.f) * 0.0625f; color = color + T(0.f, 1.5f) * 0.0625f; color = color + T(0.f, -1.5f) * 0.0625f;
+        color = color + T(1.5f, 1.5f) * 0.03125f; color = color + T(1.5f, -1.5f) * 0.03125f; color = color + T(-1.5f, 1.5f) * 0.03125f; color = color + T(-1.5f, -1.5f) * 0.03125f;
+        storeR11(target, ix, iy, color);
+        return;
+    }
+    AxisTap X[5], Y[5];
+    const float off[5] = {0.f, 0.5f, -0.5f, 1.5f, -1.5f};
+#pragma unroll
+    for (int k = 0; k < 5; k++) {
+        X[k] = axisTapT<false, true>(k == 0 ? uv.x : uv.x + texelSize.x * off[k], source.w, sx0);
+        Y[k] = axisTapT<false, true>(k == 0 ? uv.y : uv.y + texelSize.y * off[k], source.h, sy0);
+    }
+    bool inside = true;
+#pragma unroll
+    for (int k = 0; k < 5; k++) inside = inside && X[k].l0 < (unsigned)(TW - 1) && Y[k].l0 < (unsigned)(TH - 1);
+    if (!inside) { bloomDownsampleGeneric(target, source, nullptr, source.w + TW, source.h + TH, ix, iy); return; }  // taps from the image itself
+#pragma unroll
+    for (int k = 0; k < 5; k++) { X[k].l0 = tileSwizzle<TW>(X[k].l0); X[k].l1 = tileSwizzle<TW>(X[k].l1); }
+    vec3 color = v3(0.f);
+    auto T = [&](int kx, int ky) { return tapR11TileInside(tile, X[kx], Y[ky]); };
+    color = color + T(0, 0) * 0.125f;
+    color = color + T(1, 1) * 0.125f; color = color + T(1, 2) * 0.125f; color = color + T(2, 1) * 0.125f; color = color + T(2, 2) * 0.125f;
+    color = color + T(3, 0) * 0.0625f; color = color + T(4, 0) * 0.0625f; color = color + T(0, 3) * 0.0625f; color = color + T(0, 4) * 0.0625f;
+    color = color + T(3, 3) * 0.03125f; color = color + T(3, 4) * 0.03125f; color = color + T(4, 3) * 0.03125f; color = color + T(4, 4) * 0.03125f;
+    storeR11(target, ix, iy, color);
+}
+// 2-D tensor map of one R11G11B10 mip level (32-bit texels, tightly packed rows), box = the staged tile, out-of-image texels zero
+static bool makeTileTensorMap(CUtensorMap* map, const ImgView& img, int boxW, int boxH) {
+    static PFN_cuTensorMapEncodeTiled encode = nullptr;
+    if (!encode) {
+        cudaDriverEntryPointQueryResult q;
+        void* fn = nullptr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess || !fn) return false;
+        encode = (PFN_cuTensorMapEncodeTiled)fn;
+    }
+    const cuuint64_t dims[2] = {(cuuint64_t)img.w, (cuuint64_t)img.h};
+    const cuuint64_t strides[1] = {(cuuint64_t)img.w * 4};  // bytes, dimension 1 (must be a multiple of 16)
+    const cuuint32_t box[2] = {(cuuint32_t)boxW, (cuuint32_t)boxH}, elemStrides[2] = {1, 1};
+    return encode(map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, img.ptr, dims, strides, box, elemStrides, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
 PLAIN_PASS(launch_bloomDownsample, "bloomDownsample.comp") {
     const ImgView target = c.storage(0, PLAIN_FORMAT_R11G11B10_UFLOAT), source = c.sampled(1, PLAIN_FORMAT_R11G11B10_UFLOAT);
     if (c.failed) return;
@@ -108,7 +208,16 @@ PLAIN_PASS(launch_bloomDownsample, "bloomDownsample.comp") {
     int y0, y1;
     c.window(target.h, y0, y1);
     if (y1 <= y0) return;
-    PLAIN_LAUNCH(c, bloomDownsampleKernel, dim3(ceilDiv(target.w, 32), ceilDiv((unsigned)(y1 - y0), 8)), 256, 0, target, source, y0, y1);
+    const dim3 grid(ceilDiv(target.w, 32), ceilDiv((unsigned)(y1 - y0), 8));
+    static const bool useTma = !getenv("PLAIN_BLOOM_TMA") || atoi(getenv("PLAIN_BLOOM_TMA")) != 0;  // on by default: 3.7 % faster at 4K (profiles/r2_tma_ab.md)
+    if (useTma && (source.w % 4) == 0 && ((uintptr_t)source.ptr % 16) == 0 && source.w >= BLOOM_DOWN_TW / 4) {
+        CUtensorMap map;
+        if (makeTileTensorMap(&map, source, BLOOM_DOWN_TMA_TW, BLOOM_DOWN_TH)) {
+            PLAIN_LAUNCH(c, bloomDownsampleTmaKernel, grid, 256, 0, map, target, source, y0, y1);
+            return;
+        }
+    }
+    PLAIN_LAUNCH(c, bloomDownsampleKernel, grid, 256, 0, target, source, y0, y1);
 }
 
 // bloomUpsample.comp: 9-tap tent of the coarser downsample mip (+ 4-tap box of the coarser upsample mip)
@@ -132,7 +241,7 @@ __device__ __noinline__ void bloomUpsampleGeneric(ImgView target, ImgView target
     }
     storeR11(target, ix, iy, color);
 }
-__global__ void __launch_bounds__(256) bloomUpsampleKernel(ImgView target, ImgView targetPreviousMip, ImgView source, int isLowestMip, float blurRadius, int fastAllowed, int yBegin, int yEnd) {
+__global__ void __launch_bounds__(256, 4) bloomUpsampleKernel(ImgView target, ImgView targetPreviousMip, ImgView source, int isLowestMip, float blurRadius, int fastAllowed, int yBegin, int yEnd) {
     constexpr int TW = BLOOM_UP_TW, TH = BLOOM_UP_TH;
     __shared__ float4 sSrc[TW * TH], sPrev[TW * TH];
     const int bx = blockIdx.x * 32, by = yBegin + blockIdx.y * 8;
@@ -451,7 +560,7 @@ __device__ __noinline__ void temporalFilterPixelGeneric(const TaaParams& p, cons
     temporalFilterPixel<TONEMAP, TECH, false>(p, sCur, sHis, sRw);
 }
 template <bool TONEMAP, int TECH>
-__global__ void __launch_bounds__(256, 3) temporalFilterKernel(const __grid_constant__ TaaParams p) {
+__global__ void __launch_bounds__(256, 4) temporalFilterKernel(const __grid_constant__ TaaParams p) {
     __shared__ float4 sCur[TAA_CUR_W * TAA_CUR_H];
     __shared__ float4 sHis[TAA_HIS_W * TAA_HIS_H];
     __shared__ float sRw[9];

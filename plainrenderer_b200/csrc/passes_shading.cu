@@ -99,14 +99,24 @@ __device__ __forceinline__ float calcShadow(const ImgView& shadowMap, const floa
     const vec2 offsetScale = PB_SHADOW_SAMPLE_RADIUS * lightSpaceScale;
     float shadow = 0.f;
     const float sampleCount = 12.f;
+    // shadowTest (:84-87) compares actualDepth with the D16 texel decoded as float(code) / 65535. The decode is monotonic in the code, so
+    // the twelve comparisons are integer comparisons against ONE threshold: the largest code whose decoded value does not exceed
+    // actualDepth (found among three candidates with the same IEEE division: truncation of actualDepth * 65535 is off by at most one).
+    // actualDepth is in [0, 1] (a NaN was clamped to 0), so the black border (0) always passes.
+    const int c0 = (int)(actualDepth * 65535.f);
+    const int c1 = imin(c0 + 1, 65535);
+    const int codeMax = ((float)c1 / 65535.f <= actualDepth) ? c1 : (((float)c0 / 65535.f <= actualDepth) ? c0 : c0 - 1);
+    const uint16_t* texels = (const uint16_t*)shadowMap.ptr;
 #pragma unroll
     for (int i = 0; i < 12; i++) {
         const float4 e = __ldg(pcfRow + i);  // {cos(angle), sin(angle), sqrt(d)}
         vec2 offset = v2(e.x, e.y);
         offset = offset * (offsetScale * e.z);
         const vec2 samplePosition = plsXY + offset;
-        const float depthTexel = sampleNearest2D<WRAP_BORDER, float>([&](int x, int y) { return loadD16(shadowMap, x, y); }, shadowMap.w, shadowMap.h, samplePosition, 0.f);
-        shadow += (actualDepth >= depthTexel) ? 1.f : 0.f;  // shadowTest :84-87
+        const ivec2 t = nearestTexelUnsanitized(samplePosition, shadowMap.w, shadowMap.h);  // nearest + border sampler (image_view.h)
+        const bool inside = (unsigned)t.x < (unsigned)shadowMap.w && (unsigned)t.y < (unsigned)shadowMap.h;
+        const bool lit = inside ? ((int)ldg(texels + t.y * shadowMap.w + t.x) <= codeMax) : true;
+        shadow += lit ? 1.f : 0.f;
     }
     return shadow / sampleCount;
 }
@@ -273,7 +283,7 @@ __device__ __forceinline__ vec3 shadeSky(const ShadingParams& p, int x, int y, v
 }
 
 template <int DIFFUSE, int MULTI, int GEOAA, int TECH>
-__global__ void __launch_bounds__(256) gbufferShadingKernel(const __grid_constant__ ShadingParams p, int limitX, int limitY, int y0) {
+__global__ void __launch_bounds__(256, 4) gbufferShadingKernel(const __grid_constant__ ShadingParams p, int limitX, int limitY, int y0) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int x = blockIdx.x * 32 + (warp & 1) * 16 + (lane & 15);
     const int y = y0 + blockIdx.y * 8 + (warp >> 1) * 2 + (lane >> 4);  // y0: first row of the launch (even; row sharding)

@@ -37,8 +37,13 @@ __device__ __forceinline__ bool r11TexelIsSpecial(uint32_t v) {
 // Thread t owns column t % TW of rows t / TW, t / TW + 256 / TW, ...: one division per tile instead of one per texel, constant
 // strides from row to row. INTERIOR: the rectangle lies inside the image (no bounds tests). Returns whether one of the texels
 // this thread staged holds an inf / NaN channel.
-template <int TW, int TH, bool INTERIOR = false>
+// SWIZZLE: a row stores its even columns first, then its odd columns (tileSwizzle). A 2:1 downsampling stencil reads columns two
+// apart in neighbouring lanes: with the plain layout a quarter warp's 128-bit reads hit every bank twice, with this one they are
+// consecutive. The taps must then address columns through tileSwizzle too.
+template <int TW> __device__ __forceinline__ unsigned tileSwizzle(unsigned column) { return (column >> 1) + (column & 1u) * (unsigned)(TW / 2); }
+template <int TW, int TH, bool INTERIOR = false, bool SWIZZLE = false>
 __device__ __forceinline__ bool tileLoadR11(float4* smem, const ImgView& img, int x0, int y0) {
+    static_assert(!SWIZZLE || (TW % 2) == 0, "swizzled tiles have an even width");
     constexpr int RPP = 256 / TW;  // rows per pass
     static_assert(RPP >= 1, "tile wider than the block");
     const int tx = (int)threadIdx.x % TW, tyBase = (int)threadIdx.x / TW;
@@ -47,7 +52,7 @@ __device__ __forceinline__ bool tileLoadR11(float4* smem, const ImgView& img, in
         const int ax = x0 + tx;
         const bool colOk = INTERIOR || (ax >= 0 && ax < img.w);
         const uint32_t* src = (const uint32_t*)img.ptr + (y0 + tyBase) * img.w + ax;
-        float4* dst = smem + tyBase * TW + tx;
+        float4* dst = smem + tyBase * TW + (SWIZZLE ? (int)tileSwizzle<TW>((unsigned)tx) : tx);
 #pragma unroll
         for (int r = 0; r < (TH + RPP - 1) / RPP; r++) {
             const int ty = tyBase + r * RPP;

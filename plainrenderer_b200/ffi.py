@@ -167,7 +167,7 @@ BACKEND_SYMBOLS = [
     "write_image_async", "read_image_async", "write_image_rows_async", "read_image_rows_async", "get_image_device_pointer", "get_storage_buffer_device_pointer", "get_last_frame_launch_count",
     "set_graph_replay_enabled", "set_concurrent_passes_enabled", "join_transfers", "get_stream",
     "peer_init", "peer_get_sync_handle", "peer_open_sync", "peer_get_image_handle", "peer_open_image", "peer_image_ready", "peer_push_rows", "peer_barrier",
-    "peer_allreduce_sum_u32", "peer_error", "device_selftest"]
+    "peer_allreduce_sum_u32", "peer_error", "peer_error_poll", "device_selftest"]
 FRONTEND_SYMBOLS = [
     "default_settings", "create", "destroy", "last_error", "backend", "register_sdf_mesh", "set_mesh_geometry", "set_scene", "render_frame", "begin_frame", "run_segment", "set_peer_exchange", "shard_band",
     "read_output_rows", "read_output", "get_image",

@@ -146,13 +146,16 @@ class DistComm:
                     buf = (C.c_uint8 * 64).from_buffer_copy(hb)
                     be._check(self.api.b["peer_open_image"](be.ctx, img, ffi.u32(r), buf), "peer_open_image")
 
-    def check_peer_error(self):
+    def check_peer_error(self, blocking=True):
+        """Raises when a peer barrier gave up waiting (the frame consumed incomplete exchanges). blocking=False is the per-frame poll:
+        no synchronisation, the value is at most one frame old (the error word is sticky)."""
         if not self.peer:
             return
         e = ffi.u32()
-        self.fe.backend._check(self.api.b["peer_error"](self.fe.backend.ctx, C.byref(e)), "peer_error")
+        name = "peer_error" if blocking else "peer_error_poll"
+        self.fe.backend._check(self.api.b[name](self.fe.backend.ctx, C.byref(e)), name)
         if e.value:
-            raise RuntimeError("peer exchange: a barrier timed out waiting for another rank")
+            raise RuntimeError("peer exchange: a barrier timed out waiting for another rank - the frames since the previous check are invalid")
 
     def bands(self, rows, divisor):
         return [shard_band(self.api, self.H, self.world, r, divisor, rows) for r in range(self.world)]
@@ -237,6 +240,8 @@ def run_frame(fe, comm, cam, time, delta_time, inputs=None, async_upload=False, 
     while True:
         x = fe.run_segment()
         if x is None:
+            if hasattr(comm, "check_peer_error"):
+                comm.check_peer_error(blocking=False)  # every frame, without a synchronisation
             return n
         comm.exchange(x)
         n += 1

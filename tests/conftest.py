@@ -80,7 +80,7 @@ def random_r11g11b10(rng, n, finite=True):
 CAMERA = ((-13.0, -1.7, 0.5), (1.0, 0.0, 0.0), (0.0, 0.0, 1.0), (0.0, -1.0, 0.0))
 ALL_IMAGES = ["skyTransmission", "skyMultiscatter", "skyLut", "hiz", "depthHalf", "giY0", "giC0", "giY1", "giC1", "giHistY0", "giHistC0", "giHistY1", "giHistC1", "giFullY", "giFullC",
               "froxelMaterial", "froxelScatter", "froxelHist0", "froxelHist1", "froxelIntegration", "color0", "color1", "taaHist0", "taaHist1", "taaLum0", "taaLum1", "post0", "post1", "brdfLut", "output"]
-ALL_BUFFERS = [("histogram", 512), ("light", 20), ("sunShadowInfo", 304)]
+ALL_BUFFERS = [("histogram", 512), ("light", 20), ("sunShadowInfo", 304), ("sdfCulled", None), ("sdfTiles", None)]  # None: the whole buffer (S3: instance culling lists)
 # the non-default passes beside the frame path (temporalSupersampling.comp + colorToLuminance.comp, sdfDebugVisualisation.comp)
 N4_VARIANTS = [dict(taa_use_separate_supersampling=1), dict(taa_use_separate_supersampling=1, taa_supersample_use_tonemapping=0),
                dict(sdf_debug_mode=1), dict(sdf_debug_mode=2), dict(sdf_debug_mode=3), dict(sdf_debug_mode=4),
@@ -133,8 +133,19 @@ class Sequence:
             for mip in range(image_mips(self.fe, h)):
                 out["%s/%d" % (name, mip)] = self.fe.backend.read_image(h, mip).copy()
         for name, size in buffers:
+            if size is None:
+                size = self.buffer_bytes(name)
             out["buf:" + name] = self.fe.backend.read_storage_buffer(self.fe.storage_buffer(name), size).copy()
         return out
+
+    def buffer_bytes(self, name):
+        """sizes of the SDF culling buffers as SDFGI::init allocates them (Techniques.cpp: SDFGI.cpp:139-151)"""
+        if name == "sdfCulled":
+            return 4 + 4 * 1200  # maxObjectCountMainScene u32 + the count
+        if name == "sdfTiles":
+            tw, th = (self.w + 31) // 32, (self.h + 31) // 32
+            return tw * th * 404
+        raise KeyError(name)
 
     def close(self):
         self.scene.close()
@@ -205,6 +216,7 @@ class PlainSceneSequence:
         self.frame += 1
 
     RASTER_IMAGES = ["depth0", "depth1", "motion0", "motion1", "motion2", "normal", "gbuffer", "shadow0", "shadow1", "shadow2"]
+    buffer_bytes = Sequence.buffer_bytes
 
     def snapshot(self, images=None, buffers=ALL_BUFFERS):
         return Sequence.snapshot(self, images or (self.RASTER_IMAGES + ALL_IMAGES), buffers)

@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 
 import passes
-from conftest import N4_VARIANTS, Sequence, assert_snapshots_equal, decode_r11g11b10, random_r11g11b10
+from conftest import ALL_BUFFERS, ALL_IMAGES, N4_VARIANTS, Sequence, assert_snapshots_equal, decode_r11g11b10, image_mips, random_r11g11b10
 
 pytestmark = pytest.mark.gpu
 
@@ -169,6 +169,38 @@ def test_concurrent_pass_schedule_is_identical(ffi, cuda):
         outs.append(s.snapshot())
         s.close()
     assert_snapshots_equal(outs[0], outs[1], "concurrent pass schedule")
+
+
+# ---------------- full size (BASELINE 3840x2160) against the oracle ----------------
+def test_frame_4k_equals_oracle(ffi, cuda, oracle):
+    """BASELINE configs[2] itself: 3840x2160, 100 SDF instances, two frames (the second consumes every history of the first), every image and
+    buffer of the frame compared with the oracle bit for bit. The reference's resolution-capped buffers (SDFGI.cpp:146-151,
+    RenderFrontend.cpp:1069-1070, sdfCulling.inc:17-20) only matter at this size. ~12 s per oracle frame on 16 host threads."""
+    W, H = 3840, 2160
+    a, b = Sequence(ffi, cuda, W, H, 100), Sequence(ffi, oracle, W, H, 100)
+    try:
+        inputs = None
+        for f in range(2):
+            inputs = a.step(inputs=inputs) if inputs is not None else a.step()  # static camera: the inputs of frame 0 serve both frames
+            b.step(inputs=inputs)
+        # one image at a time: a full snapshot of both sides would hold ~4 GB
+        bad = []
+        for name in ALL_IMAGES:
+            ha, hb = a.fe.image(name), b.fe.image(name)
+            for mip in range(image_mips(a.fe, ha)):
+                x, y = a.fe.backend.read_image(ha, mip), b.fe.backend.read_image(hb, mip)
+                n = int((x != y).sum())
+                if n:
+                    bad.append("%s/%d: %d of %d bytes" % (name, mip, n, x.size))
+        for name, size in ALL_BUFFERS:
+            size = a.buffer_bytes(name) if size is None else size
+            x, y = a.fe.backend.read_storage_buffer(a.fe.storage_buffer(name), size), b.fe.backend.read_storage_buffer(b.fe.storage_buffer(name), size)
+            if not np.array_equal(x, y):
+                bad.append("buf:" + name)
+        assert not bad, "3840x2160 frame differs from the oracle: " + "; ".join(bad)
+    finally:
+        a.close()
+        b.close()
 
 
 # ---------------- full size (BASELINE 3840x2160): size-independent properties ----------------
