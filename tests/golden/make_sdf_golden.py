@@ -27,7 +27,11 @@ CASES = {
     "cube": (np.eye(3), np.zeros(3)),                                                        # 2 m cube -> 16^3
     "slab": (np.array([[3.0, 0.4, 0.0], [0.0, 1.0, 0.3], [0.2, 0.0, 1.7]]), np.array([0.5, -0.25, 1.0])),  # sheared, off-centre -> 32 x 16 x 16
     "tall": (np.array([[0.8, 0.0, 0.1], [0.3, 4.5, 0.0], [0.0, 0.2, 1.1]]), np.array([-1.0, 2.0, 0.0])),   # -> 16 x 64 x 16
+    # BASELINE configs[0]: the cube scaled x8 (16 m edge) -> 64^3, the reference's maximum (SceneSDF.cpp:120-131). 25 s on one core.
+    # Only its sha256 is committed (cube64.dds.sha256; the brick itself is 512 KB) together with the mesh the bake saw (cube64.plain).
+    "cube64": (np.eye(3) * 8.0, np.zeros(3)),
 }
+HASH_ONLY = {"cube64"}
 
 
 def run_case(name, matrix, offset):
@@ -65,8 +69,14 @@ def run_case(name, matrix, offset):
         raise SystemExit("reference asset pipeline produced no brick for %s:\n%s" % (name, "\n".join(log)))
     OUT.mkdir(parents=True, exist_ok=True)
     shutil.copy(model_dir / "Cube.plain", OUT / (name + ".plain"))
-    shutil.copy(dds, OUT / (name + ".dds"))
-    hdr = (OUT / (name + ".dds")).read_bytes()[:148]
+    if name in HASH_ONLY:
+        import hashlib
+        raw = dds.read_bytes()
+        (OUT / (name + ".dds.sha256")).write_text("%s  file (%d bytes)\n%s  texels (the %d bytes after the 148-byte DDS + DX10 header)\n"
+                                                   % (hashlib.sha256(raw).hexdigest(), len(raw), hashlib.sha256(raw[148:]).hexdigest(), len(raw) - 148))
+    else:
+        shutil.copy(dds, OUT / (name + ".dds"))
+    hdr = dds.read_bytes()[:148]
     h, w, d = struct.unpack_from("<I", hdr, 12)[0], struct.unpack_from("<I", hdr, 16)[0], struct.unpack_from("<I", hdr, 24)[0]
     print("%s: brick %dx%dx%d, %s" % (name, w, h, d, [l for l in log if "SDF computation time" in l]))
     shutil.rmtree(work, ignore_errors=True)

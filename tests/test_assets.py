@@ -87,6 +87,17 @@ def test_oracle_bake_reproduces_the_reference_bricks(oracle_assets, name):
     assert (want >> 15).any() and not (want >> 15).all()  # the fixture has texels inside (negative) and outside the mesh
 
 
+def test_oracle_bake_reproduces_the_reference_brick_at_64_cubed(oracle_assets):
+    """BASELINE configs[0] itself: the cube scaled x8 -> 64^3, the reference's maximum resolution (SceneSDF.cpp:120-131). The reference
+    binary's brick is pinned by its sha256 (tests/golden/sdf/cube64.dds.sha256, written by make_sdf_golden.py; the brick is 512 KB)."""
+    import hashlib
+    mesh = oracle_assets.load_scene(GOLD / "cube64.plain").meshes[0]
+    assert oracle_assets.resolution(mesh.bb_min, mesh.bb_max) == (64, 64, 64)
+    got, _ = oracle_assets.bake(mesh)
+    want = (GOLD / "cube64.dds.sha256").read_text().splitlines()[1].split()[0]
+    assert hashlib.sha256(np.ascontiguousarray(got).tobytes()).hexdigest() == want
+
+
 def test_bake_has_no_cpu_fallback(product_assets):
     import torch
     if torch.cuda.is_available():

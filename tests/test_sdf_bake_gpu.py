@@ -54,6 +54,18 @@ def test_cuda_bake_equals_the_pinned_oracle(libs, seed, triangles, extent):
     assert np.array_equal(got, want), "%d of %d texels differ from the oracle" % ((got != want).sum(), want.size)
 
 
+def test_full_size_brick_equals_the_reference_binary(libs):
+    """BASELINE configs[0]: the 64^3 brick of the x8 cube from the CUDA bake, bit for bit the one the reference binary wrote (sha256)."""
+    import hashlib
+    cuda, _ = libs
+    mesh = cuda.load_scene(GOLD / "cube64.plain").meshes[0]
+    got, ms = cuda.bake(mesh)
+    assert got.shape == (64, 64, 64)
+    want = (GOLD / "cube64.dds.sha256").read_text().splitlines()[1].split()[0]
+    assert hashlib.sha256(np.ascontiguousarray(got).tobytes()).hexdigest() == want
+    print("64^3 bake: %.2f ms on the device" % ms)
+
+
 def test_full_size_brick_properties(libs):
     """64^3 (the reference's maximum, BASELINE configs[0]): the scaled cube of the first fixture. Size-independent checks: sign
     inside/outside, distances bounded by the padded box diagonal, symmetric about the cube's mirror planes up to half precision."""
