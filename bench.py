@@ -234,7 +234,7 @@ def workload_config(n_gpus):
     name = "configs[2]" if (WIDTH, HEIGHT) == (3840, 2160) else "configs[4] (GI-trace-bound stress; not the headline metric)"
     return {"workload": "%s: %dx%d synthetic Sponza-sized scene (%d SDF instances), full pipeline (GI/TAA/sky/volumetrics/bloom), static camera with TAA jitter" % (name, WIDTH, HEIGHT, INSTANCES),
             "resolution": [WIDTH, HEIGHT], "sdf_instances": INSTANCES,
-            "parallelism": "1 GPU" if n_gpus == 1 else "%d GPUs: every frame split into %d screen-space row bands (multiples of 32 rows), 10 exchanges per frame over NVLink (histogram all-reduce, row all-gathers, halos); sky LUTs, culling lists and bloom mips >= 2 replicated" % (n_gpus, n_gpus),
+            "parallelism": "1 GPU" if n_gpus == 1 else "%d GPUs: every frame split into %d screen-space row bands (multiples of 32 rows), 5 exchanges per frame on the critical path over NVLink (histogram all-reduce, 4 row all-gathers) + 3 all-gathers of next-frame data behind the frame; sky LUTs, culling lists and bloom mips >= 2 replicated" % (n_gpus, n_gpus),
             "l2": "per-frame working set (>1.5 GB touched, G-buffer alone 133 MB) exceeds the 126 MB L2; no flush needed"}
 
 
@@ -378,7 +378,8 @@ def run_ours(args, rank, world, local_rank):
         fps = 1000.0 / ms_step      # N > 1: the SAME frame is split over the N GPUs (strong scaling)
         ms_step_e2e = ms_e2e / args.steps
         fps_e2e = 1000.0 / ms_step_e2e
-        h2d = WIDTH * (upload_rows[1] - upload_rows[0]) * (4 + 4 + 16) + WIDTH * HEIGHT * 4  # per rank: band + halo of depth/normal/G-buffer, motion whole
+        # per rank: band + halo of depth / normal / G-buffer / motion (a sharded rank all-gathers the motion vectors over NVLink); 1 GPU: whole images
+        h2d = WIDTH * (upload_rows[1] - upload_rows[0]) * (4 + 4 + 16 + 4)
         d2h = WIDTH * (band[1] - band[0]) * 4
         peak, peak_src = measured_hbm_peak()
         alg_frame = algorithmic_bytes(WIDTH, HEIGHT)
@@ -425,7 +426,7 @@ def run_ours(args, rank, world, local_rank):
             line["config"]["numeric_contract"] = "fast: SFU approximations + contraction in the floating-point passes (libplain_b200_fast.so)"
         if sharded:
             comm.check_peer_error()
-            line["sharding"] = {"rows_of_rank0": list(band), "exchanges_per_frame": 10, "bytes_sent_per_frame_rank0": bytes_first_frame[0],
+            line["sharding"] = {"rows_of_rank0": list(band), "exchanges_per_frame": 8, "exchanges_on_the_critical_path": 5, "exchanges_deferred_behind_the_frame": 3, "bytes_sent_per_frame_rank0": bytes_first_frame[0],
                                 "transport": "peer pushes over NVLink (CUDA IPC) + flag barriers, enqueued by run_segment" if comm.peer else "NCCL send/recv batches issued from Python",
                                 "exchanges_through_python": comm.python_exchanges,
                                 "note": "passes_ms are rank 0's kernels only (its band); e2e byte counts are per rank"}

@@ -291,6 +291,13 @@ PLAIN_EXPORT int PLAIN_FN(peer_push_rows)(plain_ctx* ctx, uint32_t n, const plai
 /* every rank signals every other rank and waits for all of them: pushes enqueued before it on any rank are visible to the
  * passes enqueued after it on every rank */
 PLAIN_EXPORT int PLAIN_FN(peer_barrier)(plain_ctx* ctx);
+/* Deferred exchange, for rows that only the NEXT frame reads (GI / froxel / TAA history): the push is enqueued on a separate stream
+ * behind the passes submitted so far and overlaps the rest of the frame; peer_flush_deferred (once per frame, after the last pass)
+ * closes the frame's deferred pushes with one barrier on a second flag set. The first submission after the next new_frame - and any
+ * read-back or wait_for_gpu_idle - waits for it. Rule for the caller: at least one peer_barrier / peer_allreduce_sum_u32 of the same
+ * frame precedes the first deferred push (it orders the peers' readers of the previous contents before the new rows arrive). */
+PLAIN_EXPORT int PLAIN_FN(peer_push_rows_deferred)(plain_ctx* ctx, uint32_t n, const plain_peer_push* pushes);
+PLAIN_EXPORT int PLAIN_FN(peer_flush_deferred)(plain_ctx* ctx);
 /* element-wise sum over the ranks of `count` (<= 256) u32 at the start of a storage buffer; includes its own barrier */
 PLAIN_EXPORT int PLAIN_FN(peer_allreduce_sum_u32)(plain_ctx* ctx, plain_handle storage_buffer, uint32_t count);
 /* non-zero once a barrier gave up waiting for a peer (about 2 s): the frame is invalid, the caller must abort */

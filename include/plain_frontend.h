@@ -137,6 +137,8 @@ typedef struct {
     plain_handle buffer;         /* ALLREDUCE: the storage buffer */
     uint32_t depth[4];           /* slices of the level (1 for 2-D images): a row range means those rows in EVERY slice; slices are
                                     rows * row_pitch_bytes apart */
+    uint32_t deferred;           /* 1: only the NEXT frame reads the gathered rows - the exchange may complete any time before the next
+                                    begin_frame (over peer exchange it runs behind the frame; a caller may also perform it right away) */
 } plain_exchange;
 PLAIN_EXPORT int PLAIN_FE(begin_frame)(plain_frontend* fe, const plain_camera_extrinsic* camera, float time, float delta_time, const plain_frame_inputs* inputs);
 PLAIN_EXPORT int PLAIN_FE(run_segment)(plain_frontend* fe, plain_exchange* out);

@@ -466,6 +466,8 @@ int PLAIN_FN(peer_open_image)(plain_ctx* ctx, plain_image_handle, uint32_t, cons
 int PLAIN_FN(peer_image_ready)(plain_ctx*, plain_image_handle) { return 0; }
 int PLAIN_FN(peer_push_rows)(plain_ctx* ctx, uint32_t, const plain_peer_push*) { return peerUnsupported(ctx); }
 int PLAIN_FN(peer_barrier)(plain_ctx* ctx) { return peerUnsupported(ctx); }
+int PLAIN_FN(peer_push_rows_deferred)(plain_ctx* ctx, uint32_t, const plain_peer_push*) { return peerUnsupported(ctx); }
+int PLAIN_FN(peer_flush_deferred)(plain_ctx* ctx) { return peerUnsupported(ctx); }
 int PLAIN_FN(peer_allreduce_sum_u32)(plain_ctx* ctx, plain_handle, uint32_t) { return peerUnsupported(ctx); }
 int PLAIN_FN(peer_error)(plain_ctx*, uint32_t* out_error) { *out_error = 0; return 0; }
 int PLAIN_FN(peer_error_poll)(plain_ctx*, uint32_t* out_error) { *out_error = 0; return 0; }

@@ -75,11 +75,20 @@ struct Backend {
     //   u32 error                    set when a barrier gave up waiting
     //   u32 scratch[2][PLAIN_MAX_PEERS][kPeerReduceMax]   all-reduce partials, double-buffered by all-reduce parity
     static const uint32_t kPeerReduceMax = 256;
+    //   u32 flagsDeferred[PLAIN_MAX_PEERS]   the same for the barrier of the deferred (next-frame) exchanges, which runs on its own stream
     static const size_t kPeerFlagsOffset = 0, kPeerErrorOffset = PLAIN_MAX_PEERS, kPeerScratchOffset = 2 * PLAIN_MAX_PEERS;
-    static const size_t kPeerSyncWords = 2 * PLAIN_MAX_PEERS + 2 * PLAIN_MAX_PEERS * kPeerReduceMax;
+    static const size_t kPeerFlagsDeferredOffset = 2 * PLAIN_MAX_PEERS + 2 * PLAIN_MAX_PEERS * kPeerReduceMax;
+    static const size_t kPeerSyncWords = kPeerFlagsDeferredOffset + PLAIN_MAX_PEERS;
     uint32_t peerRank = 0, peerCount = 0;
     uint32_t* peerSync[PLAIN_MAX_PEERS] = {};  // [peerRank] = own block
     uint32_t peerEpoch = 0, peerReduceCount = 0;
+    // Deferred exchanges: rows that only the NEXT frame reads (GI history, froxel history, TAA history) are pushed on peerStream,
+    // behind an event of the pass stream, while the rest of the frame runs; one barrier on the deferred flag set closes them
+    // (peer_flush_deferred) and the first submission of the next frame waits for it.
+    cudaStream_t peerStream = nullptr;
+    cudaEvent_t peerFork = nullptr, peerDeferredDone = nullptr;
+    uint32_t peerEpochDeferred = 0;
+    bool peerDeferredDirty = false, peerDeferredPending = false, frameFresh = false;
     std::vector<DeviceImage> images, transientImages;
     // two presentable images, flipped by new_frame (a swapchain hands out a different image every frame): the read-back of
     // frame N does not hold up the tonemapping pass of frame N+1
@@ -314,6 +323,7 @@ static cudaStream_t transferStream(Backend& b, DeviceImage& img, bool toDevice) 
     }
     cudaEventRecord(b.computeMark, b.stream);
     cudaStreamWaitEvent(b.downloadStream, b.computeMark, 0);
+    if (img.deferredExchange && b.peerDeferredPending) cudaStreamWaitEvent(b.downloadStream, b.peerDeferredDone, 0);  // rows the peers pushed behind the frame
     if (b.uploadsPending) {  // a read-back of an image that is being uploaded sees the upload
         cudaEventRecord(b.uploadsDone, b.uploadStream);
         cudaStreamWaitEvent(b.downloadStream, b.uploadsDone, 0);
@@ -532,6 +542,7 @@ static void updateBindless(Backend& b, uint32_t index) {
 }
 
 extern "C" {
+static int joinDeferredExchanges(plain_ctx* ctx, cudaStream_t stream);
 
 int PLAIN_FN(backend_create)(int device, uint32_t width, uint32_t height, plain_ctx** out_ctx) {
     if (!out_ctx) return 1;
@@ -577,6 +588,7 @@ void PLAIN_FN(backend_destroy)(plain_ctx* ctx) {
     cudaStreamSynchronize(b.uploadStream);
     cudaStreamSynchronize(b.downloadStream);
     cudaStreamSynchronize(b.stream);
+    if (b.peerStream) cudaStreamSynchronize(b.peerStream);
     for (auto& g : b.graphs) if (g.second.exec) cudaGraphExecDestroy(g.second.exec);
     for (uint32_t p = 0; p < b.peerCount; p++) {
         for (auto& i : b.images) if (i.peerPtr[p]) cudaIpcCloseMemHandle(i.peerPtr[p]);
@@ -599,6 +611,7 @@ void PLAIN_FN(backend_destroy)(plain_ctx* ctx) {
     cudaFreeHost(b.stagingHost);
     cudaFree(b.bindlessDevice);
     if (b.peerErrorHost) cudaFreeHost(b.peerErrorHost);
+    if (b.peerStream) { cudaStreamDestroy(b.peerStream); cudaEventDestroy(b.peerFork); cudaEventDestroy(b.peerDeferredDone); }
     cudaFree(b.tablesDevice);
     cudaEventDestroy(b.stagingConsumed);
     for (auto& e : b.submissionDone) cudaEventDestroy(e);
@@ -758,6 +771,7 @@ int PLAIN_FN(new_frame)(plain_ctx* ctx) {
     ctx->b.launchCounter = 0;  // kernels of the frame: all submissions + the peer exchange kernels between them
     ctx->b.timings.clear();  // pass timings accumulate over the submissions of a frame (a row-sharded frame has one per segment)
     ctx->b.swapchainCurrent ^= 1;  // the next presentable image (RenderBackend.cpp:608-612 getSwapchainInputImage)
+    ctx->b.frameFresh = true;
     for (auto& t : ctx->b.transientImages) t.inUse = false;
     return 0;
 }
@@ -954,6 +968,11 @@ int PLAIN_FN(render_frame)(plain_ctx* ctx, int present) {
     Backend& b = ctx->b;
     cudaSetDevice(b.device);
     joinTransfers(b);  // uploads issued before this submission are visible to its passes; read-backs in flight keep their source
+    if (b.frameFresh) {  // the previous frame's deferred exchanges (next-frame data) have landed before this frame's first pass
+        b.frameFresh = false;
+        if (joinDeferredExchanges(ctx, b.stream)) return 1;
+        b.peerDeferredPending = false;
+    }
     refreshCornerBricks(b);  // SDF bricks written since the last submission (direct launches, outside the captured graph)
     while (b.passEvents.size() < b.execs.size()) { cudaEvent_t x; cudaEventCreateWithFlags(&x, cudaEventDisableTiming); b.passEvents.push_back(x); }
     if (prepareRaster(ctx)) return 1;
@@ -1037,6 +1056,8 @@ int PLAIN_FN(submit_recorded_passes)(plain_ctx* ctx) {
 }
 int PLAIN_FN(wait_for_gpu_idle)(plain_ctx* ctx) {
     cudaSetDevice(ctx->b.device);
+    if (joinDeferredExchanges(ctx, ctx->b.stream)) return 1;  // a read of an exchanged image after this call sees the peers' rows
+    ctx->b.peerDeferredPending = false;
     drainTransfers(ctx->b);
     CU_CHECK(ctx, cudaStreamSynchronize(ctx->b.stream));
     return 0;
@@ -1065,6 +1086,7 @@ static int imageCopy(plain_ctx* ctx, plain_image_handle image, uint32_t mip, voi
     if (size != img->mips[mip].bytes) return fail(ctx, std::string(what) + ": size mismatch");
     unsigned char* dev = img->ptr + img->mips[mip].offset;
     if (sync) drainTransfers(b);
+    if (sync && img->deferredExchange && joinDeferredExchanges(ctx, b.stream)) return 1;
     cudaStream_t st = sync ? b.stream : transferStream(b, *img, toDevice);
     if (toDevice) CU_CHECK(ctx, cudaMemcpyAsync(dev, host, size, cudaMemcpyHostToDevice, st));
     else CU_CHECK(ctx, cudaMemcpyAsync(host, dev, size, cudaMemcpyDeviceToHost, st));
@@ -1190,7 +1212,7 @@ int PLAIN_FN(peer_image_ready)(plain_ctx* ctx, plain_image_handle image) {
         if (p != b.peerRank && !img->peerPtr[p]) return 0;
     return 1;
 }
-int PLAIN_FN(peer_push_rows)(plain_ctx* ctx, uint32_t n, const plain_peer_push* pushes) {
+static int peerPushRows(plain_ctx* ctx, uint32_t n, const plain_peer_push* pushes, cudaStream_t stream, int blocksPerSm) {
     Backend& b = ctx->b;
     cudaSetDevice(b.device);
     if (b.peerCount < 2) return fail(ctx, "peer_push_rows: peer_init first");
@@ -1198,8 +1220,8 @@ int PLAIN_FN(peer_push_rows)(plain_ctx* ctx, uint32_t n, const plain_peer_push* 
     int used = 0;
     auto flush = [&]() {
         if (!used) return;
-        const unsigned blocksPerSegment = (unsigned)std::max(1, 4 * b.smCount / used);
-        peerPushKernel<<<dim3(blocksPerSegment, (unsigned)used), 256, 0, b.stream>>>(args);
+        const unsigned blocksPerSegment = (unsigned)std::max(1, blocksPerSm * b.smCount / used);
+        peerPushKernel<<<dim3(blocksPerSegment, (unsigned)used), 256, 0, stream>>>(args);
         b.launchCounter++;
         used = 0;
     };
@@ -1224,23 +1246,63 @@ int PLAIN_FN(peer_push_rows)(plain_ctx* ctx, uint32_t n, const plain_peer_push* 
     if (e != cudaSuccess) return fail(ctx, std::string("peer_push_rows: ") + cudaGetErrorString(e));
     return 0;
 }
-static int peerBarrier(plain_ctx* ctx) {
+int PLAIN_FN(peer_push_rows)(plain_ctx* ctx, uint32_t n, const plain_peer_push* pushes) { return peerPushRows(ctx, n, pushes, ctx->b.stream, 4); }
+static int peerBarrier(plain_ctx* ctx, bool deferred = false) {
     Backend& b = ctx->b;
     BarrierArgs a{};
     for (uint32_t p = 0; p < b.peerCount; p++) {
         if (!b.peerSync[p]) return fail(ctx, "peer_barrier: sync block of a peer not mapped (peer_open_sync)");
-        a.peerFlags[p] = b.peerSync[p] + Backend::kPeerFlagsOffset;
+        a.peerFlags[p] = b.peerSync[p] + (deferred ? Backend::kPeerFlagsDeferredOffset : Backend::kPeerFlagsOffset);
     }
     a.localError = b.peerSync[b.peerRank] + Backend::kPeerErrorOffset;
-    a.rank = b.peerRank; a.count = b.peerCount; a.epoch = ++b.peerEpoch;
+    a.rank = b.peerRank; a.count = b.peerCount; a.epoch = deferred ? ++b.peerEpochDeferred : ++b.peerEpoch;
     // a rank that is late on the host (first graph instantiation, lazy IPC mapping, CPU contention) must not trip the others: 20 s by
     // default, PLAIN_PEER_TIMEOUT_MS to change it. A timeout sets the sticky error word; callers poll it every frame (peer_error_poll)
     static const long long timeoutMs = getenv("PLAIN_PEER_TIMEOUT_MS") ? atoll(getenv("PLAIN_PEER_TIMEOUT_MS")) : 20000ll;
     a.timeoutCycles = timeoutMs * 1900000ll;  // SM clock ~1.9 GHz
-    peerBarrierKernel<<<1, 32, 0, b.stream>>>(a);
+    peerBarrierKernel<<<1, 32, 0, deferred ? b.peerStream : b.stream>>>(a);
     b.launchCounter++;
     cudaError_t e = cudaPeekAtLastError();
     if (e != cudaSuccess) return fail(ctx, std::string("peer_barrier: ") + cudaGetErrorString(e));
+    return 0;
+}
+// Rows that only the next frame reads: pushed on peerStream behind everything the pass stream holds so far, next to the passes that
+// follow. Fewer blocks than a synchronous push: the copy shares the SMs with the frame's kernels and has most of a frame to finish.
+int PLAIN_FN(peer_push_rows_deferred)(plain_ctx* ctx, uint32_t n, const plain_peer_push* pushes) {
+    Backend& b = ctx->b;
+    cudaSetDevice(b.device);
+    if (b.peerCount < 2) return fail(ctx, "peer_push_rows_deferred: peer_init first");
+    if (!b.peerStream) {
+        CU_CHECK(ctx, cudaStreamCreateWithFlags(&b.peerStream, cudaStreamNonBlocking));
+        CU_CHECK(ctx, cudaEventCreateWithFlags(&b.peerFork, cudaEventDisableTiming));
+        CU_CHECK(ctx, cudaEventCreateWithFlags(&b.peerDeferredDone, cudaEventDisableTiming));
+    }
+    CU_CHECK(ctx, cudaEventRecord(b.peerFork, b.stream));
+    CU_CHECK(ctx, cudaStreamWaitEvent(b.peerStream, b.peerFork, 0));
+    if (peerPushRows(ctx, n, pushes, b.peerStream, 1)) return 1;
+    for (uint32_t i = 0; i < n; i++) if (DeviceImage* img = b.resolve(pushes[i].image)) img->deferredExchange = true;
+    b.peerDeferredDirty = true;
+    return 0;
+}
+// closes the deferred pushes of the frame: one barrier on the deferred flag set, on peerStream. The next frame's first submission
+// (and any read-back) waits for it - by then every peer's rows have landed here and every peer has read what this rank will overwrite.
+int PLAIN_FN(peer_flush_deferred)(plain_ctx* ctx) {
+    Backend& b = ctx->b;
+    cudaSetDevice(b.device);
+    if (!b.peerDeferredDirty) return 0;
+    // the barrier also orders this rank's consumers of the images (this frame's passes) before the peers' next pushes into them
+    CU_CHECK(ctx, cudaEventRecord(b.peerFork, b.stream));
+    CU_CHECK(ctx, cudaStreamWaitEvent(b.peerStream, b.peerFork, 0));
+    if (peerBarrier(ctx, true)) return 1;
+    CU_CHECK(ctx, cudaEventRecord(b.peerDeferredDone, b.peerStream));
+    b.peerDeferredDirty = false;
+    b.peerDeferredPending = true;
+    return 0;
+}
+static int joinDeferredExchanges(plain_ctx* ctx, cudaStream_t stream) {
+    Backend& b = ctx->b;
+    if (b.peerDeferredDirty && PLAIN_FN(peer_flush_deferred)(ctx)) return 1;
+    if (b.peerDeferredPending) CU_CHECK(ctx, cudaStreamWaitEvent(stream, b.peerDeferredDone, 0));
     return 0;
 }
 int PLAIN_FN(peer_barrier)(plain_ctx* ctx) {

@@ -42,6 +42,7 @@ struct DeviceImage {
     unsigned char* peerPtr[PLAIN_MAX_PEERS] = {};  // the other ranks' copies of this image (CUDA IPC mappings), row sharding
     cudaEvent_t downloadDone = nullptr; // recorded after the last asynchronous read-back of the image (created on first use)
     bool downloadPending = false;       // that read-back has not been ordered before a later writer yet
+    bool deferredExchange = false;      // peers push rows of this image behind the frame (peer_push_rows_deferred): a read-back waits for them
 };
 struct DeviceBuffer {
     unsigned char* ptr = nullptr;

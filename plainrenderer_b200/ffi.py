@@ -150,7 +150,7 @@ EXCHANGE_NONE, EXCHANGE_ALLREDUCE_SUM_U32, EXCHANGE_ALLGATHER_ROWS, EXCHANGE_HAL
 
 class Exchange(C.Structure):  # include/plain_frontend.h plain_exchange
     _fields_ = [("kind", u32), ("n_images", u32), ("device_ptr", C.c_void_p * 4), ("row_pitch_bytes", u32 * 4), ("rows", u32 * 4), ("row_divisor", u32 * 4),
-                ("halo_rows", u32), ("element_count", u32), ("name", C.c_char * 32), ("image", ImageHandle * 4), ("mip_level", u32 * 4), ("buffer", u32), ("depth", u32 * 4)]
+                ("halo_rows", u32), ("element_count", u32), ("name", C.c_char * 32), ("image", ImageHandle * 4), ("mip_level", u32 * 4), ("buffer", u32), ("depth", u32 * 4), ("deferred", u32)]
 
 
 class CameraExtrinsic(C.Structure):
@@ -166,7 +166,7 @@ BACKEND_SYMBOLS = [
     "create_meshes", "create_graphic_pass", "set_graphic_pass_execution", "draw_meshes",
     "write_image_async", "read_image_async", "write_image_rows_async", "read_image_rows_async", "get_image_device_pointer", "get_storage_buffer_device_pointer", "get_last_frame_launch_count",
     "set_graph_replay_enabled", "set_concurrent_passes_enabled", "join_transfers", "get_stream",
-    "peer_init", "peer_get_sync_handle", "peer_open_sync", "peer_get_image_handle", "peer_open_image", "peer_image_ready", "peer_push_rows", "peer_barrier",
+    "peer_init", "peer_get_sync_handle", "peer_open_sync", "peer_get_image_handle", "peer_open_image", "peer_image_ready", "peer_push_rows", "peer_barrier", "peer_push_rows_deferred", "peer_flush_deferred",
     "peer_allreduce_sum_u32", "peer_error", "peer_error_poll", "device_selftest"]
 FRONTEND_SYMBOLS = [
     "default_settings", "create", "destroy", "last_error", "backend", "register_sdf_mesh", "set_mesh_geometry", "set_scene", "render_frame", "begin_frame", "run_segment", "set_peer_exchange", "shard_band",

@@ -4,6 +4,7 @@
 // throw std::runtime_error carrying plain_last_error() (the reference prints and throws, RenderBackend.cpp:442-445).
 #pragma once
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <stdexcept>
 #include <string>
@@ -84,6 +85,7 @@ struct ExchangeRequest {
     std::vector<ImageHandle> images;
     std::vector<uint32_t> mips, divisors;
     uint32_t buffer = PLAIN_INVALID_INDEX, elementCount = 0, haloRows = 0;
+    bool deferred = false;  // only the NEXT frame reads the rows: the peer exchange may run behind the frame (peer_push_rows_deferred)
     std::string name;
 };
 struct ShardInfo {
@@ -194,6 +196,7 @@ public:
             out->kind = r.exchange.kind;
             out->halo_rows = r.exchange.haloRows;
             out->element_count = r.exchange.elementCount;
+            out->deferred = r.exchange.deferred ? 1u : 0u;
             std::snprintf(out->name, sizeof(out->name), "%s", r.exchange.name.c_str());
             if (r.exchange.kind == PLAIN_EXCHANGE_ALLREDUCE_SUM_U32) {
                 size_t size = 0;
@@ -222,10 +225,13 @@ public:
             return true;
         }
         check(PLAIN_FN(render_frame)(m_ctx, 1));
+        if (m_deferredIssued) { check(PLAIN_FN(peer_flush_deferred)(m_ctx)); m_deferredIssued = false; }  // one barrier for the frame's deferred pushes
         return false;
     }
     // ---- peer exchange over NVLink (include/plain_b200.h): the sends of sharding.plan_row_exchange as row pushes ----
     bool m_peerExchange = false;
+    bool m_peerDeferred = !(std::getenv("PLAIN_PEER_DEFERRED") && std::atoi(std::getenv("PLAIN_PEER_DEFERRED")) == 0);  // A / B switch
+    bool m_deferredIssued = false;
     void bandOf(uint32_t rank, uint32_t divisor, uint32_t rows, uint32_t* a, uint32_t* b) const {
         uint32_t y0 = 0, y1 = shard.fullHeight;
         shardBandRows(shard.fullHeight, shard.count, rank, &y0, &y1);
@@ -263,6 +269,11 @@ public:
                 if (shard.rank > 0) push(shard.rank - 1, a, a + halo < b ? a + halo : b);                // the neighbour above needs my first rows
                 if (shard.rank + 1 < shard.count) push(shard.rank + 1, b > a + halo ? b - halo : a, b);  // the neighbour below my last rows
             }
+        }
+        if (x.deferred && m_peerDeferred && x.kind == PLAIN_EXCHANGE_ALLGATHER_ROWS) {
+            check(PLAIN_FN(peer_push_rows_deferred)(m_ctx, (uint32_t)pushes.size(), pushes.data()));
+            m_deferredIssued = true;
+            return true;
         }
         check(PLAIN_FN(peer_push_rows)(m_ctx, (uint32_t)pushes.size(), pushes.data()));
         check(PLAIN_FN(peer_barrier)(m_ctx));

@@ -451,11 +451,13 @@ void RenderFrontend::prepareRenderpasses() {
     m_sky.updateSkyLut(backend, m_lightBuffer, m_atmosphereSettings);
     // depth / motion / normal / G-buffer / shadow maps of this frame: rasterised from the meshes (m_rasterInputs) or uploaded
     if (m_rasterInputs) renderDepthPrepass(currentRenderTarget.depthBuffer, worldSpaceNormalImage(), currentRenderTarget.motionBuffer);
-    computeDepthPyramid(currentRenderTarget.depthBuffer);
+    // row-sharded: the half-resolution depth is produced next to the pyramid's local levels and gathered in the same exchange
+    const bool downscaleWithPyramid = backend.shard.active() && m_shadingConfig.indirectLightingTech == IndirectLightingTech::SDFTrace && m_sdfTraceSettings.halfResTrace;
+    computeDepthPyramid(currentRenderTarget.depthBuffer, downscaleWithPyramid ? &currentRenderTarget : nullptr);
     computeSunLightMatrices();
     if (m_rasterInputs) renderSunShadowCascades();
     if (m_shadingConfig.indirectLightingTech == IndirectLightingTech::SDFTrace) {
-        if (m_sdfTraceSettings.halfResTrace) downscaleDepth(currentRenderTarget);
+        if (m_sdfTraceSettings.halfResTrace && !downscaleWithPyramid) downscaleDepth(currentRenderTarget);
         m_sdfGi.computeIndirectLighting(backend, fillOutSdfGiDependencies(), m_sdfTraceSettings, m_frameIndex);
     }
     Volumetrics::Dependencies vd;
@@ -721,7 +723,7 @@ void RenderFrontend::computeExposure() {
     backend.setComputePassExecution(e);
 }
 
-void RenderFrontend::computeDepthPyramid(ImageHandle depthBuffer) {
+void RenderFrontend::computeDepthPyramid(ImageHandle depthBuffer, const FrameRenderTargets* alsoDownscale) {
     ComputePassExecution e;
     e.genericInfo.handle = m_depthPyramidPass;
     const uint32_t width = m_screenWidth / 2, height = m_screenHeight / 2;
@@ -740,6 +742,7 @@ void RenderFrontend::computeDepthPyramid(ImageHandle depthBuffer) {
     }
     if (!backend.shard.active()) {
         backend.setComputePassExecution(e);
+        if (alsoDownscale) downscaleDepth(*alsoDownscale, true);
         return;
     }
     // sharded: the levels reduced from a rank's own depth rows (up to four: band boundaries are multiples of 32 rows), then
@@ -750,7 +753,17 @@ void RenderFrontend::computeDepthPyramid(ImageHandle depthBuffer) {
     local.shardPhase = 1;
     setRows(backend, local, 2, height);
     backend.setComputePassExecution(local);
-    backend.addExchange(gatherRows("hiz", {m_minMaxDepthPyramid}, fused - 1, 2u << (fused - 1)));
+    ExchangeRequest x = gatherRows("hiz", {m_minMaxDepthPyramid}, fused - 1, 2u << (fused - 1));
+    if (alsoDownscale) {  // the depth downscale does not depend on the pyramid: its all-gather shares this exchange's barrier
+        downscaleDepth(*alsoDownscale, false);
+        x.name = "hiz+depthHalf";
+        x.images.push_back(m_depthHalfRes); x.mips.push_back(0); x.divisors.push_back(2);
+    }
+    if (m_motionRowsOnly && !m_rasterInputs) {  // the uploaded band of motion vectors rides on the same barrier
+        x.name += "+motion";
+        x.images.push_back(m_frameRenderTargets[m_sceneRenderTargetIndex].motionBuffer); x.mips.push_back(0); x.divisors.push_back(1);
+    }
+    backend.addExchange(x);
     ComputePassExecution rest = e;
     rest.shardPhase = 2;
     backend.setComputePassExecution(rest);
@@ -770,7 +783,7 @@ void RenderFrontend::computeSunLightMatrices() {
     backend.setComputePassExecution(e);
 }
 
-void RenderFrontend::downscaleDepth(const FrameRenderTargets& current) {
+void RenderFrontend::downscaleDepth(const FrameRenderTargets& current, bool exchange) {
     ComputePassExecution e;
     e.genericInfo.handle = m_depthDownscalePass;
     e.dispatchCount[0] = ceilDiv(m_screenWidth / 2, 8);
@@ -779,7 +792,7 @@ void RenderFrontend::downscaleDepth(const FrameRenderTargets& current) {
     e.genericInfo.resources.sampledImages = {ImageResource(current.depthBuffer, 0, 1)};
     setRows(backend, e, 2, m_screenHeight / 2);
     backend.setComputePassExecution(e);
-    backend.addExchange(gatherRows("depthHalf", {m_depthHalfRes}, 0, 2));  // the spatial GI filter reads it at arbitrary rows
+    if (exchange) backend.addExchange(gatherRows("depthHalf", {m_depthHalfRes}, 0, 2));  // the spatial GI filter reads it at arbitrary rows
 }
 
 // renderForwardShading :894-929 + Sky::renderSky (Sky.cpp:318-352), as one full-screen pass over the G-buffer.

@@ -190,6 +190,7 @@ public:
     // with m_rasterInputs the depth prepass, the sun shadow cascades and the G-buffer are rasterised from the
     // registered meshes by the backend's graphic passes instead of being uploaded
     bool m_rasterInputs = false;
+    bool m_motionRowsOnly = false;  // row-sharded, uploaded inputs: only this rank's rows of the motion vectors were uploaded (all-gathered with the pyramid level)
     void setMeshGeometry(uint32_t mesh, const MeshBinary& geometry, const Material* material);  // registerMeshes :456-531 (geometry + material part)
     DefaultTextures m_defaultTextures;
     uint32_t m_currentMainPassDrawcallCount = 0, m_currentShadowPassDrawcallCount = 0;
@@ -238,9 +239,9 @@ private:
     void prepareRenderpasses();
     void computeColorBufferHistogram(ImageHandle lastFrameColor);
     void computeExposure();
-    void computeDepthPyramid(ImageHandle depthBuffer);
+    void computeDepthPyramid(ImageHandle depthBuffer, const FrameRenderTargets* alsoDownscale = nullptr);
     void computeSunLightMatrices();
-    void downscaleDepth(const FrameRenderTargets& current);
+    void downscaleDepth(const FrameRenderTargets& current, bool exchange = true);
     void shadeGBuffer(ImageHandle colorTarget);
     void renderDepthPrepass(ImageHandle depth, ImageHandle normal, ImageHandle motion);  // :792-802
     void renderSunShadowCascades();                                                     // :760-775

@@ -160,10 +160,10 @@ void SDFGI::filterIndirectDiffuse(RenderBackend& b, const SDFTraceDependencies& 
         e.genericInfo.resources.sampledImages = {ImageResource(m_indirectDiffuse_Y_SH[0], 0, 2), ImageResource(m_indirectDiffuse_CoCg[0], 0, 3), ImageResource(depthSrc, 0, 4),
                                                  ImageResource(d.worldSpaceNormals, 0, 5)};
         e.dispatchCount[0] = gx; e.dispatchCount[1] = gy;
-        setRows(b, e, div, target.height);
+        // the temporal filter reads its input bilinearly at the pixel's own position, one row beyond the band: overlapped computation
+        // (two more rows of the filter on either side; its inputs are gathered or within the uploaded halo) instead of a halo exchange
+        setRows(b, e, div, target.height, 2);
         b.setComputePassExecution(e);
-        // the temporal filter reads its input bilinearly at the pixel's own position: one row beyond the band
-        b.addExchange(exchangeRows(PLAIN_EXCHANGE_HALO_ROWS, "giSpatial0", {m_indirectDiffuse_Y_SH[1], m_indirectDiffuse_CoCg[1]}, 0, div, 2));
     }
     {   // temporal filter
         ComputePassExecution e;
@@ -185,10 +185,15 @@ void SDFGI::filterIndirectDiffuse(RenderBackend& b, const SDFTraceDependencies& 
         e.genericInfo.resources.sampledImages = {ImageResource(m_indirectDiffuseHistory_Y_SH[1], 0, 2), ImageResource(m_indirectDiffuseHistory_CoCg[1], 0, 3), ImageResource(depthSrc, 0, 4),
                                                  ImageResource(d.worldSpaceNormals, 0, 5)};
         e.dispatchCount[0] = gx; e.dispatchCount[1] = gy;
-        setRows(b, e, div, target.height);
+        // read by the upscale and, reprojected, by the NEXT frame's temporal filter: the all-gather is deferred (it overlaps upscale /
+        // froxels / shading / TAA / bloom). The upscale runs 8 full-resolution rows beyond the band (for the shading pass) and gathers
+        // half-resolution rows floor(y / 2 - 0.25) .. + 1 plus the closest-depth texel one row further: 5 rows beyond the band here,
+        // computed by this rank itself (6 with a spare; the filter's own inputs are gathered or inside the 16 uploaded halo rows)
+        setRows(b, e, div, target.height, s.halfResTrace ? 6 : 8);  // full-resolution trace: the shading pass reads this image itself, 8 rows beyond the band
         b.setComputePassExecution(e);
-        // read by the upscale (+-1 row) and, reprojected, by the next frame's temporal filter
-        b.addExchange(exchangeRows(PLAIN_EXCHANGE_ALLGATHER_ROWS, "giSpatial1", {m_indirectDiffuseHistory_Y_SH[0], m_indirectDiffuseHistory_CoCg[0]}, 0, div));
+        ExchangeRequest x = exchangeRows(PLAIN_EXCHANGE_ALLGATHER_ROWS, "giSpatial1", {m_indirectDiffuseHistory_Y_SH[0], m_indirectDiffuseHistory_CoCg[0]}, 0, div);
+        x.deferred = true;
+        b.addExchange(x);
     }
     if (s.halfResTrace) {  // upscale
         ComputePassExecution e;
@@ -300,7 +305,9 @@ void TAA::computeTemporalFilter(RenderBackend& b, ImageHandle colorSrc, const Fr
     setRows(b, e, 1, td.height, 4);  // 4 rows beyond the band: the first bloom downsample reads +-3 rows of the resolved image
     b.setComputePassExecution(e);
     // next frame's resolve reads the history at reprojected positions
-    b.addExchange(exchangeRows(PLAIN_EXCHANGE_ALLGATHER_ROWS, "taaHistory", {m_historyBuffers[(m2 + 1) % 2]}, 0, 1));
+    ExchangeRequest x = exchangeRows(PLAIN_EXCHANGE_ALLGATHER_ROWS, "taaHistory", {m_historyBuffers[(m2 + 1) % 2]}, 0, 1);
+    x.deferred = true;
+    b.addExchange(x);
 }
 hm::Vec2 TAA::computeProjectionMatrixJitter(const FrameIndex& fi) const {  // TAA.cpp:168-170
     hm::Vec2 h = hammersley2D((uint32_t)fi.mod8());
@@ -474,7 +481,9 @@ void Volumetrics::computeVolumetricLighting(RenderBackend& b, const VolumetricsS
         b.setComputePassExecution(e);
     }
     // next frame's reprojection history: every rank contributes the froxel rows of its band (in every z slice)
-    b.addExchange(exchangeRows(PLAIN_EXCHANGE_ALLGATHER_ROWS, "froxelHistory", {reprojectionTarget}, 0, froxelRowPixels));
+    ExchangeRequest x = exchangeRows(PLAIN_EXCHANGE_ALLGATHER_ROWS, "froxelHistory", {reprojectionTarget}, 0, froxelRowPixels);
+    x.deferred = true;
+    b.addExchange(x);
 }
 
 // =============================== Bloom ===============================

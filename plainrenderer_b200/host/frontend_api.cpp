@@ -126,6 +126,9 @@ int PLAIN_FE(set_scene)(plain_frontend* fe, uint32_t n, const uint32_t* meshes, 
 
 static void beginFrame(plain_frontend* fe, const plain_camera_extrinsic* cam, float time, float deltaTime, const plain_frame_inputs* in) {
     RenderFrontend& f = fe->fe;
+    // a row-sharded caller that uploads only its rows also uploads only its rows of the motion vectors: the ranks all-gather them over
+    // NVLink (they are read at reprojected positions) instead of every rank pulling the whole buffer through the host
+    f.m_motionRowsOnly = in && in->motion && f.backend.shard.active() && !(in->row_begin == 0 && in->row_end == 0);
     f.markNewFrame(time, deltaTime);
     f.prepareNewFrame();
     if (in) {  // what depthPrepass / sunShadow / the G-buffer producer write during the frame
@@ -148,7 +151,8 @@ static void beginFrame(plain_frontend* fe, const plain_camera_extrinsic* cam, fl
         upRows(t.depthBuffer, in->depth, 4);
         upRows(f.worldSpaceNormalImage(), in->normal, 4);
         upRows(f.gbuffer(), in->gbuffer, 16);
-        up(t.motionBuffer, in->motion, W * H * 4);
+        if (f.m_motionRowsOnly) upRows(t.motionBuffer, in->motion, 4);
+        else up(t.motionBuffer, in->motion, W * H * 4);
         for (int i = 0; i < 4; i++) up(f.m_shadowMaps[i], in->shadow_maps[i], (size_t)2048 * 2048 * 2);
     }
     CameraExtrinsic e;

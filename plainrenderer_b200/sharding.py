@@ -232,6 +232,13 @@ class LocalComm:
             torch.cuda.synchronize()
 
 
+def copy_exchange(x):
+    """run_segment reuses one descriptor per frontend: a deferred exchange is kept by value."""
+    y = type(x)()
+    C.memmove(C.byref(y), C.byref(x), C.sizeof(x))
+    return y
+
+
 def run_frame(fe, comm, cam, time, delta_time, inputs=None, async_upload=False, upload_rows=None):
     """One frame of one rank (DistComm)."""
     i = inputs or {}
@@ -253,10 +260,17 @@ def run_frame_local(fes, comm, cam, time, delta_time, inputs=None, upload_rows=N
     for r, fe in enumerate(fes):
         fe.begin_frame(cam, time, delta_time, i.get("depth"), i.get("motion"), i.get("normal"), i.get("gbuffer"), i.get("shadow_maps"), rows=upload_rows[r] if upload_rows else None)
     n = 0
+    late = []  # deferred exchanges (next-frame data) are performed AFTER the frame's last pass, as the peer exchange may: a pass of this
+    #            frame that needed their rows would read stale data here and fail the parity tests
     while True:
         xs = [fe.run_segment() for fe in fes]
         if xs[0] is None:
             assert all(x is None for x in xs)
+            for held in late:
+                comm.exchange_all(held)
             return n
-        comm.exchange_all(xs)
+        if xs[0].deferred:
+            late.append([copy_exchange(x) for x in xs])
+        else:
+            comm.exchange_all(xs)
         n += 1

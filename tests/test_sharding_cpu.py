@@ -119,8 +119,8 @@ def test_exchanges_over_gloo_world_size_2(cuda):
 
 
 def test_exchange_schedule_of_a_sharded_frame(ffi, oracle):
-    """the exchanges a row-sharded frontend asks for, in order - with uploaded inputs (10) and with rasterised inputs (the motion
-    vectors become an 11th, right after the depth prepass). Driven against the CPU backend: the schedule is host-side logic."""
+    """the exchanges a row-sharded frontend asks for, in order - with uploaded inputs (8) and with rasterised inputs (the motion
+    vectors become a 9th, right after the depth prepass). Driven against the CPU backend: the schedule is host-side logic."""
     from conftest import PlainSceneSequence
     from plainrenderer_b200 import assets
 
@@ -143,7 +143,11 @@ def test_exchange_schedule_of_a_sharded_frame(ffi, oracle):
     uploaded = schedule(fe, ffi.camera((-13.0, -1.7, 0.5), (1, 0, 0), (0, 0, 1), (0, -1, 0)))
     scene.close()
     fe.close()
-    assert [n for n, _, _ in uploaded] == ["histogram", "hiz", "depthHalf", "giTrace", "giSpatial0", "giTemporal", "giSpatial1", "froxelHistory", "taaHistory", "bloomMip1"]
+    # round 2: the half-res depth travels with the pyramid level (one barrier), the 2-row halo of the first spatial filter became overlapped
+    # computation, and the three exchanges of next-frame data (giSpatial1, froxelHistory, taaHistory) are marked deferred - over peer
+    # exchange they run behind the frame; through Python (this test, NCCL, LocalComm) they are ordinary all-gathers at the same place
+    assert [n for n, _, _ in uploaded] == ["histogram", "hiz+depthHalf", "giTrace", "giTemporal", "giSpatial1", "froxelHistory", "taaHistory", "bloomMip1"]
+    assert dict((n, c) for n, _, c in uploaded)["hiz+depthHalf"] == 2
     assert [n for n, _, _ in raster] == ["histogram", "motion"] + [n for n, _, _ in uploaded][1:]
     assert dict((n, k) for n, k, _ in raster)["motion"] == ffi.EXCHANGE_ALLGATHER_ROWS
     assert uploaded[0][1] == ffi.EXCHANGE_ALLREDUCE_SUM_U32

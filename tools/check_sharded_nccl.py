@@ -64,6 +64,17 @@ def main():
     upload = (max(band[0] - 16, 0), min(band[1] + 16, H))
     ok = True
     prev = None
+    skew = [a for a in sys.argv[1:] if a.startswith("--skew=")]  # --skew=RANK:MS: that rank is late on the host by MS before every frame and mid-frame
+    skew_rank, skew_ms = (int(skew[0][7:].split(":")[0]), float(skew[0][7:].split(":")[1])) if skew else (-1, 0.0)
+    if rank == skew_rank:
+        import time
+        real_exchange = comm.exchange
+        orig_run_segment = fe.run_segment
+
+        def slow_run_segment():
+            time.sleep(skew_ms * 1e-3)
+            return orig_run_segment()
+        fe.run_segment = slow_run_segment
     for f in range(frames):
         p, fw, r, u = CAMERA
         cam = ffi.camera((p[0] + 0.02 * f, p[1], p[2] + 0.01 * f), fw, r, u)
@@ -85,7 +96,11 @@ def main():
         hist_g = fe.backend.read_storage_buffer(fe.storage_buffer("histogram"), 512)
         hname = "taaHist%d" % (f % 2)
         same_hist = np.array_equal(hist_w, hist_g)
-        same_taa = np.array_equal(ref.backend.read_image(ref.image(hname)), fe.backend.read_image(fe.image(hname)))
+        taa_w, taa_g = ref.backend.read_image(ref.image(hname)), fe.backend.read_image(fe.image(hname))
+        same_taa = np.array_equal(taa_w, taa_g)
+        if not same_taa:  # which rows: the rank's own band, its overlapped rows or rows a peer pushed
+            bad = np.nonzero((taa_w.reshape(H, -1) != taa_g.reshape(H, -1)).any(axis=1))[0]
+            print("rank %d frame %d: TAA history differs in %d rows, first %d last %d (band [%d,%d))" % (rank, f, len(bad), bad[0], bad[-1], band[0], band[1]), flush=True)
         if raster:  # the all-gathered motion vectors of this frame
             mname = "motion%d" % ((f + 1) % 3)
             same_taa = same_taa and np.array_equal(ref.backend.read_image(ref.image(mname)), fe.backend.read_image(fe.image(mname)))
