@@ -181,7 +181,7 @@ public:
     }
     void addExchange(const ExchangeRequest& x) { if (m_recording && shard.active()) m_recorded.push_back(Recorded{true, ComputePassExecution(), x}); }
     // deferred frames: executions are kept on the host and sent segment by segment (run until the next exchange)
-    void beginRecording() { m_recording = true; m_recorded.clear(); m_cursor = 0; }
+    void beginRecording() { m_recording = true; m_recorded.clear(); m_pendingDeferred.clear(); m_cursor = 0; }
     void endRecording() { m_recording = false; }
     bool hasRecorded() const { return m_cursor < m_recorded.size(); }
     // sends executions up to the next exchange and submits them; returns true and fills `out` when an exchange is pending
@@ -190,8 +190,18 @@ public:
             const Recorded& r = m_recorded[m_cursor++];
             if (r.isGraphic) { sendGraphic(r); continue; }
             if (!r.isExchange) { sendExecution(r.exec); continue; }
+            // a deferred exchange over peer memory does not end the submission: its pushes are issued behind the submission it falls
+            // into (they only have to land before the next frame), so the passes around it stay in one graph with its parallel branches
+            if (r.exchange.deferred && deferredOnDevice(r.exchange)) { m_pendingDeferred.push_back(&r.exchange); continue; }
             check(PLAIN_FN(submit_recorded_passes)(m_ctx));
-            if (peerExchange(r.exchange)) continue;  // done on the device: rows pushed into the peers' images + flag barrier
+            issuePendingDeferred();
+            // two exchanges back to back share the second one's barrier (pushes enqueued before a barrier on any rank are visible after it)
+            bool nextHasBarrier = false;
+            if (m_cursor < m_recorded.size() && m_recorded[m_cursor].isExchange && !m_recorded[m_cursor].exchange.deferred) {
+                const ExchangeRequest& nx = m_recorded[m_cursor].exchange;
+                nextHasBarrier = m_peerExchange && shard.active() && (nx.kind == PLAIN_EXCHANGE_ALLREDUCE_SUM_U32 || imagesMapped(nx));
+            }
+            if (peerExchange(r.exchange, nextHasBarrier)) continue;  // done on the device: rows pushed into the peers' images + flag barrier
             std::memset(out, 0, sizeof(*out));
             out->kind = r.exchange.kind;
             out->halo_rows = r.exchange.haloRows;
@@ -225,6 +235,7 @@ public:
             return true;
         }
         check(PLAIN_FN(render_frame)(m_ctx, 1));
+        issuePendingDeferred();
         if (m_deferredIssued) { check(PLAIN_FN(peer_flush_deferred)(m_ctx)); m_deferredIssued = false; }  // one barrier for the frame's deferred pushes
         return false;
     }
@@ -241,7 +252,25 @@ public:
         if (lo > hi) lo = hi;
         *a = lo; *b = hi;
     }
-    bool peerExchange(const ExchangeRequest& x) {
+    std::vector<const ExchangeRequest*> m_pendingDeferred;
+    bool imagesMapped(const ExchangeRequest& x) {
+        for (size_t i = 0; i < x.images.size(); i++) {
+            plain_image_handle h;
+            h.type = (uint32_t)x.images[i].type;
+            h.index = x.images[i].index;
+            if (!PLAIN_FN(peer_image_ready)(m_ctx, h)) return false;
+        }
+        return true;
+    }
+    bool deferredOnDevice(const ExchangeRequest& x) {
+        return m_peerExchange && m_peerDeferred && shard.active() && x.kind == PLAIN_EXCHANGE_ALLGATHER_ROWS && imagesMapped(x);
+    }
+    void issuePendingDeferred() {
+        for (const ExchangeRequest* x : m_pendingDeferred)
+            if (!peerExchange(*x)) throw std::runtime_error("deferred peer exchange: image not mapped");
+        m_pendingDeferred.clear();
+    }
+    bool peerExchange(const ExchangeRequest& x, bool skipBarrier = false) {
         if (!m_peerExchange || !shard.active()) return false;
         if (x.kind == PLAIN_EXCHANGE_ALLREDUCE_SUM_U32) {
             check(PLAIN_FN(peer_allreduce_sum_u32)(m_ctx, x.buffer, x.elementCount));
@@ -276,7 +305,7 @@ public:
             return true;
         }
         check(PLAIN_FN(peer_push_rows)(m_ctx, (uint32_t)pushes.size(), pushes.data()));
-        check(PLAIN_FN(peer_barrier)(m_ctx));
+        if (!skipBarrier) check(PLAIN_FN(peer_barrier)(m_ctx));
         return true;
     }
     void sendGraphic(const Recorded& r);

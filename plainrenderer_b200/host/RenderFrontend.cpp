@@ -445,26 +445,46 @@ void RenderFrontend::prepareRenderpasses() {
         return;
     }
 
-    computeColorBufferHistogram(previousRenderTarget.colorBuffer);
-    m_sky.updateTransmissionLut(backend);
-    computeExposure();
-    m_sky.updateSkyLut(backend, m_lightBuffer, m_atmosphereSettings);
-    // depth / motion / normal / G-buffer / shadow maps of this frame: rasterised from the meshes (m_rasterInputs) or uploaded
-    if (m_rasterInputs) renderDepthPrepass(currentRenderTarget.depthBuffer, worldSpaceNormalImage(), currentRenderTarget.motionBuffer);
     // row-sharded: the half-resolution depth is produced next to the pyramid's local levels and gathered in the same exchange
     const bool downscaleWithPyramid = backend.shard.active() && m_shadingConfig.indirectLightingTech == IndirectLightingTech::SDFTrace && m_sdfTraceSettings.halfResTrace;
-    computeDepthPyramid(currentRenderTarget.depthBuffer, downscaleWithPyramid ? &currentRenderTarget : nullptr);
+    // row-sharded with uploaded inputs: the rank's share of the histogram, of the pyramid and of the half-resolution depth need nothing
+    // but last frame's colour and this frame's depth, so they are recorded first and their two exchanges (row all-gather, counter
+    // all-reduce) share ONE barrier; everything up to the SDF trace - exposure, the three sky LUTs, the small pyramid levels, light
+    // matrices, the froxel chain, instance culling - then forms one submission whose independent chains run side by side
+    const bool exchangesFirst = backend.shard.active() && !m_rasterInputs;
+    if (exchangesFirst) {
+        computeColorBufferHistogram(previousRenderTarget.colorBuffer, false);
+        computeDepthPyramid(currentRenderTarget.depthBuffer, downscaleWithPyramid ? &currentRenderTarget : nullptr, true);
+        backend.addExchange(m_pendingHistogramExchange);
+        m_sky.updateTransmissionLut(backend);
+        computeExposure();
+        m_sky.updateSkyLut(backend, m_lightBuffer, m_atmosphereSettings);
+        backend.setComputePassExecution(m_pendingPyramidRest);
+    } else {
+        computeColorBufferHistogram(previousRenderTarget.colorBuffer);
+        m_sky.updateTransmissionLut(backend);
+        computeExposure();
+        m_sky.updateSkyLut(backend, m_lightBuffer, m_atmosphereSettings);
+        // depth / motion / normal / G-buffer / shadow maps of this frame: rasterised from the meshes (m_rasterInputs) or uploaded
+        if (m_rasterInputs) renderDepthPrepass(currentRenderTarget.depthBuffer, worldSpaceNormalImage(), currentRenderTarget.motionBuffer);
+        computeDepthPyramid(currentRenderTarget.depthBuffer, downscaleWithPyramid ? &currentRenderTarget : nullptr);
+    }
     computeSunLightMatrices();
     if (m_rasterInputs) renderSunShadowCascades();
-    if (m_shadingConfig.indirectLightingTech == IndirectLightingTech::SDFTrace) {
-        if (m_sdfTraceSettings.halfResTrace && !downscaleWithPyramid) downscaleDepth(currentRenderTarget);
-        m_sdfGi.computeIndirectLighting(backend, fillOutSdfGiDependencies(), m_sdfTraceSettings, m_frameIndex);
-    }
     Volumetrics::Dependencies vd;
     vd.lightBuffer = m_lightBuffer;
     vd.shadowMap = m_shadowMaps[m_shadingConfig.sunShadowCascadeCount - 1];
     vd.sunShadowInfoBuffer = m_sunShadowInfoBuffer;
-    m_volumetrics.computeVolumetricLighting(backend, m_volumetricsSettings, m_windSettings, vd, m_frameIndex, m_deltaTime);
+    // row-sharded: a submission ends at every exchange, so the froxel chain (which depends on the light matrices and the exposure only)
+    // is recorded next to the SDF trace instead of behind the GI chain - the backend's scheduler runs it on a side stream beside the
+    // trace, as it does in the unsharded frame's single submission. Same passes, same inputs, same bits.
+    const bool volumetricsFirst = backend.shard.active();
+    if (volumetricsFirst) m_volumetrics.computeVolumetricLighting(backend, m_volumetricsSettings, m_windSettings, vd, m_frameIndex, m_deltaTime);
+    if (m_shadingConfig.indirectLightingTech == IndirectLightingTech::SDFTrace) {
+        if (m_sdfTraceSettings.halfResTrace && !downscaleWithPyramid) downscaleDepth(currentRenderTarget);
+        m_sdfGi.computeIndirectLighting(backend, fillOutSdfGiDependencies(), m_sdfTraceSettings, m_frameIndex);
+    }
+    if (!volumetricsFirst) m_volumetrics.computeVolumetricLighting(backend, m_volumetricsSettings, m_windSettings, vd, m_frameIndex, m_deltaTime);
 
     if (m_rasterInputs) fillGBuffer(gbuffer(), currentRenderTarget.depthBuffer);
     shadeGBuffer(currentRenderTarget.colorBuffer);  // renderForwardShading + m_sky.renderSky
@@ -673,7 +693,7 @@ uint32_t RenderFrontend::registerSdfMesh(const uint16_t* texels, uint32_t rx, ui
     return (uint32_t)m_frontendMeshes.size() - 1;
 }
 
-void RenderFrontend::computeColorBufferHistogram(ImageHandle lastFrameColor) {
+void RenderFrontend::computeColorBufferHistogram(ImageHandle lastFrameColor, bool exchange) {
     StorageBufferResource histogramPerTileResource(m_histogramPerTileBuffer, false, 0);
     StorageBufferResource histogramResource(m_histogramBuffer, false, 1);
     {
@@ -712,7 +732,8 @@ void RenderFrontend::computeColorBufferHistogram(ImageHandle lastFrameColor) {
     x.name = "histogram";
     x.buffer = m_histogramBuffer.index;
     x.elementCount = nHistogramBins;
-    backend.addExchange(x);
+    if (exchange) backend.addExchange(x);
+    else m_pendingHistogramExchange = x;
 }
 
 void RenderFrontend::computeExposure() {
@@ -723,7 +744,7 @@ void RenderFrontend::computeExposure() {
     backend.setComputePassExecution(e);
 }
 
-void RenderFrontend::computeDepthPyramid(ImageHandle depthBuffer, const FrameRenderTargets* alsoDownscale) {
+void RenderFrontend::computeDepthPyramid(ImageHandle depthBuffer, const FrameRenderTargets* alsoDownscale, bool holdRest) {
     ComputePassExecution e;
     e.genericInfo.handle = m_depthPyramidPass;
     const uint32_t width = m_screenWidth / 2, height = m_screenHeight / 2;
@@ -766,7 +787,8 @@ void RenderFrontend::computeDepthPyramid(ImageHandle depthBuffer, const FrameRen
     backend.addExchange(x);
     ComputePassExecution rest = e;
     rest.shardPhase = 2;
-    backend.setComputePassExecution(rest);
+    if (holdRest) m_pendingPyramidRest = rest;  // emitted by the caller after the exchange that follows (prepareRenderpasses)
+    else backend.setComputePassExecution(rest);
 }
 
 void RenderFrontend::computeSunLightMatrices() {

@@ -237,9 +237,11 @@ private:
     void initBuffers();
     void initRenderpasses();
     void prepareRenderpasses();
-    void computeColorBufferHistogram(ImageHandle lastFrameColor);
+    void computeColorBufferHistogram(ImageHandle lastFrameColor, bool exchange = true);
     void computeExposure();
-    void computeDepthPyramid(ImageHandle depthBuffer, const FrameRenderTargets* alsoDownscale = nullptr);
+    void computeDepthPyramid(ImageHandle depthBuffer, const FrameRenderTargets* alsoDownscale = nullptr, bool holdRest = false);
+    ComputePassExecution m_pendingPyramidRest;
+    ExchangeRequest m_pendingHistogramExchange;
     void computeSunLightMatrices();
     void downscaleDepth(const FrameRenderTargets& current, bool exchange = true);
     void shadeGBuffer(ImageHandle colorTarget);

@@ -146,8 +146,13 @@ def test_exchange_schedule_of_a_sharded_frame(ffi, oracle):
     # round 2: the half-res depth travels with the pyramid level (one barrier), the 2-row halo of the first spatial filter became overlapped
     # computation, and the three exchanges of next-frame data (giSpatial1, froxelHistory, taaHistory) are marked deferred - over peer
     # exchange they run behind the frame; through Python (this test, NCCL, LocalComm) they are ordinary all-gathers at the same place
-    assert [n for n, _, _ in uploaded] == ["histogram", "hiz+depthHalf", "giTrace", "giTemporal", "giSpatial1", "froxelHistory", "taaHistory", "bloomMip1"]
+    # round 2: the half-res depth travels with the pyramid level, the 2-row halo of the first spatial filter became overlapped
+    # computation, the three exchanges of next-frame data (froxelHistory, giSpatial1, taaHistory) are marked deferred - over peer exchange
+    # they run behind the frame; through Python (this test, NCCL, LocalComm) they are ordinary all-gathers - and with uploaded inputs the
+    # rank-local work is recorded first so that the row all-gather and the histogram all-reduce are back to back (one barrier on the device)
+    tail = ["froxelHistory", "giTrace", "giTemporal", "giSpatial1", "taaHistory", "bloomMip1"]  # the froxel chain is recorded beside the trace
+    assert [n for n, _, _ in uploaded] == ["hiz+depthHalf", "histogram"] + tail
     assert dict((n, c) for n, _, c in uploaded)["hiz+depthHalf"] == 2
-    assert [n for n, _, _ in raster] == ["histogram", "motion"] + [n for n, _, _ in uploaded][1:]
+    assert [n for n, _, _ in raster] == ["histogram", "motion", "hiz+depthHalf"] + tail
     assert dict((n, k) for n, k, _ in raster)["motion"] == ffi.EXCHANGE_ALLGATHER_ROWS
-    assert uploaded[0][1] == ffi.EXCHANGE_ALLREDUCE_SUM_U32
+    assert uploaded[1][1] == ffi.EXCHANGE_ALLREDUCE_SUM_U32
