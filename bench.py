@@ -385,6 +385,12 @@ def run_ours(args, rank, world, local_rank):
         alg_frame = algorithmic_bytes(WIDTH, HEIGHT)
         # rank 0's kernels cover rank 0's band: the bytes a launch moves are the band's share of the pass (replicated passes move all of them)
         band_share = (band[1] - band[0]) / float(HEIGHT)
+        if acc.get("Indirect lighting upscale", 1.0) < 0.004:
+            # pass fusion (the product's default): the upscale is folded into the shading kernel - its two full-resolution images
+            # (12 bytes per pixel written, 12 read) do not exist; shading reads the upscale's inputs instead (full-res depth + half-res GI / depth)
+            N_, n_ = WIDTH * HEIGHT, (WIDTH // 2) * (HEIGHT // 2)
+            alg_frame["Forward shading"] += 4 * N_ + 14 * n_ - 12 * N_
+            alg_frame["Indirect lighting upscale"] = 0
         alg = {k: (v if (not sharded or k.startswith(REPLICATED_PASSES)) else int(v * band_share)) for k, v in alg_frame.items()}
         top = max(acc, key=lambda k: acc[k])
         launches_of_top = 2 if top == "Indirect diffuse spatial filter" else 1

@@ -456,6 +456,7 @@ int PLAIN_FN(get_storage_buffer_device_pointer)(plain_ctx* ctx, plain_handle buf
 }
 int PLAIN_FN(get_last_frame_launch_count)(plain_ctx* ctx, uint32_t* out) { (void)ctx; *out = 0; return 0; }
 int PLAIN_FN(set_graph_replay_enabled)(plain_ctx* ctx, int enabled) { (void)ctx; (void)enabled; return 0; }
+int PLAIN_FN(set_pass_fusion_enabled)(plain_ctx*, int) { return 0; }  // the oracle runs every pass as recorded
 // peer exchange over NVLink: CUDA backend only
 static int peerUnsupported(plain_ctx* ctx) { ctx->c.lastError = "peer exchange is not available in the CPU oracle"; return 1; }
 int PLAIN_FN(peer_init)(plain_ctx* ctx, uint32_t, uint32_t) { return peerUnsupported(ctx); }

@@ -124,6 +124,7 @@ struct Backend {
     std::vector<cudaEvent_t> timingEvents;
 
     bool graphEnabled = false;
+    bool fusionEnabled = true;  // planFusions: indirectLightUpscale.comp folded into gbufferShading.comp (set_pass_fusion_enabled)
     std::unordered_map<uint64_t, CachedGraph> graphs;
     static const size_t kMaxCachedGraphs = 32;
     uint64_t graphUseCounter = 0;
@@ -251,6 +252,8 @@ const void* LaunchCtx::ubufRaw(uint32_t binding) {
     return nullptr;
 }
 void LaunchCtx::countLaunch(int n) { be->launchCounter += (uint32_t)n; }
+const ExecRecord* LaunchCtx::be_exec(int index) const { return &be->execs[(size_t)index]; }
+const PassRecord* LaunchCtx::be_pass(uint32_t p) const { return &be->passes[p]; }
 size_t LaunchCtx::be_imageCount() const { return be->images.size(); }
 int LaunchCtx::be_imageFormat(uint32_t index) const { return index < be->images.size() ? (int)be->images[index].desc.format : -1; }
 
@@ -375,6 +378,44 @@ static void passDependencies(Backend& b, std::vector<std::vector<int>>& deps) {
     }
 }
 
+// Pass fusion. indirectLightUpscale.comp writes two full-resolution images (12 bytes per pixel) that gbufferShading.comp reads back at
+// the pixel's own texel (triangle.frag:294-320): when both are in one submission, nothing else in it touches the two images and they
+// have the colour target's extent, the shading kernel computes the upscaled texel itself (giUpscalePixel, rounded through binary16 like
+// the store) and the upscale is not launched. The images then keep their previous contents: callers that read them back (tests,
+// debugging) switch fusion off with set_pass_fusion_enabled(ctx, 0). The producer keeps its place in the dependency order, so the
+// consumer still waits for everything the producer's inputs depend on, and for the same row window.
+static void planFusions(Backend& b) {
+    for (auto& e : b.execs) { e.fusedProducer = -1; e.fusedAway = false; }
+    if (!b.fusionEnabled) return;
+    auto same = [](const plain_image_resource& a, const plain_image_resource& c) { return a.image.type == c.image.type && a.image.index == c.image.index && a.mip_level == c.mip_level; };
+    auto find = [](const std::vector<plain_image_resource>& v, uint32_t binding) -> const plain_image_resource* { for (auto& r : v) if (r.binding == binding) return &r; return nullptr; };
+    for (size_t j = 0; j < b.execs.size(); j++) {
+        ExecRecord& consumer = b.execs[j];
+        if (b.passes[consumer.pass].graphic || b.passes[consumer.pass].shader != "gbufferShading.comp") continue;
+        const plain_image_resource* y = find(consumer.sampledImages, 15), *cg = find(consumer.sampledImages, 16);
+        if (!y || !cg) continue;
+        int producer = -1;
+        for (size_t i = 0; i < j; i++) {
+            const ExecRecord& e = b.execs[i];
+            if (b.passes[e.pass].graphic || b.passes[e.pass].shader != "indirectLightUpscale.comp") continue;
+            const plain_image_resource* oy = find(e.storageImages, 0), *oc = find(e.storageImages, 1);
+            if (oy && oc && same(*oy, *y) && same(*oc, *cg)) producer = (int)i;
+        }
+        if (producer < 0) continue;
+        const ExecRecord& pe = b.execs[(size_t)producer];
+        if (pe.rowBegin != consumer.rowBegin || pe.rowEnd != consumer.rowEnd) continue;  // both cover the same rows (row sharding: band + 8)
+        bool othersTouch = false;
+        for (size_t k = 0; k < b.execs.size() && !othersTouch; k++) {
+            if ((int)k == producer || k == j) continue;
+            for (auto& r : b.execs[k].sampledImages) othersTouch = othersTouch || same(r, *y) || same(r, *cg);
+            for (auto& r : b.execs[k].storageImages) othersTouch = othersTouch || same(r, *y) || same(r, *cg);
+        }
+        if (othersTouch) continue;
+        consumer.fusedProducer = producer;
+        b.execs[(size_t)producer].fusedAway = true;
+    }
+}
+
 #define SCHED_CHECK(call, what)                                                                                         \
     do {                                                                                                                \
         cudaError_t e__ = (call);                                                                                       \
@@ -431,7 +472,7 @@ static bool runPasses(Backend& b, bool withTiming) {
             while (b.timingEvents.size() < ev + 2) { cudaEvent_t x; cudaEventCreate(&x); b.timingEvents.push_back(x); }
             cudaEventRecord(b.timingEvents[ev], b.stream);
         }
-        c.pass->fn(c);
+        if (!e.fusedAway) c.pass->fn(c);  // a fused-away producer keeps its events: its consumer inherits its dependencies through them
         if (withTiming) { cudaEventRecord(b.timingEvents[ev + 1], b.stream); ev += 2; }
         if (concurrent) SCHED_CHECK(cudaEventRecord(b.passEvents[i], c.stream), "pass event record");
         if (c.failed) { b.lastError = c.error; if (concurrent) for (int k = 1; k <= Backend::kSideStreams; k++) if (forked[k] && tail[k] >= 0) cudaStreamWaitEvent(b.stream, b.passEvents[(size_t)tail[k]], 0); return false; }
@@ -1003,6 +1044,7 @@ int PLAIN_FN(render_frame)(plain_ctx* ctx, int present) {
         b.stagingUsed = kStagingHeader;
     }
     const uint32_t fillLaunches = b.launchCounter;
+    planFusions(b);
     if (b.timingEnabled) {
         if (!runPasses(b, true)) return 1;
         CU_CHECK(ctx, cudaStreamSynchronize(b.stream));
@@ -1143,6 +1185,7 @@ int PLAIN_FN(get_storage_buffer_device_pointer)(plain_ctx* ctx, plain_handle buf
 }
 int PLAIN_FN(get_last_frame_launch_count)(plain_ctx* ctx, uint32_t* out) { *out = ctx->b.lastFrameLaunches; return 0; }
 int PLAIN_FN(set_graph_replay_enabled)(plain_ctx* ctx, int enabled) { ctx->b.graphEnabled = enabled != 0; return 0; }
+int PLAIN_FN(set_pass_fusion_enabled)(plain_ctx* ctx, int enabled) { ctx->b.fusionEnabled = enabled != 0; ctx->b.passEpoch++; return 0; }
 int PLAIN_FN(set_concurrent_passes_enabled)(plain_ctx* ctx, int enabled) {
     if ((enabled != 0) != ctx->b.concurrentPasses) ctx->b.passEpoch++;  // cached graphs were captured with the other schedule
     ctx->b.concurrentPasses = enabled != 0;

@@ -82,6 +82,9 @@ struct ExecRecord {
     std::vector<uint8_t> pushConstants;
     uint32_t dispatch[3];
     uint32_t rowBegin = 0, rowEnd = 0, shardPhase = 0;  // row sharding (plain_compute_pass_execution), 0/0/0 = whole pass
+    // pass fusion (backend.cu planFusions): a producer whose only consumer in the submission computes its texels inline
+    int fusedProducer = -1;   // consumer: index of the execution it absorbed
+    bool fusedAway = false;   // producer: no launch (its place in the dependency order is kept)
 };
 
 struct Backend;
@@ -145,6 +148,8 @@ struct LaunchCtx {
         if (y1 < y0) y1 = y0;
     }
     void countLaunch(int n = 1);
+    const ExecRecord* be_exec(int index) const;  // another execution of the same submission (pass fusion)
+    const PassRecord* be_pass(uint32_t pass) const;
     size_t be_imageCount() const;               // image table of the backend (bindless slot == image handle index)
     int be_imageFormat(uint32_t index) const;
 };

@@ -1296,48 +1296,17 @@ PLAIN_PASS(launch_giTemporalFilter, "filterIndirectDiffuseTemporal.comp") {
 
 // ---------------- indirectLightUpscale.comp ----------------
 struct UpscaleParams {
-    ImgView dstYSH, dstCoCg, srcYSH, srcCoCg, fullResDepth, halfResDepth;
+    ImgView dstYSH, dstCoCg;
+    UpscaleSource src;
     const plain_global_shader_info* g;
     int y0, y1;  // rows to produce (row sharding)
 };
 __global__ void __launch_bounds__(256) giUpscaleKernel(const __grid_constant__ UpscaleParams p) {
     const int ix = blockIdx.x * 32 + (threadIdx.x & 31), iy = p.y0 + blockIdx.y * 8 + (threadIdx.x >> 5);
     if (ix >= p.dstYSH.w || iy >= p.y1) return;
-    const plain_global_shader_info* g = p.g;
-    const float nearP = g->nearPlane, farP = g->farPlane;
-    const vec2 uv = (v2((float)ix, (float)iy) + 0.5f) / v2((float)g->screenResolution[0], (float)g->screenResolution[1]);
-    float fullResDepth = sampleNearest2D<WRAP_CLAMP, float>([&](int x, int y) { return loadD32(p.fullResDepth, x, y); }, p.fullResDepth.w, p.fullResDepth.h, uv, 0.f);
-    fullResDepth = linearizeDepth(fullResDepth, nearP, farP);
-    const vec2 halfResTexelSize = 1.f / v2((float)p.halfResDepth.w, (float)p.halfResDepth.h);
-    // textureGather: (i0,j1), (i1,j1), (i1,j0), (i0,j0) with i0 = floor(u*w - 0.5), clamp-to-edge
-    const int gx0 = f2i(floorf_(sanitizeCoord(uv.x) * (float)p.halfResDepth.w - 0.5f));
-    const int gy0 = f2i(floorf_(sanitizeCoord(uv.y) * (float)p.halfResDepth.h - 0.5f));
-    auto G4 = [&](int x, int y) { return loadR16F(p.halfResDepth, iclamp(x, 0, p.halfResDepth.w - 1), iclamp(y, 0, p.halfResDepth.h - 1)); };
-    float depthSamples[4] = {G4(gx0, gy0 + 1), G4(gx0 + 1, gy0 + 1), G4(gx0 + 1, gy0), G4(gx0, gy0)};
-    for (int i = 0; i < 4; i++) depthSamples[i] = linearizeDepth(depthSamples[i], nearP, farP);
-    float minDepthDiff = 1000.f;
-    vec2 closestDepthTexel = v2(0.f);
-    const float edgeDepthThreshold = 0.5f;
-    bool isEdge = false;
-    const float offX[4] = {0.f, 1.f, 1.f, 0.f}, offY[4] = {1.f, 1.f, 0.f, 0.f};
-    for (int i = 0; i < 4; i++) {
-        const float depthDiff = absf(depthSamples[i] - fullResDepth);
-        isEdge = isEdge || depthDiff > edgeDepthThreshold;
-        if (depthDiff < minDepthDiff) {
-            minDepthDiff = depthDiff;
-            closestDepthTexel = v2(offX[i], offY[i]);
-        }
-    }
-    const vec2 uvClosestTexel = uv + closestDepthTexel * halfResTexelSize;
     vec4 result_Y_SH;
     vec2 result_CoCg;
-    if (isEdge) {
-        result_Y_SH = sampleNearest2D<WRAP_CLAMP, vec4>([&](int x, int y) { return loadRGBA16F(p.srcYSH, x, y); }, p.srcYSH.w, p.srcYSH.h, uvClosestTexel, v4(0.f));
-        result_CoCg = sampleNearest2D<WRAP_CLAMP, vec2>([&](int x, int y) { return loadRG16F(p.srcCoCg, x, y); }, p.srcCoCg.w, p.srcCoCg.h, uvClosestTexel, v2(0.f));
-    } else {
-        result_Y_SH = sampleRGBA16FLinearClamp(p.srcYSH, uv);
-        result_CoCg = sampleRG16FLinearClamp(p.srcCoCg, uv);
-    }
+    giUpscalePixel(p.src, p.g, ix, iy, result_Y_SH, result_CoCg);
     storeRGBA16F(p.dstYSH, ix, iy, 0, result_Y_SH);
     if (inRange(p.dstCoCg, ix, iy)) storeRG16F(p.dstCoCg, ix, iy, result_CoCg);
 }
@@ -1345,10 +1314,10 @@ PLAIN_PASS(launch_giUpscale, "indirectLightUpscale.comp") {
     UpscaleParams p;
     p.dstYSH = c.storage(0, PLAIN_FORMAT_RGBA16_SFLOAT);
     p.dstCoCg = c.storage(1, PLAIN_FORMAT_RG16_SFLOAT);
-    p.srcYSH = c.sampled(2, PLAIN_FORMAT_RGBA16_SFLOAT);
-    p.srcCoCg = c.sampled(3, PLAIN_FORMAT_RG16_SFLOAT);
-    p.fullResDepth = c.sampled(4, PLAIN_FORMAT_DEPTH32);
-    p.halfResDepth = c.sampled(5, PLAIN_FORMAT_R16_SFLOAT);
+    p.src.srcYSH = c.sampled(2, PLAIN_FORMAT_RGBA16_SFLOAT);
+    p.src.srcCoCg = c.sampled(3, PLAIN_FORMAT_RG16_SFLOAT);
+    p.src.fullResDepth = c.sampled(4, PLAIN_FORMAT_DEPTH32);
+    p.src.halfResDepth = c.sampled(5, PLAIN_FORMAT_R16_SFLOAT);
     p.g = c.g;
     if (c.failed) return;
     if ((int)c.exec->dispatch[0] * 8 < p.dstYSH.w || (int)c.exec->dispatch[1] * 8 < p.dstYSH.h) { c.fail("indirectLightUpscale.comp: dispatch does not cover the target"); return; }

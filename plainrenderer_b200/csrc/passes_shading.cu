@@ -49,6 +49,7 @@ struct ShadingParams {
     uint32_t sunShadowCascadeCount;
     float sunSpriteModel[16];
     int hasSunSprite;
+    UpscaleSource upscale;  // FUSED: the inputs of the indirectLightUpscale.comp execution this kernel absorbed (ySH / coCg are then only extents)
 };
 
 __device__ __forceinline__ vec3 decodeOctNormal(uint32_t packed) {
@@ -121,7 +122,7 @@ __device__ __forceinline__ float calcShadow(const ImgView& shadowMap, const floa
     return shadow / sampleCount;
 }
 
-template <int DIFFUSE, int MULTI, int GEOAA, int TECH>
+template <int DIFFUSE, int MULTI, int GEOAA, int TECH, bool FUSED>
 __device__ __forceinline__ vec3 shadeGeometry(const ShadingParams& p, const Globals& G, int x, int y, uint4 texel, vec3 N, vec3 N_U, vec3 N_V, vec3 cameraToPixel, uint32_t noiseBytes) {
     const plain_global_shader_info* g = p.g;
     const vec2 fragCoord = v2((float)x + 0.5f, (float)y + 0.5f);
@@ -199,9 +200,25 @@ __device__ __forceinline__ vec3 shadeGeometry(const ShadingParams& p, const Glob
     const vec2 screenRes = v2((float)g->screenResolution[0], (float)g->screenResolution[1]);
     if ((TECH >= 0 ? TECH : p.indirectLightingTech) == 0) {  // :295-322
         const vec2 screenUV = fragCoord / screenRes;
-        const vec4 irradiance_Y_SH = sampleNearest2D<WRAP_CLAMP, vec4>([&](int tx, int ty) { return loadRGBA16F(p.ySH, tx, ty); }, p.ySH.w, p.ySH.h, screenUV, v4(0.f));
+        vec4 irradiance_Y_SH;
+        vec2 irradiance_CoCg;
+        if (FUSED) {
+            // the upscale pass folded into its consumer (indirectLightUpscale.comp:17-71 -> triangle.frag:294-320): the nearest texel the two
+            // lookups below would have fetched is computed here for that texel, and rounded through binary16 exactly as its store +
+            // load would have done. 28 bytes per pixel (12 written, 12 + 4 read) and one launch less; the launcher checked that the
+            // full-resolution GI images have the colour target's extent, so both lookups address the same texel
+            ivec2 zero; zero.x = 0; zero.y = 0;
+            const ivec2 t = sampleNearest2D<WRAP_CLAMP, ivec2>([&](int tx, int ty) { ivec2 r; r.x = tx; r.y = ty; return r; }, p.ySH.w, p.ySH.h, screenUV, zero);  // the sampler's own texel selection
+            vec4 up_Y_SH;
+            vec2 up_CoCg;
+            giUpscalePixel(p.upscale, g, t.x, t.y, up_Y_SH, up_CoCg);
+            irradiance_Y_SH = v4(halfToFloat(floatToHalf(up_Y_SH.x)), halfToFloat(floatToHalf(up_Y_SH.y)), halfToFloat(floatToHalf(up_Y_SH.z)), halfToFloat(floatToHalf(up_Y_SH.w)));
+            irradiance_CoCg = v2(halfToFloat(floatToHalf(up_CoCg.x)), halfToFloat(floatToHalf(up_CoCg.y)));
+        } else {
+            irradiance_Y_SH = sampleNearest2D<WRAP_CLAMP, vec4>([&](int tx, int ty) { return loadRGBA16F(p.ySH, tx, ty); }, p.ySH.w, p.ySH.h, screenUV, v4(0.f));
+            irradiance_CoCg = sampleNearest2D<WRAP_CLAMP, vec2>([&](int tx, int ty) { return loadRG16F(p.coCg, tx, ty); }, p.coCg.w, p.coCg.h, screenUV, v2(0.f));
+        }
         const float irradiance_Y = dot(irradiance_Y_SH, directionToSH_L1(N));
-        const vec2 irradiance_CoCg = sampleNearest2D<WRAP_CLAMP, vec2>([&](int tx, int ty) { return loadRG16F(p.coCg, tx, ty); }, p.coCg.w, p.coCg.h, screenUV, v2(0.f));
         const vec3 irradiance = YCoCgToLinear(v3(irradiance_Y, irradiance_CoCg.x, irradiance_CoCg.y));
         const vec3 diffuseIndirect = irradiance * diffuseColor * diffuseBRDFIntegral;
 
@@ -282,7 +299,7 @@ __device__ __forceinline__ vec3 shadeSky(const ShadingParams& p, int x, int y, v
     return color;
 }
 
-template <int DIFFUSE, int MULTI, int GEOAA, int TECH>
+template <int DIFFUSE, int MULTI, int GEOAA, int TECH, bool FUSED = false>
 __global__ void __launch_bounds__(256, 4) gbufferShadingKernel(const __grid_constant__ ShadingParams p, int limitX, int limitY, int y0) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int x = blockIdx.x * 32 + (warp & 1) * 16 + (lane & 15);
@@ -317,7 +334,7 @@ __global__ void __launch_bounds__(256, 4) gbufferShadingKernel(const __grid_cons
         const ImgView noiseTex = p.bindless[g->noiseTextureIndices[g->frameIndexMod4]].view;
         const vec2 noiseUV = v2((float)x + 0.5f, (float)y + 0.5f) / v2((float)noiseTex.w, (float)noiseTex.h);
         const uint32_t noiseBytes = sampleNearest2D<WRAP_REPEAT, uint32_t>([&](int tx, int ty) { return (uint32_t)ldg((const uint16_t*)noiseTex.ptr + texelIndex(noiseTex, tx, ty)); }, noiseTex.w, noiseTex.h, noiseUV, 0u);
-        color = shadeGeometry<DIFFUSE, MULTI, GEOAA, TECH>(p, G, x, y, texel, N, N_U, N_V, cameraToPixel, noiseBytes);
+        color = shadeGeometry<DIFFUSE, MULTI, GEOAA, TECH, FUSED>(p, G, x, y, texel, N, N_U, N_V, cameraToPixel, noiseBytes);
     }
     storeR11(p.colorOut, x, y, color);
 }
@@ -356,7 +373,24 @@ PLAIN_PASS(launch_gbufferShading, "gbufferShading.comp") {
     if (y0 % 2 != 0) { c.fail("gbufferShading.comp: row window must start at an even row (2x2 quads)"); return; }
     if (y1 <= y0) return;
     dim3 grid(ceilDiv(p.colorOut.w, 32), ceilDiv((unsigned)(y1 - y0), 8));
-    if (p.diffuseBRDF == 2 && p.directMultiscatterBRDF == 0 && p.geometricAA && p.indirectLightingTech == 0)
+    // the backend folded the execution that produces ySH / coCg (indirectLightUpscale.comp) into this one: its inputs travel in p.upscale
+    bool fused = false;
+    if (c.exec->fusedProducer >= 0 && p.indirectLightingTech == 0 && p.ySH.w == p.colorOut.w && p.ySH.h == p.colorOut.h && p.coCg.w == p.colorOut.w && p.coCg.h == p.colorOut.h) {
+        LaunchCtx u = c;
+        u.exec = c.be_exec(c.exec->fusedProducer);
+        u.pass = c.be_pass(u.exec->pass);
+        p.upscale.srcYSH = u.sampled(2, PLAIN_FORMAT_RGBA16_SFLOAT);
+        p.upscale.srcCoCg = u.sampled(3, PLAIN_FORMAT_RG16_SFLOAT);
+        p.upscale.fullResDepth = u.sampled(4, PLAIN_FORMAT_DEPTH32);
+        p.upscale.halfResDepth = u.sampled(5, PLAIN_FORMAT_R16_SFLOAT);
+        if (u.failed) { c.fail(u.error); return; }
+        fused = true;
+    } else if (c.exec->fusedProducer >= 0) { c.fail("gbufferShading.comp: an upscale execution was folded into a configuration that does not read it"); return; }
+    if (fused && p.diffuseBRDF == 2 && p.directMultiscatterBRDF == 0 && p.geometricAA)
+        PLAIN_LAUNCH(c, (gbufferShadingKernel<2, 0, 1, 0, true>), grid, 256, 0, p, limX, y1, y0);
+    else if (fused)
+        PLAIN_LAUNCH(c, (gbufferShadingKernel<-1, -1, -1, 0, true>), grid, 256, 0, p, limX, y1, y0);
+    else if (p.diffuseBRDF == 2 && p.directMultiscatterBRDF == 0 && p.geometricAA && p.indirectLightingTech == 0)
         PLAIN_LAUNCH(c, (gbufferShadingKernel<2, 0, 1, 0>), grid, 256, 0, p, limX, y1, y0);
     else if (p.diffuseBRDF == 2 && p.directMultiscatterBRDF == 0 && p.geometricAA && p.indirectLightingTech == 1)
         PLAIN_LAUNCH(c, (gbufferShadingKernel<2, 0, 1, 1>), grid, 256, 0, p, limX, y1, y0);

@@ -94,6 +94,44 @@ PV_HD vec3 calculateViewDirectionFromPixel(vec2 pixelNDC, vec3 cameraForward, ve
 }
 __device__ __forceinline__ vec3 viewDirFromNDC(const Globals& G, vec2 ndc) { return calculateViewDirectionFromPixel(ndc, G.fwd, G.up, G.right, G.tanFovHalf, G.aspect); }
 
+// indirectLightUpscale.comp:17-71 for one full-resolution pixel: depth-aware upscale of the half-resolution GI (Y_SH RGBA16F + CoCg RG16F).
+// Shared by giUpscaleKernel (passes_gi.cu) and by the shading kernel when the backend folds the upscale into its consumer (triangle.frag:294-320).
+struct UpscaleSource { ImgView srcYSH, srcCoCg, fullResDepth, halfResDepth; };
+__device__ __forceinline__ void giUpscalePixel(const UpscaleSource& p, const plain_global_shader_info* __restrict__ g, int ix, int iy, vec4& result_Y_SH, vec2& result_CoCg) {
+    const float nearP = g->nearPlane, farP = g->farPlane;
+    const vec2 uv = (v2((float)ix, (float)iy) + 0.5f) / v2((float)g->screenResolution[0], (float)g->screenResolution[1]);
+    float fullResDepth = sampleNearest2D<WRAP_CLAMP, float>([&](int x, int y) { return loadD32(p.fullResDepth, x, y); }, p.fullResDepth.w, p.fullResDepth.h, uv, 0.f);
+    fullResDepth = linearizeDepth(fullResDepth, nearP, farP);
+    const vec2 halfResTexelSize = 1.f / v2((float)p.halfResDepth.w, (float)p.halfResDepth.h);
+    // textureGather: (i0,j1), (i1,j1), (i1,j0), (i0,j0) with i0 = floor(u*w - 0.5), clamp-to-edge
+    const int gx0 = f2i(floorf_(sanitizeCoord(uv.x) * (float)p.halfResDepth.w - 0.5f));
+    const int gy0 = f2i(floorf_(sanitizeCoord(uv.y) * (float)p.halfResDepth.h - 0.5f));
+    auto G4 = [&](int x, int y) { return loadR16F(p.halfResDepth, iclamp(x, 0, p.halfResDepth.w - 1), iclamp(y, 0, p.halfResDepth.h - 1)); };
+    float depthSamples[4] = {G4(gx0, gy0 + 1), G4(gx0 + 1, gy0 + 1), G4(gx0 + 1, gy0), G4(gx0, gy0)};
+    for (int i = 0; i < 4; i++) depthSamples[i] = linearizeDepth(depthSamples[i], nearP, farP);
+    float minDepthDiff = 1000.f;
+    vec2 closestDepthTexel = v2(0.f);
+    const float edgeDepthThreshold = 0.5f;
+    bool isEdge = false;
+    const float offX[4] = {0.f, 1.f, 1.f, 0.f}, offY[4] = {1.f, 1.f, 0.f, 0.f};
+    for (int i = 0; i < 4; i++) {
+        const float depthDiff = absf(depthSamples[i] - fullResDepth);
+        isEdge = isEdge || depthDiff > edgeDepthThreshold;
+        if (depthDiff < minDepthDiff) {
+            minDepthDiff = depthDiff;
+            closestDepthTexel = v2(offX[i], offY[i]);
+        }
+    }
+    const vec2 uvClosestTexel = uv + closestDepthTexel * halfResTexelSize;
+    if (isEdge) {
+        result_Y_SH = sampleNearest2D<WRAP_CLAMP, vec4>([&](int x, int y) { return loadRGBA16F(p.srcYSH, x, y); }, p.srcYSH.w, p.srcYSH.h, uvClosestTexel, v4(0.f));
+        result_CoCg = sampleNearest2D<WRAP_CLAMP, vec2>([&](int x, int y) { return loadRG16F(p.srcCoCg, x, y); }, p.srcCoCg.w, p.srcCoCg.h, uvClosestTexel, v2(0.f));
+    } else {
+        result_Y_SH = sampleRGBA16FLinearClamp(p.srcYSH, uv);
+        result_CoCg = sampleRG16FLinearClamp(p.srcCoCg, uv);
+    }
+}
+
 // ---- brdf.inc ----
 PV_HD float D_GGX(float NoH, float r) {  // :4-8
     const float a = NoH * r;

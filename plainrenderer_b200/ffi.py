@@ -165,7 +165,7 @@ BACKEND_SYMBOLS = [
     "render_frame", "submit_recorded_passes", "wait_for_gpu_idle", "get_renderpass_timings", "set_timing_enabled", "write_image", "read_image", "read_storage_buffer",
     "create_meshes", "create_graphic_pass", "set_graphic_pass_execution", "draw_meshes",
     "write_image_async", "read_image_async", "write_image_rows_async", "read_image_rows_async", "get_image_device_pointer", "get_storage_buffer_device_pointer", "get_last_frame_launch_count",
-    "set_graph_replay_enabled", "set_concurrent_passes_enabled", "join_transfers", "get_stream",
+    "set_graph_replay_enabled", "set_pass_fusion_enabled", "set_concurrent_passes_enabled", "join_transfers", "get_stream",
     "peer_init", "peer_get_sync_handle", "peer_open_sync", "peer_get_image_handle", "peer_open_image", "peer_image_ready", "peer_push_rows", "peer_barrier", "peer_push_rows_deferred", "peer_flush_deferred",
     "peer_allreduce_sum_u32", "peer_error", "peer_error_poll", "device_selftest"]
 FRONTEND_SYMBOLS = [

@@ -80,6 +80,7 @@ def random_r11g11b10(rng, n, finite=True):
 CAMERA = ((-13.0, -1.7, 0.5), (1.0, 0.0, 0.0), (0.0, 0.0, 1.0), (0.0, -1.0, 0.0))
 ALL_IMAGES = ["skyTransmission", "skyMultiscatter", "skyLut", "hiz", "depthHalf", "giY0", "giC0", "giY1", "giC1", "giHistY0", "giHistC0", "giHistY1", "giHistC1", "giFullY", "giFullC",
               "froxelMaterial", "froxelScatter", "froxelHist0", "froxelHist1", "froxelIntegration", "color0", "color1", "taaHist0", "taaHist1", "taaLum0", "taaLum1", "post0", "post1", "brdfLut", "output"]
+FUSED_AWAY_IMAGES = ("giFullY", "giFullC")  # outputs of indirectLightUpscale.comp: not written when the pass is folded into the shading kernel
 ALL_BUFFERS = [("histogram", 512), ("light", 20), ("sunShadowInfo", 304), ("sdfCulled", None), ("sdfTiles", None)]  # None: the whole buffer (S3: instance culling lists)
 # the non-default passes beside the frame path (temporalSupersampling.comp + colorToLuminance.comp, sdfDebugVisualisation.comp)
 N4_VARIANTS = [dict(taa_use_separate_supersampling=1), dict(taa_use_separate_supersampling=1, taa_supersample_use_tonemapping=0),
@@ -99,11 +100,15 @@ def image_mips(fe, h):
 class Sequence:
     """Drives the same frame sequence through one library (CUDA product or CPU oracle)."""
 
-    def __init__(self, ffi, api, w, h, instances=12, frames=None, **settings):
+    def __init__(self, ffi, api, w, h, instances=12, frames=None, pass_fusion=False, **settings):
         self.ffi, self.api, self.w, self.h = ffi, api, w, h
         settings.setdefault("sun_direction_deg", (40.0, 35.0))
         self.s = ffi.default_settings(api, w, h, **settings)
         self.fe = ffi.Frontend(api, self.s)
+        # pass fusion is the product's default; with it the images in FUSED_AWAY_IMAGES are not written, so the sequences that compare
+        # EVERY image run unfused and the fused path is compared on everything else (run_both does both)
+        self.pass_fusion = pass_fusion
+        self.fe.backend._check(api.b["set_pass_fusion_enabled"](self.fe.backend.ctx, 1 if pass_fusion else 0), "set_pass_fusion_enabled")
         self.scene = ffi.SyntheticScene(api, n_instances=instances)
         self.scene.attach(self.fe)
         self.fe.set_exposure(2e-5)
@@ -126,9 +131,11 @@ class Sequence:
         self.frame += 1
         return inputs
 
-    def snapshot(self, images=ALL_IMAGES, buffers=ALL_BUFFERS):
+    def snapshot(self, images=ALL_IMAGES, buffers=ALL_BUFFERS, skip=()):
         out = {}
         for name in images:
+            if name in skip:
+                continue
             h = self.fe.image(name)
             for mip in range(image_mips(self.fe, h)):
                 out["%s/%d" % (name, mip)] = self.fe.backend.read_image(h, mip).copy()
@@ -173,6 +180,7 @@ class PlainSceneSequence:
         settings.setdefault("sun_direction_deg", (40.0, 35.0))
         self.s = ffi.default_settings(api, w, h, raster_inputs=1, **settings)
         self.fe = ffi.Frontend(api, self.s, device=device)
+        self.fe.backend._check(api.b["set_pass_fusion_enabled"](self.fe.backend.ctx, 0), "set_pass_fusion_enabled")  # every image is compared
         be = self.fe.backend
         rng = np.random.default_rng(5)
         checker = np.zeros((4, 4, 4), np.uint8)

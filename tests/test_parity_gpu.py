@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 
 import passes
-from conftest import ALL_BUFFERS, ALL_IMAGES, N4_VARIANTS, Sequence, assert_snapshots_equal, decode_r11g11b10, image_mips, random_r11g11b10
+from conftest import ALL_BUFFERS, ALL_IMAGES, FUSED_AWAY_IMAGES, N4_VARIANTS, Sequence, assert_snapshots_equal, decode_r11g11b10, image_mips, random_r11g11b10
 
 pytestmark = pytest.mark.gpu
 
@@ -82,15 +82,22 @@ def test_temporal_supersampling_bit_exact(ffi, cuda, oracle, w, h, use_tonemap):
 
 # ---------------- whole frames: every resource of every pass ----------------
 def run_both(ffi, cuda, oracle, w, h, frames, moving, instances=12, **settings):
+    """the CUDA product twice - every pass launched (all images compared) and with pass fusion, the product's default (the images the
+    fused-away pass would have written are skipped) - against one run of the oracle"""
     a, b = Sequence(ffi, cuda, w, h, instances, **settings), Sequence(ffi, oracle, w, h, instances, **settings)
+    fused = Sequence(ffi, cuda, w, h, instances, pass_fusion=True, **settings)
     try:
         for f in range(frames):
             inputs = a.step(moving=moving)
             b.step(moving=moving, inputs=inputs)
-            assert_snapshots_equal(a.snapshot(), b.snapshot(), "frame %d of %dx%d %s" % (f, w, h, settings))
+            fused.step(moving=moving, inputs=inputs)
+            want = b.snapshot()
+            assert_snapshots_equal(a.snapshot(), want, "frame %d of %dx%d %s" % (f, w, h, settings))
+            assert_snapshots_equal(fused.snapshot(skip=FUSED_AWAY_IMAGES), want, "frame %d of %dx%d %s (pass fusion)" % (f, w, h, settings))
     finally:
         a.close()
         b.close()
+        fused.close()
 
 
 @pytest.mark.parametrize("w,h", [(256, 144), (200, 120), (250, 142)])
@@ -177,7 +184,7 @@ def test_frame_4k_equals_oracle(ffi, cuda, oracle):
     buffer of the frame compared with the oracle bit for bit. The reference's resolution-capped buffers (SDFGI.cpp:146-151,
     RenderFrontend.cpp:1069-1070, sdfCulling.inc:17-20) only matter at this size. ~12 s per oracle frame on 16 host threads."""
     W, H = 3840, 2160
-    a, b = Sequence(ffi, cuda, W, H, 100), Sequence(ffi, oracle, W, H, 100)
+    a, b = Sequence(ffi, cuda, W, H, 100, pass_fusion=True), Sequence(ffi, oracle, W, H, 100)  # as benchmarked: the upscale folded into the shading kernel
     try:
         inputs = None
         for f in range(2):
@@ -186,6 +193,8 @@ def test_frame_4k_equals_oracle(ffi, cuda, oracle):
         # one image at a time: a full snapshot of both sides would hold ~4 GB
         bad = []
         for name in ALL_IMAGES:
+            if name in FUSED_AWAY_IMAGES:
+                continue  # compared unfused at smaller sizes (run_both); their consumer's output (color0 / color1) is compared here
             ha, hb = a.fe.image(name), b.fe.image(name)
             for mip in range(image_mips(a.fe, ha)):
                 x, y = a.fe.backend.read_image(ha, mip), b.fe.backend.read_image(hb, mip)

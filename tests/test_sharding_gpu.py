@@ -13,9 +13,10 @@ BANDED_IMAGES = [("hiz", 2, 0), ("hiz", 2, 1), ("hiz", 2, 2), ("output", 1, 0), 
                  ("giY0", 2, 0), ("giC0", 2, 0), ("color0", 1, 0), ("color1", 1, 0)]  # giY0/giC0: the temporal filter overwrites the gathered trace result with its banded target  # (name, divisor, mip): compared on the rank's own rows
 
 
-def make(ffi, api, W, H, instances, rank=0, count=1, **settings):
+def make(ffi, api, W, H, instances, rank=0, count=1, pass_fusion=False, **settings):
     s = ffi.default_settings(api, W, H, sun_direction_deg=(40.0, 35.0), shard_rank=rank, shard_count=count, **settings)
     fe = ffi.Frontend(api, s)
+    fe.backend._check(api.b["set_pass_fusion_enabled"](fe.backend.ctx, 1 if pass_fusion else 0), "set_pass_fusion_enabled")  # off: giFullY / giFullC are compared
     scene = ffi.SyntheticScene(api, n_instances=instances)
     scene.attach(fe)
     fe.set_exposure(2e-5)
@@ -29,12 +30,12 @@ def camera(ffi, f, moving):
     return ffi.camera(p, fw, r, u)
 
 
-@pytest.mark.parametrize("W,H,R,moving", [(256, 192, 2, False), (256, 192, 3, True), (320, 256, 4, True)])
-def test_sharded_frame_equals_unsharded(ffi, cuda, W, H, R, moving):
+@pytest.mark.parametrize("W,H,R,moving,fused", [(256, 192, 2, False, False), (256, 192, 3, True, False), (320, 256, 4, True, False), (320, 256, 4, True, True)])
+def test_sharded_frame_equals_unsharded(ffi, cuda, W, H, R, moving, fused):
     import torch
     from plainrenderer_b200 import sharding
-    s0, ref, scene0 = make(ffi, cuda, W, H, 14)
-    ranks = [make(ffi, cuda, W, H, 14, rank=r, count=R) for r in range(R)]
+    s0, ref, scene0 = make(ffi, cuda, W, H, 14)  # the unsharded reference always runs every pass
+    ranks = [make(ffi, cuda, W, H, 14, rank=r, count=R, pass_fusion=fused) for r in range(R)]
     fes = [x[1] for x in ranks]
     comm = sharding.LocalComm(cuda, H, R, torch.device("cuda", 0))
     prev = None
@@ -67,6 +68,8 @@ def test_sharded_frame_equals_unsharded(ffi, cuda, W, H, R, moving):
                 assert np.array_equal(fe.backend.read_storage_buffer(fe.storage_buffer(name), size), want), "frame %d rank %d: buffer %s" % (f, r, name)
         # images a rank holds for its own rows
         for name, div, mip in BANDED_IMAGES:
+            if fused and name in ("giFullY", "giFullC"):
+                continue  # not written when the upscale is folded into the shading kernel; color0 / color1 below are its consumer's output
             h = ref.image(name)
             d = ref.backend.image_description(h)
             rows = d.height >> mip
