@@ -1186,6 +1186,128 @@ __global__ void __launch_bounds__(256, 4) giSpatialFilterKernel(const __grid_con
             }
         }
     };
+#if defined(PV_F32X2)
+    // ---- pair path (round 2): two disc samples per iteration in the two halves of packed binary32 arithmetic ----
+    // Every multiply / add / fma of the per-sample chain (:72-112) is issued once for samples (i, i + 1) as FMUL2 / FFMA2: the operations,
+    // their operands and their order are those of fetchSample / accumulate above, per half. The three reciprocals, the square root and the
+    // two divisions of a sample run as their unguarded fast paths (pvec.h rcp2_normal / sqrt2_normal / div2_normal), and the range tests
+    // that make those valid are collected in ONE flag per pixel: if any such operand of any sample was outside 2^-60 .. 2^60 the results
+    // of this loop are discarded and the spelled-out loop below runs instead (never, for a sane camera and depth buffer).
+    // Sample i + 1's radius depends on whether sample i landed off screen (:101-106): it is computed assuming it did not, and recomputed
+    // when it did (only pixels whose world-space disc leaves the screen).
+    bool pairOk = true;
+    {
+        const float nearFar = G.nearPlane * G.farPlane, nearMinusFar = G.nearPlane - G.farPlane, tanAspect = G.tanFovHalf * G.aspect;
+        auto P = [](float v) { return pk2(v, v); };
+        struct PairPos { float2 u, v; int texelA, texelB; bool outsideA, outsideB; };
+        auto positions = [&](int i, float lmA, float lmB) {
+            PairPos r;
+            const float4 dA = sDisc[i], dB = sDisc[i + 1];
+            const float2 d = mul2(pk2(dA.x, dB.x), pk2(lmA, lmB));
+            const float2 ox = mul2(pk2(dA.y, dB.y), d), oy = mul2(pk2(dA.z, dB.z), d);
+            // sampleWorld = pCenter + radiusWorld * (offset.x * tangent + offset.y * bitangent)
+            const float2 wx = add2(P(pCenter.x), mul2(P(radiusWorld), add2(mul2(ox, P(tangent.x)), mul2(oy, P(bitangent.x)))));
+            const float2 wy = add2(P(pCenter.y), mul2(P(radiusWorld), add2(mul2(ox, P(tangent.y)), mul2(oy, P(bitangent.y)))));
+            const float2 wz = add2(P(pCenter.z), mul2(P(radiusWorld), add2(mul2(ox, P(tangent.z)), mul2(oy, P(bitangent.z)))));
+            const float2 one = P(1.f);
+            const float2 px = __ffma2_rn(P(sVP[12]), one, __ffma2_rn(P(sVP[8]), wz, __ffma2_rn(P(sVP[4]), wy, mul2(P(sVP[0]), wx))));
+            const float2 py = __ffma2_rn(P(sVP[13]), one, __ffma2_rn(P(sVP[9]), wz, __ffma2_rn(P(sVP[5]), wy, mul2(P(sVP[1]), wx))));
+            const float2 pw = __ffma2_rn(P(sVP[15]), one, __ffma2_rn(P(sVP[11]), wz, __ffma2_rn(P(sVP[7]), wy, mul2(P(sVP[3]), wx))));
+            pairOk = pairOk && moderate_(pw.x) && moderate_(pw.y);
+            const float2 rw = rcp2_normal(pw);
+            float2 su = add2(mul2(mul2(px, rw), P(0.5f)), P(0.5f)), sv = add2(mul2(mul2(py, rw), P(0.5f)), P(0.5f));
+            const float2 altX = sub2(P(uv.x), ox), altY = sub2(P(uv.y), oy);
+            su.x = (su.x < 0.f || su.x > 1.f) ? altX.x : su.x;
+            su.y = (su.y < 0.f || su.y > 1.f) ? altX.y : su.y;
+            sv.x = (sv.x < 0.f || sv.x > 1.f) ? altY.x : sv.x;
+            sv.y = (sv.y < 0.f || sv.y > 1.f) ? altY.y : sv.y;
+            r.u = su; r.v = sv;
+            const float2 tu = mul2(su, P(dW)), tv = mul2(sv, P(dH));
+            r.texelA = iclamp(floor2i(tv.x), 0, dHm1) * p.depthTexture.w + iclamp(floor2i(tu.x), 0, dWm1);
+            r.texelB = iclamp(floor2i(tv.y), 0, dHm1) * p.depthTexture.w + iclamp(floor2i(tu.y), 0, dWm1);
+            r.outsideA = su.x < 0.f || sv.x < 0.f || su.x > 1.f || sv.x > 1.f;
+            r.outsideB = su.y < 0.f || sv.y < 0.f || su.y > 1.f || sv.y > 1.f;
+            return r;
+        };
+        auto nearest = [&](vec2 at, const ImgView& img) { const ivec2 t = nearestClampTexel(at, img.w, img.h); return texelIndex(img, t.x, t.y); };
+#pragma unroll 1
+        for (int i = 0; i < 32; i += 2) {
+            const float lmA = lengthModifier;
+            PairPos q = positions(i, lmA, lmA);
+            if (q.outsideA) {  // sample i + 1 starts from the reduced radius (sample i's half is recomputed to the same bits)
+                lengthModifier = lmA * 0.98f;
+                q = positions(i, lmA, lengthModifier);
+            }
+            if (q.outsideB) lengthModifier *= 0.98f;
+            // the three texels of both samples (clamped addresses are always valid; Y_SH / CoCg are only used where the reference samples them)
+            uint32_t depthA, depthB, cocgA, cocgB;
+            uint2 yshA, yshB;
+            depthA = DEPTH_IS_R16F ? (uint32_t)ldg((const uint16_t*)p.depthTexture.ptr + q.texelA) : ldg((const uint32_t*)p.depthTexture.ptr + q.texelA);
+            depthB = DEPTH_IS_R16F ? (uint32_t)ldg((const uint16_t*)p.depthTexture.ptr + q.texelB) : ldg((const uint32_t*)p.depthTexture.ptr + q.texelB);
+            if (SAME_EXTENT) {
+                yshA = ldg((const uint2*)p.texYSH.ptr + q.texelA); cocgA = ldg((const uint32_t*)p.texCoCg.ptr + q.texelA);
+                yshB = ldg((const uint2*)p.texYSH.ptr + q.texelB); cocgB = ldg((const uint32_t*)p.texCoCg.ptr + q.texelB);
+            } else {
+                const vec2 atA = v2(q.u.x, q.v.x), atB = v2(q.u.y, q.v.y);
+                yshA = ldg((const uint2*)p.texYSH.ptr + nearest(atA, p.texYSH)); cocgA = ldg((const uint32_t*)p.texCoCg.ptr + nearest(atA, p.texCoCg));
+                yshB = ldg((const uint2*)p.texYSH.ptr + nearest(atB, p.texYSH)); cocgB = ldg((const uint32_t*)p.texCoCg.ptr + nearest(atB, p.texCoCg));
+            }
+            // giDepthToWorld for both samples (:21-28): linearizeDepth, the view vector through the sample's uv, the world position
+            const float2 depth = DEPTH_IS_R16F ? pk2(halfToFloat((uint16_t)depthA), halfToFloat((uint16_t)depthB)) : pk2(dm::u2f(depthA), dm::u2f(depthB));
+            const float2 den = add2(P(G.farPlane), mul2(add2(neg2(depth), P(1.f)), P(nearMinusFar)));
+            const float2 ndcX = sub2(mul2(q.u, P(2.f)), P(1.f)), ndcY = sub2(mul2(q.v, P(2.f)), P(1.f));
+            const float2 kUp = mul2(P(G.tanFovHalf), ndcY), kRight = mul2(P(tanAspect), ndcX);
+            float2 Vx = sub2(add2(P(-G.fwd.x), mul2(kUp, P(G.up.x))), mul2(kRight, P(G.right.x)));
+            float2 Vy = sub2(add2(P(-G.fwd.y), mul2(kUp, P(G.up.y))), mul2(kRight, P(G.right.y)));
+            float2 Vz = sub2(add2(P(-G.fwd.z), mul2(kUp, P(G.up.z))), mul2(kRight, P(G.right.z)));
+            const float2 len2 = __ffma2_rn(Vz, Vz, __ffma2_rn(Vy, Vy, mul2(Vx, Vx)));
+            pairOk = pairOk && moderate_(den.x) && moderate_(den.y) && moderate_(len2.x) && moderate_(len2.y);
+            const float2 depthLinear = div2_normal(P(nearFar), den);
+            const float2 rl = rcp2_normal(sqrt2_normal(len2));
+            // cameraToPixel = -normalize(V)
+            const float2 cx = neg2(mul2(Vx, rl)), cy = neg2(mul2(Vy, rl)), cz = neg2(mul2(Vz, rl));
+            const float2 cf = __ffma2_rn(cz, P(G.fwd.z), __ffma2_rn(cy, P(G.fwd.y), mul2(cx, P(G.fwd.x))));
+            pairOk = pairOk && moderate_(cf.x) && moderate_(cf.y);
+            const float2 rcf = rcp2_normal(cf);
+            const float2 wX = add2(P(G.camPos.x), mul2(mul2(cx, rcf), depthLinear));
+            const float2 wY = add2(P(G.camPos.y), mul2(mul2(cy, rcf), depthLinear));
+            const float2 wZ = add2(P(G.camPos.z), mul2(mul2(cz, rcf), depthLinear));
+            const float2 dX = sub2(wX, P(pCenter.x)), dY = sub2(wY, P(pCenter.y)), dZ = sub2(wZ, P(pCenter.z));
+            const float2 nd = __ffma2_rn(P(N.z), dZ, __ffma2_rn(P(N.y), dY, mul2(P(N.x), dX)));
+            const float2 dist = pk2(fmaxf(absf(nd.x), 0.0001f), fmaxf(absf(nd.y), 0.0001f));
+            pairOk = pairOk && dist.x <= 1.1529215e18f && dist.y <= 1.1529215e18f;
+            float2 weight = div2_normal(P(0.25f), dist);
+            weight = pk2(fminf(weight.x, 1.f), fminf(weight.y, 1.f));
+            weight = mul2(weight, weight);
+            // accumulate in sample order (:118-135)
+            if (!q.outsideA && weight.x > 0.f) {
+                const vec4 sample_Y_SH = v4(halfToFloat((uint16_t)(yshA.x & 0xffffu)), halfToFloat((uint16_t)(yshA.x >> 16)), halfToFloat((uint16_t)(yshA.y & 0xffffu)), halfToFloat((uint16_t)(yshA.y >> 16)));
+                const vec2 sample_CoCg = v2(halfToFloat((uint16_t)(cocgA & 0xffffu)), halfToFloat((uint16_t)(cocgA >> 16)));
+                if (!(anynan(sample_Y_SH) || anynan(sample_CoCg))) {
+                    result_Y_SH = result_Y_SH + weight.x * sample_Y_SH;
+                    result_CoCg = result_CoCg + weight.x * sample_CoCg;
+                    weightTotal += weight.x;
+                }
+            }
+            if (!q.outsideB && weight.y > 0.f) {
+                const vec4 sample_Y_SH = v4(halfToFloat((uint16_t)(yshB.x & 0xffffu)), halfToFloat((uint16_t)(yshB.x >> 16)), halfToFloat((uint16_t)(yshB.y & 0xffffu)), halfToFloat((uint16_t)(yshB.y >> 16)));
+                const vec2 sample_CoCg = v2(halfToFloat((uint16_t)(cocgB & 0xffffu)), halfToFloat((uint16_t)(cocgB >> 16)));
+                if (!(anynan(sample_Y_SH) || anynan(sample_CoCg))) {
+                    result_Y_SH = result_Y_SH + weight.y * sample_Y_SH;
+                    result_CoCg = result_CoCg + weight.y * sample_CoCg;
+                    weightTotal += weight.y;
+                }
+            }
+        }
+    }
+    if (!pairOk) {  // an operand outside the fast sequences' range somewhere in this pixel: everything again, spelled out
+        result_Y_SH = v4(0.f);
+        result_CoCg = v2(0.f);
+        weightTotal = 0.f;
+        lengthModifier = 1.f;
+#else
+    {
+#endif
     SpatialFetch A = fetchSample(0, lengthModifier), B;
 #pragma unroll 1
     for (int i = 0; i < 32; i += 2) {
@@ -1197,6 +1319,7 @@ __global__ void __launch_bounds__(256, 4) giSpatialFilterKernel(const __grid_con
         if (outsideB) lengthModifier *= 0.98f;
         if (i + 2 < 32) A = fetchSample(i + 2, lengthModifier);
         accumulate(B, outsideB);
+    }
     }
     weightTotal = fmaxp(weightTotal, 0.00001f);
     result_Y_SH = result_Y_SH / weightTotal;

@@ -29,6 +29,41 @@ __global__ void selftestAllFloatsKernel(unsigned long long* out) {
     if (bad2) atomicAdd(out + 2, bad2);
     if (bad4) atomicAdd(out + 4, bad4);
 }
+// [6] sqrtf_normal / sqrt2_normal against sqrtf over every x with 2^-60 <= x <= 2^60; [7] divf_normal / div2_normal against IEEE division: every
+// such divisor under the numerators the frame uses (0.25, near * far = 30, and four others), and pseudo-random moderate operand pairs
+__global__ void selftestNormalRangeKernel(unsigned long long* out) {
+#if defined(__CUDA_ARCH__)  // the sequences under test are device-only (inline PTX)
+    unsigned long long bad6 = 0, bad7 = 0;
+    const uint32_t lo = 0x21800000u, hi = 0x5d800000u;  // 2^-60 .. 2^60
+    const uint32_t stride = gridDim.x * blockDim.x;
+    const float numerators[6] = {0.25f, 30.f, 1.f, 3.1415927f, 1.0e-12f, 7.7e11f};
+    for (uint32_t u = lo + blockIdx.x * blockDim.x + threadIdx.x; u <= hi; u += stride) {
+        const float x = dm::u2f(u), nx = -x;
+        if (!sameBits(sqrtf_normal(x), sqrtf(x))) bad6++;
+        const float2 s2 = sqrt2_normal(make_float2(x, x * 1.5f));  // (x * 1.5 <= 2^60.6: inside the sequence's own range)
+        if (!sameBits(s2.x, sqrtf(x)) || !sameBits(s2.y, sqrtf(x * 1.5f))) bad6++;
+#pragma unroll
+        for (int k = 0; k < 6; k++) {
+            const float a = numerators[k];
+            if (!sameBits(divf_normal(a, x), a / x) || !sameBits(divf_normal(a, nx), a / nx)) bad7++;
+        }
+        const float2 d2 = div2_normal(make_float2(0.25f, 30.f), make_float2(x, nx));
+        if (!sameBits(d2.x, 0.25f / x) || !sameBits(d2.y, 30.f / nx)) bad7++;
+        const float2 r2 = rcp2_normal(make_float2(x, nx));
+        if (!sameBits(r2.x, __frcp_rn(x)) || !sameBits(r2.y, __frcp_rn(nx))) bad7++;
+    }
+    uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x + 1u) * 2654435761u;
+    for (int k = 0; k < (1 << 16); k++) {  // 2^16 threads x 2^16 pairs
+        s ^= s << 13; s ^= s >> 17; s ^= s << 5;
+        const float a = dm::u2f((lo + s % (hi - lo + 1u)) | (s & 0x80000000u));
+        s ^= s << 13; s ^= s >> 17; s ^= s << 5;
+        const float b = dm::u2f((lo + s % (hi - lo + 1u)) | (s & 0x80000000u));
+        if (!sameBits(divf_normal(a, b), a / b)) bad7++;
+    }
+    if (bad6) atomicAdd(out + 6, bad6);
+    if (bad7) atomicAdd(out + 7, bad7);
+#endif
+}
 // [3] decoders over every code, [5] FMNMX against the pinned min / max over pseudo-random operand pairs without -0
 __global__ void selftestCodesKernel(unsigned long long* out) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -58,6 +93,7 @@ bool runDeviceSelftest(cudaStream_t stream, unsigned long long* hostOut8, std::s
     cudaMemsetAsync(d, 0, 8 * sizeof(unsigned long long), stream);
     selftestAllFloatsKernel<<<16, 256, 0, stream>>>(d);
     selftestCodesKernel<<<256, 256, 0, stream>>>(d);
+    selftestNormalRangeKernel<<<256, 256, 0, stream>>>(d);
     cudaError_t e = cudaMemcpyAsync(hostOut8, d, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
     cudaFree(d);

@@ -10,7 +10,7 @@ import pytest
 pytestmark = [pytest.mark.gpu]
 
 NAMES = ["rcpf_nz vs __frcp_rn", "rcpf_normal vs __frcp_rn", "lean R11G11B10 encoder", "lean R11G11B10 decoder", "floor2i + int->float vs floor_ + f2i",
-         "FMNMX vs pinned min/max (no -0)"]
+         "FMNMX vs pinned min/max (no -0)", "sqrtf_normal / sqrt2_normal vs sqrtf (2^-60..2^60)", "divf_normal / div2_normal / rcp2_normal vs IEEE division / __frcp_rn (2^-60..2^60)"]
 
 
 def test_lean_device_sequences_equal_the_contract_functions(ffi, cuda):
