@@ -456,13 +456,12 @@ __device__ __forceinline__ void shadeWinner2(const TraceInst2& inst, vec3 raySta
 }
 
 // State of a hit as its marching lane leaves it for the ray's own thread: what shadeWinner2 needs (SDF.inc:165-176)
-struct HitRecord {
-    vec3 samplePos, rayDirection;
+struct HitRecord {  // 20 bytes: the local ray direction is recomputed from the ray and the instance (the expression of traceSetup: same operands, same
+    vec3 samplePos; //           bits), the march count is not used by the diffuse trace - so the pool holds 416 records instead of 192 in the same space
     float d, dLast;
-    int hitCount;
 };
 #define TRACE_PAIR_CAP 2560  // (ray, candidate) pairs of one batch of rays; a ray has at most 100
-#define TRACE_HIT_POOL 192   // hit records per block; a block that reports more re-marches the winners that did not get one
+#define TRACE_HIT_POOL 416   // hit records per block (ncu, round 2: an indoor scene reports ~330 per 256 rays; with 192 the winners without a record cost 6 % of the kernel); a block that reports more re-marches those winners
 #define TRACE_QUEUE_CAP 896  // marches waiting for a lane (pairs whose ray enters the box), per batch; more are marched on the spot
 #define TRACE_LONG_CAP 16    // marches parked between two slices (<= 256: the compaction uses one thread per slot); slicing is off by default
 struct LongMarch {           // a march parked between two slices: the whole MarchState
@@ -612,14 +611,21 @@ __global__ void __launch_bounds__(256, 3) sdfDiffuseTraceKernel(const __grid_con
         rayOrigin = pWorld + N * 0.2f;
         L = importanceSampleCosine(xi, N);
         const float invLen2 = 1.f / dot(L, L);
+        // the bounding-sphere test pays in crowded tiles (it is five times cheaper than the slab rejection of D1a that follows); in a tile
+        // with a handful of instances it rejects next to nothing (ncu, round 2: 7.3 instances per tile, 8 pairs per ray survive) and is skipped
+        const bool sphereTest = !(p.variant & 32) || objectCount > 12u;
 #pragma unroll
         for (int w = 0; w < 4; w++) {
             uint32_t m = 0u;
             const uint32_t base = (uint32_t)w * 32u;
             if (base < objectCount) {
                 const uint32_t n = min(32u, objectCount - base);
-                for (uint32_t b = 0; b < n; b++)
-                    if (!rayMissesSphere(sInst[base + b], rayOrigin, L, invLen2)) m |= 1u << b;
+                if (sphereTest) {
+                    for (uint32_t b = 0; b < n; b++)
+                        if (!rayMissesSphere(sInst[base + b], rayOrigin, L, invLen2)) m |= 1u << b;
+                } else {
+                    m = n >= 32u ? 0xffffffffu : ((1u << n) - 1u);
+                }
             }
             cand[w] = m;
         }
@@ -671,10 +677,12 @@ __global__ void __launch_bounds__(256, 3) sdfDiffuseTraceKernel(const __grid_con
             auto recordHit = [&](int ray, int cur) {
                 sHit[ray] = 1;
                 if (tr.winner != cur) return;  // d < threshold, but not closer than the closest hit known when the pair was taken
+                // another lane may have reported a closer hit (or an equal one listed earlier) since: this one cannot win, no record needed
+                if ((traceKey(tr.closestHitDistance, cur, 0u) >> 16) >= (sKey[ray] >> 16)) return;
                 uint32_t slot = (uint32_t)atomicAdd(&sHitCount, 1);
                 if (slot < (uint32_t)TRACE_HIT_POOL) {
                     HitRecord h;
-                    h.samplePos = tr.winnerSamplePos; h.rayDirection = tr.winnerRayDirection; h.d = tr.winnerD; h.dLast = tr.winnerDLast; h.hitCount = tr.hitCount;
+                    h.samplePos = tr.winnerSamplePos; h.d = tr.winnerD; h.dLast = tr.winnerDLast;
                     sHitPool[slot] = h;
                 } else {
                     slot = TRACE_NO_SLOT;
@@ -759,7 +767,10 @@ __global__ void __launch_bounds__(256, 3) sdfDiffuseTraceKernel(const __grid_con
 #pragma unroll 1
             for (int round = 0; round < 3; round++) {
                 const int sliceEnd = (p.variant & 2) ? (round == 0 ? 8 : (round == 1 ? 32 : 128)) : 128;  // a march of this round stops when st.k reaches it
-                bool marching = false, done = false;
+                // PLAIN_TRACE_VARIANT bits 3 / 4: only the first 4 / 6 warps march (more jobs per lane: the longest lane of a warp is closer to
+                // the average), the others wait at the barrier without using issue slots
+                const int marchWarps = (p.variant & 8) ? 4 : ((p.variant & 16) ? 6 : 8);
+                bool marching = false, done = warp >= marchWarps;
                 int ray = 0, cur = 0, slotLong = -1;
                 MarchState st;
                 st.localSamplePos = v3(0.f); st.rayDirection = v3(0.f); st.hitDistanceLocal = 0.f; st.d = 0.f; st.dLast = 0.f; st.k = 0;
@@ -844,7 +855,12 @@ __global__ void __launch_bounds__(256, 3) sdfDiffuseTraceKernel(const __grid_con
             const uint32_t slot = (uint32_t)(key & 0xffffu);
             if (slot != TRACE_NO_SLOT) {
                 const HitRecord h = sHitPool[slot];
-                tr.winnerSamplePos = h.samplePos; tr.winnerRayDirection = h.rayDirection; tr.winnerD = h.d; tr.winnerDLast = h.dLast; tr.hitCount = h.hitCount;
+                tr.winnerSamplePos = h.samplePos; tr.winnerD = h.d; tr.winnerDLast = h.dLast;
+                // the local ray direction of this (ray, instance), SDF.inc:103-107: the expression traceSetup evaluated for the march
+                const TraceInst2& wi = sInst[tr.winner];
+                const vec3 startLocal = xyz(mulm4(wi.worldToLocal, v4(rayOrigin, 1.f))), endLocal = xyz(mulm4(wi.worldToLocal, v4(rayOrigin + L, 1.f)));
+                const vec3 dirLocal = endLocal - startLocal;
+                tr.winnerRayDirection = dirLocal / length(dirLocal);
             } else {  // the block ran out of hit records: march the winning pair again (same operations, same state)
                 TraceResult again;
                 again.hit = false; again.closestHitDistance = 10000.f; again.hitCount = 0; again.winner = -1;
