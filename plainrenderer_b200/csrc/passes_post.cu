@@ -343,8 +343,8 @@ __device__ __forceinline__ vec3 taaTonemapReverse(vec3 color) { return color / (
 __device__ __forceinline__ vec3 taaTonemapFiniteNonNegative(vec3 color) { return color * rcpf_normal(1.f + computeLuminance(color)); }
 struct Nb { vec3 v[3][3]; };  // v[x+1][y+1]
 // FAST (block-uniform, decided after staging): the tile lies inside the image and holds no inf / NaN texel.
-template <bool TONEMAP, bool FAST, int TW, int TH>
-__device__ __forceinline__ void sampleNeighbourhood(const TileR11<TW, TH>& tile, const ImgView& tex, vec2 uv, vec2 texelSize, Nb& n) {  // :42-52
+template <bool TONEMAP, bool FAST, int TW, int TH, typename Store>
+__device__ __forceinline__ void sampleNeighbourhoodTo(const TileR11<TW, TH>& tile, const ImgView& tex, vec2 uv, vec2 texelSize, Store store) {  // :42-52; store(x, y, tap)
     AxisTap X[3], Y[3];  // separable set-up of the nine taps (tile.cuh)
 #pragma unroll
     for (int i = 0; i < 3; i++) {
@@ -354,7 +354,7 @@ __device__ __forceinline__ void sampleNeighbourhood(const TileR11<TW, TH>& tile,
     }
     if (FAST) {
         if (window3x3Applies<TW, TH>(X, Y)) {
-            window3x3(tile, X, Y, [&](int x, int y, vec3 color) { n.v[x][y] = TONEMAP ? taaTonemapFiniteNonNegative(color) : color; });
+            window3x3(tile, X, Y, [&](int x, int y, vec3 color) { store(x, y, TONEMAP ? taaTonemapFiniteNonNegative(color) : color); });
         } else {  // a tap leaves the tile (fast motion): every tap on its own, out of line
             AxisTap Xc[3] = {X[0], X[1], X[2]}, Yc[3] = {Y[0], Y[1], Y[2]};
             vec3 taps[9];
@@ -362,7 +362,7 @@ __device__ __forceinline__ void sampleNeighbourhood(const TileR11<TW, TH>& tile,
 #pragma unroll
             for (int x = 0; x < 3; x++)
 #pragma unroll
-                for (int y = 0; y < 3; y++) n.v[x][y] = TONEMAP ? taaTonemapFiniteNonNegative(taps[x * 3 + y]) : taps[x * 3 + y];
+                for (int y = 0; y < 3; y++) store(x, y, TONEMAP ? taaTonemapFiniteNonNegative(taps[x * 3 + y]) : taps[x * 3 + y]);
         }
     } else {
 #pragma unroll
@@ -370,9 +370,24 @@ __device__ __forceinline__ void sampleNeighbourhood(const TileR11<TW, TH>& tile,
 #pragma unroll
             for (int y = 0; y < 3; y++) {
                 const vec3 color = tapR11Tile(tile, tex, X[x], Y[y]);
-                n.v[x][y] = TONEMAP ? taaTonemap(color) : color;
+                store(x, y, TONEMAP ? taaTonemap(color) : color);
             }
     }
+}
+template <bool TONEMAP, bool FAST, int TW, int TH>
+__device__ __forceinline__ void sampleNeighbourhood(const TileR11<TW, TH>& tile, const ImgView& tex, vec2 uv, vec2 texelSize, Nb& n) {
+    sampleNeighbourhoodTo<TONEMAP, FAST>(tile, tex, uv, texelSize, [&](int x, int y, vec3 tap) { n.v[x][y] = tap; });
+}
+// the history neighbourhood only feeds its luminance contrast (temporalFilter.comp:150, the reference's own TODO): nine luminances are kept
+// instead of nine colours - computeLuminance of the same tap, summed in neighbourhoodContrast's order
+struct NbLum { float l[3][3]; };
+template <bool TONEMAP, bool FAST, int TW, int TH>
+__device__ __forceinline__ float neighbourhoodContrastAt(const TileR11<TW, TH>& tile, const ImgView& tex, vec2 uv, vec2 texelSize) {
+    NbLum n;
+    sampleNeighbourhoodTo<TONEMAP, FAST>(tile, tex, uv, texelSize, [&](int x, int y, vec3 tap) { n.l[x][y] = computeLuminance(tap); });
+    const float c11 = n.l[1][1];
+    return absf(n.l[0][0] - c11) + absf(n.l[1][0] - c11) + absf(n.l[2][0] - c11) + absf(n.l[0][2] - c11) + absf(n.l[1][2] - c11) + absf(n.l[2][2] - c11) +
+           absf(n.l[0][1] - c11) + absf(n.l[2][1] - c11);
 }
 template <bool FAST>
 __device__ __forceinline__ vec3 clipAABB(vec3 target, vec3 bbMin, vec3 bbMax) {  // :8-30
@@ -536,9 +551,7 @@ __device__ __forceinline__ void temporalFilterPixel(const TaaParams& p, const fl
     // gaussianFilteredNeighbourhood :71-82, used below when the history lies outside the image (same operands either way)
     const vec3 gaussian = nb.v[0][0] * 0.0625f + nb.v[0][2] * 0.0625f + nb.v[2][0] * 0.0625f + nb.v[2][2] * 0.0625f + nb.v[1][0] * 0.125f +
                           nb.v[0][1] * 0.125f + nb.v[1][2] * 0.125f + nb.v[2][1] * 0.125f + nb.v[1][1] * 0.25f;
-    Nb lastNb;
-    sampleNeighbourhood<TONEMAP, FAST>(hisTile, p.historySrc, uv + motion, texelSize, lastNb);
-    const float lastContrast = neighbourhoodContrast(lastNb);
+    const float lastContrast = neighbourhoodContrastAt<TONEMAP, FAST>(hisTile, p.historySrc, uv + motion, texelSize);
     float contrastChange = absf(currentContrast - lastContrast);
     contrastChange = clampf(contrastChange, 0.f, 1.f);
     const float blendMin = 0.03f, blendMax = 0.13f;
