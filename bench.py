@@ -87,7 +87,7 @@ def ncu_traffic(pass_name):
     want = NCU_KERNEL_OF_PASS.get(pass_name)
     if not want:
         return None, None
-    for f in sorted((ROOT / "profiles").glob("r2*_ncu_*.json"), reverse=True):
+    for f in sorted((ROOT / "profiles").glob("r[2-9]*_ncu_*.json"), reverse=True):
         try:
             rows = [r for r in json.loads(f.read_text()) if want in r["kernel"]]
         except Exception:
