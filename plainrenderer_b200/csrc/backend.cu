@@ -172,7 +172,11 @@ static int computeMipCount(const plain_image_desc& d) {
 
 static bool hasCornerBrick(const plain_image_desc& d) { return d.type == PLAIN_IMAGE_TYPE_3D && d.format == PLAIN_FORMAT_R16_SFLOAT; }
 static bool allocateImage(Backend& b, DeviceImage& img, const plain_image_desc& d) {
-    if (img.ptr) { cudaStreamSynchronize(b.uploadStream); cudaStreamSynchronize(b.downloadStream); cudaStreamSynchronize(b.stream); cudaFree(img.ptr); img.ptr = nullptr; }
+    if (img.ptr) { cudaStreamSynchronize(b.uploadStream); cudaStreamSynchronize(b.downloadStream); cudaStreamSynchronize(b.stream); if (b.peerStream) cudaStreamSynchronize(b.peerStream); cudaFree(img.ptr); img.ptr = nullptr; }
+    // the peers' copies were mapped for the old allocation (and the peers hold mappings of it): drop this rank's mappings so that
+    // peer_image_ready turns false and the next exchange of the image goes back through the caller, which re-maps it on every rank
+    for (uint32_t pr = 0; pr < PLAIN_MAX_PEERS; pr++) if (img.peerPtr[pr]) { cudaIpcCloseMemHandle(img.peerPtr[pr]); img.peerPtr[pr] = nullptr; }
+    img.deferredExchange = false;
     if (img.corners) { cudaFree(img.corners); img.corners = nullptr; }
     img.desc = d;
     const int n = computeMipCount(d), bpt = formatBytesPerTexel(d.format);

@@ -74,7 +74,8 @@ int PLAIN_ASSET(scene_load)(const char* path, plain_scene** out) {
             if (!need(4)) { delete s; return failAsset("scene_load: truncated path"); }
             rd(&len, 4);
             if (!need(len)) { delete s; return failAsset("scene_load: truncated path"); }
-            const size_t n = len < 255 ? len : 255;
+            if (len > 255) { delete s; return failAsset("scene_load: a texture / SDF path is longer than 255 bytes (plain_mesh_info holds 256)"); }
+            const size_t n = len;
             std::memcpy(paths[k], d.data() + p, n);
             paths[k][n] = 0;
             p += len;
