@@ -354,7 +354,9 @@ def run_ours(args, rank, world, local_rank):
     be.set_graph_replay_enabled(not args.no_graph)
     # at least 6 untimed frames: a frame's pass list is replayed as a CUDA graph keyed by its resources, and those cycle with period 6 (two
     # presentable / ping-pong images x three motion buffers) - with fewer, a graph would be instantiated inside the timed region
-    warmup_frames = max(args.warmup, 6, n_phases if n_phases <= 8 else 8)
+    # row-sharded: the first three frames also map the exchanged images (three motion buffers) and run their exchanges through Python; the
+    # submissions only take their final shape - and their graphs get instantiated - in the six frames after that
+    warmup_frames = max(args.warmup, 6 if not sharded else 14, n_phases if n_phases <= 8 else 8)
     for _ in range(warmup_frames):
         step(True, True)
     barrier()
