@@ -124,6 +124,7 @@ struct Backend {
     std::vector<cudaEvent_t> timingEvents;
 
     bool graphEnabled = false;
+    unsigned int* fusionCounters = nullptr;  // device scratch of fused runs (grid-barrier counters + error word)
     bool fusionEnabled = true;  // planFusions: indirectLightUpscale.comp folded into gbufferShading.comp (set_pass_fusion_enabled)
     std::unordered_map<uint64_t, CachedGraph> graphs;
     static const size_t kMaxCachedGraphs = 32;
@@ -257,6 +258,7 @@ const void* LaunchCtx::ubufRaw(uint32_t binding) {
 }
 void LaunchCtx::countLaunch(int n) { be->launchCounter += (uint32_t)n; }
 const ExecRecord* LaunchCtx::be_exec(int index) const { return &be->execs[(size_t)index]; }
+unsigned int* LaunchCtx::be_fusionCounters() const { return be->fusionCounters; }
 const PassRecord* LaunchCtx::be_pass(uint32_t p) const { return &be->passes[p]; }
 size_t LaunchCtx::be_imageCount() const { return be->images.size(); }
 int LaunchCtx::be_imageFormat(uint32_t index) const { return index < be->images.size() ? (int)be->images[index].desc.format : -1; }
@@ -389,8 +391,28 @@ static void passDependencies(Backend& b, std::vector<std::vector<int>>& deps) {
 // debugging) switch fusion off with set_pass_fusion_enabled(ctx, 0). The producer keeps its place in the dependency order, so the
 // consumer still waits for everything the producer's inputs depend on, and for the same row window.
 static void planFusions(Backend& b) {
-    for (auto& e : b.execs) { e.fusedProducer = -1; e.fusedAway = false; }
+    for (auto& e : b.execs) { e.fusedProducer = -1; e.fusedAway = false; e.fusedRun.clear(); }
     if (!b.fusionEnabled) return;
+    // runs of consecutive bloomDownsample / bloomUpsample executions over WHOLE small levels (<= 600 K texels: mips >= 2 at 3840x2160;
+    // Bloom.cpp:65-122 emits them back to back and each reads what the previous ones wrote): one persistent launch (passes_post.cu bloomTailKernel)
+    for (size_t i = 0; i < b.execs.size();) {
+        auto smallBloomLevel = [&](const ExecRecord& e) {
+            if (b.passes[e.pass].graphic || (b.passes[e.pass].shader != "bloomDownsample.comp" && b.passes[e.pass].shader != "bloomUpsample.comp")) return false;
+            if (e.rowBegin != 0 || e.rowEnd != 0 || e.storageImages.empty()) return false;
+            DeviceImage* img = b.resolve(e.storageImages[0].image);
+            if (!img || e.storageImages[0].mip_level >= img->mips.size()) return false;
+            const MipInfo& m = img->mips[e.storageImages[0].mip_level];
+            return (size_t)m.w * m.h <= 600000u && m.d == 1;
+        };
+        size_t j = i;
+        while (j < b.execs.size() && smallBloomLevel(b.execs[j]) && j - i < 10) j++;
+        if (j - i >= 2) {
+            for (size_t k = i; k < j; k++) { b.execs[i].fusedRun.push_back((int)k); if (k > i) b.execs[k].fusedAway = true; }
+            i = j;
+        } else {
+            i = j > i ? j : i + 1;
+        }
+    }
     auto same = [](const plain_image_resource& a, const plain_image_resource& c) { return a.image.type == c.image.type && a.image.index == c.image.index && a.mip_level == c.mip_level; };
     auto find = [](const std::vector<plain_image_resource>& v, uint32_t binding) -> const plain_image_resource* { for (auto& r : v) if (r.binding == binding) return &r; return nullptr; };
     for (size_t j = 0; j < b.execs.size(); j++) {
@@ -618,6 +640,8 @@ int PLAIN_FN(backend_create)(int device, uint32_t width, uint32_t height, plain_
     }
     cudaMemsetAsync(b.bindlessDevice, 0, sizeof(BindlessEntry) * Backend::kMaxBindless, b.stream);
     buildShadingTables(b.tablesDevice, b.stream);
+    if (cudaMalloc(&b.fusionCounters, 64 * sizeof(unsigned int)) != cudaSuccess) { delete ctx; return 1; }
+    cudaMemsetAsync(b.fusionCounters, 0, 64 * sizeof(unsigned int), b.stream);
     plain_image_desc d{};
     d.width = width; d.height = height; d.depth = 1;
     d.type = PLAIN_IMAGE_TYPE_2D; d.format = PLAIN_FORMAT_BGRA8_UNORM;  // VulkanSurface.cpp:41-46
@@ -658,6 +682,7 @@ void PLAIN_FN(backend_destroy)(plain_ctx* ctx) {
     if (b.peerErrorHost) cudaFreeHost(b.peerErrorHost);
     if (b.peerStream) { cudaStreamDestroy(b.peerStream); cudaEventDestroy(b.peerFork); cudaEventDestroy(b.peerDeferredDone); }
     cudaFree(b.tablesDevice);
+    cudaFree(b.fusionCounters);
     cudaEventDestroy(b.stagingConsumed);
     for (auto& e : b.submissionDone) cudaEventDestroy(e);
     for (auto& st : b.sideStreams) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }

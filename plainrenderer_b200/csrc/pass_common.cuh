@@ -85,6 +85,7 @@ struct ExecRecord {
     // pass fusion (backend.cu planFusions): a producer whose only consumer in the submission computes its texels inline
     int fusedProducer = -1;   // consumer: index of the execution it absorbed
     bool fusedAway = false;   // producer: no launch (its place in the dependency order is kept)
+    std::vector<int> fusedRun; // leader of a run of dependent small passes executed by ONE persistent launch (bloom mips >= 2): the run's executions in order, itself first
 };
 
 struct Backend;
@@ -149,6 +150,7 @@ struct LaunchCtx {
     }
     void countLaunch(int n = 1);
     const ExecRecord* be_exec(int index) const;  // another execution of the same submission (pass fusion)
+    unsigned int* be_fusionCounters() const;      // 64 u32 of device scratch for the grid barriers of a fused run
     const PassRecord* be_pass(uint32_t pass) const;
     size_t be_imageCount() const;               // image table of the backend (bindless slot == image handle index)
     int be_imageFormat(uint32_t index) const;

@@ -69,10 +69,10 @@ __device__ __noinline__ void bloomDownsampleGeneric(ImgView target, ImgView sour
     color = color + T(1.5f, 1.5f) * 0.03125f; color = color + T(1.5f, -1.5f) * 0.03125f; color = color + T(-1.5f, 1.5f) * 0.03125f; color = color + T(-1.5f, -1.5f) * 0.03125f;
     storeR11(target, ix, iy, color);
 }
-__global__ void __launch_bounds__(256) bloomDownsampleKernel(ImgView target, ImgView source, int yBegin, int yEnd) {
+// one 32x8 block of target texels at (bx, by); sSrc: BLOOM_DOWN_TW x BLOOM_DOWN_TH float4. Called by the per-level kernel and by the
+// persistent kernel of the small levels (bloomTailKernel): every thread of the block calls it, returning early is fine (no exit)
+__device__ __forceinline__ void bloomDownsampleTile(const ImgView& target, const ImgView& source, int bx, int by, int yEnd, float4* sSrc) {
     constexpr int TW = BLOOM_DOWN_TW, TH = BLOOM_DOWN_TH;
-    __shared__ float4 sSrc[TW * TH];
-    const int bx = blockIdx.x * 32, by = yBegin + blockIdx.y * 8;
     const int sx0 = (int)(((long long)bx * source.w) / target.w) - 3, sy0 = (int)(((long long)by * source.h) / target.h) - 3;
     const bool interior = tileIsInterior<TW, TH>(source, sx0, sy0);
     if (interior) tileLoadR11<TW, TH, true, true>(sSrc, source, sx0, sy0);  // swizzled columns: neighbouring lanes read columns two apart
@@ -108,6 +108,10 @@ __global__ void __launch_bounds__(256) bloomDownsampleKernel(ImgView target, Img
     color = color + T(3, 0) * 0.0625f; color = color + T(4, 0) * 0.0625f; color = color + T(0, 3) * 0.0625f; color = color + T(0, 4) * 0.0625f;
     color = color + T(3, 3) * 0.03125f; color = color + T(3, 4) * 0.03125f; color = color + T(4, 3) * 0.03125f; color = color + T(4, 4) * 0.03125f;
     storeR11(target, ix, iy, color);
+}
+__global__ void __launch_bounds__(256) bloomDownsampleKernel(ImgView target, ImgView source, int yBegin, int yEnd) {
+    __shared__ float4 sSrc[BLOOM_DOWN_TW * BLOOM_DOWN_TH];
+    bloomDownsampleTile(target, source, blockIdx.x * 32, yBegin + blockIdx.y * 8, yEnd, sSrc);
 }
 // ---- the same pass with the source tile staged by TMA (the default when the source rows are 16-byte multiples; PLAIN_BLOOM_TMA=0
 //      selects the plain loader; A / B in profiles/r2_tma_ab.md) ----
@@ -201,7 +205,9 @@ static bool makeTileTensorMap(CUtensorMap* map, const ImgView& img, int boxW, in
     return encode(map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, img.ptr, dims, strides, box, elemStrides, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
+static bool launchBloomTail(LaunchCtx& c);  // after bloomTailKernel, below
 PLAIN_PASS(launch_bloomDownsample, "bloomDownsample.comp") {
+    if (!c.exec->fusedRun.empty() && launchBloomTail(c)) return;
     const ImgView target = c.storage(0, PLAIN_FORMAT_R11G11B10_UFLOAT), source = c.sampled(1, PLAIN_FORMAT_R11G11B10_UFLOAT);
     if (c.failed) return;
     if ((int)c.exec->dispatch[0] * 8 < target.w || (int)c.exec->dispatch[1] * 8 < target.h) { c.fail("bloomDownsample.comp: dispatch does not cover the target"); return; }
@@ -241,10 +247,9 @@ __device__ __noinline__ void bloomUpsampleGeneric(ImgView target, ImgView target
     }
     storeR11(target, ix, iy, color);
 }
-__global__ void __launch_bounds__(256, 4) bloomUpsampleKernel(ImgView target, ImgView targetPreviousMip, ImgView source, int isLowestMip, float blurRadius, int fastAllowed, int yBegin, int yEnd) {
+__device__ __forceinline__ void bloomUpsampleTile(const ImgView& target, const ImgView& targetPreviousMip, const ImgView& source, int isLowestMip, float blurRadius, int fastAllowed,
+                                                  int bx, int by, int yEnd, float4* sSrc, float4* sPrev) {
     constexpr int TW = BLOOM_UP_TW, TH = BLOOM_UP_TH;
-    __shared__ float4 sSrc[TW * TH], sPrev[TW * TH];
-    const int bx = blockIdx.x * 32, by = yBegin + blockIdx.y * 8;
     const int sx0 = (int)(((long long)bx * source.w) / target.w) - 3, sy0 = (int)(((long long)by * source.h) / target.h) - 3;
     // fastAllowed (launcher): the previous mip has the source's extent and blurRadius is a small finite number (bounded coordinates)
     const bool interior = fastAllowed && tileIsInterior<TW, TH>(source, sx0, sy0);
@@ -293,6 +298,78 @@ __global__ void __launch_bounds__(256, 4) bloomUpsampleKernel(ImgView target, Im
         color = color + P(0, 0) * 0.25f; color = color + P(0, 1) * 0.25f; color = color + P(1, 0) * 0.25f; color = color + P(1, 1) * 0.25f;
     }
     storeR11(target, ix, iy, color);
+}
+__global__ void __launch_bounds__(256, 4) bloomUpsampleKernel(ImgView target, ImgView targetPreviousMip, ImgView source, int isLowestMip, float blurRadius, int fastAllowed, int yBegin, int yEnd) {
+    __shared__ float4 sSrc[BLOOM_UP_TW * BLOOM_UP_TH], sPrev[BLOOM_UP_TW * BLOOM_UP_TH];
+    bloomUpsampleTile(target, targetPreviousMip, source, isLowestMip, blurRadius, fastAllowed, blockIdx.x * 32, yBegin + blockIdx.y * 8, yEnd, sSrc, sPrev);
+}
+
+// ---- the small levels of the chain in ONE launch (Bloom.cpp:65-122: downsample mips >= 2, then upsample back to mip 2) ----
+// At 3840x2160 those are seven dependent launches of 36 .. 2025 blocks, 8 - 29 us each and mostly launch latency and tail. The backend
+// (planFusions) hands the whole run to a persistent kernel: two blocks per SM walk the 32x8 tiles of a level, a grid-wide barrier (one
+// counter per level in global memory, zeroed by the launcher) separates the levels. Same tile functions, same bits. The barrier gives up
+// after ~50 ms into an error word instead of hanging the device if the grid is ever not co-resident.
+#define BLOOM_TAIL_MAX_LEVELS 10
+struct BloomTailLevel { ImgView target, source, prev; int isUpsample, isLowestMip, fastAllowed; float blurRadius; };
+struct BloomTailParams { BloomTailLevel lv[BLOOM_TAIL_MAX_LEVELS]; int nLevels; unsigned int* counters; };  // counters[0 .. nLevels): barrier arrivals, [nLevels]: error
+__global__ void __launch_bounds__(256, 4) bloomTailKernel(const __grid_constant__ BloomTailParams p) {
+    __shared__ float4 sTile[BLOOM_DOWN_TW * BLOOM_DOWN_TH];  // the upsample's two 24x12 tiles fit in it
+    static_assert(2 * BLOOM_UP_TW * BLOOM_UP_TH <= BLOOM_DOWN_TW * BLOOM_DOWN_TH, "tile sizes");
+    for (int l = 0; l < p.nLevels; l++) {
+        const BloomTailLevel& L = p.lv[l];
+        const int tilesX = (L.target.w + 31) / 32, tilesY = (L.target.h + 7) / 8;
+        for (int t = blockIdx.x; t < tilesX * tilesY; t += gridDim.x) {
+            const int bx = (t % tilesX) * 32, by = (t / tilesX) * 8;
+            if (L.isUpsample) bloomUpsampleTile(L.target, L.prev, L.source, L.isLowestMip, L.blurRadius, L.fastAllowed, bx, by, L.target.h, sTile, sTile + BLOOM_UP_TW * BLOOM_UP_TH);
+            else bloomDownsampleTile(L.target, L.source, bx, by, L.target.h, sTile);
+            __syncthreads();  // the tile is reused
+        }
+        if (l + 1 < p.nLevels) {  // grid barrier: this level's stores are visible to every block before the next level reads them
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                __threadfence();
+                atomicAdd(p.counters + l, 1u);
+                const long long start = clock64();
+                while (*(volatile unsigned int*)(p.counters + l) < gridDim.x) {
+                    if (clock64() - start > 100000000ll) { atomicExch(p.counters + p.nLevels, 1u); break; }
+                    __nanosleep(32);
+                }
+                __threadfence();
+            }
+            __syncthreads();
+        }
+    }
+}
+// a run of small levels handed over by the backend (ExecRecord::fusedRun): one persistent launch, two blocks per SM
+static bool launchBloomTail(LaunchCtx& c) {
+    BloomTailParams p;
+    p.nLevels = 0;
+    for (int index : c.exec->fusedRun) {
+        LaunchCtx m = c;
+        m.exec = c.be_exec(index);
+        m.pass = c.be_pass(m.exec->pass);
+        BloomTailLevel& L = p.lv[p.nLevels++];
+        L.isUpsample = m.pass->shader == "bloomUpsample.comp" ? 1 : 0;
+        L.target = m.storage(0, PLAIN_FORMAT_R11G11B10_UFLOAT);
+        if (L.isUpsample) {
+            L.prev = m.sampled(1, PLAIN_FORMAT_R11G11B10_UFLOAT);
+            L.source = m.sampled(2, PLAIN_FORMAT_R11G11B10_UFLOAT);
+            L.isLowestMip = m.specBool(0, false) ? 1 : 0;
+            L.blurRadius = m.push<float>(0);
+            L.fastAllowed = (L.isLowestMip || (L.prev.w == L.source.w && L.prev.h == L.source.h)) && L.blurRadius == L.blurRadius && std::fabs(L.blurRadius) <= 64.f;
+        } else {
+            L.source = m.sampled(1, PLAIN_FORMAT_R11G11B10_UFLOAT);
+            L.prev = L.source;
+            L.isLowestMip = 0; L.fastAllowed = 0; L.blurRadius = 0.f;
+        }
+        if (m.failed) { c.fail(m.error); return true; }
+        if ((int)m.exec->dispatch[0] * 8 < L.target.w || (int)m.exec->dispatch[1] * 8 < L.target.h) { c.fail("bloom chain: dispatch does not cover the target"); return true; }
+    }
+    p.counters = c.be_fusionCounters();
+    if (!p.counters) return false;
+    if (cudaMemsetAsync(p.counters, 0, (size_t)(p.nLevels + 1) * sizeof(unsigned int), c.stream) != cudaSuccess) return false;
+    PLAIN_LAUNCH(c, bloomTailKernel, dim3((unsigned)(4 * c.smCount)), 256, 0, p);
+    return true;
 }
 PLAIN_PASS(launch_bloomUpsample, "bloomUpsample.comp") {
     const ImgView target = c.storage(0, PLAIN_FORMAT_R11G11B10_UFLOAT);
