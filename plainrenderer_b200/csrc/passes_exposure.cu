@@ -126,20 +126,55 @@ __device__ float offsetFromSceneEV(float sceneEV100) {  // :28-38
 }
 __global__ void preExposeLightsKernel(plain_light_buffer* lightBuffer, const uint32_t* __restrict__ histogram, ImgView transmissionLut,
                                       const plain_global_shader_info* __restrict__ g, int nBins, float minLuminance, float maxLuminance) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    // one warp (round 2): the per-bin work of :28-38 - the running pixel count (an exact integer prefix sum), the percentage test, the bin's
+    // luminance exp(...) and the product count * luminance - is done by the lanes, four bins each; lane 0 then adds the products up in bin
+    // order, which is the only serial part (the sum's rounding depends on the order). A single thread took 25 us on the critical path of a
+    // row-sharded frame. More than 128 bins (never: nHistogramBins = 128) fall back to the serial loop.
+    if (blockIdx.x != 0 || threadIdx.x >= 32) return;
     const float minLuminanceLog = dm::log(minLuminance), maxLuminanceLog = dm::log(maxLuminance);
     const uint32_t pixelCount = (uint32_t)(g->screenResolution[0] * g->screenResolution[1]);
     float mean = 0.f;
-    uint32_t countedPixels = 0, currentPixelCount = 0;
-    for (int i = 0; i < nBins; i++) {
-        const uint32_t h = histogram[i];
-        currentPixelCount += h;
-        const float percentage = (float)currentPixelCount / (float)pixelCount;
-        if (percentage < 0.95f && percentage >= 0.5f) {
-            const float binValueLog = minLuminanceLog + (maxLuminanceLog - minLuminanceLog) * (float)i / ((float)nBins - 1.f);
-            const float binValueLinear = dm::exp(binValueLog);
-            mean += (float)h * binValueLinear;
-            countedPixels += h;
+    uint32_t countedPixels = 0;
+    __shared__ float sTerm[128];
+    __shared__ uint32_t sCounted[128];
+    if (nBins <= 128) {
+        const int lane = threadIdx.x, base = lane * 4;
+        uint32_t h[4], mine = 0;
+        for (int k = 0; k < 4; k++) { h[k] = base + k < nBins ? histogram[base + k] : 0u; mine += h[k]; }
+        uint32_t incl = mine;
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+        uint32_t currentPixelCount = incl - mine;
+        for (int k = 0; k < 4; k++) {
+            const int i = base + k;
+            currentPixelCount += h[k];
+            const float percentage = (float)currentPixelCount / (float)pixelCount;
+            float term = 0.f;
+            uint32_t counted = 0xffffffffu;  // marker: the bin is outside the window
+            if (i < nBins && percentage < 0.95f && percentage >= 0.5f) {
+                const float binValueLog = minLuminanceLog + (maxLuminanceLog - minLuminanceLog) * (float)i / ((float)nBins - 1.f);
+                const float binValueLinear = dm::exp(binValueLog);
+                term = (float)h[k] * binValueLinear;
+                counted = h[k];
+            }
+            sTerm[i] = term; sCounted[i] = counted;
+        }
+        __syncwarp();
+        if (lane != 0) return;
+        for (int i = 0; i < nBins; i++)
+            if (sCounted[i] != 0xffffffffu) { mean += sTerm[i]; countedPixels += sCounted[i]; }
+    } else {
+        if (threadIdx.x != 0) return;
+        uint32_t currentPixelCount = 0;
+        for (int i = 0; i < nBins; i++) {
+            const uint32_t h = histogram[i];
+            currentPixelCount += h;
+            const float percentage = (float)currentPixelCount / (float)pixelCount;
+            if (percentage < 0.95f && percentage >= 0.5f) {
+                const float binValueLog = minLuminanceLog + (maxLuminanceLog - minLuminanceLog) * (float)i / ((float)nBins - 1.f);
+                const float binValueLinear = dm::exp(binValueLog);
+                mean += (float)h * binValueLinear;
+                countedPixels += h;
+            }
         }
     }
     mean /= (float)countedPixels;
@@ -171,9 +206,17 @@ PLAIN_PASS(launch_preExposeLights, "preExposeLights.comp") {
 }
 
 // ---------------- skyTransmissionLut.comp:16-48 ----------------
-__global__ void __launch_bounds__(64) skyTransmissionLutKernel(ImgView lut, const plain_atmosphere_settings* __restrict__ ap, int limitX, int limitY) {
-    const int ux = blockIdx.x * 8 + threadIdx.x, uy = blockIdx.y * 8 + threadIdx.y;
-    if (ux >= limitX || uy >= limitY || ux >= lut.w || uy >= lut.h) return;
+// eight lanes per texel like skyLutKernel below: lane l evaluates the decay factors of steps [5l, 5l + 5), lane 0 multiplies them up in step order
+#define SKYT_LANES 8
+#define SKYT_TEXELS_PER_BLOCK 16
+__global__ void __launch_bounds__(SKYT_LANES * SKYT_TEXELS_PER_BLOCK) skyTransmissionLutKernel(ImgView lut, const plain_atmosphere_settings* __restrict__ ap, int limitX, int limitY) {
+    constexpr int sampleCount = 40;
+    __shared__ float sDecay[SKYT_TEXELS_PER_BLOCK][sampleCount][3];
+    const int local = threadIdx.x / SKYT_LANES, l = threadIdx.x % SKYT_LANES;
+    const int wLim = min(limitX, lut.w), hLim = min(limitY, lut.h);
+    const int texel = blockIdx.x * SKYT_TEXELS_PER_BLOCK + local;
+    const bool active = texel < wLim * hLim;
+    const int ux = active ? texel % wLim : 0, uy = active ? texel / wLim : 0;
     const plain_atmosphere_settings a = *ap;
     const float x = (float)ux / (float)(lut.w - 1);
     const float y = (float)uy / (float)(lut.h - 1);
@@ -185,17 +228,24 @@ __global__ void __launch_bounds__(64) skyTransmissionLutKernel(ImgView lut, cons
     const vec3 earthCenter = v3(0.f);
     const Intersection intersection = rayEarthIntersection(P - 0.01f, V, earthCenter, a.earthRadius, a.atmosphereHeight);
     const float pathLength = fmaxp(length(intersection.pos - P), 0.01f);
-    const int sampleCount = 40;
     const float stepLength = pathLength / (float)sampleCount;
     vec3 currentPos = intersection.pos;
-    vec3 absorption = v3(1.f);
     const vec3 step = V * stepLength;
-    for (int i = 0; i < sampleCount; i++) {
-        currentPos = currentPos - step;
-        const float currentHeight = fmaxp(length(earthCenter - currentPos) - a.earthRadius, 0.f);
-        const AtmosphereCoefficients co = calculateCoefficients(currentHeight, a);
-        absorption = absorption * vexp(-co.extinction * stepLength);
+    const int first = 5 * l, last = first + 5;
+    for (int i = 0; i < first; i++) currentPos = currentPos - step;  // where the serial loop stands before step `first`
+    if (active) {
+        for (int i = first; i < last; i++) {
+            currentPos = currentPos - step;
+            const float currentHeight = fmaxp(length(earthCenter - currentPos) - a.earthRadius, 0.f);
+            const AtmosphereCoefficients co = calculateCoefficients(currentHeight, a);
+            const vec3 decay = vexp(-co.extinction * stepLength);
+            sDecay[local][i][0] = decay.x; sDecay[local][i][1] = decay.y; sDecay[local][i][2] = decay.z;
+        }
     }
+    __syncthreads();
+    if (!active || l != 0) return;
+    vec3 absorption = v3(1.f);
+    for (int i = 0; i < sampleCount; i++) absorption = absorption * v3(sDecay[local][i][0], sDecay[local][i][1], sDecay[local][i][2]);
     absorption = intersection.hitEarth ? v3(0.f) : absorption;
     storeR11(lut, ux, uy, absorption);
 }
@@ -203,15 +253,17 @@ PLAIN_PASS(launch_skyTransmissionLut, "skyTransmissionLut.comp") {
     const ImgView lut = c.storage(0, PLAIN_FORMAT_R11G11B10_UFLOAT);
     const plain_atmosphere_settings* a = c.ubuf<plain_atmosphere_settings>(1);
     if (c.failed) return;
-    dim3 grid(c.exec->dispatch[0], c.exec->dispatch[1]);
-    PLAIN_LAUNCH(c, skyTransmissionLutKernel, grid, dim3(8, 8), 0, lut, a, (int)grid.x * 8, (int)grid.y * 8);
+    const int limX = (int)c.exec->dispatch[0] * 8, limY = (int)c.exec->dispatch[1] * 8;
+    const int texels = std::min(limX, lut.w) * std::min(limY, lut.h);
+    if (texels <= 0) return;
+    PLAIN_LAUNCH(c, skyTransmissionLutKernel, dim3(ceilDiv((unsigned)texels, SKYT_TEXELS_PER_BLOCK)), SKYT_LANES * SKYT_TEXELS_PER_BLOCK, 0, lut, a, limX, limY);
 }
 
 // ---------------- skyMultiscatterLut.comp:19-124 ('approximation' path) ----------------
-// One warp per LUT texel: the 64 (i, j) directions are spread over the lanes (two each) and the two partial sums are
+// One block of 64 threads per LUT texel: the 64 (i, j) directions are spread over the threads (one each) and the two partial sums are
 // combined in the reference's (i, j) order by a serial pass of lane 0 over the per-direction terms, so the result
 // does not depend on the lane mapping.
-__global__ void __launch_bounds__(32) skyMultiscatterLutKernel(ImgView multiscatterLut, ImgView transmissionLut, const plain_atmosphere_settings* __restrict__ ap, int limitX, int limitY) {
+__global__ void __launch_bounds__(64) skyMultiscatterLutKernel(ImgView multiscatterLut, ImgView transmissionLut, const plain_atmosphere_settings* __restrict__ ap, int limitX, int limitY) {
     __shared__ float terms[64][6];
     const int ux = blockIdx.x, uy = blockIdx.y;
     if (ux >= limitX || uy >= limitY || ux >= multiscatterLut.w || uy >= multiscatterLut.h) return;
@@ -226,7 +278,7 @@ __global__ void __launch_bounds__(32) skyMultiscatterLutKernel(ImgView multiscat
     const float isotropicPhase = 1.f / (4.f * PV_PI);
     const int sampleCountSqrt = 8;
     const float sampleCountSqrtRcp = 1.f / (float)sampleCountSqrt;
-    for (int dirIdx = threadIdx.x; dirIdx < 64; dirIdx += 32) {
+    for (int dirIdx = threadIdx.x; dirIdx < 64; dirIdx += 64) {  // one direction per thread (round 2: two per lane of one warp took twice as long on the critical path of a sharded frame)
         const int i = dirIdx / 8;
         const float theta = PV_PI * (float)i * sampleCountSqrtRcp;
         const float sinTheta = dm::sin(theta), cosTheta = dm::cos(theta);
@@ -267,7 +319,7 @@ __global__ void __launch_bounds__(32) skyMultiscatterLutKernel(ImgView multiscat
         terms[dirIdx][0] = fTerm.x; terms[dirIdx][1] = fTerm.y; terms[dirIdx][2] = fTerm.z;
         terms[dirIdx][3] = lTerm.x; terms[dirIdx][4] = lTerm.y; terms[dirIdx][5] = lTerm.z;
     }
-    __syncwarp();
+    __syncthreads();
     if (threadIdx.x == 0) {
         vec3 f_ms = v3(0.f), L_2nd = v3(0.f);
         for (int d = 0; d < 64; d++) {
@@ -288,7 +340,7 @@ PLAIN_PASS(launch_skyMultiscatterLut, "skyMultiscatterLut.comp") {
     if (c.failed) return;
     const int limX = (int)c.exec->dispatch[0] * 8, limY = (int)c.exec->dispatch[1] * 8;
     dim3 grid(std::min(limX, lut.w), std::min(limY, lut.h));
-    PLAIN_LAUNCH(c, skyMultiscatterLutKernel, grid, 32, 0, lut, transmission, a, limX, limY);
+    PLAIN_LAUNCH(c, skyMultiscatterLutKernel, grid, 64, 0, lut, transmission, a, limX, limY);
 }
 
 // ---------------- skyLut.comp:24-97 ----------------
@@ -300,10 +352,23 @@ __device__ float skyShadowRay(vec3 P, vec3 D, vec3 C, float earthRadius) {  // :
     const float t_earth = t_ca - t_hc_earth;
     return t_earth > 0.f ? 0.f : 1.f;
 }
-__global__ void __launch_bounds__(64) skyLutKernel(ImgView skyLut, ImgView transmissionLut, ImgView multiscatterLut, const plain_atmosphere_settings* __restrict__ ap,
+// Eight lanes per LUT texel (round 2): the 30 march steps of a texel (:52-93) are a serial chain only through `color` and `absorption`; what a
+// step costs - the position's height, two LUT lookups, the shadow ray, the coefficients, three exponentials - depends on the step's position
+// alone. Lane l evaluates steps [4l, 4l + 4) (lanes 6, 7: three each) from the position the serial loop would have reached (the same repeated
+// additions), leaves each step's three vectors in shared memory, and lane 0 then runs the serial accumulation in step order. Same operations,
+// same order per accumulator, a sixth of the latency: the kernel is 300 threads of pure dependency chain otherwise (ncu: 6 % occupancy, 55 us) -
+// hidden beside the trace on one GPU, on the critical path of a row-sharded frame, where every rank computes the whole LUT.
+#define SKY_LANES 8
+#define SKY_TEXELS_PER_BLOCK 16
+__global__ void __launch_bounds__(SKY_LANES * SKY_TEXELS_PER_BLOCK) skyLutKernel(ImgView skyLut, ImgView transmissionLut, ImgView multiscatterLut, const plain_atmosphere_settings* __restrict__ ap,
                                                     const plain_light_buffer* __restrict__ light, const plain_global_shader_info* __restrict__ g, int limitX, int limitY) {
-    const int ux = blockIdx.x * 8 + threadIdx.x, uy = blockIdx.y * 8 + threadIdx.y;
-    if (ux >= limitX || uy >= limitY || ux >= skyLut.w || uy >= skyLut.h) return;  // the dispatch truncates: rows 96-99 stay unwritten (Sky.cpp:311-312)
+    constexpr int sampleCount = 30;
+    __shared__ float sStep[SKY_TEXELS_PER_BLOCK][sampleCount][9];  // per step: scatterIntegral, exp(-extinction * stepSize), the multiscattering term
+    const int local = threadIdx.x / SKY_LANES, l = threadIdx.x % SKY_LANES;
+    const int wLim = min(limitX, skyLut.w), hLim = min(limitY, skyLut.h);  // the dispatch truncates: rows 96-99 stay unwritten (Sky.cpp:311-312)
+    const int texel = blockIdx.x * SKY_TEXELS_PER_BLOCK + local;
+    const bool active = texel < wLim * hLim;
+    const int ux = active ? texel % wLim : 0, uy = active ? texel / wLim : 0;
     const plain_atmosphere_settings a = *ap;
     const float sunStrengthExposed = light->sunStrengthExposed;
     const float x = (float)ux / (float)skyLut.w;
@@ -313,35 +378,49 @@ __global__ void __launch_bounds__(64) skyLutKernel(ImgView skyLut, ImgView trans
     const float bias = 0.002f;
     const vec3 P = v3(0.f, -a.earthRadius - bias, 0.f);
     const Intersection intersection = rayEarthIntersection(P, V, earthCenter, a.earthRadius, a.atmosphereHeight);
-    const int sampleCount = 30;
     const float stepSize = intersection.distance / (float)sampleCount;
     const vec3 L = v3(g->sunDirection[0], g->sunDirection[1], g->sunDirection[2]);
     const float VoL = dot(V, L);
     const float phaseR = phaseRayleigh(VoL);
     const float phaseMie = cornetteShanksPhase(VoL, a.mieScatteringExponent);
+    const vec3 step = V * stepSize;
+    const int first = l < 6 ? 4 * l : 24 + 3 * (l - 6), last = l < 6 ? first + 4 : first + 3;
     vec3 currentPosition = P;
+    for (int i = 0; i < first; i++) currentPosition = currentPosition + step;  // where the serial loop stands before step `first`
+    if (active) {
+        for (int i = first; i < last; i++) {
+            currentPosition = currentPosition + step;
+            vec3 up = currentPosition - earthCenter;
+            const float upLength = length(up);
+            const float currentHeight = upLength - a.earthRadius;
+            up = up / upLength;
+            const vec2 lutUV = computeLutUV(currentHeight, a.atmosphereHeight, up, L);
+            const vec3 transmission = sampleR11LinearClamp(transmissionLut, lutUV);
+            vec3 incomingLight = sunStrengthExposed * transmission;
+            incomingLight = incomingLight * skyShadowRay(currentPosition, L, earthCenter, a.earthRadius);
+            const AtmosphereCoefficients co = calculateCoefficients(currentHeight, a);
+            const vec3 inscatteringRayleight = co.scatterRayleigh * incomingLight * phaseR;
+            const vec3 inscatteringMie = co.scatterMie * incomingLight * phaseMie;
+            const vec3 inscattering = inscatteringRayleight + inscatteringMie;
+            const vec3 scatterIntegral = integrateInscattering(inscattering, co.extinction, stepSize);
+            const vec3 decay = vexp(-co.extinction * stepSize);
+            const vec3 multiscattering = sampleR11LinearClamp(multiscatterLut, lutUV);
+            const vec3 ms = multiscattering * incomingLight * (co.scatterRayleigh + co.scatterMie) * stepSize * transmission;
+            float* o = sStep[local][i];
+            o[0] = scatterIntegral.x; o[1] = scatterIntegral.y; o[2] = scatterIntegral.z;
+            o[3] = decay.x; o[4] = decay.y; o[5] = decay.z;
+            o[6] = ms.x; o[7] = ms.y; o[8] = ms.z;
+        }
+    }
+    __syncthreads();
+    if (!active || l != 0) return;
     vec3 absorption = v3(1.f);
     vec3 color = v3(0.f);
-    const vec3 step = V * stepSize;
-    for (int i = 0; i < sampleCount; i++) {
-        currentPosition = currentPosition + step;
-        vec3 up = currentPosition - earthCenter;
-        const float upLength = length(up);
-        const float currentHeight = upLength - a.earthRadius;
-        up = up / upLength;
-        const vec2 lutUV = computeLutUV(currentHeight, a.atmosphereHeight, up, L);
-        const vec3 transmission = sampleR11LinearClamp(transmissionLut, lutUV);
-        vec3 incomingLight = sunStrengthExposed * transmission;
-        incomingLight = incomingLight * skyShadowRay(currentPosition, L, earthCenter, a.earthRadius);
-        const AtmosphereCoefficients co = calculateCoefficients(currentHeight, a);
-        const vec3 inscatteringRayleight = co.scatterRayleigh * incomingLight * phaseR;
-        const vec3 inscatteringMie = co.scatterMie * incomingLight * phaseMie;
-        const vec3 inscattering = inscatteringRayleight + inscatteringMie;
-        const vec3 scatterIntegral = integrateInscattering(inscattering, co.extinction, stepSize);
-        color = color + scatterIntegral * absorption;
-        absorption = absorption * vexp(-co.extinction * stepSize);
-        const vec3 multiscattering = sampleR11LinearClamp(multiscatterLut, lutUV);
-        color = color + multiscattering * incomingLight * (co.scatterRayleigh + co.scatterMie) * stepSize * transmission;
+    for (int i = 0; i < sampleCount; i++) {  // :84-92 in step order
+        const float* o = sStep[local][i];
+        color = color + v3(o[0], o[1], o[2]) * absorption;
+        absorption = absorption * v3(o[3], o[4], o[5]);
+        color = color + v3(o[6], o[7], o[8]);
     }
     storeR11(skyLut, ux, uy, color);
 }
@@ -351,8 +430,10 @@ PLAIN_PASS(launch_skyLut, "skyLut.comp") {
     const plain_atmosphere_settings* a = c.ubuf<plain_atmosphere_settings>(4);
     const plain_light_buffer* light = c.sbuf<plain_light_buffer>(5);
     if (c.failed) return;
-    dim3 grid(c.exec->dispatch[0], c.exec->dispatch[1]);
-    PLAIN_LAUNCH(c, skyLutKernel, grid, dim3(8, 8), 0, lut, transmission, multiscatter, a, light, c.g, (int)grid.x * 8, (int)grid.y * 8);
+    const int limX = (int)c.exec->dispatch[0] * 8, limY = (int)c.exec->dispatch[1] * 8;
+    const int texels = std::min(limX, lut.w) * std::min(limY, lut.h);
+    if (texels <= 0) return;
+    PLAIN_LAUNCH(c, skyLutKernel, dim3(ceilDiv((unsigned)texels, SKY_TEXELS_PER_BLOCK)), SKY_LANES * SKY_TEXELS_PER_BLOCK, 0, lut, transmission, multiscatter, a, light, c.g, limX, limY);
 }
 
 }  // namespace pb
