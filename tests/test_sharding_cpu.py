@@ -124,6 +124,8 @@ def test_exchange_schedule_of_a_sharded_frame(ffi, oracle):
     from conftest import PlainSceneSequence
     from plainrenderer_b200 import assets
 
+    deferred = {}
+
     def schedule(fe, cam):
         names = []
         fe.begin_frame(cam, 1 / 60.0, 1 / 60.0)
@@ -132,6 +134,7 @@ def test_exchange_schedule_of_a_sharded_frame(ffi, oracle):
             if x is None:
                 return names
             names.append((x.name.decode(), x.kind, x.n_images))
+            deferred[x.name.decode()] = int(x.deferred)
     lib = assets.Assets(ROOT / "oracle" / "_build" / "liboracle.so", "oracle_asset_")
     seq = PlainSceneSequence(ffi, oracle, lib, 64, 64, shard_rank=0, shard_count=2)
     raster = schedule(seq.fe, seq.camera_at(0, False))
@@ -156,3 +159,5 @@ def test_exchange_schedule_of_a_sharded_frame(ffi, oracle):
     assert [n for n, _, _ in raster] == ["histogram", "motion", "hiz+depthHalf"] + tail
     assert dict((n, k) for n, k, _ in raster)["motion"] == ffi.EXCHANGE_ALLGATHER_ROWS
     assert uploaded[1][1] == ffi.EXCHANGE_ALLREDUCE_SUM_U32
+    # exactly the three all-gathers of next-frame data carry the deferred mark (include/plain_frontend.h plain_exchange.deferred)
+    assert sorted(n for n, d in deferred.items() if d) == ["froxelHistory", "giSpatial1", "taaHistory"]
