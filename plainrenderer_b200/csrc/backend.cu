@@ -89,6 +89,7 @@ struct Backend {
     cudaEvent_t peerFork = nullptr, peerDeferredDone = nullptr;
     uint32_t peerEpochDeferred = 0;
     bool peerDeferredDirty = false, peerDeferredPending = false, frameFresh = false;
+    uint32_t peerBarriersThisFrame = 0;  // synchronous barriers since new_frame: a deferred push needs at least one before it (write-after-read across frames)
     std::vector<DeviceImage> images, transientImages;
     // two presentable images, flipped by new_frame (a swapchain hands out a different image every frame): the read-back of
     // frame N does not hold up the tonemapping pass of frame N+1
@@ -842,6 +843,7 @@ int PLAIN_FN(new_frame)(plain_ctx* ctx) {
     ctx->b.timings.clear();  // pass timings accumulate over the submissions of a frame (a row-sharded frame has one per segment)
     ctx->b.swapchainCurrent ^= 1;  // the next presentable image (RenderBackend.cpp:608-612 getSwapchainInputImage)
     ctx->b.frameFresh = true;
+    ctx->b.peerBarriersThisFrame = 0;
     for (auto& t : ctx->b.transientImages) t.inUse = false;
     return 0;
 }
@@ -1131,6 +1133,14 @@ int PLAIN_FN(wait_for_gpu_idle)(plain_ctx* ctx) {
     ctx->b.peerDeferredPending = false;
     drainTransfers(ctx->b);
     CU_CHECK(ctx, cudaStreamSynchronize(ctx->b.stream));
+    if (ctx->b.fusionCounters) {  // the grid barrier of a fused run gave up (its blocks were not co-resident for 50 ms): frames since the last check are invalid
+        unsigned int fusionError = 0;
+        CU_CHECK(ctx, cudaMemcpy(&fusionError, ctx->b.fusionCounters + 63, sizeof(fusionError), cudaMemcpyDeviceToHost));
+        if (fusionError) {
+            cudaMemset(ctx->b.fusionCounters + 63, 0, sizeof(fusionError));
+            return fail(ctx, "wait_for_gpu_idle: the grid barrier of a fused pass run (bloom mips >= 2) timed out; disable it with set_pass_fusion_enabled(ctx, 0)");
+        }
+    }
     return 0;
 }
 int PLAIN_FN(join_transfers)(plain_ctx* ctx) {  // the compute stream waits for every asynchronous upload and read-back issued so far
@@ -1328,6 +1338,7 @@ static int peerBarrier(plain_ctx* ctx, bool deferred = false) {
     }
     a.localError = b.peerSync[b.peerRank] + Backend::kPeerErrorOffset;
     a.rank = b.peerRank; a.count = b.peerCount; a.epoch = deferred ? ++b.peerEpochDeferred : ++b.peerEpoch;
+    if (!deferred) b.peerBarriersThisFrame++;
     // a rank that is late on the host (first graph instantiation, lazy IPC mapping, CPU contention) must not trip the others: 20 s by
     // default, PLAIN_PEER_TIMEOUT_MS to change it. A timeout sets the sticky error word; callers poll it every frame (peer_error_poll)
     static const long long timeoutMs = getenv("PLAIN_PEER_TIMEOUT_MS") ? atoll(getenv("PLAIN_PEER_TIMEOUT_MS")) : 20000ll;
@@ -1344,6 +1355,7 @@ int PLAIN_FN(peer_push_rows_deferred)(plain_ctx* ctx, uint32_t n, const plain_pe
     Backend& b = ctx->b;
     cudaSetDevice(b.device);
     if (b.peerCount < 2) return fail(ctx, "peer_push_rows_deferred: peer_init first");
+    if (b.peerBarriersThisFrame == 0) return fail(ctx, "peer_push_rows_deferred: no synchronous peer barrier in this frame yet - the peers may still be reading the rows' previous contents");
     if (!b.peerStream) {
         CU_CHECK(ctx, cudaStreamCreateWithFlags(&b.peerStream, cudaStreamNonBlocking));
         CU_CHECK(ctx, cudaEventCreateWithFlags(&b.peerFork, cudaEventDisableTiming));

@@ -311,7 +311,7 @@ __global__ void __launch_bounds__(256, 4) bloomUpsampleKernel(ImgView target, Im
 // after ~50 ms into an error word instead of hanging the device if the grid is ever not co-resident.
 #define BLOOM_TAIL_MAX_LEVELS 10
 struct BloomTailLevel { ImgView target, source, prev; int isUpsample, isLowestMip, fastAllowed; float blurRadius; };
-struct BloomTailParams { BloomTailLevel lv[BLOOM_TAIL_MAX_LEVELS]; int nLevels; unsigned int* counters; };  // counters[0 .. nLevels): barrier arrivals, [nLevels]: error
+struct BloomTailParams { BloomTailLevel lv[BLOOM_TAIL_MAX_LEVELS]; int nLevels; unsigned int* counters; };  // counters[0 .. nLevels): barrier arrivals; counters[63]: sticky error word (wait_for_gpu_idle reports it)
 __global__ void __launch_bounds__(256, 4) bloomTailKernel(const __grid_constant__ BloomTailParams p) {
     __shared__ float4 sTile[BLOOM_DOWN_TW * BLOOM_DOWN_TH];  // the upsample's two 24x12 tiles fit in it
     static_assert(2 * BLOOM_UP_TW * BLOOM_UP_TH <= BLOOM_DOWN_TW * BLOOM_DOWN_TH, "tile sizes");
@@ -331,7 +331,7 @@ __global__ void __launch_bounds__(256, 4) bloomTailKernel(const __grid_constant_
                 atomicAdd(p.counters + l, 1u);
                 const long long start = clock64();
                 while (*(volatile unsigned int*)(p.counters + l) < gridDim.x) {
-                    if (clock64() - start > 100000000ll) { atomicExch(p.counters + p.nLevels, 1u); break; }
+                    if (clock64() - start > 100000000ll) { atomicExch(p.counters + 63, 1u); break; }
                     __nanosleep(32);
                 }
                 __threadfence();
@@ -367,7 +367,7 @@ static bool launchBloomTail(LaunchCtx& c) {
     }
     p.counters = c.be_fusionCounters();
     if (!p.counters) return false;
-    if (cudaMemsetAsync(p.counters, 0, (size_t)(p.nLevels + 1) * sizeof(unsigned int), c.stream) != cudaSuccess) return false;
+    if (cudaMemsetAsync(p.counters, 0, (size_t)p.nLevels * sizeof(unsigned int), c.stream) != cudaSuccess) return false;
     PLAIN_LAUNCH(c, bloomTailKernel, dim3((unsigned)(4 * c.smCount)), 256, 0, p);
     return true;
 }
