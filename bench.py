@@ -396,6 +396,15 @@ def run_ours(args, rank, world, local_rank):
             N_, n_ = WIDTH * HEIGHT, (WIDTH // 2) * (HEIGHT // 2)
             alg_frame["Forward shading"] += 4 * N_ + 14 * n_ - 12 * N_
             alg_frame["Indirect lighting upscale"] = 0
+        froxel_chain = ("Froxel volume material", "Froxel light scattering", "Volumetric lighting reprojection")
+        if all(acc.get(k, 1.0) < 0.004 for k in froxel_chain):
+            # pass fusion: the four froxel passes run as ONE launch over froxel columns in the place of the integration pass - the material and scattering
+            # volumes are never written, the reprojected texel goes from registers into the integration: history read 8 + history write 8 + integrated write 8
+            # bytes per froxel (531 -> 199 MB at 3840x2160)
+            F_ = ((WIDTH + 7) // 8) * ((HEIGHT + 7) // 8) * 64
+            for k in froxel_chain:
+                alg_frame[k] = 0
+            alg_frame["Volumetric light integration"] = 24 * F_
         alg = {k: (v if (not sharded or k.startswith(REPLICATED_PASSES)) else int(v * band_share)) for k, v in alg_frame.items()}
         top = max(acc, key=lambda k: acc[k])
         launches_of_top = 2 if top == "Indirect diffuse spatial filter" else 1

@@ -256,8 +256,10 @@ PLAIN_EXPORT int PLAIN_FN(get_last_frame_launch_count)(plain_ctx* ctx, uint32_t*
 /* enable replay of an unchanged pass list through a captured CUDA graph (CUDA backend; no-op in the oracle) */
 PLAIN_EXPORT int PLAIN_FN(set_graph_replay_enabled)(plain_ctx* ctx, int enabled);
 /* Pass fusion (default on): a producer pass whose only consumer in the submission can compute its texels inline is not launched.
- * Today: indirectLightUpscale.comp folded into gbufferShading.comp (the two full-resolution GI images are then NOT written - switch
- * fusion off when they are to be read back). Results are bit-identical either way. No-op in the oracle. */
+ * Today: indirectLightUpscale.comp folded into gbufferShading.comp (the two full-resolution GI images are then NOT written); the small
+ * levels of the bloom chain as one launch; the froxel chain froxelVolumeMaterial -> froxelLightScattering -> volumeLightingReprojection ->
+ * volumetricLightingIntegration as one launch over froxel columns (the material and scattering volumes are then NOT written). Switch
+ * fusion off when those images are to be read back. Results are bit-identical either way. No-op in the oracle. */
 PLAIN_EXPORT int PLAIN_FN(set_pass_fusion_enabled)(plain_ctx* ctx, int enabled);
 /* schedule the passes of a submission onto several streams from the hazards between their declared resources (default on):
  * a pass waits only for the passes it conflicts with, like the barriers the reference derives (RenderBackend.cpp:632-767).

@@ -441,6 +441,59 @@ static void planFusions(Backend& b) {
         consumer.fusedProducer = producer;
         b.execs[(size_t)producer].fusedAway = true;
     }
+    // The froxel chain (Volumetrics.cpp:151-246 emits froxelVolumeMaterial -> froxelLightScattering -> volumeLightingReprojection ->
+    // volumetricLightingIntegration back to back, each reading its predecessor's volume at its own froxel only): ONE launch over froxel
+    // columns (passes_volumetrics.cu froxelColumnKernel), issued in the place of the LAST execution - by then the stream has waited for
+    // everything the four depend on. The material and scattering volumes are then not written (nothing else in the submission may touch them).
+    static const bool fuseFroxels = !getenv("PLAIN_FROXEL_FUSION") || atoi(getenv("PLAIN_FROXEL_FUSION")) != 0;  // A / B switch: 0 = the four kernels
+    for (size_t i = 0; fuseFroxels && i + 3 < b.execs.size(); i++) {
+        static const char* const chain[4] = {"froxelVolumeMaterial.comp", "froxelLightScattering.comp", "volumeLightingReprojection.comp", "volumetricLightingIntegration.comp"};
+        bool ok = true;
+        for (size_t k = 0; k < 4 && ok; k++) {
+            const ExecRecord& e = b.execs[i + k];
+            ok = !b.passes[e.pass].graphic && b.passes[e.pass].shader == chain[k] && !e.fusedAway && e.fusedRun.empty() && e.fusedProducer < 0 &&
+                 e.rowBegin == b.execs[i].rowBegin && e.rowEnd == b.execs[i].rowEnd;
+        }
+        if (!ok) continue;
+        const ExecRecord &mat = b.execs[i], &sca = b.execs[i + 1], &rep = b.execs[i + 2], &itg = b.execs[i + 3];
+        const plain_image_resource *matOut = find(mat.storageImages, 0), *scaOut = find(sca.storageImages, 0), *scaIn = find(sca.sampledImages, 2);
+        const plain_image_resource *repOut = find(rep.storageImages, 0), *repIn = find(rep.sampledImages, 1), *repHistory = find(rep.sampledImages, 2);
+        const plain_image_resource *itgOut = find(itg.storageImages, 0), *itgIn = find(itg.sampledImages, 1);
+        if (!matOut || !scaOut || !scaIn || !repOut || !repIn || !repHistory || !itgOut || !itgIn) continue;
+        if (!same(*matOut, *scaIn) || !same(*scaOut, *repIn) || !same(*repOut, *itgIn)) continue;
+        const plain_image_resource* written[4] = {matOut, scaOut, repOut, itgOut};
+        bool distinct = true;
+        for (int a = 0; a < 4; a++) {
+            distinct = distinct && !same(*written[a], *repHistory);  // the history is sampled at reprojected positions: it must not be a volume the launch writes
+            for (int c = a + 1; c < 4; c++) distinct = distinct && !same(*written[a], *written[c]);
+        }
+        if (!distinct) continue;
+        auto level = [&](const plain_image_resource& r) -> const MipInfo* {
+            DeviceImage* img = b.resolve(r.image);
+            return img && r.mip_level < img->mips.size() ? &img->mips[r.mip_level] : nullptr;
+        };
+        const MipInfo* ref = level(*repOut);
+        if (!ref || ref->d > 128) continue;
+        bool sameExtent = true;
+        for (int a = 0; a < 4; a++) { const MipInfo* m = level(*written[a]); sameExtent = sameExtent && m && m->w == ref->w && m->h == ref->h && m->d == ref->d; }
+        if (!sameExtent) continue;
+        bool covered = (int)itg.dispatch[0] * 8 >= ref->w && (int)itg.dispatch[1] * 8 >= ref->h;
+        for (size_t k = 0; k < 3; k++) covered = covered && (int)b.execs[i + k].dispatch[0] * 4 >= ref->w && (int)b.execs[i + k].dispatch[1] * 4 >= ref->h && (int)b.execs[i + k].dispatch[2] * 4 >= ref->d;
+        if (!covered) continue;
+        auto settingsBuffer = [](const ExecRecord& e, uint32_t binding) -> long long { for (auto& r : e.uniformBuffers) if (r.binding == binding) return (long long)r.buffer; return -1 - (long long)binding; };
+        const long long settings = settingsBuffer(mat, 2);
+        if (settings < 0 || settingsBuffer(sca, 5) != settings || settingsBuffer(rep, 3) != settings || settingsBuffer(itg, 2) != settings) continue;
+        bool othersTouch = false;
+        for (size_t k = 0; k < b.execs.size() && !othersTouch; k++) {
+            if (k >= i && k < i + 4) continue;
+            for (auto& r : b.execs[k].sampledImages) othersTouch = othersTouch || same(r, *matOut) || same(r, *scaOut);
+            for (auto& r : b.execs[k].storageImages) othersTouch = othersTouch || same(r, *matOut) || same(r, *scaOut);
+        }
+        if (othersTouch) continue;
+        for (size_t k = 0; k < 4; k++) b.execs[i + 3].fusedRun.push_back((int)(i + k));
+        for (size_t k = 0; k < 3; k++) b.execs[i + k].fusedAway = true;
+        i += 3;
+    }
 }
 
 #define SCHED_CHECK(call, what)                                                                                         \

@@ -85,7 +85,8 @@ struct ExecRecord {
     // pass fusion (backend.cu planFusions): a producer whose only consumer in the submission computes its texels inline
     int fusedProducer = -1;   // consumer: index of the execution it absorbed
     bool fusedAway = false;   // producer: no launch (its place in the dependency order is kept)
-    std::vector<int> fusedRun; // leader of a run of dependent small passes executed by ONE persistent launch (bloom mips >= 2): the run's executions in order, itself first
+    std::vector<int> fusedRun; // the execution that launches a run of dependent passes as ONE kernel, the run's executions in order: bloom mips >= 2 (one persistent
+                               // launch by the run's FIRST execution), the froxel chain (one launch over froxel columns by the run's LAST execution)
 };
 
 struct Backend;
@@ -197,7 +198,7 @@ struct Globals {  // the fields of the global UBO (global.inc:4-33) most kernels
     vec3 camPos, fwd, up, right;
     float tanFovHalf, aspect, nearPlane, farPlane;
 };
-__device__ __forceinline__ Globals loadGlobals(const plain_global_shader_info* __restrict__ g) {
+PV_HD Globals loadGlobals(const plain_global_shader_info* __restrict__ g) {
     Globals r;
     r.camPos = v3(g->cameraPosition[0], g->cameraPosition[1], g->cameraPosition[2]);
     r.fwd = v3(g->cameraForward[0], g->cameraForward[1], g->cameraForward[2]);

@@ -2,15 +2,11 @@
 //   froxelVolumeMaterial.comp:17-44, froxelLightScattering.comp:31-64, volumeLightingReprojection.comp:19-62,
 //   volumetricLightingIntegration.comp:18-43, volumetricFroxelLighting.inc:1-55
 // Froxel volumes are RGBA16F, x fastest: a warp covers 32 consecutive froxels of one row (256 contiguous bytes).
-#include "shader_inc.cuh"
+// The per-froxel bodies live in froxel_inc.cuh (host+device); this file holds the four per-pass kernels and the fused column
+// kernel the backend launches instead of them when the four executions form one chain (backend.cu planFusions).
+#include "froxel_inc.cuh"
 
 namespace pb {
-
-__device__ __forceinline__ vec3 froxelWorldPos(const Globals& G, vec3 uv, float maxDistance) {
-    const vec3 ndc = 2.f * (uv - 0.5f);
-    const vec3 V = viewDirFromNDC(G, v2(ndc.x, ndc.y));
-    return G.camPos - V / dot(-V, G.fwd) * froxelUVToDepth(uv.z, maxDistance);
-}
 
 // yBegin / limY: froxel rows [yBegin, limY) of this launch (row sharding: the rank's band of froxel rows + a few rows of overlap)
 #define FROXEL_COORDS(vol)                                                                                     \
@@ -26,17 +22,7 @@ __global__ void __launch_bounds__(128) froxelVolumeMaterialKernel(ImgView materi
     const vec3 volumeRes = v3((float)materialVolume.w, (float)materialVolume.h, (float)materialVolume.d);
     const vec3 uv = (v3((float)x, (float)y, (float)z) + 0.5f + s.sampleOffset) / volumeRes;
     const vec3 posWorld = froxelWorldPos(G, uv, s.maxDistance);
-    const float noiseScale = 0.5f;
-    const vec3 noiseSample = posWorld * noiseScale + ld3(s.windSampleOffset);
-    const float noise = sampleLinear3D<WRAP_REPEAT, float>([&](int tx, int ty, int tz) { return loadR8(noiseTexture, tx, ty, tz); }, noiseTexture.w, noiseTexture.h, noiseTexture.d, noiseSample, 0.f);
-    vec3 scatteringCoefficient = ld3(s.scatteringCoefficients);
-    float absorptionCoefficient = s.absorptionCoefficient;
-    float densityMultiplier = s.baseDensity;
-    densityMultiplier += s.densityNoiseRange * (noise - 0.5f);
-    densityMultiplier = fmaxp(densityMultiplier, 0.f);
-    scatteringCoefficient = scatteringCoefficient * densityMultiplier;
-    absorptionCoefficient *= densityMultiplier;
-    storeRGBA16F(materialVolume, x, y, z, v4(scatteringCoefficient, absorptionCoefficient));
+    storeRGBA16F(materialVolume, x, y, z, froxelMaterialAt(s, noiseTexture, posWorld));
 }
 PLAIN_PASS(launch_froxelVolumeMaterial, "froxelVolumeMaterial.comp") {
     const ImgView vol = c.storage(0, PLAIN_FORMAT_RGBA16_SFLOAT), noise = c.sampled(1, PLAIN_FORMAT_R8);
@@ -62,19 +48,8 @@ __global__ void __launch_bounds__(128) froxelLightScatteringKernel(ImgView outVo
     const vec3 ndc = 2.f * uv - 1.f;  // :40 (the other froxel passes use 2 * (uv - 0.5))
     const vec3 V = viewDirFromNDC(G, v2(ndc.x, ndc.y));
     const vec3 posWorld = G.camPos - V / dot(-V, G.fwd) * froxelUVToDepth(uv.z, s.maxDistance);
-    const float shadow = simpleShadow<false>(posWorld, cascades->lightMatrices[2], sunShadowMap);  // hard-coded cascade 2 (:45)
-    const float sunStrength = shadow * light->sunStrengthExposed;
-    const vec3 L = v3(g->sunDirection[0], g->sunDirection[1], g->sunDirection[2]);
-    const float VoL = dot(-V, L);
-    const float phase = phaseGreenstein(VoL, s.phaseFunctionG);
     const vec4 sa = inRange(materialVolume, x, y, z) ? loadRGBA16F(materialVolume, x, y, z) : v4(0.f);
-    const vec3 scatteringCoefficient = xyz(sa);
-    const float absorptionCoefficient = sa.w;
-    const vec3 constantAmbientLighting = v3(0.02f);
-    const vec3 inscattering = (sunStrength * phase * ld3(light->sunColor) + constantAmbientLighting) * scatteringCoefficient;
-    const vec3 extinctionCoefficient = scatteringCoefficient + absorptionCoefficient;
-    const float transmittance = computeLuminance(extinctionCoefficient);
-    storeRGBA16F(outVolume, x, y, z, v4(inscattering, transmittance));
+    storeRGBA16F(outVolume, x, y, z, froxelScatteringAt(g, s, cascades, light, sunShadowMap, V, posWorld, sa));
 }
 PLAIN_PASS(launch_froxelLightScattering, "froxelLightScattering.comp") {
     const ImgView out = c.storage(0, PLAIN_FORMAT_RGBA16_SFLOAT);
@@ -101,18 +76,7 @@ __global__ void __launch_bounds__(128) volumeLightingReprojectionKernel(ImgView 
     const vec3 volumeRes = v3((float)targetImage.w, (float)targetImage.h, (float)targetImage.d);
     const vec3 uv = (v3((float)x, (float)y, (float)z) + 0.5f) / volumeRes;
     const vec3 posWorld = froxelWorldPos(G, uv, maxDistance);
-    const vec4 ndcPrevious = mulm4(g->viewProjectionPrevious, v4(posWorld, 1.f));
-    const vec3 ndcP = xyz(ndcPrevious) / ndcPrevious.w;
-    const vec3 camPosPrev = v3(g->cameraPositionPrevious[0], g->cameraPositionPrevious[1], g->cameraPositionPrevious[2]);
-    const vec3 V_history = normalize(camPosPrev - posWorld);
-    const float historyDistance = length(posWorld - camPosPrev);
-    const float historyDepth = historyDistance * dot(-V_history, v3(g->cameraForwardPrevious[0], g->cameraForwardPrevious[1], g->cameraForwardPrevious[2]));
-    const vec3 historyUV = v3(ndcP.x * 0.5f + 0.5f, ndcP.y * 0.5f + 0.5f, depthToFroxelUVZ(historyDepth, maxDistance));
-    vec4 history = sampleRGBA16FLinearClamp3D(historyVolume, historyUV);
-    float alpha = 0.95f;
-    if (historyUV.x > 1.f || historyUV.y > 1.f || historyUV.z > 1.f || historyUV.x < 0.f || historyUV.y < 0.f || historyUV.z < 0.f) alpha = 0.f;
-    if (g->cameraCut) history = current;
-    storeRGBA16F(targetImage, x, y, z, vmix(current, history, alpha));
+    storeRGBA16F(targetImage, x, y, z, froxelReprojectionAt(g, maxDistance, historyVolume, posWorld, current));
 }
 PLAIN_PASS(launch_volumeLightingReprojection, "volumeLightingReprojection.comp") {
     const ImgView target = c.storage(0, PLAIN_FORMAT_RGBA16_SFLOAT);
@@ -143,14 +107,63 @@ __global__ void __launch_bounds__(128) volumetricLightingIntegrationKernel(ImgVi
         const vec4 it = inRange(scatteringTransmittanceVolume, x, y, z) ? loadRGBA16F(scatteringTransmittanceVolume, x, y, z) : v4(0.f);
         const float depthEnd = froxelUVToDepth((float)(z + 1) / (float)resZ, maxDistance);
         const float segmentLength = depthEnd - depthStart;
-        const vec3 inscattering = integrateInscattering(xyz(it), v3(it.w), segmentLength);
-        inscatteringTotal = inscatteringTotal + inscattering;
-        transmittance *= dm::exp(-it.w * segmentLength);
+        const vec4 terms = froxelSegmentTerms(it, segmentLength);
+        inscatteringTotal = inscatteringTotal + xyz(terms);
+        transmittance *= terms.w;
         storeRGBA16F(integrationVolume, x, y, z, v4(inscatteringTotal, transmittance));
         depthStart = depthEnd;  // froxelUVToDepth(z / resZ) of the next slice is the same expression as this slice's end
     }
 }
+
+// ---------------- the four passes as ONE launch (backend.cu planFusions hands the chain over as ExecRecord::fusedRun) ----------------
+// Block = 8 columns x 64 z lanes of one froxel row; the phases are in froxel_inc.cuh (froxelBlockPrologue / Phase1 / Phase2 / Phase3), one call
+// per thread and phase with a barrier in between.
+// Algorithmic bytes per froxel: history read 8 + history write 8 + integrated write 8 = 24 (the four passes: 8 + 16 + 24 + 16 = 64); the material
+// and scattering volumes are not written (tests that compare them run unfused: plain_set_pass_fusion_enabled).
+__global__ void __launch_bounds__(FROXEL_BLOCK_THREADS, 2) froxelColumnKernel(const __grid_constant__ FroxelFusedParams p) {
+    __shared__ FroxelBlockShared sh;
+    const int tid = threadIdx.x, blockX = blockIdx.x, y = p.yBegin + blockIdx.y;
+    const plain_volumetric_lighting_settings s = *p.settings;
+    const Globals G = loadGlobals(p.in.g);
+    froxelBlockPrologue(sh, p, G, s, tid, blockX, y);
+    __syncthreads();
+    froxelBlockPhase1<false>(sh, p, G, s, tid, blockX, y);
+    __syncthreads();
+    froxelBlockPhase2(sh, p, tid, blockX);
+    __syncthreads();
+    froxelBlockPhase3(sh, p, tid, blockX, y);
+}
+// c = the chain's last execution (volumetricLightingIntegration.comp); c.exec->fusedRun = material, scattering, reprojection, integration
+static void launchFroxelColumns(LaunchCtx& c) {
+    if (c.exec->fusedRun.size() != 4) { c.fail("froxel chain: a fused run of four executions expected"); return; }
+    LaunchCtx m[4] = {c, c, c, c};
+    for (int k = 0; k < 4; k++) {
+        m[k].exec = c.be_exec(c.exec->fusedRun[(size_t)k]);
+        m[k].pass = c.be_pass(m[k].exec->pass);
+    }
+    FroxelFusedParams p;
+    p.materialVolume = m[0].storage(0, PLAIN_FORMAT_RGBA16_SFLOAT);
+    p.scatteringVolume = m[1].storage(0, PLAIN_FORMAT_RGBA16_SFLOAT);
+    p.in.noiseTexture = m[0].sampled(1, PLAIN_FORMAT_R8);
+    p.settings = m[0].ubuf<plain_volumetric_lighting_settings>(2);
+    p.in.sunShadowMap = m[1].sampled(1, PLAIN_FORMAT_DEPTH16);
+    p.in.cascades = m[1].sbuf<plain_shadow_cascade_info>(3);
+    p.in.light = m[1].sbuf<plain_light_buffer>(4);
+    p.historyTarget = m[2].storage(0, PLAIN_FORMAT_RGBA16_SFLOAT);
+    p.in.historyVolume = m[2].sampled(2, PLAIN_FORMAT_RGBA16_SFLOAT);
+    p.integrationVolume = m[3].storage(0, PLAIN_FORMAT_RGBA16_SFLOAT);
+    p.in.g = c.g;
+    for (int k = 0; k < 4; k++) if (m[k].failed) { c.fail(m[k].error); return; }
+    auto sameExtent = [&](const ImgView& v) { return v.w == p.historyTarget.w && v.h == p.historyTarget.h && v.d == p.historyTarget.d; };
+    if (!sameExtent(p.materialVolume) || !sameExtent(p.scatteringVolume) || !sameExtent(p.integrationVolume) || p.historyTarget.d > FROXEL_MAX_DEPTH) { c.fail("froxel chain: fused volumes of different extents"); return; }
+    int y0, y1;
+    c.window(p.historyTarget.h, y0, y1);
+    if (y1 <= y0) return;
+    p.yBegin = y0;
+    PLAIN_LAUNCH(c, froxelColumnKernel, dim3(ceilDiv(p.historyTarget.w, FROXEL_COLS), (unsigned)(y1 - y0)), FROXEL_BLOCK_THREADS, 0, p);
+}
 PLAIN_PASS(launch_volumetricLightingIntegration, "volumetricLightingIntegration.comp") {
+    if (!c.exec->fusedRun.empty()) { launchFroxelColumns(c); return; }
     const ImgView integration = c.storage(0, PLAIN_FORMAT_RGBA16_SFLOAT), src = c.sampled(1, PLAIN_FORMAT_RGBA16_SFLOAT);
     const plain_volumetric_lighting_settings* s = c.ubuf<plain_volumetric_lighting_settings>(2);
     if (c.failed) return;

@@ -92,7 +92,7 @@ PV_HD vec3 calculateViewDirectionFromPixel(vec2 pixelNDC, vec3 cameraForward, ve
     V = V - cameraTanFovHalf * aspectRatio * pixelNDC.x * cameraRight;
     return normalize(V);
 }
-__device__ __forceinline__ vec3 viewDirFromNDC(const Globals& G, vec2 ndc) { return calculateViewDirectionFromPixel(ndc, G.fwd, G.up, G.right, G.tanFovHalf, G.aspect); }
+PV_HD vec3 viewDirFromNDC(const Globals& G, vec2 ndc) { return calculateViewDirectionFromPixel(ndc, G.fwd, G.up, G.right, G.tanFovHalf, G.aspect); }
 
 // indirectLightUpscale.comp:17-71 for one full-resolution pixel: depth-aware upscale of the half-resolution GI (Y_SH RGBA16F + CoCg RG16F).
 // Shared by giUpscaleKernel (passes_gi.cu) and by the shading kernel when the backend folds the upscale into its consumer (triangle.frag:294-320).

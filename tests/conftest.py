@@ -80,7 +80,9 @@ def random_r11g11b10(rng, n, finite=True):
 CAMERA = ((-13.0, -1.7, 0.5), (1.0, 0.0, 0.0), (0.0, 0.0, 1.0), (0.0, -1.0, 0.0))
 ALL_IMAGES = ["skyTransmission", "skyMultiscatter", "skyLut", "hiz", "depthHalf", "giY0", "giC0", "giY1", "giC1", "giHistY0", "giHistC0", "giHistY1", "giHistC1", "giFullY", "giFullC",
               "froxelMaterial", "froxelScatter", "froxelHist0", "froxelHist1", "froxelIntegration", "color0", "color1", "taaHist0", "taaHist1", "taaLum0", "taaLum1", "post0", "post1", "brdfLut", "output"]
-FUSED_AWAY_IMAGES = ("giFullY", "giFullC")  # outputs of indirectLightUpscale.comp: not written when the pass is folded into the shading kernel
+# not written under pass fusion: the outputs of indirectLightUpscale.comp (folded into the shading kernel) and the material / scattering volumes of
+# the froxel chain (one launch over froxel columns keeps them in registers)
+FUSED_AWAY_IMAGES = ("giFullY", "giFullC", "froxelMaterial", "froxelScatter")
 ALL_BUFFERS = [("histogram", 512), ("light", 20), ("sunShadowInfo", 304), ("sdfCulled", None), ("sdfTiles", None)]  # None: the whole buffer (S3: instance culling lists)
 # the non-default passes beside the frame path (temporalSupersampling.comp + colorToLuminance.comp, sdfDebugVisualisation.comp)
 N4_VARIANTS = [dict(taa_use_separate_supersampling=1), dict(taa_use_separate_supersampling=1, taa_supersample_use_tonemapping=0),

@@ -398,16 +398,19 @@ def gi_upscale(ffi, api, y_sh, co_cg, depth_full, depth_half):
     return res
 
 
-def froxels(ffi, api, res, noise_r8, shadow_d16, light_matrix2, light, settings13, history, camera, prev, sun_direction, camera_cut=False):
+def froxels(ffi, api, res, noise_r8, shadow_d16, light_matrix2, light, settings13, history, camera, prev, sun_direction, camera_cut=False, pass_fusion=False):
     """The four froxel passes with the bindings of Volumetrics::computeVolumetricLighting (Volumetrics.cpp:136-247) in one frame:
     froxelVolumeMaterial -> froxelLightScattering -> volumeLightingReprojection -> volumetricLightingIntegration.
     res = (w, h, d) of the volumes; noise_r8 (n, n, n) uint8; shadow_d16 (s, s) uint16; light_matrix2 = column-major 16 floats of cascade 2;
     light = (sunColor rgb, previousFrameExposure, sunStrengthExposed) (lightBuffer.inc:4-8); settings13 = the 13 floats of VolumetricLightingSettings;
     history (d, h, w, 4) float16; camera = dict(position, forward, up, right, tan_fov_half, aspect); prev = dict(view_projection (4x4, row-major
-    numpy), position, forward). Returns (material, scattering, reprojected, integrated) float16 volumes (d, h, w, 4) and the globals."""
+    numpy), position, forward). Returns (material, scattering, reprojected, integrated) float16 volumes (d, h, w, 4) and the globals.
+    pass_fusion: the product runs the chain as one launch over froxel columns (backend.cu planFusions) - material and scattering are then
+    not written and come back as zeros."""
     w, h, d = res
     rig = PassRig(ffi, api, w * 8, h * 8)
     be, g = rig.be, rig.g
+    be._check(api.b["set_pass_fusion_enabled"](be.ctx, 1 if pass_fusion else 0), "set_pass_fusion_enabled")
     for i in range(3):
         g.cameraPosition[i], g.cameraForward[i], g.cameraUp[i], g.cameraRight[i] = (float(camera[k][i]) for k in ("position", "forward", "up", "right"))
         g.cameraPositionPrevious[i], g.cameraForwardPrevious[i] = float(prev["position"][i]), float(prev["forward"][i])

@@ -40,8 +40,10 @@ def test_gi_upscale_bit_exact(ffi, cuda, oracle, W, H):
     assert np.array_equal(a[0].view(np.uint16), b[0].view(np.uint16)) and np.array_equal(a[1].view(np.uint16), b[1].view(np.uint16))
 
 
-@pytest.mark.parametrize("res,moving,cut", [((12, 7, 16), False, False), ((10, 6, 8), True, False), ((9, 5, 8), True, True), ((60, 34, 64), True, False)])
+@pytest.mark.parametrize("res,moving,cut", [((12, 7, 16), False, False), ((10, 6, 8), True, False), ((9, 5, 8), True, True), ((60, 34, 64), True, False), ((19, 9, 70), True, False)])
 def test_froxel_passes_bit_exact(ffi, cuda, oracle, res, moving, cut):
+    """the four froxel passes launched one by one (all four volumes compared) and as the fused column launch, the product's default (the
+    reprojected and the integrated volume compared; the launch leaves the material and scattering volumes alone)"""
     from test_froxels_numpy import scene
     cam, prev, noise, shadow, L, settings, light, history, sun = scene(res[0] * 10 + res[2], res, moving)
     history[1, 2, 3, :] = np.nan
@@ -49,6 +51,10 @@ def test_froxel_passes_bit_exact(ffi, cuda, oracle, res, moving, cut):
     b = passes.froxels(ffi, oracle, res, noise, shadow, L.T.ravel(), light, settings, history, cam, prev, sun, camera_cut=cut)
     for name, x, y in zip(("material", "scattering", "reprojection", "integration"), a, b):
         assert np.array_equal(x.view(np.uint16), y.view(np.uint16)), name
+    fused = passes.froxels(ffi, cuda, res, noise, shadow, L.T.ravel(), light, settings, history, cam, prev, sun, camera_cut=cut, pass_fusion=True)
+    for name, x, y in list(zip(("material", "scattering", "reprojection", "integration"), fused, b))[2:]:
+        assert np.array_equal(x.view(np.uint16), y.view(np.uint16)), name + " (fused column launch)"
+    assert not fused[0].view(np.uint16).any() and not fused[1].view(np.uint16).any(), "the fused launch wrote the material / scattering volume"
 
 
 @pytest.mark.parametrize("w,h,radius,strength", [(64, 48, 1.5, 0.05), (100, 75, 1.0, 0.3), (33, 17, 2.5, 1.0)])
