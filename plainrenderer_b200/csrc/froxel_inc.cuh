@@ -21,11 +21,31 @@ PV_HD vec3 froxelWorldPos(const Globals& G, vec3 uv, float maxDistance) {
     return G.camPos - V / dot(-V, G.fwd) * froxelUVToDepth(uv.z, maxDistance);
 }
 
+// trilinear sample of the R8 density noise with repeat addressing (sampleLinear3D<WRAP_REPEAT> of image_view.h: same set-up, same blend). When all
+// three extents are powers of two (the 32^3 volume of Volumetrics.cpp:60-75) the six index wraps are masks instead of integer remainders:
+// for size = 2^k, i & (size - 1) IS the non-negative remainder of the two's complement i - an integer identity, no arithmetic changes.
+PV_HD float froxelNoiseSample(const ImgView& t, vec3 uvw) {
+    const int w = t.w, h = t.h, d = t.d;
+    if (((w & (w - 1)) | (h & (h - 1)) | (d & (d - 1))) != 0 || w <= 0 || h <= 0 || d <= 0)
+        return sampleLinear3D<WRAP_REPEAT, float>([&](int tx, int ty, int tz) { return loadR8(t, tx, ty, tz); }, w, h, d, uvw, 0.f);
+    const Bilerp b = bilerpSetup(v2(uvw.x, uvw.y), w, h);
+    const float fz = fmaf_(sanitizeCoord(uvw.z), (float)d, -0.5f);
+    const float z0f = floorf_(fz);
+    const float az = fz - z0f, bz = 1.f - az;
+    const int z0i = f2i(z0f);
+    const int x0 = b.x0 & (w - 1), x1 = (b.x0 + 1) & (w - 1), y0 = b.y0 & (h - 1), y1 = (b.y0 + 1) & (h - 1), z0 = z0i & (d - 1), z1 = (z0i + 1) & (d - 1);
+    const float a00 = loadR8(t, x0, y0, z0), a10 = loadR8(t, x1, y0, z0), a01 = loadR8(t, x0, y1, z0), a11 = loadR8(t, x1, y1, z0);
+    const float b00 = loadR8(t, x0, y0, z1), b10 = loadR8(t, x1, y0, z1), b01 = loadR8(t, x0, y1, z1), b11 = loadR8(t, x1, y1, z1);
+    const float s0 = vfma(a11, b.w11, vfma(a01, b.w01, vfma(a10, b.w10, a00 * b.w00)));
+    const float s1 = vfma(b11, b.w11, vfma(b01, b.w01, vfma(b10, b.w10, b00 * b.w00)));
+    return vfma(s1, az, s0 * bz);
+}
+
 // ---------------- froxelVolumeMaterial.comp:24-43, from the world position on ----------------
 PV_HD vec4 froxelMaterialAt(const plain_volumetric_lighting_settings& s, const ImgView& noiseTexture, vec3 posWorld) {
     const float noiseScale = 0.5f;
     const vec3 noiseSample = posWorld * noiseScale + ld3(s.windSampleOffset);
-    const float noise = sampleLinear3D<WRAP_REPEAT, float>([&](int tx, int ty, int tz) { return loadR8(noiseTexture, tx, ty, tz); }, noiseTexture.w, noiseTexture.h, noiseTexture.d, noiseSample, 0.f);
+    const float noise = froxelNoiseSample(noiseTexture, noiseSample);
     vec3 scatteringCoefficient = ld3(s.scatteringCoefficients);
     float absorptionCoefficient = s.absorptionCoefficient;
     float densityMultiplier = s.baseDensity;
@@ -120,13 +140,13 @@ PV_HD void froxelFusedTexel(const FroxelFusedInputs& in, const Globals& G, const
 }
 
 
-// ---- one block of the fused launch: 8 columns x 64 z lanes of one froxel row, a thread owns the froxels (x, y, z = lane, lane + 64, ..) of its
-// column. The phases are functions of the thread index so that the kernel (passes_volumetrics.cu froxelColumnKernel: one call per thread and
+// ---- one block of the fused launch: 8 columns x ZLANES z lanes of one froxel row, a thread owns the froxels (x, y, z = lane, lane + ZLANES, ..) of
+// its column. The phases are functions of the thread index so that the kernel (passes_volumetrics.cu froxelColumnKernel: one call per thread and
 // phase, __syncthreads between the phases) and the CPU check (tests/emul/froxel_fusion_host.cu: a loop over the thread indices per phase) run the
 // same statements. ----
 #define FROXEL_COLS 8
-#define FROXEL_ZLANES 64
-#define FROXEL_BLOCK_THREADS (FROXEL_COLS * FROXEL_ZLANES)
+// ZLANES (template parameter of the phases): z lanes of a block, 64 / 32 / 16 = 512 / 256 / 128 threads; the smaller the block, the more blocks
+// share an SM and cover each other's barrier phases (the froxels a thread owns grow accordingly: z = lane, lane + ZLANES, ..)
 #define FROXEL_MAX_DEPTH 128  // planFusions (backend.cu) does not fuse deeper volumes
 struct FroxelBlockShared {
     float depth[3 * FROXEL_MAX_DEPTH + 1];          // froxelDepthTableEntry
@@ -142,7 +162,7 @@ struct FroxelFusedParams {
 };
 // prologue: 24 threads form the three (V, W) pairs of the block's 8 columns, the other warps the three depth tables (3 d + 1 exponentials per block
 // instead of four to five per froxel)
-PV_HD void froxelBlockPrologue(FroxelBlockShared& sh, const FroxelFusedParams& p, const Globals& G, const plain_volumetric_lighting_settings& s, int tid, int blockX, int y) {
+template <int ZLANES> PV_HD void froxelBlockPrologue(FroxelBlockShared& sh, const FroxelFusedParams& p, const Globals& G, const plain_volumetric_lighting_settings& s, int tid, int blockX, int y) {
     const int resX = p.historyTarget.w, resY = p.historyTarget.h, resZ = p.historyTarget.d;
     if (tid < 3 * FROXEL_COLS) {
         const int variant = tid / FROXEL_COLS, xl = tid % FROXEL_COLS;
@@ -151,12 +171,12 @@ PV_HD void froxelBlockPrologue(FroxelBlockShared& sh, const FroxelFusedParams& p
         float* c = sh.column[variant][xl];
         c[0] = V.x; c[1] = V.y; c[2] = V.z; c[3] = W.x; c[4] = W.y; c[5] = W.z;
     } else if (tid >= 32) {
-        for (int j = tid - 32; j <= 3 * resZ; j += FROXEL_BLOCK_THREADS - 32) sh.depth[j] = froxelDepthTableEntry(j, resZ, s.sampleOffset, s.maxDistance);
+        for (int j = tid - 32; j <= 3 * resZ; j += FROXEL_COLS * ZLANES - 32) sh.depth[j] = froxelDepthTableEntry(j, resZ, s.sampleOffset, s.maxDistance);
     }
 }
 // phase 1: material -> scattering -> reprojection of the thread's froxels in registers; the reprojected texel (= next frame's history) is stored, the
 // slice's integration terms are left in shared memory
-template <bool WRITE_INTERMEDIATES> PV_HD void froxelBlockPhase1(FroxelBlockShared& sh, const FroxelFusedParams& p, const Globals& G, const plain_volumetric_lighting_settings& s, int tid, int blockX, int y) {
+template <int ZLANES, bool WRITE_INTERMEDIATES> PV_HD void froxelBlockPhase1(FroxelBlockShared& sh, const FroxelFusedParams& p, const Globals& G, const plain_volumetric_lighting_settings& s, int tid, int blockX, int y) {
     const int xl = tid % FROXEL_COLS, zl = tid / FROXEL_COLS, x = blockX * FROXEL_COLS + xl;
     const int resZ = p.historyTarget.d;
     if (x >= p.historyTarget.w) return;
@@ -164,7 +184,7 @@ template <bool WRITE_INTERMEDIATES> PV_HD void froxelBlockPhase1(FroxelBlockShar
     const float* cs = sh.column[1][xl];
     const float* cr = sh.column[2][xl];
     const vec3 Wm = v3(cm[3], cm[4], cm[5]), Vs = v3(cs[0], cs[1], cs[2]), Ws = v3(cs[3], cs[4], cs[5]), Wr = v3(cr[3], cr[4], cr[5]);
-    for (int z = zl; z < resZ; z += FROXEL_ZLANES) {
+    for (int z = zl; z < resZ; z += ZLANES) {
         vec4 material, scattering, reprojected;
         froxelFusedTexel(p.in, G, s, Wm, Vs, Ws, Wr, sh.depth[z], sh.depth[resZ + z], material, scattering, reprojected);
         storeRGBA16F(p.historyTarget, x, y, z, reprojected);
@@ -197,10 +217,10 @@ PV_HD void froxelBlockPhase2(FroxelBlockShared& sh, const FroxelFusedParams& p, 
     }
 }
 // phase 3: every thread stores its froxels of the integrated volume
-PV_HD void froxelBlockPhase3(const FroxelBlockShared& sh, const FroxelFusedParams& p, int tid, int blockX, int y) {
+template <int ZLANES> PV_HD void froxelBlockPhase3(const FroxelBlockShared& sh, const FroxelFusedParams& p, int tid, int blockX, int y) {
     const int xl = tid % FROXEL_COLS, zl = tid / FROXEL_COLS, x = blockX * FROXEL_COLS + xl;
     if (x >= p.historyTarget.w) return;
-    for (int z = zl; z < p.historyTarget.d; z += FROXEL_ZLANES) {
+    for (int z = zl; z < p.historyTarget.d; z += ZLANES) {
         const float4 t = sh.terms[z][xl];
         storeRGBA16F(p.integrationVolume, x, y, z, v4(t.x, t.y, t.z, t.w));
     }

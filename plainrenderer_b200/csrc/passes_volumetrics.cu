@@ -4,6 +4,7 @@
 // Froxel volumes are RGBA16F, x fastest: a warp covers 32 consecutive froxels of one row (256 contiguous bytes).
 // The per-froxel bodies live in froxel_inc.cuh (host+device); this file holds the four per-pass kernels and the fused column
 // kernel the backend launches instead of them when the four executions form one chain (backend.cu planFusions).
+#include <cstdlib>
 #include "froxel_inc.cuh"
 
 namespace pb {
@@ -120,18 +121,18 @@ __global__ void __launch_bounds__(128) volumetricLightingIntegrationKernel(ImgVi
 // per thread and phase with a barrier in between.
 // Algorithmic bytes per froxel: history read 8 + history write 8 + integrated write 8 = 24 (the four passes: 8 + 16 + 24 + 16 = 64); the material
 // and scattering volumes are not written (tests that compare them run unfused: plain_set_pass_fusion_enabled).
-__global__ void __launch_bounds__(FROXEL_BLOCK_THREADS, 2) froxelColumnKernel(const __grid_constant__ FroxelFusedParams p) {
+template <int ZLANES> __global__ void __launch_bounds__(FROXEL_COLS * ZLANES, 1024 / (FROXEL_COLS * ZLANES)) froxelColumnKernel(const __grid_constant__ FroxelFusedParams p) {
     __shared__ FroxelBlockShared sh;
     const int tid = threadIdx.x, blockX = blockIdx.x, y = p.yBegin + blockIdx.y;
     const plain_volumetric_lighting_settings s = *p.settings;
     const Globals G = loadGlobals(p.in.g);
-    froxelBlockPrologue(sh, p, G, s, tid, blockX, y);
+    froxelBlockPrologue<ZLANES>(sh, p, G, s, tid, blockX, y);
     __syncthreads();
-    froxelBlockPhase1<false>(sh, p, G, s, tid, blockX, y);
+    froxelBlockPhase1<ZLANES, false>(sh, p, G, s, tid, blockX, y);
     __syncthreads();
     froxelBlockPhase2(sh, p, tid, blockX);
     __syncthreads();
-    froxelBlockPhase3(sh, p, tid, blockX, y);
+    froxelBlockPhase3<ZLANES>(sh, p, tid, blockX, y);
 }
 // c = the chain's last execution (volumetricLightingIntegration.comp); c.exec->fusedRun = material, scattering, reprojection, integration
 static void launchFroxelColumns(LaunchCtx& c) {
@@ -160,7 +161,11 @@ static void launchFroxelColumns(LaunchCtx& c) {
     c.window(p.historyTarget.h, y0, y1);
     if (y1 <= y0) return;
     p.yBegin = y0;
-    PLAIN_LAUNCH(c, froxelColumnKernel, dim3(ceilDiv(p.historyTarget.w, FROXEL_COLS), (unsigned)(y1 - y0)), FROXEL_BLOCK_THREADS, 0, p);
+    static const int zLanes = getenv("PLAIN_FROXEL_ZLANES") ? atoi(getenv("PLAIN_FROXEL_ZLANES")) : 64;  // A / B switch: 64 (default) / 32 / 16 z lanes per block
+    const dim3 grid(ceilDiv(p.historyTarget.w, FROXEL_COLS), (unsigned)(y1 - y0));
+    if (zLanes == 16) PLAIN_LAUNCH(c, froxelColumnKernel<16>, grid, FROXEL_COLS * 16, 0, p);
+    else if (zLanes == 32) PLAIN_LAUNCH(c, froxelColumnKernel<32>, grid, FROXEL_COLS * 32, 0, p);
+    else PLAIN_LAUNCH(c, froxelColumnKernel<64>, grid, FROXEL_COLS * 64, 0, p);
 }
 PLAIN_PASS(launch_volumetricLightingIntegration, "volumetricLightingIntegration.comp") {
     if (!c.exec->fusedRun.empty()) { launchFroxelColumns(c); return; }

@@ -39,11 +39,11 @@ def host_lib():
                         "-o", str(lib), str(src)], check=True, capture_output=True)
     h = C.CDLL(str(lib))
     h.froxel_fused_host.restype = C.c_int
-    h.froxel_fused_host.argtypes = [C.c_int] * 3 + [C.c_void_p, C.c_int, C.c_void_p, C.c_int] + [C.c_void_p] * 5 + [C.c_int] * 2 + [C.c_void_p] * 4
+    h.froxel_fused_host.argtypes = [C.c_int] * 3 + [C.c_void_p, C.c_int, C.c_void_p, C.c_int] + [C.c_void_p] * 5 + [C.c_int] * 3 + [C.c_void_p] * 4
     return h
 
 
-def fused_on_host(h, ffi, res, noise, shadow, light_matrix2, light, settings, history, g, rows=None):
+def fused_on_host(h, ffi, res, noise, shadow, light_matrix2, light, settings, history, g, rows=None, z_lanes=64):
     w, hh, d = res
     lm = np.zeros((4, 16), np.float32)
     lm[2] = np.asarray(light_matrix2, np.float32)
@@ -57,18 +57,23 @@ def fused_on_host(h, ffi, res, noise, shadow, light_matrix2, light, settings, hi
     outs = [np.zeros((d, hh, w, 4), np.float16) for _ in range(4)]
     y0, y1 = rows or (0, hh)
     rc = h.froxel_fused_host(w, hh, d, noise.ctypes.data, noise.shape[0], shadow.ctypes.data, shadow.shape[0], info.ctypes.data, light.ctypes.data, settings.ctypes.data,
-                             hist.ctypes.data, gbytes.ctypes.data, y0, y1, *[o.ctypes.data for o in outs])
+                             hist.ctypes.data, gbytes.ctypes.data, y0, y1, z_lanes, *[o.ctypes.data for o in outs])
     assert rc == 0
     return outs
 
 
-@pytest.mark.parametrize("res,moving,cut", [((12, 7, 16), False, False), ((10, 6, 8), True, False), ((9, 5, 8), True, True), ((19, 9, 64), True, False), ((8, 3, 70), True, False)])
-def test_fused_froxel_columns_equal_the_oracles_four_passes(ffi, oracle, host_lib, res, moving, cut):
+@pytest.mark.parametrize("z_lanes", [64, 32, 16])
+@pytest.mark.parametrize("res,moving,cut,noise_size", [((12, 7, 16), False, False, 8), ((10, 6, 8), True, False, 8), ((9, 5, 8), True, True, 8), ((19, 9, 64), True, False, 8),
+                                                       ((8, 3, 70), True, False, 8), ((11, 6, 16), True, False, 6), ((9, 4, 24), False, False, 32)])
+def test_fused_froxel_columns_equal_the_oracles_four_passes(ffi, oracle, host_lib, res, moving, cut, noise_size, z_lanes):
+    """noise_size 6: the generic repeat addressing of the density noise; 8 / 32: the power-of-two masks (froxelNoiseSample)"""
     cam, prev, noise, shadow, L, settings, light, history, sun = scene(res[0] * 10 + res[2], res, moving)
+    if noise_size != noise.shape[0]:
+        noise = np.random.default_rng(noise_size).integers(0, 256, (noise_size,) * 3, dtype=np.uint8)
     history[1, 2, 3, :] = np.nan
     history[2, 1, 0, 3] = np.inf
     want = passes.froxels(ffi, oracle, res, noise, shadow, L.T.ravel(), light, settings, history, cam, prev, sun, camera_cut=cut)
-    got = fused_on_host(host_lib, ffi, res, noise, shadow, L.T.ravel(), light, settings, history, want[4])
+    got = fused_on_host(host_lib, ffi, res, noise, shadow, L.T.ravel(), light, settings, history, want[4], z_lanes=z_lanes)
     for name, x, y in zip(("material", "scattering", "reprojection", "integration"), got, want):
         assert np.array_equal(x.view(np.uint16), y.view(np.uint16)), "%s: %d of %d halves differ" % (name, int((x.view(np.uint16) != y.view(np.uint16)).sum()), x.size)
 
