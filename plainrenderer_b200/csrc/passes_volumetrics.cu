@@ -161,11 +161,13 @@ static void launchFroxelColumns(LaunchCtx& c) {
     c.window(p.historyTarget.h, y0, y1);
     if (y1 <= y0) return;
     p.yBegin = y0;
-    static const int zLanes = getenv("PLAIN_FROXEL_ZLANES") ? atoi(getenv("PLAIN_FROXEL_ZLANES")) : 64;  // A / B switch: 64 (default) / 32 / 16 z lanes per block
+    // z lanes per block, A / B switch: 64 / 32 / 16 (default). Measured at 3840x2160 (profiles/r4b_froxel_lanes.md): 0.430 / 0.357 / 0.338 ms - eight
+    // 128-thread blocks per SM cover each other's barrier phases (prologue, running sums), two 512-thread blocks do not
+    static const int zLanes = getenv("PLAIN_FROXEL_ZLANES") ? atoi(getenv("PLAIN_FROXEL_ZLANES")) : 16;
     const dim3 grid(ceilDiv(p.historyTarget.w, FROXEL_COLS), (unsigned)(y1 - y0));
-    if (zLanes == 16) PLAIN_LAUNCH(c, froxelColumnKernel<16>, grid, FROXEL_COLS * 16, 0, p);
+    if (zLanes == 64) PLAIN_LAUNCH(c, froxelColumnKernel<64>, grid, FROXEL_COLS * 64, 0, p);
     else if (zLanes == 32) PLAIN_LAUNCH(c, froxelColumnKernel<32>, grid, FROXEL_COLS * 32, 0, p);
-    else PLAIN_LAUNCH(c, froxelColumnKernel<64>, grid, FROXEL_COLS * 64, 0, p);
+    else PLAIN_LAUNCH(c, froxelColumnKernel<16>, grid, FROXEL_COLS * 16, 0, p);
 }
 PLAIN_PASS(launch_volumetricLightingIntegration, "volumetricLightingIntegration.comp") {
     if (!c.exec->fusedRun.empty()) { launchFroxelColumns(c); return; }
