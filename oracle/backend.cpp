@@ -17,8 +17,15 @@ static std::map<std::string, PassFn>& registry() {
     static std::map<std::string, PassFn> r;
     return r;
 }
+static std::map<std::string, PassFn>& overrides() {
+    static std::map<std::string, PassFn> r;
+    return r;
+}
 PassRegistration::PassRegistration(const char* shader, PassFn fn) { registry()[shader] = fn; }
+PassOverride::PassOverride(const char* shader, PassFn fn) { overrides()[shader] = fn; }
 PassFn findPass(const std::string& shader) {
+    auto ov = overrides().find(shader);
+    if (ov != overrides().end()) return ov->second;
     auto it = registry().find(shader);
     return it == registry().end() ? nullptr : it->second;
 }

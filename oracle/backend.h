@@ -119,6 +119,9 @@ struct PassCtx {
 
 PassFn findPass(const std::string& shader);
 struct PassRegistration { PassRegistration(const char* shader, PassFn fn); };
+// a pass that takes precedence over the registered one of the same shader name: oracle/_ref/liboracle_refmain.so (oracle/ref/ref_shader_passes.cpp)
+// runs the reference's own main() for the shaders that compile as C++; liboracle.so itself registers no override
+struct PassOverride { PassOverride(const char* shader, PassFn fn); };
 #define ORACLE_PASS(fnname, shader) static void fnname(PassCtx& c); static PassRegistration reg_##fnname(shader, fnname); static void fnname(PassCtx& c)
 
 }  // namespace orc

@@ -30,6 +30,32 @@ if [ -d "$REF/resources/shaders" ]; then
         echo "built $OUT/libref_glsl.so"
     fi
 fi
+# whole compute shaders of the reference (main() included) compiled as C++ from where they lie and registered as overrides of the oracle's own
+# passes: oracle/_ref/liboracle_refmain.so = the oracle's objects + oracle/ref/ref_shader_passes.cpp (tests/test_oracle_vs_reference_shaders.py).
+# The generated headers are build products under _ref/glsl/, never committed.
+REF_SHADERS="$(cat "$HERE/ref/ref_shaders.txt" | grep -v '^#' | tr '\n' ' ')"
+if [ -d "$REF/resources/shaders" ] && [ -n "$REF_SHADERS" ]; then
+    make -C "$HERE" >/dev/null
+    NEWEST_OBJ=$(ls -t "$HERE"/_build/o_*.o "$HERE"/_build/h_*.o | head -1)
+    if [ ! -f "$OUT/liboracle_refmain.so" ] || [ "$HERE/ref/ref_shader_passes.cpp" -nt "$OUT/liboracle_refmain.so" ] || [ "$HERE/ref/glsl_shader.h" -nt "$OUT/liboracle_refmain.so" ] || \
+       [ "$HERE/ref/glsl_ref.h" -nt "$OUT/liboracle_refmain.so" ] || [ "$HERE/ref/glsl_shader_to_cpp.py" -nt "$OUT/liboracle_refmain.so" ] || [ "$HERE/ref/glsl_to_cpp.py" -nt "$OUT/liboracle_refmain.so" ] || \
+       [ "$HERE/ref/ref_shaders.txt" -nt "$OUT/liboracle_refmain.so" ] || [ "$NEWEST_OBJ" -nt "$OUT/liboracle_refmain.so" ]; then
+        mkdir -p "$OUT/glsl"
+        python3 "$HERE/ref/glsl_shader_to_cpp.py" "$REF/resources/shaders" "$OUT/glsl" $REF_SHADERS
+        : > "$OUT/glsl/shaders_generated.h"; : > "$OUT/glsl/shaders_registered.h"
+        for s in $REF_SHADERS; do
+            n="${s%.comp}"
+            echo "#include \"shader_$n.h\"" >> "$OUT/glsl/shaders_generated.h"
+            echo "REF_SHADER($n, \"$s\")" >> "$OUT/glsl/shaders_registered.h"
+        done
+        echo "#define REF_SHADER_LIST \"$REF_SHADERS\"" >> "$OUT/glsl/shaders_registered.h"
+        FMA=""; [ "$(uname -m)" = "x86_64" ] && FMA="-mfma"
+        g++ -std=c++17 -O2 -ffp-contract=off $FMA -fno-fast-math -fPIC -fvisibility=hidden -w -DPLAIN_FN_PREFIX=oracle_ -DPLAIN_FRONTEND_PREFIX=oracle_frontend_ -DPLAIN_ASSET_PREFIX=oracle_asset_ \
+            -I"$HERE" -I"$HERE/ref" -I"$OUT/glsl" -I"$HERE/../include" -I"$HERE/../plainrenderer_b200/csrc" -c "$HERE/ref/ref_shader_passes.cpp" -o "$OUT/glsl/ref_shader_passes.o"
+        g++ -shared -o "$OUT/liboracle_refmain.so" "$HERE"/_build/o_*.o "$HERE"/_build/h_*.o "$OUT/glsl/ref_shader_passes.o" -lpthread
+        echo "built $OUT/liboracle_refmain.so ($REF_SHADERS)"
+    fi
+fi
 [ -x "$OUT/PlainAssetPipeline" ] && [ "$OUT/PlainAssetPipeline" -nt "$HERE/build_ref.sh" ] && { echo "up to date: $OUT/PlainAssetPipeline"; exit 0; }
 # -include math.h / stdlib.h: libstdc++'s C++ wrappers pull the float overloads of abs/sin/cos/sqrt into the global namespace, as
 # MSVC's headers do for the reference's own build. Without them the unqualified abs(float) calls of SceneSDF.cpp resolve to

@@ -1,0 +1,69 @@
+// ORACLE - test infrastructure only. What whole compute shaders of the reference need beyond oracle/ref/glsl_ref.h to compile as C++
+// (oracle/ref/ref_shader_passes.cpp): storage images, the compute built-in variables, unsigned-vector spelling, swizzle stores.
+// Every arithmetic operation is oracle/glsl.h's (the numeric contract) and every texel access oracle/image.h's (the sampler the
+// oracle's own passes use): this header only adds spelling.
+#pragma once
+#include "glsl_ref.h"
+#include "backend.h"
+
+namespace refglsl {
+
+// ---- compute built-ins, set by dispatch() below ----
+static uvec3 gl_GlobalInvocationID, gl_WorkGroupID, gl_LocalInvocationID, gl_NumWorkGroups;
+static uint gl_LocalInvocationIndex;
+
+// ---- storage images ----
+struct image2D { View v; image2D() {} explicit image2D(View view) : v(view) {} };
+struct image3D { View v; image3D() {} explicit image3D(View view) : v(view) {} };
+inline ivec2 imageSize(const image2D& i) { return ivec2(i.v.w(), i.v.h()); }
+inline ivec3 imageSize(const image3D& i) { return ivec3(i.v.w(), i.v.h(), i.v.d()); }
+inline vec4 imageLoad(const image2D& i, ivec2 p) { return i.v.fetch(p.x, p.y, 0); }
+inline vec4 imageLoad(const image3D& i, ivec3 p) { return i.v.fetch(p.x, p.y, p.z); }
+inline void imageStore(const image2D& i, ivec2 p, vec4 c) { i.v.store(p.x, p.y, 0, c); }
+inline void imageStore(const image3D& i, ivec3 p, vec4 c) { i.v.store(p.x, p.y, p.z, c); }
+inline vec4 texelFetch(sampler3D s, ivec3 p, int) { return s.t->fetch(p.x, p.y, p.z); }
+inline ivec2 textureSize(sampler2D s, int) { return ivec2(s.t->w(), s.t->h()); }
+inline vec4 textureLod(sampler2D s, gl::vec2 uv, float) { return orc::texture(*s.t, *s.s, uv); }  // views are single mip levels
+inline vec4 textureGather(sampler2D s, gl::vec2 uv, int = 0) { return orc::textureGather(*s.t, *s.s, uv); }
+
+// ---- unsigned / signed vector spelling (GLSL converts implicitly; integer -> float conversions are exact below 2^24) ----
+inline gl::vec3 operator+(uvec3 a, float b) { return gl::vec3((float)a.x + b, (float)a.y + b, (float)a.z + b); }
+inline gl::vec2 operator+(uvec2 a, float b) { return gl::vec2((float)a.x + b, (float)a.y + b); }
+inline gl::vec3 operator/(gl::vec3 a, uvec3 b) { return a / gl::vec3((float)b.x, (float)b.y, (float)b.z); }
+inline gl::vec2 operator/(gl::vec2 a, uvec2 b) { return a / gl::vec2((float)b.x, (float)b.y); }
+inline gl::vec2 operator/(gl::vec2 a, gl::ivec2 b) { return a / gl::vec2((float)b.x, (float)b.y); }
+inline gl::vec2 operator+(gl::ivec2 a, float b) { return gl::vec2((float)a.x + b, (float)a.y + b); }
+inline gl::vec2 operator-(gl::ivec2 a, float b) { return gl::vec2((float)a.x - b, (float)a.y - b); }
+inline gl::vec2 operator/(float a, gl::ivec2 b) { return a / gl::vec2((float)b.x, (float)b.y); }
+inline gl::vec2 operator*(gl::vec2 a, gl::ivec2 b) { return a * gl::vec2((float)b.x, (float)b.y); }
+struct bvec2 { bool x, y; };
+inline bvec2 greaterThan(gl::ivec2 a, gl::ivec2 b) { return bvec2{a.x > b.x, a.y > b.y}; }
+inline bvec2 lessThan(gl::ivec2 a, gl::ivec2 b) { return bvec2{a.x < b.x, a.y < b.y}; }
+inline bvec3 greaterThanEqual(uvec3 a, uvec3 b) { return bvec3{a.x >= b.x, a.y >= b.y, a.z >= b.z}; }
+inline bvec2 greaterThanEqual(uvec2 a, uvec2 b) { return bvec2{a.x >= b.x, a.y >= b.y}; }
+inline bvec2 greaterThanEqual(gl::ivec2 a, gl::ivec2 b) { return bvec2{a.x >= b.x, a.y >= b.y}; }
+inline bool any(bvec2 v) { return v.x || v.y; }
+
+// ---- swizzle stores: X.xy = E; X.xyz = E; ----
+template <typename V> inline void assign_xy(V& v, gl::vec2 e) { v.x = e.x; v.y = e.y; }
+template <typename V> inline void assign_xyz(V& v, gl::vec3 e) { v.x = e.x; v.y = e.y; v.z = e.z; }
+
+// run body() for every invocation of the execution's dispatch, in invocation order (single thread: the variables above are globals)
+template <typename F> inline void dispatch(const orc::PassCtx& c, const int local[3], F body) {
+    gl_NumWorkGroups = uvec3(c.exec->dispatch[0], c.exec->dispatch[1], c.exec->dispatch[2]);
+    for (uint gz = 0; gz < c.exec->dispatch[2]; gz++)
+        for (uint gy = 0; gy < c.exec->dispatch[1]; gy++)
+            for (uint gx = 0; gx < c.exec->dispatch[0]; gx++) {
+                gl_WorkGroupID = uvec3(gx, gy, gz);
+                for (int lz = 0; lz < local[2]; lz++)
+                    for (int ly = 0; ly < local[1]; ly++)
+                        for (int lx = 0; lx < local[0]; lx++) {
+                            gl_LocalInvocationID = uvec3((uint)lx, (uint)ly, (uint)lz);
+                            gl_LocalInvocationIndex = (uint)((lz * local[1] + ly) * local[0] + lx);
+                            gl_GlobalInvocationID = uvec3(gx * local[0] + lx, gy * local[1] + ly, gz * local[2] + lz);
+                            body();
+                        }
+            }
+}
+
+}  // namespace refglsl

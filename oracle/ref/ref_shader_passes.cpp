@@ -1,0 +1,27 @@
+// ORACLE - test infrastructure only. Whole compute shaders of the reference (resources/shaders/*.comp with their include files), compiled
+// as C++ from where they lie under /root/reference (oracle/ref/glsl_shader_to_cpp.py adapts spelling and turns the interface declarations
+// into variables; oracle/build_ref.sh builds this file + the oracle's own objects into oracle/_ref/liboracle_refmain.so). Each shader is
+// registered as an OVERRIDE of the oracle's restatement of that pass: the library is the oracle with these passes executed by the
+// reference's own main(). tests/test_oracle_vs_reference_shaders.py renders the same frames through liboracle.so and through this library
+// and compares every image and buffer bit for bit - which pins the oracle's main() bodies, not only its include functions.
+#include "glsl_shader.h"
+
+namespace refglsl {
+#include "shaders_generated.h"
+}  // namespace refglsl
+
+namespace {
+int g_runs = 0;  // executions that went through a reference main()
+}
+#define REF_SHADER(name, file)                                                                             \
+    static void run_##name(orc::PassCtx& c) {                                                              \
+        refglsl::ref_##name::bind(c);                                                                      \
+        refglsl::dispatch(c, refglsl::ref_##name::local_size, [] { refglsl::ref_##name::shader_main(); }); \
+        refglsl::ref_##name::unbind(c);                                                                    \
+        g_runs++;                                                                                          \
+    }                                                                                                      \
+    static orc::PassOverride override_##name(file, run_##name);
+#include "shaders_registered.h"
+
+extern "C" __attribute__((visibility("default"))) int oracle_refmain_runs() { return g_runs; }
+extern "C" __attribute__((visibility("default"))) const char* oracle_refmain_shaders() { return REF_SHADER_LIST; }

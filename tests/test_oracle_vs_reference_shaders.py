@@ -1,0 +1,80 @@
+"""The oracle's passes against the reference's OWN compute shaders, main() included.
+
+oracle/_ref/liboracle_refmain.so is the oracle with the shaders listed in oracle/ref/ref_shaders.txt executed by the reference's GLSL: the
+.comp files and the include files they name are compiled as C++ from where they lie under /root/reference (oracle/ref/glsl_shader_to_cpp.py
+adapts spelling only and turns the `layout(...)` interface declarations into variables; arithmetic and texel access are oracle/glsl.h and
+oracle/image.h, the contract both sides share) and registered as overrides of the oracle's restatements. The same frames rendered through
+liboracle.so and through that library must agree in every image and buffer, bit for bit: that pins the statement order of every listed
+main(), where tests/test_oracle_vs_reference_glsl.py pins the include functions one by one.
+
+/root/reference does not travel: where neither the library nor the reference exists the tests skip (CPU suite only; no GPU test needs it)."""
+import ctypes as C
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import passes
+from conftest import ROOT, Sequence, assert_snapshots_equal
+
+LIB = ROOT / "oracle" / "_ref" / "liboracle_refmain.so"
+
+
+@pytest.fixture(scope="module")
+def refmain(ffi, oracle):
+    if Path("/root/reference/resources/shaders").exists():
+        subprocess.run(["bash", str(ROOT / "oracle" / "build_ref.sh")], check=True, capture_output=True)  # up to date: returns at once
+    if not LIB.exists():
+        pytest.skip("oracle/_ref/liboracle_refmain.so not built and /root/reference not present")
+    api = ffi.Api(str(LIB), "oracle_", "oracle_frontend_")
+    h = C.CDLL(str(LIB))
+    h.oracle_refmain_shaders.restype = C.c_char_p
+    api.refmain_runs = h.oracle_refmain_runs
+    api.refmain_shaders = h.oracle_refmain_shaders().decode().split()
+    return api
+
+
+def listed():
+    return [l.strip() for l in (ROOT / "oracle" / "ref" / "ref_shaders.txt").read_text().splitlines() if l.strip() and not l.startswith("#")]
+
+
+def test_every_listed_shader_is_compiled_in(refmain):
+    assert refmain.refmain_shaders == listed()
+    assert len(refmain.refmain_shaders) >= 10
+
+
+@pytest.mark.parametrize("res,moving,cut", [((12, 7, 16), False, False), ((10, 6, 8), True, False), ((9, 5, 8), True, True), ((19, 9, 64), True, False)])
+def test_froxel_shaders(ffi, oracle, refmain, res, moving, cut):
+    from test_froxels_numpy import scene
+    cam, prev, noise, shadow, L, settings, light, history, sun = scene(res[0] * 10 + res[2], res, moving)
+    history[1, 2, 3, :] = np.nan
+    before = refmain.refmain_runs()
+    a = passes.froxels(ffi, oracle, res, noise, shadow, L.T.ravel(), light, settings, history, cam, prev, sun, camera_cut=cut)
+    b = passes.froxels(ffi, refmain, res, noise, shadow, L.T.ravel(), light, settings, history, cam, prev, sun, camera_cut=cut)
+    assert refmain.refmain_runs() - before == 4, "the four froxel passes did not go through the reference's main()"
+    for name, x, y in zip(("material", "scattering", "reprojection", "integration"), a, b):
+        assert np.array_equal(x.view(np.uint16), y.view(np.uint16)), name
+
+
+@pytest.mark.parametrize("w,h,frames,moving,instances,settings", [
+    (96, 64, 3, False, 8, {}),
+    (120, 72, 4, True, 14, {}),
+    (100, 60, 3, True, 10, dict(taa_use_clipping=0, taa_use_motion_vector_dilation=0)),
+])
+def test_frames_through_the_reference_shaders(ffi, oracle, refmain, w, h, frames, moving, instances, settings):
+    """whole frame sequences (every history fed back): the oracle against the oracle with the listed passes run by the reference's GLSL"""
+    try:
+        a, b = Sequence(ffi, oracle, w, h, instances, **settings), Sequence(ffi, refmain, w, h, instances, **settings)
+    except Exception as e:  # a setting this frontend does not know
+        pytest.skip(str(e))
+    before = refmain.refmain_runs()
+    try:
+        for f in range(frames):
+            inputs = a.step(moving=moving)
+            b.step(moving=moving, inputs=inputs)
+            assert_snapshots_equal(b.snapshot(), a.snapshot(), "frame %d of %dx%d through the reference's shaders" % (f, w, h))
+    finally:
+        a.close()
+        b.close()
+    assert refmain.refmain_runs() - before >= frames * len(refmain.refmain_shaders) // 2
