@@ -14,7 +14,7 @@ using orc::Sampler;
 
 // ---- integer / unsigned vectors (float -> int conversions saturate like the contract's f2int / f2uint) ----
 struct uvec2; struct uvec3;
-struct ivec2 : gl::ivec2 { using gl::ivec2::ivec2; ivec2() {} ivec2(gl::ivec2 v) : gl::ivec2(v) {} explicit ivec2(gl::vec2 v) : gl::ivec2(f2int(v.x), f2int(v.y)) {} explicit inline ivec2(const uvec2& v); };
+struct ivec2 : gl::ivec2 { using gl::ivec2::ivec2; ivec2() {} ivec2(gl::ivec2 v) : gl::ivec2(v) {} explicit ivec2(gl::vec2 v) : gl::ivec2(f2int(v.x), f2int(v.y)) {} explicit inline ivec2(const uvec2& v); ivec2 xy() const { return *this; } };
 struct ivec3 { int x, y, z; ivec3() : x(0), y(0), z(0) {} ivec3(int a, int b, int c) : x(a), y(b), z(c) {} explicit ivec3(gl::vec3 v) : x(f2int(v.x)), y(f2int(v.y)), z(f2int(v.z)) {}
     ivec3(ivec2 v, int c) : x(v.x), y(v.y), z(c) {} explicit inline ivec3(const uvec3& v); inline ivec3(const uvec2& v, int c); };
 struct ivec4 { int x, y, z, w; ivec4() : x(0), y(0), z(0), w(0) {} ivec4(int a, int b, int c, int d) : x(a), y(b), z(c), w(d) {} };

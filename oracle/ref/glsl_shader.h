@@ -43,6 +43,14 @@ inline bvec3 greaterThanEqual(uvec3 a, uvec3 b) { return bvec3{a.x >= b.x, a.y >
 inline bvec2 greaterThanEqual(uvec2 a, uvec2 b) { return bvec2{a.x >= b.x, a.y >= b.y}; }
 inline bvec2 greaterThanEqual(gl::ivec2 a, gl::ivec2 b) { return bvec2{a.x >= b.x, a.y >= b.y}; }
 inline bool any(bvec2 v) { return v.x || v.y; }
+inline bvec2 greaterThan(gl::vec2 a, gl::vec2 b) { return bvec2{a.x > b.x, a.y > b.y}; }
+inline bvec2 lessThan(gl::vec2 a, gl::vec2 b) { return bvec2{a.x < b.x, a.y < b.y}; }
+struct bvec4 { bool x, y, z, w; };
+inline bool any(bvec4 v) { return v.x || v.y || v.z || v.w; }
+using gl::isnan;
+inline bvec2 isnan(gl::vec2 a) { return bvec2{gl::isnan(a.x), gl::isnan(a.y)}; }
+inline bvec3 isnan(gl::vec3 a) { return bvec3{gl::isnan(a.x), gl::isnan(a.y), gl::isnan(a.z)}; }
+inline bvec4 isnan(gl::vec4 a) { return bvec4{gl::isnan(a.x), gl::isnan(a.y), gl::isnan(a.z), gl::isnan(a.w)}; }
 
 // ---- swizzle stores: X.xy = E; X.xyz = E; ----
 template <typename V> inline void assign_xy(V& v, gl::vec2 e) { v.x = e.x; v.y = e.y; }

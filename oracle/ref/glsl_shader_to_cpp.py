@@ -239,6 +239,7 @@ def convert_shader(shader_dir, shader):
     text = re.sub(r"^(\s*)([\w.\[\]]+)\.%s\s*=(?!=)\s*([^;]+);" % sw, lambda m: "%sassign_%s(%s, %s);" % (m.group(1), {"rg": "xy", "rgb": "xyz"}.get(m.group(3), m.group(3)), m.group(2), m.group(4)), text, flags=re.M)
     text = re.sub(r"^(\s*)([\w.\[\]]+)\.%s\s*([-+*/])=\s*([^;]+);" % sw,
                   lambda m: "%sassign_%s(%s, %s.%s %s (%s));" % (m.group(1), {"rg": "xy", "rgb": "xyz"}.get(m.group(3), m.group(3)), m.group(2), m.group(2), m.group(3), m.group(4), m.group(5)), text, flags=re.M)
+    text = re.sub(r"\bvec3\s+(\w+)\s*\[3\]\s*\[3\]", r"vec3[3][3] \1", text)  # C-style array declarator -> the type spelling glsl_to_cpp.py maps to Nb33
     text = re.sub(r"\bvoid\s+main\s*\(\s*\)", "static void shader_main()", text)
     text = convert_spelling(text)
     head = "// GENERATED by oracle/ref/glsl_shader_to_cpp.py from %s - build output, not source. Do not commit.\n" % (shader_dir / shader)
