@@ -60,11 +60,17 @@ inline gl::vec3 clamp(gl::vec3 x, int lo, int hi) { return gl::clamp(x, (float)l
 inline gl::vec3 operator/(gl::vec3 a, ivec3 b) { return a / gl::vec3((float)b.x, (float)b.y, (float)b.z); }
 
 // ---- matrices ----
+struct mat4 : gl::mat4 {  // mat4(d), mat4 M = {{..}, {..}, {..}, {..}} (columns)
+    mat4() {}
+    mat4(const gl::mat4& m) : gl::mat4(m) {}
+    explicit mat4(float d) : gl::mat4(gl::mat4_diag(d)) {}
+    mat4(gl::vec4 c0, gl::vec4 c1, gl::vec4 c2, gl::vec4 c3) { c[0] = c0; c[1] = c1; c[2] = c2; c[3] = c3; }
+};
 struct mat3 : gl::mat3 {
     mat3() {}
     mat3(const gl::mat3& m) : gl::mat3(m) {}
     mat3(gl::vec3 c0, gl::vec3 c1, gl::vec3 c2) { c[0] = c0; c[1] = c1; c[2] = c2; }
-    explicit mat3(const mat4& m) { for (int i = 0; i < 3; i++) c[i] = m.c[i].xyz(); }
+    explicit mat3(const gl::mat4& m) { for (int i = 0; i < 3; i++) c[i] = m.c[i].xyz(); }
 };
 
 // ---- bool vectors ----

@@ -52,6 +52,11 @@ inline bvec2 isnan(gl::vec2 a) { return bvec2{gl::isnan(a.x), gl::isnan(a.y)}; }
 inline bvec3 isnan(gl::vec3 a) { return bvec3{gl::isnan(a.x), gl::isnan(a.y), gl::isnan(a.z)}; }
 inline bvec4 isnan(gl::vec4 a) { return bvec4{gl::isnan(a.x), gl::isnan(a.y), gl::isnan(a.z), gl::isnan(a.w)}; }
 
+// ---- atomics (the dispatch runs on one thread, in invocation order) ----
+inline uint atomicAdd(uint& mem, uint v) { const uint old = mem; mem += v; return old; }
+inline uint atomicMax(uint& mem, uint v) { const uint old = mem; if (v > mem) mem = v; return old; }
+inline uint atomicMin(uint& mem, uint v) { const uint old = mem; if (v < mem) mem = v; return old; }
+
 // ---- swizzle stores: X.xy = E; X.xyz = E; ----
 template <typename V> inline void assign_xy(V& v, gl::vec2 e) { v.x = e.x; v.y = e.y; }
 template <typename V> inline void assign_xyz(V& v, gl::vec3 e) { v.x = e.x; v.y = e.y; v.z = e.z; }

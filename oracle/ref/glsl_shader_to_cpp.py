@@ -52,7 +52,10 @@ class Layout:
             return None  # unsized
         if text in self.consts:
             return int(self.consts[text])
-        return int(text)
+        try:
+            return int(text)
+        except ValueError:
+            return None  # sized by specialisation constants (histogramCombineTiles.comp:15): bound as a pointer into the buffer
 
     def type_info(self, t):
         """(align, size, leaves) with leaves = [(suffix, scalar, offset)]"""
@@ -92,7 +95,7 @@ class Layout:
         return a, stride * n, leaves
 
 
-MEMBER = re.compile(r"\s*(\w+)\s+(\w+)\s*(?:\[\s*(\w*)\s*\])?\s*;")
+MEMBER = re.compile(r"\s*(\w+)\s+(\w+)\s*(?:\[\s*([^\]]*?)\s*\])?\s*;")
 
 
 def parse_members(body):
@@ -105,8 +108,14 @@ def parse_members(body):
 def gather(shader_dir, name, seen):
     """the shader text with its includes spliced in (each file once, in first-use order)"""
     text = strip_comments((shader_dir / name).read_text())
-    text = re.sub(r"^\s*#\s*(version|extension|ifndef|endif)\b[^\n]*$", "", text, flags=re.M)
-    text = re.sub(r"^\s*#\s*define\s+\w+\s*$", "", text, flags=re.M)  # include guards; macros with a value stay (C++ spells them the same)
+    text = re.sub(r"^\s*#\s*(version|extension)\b[^\n]*$", "", text, flags=re.M)
+    # the include guard (#ifndef G / #define G ... #endif) goes, files are spliced once; every other preprocessor line stays - the C++ preprocessor
+    # reads #define / #ifdef / #else / #endif the same way (the macros are #undef'd at the end of the generated header)
+    g = re.match(r"\s*#\s*ifndef\s+(\w+)\s*\n\s*#\s*define\s+(\w+)[^\n]*\n", text)
+    if g and g.group(1) == g.group(2):
+        text = text[g.end():]
+        k = text.rfind("#endif")
+        text = text[:k] + re.sub(r"^#endif[^\n]*", "", text[k:])
 
     def splice(m):
         inc = m.group(1)
@@ -120,7 +129,9 @@ def gather(shader_dir, name, seen):
 def convert_shader(shader_dir, shader):
     ns = "ref_" + re.sub(r"\W", "_", Path(shader).stem)
     text = gather(shader_dir, shader, set())
-    consts = dict(re.findall(r"const\s+(?:int|uint)\s+(\w+)\s*=\s*(\d+)\s*;", text))
+    # compile-time constants that may size an array; specialisation constants are NOT among them (their value comes with the pass), so an
+    # array they size is bound as a pointer into the buffer
+    consts = dict(re.findall(r"^\s*const\s+(?:int|uint)\s+(\w+)\s*=\s*(\d+)\s*;", text, flags=re.M))
     structs = {}
     for m in re.finditer(r"\bstruct\s+(\w+)\s*\{(.*?)\}\s*;", text, flags=re.S):
         structs[m.group(1)] = parse_members(m.group(2))
@@ -206,8 +217,12 @@ def convert_shader(shader_dir, shader):
         for mt, mn, ml in members:
             a, s, lv = lay.member_info(mt, ml)
             off = round_up(off, a)
-            if lv and lv[0][0] == "[]":  # unsized array at the end of a buffer block: a pointer into the buffer
+            if lv and lv[0][0] == "[]":  # unsized array / array sized by a specialisation constant: a pointer into the buffer
                 elem = lv[0][1]
+                if (mt, mn, ml) != members[-1]:
+                    raise ValueError("%s: the array %s of unknown size is not the last member of its block" % (shader, mn))
+                if elem not in SCALARS:
+                    raise ValueError("%s: the array %s of unknown size has elements of type %s" % (shader, mn, elem))
                 out.append("static %s* %s;" % (elem, mn) if not inst else "%s* %s;" % (elem, mn))
                 bind.append("    %s%s = (%s*)(%s + %d);" % (prefix, mn, elem, base, off))
                 continue
@@ -239,9 +254,31 @@ def convert_shader(shader_dir, shader):
     text = re.sub(r"^(\s*)([\w.\[\]]+)\.%s\s*=(?!=)\s*([^;]+);" % sw, lambda m: "%sassign_%s(%s, %s);" % (m.group(1), {"rg": "xy", "rgb": "xyz"}.get(m.group(3), m.group(3)), m.group(2), m.group(4)), text, flags=re.M)
     text = re.sub(r"^(\s*)([\w.\[\]]+)\.%s\s*([-+*/])=\s*([^;]+);" % sw,
                   lambda m: "%sassign_%s(%s, %s.%s %s (%s));" % (m.group(1), {"rg": "xy", "rgb": "xyz"}.get(m.group(3), m.group(3)), m.group(2), m.group(2), m.group(3), m.group(4), m.group(5)), text, flags=re.M)
+    # GLSL: a local variable is not in scope in its own initialiser - `float phase = phase(x);` calls the function. C++ would call the float:
+    # the local gets a suffix from its declaration to the end of the enclosing block
+    while True:
+        m = re.search(r"\b(float|int|uint|vec[234])\s+(\w+)\s*=\s*\2\s*\(", text)
+        if not m:
+            break
+        name, depth, end = m.group(2), 0, len(text)
+        for k in range(m.start(), len(text)):
+            if text[k] == "{":
+                depth += 1
+            elif text[k] == "}":
+                depth -= 1
+                if depth < 0:
+                    end = k
+                    break
+        block = text[m.start():end]
+        block = block.replace(m.group(0), "%s %s_v = %s(" % (m.group(1), name, name), 1)
+        block = re.sub(r"\b%s\b(?!\s*\(|_v)" % name, name + "_v", block)
+        text = text[:m.start()] + block + text[end:]
+    text = re.sub(r"\b(?:inout|out)\s+(\w+)\s*\[(\d+)\]\s+(\w+)", r"\1 (&\3)[\2]", text)   # `inout vec3[8] p` -> a reference to an array
     text = re.sub(r"\bvec3\s+(\w+)\s*\[3\]\s*\[3\]", r"vec3[3][3] \1", text)  # C-style array declarator -> the type spelling glsl_to_cpp.py maps to Nb33
     text = re.sub(r"\bvoid\s+main\s*\(\s*\)", "static void shader_main()", text)
     text = convert_spelling(text)
+    macros = sorted(set(re.findall(r"^\s*#\s*define\s+(\w+)", text, flags=re.M)))
+    text += "\n" + "".join("#undef %s\n" % m for m in macros)
     head = "// GENERATED by oracle/ref/glsl_shader_to_cpp.py from %s - build output, not source. Do not commit.\n" % (shader_dir / shader)
     body = "namespace %s {\n%s\nstatic const int local_size[3] = {%d, %d, %d};\nstatic void bind(orc::PassCtx& c) {\n%s\n}\nstatic void unbind(orc::PassCtx& c) {\n%s\n}\n}  // namespace %s\n" % (
         ns, text, local[0], local[1], local[2], "\n".join(bind), "\n".join(unbind) if unbind else "    (void)c;", ns)
