@@ -9,8 +9,8 @@
 namespace refglsl {
 
 // ---- compute built-ins, set by dispatch() below ----
-static uvec3 gl_GlobalInvocationID, gl_WorkGroupID, gl_LocalInvocationID, gl_NumWorkGroups;
-static uint gl_LocalInvocationIndex;
+static thread_local uvec3 gl_GlobalInvocationID, gl_WorkGroupID, gl_LocalInvocationID, gl_NumWorkGroups;
+static thread_local uint gl_LocalInvocationIndex;
 
 // ---- storage images ----
 struct image2D { View v; image2D() {} explicit image2D(View view) : v(view) {} };
@@ -36,7 +36,10 @@ inline gl::vec2 operator+(gl::ivec2 a, float b) { return gl::vec2((float)a.x + b
 inline gl::vec2 operator-(gl::ivec2 a, float b) { return gl::vec2((float)a.x - b, (float)a.y - b); }
 inline gl::vec2 operator/(float a, gl::ivec2 b) { return a / gl::vec2((float)b.x, (float)b.y); }
 inline gl::vec2 operator*(gl::vec2 a, gl::ivec2 b) { return a * gl::vec2((float)b.x, (float)b.y); }
+inline gl::vec2 operator/(gl::ivec2 a, gl::vec2 b) { return gl::vec2((float)a.x, (float)a.y) / b; }
+inline float ceil(float x) { const float f = gl::floor(x); return f < x ? f + 1.f : f; }  // exact either way
 struct bvec2 { bool x, y; };
+inline bvec2 greaterThanEqual(gl::ivec2 a, uvec2 b) { return bvec2{(uint)a.x >= b.x, (uint)a.y >= b.y}; }  /* GLSL converts int -> uint implicitly */
 inline bvec2 greaterThan(gl::ivec2 a, gl::ivec2 b) { return bvec2{a.x > b.x, a.y > b.y}; }
 inline bvec2 lessThan(gl::ivec2 a, gl::ivec2 b) { return bvec2{a.x < b.x, a.y < b.y}; }
 inline bvec3 greaterThanEqual(uvec3 a, uvec3 b) { return bvec3{a.x >= b.x, a.y >= b.y, a.z >= b.z}; }
@@ -61,22 +64,27 @@ inline uint atomicMin(uint& mem, uint v) { const uint old = mem; if (v < mem) me
 template <typename V> inline void assign_xy(V& v, gl::vec2 e) { v.x = e.x; v.y = e.y; }
 template <typename V> inline void assign_xyz(V& v, gl::vec3 e) { v.x = e.x; v.y = e.y; v.z = e.z; }
 
-// run body() for every invocation of the execution's dispatch, in invocation order (single thread: the variables above are globals)
-template <typename F> inline void dispatch(const orc::PassCtx& c, const int local[3], F body) {
-    gl_NumWorkGroups = uvec3(c.exec->dispatch[0], c.exec->dispatch[1], c.exec->dispatch[2]);
-    for (uint gz = 0; gz < c.exec->dispatch[2]; gz++)
-        for (uint gy = 0; gy < c.exec->dispatch[1]; gy++)
-            for (uint gx = 0; gx < c.exec->dispatch[0]; gx++) {
-                gl_WorkGroupID = uvec3(gx, gy, gz);
-                for (int lz = 0; lz < local[2]; lz++)
-                    for (int ly = 0; ly < local[1]; ly++)
-                        for (int lx = 0; lx < local[0]; lx++) {
-                            gl_LocalInvocationID = uvec3((uint)lx, (uint)ly, (uint)lz);
-                            gl_LocalInvocationIndex = (uint)((lz * local[1] + ly) * local[0] + lx);
-                            gl_GlobalInvocationID = uvec3(gx * local[0] + lx, gy * local[1] + ly, gz * local[2] + lz);
-                            body();
-                        }
-            }
+// run body() for every invocation of the execution's dispatch. serial (shaders with atomics: the append order is the invocation order, as in the
+// oracle's restatement): one thread, invocation order. Otherwise the workgroups are spread over the oracle's threads (PassCtx::forEachGroup) - the
+// built-in variables above are thread_local, everything else a shader reads is bound before the dispatch and not written during it.
+template <typename F> inline void dispatch(const orc::PassCtx& c, const int local[3], bool serial, F body) {
+    const uvec3 groups(c.exec->dispatch[0], c.exec->dispatch[1], c.exec->dispatch[2]);
+    auto group = [&](int gx, int gy, int gz) {
+        gl_NumWorkGroups = groups;
+        gl_WorkGroupID = uvec3((uint)gx, (uint)gy, (uint)gz);
+        for (int lz = 0; lz < local[2]; lz++)
+            for (int ly = 0; ly < local[1]; ly++)
+                for (int lx = 0; lx < local[0]; lx++) {
+                    gl_LocalInvocationID = uvec3((uint)lx, (uint)ly, (uint)lz);
+                    gl_LocalInvocationIndex = (uint)((lz * local[1] + ly) * local[0] + lx);
+                    gl_GlobalInvocationID = uvec3((uint)(gx * local[0] + lx), (uint)(gy * local[1] + ly), (uint)(gz * local[2] + lz));
+                    body();
+                }
+    };
+    if (!serial) { c.forEachGroup(group); return; }
+    for (uint gz = 0; gz < groups.z; gz++)
+        for (uint gy = 0; gy < groups.y; gy++)
+            for (uint gx = 0; gx < groups.x; gx++) group((int)gx, (int)gy, (int)gz);
 }
 
 }  // namespace refglsl

@@ -79,6 +79,29 @@ class Layout:
             return align, round_up(off, align), leaves
         raise ValueError("unknown GLSL type in a block: " + t)
 
+    def natural(self, t):
+        """(size, leaves) of the C++ struct the converted GLSL text declares: members packed at 4-byte alignment"""
+        if t in SCALARS:
+            return 4, [("", t, 0)]
+        if t in VECS:
+            sc, n = VECS[t]
+            return 4 * n, [("." + COMP[i], sc, 4 * i) for i in range(n)]
+        if t in ("mat4", "mat4x4"):
+            return 64, [(".c[%d].%s" % (c, COMP[r]), "float", 16 * c + 4 * r) for c in range(4) for r in range(4)]
+        off, leaves = 0, []
+        for mt, mn, ml in self.structs[t]:
+            s, lv = self.natural(mt)
+            for i in range(1 if ml is None else self.array_len(ml)):
+                sfx = "" if ml is None else "[%d]" % i
+                leaves += [("." + mn + sfx + x, sc, off + o) for x, sc, o in lv]
+                off += s
+        return off, leaves
+
+    def same_as_natural(self, t):
+        a, s, lv = self.type_info(t)
+        ns, nlv = self.natural(t)
+        return round_up(s, a) == ns and lv == nlv
+
     def member_info(self, t, arr):
         a, s, lv = self.type_info(t)
         if arr is None:
@@ -221,8 +244,8 @@ def convert_shader(shader_dir, shader):
                 elem = lv[0][1]
                 if (mt, mn, ml) != members[-1]:
                     raise ValueError("%s: the array %s of unknown size is not the last member of its block" % (shader, mn))
-                if elem not in SCALARS:
-                    raise ValueError("%s: the array %s of unknown size has elements of type %s" % (shader, mn, elem))
+                if elem not in SCALARS and not (elem in structs and lay.same_as_natural(elem)):
+                    raise ValueError("%s: the array %s of unknown size has elements of type %s whose block layout differs from the C++ struct's" % (shader, mn, elem))
                 out.append("static %s* %s;" % (elem, mn) if not inst else "%s* %s;" % (elem, mn))
                 bind.append("    %s%s = (%s*)(%s + %d);" % (prefix, mn, elem, base, off))
                 continue
@@ -273,6 +296,7 @@ def convert_shader(shader_dir, shader):
         block = block.replace(m.group(0), "%s %s_v = %s(" % (m.group(1), name, name), 1)
         block = re.sub(r"\b%s\b(?!\s*\(|_v)" % name, name + "_v", block)
         text = text[:m.start()] + block + text[end:]
+    text = re.sub(r"\b(cullingTileSize)\.x\b", r"\1", text)  # GLSL lets a scalar be swizzled: s.x is s
     text = re.sub(r"\b(?:inout|out)\s+(\w+)\s*\[(\d+)\]\s+(\w+)", r"\1 (&\3)[\2]", text)   # `inout vec3[8] p` -> a reference to an array
     text = re.sub(r"\bvec3\s+(\w+)\s*\[3\]\s*\[3\]", r"vec3[3][3] \1", text)  # C-style array declarator -> the type spelling glsl_to_cpp.py maps to Nb33
     text = re.sub(r"\bvoid\s+main\s*\(\s*\)", "static void shader_main()", text)
@@ -280,8 +304,9 @@ def convert_shader(shader_dir, shader):
     macros = sorted(set(re.findall(r"^\s*#\s*define\s+(\w+)", text, flags=re.M)))
     text += "\n" + "".join("#undef %s\n" % m for m in macros)
     head = "// GENERATED by oracle/ref/glsl_shader_to_cpp.py from %s - build output, not source. Do not commit.\n" % (shader_dir / shader)
-    body = "namespace %s {\n%s\nstatic const int local_size[3] = {%d, %d, %d};\nstatic void bind(orc::PassCtx& c) {\n%s\n}\nstatic void unbind(orc::PassCtx& c) {\n%s\n}\n}  // namespace %s\n" % (
-        ns, text, local[0], local[1], local[2], "\n".join(bind), "\n".join(unbind) if unbind else "    (void)c;", ns)
+    serial = "true" if re.search(r"\batomic\w+\s*\(", text) else "false"  # appends keep the invocation order
+    body = "namespace %s {\n%s\nstatic const int local_size[3] = {%d, %d, %d};\nstatic const bool serial = %s;\nstatic void bind(orc::PassCtx& c) {\n%s\n}\nstatic void unbind(orc::PassCtx& c) {\n%s\n}\n}  // namespace %s\n" % (
+        ns, text, local[0], local[1], local[2], serial, "\n".join(bind), "\n".join(unbind) if unbind else "    (void)c;", ns)
     return head + body
 
 

@@ -16,7 +16,7 @@ int g_runs = 0;  // executions that went through a reference main()
 #define REF_SHADER(name, file)                                                                             \
     static void run_##name(orc::PassCtx& c) {                                                              \
         refglsl::ref_##name::bind(c);                                                                      \
-        refglsl::dispatch(c, refglsl::ref_##name::local_size, [] { refglsl::ref_##name::shader_main(); }); \
+        refglsl::dispatch(c, refglsl::ref_##name::local_size, refglsl::ref_##name::serial, [] { refglsl::ref_##name::shader_main(); }); \
         refglsl::ref_##name::unbind(c);                                                                    \
         g_runs++;                                                                                          \
     }                                                                                                      \

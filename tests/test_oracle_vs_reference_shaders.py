@@ -58,9 +58,9 @@ def test_froxel_shaders(ffi, oracle, refmain, res, moving, cut):
 
 
 @pytest.mark.parametrize("w,h,frames,moving,instances,settings", [
-    (96, 64, 3, False, 8, {}),
     (120, 72, 4, True, 14, {}),
     (100, 60, 3, True, 10, dict(taa_use_clipping=0, taa_use_motion_vector_dilation=0)),
+    (96, 56, 3, True, 10, dict(taa_use_separate_supersampling=1)),  # temporalSupersampling.comp + colorToLuminance.comp
 ])
 def test_frames_through_the_reference_shaders(ffi, oracle, refmain, w, h, frames, moving, instances, settings):
     """whole frame sequences (every history fed back): the oracle against the oracle with the listed passes run by the reference's GLSL"""
