@@ -17,7 +17,7 @@ struct uvec2; struct uvec3;
 struct ivec2 : gl::ivec2 { using gl::ivec2::ivec2; ivec2() {} ivec2(gl::ivec2 v) : gl::ivec2(v) {} explicit ivec2(gl::vec2 v) : gl::ivec2(f2int(v.x), f2int(v.y)) {} explicit inline ivec2(const uvec2& v); ivec2 xy() const { return *this; } };
 struct ivec3 { int x, y, z; ivec3() : x(0), y(0), z(0) {} ivec3(int a, int b, int c) : x(a), y(b), z(c) {} explicit ivec3(gl::vec3 v) : x(f2int(v.x)), y(f2int(v.y)), z(f2int(v.z)) {}
     ivec3(ivec2 v, int c) : x(v.x), y(v.y), z(c) {} explicit inline ivec3(const uvec3& v); inline ivec3(const uvec2& v, int c); };
-struct ivec4 { int x, y, z, w; ivec4() : x(0), y(0), z(0), w(0) {} ivec4(int a, int b, int c, int d) : x(a), y(b), z(c), w(d) {} };
+struct ivec4 { int x, y, z, w; ivec4() : x(0), y(0), z(0), w(0) {} ivec4(int a, int b, int c, int d) : x(a), y(b), z(c), w(d) {} int operator[](int i) const { return (&x)[i]; } };
 struct uvec2 { uint x, y; uvec2() : x(0), y(0) {} uvec2(uint a, uint b) : x(a), y(b) {} explicit uvec2(gl::vec2 v) : x(f2uint(v.x)), y(f2uint(v.y)) {} uvec2 xy() const { return *this; } };
 struct uvec3 { uint x, y, z; uvec3() : x(0), y(0), z(0) {} uvec3(uint a, uint b, uint c) : x(a), y(b), z(c) {} uvec3(ivec3 v) : x((uint)v.x), y((uint)v.y), z((uint)v.z) {}  /* uvec3 v = imageSize(image3D): GLSL converts implicitly */
     uvec2 xy() const { return uvec2(x, y); } uvec3 xyz() const { return *this; } };
@@ -27,7 +27,7 @@ inline ivec3::ivec3(const uvec2& v, int c) : x((int)v.x), y((int)v.y), z(c) {}
 inline uvec3 operator*(uvec3 a, uvec3 b) { return uvec3(a.x * b.x, a.y * b.y, a.z * b.z); }
 inline uvec3 operator*(uint a, uvec3 b) { return uvec3(a * b.x, a * b.y, a * b.z); }
 // vec3(uvec3), vec2(uvec2): GLSL constructors the converter leaves as written
-struct vec3 : gl::vec3 { using gl::vec3::vec3; vec3() {} vec3(gl::vec3 v) : gl::vec3(v) {} explicit vec3(uvec3 n) : gl::vec3((float)n.x, (float)n.y, (float)n.z) {} };
+struct vec3 : gl::vec3 { using gl::vec3::vec3; vec3() {} vec3(gl::vec3 v) : gl::vec3(v) {} explicit vec3(uvec3 n) : gl::vec3((float)n.x, (float)n.y, (float)n.z) {} gl::vec2 yz() const { return gl::vec2(y, z); } };
 struct vec2 : gl::vec2 { using gl::vec2::vec2; vec2() {} vec2(gl::vec2 v) : gl::vec2(v) {} vec2(uvec2 n) : gl::vec2((float)n.x, (float)n.y) {}  /* GLSL converts uvec2 -> vec2 implicitly (dither.inc:7) */
     explicit vec2(gl::ivec2 n) : gl::vec2((float)n.x, (float)n.y) {} };
 struct vec4 : gl::vec4 { using gl::vec4::vec4; vec4() {} vec4(gl::vec4 v) : gl::vec4(v) {} vec4(float a, gl::vec3 v) : gl::vec4(a, v.x, v.y, v.z) {} vec4(gl::vec2 a, gl::vec2 b) : gl::vec4(a.x, a.y, b.x, b.y) {}
@@ -36,6 +36,11 @@ inline ivec2 operator*(ivec2 a, int b) { return ivec2(a.x * b, a.y * b); }
 inline ivec2 operator+(ivec2 a, ivec2 b) { return ivec2(a.x + b.x, a.y + b.y); }
 inline ivec2 operator-(ivec2 a, ivec2 b) { return ivec2(a.x - b.x, a.y - b.y); }
 inline ivec2 operator/(ivec2 a, int b) { return ivec2(a.x / b, a.y / b); }
+inline ivec2 operator/(ivec2 a, ivec2 b) { return ivec2(a.x / b.x, a.y / b.y); }
+inline ivec2 operator*(ivec2 a, ivec2 b) { return ivec2(a.x * b.x, a.y * b.y); }
+inline ivec2 max(ivec2 a, ivec2 b) { return ivec2(a.x > b.x ? a.x : b.x, a.y > b.y ? a.y : b.y); }
+inline ivec2 min(ivec2 a, ivec2 b) { return ivec2(a.x < b.x ? a.x : b.x, a.y < b.y ? a.y : b.y); }
+inline gl::vec2 operator*(ivec2 a, gl::vec2 b) { return gl::vec2((float)a.x * b.x, (float)a.y * b.y); }
 inline gl::vec2 operator*(ivec2 a, float b) { return gl::vec2((float)a.x * b, (float)a.y * b); }
 inline gl::vec2 operator+(ivec2 a, gl::vec2 b) { return gl::vec2((float)a.x + b.x, (float)a.y + b.y); }
 

@@ -181,6 +181,15 @@ def convert_shader(shader_dir, shader):
                 if writable:
                     unbind.append("    memcpy(%s + %d, &%s, 4);" % (base, off, lv))
 
+    # set 2: the global texture array, `uniform texture3D[] textures;` -> one table of views over every image of the backend
+    def bindless(m):
+        bind.append("    %s.bind(c);" % m.group(2))
+        return "static BindlessTextures %s;" % m.group(2)
+    text = re.sub(r"layout\s*\(\s*set\s*=\s*2[^)]*\)\s*uniform\s+(texture[23]D)\s*\[\s*\]\s*(\w+)\s*;", bindless, text)
+    # workgroup-shared variables: a workgroup runs on one OS thread (glsl_shader.h Fibers)
+    text = re.sub(r"^\s*shared\s+(\w+)\s*((?:\[\d+\])+)\s*(\w+)\s*;", r"static thread_local \1 \3\2;", text, flags=re.M)
+    text = re.sub(r"^\s*shared\s+(\w+)\s+(\w+)\s*\[\s*([A-Za-z_]\w*)\s*\]\s*;", r"static thread_local \1 \2[4096];  // sized by the specialisation constant \3", text, flags=re.M)
+    text = re.sub(r"^\s*shared\s+(\w+)\s+(\w+)\s*((?:\[\w+\])*)\s*;", r"static thread_local \1 \2\3;", text, flags=re.M)
     # resources: images / textures / samplers
     def resource(m):
         quals, typ, name, arr = m.group(1), m.group(2), m.group(3), m.group(4)
@@ -257,7 +266,7 @@ def convert_shader(shader_dir, shader):
         if inst:
             return "struct %s_t { %s }; static %s_t %s;" % (bname, " ".join(out), bname, inst)
         return "\n".join(out)
-    text = re.sub(r"layout\s*\(([^)]*)\)\s*(uniform|buffer)\s+(\w+)\s*\{(.*?)\}\s*(\w*)\s*;", block, text, flags=re.S)
+    text = re.sub(r"layout\s*\(([^)]*)\)\s*(?:(?:readonly|writeonly|coherent|restrict|volatile)\s+)*(uniform|buffer)\s+(\w+)\s*\{(.*?)\}\s*(\w*)\s*;", block, text, flags=re.S)
 
     # GLSL: a local variable is not in scope in its own initialiser, so `float depth = texture(sampler2D(depth, s), uv).r;` reads the texture
     # of the same name; C++ would read the local. Such textures get a suffix in their declaration and wherever a sampler is built from them.
@@ -269,8 +278,8 @@ def convert_shader(shader_dir, shader):
                 bind[k] = line.replace("%s = &%s_view;" % (name, name), "%s_tex = &%s_view;" % (name, name))
     if re.search(r"\blayout\s*\(", text):
         raise ValueError("%s: an interface declaration was not understood: %s" % (shader, re.search(r"\blayout\s*\([^\n]*", text).group(0)))
-    if re.search(r"\bshared\b|\bbarrier\s*\(", text):
-        raise ValueError("%s: shared memory / barriers are not supported by this converter" % shader)
+    if re.search(r"^\s*shared\b", text, flags=re.M):
+        raise ValueError("%s: a shared declaration was not understood: %s" % (shader, re.search(r"^\s*shared\b[^\n]*", text, flags=re.M).group(0)))
 
     # swizzle stores, before the spelling pass turns swizzles into calls
     sw = r"(xy|xyz|rg|rgb)"
@@ -305,8 +314,10 @@ def convert_shader(shader_dir, shader):
     text += "\n" + "".join("#undef %s\n" % m for m in macros)
     head = "// GENERATED by oracle/ref/glsl_shader_to_cpp.py from %s - build output, not source. Do not commit.\n" % (shader_dir / shader)
     serial = "true" if re.search(r"\batomic\w+\s*\(", text) else "false"  # appends keep the invocation order
-    body = "namespace %s {\n%s\nstatic const int local_size[3] = {%d, %d, %d};\nstatic const bool serial = %s;\nstatic void bind(orc::PassCtx& c) {\n%s\n}\nstatic void unbind(orc::PassCtx& c) {\n%s\n}\n}  // namespace %s\n" % (
-        ns, text, local[0], local[1], local[2], serial, "\n".join(bind), "\n".join(unbind) if unbind else "    (void)c;", ns)
+    fibers = "true" if re.search(r"\bbarrier\s*\(", text) else "false"
+    text = "static const uvec3 gl_WorkGroupSize(%d, %d, %d);\n" % tuple(local) + text
+    body = "namespace %s {\n%s\nstatic const int local_size[3] = {%d, %d, %d};\nstatic const bool serial = %s, fibers = %s;\nstatic void bind(orc::PassCtx& c) {\n%s\n}\nstatic void unbind(orc::PassCtx& c) {\n%s\n}\n}  // namespace %s\n" % (
+        ns, text, local[0], local[1], local[2], serial, fibers, "\n".join(bind), "\n".join(unbind) if unbind else "    (void)c;", ns)
     return head + body
 
 

@@ -10,18 +10,23 @@ namespace refglsl {
 #include "shaders_generated.h"
 }  // namespace refglsl
 
+#include <map>
+#include <string>
 namespace {
 int g_runs = 0;  // executions that went through a reference main()
+std::map<std::string, int>& runsOf() { static std::map<std::string, int> m; return m; }
 }
 #define REF_SHADER(name, file)                                                                             \
     static void run_##name(orc::PassCtx& c) {                                                              \
         refglsl::ref_##name::bind(c);                                                                      \
-        refglsl::dispatch(c, refglsl::ref_##name::local_size, refglsl::ref_##name::serial, [] { refglsl::ref_##name::shader_main(); }); \
+        refglsl::dispatch(c, refglsl::ref_##name::local_size, refglsl::ref_##name::serial, refglsl::ref_##name::fibers, refglsl::ref_##name::shader_main); \
         refglsl::ref_##name::unbind(c);                                                                    \
         g_runs++;                                                                                          \
+        runsOf()[file]++;                                                                                  \
     }                                                                                                      \
     static orc::PassOverride override_##name(file, run_##name);
 #include "shaders_registered.h"
 
 extern "C" __attribute__((visibility("default"))) int oracle_refmain_runs() { return g_runs; }
+extern "C" __attribute__((visibility("default"))) int oracle_refmain_runs_of(const char* shader) { return runsOf()[shader]; }
 extern "C" __attribute__((visibility("default"))) const char* oracle_refmain_shaders() { return REF_SHADER_LIST; }
