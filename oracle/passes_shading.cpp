@@ -7,6 +7,7 @@
 #include <tuple>
 #include "backend.h"
 #include "shader_inc.h"
+#include "shading_hook.h"
 
 namespace orc {
 
@@ -123,6 +124,8 @@ static GBufferTexel decodeGBuffer(const View& gb, int x, int y) {
     return g;
 }
 
+ShadeGeometryHook g_shadeGeometryHook = {nullptr, nullptr};
+
 struct ShadingResources {
     View gbuffer, brdfLut, shadowMaps[4], ySH, coCg, volumetricLUT, skyLut, transmissionLut, noise;
     plain_light_buffer light;
@@ -219,6 +222,15 @@ static vec3 shadeGeometry(const ShadingResources& R, int x, int y, const GBuffer
     // passPos: world position reconstructed from depth (as sdfDiffuseTrace.comp:122-126)
     float depthLinear = linearizeDepth(gbt.depth, g.nearPlane, g.farPlane);
     vec3 passPos = cameraPosition + cameraToPixel / dot(cameraToPixel, cameraForward) * depthLinear;
+    if (g_shadeGeometryHook.shade) {  // liboracle_refmain.so: the rest of this function is the reference's own triangle.frag main()
+        FragmentInputs in;
+        in.x = x; in.y = y; in.passPos = passPos; in.N = gbt.N; in.albedoTexel = gbt.albedoTexel; in.specG = gbt.specG; in.specB = gbt.specB;
+        const View& gb = R.gbuffer;  // the quad's partners as modifiedRoughnessGeometricAA below defines them
+        const int x0 = x & ~1, y0 = y & ~1, x1 = (x0 + 1 < gb.w()) ? x0 + 1 : x0, y1 = (y0 + 1 < gb.h()) ? y0 + 1 : y0;
+        in.dxN[0] = decodeGBuffer(gb, x0, y).N; in.dxN[1] = decodeGBuffer(gb, x1, y).N;
+        in.dyN[0] = decodeGBuffer(gb, x, y0).N; in.dyN[1] = decodeGBuffer(gb, x, y1).N;
+        return g_shadeGeometryHook.shade(in);
+    }
 
     // triangle.frag:184-193
     float metalic = gbt.specB;
@@ -399,6 +411,7 @@ ORACLE_PASS(pass_gbufferShading, "gbufferShading.comp") {
     }
     const plain_global_shader_info& g = c.g;
     vec3 fwd = c.gv3(g.cameraForward), up = c.gv3(g.cameraUp), right = c.gv3(g.cameraRight);
+    if (g_shadeGeometryHook.beginPass) g_shadeGeometryHook.beginPass(c);
     c.forEachInvocation(8, 8, 1, [&](int x, int y, int) {
         if (x >= colorOut.w() || y >= colorOut.h()) return;
         GBufferTexel gbt = decodeGBuffer(R.gbuffer, x, y);

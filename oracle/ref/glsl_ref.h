@@ -27,7 +27,8 @@ inline ivec3::ivec3(const uvec2& v, int c) : x((int)v.x), y((int)v.y), z(c) {}
 inline uvec3 operator*(uvec3 a, uvec3 b) { return uvec3(a.x * b.x, a.y * b.y, a.z * b.z); }
 inline uvec3 operator*(uint a, uvec3 b) { return uvec3(a * b.x, a * b.y, a * b.z); }
 // vec3(uvec3), vec2(uvec2): GLSL constructors the converter leaves as written
-struct vec3 : gl::vec3 { using gl::vec3::vec3; vec3() {} vec3(gl::vec3 v) : gl::vec3(v) {} explicit vec3(uvec3 n) : gl::vec3((float)n.x, (float)n.y, (float)n.z) {} gl::vec2 yz() const { return gl::vec2(y, z); } };
+struct vec3 : gl::vec3 { using gl::vec3::vec3; vec3() {} vec3(gl::vec3 v) : gl::vec3(v) {} explicit vec3(uvec3 n) : gl::vec3((float)n.x, (float)n.y, (float)n.z) {} gl::vec2 yz() const { return gl::vec2(y, z); }
+    vec3(float a, gl::vec2 b) : gl::vec3(a, b.x, b.y) {} };
 struct vec2 : gl::vec2 { using gl::vec2::vec2; vec2() {} vec2(gl::vec2 v) : gl::vec2(v) {} vec2(uvec2 n) : gl::vec2((float)n.x, (float)n.y) {}  /* GLSL converts uvec2 -> vec2 implicitly (dither.inc:7) */
     explicit vec2(gl::ivec2 n) : gl::vec2((float)n.x, (float)n.y) {} };
 struct vec4 : gl::vec4 { using gl::vec4::vec4; vec4() {} vec4(gl::vec4 v) : gl::vec4(v) {} vec4(float a, gl::vec3 v) : gl::vec4(a, v.x, v.y, v.z) {} vec4(gl::vec2 a, gl::vec2 b) : gl::vec4(a.x, a.y, b.x, b.y) {}
@@ -61,6 +62,7 @@ inline float max(float a, int b) { return gl::max(a, (float)b); }
 inline float min(int a, float b) { return gl::min((float)a, b); }
 inline float min(float a, int b) { return gl::min(a, (float)b); }
 inline float clamp(float x, int lo, int hi) { return gl::clamp(x, (float)lo, (float)hi); }
+inline float clamp(float x, float lo, int hi) { return gl::clamp(x, lo, (float)hi); }
 inline gl::vec3 clamp(gl::vec3 x, int lo, int hi) { return gl::clamp(x, (float)lo, (float)hi); }
 inline gl::vec3 operator/(gl::vec3 a, ivec3 b) { return a / gl::vec3((float)b.x, (float)b.y, (float)b.z); }
 

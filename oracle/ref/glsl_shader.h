@@ -14,6 +14,17 @@ namespace refglsl {
 static thread_local uvec3 gl_GlobalInvocationID, gl_WorkGroupID, gl_LocalInvocationID, gl_NumWorkGroups;
 static thread_local uint gl_LocalInvocationIndex;
 
+// ---- fragment-shader inputs (triangle.frag through oracle/shading_hook.h): set per pixel by the hook ----
+static thread_local vec4 gl_FragCoord;
+static thread_local gl::vec3 g_dxN[2], g_dyN[2];                 // the quad's values of the one quantity the shader differentiates (the normal)
+inline gl::vec3 dFdxFine(gl::vec3) { return g_dxN[1] - g_dxN[0]; }  // right - left in the pixel's row
+inline gl::vec3 dFdyFine(gl::vec3) { return g_dyN[1] - g_dyN[0]; }  // bottom - top in its column
+struct textureCube {};                                            // declared by triangle.frag, not read by its main()
+// the three material fetches of triangle.frag:178-180 return what the G-buffer texel says they returned: the bindless table hands out these
+// slots for the (negative) material indices the hook sets, and texture(sampler, uv, bias) recognises them
+static View g_materialSlot[3];
+static thread_local vec4 g_materialTexel[3];
+
 // ---- storage images ----
 struct image2D { View v; image2D() {} explicit image2D(View view) : v(view) {} };
 struct image3D { View v; image3D() {} explicit image3D(View view) : v(view) {} };
@@ -29,6 +40,10 @@ inline vec4 textureLod(sampler2D s, gl::vec2 uv, float lod) {  // an explicit le
     View v = *s.t;
     v.mip += (int)lod;
     return orc::texture(v, *s.s, uv);
+}
+inline vec4 texture(sampler2D s, gl::vec2 uv, float /*bias*/) {  // views are single mip levels; material slots: see above
+    if (s.t >= g_materialSlot && s.t < g_materialSlot + 3) return g_materialTexel[s.t - g_materialSlot];
+    return orc::texture(*s.t, *s.s, uv);
 }
 inline vec4 textureGather(sampler2D s, gl::vec2 uv, int = 0) { return orc::textureGather(*s.t, *s.s, uv); }
 
@@ -144,7 +159,7 @@ inline void dispatch(const orc::PassCtx& c, const int local[3], bool serial, boo
 struct BindlessTextures {
     std::vector<View> views;
     void bind(const orc::PassCtx& c) { views.resize(c.ctx->images.size()); for (size_t i = 0; i < views.size(); i++) views[i] = c.bindless((uint32_t)i); }
-    const View* operator[](int i) const { return &views[(size_t)i]; }
+    const View* operator[](int i) const { return i < 0 ? &g_materialSlot[-i - 1] : &views[(size_t)i]; }
 };
 inline bool all(bvec2 v) { return v.x && v.y; }
 inline bool all(bvec3 v) { return v.x && v.y && v.z; }

@@ -33,7 +33,7 @@ SCALARS = {"float": "float", "int": "int", "uint": "uint", "bool": "bool"}
 VECS = {"vec2": ("float", 2), "vec3": ("float", 3), "vec4": ("float", 4), "ivec2": ("int", 2), "ivec3": ("int", 3), "ivec4": ("int", 4),
         "uvec2": ("uint", 2), "uvec3": ("uint", 3), "uvec4": ("uint", 4)}
 COMP = "xyzw"
-RESOURCE_TYPES = ("image2D", "image3D", "texture2D", "texture3D", "sampler")
+RESOURCE_TYPES = ("image2D", "image3D", "texture2D", "texture3D", "textureCube", "sampler")
 
 
 def round_up(x, a):
@@ -199,6 +199,8 @@ def convert_shader(shader_dir, shader):
             raise ValueError("resource arrays (bindless textures) are not supported: " + name)
         if typ == "sampler":
             return "static const sampler %s = &orc::s_%s;" % (name, name.replace("g_sampler_", ""))
+        if typ == "textureCube":
+            return "static textureCube %s;" % name
         decls.append((typ, name))
         if typ.startswith("image"):
             bind.append("    %s = %s(c.storage(%d));" % (name, typ, binding))
@@ -209,6 +211,8 @@ def convert_shader(shader_dir, shader):
         return "static %s %s;" % (typ, name)
     text = re.sub(r"layout\s*\(([^)]*)\)\s*uniform\s+(%s)\s+(\w+)\s*(\[\s*\w*\s*\])?\s*;" % "|".join(RESOURCE_TYPES), resource, text)
 
+    # fragment-shader varyings and outputs (triangle.frag): per-pixel variables the hook of oracle/shading_hook.h sets / reads
+    text = re.sub(r"layout\s*\(\s*location\s*=\s*\d+\s*\)\s*(?:in|out)\s+(\w+)\s+(\w+)\s*;", r"static thread_local \1 \2;", text)
     # specialisation constants
     def spec(m):
         cid, typ, name, val = int(m.group(1)), m.group(2), m.group(3), m.group(4).strip()
@@ -228,7 +232,7 @@ def convert_shader(shader_dir, shader):
         lay = Layout(structs, consts, std)
         if push:
             base, writable = "push", False
-            pre = "    const uint8_t* push = c.exec->pushConstants.data(); (void)push;"
+            pre = "    uint8_t push[256] = {0}; memcpy(push, c.exec->pushConstants.data(), c.exec->pushConstants.size() < 256 ? c.exec->pushConstants.size() : 256);"
         else:
             set_ = int(re.search(r"set\s*=\s*(\d+)", quals).group(1)) if re.search(r"set\s*=", quals) else 0
             binding = int(re.search(r"binding\s*=\s*(\d+)", quals).group(1))

@@ -6,8 +6,11 @@
 // and compares every image and buffer bit for bit - which pins the oracle's main() bodies, not only its include functions.
 #include "glsl_shader.h"
 
+#include "shading_hook.h"
+
 namespace refglsl {
 #include "shaders_generated.h"
+#include "shader_triangle.h"  // triangle.frag: not a pass of its own here, see the hook at the end of this file
 }  // namespace refglsl
 
 #include <map>
@@ -48,3 +51,38 @@ static bool lutCached(orc::PassCtx& c, const char* file, bool store) {
 extern "C" __attribute__((visibility("default"))) int oracle_refmain_runs() { return g_runs; }
 extern "C" __attribute__((visibility("default"))) int oracle_refmain_runs_of(const char* shader) { return runsOf()[shader]; }
 extern "C" __attribute__((visibility("default"))) const char* oracle_refmain_shaders() { return REF_SHADER_LIST; }
+
+// ---- triangle.frag: the reference's fragment shader behind the geometry branch of gbufferShading.comp (oracle/shading_hook.h) ----
+// The pass binds what triangle.frag binds, under the same numbers (RenderFrontend.cpp shading execution); the fragment's varyings come from the
+// G-buffer texel: passPos = the reconstructed world position, the normal map fetch returns NaN so that main() takes its own fallback
+// `N = passTBN[2]` (triangle.frag:195-197) with passTBN[2] = the G-buffer's normal, the albedo / specular fetches return the stored texels.
+namespace {
+int g_triangleRuns = 0;
+void beginTriangle(orc::PassCtx& c) {
+    using namespace refglsl::ref_triangle;
+    bind(c);
+    albedoTextureIndex = -1;
+    specularTextureIndex = -2;
+    normalTextureIndex = -3;
+    runsOf()["triangle.frag"]++;
+    g_triangleRuns++;
+    g_runs++;
+}
+gl::vec3 shadeTriangle(const orc::FragmentInputs& in) {
+    using namespace refglsl::ref_triangle;
+    const float nan = dm::u2f(0x7fc00000u);
+    refglsl::gl_FragCoord = refglsl::vec4((float)in.x + 0.5f, (float)in.y + 0.5f, 0.f, 1.f);
+    refglsl::g_materialTexel[0] = refglsl::vec4(in.albedoTexel.x, in.albedoTexel.y, in.albedoTexel.z, 1.f);
+    refglsl::g_materialTexel[1] = refglsl::vec4(0.f, in.specG, in.specB, 1.f);
+    refglsl::g_materialTexel[2] = refglsl::vec4(nan, nan, 0.f, 1.f);
+    for (int k = 0; k < 2; k++) { refglsl::g_dxN[k] = in.dxN[k]; refglsl::g_dyN[k] = in.dyN[k]; }
+    passUV = refglsl::vec2(0.f, 0.f);
+    passPos = in.passPos;
+    passTBN[0] = gl::vec3(0.f, 0.f, 0.f);
+    passTBN[1] = gl::vec3(0.f, 0.f, 0.f);
+    passTBN[2] = in.N;
+    shader_main();
+    return color;
+}
+struct InstallTriangle { InstallTriangle() { orc::g_shadeGeometryHook.beginPass = beginTriangle; orc::g_shadeGeometryHook.shade = shadeTriangle; } } g_installTriangle;
+}  // namespace

@@ -81,7 +81,27 @@ def test_frames_through_the_reference_shaders(ffi, oracle, refmain, w, h, frames
     assert refmain.refmain_runs() - before >= 10 * frames, "the frames did not go through the reference's main()s"
 
 
+@pytest.mark.parametrize("settings", [
+    dict(diffuse_brdf=0, direct_multiscatter=1, taa_history_sampling_tech=1, half_res_trace=0),
+    dict(diffuse_brdf=1, direct_multiscatter=2, use_geometry_aa=0, taa_history_sampling_tech=2, strict_influence_radius_cutoff=0),
+    dict(diffuse_brdf=3, direct_multiscatter=3, taa_history_sampling_tech=3, sun_shadow_cascade_count=4, strict_influence_radius_cutoff=1),
+    dict(indirect_lighting_tech=1, taa_filter_use_tonemapping=0, taa_history_sampling_tech=4, sun_direction_deg=(200.0, 80.0)),
+])
+def test_setting_variants_through_the_reference_shaders(ffi, oracle, refmain, settings):
+    """the specialisation-constant variants of the shaders: the four diffuse BRDFs and multiscatter lobes of triangle.frag (+ geometric AA off,
+    constant ambient), the bicubic history samplers of the TAA resolve, full-resolution trace, strict influence cut-off, 4 shadow cascades"""
+    a, b = Sequence(ffi, oracle, 88, 52, 9, **settings), Sequence(ffi, refmain, 88, 52, 9, **settings)
+    try:
+        for f in range(3):
+            inputs = a.step(moving=True)
+            b.step(moving=True, inputs=inputs)
+            assert_snapshots_equal(b.snapshot(), a.snapshot(), "frame %d with %s through the reference's shaders" % (f, settings))
+    finally:
+        a.close()
+        b.close()
+
+
 def test_zz_every_listed_shader_ran(refmain):
     """after the tests above: each listed shader was executed by the reference's main() at least once (none fell back to the oracle's restatement)"""
-    idle = [s for s in refmain.refmain_shaders if refmain.refmain_runs_of(s) == 0]
+    idle = [s for s in refmain.refmain_shaders + ["triangle.frag"] if refmain.refmain_runs_of(s) == 0]  # triangle.frag: behind gbufferShading.comp (oracle/shading_hook.h)
     assert not idle, "never executed through the reference's main(): %s" % idle
