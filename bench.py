@@ -443,7 +443,7 @@ def run_ours(args, rank, world, local_rank):
             line["passes_roofline"] = {"error": str(e)}
         if args.contract != "exact":
             # never the headline by default: the fast contract matches the oracle within a tolerance, not bit for bit
-            line["config"]["numeric_contract"] = "fast: SFU approximations + contraction in the floating-point passes (libplain_b200_fast.so)"
+            line["config"]["numeric_contract"] = "fast (EXPERIMENTAL, not the product's contract): SFU approximations + contraction in the floating-point passes (libplain_b200_fast.so)"
         if sharded:
             comm.check_peer_error()
             line["sharding"] = {"rows_of_rank0": list(band), "exchanges_per_frame": 8, "exchanges_on_the_critical_path": 5, "exchanges_deferred_behind_the_frame": 3, "bytes_sent_per_frame_rank0": bytes_first_frame[0],
