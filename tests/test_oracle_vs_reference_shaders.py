@@ -105,3 +105,35 @@ def test_zz_every_listed_shader_ran(refmain):
     """after the tests above: each listed shader was executed by the reference's main() at least once (none fell back to the oracle's restatement)"""
     idle = [s for s in refmain.refmain_shaders + ["triangle.frag"] if refmain.refmain_runs_of(s) == 0]  # triangle.frag: behind gbufferShading.comp (oracle/shading_hook.h)
     assert not idle, "never executed through the reference's main(): %s" % idle
+
+
+def test_block_layouts_of_the_converter_match_the_c_abi_structs(ffi):
+    """the std140 / std430 offsets oracle/ref/glsl_shader_to_cpp.py computes for the reference's interface blocks against the C structs of
+    include/plain_frame_types.h (the layouts the backend's buffers actually have): the global uniform block member by member, the sizes of
+    the others"""
+    import re
+    import sys
+    shaders = Path("/root/reference/resources/shaders")
+    if not shaders.exists():
+        pytest.skip("/root/reference not present")
+    sys.path.insert(0, str(ROOT / "oracle" / "ref"))
+    import glsl_shader_to_cpp as conv
+    text = conv.gather(shaders, "sdfDiffuseTrace.comp", set()) + conv.gather(shaders, "skyLut.comp", set()) + conv.gather(shaders, "froxelVolumeMaterial.comp", set())
+    structs = {m.group(1): conv.parse_members(m.group(2)) for m in re.finditer(r"\bstruct\s+(\w+)\s*\{(.*?)\}\s*;", text, flags=re.S)}
+    consts = dict(re.findall(r"^\s*const\s+(?:int|uint)\s+(\w+)\s*=\s*(\d+)\s*;", text, flags=re.M))
+    block = re.search(r"uniform\s+global\s*\{(.*?)\}\s*;", text, flags=re.S).group(1)
+    lay = conv.Layout(structs, consts, "std140")
+    off, got = 0, {}
+    for mt, mn, ml in conv.parse_members(block):
+        a, s, _ = lay.member_info(mt, ml)
+        off = conv.round_up(off, a)
+        got[mn] = off
+        off += s
+    G = ffi.GlobalShaderInfo
+    want = {"g_" + name: getattr(G, name).offset for name, _ in G._fields_}
+    assert got == want and off == C.sizeof(G) == 340
+    std430 = conv.Layout(structs, consts, "std430")
+    assert std430.type_info("ShadowCascadeInfo")[1] == C.sizeof(ffi.ShadowCascadeInfo) == 304
+    assert std430.type_info("LightBuffer")[1] in (20, 32)  # 20 bytes of members; the struct's own alignment rounds its array stride to 32
+    assert conv.Layout(structs, consts, "std140").type_info("VolumetricLightingSettings")[2][-1][2] == 48  # phaseFunctionG, the 13th float
+    assert std430.same_as_natural("BoundingBox") and std430.same_as_natural("CulledInstancesPerTile") and std430.same_as_natural("SDFInstance")
