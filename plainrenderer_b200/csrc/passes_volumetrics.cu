@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(128) volumetricLightingIntegrationKernel(ImgVi
 }
 
 // ---------------- the four passes as ONE launch (backend.cu planFusions hands the chain over as ExecRecord::fusedRun) ----------------
-// Block = 8 columns x 64 z lanes of one froxel row; the phases are in froxel_inc.cuh (froxelBlockPrologue / Phase1 / Phase2 / Phase3), one call
+// Block = 8 columns x ZLANES z lanes of one froxel row (16 by default: 128 threads); the phases are in froxel_inc.cuh (froxelBlockPrologue / Phase1 / Phase2 / Phase3), one call
 // per thread and phase with a barrier in between.
 // Algorithmic bytes per froxel: history read 8 + history write 8 + integrated write 8 = 24 (the four passes: 8 + 16 + 24 + 16 = 64); the material
 // and scattering volumes are not written (tests that compare them run unfused: plain_set_pass_fusion_enabled).
@@ -161,7 +161,7 @@ static void launchFroxelColumns(LaunchCtx& c) {
     c.window(p.historyTarget.h, y0, y1);
     if (y1 <= y0) return;
     p.yBegin = y0;
-    // z lanes per block, A / B switch: 64 / 32 / 16 (default). Measured at 3840x2160 (profiles/r4b_froxel_lanes.md): 0.430 / 0.357 / 0.338 ms - eight
+    // z lanes per block, A / B switch: 64 / 32 / 16 (default). Measured at 3840x2160 (profiles/r4_froxel_fusion.md): 0.430 / 0.357 / 0.338 ms - eight
     // 128-thread blocks per SM cover each other's barrier phases (prologue, running sums), two 512-thread blocks do not
     static const int zLanes = getenv("PLAIN_FROXEL_ZLANES") ? atoi(getenv("PLAIN_FROXEL_ZLANES")) : 16;
     const dim3 grid(ceilDiv(p.historyTarget.w, FROXEL_COLS), (unsigned)(y1 - y0));
