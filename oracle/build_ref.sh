@@ -41,7 +41,7 @@ if [ -d "$REF/resources/shaders" ] && [ -n "$REF_SHADERS" ]; then
        [ "$HERE/ref/glsl_ref.h" -nt "$OUT/liboracle_refmain.so" ] || [ "$HERE/ref/glsl_shader_to_cpp.py" -nt "$OUT/liboracle_refmain.so" ] || [ "$HERE/ref/glsl_to_cpp.py" -nt "$OUT/liboracle_refmain.so" ] || \
        [ "$HERE/ref/ref_shaders.txt" -nt "$OUT/liboracle_refmain.so" ] || [ "$NEWEST_OBJ" -nt "$OUT/liboracle_refmain.so" ]; then
         mkdir -p "$OUT/glsl"
-        python3 "$HERE/ref/glsl_shader_to_cpp.py" "$REF/resources/shaders" "$OUT/glsl" $REF_SHADERS triangle.frag  # triangle.frag: behind oracle/shading_hook.h
+        python3 "$HERE/ref/glsl_shader_to_cpp.py" "$REF/resources/shaders" "$OUT/glsl" $REF_SHADERS triangle.frag depthPrepass.frag  # the two fragment shaders: behind oracle/shading_hook.h
         : > "$OUT/glsl/shaders_generated.h"; : > "$OUT/glsl/shaders_registered.h"
         for s in $REF_SHADERS; do
             n="${s%.comp}"

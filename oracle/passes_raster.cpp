@@ -24,8 +24,11 @@
 #include <cmath>
 #include "backend.h"
 #include "shader_inc.h"
+#include "shading_hook.h"
 
 namespace orc {
+
+PrepassFragmentHook g_prepassFragmentHook = {nullptr, nullptr};
 
 struct D3 { double x, y, z; };
 static D3 crossd(D3 a, D3 b) { return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
@@ -212,6 +215,7 @@ ORACLE_PASS(pass_depthPrepass, "depthPrepass.vert+depthPrepass.frag") {
     const RasterTarget rt{W, H, !c.pass->clampDepth, c.pass->clampDepth != 0, c.pass->cullMode, vis.data()};
     rasterDraws(c, draws, rt, [&](const DrawInfo& d) { return c.gm4(transforms[pushU32(d, 3)].mvp); });
     const plain_global_shader_info& g = c.g;
+    if (g_prepassFragmentHook.beginPass) g_prepassFragmentHook.beginPass(c);
     parallelFor(c.ctx->threads, H, [&](int iy) {
         for (int ix = 0; ix < W; ix++) {
             const uint64_t key = vis[(size_t)iy * W + ix];
@@ -237,6 +241,17 @@ ORACLE_PASS(pass_depthPrepass, "depthPrepass.vert+depthPrepass.frag") {
                 const vec3 pos(lerp3(l, passPos[0].x, passPos[1].x, passPos[2].x), lerp3(l, passPos[0].y, passPos[1].y, passPos[2].y), lerp3(l, passPos[0].w, passPos[1].w, passPos[2].w));
                 const vec3 posPrev(lerp3(l, passPosPrevious[0].x, passPosPrevious[1].x, passPosPrevious[2].x), lerp3(l, passPosPrevious[0].y, passPosPrevious[1].y, passPosPrevious[2].y),
                                    lerp3(l, passPosPrevious[0].w, passPosPrevious[1].w, passPosPrevious[2].w));
+                if (g_prepassFragmentHook.shade) {  // liboracle_refmain.so: the fragment stage is the reference's own depthPrepass.frag main()
+                    vec2 mvRef;
+                    vec3 nRef;
+                    g_prepassFragmentHook.shade(vec4(pos.x, pos.y, 0.f, pos.z), vec4(posPrev.x, posPrev.y, 0.f, posPrev.z), lerp3(l, N[0], N[1], N[2]), mvRef, nRef);
+                    motion[0] = toSnorm16(mvRef.x); motion[1] = toSnorm16(mvRef.y);
+                    normal[0] = floatToUnorm8(nRef.x); normal[1] = floatToUnorm8(nRef.y); normal[2] = floatToUnorm8(nRef.z);
+                    memcpy(depthT.texelPtr(ix, iy, 0), &depth, 4);
+                    memcpy(motionT.texelPtr(ix, iy, 0), motion, 4);
+                    memcpy(normalT.texelPtr(ix, iy, 0), normal, 4);
+                    continue;
+                }
                 vec2 ndcCurrent = vec2(pos.x, pos.y) / pos.z;
                 vec2 ndcPrevious = vec2(posPrev.x, posPrev.y) / posPrev.z;
                 ndcCurrent += vec2(g.currentFrameCameraJitter[0], g.currentFrameCameraJitter[1]);

@@ -19,6 +19,7 @@ static thread_local vec4 gl_FragCoord;
 static thread_local gl::vec3 g_dxN[2], g_dyN[2];                 // the quad's values of the one quantity the shader differentiates (the normal)
 inline gl::vec3 dFdxFine(gl::vec3) { return g_dxN[1] - g_dxN[0]; }  // right - left in the pixel's row
 inline gl::vec3 dFdyFine(gl::vec3) { return g_dyN[1] - g_dyN[0]; }  // bottom - top in its column
+static thread_local bool g_discarded;                             // `discard;` (the converter spells it { g_discarded = true; return; })
 struct textureCube {};                                            // declared by triangle.frag, not read by its main()
 // the three material fetches of triangle.frag:178-180 return what the G-buffer texel says they returned: the bindless table hands out these
 // slots for the (negative) material indices the hook sets, and texture(sampler, uv, bias) recognises them

@@ -312,6 +312,7 @@ def convert_shader(shader_dir, shader):
     text = re.sub(r"\b(cullingTileSize)\.x\b", r"\1", text)  # GLSL lets a scalar be swizzled: s.x is s
     text = re.sub(r"\b(?:inout|out)\s+(\w+)\s*\[(\d+)\]\s+(\w+)", r"\1 (&\3)[\2]", text)   # `inout vec3[8] p` -> a reference to an array
     text = re.sub(r"\bvec3\s+(\w+)\s*\[3\]\s*\[3\]", r"vec3[3][3] \1", text)  # C-style array declarator -> the type spelling glsl_to_cpp.py maps to Nb33
+    text = re.sub(r"\bdiscard\s*;", "{ g_discarded = true; return; }", text)  # fragment shaders
     text = re.sub(r"\bvoid\s+main\s*\(\s*\)", "static void shader_main()", text)
     text = convert_spelling(text)
     macros = sorted(set(re.findall(r"^\s*#\s*define\s+(\w+)", text, flags=re.M)))

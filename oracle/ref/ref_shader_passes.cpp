@@ -11,6 +11,7 @@
 namespace refglsl {
 #include "shaders_generated.h"
 #include "shader_triangle.h"  // triangle.frag: not a pass of its own here, see the hook at the end of this file
+#include "shader_depthPrepass.h"  // depthPrepass.frag: likewise
 }  // namespace refglsl
 
 #include <map>
@@ -85,4 +86,34 @@ gl::vec3 shadeTriangle(const orc::FragmentInputs& in) {
     return color;
 }
 struct InstallTriangle { InstallTriangle() { orc::g_shadeGeometryHook.beginPass = beginTriangle; orc::g_shadeGeometryHook.shade = shadeTriangle; } } g_installTriangle;
+}  // namespace
+
+// ---- depthPrepass.frag: the fragment stage behind the resolve step of the oracle's depth prepass (oracle/shading_hook.h) ----
+// The fragment reached the resolve step, so its alpha test has passed: the albedo fetch returns alpha 1; the normal-map fetch is irrelevant
+// (depthPrepass.frag:48 overwrites the normal-mapped normal with the geometric one).
+namespace {
+void beginPrepass(orc::PassCtx& c) {
+    using namespace refglsl::ref_depthPrepass;
+    bind(c);
+    albedoTextureIndex = -1;
+    normalTextureIndex = -3;
+    runsOf()["depthPrepass.frag"]++;
+    g_runs++;
+}
+void shadePrepass(gl::vec4 pos, gl::vec4 posPrevious, gl::vec3 n, gl::vec2& motionOut, gl::vec3& normalOut) {
+    using namespace refglsl::ref_depthPrepass;
+    refglsl::g_materialTexel[0] = refglsl::vec4(0.f, 0.f, 0.f, 1.f);
+    refglsl::g_materialTexel[2] = refglsl::vec4(0.5f, 0.5f, 0.f, 1.f);
+    refglsl::g_discarded = false;
+    passUV = refglsl::vec2(0.f, 0.f);
+    passPos = pos;
+    passPosPrevious = posPrevious;
+    passTBN[0] = gl::vec3(1.f, 0.f, 0.f);
+    passTBN[1] = gl::vec3(0.f, 1.f, 0.f);
+    passTBN[2] = n;
+    shader_main();
+    motionOut = motion;
+    normalOut = normal;
+}
+struct InstallPrepass { InstallPrepass() { orc::g_prepassFragmentHook.beginPass = beginPrepass; orc::g_prepassFragmentHook.shade = shadePrepass; } } g_installPrepass;
 }  // namespace

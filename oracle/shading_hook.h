@@ -22,4 +22,12 @@ struct ShadeGeometryHook {
 };
 extern ShadeGeometryHook g_shadeGeometryHook;
 
+// depthPrepass.frag behind the resolve step of the oracle's depth prepass (passes_raster.cpp): the fragment that won the pixel, with the varyings
+// the rasteriser interpolated (clip-space position this frame / last frame, geometric normal = passTBN[2]) -> motion vector and encoded normal
+struct PrepassFragmentHook {
+    void (*beginPass)(PassCtx& c);
+    void (*shade)(vec4 passPos, vec4 passPosPrevious, vec3 passNormal, vec2& motion, vec3& normal);  // any thread
+};
+extern PrepassFragmentHook g_prepassFragmentHook;
+
 }  // namespace orc

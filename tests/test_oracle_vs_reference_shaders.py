@@ -101,9 +101,29 @@ def test_setting_variants_through_the_reference_shaders(ffi, oracle, refmain, se
         b.close()
 
 
+def test_frames_from_meshes_through_the_reference_shaders(ffi, oracle, refmain):
+    """frames rendered end to end from `.plain` meshes (raster_inputs = 1): the depth prepass resolves its fragments through the reference's
+    depthPrepass.frag main() (motion vectors, encoded normal) and every later pass through its own shader - moving camera, so the motion
+    vectors are not zero"""
+    from conftest import PlainSceneSequence
+    from plainrenderer_b200 import assets
+    a = PlainSceneSequence(ffi, oracle, assets.Assets(ROOT / "oracle" / "_build" / "liboracle.so", "oracle_asset_"), 112, 64)
+    b = PlainSceneSequence(ffi, refmain, assets.Assets(LIB, "oracle_asset_"), 112, 64)
+    try:
+        for f in range(3):
+            a.step(moving=True)
+            b.step(moving=True)
+            sa = a.snapshot()
+            assert_snapshots_equal(b.snapshot(), sa, "frame %d from meshes through the reference's shaders" % f)
+        assert sa["motion%d/0" % ((a.frame - 1) % 3)].any() or sa["motion0/0"].any() or sa["motion1/0"].any(), "the motion vectors of a moving camera are all zero"
+    finally:
+        a.close()
+        b.close()
+
+
 def test_zz_every_listed_shader_ran(refmain):
     """after the tests above: each listed shader was executed by the reference's main() at least once (none fell back to the oracle's restatement)"""
-    idle = [s for s in refmain.refmain_shaders + ["triangle.frag"] if refmain.refmain_runs_of(s) == 0]  # triangle.frag: behind gbufferShading.comp (oracle/shading_hook.h)
+    idle = [s for s in refmain.refmain_shaders + ["triangle.frag", "depthPrepass.frag"] if refmain.refmain_runs_of(s) == 0]  # the fragment shaders: behind oracle/shading_hook.h
     assert not idle, "never executed through the reference's main(): %s" % idle
 
 
