@@ -21,6 +21,17 @@ Rewrites beyond glsl_to_cpp.py (each mechanical):
   * block members are filled leaf by leaf at their std140 / std430 offsets (computed here), never by copying a C++ struct
   * `void main()` -> `static void shader_main()`; `X.xy = E;` / `X.xyz = E;` / `X.rgb = E;` (swizzle stores) -> `assign_xy(X, E);` ...;
     `X.xy op= E;` likewise; `T name[N] = { .. };` initialiser lists stay (C++ aggregate initialisation)
+  * include guards (#ifndef G / #define G / #endif) go - files are spliced once; every other preprocessor line stays (skyMultiscatterLut.comp
+    switches code with #define / #ifdef) and the macros are #undef'd at the end of the generated header
+  * arrays sized by a specialisation constant or unsized (`uint histogram[constNBins]`, `BoundingBox instanceBBs[]`) are pointers into the bound
+    buffer (struct elements only when their std430 layout equals the C++ struct's, checked here)
+  * `layout(set = 2, ..) uniform texture2D[] textures;` -> one table of views over the backend's images (glsl_shader.h BindlessTextures)
+  * `shared T x[..];` -> `static thread_local` (a workgroup runs on one OS thread); `barrier()` yields to the workgroup's fiber scheduler
+  * GLSL scoping: a local is not in scope in its own initialiser, C++'s is - `float depth = texture(sampler2D(depth, s), uv).r;` and
+    `float phase = phase(x);` get the texture / the local renamed (suffix _tex / _v)
+  * `inout vec3[8] p` -> `vec3 (&p)[8]`; `vec3 n[3][3]` parameters -> the Nb33 type of glsl_to_cpp.py; `cullingTileSize.x` (a swizzled scalar) -> the scalar
+  * fragment shaders (triangle.frag, depthPrepass.frag, run behind oracle/shading_hook.h): `layout(location = N) in / out T x;` -> `static thread_local T x;`,
+    `discard;` -> `{ g_discarded = true; return; }`, textureCube resources are declared and left unbound
 """
 import re
 import sys
